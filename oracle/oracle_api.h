@@ -1,0 +1,86 @@
+// TEST INFRASTRUCTURE — not product code.
+//
+// One C ABI, exported by BOTH CPU checkers so the tests can run them side by side:
+//   oracle/_ref/libviltrum_ref.so  vo_kind() == "reference"  (unmodified reference headers, ref_harness_*.cpp)
+//   oracle/liboracle.so            vo_kind() == "port"       (plain restatement, oracle.cpp)
+// All bins / per-bin records are flat arrays in viltrum::tensor layout (dim-0-fastest,
+// reference src/tensor.h:17-23).  Every function returns 0 on success, <0 on error
+// (-1 unknown integrand, -2 unsupported dimension/rule combination, -3 buffer too small).
+// Optional output pointers may be NULL.
+#pragma once
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* vo_kind(void);
+// dimension of a named integrand; -1 for infinite-dimensional ones, 0 if unknown
+int vo_integrand_dim(const char* integrand);
+
+// reference monte_carlo_per_bin_parallel(spp,seed) — src/monte-carlo/monte-carlo-per-bin-parallel.h:41-71
+// bins: in/out, accumulated with '+='.  rec_samples [nbins*spp*dim], rec_sum/rec_sum2 [nbins] = sum f, sum f^2.
+int vo_mc_per_bin_parallel(const char* integrand, int dimbins, const uint64_t* res,
+                           const float* rmin, const float* rmax, uint64_t spp, uint64_t seed,
+                           float* bins, float* rec_samples, double* rec_sum, double* rec_sum2);
+
+// reference integrator_per_bin_parallel(monte_carlo(spp,seed)) — src/integrator-per-bin-parallel.h:16-35,
+// src/monte-carlo/monte-carlo.h:39-63.  bins overwritten ('=').
+int vo_per_bin_parallel_mc(const char* integrand, int dimbins, const uint64_t* res,
+                           const float* rmin, const float* rmax, uint64_t spp, uint64_t seed,
+                           float* bins, float* rec_samples, double* rec_sum, double* rec_sum2);
+
+// reference monte_carlo(samples,seed) global scatter — src/monte-carlo/monte-carlo.h:39-63.  '+='.
+int vo_monte_carlo(const char* integrand, int dimbins, const uint64_t* res,
+                   const float* rmin, const float* rmax, uint64_t samples, uint64_t seed,
+                   float* bins, float* rec_samples);
+
+// reference monte_carlo_per_bin_parallel(spp,seed) over RangeInfinite —
+// src/monte-carlo/monte-carlo-per-bin-parallel.h:73-100, src/monte-carlo/random-sequence-ref-dis.h:11-44.
+// rmin/rmax have nrange entries (implicit [0,1] tail).  rec_len [nbins*spp] = sequence elements the
+// integrand consumed for that path; rec_elems (capacity rec_cap floats) = those elements back to back in
+// bin-major (tensor order), sample-minor order; *rec_used = floats needed.
+int vo_mc_per_bin_parallel_inf(const char* integrand, int dimbins, const uint64_t* res,
+                               const float* rmin, const float* rmax, int nrange,
+                               uint64_t spp, uint64_t seed, float* bins,
+                               double* rec_sum, double* rec_sum2,
+                               uint32_t* rec_len, float* rec_elems, uint64_t rec_cap, uint64_t* rec_used);
+
+// reference integrator_newton_cotes(rule) — src/newton-cotes/newton-cotes.h:11-14. rule in
+// {"trapezoidal","simpson","boole"}.  '+='.
+int vo_newton_cotes(const char* integrand, const char* rule, int dimbins, const uint64_t* res,
+                    const float* rmin, const float* rmax, float* bins);
+
+// reference integrator_adaptive_iterations(nested(H,L), heuristic, iterations) —
+// src/nested/integrator-adaptive-iterations.h:12-15, src/nested/regions-generator-adaptive-heap.h:18-45,
+// src/newton-cotes/regions-integrator-sequential.h:38-58.
+//   rule      in {"simpson_trapezoidal","boole_simpson"}
+//   heuristic in {"default_absolute","default_relative","size_absolute","size_relative"}
+//   size_weight only used by size_* (reference default 1e-5)
+// Region list (iterations+1 regions, in the reference's heap-array order):
+//   reg_min/reg_max [n*dim], reg_err [n], reg_dim [n], reg_data [n*S^dim] (dim-0-fastest samples).
+int vo_adaptive_iterations(const char* integrand, const char* rule, const char* heuristic, double size_weight,
+                           uint64_t iterations, int dimbins, const uint64_t* res,
+                           const float* rmin, const float* rmax, float* bins,
+                           float* reg_min, float* reg_max, float* reg_err, uint32_t* reg_dim, float* reg_data);
+
+// reference integrator_crespo2021(iterations,spp,seed) — src/control-variates/integrator-crespo2021.h:7-22,
+// src/control-variates/regions-integrator-parallel-variance-reduction.h:32-109.  bins overwritten ('=').
+// Records (per bin, tensor order): rec_nregions [nbins]; rec_approx [nbins] (control-variate integral);
+// rec_chosen [nbins*spp] index into the region list; rec_samples [nbins*spp*dim].
+// Region list outputs as in vo_adaptive_iterations (rule = simpson_trapezoidal, S=3).
+int vo_crespo2021(const char* integrand, uint64_t iterations, uint64_t spp, uint64_t seed,
+                  int dimbins, const uint64_t* res, const float* rmin, const float* rmax, float* bins,
+                  uint32_t* rec_nregions, float* rec_approx, uint32_t* rec_chosen, float* rec_samples,
+                  float* reg_min, float* reg_max, float* reg_err, uint32_t* reg_dim, float* reg_data);
+
+// Multi-threaded CPU baseline used by bench.py (--impl reference / cpu_baseline): slabs the bin grid along the
+// LAST bin dimension over nthreads std::threads, each calling the single-threaded entry point above on its
+// slab with seed+slab.  path in {"mc_per_bin_parallel","per_bin_parallel_mc",
+// "mc_per_bin_parallel_inf"}.
+int vo_mt_per_bin(const char* path, const char* integrand, int dimbins, const uint64_t* res,
+                  const float* rmin, const float* rmax, int nrange, uint64_t spp, uint64_t seed,
+                  int nthreads, float* bins);
+
+#ifdef __cplusplus
+}
+#endif

@@ -1,0 +1,61 @@
+// TEST INFRASTRUCTURE — not product code.
+// Newton-Cotes and adaptive (greedy heap) entry points of oracle/_ref/libviltrum_ref.so.
+#include "ref_regions.h"
+
+using namespace vref;
+
+extern "C" int vo_newton_cotes(const char* integrand, const char* rule, int dimbins, const uint64_t* res,
+                    const float* rmin, const float* rmax, float* bins) {
+    return dispatch_finite_bins(integrand, dimbins, [&] (auto f, auto dbc) -> int {
+        using F = decltype(f);
+        constexpr std::size_t D = F::dim;
+        constexpr std::size_t DB = decltype(dbc)::value;
+        auto r = res_array<DB>(res);
+        auto range = range_array<D>(rmin, rmax);
+        auto acc = [&] (const std::array<std::size_t,DB>& p) -> float& { return bins[tensor_pos(p,r)]; };
+        if (!std::strcmp(rule,"trapezoidal")) viltrum::integrate(viltrum::integrator_newton_cotes(viltrum::trapezoidal), acc, r, f, range);
+        else if (!std::strcmp(rule,"simpson")) viltrum::integrate(viltrum::integrator_newton_cotes(viltrum::simpson), acc, r, f, range);
+        else if (!std::strcmp(rule,"boole"))   viltrum::integrate(viltrum::integrator_newton_cotes(viltrum::boole), acc, r, f, range);
+        else return -2;
+        return 0;
+    });
+}
+
+namespace {
+template<typename F, std::size_t DB, typename Rule, typename EH>
+int run_adaptive(const F& f, const Rule& rule, const EH& eh, uint64_t iterations, const uint64_t* res,
+                 const float* rmin, const float* rmax, float* bins, RegionSink& sink) {
+    constexpr std::size_t D = F::dim;
+    auto r = res_array<DB>(res);
+    auto range = range_array<D>(rmin, rmax);
+    auto acc = [&] (const std::array<std::size_t,DB>& p) -> float& { return bins[tensor_pos(p,r)]; };
+    DumpLogger logger(&sink);
+    viltrum::integrate(viltrum::integrator_adaptive_iterations(rule, eh, std::size_t(iterations)), acc, r, f, range, logger);
+    return 0;
+}
+}
+
+extern "C" int vo_adaptive_iterations(const char* integrand, const char* rule, const char* heuristic, double size_weight,
+                           uint64_t iterations, int dimbins, const uint64_t* res,
+                           const float* rmin, const float* rmax, float* bins,
+                           float* reg_min, float* reg_max, float* reg_err, uint32_t* reg_dim, float* reg_data) {
+    RegionSink sink; sink.reg_min=reg_min; sink.reg_max=reg_max; sink.reg_err=reg_err; sink.reg_dim=reg_dim; sink.reg_data=reg_data;
+    return dispatch_finite_bins(integrand, dimbins, [&] (auto f, auto dbc) -> int {
+        constexpr std::size_t DB = decltype(dbc)::value;
+        using namespace viltrum;
+        auto with_rule = [&] (auto rule) -> int {
+            if (!std::strcmp(heuristic,"default_absolute"))
+                return run_adaptive<decltype(f),DB>(f, rule, error_heuristic_default(error_metric_absolute()), iterations,res,rmin,rmax,bins,sink);
+            if (!std::strcmp(heuristic,"default_relative"))
+                return run_adaptive<decltype(f),DB>(f, rule, error_heuristic_default(error_metric_relative()), iterations,res,rmin,rmax,bins,sink);
+            if (!std::strcmp(heuristic,"size_absolute"))
+                return run_adaptive<decltype(f),DB>(f, rule, error_heuristic_size(error_metric_absolute(),size_weight), iterations,res,rmin,rmax,bins,sink);
+            if (!std::strcmp(heuristic,"size_relative"))
+                return run_adaptive<decltype(f),DB>(f, rule, error_heuristic_size(error_metric_relative(),size_weight), iterations,res,rmin,rmax,bins,sink);
+            return -2;
+        };
+        if (!std::strcmp(rule,"simpson_trapezoidal")) return with_rule(nested(simpson,trapezoidal));
+        if (!std::strcmp(rule,"boole_simpson"))       return with_rule(nested(boole,simpson));
+        return -2;
+    });
+}
