@@ -1,0 +1,737 @@
+// TEST INFRASTRUCTURE — not product code.  Builds into oracle/liboracle.so (vo_kind() == "port").
+//
+// Plain CPU restatement of the reference's per-bin integration hot path, written as
+// straight loops over flat arrays with run-time dimensions: no templates over rules/regions, no lazy
+// expression views.  Every function cites the reference file:line it restates.  It exists to be the
+// checker the CUDA path is compared against on machines where /root/reference is absent (the GPU box);
+// it is itself pinned bit-for-bit against oracle/_ref/libviltrum_ref.so (the unmodified reference) by
+// tests/test_oracle_vs_reference.py and against tests/golden/*.json (vectors generated from the reference).
+//
+// Third-party arithmetic the reference takes from the C++ standard library (libstdc++ 13, GCC 13.3 — the
+// reference pins no version) is restated here explicitly so the oracle does not depend on which standard
+// library it is built with:
+//   * std::mt19937                     — [rand.eng.mers] MT19937, Matsumoto & Nishimura 1998
+//   * std::uniform_real_distribution   — libstdc++ bits/random.h operator(): canonical*(b-a)+a,
+//     std::generate_canonical<float,24>  bits/random.tcc:3349-3381: float(u32)/2^32, clamped to nextafter(1,0)
+//   * std::uniform_int_distribution    — libstdc++ bits/uniform_int_dist.h:240-330 (Lemire nearly-divisionless)
+//   * std::push_heap / std::pop_heap   — libstdc++ bits/stl_heap.h:135-267
+//
+// Numerics: built with -ffp-contract=off; float/double promotions mirror the reference expression by
+// expression — that is what makes the bit-exact parity modes possible.
+#include <cstdint>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include <array>
+#include <thread>
+#include <algorithm>
+#include <functional>
+#include "integrands.h"
+#include "oracle_api.h"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------
+// RNG restatement
+// ---------------------------------------------------------------------------------------------------------
+struct MT19937 {
+    uint32_t x[624]; int p;
+    explicit MT19937(uint64_t sd = 5489u) { seed(sd); }
+    void seed(uint64_t sd) {                       // seed taken mod 2^32 (bits/random.tcc mersenne_twister_engine::seed)
+        x[0] = uint32_t(sd);
+        for (int i=1;i<624;++i) x[i] = 1812433253u*(x[i-1]^(x[i-1]>>30)) + uint32_t(i);
+        p = 624;
+    }
+    uint32_t operator()() {
+        if (p >= 624) {
+            for (int k=0;k<624;++k) {
+                uint32_t y = (x[k]&0x80000000u) | (x[(k+1)%624]&0x7fffffffu);
+                x[k] = x[(k+397)%624] ^ (y>>1) ^ ((y&1u)?0x9908b0dfu:0u);
+            }
+            p = 0;
+        }
+        uint32_t z = x[p++];
+        z ^= (z>>11); z ^= (z<<7)&0x9d2c5680u; z ^= (z<<15)&0xefc60000u; z ^= (z>>18);
+        return z;
+    }
+};
+
+inline float canonical(MT19937& g) {              // generate_canonical<float,24>, one 32-bit draw
+    float r = float(g()) / 4294967296.0f;
+    if (r >= 1.0f) r = std::nextafter(1.0f, 0.0f);
+    return r;
+}
+inline float uniform_real(MT19937& g, float a, float b) { return canonical(g)*(b-a)+a; }
+
+inline uint64_t uniform_int(MT19937& g, uint64_t a, uint64_t b) {  // uniform_int_distribution<size_t>(a,b), 32-bit urng
+    uint64_t urange = b-a;
+    // (the reference only ever asks for ranges far below 2^32: number of regions in a bin)
+    uint32_t range = uint32_t(urange+1);
+    uint64_t product = uint64_t(g())*uint64_t(range);
+    uint32_t low = uint32_t(product);
+    if (low < range) {
+        uint32_t threshold = uint32_t(-range) % range;
+        while (low < threshold) { product = uint64_t(g())*uint64_t(range); low = uint32_t(product); }
+    }
+    return (product>>32) + a;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// integrands by name (finite ones evaluate a float[dim] point)
+// ---------------------------------------------------------------------------------------------------------
+typedef float (*FiniteFn)(const float*);
+template<typename F> float call_finite(const float* x) {
+    std::array<float,F::dim> a; for (int i=0;i<F::dim;++i) a[i]=x[i];
+    return F()(a);
+}
+struct FiniteIntegrand { const char* name; int dim; FiniteFn fn; };
+const FiniteIntegrand FINITE[] = {
+    {"x2y2",2,call_finite<vo::X2Y2>}, {"ind2",2,call_finite<vo::Ind2>}, {"cubic1",1,call_finite<vo::Cubic1>},
+    {"poly3",3,call_finite<vo::Poly3>}, {"shade4_64",4,call_finite<vo::Shade4<64>>}, {"shade4_16",4,call_finite<vo::Shade4<16>>},
+    {"shade5_64",5,call_finite<vo::Shade5<64>>}, {"shade5_16",5,call_finite<vo::Shade5<16>>}, {"smooth_edge2",2,call_finite<vo::SmoothEdge2>},
+};
+const FiniteIntegrand* find_finite(const char* n) { for (auto& f : FINITE) if (!std::strcmp(f.name,n)) return &f; return nullptr; }
+
+// lazy sequence protocol of reference random-sequence-ref-dis.h:20-38, over a generator callback
+struct LazySeq {
+    std::function<float()> next;
+    struct It { const LazySeq* s; float n; const float& operator*() const { return n; } It& operator++() { n = s->next(); return *this; } };
+    It begin() const { return It{this, next()}; }
+};
+typedef float (*InfFn)(const LazySeq&);
+template<typename F> float call_inf(const LazySeq& s) { return F()(s); }
+struct InfIntegrand { const char* name; InfFn fn; };
+const InfIntegrand INFINITE[] = { {"walk",call_inf<vo::Walk>}, {"decay",call_inf<vo::Decay>} };
+const InfIntegrand* find_inf(const char* n) { for (auto& f : INFINITE) if (!std::strcmp(f.name,n)) return &f; return nullptr; }
+
+// ---------------------------------------------------------------------------------------------------------
+// bins: tensor layout, multidimensional_range iteration (dim 0 fastest)   reference tensor.h:17-23,
+// multidimensional-range.h:33-40
+// ---------------------------------------------------------------------------------------------------------
+inline uint64_t nbins_of(int db, const uint64_t* res) { uint64_t n=1; for (int i=0;i<db;++i) n*=res[i]; return n; }
+inline void unflatten(uint64_t lin, int db, const uint64_t* res, uint64_t* pos) { for (int i=0;i<db;++i) { pos[i]=lin%res[i]; lin/=res[i]; } }
+
+// Range<float,D>::volume  (range.h:21-25): product in float, starting from 1
+inline float volume_of(int d, const float* a, const float* b) { float v=1.0f; for (int i=0;i<d;++i) v*=(b[i]-a[i]); return v; }
+
+// bin sub-box of the first `db` dims (monte-carlo-per-bin-parallel.h:45-47,59-61; same expression in every
+// per-bin integrator): drange = (max-min)/float(res); [min+float(pos)*drange, min+float(pos+1)*drange]
+inline void bin_box(int d, int db, const float* rmin, const float* rmax, const uint64_t* res, const uint64_t* pos, float* a, float* b) {
+    for (int i=0;i<d;++i) { a[i]=rmin[i]; b[i]=rmax[i]; }
+    for (int i=0;i<db;++i) {
+        float drange = (rmax[i]-rmin[i])/float(res[i]);
+        a[i] = rmin[i] + float(pos[i])*drange;
+        b[i] = rmin[i] + float(pos[i]+1)*drange;
+    }
+}
+
+} // namespace
+
+extern "C" const char* vo_kind(void) { return "port"; }
+extern "C" int vo_integrand_dim(const char* name) {
+    if (auto f = find_finite(name)) return f->dim;
+    if (find_inf(name)) return -1;
+    return 0;
+}
+
+// =========================================================================================================
+// Monte Carlo
+// =========================================================================================================
+
+// monte-carlo-per-bin-parallel.h:41-71
+extern "C" int vo_mc_per_bin_parallel(const char* integrand, int dimbins, const uint64_t* res,
+                           const float* rmin, const float* rmax, uint64_t spp, uint64_t seed,
+                           float* bins, float* rec_samples, double* rec_sum, double* rec_sum2) {
+    auto F = find_finite(integrand); if (!F) return -1;
+    int D = F->dim; if (dimbins<1 || dimbins>D) return -2;
+    uint64_t nb = nbins_of(dimbins,res);
+    double factor = volume_of(D,rmin,rmax)/double(spp);                       // :45
+    MT19937 master(seed);
+    std::vector<uint32_t> perbin_seed(nb);
+    for (uint64_t k=0;k<nb;++k) perbin_seed[k] = uint32_t(master());          // :50-54 (sequential, dim-0-fastest)
+    for (uint64_t k=0;k<nb;++k) {                                             // :56-70 (bins are independent)
+        uint64_t pos[8]; unflatten(k,dimbins,res,pos);
+        MT19937 local(perbin_seed[k]);
+        float a[8], b[8]; bin_box(D,dimbins,rmin,rmax,res,pos,a,b);
+        double s1=0, s2=0;
+        for (uint64_t s=0;s<spp;++s) {
+            float x[8];
+            for (int i=0;i<D;++i) x[i] = uniform_real(local,a[i],b[i]);       // :64-67
+            float v = F->fn(x);
+            bins[k] = float(double(bins[k]) + double(v)*factor);              // :68  float += float*double
+            if (rec_samples) for (int i=0;i<D;++i) rec_samples[(k*spp+s)*D+i]=x[i];
+            s1 += double(v); s2 += double(v)*double(v);
+        }
+        if (rec_sum) rec_sum[k]=s1;
+        if (rec_sum2) rec_sum2[k]=s2;
+    }
+    return 0;
+}
+
+// integrator-per-bin-parallel.h:16-35 wrapping monte-carlo.h:39-63 through integrate.h:105-113
+extern "C" int vo_per_bin_parallel_mc(const char* integrand, int dimbins, const uint64_t* res,
+                           const float* rmin, const float* rmax, uint64_t spp, uint64_t seed,
+                           float* bins, float* rec_samples, double* rec_sum, double* rec_sum2) {
+    auto F = find_finite(integrand); if (!F) return -1;
+    int D = F->dim; if (dimbins<1 || dimbins>D) return -2;
+    uint64_t nb = nbins_of(dimbins,res);
+    // monte_carlo(spp,seed) holds mt19937(seed); wrapping it copies it once (copy ctor reseeds from the source
+    // stream, monte-carlo.h:32-33; integrator-per-bin-parallel.h:37-38), then one more reseeding copy per bin
+    // into tensor<Integrator> in tensor order (integrator-per-bin-parallel.h:24).
+    MT19937 user(seed);
+    MT19937 master{uint64_t(user())};
+    std::vector<uint32_t> perbin_seed(nb);
+    for (uint64_t k=0;k<nb;++k) perbin_seed[k] = master();
+    for (uint64_t k=0;k<nb;++k) {
+        uint64_t pos[8]; unflatten(k,dimbins,res,pos);
+        MT19937 local(perbin_seed[k]);
+        float a[8], b[8]; bin_box(D,dimbins,rmin,rmax,res,pos,a,b);
+        double factor = 1.0*volume_of(D,a,b)/double(spp);                     // monte-carlo.h:43-45 with one bin
+        float sol = 0.0f;                                                     // integrate.h:108
+        double s1=0, s2=0;
+        for (uint64_t s=0;s<spp;++s) {
+            float x[8];
+            for (int i=0;i<D;++i) x[i] = uniform_real(local,a[i],b[i]);       // monte-carlo.h:50-53
+            // is_inside (monte-carlo.h:54) is always true for points drawn inside [a,b]
+            float v = F->fn(x);
+            sol = float(double(sol) + double(v)*factor);                      // monte-carlo.h:59
+            if (rec_samples) for (int i=0;i<D;++i) rec_samples[(k*spp+s)*D+i]=x[i];
+            s1 += double(v); s2 += double(v)*double(v);
+        }
+        bins[k] = float(double(nb)*double(sol));                              // integrator-per-bin-parallel.h:33 ('=')
+        if (rec_sum) rec_sum[k]=s1;
+        if (rec_sum2) rec_sum2[k]=s2;
+    }
+    return 0;
+}
+
+// monte-carlo.h:39-63
+extern "C" int vo_monte_carlo(const char* integrand, int dimbins, const uint64_t* res,
+                   const float* rmin, const float* rmax, uint64_t samples, uint64_t seed,
+                   float* bins, float* rec_samples) {
+    auto F = find_finite(integrand); if (!F) return -1;
+    int D = F->dim; if (dimbins<1 || dimbins>D) return -2;
+    double resolution_factor = 1; for (int i=0;i<dimbins;++i) resolution_factor *= double(res[i]);
+    double factor = resolution_factor*double(volume_of(D,rmin,rmax))/double(samples);   // :45
+    MT19937 rng(seed);
+    for (uint64_t s=0;s<samples;++s) {
+        float x[8];
+        for (int i=0;i<D;++i) x[i] = uniform_real(rng,rmin[i],rmax[i]);       // :50-53
+        if (rec_samples) for (int i=0;i<D;++i) rec_samples[s*D+i]=x[i];
+        uint64_t lin=0, prod=1; bool ok=true;
+        for (int i=0;i<dimbins;++i) {
+            uint64_t p = uint64_t(float(res[i])*(x[i]-rmin[i])/(rmax[i]-rmin[i]));   // :57
+            if (p>=res[i]) ok=false;   // the reference would write out of bounds here (x rounded up to max); never hit in tests
+            lin += p*prod; prod *= res[i];
+        }
+        float v = F->fn(x);
+        if (ok) bins[lin] = float(double(bins[lin]) + double(v)*factor);      // :59
+    }
+    return 0;
+}
+
+// monte-carlo-per-bin-parallel.h:73-100 + random-sequence-ref-dis.h:11-44 + range-infinite.h:16-64
+extern "C" int vo_mc_per_bin_parallel_inf(const char* integrand, int dimbins, const uint64_t* res,
+                               const float* rmin, const float* rmax, int nrange,
+                               uint64_t spp, uint64_t seed, float* bins,
+                               double* rec_sum, double* rec_sum2,
+                               uint32_t* rec_len, float* rec_elems, uint64_t rec_cap, uint64_t* rec_used) {
+    auto F = find_inf(integrand); if (!F) return -1;
+    if (dimbins<1 || dimbins>8) return -2;
+    auto rmin_at = [&] (int i) { return i<nrange ? rmin[i] : 0.0f; };       // range-infinite.h:31-37
+    auto rmax_at = [&] (int i) { return i<nrange ? rmax[i] : 1.0f; };
+    float vol = 1.0f; for (int i=0;i<nrange;++i) vol *= (rmax_at(i)-rmin_at(i));        // range-infinite.h:22-23
+    double factor = vol/double(spp);                                          // :77
+    uint64_t nb = nbins_of(dimbins,res);
+    MT19937 master(seed);
+    std::vector<uint32_t> perbin_seed(nb);
+    for (uint64_t k=0;k<nb;++k) perbin_seed[k] = uint32_t(master());          // :83-87
+    uint64_t used = 0; int rc = 0;
+    for (uint64_t k=0;k<nb;++k) {
+        uint64_t pos[8]; unflatten(k,dimbins,res,pos);
+        MT19937 local(perbin_seed[k]);
+        int nsub = std::max(nrange,dimbins);
+        std::vector<float> a(nsub), b(nsub);
+        for (int i=0;i<nsub;++i) { a[i]=rmin_at(i); b[i]=rmax_at(i); }
+        for (int i=0;i<dimbins;++i) {                                          // :79,93-94
+            float drange = (rmax_at(i)-rmin_at(i))/float(res[i]);
+            a[i] = rmin_at(i)+float(pos[i])*drange; b[i] = rmin_at(i)+float(pos[i]+1)*drange;
+        }
+        double s1=0, s2=0;
+        for (uint64_t s=0;s<spp;++s) {
+            uint32_t count = 0; int idx = 0;
+            LazySeq seq;
+            seq.next = [&] () -> float {                                      // random-sequence-ref-dis.h:28,32
+                int i = idx++;
+                float lo = i<nsub ? a[i] : 0.0f, hi = i<nsub ? b[i] : 1.0f;
+                float n = uniform_real(local,0.0f,1.0f)*(hi-lo)+lo;
+                ++count;
+                if (rec_elems) { if (used < rec_cap) rec_elems[used] = n; else rc = -3; }
+                ++used;
+                return n;
+            };
+            float v = F->fn(seq);
+            bins[k] = float(double(bins[k]) + double(v)*factor);              // :96
+            if (rec_len) rec_len[k*spp+s] = count;
+            s1 += double(v); s2 += double(v)*double(v);
+        }
+        if (rec_sum) rec_sum[k]=s1;
+        if (rec_sum2) rec_sum2[k]=s2;
+    }
+    if (rec_used) *rec_used = used;
+    return rc;
+}
+
+// =========================================================================================================
+// Newton-Cotes rules (rules.h), nested pairs (nested.h), error metrics / heuristics (error-*.h)
+// =========================================================================================================
+namespace {
+
+enum Rule { TRAPEZOIDAL=2, SIMPSON=3, BOOLE=5 };   // value == samples per dimension
+
+// rules.h:14 / :64 / :256 — literals are double, result rounded to float at return
+inline float rule_apply(int S, const float* p) {
+    switch (S) {
+        case 2: return float((p[0]+p[1])/2.0);                                               // float add, double divide
+        case 3: return float((double(p[0])+4.0*double(p[1])+double(p[2]))/6.0);
+        default: return float((7.0*double(p[0])+32.0*double(p[1])+12.0*double(p[2])+32.0*double(p[3])+7.0*double(p[4]))/90.0);
+    }
+}
+// rules.h:27-32 / :77-83 / :272-280 — integer literals: float arithmetic, left to right
+inline void rule_coefficients(int S, const float* p, float* c) {
+    switch (S) {
+        case 2: c[0]=p[0]; c[1]=p[1]-p[0]; break;
+        case 3: c[0]=p[0]; c[1]=-3*p[0]+4*p[1]-p[2]; c[2]=2*p[0]-4*p[1]+2*p[2]; break;
+        default:
+            c[0]=p[0];
+            c[1]=-25*p[0]/3+ 16*p[1] - 12*p[2] +16*p[3]/3 - p[4];
+            c[2]=70*p[0]/3 -208*p[1]/3 + 76*p[2] -112*p[3]/3 + 22*p[4]/3;
+            c[3]=-80*p[0]/3 + 96*p[1] - 128*p[2] + 224*p[3]/3 - 16*p[4];
+            c[4]=32*p[0]/3 - 128*p[1]/3 + 64*p[2] - 128*p[3]/3 + 32*p[4]/3;
+    }
+}
+// rules.h:35-38 / :86-89 / :283-286 — Horner in float
+inline float rule_at(int S, float t, const float* p) {
+    float c[5]; rule_coefficients(S,p,c);
+    switch (S) {
+        case 2: return c[1]*t + c[0];
+        case 3: return (c[2]*t + c[1])*t + c[0];
+        default: return (((c[4]*t + c[3])*t + c[2])*t + c[1])*t + c[0];
+    }
+}
+// rules.h:41-44 / :97-100 / :289-293 — antiderivative difference; c*b is float, the /k.0 promotes to double
+inline float rule_subrange(int S, float a, float b, const float* p) {
+    float c[5]; rule_coefficients(S,p,c);
+    switch (S) {
+        case 2: return float((c[1]*b/2.0 + c[0])*b - (c[1]*a/2.0 + c[0])*a);
+        case 3: return float(((c[2]*b/3.0 + c[1]/2.0)*b + c[0])*b - ((c[2]*a/3.0 + c[1]/2.0)*a + c[0])*a);
+        default: return float(((((c[4]*b/5.0 + c[3]/4.0)*b + c[2]/3.0)*b + c[1]/2.0)*b + c[0])*b -
+                              ((((c[4]*a/5.0 + c[3]/4.0)*a + c[2]/3.0)*a + c[1]/2.0)*a + c[0])*a);
+    }
+}
+// nested.h:17-23
+inline float nested_low(int SH, int SL, const float* p) {
+    float plow[5];
+    for (int i=0;i<SL;++i) plow[i] = p[i*(SH-1)/(SL-1)];
+    return rule_apply(SL,plow);
+}
+// error-metric.h:10-13 / :30-37
+inline float metric_absolute(float a, float b) { return std::abs(b-a); }
+inline float metric_relative(float a, float b) {
+    const double min_val = 1.e-37;
+    if (std::max(std::abs(a),std::abs(b)) < min_val) return std::abs(b-a);
+    else return std::abs(b-a)/std::max(std::abs(a),std::abs(b));
+}
+
+inline uint64_t ipow(int s, int d) { uint64_t r=1; for (int i=0;i<d;++i) r*=uint64_t(s); return r; }
+
+// A region = box + S^D samples, dim-0-fastest (region.h:23-68, multiarray.h:20-25)
+struct Region {
+    std::vector<float> rmin, rmax, data;
+    float volume;                     // Range::_volume, float product
+    float err = 0.0f; uint32_t errdim = 0;
+};
+
+// fold a multiarray along dimension `dim` with a per-line functor; shape in/out are S^nd / S^(nd-1), dim-0-fastest
+// (fold.h:24-35: result index = base index with `dim` removed)
+template<typename LineFn>
+std::vector<float> fold_dim(const std::vector<float>& in, int S, int nd, int dim, LineFn&& fn) {
+    uint64_t inner = ipow(S,dim), outer = ipow(S,nd-1-dim);
+    std::vector<float> out(inner*outer);
+    float line[5];
+    for (uint64_t o=0;o<outer;++o) for (uint64_t i=0;i<inner;++i) {
+        for (int e=0;e<S;++e) line[e] = in[i + uint64_t(e)*inner + o*inner*uint64_t(S)];
+        out[i + o*inner] = fn(line);
+    }
+    return out;
+}
+// fold_all(q): fold dimension 0 repeatedly (fold.h:87-108) — the lowest remaining dim is always innermost
+inline float fold_all_rule(std::vector<float> v, int S, int nd) {
+    while (nd>0) { v = fold_dim(v,S,nd,0,[&] (const float* l) { return rule_apply(S,l); }); --nd; }
+    return v[0];
+}
+
+// region.h:40-46 (f_in_range) + fill.h:45-72: normalised coords double(i)/double(S-1), mapped in double, rounded to float
+inline void region_point(const Region& r, int D, const double* p, float* x) {
+    for (int i=0;i<D;++i) x[i] = float(p[i]*double(r.rmax[i]-r.rmin[i]) + double(r.rmin[i]));
+}
+Region make_region(FiniteFn f, int S, int D, const float* a, const float* b) {
+    Region r; r.rmin.assign(a,a+D); r.rmax.assign(b,b+D); r.volume = volume_of(D,a,b);
+    uint64_t n = ipow(S,D); r.data.resize(n);
+    for (uint64_t k=0;k<n;++k) {
+        double p[8]; float x[8]; uint64_t t=k;
+        for (int d=0;d<D;++d) { p[d] = double(t%uint64_t(S))/double(S-1); t/=uint64_t(S); }
+        region_point(r,D,p,x);
+        r.data[k] = f(x);
+    }
+    return r;
+}
+
+// region.h:345-359 + split.h:13-49, parts == 2.  Children reuse the parent's samples at even positions along
+// `dim` and evaluate f at the odd ones with coordinates derived from the PARENT range (v = i/(2(S-1))).
+void split_region(FiniteFn f, int S, int D, const Region& r, int dim, Region out[2]) {
+    uint64_t n = ipow(S,D), inner = ipow(S,dim);
+    int full = 2*(S-1)+1;
+    for (int c=0;c<2;++c) { out[c].rmin=r.rmin; out[c].rmax=r.rmax; out[c].data.assign(n,0.0f); }
+    // slab(i) of the conceptual (2S-1)-wide array: from parent if i even, fresh evaluations if odd
+    for (int i=0;i<full;++i) {
+        for (uint64_t k=0;k<n/uint64_t(S);++k) {           // index over the other D-1 dims, dim-0-fastest
+            uint64_t lo = k%inner, hi = k/inner;            // position below / above `dim`
+            float v;
+            if (i%2==0) v = r.data[lo + uint64_t(i/2)*inner + hi*inner*uint64_t(S)];
+            else {
+                double p[8]; float x[8]; uint64_t t=k;
+                for (int d=0;d<D;++d) {
+                    if (d==dim) p[d] = double(i)/double(full-1);
+                    else { p[d] = double(t%uint64_t(S))/double(S-1); t/=uint64_t(S); }
+                }
+                region_point(r,D,p,x);
+                v = f(x);
+            }
+            if (i<=S-1) out[0].data[lo + uint64_t(i)*inner + hi*inner*uint64_t(S)] = v;
+            if (i>=S-1) out[1].data[lo + uint64_t(i-(S-1))*inner + hi*inner*uint64_t(S)] = v;
+        }
+    }
+    float d = (r.rmax[dim]-r.rmin[dim])/float(2);                              // region.h:351
+    float mid = r.rmin[dim] + d*float(1);                                      // :353 (i+1 == 1)
+    out[0].rmax[dim] = mid; out[1].rmin[dim] = mid;                            // :353-355 ; last child keeps parent max
+    for (int c=0;c<2;++c) out[c].volume = volume_of(D,out[c].rmin.data(),out[c].rmax.data());
+}
+
+// region.h:387-393: volume * fold(error along dim).fold_all(high rule)
+float region_error(const Region& r, int SH, int SL, int D, int dim, bool relative) {
+    auto e = fold_dim(r.data,SH,D,dim,[&] (const float* l) {
+        float h = rule_apply(SH,l), lo = nested_low(SH,SL,l);
+        return relative ? metric_relative(h,lo) : metric_absolute(h,lo);       // nested.h:31-33
+    });
+    return r.volume*fold_all_rule(e,SH,D-1);
+}
+// error-heuristic.h:15-18 -> region.h:401-411 (first maximal dim, strict >)
+void heuristic_default(Region& r, int SH, int SL, int D, bool relative) {
+    float max_err = 0; uint32_t max_dim = 0;
+    for (int d=0; d<D; ++d) { float err = region_error(r,SH,SL,D,d,relative); if (err>max_err) { max_err=err; max_dim=uint32_t(d); } }
+    r.err = max_err; r.errdim = max_dim;
+}
+// error-heuristic.h:29-46 (last maximal dim, >=)
+void heuristic_size(Region& r, int SH, int SL, int D, bool relative, double size_weight) {
+    const double min_size = 1.e-37;
+    float max_err = region_error(r,SH,SL,D,0,relative);
+    float w0 = r.rmax[0]-r.rmin[0];
+    if (w0<min_size || std::isnan(w0)) max_err = 0;
+    else max_err = float(double(max_err) + size_weight*double(std::abs(r.rmax[0]-r.rmin[0])));
+    uint32_t max_dim = 0;
+    float err = max_err;
+    for (int d=1; d<D; ++d) {
+        err = float(double(region_error(r,SH,SL,D,d,relative)) + size_weight*double(std::abs(r.rmax[d]-r.rmin[d])));
+        if ((r.rmax[d]-r.rmin[d])<min_size) err = 0;
+        if (err>=max_err) { max_err=err; max_dim=uint32_t(d); }
+    }
+    r.err = max_err; r.errdim = max_dim;
+}
+
+struct Heuristic { bool size; bool relative; double size_weight; };
+bool parse_heuristic(const char* h, double sw, Heuristic& out) {
+    out.size_weight = sw;
+    if (!std::strcmp(h,"default_absolute")) { out.size=false; out.relative=false; return true; }
+    if (!std::strcmp(h,"default_relative")) { out.size=false; out.relative=true;  return true; }
+    if (!std::strcmp(h,"size_absolute"))    { out.size=true;  out.relative=false; return true; }
+    if (!std::strcmp(h,"size_relative"))    { out.size=true;  out.relative=true;  return true; }
+    return false;
+}
+void apply_heuristic(Region& r, int SH, int SL, int D, const Heuristic& h) {
+    if (h.size) heuristic_size(r,SH,SL,D,h.relative,h.size_weight); else heuristic_default(r,SH,SL,D,h.relative);
+}
+
+// libstdc++ bits/stl_heap.h:135-148 (__push_heap) with comparator a.err < b.err
+void heap_push(std::vector<Region>& h) {
+    std::size_t hole = h.size()-1; Region value = std::move(h[hole]);
+    std::size_t parent = (hole-1)/2;
+    while (hole>0 && h[parent].err < value.err) { h[hole] = std::move(h[parent]); hole = parent; parent = (hole-1)/2; }
+    h[hole] = std::move(value);
+}
+// libstdc++ bits/stl_heap.h:254-267 (pop_heap -> __pop_heap) + :224-250 (__adjust_heap); caller pops the back
+void heap_pop(std::vector<Region>& h) {
+    if (h.size()<2) return;
+    std::size_t last = h.size()-1;
+    Region value = std::move(h[last]); h[last] = std::move(h[0]);
+    std::size_t len = last, hole = 0, child = 0;
+    while (child < (len-1)/2) {
+        child = 2*(child+1);
+        if (h[child].err < h[child-1].err) --child;
+        h[hole] = std::move(h[child]); hole = child;
+    }
+    if ((len&1)==0 && child==(len-2)/2) { child = 2*(child+1); h[hole] = std::move(h[child-1]); hole = child-1; }
+    // __push_heap(first, hole, top=0, value)
+    std::size_t parent = (hole-1)/2;
+    while (hole>0 && h[parent].err < value.err) { h[hole] = std::move(h[parent]); hole = parent; parent = (hole-1)/2; }
+    h[hole] = std::move(value);
+}
+
+// regions-generator-adaptive-heap.h:18-45
+std::vector<Region> generate_adaptive(FiniteFn f, int SH, int SL, int D, const float* rmin, const float* rmax,
+                                      const Heuristic& h, uint64_t iterations) {
+    std::vector<Region> heap; heap.reserve(iterations+1);
+    heap.push_back(make_region(f,SH,D,rmin,rmax));
+    apply_heuristic(heap[0],SH,SL,D,h);
+    for (uint64_t i=0;i<iterations;++i) {
+        Region r = heap.front();                                               // :33
+        Region sub[2]; split_region(f,SH,D,r,int(r.errdim),sub);               // :34
+        heap_pop(heap); heap.pop_back();                                       // :35
+        for (int c=0;c<2;++c) {                                                // :36-40
+            apply_heuristic(sub[c],SH,SL,D,h);
+            heap.push_back(std::move(sub[c])); heap_push(heap);
+        }
+    }
+    return heap;
+}
+
+// range.h:45-53
+inline float pos_in_range1(float lo, float hi, float p) { return (lo>=hi) ? lo : (p-lo)/(hi-lo); }
+
+// region.h:141-169 (integral_subrange -> sub_last): fold subrange(a_d,b_d) over dim D-1, ..., 0; times volume
+float region_integral_subrange(const Region& r, int S, int D, const float* a, const float* b) {
+    std::vector<float> v = r.data;
+    for (int d=D-1; d>=0; --d) {
+        float na = pos_in_range1(r.rmin[d],r.rmax[d],a[d]), nb = pos_in_range1(r.rmin[d],r.rmax[d],b[d]);
+        v = fold_dim(v,S,d+1,d,[&] (const float* l) { return rule_subrange(S,na,nb,l); });
+    }
+    return r.volume*v[0];
+}
+// region.h:86-112 (approximation_at -> app_at): fold at(pos_d) over dim 0, 1, ..., D-1; times volume_from(D) == 1
+float region_approximation_at(const Region& r, int S, int D, const float* pos) {
+    std::vector<float> v = r.data;
+    for (int d=0; d<D; ++d) {
+        float t = pos_in_range1(r.rmin[d],r.rmax[d],pos[d]);
+        v = fold_dim(v,S,D-d,0,[&] (const float* l) { return rule_at(S,t,l); });
+    }
+    return v[0]*1.0f;
+}
+
+// region.h:454-463
+void pixels_in_region(const Region& r, int db, const uint64_t* res, const float* rmin, const float* rmax, uint64_t* start, uint64_t* end) {
+    for (int i=0;i<db;++i) {
+        start[i] = std::max(uint64_t(0), uint64_t(float(res[i])*(r.rmin[i]-rmin[i])/(rmax[i]-rmin[i])));
+        end[i]   = std::max(start[i]+1, std::min(res[i], uint64_t(0.99f + (float(res[i])*(r.rmax[i]-rmin[i])/(rmax[i]-rmin[i])))));
+    }
+}
+// range.h:92-101 ; false when the intersection is empty (range.h:70-75)
+bool intersect(int D, const float* a1, const float* b1, const float* a2, const float* b2, float* a, float* b) {
+    bool empty = false;
+    for (int d=0;d<D;++d) { a[d] = std::max(a1[d],a2[d]); b[d] = std::max(a[d], std::min(b1[d],b2[d])); if (a[d]>=b[d]) empty = true; }
+    return !empty;
+}
+
+// regions-integrator-sequential.h:38-58
+void integrate_regions_sequential(const std::vector<Region>& regions, int S, int D, int db, const uint64_t* res,
+                                  const float* rmin, const float* rmax, float* bins) {
+    uint64_t factor = nbins_of(db,res);
+    for (const Region& r : regions) {
+        uint64_t st[8], en[8]; pixels_in_region(r,db,res,rmin,rmax,st,en);
+        uint64_t pos[8]; for (int i=0;i<db;++i) pos[i]=st[i];
+        while (true) {
+            float ba[8], bb[8], ia[8], ib[8];
+            bin_box(D,db,rmin,rmax,res,pos,ba,bb);
+            if (intersect(D,ba,bb,r.rmin.data(),r.rmax.data(),ia,ib)) {
+                uint64_t lin=0, prod=1; for (int i=0;i<db;++i) { lin+=pos[i]*prod; prod*=res[i]; }
+                bins[lin] = float(double(bins[lin]) + double(factor)*double(region_integral_subrange(r,S,D,ia,ib)));   // :54
+            }
+            int d=0; for (; d<db; ++d) { if (++pos[d] >= en[d]) pos[d]=st[d]; else break; }
+            if (d==db) break;
+        }
+    }
+}
+
+void export_regions(const std::vector<Region>& regions, int D,
+                    float* reg_min, float* reg_max, float* reg_err, uint32_t* reg_dim, float* reg_data) {
+    uint64_t n = 0;
+    for (const Region& r : regions) {
+        if (reg_min) std::copy(r.rmin.begin(), r.rmin.end(), reg_min+n*uint64_t(D));
+        if (reg_max) std::copy(r.rmax.begin(), r.rmax.end(), reg_max+n*uint64_t(D));
+        if (reg_err) reg_err[n] = r.err;
+        if (reg_dim) reg_dim[n] = r.errdim;
+        if (reg_data) std::copy(r.data.begin(), r.data.end(), reg_data+n*r.data.size());
+        ++n;
+    }
+}
+
+} // namespace
+
+// newton-cotes.h:11-14 = regions-generator-single.h:12-20 + regions-integrator-sequential.h:38-58
+extern "C" int vo_newton_cotes(const char* integrand, const char* rule, int dimbins, const uint64_t* res,
+                    const float* rmin, const float* rmax, float* bins) {
+    auto F = find_finite(integrand); if (!F) return -1;
+    int D = F->dim; if (dimbins<1 || dimbins>D) return -2;
+    int S = !std::strcmp(rule,"trapezoidal") ? 2 : !std::strcmp(rule,"simpson") ? 3 : !std::strcmp(rule,"boole") ? 5 : 0;
+    if (!S) return -2;
+    std::vector<Region> regions; regions.push_back(make_region(F->fn,S,D,rmin,rmax));
+    integrate_regions_sequential(regions,S,D,dimbins,res,rmin,rmax,bins);
+    return 0;
+}
+
+extern "C" int vo_adaptive_iterations(const char* integrand, const char* rule, const char* heuristic, double size_weight,
+                           uint64_t iterations, int dimbins, const uint64_t* res,
+                           const float* rmin, const float* rmax, float* bins,
+                           float* reg_min, float* reg_max, float* reg_err, uint32_t* reg_dim, float* reg_data) {
+    auto F = find_finite(integrand); if (!F) return -1;
+    int D = F->dim; if (dimbins<1 || dimbins>D) return -2;
+    int SH, SL;
+    if (!std::strcmp(rule,"simpson_trapezoidal")) { SH=3; SL=2; }
+    else if (!std::strcmp(rule,"boole_simpson")) { SH=5; SL=3; }
+    else return -2;
+    Heuristic h; if (!parse_heuristic(heuristic,size_weight,h)) return -2;
+    auto regions = generate_adaptive(F->fn,SH,SL,D,rmin,rmax,h,iterations);
+    export_regions(regions,D,reg_min,reg_max,reg_err,reg_dim,reg_data);
+    if (bins) integrate_regions_sequential(regions,SH,D,dimbins,res,rmin,rmax,bins);
+    return 0;
+}
+
+// =========================================================================================================
+// Control variates: integrator-crespo2021.h:7-22 -> regions-integrator-parallel-variance-reduction.h:32-109
+// =========================================================================================================
+extern "C" int vo_crespo2021(const char* integrand, uint64_t iterations, uint64_t spp, uint64_t seed,
+                  int dimbins, const uint64_t* res, const float* rmin, const float* rmax, float* bins,
+                  uint32_t* rec_nregions, float* rec_approx, uint32_t* rec_chosen, float* rec_samples,
+                  float* reg_min, float* reg_max, float* reg_err, uint32_t* reg_dim, float* reg_data) {
+    auto F = find_finite(integrand); if (!F) return -1;
+    int D = F->dim; if (dimbins<1 || dimbins>D) return -2;
+    const int S = 3, SL = 2;
+    Heuristic h{true,true,1.e-5};                                              // integrator-crespo2021.h:12
+    auto regions = generate_adaptive(F->fn,S,SL,D,rmin,rmax,h,iterations);
+    export_regions(regions,D,reg_min,reg_max,reg_err,reg_dim,reg_data);
+
+    uint64_t nb = nbins_of(dimbins,res);
+    uint64_t factor = nb;
+    // bin -> region lists, regions visited in list order (:53-57, serial PSTL backend)
+    std::vector<std::vector<uint32_t>> perbin(nb);
+    for (uint32_t ri=0; ri<regions.size(); ++ri) {
+        uint64_t st[8], en[8]; pixels_in_region(regions[ri],dimbins,res,rmin,rmax,st,en);
+        uint64_t pos[8]; for (int i=0;i<dimbins;++i) pos[i]=st[i];
+        while (true) {
+            uint64_t lin=0, prod=1; for (int i=0;i<dimbins;++i) { lin+=pos[i]*prod; prod*=res[i]; }
+            perbin[lin].push_back(ri);
+            int d=0; for (; d<dimbins; ++d) { if (++pos[d] >= en[d]) pos[d]=st[d]; else break; }
+            if (d==dimbins) break;
+        }
+    }
+    // one RNG per bin, seeded sequentially in tensor order from the integrator's mt19937(seed) (:59-63)
+    MT19937 master(seed);
+    std::vector<uint32_t> bin_seed(nb);
+    for (uint64_t k=0;k<nb;++k) bin_seed[k] = master();
+
+    for (uint64_t k=0;k<nb;++k) {                                              // variance_reduction(pos) :67-103
+        uint64_t pos[8]; unflatten(k,dimbins,res,pos);
+        MT19937 rng{uint64_t(bin_seed[k])};
+        (void)rng();        // monte_carlo_per_bin(rng,1) reseeds itself from the bin RNG: one draw (:69, monte-carlo-per-bin.h:28)
+        float ba[8], bb[8]; bin_box(D,dimbins,rmin,rmax,res,pos,ba,bb);       // :71-73
+        const auto& list = perbin[k];
+        std::size_t n = list.size();
+        std::vector<std::array<float,8>> ia(n), ib(n);
+        float approximation = 0.0f;                                            // :77
+        for (std::size_t i=0;i<n;++i) {                                        // :78-88
+            const Region& r = regions[list[i]];
+            if (intersect(D,ba,bb,r.rmin.data(),r.rmax.data(),ia[i].data(),ib[i].data()))
+                approximation = float(double(approximation) + double(factor)*double(region_integral_subrange(r,S,D,ia[i].data(),ib[i].data())));
+        }
+        if (rec_nregions) rec_nregions[k] = uint32_t(n);
+        if (rec_approx) rec_approx[k] = approximation;
+        // cv_optimize_weight accumulator (weight-strategy.h:40-101)
+        float sum_f=0.0f, sum_app=0.0f; uint64_t size=0;
+        double k_f=0,k_app=0,e_f=0,e_ap=0,e_ap2=0,e_fap=0;
+        for (uint64_t s=0;s<spp;++s) {                                         // :92-101
+            uint64_t chosen = uniform_int(rng,0,n-1);                          // region-russian-roulette.h:14,18-21
+            double rrfactor = double(n);
+            const Region& r = regions[list[chosen]];
+            float x[8];
+            for (int i=0;i<D;++i) x[i] = uniform_real(rng,ia[chosen][i],ib[chosen][i]);   // region-sampling.h:13-17
+            float sfactor = volume_of(D,ia[chosen].data(),ib[chosen].data());              // :18
+            if (rec_chosen) rec_chosen[k*spp+s] = list[chosen];
+            if (rec_samples) for (int i=0;i<D;++i) rec_samples[(k*spp+s)*D+i] = x[i];
+            float fs = float(double(F->fn(x))*double(factor)*rrfactor*double(sfactor));                      // :98
+            float as = float(double(region_approximation_at(r,S,D,x))*double(factor)*rrfactor*double(sfactor)); // :99
+            // push (weight-strategy.h:56-69); NormDefault = abs (norm.h:12)
+            if (size==0) { k_f = std::abs(fs); k_app = std::abs(as); }
+            e_f   += (std::abs(fs) - k_f);
+            e_ap  += (std::abs(as) - k_app);
+            e_ap2 += (std::abs(as) - k_app)*(std::abs(as) - k_app);
+            e_fap += (std::abs(fs) - k_f)*(std::abs(as) - k_app);
+            sum_f += fs; sum_app += as;
+            ++size;
+        }
+        // integral (weight-strategy.h:71-101)
+        float result;
+        if (size<2) result = approximation;
+        else {
+            double covariance = (e_fap - (e_f*e_ap)/double(size))/double(size-1);
+            double variance   = (e_ap2 - (e_ap*e_ap)/double(size))/double(size-1);
+            double alpha;
+            double v = std::max(0.0,variance);
+            if (v<=0.0) alpha = 1.0;
+            else { double c = std::min(v,std::max(0.0,covariance)); alpha = c/v; }
+            result = float((double(sum_f) - alpha*double(sum_app))/double(size) + alpha*double(approximation));
+        }
+        bins[k] = result;                                                      // :102 ('=')
+    }
+    return 0;
+}
+
+// Thread-pool driver used as the "port" CPU baseline (same slabbing as the reference-side harness).
+extern "C" int vo_mt_per_bin(const char* path, const char* integrand, int dimbins, const uint64_t* res,
+                  const float* rmin, const float* rmax, int nrange, uint64_t spp, uint64_t seed,
+                  int nthreads, float* bins) {
+    if (dimbins < 1 || dimbins > 2) return -2;
+    int last = dimbins-1;
+    uint64_t rows = res[last];
+    if (nthreads < 1) nthreads = 1;
+    if (uint64_t(nthreads) > rows) nthreads = int(rows);
+    uint64_t stride = (dimbins==2) ? res[0] : 1;
+    int dim = vo_integrand_dim(integrand);
+    if (dim == 0) return -1;
+    bool inf = (dim == -1);
+    int have = inf ? nrange : dim;
+    int nr = inf ? std::max(nrange, dimbins) : dim;
+    std::vector<int> rc(nthreads, 0);
+    std::vector<std::thread> th;
+    for (int t=0;t<nthreads;++t) th.emplace_back([&,t] () {
+        uint64_t lo = rows*uint64_t(t)/uint64_t(nthreads), hi = rows*uint64_t(t+1)/uint64_t(nthreads);
+        std::vector<float> a(nr), b(nr);
+        for (int i=0;i<nr;++i) { a[i] = (i<have) ? rmin[i] : 0.0f; b[i] = (i<have) ? rmax[i] : 1.0f; }
+        float d = (b[last]-a[last])/float(rows);
+        float amin = a[last];
+        a[last] = amin + float(lo)*d; b[last] = amin + float(hi)*d;
+        uint64_t r2[2] = { res[0], res[dimbins>1?1:0] }; r2[last] = hi-lo;
+        float* out = bins + lo*stride;
+        if (!std::strcmp(path,"mc_per_bin_parallel"))
+            rc[t] = vo_mc_per_bin_parallel(integrand,dimbins,r2,a.data(),b.data(),spp,seed+uint64_t(t),out,nullptr,nullptr,nullptr);
+        else if (!std::strcmp(path,"per_bin_parallel_mc"))
+            rc[t] = vo_per_bin_parallel_mc(integrand,dimbins,r2,a.data(),b.data(),spp,seed+uint64_t(t),out,nullptr,nullptr,nullptr);
+        else if (!std::strcmp(path,"mc_per_bin_parallel_inf"))
+            rc[t] = vo_mc_per_bin_parallel_inf(integrand,dimbins,r2,a.data(),b.data(),nr,spp,seed+uint64_t(t),out,nullptr,nullptr,nullptr,nullptr,0,nullptr);
+        else rc[t] = -2;
+        // bins hold densities scaled by the bin count of the call: rescale slab -> full grid
+        float scale = float(rows)/float(hi-lo);
+        for (uint64_t k=0;k<(hi-lo)*stride;++k) out[k] *= scale;
+    });
+    for (auto& x : th) x.join();
+    for (int x : rc) if (x) return x;
+    return 0;
+}

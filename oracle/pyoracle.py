@@ -1,0 +1,177 @@
+"""TEST INFRASTRUCTURE — not product code.
+
+ctypes loader for the two CPU checkers (see oracle/oracle_api.h):
+
+  * ``load("port")``       -> oracle/liboracle.so            plain restatement (oracle/oracle.cpp)
+  * ``load("reference")``  -> oracle/_ref/libviltrum_ref.so  the unmodified reference
+
+Only tests/, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` legs may import
+this module.  Nothing under viltrum_b200/ does.
+"""
+import ctypes
+import os
+import subprocess
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PORT_SO = os.path.join(HERE, "liboracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libviltrum_ref.so")
+REFERENCE_ROOT = "/root/reference"
+
+RULE_SAMPLES = {"trapezoidal": 2, "simpson": 3, "boole": 5, "simpson_trapezoidal": 3, "boole_simpson": 5}
+
+
+def build(kind="port"):
+    """(Re)build a checker with oracle/Makefile.  'reference' needs /root/reference (authoring container only)."""
+    target = {"port": "port", "reference": "ref"}[kind]
+    if kind == "reference" and not os.path.isdir(REFERENCE_ROOT):
+        raise RuntimeError("/root/reference is absent: the reference checker can only be built in the authoring container")
+    subprocess.run(["make", "-s", "-j8", "-C", HERE, target], check=True)
+
+
+def available(kind):
+    return os.path.exists(PORT_SO if kind == "port" else REF_SO)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _f32(x):
+    return np.ascontiguousarray(np.asarray(x, dtype=np.float32))
+
+
+class Oracle:
+    """Thin numpy front end over the vo_* C ABI.  Bins are flat float32 arrays in viltrum::tensor order
+    (dim 0 fastest); ``res`` is the per-dimension bin count."""
+
+    def __init__(self, path):
+        self.lib = ctypes.CDLL(path)
+        self.lib.vo_kind.restype = ctypes.c_char_p
+        self.kind = self.lib.vo_kind().decode()
+        for name in ("vo_mc_per_bin_parallel", "vo_per_bin_parallel_mc", "vo_monte_carlo", "vo_mc_per_bin_parallel_inf",
+                     "vo_newton_cotes", "vo_adaptive_iterations", "vo_crespo2021", "vo_mt_per_bin", "vo_integrand_dim"):
+            getattr(self.lib, name).restype = ctypes.c_int
+
+    def dim(self, integrand):
+        return self.lib.vo_integrand_dim(integrand.encode())
+
+    @staticmethod
+    def _setup(res, rmin, rmax):
+        res = np.ascontiguousarray(np.asarray(res, dtype=np.uint64))
+        return res, _f32(rmin), _f32(rmax), int(np.prod(res))
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed in {self.kind} oracle: rc={rc}")
+
+    def _per_bin(self, fn, integrand, res, rmin, rmax, spp, seed, bins, record):
+        res, rmin, rmax, nb = self._setup(res, rmin, rmax)
+        d = self.dim(integrand)
+        bins = np.zeros(nb, np.float32) if bins is None else np.ascontiguousarray(bins, dtype=np.float32).copy()
+        samples = np.zeros((nb, spp, d), np.float32) if record else None
+        s1 = np.zeros(nb, np.float64) if record else None
+        s2 = np.zeros(nb, np.float64) if record else None
+        rc = fn(integrand.encode(), len(res), _p(res), _p(rmin), _p(rmax), ctypes.c_uint64(spp), ctypes.c_uint64(seed),
+                _p(bins), _p(samples), _p(s1), _p(s2))
+        self._check(rc, fn.__name__)
+        return (bins, samples, s1, s2) if record else bins
+
+    def mc_per_bin_parallel(self, integrand, res, rmin, rmax, spp, seed, bins=None, record=False):
+        return self._per_bin(self.lib.vo_mc_per_bin_parallel, integrand, res, rmin, rmax, spp, seed, bins, record)
+
+    def per_bin_parallel_mc(self, integrand, res, rmin, rmax, spp, seed, bins=None, record=False):
+        return self._per_bin(self.lib.vo_per_bin_parallel_mc, integrand, res, rmin, rmax, spp, seed, bins, record)
+
+    def monte_carlo(self, integrand, res, rmin, rmax, samples, seed, bins=None, record=False):
+        res, rmin, rmax, nb = self._setup(res, rmin, rmax)
+        d = self.dim(integrand)
+        bins = np.zeros(nb, np.float32) if bins is None else np.ascontiguousarray(bins, dtype=np.float32).copy()
+        rec = np.zeros((samples, d), np.float32) if record else None
+        rc = self.lib.vo_monte_carlo(integrand.encode(), len(res), _p(res), _p(rmin), _p(rmax), ctypes.c_uint64(samples),
+                                     ctypes.c_uint64(seed), _p(bins), _p(rec))
+        self._check(rc, "vo_monte_carlo")
+        return (bins, rec) if record else bins
+
+    def mc_per_bin_parallel_inf(self, integrand, res, spp, seed, rmin=(), rmax=(), bins=None, record=False, rec_cap=None):
+        res = np.ascontiguousarray(np.asarray(res, dtype=np.uint64))
+        nb = int(np.prod(res))
+        rmin, rmax = _f32(rmin), _f32(rmax)
+        bins = np.zeros(nb, np.float32) if bins is None else np.ascontiguousarray(bins, dtype=np.float32).copy()
+        s1 = s2 = lens = elems = None
+        used = ctypes.c_uint64(0)
+        cap = 0
+        if record:
+            s1 = np.zeros(nb, np.float64); s2 = np.zeros(nb, np.float64)
+            lens = np.zeros(nb * spp, np.uint32)
+            cap = rec_cap if rec_cap is not None else nb * spp * 64
+            elems = np.zeros(cap, np.float32)
+        rc = self.lib.vo_mc_per_bin_parallel_inf(integrand.encode(), len(res), _p(res), _p(rmin), _p(rmax), len(rmin),
+                                                 ctypes.c_uint64(spp), ctypes.c_uint64(seed), _p(bins), _p(s1), _p(s2),
+                                                 _p(lens), _p(elems), ctypes.c_uint64(cap), ctypes.byref(used))
+        self._check(rc, "vo_mc_per_bin_parallel_inf")
+        if record:
+            return bins, s1, s2, lens, elems[: used.value]
+        return bins
+
+    def newton_cotes(self, integrand, rule, res, rmin, rmax, bins=None):
+        res, rmin, rmax, nb = self._setup(res, rmin, rmax)
+        bins = np.zeros(nb, np.float32) if bins is None else np.ascontiguousarray(bins, dtype=np.float32).copy()
+        rc = self.lib.vo_newton_cotes(integrand.encode(), rule.encode(), len(res), _p(res), _p(rmin), _p(rmax), _p(bins))
+        self._check(rc, "vo_newton_cotes")
+        return bins
+
+    def _region_buffers(self, integrand, rule, iterations):
+        d = self.dim(integrand); n = iterations + 1; sd = RULE_SAMPLES[rule] ** d
+        return dict(min=np.zeros((n, d), np.float32), max=np.zeros((n, d), np.float32), err=np.zeros(n, np.float32),
+                    dim=np.zeros(n, np.uint32), data=np.zeros((n, sd), np.float32))
+
+    def adaptive_iterations(self, integrand, rule, heuristic, iterations, res, rmin, rmax, size_weight=1e-5, bins=None):
+        """returns (bins, regions) with regions = dict(min,max,err,dim,data) in the reference's heap-array order"""
+        res, rmin, rmax, nb = self._setup(res, rmin, rmax)
+        bins = np.zeros(nb, np.float32) if bins is None else np.ascontiguousarray(bins, dtype=np.float32).copy()
+        reg = self._region_buffers(integrand, rule, iterations)
+        rc = self.lib.vo_adaptive_iterations(integrand.encode(), rule.encode(), heuristic.encode(), ctypes.c_double(size_weight),
+                                             ctypes.c_uint64(iterations), len(res), _p(res), _p(rmin), _p(rmax), _p(bins),
+                                             _p(reg["min"]), _p(reg["max"]), _p(reg["err"]), _p(reg["dim"]), _p(reg["data"]))
+        self._check(rc, "vo_adaptive_iterations")
+        return bins, reg
+
+    def crespo2021(self, integrand, iterations, spp, seed, res, rmin, rmax, record=False):
+        res, rmin, rmax, nb = self._setup(res, rmin, rmax)
+        d = self.dim(integrand)
+        bins = np.zeros(nb, np.float32)
+        reg = self._region_buffers(integrand, "simpson_trapezoidal", iterations)
+        nreg = approx = chosen = samples = None
+        if record:
+            nreg = np.zeros(nb, np.uint32); approx = np.zeros(nb, np.float32)
+            chosen = np.zeros((nb, spp), np.uint32); samples = np.zeros((nb, spp, d), np.float32)
+        rc = self.lib.vo_crespo2021(integrand.encode(), ctypes.c_uint64(iterations), ctypes.c_uint64(spp), ctypes.c_uint64(seed),
+                                    len(res), _p(res), _p(rmin), _p(rmax), _p(bins), _p(nreg), _p(approx), _p(chosen), _p(samples),
+                                    _p(reg["min"]), _p(reg["max"]), _p(reg["err"]), _p(reg["dim"]), _p(reg["data"]))
+        self._check(rc, "vo_crespo2021")
+        if record:
+            return bins, reg, dict(nregions=nreg, approx=approx, chosen=chosen, samples=samples)
+        return bins, reg
+
+    def mt_per_bin(self, path, integrand, res, spp, seed, nthreads, rmin=(), rmax=()):
+        res = np.ascontiguousarray(np.asarray(res, dtype=np.uint64))
+        rmin, rmax = _f32(rmin), _f32(rmax)
+        bins = np.zeros(int(np.prod(res)), np.float32)
+        rc = self.lib.vo_mt_per_bin(path.encode(), integrand.encode(), len(res), _p(res), _p(rmin), _p(rmax), len(rmin),
+                                    ctypes.c_uint64(spp), ctypes.c_uint64(seed), int(nthreads), _p(bins))
+        self._check(rc, "vo_mt_per_bin")
+        return bins
+
+
+_cache = {}
+
+
+def load(kind="port"):
+    """kind: 'port' (restatement, built on demand) or 'reference' (prebuilt .so, or built when /root/reference exists)."""
+    if kind not in _cache:
+        path = PORT_SO if kind == "port" else REF_SO
+        if not os.path.exists(path):
+            build(kind)
+        _cache[kind] = Oracle(path)
+    return _cache[kind]

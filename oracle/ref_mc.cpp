@@ -187,6 +187,9 @@ extern "C" int vo_mt_per_bin(const char* path, const char* integrand, int dimbin
         else if (!std::strcmp(path,"mc_per_bin_parallel_inf"))
             rc[t] = vo_mc_per_bin_parallel_inf(integrand,dimbins,r2,a.data(),b.data(),nr,spp,seed+uint64_t(t),out,nullptr,nullptr,nullptr,nullptr,0,nullptr);
         else rc[t] = -2;
+        // bins hold densities scaled by the bin count of the call: rescale slab -> full grid
+        float scale = float(rows)/float(hi-lo);
+        for (uint64_t k=0;k<(hi-lo)*stride;++k) out[k] *= scale;
     });
     for (auto& x : th) x.join();
     for (int x : rc) if (x) return x;
