@@ -1,0 +1,317 @@
+/* viltrum_b200 — C ABI of the B200-native per-bin integration hot path (libviltrum_b200.so).
+ *
+ * This is the drop-in boundary SURVEY.md §8(b) describes: plain pointers, sizes and POD structs, no C++
+ * types, no torch types.  The reference (adolfomunoz/viltrum, header-only C++17) has no FFI of its own; the
+ * "binding" is the set of integrator classes whose
+ *     integrate(bins, bin_resolution, f, range, logger) const
+ * member viltrum::integrate dispatches to (reference src/integrate.h:72-90).  Each driver below replaces one
+ * such member; include/viltrum_b200/viltrum.h re-creates the reference's C++ vocabulary on top of it
+ * (see INTEGRATION.md).
+ *
+ * Conventions
+ *   - one vb200_ctx per process and GPU (one process per GPU; multi-GPU = bin-grid sharding through
+ *     vb200_shard, no data-path collective — SURVEY.md §8(e));
+ *   - bins are flat float arrays in the reference's tensor layout, dimension 0 fastest
+ *     (reference src/tensor.h:17-23), addressed from the base of the FULL grid even when a call only
+ *     integrates a shard of it;
+ *   - every pointer argument carries a memory-space flag: VB200_HOST pointers are staged through device
+ *     scratch inside the call (the reference-facing, end-to-end path), VB200_DEVICE pointers are used in place
+ *     (the resident path);
+ *   - all entry points return VB200_OK (0) or a negative vb200_status; vb200_last_error() gives the text.
+ *     The reference's hot path returns void and throws nothing (SURVEY.md §8b "Errors"); the C++ wrapper turns
+ *     a non-zero status into std::runtime_error;
+ *   - there is NO CPU fallback: without a CUDA device vb200_create fails with VB200_ERR_NO_DEVICE.
+ *
+ * Integrands are C++ functors compiled by nvcc in the USER's translation unit.  They cross this ABI as a
+ * vb200_integrand: the functor's bytes (trivially copyable) plus a table of launch thunks instantiated from
+ * the kernel templates in include/viltrum_b200/device/ (viltrum::b200::make_integrand<F,DIM>()).  The
+ * library also ships the synthetic integrands of SURVEY.md §8(d) (vb200_builtin_integrand) so that C, Python
+ * (ctypes) and the benchmark can drive every path without an nvcc TU of their own.
+ */
+#ifndef VILTRUM_B200_H
+#define VILTRUM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VB200_ABI_VERSION 1u
+#define VB200_MAX_DIM      8     /* finite integrands: 1..8 dimensions (reference VILTRUM_MAX_DIMENSIONS_REGION = 6, region.h:16-18) */
+#define VB200_MAX_DIMBINS  3     /* reference binned overloads go up to 3-D containers (integrate.h:132-167) */
+
+typedef enum vb200_status {
+    VB200_OK = 0,
+    VB200_ERR_NO_DEVICE = -1,      /* no CUDA device / driver: the product never falls back to the CPU */
+    VB200_ERR_INVALID = -2,        /* bad argument (dimension mismatch is a compile error upstream, integrate.h:75-77) */
+    VB200_ERR_CUDA = -3,           /* a CUDA runtime call or kernel failed; see vb200_last_error */
+    VB200_ERR_UNSUPPORTED = -4,    /* combination not implemented for this integrand (missing thunk) */
+    VB200_ERR_NOMEM = -5
+} vb200_status;
+
+typedef enum vb200_mem { VB200_HOST = 0, VB200_DEVICE = 1 } vb200_mem;
+
+typedef struct vb200_ctx vb200_ctx;
+
+/* ---- context ------------------------------------------------------------------------------------------ */
+int         vb200_create(int device, vb200_ctx** out);
+void        vb200_destroy(vb200_ctx* ctx);
+const char* vb200_last_error(const vb200_ctx* ctx);      /* ctx may be NULL: error of the last failed vb200_create */
+/* stream all work of this context is enqueued on (a cudaStream_t); calls with VB200_HOST outputs synchronise it
+ * before returning, calls whose outputs are all VB200_DEVICE return with the work enqueued. */
+void*       vb200_stream(vb200_ctx* ctx);
+int         vb200_synchronize(vb200_ctx* ctx);
+int         vb200_sm_count(const vb200_ctx* ctx);
+/* kernels launched by this context since creation (bench.py's gpu_launches) */
+uint64_t    vb200_launch_count(const vb200_ctx* ctx);
+
+/* Host-side evaluation of the library's counter-based generator (Philox4x32-10, include/viltrum_b200/device/philox.cuh),
+ * for known-answer tests and for callers that want to predict which sample a (seed, bin, sample) triple maps to. */
+void        vb200_philox4x32_10(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]);
+
+/* ---- integrands --------------------------------------------------------------------------------------- */
+struct vb200_integrand;
+/* launch thunk: enqueue one kernel instantiated for the integrand's functor type.  `args` points at the
+ * launch struct of that kernel kind (below).  Returns a cudaError_t value (0 = success). */
+typedef int (*vb200_launch_fn)(const struct vb200_integrand* self, const void* args, void* stream);
+
+enum {
+    VB200_K_MC_PER_BIN = 0,        /* vb200_mc_launch      : Philox per-bin sampler (fused draw/eval/reduce/store) */
+    VB200_K_MC_REPLAY = 1,         /* vb200_replay_launch  : recorded samples, sequential reference arithmetic    */
+    VB200_K_WALK = 2,              /* vb200_walk_launch    : infinite-dimensional lazy-sequence paths             */
+    VB200_K_WALK_REPLAY = 3,       /* vb200_walk_replay_launch                                                     */
+    VB200_K_EVAL_POINTS = 4,       /* vb200_eval_launch    : values[i] = f(points[i]) — region fill / batched splits / CV residual */
+    VB200_K_ADAPTIVE_EXACT = 5,    /* vb200_greedy_launch  : persistent single-CTA greedy heap refinement (batch size 1) */
+    VB200_K_MC_SCATTER = 6,        /* vb200_scatter_launch : global sampler scattering into bins (monte-carlo.h:39-63) */
+    VB200_K_COUNT = 8
+};
+
+#define VB200_INTEGRAND_EXACT 1u   /* thunks were compiled with --fmad=false: bit-exact twin of a CPU build with -ffp-contract=off */
+
+typedef struct vb200_integrand {
+    uint32_t        abi_version;    /* VB200_ABI_VERSION */
+    int32_t         dim;            /* >0: f(std::array<float,dim>) ; -1: f(sequence) over an infinite range */
+    const void*     functor;        /* trivially copyable functor object, passed to kernels by value */
+    uint32_t        functor_bytes;
+    uint32_t        flags;          /* VB200_INTEGRAND_* */
+    const char*     name;           /* for error messages */
+    vb200_launch_fn launch[VB200_K_COUNT];   /* NULL = kind not available for this integrand */
+} vb200_integrand;
+
+/* Synthetic integrands compiled into the library: "x2y2", "ind2", "cubic1", "poly3",
+ * "shade4_16", "shade4_64", "shade5_16", "shade5_64", "smooth_edge2", "walk", "decay".  exact != 0 selects the
+ * --fmad=false instantiation.  Returns NULL if unknown. */
+const vb200_integrand* vb200_builtin_integrand(const char* name, int exact);
+int                    vb200_builtin_count(void);
+const char*            vb200_builtin_name(int index);
+
+/* ---- shared parameter blocks -------------------------------------------------------------------------- */
+/* Integration box + bin grid.  For infinite ranges `dim` is the number of explicit entries of rmin/rmax
+ * (reference RangeInfinite: implicit [0,1] tail, range-infinite.h:31-37) and may be 0. */
+typedef struct vb200_domain {
+    int32_t  dim;
+    int32_t  dimbins;                      /* bins span the FIRST dimbins dimensions (README.md:69-71) */
+    float    rmin[VB200_MAX_DIM];
+    float    rmax[VB200_MAX_DIM];
+    uint64_t res[VB200_MAX_DIMBINS];       /* bins per dimension */
+} vb200_domain;
+
+/* Bin-grid shard handled by one call/GPU: linear bin indices [begin,end) in tensor order.  {0,0} = whole grid.
+ * Philox counters are keyed by the GLOBAL bin index, so results do not depend on how the grid is sharded. */
+typedef struct vb200_shard { uint64_t begin, end; } vb200_shard;
+
+typedef enum vb200_mc_flavor {
+    VB200_MC_PER_BIN = 0,     /* monte_carlo_per_bin_parallel(spp,seed): bins(p) += sum f * vol(range)/spp
+                                 (reference src/monte-carlo/monte-carlo-per-bin-parallel.h:41-71 and :73-100) */
+    VB200_PER_BIN_MC = 1      /* integrator_per_bin_parallel(monte_carlo(spp,seed)): bins(p) = nbins * (sum f * vol(bin box)/spp)
+                                 (reference src/integrator-per-bin-parallel.h:16-35 + src/monte-carlo/monte-carlo.h:39-63) */
+} vb200_mc_flavor;
+
+/* ---- per-bin Monte Carlo (SURVEY.md §8a rows a2,a3,a4) ------------------------------------------------- */
+typedef struct vb200_mc_params {
+    vb200_domain domain;
+    vb200_shard  shard;
+    uint64_t     spp;
+    uint64_t     seed;          /* Philox key; counter = (bin index, sample index, draw block) */
+    int32_t      flavor;        /* vb200_mc_flavor: also fixes the write semantics ('+=' vs '=') */
+    int32_t      reserved;
+} vb200_mc_params;
+
+/* bins: base of the full grid.  sum_f / sum_f2 (optional, may be NULL; same memory space as bins): raw per-bin
+ * sum f and sum f^2 of the shard's bins, for the tests' 3-sigma gate. */
+int vb200_mc_per_bin(vb200_ctx* ctx, const vb200_integrand* f, const vb200_mc_params* p,
+                     float* bins, int bins_mem, float* sum_f, float* sum_f2);
+
+/* Sample-replay mode (BASELINE.json north_star: "match exactly in a sample-replay mode that feeds the
+ * reference's sample points").  samples: [nbins_of_shard][spp][dim] floats, bin-major in tensor order starting
+ * at shard.begin.  One thread per bin accumulates sequentially with the reference's promotions
+ * (float(double(acc)+double(f)*factor)); with an EXACT integrand the result is bit-identical to the reference. */
+int vb200_mc_per_bin_replay(vb200_ctx* ctx, const vb200_integrand* f, const vb200_mc_params* p,
+                            const float* samples, int samples_mem, float* bins, int bins_mem);
+
+/* ---- infinite-dimensional paths (rows a5, a20) --------------------------------------------------------- */
+/* domain.dim = explicit range entries (0..VB200_MAX_DIM); flavor VB200_MC_PER_BIN only.
+ * Sequence element i of sample s in bin b = u * (max_i - min_i) + min_i with u drawn from
+ * Philox(key=seed, counter=(b, s, i/4))[i%4]; the first dimbins elements are confined to the bin. */
+int vb200_mc_per_bin_inf(vb200_ctx* ctx, const vb200_integrand* f, const vb200_mc_params* p,
+                         float* bins, int bins_mem, float* sum_f, float* sum_f2);
+
+/* Replay of recorded lazy sequences: elems holds every path's elements back to back (bin-major, sample-minor),
+ * offsets [nbins_of_shard*spp + 1] are prefix sums of the per-path lengths.  Reading past a path's recorded
+ * length yields NaN and sets a sticky error (VB200_ERR_INVALID on return). */
+int vb200_mc_per_bin_inf_replay(vb200_ctx* ctx, const vb200_integrand* f, const vb200_mc_params* p,
+                                const uint64_t* offsets, const float* elems, int mem, float* bins, int bins_mem);
+
+/* ---- global Monte Carlo with scatter binning (row a6; SURVEY.md §8f "next" #1) -------------------------- */
+/* monte_carlo(samples,seed): bins(pos(x)) += f(x) * nbins*vol/samples   (reference src/monte-carlo/monte-carlo.h:39-63).
+ * shard selects a SAMPLE index range [begin,end) here (split-bin mode: every GPU draws part of the samples and
+ * the caller sums the partial grids — the one allreduce the design allows). */
+int vb200_monte_carlo(vb200_ctx* ctx, const vb200_integrand* f, const vb200_mc_params* p /* spp = total samples */,
+                      float* bins, int bins_mem);
+
+/* ---- region tables (rows a7-a14) ----------------------------------------------------------------------- */
+typedef enum vb200_rule {
+    VB200_RULE_TRAPEZOIDAL = 2, VB200_RULE_SIMPSON = 3, VB200_RULE_BOOLE = 5,       /* value = samples per dimension (rules.h) */
+    VB200_RULE_SIMPSON_TRAPEZOIDAL = 32, VB200_RULE_BOOLE_SIMPSON = 53              /* nested(high,low) pairs (nested.h:7-34) */
+} vb200_rule;
+typedef enum vb200_heuristic { VB200_HEURISTIC_DEFAULT = 0, VB200_HEURISTIC_SIZE = 1 } vb200_heuristic;   /* error-heuristic.h:10-46 */
+typedef enum vb200_metric { VB200_METRIC_ABSOLUTE = 0, VB200_METRIC_RELATIVE = 1 } vb200_metric;         /* error-metric.h:10-41 */
+
+/* Leaf table produced by a generator ("region tree" of north_star = this flat table).
+ * Device resident, SoA; order is the reference's heap-array order in exact mode. */
+typedef struct vb200_regions vb200_regions;
+
+typedef struct vb200_adaptive_params {
+    vb200_domain domain;        /* dimbins/res unused by the generator */
+    int32_t  rule;              /* nested pair */
+    int32_t  heuristic;         /* vb200_heuristic */
+    int32_t  metric;            /* vb200_metric */
+    int32_t  batch;             /* 1 = exact greedy order (reference regions-generator-adaptive-heap.h:18-45, bit-exact with an
+                                   EXACT integrand); 0 = batched top-k refinement (throughput mode, auto batch size);
+                                   >1 = batched with at most this many splits per round */
+    double   size_weight;       /* error_heuristic_size weight (reference default 1e-5) */
+    uint64_t iterations;        /* number of splits: the table ends with iterations+1 regions */
+} vb200_adaptive_params;
+
+int vb200_regions_generate_adaptive(vb200_ctx* ctx, const vb200_integrand* f, const vb200_adaptive_params* p, vb200_regions** out);
+/* regions_generator_single (reference src/newton-cotes/regions-generator-single.h:12-20): one region over the range */
+int vb200_regions_generate_single(vb200_ctx* ctx, const vb200_integrand* f, const vb200_domain* domain, int rule, vb200_regions** out);
+/* upload an externally produced table (tests: the reference's own region list) */
+int vb200_regions_upload(vb200_ctx* ctx, int dim, int rule, uint64_t count,
+                         const float* rmin, const float* rmax, const float* err, const uint32_t* errdim, const float* data,
+                         vb200_regions** out);
+uint64_t vb200_regions_count(const vb200_regions* r);
+int      vb200_regions_dim(const vb200_regions* r);
+int      vb200_regions_samples(const vb200_regions* r);     /* S^dim values per region */
+/* host copies, AoS like the reference's Logger::log view: rmin/rmax [n*dim], err [n], errdim [n], data [n*S^dim]; any may be NULL */
+int      vb200_regions_download(vb200_ctx* ctx, const vb200_regions* r, float* rmin, float* rmax, float* err, uint32_t* errdim, float* data);
+void     vb200_regions_free(vb200_regions* r);
+
+/* RegionsIntegratorSequential (reference src/newton-cotes/regions-integrator-sequential.h:38-58):
+ * bins(pos) += nbins * region.integral_subrange(bin ∩ region) for every region and touched bin
+ * (pixels_in_region incl. its 0.99f rule, region.h:454-463).  Bin-major, regions visited in table order per bin,
+ * so the float summation order — and the bits — match the reference.  Also serves RegionsIntegratorParallelRegions. */
+int vb200_regions_integrate_bins(vb200_ctx* ctx, const vb200_regions* r, const vb200_domain* domain, const vb200_shard* shard,
+                                 float* bins, int bins_mem);
+
+/* ---- control variates + residual Monte Carlo (rows a15-a18) --------------------------------------------- */
+typedef struct vb200_cv_params {
+    vb200_domain domain;
+    vb200_shard  shard;
+    uint64_t     spp;
+    uint64_t     seed;
+} vb200_cv_params;
+
+/* RegionsIntegratorParallelVarianceReduction with rr_uniform_region / cv_optimize_weight / region_sampling_uniform
+ * (reference src/control-variates/regions-integrator-parallel-variance-reduction.h:32-109; the integrator_crespo2021
+ * preset, integrator-crespo2021.h:7-22).  bins overwritten ('=').  Optional per-bin records (same memory space as
+ * bins, may be NULL): nregions (uint32), approx (float, the control-variate integral). */
+int vb200_cv_integrate(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r, const vb200_cv_params* p,
+                       float* bins, int bins_mem, uint32_t* nregions, float* approx);
+
+/* Replay: chosen [nbins_of_shard*spp] = index into the region table, samples [nbins_of_shard*spp*dim]; accumulates
+ * the reference's online moments sequentially in double — bit-identical bins with an EXACT integrand. */
+int vb200_cv_replay(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r, const vb200_cv_params* p,
+                    const uint32_t* chosen, const float* samples, int mem, float* bins, int bins_mem);
+
+/* ---- kernel launch structs (filled by the library, consumed by the thunks) ------------------------------ */
+typedef struct vb200_mc_launch {
+    vb200_domain domain;
+    uint64_t bin_begin, bin_end;      /* shard */
+    uint64_t nbins_total;
+    uint32_t spp;
+    uint32_t lanes_per_bin;           /* power of two, 1..32 */
+    uint32_t key0, key1;              /* Philox key */
+    int32_t  flavor;
+    int32_t  accumulate;              /* 1: out[b] = float(double(out[b]) + v) ; 0: out[b] = v */
+    double   factor;                  /* flavor 0: vol(range)/spp */
+    float*   out;                     /* device, base of full grid */
+    float*   sum_f;                   /* device or NULL, base of shard */
+    float*   sum_f2;
+    int32_t  grid_hint;               /* CTAs to launch (0 = let the thunk size it from occupancy) */
+    int32_t  reserved;
+} vb200_mc_launch;
+
+typedef struct vb200_replay_launch {
+    vb200_domain domain;
+    uint64_t bin_begin, bin_end, nbins_total;
+    uint32_t spp; int32_t flavor;
+    double   factor;
+    const float* samples;             /* device, [nbins_of_shard][spp][dim] */
+    float*   out;                     /* device, base of full grid; read-modify-write for flavor 0 */
+} vb200_replay_launch;
+
+typedef struct vb200_walk_launch {
+    vb200_domain domain;              /* dim = explicit range entries */
+    uint64_t bin_begin, bin_end, nbins_total;
+    uint32_t spp; uint32_t lanes_per_bin;
+    uint32_t key0, key1;
+    int32_t  accumulate; int32_t grid_hint;
+    double   factor;
+    float*   out; float* sum_f; float* sum_f2;
+} vb200_walk_launch;
+
+typedef struct vb200_walk_replay_launch {
+    vb200_domain domain;
+    uint64_t bin_begin, bin_end, nbins_total;
+    uint32_t spp; int32_t reserved;
+    double   factor;
+    const uint64_t* offsets; const float* elems;
+    float*   out;
+    int32_t* error_flag;              /* device int, set to 1 when a path reads past its recorded length */
+} vb200_walk_replay_launch;
+
+typedef struct vb200_eval_launch {
+    uint64_t n;
+    int32_t  dim; int32_t reserved;
+    const float* points;              /* device, SoA: points[d*n + i] */
+    float*   values;                  /* device, [n] */
+} vb200_eval_launch;
+
+typedef struct vb200_greedy_launch {
+    int32_t  dim, rule, heuristic, metric;
+    double   size_weight;
+    uint64_t iterations;
+    uint64_t capacity;                /* region slots (>= iterations*2+1: parents are not recycled) */
+    float*   rmin; float* rmax;       /* device SoA [dim][capacity] */
+    float*   data;                    /* device SoA [S^dim][capacity] */
+    float*   err;  uint32_t* errdim;  /* device [capacity] */
+    float*   heap_key; uint32_t* heap_id;   /* device [iterations+1]: the binary heap, array order = output order */
+    float    range_min[VB200_MAX_DIM], range_max[VB200_MAX_DIM];
+} vb200_greedy_launch;
+
+typedef struct vb200_scatter_launch {
+    vb200_domain domain;
+    uint64_t sample_begin, sample_end, nbins_total;
+    uint32_t key0, key1;
+    double   factor;
+    float*   out;
+    int32_t  grid_hint; int32_t reserved;
+} vb200_scatter_launch;
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VILTRUM_B200_H */

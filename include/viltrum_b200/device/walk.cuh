@@ -1,0 +1,146 @@
+// K3 — infinite-dimensional (RangeInfinite) per-bin Monte Carlo, replacing the reference's
+//   MonteCarloPerBinParallel::integrate(RangeInfinite)   src/monte-carlo/monte-carlo-per-bin-parallel.h:73-100
+//   RandomSequenceRefDis (lazy sequence over the bin RNG)  src/monte-carlo/random-sequence-ref-dis.h:11-44
+//   RangeInfinite (implicit [0,1] tail)                    src/range-infinite.h:16-64
+// The integrand is a functor over a *sequence* (seq.begin(), *it, ++it; never-ending), exactly the reference's
+// protocol.  On the GPU the sequence is stateless: element i of sample s in bin b is
+//   u01(Philox4x32-10(key=seed, counter=(b, s, i/4))[i%4]) * (max_i - min_i) + min_i
+// so a lane needs no per-bin generator state and any lane can produce any element.  Each lane owns whole paths
+// and runs its own Russian roulette inside the user's functor.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include "../../viltrum_b200.h"
+#include "philox.cuh"
+#include "mc_per_bin.cuh"
+
+namespace viltrum { namespace b200 { namespace device {
+
+template<int DIMBINS>
+struct PhiloxSequence {
+    uint32_t b0, b1, s, k0, k1;
+    float lo[DIMBINS], ext[DIMBINS];        // the bin's box in the binned dimensions
+    const vb200_domain* dom;                 // explicit entries beyond the binned dims (kernel parameter space)
+
+    class const_iterator {
+        const PhiloxSequence* q; uint32_t i; u32x4 blk; float n;
+        __device__ __forceinline__ void load() {
+            if ((i & 3u) == 0u) blk = philox4x32<10>(u32x4{q->b0, q->b1, q->s, i >> 2}, q->k0, q->k1);
+            const float u = pick(blk, int(i & 3u));
+            float v = u;                                                   // default range [0,1): u*(1-0)+0 == u
+            bool binned = false;
+#pragma unroll
+            for (int d = 0; d < DIMBINS; ++d) if (i == uint32_t(d)) { v = fmaf(u, q->ext[d], q->lo[d]); binned = true; }
+            if (!binned && int(i) < q->dom->dim) v = fmaf(u, q->dom->rmax[i] - q->dom->rmin[i], q->dom->rmin[i]);
+            n = v;
+        }
+    public:
+        __device__ __forceinline__ const_iterator(const PhiloxSequence* q_) : q(q_), i(0) { load(); }
+        __device__ __forceinline__ const float& operator*() const { return n; }
+        __device__ __forceinline__ const_iterator& operator++() { ++i; load(); return *this; }
+        __device__ __forceinline__ bool operator!=(const const_iterator&) const { return true; }   // infinite list
+        __device__ __forceinline__ bool operator==(const const_iterator&) const { return false; }
+    };
+    __device__ __forceinline__ const_iterator begin() const { return const_iterator(this); }
+    __device__ __forceinline__ const_iterator end() const { return const_iterator(this); }
+};
+
+template<int DIMBINS>
+__device__ __forceinline__ void walk_bin_box(const vb200_domain& dom, uint64_t bin, float (&lo)[DIMBINS], float (&ext)[DIMBINS]) {
+    uint32_t pos[VB200_MAX_DIMBINS];
+    unflatten_bin<DIMBINS>(bin, dom, pos);
+#pragma unroll
+    for (int i = 0; i < DIMBINS; ++i) {
+        // RangeInfinite::min/max default to 0/1 beyond the explicit entries (range-infinite.h:31-37)
+        const float rmin = i < dom.dim ? dom.rmin[i] : 0.0f, rmax = i < dom.dim ? dom.rmax[i] : 1.0f;
+        const float drange = __fdiv_rn(rmax - rmin, float(dom.res[i]));
+        const float a = __fadd_rn(rmin, __fmul_rn(float(pos[i]), drange));
+        const float b = __fadd_rn(rmin, __fmul_rn(float(pos[i] + 1u), drange));
+        lo[i] = a; ext[i] = b - a;
+    }
+}
+
+template<class F, int DIMBINS, bool MOMENTS, bool EXACT>
+__global__ void __launch_bounds__(MC_THREADS)
+walk_kernel(const F f, const vb200_walk_launch a) {
+    __shared__ float s_val[2][MC_THREADS];
+    __shared__ float s_m1[MOMENTS ? MC_THREADS : 1];
+    __shared__ float s_m2[MOMENTS ? MC_THREADS : 1];
+    const uint32_t lpb = a.lanes_per_bin;
+    const uint32_t bins_per_tile = MC_THREADS / lpb;
+    const uint32_t tid = threadIdx.x, slot = tid / lpb, sub = tid % lpb;
+    const uint64_t nshard = a.bin_end - a.bin_begin;
+    const uint64_t ntiles = (nshard + bins_per_tile - 1) / bins_per_tile;
+    int buf = 0;
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+        const uint64_t bin = a.bin_begin + tile * bins_per_tile + slot;
+        float sum = 0.0f, sum2 = 0.0f;
+        if (bin < a.bin_end) {
+            PhiloxSequence<DIMBINS> seq;
+            seq.b0 = uint32_t(bin); seq.b1 = uint32_t(bin >> 32); seq.k0 = a.key0; seq.k1 = a.key1; seq.dom = &a.domain;
+            walk_bin_box<DIMBINS>(a.domain, bin, seq.lo, seq.ext);
+            for (uint32_t s = sub; s < a.spp; s += lpb) {
+                seq.s = s;
+                const float v = f(seq);
+                sum += v;
+                if (MOMENTS) sum2 = fmaf(v, v, sum2);
+            }
+        }
+        for (uint32_t off = lpb >> 1; off > 0; off >>= 1) {
+            sum += __shfl_xor_sync(0xffffffffu, sum, off);
+            if (MOMENTS) sum2 += __shfl_xor_sync(0xffffffffu, sum2, off);
+        }
+        if (sub == 0) {
+            s_val[buf][slot] = float(double(sum) * a.factor);            // monte-carlo-per-bin-parallel.h:77,96
+            if (MOMENTS) { s_m1[slot] = sum; s_m2[slot] = sum2; }
+        }
+        __syncthreads();
+        if (tid < bins_per_tile) {
+            const uint64_t ob = a.bin_begin + tile * bins_per_tile + tid;
+            if (ob < a.bin_end) {
+                const float v = s_val[buf][tid];
+                a.out[ob] = a.accumulate ? float(double(a.out[ob]) + double(v)) : v;
+                if (MOMENTS) {
+                    if (a.sum_f)  a.sum_f[ob - a.bin_begin]  = s_m1[tid];
+                    if (a.sum_f2) a.sum_f2[ob - a.bin_begin] = s_m2[tid];
+                }
+            }
+        }
+        if (MOMENTS) __syncthreads();
+    }
+}
+
+// Replay of recorded sequences (the reference's own element values): one thread per bin, paths in order,
+// bins(p) += f(seq)*factor with float(double(acc)+double(f)*factor)  (monte-carlo-per-bin-parallel.h:96).
+struct RecordedSequence {
+    const float* e; uint32_t len; int32_t* error_flag;
+    class const_iterator {
+        const RecordedSequence* q; uint32_t i; float n;
+        __device__ __forceinline__ void load() {
+            if (i < q->len) n = q->e[i]; else { n = CUDART_NAN_F; *q->error_flag = 1; }
+        }
+    public:
+        __device__ __forceinline__ const_iterator(const RecordedSequence* q_) : q(q_), i(0) { load(); }
+        __device__ __forceinline__ const float& operator*() const { return n; }
+        __device__ __forceinline__ const_iterator& operator++() { ++i; load(); return *this; }
+    };
+    __device__ __forceinline__ const_iterator begin() const { return const_iterator(this); }
+};
+
+template<class F, bool EXACT>
+__global__ void __launch_bounds__(128)
+walk_replay_kernel(const F f, const vb200_walk_replay_launch a) {
+    const uint64_t k = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const uint64_t bin = a.bin_begin + k;
+    if (bin >= a.bin_end) return;
+    float acc = a.out[bin];
+    for (uint32_t s = 0; s < a.spp; ++s) {
+        const uint64_t p = k * a.spp + s;
+        RecordedSequence seq{a.elems + a.offsets[p], uint32_t(a.offsets[p + 1] - a.offsets[p]), a.error_flag};
+        const float v = f(seq);
+        acc = __double2float_rn(__dadd_rn(double(acc), __dmul_rn(double(v), a.factor)));
+    }
+    a.out[bin] = acc;
+}
+
+}}} // namespace viltrum::b200::device

@@ -1,0 +1,9 @@
+"""viltrum_b200 — B200-native per-bin integration hot path of adolfomunoz/viltrum behind the reference's own
+vocabulary.  The product is the CUDA library (viltrum_b200/csrc -> libviltrum_b200.so, C ABI in
+include/viltrum_b200.h) and the C++17 drop-in headers (include/viltrum_b200/viltrum.h); this Python package is
+the thin host-side mirror used by the tests and the benchmark (ctypes over the C ABI, numpy/torch buffers)."""
+from .host import (Context, Regions, integrate, monte_carlo, monte_carlo_per_bin_parallel, integrator_per_bin_parallel,  # noqa: F401
+                   integrator_newton_cotes, integrator_adaptive_iterations, integrator_crespo2021, nested,
+                   error_heuristic_default, error_heuristic_size, error_metric_absolute, error_metric_relative,
+                   range_primary, range_primary_infinite, Range, RangeInfinite, builtin_names)
+from ._capi import Vb200Error  # noqa: F401

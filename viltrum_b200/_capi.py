@@ -1,0 +1,114 @@
+"""ctypes binding of the C ABI in include/viltrum_b200.h (libviltrum_b200.so).  No torch types cross this
+boundary: pointers are integers / numpy buffers, sizes are plain ints.  The library has no CPU path — importing
+works anywhere, creating a Context needs a CUDA device and raises otherwise."""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libviltrum_b200.so")
+
+MAX_DIM, MAX_DIMBINS, K_COUNT = 8, 3, 8
+HOST, DEVICE = 0, 1
+MC_PER_BIN, PER_BIN_MC = 0, 1
+RULES = {"trapezoidal": 2, "simpson": 3, "boole": 5, "simpson_trapezoidal": 32, "boole_simpson": 53}
+RULE_SAMPLES = {2: 2, 3: 3, 5: 5, 32: 3, 53: 5}
+HEURISTICS = {"default": 0, "size": 1}
+METRICS = {"absolute": 0, "relative": 1}
+
+STATUS = {0: "VB200_OK", -1: "VB200_ERR_NO_DEVICE", -2: "VB200_ERR_INVALID", -3: "VB200_ERR_CUDA",
+          -4: "VB200_ERR_UNSUPPORTED", -5: "VB200_ERR_NOMEM"}
+
+# every symbol include/viltrum_b200.h declares (tests/test_capi_symbols.py checks the header against this list and the .so)
+SYMBOLS = [
+    "vb200_create", "vb200_destroy", "vb200_last_error", "vb200_stream", "vb200_synchronize", "vb200_sm_count",
+    "vb200_launch_count", "vb200_philox4x32_10", "vb200_builtin_integrand", "vb200_builtin_count", "vb200_builtin_name",
+    "vb200_mc_per_bin", "vb200_mc_per_bin_replay", "vb200_mc_per_bin_inf", "vb200_mc_per_bin_inf_replay",
+    "vb200_monte_carlo", "vb200_regions_generate_adaptive", "vb200_regions_generate_single", "vb200_regions_upload",
+    "vb200_regions_count", "vb200_regions_dim", "vb200_regions_samples", "vb200_regions_download", "vb200_regions_free",
+    "vb200_regions_integrate_bins", "vb200_cv_integrate", "vb200_cv_replay",
+]
+
+
+class Domain(ctypes.Structure):
+    _fields_ = [("dim", ctypes.c_int32), ("dimbins", ctypes.c_int32), ("rmin", ctypes.c_float * MAX_DIM),
+                ("rmax", ctypes.c_float * MAX_DIM), ("res", ctypes.c_uint64 * MAX_DIMBINS)]
+
+
+class Shard(ctypes.Structure):
+    _fields_ = [("begin", ctypes.c_uint64), ("end", ctypes.c_uint64)]
+
+
+class McParams(ctypes.Structure):
+    _fields_ = [("domain", Domain), ("shard", Shard), ("spp", ctypes.c_uint64), ("seed", ctypes.c_uint64),
+                ("flavor", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+class AdaptiveParams(ctypes.Structure):
+    _fields_ = [("domain", Domain), ("rule", ctypes.c_int32), ("heuristic", ctypes.c_int32), ("metric", ctypes.c_int32),
+                ("batch", ctypes.c_int32), ("size_weight", ctypes.c_double), ("iterations", ctypes.c_uint64)]
+
+
+class CvParams(ctypes.Structure):
+    _fields_ = [("domain", Domain), ("shard", Shard), ("spp", ctypes.c_uint64), ("seed", ctypes.c_uint64)]
+
+
+class Vb200Error(RuntimeError):
+    def __init__(self, status, text):
+        super().__init__(f"{STATUS.get(status, status)}: {text}")
+        self.status = status
+
+
+_lib = None
+
+
+def lib():
+    """Loads libviltrum_b200.so (built in-tree by viltrum_b200.build).  Fails loudly if it is missing: there is no
+    fallback implementation."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `python -m viltrum_b200.build` (no fallback path exists)")
+        L = ctypes.CDLL(LIB_PATH)
+        vp, i32, u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64
+        L.vb200_create.argtypes = [i32, ctypes.POINTER(vp)]; L.vb200_create.restype = i32
+        L.vb200_destroy.argtypes = [vp]; L.vb200_destroy.restype = None
+        L.vb200_last_error.argtypes = [vp]; L.vb200_last_error.restype = ctypes.c_char_p
+        L.vb200_stream.argtypes = [vp]; L.vb200_stream.restype = vp
+        L.vb200_synchronize.argtypes = [vp]; L.vb200_synchronize.restype = i32
+        L.vb200_sm_count.argtypes = [vp]; L.vb200_sm_count.restype = i32
+        L.vb200_launch_count.argtypes = [vp]; L.vb200_launch_count.restype = u64
+        L.vb200_philox4x32_10.argtypes = [ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]; L.vb200_philox4x32_10.restype = None
+        L.vb200_builtin_integrand.argtypes = [ctypes.c_char_p, i32]; L.vb200_builtin_integrand.restype = vp
+        L.vb200_builtin_count.argtypes = []; L.vb200_builtin_count.restype = i32
+        L.vb200_builtin_name.argtypes = [i32]; L.vb200_builtin_name.restype = ctypes.c_char_p
+        L.vb200_mc_per_bin.argtypes = [vp, vp, ctypes.POINTER(McParams), vp, i32, vp, vp]; L.vb200_mc_per_bin.restype = i32
+        L.vb200_mc_per_bin_replay.argtypes = [vp, vp, ctypes.POINTER(McParams), vp, i32, vp, i32]; L.vb200_mc_per_bin_replay.restype = i32
+        L.vb200_mc_per_bin_inf.argtypes = [vp, vp, ctypes.POINTER(McParams), vp, i32, vp, vp]; L.vb200_mc_per_bin_inf.restype = i32
+        L.vb200_mc_per_bin_inf_replay.argtypes = [vp, vp, ctypes.POINTER(McParams), vp, vp, i32, vp, i32]; L.vb200_mc_per_bin_inf_replay.restype = i32
+        L.vb200_monte_carlo.argtypes = [vp, vp, ctypes.POINTER(McParams), vp, i32]; L.vb200_monte_carlo.restype = i32
+        L.vb200_regions_generate_adaptive.argtypes = [vp, vp, ctypes.POINTER(AdaptiveParams), ctypes.POINTER(vp)]; L.vb200_regions_generate_adaptive.restype = i32
+        L.vb200_regions_generate_single.argtypes = [vp, vp, ctypes.POINTER(Domain), i32, ctypes.POINTER(vp)]; L.vb200_regions_generate_single.restype = i32
+        L.vb200_regions_upload.argtypes = [vp, i32, i32, u64, vp, vp, vp, vp, vp, ctypes.POINTER(vp)]; L.vb200_regions_upload.restype = i32
+        L.vb200_regions_count.argtypes = [vp]; L.vb200_regions_count.restype = u64
+        L.vb200_regions_dim.argtypes = [vp]; L.vb200_regions_dim.restype = i32
+        L.vb200_regions_samples.argtypes = [vp]; L.vb200_regions_samples.restype = i32
+        L.vb200_regions_download.argtypes = [vp, vp, vp, vp, vp, vp, vp]; L.vb200_regions_download.restype = i32
+        L.vb200_regions_free.argtypes = [vp]; L.vb200_regions_free.restype = None
+        L.vb200_regions_integrate_bins.argtypes = [vp, vp, ctypes.POINTER(Domain), ctypes.POINTER(Shard), vp, i32]; L.vb200_regions_integrate_bins.restype = i32
+        L.vb200_cv_integrate.argtypes = [vp, vp, vp, ctypes.POINTER(CvParams), vp, i32, vp, vp]; L.vb200_cv_integrate.restype = i32
+        L.vb200_cv_replay.argtypes = [vp, vp, vp, ctypes.POINTER(CvParams), vp, vp, i32, vp, i32]; L.vb200_cv_replay.restype = i32
+        _lib = L
+    return _lib
+
+
+def make_domain(dim, res, rmin=(), rmax=()):
+    d = Domain()
+    d.dim = int(dim); d.dimbins = len(res)
+    if len(res) > MAX_DIMBINS:
+        raise ValueError(f"at most {MAX_DIMBINS} binned dimensions")
+    for i, r in enumerate(res):
+        d.res[i] = int(r)
+    for i in range(MAX_DIM):
+        d.rmin[i] = float(rmin[i]) if i < len(rmin) else 0.0
+        d.rmax[i] = float(rmax[i]) if i < len(rmax) else 1.0
+    return d

@@ -1,0 +1,60 @@
+// Device twins of the synthetic integrands of SURVEY.md §8(d) / Appendix D (shade4<K>, shade5<K>, smooth_edge2,
+// walk) plus the small analytic ones the reference's own examples use (x^2+y^2: main/doc/montecarlo-2d.cc:10;
+// (x+y<1): main/compilation-tests/array-parameter.cc:11-14; geometric-series walk: main/doc/montecarlo-infd.cc:8-22).
+// Transcendental-free fp32, so a --fmad=false build evaluates them to the same bits as a CPU build with
+// -ffp-contract=off.  Written from the formulas in SURVEY.md; nothing here comes from oracle/.
+#pragma once
+#include <array>
+
+namespace viltrum { namespace b200 { namespace builtin {
+
+struct X2Y2 { __host__ __device__ float operator()(const std::array<float,2>& x) const { return x[0]*x[0] + x[1]*x[1]; } };
+struct Ind2 { __host__ __device__ float operator()(const std::array<float,2>& x) const { return ((x[0]+x[1])<1.0f)?1.0f:0.0f; } };
+struct Cubic1 { __host__ __device__ float operator()(const std::array<float,1>& x) const { return (4.0f*x[0]*x[0]-1.0f)*x[0] + 0.25f; } };
+struct Poly3 { __host__ __device__ float operator()(const std::array<float,3>& x) const { return x[0]*x[1] + x[1]*x[2]*x[2] + 0.5f; } };
+
+template<int K> struct Shade4 {
+    __host__ __device__ float operator()(const std::array<float,4>& x) const {
+        const float a = x[0]-.5f, b = x[1]-.5f;
+        const float edge = .55f+.35f*(a*a-b*b)+.2f*a*b;
+        const float vis = (x[2]+.5f*x[3]<edge)?1.0f:0.0f;
+        const float t = x[2]*(1.0f-x[3]);
+        float lobe = 1.0f/float(K);
+#pragma unroll
+        for (int k=K-2;k>=0;--k) lobe = lobe*t+1.0f/float(k+1);      // Horner, c_k = 1/(k+1)
+        const float alb = .25f+.75f*x[0]*x[1];
+        return vis*lobe*alb;
+    }
+};
+template<int K> struct Shade5 {
+    __host__ __device__ float operator()(const std::array<float,5>& x) const {
+        return Shade4<K>()(std::array<float,4>{x[0],x[1],x[2],x[3]})*(.5f+x[4]);
+    }
+};
+struct SmoothEdge2 {
+    __host__ __device__ float operator()(const std::array<float,2>& p) const {
+        const float x = p[0], y = p[1];
+        const float s = .5f+8.0f*x*(1.0f-x)*y*(1.0f-y)*(1.0f-2.0f*(x-y)*(x-y));
+        const float dx = x-.45f, dy = y-.55f;
+        return s+((dx*dx+dy*dy<.09f)?.75f:0.0f);
+    }
+};
+struct Walk {
+    template<typename Seq> __host__ __device__ float operator()(const Seq& seq) const {
+        auto it = seq.begin(); const float px = *it; ++it; const float py = *it; ++it;
+        const float alb = .4f+.5f*(4.0f*px*(1.0f-px))*(.25f+.75f*py);
+        float pos = .5f, L = 0.0f;
+        while (true) { const float u = *it; ++it; if (u>=alb) break;
+                       const float s = *it; ++it; pos = .5f*pos+.5f*s; L += .25f+pos*pos; }
+        return L;
+    }
+};
+struct Decay {
+    template<typename Seq> __host__ __device__ float operator()(const Seq& seq) const {
+        auto x = seq.begin(); float sum = 0.0f, term = 1.0f;
+        while ((*x) < 0.75f) { ++x; term *= 2.0f*(*x); ++x; sum += term; }
+        return sum;
+    }
+};
+
+}}} // namespace viltrum::b200::builtin

@@ -1,0 +1,347 @@
+// libviltrum_b200.so — context, argument staging and the Monte-Carlo drivers of the C ABI (include/viltrum_b200.h).
+// Nothing in here evaluates an integrand: kernels templated on the functor are reached through the launch thunks
+// in the vb200_integrand table.  There is no CPU fallback anywhere in this library.
+#include "context.h"
+#include <viltrum_b200/device/philox.cuh>
+#include <cstring>
+#include <cmath>
+#include <new>
+
+namespace {
+thread_local std::string g_create_error;
+}
+
+namespace vb200 {
+
+int fail(vb200_ctx* ctx, int status, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    if (ctx) ctx->error = buf; else g_create_error = buf;
+    return status;
+}
+
+int reserve(vb200_ctx* ctx, int slot, size_t bytes, void** out) {
+    if (bytes > ctx->scratch_bytes[slot]) {
+        if (ctx->scratch[slot]) { VB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); VB200_CUDA(ctx, cudaFree(ctx->scratch[slot])); ctx->scratch[slot] = nullptr; ctx->scratch_bytes[slot] = 0; }
+        size_t want = bytes + bytes / 4 + 256;
+        if (cudaMalloc(&ctx->scratch[slot], want) != cudaSuccess) { cudaGetLastError(); return fail(ctx, VB200_ERR_NOMEM, "cudaMalloc of %zu scratch bytes failed", want); }
+        ctx->scratch_bytes[slot] = want;
+    }
+    *out = ctx->scratch[slot];
+    return VB200_OK;
+}
+
+int reserve_pinned(vb200_ctx* ctx, size_t bytes, void** out) {
+    if (bytes > ctx->pinned_bytes) {
+        if (ctx->pinned) { VB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); VB200_CUDA(ctx, cudaFreeHost(ctx->pinned)); ctx->pinned = nullptr; ctx->pinned_bytes = 0; }
+        size_t want = bytes + bytes / 4 + 256;
+        if (cudaMallocHost(&ctx->pinned, want) != cudaSuccess) { cudaGetLastError(); return fail(ctx, VB200_ERR_NOMEM, "cudaMallocHost of %zu bytes failed", want); }
+        ctx->pinned_bytes = want;
+    }
+    *out = ctx->pinned;
+    return VB200_OK;
+}
+
+int check_domain(vb200_ctx* ctx, const vb200_domain& d, int integrand_dim) {
+    if (d.dimbins < 1 || d.dimbins > VB200_MAX_DIMBINS) return fail(ctx, VB200_ERR_INVALID, "dimbins=%d outside 1..%d", d.dimbins, VB200_MAX_DIMBINS);
+    if (integrand_dim > 0) {
+        if (d.dim != integrand_dim) return fail(ctx, VB200_ERR_INVALID, "range has %d dimensions, integrand takes %d", d.dim, integrand_dim);
+        if (d.dimbins > d.dim) return fail(ctx, VB200_ERR_INVALID, "dimbins=%d exceeds range dimensions %d", d.dimbins, d.dim);
+    } else if (d.dim < 0 || d.dim > VB200_MAX_DIM) return fail(ctx, VB200_ERR_INVALID, "infinite range with %d explicit entries (max %d)", d.dim, VB200_MAX_DIM);
+    for (int i = 0; i < d.dimbins; ++i) if (d.res[i] == 0 || d.res[i] > 0xffffffffull) return fail(ctx, VB200_ERR_INVALID, "resolution[%d]=%llu invalid", i, (unsigned long long)d.res[i]);
+    return VB200_OK;
+}
+
+int resolve_shard(vb200_ctx* ctx, const vb200_shard& s, uint64_t total, uint64_t* begin, uint64_t* end) {
+    if (s.begin == 0 && s.end == 0) { *begin = 0; *end = total; return VB200_OK; }
+    if (s.begin > s.end || s.end > total) return fail(ctx, VB200_ERR_INVALID, "shard [%llu,%llu) outside [0,%llu)", (unsigned long long)s.begin, (unsigned long long)s.end, (unsigned long long)total);
+    *begin = s.begin; *end = s.end;
+    return VB200_OK;
+}
+
+int call_thunk(vb200_ctx* ctx, const vb200_integrand* f, int kind, const void* args) {
+    if (!f || f->abi_version != VB200_ABI_VERSION) return fail(ctx, VB200_ERR_INVALID, "integrand descriptor missing or built against another ABI version");
+    if (!f->launch[kind]) return fail(ctx, VB200_ERR_UNSUPPORTED, "integrand '%s' has no kernel of kind %d", f->name ? f->name : "?", kind);
+    int e = f->launch[kind](f, args, ctx->stream);
+    if (e != 0) return fail(ctx, VB200_ERR_CUDA, "kernel launch (kind %d, integrand '%s') failed: %s", kind, f->name ? f->name : "?", cudaGetErrorString(cudaError_t(e)));
+    ctx->launches++;
+    return VB200_OK;
+}
+
+// lanes of one warp that share a bin: aim for >= 8 samples per lane so the per-bin setup (bin box, shuffles)
+// amortises, and for enough lanes that small bin grids still fill the chip
+uint32_t pick_lanes_per_bin(uint64_t spp) {
+    uint32_t lpb = 1;
+    while (lpb < 32 && uint64_t(lpb) * 16 <= spp) lpb <<= 1;
+    return lpb;
+}
+
+int stage_bins_in(vb200_ctx* ctx, float* bins, int mem, uint64_t begin, uint64_t end, bool upload, BinStage* st) {
+    st->begin = begin; st->end = end; st->host = nullptr; st->staged = false;
+    if (!bins) return fail(ctx, VB200_ERR_INVALID, "bins pointer is NULL");
+    if (mem == VB200_DEVICE) { st->dev_base = bins; return VB200_OK; }
+    if (mem != VB200_HOST) return fail(ctx, VB200_ERR_INVALID, "bad memory-space flag %d", mem);
+    const uint64_t n = end - begin;
+    void* d = nullptr;
+    int rc = reserve(ctx, 0, n * sizeof(float), &d); if (rc) return rc;
+    if (upload) VB200_CUDA(ctx, cudaMemcpyAsync(d, bins + begin, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    st->dev_base = static_cast<float*>(d) - begin;      // kernels index from the base of the full grid
+    st->staged = true; st->host = bins;
+    return VB200_OK;
+}
+
+int stage_bins_out(vb200_ctx* ctx, const BinStage& st) {
+    if (!st.staged) return VB200_OK;
+    const uint64_t n = st.end - st.begin;
+    VB200_CUDA(ctx, cudaMemcpyAsync(st.host + st.begin, st.dev_base + st.begin, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    VB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VB200_OK;
+}
+
+} // namespace vb200
+
+using namespace vb200;
+
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int vb200_create(int device, vb200_ctx** out) {
+    if (!out) return fail(nullptr, VB200_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) { cudaGetLastError(); return fail(nullptr, VB200_ERR_NO_DEVICE, "no CUDA device available (%s); viltrum_b200 has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"); }
+    if (device < 0 || device >= n) return fail(nullptr, VB200_ERR_INVALID, "device %d outside 0..%d", device, n - 1);
+    vb200_ctx* ctx = new (std::nothrow) vb200_ctx;
+    if (!ctx) return fail(nullptr, VB200_ERR_NOMEM, "out of host memory");
+    ctx->device = device;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess ||
+        (e = cudaMalloc(&ctx->d_flag, sizeof(int32_t))) != cudaSuccess) {
+        int rc = fail(nullptr, VB200_ERR_CUDA, "context setup on device %d failed: %s", device, cudaGetErrorString(e));
+        delete ctx; return rc;
+    }
+    *out = ctx;
+    return VB200_OK;
+}
+
+extern "C" void vb200_destroy(vb200_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto& s : ctx->scratch) if (s) cudaFree(s);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->d_flag) cudaFree(ctx->d_flag);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char* vb200_last_error(const vb200_ctx* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+extern "C" void* vb200_stream(vb200_ctx* ctx) { return ctx ? ctx->stream : nullptr; }
+extern "C" int vb200_synchronize(vb200_ctx* ctx) { if (!ctx) return VB200_ERR_INVALID; VB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); return VB200_OK; }
+extern "C" int vb200_sm_count(const vb200_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+extern "C" uint64_t vb200_launch_count(const vb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" void vb200_philox4x32_10(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]) {
+    const viltrum::b200::u32x4 r = viltrum::b200::philox4x32<10>(viltrum::b200::u32x4{counter[0], counter[1], counter[2], counter[3]}, key[0], key[1]);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+// ---- built-in integrands ----------------------------------------------------------------------------------
+struct BuiltinEntry { const char* name; const vb200_integrand* desc; };
+extern "C" const BuiltinEntry* builtin_table_fast(int* count);
+extern "C" const BuiltinEntry* builtin_table_exact(int* count);
+
+extern "C" const vb200_integrand* vb200_builtin_integrand(const char* name, int exact) {
+    if (!name) return nullptr;
+    int n = 0; const BuiltinEntry* t = exact ? builtin_table_exact(&n) : builtin_table_fast(&n);
+    for (int i = 0; i < n; ++i) if (!std::strcmp(t[i].name, name)) return t[i].desc;
+    return nullptr;
+}
+extern "C" int vb200_builtin_count(void) { int n = 0; builtin_table_fast(&n); return n; }
+extern "C" const char* vb200_builtin_name(int index) { int n = 0; const BuiltinEntry* t = builtin_table_fast(&n); return (index >= 0 && index < n) ? t[index].name : nullptr; }
+
+// ---- per-bin Monte Carlo ----------------------------------------------------------------------------------
+namespace {
+// Range::volume(): float product over the dimensions in order, starting from 1 (reference src/range.h:21-25)
+float range_volume(const vb200_domain& d, int n) { float v = 1.0f; for (int i = 0; i < n; ++i) v *= (d.rmax[i] - d.rmin[i]); return v; }
+
+int stage_moments(vb200_ctx* ctx, float* p, int mem, int slot, uint64_t n, float** dev) {
+    *dev = nullptr;
+    if (!p) return VB200_OK;
+    if (mem == VB200_DEVICE) { *dev = p; return VB200_OK; }
+    void* d = nullptr; int rc = reserve(ctx, slot, n * sizeof(float), &d); if (rc) return rc;
+    *dev = static_cast<float*>(d);
+    return VB200_OK;
+}
+}
+
+extern "C" int vb200_mc_per_bin(vb200_ctx* ctx, const vb200_integrand* f, const vb200_mc_params* p,
+                                float* bins, int bins_mem, float* sum_f, float* sum_f2) {
+    if (!ctx || !f || !p) return fail(ctx, VB200_ERR_INVALID, "NULL argument");
+    VB200_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (f->dim <= 0) return fail(ctx, VB200_ERR_INVALID, "vb200_mc_per_bin needs a finite-dimensional integrand (use vb200_mc_per_bin_inf)");
+    int rc = check_domain(ctx, p->domain, f->dim); if (rc) return rc;
+    if (p->spp == 0 || p->spp > 0xffffffffull) return fail(ctx, VB200_ERR_INVALID, "spp=%llu invalid", (unsigned long long)p->spp);
+    if (p->flavor != VB200_MC_PER_BIN && p->flavor != VB200_PER_BIN_MC) return fail(ctx, VB200_ERR_INVALID, "unknown flavor %d", p->flavor);
+    const uint64_t total = nbins_of(p->domain);
+    uint64_t begin, end; rc = resolve_shard(ctx, p->shard, total, &begin, &end); if (rc) return rc;
+    if (begin == end) return VB200_OK;
+
+    vb200_mc_launch a; std::memset(&a, 0, sizeof(a));
+    a.domain = p->domain; a.bin_begin = begin; a.bin_end = end; a.nbins_total = total;
+    a.spp = uint32_t(p->spp); a.lanes_per_bin = pick_lanes_per_bin(p->spp);
+    a.key0 = uint32_t(p->seed); a.key1 = uint32_t(p->seed >> 32);
+    a.flavor = p->flavor;
+    a.factor = double(range_volume(p->domain, p->domain.dim)) / double(p->spp);     // monte-carlo-per-bin-parallel.h:45
+    // '+=' for MonteCarloPerBinParallel, '=' for IntegratorPerBinParallel.  With host bins the
+    // kernel writes the shard's estimate into scratch and the '+=' happens on the host after the copy back.
+    const bool accumulate = (p->flavor == VB200_MC_PER_BIN);
+    BinStage st; rc = stage_bins_in(ctx, bins, bins_mem, begin, end, /*upload=*/false, &st); if (rc) return rc;
+    a.accumulate = (accumulate && !st.staged) ? 1 : 0;
+    a.out = st.dev_base;
+    rc = stage_moments(ctx, sum_f, bins_mem, 1, end - begin, &a.sum_f); if (rc) return rc;
+    rc = stage_moments(ctx, sum_f2, bins_mem, 2, end - begin, &a.sum_f2); if (rc) return rc;
+    rc = call_thunk(ctx, f, VB200_K_MC_PER_BIN, &a); if (rc) return rc;
+    if (st.staged) {
+        const uint64_t n = end - begin;
+        float* h = nullptr; rc = reserve_pinned(ctx, n * sizeof(float) * 3, reinterpret_cast<void**>(&h)); if (rc) return rc;
+        VB200_CUDA(ctx, cudaMemcpyAsync(h, st.dev_base + begin, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        if (sum_f)  VB200_CUDA(ctx, cudaMemcpyAsync(h + n, a.sum_f, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        if (sum_f2) VB200_CUDA(ctx, cudaMemcpyAsync(h + 2 * n, a.sum_f2, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        VB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        float* dst = bins + begin;
+        if (accumulate) for (uint64_t i = 0; i < n; ++i) dst[i] = float(double(dst[i]) + double(h[i]));
+        else std::memcpy(dst, h, n * sizeof(float));
+        if (sum_f)  std::memcpy(sum_f, h + n, n * sizeof(float));
+        if (sum_f2) std::memcpy(sum_f2, h + 2 * n, n * sizeof(float));
+    }
+    return VB200_OK;
+}
+
+extern "C" int vb200_mc_per_bin_replay(vb200_ctx* ctx, const vb200_integrand* f, const vb200_mc_params* p,
+                                       const float* samples, int samples_mem, float* bins, int bins_mem) {
+    if (!ctx || !f || !p || !samples) return fail(ctx, VB200_ERR_INVALID, "NULL argument");
+    VB200_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (f->dim <= 0) return fail(ctx, VB200_ERR_INVALID, "replay of finite samples needs a finite-dimensional integrand");
+    int rc = check_domain(ctx, p->domain, f->dim); if (rc) return rc;
+    if (p->spp == 0 || p->spp > 0xffffffffull) return fail(ctx, VB200_ERR_INVALID, "spp invalid");
+    const uint64_t total = nbins_of(p->domain);
+    uint64_t begin, end; rc = resolve_shard(ctx, p->shard, total, &begin, &end); if (rc) return rc;
+    if (begin == end) return VB200_OK;
+    vb200_replay_launch a; std::memset(&a, 0, sizeof(a));
+    a.domain = p->domain; a.bin_begin = begin; a.bin_end = end; a.nbins_total = total; a.spp = uint32_t(p->spp); a.flavor = p->flavor;
+    a.factor = double(range_volume(p->domain, p->domain.dim)) / double(p->spp);
+    const size_t sbytes = size_t(end - begin) * p->spp * size_t(f->dim) * sizeof(float);
+    if (samples_mem == VB200_HOST) {
+        void* d = nullptr; rc = reserve(ctx, 1, sbytes, &d); if (rc) return rc;
+        VB200_CUDA(ctx, cudaMemcpyAsync(d, samples, sbytes, cudaMemcpyHostToDevice, ctx->stream));
+        a.samples = static_cast<const float*>(d);
+    } else a.samples = samples;
+    // replay continues the reference's running '+=' from the bins' current contents: upload them
+    BinStage st; rc = stage_bins_in(ctx, bins, bins_mem, begin, end, /*upload=*/true, &st); if (rc) return rc;
+    a.out = st.dev_base;
+    rc = call_thunk(ctx, f, VB200_K_MC_REPLAY, &a); if (rc) return rc;
+    return stage_bins_out(ctx, st);
+}
+
+// ---- infinite-dimensional paths ---------------------------------------------------------------------------
+extern "C" int vb200_mc_per_bin_inf(vb200_ctx* ctx, const vb200_integrand* f, const vb200_mc_params* p,
+                                    float* bins, int bins_mem, float* sum_f, float* sum_f2) {
+    if (!ctx || !f || !p) return fail(ctx, VB200_ERR_INVALID, "NULL argument");
+    VB200_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (f->dim != -1) return fail(ctx, VB200_ERR_INVALID, "vb200_mc_per_bin_inf needs a sequence integrand");
+    int rc = check_domain(ctx, p->domain, -1); if (rc) return rc;
+    if (p->spp == 0 || p->spp > 0xffffffffull) return fail(ctx, VB200_ERR_INVALID, "spp invalid");
+    if (p->flavor != VB200_MC_PER_BIN) return fail(ctx, VB200_ERR_UNSUPPORTED, "infinite ranges: only the monte_carlo_per_bin_parallel flavor is implemented");
+    const uint64_t total = nbins_of(p->domain);
+    uint64_t begin, end; rc = resolve_shard(ctx, p->shard, total, &begin, &end); if (rc) return rc;
+    if (begin == end) return VB200_OK;
+    vb200_walk_launch a; std::memset(&a, 0, sizeof(a));
+    a.domain = p->domain; a.bin_begin = begin; a.bin_end = end; a.nbins_total = total;
+    a.spp = uint32_t(p->spp); a.lanes_per_bin = pick_lanes_per_bin(p->spp);
+    a.key0 = uint32_t(p->seed); a.key1 = uint32_t(p->seed >> 32);
+    a.factor = double(range_volume(p->domain, p->domain.dim)) / double(p->spp);      // range-infinite.h:22-23; :77
+    BinStage st; rc = stage_bins_in(ctx, bins, bins_mem, begin, end, false, &st); if (rc) return rc;
+    a.accumulate = st.staged ? 0 : 1;
+    a.out = st.dev_base;
+    rc = stage_moments(ctx, sum_f, bins_mem, 1, end - begin, &a.sum_f); if (rc) return rc;
+    rc = stage_moments(ctx, sum_f2, bins_mem, 2, end - begin, &a.sum_f2); if (rc) return rc;
+    rc = call_thunk(ctx, f, VB200_K_WALK, &a); if (rc) return rc;
+    if (st.staged) {
+        const uint64_t n = end - begin;
+        float* h = nullptr; rc = reserve_pinned(ctx, n * sizeof(float) * 3, reinterpret_cast<void**>(&h)); if (rc) return rc;
+        VB200_CUDA(ctx, cudaMemcpyAsync(h, st.dev_base + begin, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        if (sum_f)  VB200_CUDA(ctx, cudaMemcpyAsync(h + n, a.sum_f, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        if (sum_f2) VB200_CUDA(ctx, cudaMemcpyAsync(h + 2 * n, a.sum_f2, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        VB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        float* dst = bins + begin;
+        for (uint64_t i = 0; i < n; ++i) dst[i] = float(double(dst[i]) + double(h[i]));
+        if (sum_f)  std::memcpy(sum_f, h + n, n * sizeof(float));
+        if (sum_f2) std::memcpy(sum_f2, h + 2 * n, n * sizeof(float));
+    }
+    return VB200_OK;
+}
+
+extern "C" int vb200_mc_per_bin_inf_replay(vb200_ctx* ctx, const vb200_integrand* f, const vb200_mc_params* p,
+                                           const uint64_t* offsets, const float* elems, int mem, float* bins, int bins_mem) {
+    if (!ctx || !f || !p || !offsets || !elems) return fail(ctx, VB200_ERR_INVALID, "NULL argument");
+    VB200_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (f->dim != -1) return fail(ctx, VB200_ERR_INVALID, "sequence replay needs a sequence integrand");
+    int rc = check_domain(ctx, p->domain, -1); if (rc) return rc;
+    const uint64_t total = nbins_of(p->domain);
+    uint64_t begin, end; rc = resolve_shard(ctx, p->shard, total, &begin, &end); if (rc) return rc;
+    if (begin == end) return VB200_OK;
+    const uint64_t npaths = (end - begin) * p->spp;
+    vb200_walk_replay_launch a; std::memset(&a, 0, sizeof(a));
+    a.domain = p->domain; a.bin_begin = begin; a.bin_end = end; a.nbins_total = total; a.spp = uint32_t(p->spp);
+    a.factor = double(range_volume(p->domain, p->domain.dim)) / double(p->spp);
+    if (mem == VB200_HOST) {
+        const uint64_t nel = offsets[npaths];
+        void *d0 = nullptr, *d1 = nullptr;
+        rc = reserve(ctx, 1, (npaths + 1) * sizeof(uint64_t), &d0); if (rc) return rc;
+        rc = reserve(ctx, 2, (nel + 1) * sizeof(float), &d1); if (rc) return rc;
+        VB200_CUDA(ctx, cudaMemcpyAsync(d0, offsets, (npaths + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+        VB200_CUDA(ctx, cudaMemcpyAsync(d1, elems, nel * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        a.offsets = static_cast<const uint64_t*>(d0); a.elems = static_cast<const float*>(d1);
+    } else { a.offsets = offsets; a.elems = elems; }
+    VB200_CUDA(ctx, cudaMemsetAsync(ctx->d_flag, 0, sizeof(int32_t), ctx->stream));
+    a.error_flag = ctx->d_flag;
+    BinStage st; rc = stage_bins_in(ctx, bins, bins_mem, begin, end, true, &st); if (rc) return rc;
+    a.out = st.dev_base;
+    rc = call_thunk(ctx, f, VB200_K_WALK_REPLAY, &a); if (rc) return rc;
+    rc = stage_bins_out(ctx, st); if (rc) return rc;
+    int32_t flag = 0;
+    VB200_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->d_flag, sizeof(flag), cudaMemcpyDeviceToHost, ctx->stream));
+    VB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (flag) return fail(ctx, VB200_ERR_INVALID, "sequence replay: the integrand read past the recorded length of a path");
+    return VB200_OK;
+}
+
+// ---- global Monte Carlo (scatter) ---------------------------------------------------------------------------
+extern "C" int vb200_monte_carlo(vb200_ctx* ctx, const vb200_integrand* f, const vb200_mc_params* p, float* bins, int bins_mem) {
+    if (!ctx || !f || !p) return fail(ctx, VB200_ERR_INVALID, "NULL argument");
+    VB200_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (f->dim <= 0) return fail(ctx, VB200_ERR_UNSUPPORTED, "global Monte Carlo over infinite ranges is not implemented");
+    int rc = check_domain(ctx, p->domain, f->dim); if (rc) return rc;
+    if (p->spp == 0) return fail(ctx, VB200_ERR_INVALID, "samples=0");
+    const uint64_t total = nbins_of(p->domain);
+    uint64_t sb, se; rc = resolve_shard(ctx, p->shard, p->spp, &sb, &se); if (rc) return rc;
+    vb200_scatter_launch a; std::memset(&a, 0, sizeof(a));
+    a.domain = p->domain; a.sample_begin = sb; a.sample_end = se; a.nbins_total = total;
+    a.key0 = uint32_t(p->seed); a.key1 = uint32_t(p->seed >> 32);
+    a.factor = double(total) * double(range_volume(p->domain, p->domain.dim)) / double(p->spp);     // monte-carlo.h:43-45
+    float* dev = bins;
+    if (bins_mem == VB200_HOST) {
+        void* d = nullptr; rc = reserve(ctx, 0, total * sizeof(float), &d); if (rc) return rc;
+        dev = static_cast<float*>(d);
+        VB200_CUDA(ctx, cudaMemsetAsync(dev, 0, total * sizeof(float), ctx->stream));
+    }
+    a.out = dev;
+    if (se > sb) { rc = call_thunk(ctx, f, VB200_K_MC_SCATTER, &a); if (rc) return rc; }
+    if (bins_mem == VB200_HOST) {
+        float* h = nullptr; rc = reserve_pinned(ctx, total * sizeof(float), reinterpret_cast<void**>(&h)); if (rc) return rc;
+        VB200_CUDA(ctx, cudaMemcpyAsync(h, dev, total * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        VB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (uint64_t i = 0; i < total; ++i) bins[i] = float(double(bins[i]) + double(h[i]));        // '+=' (monte-carlo.h:59)
+    }
+    return VB200_OK;
+}

@@ -1,0 +1,437 @@
+"""Host-side mirror of the reference's integrator vocabulary for the hot path, over the C ABI.
+
+The reference is header-only C++ (viltrum::integrate(integrator, bins, resolution, f, range), reference
+src/integrate.h:72-173); its real drop-in lives in include/viltrum_b200/viltrum.h.  This module re-states the same
+names in Python so that the parity tests and bench.py read like the reference's own examples:
+
+    ctx  = Context(0)
+    bins = numpy.zeros(1024*1024, numpy.float32)                      # host bins  -> end-to-end path
+    integrate(monte_carlo_per_bin_parallel(64, seed=0), bins, [1024, 1024], "shade4_64", range_primary(4), ctx=ctx)
+
+Integrands are the library's built-in synthetic functors, named by string (a Python callable cannot run on the
+GPU; C++ users pass their own __device__ functors through the headers).  ``bins`` is a flat float32 buffer in the
+reference's tensor layout (dim 0 fastest): a numpy array (staged through the device inside the call) or a CUDA
+torch tensor / DevicePtr (used in place).  Write semantics follow the reference integrator by integrator
+('+=' vs '=').  Everything runs on the GPU; there is no CPU fallback.
+"""
+import ctypes
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _capi as C
+
+
+# ---- ranges (reference src/range.h, src/range-infinite.h) ------------------------------------------------------
+@dataclass
+class Range:
+    min: Sequence[float]
+    max: Sequence[float]
+
+    @property
+    def dim(self):
+        return len(self.min)
+
+
+@dataclass
+class RangeInfinite:
+    min: Sequence[float] = ()
+    max: Sequence[float] = ()
+
+
+def range_primary(n):
+    """range_primary<N>() — the unit box (reference src/range.h:196-199)"""
+    return Range([0.0] * n, [1.0] * n)
+
+
+def range_primary_infinite():
+    """range_primary_infinite<float>() (reference src/range-infinite.h:129-132)"""
+    return RangeInfinite()
+
+
+# ---- device buffers ----------------------------------------------------------------------------------------------
+@dataclass
+class DevicePtr:
+    """A raw device pointer + element count (for callers that manage device memory themselves)."""
+    ptr: int
+    numel: int
+
+
+def _buffer(x, dtype=np.float32):
+    """-> (address, memory-space flag, keepalive)"""
+    if x is None:
+        return None, C.HOST, None
+    if isinstance(x, DevicePtr):
+        return x.ptr, C.DEVICE, x
+    if isinstance(x, np.ndarray):
+        if x.dtype != dtype or not x.flags["C_CONTIGUOUS"]:
+            raise TypeError(f"host buffers must be C-contiguous {np.dtype(dtype).name} arrays (got {x.dtype})")
+        return x.ctypes.data, C.HOST, x
+    if hasattr(x, "data_ptr") and hasattr(x, "is_cuda"):      # torch tensor, used as plain device memory
+        if not x.is_contiguous():
+            raise TypeError("tensors must be contiguous")
+        return x.data_ptr(), (C.DEVICE if x.is_cuda else C.HOST), x
+    raise TypeError(f"unsupported buffer type {type(x)}")
+
+
+def builtin_names():
+    L = C.lib()
+    return [L.vb200_builtin_name(i).decode() for i in range(L.vb200_builtin_count())]
+
+
+class Context:
+    """One per process and GPU (vb200_create).  Raises Vb200Error(VB200_ERR_NO_DEVICE) without a CUDA device."""
+
+    def __init__(self, device=0):
+        self._L = C.lib()
+        h = ctypes.c_void_p()
+        rc = self._L.vb200_create(int(device), ctypes.byref(h))
+        if rc != 0:
+            raise C.Vb200Error(rc, self._L.vb200_last_error(None).decode())
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.vb200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc != 0:
+            raise C.Vb200Error(rc, self._L.vb200_last_error(self._h).decode())
+
+    def synchronize(self):
+        self.check(self._L.vb200_synchronize(self._h))
+
+    @property
+    def stream(self):
+        """cudaStream_t (as int) every call of this context is enqueued on"""
+        return self._L.vb200_stream(self._h)
+
+    @property
+    def sm_count(self):
+        return self._L.vb200_sm_count(self._h)
+
+    @property
+    def launch_count(self):
+        return self._L.vb200_launch_count(self._h)
+
+    def integrand(self, name, exact=False):
+        p = self._L.vb200_builtin_integrand(name.encode(), 1 if exact else 0)
+        if not p:
+            raise KeyError(f"unknown built-in integrand '{name}' (have: {builtin_names()})")
+        return p
+
+    # -- raw drivers (1:1 with the C ABI) --------------------------------------------------------------------------
+    def _mc_params(self, dim, res, rng, spp, seed, flavor, shard):
+        p = C.McParams()
+        p.domain = C.make_domain(dim, res, rng.min, rng.max)
+        p.shard.begin, p.shard.end = (shard if shard else (0, 0))
+        p.spp, p.seed, p.flavor = int(spp), int(seed) & 0xFFFFFFFFFFFFFFFF, flavor
+        return p
+
+    def mc_per_bin(self, f, bins, res, rng, spp, seed, flavor=C.MC_PER_BIN, shard=None, sum_f=None, sum_f2=None, exact=False):
+        b, mem, _k = _buffer(bins)
+        s1, m1, _k1 = _buffer(sum_f); s2, m2, _k2 = _buffer(sum_f2)
+        p = self._mc_params(len(rng.min), res, rng, spp, seed, flavor, shard)
+        self.check(self._L.vb200_mc_per_bin(self._h, self.integrand(f, exact), ctypes.byref(p), b, mem, s1, s2))
+
+    def mc_per_bin_replay(self, f, bins, res, rng, spp, samples, flavor=C.MC_PER_BIN, shard=None, exact=True):
+        b, mem, _k = _buffer(bins); s, smem, _ks = _buffer(samples)
+        p = self._mc_params(len(rng.min), res, rng, spp, 0, flavor, shard)
+        self.check(self._L.vb200_mc_per_bin_replay(self._h, self.integrand(f, exact), ctypes.byref(p), s, smem, b, mem))
+
+    def mc_per_bin_inf(self, f, bins, res, rng, spp, seed, shard=None, sum_f=None, sum_f2=None, exact=False):
+        b, mem, _k = _buffer(bins)
+        s1, m1, _k1 = _buffer(sum_f); s2, m2, _k2 = _buffer(sum_f2)
+        p = self._mc_params(len(rng.min), res, rng, spp, seed, C.MC_PER_BIN, shard)
+        self.check(self._L.vb200_mc_per_bin_inf(self._h, self.integrand(f, exact), ctypes.byref(p), b, mem, s1, s2))
+
+    def mc_per_bin_inf_replay(self, f, bins, res, rng, spp, offsets, elems, shard=None, exact=True):
+        b, mem, _k = _buffer(bins)
+        o, omem, _ko = _buffer(offsets, np.uint64); e, emem, _ke = _buffer(elems)
+        p = self._mc_params(len(rng.min), res, rng, spp, 0, C.MC_PER_BIN, shard)
+        self.check(self._L.vb200_mc_per_bin_inf_replay(self._h, self.integrand(f, exact), ctypes.byref(p), o, e, emem, b, mem))
+
+    def monte_carlo(self, f, bins, res, rng, samples, seed, shard=None, exact=False):
+        b, mem, _k = _buffer(bins)
+        p = self._mc_params(len(rng.min), res, rng, samples, seed, C.MC_PER_BIN, shard)
+        self.check(self._L.vb200_monte_carlo(self._h, self.integrand(f, exact), ctypes.byref(p), b, mem))
+
+    def regions_generate_adaptive(self, f, rng, rule, heuristic, metric, iterations, size_weight=1e-5, batch=1, exact=True):
+        p = C.AdaptiveParams()
+        p.domain = C.make_domain(len(rng.min), [1], rng.min, rng.max)
+        p.rule, p.heuristic, p.metric = C.RULES[rule], C.HEURISTICS[heuristic], C.METRICS[metric]
+        p.batch, p.size_weight, p.iterations = int(batch), float(size_weight), int(iterations)
+        h = ctypes.c_void_p()
+        self.check(self._L.vb200_regions_generate_adaptive(self._h, self.integrand(f, exact), ctypes.byref(p), ctypes.byref(h)))
+        return Regions(self, h)
+
+    def regions_generate_single(self, f, rng, rule, exact=True):
+        d = C.make_domain(len(rng.min), [1], rng.min, rng.max)
+        h = ctypes.c_void_p()
+        self.check(self._L.vb200_regions_generate_single(self._h, self.integrand(f, exact), ctypes.byref(d), C.RULES[rule], ctypes.byref(h)))
+        return Regions(self, h)
+
+    def regions_upload(self, rule, rmin, rmax, err, errdim, data):
+        rmin = np.ascontiguousarray(rmin, np.float32); rmax = np.ascontiguousarray(rmax, np.float32)
+        n, dim = rmin.shape
+        err = np.ascontiguousarray(err if err is not None else np.zeros(n), np.float32)
+        errdim = np.ascontiguousarray(errdim if errdim is not None else np.zeros(n), np.uint32)
+        data = np.ascontiguousarray(data, np.float32)
+        h = ctypes.c_void_p()
+        self.check(self._L.vb200_regions_upload(self._h, dim, C.RULES[rule], n, rmin.ctypes.data, rmax.ctypes.data, err.ctypes.data,
+                                                errdim.ctypes.data, data.ctypes.data, ctypes.byref(h)))
+        return Regions(self, h)
+
+
+class Regions:
+    """Device-resident leaf table (vb200_regions)."""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self._h = ctx, handle
+
+    def __len__(self):
+        return int(self.ctx._L.vb200_regions_count(self._h))
+
+    @property
+    def dim(self):
+        return self.ctx._L.vb200_regions_dim(self._h)
+
+    @property
+    def samples(self):
+        return self.ctx._L.vb200_regions_samples(self._h)
+
+    def download(self):
+        n, d, sd = len(self), self.dim, self.samples
+        out = dict(min=np.zeros((n, d), np.float32), max=np.zeros((n, d), np.float32), err=np.zeros(n, np.float32),
+                   dim=np.zeros(n, np.uint32), data=np.zeros((n, sd), np.float32))
+        self.ctx.check(self.ctx._L.vb200_regions_download(self.ctx._h, self._h, out["min"].ctypes.data, out["max"].ctypes.data,
+                                                          out["err"].ctypes.data, out["dim"].ctypes.data, out["data"].ctypes.data))
+        return out
+
+    def integrate_bins(self, bins, res, rng, shard=None):
+        b, mem, _k = _buffer(bins)
+        d = C.make_domain(len(rng.min), res, rng.min, rng.max)
+        s = C.Shard(); s.begin, s.end = (shard if shard else (0, 0))
+        self.ctx.check(self.ctx._L.vb200_regions_integrate_bins(self.ctx._h, self._h, ctypes.byref(d), ctypes.byref(s), b, mem))
+
+    def _cv_params(self, res, rng, spp, seed, shard):
+        p = C.CvParams()
+        p.domain = C.make_domain(len(rng.min), res, rng.min, rng.max)
+        p.shard.begin, p.shard.end = (shard if shard else (0, 0))
+        p.spp, p.seed = int(spp), int(seed) & 0xFFFFFFFFFFFFFFFF
+        return p
+
+    def cv_integrate(self, f, bins, res, rng, spp, seed, shard=None, nregions=None, approx=None, exact=False):
+        b, mem, _k = _buffer(bins)
+        n, _m, _kn = _buffer(nregions, np.uint32); a, _m2, _ka = _buffer(approx)
+        p = self._cv_params(res, rng, spp, seed, shard)
+        self.ctx.check(self.ctx._L.vb200_cv_integrate(self.ctx._h, self.ctx.integrand(f, exact), self._h, ctypes.byref(p), b, mem, n, a))
+
+    def cv_replay(self, f, bins, res, rng, spp, chosen, samples, shard=None, exact=True):
+        b, mem, _k = _buffer(bins)
+        c, cmem, _kc = _buffer(chosen, np.uint32); s, _sm, _ks = _buffer(samples)
+        p = self._cv_params(res, rng, spp, 0, shard)
+        self.ctx.check(self.ctx._L.vb200_cv_replay(self.ctx._h, self.ctx.integrand(f, exact), self._h, ctypes.byref(p), c, s, cmem, b, mem))
+
+    def free(self):
+        if self._h:
+            self.ctx._L.vb200_regions_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+# ---- integrators: same factory names and argument meaning as the reference ---------------------------------------
+@dataclass
+class MonteCarlo:
+    """monte_carlo(samples, seed) — reference src/monte-carlo/monte-carlo.h:88-95"""
+    samples: int
+    seed: int = 0
+
+    def integrate(self, ctx, bins, res, f, rng, shard=None, **kw):
+        ctx.monte_carlo(f, bins, res, rng, self.samples, self.seed, shard=shard, **kw)
+
+
+@dataclass
+class MonteCarloPerBinParallel:
+    """monte_carlo_per_bin_parallel(spp, seed) — reference src/monte-carlo/monte-carlo-per-bin-parallel.h:104-111 ('+=')"""
+    spp: int
+    seed: int = 0
+
+    def integrate(self, ctx, bins, res, f, rng, shard=None, **kw):
+        if isinstance(rng, RangeInfinite):
+            ctx.mc_per_bin_inf(f, bins, res, rng, self.spp, self.seed, shard=shard, **kw)
+        else:
+            ctx.mc_per_bin(f, bins, res, rng, self.spp, self.seed, C.MC_PER_BIN, shard=shard, **kw)
+
+
+@dataclass
+class IntegratorPerBinParallel:
+    """integrator_per_bin_parallel(inner) — reference src/integrator-per-bin-parallel.h:37-38 ('=')"""
+    inner: MonteCarlo
+
+    def integrate(self, ctx, bins, res, f, rng, shard=None, **kw):
+        if not isinstance(self.inner, MonteCarlo):
+            raise NotImplementedError("integrator_per_bin_parallel: only monte_carlo(...) inner integrators are on the hot path")
+        ctx.mc_per_bin(f, bins, res, rng, self.inner.samples, self.inner.seed, C.PER_BIN_MC, shard=shard, **kw)
+
+
+@dataclass
+class Nested:
+    high: str
+    low: str
+
+    @property
+    def name(self):
+        return f"{self.high}_{self.low}"
+
+
+@dataclass
+class ErrorMetric:
+    kind: str
+
+
+@dataclass
+class ErrorHeuristic:
+    kind: str
+    metric: ErrorMetric
+    size_weight: float = 1e-5
+
+
+def nested(high, low):
+    """nested(high, low) — reference src/nested/nested.h:42-45; rules are named 'trapezoidal' | 'simpson' | 'boole'"""
+    return Nested(high, low)
+
+
+def error_metric_absolute():
+    return ErrorMetric("absolute")
+
+
+def error_metric_relative():
+    return ErrorMetric("relative")
+
+
+def error_heuristic_default(metric):
+    return ErrorHeuristic("default", metric)
+
+
+def error_heuristic_size(metric, size_weight=1e-5):
+    return ErrorHeuristic("size", metric, size_weight)
+
+
+@dataclass
+class IntegratorNewtonCotes:
+    """integrator_newton_cotes(rule) — reference src/newton-cotes/newton-cotes.h:11-14 ('+=')"""
+    rule: str
+
+    def integrate(self, ctx, bins, res, f, rng, shard=None, exact=True, **kw):
+        regs = ctx.regions_generate_single(f, rng, self.rule, exact=exact)
+        try:
+            regs.integrate_bins(bins, res, rng, shard=shard)
+        finally:
+            regs.free()
+
+
+@dataclass
+class IntegratorAdaptiveIterations:
+    """integrator_adaptive_iterations(nested_rule, error_heuristic, iterations) — reference
+    src/nested/integrator-adaptive-iterations.h:12-15 ('+=').  batch=1 reproduces the reference's greedy order."""
+    rule: Nested
+    heuristic: ErrorHeuristic
+    iterations: int
+    batch: int = 1
+    last_regions: Optional[Regions] = field(default=None, repr=False)
+
+    def generate(self, ctx, f, rng, exact=True):
+        return ctx.regions_generate_adaptive(f, rng, self.rule.name, self.heuristic.kind, self.heuristic.metric.kind,
+                                             self.iterations, self.heuristic.size_weight, self.batch, exact=exact)
+
+    def integrate(self, ctx, bins, res, f, rng, shard=None, exact=True, logger=None, **kw):
+        regs = self.generate(ctx, f, rng, exact=exact)
+        if logger is not None:
+            logger.log(regs)          # the reference hands the region list to Logger::log (integrator-region-based.h:19)
+        try:
+            regs.integrate_bins(bins, res, rng, shard=shard)
+        finally:
+            if logger is None:
+                regs.free()
+
+
+@dataclass
+class IntegratorCrespo2021:
+    """integrator_crespo2021(iterations, spp, seed) — reference src/control-variates/integrator-crespo2021.h:7-22 ('=')"""
+    iterations: int
+    spp: int
+    seed: int = 0
+    batch: int = 1
+
+    def integrate(self, ctx, bins, res, f, rng, shard=None, exact=False, logger=None, **kw):
+        gen = IntegratorAdaptiveIterations(nested("simpson", "trapezoidal"), error_heuristic_size(error_metric_relative(), 1e-5),
+                                           self.iterations, self.batch)
+        regs = gen.generate(ctx, f, rng, exact=True)
+        if logger is not None:
+            logger.log(regs)
+        try:
+            regs.cv_integrate(f, bins, res, rng, self.spp, self.seed, shard=shard, exact=exact, **kw)
+        finally:
+            if logger is None:
+                regs.free()
+
+
+def monte_carlo(samples, seed=0):
+    return MonteCarlo(samples, seed)
+
+
+def monte_carlo_per_bin_parallel(spp, seed=0):
+    return MonteCarloPerBinParallel(spp, seed)
+
+
+def integrator_per_bin_parallel(inner):
+    return IntegratorPerBinParallel(inner)
+
+
+def integrator_newton_cotes(rule):
+    return IntegratorNewtonCotes(rule)
+
+
+def integrator_adaptive_iterations(rule, heuristic=None, iterations=None, batch=1):
+    if iterations is None:            # integrator_adaptive_iterations(rule, iterations) overload (integrator-adaptive-iterations.h:22-25)
+        heuristic, iterations = error_heuristic_default(error_metric_absolute()), heuristic
+    return IntegratorAdaptiveIterations(rule, heuristic, iterations, batch)
+
+
+def integrator_crespo2021(iterations, spp, seed=0, batch=1):
+    return IntegratorCrespo2021(iterations, spp, seed, batch)
+
+
+_default_ctx = {}
+
+
+def default_context(device=0):
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+def integrate(integrator, bins, resolution, f, rng, ctx=None, **kw):
+    """viltrum::integrate(integrator, bins, resolution, f, range) — reference src/integrate.h:72-103.
+    ``bins`` is flat (tensor order); pass ``resolution=None`` for the std::vector overload (1-D, res = len(bins),
+    integrate.h:132-137)."""
+    if resolution is None:
+        resolution = [bins.numel() if hasattr(bins, "numel") and callable(bins.numel) else len(bins)]
+    ctx = ctx or default_context()
+    integrator.integrate(ctx, bins, list(resolution), f, rng, **kw)
+    return bins
