@@ -18,7 +18,6 @@ reference's CPU path timed on this box's host cores (rank 0, N=1, bounded sample
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -43,43 +42,45 @@ def dist_env():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region through NVML (same data as the nvidia-smi
+    clocks line of B200_PROFILING.md, but at ~1 kHz so that a millisecond-scale timed region still gets samples)."""
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.reasons, self.stop_flag, self.err = index, [], 0, False, None
+        self.sm_max = None
+
+    def _loop(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if visible:
+                try:
+                    idx = int(visible.split(",")[self.index])
+                except Exception:
+                    pass
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            while not self.stop_flag:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.reasons |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                time.sleep(0.001)
+        except Exception as ex:
+            self.err = str(ex)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+        self.t = threading.Thread(target=self._loop, daemon=True); self.t.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        self.stop_flag = True
+        self.t.join(timeout=2)
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
+        reasons = sorted(n for bit, n in names.items() if self.reasons & bit)
+        out = {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.sm_max, "reasons": reasons, "samples": len(self.sm)}
+        if self.err:
+            out["error"] = self.err
+        return out
 
 
 def cpu_threads():

@@ -160,7 +160,7 @@ int vb200_mc_per_bin_inf(vb200_ctx* ctx, const vb200_integrand* f, const vb200_m
 
 /* Replay of recorded lazy sequences: elems holds every path's elements back to back (bin-major, sample-minor),
  * offsets [nbins_of_shard*spp + 1] are prefix sums of the per-path lengths.  Reading past a path's recorded
- * length yields NaN and sets a sticky error (VB200_ERR_INVALID on return). */
+ * length yields +inf (so Russian-roulette loops end) and sets a sticky error (VB200_ERR_INVALID on return). */
 int vb200_mc_per_bin_inf_replay(vb200_ctx* ctx, const vb200_integrand* f, const vb200_mc_params* p,
                                 const uint64_t* offsets, const float* elems, int mem, float* bins, int bins_mem);
 
@@ -252,6 +252,7 @@ typedef struct vb200_mc_launch {
     float*   sum_f2;
     int32_t  grid_hint;               /* CTAs to launch (0 = let the thunk size it from occupancy) */
     int32_t  reserved;
+    unsigned long long* tile_counter; /* device, zeroed by the driver before the launch: dynamic tile scheduler */
 } vb200_mc_launch;
 
 typedef struct vb200_replay_launch {
@@ -271,6 +272,7 @@ typedef struct vb200_walk_launch {
     int32_t  accumulate; int32_t grid_hint;
     double   factor;
     float*   out; float* sum_f; float* sum_f2;
+    unsigned long long* tile_counter; /* device, zeroed by the driver before the launch */
 } vb200_walk_launch;
 
 typedef struct vb200_walk_replay_launch {

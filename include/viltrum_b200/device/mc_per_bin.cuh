@@ -6,11 +6,10 @@
 // shuffles -> scaled, coalesced store into the tensor bin layout (dim 0 fastest).  Nothing but the final bin
 // values touches HBM (4 B per bin per `spp` evaluations), so the kernel is bound by FP32 issue, not bandwidth.
 //
-// Work decomposition: a CTA of 256 threads owns one *tile* of 256/LPB consecutive bins; LPB (a power of two,
-// chosen by the driver from spp) lanes of one warp share a bin and stride over its samples.  Tiles are handed out grid-stride over a grid sized
-// to the resident CTA capacity of the chip (148 SMs x occupancy), so the tail is a fraction of one tile.
-// Each tile's bin values are staged in shared memory and written by the first 256/LPB threads as full,
-// contiguous lines.
+// Work decomposition: LPB (a power of two, chosen by the driver from spp) lanes of one warp share a bin and stride
+// over its samples; a warp therefore owns 32/LPB consecutive bins per step and writes them as one contiguous run.
+// The grid is sized to the resident CTA capacity of the chip (148 SMs x occupancy) and warps pull tiles from a
+// global counter until the shard is done.
 #pragma once
 #include <array>
 #include <cuda_runtime.h>
@@ -24,8 +23,14 @@ constexpr int MC_THREADS = 256;
 // bin position (tensor order, dim 0 fastest) -> per-dimension index; reference src/tensor.h:17-23
 template<int DIMBINS>
 __device__ __forceinline__ void unflatten_bin(uint64_t bin, const vb200_domain& dom, uint32_t (&pos)[VB200_MAX_DIMBINS]) {
+    if ((bin >> 32) == 0) {       // 32-bit division: the 64-bit one is a ~100-instruction subroutine
+        uint32_t b = uint32_t(bin);
 #pragma unroll
-    for (int i = 0; i < DIMBINS; ++i) { uint64_t r = dom.res[i]; pos[i] = uint32_t(bin % r); bin /= r; }
+        for (int i = 0; i < DIMBINS; ++i) { const uint32_t r = uint32_t(dom.res[i]); pos[i] = b % r; b /= r; }
+    } else {
+#pragma unroll
+        for (int i = 0; i < DIMBINS; ++i) { const uint64_t r = dom.res[i]; pos[i] = uint32_t(bin % r); bin /= r; }
+    }
 }
 
 // Bin sub-box exactly as the reference computes it (monte-carlo-per-bin-parallel.h:45-47,59-61):
@@ -50,52 +55,76 @@ __device__ __forceinline__ void bin_box(const vb200_domain& dom, uint64_t bin, f
 
 // EXACT only tags the instantiation (the same template is compiled twice into the library, once in a TU built
 // with --fmad=false); it keeps the two sets of kernel symbols apart.
+//
+// Design notes (measured on B200, profiles/exp/mc_variants.cu -> profiles/mc_variants_r1.txt):
+//   * warp-autonomous tiles: a warp owns G = 32/LPB consecutive bins per step and never meets a CTA barrier
+//     (the first version staged a CTA tile through shared memory behind __syncthreads: 11 % of warp samples sat
+//     in stall_barrier);
+//   * tiles are handed out through one global atomic per warp and tile (a.tile_counter, zeroed by the driver before
+//     the launch), so the tail is one tile long instead of one static share;
+//   * two samples per lane are in flight (independent Philox + Horner chains) — +4 % over one;
+//   * the u32 -> [0,1) scaling (2^-24) is folded into the bin extent, so a coordinate costs SHF + I2FP + FFMA.
+template<class F, int DIM>
+__device__ __forceinline__ float mc_sample(const F& f, uint32_t b0, uint32_t b1, uint32_t s, uint32_t k0, uint32_t k1,
+                                           const float (&lo)[DIM], const float (&ext24)[DIM]) {
+    std::array<float, DIM> x;
+#pragma unroll
+    for (int blk = 0; blk < (DIM + 3) / 4; ++blk) {
+        const u32x4 r = philox4x32<10>(u32x4{b0, b1, s, uint32_t(blk)}, k0, k1);
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = blk * 4 + j;
+            // u*(b-a)+a as std::uniform_real_distribution, u = (w>>8)*2^-24 in [0,1); ext24 = (b-a)*2^-24 (exact scaling)
+            if (i < DIM) x[i] = fmaf(float(w[j] >> 8), ext24[i], lo[i]);
+        }
+    }
+    return f(x);
+}
+
 template<class F, int DIM, int DIMBINS, bool MOMENTS, bool EXACT>
 __global__ void __launch_bounds__(MC_THREADS)
 mc_per_bin_kernel(const F f, const vb200_mc_launch a) {
-    __shared__ float s_val[2][MC_THREADS];
-    __shared__ float s_m1[MOMENTS ? MC_THREADS : 1];
-    __shared__ float s_m2[MOMENTS ? MC_THREADS : 1];
-
     const uint32_t LPB = a.lanes_per_bin;     // power of two <= 32: the lanes of a bin sit in one warp
-    const uint32_t BINS_PER_TILE = MC_THREADS / LPB;
-    const uint32_t tid = threadIdx.x;
-    const uint32_t slot = tid / LPB;          // bin within the tile
-    const uint32_t sub = tid % LPB;           // lane within the bin
+    const uint32_t G = 32u / LPB;             // bins per warp step
+    const uint32_t lane = threadIdx.x & 31u, sub = lane % LPB, grp = lane / LPB;
     const uint64_t nshard = a.bin_end - a.bin_begin;
-    const uint64_t ntiles = (nshard + BINS_PER_TILE - 1) / BINS_PER_TILE;
-    int buf = 0;
+    const uint64_t ntiles = (nshard + G - 1) / G;
 
-    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
-        const uint64_t bin = a.bin_begin + tile * BINS_PER_TILE + slot;
+    uint64_t tile = 0;
+    if (lane == 0) tile = atomicAdd(a.tile_counter, 1ull);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    while (tile < ntiles) {
+        const uint64_t bin = a.bin_begin + tile * G + grp;
         const bool live = bin < a.bin_end;
         float sum = 0.0f, sum2 = 0.0f, volume = 1.0f;
         if (live) {
             float lo[DIM], ext[DIM];
             bin_box<DIM, DIMBINS>(a.domain, bin, lo, ext, volume);
+#pragma unroll
+            for (int i = 0; i < DIM; ++i) ext[i] *= 5.9604644775390625e-08f;
             const uint32_t b0 = uint32_t(bin), b1 = uint32_t(bin >> 32);
-            for (uint32_t s = sub; s < a.spp; s += LPB) {
-                std::array<float, DIM> x;
-#pragma unroll
-                for (int blk = 0; blk < (DIM + 3) / 4; ++blk) {
-                    const u32x4 r = philox4x32<10>(u32x4{b0, b1, s, uint32_t(blk)}, a.key0, a.key1);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int i = blk * 4 + j;
-                        if (i < DIM) x[i] = fmaf(pick(r, j), ext[i], lo[i]);   // u*(b-a)+a, as uniform_real_distribution
-                    }
-                }
-                const float v = f(x);
-                sum += v;
-                if (MOMENTS) sum2 = fmaf(v, v, sum2);
+            float sumb = 0.0f, sum2b = 0.0f;
+            uint32_t s = sub;
+            for (; s + LPB < a.spp; s += 2u * LPB) {      // two independent samples in flight per lane
+                const float v0 = mc_sample<F, DIM>(f, b0, b1, s, a.key0, a.key1, lo, ext);
+                const float v1 = mc_sample<F, DIM>(f, b0, b1, s + LPB, a.key0, a.key1, lo, ext);
+                sum += v0; sumb += v1;
+                if (MOMENTS) { sum2 = fmaf(v0, v0, sum2); sum2b = fmaf(v1, v1, sum2b); }
             }
+            if (s < a.spp) {
+                const float v0 = mc_sample<F, DIM>(f, b0, b1, s, a.key0, a.key1, lo, ext);
+                sum += v0;
+                if (MOMENTS) sum2 = fmaf(v0, v0, sum2);
+            }
+            sum += sumb; sum2 += sum2b;
         }
         // in-bin reduction across the LPB lanes that share the bin (all inside one warp)
         for (uint32_t off = LPB >> 1; off > 0; off >>= 1) {
             sum += __shfl_xor_sync(0xffffffffu, sum, off);
             if (MOMENTS) sum2 += __shfl_xor_sync(0xffffffffu, sum2, off);
         }
-        if (sub == 0) {
+        if (live && sub == 0) {       // G consecutive bins per warp: one contiguous 4*G-byte store
             float v;
             if (a.flavor == VB200_PER_BIN_MC) {
                 // sol = sum f * (vol(bin box)/spp) ; bins = double(nbins)*sol   (monte-carlo.h:43-45,59; integrator-per-bin-parallel.h:33)
@@ -104,22 +133,14 @@ mc_per_bin_kernel(const F f, const vb200_mc_launch a) {
             } else {
                 v = float(double(sum) * a.factor);                              // monte-carlo-per-bin-parallel.h:45,68
             }
-            s_val[buf][slot] = v;
-            if (MOMENTS) { s_m1[slot] = sum; s_m2[slot] = sum2; }
-        }
-        __syncthreads();
-        if (tid < BINS_PER_TILE) {
-            const uint64_t ob = a.bin_begin + tile * BINS_PER_TILE + tid;
-            if (ob < a.bin_end) {
-                const float v = s_val[buf][tid];
-                a.out[ob] = a.accumulate ? float(double(a.out[ob]) + double(v)) : v;   // '+=' vs '=' 
-                if (MOMENTS) {
-                    if (a.sum_f)  a.sum_f[ob - a.bin_begin]  = s_m1[tid];
-                    if (a.sum_f2) a.sum_f2[ob - a.bin_begin] = s_m2[tid];
-                }
+            a.out[bin] = a.accumulate ? float(double(a.out[bin]) + double(v)) : v;   // '+=' vs '=' 
+            if (MOMENTS) {
+                if (a.sum_f)  a.sum_f[bin - a.bin_begin]  = sum;
+                if (a.sum_f2) a.sum_f2[bin - a.bin_begin] = sum2;
             }
         }
-        if (MOMENTS) __syncthreads();     // s_m1/s_m2 are single-buffered
+        if (lane == 0) tile = atomicAdd(a.tile_counter, 1ull);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
     }
 }
 

@@ -55,9 +55,9 @@ struct FiniteThunks {
     template<int DB, bool MOMENTS>
     static int launch_mc(const F& f, const vb200_mc_launch& a, cudaStream_t st) {
         auto k = device::mc_per_bin_kernel<F, DIM, DB, MOMENTS, EXACT>;
-        const uint64_t bins_per_tile = device::MC_THREADS / a.lanes_per_bin;
-        const uint64_t ntiles = (a.bin_end - a.bin_begin + bins_per_tile - 1) / bins_per_tile;
-        const int grid = persistent_grid(k, device::MC_THREADS, ntiles, a.grid_hint);
+        const uint64_t bins_per_cta = uint64_t(device::MC_THREADS) / a.lanes_per_bin;     // one warp step of every warp
+        const uint64_t ctas = (a.bin_end - a.bin_begin + bins_per_cta - 1) / bins_per_cta;
+        const int grid = persistent_grid(k, device::MC_THREADS, ctas, a.grid_hint);
         k<<<grid, device::MC_THREADS, 0, st>>>(f, a);
         return int(cudaGetLastError());
     }
@@ -134,9 +134,9 @@ struct InfiniteThunks {
     template<int DB, bool MOMENTS>
     static int launch_walk(const F& f, const vb200_walk_launch& a, cudaStream_t st) {
         auto k = device::walk_kernel<F, DB, MOMENTS, EXACT>;
-        const uint64_t bins_per_tile = device::MC_THREADS / a.lanes_per_bin;
-        const uint64_t ntiles = (a.bin_end - a.bin_begin + bins_per_tile - 1) / bins_per_tile;
-        const int grid = persistent_grid(k, device::MC_THREADS, ntiles, a.grid_hint);
+        const uint64_t bins_per_cta = uint64_t(device::MC_THREADS) / a.lanes_per_bin;
+        const uint64_t ctas = (a.bin_end - a.bin_begin + bins_per_cta - 1) / bins_per_cta;
+        const int grid = persistent_grid(k, device::MC_THREADS, ctas, a.grid_hint);
         k<<<grid, device::MC_THREADS, 0, st>>>(f, a);
         return int(cudaGetLastError());
     }

@@ -63,50 +63,42 @@ __device__ __forceinline__ void walk_bin_box(const vb200_domain& dom, uint64_t b
 template<class F, int DIMBINS, bool MOMENTS, bool EXACT>
 __global__ void __launch_bounds__(MC_THREADS)
 walk_kernel(const F f, const vb200_walk_launch a) {
-    __shared__ float s_val[2][MC_THREADS];
-    __shared__ float s_m1[MOMENTS ? MC_THREADS : 1];
-    __shared__ float s_m2[MOMENTS ? MC_THREADS : 1];
-    const uint32_t lpb = a.lanes_per_bin;
-    const uint32_t bins_per_tile = MC_THREADS / lpb;
-    const uint32_t tid = threadIdx.x, slot = tid / lpb, sub = tid % lpb;
+    const uint32_t LPB = a.lanes_per_bin, G = 32u / LPB;
+    const uint32_t lane = threadIdx.x & 31u, sub = lane % LPB, grp = lane / LPB;
     const uint64_t nshard = a.bin_end - a.bin_begin;
-    const uint64_t ntiles = (nshard + bins_per_tile - 1) / bins_per_tile;
-    int buf = 0;
-    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
-        const uint64_t bin = a.bin_begin + tile * bins_per_tile + slot;
+    const uint64_t ntiles = (nshard + G - 1) / G;
+    uint64_t tile = 0;
+    if (lane == 0) tile = atomicAdd(a.tile_counter, 1ull);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    while (tile < ntiles) {
+        const uint64_t bin = a.bin_begin + tile * G + grp;
+        const bool live = bin < a.bin_end;
         float sum = 0.0f, sum2 = 0.0f;
-        if (bin < a.bin_end) {
+        if (live) {
             PhiloxSequence<DIMBINS> seq;
             seq.b0 = uint32_t(bin); seq.b1 = uint32_t(bin >> 32); seq.k0 = a.key0; seq.k1 = a.key1; seq.dom = &a.domain;
             walk_bin_box<DIMBINS>(a.domain, bin, seq.lo, seq.ext);
-            for (uint32_t s = sub; s < a.spp; s += lpb) {
+            for (uint32_t s = sub; s < a.spp; s += LPB) {
                 seq.s = s;
                 const float v = f(seq);
                 sum += v;
                 if (MOMENTS) sum2 = fmaf(v, v, sum2);
             }
         }
-        for (uint32_t off = lpb >> 1; off > 0; off >>= 1) {
+        for (uint32_t off = LPB >> 1; off > 0; off >>= 1) {
             sum += __shfl_xor_sync(0xffffffffu, sum, off);
             if (MOMENTS) sum2 += __shfl_xor_sync(0xffffffffu, sum2, off);
         }
-        if (sub == 0) {
-            s_val[buf][slot] = float(double(sum) * a.factor);            // monte-carlo-per-bin-parallel.h:77,96
-            if (MOMENTS) { s_m1[slot] = sum; s_m2[slot] = sum2; }
-        }
-        __syncthreads();
-        if (tid < bins_per_tile) {
-            const uint64_t ob = a.bin_begin + tile * bins_per_tile + tid;
-            if (ob < a.bin_end) {
-                const float v = s_val[buf][tid];
-                a.out[ob] = a.accumulate ? float(double(a.out[ob]) + double(v)) : v;
-                if (MOMENTS) {
-                    if (a.sum_f)  a.sum_f[ob - a.bin_begin]  = s_m1[tid];
-                    if (a.sum_f2) a.sum_f2[ob - a.bin_begin] = s_m2[tid];
-                }
+        if (live && sub == 0) {
+            const float v = float(double(sum) * a.factor);               // monte-carlo-per-bin-parallel.h:77,96
+            a.out[bin] = a.accumulate ? float(double(a.out[bin]) + double(v)) : v;
+            if (MOMENTS) {
+                if (a.sum_f)  a.sum_f[bin - a.bin_begin]  = sum;
+                if (a.sum_f2) a.sum_f2[bin - a.bin_begin] = sum2;
             }
         }
-        if (MOMENTS) __syncthreads();
+        if (lane == 0) tile = atomicAdd(a.tile_counter, 1ull);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
     }
 }
 
@@ -117,7 +109,9 @@ struct RecordedSequence {
     class const_iterator {
         const RecordedSequence* q; uint32_t i; float n;
         __device__ __forceinline__ void load() {
-            if (i < q->len) n = q->e[i]; else { n = CUDART_NAN_F; *q->error_flag = 1; }
+            // past the recorded end: flag the error and hand out +inf, which ends every `u < p` Russian-roulette test
+            // (NaN would make `if (u >= p) break;` spin forever)
+            if (i < q->len) n = q->e[i]; else { n = CUDART_INF_F; *q->error_flag = 1; }
         }
     public:
         __device__ __forceinline__ const_iterator(const RecordedSequence* q_) : q(q_), i(0) { load(); }

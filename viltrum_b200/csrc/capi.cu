@@ -115,7 +115,8 @@ extern "C" int vb200_create(int device, vb200_ctx** out) {
     ctx->device = device;
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess ||
-        (e = cudaMalloc(&ctx->d_flag, sizeof(int32_t))) != cudaSuccess) {
+        (e = cudaMalloc(&ctx->d_flag, sizeof(int32_t))) != cudaSuccess ||
+        (e = cudaMalloc(&ctx->d_counter, sizeof(unsigned long long))) != cudaSuccess) {
         int rc = fail(nullptr, VB200_ERR_CUDA, "context setup on device %d failed: %s", device, cudaGetErrorString(e));
         delete ctx; return rc;
     }
@@ -130,6 +131,7 @@ extern "C" void vb200_destroy(vb200_ctx* ctx) {
     for (auto& s : ctx->scratch) if (s) cudaFree(s);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->d_flag) cudaFree(ctx->d_flag);
+    if (ctx->d_counter) cudaFree(ctx->d_counter);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -200,6 +202,8 @@ extern "C" int vb200_mc_per_bin(vb200_ctx* ctx, const vb200_integrand* f, const 
     a.out = st.dev_base;
     rc = stage_moments(ctx, sum_f, bins_mem, 1, end - begin, &a.sum_f); if (rc) return rc;
     rc = stage_moments(ctx, sum_f2, bins_mem, 2, end - begin, &a.sum_f2); if (rc) return rc;
+    a.tile_counter = ctx->d_counter;
+    VB200_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), ctx->stream));
     rc = call_thunk(ctx, f, VB200_K_MC_PER_BIN, &a); if (rc) return rc;
     if (st.staged) {
         const uint64_t n = end - begin;
@@ -265,6 +269,8 @@ extern "C" int vb200_mc_per_bin_inf(vb200_ctx* ctx, const vb200_integrand* f, co
     a.out = st.dev_base;
     rc = stage_moments(ctx, sum_f, bins_mem, 1, end - begin, &a.sum_f); if (rc) return rc;
     rc = stage_moments(ctx, sum_f2, bins_mem, 2, end - begin, &a.sum_f2); if (rc) return rc;
+    a.tile_counter = ctx->d_counter;
+    VB200_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), ctx->stream));
     rc = call_thunk(ctx, f, VB200_K_WALK, &a); if (rc) return rc;
     if (st.staged) {
         const uint64_t n = end - begin;

@@ -18,6 +18,7 @@ struct vb200_ctx {
     // pinned host staging (D2H of bins lands here first so the copy is truly asynchronous)
     void* pinned = nullptr; size_t pinned_bytes = 0;
     int32_t* d_flag = nullptr;      // device error flag for replay kernels
+    unsigned long long* d_counter = nullptr;   // dynamic tile scheduler of the sampling kernels
 };
 
 namespace vb200 {
