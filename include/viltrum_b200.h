@@ -116,6 +116,9 @@ typedef struct vb200_domain {
     float    rmin[VB200_MAX_DIM];
     float    rmax[VB200_MAX_DIM];
     uint64_t res[VB200_MAX_DIMBINS];       /* bins per dimension */
+    float    drange[VB200_MAX_DIMBINS];    /* filled by the library: (max-min)/float(res), the reference's bin pitch
+                                              (monte-carlo-per-bin-parallel.h:46-47); callers may leave it 0 */
+    int32_t  reserved;
 } vb200_domain;
 
 /* Bin-grid shard handled by one call/GPU: linear bin indices [begin,end) in tensor order.  {0,0} = whole grid.

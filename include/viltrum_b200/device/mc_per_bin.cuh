@@ -44,7 +44,7 @@ __device__ __forceinline__ void bin_box(const vb200_domain& dom, uint64_t bin, f
     for (int i = 0; i < DIM; ++i) {
         float a = dom.rmin[i], b = dom.rmax[i];
         if (i < DIMBINS) {
-            float drange = __fdiv_rn(dom.rmax[i] - dom.rmin[i], float(dom.res[i]));
+            const float drange = dom.drange[i];      // (max-min)/Float(res), computed once on the host (same IEEE division)
             a = __fadd_rn(dom.rmin[i], __fmul_rn(float(pos[i]), drange));
             b = __fadd_rn(dom.rmin[i], __fmul_rn(float(pos[i] + 1u), drange));
         }

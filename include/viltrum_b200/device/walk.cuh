@@ -52,8 +52,8 @@ __device__ __forceinline__ void walk_bin_box(const vb200_domain& dom, uint64_t b
 #pragma unroll
     for (int i = 0; i < DIMBINS; ++i) {
         // RangeInfinite::min/max default to 0/1 beyond the explicit entries (range-infinite.h:31-37)
-        const float rmin = i < dom.dim ? dom.rmin[i] : 0.0f, rmax = i < dom.dim ? dom.rmax[i] : 1.0f;
-        const float drange = __fdiv_rn(rmax - rmin, float(dom.res[i]));
+        const float rmin = i < dom.dim ? dom.rmin[i] : 0.0f;
+        const float drange = dom.drange[i];
         const float a = __fadd_rn(rmin, __fmul_rn(float(pos[i]), drange));
         const float b = __fadd_rn(rmin, __fmul_rn(float(pos[i] + 1u), drange));
         lo[i] = a; ext[i] = b - a;

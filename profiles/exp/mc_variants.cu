@@ -2,10 +2,12 @@
 // choices are measured, not guessed.  nvcc -O3 -std=c++17 --expt-relaxed-constexpr -gencode arch=compute_100a,code=sm_100a
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 #include <array>
 #include <cuda_runtime.h>
 #include <viltrum_b200/device/philox.cuh>
+#include <viltrum_b200/device/mc_per_bin.cuh>
 #include "../../viltrum_b200/csrc/builtin_integrands.cuh"
 
 using namespace viltrum::b200;
@@ -152,6 +154,19 @@ int main() {
     RUN_WARP("warp LPB4 dynamic fused ILP2 minb4", 4, 10, true, 2, true, 4)
     RUN_WARP("warp LPB4 dynamic fused minb8", 4, 10, true, 1, true, 8)
     RUN_WARP("warp LPB4 dynamic fused philox7", 4, 7, true, 1, true, 1)
+    {   // the shipped product kernel, launched exactly as the library does
+        vb200_mc_launch L; memset(&L, 0, sizeof(L));
+        L.domain.dim = 4; L.domain.dimbins = 2; for (int i = 0; i < 4; ++i) { L.domain.rmin[i] = 0; L.domain.rmax[i] = 1; }
+        L.domain.res[0] = 1024; L.domain.res[1] = 1024; L.domain.drange[0] = L.domain.drange[1] = 1.0f / 1024.0f; L.bin_begin = 0; L.bin_end = a.nbins; L.nbins_total = a.nbins; L.spp = 64;
+        L.key0 = 1; L.key1 = 2; L.flavor = 0; L.accumulate = 0; L.factor = 1.0 / 64; L.out = a.out;
+        unsigned long long* ctr; cudaMalloc(&ctr, 8); L.tile_counter = ctr;
+        for (uint32_t lpb : {1u, 2u, 4u, 8u}) {
+            L.lanes_per_bin = lpb;
+            auto k = device::mc_per_bin_kernel<F, 4, 2, false, false>; int g = occ_grid(k, sms);
+            float ms = time_ms([&] { cudaMemsetAsync(ctr, 0, 8); k<<<g, 256>>>(f, L); });
+            char name[64]; snprintf(name, sizeof(name), "PRODUCT mc_per_bin_kernel LPB%u", lpb); report(name, ms, g);
+        }
+    }
     {   // FMA peaks
         int iters = 4096; int g = sms * 8;
         float ms = time_ms([&] { k_fma_peak<<<g, 256>>>(a.out, iters, 1.0001f, 0.5f); });

@@ -31,7 +31,8 @@ SYMBOLS = [
 
 class Domain(ctypes.Structure):
     _fields_ = [("dim", ctypes.c_int32), ("dimbins", ctypes.c_int32), ("rmin", ctypes.c_float * MAX_DIM),
-                ("rmax", ctypes.c_float * MAX_DIM), ("res", ctypes.c_uint64 * MAX_DIMBINS)]
+                ("rmax", ctypes.c_float * MAX_DIM), ("res", ctypes.c_uint64 * MAX_DIMBINS),
+                ("drange", ctypes.c_float * MAX_DIMBINS), ("reserved", ctypes.c_int32)]
 
 
 class Shard(ctypes.Structure):

@@ -68,11 +68,23 @@ int call_thunk(vb200_ctx* ctx, const vb200_integrand* f, int kind, const void* a
     return VB200_OK;
 }
 
-// lanes of one warp that share a bin: aim for >= 8 samples per lane so the per-bin setup (bin box, shuffles)
-// amortises, and for enough lanes that small bin grids still fill the chip
-uint32_t pick_lanes_per_bin(uint64_t spp) {
+vb200_domain finish_domain(const vb200_domain& d) {
+    vb200_domain o = d;
+    for (int i = 0; i < VB200_MAX_DIMBINS; ++i) o.drange[i] = 0.0f;
+    for (int i = 0; i < d.dimbins && i < VB200_MAX_DIMBINS; ++i) {
+        const float lo = i < d.dim ? d.rmin[i] : 0.0f, hi = i < d.dim ? d.rmax[i] : 1.0f;
+        o.drange[i] = (hi - lo) / float(d.res[i]);
+    }
+    return o;
+}
+
+// Lanes of one warp that share a bin.  Every bin costs a fixed set-up (bin box, scaling, tile ticket) worth about one
+// sample, so as few lanes per bin as possible — but enough lanes in total to fill the chip twice over when the grid is
+// small (measured: profiles/mc_variants_r1.txt).
+uint32_t pick_lanes_per_bin(const vb200_ctx* ctx, uint64_t spp, uint64_t nbins) {
+    const uint64_t want_lanes = uint64_t(ctx->sm_count) * 2048ull * 2ull;
     uint32_t lpb = 1;
-    while (lpb < 32 && uint64_t(lpb) * 16 <= spp) lpb <<= 1;
+    while (lpb < 32 && nbins * lpb < want_lanes && uint64_t(lpb) * 2 <= spp) lpb <<= 1;
     return lpb;
 }
 
@@ -116,10 +128,12 @@ extern "C" int vb200_create(int device, vb200_ctx** out) {
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess ||
         (e = cudaMalloc(&ctx->d_flag, sizeof(int32_t))) != cudaSuccess ||
-        (e = cudaMalloc(&ctx->d_counter, sizeof(unsigned long long))) != cudaSuccess) {
+        (e = cudaMalloc(&ctx->d_counter, vb200_ctx::kMaxChunks * sizeof(unsigned long long))) != cudaSuccess) {
         int rc = fail(nullptr, VB200_ERR_CUDA, "context setup on device %d failed: %s", device, cudaGetErrorString(e));
         delete ctx; return rc;
     }
+    for (auto& ev : ctx->chunk_done) if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) {
+        int rc = fail(nullptr, VB200_ERR_CUDA, "event creation failed: %s", cudaGetErrorString(e)); vb200_destroy(ctx); return rc; }
     *out = ctx;
     return VB200_OK;
 }
@@ -132,6 +146,7 @@ extern "C" void vb200_destroy(vb200_ctx* ctx) {
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->d_flag) cudaFree(ctx->d_flag);
     if (ctx->d_counter) cudaFree(ctx->d_counter);
+    for (auto& ev : ctx->chunk_done) if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -166,14 +181,50 @@ namespace {
 // Range::volume(): float product over the dimensions in order, starting from 1 (reference src/range.h:21-25)
 float range_volume(const vb200_domain& d, int n) { float v = 1.0f; for (int i = 0; i < n; ++i) v *= (d.rmax[i] - d.rmin[i]); return v; }
 
-int stage_moments(vb200_ctx* ctx, float* p, int mem, int slot, uint64_t n, float** dev) {
-    *dev = nullptr;
-    if (!p) return VB200_OK;
-    if (mem == VB200_DEVICE) { *dev = p; return VB200_OK; }
-    void* d = nullptr; int rc = reserve(ctx, slot, n * sizeof(float), &d); if (rc) return rc;
-    *dev = static_cast<float*>(d);
-    return VB200_OK;
 }
+
+// Shared tail of the two sampling drivers (finite and infinite ranges).
+//   DEVICE bins: one launch over the shard, '+=' (or '=') applied by the kernel in place; returns with work enqueued.
+//   HOST bins  : the end-to-end path.  The kernel writes its estimates straight into the context's pinned, device-mapped
+//                staging buffer (zero-copy stores ride PCIe underneath the compute — no separate D2H pass), the shard is cut
+//                into chunks with one launch + event each, and the host applies '+=' / '=' to chunk k while chunk k+1 is
+//                still being computed.
+template<class Launch>
+static int run_sampler(vb200_ctx* ctx, const vb200_integrand* f, int kind, Launch& a, bool accumulate,
+                       float* bins, int bins_mem, float* sum_f, float* sum_f2) {
+    const uint64_t begin = a.bin_begin, end = a.bin_end, n = end - begin;
+    if (bins_mem != VB200_HOST && bins_mem != VB200_DEVICE) return fail(ctx, VB200_ERR_INVALID, "bad memory-space flag %d", bins_mem);
+    if (!bins) return fail(ctx, VB200_ERR_INVALID, "bins pointer is NULL");
+    VB200_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, vb200_ctx::kMaxChunks * sizeof(unsigned long long), ctx->stream));
+    if (bins_mem == VB200_DEVICE) {
+        a.accumulate = accumulate ? 1 : 0; a.out = bins; a.sum_f = sum_f; a.sum_f2 = sum_f2; a.tile_counter = ctx->d_counter;
+        return call_thunk(ctx, f, kind, &a);
+    }
+    float* h = nullptr;
+    int rc = reserve_pinned(ctx, n * sizeof(float) * 3, reinterpret_cast<void**>(&h)); if (rc) return rc;
+    a.accumulate = 0;
+    a.out = h - begin;                                   // kernels index from the base of the full grid
+    a.sum_f = sum_f ? h + n : nullptr; a.sum_f2 = sum_f2 ? h + 2 * n : nullptr;
+    int chunks = int(n / (128u * 1024u)); if (chunks < 1) chunks = 1; if (chunks > vb200_ctx::kMaxChunks) chunks = vb200_ctx::kMaxChunks;
+    for (int c = 0; c < chunks; ++c) {
+        a.bin_begin = begin + n * uint64_t(c) / uint64_t(chunks); a.bin_end = begin + n * uint64_t(c + 1) / uint64_t(chunks);
+        a.tile_counter = ctx->d_counter + c;
+        if (a.sum_f)  a.sum_f  = h + n + (a.bin_begin - begin);      // moment arrays are indexed from the launch's first bin
+        if (a.sum_f2) a.sum_f2 = h + 2 * n + (a.bin_begin - begin);
+        rc = call_thunk(ctx, f, kind, &a); if (rc) return rc;
+        VB200_CUDA(ctx, cudaEventRecord(ctx->chunk_done[c], ctx->stream));
+    }
+    for (int c = 0; c < chunks; ++c) {
+        const uint64_t lo = n * uint64_t(c) / uint64_t(chunks), hi = n * uint64_t(c + 1) / uint64_t(chunks);
+        VB200_CUDA(ctx, cudaEventSynchronize(ctx->chunk_done[c]));
+        float* dst = bins + begin; const float* src = h;
+        // float(double(dst)+double(src)) == dst+src in fp32 (the double sum of two floats rounds to the same float)
+        if (accumulate) for (uint64_t i = lo; i < hi; ++i) dst[i] += src[i];
+        else std::memcpy(dst + lo, src + lo, (hi - lo) * sizeof(float));
+    }
+    if (sum_f)  std::memcpy(sum_f, h + n, n * sizeof(float));
+    if (sum_f2) std::memcpy(sum_f2, h + 2 * n, n * sizeof(float));
+    return VB200_OK;
 }
 
 extern "C" int vb200_mc_per_bin(vb200_ctx* ctx, const vb200_integrand* f, const vb200_mc_params* p,
@@ -189,36 +240,13 @@ extern "C" int vb200_mc_per_bin(vb200_ctx* ctx, const vb200_integrand* f, const 
     if (begin == end) return VB200_OK;
 
     vb200_mc_launch a; std::memset(&a, 0, sizeof(a));
-    a.domain = p->domain; a.bin_begin = begin; a.bin_end = end; a.nbins_total = total;
-    a.spp = uint32_t(p->spp); a.lanes_per_bin = pick_lanes_per_bin(p->spp);
+    a.domain = finish_domain(p->domain); a.bin_begin = begin; a.bin_end = end; a.nbins_total = total;
+    a.spp = uint32_t(p->spp); a.lanes_per_bin = pick_lanes_per_bin(ctx, p->spp, total);   // from the WHOLE grid: the summation order, hence the bits, must not depend on the shard
     a.key0 = uint32_t(p->seed); a.key1 = uint32_t(p->seed >> 32);
     a.flavor = p->flavor;
     a.factor = double(range_volume(p->domain, p->domain.dim)) / double(p->spp);     // monte-carlo-per-bin-parallel.h:45
-    // '+=' for MonteCarloPerBinParallel, '=' for IntegratorPerBinParallel.  With host bins the
-    // kernel writes the shard's estimate into scratch and the '+=' happens on the host after the copy back.
-    const bool accumulate = (p->flavor == VB200_MC_PER_BIN);
-    BinStage st; rc = stage_bins_in(ctx, bins, bins_mem, begin, end, /*upload=*/false, &st); if (rc) return rc;
-    a.accumulate = (accumulate && !st.staged) ? 1 : 0;
-    a.out = st.dev_base;
-    rc = stage_moments(ctx, sum_f, bins_mem, 1, end - begin, &a.sum_f); if (rc) return rc;
-    rc = stage_moments(ctx, sum_f2, bins_mem, 2, end - begin, &a.sum_f2); if (rc) return rc;
-    a.tile_counter = ctx->d_counter;
-    VB200_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), ctx->stream));
-    rc = call_thunk(ctx, f, VB200_K_MC_PER_BIN, &a); if (rc) return rc;
-    if (st.staged) {
-        const uint64_t n = end - begin;
-        float* h = nullptr; rc = reserve_pinned(ctx, n * sizeof(float) * 3, reinterpret_cast<void**>(&h)); if (rc) return rc;
-        VB200_CUDA(ctx, cudaMemcpyAsync(h, st.dev_base + begin, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-        if (sum_f)  VB200_CUDA(ctx, cudaMemcpyAsync(h + n, a.sum_f, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-        if (sum_f2) VB200_CUDA(ctx, cudaMemcpyAsync(h + 2 * n, a.sum_f2, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-        VB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        float* dst = bins + begin;
-        if (accumulate) for (uint64_t i = 0; i < n; ++i) dst[i] = float(double(dst[i]) + double(h[i]));
-        else std::memcpy(dst, h, n * sizeof(float));
-        if (sum_f)  std::memcpy(sum_f, h + n, n * sizeof(float));
-        if (sum_f2) std::memcpy(sum_f2, h + 2 * n, n * sizeof(float));
-    }
-    return VB200_OK;
+    // '+=' for MonteCarloPerBinParallel, '=' for IntegratorPerBinParallel
+    return run_sampler(ctx, f, VB200_K_MC_PER_BIN, a, p->flavor == VB200_MC_PER_BIN, bins, bins_mem, sum_f, sum_f2);
 }
 
 extern "C" int vb200_mc_per_bin_replay(vb200_ctx* ctx, const vb200_integrand* f, const vb200_mc_params* p,
@@ -232,7 +260,7 @@ extern "C" int vb200_mc_per_bin_replay(vb200_ctx* ctx, const vb200_integrand* f,
     uint64_t begin, end; rc = resolve_shard(ctx, p->shard, total, &begin, &end); if (rc) return rc;
     if (begin == end) return VB200_OK;
     vb200_replay_launch a; std::memset(&a, 0, sizeof(a));
-    a.domain = p->domain; a.bin_begin = begin; a.bin_end = end; a.nbins_total = total; a.spp = uint32_t(p->spp); a.flavor = p->flavor;
+    a.domain = finish_domain(p->domain); a.bin_begin = begin; a.bin_end = end; a.nbins_total = total; a.spp = uint32_t(p->spp); a.flavor = p->flavor;
     a.factor = double(range_volume(p->domain, p->domain.dim)) / double(p->spp);
     const size_t sbytes = size_t(end - begin) * p->spp * size_t(f->dim) * sizeof(float);
     if (samples_mem == VB200_HOST) {
@@ -260,31 +288,11 @@ extern "C" int vb200_mc_per_bin_inf(vb200_ctx* ctx, const vb200_integrand* f, co
     uint64_t begin, end; rc = resolve_shard(ctx, p->shard, total, &begin, &end); if (rc) return rc;
     if (begin == end) return VB200_OK;
     vb200_walk_launch a; std::memset(&a, 0, sizeof(a));
-    a.domain = p->domain; a.bin_begin = begin; a.bin_end = end; a.nbins_total = total;
-    a.spp = uint32_t(p->spp); a.lanes_per_bin = pick_lanes_per_bin(p->spp);
+    a.domain = finish_domain(p->domain); a.bin_begin = begin; a.bin_end = end; a.nbins_total = total;
+    a.spp = uint32_t(p->spp); a.lanes_per_bin = pick_lanes_per_bin(ctx, p->spp, total);   // from the WHOLE grid: the summation order, hence the bits, must not depend on the shard
     a.key0 = uint32_t(p->seed); a.key1 = uint32_t(p->seed >> 32);
     a.factor = double(range_volume(p->domain, p->domain.dim)) / double(p->spp);      // range-infinite.h:22-23; :77
-    BinStage st; rc = stage_bins_in(ctx, bins, bins_mem, begin, end, false, &st); if (rc) return rc;
-    a.accumulate = st.staged ? 0 : 1;
-    a.out = st.dev_base;
-    rc = stage_moments(ctx, sum_f, bins_mem, 1, end - begin, &a.sum_f); if (rc) return rc;
-    rc = stage_moments(ctx, sum_f2, bins_mem, 2, end - begin, &a.sum_f2); if (rc) return rc;
-    a.tile_counter = ctx->d_counter;
-    VB200_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), ctx->stream));
-    rc = call_thunk(ctx, f, VB200_K_WALK, &a); if (rc) return rc;
-    if (st.staged) {
-        const uint64_t n = end - begin;
-        float* h = nullptr; rc = reserve_pinned(ctx, n * sizeof(float) * 3, reinterpret_cast<void**>(&h)); if (rc) return rc;
-        VB200_CUDA(ctx, cudaMemcpyAsync(h, st.dev_base + begin, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-        if (sum_f)  VB200_CUDA(ctx, cudaMemcpyAsync(h + n, a.sum_f, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-        if (sum_f2) VB200_CUDA(ctx, cudaMemcpyAsync(h + 2 * n, a.sum_f2, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-        VB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        float* dst = bins + begin;
-        for (uint64_t i = 0; i < n; ++i) dst[i] = float(double(dst[i]) + double(h[i]));
-        if (sum_f)  std::memcpy(sum_f, h + n, n * sizeof(float));
-        if (sum_f2) std::memcpy(sum_f2, h + 2 * n, n * sizeof(float));
-    }
-    return VB200_OK;
+    return run_sampler(ctx, f, VB200_K_WALK, a, /*accumulate '+='*/ true, bins, bins_mem, sum_f, sum_f2);
 }
 
 extern "C" int vb200_mc_per_bin_inf_replay(vb200_ctx* ctx, const vb200_integrand* f, const vb200_mc_params* p,
@@ -298,7 +306,7 @@ extern "C" int vb200_mc_per_bin_inf_replay(vb200_ctx* ctx, const vb200_integrand
     if (begin == end) return VB200_OK;
     const uint64_t npaths = (end - begin) * p->spp;
     vb200_walk_replay_launch a; std::memset(&a, 0, sizeof(a));
-    a.domain = p->domain; a.bin_begin = begin; a.bin_end = end; a.nbins_total = total; a.spp = uint32_t(p->spp);
+    a.domain = finish_domain(p->domain); a.bin_begin = begin; a.bin_end = end; a.nbins_total = total; a.spp = uint32_t(p->spp);
     a.factor = double(range_volume(p->domain, p->domain.dim)) / double(p->spp);
     if (mem == VB200_HOST) {
         const uint64_t nel = offsets[npaths];
@@ -332,7 +340,7 @@ extern "C" int vb200_monte_carlo(vb200_ctx* ctx, const vb200_integrand* f, const
     const uint64_t total = nbins_of(p->domain);
     uint64_t sb, se; rc = resolve_shard(ctx, p->shard, p->spp, &sb, &se); if (rc) return rc;
     vb200_scatter_launch a; std::memset(&a, 0, sizeof(a));
-    a.domain = p->domain; a.sample_begin = sb; a.sample_end = se; a.nbins_total = total;
+    a.domain = finish_domain(p->domain); a.sample_begin = sb; a.sample_end = se; a.nbins_total = total;
     a.key0 = uint32_t(p->seed); a.key1 = uint32_t(p->seed >> 32);
     a.factor = double(total) * double(range_volume(p->domain, p->domain.dim)) / double(p->spp);     // monte-carlo.h:43-45
     float* dev = bins;

@@ -18,7 +18,9 @@ struct vb200_ctx {
     // pinned host staging (D2H of bins lands here first so the copy is truly asynchronous)
     void* pinned = nullptr; size_t pinned_bytes = 0;
     int32_t* d_flag = nullptr;      // device error flag for replay kernels
-    unsigned long long* d_counter = nullptr;   // dynamic tile scheduler of the sampling kernels
+    unsigned long long* d_counter = nullptr;   // dynamic tile schedulers of the sampling kernels: one ticket counter per chunk
+    static constexpr int kMaxChunks = 8;
+    cudaEvent_t chunk_done[kMaxChunks] = {};
 };
 
 namespace vb200 {
@@ -31,9 +33,11 @@ int reserve(vb200_ctx* ctx, int slot, size_t bytes, void** out);
 int reserve_pinned(vb200_ctx* ctx, size_t bytes, void** out);
 inline uint64_t nbins_of(const vb200_domain& d) { uint64_t n = 1; for (int i = 0; i < d.dimbins; ++i) n *= d.res[i]; return n; }
 int check_domain(vb200_ctx* ctx, const vb200_domain& d, int integrand_dim);
+// copy of the caller's domain with drange filled in: (max-min)/float(res) in fp32, implicit [0,1] beyond d.dim (infinite ranges)
+vb200_domain finish_domain(const vb200_domain& d);
 int resolve_shard(vb200_ctx* ctx, const vb200_shard& s, uint64_t total, uint64_t* begin, uint64_t* end);
 int call_thunk(vb200_ctx* ctx, const vb200_integrand* f, int kind, const void* args);
-uint32_t pick_lanes_per_bin(uint64_t spp);
+uint32_t pick_lanes_per_bin(const vb200_ctx* ctx, uint64_t spp, uint64_t nbins);
 // bins staging helpers: returns the device pointer to use as "base of the full grid"
 struct BinStage { float* dev_base = nullptr; bool staged = false; uint64_t begin = 0, end = 0; float* host = nullptr; };
 int stage_bins_in(vb200_ctx* ctx, float* bins, int mem, uint64_t begin, uint64_t end, bool upload, BinStage* st);
