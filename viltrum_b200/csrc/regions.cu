@@ -1,15 +1,483 @@
-// region tables, region->bin integration and control variates (stubs, being implemented)
-#include "context.h"
+// Region tables and region->bin integration (kernels K8-K10 of §2.2).
+// Compiled with --fmad=false; the rule arithmetic additionally uses explicit round-to-nearest intrinsics
+// (include/viltrum_b200/device/rules.cuh), so every float/double rounding of the reference happens here too and the
+// per-bin results are bit-identical to RegionsIntegratorSequential on the same region table.
+#include "regions.h"
+#include <viltrum_b200/device/rules.cuh>
+#include <vector>
+#include <cstring>
+#include <new>
+
 using namespace vb200;
-struct vb200_regions { int dim; };
+namespace R = viltrum::b200::device::rules;
+
+namespace vb200 {
+
+int rule_samples(int rule, int* SH, int* SL) {
+    switch (rule) {
+        case VB200_RULE_TRAPEZOIDAL: *SH = 2; *SL = 0; return 0;
+        case VB200_RULE_SIMPSON: *SH = 3; *SL = 0; return 0;
+        case VB200_RULE_BOOLE: *SH = 5; *SL = 0; return 0;
+        case VB200_RULE_SIMPSON_TRAPEZOIDAL: *SH = 3; *SL = 2; return 0;
+        case VB200_RULE_BOOLE_SIMPSON: *SH = 5; *SL = 3; return 0;
+    }
+    return -1;
+}
+
+int regions_alloc(vb200_ctx* ctx, int dim, int rule, uint64_t capacity, vb200_regions** out) {
+    int SH, SL;
+    if (rule_samples(rule, &SH, &SL)) return fail(ctx, VB200_ERR_INVALID, "unknown rule %d", rule);
+    if (dim < 1 || dim > VB200_MAX_DIM) return fail(ctx, VB200_ERR_INVALID, "region dimension %d outside 1..%d", dim, VB200_MAX_DIM);
+    uint64_t sd = 1; for (int i = 0; i < dim; ++i) sd *= uint64_t(SH);
+    if (sd > 15625) return fail(ctx, VB200_ERR_UNSUPPORTED, "%llu samples per region: beyond the reference's own limit (VILTRUM_MAX_DIMENSIONS_REGION, region.h:16-18)", (unsigned long long)sd);
+    vb200_regions* r = new (std::nothrow) vb200_regions;
+    if (!r) return fail(ctx, VB200_ERR_NOMEM, "out of host memory");
+    r->ctx = ctx; r->dim = dim; r->rule = rule; r->SH = SH; r->SL = SL; r->sd = int(sd); r->capacity = capacity; r->count = 0;
+    cudaError_t e;
+    if ((e = cudaMalloc(&r->rmin, capacity * dim * sizeof(float))) != cudaSuccess || (e = cudaMalloc(&r->rmax, capacity * dim * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc(&r->data, capacity * sd * sizeof(float))) != cudaSuccess || (e = cudaMalloc(&r->err, capacity * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc(&r->errdim, capacity * sizeof(uint32_t))) != cudaSuccess) {
+        cudaGetLastError(); vb200_regions_free(r);
+        return fail(ctx, VB200_ERR_NOMEM, "region table of %llu regions x %llu samples does not fit: %s", (unsigned long long)capacity, (unsigned long long)sd, cudaGetErrorString(e));
+    }
+    *out = r;
+    return VB200_OK;
+}
+
+} // namespace vb200
+
+extern "C" void vb200_regions_free(vb200_regions* r) {
+    if (!r) return;
+    if (r->ctx) cudaStreamSynchronize(r->ctx->stream);
+    cudaFree(r->rmin); cudaFree(r->rmax); cudaFree(r->data); cudaFree(r->err); cudaFree(r->errdim);
+    delete r;
+}
+extern "C" uint64_t vb200_regions_count(const vb200_regions* r) { return r ? r->count : 0; }
+extern "C" int vb200_regions_dim(const vb200_regions* r) { return r ? r->dim : 0; }
+extern "C" int vb200_regions_samples(const vb200_regions* r) { return r ? r->sd : 0; }
+
+extern "C" int vb200_regions_upload(vb200_ctx* ctx, int dim, int rule, uint64_t count,
+                                    const float* rmin, const float* rmax, const float* err, const uint32_t* errdim, const float* data,
+                                    vb200_regions** out) {
+    if (!ctx || !out || !rmin || !rmax || !data || count == 0) return fail(ctx, VB200_ERR_INVALID, "NULL/empty argument");
+    VB200_CUDA(ctx, cudaSetDevice(ctx->device));
+    vb200_regions* r = nullptr;
+    int rc = regions_alloc(ctx, dim, rule, count, &r); if (rc) return rc;
+    const uint64_t sd = uint64_t(r->sd);
+    std::vector<float> t(count * (sd > uint64_t(dim) ? sd : uint64_t(dim)));
+    auto up = [&] (float* dst, const float* src, uint64_t width) -> cudaError_t {       // AoS [count][width] -> SoA [width][count]
+        for (uint64_t i = 0; i < count; ++i) for (uint64_t k = 0; k < width; ++k) t[k * count + i] = src[i * width + k];
+        return cudaMemcpyAsync(dst, t.data(), count * width * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+    };
+    cudaError_t e;
+    if ((e = up(r->rmin, rmin, dim)) != cudaSuccess || (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess ||
+        (e = up(r->rmax, rmax, dim)) != cudaSuccess || (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess ||
+        (e = up(r->data, data, sd)) != cudaSuccess || (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) {
+        vb200_regions_free(r); return fail(ctx, VB200_ERR_CUDA, "region upload failed: %s", cudaGetErrorString(e));
+    }
+    if (err) VB200_CUDA(ctx, cudaMemcpyAsync(r->err, err, count * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    else VB200_CUDA(ctx, cudaMemsetAsync(r->err, 0, count * sizeof(float), ctx->stream));
+    if (errdim) VB200_CUDA(ctx, cudaMemcpyAsync(r->errdim, errdim, count * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    else VB200_CUDA(ctx, cudaMemsetAsync(r->errdim, 0, count * sizeof(uint32_t), ctx->stream));
+    VB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    r->count = count;
+    *out = r;
+    return VB200_OK;
+}
+
+extern "C" int vb200_regions_download(vb200_ctx* ctx, const vb200_regions* r, float* rmin, float* rmax, float* err, uint32_t* errdim, float* data) {
+    if (!ctx || !r) return fail(ctx, VB200_ERR_INVALID, "NULL argument");
+    VB200_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t n = r->count, cap = r->capacity, sd = uint64_t(r->sd), dim = uint64_t(r->dim);
+    std::vector<float> t;
+    auto down = [&] (float* dst, const float* src, uint64_t width) -> int {              // SoA [width][cap] -> AoS [n][width]
+        t.resize(width * cap);
+        VB200_CUDA(ctx, cudaMemcpyAsync(t.data(), src, width * cap * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        VB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (uint64_t i = 0; i < n; ++i) for (uint64_t k = 0; k < width; ++k) dst[i * width + k] = t[k * cap + i];
+        return VB200_OK;
+    };
+    int rc;
+    if (rmin && (rc = down(rmin, r->rmin, dim))) return rc;
+    if (rmax && (rc = down(rmax, r->rmax, dim))) return rc;
+    if (data && (rc = down(data, r->data, sd))) return rc;
+    if (err) VB200_CUDA(ctx, cudaMemcpyAsync(err, r->err, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (errdim) VB200_CUDA(ctx, cudaMemcpyAsync(errdim, r->errdim, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    VB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VB200_OK;
+}
+
+// ---- regions_generator_single: one region over the whole range (regions-generator-single.h:12-20) --------------------
+// sample points of region.h:40-46 + fill.h:45-72: p = double(i)/double(S-1); x = float(p*(max-min) + min), (max-min) a float difference
+__global__ void region_grid_points_kernel(int S, int dim, uint64_t n, const float* rmin, const float* rmax, uint64_t cap, uint64_t region, float* points) {
+    const uint64_t k = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    uint64_t t = k;
+    for (int d = 0; d < dim; ++d) {
+        const double p = R::dd(double(t % uint64_t(S)), double(S - 1)); t /= uint64_t(S);
+        const float lo = rmin[uint64_t(d) * cap + region], hi = rmax[uint64_t(d) * cap + region];
+        points[uint64_t(d) * n + k] = R::d2f(R::da(R::dm(p, double(R::fs(hi, lo))), double(lo)));
+    }
+}
+
+extern "C" int vb200_regions_generate_single(vb200_ctx* ctx, const vb200_integrand* f, const vb200_domain* domain, int rule, vb200_regions** out) {
+    if (!ctx || !f || !domain || !out) return fail(ctx, VB200_ERR_INVALID, "NULL argument");
+    VB200_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (f->dim <= 0 || domain->dim != f->dim) return fail(ctx, VB200_ERR_INVALID, "range has %d dimensions, integrand takes %d", domain->dim, f->dim);
+    vb200_regions* r = nullptr;
+    int rc = regions_alloc(ctx, f->dim, rule, 1, &r); if (rc) return rc;
+    auto bail = [&] (int code) { vb200_regions_free(r); return code; };
+    if (cudaMemcpyAsync(r->rmin, domain->rmin, f->dim * sizeof(float), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+        cudaMemcpyAsync(r->rmax, domain->rmax, f->dim * sizeof(float), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+        return bail(fail(ctx, VB200_ERR_CUDA, "range upload failed"));
+    const uint64_t n = uint64_t(r->sd);
+    void* pts = nullptr; rc = reserve(ctx, 3, n * f->dim * sizeof(float), &pts); if (rc) return bail(rc);
+    region_grid_points_kernel<<<unsigned((n + 255) / 256), 256, 0, ctx->stream>>>(r->SH, f->dim, n, r->rmin, r->rmax, 1, 0, static_cast<float*>(pts));
+    ctx->launches++;
+    vb200_eval_launch ev; std::memset(&ev, 0, sizeof(ev));
+    ev.n = n; ev.dim = f->dim; ev.points = static_cast<const float*>(pts); ev.values = r->data;       // capacity 1: data[k*1+0]
+    rc = call_thunk(ctx, f, VB200_K_EVAL_POINTS, &ev); if (rc) return bail(rc);
+    if (cudaMemsetAsync(r->err, 0, sizeof(float), ctx->stream) != cudaSuccess || cudaMemsetAsync(r->errdim, 0, sizeof(uint32_t), ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess) return bail(fail(ctx, VB200_ERR_CUDA, "single-region generation failed: %s", cudaGetErrorString(cudaGetLastError())));
+    r->count = 1;
+    *out = r;
+    return VB200_OK;
+}
+
+// =====================================================================================================================
+// Bin walk
+// =====================================================================================================================
+namespace {
+
+// one fold level of Region::sub_last over a NON-binned dimension: the bin box spans the region's whole extent there, so the
+// normalised limits are exactly 0 and 1 (pos_in_range(min)=0, pos_in_range(max)=1) and the result is the same for every
+// bin — computed once per region instead of once per (bin, region) pair.  in: [S^m][cap] -> out: [S^(m-1)][cap].
+template<int S>
+__global__ void fold_last_dim_kernel(uint64_t nregions, uint64_t cap, int lower /* S^(m-1) */, const float* __restrict__ in, float* __restrict__ out) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    if (i >= nregions) return;
+    float line[S];
+#pragma unroll
+    for (int j = 0; j < S; ++j) line[j] = in[(uint64_t(k) + uint64_t(j) * uint64_t(lower)) * cap + i];
+    out[uint64_t(k) * cap + i] = R::subrange<S>(0.0f, 1.0f, line);
+}
+
+// Range::volume (range.h:21-25) and pixels_in_region (region.h:454-463) per region
+__global__ void region_boxes_kernel(uint64_t nregions, uint64_t cap, int dim, int db, vb200_domain dom,
+                                    const float* __restrict__ rmin, const float* __restrict__ rmax,
+                                    float* __restrict__ volume, uint32_t* __restrict__ pstart, uint32_t* __restrict__ pend) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= nregions) return;
+    float v = 1.0f;
+    for (int d = 0; d < dim; ++d) v = R::fm(v, R::fs(rmax[uint64_t(d) * cap + i], rmin[uint64_t(d) * cap + i]));
+    volume[i] = v;
+    for (int d = 0; d < db; ++d) {
+        const float res = float(dom.res[d]);
+        const float ext = R::fs(dom.rmax[d], dom.rmin[d]);
+        const float fs_ = R::fd(R::fm(res, R::fs(rmin[uint64_t(d) * cap + i], dom.rmin[d])), ext);
+        const float fe_ = R::fa(0.99f, R::fd(R::fm(res, R::fs(rmax[uint64_t(d) * cap + i], dom.rmin[d])), ext));
+        // size_t(float): negative / NaN inputs are undefined upstream; clamp them to 0 here
+        uint64_t s = fs_ > 0.0f ? uint64_t(fs_) : 0ull;
+        uint64_t e = fe_ > 0.0f ? uint64_t(fe_) : 0ull;
+        if (e > dom.res[d]) e = dom.res[d];
+        if (e < s + 1) e = s + 1;
+        pstart[uint64_t(d) * cap + i] = uint32_t(s < 0xffffffffull ? s : 0xffffffffull);
+        pend[uint64_t(d) * cap + i] = uint32_t(e < 0xffffffffull ? e : 0xffffffffull);
+    }
+}
+
+struct TileGeom { uint32_t tile[3], tiles[3], res[3]; int db; };
+
+__device__ __forceinline__ void tile_origin(const TileGeom& g, uint64_t t, uint32_t (&o)[3]) {
+    for (int d = 0; d < 3; ++d) { o[d] = uint32_t(t % g.tiles[d]) * g.tile[d]; t /= g.tiles[d]; }
+}
+__device__ __forceinline__ bool tile_in_shard(const TileGeom& g, const uint32_t (&o)[3], uint64_t begin, uint64_t end) {
+    uint64_t lo = 0, hi = 0, prod = 1;
+    for (int d = 0; d < g.db; ++d) {
+        const uint32_t last = min(o[d] + g.tile[d], g.res[d]) - 1u;
+        lo += uint64_t(o[d]) * prod; hi += uint64_t(last) * prod; prod *= g.res[d];
+    }
+    return hi >= begin && lo < end;
+}
+__device__ __forceinline__ bool overlaps(const TileGeom& g, const uint32_t (&o)[3], const uint32_t* pstart, const uint32_t* pend, uint64_t cap, uint64_t r) {
+    bool ok = true;
+    for (int d = 0; d < g.db; ++d) {
+        const uint32_t s = pstart[uint64_t(d) * cap + r], e = pend[uint64_t(d) * cap + r];
+        ok = ok && (s < o[d] + g.tile[d]) && (e > o[d]);
+    }
+    return ok;
+}
+
+// one CTA per tile: count (fill == false) or write (fill == true) the ids of the regions whose pixel box meets the tile,
+// in ascending region order (ordered stream compaction: ballot + popc inside a warp, shared-memory scan across warps)
+template<bool FILL>
+__global__ void __launch_bounds__(256) tile_lists_kernel(TileGeom g, uint64_t nregions, uint64_t cap, uint64_t begin, uint64_t end,
+                                                         const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ pend,
+                                                         unsigned long long* __restrict__ counts, const uint64_t* __restrict__ offsets, uint32_t* __restrict__ list) {
+    __shared__ uint32_t s_warp[8];
+    __shared__ unsigned long long s_running;
+    const uint64_t t = blockIdx.x;
+    uint32_t o[3]; tile_origin(g, t, o);
+    if (!tile_in_shard(g, o, begin, end)) { if (!FILL && threadIdx.x == 0) counts[t] = 0; return; }
+    if (threadIdx.x == 0) s_running = 0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint64_t base_out = FILL ? offsets[t] : 0;
+    for (uint64_t base = 0; base < nregions; base += 256) {
+        const uint64_t r = base + threadIdx.x;
+        const bool hit = r < nregions && overlaps(g, o, pstart, pend, cap, r);
+        const uint32_t m = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+        for (uint32_t w = 0; w < 8; ++w) { const uint32_t c = s_warp[w]; if (w < warp) before += c; total += c; }
+        const unsigned long long running = s_running;
+        if (FILL && hit) list[base_out + running + before + __popc(m & ((1u << lane) - 1u))] = uint32_t(r);
+        __syncthreads();
+        if (threadIdx.x == 0) s_running = running + total;
+        __syncthreads();
+    }
+    if (!FILL && threadIdx.x == 0) counts[t] = s_running;
+}
+
+// closed-form integral of the region's (marginalised) tensor-product interpolant over bin ∩ region:
+// Region::integral_subrange -> sub_last (region.h:141-169), folding subrange(a_d,b_d) over the binned dims DB-1, ..., 0.
+template<int S, int DB>
+__device__ __forceinline__ float patch_subrange(const float* patch, const float (&na)[3], const float (&nb)[3]) {
+    if (DB == 1) return R::subrange<S>(na[0], nb[0], patch);
+    if (DB == 2) {
+        float t[S];
+#pragma unroll
+        for (int i0 = 0; i0 < S; ++i0) {
+            float line[S];
+#pragma unroll
+            for (int i1 = 0; i1 < S; ++i1) line[i1] = patch[i0 + S * i1];
+            t[i0] = R::subrange<S>(na[1], nb[1], line);
+        }
+        return R::subrange<S>(na[0], nb[0], t);
+    }
+    float t1[S];
+#pragma unroll
+    for (int i0 = 0; i0 < S; ++i0) {
+        float t2[S];
+#pragma unroll
+        for (int i1 = 0; i1 < S; ++i1) {
+            float line[S];
+#pragma unroll
+            for (int i2 = 0; i2 < S; ++i2) line[i2] = patch[i0 + S * i1 + S * S * i2];
+            t2[i1] = R::subrange<S>(na[2], nb[2], line);
+        }
+        t1[i0] = R::subrange<S>(na[1], nb[1], t2);
+    }
+    return R::subrange<S>(na[0], nb[0], t1);
+}
+
+template<int S, int DB> struct Staged {
+    static constexpr int P = (DB == 1 ? S : DB == 2 ? S * S : S * S * S);
+    float patch[P]; float rmin[DB], rmax[DB]; float volume; uint32_t ps[DB], pe[DB];
+};
+
+// K8/K10: one CTA per bin tile, one thread per bin.  The tile's region list is staged through shared memory in chunks
+// (patches + boxes: the "region tree" a bin needs), every thread walks the chunk in table order, keeps the regions whose
+// pixel box contains its bin and accumulates nbins * integral_subrange(bin ∩ region) with the reference's promotions:
+//   bins(pos) += double(factor) * float        (regions-integrator-sequential.h:54; ...-variance-reduction.h:80)
+template<int S, int DB>
+__global__ void __launch_bounds__(256) walk_accumulate_kernel(TileGeom g, vb200_domain dom, uint64_t cap, uint64_t begin, uint64_t end, uint64_t nbins_total,
+                                                              const float* __restrict__ patches, const float* __restrict__ rmin, const float* __restrict__ rmax,
+                                                              const float* __restrict__ volume, const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ pend,
+                                                              const uint64_t* __restrict__ offsets, const uint32_t* __restrict__ list,
+                                                              int mode, float* __restrict__ out, float* __restrict__ approx, uint32_t* __restrict__ count) {
+    using St = Staged<S, DB>;
+    constexpr int CHUNK = (St::P > 64) ? 16 : 64;
+    __shared__ St s_reg[CHUNK];
+    const uint64_t t = blockIdx.x;
+    uint32_t o[3]; tile_origin(g, t, o);
+    if (!tile_in_shard(g, o, begin, end)) return;
+    // this thread's bin
+    uint32_t pos[3] = {0, 0, 0}; { uint32_t k = threadIdx.x; for (int d = 0; d < DB; ++d) { pos[d] = o[d] + k % g.tile[d]; k /= g.tile[d]; } }
+    bool live = true; uint64_t bin = 0, prod = 1;
+    for (int d = 0; d < DB; ++d) { live = live && pos[d] < g.res[d]; bin += uint64_t(pos[d]) * prod; prod *= g.res[d]; }
+    live = live && bin >= begin && bin < end;
+    float ba[DB], bb[DB];
+#pragma unroll
+    for (int d = 0; d < DB; ++d) {       // bin box: min + float(pos)*drange (regions-integrator-sequential.h:42-51)
+        ba[d] = R::fa(dom.rmin[d], R::fm(float(pos[d]), dom.drange[d]));
+        bb[d] = R::fa(dom.rmin[d], R::fm(float(pos[d] + 1u), dom.drange[d]));
+    }
+    float acc = (mode == 0 && live) ? out[bin] : 0.0f;
+    uint32_t cnt = 0;
+    const double factor = double(nbins_total);
+    const uint64_t lo = offsets[t], hi = offsets[t + 1];
+    for (uint64_t base = lo; base < hi; base += CHUNK) {
+        const int n = int(min(uint64_t(CHUNK), hi - base));
+        __syncthreads();
+        for (int k = threadIdx.x; k < n * St::P; k += blockDim.x) {
+            const int j = k / St::P, q = k % St::P;
+            s_reg[j].patch[q] = patches[uint64_t(q) * cap + list[base + j]];
+        }
+        for (int j = threadIdx.x; j < n; j += blockDim.x) {
+            const uint64_t r = list[base + j];
+            for (int d = 0; d < DB; ++d) {
+                s_reg[j].rmin[d] = rmin[uint64_t(d) * cap + r]; s_reg[j].rmax[d] = rmax[uint64_t(d) * cap + r];
+                s_reg[j].ps[d] = pstart[uint64_t(d) * cap + r]; s_reg[j].pe[d] = pend[uint64_t(d) * cap + r];
+            }
+            s_reg[j].volume = volume[r];
+        }
+        __syncthreads();
+        if (live) {
+            for (int j = 0; j < n; ++j) {
+                const St& rg = s_reg[j];
+                bool inside = true;
+#pragma unroll
+                for (int d = 0; d < DB; ++d) inside = inside && pos[d] >= rg.ps[d] && pos[d] < rg.pe[d];
+                if (!inside) continue;
+                ++cnt;
+                // Range::intersection (range.h:92-101) in the binned dims; the other dims are the region's own extent
+                float na[3], nb[3]; bool empty = false;
+#pragma unroll
+                for (int d = 0; d < DB; ++d) {
+                    const float a = fmaxf(ba[d], rg.rmin[d]);
+                    const float b = fmaxf(a, fminf(bb[d], rg.rmax[d]));
+                    empty = empty || (a >= b);
+                    na[d] = R::pos_in_range(rg.rmin[d], rg.rmax[d], a);
+                    nb[d] = R::pos_in_range(rg.rmin[d], rg.rmax[d], b);
+                }
+                if (empty) continue;                                             // regions-integrator-sequential.h:54 `if (!empty())`
+                const float integral = R::fm(rg.volume, patch_subrange<S, DB>(rg.patch, na, nb));
+                acc = R::d2f(R::da(double(acc), R::dm(factor, double(integral))));
+            }
+        }
+    }
+    if (live) {
+        if (mode == 0) out[bin] = acc;
+        else { approx[bin - begin] = acc; count[bin - begin] = cnt; }
+    }
+}
+
+template<int S, int DB>
+int launch_accumulate(vb200_ctx* ctx, const vb200_regions* r, const BinWalk& w, const TileGeom& g, const vb200_domain& dom,
+                      uint64_t begin, uint64_t end, uint64_t total, int mode, float* out, float* approx, uint32_t* count) {
+    walk_accumulate_kernel<S, DB><<<unsigned(w.ntiles), 256, 0, ctx->stream>>>(g, dom, w.cap, begin, end, total, w.patches, r->rmin, r->rmax, w.volume,
+                                                                                w.pstart, w.pend, w.tile_offset, w.tile_list, mode, out, approx, count);
+    ctx->launches++;
+    VB200_CUDA(ctx, cudaGetLastError());
+    return VB200_OK;
+}
+
+TileGeom make_geom(const BinWalk& w, const vb200_domain& dom) {
+    TileGeom g; g.db = w.db;
+    for (int d = 0; d < 3; ++d) { g.tile[d] = w.tile[d]; g.tiles[d] = w.tiles[d]; g.res[d] = d < w.db ? uint32_t(dom.res[d]) : 1u; }
+    return g;
+}
+
+} // namespace
+
+namespace vb200 {
+
+void walk_free(BinWalk* w) {
+    cudaFree(w->patches); cudaFree(w->volume); cudaFree(w->pstart); cudaFree(w->pend); cudaFree(w->tile_offset); cudaFree(w->tile_list);
+    cudaFree(w->scratch[0]); cudaFree(w->scratch[1]);
+    *w = BinWalk();
+}
+
+int walk_build(vb200_ctx* ctx, const vb200_regions* r, const vb200_domain& dom, uint64_t begin, uint64_t end, BinWalk* w) {
+    *w = BinWalk();
+    const int S = r->SH, D = r->dim, db = dom.dimbins;
+    const uint64_t n = r->count, cap = r->capacity;
+    w->S = S; w->db = db; w->nregions = n; w->cap = cap;
+    int patch = 1; for (int i = 0; i < db; ++i) patch *= S;
+    w->patch = patch;
+    auto bail = [&] (int code) { walk_free(w); return code; };
+#define VB200_TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return bail(fail(ctx, VB200_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__))); } while (0)
+    // 1. marginalise the non-binned dimensions D-1 .. db (each fold rounds to float, exactly like the lazy reference folds)
+    const float* cur = r->data;
+    if (D > db) {
+        uint64_t biggest = 1; for (int i = 0; i < D - 1; ++i) biggest *= uint64_t(S);
+        VB200_TRY(cudaMalloc(&w->scratch[0], biggest * cap * sizeof(float)));
+        if (D - db > 1) VB200_TRY(cudaMalloc(&w->scratch[1], (biggest / uint64_t(S)) * cap * sizeof(float)));
+        int which = 0;
+        for (int m = D; m > db; --m) {
+            int lower = 1; for (int i = 0; i < m - 1; ++i) lower *= S;
+            float* dst = w->scratch[which];
+            dim3 grid(unsigned((n + 127) / 128), unsigned(lower));
+            if (S == 2) fold_last_dim_kernel<2><<<grid, 128, 0, ctx->stream>>>(n, cap, lower, cur, dst);
+            else if (S == 3) fold_last_dim_kernel<3><<<grid, 128, 0, ctx->stream>>>(n, cap, lower, cur, dst);
+            else fold_last_dim_kernel<5><<<grid, 128, 0, ctx->stream>>>(n, cap, lower, cur, dst);
+            ctx->launches++;
+            VB200_TRY(cudaGetLastError());
+            cur = dst; which ^= 1;
+        }
+    }
+    VB200_TRY(cudaMalloc(&w->patches, uint64_t(patch) * cap * sizeof(float)));
+    VB200_TRY(cudaMemcpyAsync(w->patches, cur, uint64_t(patch) * cap * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    // 2. volumes + pixel boxes
+    VB200_TRY(cudaMalloc(&w->volume, cap * sizeof(float)));
+    VB200_TRY(cudaMalloc(&w->pstart, uint64_t(db) * cap * sizeof(uint32_t)));
+    VB200_TRY(cudaMalloc(&w->pend, uint64_t(db) * cap * sizeof(uint32_t)));
+    region_boxes_kernel<<<unsigned((n + 255) / 256), 256, 0, ctx->stream>>>(n, cap, D, db, dom, r->rmin, r->rmax, w->volume, w->pstart, w->pend);
+    ctx->launches++;
+    VB200_TRY(cudaGetLastError());
+    // 3. tiles of 256 bins and their ordered region lists
+    if (db == 1) { w->tile[0] = 256; } else if (db == 2) { w->tile[0] = 16; w->tile[1] = 16; } else { w->tile[0] = 8; w->tile[1] = 8; w->tile[2] = 4; }
+    w->ntiles = 1;
+    for (int d = 0; d < 3; ++d) { w->tiles[d] = d < db ? uint32_t((dom.res[d] + w->tile[d] - 1) / w->tile[d]) : 1u; w->ntiles *= w->tiles[d]; }
+    if (w->ntiles > 0x7fffffffull) return bail(fail(ctx, VB200_ERR_UNSUPPORTED, "bin grid too large for the tile walk"));
+    const TileGeom g = make_geom(*w, dom);
+    VB200_TRY(cudaMalloc(&w->tile_offset, (w->ntiles + 1) * sizeof(uint64_t)));
+    unsigned long long* counts = reinterpret_cast<unsigned long long*>(w->tile_offset);
+    tile_lists_kernel<false><<<unsigned(w->ntiles), 256, 0, ctx->stream>>>(g, n, cap, begin, end, w->pstart, w->pend, counts, nullptr, nullptr);
+    ctx->launches++;
+    VB200_TRY(cudaGetLastError());
+    std::vector<uint64_t> h(w->ntiles + 1);
+    VB200_TRY(cudaMemcpyAsync(h.data(), counts, w->ntiles * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    VB200_TRY(cudaStreamSynchronize(ctx->stream));
+    uint64_t run = 0; for (uint64_t t = 0; t < w->ntiles; ++t) { const uint64_t c = h[t]; h[t] = run; run += c; } h[w->ntiles] = run;
+    w->pairs = run;
+    VB200_TRY(cudaMemcpyAsync(w->tile_offset, h.data(), (w->ntiles + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    VB200_TRY(cudaMalloc(&w->tile_list, (run + 1) * sizeof(uint32_t)));
+    tile_lists_kernel<true><<<unsigned(w->ntiles), 256, 0, ctx->stream>>>(g, n, cap, begin, end, w->pstart, w->pend, nullptr, w->tile_offset, w->tile_list);
+    ctx->launches++;
+    VB200_TRY(cudaGetLastError());
+    VB200_TRY(cudaStreamSynchronize(ctx->stream));       // h goes out of scope
+#undef VB200_TRY
+    return VB200_OK;
+}
+
+int walk_accumulate(vb200_ctx* ctx, const vb200_regions* r, const BinWalk& w, const vb200_domain& dom, uint64_t begin, uint64_t end,
+                    int mode, float* out, float* approx, uint32_t* count) {
+    const TileGeom g = make_geom(w, dom);
+    const uint64_t total = nbins_of(dom);
+#define VB200_WALK(SS, DD) if (w.S == SS && w.db == DD) return launch_accumulate<SS, DD>(ctx, r, w, g, dom, begin, end, total, mode, out, approx, count);
+    VB200_WALK(2, 1) VB200_WALK(2, 2) VB200_WALK(2, 3) VB200_WALK(3, 1) VB200_WALK(3, 2) VB200_WALK(3, 3) VB200_WALK(5, 1) VB200_WALK(5, 2) VB200_WALK(5, 3)
+#undef VB200_WALK
+    return fail(ctx, VB200_ERR_UNSUPPORTED, "no bin walk for rule with %d samples and %d binned dimensions", w.S, w.db);
+}
+
+} // namespace vb200
+
+extern "C" int vb200_regions_integrate_bins(vb200_ctx* ctx, const vb200_regions* r, const vb200_domain* domain, const vb200_shard* shard,
+                                            float* bins, int bins_mem) {
+    if (!ctx || !r || !domain || !bins) return fail(ctx, VB200_ERR_INVALID, "NULL argument");
+    VB200_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = check_domain(ctx, *domain, r->dim); if (rc) return rc;
+    const vb200_domain dom = finish_domain(*domain);
+    const uint64_t total = nbins_of(dom);
+    uint64_t begin, end; vb200_shard s = shard ? *shard : vb200_shard{0, 0};
+    rc = resolve_shard(ctx, s, total, &begin, &end); if (rc) return rc;
+    if (begin == end || r->count == 0) return VB200_OK;
+    // '+=' continues from the bins' current contents in the reference's float(double(acc)+...) chain: upload them
+    BinStage st; rc = stage_bins_in(ctx, bins, bins_mem, begin, end, /*upload=*/true, &st); if (rc) return rc;
+    BinWalk w;
+    rc = walk_build(ctx, r, dom, begin, end, &w); if (rc) return rc;
+    rc = walk_accumulate(ctx, r, w, dom, begin, end, 0, st.dev_base, nullptr, nullptr);
+    if (!rc) rc = stage_bins_out(ctx, st);
+    if (!rc && !st.staged) { cudaError_t e = cudaStreamSynchronize(ctx->stream); if (e != cudaSuccess) rc = fail(ctx, VB200_ERR_CUDA, "region->bin integration failed: %s", cudaGetErrorString(e)); }
+    walk_free(&w);
+    return rc;
+}
+
+// ---- still to come ------------------------------------------------------------------------------------------------------
 extern "C" int vb200_regions_generate_adaptive(vb200_ctx* ctx, const vb200_integrand*, const vb200_adaptive_params*, vb200_regions**) { return fail(ctx, VB200_ERR_UNSUPPORTED, "not implemented yet"); }
-extern "C" int vb200_regions_generate_single(vb200_ctx* ctx, const vb200_integrand*, const vb200_domain*, int, vb200_regions**) { return fail(ctx, VB200_ERR_UNSUPPORTED, "not implemented yet"); }
-extern "C" int vb200_regions_upload(vb200_ctx* ctx, int, int, uint64_t, const float*, const float*, const float*, const uint32_t*, const float*, vb200_regions**) { return fail(ctx, VB200_ERR_UNSUPPORTED, "not implemented yet"); }
-extern "C" uint64_t vb200_regions_count(const vb200_regions*) { return 0; }
-extern "C" int vb200_regions_dim(const vb200_regions*) { return 0; }
-extern "C" int vb200_regions_samples(const vb200_regions*) { return 0; }
-extern "C" int vb200_regions_download(vb200_ctx* ctx, const vb200_regions*, float*, float*, float*, uint32_t*, float*) { return fail(ctx, VB200_ERR_UNSUPPORTED, "not implemented yet"); }
-extern "C" void vb200_regions_free(vb200_regions*) {}
-extern "C" int vb200_regions_integrate_bins(vb200_ctx* ctx, const vb200_regions*, const vb200_domain*, const vb200_shard*, float*, int) { return fail(ctx, VB200_ERR_UNSUPPORTED, "not implemented yet"); }
 extern "C" int vb200_cv_integrate(vb200_ctx* ctx, const vb200_integrand*, const vb200_regions*, const vb200_cv_params*, float*, int, uint32_t*, float*) { return fail(ctx, VB200_ERR_UNSUPPORTED, "not implemented yet"); }
 extern "C" int vb200_cv_replay(vb200_ctx* ctx, const vb200_integrand*, const vb200_regions*, const vb200_cv_params*, const uint32_t*, const float*, int, float*, int) { return fail(ctx, VB200_ERR_UNSUPPORTED, "not implemented yet"); }
