@@ -299,11 +299,14 @@ typedef struct vb200_greedy_launch {
     int32_t  dim, rule, heuristic, metric;
     double   size_weight;
     uint64_t iterations;
-    uint64_t capacity;                /* region slots (>= iterations*2+1: parents are not recycled) */
-    float*   rmin; float* rmax;       /* device SoA [dim][capacity] */
-    float*   data;                    /* device SoA [S^dim][capacity] */
-    float*   err;  uint32_t* errdim;  /* device [capacity] */
-    float*   heap_key; uint32_t* heap_id;   /* device [iterations+1]: the binary heap, array order = output order */
+    uint64_t capacity;                /* region slots: 2*iterations+1 (a split retires the parent slot and opens two) */
+    /* working set of the persistent kernel, region-major so that one region is a few contiguous lines: */
+    float*   range;                   /* device [capacity][2*dim]: min[0..dim), max[0..dim) */
+    float*   data;                    /* device [capacity][S^dim], the reference's multiarray order (dim 0 fastest) */
+    float*   err;                     /* device [capacity] heuristic value */
+    unsigned long long* heap;         /* device [iterations+2]: binary heap entries (id | dim<<28) << 32 | float bits of the key;
+                                         array order = the reference's output order (regions-generator-adaptive-heap.h:44) */
+    uint64_t* heap_size;              /* device scalar: entries in the heap when the kernel ends (iterations+1) */
     float    range_min[VB200_MAX_DIM], range_max[VB200_MAX_DIM];
 } vb200_greedy_launch;
 

@@ -1,8 +1,275 @@
-// placeholder — replaced by the persistent greedy-heap refinement kernel
+// K5-K7, exact mode — greedy max-error refinement with batch size 1, replacing the reference's
+//   RegionsGeneratorAdaptiveHeap::generate    src/nested/regions-generator-adaptive-heap.h:18-45
+//   Region ctor / multiarray::fill            src/newton-cotes/region.h:62-68, src/multiarray/fill.h:45-72
+//   Region::split / detail::split             src/newton-cotes/region.h:345-359, src/multiarray/split.h:13-49
+//   Region::error, error_heuristic_*          src/newton-cotes/region.h:387-411, src/nested/error-heuristic.h:10-46
+//   std::push_heap / std::pop_heap            libstdc++ bits/stl_heap.h:135-267 (tie order is decided by these mechanics)
+// The loop is inherently serial (every iteration depends on which region the previous one made the maximum), so a launch
+// per iteration cannot work: ONE persistent CTA runs all iterations.  Inside an iteration the work is spread over the CTA:
+//   warp 0 / lane 0  pops the heap (its top levels live in shared memory, the rest in L2) while
+//   the other warps  fetch the parent region, evaluate the integrand at the (S-1)*S^(D-1) new points of the split and
+//                    build both children in shared memory;
+//   one warp per (child, dimension) evaluates the nested-rule error along that dimension and folds it over the others;
+//   then lane 0 pushes the two children.
+// With an EXACT integrand (--fmad=false) the region list — ranges, samples, errors, split dimensions and ORDER — is
+// bit-identical to the reference's (tests/test_gpu_regions.py).
 #pragma once
+#include <array>
 #include <cuda_runtime.h>
 #include "../../viltrum_b200.h"
+#include "rules.cuh"
+
 namespace viltrum { namespace b200 { namespace device {
+
+constexpr int GREEDY_THREADS = 256;
+constexpr unsigned GREEDY_ID_MASK = 0x0fffffffu;
+
+struct GreedyHeap {
+    unsigned long long* g;      // global entries
+    unsigned long long* s;      // shared-memory cache of entries [0, cached)
+    long long cached;
+    long long n;
+    __device__ __forceinline__ unsigned long long get(long long i) const { return i < cached ? s[i] : g[i]; }
+    __device__ __forceinline__ void set(long long i, unsigned long long v) { if (i < cached) s[i] = v; else g[i] = v; }
+    __device__ __forceinline__ static float key(unsigned long long e) { return __uint_as_float(unsigned(e)); }
+
+    // libstdc++ __push_heap (stl_heap.h:135-148), comparator a.err < b.err
+    __device__ void sift_up(long long hole, unsigned long long value) {
+        const float vk = key(value);
+        long long parent = (hole - 1) / 2;
+        while (hole > 0) {
+            const unsigned long long pe = get(parent);
+            if (!(key(pe) < vk)) break;
+            set(hole, pe); hole = parent; parent = (hole - 1) / 2;
+        }
+        set(hole, value);
+    }
+    __device__ void push(unsigned long long value) { ++n; sift_up(n - 1, value); }
+    // libstdc++ pop_heap -> __pop_heap -> __adjust_heap (stl_heap.h:224-267) followed by the caller's pop_back
+    __device__ void pop() {
+        if (n > 1) {
+            const unsigned long long value = get(n - 1);
+            const long long len = n - 1;
+            long long hole = 0, child = 0;
+            while (child < (len - 1) / 2) {
+                child = 2 * (child + 1);
+                unsigned long long ce = get(child); const unsigned long long le = get(child - 1);
+                if (key(ce) < key(le)) { --child; ce = le; }
+                set(hole, ce); hole = child;
+            }
+            if ((len & 1) == 0 && child == (len - 2) / 2) { child = 2 * (child + 1); set(hole, get(child - 1)); hole = child - 1; }
+            sift_up(hole, value);
+        }
+        --n;
+    }
+};
+
+template<int SH, int SL, int DIM>
+struct GreedyShape {
+    static constexpr int pow_(int b, int e) { return e == 0 ? 1 : b * pow_(b, e - 1); }
+    static constexpr int SD = pow_(SH, DIM);          // samples per region
+    static constexpr int L = pow_(SH, DIM - 1);       // lines along one dimension
+    static constexpr int WIDE = (2 * SH - 1) * L;     // samples of the two children side by side
+};
+
+// normalised grid coordinate -> point, with the PARENT's range (region.h:40-46): x = float(p*(max-min) + min)
+__device__ __forceinline__ float grid_coord(double p, float lo, float hi) {
+    return rules::d2f(rules::da(rules::dm(p, double(rules::fs(hi, lo))), double(lo)));
+}
+
+// error of one region along `dim` (region.h:387-393): per line metric(high,low), folded over the other dims with the high
+// rule, times the volume.  One warp; `work` holds L floats.
+template<int SH, int SL, int DIM>
+__device__ float region_error_warp(const float* data, float volume, int dim, bool relative, float* work, unsigned lane) {
+    using Sh = GreedyShape<SH, SL, DIM>;
+    int inner = 1; for (int i = 0; i < dim; ++i) inner *= SH;
+    for (int o = lane; o < Sh::L; o += 32) {
+        const int lo = o % inner, hi = o / inner;
+        float line[SH];
+#pragma unroll
+        for (int e = 0; e < SH; ++e) line[e] = data[lo + e * inner + hi * inner * SH];
+        work[o] = rules::line_error<SH, SL>(relative, line);
+    }
+    __syncwarp();
+    // fold_all(high rule): fold dimension 0 of the remaining array until one value is left (fold.h:87-108)
+    for (int n = Sh::L / SH; n >= 1; n /= SH) {
+        float v[(Sh::L / SH + 31) / 32 > 0 ? (Sh::L / SH + 31) / 32 : 1];
+        int c = 0;
+        for (int o = lane; o < n; o += 32, ++c) v[c] = rules::apply<SH>(work + o * SH);
+        __syncwarp();
+        c = 0;
+        for (int o = lane; o < n; o += 32, ++c) work[o] = v[c];
+        __syncwarp();
+        if (n == 1) break;
+    }
+    return rules::fm(volume, work[0]);
+}
+
+// error_heuristic_size (error-heuristic.h:29-46) / error_heuristic_default -> max_error_dimension (region.h:401-411)
+template<int DIM>
+__device__ void heuristic_pick(const float* E, const float* rng /* min[DIM], max[DIM] */, int heuristic, double size_weight, float* out_err, unsigned* out_dim) {
+    const double min_size = 1.e-37;
+    if (heuristic == VB200_HEURISTIC_SIZE) {
+        float max_err = E[0];
+        const float w0 = rules::fs(rng[DIM], rng[0]);
+        if (double(w0) < min_size || isnan(w0)) max_err = 0.0f;
+        else max_err = rules::d2f(rules::da(double(max_err), rules::dm(size_weight, double(fabsf(w0)))));
+        unsigned max_dim = 0;
+        for (int d = 1; d < DIM; ++d) {
+            const float w = rules::fs(rng[DIM + d], rng[d]);
+            float err = rules::d2f(rules::da(double(E[d]), rules::dm(size_weight, double(fabsf(w)))));
+            if (double(w) < min_size) err = 0.0f;
+            if (err >= max_err) { max_err = err; max_dim = unsigned(d); }
+        }
+        *out_err = max_err; *out_dim = max_dim;
+    } else {
+        float max_err = 0.0f; unsigned max_dim = 0;
+        for (int d = 0; d < DIM; ++d) if (E[d] > max_err) { max_err = E[d]; max_dim = unsigned(d); }
+        *out_err = max_err; *out_dim = max_dim;
+    }
+}
+
+template<class F, int DIM, int SH, int SL, bool EXACT>
+__global__ void __launch_bounds__(GREEDY_THREADS, 1)
+greedy_kernel(const F f, const vb200_greedy_launch a, const int heap_cached) {
+    using Sh = GreedyShape<SH, SL, DIM>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long* s_heap = reinterpret_cast<unsigned long long*>(smem_raw);
+    float* s_parent = reinterpret_cast<float*>(s_heap + heap_cached);       // [SD]
+    float* s_child = s_parent + Sh::SD;                                     // [2][SD]
+    float* s_work = s_child + 2 * Sh::SD;                                   // [2*DIM][L]
+    float* s_prange = s_work + 2 * DIM * Sh::L;                             // [2*DIM]
+    float* s_crange = s_prange + 2 * DIM;                                   // [2][2*DIM]
+    float* s_E = s_crange + 4 * DIM;                                        // [2][DIM]
+    float* s_vol = s_E + 2 * DIM;                                           // [2]
+    __shared__ unsigned s_top_id, s_top_dim;
+    __shared__ GreedyHeap heap;
+
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, nwarps = GREEDY_THREADS / 32;
+    const bool relative = a.metric == VB200_METRIC_RELATIVE;
+
+    // ---- initial region over the whole range (regions-generator-adaptive-heap.h:27-31) ----
+    if (tid == 0) { heap.g = a.heap; heap.s = s_heap; heap.cached = heap_cached; heap.n = 0; }
+    if (tid < 2 * DIM) s_crange[tid] = tid < DIM ? a.range_min[tid] : a.range_max[tid - DIM];
+    __syncthreads();
+    for (int k = tid; k < Sh::SD; k += GREEDY_THREADS) {
+        std::array<float, DIM> x; int t = k;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) { x[d] = grid_coord(rules::dd(double(t % SH), double(SH - 1)), s_crange[d], s_crange[DIM + d]); t /= SH; }
+        s_child[k] = f(x);
+    }
+    if (tid == 0) { float v = 1.0f; for (int d = 0; d < DIM; ++d) v = rules::fm(v, rules::fs(s_crange[DIM + d], s_crange[d])); s_vol[0] = v; }
+    __syncthreads();
+    for (int d = warp; d < DIM; d += nwarps) {
+        const float e = region_error_warp<SH, SL, DIM>(s_child, s_vol[0], d, relative, s_work + d * Sh::L, lane);
+        if (lane == 0) s_E[d] = e;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float err; unsigned dim; heuristic_pick<DIM>(s_E, s_crange, a.heuristic, a.size_weight, &err, &dim);
+        a.err[0] = err;
+        heap.push((static_cast<unsigned long long>(0u | (dim << 28)) << 32) | __float_as_uint(err));
+    }
+    for (int k = tid; k < Sh::SD; k += GREEDY_THREADS) a.data[k] = s_child[k];
+    if (tid < 2 * DIM) a.range[tid] = s_crange[tid];
+    __syncthreads();
+
+    // ---- iterations ----
+    unsigned long long next_slot = 1;
+    for (unsigned long long it = 0; it < a.iterations; ++it) {
+        if (tid == 0) { const unsigned long long e = heap.get(0); s_top_id = unsigned(e >> 32) & GREEDY_ID_MASK; s_top_dim = unsigned(e >> 60); }
+        __syncthreads();
+        const unsigned top = s_top_id; const int dim = int(s_top_dim);
+        // warp 0 pops while the others fetch the parent (the pop does not depend on the split: heap.front() was copied first, :33-35)
+        if (warp == 0) { if (lane == 0) heap.pop(); }
+        else {
+            for (int k = tid - 32; k < Sh::SD; k += GREEDY_THREADS - 32) s_parent[k] = a.data[static_cast<unsigned long long>(top) * Sh::SD + k];
+            if (tid - 32 < 2 * DIM) s_prange[tid - 32] = a.range[static_cast<unsigned long long>(top) * (2 * DIM) + (tid - 32)];
+        }
+        __syncthreads();
+        // split along `dim` (split.h:13-49): the (2S-1)-wide array; even positions are the parent's samples, odd ones new evaluations
+        int inner = 1; for (int i = 0; i < dim; ++i) inner *= SH;
+        for (int item = tid; item < Sh::WIDE; item += GREEDY_THREADS) {
+            const int i = item / Sh::L, o = item % Sh::L;            // position along `dim` (0..2S-2), index over the other dims
+            const int lo = o % inner, hi = o / inner;
+            float v;
+            if ((i & 1) == 0) v = s_parent[lo + (i / 2) * inner + hi * inner * SH];
+            else {
+                std::array<float, DIM> x; int t = o;
+#pragma unroll
+                for (int d = 0; d < DIM; ++d) {
+                    double p;
+                    if (d == dim) p = rules::dd(double(i), double(2 * (SH - 1)));
+                    else { p = rules::dd(double(t % SH), double(SH - 1)); t /= SH; }
+                    x[d] = grid_coord(p, s_prange[d], s_prange[DIM + d]);
+                }
+                v = f(x);
+            }
+            if (i <= SH - 1) s_child[lo + i * inner + hi * inner * SH] = v;
+            if (i >= SH - 1) s_child[Sh::SD + lo + (i - (SH - 1)) * inner + hi * inner * SH] = v;
+        }
+        // child ranges (region.h:349-357): d = (max-min)/Float(2); child 0 = [min, min+d*1], child 1 = [min+d*1, max]
+        if (tid < 2) {
+            const float pmin = s_prange[dim], pmax = s_prange[DIM + dim];
+            const float mid = rules::fa(pmin, rules::fm(rules::fd(rules::fs(pmax, pmin), 2.0f), 1.0f));
+            float* cr = s_crange + tid * 2 * DIM;
+            for (int d = 0; d < 2 * DIM; ++d) cr[d] = s_prange[d];
+            if (tid == 0) cr[DIM + dim] = mid; else cr[dim] = mid;
+            float v = 1.0f; for (int d = 0; d < DIM; ++d) v = rules::fm(v, rules::fs(cr[DIM + d], cr[d]));
+            s_vol[tid] = v;
+        }
+        __syncthreads();
+        // nested-rule error of both children along every dimension: one warp per (child, dimension)
+        for (int job = warp; job < 2 * DIM; job += nwarps) {
+            const int c = job / DIM, d = job % DIM;
+            const float e = region_error_warp<SH, SL, DIM>(s_child + c * Sh::SD, s_vol[c], d, relative, s_work + job * Sh::L, lane);
+            if (lane == 0) s_E[c * DIM + d] = e;
+        }
+        __syncthreads();
+        // store the children (slots next_slot, next_slot+1) and push them in ascending coordinate order (:36-40)
+        for (int k = tid; k < 2 * Sh::SD; k += GREEDY_THREADS) a.data[next_slot * Sh::SD + k] = s_child[k];
+        if (tid < 4 * DIM) a.range[next_slot * (2 * DIM) + tid] = s_crange[tid];
+        if (tid == 0) {
+            for (int c = 0; c < 2; ++c) {
+                float err; unsigned d; heuristic_pick<DIM>(s_E + c * DIM, s_crange + c * 2 * DIM, a.heuristic, a.size_weight, &err, &d);
+                a.err[next_slot + c] = err;
+                heap.push((static_cast<unsigned long long>(unsigned(next_slot + c) | (d << 28)) << 32) | __float_as_uint(err));
+            }
+        }
+        next_slot += 2;
+        __syncthreads();
+    }
+    // flush the cached top of the heap
+    const long long n = heap.n;
+    for (long long i = tid; i < n && i < heap_cached; i += GREEDY_THREADS) a.heap[i] = s_heap[i];
+    if (tid == 0) *a.heap_size = static_cast<uint64_t>(n);
+}
+
+template<class F, int DIM, int SH, int SL, bool EXACT>
+inline int launch_greedy_rule(const F& f, const vb200_greedy_launch& a, cudaStream_t st) {
+    using Sh = GreedyShape<SH, SL, DIM>;
+    if (a.capacity > GREEDY_ID_MASK) return int(cudaErrorInvalidValue);
+    auto k = greedy_kernel<F, DIM, SH, SL, EXACT>;
+    const size_t fixed = sizeof(float) * size_t(3 * Sh::SD + 2 * DIM * Sh::L + 2 * DIM + 4 * DIM + 2 * DIM + 2) + 64;
+    int dev = 0, max_smem = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (size_t(max_smem) < fixed + 1024) return int(cudaErrorInvalidConfiguration);     // region too large for the one-CTA working set
+    // cache as many complete top levels of the heap as fit: 2^k - 1 entries of 8 bytes
+    size_t room = size_t(max_smem) - fixed - 1024;
+    int cached = 1; while (size_t(2 * cached + 1) * 8 <= room && cached < (1 << 15)) cached = 2 * cached + 1;
+    const size_t smem = size_t(cached) * 8 + fixed;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return int(e);
+    k<<<1, GREEDY_THREADS, smem, st>>>(f, a, cached);
+    return int(cudaGetLastError());
+}
+
 template<class F, int DIM, bool EXACT>
-inline int launch_greedy(const F&, const vb200_greedy_launch&, cudaStream_t) { return int(cudaErrorNotSupported); }
-}}}
+inline int launch_greedy(const F& f, const vb200_greedy_launch& a, cudaStream_t st) {
+    if constexpr (DIM <= 6) { if (a.rule == VB200_RULE_SIMPSON_TRAPEZOIDAL) return launch_greedy_rule<F, DIM, 3, 2, EXACT>(f, a, st); }
+    if constexpr (DIM <= 5) { if (a.rule == VB200_RULE_BOOLE_SIMPSON) return launch_greedy_rule<F, DIM, 5, 3, EXACT>(f, a, st); }
+    return int(cudaErrorNotSupported);
+}
+
+}}} // namespace viltrum::b200::device

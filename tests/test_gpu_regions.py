@@ -92,3 +92,80 @@ def test_region_to_bin_golden_reference_tables(ctx):
         assert_same_bits(got, f32(v["bins"]), f"{v['integrand']} {v['rule']} {v['heuristic']}")
         regs.free(); n += 1
     assert n >= 20
+
+
+@pytest.mark.parametrize("integ,rule,h,it,lo,hi", [("x2y2", "boole_simpson", "size_relative", 32, 0.0, 1.0),
+                                                   ("x2y2", "simpson_trapezoidal", "default_absolute", 200, 0.05, 1.1),
+                                                   ("smooth_edge2", "boole_simpson", "size_relative", 10000, 0.0, 1.0),
+                                                   ("ind2", "boole_simpson", "default_relative", 500, 0.0, 1.0),
+                                                   ("ind2", "simpson_trapezoidal", "size_absolute", 500, 0.0, 1.0),
+                                                   ("cubic1", "boole_simpson", "size_relative", 300, -0.5, 1.25),
+                                                   ("cubic1", "simpson_trapezoidal", "default_relative", 1, 0.0, 1.0),
+                                                   ("poly3", "boole_simpson", "default_absolute", 150, 0.1, 0.9),
+                                                   ("poly3", "simpson_trapezoidal", "size_relative", 400, 0.0, 1.0),
+                                                   ("shade4_16", "simpson_trapezoidal", "size_relative", 300, 0.0, 1.0),
+                                                   ("shade4_64", "boole_simpson", "size_relative", 40, 0.0, 1.0),
+                                                   ("shade5_16", "simpson_trapezoidal", "size_relative", 600, 0.0, 1.0),
+                                                   ("shade5_64", "simpson_trapezoidal", "default_absolute", 100, 0.0, 1.0),
+                                                   ("x2y2", "simpson_trapezoidal", "size_relative", 0, 0.0, 1.0)])
+def test_greedy_refinement_reproduces_the_reference_subdivision(ctx, port, integ, rule, h, it, lo, hi):
+    """north_star: 'batch-size-1 adaptive mode must reproduce the same region subdivision bit-exactly' — ranges, samples, errors,
+    split dimensions AND order (heap-array order, decided by libstdc++'s push_heap/pop_heap tie mechanics)."""
+    d = DIMS[integ]
+    res = [4] * min(d, 2)
+    want_bins, want = port.adaptive_iterations(integ, rule, h, it, res, [lo] * d, [hi] * d)
+    heur, metric = h.split("_")
+    regs = ctx.regions_generate_adaptive(integ, _rng(integ, lo, hi), rule, heur, metric, it, 1e-5, batch=1, exact=True)
+    assert len(regs) == it + 1
+    got = regs.download()
+    for k in ("min", "max", "err", "dim", "data"):
+        assert_same_bits(got[k], want[k], f"{integ} {rule} {h} region {k}")
+    bins = np.zeros(int(np.prod(res)), np.float32)
+    regs.integrate_bins(bins, res, _rng(integ, lo, hi))
+    assert_same_bits(bins, want_bins, "bins")
+    regs.free()
+
+
+def test_greedy_refinement_golden_reference_tables(ctx):
+    """region lists dumped from the UNMODIFIED reference through Logger::log (tests/golden/reference_vectors.json)"""
+    from viltrum_b200 import Range
+    from helpers import data_checksum
+    n = 0
+    for v in load_golden():
+        if v["path"] != "adaptive_iterations":
+            continue
+        heur, metric = v["heuristic"].split("_")
+        regs = ctx.regions_generate_adaptive(v["integrand"], Range(v["rmin"], v["rmax"]), v["rule"], heur, metric, v["iterations"], v["size_weight"], batch=1, exact=True)
+        got = regs.download()
+        d = len(v["rmin"])
+        assert_same_bits(got["min"], f32(v["reg_min"]).reshape(-1, d), "min"); assert_same_bits(got["max"], f32(v["reg_max"]).reshape(-1, d), "max")
+        assert_same_bits(got["err"], f32(v["reg_err"]), "err"); assert np.array_equal(got["dim"], np.asarray(v["reg_dim"], np.uint32))
+        assert data_checksum(got["data"]) == v["reg_data_checksum"]
+        bins = np.zeros(int(np.prod(v["res"])), np.float32)
+        regs.integrate_bins(bins, v["res"], Range(v["rmin"], v["rmax"]))
+        assert_same_bits(bins, f32(v["bins"]), "bins")
+        regs.free(); n += 1
+    assert n >= 20
+
+
+def test_greedy_refinement_c3_shape_with_ties(ctx, port):
+    """config 3 shape, reduced: nested(boole,simpson), size/relative 1e-5 on smooth_edge2 — tens of thousands of iterations where
+    most heap keys are exact ties; then the public integrate() front door on 128x128 bins."""
+    from viltrum_b200 import integrate, integrator_adaptive_iterations, nested, error_heuristic_size, error_metric_relative
+    it = 60000
+    want_bins, want = port.adaptive_iterations("smooth_edge2", "boole_simpson", "size_relative", it, [128, 128], [0, 0], [1, 1])
+    assert len(np.unique(want["err"])) < 0.3 * (it + 1)
+    bins = np.zeros(128 * 128, np.float32)
+
+    class Log:
+        def log(self, regs):
+            self.regs = regs
+    lg = Log()
+    integrate(integrator_adaptive_iterations(nested("boole", "simpson"), error_heuristic_size(error_metric_relative(), 1e-5), it),
+              bins, [128, 128], "smooth_edge2", _rng("smooth_edge2"), ctx=ctx, logger=lg)
+    got = lg.regs.download()
+    for k in ("min", "max", "err", "dim", "data"):
+        assert_same_bits(got[k], want[k], k)
+    assert_same_bits(bins, want_bins, "bins")
+    assert abs(float(bins.mean()) - (0.5 + 2 / 9 - 2 / 45 + 0.75 * np.pi * 0.09)) < 1e-4
+    lg.regs.free()

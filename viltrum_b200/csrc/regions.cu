@@ -478,6 +478,66 @@ extern "C" int vb200_regions_integrate_bins(vb200_ctx* ctx, const vb200_regions*
 }
 
 // ---- still to come ------------------------------------------------------------------------------------------------------
-extern "C" int vb200_regions_generate_adaptive(vb200_ctx* ctx, const vb200_integrand*, const vb200_adaptive_params*, vb200_regions**) { return fail(ctx, VB200_ERR_UNSUPPORTED, "not implemented yet"); }
+// ---- adaptive refinement ------------------------------------------------------------------------------------------------
+// heap-array order -> region table (SoA): region h of the output is the region the h-th heap entry points at
+// (the reference returns the heap vector as is, regions-generator-adaptive-heap.h:44)
+__global__ void compact_heap_order_kernel(uint64_t n, uint64_t cap_out, int dim, int sd, const unsigned long long* __restrict__ heap,
+                                          const float* __restrict__ range, const float* __restrict__ data,
+                                          float* __restrict__ rmin, float* __restrict__ rmax, float* __restrict__ odata,
+                                          float* __restrict__ err, uint32_t* __restrict__ errdim) {
+    const uint64_t h = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (h >= n) return;
+    const unsigned long long e = heap[h];
+    const uint64_t id = (e >> 32) & 0x0fffffffull;
+    if (blockIdx.y == 0) {
+        err[h] = __uint_as_float(unsigned(e)); errdim[h] = uint32_t(e >> 60);
+        for (int d = 0; d < dim; ++d) { rmin[uint64_t(d) * cap_out + h] = range[id * uint64_t(2 * dim) + d]; rmax[uint64_t(d) * cap_out + h] = range[id * uint64_t(2 * dim) + dim + d]; }
+    }
+    for (int k = blockIdx.y; k < sd; k += gridDim.y) odata[uint64_t(k) * cap_out + h] = data[id * uint64_t(sd) + k];
+}
+
+static int generate_greedy(vb200_ctx* ctx, const vb200_integrand* f, const vb200_adaptive_params* p, vb200_regions** out) {
+    vb200_regions* r = nullptr;
+    const uint64_t n = p->iterations + 1, cap = 2 * p->iterations + 1;
+    int rc = regions_alloc(ctx, f->dim, p->rule, n, &r); if (rc) return rc;
+    const int D = f->dim; const uint64_t sd = uint64_t(r->sd);
+    float *range = nullptr, *data = nullptr, *err = nullptr; unsigned long long* heap = nullptr; uint64_t* hsize = nullptr;
+    auto cleanup = [&] () { cudaFree(range); cudaFree(data); cudaFree(err); cudaFree(heap); cudaFree(hsize); };
+    auto bail = [&] (int code) { cleanup(); vb200_regions_free(r); return code; };
+    if (cudaMalloc(&range, cap * 2 * D * sizeof(float)) != cudaSuccess || cudaMalloc(&data, cap * sd * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&err, cap * sizeof(float)) != cudaSuccess || cudaMalloc(&heap, (n + 1) * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc(&hsize, sizeof(uint64_t)) != cudaSuccess) { cudaGetLastError(); return bail(fail(ctx, VB200_ERR_NOMEM, "working set of the greedy refinement (%llu region slots) does not fit", (unsigned long long)cap)); }
+    vb200_greedy_launch a; std::memset(&a, 0, sizeof(a));
+    a.dim = D; a.rule = p->rule; a.heuristic = p->heuristic; a.metric = p->metric; a.size_weight = p->size_weight;
+    a.iterations = p->iterations; a.capacity = cap; a.range = range; a.data = data; a.err = err; a.heap = heap; a.heap_size = hsize;
+    for (int d = 0; d < D; ++d) { a.range_min[d] = p->domain.rmin[d]; a.range_max[d] = p->domain.rmax[d]; }
+    rc = call_thunk(ctx, f, VB200_K_ADAPTIVE_EXACT, &a); if (rc) return bail(rc);
+    uint64_t got = 0;
+    if (cudaMemcpyAsync(&got, hsize, sizeof(got), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+        return bail(fail(ctx, VB200_ERR_CUDA, "greedy refinement kernel failed: %s", cudaGetErrorString(cudaGetLastError())));
+    if (got != n) return bail(fail(ctx, VB200_ERR_CUDA, "greedy refinement ended with %llu regions, expected %llu", (unsigned long long)got, (unsigned long long)n));
+    dim3 grid(unsigned((n + 255) / 256), unsigned(sd < 32 ? sd : 32));
+    compact_heap_order_kernel<<<grid, 256, 0, ctx->stream>>>(n, n, D, int(sd), heap, range, data, r->rmin, r->rmax, r->data, r->err, r->errdim);
+    ctx->launches++;
+    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+        return bail(fail(ctx, VB200_ERR_CUDA, "heap-order compaction failed: %s", cudaGetErrorString(cudaGetLastError())));
+    cleanup();
+    r->count = n;
+    *out = r;
+    return VB200_OK;
+}
+
+extern "C" int vb200_regions_generate_adaptive(vb200_ctx* ctx, const vb200_integrand* f, const vb200_adaptive_params* p, vb200_regions** out) {
+    if (!ctx || !f || !p || !out) return fail(ctx, VB200_ERR_INVALID, "NULL argument");
+    VB200_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (f->dim <= 0 || p->domain.dim != f->dim) return fail(ctx, VB200_ERR_INVALID, "range has %d dimensions, integrand takes %d", p->domain.dim, f->dim);
+    int SH, SL;
+    if (rule_samples(p->rule, &SH, &SL) || SL == 0) return fail(ctx, VB200_ERR_INVALID, "adaptive refinement needs a nested(high,low) rule (got %d)", p->rule);
+    if (p->heuristic != VB200_HEURISTIC_DEFAULT && p->heuristic != VB200_HEURISTIC_SIZE) return fail(ctx, VB200_ERR_INVALID, "unknown heuristic %d", p->heuristic);
+    if (p->metric != VB200_METRIC_ABSOLUTE && p->metric != VB200_METRIC_RELATIVE) return fail(ctx, VB200_ERR_INVALID, "unknown metric %d", p->metric);
+    if (p->iterations >= (1ull << 27)) return fail(ctx, VB200_ERR_UNSUPPORTED, "more than 2^27 iterations");
+    if (p->batch == 1) return generate_greedy(ctx, f, p, out);
+    return fail(ctx, VB200_ERR_UNSUPPORTED, "batched refinement (batch=%d) is not implemented yet; batch=1 reproduces the reference's greedy order", p->batch);
+}
 extern "C" int vb200_cv_integrate(vb200_ctx* ctx, const vb200_integrand*, const vb200_regions*, const vb200_cv_params*, float*, int, uint32_t*, float*) { return fail(ctx, VB200_ERR_UNSUPPORTED, "not implemented yet"); }
 extern "C" int vb200_cv_replay(vb200_ctx* ctx, const vb200_integrand*, const vb200_regions*, const vb200_cv_params*, const uint32_t*, const float*, int, float*, int) { return fail(ctx, VB200_ERR_UNSUPPORTED, "not implemented yet"); }
