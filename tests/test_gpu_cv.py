@@ -1,0 +1,113 @@
+"""-m gpu: piecewise-polynomial control variates + residual Monte Carlo against the oracle.
+  * the per-bin control-variate integral and region counts: bit-exact (same region table, same summation order);
+  * replay mode (the oracle's recorded region choices and sample points): bit-exact bins;
+  * Philox mode: within 3 sigma of the reference estimator, sigma from independent oracle seeds (the estimator's alpha is
+    data dependent and biased at low spp, so parity is against the reference ESTIMATOR, not the true integral);
+  * golden vectors recorded from the unmodified reference."""
+import numpy as np
+import pytest
+from gpu_helpers import ctx, assert_statistically_equal   # noqa: F401
+from helpers import load_golden, f32, assert_same_bits
+
+pytestmark = pytest.mark.gpu
+
+DIMS = {"x2y2": 2, "ind2": 2, "cubic1": 1, "poly3": 3, "shade4_16": 4, "shade4_64": 4, "shade5_16": 5, "shade5_64": 5, "smooth_edge2": 2}
+CASES = [("x2y2", [5], 16, 64), ("x2y2", [12, 9], 40, 16), ("ind2", [24, 20], 300, 8), ("smooth_edge2", [32, 32], 800, 8),
+         ("shade4_16", [12, 16], 200, 8), ("shade5_16", [20, 16], 400, 8), ("shade5_64", [16, 16], 300, 4), ("cubic1", [70], 50, 4),
+         ("poly3", [9, 6], 120, 8), ("x2y2", [2, 3], 10, 1), ("shade5_16", [8, 8], 0, 4)]
+
+
+def _rng(integ, lo=0.0, hi=1.0):
+    from viltrum_b200 import Range
+    return Range([lo] * DIMS[integ], [hi] * DIMS[integ])
+
+
+@pytest.mark.parametrize("integ,res,it,spp", CASES)
+def test_replay_and_control_variate_integral_bit_exact(ctx, port, integ, res, it, spp):
+    d = DIMS[integ]
+    want, reg, rec = port.crespo2021(integ, it, spp, 11, res, [0.0] * d, [1.0] * d, record=True)
+    regs = ctx.regions_generate_adaptive(integ, _rng(integ), "simpson_trapezoidal", "size", "relative", it, 1e-5, batch=1, exact=True)
+    got_reg = regs.download()
+    assert_same_bits(got_reg["min"], reg["min"], "region table")
+    nb = int(np.prod(res))
+    # (a) control-variate integral and per-bin region counts from the Philox path's own bin walk
+    bins = np.zeros(nb, np.float32); nreg = np.zeros(nb, np.uint32); approx = np.zeros(nb, np.float32)
+    regs.cv_integrate(integ, bins, res, _rng(integ), spp, 5, nregions=nreg, approx=approx)
+    assert np.array_equal(nreg, rec["nregions"]), "regions per bin (pixels_in_region)"
+    assert_same_bits(approx, rec["approx"], "control-variate integral per bin")
+    # (b) replay of the reference's region choices and sample points
+    out = np.full(nb, 7.0, np.float32)                      # '=' semantics: previous contents must not matter
+    regs.cv_replay(integ, out, res, _rng(integ), spp, np.ascontiguousarray(rec["chosen"]), np.ascontiguousarray(rec["samples"]))
+    assert_same_bits(out, want, f"{integ} replay")
+    # sharded replay
+    if nb >= 4:
+        parts = np.zeros(nb, np.float32)
+        cut = nb // 3
+        regs.cv_replay(integ, parts, res, _rng(integ), spp, np.ascontiguousarray(rec["chosen"][:cut]), np.ascontiguousarray(rec["samples"][:cut]), shard=(0, cut))
+        regs.cv_replay(integ, parts, res, _rng(integ), spp, np.ascontiguousarray(rec["chosen"][cut:]), np.ascontiguousarray(rec["samples"][cut:]), shard=(cut, nb))
+        assert_same_bits(parts, want, "sharded replay")
+    regs.free()
+
+
+def test_replay_golden_reference_vectors(ctx):
+    from viltrum_b200 import Range
+    n = 0
+    for v in load_golden():
+        if v["path"] != "crespo2021":
+            continue
+        d = len(v["rmin"]); nb = int(np.prod(v["res"])); spp = v["spp"]
+        regs = ctx.regions_generate_adaptive(v["integrand"], Range(v["rmin"], v["rmax"]), "simpson_trapezoidal", "size", "relative", v["iterations"], 1e-5, batch=1, exact=True)
+        out = np.zeros(nb, np.float32)
+        regs.cv_replay(v["integrand"], out, v["res"], Range(v["rmin"], v["rmax"]), spp,
+                       np.asarray(v["chosen"], np.uint32).reshape(nb, spp), np.ascontiguousarray(f32(v["samples"]).reshape(nb, spp, d)))
+        assert_same_bits(out, f32(v["bins"]), f"{v['integrand']} {v['res']}")
+        bins = np.zeros(nb, np.float32); nreg = np.zeros(nb, np.uint32); approx = np.zeros(nb, np.float32)
+        regs.cv_integrate(v["integrand"], bins, v["res"], Range(v["rmin"], v["rmax"]), spp, 1, nregions=nreg, approx=approx)
+        assert np.array_equal(nreg, np.asarray(v["nregions"], np.uint32)); assert_same_bits(approx, f32(v["approx"]), "approx")
+        regs.free(); n += 1
+    assert n == 10
+
+
+@pytest.mark.parametrize("integ,res,it,spp", [("shade4_16", [24, 24], 600, 16), ("shade5_16", [16, 16], 500, 32), ("smooth_edge2", [32, 32], 500, 16),
+                                               ("ind2", [16, 16], 200, 64)])
+def test_statistical_parity_with_the_reference_estimator(ctx, port, integ, res, it, spp):
+    from viltrum_b200 import integrate, integrator_crespo2021
+    d = DIMS[integ]; nb = int(np.prod(res))
+    K = 16
+    refs = np.stack([port.crespo2021(integ, it, spp, 100 + s, res, [0.0] * d, [1.0] * d)[0] for s in range(K)]).astype(np.float64)
+    gpus = []
+    for s in range(K):
+        b = np.zeros(nb, np.float32)
+        integrate(integrator_crespo2021(it, spp, seed=s), b, res, integ, _rng(integ), ctx=ctx)
+        gpus.append(b.astype(np.float64))
+    gpus = np.stack(gpus)
+    # the two estimators' means over K seeds agree within 3 sigma of their standard errors, bin by bin
+    var_r = refs.var(axis=0, ddof=1) / K; var_g = gpus.var(axis=0, ddof=1) / K
+    assert_statistically_equal(gpus.mean(axis=0), refs.mean(axis=0), var_g, var_r, f"cv {integ}")
+    # and the noise levels match: same estimator => same variance (ratio of pooled variances near 1)
+    ratio = (gpus.var(axis=0, ddof=1).mean() + 1e-30) / (refs.var(axis=0, ddof=1).mean() + 1e-30)
+    assert 0.7 < ratio < 1.4, f"variance ratio {ratio:.3f}"
+
+
+def test_crespo2021_full_pipeline_device_bins_and_sharding(ctx):
+    """config 4 shape, reduced (shade5<64>, 128x128 bins, 4096 iterations, 16 spp): device-resident bins, shards reproduce the whole"""
+    import torch
+    from viltrum_b200 import integrate, integrator_crespo2021
+    res, it, spp = [128, 128], 4096, 16
+    nb = res[0] * res[1]
+    whole = torch.full((nb,), -1.0, dtype=torch.float32, device="cuda")
+    integrate(integrator_crespo2021(it, spp, seed=3), whole, res, "shade5_64", _rng("shade5_64"), ctx=ctx)
+    ctx.synchronize()
+    a = whole.cpu().numpy()
+    assert abs(float(a.mean(dtype=np.float64)) - 0.14326) < 2e-3            # integral of shade5<64> = that of shade4<64>
+    parts = torch.zeros(nb, dtype=torch.float32, device="cuda")
+    for lo, hi in ((0, 5000), (5000, nb)):
+        integrate(integrator_crespo2021(it, spp, seed=3), parts, res, "shade5_64", _rng("shade5_64"), ctx=ctx, shard=(lo, hi))
+    ctx.synchronize()
+    assert_same_bits(parts.cpu().numpy(), a, "sharded control variates")
+    # variance reduction is real: the CV estimate is much less noisy than plain per-bin MC at the same spp
+    mc = np.zeros(nb, np.float32)
+    ctx.mc_per_bin("shade5_64", mc, res, _rng("shade5_64"), spp, 3)
+    ref = np.zeros(nb, np.float32)
+    ctx.mc_per_bin("shade5_64", ref, res, _rng("shade5_64"), 4096, 4)
+    assert np.mean((a - ref) ** 2) < 0.5 * np.mean((mc - ref) ** 2)

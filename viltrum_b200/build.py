@@ -25,6 +25,7 @@ COMMON = ["-std=c++17", "-O3", "-lineinfo", "--expt-relaxed-constexpr", "-Xcompi
 SOURCES = [
     ("capi.cu", []),
     ("regions.cu", ["--fmad=false"]),
+    ("cv.cu", ["--fmad=false"]),
     ("builtin_fast.cu", []),
     ("builtin_exact.cu", ["--fmad=false", "-DVILTRUM_B200_EXACT"]),
 ]

@@ -1,0 +1,342 @@
+// Control variates + residual Monte Carlo (kernels K9-K11 of §2.2), replacing the reference's
+//   RegionsIntegratorParallelVarianceReduction::integrate_regions   src/control-variates/regions-integrator-parallel-variance-reduction.h:32-109
+//   rr_uniform_region / region_sampling_uniform                     src/control-variates/region-russian-roulette.h:9-28, region-sampling.h:9-20
+//   Region::approximation_at -> app_at                              src/newton-cotes/region.h:86-112
+//   cv_optimize_weight::Accumulator                                 src/control-variates/weight-strategy.h:40-110
+// Pipeline per shard of bins (all on the device; the integrand is reached through the eval thunk):
+//   1. bin walk (regions.cu): per-bin control-variate integral `approximation` and region count, regions visited in
+//      table order, region patches staged through shared memory — no bin->region CSR is materialised
+//      (1.0e9 (bin,region) pairs at BASELINE config 4);
+//   2. per-sample region choice: rank ~ U[0, count) from Philox, rank -> region id by a second walk over the tile lists
+//      (64-bit occupancy masks per staged chunk);
+//   3. residual samples: uniform point in bin ∩ region, weight vol(bin ∩ region), interpolant value approximation_at(x);
+//   4. f(x) for all samples (eval thunk), then one thread per bin folds its samples into the reference's online
+//      variance/covariance accumulator in double and writes  (sum_f - a*sum_app)/n + a*approximation.
+// Compiled with --fmad=false; rule arithmetic through explicit round-to-nearest intrinsics (rules.cuh).
+#include "regions.h"
+#include <viltrum_b200/device/rules.cuh>
+#include <viltrum_b200/device/philox.cuh>
+#include <cstring>
+#include <vector>
+
+using namespace vb200;
+namespace R = viltrum::b200::device::rules;
+using viltrum::b200::u32x4;
+using viltrum::b200::philox4x32;
+
+namespace {
+
+struct TileGeomCv { uint32_t tile[3], tiles[3], res[3]; int db; };
+TileGeomCv make_geom_cv(const BinWalk& w, const vb200_domain& dom) {
+    TileGeomCv g; g.db = w.db;
+    for (int d = 0; d < 3; ++d) { g.tile[d] = w.tile[d]; g.tiles[d] = w.tiles[d]; g.res[d] = d < w.db ? uint32_t(dom.res[d]) : 1u; }
+    return g;
+}
+
+// rank of every residual sample among its bin's regions: uniform_int_distribution(0, count-1) -> mulhi(u32, count)
+// (the reference's Lemire rejection step removes a bias of at most count/2^32, region-russian-roulette.h:14,18-21)
+__global__ void cv_ranks_kernel(uint64_t begin, uint64_t nb, uint32_t spp, uint32_t k0, uint32_t k1, const uint32_t* __restrict__ count, uint32_t* __restrict__ rank) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= nb * spp) return;
+    const uint64_t b = i % nb; const uint32_t j = uint32_t(i / nb);            // sample-major layout: [j][bin]
+    const uint64_t bin = begin + b;
+    const u32x4 r = philox4x32<10>(u32x4{uint32_t(bin), uint32_t(bin >> 32), j, 0u}, k0, k1);
+    rank[i] = __umulhi(r.x, count[b]);
+}
+
+// rank -> region id.  One CTA per bin tile, one thread per bin; the tile's ordered region list is staged in chunks of 64
+// pixel boxes, each thread builds the 64-bit mask of the regions that contain its bin and resolves the ranks that fall
+// inside the chunk with find-nth-set.
+template<int DB>
+__global__ void __launch_bounds__(256) cv_resolve_kernel(TileGeomCv g, uint64_t cap, uint64_t begin, uint64_t end, uint32_t spp,
+                                                         const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ pend,
+                                                         const uint64_t* __restrict__ offsets, const uint32_t* __restrict__ list,
+                                                         const uint32_t* __restrict__ rank, uint32_t* __restrict__ chosen) {
+    __shared__ uint32_t s_ps[64][DB], s_pe[64][DB], s_id[64];
+    const uint64_t t = blockIdx.x, nb = end - begin;
+    uint32_t o[3]; { uint64_t q = t; for (int d = 0; d < 3; ++d) { o[d] = uint32_t(q % g.tiles[d]) * g.tile[d]; q /= g.tiles[d]; } }
+    uint32_t pos[3] = {0, 0, 0}; { uint32_t k = threadIdx.x; for (int d = 0; d < DB; ++d) { pos[d] = o[d] + k % g.tile[d]; k /= g.tile[d]; } }
+    bool live = true; uint64_t bin = 0, prod = 1;
+    for (int d = 0; d < DB; ++d) { live = live && pos[d] < g.res[d]; bin += uint64_t(pos[d]) * prod; prod *= g.res[d]; }
+    live = live && bin >= begin && bin < end;
+    // does any bin of this tile belong to the shard?  (uniform per CTA)
+    if (!__syncthreads_or(live ? 1 : 0)) return;
+    const uint64_t lo = offsets[t], hi = offsets[t + 1];
+    const uint64_t b = bin - begin;
+    uint32_t c0 = 0;
+    for (uint64_t base = lo; base < hi; base += 64) {
+        const int n = int(min(uint64_t(64), hi - base));
+        __syncthreads();
+        if (int(threadIdx.x) < n) {
+            const uint32_t r = list[base + threadIdx.x]; s_id[threadIdx.x] = r;
+            for (int d = 0; d < DB; ++d) { s_ps[threadIdx.x][d] = pstart[uint64_t(d) * cap + r]; s_pe[threadIdx.x][d] = pend[uint64_t(d) * cap + r]; }
+        }
+        __syncthreads();
+        if (!live) continue;
+        uint32_t m0 = 0, m1 = 0;
+        for (int j = 0; j < n; ++j) {
+            bool inside = true;
+#pragma unroll
+            for (int d = 0; d < DB; ++d) inside = inside && pos[d] >= s_ps[j][d] && pos[d] < s_pe[j][d];
+            if (inside) { if (j < 32) m0 |= 1u << j; else m1 |= 1u << (j - 32); }
+        }
+        const uint32_t n0 = __popc(m0), c1 = c0 + n0 + __popc(m1);
+        if (c1 > c0) {
+            for (uint32_t j = 0; j < spp; ++j) {
+                const uint32_t rk = rank[uint64_t(j) * nb + b];
+                if (rk >= c0 && rk < c1) {
+                    const uint32_t k = rk - c0;
+                    const int bit = k < n0 ? __fns(m0, 0, int(k) + 1) : 32 + __fns(m1, 0, int(k - n0) + 1);
+                    chosen[uint64_t(j) * nb + b] = s_id[bit];
+                }
+            }
+        }
+        c0 = c1;
+    }
+}
+
+// SoA [sd][cap] -> region-major [n][sd], so that approximation_at reads one region as a few contiguous lines
+__global__ void regions_to_aos_kernel(uint64_t n, uint64_t cap, int sd, const float* __restrict__ soa, float* __restrict__ aos) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n * uint64_t(sd)) return;
+    const uint64_t r = i / uint64_t(sd); const int k = int(i % uint64_t(sd));
+    aos[i] = soa[uint64_t(k) * cap + r];
+}
+
+// Region::approximation_at -> app_at (region.h:86-112): fold quadrature.at(t_d, line) over dimension 0, then 1, ... ; float Horner
+template<int S, int D>
+__device__ float approximation_at(const float* __restrict__ data, const float (&t)[D]) {
+    if (D == 1) { float line[S]; for (int e = 0; e < S; ++e) line[e] = data[e]; return R::at<S>(t[0], line); }
+    int n = 1; for (int i = 0; i < D - 1; ++i) n *= S;
+    float buf[(D == 1) ? 1 : (D == 2 ? S : D == 3 ? S * S : D == 4 ? S * S * S : D == 5 ? S * S * S * S : S * S * S * S * S)];
+    for (int o = 0; o < n; ++o) {
+        float line[S];
+#pragma unroll
+        for (int e = 0; e < S; ++e) line[e] = data[o * S + e];
+        buf[o] = R::at<S>(t[0], line);
+    }
+    for (int d = 1; d < D; ++d) {
+        n /= S;
+        for (int o = 0; o < n; ++o) {
+            float line[S];
+#pragma unroll
+            for (int e = 0; e < S; ++e) line[e] = buf[o * S + e];
+            buf[o] = R::at<S>(t[d], line);      // in place: o <= o*S, reads of this group are done before the write
+        }
+    }
+    return R::fm(buf[0], 1.0f);                  // * volume_from(DIM) == 1  (region.h:47-51,91-92)
+}
+
+// residual samples: chosen region -> bin ∩ region box -> uniform point, weight, interpolant value.
+// REPLAY: points are given (AoS [bin][spp][D]), only weights/interpolant are computed.
+template<int S, int D, bool REPLAY>
+__global__ void __launch_bounds__(128) cv_samples_kernel(vb200_domain dom, uint64_t begin, uint64_t nb, uint32_t spp, uint32_t k0, uint32_t k1,
+                                                         uint64_t cap, const float* __restrict__ rmin, const float* __restrict__ rmax, const float* __restrict__ aos,
+                                                         const uint32_t* __restrict__ chosen, const float* __restrict__ replay_points,
+                                                         float* __restrict__ points, float* __restrict__ weight, float* __restrict__ app) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const uint64_t N = nb * spp;
+    if (i >= N) return;
+    const uint64_t b = i % nb; const uint32_t j = uint32_t(i / nb);
+    const uint64_t bin = begin + b;
+    const uint32_t r = chosen[i];
+    // bin box in the binned dims (…-variance-reduction.h:71-73), region extent elsewhere; Range::intersection (range.h:92-101)
+    uint32_t pos[VB200_MAX_DIMBINS]; { uint64_t q = bin; for (int d = 0; d < dom.dimbins; ++d) { pos[d] = uint32_t(q % dom.res[d]); q /= dom.res[d]; } }
+    float a[D], w[D], t[D], x[D];
+    float vol = 1.0f;
+    u32x4 rnd{0, 0, 0, 0};
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        const float lo = rmin[uint64_t(d) * cap + r], hi = rmax[uint64_t(d) * cap + r];
+        float ba = dom.rmin[d], bb = dom.rmax[d];
+        if (d < dom.dimbins) { ba = R::fa(dom.rmin[d], R::fm(float(pos[d]), dom.drange[d])); bb = R::fa(dom.rmin[d], R::fm(float(pos[d] + 1u), dom.drange[d])); }
+        const float ia = fmaxf(ba, lo), ib = fmaxf(ia, fminf(bb, hi));
+        a[d] = ia; w[d] = R::fs(ib, ia);
+        vol = R::fm(vol, w[d]);                                                   // Range::volume of bin ∩ region (region-sampling.h:18)
+        if (REPLAY) x[d] = replay_points[(b * spp + j) * D + d];
+        else {
+            if ((d & 3) == 0) rnd = philox4x32<10>(u32x4{uint32_t(bin), uint32_t(bin >> 32), j, uint32_t(1 + d / 4)}, k0, k1);
+            const uint32_t u = (d & 3) == 0 ? rnd.x : (d & 3) == 1 ? rnd.y : (d & 3) == 2 ? rnd.z : rnd.w;
+            x[d] = R::fa(R::fm(viltrum::b200::u01(u), w[d]), ia);                 // uniform_real_distribution: u*(b-a)+a (region-sampling.h:13-17)
+        }
+        t[d] = R::pos_in_range(lo, hi, x[d]);
+        points[uint64_t(d) * N + i] = x[d];
+    }
+    weight[i] = vol;
+    app[i] = approximation_at<S, D>(aos + uint64_t(r) * uint64_t(R::ipow(S, D)), t);
+}
+
+// cv_optimize_weight::Accumulator (weight-strategy.h:40-110) — one thread per bin, samples in order, moments in double
+__global__ void __launch_bounds__(128) cv_accumulate_kernel(uint64_t begin, uint64_t nb, uint32_t spp, uint64_t nbins_total,
+                                                            const uint32_t* __restrict__ count, const float* __restrict__ approx,
+                                                            const float* __restrict__ fval, const float* __restrict__ app, const float* __restrict__ weight,
+                                                            float* __restrict__ out) {
+    const uint64_t b = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    const double factor = double(nbins_total), rrfactor = double(count[b]);
+    const float approximation = approx[b];
+    float sum_f = 0.0f, sum_app = 0.0f; uint64_t size = 0;
+    double k_f = 0, k_app = 0, e_f = 0, e_ap = 0, e_ap2 = 0, e_fap = 0;
+    for (uint32_t j = 0; j < spp; ++j) {
+        const uint64_t i = uint64_t(j) * nb + b;
+        const double sf = double(weight[i]);
+        // f(sample)*double(factor)*rrfactor*sfactor, rounded to the Sample type (…-variance-reduction.h:97-100)
+        const float fs = R::d2f(R::dm(R::dm(R::dm(double(fval[i]), factor), rrfactor), sf));
+        const float as = R::d2f(R::dm(R::dm(R::dm(double(app[i]), factor), rrfactor), sf));
+        const double nf = double(fabsf(fs)), na = double(fabsf(as));                     // NormDefault (norm.h:12)
+        if (size == 0) { k_f = nf; k_app = na; }
+        e_f = R::da(e_f, R::ds(nf, k_f));
+        e_ap = R::da(e_ap, R::ds(na, k_app));
+        e_ap2 = R::da(e_ap2, R::dm(R::ds(na, k_app), R::ds(na, k_app)));
+        e_fap = R::da(e_fap, R::dm(R::ds(nf, k_f), R::ds(na, k_app)));
+        sum_f = R::fa(sum_f, fs); sum_app = R::fa(sum_app, as);
+        ++size;
+    }
+    float result;
+    if (size < 2) result = approximation;                                               // weight-strategy.h:95
+    else {
+        const double n = double(size), n1 = double(size - 1);
+        const double covariance = R::dd(R::ds(e_fap, R::dd(R::dm(e_f, e_ap), n)), n1);
+        const double variance = R::dd(R::ds(e_ap2, R::dd(R::dm(e_ap, e_ap), n)), n1);
+        double alpha;
+        const double v = fmax(0.0, variance);
+        if (v <= 0.0) alpha = 1.0;
+        else alpha = R::dd(fmin(v, fmax(0.0, covariance)), v);
+        result = R::d2f(R::da(R::dd(R::ds(double(sum_f), R::dm(alpha, double(sum_app))), n), R::dm(alpha, double(approximation))));
+    }
+    out[begin + b] = result;                                                             // '=' (…-variance-reduction.h:102)
+}
+
+__global__ void transpose_chosen_kernel(uint64_t nb, uint32_t spp, const uint32_t* __restrict__ in /* [bin][spp] */, uint32_t* __restrict__ out /* [spp][bin] */) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= nb * spp) return;
+    const uint64_t b = i % nb; const uint32_t j = uint32_t(i / nb);
+    out[i] = in[b * spp + j];
+}
+
+template<int S, int D>
+int launch_samples(vb200_ctx* ctx, bool replay, const vb200_domain& dom, uint64_t begin, uint64_t nb, uint32_t spp, uint32_t k0, uint32_t k1,
+                   const vb200_regions* r, const float* aos, const uint32_t* chosen, const float* replay_points, float* points, float* weight, float* app) {
+    const uint64_t N = nb * spp;
+    const unsigned grid = unsigned((N + 127) / 128);
+    if (replay) cv_samples_kernel<S, D, true><<<grid, 128, 0, ctx->stream>>>(dom, begin, nb, spp, k0, k1, r->capacity, r->rmin, r->rmax, aos, chosen, replay_points, points, weight, app);
+    else cv_samples_kernel<S, D, false><<<grid, 128, 0, ctx->stream>>>(dom, begin, nb, spp, k0, k1, r->capacity, r->rmin, r->rmax, aos, chosen, replay_points, points, weight, app);
+    ctx->launches++;
+    VB200_CUDA(ctx, cudaGetLastError());
+    return VB200_OK;
+}
+
+int dispatch_samples(vb200_ctx* ctx, bool replay, const vb200_domain& dom, uint64_t begin, uint64_t nb, uint32_t spp, uint32_t k0, uint32_t k1,
+                     const vb200_regions* r, const float* aos, const uint32_t* chosen, const float* replay_points, float* points, float* weight, float* app) {
+#define VB200_CVS(SS, DD) if (r->SH == SS && r->dim == DD) return launch_samples<SS, DD>(ctx, replay, dom, begin, nb, spp, k0, k1, r, aos, chosen, replay_points, points, weight, app);
+    VB200_CVS(3, 1) VB200_CVS(3, 2) VB200_CVS(3, 3) VB200_CVS(3, 4) VB200_CVS(3, 5) VB200_CVS(3, 6)
+    VB200_CVS(5, 1) VB200_CVS(5, 2) VB200_CVS(5, 3) VB200_CVS(5, 4)
+    VB200_CVS(2, 1) VB200_CVS(2, 2) VB200_CVS(2, 3) VB200_CVS(2, 4) VB200_CVS(2, 5) VB200_CVS(2, 6)
+#undef VB200_CVS
+    return fail(ctx, VB200_ERR_UNSUPPORTED, "control variates: no kernel for %d samples per dimension in %d dimensions", r->SH, r->dim);
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { cudaFree(p); }
+    int alloc(vb200_ctx* ctx, size_t bytes) { if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return fail(ctx, VB200_ERR_NOMEM, "cudaMalloc of %zu bytes failed", bytes); } return VB200_OK; }
+    template<class T> T* as() const { return static_cast<T*>(p); }
+};
+
+// bins of a shard are processed in slabs so that the per-sample buffers stay bounded (<= ~32 Mi samples at a time)
+int cv_run(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r, const vb200_cv_params* p, bool replay,
+           const uint32_t* replay_chosen, const float* replay_samples, int replay_mem,
+           float* bins, int bins_mem, uint32_t* nregions, float* approx_out) {
+    VB200_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (f->dim <= 0 || f->dim != r->dim) return fail(ctx, VB200_ERR_INVALID, "integrand takes %d dimensions, regions have %d", f->dim, r->dim);
+    int rc = check_domain(ctx, p->domain, r->dim); if (rc) return rc;
+    if (p->spp > 0xffffffffull) return fail(ctx, VB200_ERR_INVALID, "spp invalid");
+    const vb200_domain dom = finish_domain(p->domain);
+    const uint64_t total = nbins_of(dom);
+    uint64_t begin, end; rc = resolve_shard(ctx, p->shard, total, &begin, &end); if (rc) return rc;
+    if (begin == end) return VB200_OK;
+    const uint32_t spp = uint32_t(p->spp);
+    const int D = r->dim;
+    const uint64_t nshard = end - begin;
+    BinStage st; rc = stage_bins_in(ctx, bins, bins_mem, begin, end, /*upload=*/false, &st); if (rc) return rc;
+
+    DevBuf aos; rc = aos.alloc(ctx, r->count * uint64_t(r->sd) * sizeof(float)); if (rc) return rc;
+    { const uint64_t n = r->count * uint64_t(r->sd);
+      regions_to_aos_kernel<<<unsigned((n + 255) / 256), 256, 0, ctx->stream>>>(r->count, r->capacity, r->sd, r->data, aos.as<float>()); ctx->launches++; VB200_CUDA(ctx, cudaGetLastError()); }
+
+    DevBuf d_count, d_approx; rc = d_count.alloc(ctx, nshard * sizeof(uint32_t)); if (rc) return rc; rc = d_approx.alloc(ctx, nshard * sizeof(float)); if (rc) return rc;
+    BinWalk w;
+    rc = walk_build(ctx, r, dom, begin, end, &w); if (rc) return rc;
+    struct WalkGuard { BinWalk* w; ~WalkGuard() { walk_free(w); } } guard{&w};
+    rc = walk_accumulate(ctx, r, w, dom, begin, end, 1, nullptr, d_approx.as<float>(), d_count.as<uint32_t>()); if (rc) return rc;
+
+    if (spp > 0) {
+        uint64_t slab = (32ull << 20) / spp; if (slab < 1) slab = 1; if (slab > nshard) slab = nshard;
+        const uint64_t NS = slab * spp;
+        DevBuf rank, chosen, points, weight, app, fval, rchosen, rpoints;
+        if ((rc = chosen.alloc(ctx, NS * 4)) || (rc = points.alloc(ctx, NS * D * 4)) || (rc = weight.alloc(ctx, NS * 4)) || (rc = app.alloc(ctx, NS * 4)) || (rc = fval.alloc(ctx, NS * 4))) return rc;
+        if (!replay) { if ((rc = rank.alloc(ctx, NS * 4))) return rc; }
+        else if (replay_mem == VB200_HOST) { if ((rc = rchosen.alloc(ctx, NS * 4)) || (rc = rpoints.alloc(ctx, NS * D * 4))) return rc; }
+        else { if ((rc = rchosen.alloc(ctx, 4))) return rc; }
+        const TileGeomCv g = make_geom_cv(w, dom);
+        for (uint64_t s0 = begin; s0 < end; s0 += slab) {
+            const uint64_t s1 = s0 + slab < end ? s0 + slab : end, nb = s1 - s0, N = nb * spp;
+            const uint32_t* cnt = d_count.as<uint32_t>() + (s0 - begin);
+            const float* rp = nullptr;
+            if (!replay) {
+                cv_ranks_kernel<<<unsigned((N + 255) / 256), 256, 0, ctx->stream>>>(s0, nb, spp, uint32_t(p->seed), uint32_t(p->seed >> 32), cnt, rank.as<uint32_t>());
+                ctx->launches++; VB200_CUDA(ctx, cudaGetLastError());
+                VB200_CUDA(ctx, cudaMemsetAsync(chosen.p, 0, N * 4, ctx->stream));
+                if (w.db == 1) cv_resolve_kernel<1><<<unsigned(w.ntiles), 256, 0, ctx->stream>>>(g, w.cap, s0, s1, spp, w.pstart, w.pend, w.tile_offset, w.tile_list, rank.as<uint32_t>(), chosen.as<uint32_t>());
+                else if (w.db == 2) cv_resolve_kernel<2><<<unsigned(w.ntiles), 256, 0, ctx->stream>>>(g, w.cap, s0, s1, spp, w.pstart, w.pend, w.tile_offset, w.tile_list, rank.as<uint32_t>(), chosen.as<uint32_t>());
+                else cv_resolve_kernel<3><<<unsigned(w.ntiles), 256, 0, ctx->stream>>>(g, w.cap, s0, s1, spp, w.pstart, w.pend, w.tile_offset, w.tile_list, rank.as<uint32_t>(), chosen.as<uint32_t>());
+                ctx->launches++; VB200_CUDA(ctx, cudaGetLastError());
+            } else {
+                const uint32_t* src_c = replay_chosen + (s0 - begin) * spp; const float* src_p = replay_samples + (s0 - begin) * spp * D;
+                if (replay_mem == VB200_HOST) {
+                    VB200_CUDA(ctx, cudaMemcpyAsync(rchosen.p, src_c, N * 4, cudaMemcpyHostToDevice, ctx->stream));
+                    VB200_CUDA(ctx, cudaMemcpyAsync(rpoints.p, src_p, N * D * 4, cudaMemcpyHostToDevice, ctx->stream));
+                    src_c = rchosen.as<uint32_t>(); src_p = rpoints.as<float>();
+                }
+                transpose_chosen_kernel<<<unsigned((N + 255) / 256), 256, 0, ctx->stream>>>(nb, spp, src_c, chosen.as<uint32_t>());
+                ctx->launches++; VB200_CUDA(ctx, cudaGetLastError());
+                rp = src_p;
+            }
+            rc = dispatch_samples(ctx, replay, dom, s0, nb, spp, uint32_t(p->seed), uint32_t(p->seed >> 32), r, aos.as<float>(), chosen.as<uint32_t>(), rp,
+                                  points.as<float>(), weight.as<float>(), app.as<float>()); if (rc) return rc;
+            vb200_eval_launch ev; std::memset(&ev, 0, sizeof(ev));
+            ev.n = N; ev.dim = D; ev.points = points.as<float>(); ev.values = fval.as<float>();
+            rc = call_thunk(ctx, f, VB200_K_EVAL_POINTS, &ev); if (rc) return rc;
+            cv_accumulate_kernel<<<unsigned((nb + 127) / 128), 128, 0, ctx->stream>>>(s0, nb, spp, total, cnt, d_approx.as<float>() + (s0 - begin),
+                                                                                        fval.as<float>(), app.as<float>(), weight.as<float>(), st.dev_base);
+            ctx->launches++; VB200_CUDA(ctx, cudaGetLastError());
+        }
+        VB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // the slab buffers die here
+    } else {
+        // no residual samples: bins = approximation (weight-strategy.h:95, size < 2)
+        VB200_CUDA(ctx, cudaMemcpyAsync(st.dev_base + begin, d_approx.p, nshard * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    auto copy_out = [&] (void* dst, const void* src, size_t bytes) -> int {
+        VB200_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, bins_mem == VB200_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, ctx->stream));
+        return VB200_OK;
+    };
+    if (nregions && (rc = copy_out(nregions, d_count.p, nshard * sizeof(uint32_t)))) return rc;
+    if (approx_out && (rc = copy_out(approx_out, d_approx.p, nshard * sizeof(float)))) return rc;
+    rc = stage_bins_out(ctx, st); if (rc) return rc;
+    VB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VB200_OK;
+}
+
+} // namespace
+
+extern "C" int vb200_cv_integrate(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r, const vb200_cv_params* p,
+                                  float* bins, int bins_mem, uint32_t* nregions, float* approx) {
+    if (!ctx || !f || !r || !p || !bins) return fail(ctx, VB200_ERR_INVALID, "NULL argument");
+    return cv_run(ctx, f, r, p, false, nullptr, nullptr, VB200_HOST, bins, bins_mem, nregions, approx);
+}
+
+extern "C" int vb200_cv_replay(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r, const vb200_cv_params* p,
+                               const uint32_t* chosen, const float* samples, int mem, float* bins, int bins_mem) {
+    if (!ctx || !f || !r || !p || !bins || !chosen || !samples) return fail(ctx, VB200_ERR_INVALID, "NULL argument");
+    return cv_run(ctx, f, r, p, true, chosen, samples, mem, bins, bins_mem, nullptr, nullptr);
+}

@@ -477,7 +477,6 @@ extern "C" int vb200_regions_integrate_bins(vb200_ctx* ctx, const vb200_regions*
     return rc;
 }
 
-// ---- still to come ------------------------------------------------------------------------------------------------------
 // ---- adaptive refinement ------------------------------------------------------------------------------------------------
 // heap-array order -> region table (SoA): region h of the output is the region the h-th heap entry points at
 // (the reference returns the heap vector as is, regions-generator-adaptive-heap.h:44)
@@ -539,5 +538,3 @@ extern "C" int vb200_regions_generate_adaptive(vb200_ctx* ctx, const vb200_integ
     if (p->batch == 1) return generate_greedy(ctx, f, p, out);
     return fail(ctx, VB200_ERR_UNSUPPORTED, "batched refinement (batch=%d) is not implemented yet; batch=1 reproduces the reference's greedy order", p->batch);
 }
-extern "C" int vb200_cv_integrate(vb200_ctx* ctx, const vb200_integrand*, const vb200_regions*, const vb200_cv_params*, float*, int, uint32_t*, float*) { return fail(ctx, VB200_ERR_UNSUPPORTED, "not implemented yet"); }
-extern "C" int vb200_cv_replay(vb200_ctx* ctx, const vb200_integrand*, const vb200_regions*, const vb200_cv_params*, const uint32_t*, const float*, int, float*, int) { return fail(ctx, VB200_ERR_UNSUPPORTED, "not implemented yet"); }
