@@ -1,0 +1,35 @@
+// BASELINE.json config 3 — nested Newton-Cotes (Boole/Simpson) adaptive refinement with the greedy heap
+// (SURVEY.md §3.3).  Built as an EXACT twin (--fmad=false): the bins written to argv[3] are bit-identical to the
+// reference's integrator_adaptive_iterations on the same integrand (tests/test_gpu_examples.py compares them).
+#include <viltrum_b200/viltrum.h>
+#include <cstdio>
+#include <cstdlib>
+
+struct SmoothEdge2 {
+    __host__ __device__ float operator()(const std::array<float,2>& p) const {
+        float x=p[0], y=p[1];
+        float s=.5f+8.0f*x*(1.0f-x)*y*(1.0f-y)*(1.0f-2.0f*(x-y)*(x-y));
+        float dx=x-.45f, dy=y-.55f;
+        return s+((dx*dx+dy*dy<.09f)?.75f:0.0f);
+    }
+};
+struct CountLogger : viltrum::LoggerNull {           // the reference hands the region list to Logger::log (integrator-region-based.h:19)
+    std::size_t* regions;
+    template<typename Data> void log(const Data& d) { *regions = d.size(); }
+};
+
+int main(int argc, char** argv) {
+    using namespace viltrum;
+    const std::size_t w = argc > 1 ? std::atoi(argv[1]) : 64, iterations = argc > 2 ? std::atoi(argv[2]) : 20000;
+    tensor<float,2> img({w,w}, 0.0f);
+    std::size_t nregions = 0; CountLogger logger; logger.regions = &nregions;
+    integrate(integrator_adaptive_iterations(nested(boole,simpson), error_heuristic_size(error_metric_relative(),1.e-5), iterations),
+              img, img.resolution(), SmoothEdge2(), range_primary<2>(), logger);
+    std::vector<float> fixed(16, 0.0f);
+    integrate(integrator_newton_cotes(simpson), fixed, [] __host__ __device__ (float x, float y) { return x*x + y*y; }, range_primary<2>());
+    double m = 0; for (float v : img.raw_data()) m += v; m /= img.size();
+    const double analytic = 0.5 + 2.0/9.0 - 2.0/45.0 + 0.75*3.14159265358979*0.09;
+    std::printf("adaptive: %zu regions, mean of bins %.6f should be close to %.6f; simpson bin 0 %.6f\n", nregions, m, analytic, fixed[0]);
+    if (argc > 3) { FILE* f = std::fopen(argv[3], "wb"); std::fwrite(img.raw_data().data(), 4, img.size(), f); std::fclose(f); }
+    return (std::fabs(m-analytic) < 1e-3 && nregions == iterations+1) ? 0 : 1;
+}

@@ -50,7 +50,9 @@ inline int persistent_grid(K kernel, int threads, uint64_t work_items, int hint)
 template<class F, int DIM, bool EXACT>
 struct FiniteThunks {
     static_assert(std::is_trivially_copyable<F>::value, "integrand functors cross the C ABI by value: must be trivially copyable");
-    static F functor(const vb200_integrand* self) { F f; std::memcpy(&f, self->functor, sizeof(F)); return f; }
+    // the descriptor points at a live F owned by the Integrand object: copy-construct from it (closures and adapters are
+    // not default-constructible)
+    static F functor(const vb200_integrand* self) { return *static_cast<const F*>(self->functor); }
 
     template<int DB, bool MOMENTS>
     static int launch_mc(const F& f, const vb200_mc_launch& a, cudaStream_t st) {
@@ -129,7 +131,9 @@ struct FiniteThunks {
 template<class F, bool EXACT>
 struct InfiniteThunks {
     static_assert(std::is_trivially_copyable<F>::value, "integrand functors cross the C ABI by value: must be trivially copyable");
-    static F functor(const vb200_integrand* self) { F f; std::memcpy(&f, self->functor, sizeof(F)); return f; }
+    // the descriptor points at a live F owned by the Integrand object: copy-construct from it (closures and adapters are
+    // not default-constructible)
+    static F functor(const vb200_integrand* self) { return *static_cast<const F*>(self->functor); }
 
     template<int DB, bool MOMENTS>
     static int launch_walk(const F& f, const vb200_walk_launch& a, cudaStream_t st) {

@@ -1,0 +1,439 @@
+// viltrum_b200/viltrum.h — the reference's C++17 vocabulary for the per-bin integration hot path, on the GPU.
+//
+// Drop-in for `#include "viltrum.h"` of adolfomunoz/viltrum as far as the hot path goes: the same
+// namespace, free function and factories —
+//     viltrum::integrate(integrator, bins, resolution, integrand, range[, logger])        reference src/integrate.h:72-103
+//     viltrum::integrate(integrator, std::vector<T>& bins, integrand, range[, logger])    reference src/integrate.h:132-137,169-173
+//     monte_carlo, monte_carlo_per_bin_parallel, integrator_per_bin_parallel, integrator_newton_cotes,
+//     integrator_adaptive_iterations, integrator_crespo2021, nested, trapezoidal / simpson / boole,
+//     error_heuristic_default / error_heuristic_size, error_metric_absolute / error_metric_relative,
+//     range, range_all, range_primary, range_infinite, range_primary_infinite, tensor, LoggerNull, LoggerProgress
+// — with every integrator's integrate(bins, resolution, f, range, logger) member forwarding to libviltrum_b200.so through
+// the C ABI of include/viltrum_b200.h.  What changes for the caller:
+//   * the translation unit is compiled by nvcc (-std=c++17 --expt-relaxed-constexpr [--extended-lambda]
+//     -gencode arch=compute_100a,code=sm_100a) and linked with -lviltrum_b200;
+//   * integrands are __device__-callable, trivially copyable functors (or __host__ __device__ extended lambdas):
+//       finite   : float operator()(const std::array<float,DIM>&) const   — or 1..7 float arguments (integrate.h:13-69)
+//       infinite : template<class Seq> float operator()(const Seq&) const   (seq.begin(), *it, ++it — doc/integrands.md:112-143)
+//   * Float is float and the bin value type is float (the reference also allows double and vector-valued bins);
+//   * random numbers come from Philox4x32-10 keyed by (seed; bin, sample), not from std::mt19937: results agree with the
+//     reference statistically (and bit for bit in the replay / exact modes of the C ABI), not stream for stream.
+// Bin write semantics follow the reference integrator by integrator ('+=' / '=').  There is no CPU
+// fallback: without a CUDA device the first integrate() throws std::runtime_error.
+#pragma once
+#include <array>
+#include <vector>
+#include <tuple>
+#include <string>
+#include <stdexcept>
+#include <limits>
+#include <chrono>
+#include <iostream>
+#include <iomanip>
+#include <type_traits>
+#include <cstring>
+#include <cmath>
+#include "../viltrum_b200.h"
+#include "device/thunks.cuh"
+
+namespace viltrum {
+
+// ---- ranges (reference src/range.h:17-199, src/range-infinite.h:16-132) ----------------------------------------------
+template<typename T, std::size_t DIM>
+class Range : public std::array<std::array<T,DIM>,2> {
+    T _volume;
+public:
+    static constexpr std::size_t dimensions = DIM;
+    using value_type = T;
+    static constexpr std::size_t size = DIM;
+    Range(const std::array<T,DIM>& a, const std::array<T,DIM>& b) : std::array<std::array<T,DIM>,2>{a,b} {
+        _volume = T(1); for (std::size_t i = 0; i<DIM; ++i) _volume*=(b[i]-a[i]);
+    }
+    const std::array<T,DIM>& min() const { return (*this)[0]; }
+    T min(std::size_t i) const { return min()[i]; }
+    const std::array<T,DIM>& max() const { return (*this)[1]; }
+    T max(std::size_t i) const { return max()[i]; }
+    T volume() const { return _volume; }
+    bool is_inside(const std::array<T,DIM>& x) const { bool is = true; for (std::size_t i = 0; (i<DIM) && is; ++i) is = ((x[i]>=min(i)) && (x[i]<=max(i))); return is; }
+    Range<T,DIM> subrange_dimension(std::size_t dim, T a, T b) const { auto na = min(); na[dim]=a; auto nb = max(); nb[dim]=b; return Range<T,DIM>(na,nb); }
+    bool empty() const { bool e = false; for (std::size_t i = 0; (i<DIM) && (!e); ++i) e = (min(i)>=max(i)); return e; }
+};
+template<typename T, std::size_t DIM> Range<T,DIM> range(const std::array<T,DIM>& a, const std::array<T,DIM>& b) { return Range<T,DIM>(a,b); }
+template<typename T> Range<T,1> range(const T& a, const T& b, std::enable_if_t<std::is_floating_point_v<T>,int> = 0) { return Range<T,1>(std::array<T,1>{a},std::array<T,1>{b}); }
+template<typename T> Range<T,2> range(const T& a0, const T& a1, const T& b0, const T& b1) { return Range<T,2>(std::array<T,2>{a0,a1},std::array<T,2>{b0,b1}); }
+template<typename T> Range<T,3> range(const T& a0, const T& a1, const T& a2, const T& b0, const T& b1, const T& b2) { return Range<T,3>(std::array<T,3>{a0,a1,a2},std::array<T,3>{b0,b1,b2}); }
+template<std::size_t N, typename T> Range<T,N> range_all(const T& va, const T& vb) { std::array<T,N> a, b; a.fill(va); b.fill(vb); return range(a,b); }
+template<std::size_t N, typename T = float> Range<T,N> range_primary() { return range_all<N>(T(0),T(1)); }
+
+template<typename T>
+class RangeInfinite : public std::array<std::vector<T>,2> {
+    T _volume;
+public:
+    static constexpr std::size_t dimensions = std::numeric_limits<std::size_t>::max();
+    using value_type = T;
+    RangeInfinite(const std::vector<T>& a = std::vector<T>(), const std::vector<T>& b = std::vector<T>()) : std::array<std::vector<T>,2>{a,b} {
+        _volume = T(1); for (std::size_t i = 0; i<std::max(a.size(),b.size()); ++i) _volume*=(max(i)-min(i));
+    }
+    const std::vector<T>& min() const { return (*this)[0]; }
+    T min(std::size_t i) const { return (i<min().size())?(min()[i]):T(0); }
+    const std::vector<T>& max() const { return (*this)[1]; }
+    T max(std::size_t i) const { return (i<max().size())?(max()[i]):T(1); }
+    T volume() const { return _volume; }
+};
+template<typename T> RangeInfinite<T> range_infinite(const std::vector<T>& a, const std::vector<T>& b) { return RangeInfinite<T>(a,b); }
+template<typename T> RangeInfinite<T> range_infinite(const T& a, const T& b, std::enable_if_t<std::is_floating_point_v<T>,int> = 0) { return RangeInfinite<T>(std::vector<T>{a},std::vector<T>{b}); }
+template<typename T = float> RangeInfinite<T> range_primary_infinite() { return RangeInfinite<T>(); }
+
+// ---- tensor (reference src/tensor.h:8-57): flat storage, dimension 0 fastest ----------------------------------------------
+template<typename T, std::size_t DIMBINS>
+class tensor {
+    std::vector<T> data_; std::array<std::size_t, DIMBINS> res;
+    std::size_t position(const std::array<std::size_t,DIMBINS>& p) const { std::size_t pos = 0, prod = 1; for (std::size_t d = 0;d<DIMBINS; ++d) { pos += p[d]*prod; prod*=res[d]; } return pos; }
+public:
+    tensor(const std::array<std::size_t, DIMBINS>& r, const T& t = T()) : res(r) { std::size_t n(1); for (auto x : res) n*=x; data_.resize(n, t); }
+    const std::array<std::size_t, DIMBINS>& resolution() const { return res; }
+    std::size_t resolution(std::size_t i) const { return res[i]; }
+    const std::vector<T>& raw_data() const { return data_; }
+    T* data() { return data_.data(); }                       // (addition) lets the GPU back end skip the per-bin accessor loop
+    T& operator[](const std::array<std::size_t,DIMBINS>& p) { return data_[position(p)]; }
+    T& operator()(const std::array<std::size_t,DIMBINS>& p) { return data_[position(p)]; }
+    const T& operator[](const std::array<std::size_t,DIMBINS>& p) const { return data_[position(p)]; }
+    const T& operator()(const std::array<std::size_t,DIMBINS>& p) const { return data_[position(p)]; }
+    std::size_t size() const { return data_.size(); }
+};
+
+// ---- loggers (reference src/log.h:10-52) ----------------------------------------------------------------------------------
+class LoggerNull {
+public:
+    LoggerNull(const std::string& = "") {}
+    std::string name() const { return ""; }
+    void set_name(const std::string&) {}
+    template<typename Number> void log_progress(const Number&, const Number& = Number(1)) {}
+    template<typename Data> void log(const Data&) {}
+};
+class LoggerProgress {
+    std::string name_; std::chrono::time_point<std::chrono::steady_clock> start = std::chrono::steady_clock::now();
+public:
+    LoggerProgress(const std::string& n) : name_(n) {}
+    const std::string& name() const { return name_; }
+    void set_name(const std::string& name) { name_=name; }
+    template<typename Number> void log_progress(const Number& number, const Number& last = Number(1)) {
+        if (number<=Number(0)) { start = std::chrono::steady_clock::now(); std::cerr<<name()<<" -                           \r"; }
+        else if (number >= last) { auto el = std::chrono::duration_cast<std::chrono::duration<double>>(std::chrono::steady_clock::now() - start);
+            std::cerr<<name()<<" - \t [DONE]\t("<<std::setprecision(3)<<std::setw(6)<<el.count()<<" seconds)\n"; }
+    }
+    template<typename Data> void log(const Data&) {}
+};
+template<typename Logger> Logger logger_step(const Logger& logger, std::string step_name) { Logger sol = logger; sol.set_name(logger.name()+" | "+step_name); return sol; }
+
+// ---- GPU plumbing -----------------------------------------------------------------------------------------------------------
+namespace b200 {
+
+class Context {
+    vb200_ctx* h = nullptr;
+public:
+    explicit Context(int device = 0) { if (vb200_create(device, &h) != VB200_OK) throw std::runtime_error(std::string("viltrum_b200: ") + vb200_last_error(nullptr)); }
+    ~Context() { vb200_destroy(h); }
+    Context(const Context&) = delete; Context& operator=(const Context&) = delete;
+    vb200_ctx* get() const { return h; }
+    void check(int status) const { if (status != VB200_OK) throw std::runtime_error(std::string("viltrum_b200: ") + vb200_last_error(h)); }
+};
+// one context per process and device, created on first use (one process per GPU)
+inline int& current_device() { static int d = 0; return d; }
+inline Context& default_context() { static Context c(current_device()); return c; }
+// bin-grid shard handled by this process ({0,0} = whole grid): multi-GPU runs set it per rank
+inline vb200_shard& current_shard() { static vb200_shard s{0, 0}; return s; }
+
+template<typename Float, std::size_t DIM, std::size_t DIMBINS>
+inline vb200_domain make_domain(const Range<Float,DIM>& r, const std::array<std::size_t,DIMBINS>& res) {
+    static_assert(std::is_same<Float,float>::value, "viltrum_b200 computes in fp32: use Range<float,DIM>");
+    static_assert(DIM <= VB200_MAX_DIM && DIMBINS <= VB200_MAX_DIMBINS && DIMBINS <= DIM, "unsupported dimensionality");
+    vb200_domain d; std::memset(&d, 0, sizeof(d));
+    d.dim = int(DIM); d.dimbins = int(DIMBINS);
+    for (std::size_t i = 0; i < DIM; ++i) { d.rmin[i] = r.min(i); d.rmax[i] = r.max(i); }
+    for (std::size_t i = 0; i < DIMBINS; ++i) d.res[i] = res[i];
+    return d;
+}
+template<typename Float, std::size_t DIMBINS>
+inline vb200_domain make_domain(const RangeInfinite<Float>& r, const std::array<std::size_t,DIMBINS>& res) {
+    static_assert(std::is_same<Float,float>::value, "viltrum_b200 computes in fp32: use RangeInfinite<float>");
+    vb200_domain d; std::memset(&d, 0, sizeof(d));
+    const std::size_t n = std::max(r.min().size(), r.max().size());
+    if (n > VB200_MAX_DIM) throw std::runtime_error("viltrum_b200: at most 8 explicit entries in an infinite range");
+    d.dim = int(n); d.dimbins = int(DIMBINS);
+    for (std::size_t i = 0; i < n; ++i) { d.rmin[i] = r.min(i); d.rmax[i] = r.max(i); }
+    for (std::size_t i = 0; i < DIMBINS; ++i) d.res[i] = res[i];
+    return d;
+}
+template<std::size_t DIMBINS> inline std::size_t bin_count(const std::array<std::size_t,DIMBINS>& res) { std::size_t n = 1; for (auto r : res) n *= r; return n; }
+
+// applies a flat device result (tensor order) to the caller's bins through the accessor: bins(pos) op= v
+template<bool ACCUMULATE, typename Bins, std::size_t DIMBINS>
+inline void apply_bins(Bins& bins, const std::array<std::size_t,DIMBINS>& res, const std::vector<float>& flat) {
+    std::array<std::size_t,DIMBINS> pos; pos.fill(0);
+    vb200_shard sh = current_shard(); const std::size_t n = flat.size();
+    const std::size_t b = (sh.begin == 0 && sh.end == 0) ? 0 : std::size_t(sh.begin), e = (sh.begin == 0 && sh.end == 0) ? n : std::size_t(sh.end);
+    for (std::size_t k = 0; k < n; ++k) {
+        if (k >= b && k < e) { if (ACCUMULATE) bins(pos) += flat[k]; else bins(pos) = flat[k]; }
+        for (std::size_t d = 0; d < DIMBINS; ++d) { if (++pos[d] >= res[d]) pos[d] = 0; else break; }
+    }
+}
+
+// scalar-argument integrands f(x0, x1, ...) -> array integrands (reference src/integrate.h:13-69), device-callable
+template<typename F, std::size_t N> struct ScalarAdapter {
+    F f;
+    template<std::size_t... I> __host__ __device__ float call(const std::array<float,N>& x, std::index_sequence<I...>) const { return f(x[I]...); }
+    __host__ __device__ float operator()(const std::array<float,N>& x) const { return call(x, std::make_index_sequence<N>()); }
+};
+template<typename F, std::size_t N, typename = void> struct takes_array : std::false_type {};
+template<typename F, std::size_t N> struct takes_array<F, N, std::void_t<decltype(std::declval<const F&>()(std::declval<const std::array<float,N>&>()))>> : std::true_type {};
+template<std::size_t DIM, typename F>
+inline auto adapt(const F& f) {
+    if constexpr (takes_array<F, DIM>::value) return f;
+    else return ScalarAdapter<F, DIM>{f};
+}
+
+// region list handed to Logger::log (the reference passes its vector of regions, integrator-region-based.h:19)
+template<std::size_t DIM>
+struct RegionView {
+    Range<float,DIM> box; std::tuple<float,std::size_t> errdim; std::vector<float> samples;
+    const Range<float,DIM>& range() const { return box; }
+    const std::tuple<float,std::size_t>& extra() const { return errdim; }
+};
+template<std::size_t DIM>
+inline std::vector<RegionView<DIM>> download_regions(Context& ctx, const vb200_regions* r) {
+    const std::size_t n = vb200_regions_count(r), sd = std::size_t(vb200_regions_samples(r));
+    std::vector<float> mn(n*DIM), mx(n*DIM), err(n), data(n*sd); std::vector<uint32_t> dim(n);
+    ctx.check(vb200_regions_download(ctx.get(), r, mn.data(), mx.data(), err.data(), dim.data(), data.data()));
+    std::vector<RegionView<DIM>> out; out.reserve(n);
+    for (std::size_t i = 0; i < n; ++i) {
+        std::array<float,DIM> a, b; for (std::size_t d = 0; d < DIM; ++d) { a[d] = mn[i*DIM+d]; b[d] = mx[i*DIM+d]; }
+        out.push_back(RegionView<DIM>{Range<float,DIM>(a,b), std::tuple<float,std::size_t>(err[i], dim[i]), std::vector<float>(data.begin()+i*sd, data.begin()+(i+1)*sd)});
+    }
+    return out;
+}
+struct RegionsHandle { vb200_regions* r = nullptr; ~RegionsHandle() { vb200_regions_free(r); } };
+
+} // namespace b200
+
+// ---- Monte Carlo integrators -----------------------------------------------------------------------------------------------
+// monte_carlo(samples, seed) — reference src/monte-carlo/monte-carlo.h:39-63,88-95: global sampler, bins(pos) += f*factor
+class MonteCarlo {
+    unsigned long samples; std::size_t seed_;
+public:
+    MonteCarlo(unsigned long s, std::size_t seed) : samples(s), seed_(seed) {}
+    unsigned long sample_count() const { return samples; }
+    std::size_t seed() const { return seed_; }
+    template<typename Bins, std::size_t DIMBINS, typename F, typename Float, std::size_t DIM, typename Logger>
+    void integrate(Bins& bins, const std::array<std::size_t,DIMBINS>& res, const F& f, const Range<Float,DIM>& range, Logger& logger) const {
+        auto& ctx = b200::default_context();
+        b200::Integrand<F, int(DIM)> g(f);
+        vb200_mc_params p; std::memset(&p, 0, sizeof(p));
+        p.domain = b200::make_domain(range, res); p.spp = samples; p.seed = seed_; p.flavor = VB200_MC_PER_BIN;
+        std::vector<float> flat(b200::bin_count(res), 0.0f);
+        logger.log_progress(0ul, samples);
+        ctx.check(vb200_monte_carlo(ctx.get(), g.c_abi(), &p, flat.data(), VB200_HOST));
+        b200::apply_bins<true>(bins, res, flat);
+        logger.log_progress(samples, samples);
+    }
+};
+inline MonteCarlo monte_carlo(unsigned long samples, std::size_t seed = 0) { return MonteCarlo(samples, seed); }
+
+// monte_carlo_per_bin_parallel(spp, seed) — reference src/monte-carlo/monte-carlo-per-bin-parallel.h:41-100,104-111 ('+=')
+class MonteCarloPerBinParallel {
+    unsigned long samples; std::size_t seed_;
+    template<bool INF, typename Bins, std::size_t DIMBINS, typename G, typename Logger>
+    void run(Bins& bins, const std::array<std::size_t,DIMBINS>& res, const G& g, const vb200_domain& dom, Logger& logger) const {
+        auto& ctx = b200::default_context();
+        vb200_mc_params p; std::memset(&p, 0, sizeof(p));
+        p.domain = dom; p.shard = b200::current_shard(); p.spp = samples; p.seed = seed_; p.flavor = VB200_MC_PER_BIN;
+        logger.log_progress(std::size_t(0), std::size_t(1));
+        if constexpr (std::is_same<Bins, tensor<float,DIMBINS>>::value) {      // fast path: the library accumulates straight into the tensor
+            ctx.check(INF ? vb200_mc_per_bin_inf(ctx.get(), g.c_abi(), &p, bins.data(), VB200_HOST, nullptr, nullptr)
+                          : vb200_mc_per_bin(ctx.get(), g.c_abi(), &p, bins.data(), VB200_HOST, nullptr, nullptr));
+        } else {
+            std::vector<float> flat(b200::bin_count(res), 0.0f);
+            ctx.check(INF ? vb200_mc_per_bin_inf(ctx.get(), g.c_abi(), &p, flat.data(), VB200_HOST, nullptr, nullptr)
+                          : vb200_mc_per_bin(ctx.get(), g.c_abi(), &p, flat.data(), VB200_HOST, nullptr, nullptr));
+            b200::apply_bins<true>(bins, res, flat);
+        }
+        logger.log_progress(std::size_t(1), std::size_t(1));
+    }
+public:
+    MonteCarloPerBinParallel(unsigned long s, std::size_t seed) : samples(s), seed_(seed) {}
+    template<typename Bins, std::size_t DIMBINS, typename F, typename Float, std::size_t DIM, typename Logger>
+    void integrate(Bins& bins, const std::array<std::size_t,DIMBINS>& res, const F& f, const Range<Float,DIM>& range, Logger& logger) const {
+        b200::Integrand<F, int(DIM)> g(f);
+        run<false>(bins, res, g, b200::make_domain(range, res), logger);
+    }
+    template<typename Bins, std::size_t DIMBINS, typename F, typename Float, typename Logger>
+    void integrate(Bins& bins, const std::array<std::size_t,DIMBINS>& res, const F& f, const RangeInfinite<Float>& range, Logger& logger) const {
+        b200::InfiniteIntegrand<F> g(f);
+        run<true>(bins, res, g, b200::make_domain(range, res), logger);
+    }
+};
+inline MonteCarloPerBinParallel monte_carlo_per_bin_parallel(unsigned long samples, std::size_t seed = 0) { return MonteCarloPerBinParallel(samples, seed); }
+inline MonteCarloPerBinParallel monte_carlo_per_bin(unsigned long samples, std::size_t seed = 0) { return MonteCarloPerBinParallel(samples, seed); }   // monte-carlo-per-bin.h: same estimator, sequential upstream
+
+// integrator_per_bin_parallel(monte_carlo(spp, seed)) — reference src/integrator-per-bin-parallel.h:16-38 ('=')
+template<typename Integrator> class IntegratorPerBinParallel;
+template<> class IntegratorPerBinParallel<MonteCarlo> {
+    MonteCarlo inner;
+public:
+    IntegratorPerBinParallel(const MonteCarlo& m) : inner(m) {}
+    template<typename Bins, std::size_t DIMBINS, typename F, typename Float, std::size_t DIM, typename Logger>
+    void integrate(Bins& bins, const std::array<std::size_t,DIMBINS>& res, const F& f, const Range<Float,DIM>& range, Logger& logger) const {
+        auto& ctx = b200::default_context();
+        b200::Integrand<F, int(DIM)> g(f);
+        vb200_mc_params p; std::memset(&p, 0, sizeof(p));
+        p.domain = b200::make_domain(range, res); p.shard = b200::current_shard(); p.spp = inner.sample_count(); p.seed = inner.seed(); p.flavor = VB200_PER_BIN_MC;
+        std::vector<float> flat(b200::bin_count(res), 0.0f);
+        logger.log_progress(std::size_t(0), std::size_t(1));
+        ctx.check(vb200_mc_per_bin(ctx.get(), g.c_abi(), &p, flat.data(), VB200_HOST, nullptr, nullptr));
+        b200::apply_bins<false>(bins, res, flat);
+        logger.log_progress(std::size_t(1), std::size_t(1));
+    }
+};
+inline IntegratorPerBinParallel<MonteCarlo> integrator_per_bin_parallel(const MonteCarlo& m) { return IntegratorPerBinParallel<MonteCarlo>(m); }
+inline IntegratorPerBinParallel<MonteCarlo> integrator_per_bin(const MonteCarlo& m) { return IntegratorPerBinParallel<MonteCarlo>(m); }
+
+// ---- Newton-Cotes rules, nested pairs, error heuristics (reference src/newton-cotes/rules.h, src/nested/*.h) ------------------
+struct Trapezoidal { static constexpr std::size_t samples = 2; static constexpr int id = VB200_RULE_TRAPEZOIDAL; };
+struct Simpson { static constexpr std::size_t samples = 3; static constexpr int id = VB200_RULE_SIMPSON; };
+struct Boole { static constexpr std::size_t samples = 5; static constexpr int id = VB200_RULE_BOOLE; };
+static const Trapezoidal trapezoidal{}; static const Simpson simpson{}; static const Boole boole{};
+template<typename H, typename L> struct Nested {
+    static constexpr std::size_t samples = H::samples;
+    static_assert((std::is_same<H,Simpson>::value && std::is_same<L,Trapezoidal>::value) || (std::is_same<H,Boole>::value && std::is_same<L,Simpson>::value),
+                  "viltrum_b200 implements nested(simpson,trapezoidal) and nested(boole,simpson)");
+    static constexpr int id = std::is_same<H,Simpson>::value ? VB200_RULE_SIMPSON_TRAPEZOIDAL : VB200_RULE_BOOLE_SIMPSON;
+};
+template<typename H, typename L> Nested<H,L> nested(const H&, const L&) { return Nested<H,L>(); }
+struct error_metric_absolute { static constexpr int id = VB200_METRIC_ABSOLUTE; };
+struct error_metric_relative { static constexpr int id = VB200_METRIC_RELATIVE; error_metric_relative(double = 1.e-37) {} };
+template<typename EM> struct error_heuristic_default { static constexpr int id = VB200_HEURISTIC_DEFAULT; double size_weight = 0; error_heuristic_default(const EM&) {} using metric = EM; };
+template<typename EM> struct error_heuristic_size { static constexpr int id = VB200_HEURISTIC_SIZE; double size_weight; error_heuristic_size(const EM&, double sw = 1.e-5, double = 1.e-37) : size_weight(sw) {} using metric = EM; };
+
+// integrator_newton_cotes(rule) — reference src/newton-cotes/newton-cotes.h:11-19 ('+=')
+template<typename Rule> class IntegratorNewtonCotes {
+public:
+    template<typename Bins, std::size_t DIMBINS, typename F, typename Float, std::size_t DIM, typename Logger>
+    void integrate(Bins& bins, const std::array<std::size_t,DIMBINS>& res, const F& f, const Range<Float,DIM>& range, Logger& logger) const {
+        auto& ctx = b200::default_context();
+        b200::Integrand<F, int(DIM)> g(f);
+        vb200_domain dom = b200::make_domain(range, res);
+        b200::RegionsHandle regs;
+        ctx.check(vb200_regions_generate_single(ctx.get(), g.c_abi(), &dom, Rule::id, &regs.r));
+        std::vector<float> flat(b200::bin_count(res), 0.0f);
+        vb200_shard sh = b200::current_shard();
+        ctx.check(vb200_regions_integrate_bins(ctx.get(), regs.r, &dom, &sh, flat.data(), VB200_HOST));
+        b200::apply_bins<true>(bins, res, flat);
+        logger.log_progress(std::size_t(1), std::size_t(1));
+    }
+};
+template<typename R> IntegratorNewtonCotes<R> integrator_newton_cotes(const R&) { return IntegratorNewtonCotes<R>(); }
+template<typename R> IntegratorNewtonCotes<R> integrator_newton_cotes_parallel(const R&) { return IntegratorNewtonCotes<R>(); }
+
+// integrator_adaptive_iterations(nested(h,l), error_heuristic, iterations) — reference src/nested/integrator-adaptive-iterations.h:12-30,
+// src/nested/regions-generator-adaptive-heap.h:18-45 + src/newton-cotes/regions-integrator-sequential.h:38-58 ('+=').
+// batch = 1 reproduces the reference's greedy split order exactly.
+template<typename Rule, typename EH> class IntegratorAdaptiveIterations {
+    EH eh; std::size_t iterations; int batch;
+public:
+    IntegratorAdaptiveIterations(const EH& e, std::size_t it, int b = 1) : eh(e), iterations(it), batch(b) {}
+    template<typename F, typename Float, std::size_t DIM>
+    void generate(b200::Context& ctx, const b200::Integrand<F,int(DIM)>& g, const Range<Float,DIM>& range, b200::RegionsHandle& regs) const {
+        vb200_adaptive_params p; std::memset(&p, 0, sizeof(p));
+        std::array<std::size_t,1> one{1}; p.domain = b200::make_domain(range, one);
+        p.rule = Rule::id; p.heuristic = EH::id; p.metric = EH::metric::id; p.batch = batch; p.size_weight = eh.size_weight; p.iterations = iterations;
+        ctx.check(vb200_regions_generate_adaptive(ctx.get(), g.c_abi(), &p, &regs.r));
+    }
+    template<typename Bins, std::size_t DIMBINS, typename F, typename Float, std::size_t DIM, typename Logger>
+    void integrate(Bins& bins, const std::array<std::size_t,DIMBINS>& res, const F& f, const Range<Float,DIM>& range, Logger& logger) const {
+        auto& ctx = b200::default_context();
+        b200::Integrand<F, int(DIM)> g(f);
+        b200::RegionsHandle regs;
+        generate(ctx, g, range, regs);
+        if constexpr (!std::is_same<Logger, LoggerNull>::value) logger.log(b200::download_regions<DIM>(ctx, regs.r));
+        vb200_domain dom = b200::make_domain(range, res);
+        std::vector<float> flat(b200::bin_count(res), 0.0f);
+        vb200_shard sh = b200::current_shard();
+        ctx.check(vb200_regions_integrate_bins(ctx.get(), regs.r, &dom, &sh, flat.data(), VB200_HOST));
+        b200::apply_bins<true>(bins, res, flat);
+        logger.log_progress(iterations, iterations);
+    }
+};
+template<typename R, typename EH> auto integrator_adaptive_iterations(const R&, const EH& eh, std::size_t iterations) { return IntegratorAdaptiveIterations<R,EH>(eh, iterations); }
+template<typename R, typename EH> auto integrator_adaptive_iterations_parallel(const R&, const EH& eh, std::size_t iterations, std::size_t = 16) { return IntegratorAdaptiveIterations<R,EH>(eh, iterations); }
+template<typename R> auto integrator_adaptive_iterations(const R& r, std::size_t iterations) { return integrator_adaptive_iterations(r, error_heuristic_default<error_metric_absolute>(error_metric_absolute()), iterations); }
+
+// integrator_crespo2021(iterations, spp, seed) — reference src/control-variates/integrator-crespo2021.h:7-22 ('=')
+class IntegratorCrespo2021 {
+    std::size_t iterations, spp, seed_;
+public:
+    IntegratorCrespo2021(std::size_t it, std::size_t s, std::size_t seed) : iterations(it), spp(s), seed_(seed) {}
+    template<typename Bins, std::size_t DIMBINS, typename F, typename Float, std::size_t DIM, typename Logger>
+    void integrate(Bins& bins, const std::array<std::size_t,DIMBINS>& res, const F& f, const Range<Float,DIM>& range, Logger& logger) const {
+        auto& ctx = b200::default_context();
+        b200::Integrand<F, int(DIM)> g(f);
+        b200::RegionsHandle regs;
+        using EH = error_heuristic_size<error_metric_relative>;
+        IntegratorAdaptiveIterations<Nested<Simpson,Trapezoidal>, EH>(EH(error_metric_relative(), 1.e-5), iterations).generate(ctx, g, range, regs);
+        if constexpr (!std::is_same<Logger, LoggerNull>::value) logger.log(b200::download_regions<DIM>(ctx, regs.r));
+        vb200_cv_params p; std::memset(&p, 0, sizeof(p));
+        p.domain = b200::make_domain(range, res); p.shard = b200::current_shard(); p.spp = spp; p.seed = seed_;
+        std::vector<float> flat(b200::bin_count(res), 0.0f);
+        ctx.check(vb200_cv_integrate(ctx.get(), g.c_abi(), regs.r, &p, flat.data(), VB200_HOST, nullptr, nullptr));
+        b200::apply_bins<false>(bins, res, flat);
+        logger.log_progress(std::size_t(1), std::size_t(1));
+    }
+};
+inline IntegratorCrespo2021 integrator_crespo2021(std::size_t iterations, std::size_t spp, std::size_t seed = 0, std::size_t = 16) { return IntegratorCrespo2021(iterations, spp, seed); }
+
+// ---- the front door (reference src/integrate.h:72-173) ------------------------------------------------------------------------
+template<typename Integrator, typename Bins, std::size_t DIMBINS, typename F, typename Float, std::size_t DIM, typename Logger>
+void integrate(const Integrator& integrator, Bins& bins, const std::array<std::size_t,DIMBINS>& resolution, const F& function, const Range<Float,DIM>& range, Logger& logger) {
+    integrator.integrate(bins, resolution, b200::adapt<DIM>(function), range, logger);
+}
+template<typename Integrator, typename Bins, std::size_t DIMBINS, typename F, typename Float, typename Logger>
+void integrate(const Integrator& integrator, Bins& bins, const std::array<std::size_t,DIMBINS>& resolution, const F& function, const RangeInfinite<Float>& range, Logger& logger) {
+    integrator.integrate(bins, resolution, function, range, logger);
+}
+template<typename Integrator, typename Bins, std::size_t DIMBINS, typename F, typename Float, std::size_t DIM>
+void integrate(const Integrator& integrator, Bins& bins, const std::array<std::size_t,DIMBINS>& resolution, const F& function, const Range<Float,DIM>& range) {
+    LoggerNull log; integrate(integrator, bins, resolution, function, range, log);
+}
+template<typename Integrator, typename Bins, std::size_t DIMBINS, typename F, typename Float>
+void integrate(const Integrator& integrator, Bins& bins, const std::array<std::size_t,DIMBINS>& resolution, const F& function, const RangeInfinite<Float>& range) {
+    LoggerNull log; integrate(integrator, bins, resolution, function, range, log);
+}
+// single value (integrate.h:105-130): one bin
+template<typename Integrator, typename F, typename Float, std::size_t DIM, typename Logger>
+float integrate(const Integrator& integrator, const F& function, const Range<Float,DIM>& range, Logger& logger) {
+    float sol(0.0f);
+    auto bins = [&sol] (const std::array<std::size_t,1>&) -> float& { return sol; };
+    std::array<std::size_t,1> res{1};
+    integrate(integrator, bins, res, function, range, logger);
+    return sol;
+}
+template<typename Integrator, typename F, typename Float, typename Logger>
+float integrate(const Integrator& integrator, const F& function, const RangeInfinite<Float>& range, Logger& logger) {
+    float sol(0.0f);
+    auto bins = [&sol] (const std::array<std::size_t,1>&) -> float& { return sol; };
+    std::array<std::size_t,1> res{1};
+    integrate(integrator, bins, res, function, range, logger);
+    return sol;
+}
+template<typename Integrator, typename F, typename R>
+float integrate(const Integrator& integrator, const F& function, const R& range) { LoggerNull log; return integrate(integrator, function, range, log); }
+// std::vector bins (integrate.h:132-137,169-173)
+template<typename Integrator, typename T, typename F, typename R, typename Logger>
+void integrate(const Integrator& integrator, std::vector<T>& bins, const F& function, const R& range, Logger& logger) {
+    auto b = [&bins] (const std::array<std::size_t,1>& i) -> T& { return bins[i[0]]; };
+    std::array<std::size_t,1> res{bins.size()};
+    integrate(integrator, b, res, function, range, logger);
+}
+template<typename Integrator, typename T, typename F, typename R>
+void integrate(const Integrator& integrator, std::vector<T>& bins, const F& function, const R& range) { LoggerNull log; integrate(integrator, bins, function, range, log); }
+
+} // namespace viltrum
