@@ -26,6 +26,7 @@ SOURCES = [
     ("capi.cu", []),
     ("regions.cu", ["--fmad=false"]),
     ("cv.cu", ["--fmad=false"]),
+    ("refine_batched.cu", ["--fmad=false"]),
     ("builtin_fast.cu", []),
     ("builtin_exact.cu", ["--fmad=false", "-DVILTRUM_B200_EXACT"]),
 ]

@@ -1,0 +1,325 @@
+// Batched adaptive refinement — the throughput mode of the region generator (SURVEY.md §2.2 K5-K7 "batched", §7 step 6).
+// The reference refines greedily, one region per iteration (regions-generator-adaptive-heap.h:32-42); that loop is serial by
+// construction (greedy.cuh reproduces it exactly).  Here every round
+//   1. selects the B regions with the largest error heuristic with a device-side radix top-k over the float keys
+//      (four 8-bit histogram passes find the B-th largest key, an ordered compaction takes everything above it plus the
+//      first ties in table order),
+//   2. generates the (S-1)*S^(D-1) new sample points of all B splits at once, evaluates the integrand on them through the
+//      eval thunk (one launch), and
+//   3. builds both children of every split and their error heuristics, one warp per split, with the same arithmetic as the
+//      exact mode (rules.cuh) — a region produced here is bit-identical to the one the greedy mode would produce for the
+//      same split.
+// Round sizes follow from the host-known region count (B = max(1, n/4) unless params.batch caps it), so the whole
+// refinement is enqueued without a single device->host read.  With batch > 1 the leaf SET differs from the reference's
+// (equally valid: > 99 % of the keys are ties at C3 scale), so this mode is validated by convergence,
+// not bin by bin.
+#include "regions.h"
+#include <viltrum_b200/device/greedy.cuh>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+
+using namespace vb200;
+namespace R = viltrum::b200::device::rules;
+namespace D_ = viltrum::b200::device;
+
+namespace {
+
+struct SelectState { unsigned prefix_val, prefix_mask; unsigned long long k; };
+
+__global__ void select_init_kernel(SelectState* st, unsigned long long k, unsigned* hist) {
+    if (threadIdx.x == 0) { st->prefix_val = 0; st->prefix_mask = 0; st->k = k; }
+    if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+}
+// histogram of the next 8-bit digit among the keys that match the prefix found so far
+__global__ void __launch_bounds__(256) select_hist_kernel(const float* __restrict__ keys, uint64_t n, const SelectState* __restrict__ st, int shift, unsigned* __restrict__ hist) {
+    __shared__ unsigned s_hist[256];
+    s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned pv = st->prefix_val, pm = st->prefix_mask;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
+        const unsigned k = __float_as_uint(keys[i]);
+        if ((k & pm) == pv) atomicAdd(&s_hist[(k >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (s_hist[threadIdx.x]) atomicAdd(&hist[threadIdx.x], s_hist[threadIdx.x]);
+}
+// walk the digits from the top: the digit where the cumulative count reaches k holds the k-th largest key
+__global__ void select_pick_kernel(SelectState* st, int shift, unsigned* hist) {
+    if (threadIdx.x == 0) {
+        unsigned long long k = st->k, cum = 0; int d = 255;
+        for (; d > 0; --d) { if (cum + hist[d] >= k) break; cum += hist[d]; }
+        st->k = k - cum; st->prefix_val |= unsigned(d) << shift; st->prefix_mask |= 255u << shift;
+    }
+    __syncthreads();
+    if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+}
+// per-CTA counts of keys above the threshold and equal to it (CTA = 1024 consecutive regions)
+__global__ void __launch_bounds__(256) select_count_kernel(const float* __restrict__ keys, uint64_t n, const SelectState* __restrict__ st, unsigned* __restrict__ cta_gt, unsigned* __restrict__ cta_eq) {
+    __shared__ unsigned s_gt, s_eq;
+    if (threadIdx.x == 0) { s_gt = 0; s_eq = 0; }
+    __syncthreads();
+    const unsigned T = st->prefix_val;
+    unsigned gt = 0, eq = 0;
+    for (int j = 0; j < 4; ++j) {
+        const uint64_t i = uint64_t(blockIdx.x) * 1024 + j * 256 + threadIdx.x;
+        if (i < n) { const unsigned k = __float_as_uint(keys[i]); gt += k > T; eq += k == T; }
+    }
+    atomicAdd(&s_gt, gt); atomicAdd(&s_eq, eq);
+    __syncthreads();
+    if (threadIdx.x == 0) { cta_gt[blockIdx.x] = s_gt; cta_eq[blockIdx.x] = s_eq; }
+}
+// exclusive scan of the per-CTA counts (single CTA; at most a few thousand entries)
+__global__ void __launch_bounds__(1024) select_scan_kernel(unsigned* cta_gt, unsigned* cta_eq, unsigned nctas) {
+    __shared__ unsigned s_a[1024], s_b[1024];
+    unsigned run_a = 0, run_b = 0;
+    for (unsigned base = 0; base < nctas; base += 1024) {
+        const unsigned i = base + threadIdx.x;
+        const unsigned a = i < nctas ? cta_gt[i] : 0, b = i < nctas ? cta_eq[i] : 0;
+        s_a[threadIdx.x] = a; s_b[threadIdx.x] = b;
+        __syncthreads();
+        for (unsigned off = 1; off < 1024; off <<= 1) {
+            const unsigned va = threadIdx.x >= off ? s_a[threadIdx.x - off] : 0, vb = threadIdx.x >= off ? s_b[threadIdx.x - off] : 0;
+            __syncthreads();
+            s_a[threadIdx.x] += va; s_b[threadIdx.x] += vb;
+            __syncthreads();
+        }
+        if (i < nctas) { cta_gt[i] = run_a + s_a[threadIdx.x] - a; cta_eq[i] = run_b + s_b[threadIdx.x] - b; }
+        run_a += s_a[1023]; run_b += s_b[1023];
+        __syncthreads();
+    }
+}
+// ordered compaction: selected = key > T, or key == T and fewer than k_eq equal keys precede it in table order.
+// Output position: (#selected-by-'>' before) + (#selected ties before); both are monotone in the index, so sel[] is sorted.
+__global__ void __launch_bounds__(1024) select_write_kernel(const float* __restrict__ keys, uint64_t n, const SelectState* __restrict__ st,
+                                                            const unsigned* __restrict__ cta_gt, const unsigned* __restrict__ cta_eq, unsigned* __restrict__ sel) {
+    __shared__ unsigned s_wgt[32], s_weq[32];
+    const unsigned T = st->prefix_val; const unsigned long long k_eq = st->k;
+    const uint64_t i = uint64_t(blockIdx.x) * 1024 + threadIdx.x;
+    const unsigned key = i < n ? __float_as_uint(keys[i]) : 0u;
+    const bool gt = i < n && key > T, eq = i < n && key == T;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned mg = __ballot_sync(0xffffffffu, gt), me = __ballot_sync(0xffffffffu, eq);
+    if (lane == 0) { s_wgt[warp] = __popc(mg); s_weq[warp] = __popc(me); }
+    __syncthreads();
+    unsigned bg = cta_gt[blockIdx.x], be = cta_eq[blockIdx.x];
+    for (unsigned w = 0; w < warp; ++w) { bg += s_wgt[w]; be += s_weq[w]; }
+    bg += __popc(mg & ((1u << lane) - 1u)); be += __popc(me & ((1u << lane) - 1u));
+    // ties are taken in table order: tie number `be` is selected iff be < k_eq; ties before it that were selected: min(be, k_eq)
+    const unsigned long long ties_before = be < k_eq ? be : k_eq;
+    if (gt) sel[bg + ties_before] = unsigned(i);
+    else if (eq && be < k_eq) sel[bg + be] = unsigned(i);
+}
+
+// sample points of all selected splits: point q of split r = odd position i = 2*(q / L)+1 along the split dimension,
+// other-dims index o = q % L; coordinates from the PARENT range (split.h:22, region.h:40-46)
+__global__ void split_points_kernel(int S, int dim, uint64_t cap, uint64_t nsel, const unsigned* __restrict__ sel,
+                                    const float* __restrict__ rmin, const float* __restrict__ rmax, const uint32_t* __restrict__ errdim, float* __restrict__ points) {
+    int L = 1; for (int i = 0; i < dim - 1; ++i) L *= S;
+    const uint64_t Q = uint64_t(S - 1) * L, N = nsel * Q;
+    const uint64_t t = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= N) return;
+    const uint64_t r = t / Q; const int q = int(t % Q);
+    const unsigned slot = sel[r]; const int sd = int(errdim[slot]);
+    const int i = 2 * (q / L) + 1; int o = q % L;
+    for (int d = 0; d < dim; ++d) {
+        double p;
+        if (d == sd) p = R::dd(double(i), double(2 * (S - 1)));
+        else { p = R::dd(double(o % S), double(S - 1)); o /= S; }
+        points[uint64_t(d) * N + t] = D_::grid_coord(p, rmin[uint64_t(d) * cap + slot], rmax[uint64_t(d) * cap + slot]);
+    }
+}
+
+// one warp per split: build both children (region.h:345-359, split.h:13-49), store child 0 over the parent and child 1 in a
+// new slot, then evaluate both children's error heuristics (region.h:387-411, error-heuristic.h:10-46)
+template<int SH, int SL, int DIM>
+__global__ void split_children_kernel(uint64_t cap, uint64_t nsel, uint64_t n_old, const unsigned* __restrict__ sel, const float* __restrict__ vals,
+                                      float* __restrict__ rmin, float* __restrict__ rmax, float* __restrict__ data, float* __restrict__ err, uint32_t* __restrict__ errdim,
+                                      int heuristic, int metric, double size_weight) {
+    using Sh = D_::GreedyShape<SH, SL, DIM>;
+    extern __shared__ float smem[];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    float* s_parent = smem + size_t(warp) * (3 * Sh::SD + Sh::L + 4 * DIM + 2 * DIM + 2);
+    float* s_child = s_parent + Sh::SD;
+    float* s_work = s_child + 2 * Sh::SD;
+    float* s_crange = s_work + Sh::L;          // [2][2*DIM]
+    float* s_E = s_crange + 4 * DIM;           // [2][DIM]
+    float* s_vol = s_E + 2 * DIM;              // [2]
+    const uint64_t r = uint64_t(blockIdx.x) * wpc + warp;
+    if (r >= nsel) return;
+    const unsigned slot = sel[r]; const uint64_t slot1 = n_old + r;
+    const int dim = int(errdim[slot]);
+    for (int k = lane; k < Sh::SD; k += 32) s_parent[k] = data[uint64_t(k) * cap + slot];
+    float prange[2 * DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) { prange[d] = rmin[uint64_t(d) * cap + slot]; prange[DIM + d] = rmax[uint64_t(d) * cap + slot]; }
+    __syncwarp();
+    int inner = 1; for (int i = 0; i < dim; ++i) inner *= SH;
+    constexpr int Q = (SH - 1) * Sh::L;
+    for (int item = lane; item < Sh::WIDE; item += 32) {
+        const int i = item / Sh::L, o = item % Sh::L;
+        const int lo = o % inner, hi = o / inner;
+        const float v = (i & 1) == 0 ? s_parent[lo + (i / 2) * inner + hi * inner * SH] : vals[r * uint64_t(Q) + uint64_t((i / 2) * Sh::L + o)];
+        if (i <= SH - 1) s_child[lo + i * inner + hi * inner * SH] = v;
+        if (i >= SH - 1) s_child[Sh::SD + lo + (i - (SH - 1)) * inner + hi * inner * SH] = v;
+    }
+    if (lane < 2) {
+        const float pmin = prange[dim], pmax = prange[DIM + dim];
+        const float mid = R::fa(pmin, R::fm(R::fd(R::fs(pmax, pmin), 2.0f), 1.0f));
+        float* cr = s_crange + lane * 2 * DIM;
+        for (int d = 0; d < 2 * DIM; ++d) cr[d] = prange[d];
+        if (lane == 0) cr[DIM + dim] = mid; else cr[dim] = mid;
+        float v = 1.0f; for (int d = 0; d < DIM; ++d) v = R::fm(v, R::fs(cr[DIM + d], cr[d]));
+        s_vol[lane] = v;
+    }
+    __syncwarp();
+    for (int k = lane; k < Sh::SD; k += 32) { data[uint64_t(k) * cap + slot] = s_child[k]; data[uint64_t(k) * cap + slot1] = s_child[Sh::SD + k]; }
+    if (lane < DIM) {
+        rmin[uint64_t(lane) * cap + slot] = s_crange[lane]; rmax[uint64_t(lane) * cap + slot] = s_crange[DIM + lane];
+        rmin[uint64_t(lane) * cap + slot1] = s_crange[2 * DIM + lane]; rmax[uint64_t(lane) * cap + slot1] = s_crange[3 * DIM + lane];
+    }
+    for (int c = 0; c < 2; ++c) for (int d = 0; d < DIM; ++d) {
+        const float e = D_::region_error_warp<SH, SL, DIM>(s_child + c * Sh::SD, s_vol[c], d, metric == VB200_METRIC_RELATIVE, s_work, lane);
+        if (lane == 0) s_E[c * DIM + d] = e;
+        __syncwarp();
+    }
+    if (lane < 2) {
+        float e; unsigned d;
+        D_::heuristic_pick<DIM>(s_E + lane * DIM, s_crange + lane * 2 * DIM, heuristic, size_weight, &e, &d);
+        const uint64_t s = lane == 0 ? uint64_t(slot) : slot1;
+        err[s] = e; errdim[s] = d;
+    }
+}
+
+// the root region: samples are already in data[.][0]; compute its heuristic
+template<int SH, int SL, int DIM>
+__global__ void root_error_kernel(uint64_t cap, const float* __restrict__ rmin, const float* __restrict__ rmax, const float* __restrict__ data,
+                                  float* __restrict__ err, uint32_t* __restrict__ errdim, int heuristic, int metric, double size_weight) {
+    using Sh = D_::GreedyShape<SH, SL, DIM>;
+    extern __shared__ float smem[];
+    float* s_data = smem; float* s_work = s_data + Sh::SD; float* s_range = s_work + Sh::L; float* s_E = s_range + 2 * DIM;
+    const unsigned lane = threadIdx.x;
+    for (int k = lane; k < Sh::SD; k += 32) s_data[k] = data[uint64_t(k) * cap];
+    if (lane < DIM) { s_range[lane] = rmin[uint64_t(lane) * cap]; s_range[DIM + lane] = rmax[uint64_t(lane) * cap]; }
+    __syncwarp();
+    float vol = 1.0f; for (int d = 0; d < DIM; ++d) vol = R::fm(vol, R::fs(s_range[DIM + d], s_range[d]));
+    for (int d = 0; d < DIM; ++d) {
+        const float e = D_::region_error_warp<SH, SL, DIM>(s_data, vol, d, metric == VB200_METRIC_RELATIVE, s_work, lane);
+        if (lane == 0) s_E[d] = e;
+        __syncwarp();
+    }
+    if (lane == 0) { float e; unsigned d; D_::heuristic_pick<DIM>(s_E, s_range, heuristic, size_weight, &e, &d); err[0] = e; errdim[0] = d; }
+}
+
+template<int SH, int SL, int DIM>
+int run_rounds(vb200_ctx* ctx, const vb200_integrand* f, const vb200_adaptive_params* p, vb200_regions* r,
+               SelectState* st, unsigned* hist, unsigned* cta_gt, unsigned* cta_eq, unsigned* sel, float* points, float* vals, uint64_t max_batch) {
+    using Sh = D_::GreedyShape<SH, SL, DIM>;
+    const uint64_t cap = r->capacity;
+    cudaStream_t s = ctx->stream;
+    root_error_kernel<SH, SL, DIM><<<1, 32, (Sh::SD + Sh::L + 4 * DIM) * sizeof(float), s>>>(cap, r->rmin, r->rmax, r->data, r->err, r->errdim, p->heuristic, p->metric, p->size_weight);
+    ctx->launches++;
+    VB200_CUDA(ctx, cudaGetLastError());
+    const size_t per_warp = (3 * Sh::SD + Sh::L + 4 * DIM + 2 * DIM + 2) * sizeof(float);
+    int wpc = int((96u << 10) / per_warp); if (wpc > 8) wpc = 8; if (wpc < 1) wpc = 1;
+    auto kchild = split_children_kernel<SH, SL, DIM>;
+    VB200_CUDA(ctx, cudaFuncSetAttribute(kchild, cudaFuncAttributeMaxDynamicSharedMemorySize, int(per_warp * wpc)));
+    const uint64_t Q = uint64_t(SH - 1) * Sh::L;
+    uint64_t n = 1, left = p->iterations;
+    while (left > 0) {
+        uint64_t B = n / 4; if (B < 1) B = 1; if (B > left) B = left; if (B > max_batch) B = max_batch;
+        if (p->batch > 1 && B > uint64_t(p->batch)) B = uint64_t(p->batch);
+        // 1. radix top-k
+        select_init_kernel<<<1, 256, 0, s>>>(st, B, hist);
+        const unsigned hgrid = unsigned(std::min<uint64_t>((n + 255) / 256, uint64_t(ctx->sm_count) * 8));
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            select_hist_kernel<<<hgrid, 256, 0, s>>>(r->err, n, st, shift, hist);
+            select_pick_kernel<<<1, 256, 0, s>>>(st, shift, hist);
+        }
+        const unsigned nctas = unsigned((n + 1023) / 1024);
+        select_count_kernel<<<nctas, 256, 0, s>>>(r->err, n, st, cta_gt, cta_eq);
+        select_scan_kernel<<<1, 1024, 0, s>>>(cta_gt, cta_eq, nctas);
+        select_write_kernel<<<nctas, 1024, 0, s>>>(r->err, n, st, cta_gt, cta_eq, sel);
+        // 2. new sample points of all B splits, one integrand launch
+        const uint64_t N = B * Q;
+        split_points_kernel<<<unsigned((N + 255) / 256), 256, 0, s>>>(SH, DIM, cap, B, sel, r->rmin, r->rmax, r->errdim, points);
+        ctx->launches += 13;
+        VB200_CUDA(ctx, cudaGetLastError());
+        vb200_eval_launch ev; std::memset(&ev, 0, sizeof(ev));
+        ev.n = N; ev.dim = DIM; ev.points = points; ev.values = vals;
+        int rc = call_thunk(ctx, f, VB200_K_EVAL_POINTS, &ev); if (rc) return rc;
+        // 3. children + heuristics
+        kchild<<<unsigned((B + wpc - 1) / wpc), wpc * 32, per_warp * wpc, s>>>(cap, B, n, sel, vals, r->rmin, r->rmax, r->data, r->err, r->errdim,
+                                                                               p->heuristic, p->metric, p->size_weight);
+        ctx->launches++;
+        VB200_CUDA(ctx, cudaGetLastError());
+        n += B; left -= B;
+    }
+    r->count = n;
+    return VB200_OK;
+}
+
+} // namespace
+
+namespace vb200 {
+
+__global__ void root_points_kernel(int S, int dim, uint64_t n, const float* rmin, const float* rmax, float* points) {
+    const uint64_t k = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    uint64_t t = k;
+    for (int d = 0; d < dim; ++d) {
+        const double p = R::dd(double(t % uint64_t(S)), double(S - 1)); t /= uint64_t(S);
+        points[uint64_t(d) * n + k] = D_::grid_coord(p, rmin[d], rmax[d]);
+    }
+}
+__global__ void scatter_root_kernel(uint64_t n, uint64_t cap, int dim, const float* vals, const float* lo, const float* hi, float* data, float* rmin, float* rmax) {
+    const uint64_t k = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (k < n) data[k * cap] = vals[k];
+    if (k < uint64_t(dim)) { rmin[k * cap] = lo[k]; rmax[k * cap] = hi[k]; }
+}
+
+int generate_batched(vb200_ctx* ctx, const vb200_integrand* f, const vb200_adaptive_params* p, vb200_regions** out) {
+    vb200_regions* r = nullptr;
+    const uint64_t cap = p->iterations + 1;
+    int rc = regions_alloc(ctx, f->dim, p->rule, cap, &r); if (rc) return rc;
+    const int D = f->dim, S = r->SH; const uint64_t sd = uint64_t(r->sd);
+    uint64_t L = 1; for (int i = 0; i < D - 1; ++i) L *= uint64_t(S);
+    const uint64_t Q = uint64_t(S - 1) * L;
+    // bound the per-round buffers: at most ~32 Mi new sample points per round
+    uint64_t max_batch = (32ull << 20) / Q; if (max_batch < 1) max_batch = 1;
+    const uint64_t maxN = std::max<uint64_t>(std::min<uint64_t>(max_batch, cap) * Q, sd);
+    SelectState* st = nullptr; unsigned *hist = nullptr, *cta_gt = nullptr, *cta_eq = nullptr, *sel = nullptr; float *points = nullptr, *vals = nullptr, *lohi = nullptr;
+    auto cleanup = [&] () { cudaFree(st); cudaFree(hist); cudaFree(cta_gt); cudaFree(cta_eq); cudaFree(sel); cudaFree(points); cudaFree(vals); cudaFree(lohi); };
+    auto bail = [&] (int code) { cudaStreamSynchronize(ctx->stream); cleanup(); vb200_regions_free(r); return code; };
+    const uint64_t nctas_max = (cap + 1023) / 1024;
+    if (cudaMalloc(&st, sizeof(SelectState)) != cudaSuccess || cudaMalloc(&hist, 256 * sizeof(unsigned)) != cudaSuccess ||
+        cudaMalloc(&cta_gt, nctas_max * sizeof(unsigned)) != cudaSuccess || cudaMalloc(&cta_eq, nctas_max * sizeof(unsigned)) != cudaSuccess ||
+        cudaMalloc(&sel, std::min<uint64_t>(max_batch, cap) * sizeof(unsigned)) != cudaSuccess || cudaMalloc(&points, maxN * D * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&vals, maxN * sizeof(float)) != cudaSuccess || cudaMalloc(&lohi, 2 * VB200_MAX_DIM * sizeof(float)) != cudaSuccess) {
+        cudaGetLastError(); return bail(fail(ctx, VB200_ERR_NOMEM, "working set of the batched refinement does not fit")); }
+    // root region (regions-generator-adaptive-heap.h:27)
+    float h_lohi[2 * VB200_MAX_DIM];
+    for (int d = 0; d < D; ++d) { h_lohi[d] = p->domain.rmin[d]; h_lohi[VB200_MAX_DIM + d] = p->domain.rmax[d]; }
+    if (cudaMemcpyAsync(lohi, h_lohi, sizeof(h_lohi), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return bail(fail(ctx, VB200_ERR_CUDA, "range upload failed"));
+    root_points_kernel<<<unsigned((sd + 255) / 256), 256, 0, ctx->stream>>>(S, D, sd, lohi, lohi + VB200_MAX_DIM, points);
+    ctx->launches++;
+    vb200_eval_launch ev; std::memset(&ev, 0, sizeof(ev));
+    ev.n = sd; ev.dim = D; ev.points = points; ev.values = vals;
+    rc = call_thunk(ctx, f, VB200_K_EVAL_POINTS, &ev); if (rc) return bail(rc);
+    scatter_root_kernel<<<unsigned((std::max<uint64_t>(sd, uint64_t(D)) + 255) / 256), 256, 0, ctx->stream>>>(sd, cap, D, vals, lohi, lohi + VB200_MAX_DIM, r->data, r->rmin, r->rmax);
+    ctx->launches++;
+    rc = VB200_ERR_UNSUPPORTED;
+#define VB200_RB(SH_, SL_, DD) if (r->SH == SH_ && r->SL == SL_ && D == DD) rc = run_rounds<SH_, SL_, DD>(ctx, f, p, r, st, hist, cta_gt, cta_eq, sel, points, vals, max_batch);
+    VB200_RB(3, 2, 1) VB200_RB(3, 2, 2) VB200_RB(3, 2, 3) VB200_RB(3, 2, 4) VB200_RB(3, 2, 5) VB200_RB(3, 2, 6)
+    VB200_RB(5, 3, 1) VB200_RB(5, 3, 2) VB200_RB(5, 3, 3) VB200_RB(5, 3, 4) VB200_RB(5, 3, 5)
+#undef VB200_RB
+    if (rc == VB200_ERR_UNSUPPORTED) return bail(fail(ctx, VB200_ERR_UNSUPPORTED, "batched refinement: rule/dimension combination not instantiated"));
+    if (rc) return bail(rc);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return bail(fail(ctx, VB200_ERR_CUDA, "batched refinement failed: %s", cudaGetErrorString(e)));
+    cleanup();
+    *out = r;
+    return VB200_OK;
+}
+
+} // namespace vb200

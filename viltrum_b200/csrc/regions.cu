@@ -536,5 +536,6 @@ extern "C" int vb200_regions_generate_adaptive(vb200_ctx* ctx, const vb200_integ
     if (p->metric != VB200_METRIC_ABSOLUTE && p->metric != VB200_METRIC_RELATIVE) return fail(ctx, VB200_ERR_INVALID, "unknown metric %d", p->metric);
     if (p->iterations >= (1ull << 27)) return fail(ctx, VB200_ERR_UNSUPPORTED, "more than 2^27 iterations");
     if (p->batch == 1) return generate_greedy(ctx, f, p, out);
-    return fail(ctx, VB200_ERR_UNSUPPORTED, "batched refinement (batch=%d) is not implemented yet; batch=1 reproduces the reference's greedy order", p->batch);
+    if (p->batch < 0) return fail(ctx, VB200_ERR_INVALID, "batch=%d", p->batch);
+    return generate_batched(ctx, f, p, out);
 }
