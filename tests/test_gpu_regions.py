@@ -213,3 +213,26 @@ def test_batched_refinement_converges(ctx, port, integ, rule, res, it, mean_tol,
     assert abs(float(bins.mean()) - float(fine.mean())) < mean_tol * max(1.0, abs(float(fine.mean())))
     assert np.allclose(bins, fine, rtol=2e-2, atol=bin_tol)
     regs.free()
+
+
+@pytest.mark.parametrize("integ,res,rule,it", [("smooth_edge2", [64, 64], "boole_simpson", 3000), ("shade5_16", [40, 36], "simpson_trapezoidal", 500),
+                                               ("poly3", [20, 18, 10], "simpson_trapezoidal", 300), ("x2y2", [600], "simpson_trapezoidal", 70000)])
+def test_region_major_tile_lists_keep_table_order(ctx, port, integ, res, rule, it, monkeypatch):
+    """large tables bin regions into tiles with atomics and sort every tile list back into table order (shared-memory bitonic
+    sort; global-memory fallback beyond 32768 regions per tile — the 1-D case): bins stay bit-identical to the brute-force path."""
+    d = DIMS[integ]
+    if len(res) <= 2:
+        want, reg = port.adaptive_iterations(integ, rule, "size_relative", it, res, [0.0] * d, [1.0] * d)
+    else:
+        _, reg = port.adaptive_iterations(integ, rule, "size_relative", it, res[:2], [0.0] * d, [1.0] * d)
+        want = None
+    regs = ctx.regions_upload(rule, reg["min"], reg["max"], reg["err"], reg["dim"], reg["data"])
+    brute = np.zeros(int(np.prod(res)), np.float32)
+    regs.integrate_bins(brute, res, _rng(integ))
+    monkeypatch.setenv("VB200_TILE_PAIR_LIMIT", "1")
+    major = np.zeros(int(np.prod(res)), np.float32)
+    regs.integrate_bins(major, res, _rng(integ))
+    assert_same_bits(major, brute, "region-major == brute force")
+    if want is not None:
+        assert_same_bits(major, want, "== oracle")
+    regs.free()

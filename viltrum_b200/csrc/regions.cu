@@ -6,6 +6,7 @@
 #include <viltrum_b200/device/rules.cuh>
 #include <vector>
 #include <cstring>
+#include <cstdlib>
 #include <new>
 
 using namespace vb200;
@@ -241,6 +242,60 @@ __global__ void __launch_bounds__(256) tile_lists_kernel(TileGeom g, uint64_t nr
     if (!FILL && threadIdx.x == 0) counts[t] = s_running;
 }
 
+// ---- region-major binning (used when regions x tiles is too large to test every pair) -------------------------------------
+// tiles a region's pixel box touches, restricted to tiles that intersect the shard
+__device__ __forceinline__ void region_tile_box(const TileGeom& g, const uint32_t* pstart, const uint32_t* pend, uint64_t cap, uint64_t r, uint32_t (&t0)[3], uint32_t (&t1)[3]) {
+    for (int d = 0; d < 3; ++d) { t0[d] = 0; t1[d] = 1; }
+    for (int d = 0; d < g.db; ++d) {
+        const uint32_t s = pstart[uint64_t(d) * cap + r], e = pend[uint64_t(d) * cap + r];
+        t0[d] = s / g.tile[d]; t1[d] = min((e + g.tile[d] - 1) / g.tile[d], g.tiles[d]);
+    }
+}
+template<bool FILL>
+__global__ void region_major_kernel(TileGeom g, uint64_t nregions, uint64_t cap, uint64_t begin, uint64_t end,
+                                    const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ pend,
+                                    unsigned long long* __restrict__ counts, const uint64_t* __restrict__ offsets, unsigned long long* __restrict__ cursor, uint32_t* __restrict__ list) {
+    const uint64_t r = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (r >= nregions) return;
+    uint32_t t0[3], t1[3]; region_tile_box(g, pstart, pend, cap, r, t0, t1);
+    for (uint32_t z = t0[2]; z < t1[2]; ++z) for (uint32_t y = t0[1]; y < t1[1]; ++y) for (uint32_t x = t0[0]; x < t1[0]; ++x) {
+        const uint32_t o[3] = {x * g.tile[0], y * g.tile[1], z * g.tile[2]};
+        if (!tile_in_shard(g, o, begin, end)) continue;
+        const uint64_t t = uint64_t(x) + uint64_t(g.tiles[0]) * (uint64_t(y) + uint64_t(g.tiles[1]) * z);
+        if (!FILL) atomicAdd(&counts[t], 1ull);
+        else list[offsets[t] + atomicAdd(&cursor[t], 1ull)] = uint32_t(r);
+    }
+}
+// restore table order inside every tile list: bitonic sort, in shared memory when the list fits (<= 32768 ids), in place
+// in global memory otherwise (rare: one tile touched by more than 32768 regions)
+__global__ void __launch_bounds__(1024) tile_sort_kernel(const uint64_t* __restrict__ offsets, uint32_t* __restrict__ list) {
+    extern __shared__ uint32_t s_ids[];
+    const uint64_t lo = offsets[blockIdx.x], len = offsets[blockIdx.x + 1] - lo;
+    if (len < 2) return;
+    uint64_t P = 1; while (P < len) P <<= 1;
+    uint32_t* a = list + lo;
+    const bool in_smem = P <= 32768;
+    if (in_smem) {
+        for (uint64_t i = threadIdx.x; i < P; i += blockDim.x) s_ids[i] = i < len ? a[i] : 0xffffffffu;
+        __syncthreads();
+    }
+    for (uint64_t k = 2; k <= P; k <<= 1) for (uint64_t j = k >> 1; j > 0; j >>= 1) {
+        for (uint64_t i = threadIdx.x; i < P; i += blockDim.x) {
+            const uint64_t l = i ^ j;
+            if (l > i) {
+                const bool up = (i & k) == 0;
+                if (in_smem) { const uint32_t x = s_ids[i], y = s_ids[l]; if ((x > y) == up) { s_ids[i] = y; s_ids[l] = x; } }
+                else {      // virtual padding: positions >= len hold +inf
+                    const uint32_t x = i < len ? a[i] : 0xffffffffu, y = l < len ? a[l] : 0xffffffffu;
+                    if ((x > y) == up) { if (i < len) a[i] = y; if (l < len) a[l] = x; }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (in_smem) for (uint64_t i = threadIdx.x; i < len; i += blockDim.x) a[i] = s_ids[i];
+}
+
 // closed-form integral of the region's (marginalised) tensor-product interpolant over bin ∩ region:
 // Region::integral_subrange -> sub_last (region.h:141-169), folding subrange(a_d,b_d) over the binned dims DB-1, ..., 0.
 template<int S, int DB>
@@ -426,7 +481,17 @@ int walk_build(vb200_ctx* ctx, const vb200_regions* r, const vb200_domain& dom, 
     const TileGeom g = make_geom(*w, dom);
     VB200_TRY(cudaMalloc(&w->tile_offset, (w->ntiles + 1) * sizeof(uint64_t)));
     unsigned long long* counts = reinterpret_cast<unsigned long long*>(w->tile_offset);
-    tile_lists_kernel<false><<<unsigned(w->ntiles), 256, 0, ctx->stream>>>(g, n, cap, begin, end, w->pstart, w->pend, counts, nullptr, nullptr);
+    // every (tile, region) pair tested by brute force keeps table order for free; beyond ~2.7e8 pairs bin the regions into
+    // their tiles with atomics instead and sort each tile list back into table order
+    uint64_t pair_limit = 1ull << 28;
+    if (const char* env = std::getenv("VB200_TILE_PAIR_LIMIT")) pair_limit = std::strtoull(env, nullptr, 10);     // test knob
+    const bool region_major = w->ntiles * n > pair_limit && w->ntiles > 1;
+    if (region_major) {
+        VB200_TRY(cudaMemsetAsync(counts, 0, (w->ntiles + 1) * sizeof(uint64_t), ctx->stream));
+        region_major_kernel<false><<<unsigned((n + 255) / 256), 256, 0, ctx->stream>>>(g, n, cap, begin, end, w->pstart, w->pend, counts, nullptr, nullptr, nullptr);
+    } else {
+        tile_lists_kernel<false><<<unsigned(w->ntiles), 256, 0, ctx->stream>>>(g, n, cap, begin, end, w->pstart, w->pend, counts, nullptr, nullptr);
+    }
     ctx->launches++;
     VB200_TRY(cudaGetLastError());
     std::vector<uint64_t> h(w->ntiles + 1);
@@ -436,10 +501,23 @@ int walk_build(vb200_ctx* ctx, const vb200_regions* r, const vb200_domain& dom, 
     w->pairs = run;
     VB200_TRY(cudaMemcpyAsync(w->tile_offset, h.data(), (w->ntiles + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
     VB200_TRY(cudaMalloc(&w->tile_list, (run + 1) * sizeof(uint32_t)));
-    tile_lists_kernel<true><<<unsigned(w->ntiles), 256, 0, ctx->stream>>>(g, n, cap, begin, end, w->pstart, w->pend, nullptr, w->tile_offset, w->tile_list);
-    ctx->launches++;
-    VB200_TRY(cudaGetLastError());
-    VB200_TRY(cudaStreamSynchronize(ctx->stream));       // h goes out of scope
+    if (region_major) {
+        unsigned long long* cursor = nullptr;
+        VB200_TRY(cudaMalloc(&cursor, w->ntiles * sizeof(unsigned long long)));
+        cudaError_t e1 = cudaMemsetAsync(cursor, 0, w->ntiles * sizeof(unsigned long long), ctx->stream);
+        region_major_kernel<true><<<unsigned((n + 255) / 256), 256, 0, ctx->stream>>>(g, n, cap, begin, end, w->pstart, w->pend, nullptr, w->tile_offset, cursor, w->tile_list);
+        cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4);
+        tile_sort_kernel<<<unsigned(w->ntiles), 1024, 32768 * 4, ctx->stream>>>(w->tile_offset, w->tile_list);
+        ctx->launches += 2;
+        cudaError_t e2 = cudaGetLastError(), e3 = cudaStreamSynchronize(ctx->stream);
+        cudaFree(cursor);
+        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) return bail(fail(ctx, VB200_ERR_CUDA, "tile list construction failed: %s", cudaGetErrorString(e3 != cudaSuccess ? e3 : e2 != cudaSuccess ? e2 : e1)));
+    } else {
+        tile_lists_kernel<true><<<unsigned(w->ntiles), 256, 0, ctx->stream>>>(g, n, cap, begin, end, w->pstart, w->pend, nullptr, w->tile_offset, w->tile_list);
+        ctx->launches++;
+        VB200_TRY(cudaGetLastError());
+        VB200_TRY(cudaStreamSynchronize(ctx->stream));       // h goes out of scope
+    }
 #undef VB200_TRY
     return VB200_OK;
 }
