@@ -157,7 +157,9 @@ def main():
     nb_local = res[0] * res[1]
     # weak scaling: the global grid is res[0] x (res[1]*world); this rank owns rows [rank*res[1], (rank+1)*res[1])
     gres = [res[0], res[1] * world]
-    shard = (rank * nb_local, (rank + 1) * nb_local)
+    from viltrum_b200 import shard_for_rank
+    shard = shard_for_rank(gres, rank, world)
+    assert shard == (rank * nb_local, (rank + 1) * nb_local)
     rng = RangeInfinite() if inf else Range([0.0] * 4, [1.0] * 4)
     d_bins = torch.zeros(gres[0] * gres[1], dtype=torch.float32, device="cuda")
     h_bins = np.zeros(gres[0] * gres[1], np.float32)

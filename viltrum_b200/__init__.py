@@ -5,5 +5,5 @@ the thin host-side mirror used by the tests and the benchmark (ctypes over the C
 from .host import (Context, Regions, integrate, monte_carlo, monte_carlo_per_bin_parallel, integrator_per_bin_parallel,  # noqa: F401
                    integrator_newton_cotes, integrator_adaptive_iterations, integrator_crespo2021, nested,
                    error_heuristic_default, error_heuristic_size, error_metric_absolute, error_metric_relative,
-                   range_primary, range_primary_infinite, Range, RangeInfinite, builtin_names)
+                   range_primary, range_primary_infinite, Range, RangeInfinite, builtin_names, shard_for_rank, sample_shard_for_rank)
 from ._capi import Vb200Error  # noqa: F401

@@ -137,7 +137,14 @@ class Context:
         p.spp, p.seed, p.flavor = int(spp), int(seed) & 0xFFFFFFFFFFFFFFFF, flavor
         return p
 
+    @staticmethod
+    def _empty(shard):
+        """an explicit empty shard (a rank with no rows): nothing to do — {0,0} in the C ABI means 'whole grid'"""
+        return shard is not None and shard[0] == shard[1]
+
     def mc_per_bin(self, f, bins, res, rng, spp, seed, flavor=C.MC_PER_BIN, shard=None, sum_f=None, sum_f2=None, exact=False):
+        if self._empty(shard):
+            return
         b, mem, _k = _buffer(bins)
         s1, m1, _k1 = _buffer(sum_f); s2, m2, _k2 = _buffer(sum_f2)
         p = self._mc_params(len(rng.min), res, rng, spp, seed, flavor, shard)
@@ -149,6 +156,8 @@ class Context:
         self.check(self._L.vb200_mc_per_bin_replay(self._h, self.integrand(f, exact), ctypes.byref(p), s, smem, b, mem))
 
     def mc_per_bin_inf(self, f, bins, res, rng, spp, seed, shard=None, sum_f=None, sum_f2=None, exact=False):
+        if self._empty(shard):
+            return
         b, mem, _k = _buffer(bins)
         s1, m1, _k1 = _buffer(sum_f); s2, m2, _k2 = _buffer(sum_f2)
         p = self._mc_params(len(rng.min), res, rng, spp, seed, C.MC_PER_BIN, shard)
@@ -218,6 +227,8 @@ class Regions:
         return out
 
     def integrate_bins(self, bins, res, rng, shard=None):
+        if Context._empty(shard):
+            return
         b, mem, _k = _buffer(bins)
         d = C.make_domain(len(rng.min), res, rng.min, rng.max)
         s = C.Shard(); s.begin, s.end = (shard if shard else (0, 0))
@@ -231,6 +242,8 @@ class Regions:
         return p
 
     def cv_integrate(self, f, bins, res, rng, spp, seed, shard=None, nregions=None, approx=None, exact=False):
+        if Context._empty(shard):
+            return
         b, mem, _k = _buffer(bins)
         n, _m, _kn = _buffer(nregions, np.uint32); a, _m2, _ka = _buffer(approx)
         p = self._cv_params(res, rng, spp, seed, shard)
@@ -415,6 +428,27 @@ def integrator_adaptive_iterations(rule, heuristic=None, iterations=None, batch=
 
 def integrator_crespo2021(iterations, spp, seed=0, batch=1):
     return IntegratorCrespo2021(iterations, spp, seed, batch)
+
+
+# ---- multi-GPU partitioning (one process per GPU) ---------------------------------------------------
+def shard_for_rank(resolution, rank, world):
+    """Bin-grid slab of `rank`: a contiguous range [begin, end) of linear bin indices (tensor order) made of whole rows of the
+    LAST bin dimension, so that every rank owns one contiguous block of the flat bin array.  Ranks beyond the number of rows
+    get an empty shard (begin == end != 0 is passed explicitly; {0,0} would mean 'whole grid')."""
+    resolution = [int(r) for r in resolution]
+    rows = resolution[-1]
+    stride = 1
+    for r in resolution[:-1]:
+        stride *= r
+    lo = rows * rank // world
+    hi = rows * (rank + 1) // world
+    return lo * stride, hi * stride
+
+
+def sample_shard_for_rank(samples, rank, world):
+    """Sample-index range of `rank` for the split-sample mode of monte_carlo (few bins, many samples): every rank draws its own
+    range of the global sample counter and the partial grids are summed (the one allreduce of the design)."""
+    return int(samples) * rank // world, int(samples) * (rank + 1) // world
 
 
 _default_ctx = {}
