@@ -135,9 +135,12 @@ struct InfiniteThunks {
     // not default-constructible)
     static F functor(const vb200_integrand* self) { return *static_cast<const F*>(self->functor); }
 
+    template<int DB, bool MOMENTS> static auto wavefront_or_plain(std::true_type) { return device::walk_wavefront_kernel<F, DB, MOMENTS, EXACT>; }
+    template<int DB, bool MOMENTS> static auto wavefront_or_plain(std::false_type) { return device::walk_kernel<F, DB, MOMENTS, EXACT>; }
     template<int DB, bool MOMENTS>
     static int launch_walk(const F& f, const vb200_walk_launch& a, cudaStream_t st) {
-        auto k = device::walk_kernel<F, DB, MOMENTS, EXACT>;
+        // functors that also describe themselves as a state machine get the wavefront kernel (lane refill)
+        auto k = wavefront_or_plain<DB, MOMENTS>(std::integral_constant<bool, device::has_steps<F>::value>());
         const uint64_t bins_per_cta = uint64_t(device::MC_THREADS) / a.lanes_per_bin;
         const uint64_t ctas = (a.bin_end - a.bin_begin + bins_per_cta - 1) / bins_per_cta;
         const int grid = persistent_grid(k, device::MC_THREADS, ctas, a.grid_hint);

@@ -8,6 +8,7 @@
 // so a lane needs no per-bin generator state and any lane can produce any element.  Each lane owns whole paths
 // and runs its own Russian roulette inside the user's functor.
 #pragma once
+#include <type_traits>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include "../../viltrum_b200.h"
@@ -36,6 +37,7 @@ struct PhiloxSequence {
         }
     public:
         __device__ __forceinline__ const_iterator(const PhiloxSequence* q_) : q(q_), i(0) { load(); }
+        __device__ __forceinline__ const_iterator(const PhiloxSequence* q_, int) : q(q_), i(0), blk{0, 0, 0, 0}, n(0.0f) {}      // unarmed (wavefront kernel)
         __device__ __forceinline__ const float& operator*() const { return n; }
         __device__ __forceinline__ const_iterator& operator++() { ++i; load(); return *this; }
         __device__ __forceinline__ bool operator!=(const const_iterator&) const { return true; }   // infinite list
@@ -91,6 +93,87 @@ walk_kernel(const F f, const vb200_walk_launch a) {
         }
         if (live && sub == 0) {
             const float v = float(double(sum) * a.factor);               // monte-carlo-per-bin-parallel.h:77,96
+            a.out[bin] = a.accumulate ? float(double(a.out[bin]) + double(v)) : v;
+            if (MOMENTS) {
+                if (a.sum_f)  a.sum_f[bin - a.bin_begin]  = sum;
+                if (a.sum_f2) a.sum_f2[bin - a.bin_begin] = sum2;
+            }
+        }
+        if (lane == 0) tile = atomicAdd(a.tile_counter, 1ull);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+    }
+}
+
+// ---- wavefront variant: per-lane Russian roulette with lane refill ---------------------------------------------------------
+// A functor may ALSO describe itself as a state machine (besides the reference's operator()(seq)):
+//     struct State {...};
+//     template<class It> __device__ State begin(It& it) const;          // start of a path: consumes its first elements
+//     template<class It> __device__ bool  step(State& s, It& it) const; // one roulette round; false = the path ended
+//     __device__ float end(const State& s) const;                       // the path's value
+// with begin/step/end performing exactly the arithmetic of operator().  Then a lane whose path has ended does not idle until the
+// longest path of its warp is done: dead lanes are re-armed with their next sample as soon as REFILL of the 32 lanes are dead,
+// and all live lanes execute step() together.  Paths consume the same Philox elements in the same order as in the generic kernel
+// and a lane adds its samples in the same order, so the bins are bit-identical to walk_kernel's.
+template<class F, class = void> struct has_steps : std::false_type {};
+template<class F> struct has_steps<F, std::void_t<typename F::State>> : std::true_type {};
+
+// REFILL: dead lanes needed before a re-arm round; STEPS: roulette rounds per loop iteration.  A path consumes a fixed number of
+// sequence elements per begin()/step(); when STEPS*elements-per-step is a multiple of 4 every live lane crosses its Philox block
+// boundary at the same instruction, so the generator runs once per iteration at full lane utilisation instead of once per step
+// at half (measured: profiles/walk_variants_r1.txt).
+template<class F, int DIMBINS, bool MOMENTS, bool EXACT, int REFILL = 8, int STEPS = 2>
+__global__ void __launch_bounds__(MC_THREADS)
+walk_wavefront_kernel(const F f, const vb200_walk_launch a) {
+    const uint32_t LPB = a.lanes_per_bin, G = 32u / LPB;
+    const uint32_t lane = threadIdx.x & 31u, sub = lane % LPB, grp = lane / LPB;
+    const uint64_t nshard = a.bin_end - a.bin_begin;
+    const uint64_t ntiles = (nshard + G - 1) / G;
+    uint64_t tile = 0;
+    if (lane == 0) tile = atomicAdd(a.tile_counter, 1ull);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    while (tile < ntiles) {
+        const uint64_t bin = a.bin_begin + tile * G + grp;
+        const bool live = bin < a.bin_end;
+        float sum = 0.0f, sum2 = 0.0f;
+        PhiloxSequence<DIMBINS> seq;
+        seq.b0 = uint32_t(bin); seq.b1 = uint32_t(bin >> 32); seq.k0 = a.key0; seq.k1 = a.key1; seq.dom = &a.domain; seq.s = 0;
+        if (live) walk_bin_box<DIMBINS>(a.domain, bin, seq.lo, seq.ext);
+        else { for (int d = 0; d < DIMBINS; ++d) { seq.lo[d] = 0.0f; seq.ext[d] = 1.0f; } }
+        uint32_t next = live ? sub : a.spp;          // next sample this lane will start
+        bool alive = false;
+        typename F::State st;
+        typename PhiloxSequence<DIMBINS>::const_iterator it(&seq, 0);      // unarmed
+        while (true) {
+            const unsigned alive_mask = __ballot_sync(0xffffffffu, alive);
+            const unsigned want_mask = __ballot_sync(0xffffffffu, !alive && next < a.spp);
+            if (alive_mask == 0u && want_mask == 0u) break;
+            // re-arm dead lanes in batches: when enough of them wait, or when nobody is alive any more
+            if (want_mask != 0u && (__popc(want_mask) >= REFILL || alive_mask == 0u)) {
+                if (!alive && next < a.spp) {
+                    seq.s = next; next += LPB;
+                    it = seq.begin();
+                    st = f.begin(it);
+                    alive = true;
+                }
+            }
+#pragma unroll
+            for (int rep = 0; rep < STEPS; ++rep) {
+                if (alive) {
+                    if (!f.step(st, it)) {
+                        const float v = f.end(st);
+                        sum += v;
+                        if (MOMENTS) sum2 = fmaf(v, v, sum2);
+                        alive = false;
+                    }
+                }
+            }
+        }
+        for (uint32_t off = LPB >> 1; off > 0; off >>= 1) {
+            sum += __shfl_xor_sync(0xffffffffu, sum, off);
+            if (MOMENTS) sum2 += __shfl_xor_sync(0xffffffffu, sum2, off);
+        }
+        if (live && sub == 0) {
+            const float v = float(double(sum) * a.factor);
             a.out[bin] = a.accumulate ? float(double(a.out[bin]) + double(v)) : v;
             if (MOMENTS) {
                 if (a.sum_f)  a.sum_f[bin - a.bin_begin]  = sum;

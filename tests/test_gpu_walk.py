@@ -119,3 +119,15 @@ def test_global_scatter_split_samples_sum_to_whole(ctx):
     tot = sum(p.double() for p in parts)
     assert torch.allclose(tot, whole.double(), rtol=1e-4, atol=1e-5)      # float atomics: order differs, values agree
     assert abs(float(whole.mean()) - 0.1430) < 5e-3
+
+
+def test_wavefront_kernel_equals_generic_kernel(ctx):
+    """'walk' carries the state-machine form (wavefront kernel, lane refill), 'walk_plain' only operator()(seq) (generic per-lane
+    kernel): same Philox elements, same per-lane summation order -> bit-identical bins."""
+    from viltrum_b200 import RangeInfinite
+    for res, spp in (([64, 48], 256), ([100], 37), ([9, 7, 5], 64)):
+        nb = int(np.prod(res))
+        a = np.zeros(nb, np.float32); b = np.zeros(nb, np.float32)
+        ctx.mc_per_bin_inf("walk", a, res, RangeInfinite(), spp, 5)
+        ctx.mc_per_bin_inf("walk_plain", b, res, RangeInfinite(), spp, 5)
+        assert_same_bits(a, b, f"wavefront vs generic {res}")

@@ -48,6 +48,22 @@ struct Walk {
                        const float s = *it; ++it; pos = .5f*pos+.5f*s; L += .25f+pos*pos; }
         return L;
     }
+    // the same path as a state machine (include/viltrum_b200/device/walk.cuh, wavefront kernel): identical arithmetic
+    struct State { float alb, pos, L; };
+    template<typename It> __host__ __device__ State begin(It& it) const {
+        const float px = *it; ++it; const float py = *it; ++it;
+        return State{.4f+.5f*(4.0f*px*(1.0f-px))*(.25f+.75f*py), .5f, 0.0f};
+    }
+    template<typename It> __host__ __device__ bool step(State& st, It& it) const {
+        const float u = *it; ++it; if (u>=st.alb) return false;
+        const float s = *it; ++it; st.pos = .5f*st.pos+.5f*s; st.L += .25f+st.pos*st.pos;
+        return true;
+    }
+    __host__ __device__ float end(const State& st) const { return st.L; }
+};
+// same integrand WITHOUT the state-machine form: keeps the generic per-lane kernel measurable and tested
+struct WalkPlain {
+    template<typename Seq> __host__ __device__ float operator()(const Seq& seq) const { return Walk()(seq); }
 };
 struct Decay {
     template<typename Seq> __host__ __device__ float operator()(const Seq& seq) const {
