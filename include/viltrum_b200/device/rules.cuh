@@ -96,6 +96,6 @@ template<int SH, int SL> __device__ __forceinline__ float line_error(bool relati
 // range.h:45-53
 __device__ __forceinline__ float pos_in_range(float lo, float hi, float p) { return (lo >= hi) ? lo : fd(fs(p, lo), fs(hi, lo)); }
 
-__device__ __forceinline__ int ipow(int s, int d) { int r = 1; for (int i = 0; i < d; ++i) r *= s; return r; }
+__host__ __device__ constexpr int ipow(int s, int d) { return d <= 0 ? 1 : s * ipow(s, d - 1); }
 
 }}}} // namespace viltrum::b200::device::rules

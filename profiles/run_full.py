@@ -6,6 +6,7 @@ import numpy as np
 import torch
 from viltrum_b200 import Context, Range
 which = sys.argv[1] if len(sys.argv) > 1 else "c3"
+batch = int(os.environ.get("BATCH", "1"))
 ctx = Context(0)
 def tic(): ctx.synchronize(); return time.perf_counter()
 if which == "c3":
@@ -14,7 +15,7 @@ if which == "c3":
     rng = Range([0, 0], [1, 1])
     for rep in range(2):
         t0 = tic()
-        regs = ctx.regions_generate_adaptive("smooth_edge2", rng, "boole_simpson", "size", "relative", it, 1e-5, batch=1, exact=True)
+        regs = ctx.regions_generate_adaptive("smooth_edge2", rng, "boole_simpson", "size", "relative", it, 1e-5, batch=batch, exact=True)
         t1 = tic()
         bins = torch.zeros(w * w, dtype=torch.float32, device="cuda")
         regs.integrate_bins(bins, [w, w], rng)
@@ -28,7 +29,7 @@ elif which == "c4":
     rng = Range([0] * 5, [1] * 5)
     for rep in range(2):
         t0 = tic()
-        regs = ctx.regions_generate_adaptive("shade5_64", rng, "simpson_trapezoidal", "size", "relative", it, 1e-5, batch=1, exact=True)
+        regs = ctx.regions_generate_adaptive("shade5_64", rng, "simpson_trapezoidal", "size", "relative", it, 1e-5, batch=batch, exact=True)
         t1 = tic()
         bins = torch.zeros(w * w, dtype=torch.float32, device="cuda")
         nreg = torch.zeros(w * w, dtype=torch.int32, device="cuda")

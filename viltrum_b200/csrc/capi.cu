@@ -31,6 +31,12 @@ int reserve(vb200_ctx* ctx, int slot, size_t bytes, void** out) {
     return VB200_OK;
 }
 
+cudaError_t dmalloc_bytes(vb200_ctx* ctx, void** p, size_t bytes) {
+    *p = nullptr;
+    return cudaMallocAsync(p, bytes ? bytes : 1, ctx->stream);
+}
+void dfree(vb200_ctx* ctx, void* p) { if (p) cudaFreeAsync(p, ctx->stream); }
+
 int reserve_pinned(vb200_ctx* ctx, size_t bytes, void** out) {
     if (bytes > ctx->pinned_bytes) {
         if (ctx->pinned) { VB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); VB200_CUDA(ctx, cudaFreeHost(ctx->pinned)); ctx->pinned = nullptr; ctx->pinned_bytes = 0; }
@@ -131,6 +137,11 @@ extern "C" int vb200_create(int device, vb200_ctx** out) {
         (e = cudaMalloc(&ctx->d_counter, vb200_ctx::kMaxChunks * sizeof(unsigned long long))) != cudaSuccess) {
         int rc = fail(nullptr, VB200_ERR_CUDA, "context setup on device %d failed: %s", device, cudaGetErrorString(e));
         delete ctx; return rc;
+    }
+    {   // keep freed blocks in the device's default memory pool instead of returning them to the OS at every synchronisation
+        cudaMemPool_t pool = nullptr; unsigned long long keep = ~0ull;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        cudaGetLastError();
     }
     for (auto& ev : ctx->chunk_done) if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) {
         int rc = fail(nullptr, VB200_ERR_CUDA, "event creation failed: %s", cudaGetErrorString(e)); vb200_destroy(ctx); return rc; }

@@ -30,6 +30,12 @@ int fail(vb200_ctx* ctx, int status, const char* fmt, ...);
     return vb200::fail(ctx, VB200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); } while (0)
 
 int reserve(vb200_ctx* ctx, int slot, size_t bytes, void** out);
+// Stream-ordered device memory from the device's default CUDA memory pool (cudaMallocAsync on the context's stream; the pool's
+// release threshold is raised at context creation so freed blocks stay cached): the region pipelines allocate and free
+// hundreds of MB per call, and plain cudaMalloc/cudaFree (each an implicit device synchronisation) dominated their wall time.
+cudaError_t dmalloc_bytes(vb200_ctx* ctx, void** p, size_t bytes);
+template<class T> inline cudaError_t dmalloc(vb200_ctx* ctx, T** p, size_t bytes) { return dmalloc_bytes(ctx, reinterpret_cast<void**>(p), bytes); }
+void dfree(vb200_ctx* ctx, void* p);
 int reserve_pinned(vb200_ctx* ctx, size_t bytes, void** out);
 inline uint64_t nbins_of(const vb200_domain& d) { uint64_t n = 1; for (int i = 0; i < d.dimbins; ++i) n *= d.res[i]; return n; }
 int check_domain(vb200_ctx* ctx, const vb200_domain& d, int integrand_dim);

@@ -103,28 +103,29 @@ __global__ void regions_to_aos_kernel(uint64_t n, uint64_t cap, int sd, const fl
     aos[i] = soa[uint64_t(k) * cap + r];
 }
 
-// Region::approximation_at -> app_at (region.h:86-112): fold quadrature.at(t_d, line) over dimension 0, then 1, ... ; float Horner
+// Region::approximation_at -> app_at (region.h:86-112): fold quadrature.at(t_d, line) over dimension 0, then 1, ... ; float Horner.
+// Evaluated depth-first (the value at level d needs S values of level d-1), so only S floats per level are live — registers, no
+// local-memory scratch — while every at() sees exactly the inputs the reference's lazy folds give it.
+template<int S, int LEVEL> struct ApproxLevel {
+    static constexpr int STRIDE = R::ipow(S, LEVEL);       // distance between consecutive indices of dimension LEVEL
+    __device__ __forceinline__ static float eval(const float* __restrict__ data, const float* t) {
+        float v[S];
+#pragma unroll
+        for (int e = 0; e < S; ++e) v[e] = ApproxLevel<S, LEVEL - 1>::eval(data + e * STRIDE, t);
+        return R::at<S>(t[LEVEL], v);
+    }
+};
+template<int S> struct ApproxLevel<S, 0> {
+    __device__ __forceinline__ static float eval(const float* __restrict__ data, const float* t) {
+        float v[S];
+#pragma unroll
+        for (int e = 0; e < S; ++e) v[e] = __ldg(data + e);
+        return R::at<S>(t[0], v);
+    }
+};
 template<int S, int D>
-__device__ float approximation_at(const float* __restrict__ data, const float (&t)[D]) {
-    if (D == 1) { float line[S]; for (int e = 0; e < S; ++e) line[e] = data[e]; return R::at<S>(t[0], line); }
-    int n = 1; for (int i = 0; i < D - 1; ++i) n *= S;
-    float buf[(D == 1) ? 1 : (D == 2 ? S : D == 3 ? S * S : D == 4 ? S * S * S : D == 5 ? S * S * S * S : S * S * S * S * S)];
-    for (int o = 0; o < n; ++o) {
-        float line[S];
-#pragma unroll
-        for (int e = 0; e < S; ++e) line[e] = data[o * S + e];
-        buf[o] = R::at<S>(t[0], line);
-    }
-    for (int d = 1; d < D; ++d) {
-        n /= S;
-        for (int o = 0; o < n; ++o) {
-            float line[S];
-#pragma unroll
-            for (int e = 0; e < S; ++e) line[e] = buf[o * S + e];
-            buf[o] = R::at<S>(t[d], line);      // in place: o <= o*S, reads of this group are done before the write
-        }
-    }
-    return R::fm(buf[0], 1.0f);                  // * volume_from(DIM) == 1  (region.h:47-51,91-92)
+__device__ __forceinline__ float approximation_at(const float* __restrict__ data, const float (&t)[D]) {
+    return R::fm(ApproxLevel<S, D - 1>::eval(data, t), 1.0f);      // * volume_from(DIM) == 1  (region.h:47-51,91-92)
 }
 
 // residual samples: chosen region -> bin ∩ region box -> uniform point, weight, interpolant value.
@@ -237,9 +238,9 @@ int dispatch_samples(vb200_ctx* ctx, bool replay, const vb200_domain& dom, uint6
 }
 
 struct DevBuf {
-    void* p = nullptr;
-    ~DevBuf() { cudaFree(p); }
-    int alloc(vb200_ctx* ctx, size_t bytes) { if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return fail(ctx, VB200_ERR_NOMEM, "cudaMalloc of %zu bytes failed", bytes); } return VB200_OK; }
+    void* p = nullptr; vb200_ctx* owner = nullptr;
+    ~DevBuf() { if (owner) dfree(owner, p); }
+    int alloc(vb200_ctx* ctx, size_t bytes) { owner = ctx; if (dmalloc(ctx, &p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return fail(ctx, VB200_ERR_NOMEM, "cudaMalloc of %zu bytes failed", bytes); } return VB200_OK; }
     template<class T> T* as() const { return static_cast<T*>(p); }
 };
 

@@ -46,9 +46,12 @@ __global__ void __launch_bounds__(256) select_hist_kernel(const float* __restric
 }
 // walk the digits from the top: the digit where the cumulative count reaches k holds the k-th largest key
 __global__ void select_pick_kernel(SelectState* st, int shift, unsigned* hist) {
+    __shared__ unsigned s_h[256];
+    s_h[threadIdx.x] = hist[threadIdx.x];
+    __syncthreads();
     if (threadIdx.x == 0) {
         unsigned long long k = st->k, cum = 0; int d = 255;
-        for (; d > 0; --d) { if (cum + hist[d] >= k) break; cum += hist[d]; }
+        for (; d > 0; --d) { if (cum + s_h[d] >= k) break; cum += s_h[d]; }
         st->k = k - cum; st->prefix_val |= unsigned(d) << shift; st->prefix_mask |= 255u << shift;
     }
     __syncthreads();
@@ -289,13 +292,13 @@ int generate_batched(vb200_ctx* ctx, const vb200_integrand* f, const vb200_adapt
     uint64_t max_batch = (32ull << 20) / Q; if (max_batch < 1) max_batch = 1;
     const uint64_t maxN = std::max<uint64_t>(std::min<uint64_t>(max_batch, cap) * Q, sd);
     SelectState* st = nullptr; unsigned *hist = nullptr, *cta_gt = nullptr, *cta_eq = nullptr, *sel = nullptr; float *points = nullptr, *vals = nullptr, *lohi = nullptr;
-    auto cleanup = [&] () { cudaFree(st); cudaFree(hist); cudaFree(cta_gt); cudaFree(cta_eq); cudaFree(sel); cudaFree(points); cudaFree(vals); cudaFree(lohi); };
+    auto cleanup = [&] () { dfree(ctx, st); dfree(ctx, hist); dfree(ctx, cta_gt); dfree(ctx, cta_eq); dfree(ctx, sel); dfree(ctx, points); dfree(ctx, vals); dfree(ctx, lohi); };
     auto bail = [&] (int code) { cudaStreamSynchronize(ctx->stream); cleanup(); vb200_regions_free(r); return code; };
     const uint64_t nctas_max = (cap + 1023) / 1024;
-    if (cudaMalloc(&st, sizeof(SelectState)) != cudaSuccess || cudaMalloc(&hist, 256 * sizeof(unsigned)) != cudaSuccess ||
-        cudaMalloc(&cta_gt, nctas_max * sizeof(unsigned)) != cudaSuccess || cudaMalloc(&cta_eq, nctas_max * sizeof(unsigned)) != cudaSuccess ||
-        cudaMalloc(&sel, std::min<uint64_t>(max_batch, cap) * sizeof(unsigned)) != cudaSuccess || cudaMalloc(&points, maxN * D * sizeof(float)) != cudaSuccess ||
-        cudaMalloc(&vals, maxN * sizeof(float)) != cudaSuccess || cudaMalloc(&lohi, 2 * VB200_MAX_DIM * sizeof(float)) != cudaSuccess) {
+    if (dmalloc(ctx, &st, sizeof(SelectState)) != cudaSuccess || dmalloc(ctx, &hist, 256 * sizeof(unsigned)) != cudaSuccess ||
+        dmalloc(ctx, &cta_gt, nctas_max * sizeof(unsigned)) != cudaSuccess || dmalloc(ctx, &cta_eq, nctas_max * sizeof(unsigned)) != cudaSuccess ||
+        dmalloc(ctx, &sel, std::min<uint64_t>(max_batch, cap) * sizeof(unsigned)) != cudaSuccess || dmalloc(ctx, &points, maxN * D * sizeof(float)) != cudaSuccess ||
+        dmalloc(ctx, &vals, maxN * sizeof(float)) != cudaSuccess || dmalloc(ctx, &lohi, 2 * VB200_MAX_DIM * sizeof(float)) != cudaSuccess) {
         cudaGetLastError(); return bail(fail(ctx, VB200_ERR_NOMEM, "working set of the batched refinement does not fit")); }
     // root region (regions-generator-adaptive-heap.h:27)
     float h_lohi[2 * VB200_MAX_DIM];

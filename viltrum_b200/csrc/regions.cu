@@ -35,9 +35,9 @@ int regions_alloc(vb200_ctx* ctx, int dim, int rule, uint64_t capacity, vb200_re
     if (!r) return fail(ctx, VB200_ERR_NOMEM, "out of host memory");
     r->ctx = ctx; r->dim = dim; r->rule = rule; r->SH = SH; r->SL = SL; r->sd = int(sd); r->capacity = capacity; r->count = 0;
     cudaError_t e;
-    if ((e = cudaMalloc(&r->rmin, capacity * dim * sizeof(float))) != cudaSuccess || (e = cudaMalloc(&r->rmax, capacity * dim * sizeof(float))) != cudaSuccess ||
-        (e = cudaMalloc(&r->data, capacity * sd * sizeof(float))) != cudaSuccess || (e = cudaMalloc(&r->err, capacity * sizeof(float))) != cudaSuccess ||
-        (e = cudaMalloc(&r->errdim, capacity * sizeof(uint32_t))) != cudaSuccess) {
+    if ((e = dmalloc(ctx, &r->rmin, capacity * dim * sizeof(float))) != cudaSuccess || (e = dmalloc(ctx, &r->rmax, capacity * dim * sizeof(float))) != cudaSuccess ||
+        (e = dmalloc(ctx, &r->data, capacity * sd * sizeof(float))) != cudaSuccess || (e = dmalloc(ctx, &r->err, capacity * sizeof(float))) != cudaSuccess ||
+        (e = dmalloc(ctx, &r->errdim, capacity * sizeof(uint32_t))) != cudaSuccess) {
         cudaGetLastError(); vb200_regions_free(r);
         return fail(ctx, VB200_ERR_NOMEM, "region table of %llu regions x %llu samples does not fit: %s", (unsigned long long)capacity, (unsigned long long)sd, cudaGetErrorString(e));
     }
@@ -49,8 +49,8 @@ int regions_alloc(vb200_ctx* ctx, int dim, int rule, uint64_t capacity, vb200_re
 
 extern "C" void vb200_regions_free(vb200_regions* r) {
     if (!r) return;
-    if (r->ctx) cudaStreamSynchronize(r->ctx->stream);
-    cudaFree(r->rmin); cudaFree(r->rmax); cudaFree(r->data); cudaFree(r->err); cudaFree(r->errdim);
+    vb200_ctx* ctx = r->ctx;       // stream-ordered frees: work already enqueued on the context's stream still sees the table
+    dfree(ctx, r->rmin); dfree(ctx, r->rmax); dfree(ctx, r->data); dfree(ctx, r->err); dfree(ctx, r->errdim);
     delete r;
 }
 extern "C" uint64_t vb200_regions_count(const vb200_regions* r) { return r ? r->count : 0; }
@@ -431,13 +431,16 @@ TileGeom make_geom(const BinWalk& w, const vb200_domain& dom) {
 namespace vb200 {
 
 void walk_free(BinWalk* w) {
-    cudaFree(w->patches); cudaFree(w->volume); cudaFree(w->pstart); cudaFree(w->pend); cudaFree(w->tile_offset); cudaFree(w->tile_list);
-    cudaFree(w->scratch[0]); cudaFree(w->scratch[1]);
+    vb200_ctx* ctx = w->ctx;
+    if (!ctx) { *w = BinWalk(); return; }
+    dfree(ctx, w->patches); dfree(ctx, w->volume); dfree(ctx, w->pstart); dfree(ctx, w->pend); dfree(ctx, w->tile_offset); dfree(ctx, w->tile_list);
+    dfree(ctx, w->scratch[0]); dfree(ctx, w->scratch[1]);
     *w = BinWalk();
 }
 
 int walk_build(vb200_ctx* ctx, const vb200_regions* r, const vb200_domain& dom, uint64_t begin, uint64_t end, BinWalk* w) {
     *w = BinWalk();
+    w->ctx = ctx;
     const int S = r->SH, D = r->dim, db = dom.dimbins;
     const uint64_t n = r->count, cap = r->capacity;
     w->S = S; w->db = db; w->nregions = n; w->cap = cap;
@@ -449,8 +452,8 @@ int walk_build(vb200_ctx* ctx, const vb200_regions* r, const vb200_domain& dom, 
     const float* cur = r->data;
     if (D > db) {
         uint64_t biggest = 1; for (int i = 0; i < D - 1; ++i) biggest *= uint64_t(S);
-        VB200_TRY(cudaMalloc(&w->scratch[0], biggest * cap * sizeof(float)));
-        if (D - db > 1) VB200_TRY(cudaMalloc(&w->scratch[1], (biggest / uint64_t(S)) * cap * sizeof(float)));
+        VB200_TRY(dmalloc(ctx, &w->scratch[0], biggest * cap * sizeof(float)));
+        if (D - db > 1) VB200_TRY(dmalloc(ctx, &w->scratch[1], (biggest / uint64_t(S)) * cap * sizeof(float)));
         int which = 0;
         for (int m = D; m > db; --m) {
             int lower = 1; for (int i = 0; i < m - 1; ++i) lower *= S;
@@ -464,12 +467,12 @@ int walk_build(vb200_ctx* ctx, const vb200_regions* r, const vb200_domain& dom, 
             cur = dst; which ^= 1;
         }
     }
-    VB200_TRY(cudaMalloc(&w->patches, uint64_t(patch) * cap * sizeof(float)));
+    VB200_TRY(dmalloc(ctx, &w->patches, uint64_t(patch) * cap * sizeof(float)));
     VB200_TRY(cudaMemcpyAsync(w->patches, cur, uint64_t(patch) * cap * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
     // 2. volumes + pixel boxes
-    VB200_TRY(cudaMalloc(&w->volume, cap * sizeof(float)));
-    VB200_TRY(cudaMalloc(&w->pstart, uint64_t(db) * cap * sizeof(uint32_t)));
-    VB200_TRY(cudaMalloc(&w->pend, uint64_t(db) * cap * sizeof(uint32_t)));
+    VB200_TRY(dmalloc(ctx, &w->volume, cap * sizeof(float)));
+    VB200_TRY(dmalloc(ctx, &w->pstart, uint64_t(db) * cap * sizeof(uint32_t)));
+    VB200_TRY(dmalloc(ctx, &w->pend, uint64_t(db) * cap * sizeof(uint32_t)));
     region_boxes_kernel<<<unsigned((n + 255) / 256), 256, 0, ctx->stream>>>(n, cap, D, db, dom, r->rmin, r->rmax, w->volume, w->pstart, w->pend);
     ctx->launches++;
     VB200_TRY(cudaGetLastError());
@@ -479,7 +482,7 @@ int walk_build(vb200_ctx* ctx, const vb200_regions* r, const vb200_domain& dom, 
     for (int d = 0; d < 3; ++d) { w->tiles[d] = d < db ? uint32_t((dom.res[d] + w->tile[d] - 1) / w->tile[d]) : 1u; w->ntiles *= w->tiles[d]; }
     if (w->ntiles > 0x7fffffffull) return bail(fail(ctx, VB200_ERR_UNSUPPORTED, "bin grid too large for the tile walk"));
     const TileGeom g = make_geom(*w, dom);
-    VB200_TRY(cudaMalloc(&w->tile_offset, (w->ntiles + 1) * sizeof(uint64_t)));
+    VB200_TRY(dmalloc(ctx, &w->tile_offset, (w->ntiles + 1) * sizeof(uint64_t)));
     unsigned long long* counts = reinterpret_cast<unsigned long long*>(w->tile_offset);
     // every (tile, region) pair tested by brute force keeps table order for free; beyond ~2.7e8 pairs bin the regions into
     // their tiles with atomics instead and sort each tile list back into table order
@@ -500,17 +503,17 @@ int walk_build(vb200_ctx* ctx, const vb200_regions* r, const vb200_domain& dom, 
     uint64_t run = 0; for (uint64_t t = 0; t < w->ntiles; ++t) { const uint64_t c = h[t]; h[t] = run; run += c; } h[w->ntiles] = run;
     w->pairs = run;
     VB200_TRY(cudaMemcpyAsync(w->tile_offset, h.data(), (w->ntiles + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
-    VB200_TRY(cudaMalloc(&w->tile_list, (run + 1) * sizeof(uint32_t)));
+    VB200_TRY(dmalloc(ctx, &w->tile_list, (run + 1) * sizeof(uint32_t)));
     if (region_major) {
         unsigned long long* cursor = nullptr;
-        VB200_TRY(cudaMalloc(&cursor, w->ntiles * sizeof(unsigned long long)));
+        VB200_TRY(dmalloc(ctx, &cursor, w->ntiles * sizeof(unsigned long long)));
         cudaError_t e1 = cudaMemsetAsync(cursor, 0, w->ntiles * sizeof(unsigned long long), ctx->stream);
         region_major_kernel<true><<<unsigned((n + 255) / 256), 256, 0, ctx->stream>>>(g, n, cap, begin, end, w->pstart, w->pend, nullptr, w->tile_offset, cursor, w->tile_list);
         cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4);
         tile_sort_kernel<<<unsigned(w->ntiles), 1024, 32768 * 4, ctx->stream>>>(w->tile_offset, w->tile_list);
         ctx->launches += 2;
         cudaError_t e2 = cudaGetLastError(), e3 = cudaStreamSynchronize(ctx->stream);
-        cudaFree(cursor);
+        dfree(ctx, cursor);
         if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) return bail(fail(ctx, VB200_ERR_CUDA, "tile list construction failed: %s", cudaGetErrorString(e3 != cudaSuccess ? e3 : e2 != cudaSuccess ? e2 : e1)));
     } else {
         tile_lists_kernel<true><<<unsigned(w->ntiles), 256, 0, ctx->stream>>>(g, n, cap, begin, end, w->pstart, w->pend, nullptr, w->tile_offset, w->tile_list);
@@ -579,11 +582,11 @@ static int generate_greedy(vb200_ctx* ctx, const vb200_integrand* f, const vb200
     int rc = regions_alloc(ctx, f->dim, p->rule, n, &r); if (rc) return rc;
     const int D = f->dim; const uint64_t sd = uint64_t(r->sd);
     float *range = nullptr, *data = nullptr, *err = nullptr; unsigned long long* heap = nullptr; uint64_t* hsize = nullptr;
-    auto cleanup = [&] () { cudaFree(range); cudaFree(data); cudaFree(err); cudaFree(heap); cudaFree(hsize); };
+    auto cleanup = [&] () { dfree(ctx, range); dfree(ctx, data); dfree(ctx, err); dfree(ctx, heap); dfree(ctx, hsize); };
     auto bail = [&] (int code) { cleanup(); vb200_regions_free(r); return code; };
-    if (cudaMalloc(&range, cap * 2 * D * sizeof(float)) != cudaSuccess || cudaMalloc(&data, cap * sd * sizeof(float)) != cudaSuccess ||
-        cudaMalloc(&err, cap * sizeof(float)) != cudaSuccess || cudaMalloc(&heap, (n + 1) * sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMalloc(&hsize, sizeof(uint64_t)) != cudaSuccess) { cudaGetLastError(); return bail(fail(ctx, VB200_ERR_NOMEM, "working set of the greedy refinement (%llu region slots) does not fit", (unsigned long long)cap)); }
+    if (dmalloc(ctx, &range, cap * 2 * D * sizeof(float)) != cudaSuccess || dmalloc(ctx, &data, cap * sd * sizeof(float)) != cudaSuccess ||
+        dmalloc(ctx, &err, cap * sizeof(float)) != cudaSuccess || dmalloc(ctx, &heap, (n + 1) * sizeof(unsigned long long)) != cudaSuccess ||
+        dmalloc(ctx, &hsize, sizeof(uint64_t)) != cudaSuccess) { cudaGetLastError(); return bail(fail(ctx, VB200_ERR_NOMEM, "working set of the greedy refinement (%llu region slots) does not fit", (unsigned long long)cap)); }
     vb200_greedy_launch a; std::memset(&a, 0, sizeof(a));
     a.dim = D; a.rule = p->rule; a.heuristic = p->heuristic; a.metric = p->metric; a.size_weight = p->size_weight;
     a.iterations = p->iterations; a.capacity = cap; a.range = range; a.data = data; a.err = err; a.heap = heap; a.heap_size = hsize;

@@ -25,6 +25,7 @@ int generate_batched(vb200_ctx* ctx, const vb200_integrand* f, const vb200_adapt
 // regions marginalised over the non-binned dimensions (patches), their pixel boxes (region.h:454-463) and per-tile
 // ordered region lists.  All device memory, freed by walk_free.
 struct BinWalk {
+    vb200_ctx* ctx = nullptr;
     int S = 0, db = 0, patch = 0;          // patch = S^db values per region
     uint64_t nregions = 0, cap = 0;
     float* patches = nullptr;              // [patch][cap]
