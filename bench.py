@@ -35,6 +35,9 @@ WORKLOADS = {
     "c5": ("range_infinite random walk with Russian roulette, 2048x2048 bins, 256 spp (BASELINE configs[4])", "walk", [2048, 2048], 256, "mc_per_bin_parallel_inf", None, True),
 }
 METRIC = "integrand evals/sec (per-bin MC, 1024x1024 bins x 64 spp, shade4<64>)"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the ncu --set full capture summarised in
+# profiles/ncu_c2_mc_per_bin_r1.txt / profiles/ncu_c5_walk_r1.txt (algorithmic bytes: 4 B per bin)
+NCU_TRAFFIC_BYTES = {"c2": 4213504, "c5": 16792576}
 
 
 def dist_env():
@@ -225,7 +228,7 @@ def main():
     roof = None
     if flops:
         achieved = (nb_local * spp / (ms_dev * 1e-3)) * flops / 1e12 if world == 1 else value / world * flops / 1e12
-        roof = {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak, "traffic": None,
+        roof = {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak, "traffic": NCU_TRAFFIC_BYTES.get(args.workload),
                 "peak_source": f"nominal FP32 (non-tensor) peak 2*128*{ctx.sm_count} SMs*{sm_max:.0f} MHz; MEASURED_PEAKS.json has no FP32 entry (hbm_gbs/bf16 only)",
                 "flops_per_eval": flops, "hbm_gbs_achieved": nb_local * 4 / (ms_dev * 1e-3) / 1e9, "hbm_gbs_peak": peaks.get("hbm_gbs")}
     cb = None
