@@ -217,7 +217,8 @@ static int run_sampler(vb200_ctx* ctx, const vb200_integrand* f, int kind, Launc
     a.accumulate = 0;
     a.out = h - begin;                                   // kernels index from the base of the full grid
     a.sum_f = sum_f ? h + n : nullptr; a.sum_f2 = sum_f2 ? h + 2 * n : nullptr;
-    int chunks = int(n / (256u * 1024u)); if (chunks < 1) chunks = 1;     // measured: 4 chunks of 256 Ki bins at C2 (profiles/results_r1.md) if (chunks > vb200_ctx::kMaxChunks) chunks = vb200_ctx::kMaxChunks;
+    // measured: 4 chunks of 256 Ki bins are the best trade at C2 (profiles/results_r1.md)
+    int chunks = int(n / (256u * 1024u)); if (chunks < 1) chunks = 1; if (chunks > vb200_ctx::kMaxChunks) chunks = vb200_ctx::kMaxChunks;
     if (const char* env = std::getenv("VB200_E2E_CHUNKS")) { chunks = std::atoi(env); if (chunks < 1) chunks = 1; if (chunks > vb200_ctx::kMaxChunks) chunks = vb200_ctx::kMaxChunks; }   // tuning knob
     for (int c = 0; c < chunks; ++c) {
         a.bin_begin = begin + n * uint64_t(c) / uint64_t(chunks); a.bin_end = begin + n * uint64_t(c + 1) / uint64_t(chunks);
