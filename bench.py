@@ -226,11 +226,16 @@ def main():
     sm_max = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
     fp32_peak = 2 * 128 * ctx.sm_count * sm_max * 1e6 / 1e12             # TFLOP/s nominal: 2 x 128 lanes x SMs x f (SURVEY.md §8d "Peaks")
     roof = None
+    fma_peak = None
+    try:
+        fma_peak = ctx.measure_fp32_peak(5)
+    except Exception:
+        pass
     if flops:
         achieved = (nb_local * spp / (ms_dev * 1e-3)) * flops / 1e12 if world == 1 else value / world * flops / 1e12
         roof = {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak, "traffic": NCU_TRAFFIC_BYTES.get(args.workload),
                 "peak_source": f"nominal FP32 (non-tensor) peak 2*128*{ctx.sm_count} SMs*{sm_max:.0f} MHz; MEASURED_PEAKS.json has no FP32 entry (hbm_gbs/bf16 only)",
-                "flops_per_eval": flops, "hbm_gbs_achieved": nb_local * 4 / (ms_dev * 1e-3) / 1e9, "hbm_gbs_peak": peaks.get("hbm_gbs")}
+                "peak_measured_fma": fma_peak, "frac_of_measured_fma": (achieved / fma_peak) if fma_peak else None, "flops_per_eval": flops, "hbm_gbs_achieved": nb_local * 4 / (ms_dev * 1e-3) / 1e9, "hbm_gbs_peak": peaks.get("hbm_gbs")}
     cb = None
     if world == 1 and not args.no_cpu_baseline:
         try:

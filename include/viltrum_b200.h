@@ -67,6 +67,11 @@ int         vb200_sm_count(const vb200_ctx* ctx);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 uint64_t    vb200_launch_count(const vb200_ctx* ctx);
 
+/* Measured FP32 (non-tensor) peak of the device: a dependent-FFMA chain kernel (8 independent chains per thread, all SMs fully
+ * occupied), timed with CUDA events on the context's stream; best of `reps`.  This is the roofline denominator bench.py reports
+ * next to the nominal 2*128*SMs*clock figure (MEASURED_PEAKS.json carries HBM and bf16-tensor peaks only). */
+int         vb200_measure_fp32_peak(vb200_ctx* ctx, int reps, double* tflops);
+
 /* Host-side evaluation of the library's counter-based generator (Philox4x32-10, include/viltrum_b200/device/philox.cuh),
  * for known-answer tests and for callers that want to predict which sample a (seed, bin, sample) triple maps to. */
 void        vb200_philox4x32_10(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]);

@@ -169,6 +169,43 @@ extern "C" int vb200_synchronize(vb200_ctx* ctx) { if (!ctx) return VB200_ERR_IN
 extern "C" int vb200_sm_count(const vb200_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 extern "C" uint64_t vb200_launch_count(const vb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+namespace {
+__global__ void __launch_bounds__(256) fma_chain_kernel(float* out, int iters, float a, float b) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = float(threadIdx.x + i);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], a, b);
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += v[i];
+    if (s == 12345.678f) out[0] = s;      // never true: keeps the chain alive
+}
+}
+
+extern "C" int vb200_measure_fp32_peak(vb200_ctx* ctx, int reps, double* tflops) {
+    if (!ctx || !tflops) return fail(ctx, VB200_ERR_INVALID, "NULL argument");
+    VB200_CUDA(ctx, cudaSetDevice(ctx->device));
+    void* scratch = nullptr; int rc = reserve(ctx, 3, 256, &scratch); if (rc) return rc;
+    cudaEvent_t e0, e1; VB200_CUDA(ctx, cudaEventCreate(&e0)); VB200_CUDA(ctx, cudaEventCreate(&e1));
+    const int iters = 8192, grid = ctx->sm_count * 8;
+    float best = 1e30f;
+    for (int r = 0; r < (reps < 1 ? 1 : reps) + 1; ++r) {
+        cudaEventRecord(e0, ctx->stream);
+        fma_chain_kernel<<<grid, 256, 0, ctx->stream>>>(static_cast<float*>(scratch), iters, 1.0001f, 0.5f);
+        cudaEventRecord(e1, ctx->stream);
+        cudaError_t e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) { cudaEventDestroy(e0); cudaEventDestroy(e1); return fail(ctx, VB200_ERR_CUDA, "FMA peak kernel failed: %s", cudaGetErrorString(e)); }
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        if (r > 0 && ms < best) best = ms;      // first launch is warm-up
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *tflops = double(grid) * 256.0 * double(iters) * 8.0 * 2.0 / (double(best) * 1e-3) / 1e12;
+    return VB200_OK;
+}
+
 extern "C" void vb200_philox4x32_10(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]) {
     const viltrum::b200::u32x4 r = viltrum::b200::philox4x32<10>(viltrum::b200::u32x4{counter[0], counter[1], counter[2], counter[3]}, key[0], key[1]);
     out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;

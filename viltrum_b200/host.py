@@ -123,6 +123,12 @@ class Context:
     def launch_count(self):
         return self._L.vb200_launch_count(self._h)
 
+    def measure_fp32_peak(self, reps=5):
+        """measured dependent-FFMA peak of this GPU in TFLOP/s (vb200_measure_fp32_peak)"""
+        out = ctypes.c_double(0.0)
+        self.check(self._L.vb200_measure_fp32_peak(self._h, int(reps), ctypes.byref(out)))
+        return out.value
+
     def integrand(self, name, exact=False):
         p = self._L.vb200_builtin_integrand(name.encode(), 1 if exact else 0)
         if not p:
