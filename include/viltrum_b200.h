@@ -90,6 +90,7 @@ enum {
     VB200_K_EVAL_POINTS = 4,       /* vb200_eval_launch    : values[i] = f(points[i]) — region fill / batched splits / CV residual */
     VB200_K_ADAPTIVE_EXACT = 5,    /* vb200_greedy_launch  : persistent single-CTA greedy heap refinement (batch size 1) */
     VB200_K_MC_SCATTER = 6,        /* vb200_scatter_launch : global sampler scattering into bins (monte-carlo.h:39-63) */
+    VB200_K_WALK_SCATTER = 7,      /* vb200_scatter_launch : the same over an infinite range (monte-carlo.h:65-84) */
     VB200_K_COUNT = 8
 };
 
@@ -160,7 +161,8 @@ int vb200_mc_per_bin_replay(vb200_ctx* ctx, const vb200_integrand* f, const vb20
                             const float* samples, int samples_mem, float* bins, int bins_mem);
 
 /* ---- infinite-dimensional paths (rows a5, a20) --------------------------------------------------------- */
-/* domain.dim = explicit range entries (0..VB200_MAX_DIM); flavor VB200_MC_PER_BIN only.
+/* domain.dim = explicit range entries (0..VB200_MAX_DIM); both flavors (VB200_PER_BIN_MC = row a20:
+ * integrator_per_bin_parallel(monte_carlo) over RangeInfinite, monte-carlo.h:65-84, bins(p) = nbins * sum f * vol(bin box)/spp).
  * Sequence element i of sample s in bin b = u * (max_i - min_i) + min_i with u drawn from
  * Philox(key=seed, counter=(b, s, i/4))[i%4]; the first dimbins elements are confined to the bin. */
 int vb200_mc_per_bin_inf(vb200_ctx* ctx, const vb200_integrand* f, const vb200_mc_params* p,
@@ -174,6 +176,7 @@ int vb200_mc_per_bin_inf_replay(vb200_ctx* ctx, const vb200_integrand* f, const 
 
 /* ---- global Monte Carlo with scatter binning (row a6; SURVEY.md §8f "next" #1) -------------------------- */
 /* monte_carlo(samples,seed): bins(pos(x)) += f(x) * nbins*vol/samples   (reference src/monte-carlo/monte-carlo.h:39-63).
+ * Sequence integrands (infinite ranges, monte-carlo.h:65-84) take the bin from the first dimbins sequence elements.
  * shard selects a SAMPLE index range [begin,end) here (split-bin mode: every GPU draws part of the samples and
  * the caller sums the partial grids — the one allreduce the design allows). */
 int vb200_monte_carlo(vb200_ctx* ctx, const vb200_integrand* f, const vb200_mc_params* p /* spp = total samples */,
@@ -281,12 +284,13 @@ typedef struct vb200_walk_launch {
     double   factor;
     float*   out; float* sum_f; float* sum_f2;
     unsigned long long* tile_counter; /* device, zeroed by the driver before the launch */
+    int32_t  flavor; int32_t reserved;
 } vb200_walk_launch;
 
 typedef struct vb200_walk_replay_launch {
     vb200_domain domain;
     uint64_t bin_begin, bin_end, nbins_total;
-    uint32_t spp; int32_t reserved;
+    uint32_t spp; int32_t flavor;
     double   factor;
     const uint64_t* offsets; const float* elems;
     float*   out;

@@ -164,8 +164,32 @@ struct InfiniteThunks {
     static int walk_replay(const vb200_integrand* self, const void* args, void* stream) {
         const vb200_walk_replay_launch& a = *static_cast<const vb200_walk_replay_launch*>(args);
         const uint64_t n = a.bin_end - a.bin_begin;
-        device::walk_replay_kernel<F, EXACT><<<unsigned((n + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(functor(self), a);
+        const unsigned grid = unsigned((n + 127) / 128); cudaStream_t st = static_cast<cudaStream_t>(stream);
+        switch (a.domain.dimbins) {
+            case 1: device::walk_replay_kernel<F, 1, EXACT><<<grid, 128, 0, st>>>(functor(self), a); break;
+            case 2: device::walk_replay_kernel<F, 2, EXACT><<<grid, 128, 0, st>>>(functor(self), a); break;
+            case 3: device::walk_replay_kernel<F, 3, EXACT><<<grid, 128, 0, st>>>(functor(self), a); break;
+            default: return int(cudaErrorInvalidValue);
+        }
         return int(cudaGetLastError());
+    }
+    template<int DB>
+    static int launch_walk_scatter(const F& f, const vb200_scatter_launch& a, cudaStream_t st) {
+        auto k = device::walk_scatter_kernel<F, DB, EXACT>;
+        const uint64_t n = a.sample_end - a.sample_begin;
+        const int grid = persistent_grid(k, 256, (n + 255) / 256, a.grid_hint);
+        k<<<grid, 256, 0, st>>>(f, a);
+        return int(cudaGetLastError());
+    }
+    static int walk_scatter(const vb200_integrand* self, const void* args, void* stream) {
+        const vb200_scatter_launch& a = *static_cast<const vb200_scatter_launch*>(args);
+        const F f = functor(self); cudaStream_t st = static_cast<cudaStream_t>(stream);
+        switch (a.domain.dimbins) {
+            case 1: return launch_walk_scatter<1>(f, a, st);
+            case 2: return launch_walk_scatter<2>(f, a, st);
+            case 3: return launch_walk_scatter<3>(f, a, st);
+        }
+        return int(cudaErrorInvalidValue);
     }
 };
 
@@ -203,6 +227,7 @@ class InfiniteIntegrand {
         using T = detail::InfiniteThunks<F, EXACT>;
         d_.launch[VB200_K_WALK] = &T::walk;
         d_.launch[VB200_K_WALK_REPLAY] = &T::walk_replay;
+        d_.launch[VB200_K_WALK_SCATTER] = &T::walk_scatter;
     }
 public:
     explicit InfiniteIntegrand(const F& f, const char* name = "user integrand") : f_(f) { bind(name); }

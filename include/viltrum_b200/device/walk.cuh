@@ -47,8 +47,9 @@ struct PhiloxSequence {
     __device__ __forceinline__ const_iterator end() const { return const_iterator(this); }
 };
 
+// returns RangeInfinite::_volume of the bin sub-range: float product over its explicit entries, in order (range-infinite.h:22-23)
 template<int DIMBINS>
-__device__ __forceinline__ void walk_bin_box(const vb200_domain& dom, uint64_t bin, float (&lo)[DIMBINS], float (&ext)[DIMBINS]) {
+__device__ __forceinline__ float walk_bin_box(const vb200_domain& dom, uint64_t bin, float (&lo)[DIMBINS], float (&ext)[DIMBINS]) {
     uint32_t pos[VB200_MAX_DIMBINS];
     unflatten_bin<DIMBINS>(bin, dom, pos);
 #pragma unroll
@@ -60,6 +61,21 @@ __device__ __forceinline__ void walk_bin_box(const vb200_domain& dom, uint64_t b
         const float b = __fadd_rn(rmin, __fmul_rn(float(pos[i] + 1u), drange));
         lo[i] = a; ext[i] = b - a;
     }
+    float volume = 1.0f;
+#pragma unroll
+    for (int i = 0; i < DIMBINS; ++i) volume = __fmul_rn(volume, ext[i]);
+    for (int i = DIMBINS; i < dom.dim; ++i) volume = __fmul_rn(volume, dom.rmax[i] - dom.rmin[i]);
+    return volume;
+}
+
+// value written for a bin: flavor 0  sum f * vol(range)/spp                       (monte-carlo-per-bin-parallel.h:77,96)
+//                          flavor 1  nbins * float(sum f * (vol(bin box)/spp))      (monte-carlo.h:70-72,81; integrator-per-bin-parallel.h:33)
+__device__ __forceinline__ float walk_bin_value(const vb200_walk_launch& a, float sum, float volume) {
+    if (a.flavor == VB200_PER_BIN_MC) {
+        const float sol = float(double(sum) * (double(volume) / double(a.spp)));
+        return float(double(a.nbins_total) * double(sol));
+    }
+    return float(double(sum) * a.factor);
 }
 
 template<class F, int DIMBINS, bool MOMENTS, bool EXACT>
@@ -75,11 +91,11 @@ walk_kernel(const F f, const vb200_walk_launch a) {
     while (tile < ntiles) {
         const uint64_t bin = a.bin_begin + tile * G + grp;
         const bool live = bin < a.bin_end;
-        float sum = 0.0f, sum2 = 0.0f;
+        float sum = 0.0f, sum2 = 0.0f, volume = 1.0f;
         if (live) {
             PhiloxSequence<DIMBINS> seq;
             seq.b0 = uint32_t(bin); seq.b1 = uint32_t(bin >> 32); seq.k0 = a.key0; seq.k1 = a.key1; seq.dom = &a.domain;
-            walk_bin_box<DIMBINS>(a.domain, bin, seq.lo, seq.ext);
+            volume = walk_bin_box<DIMBINS>(a.domain, bin, seq.lo, seq.ext);
             for (uint32_t s = sub; s < a.spp; s += LPB) {
                 seq.s = s;
                 const float v = f(seq);
@@ -92,7 +108,7 @@ walk_kernel(const F f, const vb200_walk_launch a) {
             if (MOMENTS) sum2 += __shfl_xor_sync(0xffffffffu, sum2, off);
         }
         if (live && sub == 0) {
-            const float v = float(double(sum) * a.factor);               // monte-carlo-per-bin-parallel.h:77,96
+            const float v = walk_bin_value(a, sum, volume);
             a.out[bin] = a.accumulate ? float(double(a.out[bin]) + double(v)) : v;
             if (MOMENTS) {
                 if (a.sum_f)  a.sum_f[bin - a.bin_begin]  = sum;
@@ -134,10 +150,10 @@ walk_wavefront_kernel(const F f, const vb200_walk_launch a) {
     while (tile < ntiles) {
         const uint64_t bin = a.bin_begin + tile * G + grp;
         const bool live = bin < a.bin_end;
-        float sum = 0.0f, sum2 = 0.0f;
+        float sum = 0.0f, sum2 = 0.0f, volume = 1.0f;
         PhiloxSequence<DIMBINS> seq;
         seq.b0 = uint32_t(bin); seq.b1 = uint32_t(bin >> 32); seq.k0 = a.key0; seq.k1 = a.key1; seq.dom = &a.domain; seq.s = 0;
-        if (live) walk_bin_box<DIMBINS>(a.domain, bin, seq.lo, seq.ext);
+        if (live) volume = walk_bin_box<DIMBINS>(a.domain, bin, seq.lo, seq.ext);
         else { for (int d = 0; d < DIMBINS; ++d) { seq.lo[d] = 0.0f; seq.ext[d] = 1.0f; } }
         uint32_t next = live ? sub : a.spp;          // next sample this lane will start
         bool alive = false;
@@ -173,7 +189,7 @@ walk_wavefront_kernel(const F f, const vb200_walk_launch a) {
             if (MOMENTS) sum2 += __shfl_xor_sync(0xffffffffu, sum2, off);
         }
         if (live && sub == 0) {
-            const float v = float(double(sum) * a.factor);
+            const float v = walk_bin_value(a, sum, volume);
             a.out[bin] = a.accumulate ? float(double(a.out[bin]) + double(v)) : v;
             if (MOMENTS) {
                 if (a.sum_f)  a.sum_f[bin - a.bin_begin]  = sum;
@@ -204,20 +220,74 @@ struct RecordedSequence {
     __device__ __forceinline__ const_iterator begin() const { return const_iterator(this); }
 };
 
-template<class F, bool EXACT>
+template<class F, int DIMBINS, bool EXACT>
 __global__ void __launch_bounds__(128)
 walk_replay_kernel(const F f, const vb200_walk_replay_launch a) {
     const uint64_t k = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const uint64_t bin = a.bin_begin + k;
     if (bin >= a.bin_end) return;
-    float acc = a.out[bin];
+    const bool per_bin_mc = a.flavor == VB200_PER_BIN_MC;
+    double factor = a.factor;
+    if (per_bin_mc) { float lo[DIMBINS], ext[DIMBINS]; factor = __ddiv_rn(double(walk_bin_box<DIMBINS>(a.domain, bin, lo, ext)), double(a.spp)); }
+    float acc = per_bin_mc ? 0.0f : a.out[bin];
     for (uint32_t s = 0; s < a.spp; ++s) {
         const uint64_t p = k * a.spp + s;
         RecordedSequence seq{a.elems + a.offsets[p], uint32_t(a.offsets[p + 1] - a.offsets[p]), a.error_flag};
         const float v = f(seq);
-        acc = __double2float_rn(__dadd_rn(double(acc), __dmul_rn(double(v), a.factor)));
+        acc = __double2float_rn(__dadd_rn(double(acc), __dmul_rn(double(v), factor)));
     }
-    a.out[bin] = acc;
+    a.out[bin] = per_bin_mc ? __double2float_rn(__dmul_rn(double(a.nbins_total), double(acc))) : acc;
+}
+
+// K4 over an infinite range — reference MonteCarlo::integrate(RangeInfinite), src/monte-carlo/monte-carlo.h:65-84: every sample is
+// its own lazy sequence (upstream: a fresh mt19937 per sample; here Philox keyed by the global sample index), the bin comes from
+// its first DIMBINS elements (:76-80) and bins(pos) += f(seq)*factor.  Same privatised-histogram scheme as mc_scatter_kernel.
+struct GlobalSequence {
+    uint32_t s0, s1, k0, k1; const vb200_domain* dom;
+    class const_iterator {
+        const GlobalSequence* q; uint32_t i; u32x4 blk; float n;
+        __device__ __forceinline__ void load() {
+            if ((i & 3u) == 0u) blk = philox4x32<10>(u32x4{q->s0, q->s1, 0xfffffffeu, i >> 2}, q->k0, q->k1);
+            const float u = pick(blk, int(i & 3u));
+            n = int(i) < q->dom->dim ? fmaf(u, q->dom->rmax[i] - q->dom->rmin[i], q->dom->rmin[i]) : u;
+        }
+    public:
+        __device__ __forceinline__ const_iterator(const GlobalSequence* q_) : q(q_), i(0) { load(); }
+        __device__ __forceinline__ const float& operator*() const { return n; }
+        __device__ __forceinline__ const_iterator& operator++() { ++i; load(); return *this; }
+    };
+    __device__ __forceinline__ const_iterator begin() const { return const_iterator(this); }
+};
+
+template<class F, int DIMBINS, bool EXACT>
+__global__ void __launch_bounds__(256)
+walk_scatter_kernel(const F f, const vb200_scatter_launch a) {
+    constexpr int SMEM_BINS = 8192;
+    __shared__ float s_hist[SMEM_BINS];
+    const bool priv = a.nbins_total <= uint64_t(SMEM_BINS);
+    if (priv) { for (uint32_t i = threadIdx.x; i < a.nbins_total; i += blockDim.x) s_hist[i] = 0.0f; __syncthreads(); }
+    const float factor = float(a.factor);
+    for (uint64_t s = a.sample_begin + uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; s < a.sample_end; s += uint64_t(gridDim.x) * blockDim.x) {
+        GlobalSequence seq{uint32_t(s), uint32_t(s >> 32), a.key0, a.key1, &a.domain};
+        uint64_t lin = 0, prod = 1;
+        {
+            auto it = seq.begin();
+#pragma unroll
+            for (int i = 0; i < DIMBINS; ++i) {
+                const float lo = i < a.domain.dim ? a.domain.rmin[i] : 0.0f, hi = i < a.domain.dim ? a.domain.rmax[i] : 1.0f;
+                const float t = float(a.domain.res[i]) * (*it - lo) / (hi - lo);          // monte-carlo.h:79
+                uint64_t p = uint64_t(t); if (p >= a.domain.res[i]) p = a.domain.res[i] - 1;
+                lin += p * prod; prod *= a.domain.res[i];
+                if (i + 1 < DIMBINS) ++it;
+            }
+        }
+        const float v = f(seq) * factor;
+        if (priv) atomicAdd(&s_hist[lin], v); else atomicAdd(&a.out[lin], v);
+    }
+    if (priv) {
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < a.nbins_total; i += blockDim.x) { const float v = s_hist[i]; if (v != 0.0f) atomicAdd(&a.out[i], v); }
+    }
 }
 
 }}} // namespace viltrum::b200::device

@@ -236,6 +236,18 @@ public:
         b200::apply_bins<true>(bins, res, flat);
         logger.log_progress(samples, samples);
     }
+    // global sampler over an infinite range (monte-carlo.h:65-84): the bin comes from the first DIMBINS sequence elements
+    template<typename Bins, std::size_t DIMBINS, typename F, typename Float, typename Logger>
+    void integrate(Bins& bins, const std::array<std::size_t,DIMBINS>& res, const F& f, const RangeInfinite<Float>& range, Logger& logger) const {
+        auto& ctx = b200::default_context();
+        b200::InfiniteIntegrand<F> g(f);
+        vb200_mc_params p; std::memset(&p, 0, sizeof(p));
+        p.domain = b200::make_domain(range, res); p.spp = samples; p.seed = seed_; p.flavor = VB200_MC_PER_BIN;
+        std::vector<float> flat(b200::bin_count(res), 0.0f);
+        ctx.check(vb200_monte_carlo(ctx.get(), g.c_abi(), &p, flat.data(), VB200_HOST));
+        b200::apply_bins<true>(bins, res, flat);
+        logger.log_progress(samples, samples);
+    }
 };
 inline MonteCarlo monte_carlo(unsigned long samples, std::size_t seed = 0) { return MonteCarlo(samples, seed); }
 
@@ -290,6 +302,18 @@ public:
         std::vector<float> flat(b200::bin_count(res), 0.0f);
         logger.log_progress(std::size_t(0), std::size_t(1));
         ctx.check(vb200_mc_per_bin(ctx.get(), g.c_abi(), &p, flat.data(), VB200_HOST, nullptr, nullptr));
+        b200::apply_bins<false>(bins, res, flat);
+        logger.log_progress(std::size_t(1), std::size_t(1));
+    }
+    // row a20: the wrapper spelling over an infinite range (monte-carlo.h:65-84 per bin), '='
+    template<typename Bins, std::size_t DIMBINS, typename F, typename Float, typename Logger>
+    void integrate(Bins& bins, const std::array<std::size_t,DIMBINS>& res, const F& f, const RangeInfinite<Float>& range, Logger& logger) const {
+        auto& ctx = b200::default_context();
+        b200::InfiniteIntegrand<F> g(f);
+        vb200_mc_params p; std::memset(&p, 0, sizeof(p));
+        p.domain = b200::make_domain(range, res); p.shard = b200::current_shard(); p.spp = inner.sample_count(); p.seed = inner.seed(); p.flavor = VB200_PER_BIN_MC;
+        std::vector<float> flat(b200::bin_count(res), 0.0f);
+        ctx.check(vb200_mc_per_bin_inf(ctx.get(), g.c_abi(), &p, flat.data(), VB200_HOST, nullptr, nullptr));
         b200::apply_bins<false>(bins, res, flat);
         logger.log_progress(std::size_t(1), std::size_t(1));
     }

@@ -282,6 +282,96 @@ extern "C" int vo_mc_per_bin_parallel_inf(const char* integrand, int dimbins, co
     return rc;
 }
 
+// integrator-per-bin-parallel.h:16-35 wrapping monte-carlo.h:65-84 (RangeInfinite) through integrate.h:115-123;
+// sequences are RandomSequenceRNG (random-sequence-rng.h:11-45): a fresh mt19937(seed) per sample, element i =
+// uniform_real_distribution(min_i,max_i)(rng)
+extern "C" int vo_per_bin_parallel_mc_inf(const char* integrand, int dimbins, const uint64_t* res,
+                               const float* rmin, const float* rmax, int nrange,
+                               uint64_t spp, uint64_t seed, float* bins,
+                               double* rec_sum, double* rec_sum2,
+                               uint32_t* rec_len, float* rec_elems, uint64_t rec_cap, uint64_t* rec_used) {
+    auto F = find_inf(integrand); if (!F) return -1;
+    if (dimbins<1 || dimbins>8) return -2;
+    auto rmin_at = [&] (int i) { return i<nrange ? rmin[i] : 0.0f; };
+    auto rmax_at = [&] (int i) { return i<nrange ? rmax[i] : 1.0f; };
+    uint64_t nb = nbins_of(dimbins,res);
+    MT19937 user(seed);
+    MT19937 master{uint64_t(user())};                                          // copy into the wrapper reseeds (monte-carlo.h:32-33)
+    std::vector<uint32_t> perbin_seed(nb);
+    for (uint64_t k=0;k<nb;++k) perbin_seed[k] = master();                     // tensor<Integrator> copies, tensor order
+    uint64_t used = 0; int rc = 0;
+    for (uint64_t k=0;k<nb;++k) {
+        uint64_t pos[8]; unflatten(k,dimbins,res,pos);
+        MT19937 binrng(perbin_seed[k]);
+        int nsub = std::max(nrange,dimbins);
+        std::vector<float> a(nsub), b(nsub);
+        for (int i=0;i<nsub;++i) { a[i]=rmin_at(i); b[i]=rmax_at(i); }
+        for (int i=0;i<dimbins;++i) {
+            float drange = (rmax_at(i)-rmin_at(i))/float(res[i]);
+            a[i] = rmin_at(i)+float(pos[i])*drange; b[i] = rmin_at(i)+float(pos[i]+1)*drange;
+        }
+        float vol = 1.0f; for (int i=0;i<nsub;++i) vol *= (b[i]-a[i]);          // RangeInfinite::_volume of the bin sub-range
+        double factor = 1.0*double(vol)/double(spp);                           // monte-carlo.h:70-72, one bin
+        float sol = 0.0f;
+        double s1=0, s2=0;
+        for (uint64_t s=0;s<spp;++s) {
+            MT19937 seqrng{uint64_t(uint32_t(binrng()))};                       // random_sequence(range, unsigned seed) -> mt19937(seed)  (:75)
+            // (:76-80 walks a separate copy of the stream to find the bin position — always bin 0 here — no effect on f's stream)
+            uint32_t count = 0; int idx = 0;
+            LazySeq seq;
+            seq.next = [&] () -> float {
+                int i = idx++;
+                float lo = i<nsub ? a[i] : 0.0f, hi = i<nsub ? b[i] : 1.0f;
+                float n = uniform_real(seqrng,lo,hi);                           // random-sequence-rng.h:30,35
+                ++count;
+                if (rec_elems) { if (used < rec_cap) rec_elems[used] = n; else rc = -3; }
+                ++used;
+                return n;
+            };
+            float v = F->fn(seq);
+            sol = float(double(sol) + double(v)*factor);                       // :81
+            if (rec_len) rec_len[k*spp+s] = count;
+            s1 += double(v); s2 += double(v)*double(v);
+        }
+        bins[k] = float(double(nb)*double(sol));                               // integrator-per-bin-parallel.h:33
+        if (rec_sum) rec_sum[k]=s1;
+        if (rec_sum2) rec_sum2[k]=s2;
+    }
+    if (rec_used) *rec_used = used;
+    return rc;
+}
+
+// monte-carlo.h:65-84 — global sampler over RangeInfinite, bin from the first dimbins sequence elements
+extern "C" int vo_monte_carlo_inf(const char* integrand, int dimbins, const uint64_t* res,
+                       const float* rmin, const float* rmax, int nrange, uint64_t samples, uint64_t seed, float* bins) {
+    auto F = find_inf(integrand); if (!F) return -1;
+    if (dimbins<1 || dimbins>8) return -2;
+    auto rmin_at = [&] (int i) { return i<nrange ? rmin[i] : 0.0f; };
+    auto rmax_at = [&] (int i) { return i<nrange ? rmax[i] : 1.0f; };
+    double resolution_factor = 1; for (int i=0;i<dimbins;++i) resolution_factor *= double(res[i]);
+    float vol = 1.0f; for (int i=0;i<nrange;++i) vol *= (rmax_at(i)-rmin_at(i));
+    double factor = resolution_factor*double(vol)/double(samples);             // :70-72
+    MT19937 rng(seed);
+    for (uint64_t s=0;s<samples;++s) {
+        uint32_t sd = uint32_t(rng());                                          // :75
+        MT19937 posrng{uint64_t(sd)};                                           // :76-80: a copy of the stream gives the bin position
+        uint64_t lin=0, prod=1; bool ok=true;
+        for (int i=0;i<dimbins;++i) {
+            float e = uniform_real(posrng,rmin_at(i),rmax_at(i));
+            uint64_t p = uint64_t(float(res[i])*(e-rmin_at(i))/(rmax_at(i)-rmin_at(i)));
+            if (p>=res[i]) ok=false;
+            lin += p*prod; prod *= res[i];
+        }
+        MT19937 seqrng{uint64_t(sd)};
+        int idx = 0;
+        LazySeq seq;
+        seq.next = [&] () -> float { int i = idx++; return uniform_real(seqrng,rmin_at(i),rmax_at(i)); };
+        float v = F->fn(seq);
+        if (ok) bins[lin] = float(double(bins[lin]) + double(v)*factor);       // :81
+    }
+    return 0;
+}
+
 // =========================================================================================================
 // Newton-Cotes rules (rules.h), nested pairs (nested.h), error metrics / heuristics (error-*.h)
 // =========================================================================================================

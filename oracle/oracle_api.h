@@ -45,6 +45,19 @@ int vo_mc_per_bin_parallel_inf(const char* integrand, int dimbins, const uint64_
                                double* rec_sum, double* rec_sum2,
                                uint32_t* rec_len, float* rec_elems, uint64_t rec_cap, uint64_t* rec_used);
 
+// reference integrator_per_bin_parallel(monte_carlo(spp,seed)) over RangeInfinite — src/integrator-per-bin-parallel.h:16-35 +
+// src/monte-carlo/monte-carlo.h:65-84 + src/monte-carlo/random-sequence-rng.h:11-45 (a fresh mt19937 per sample).  '='.
+// Records as vo_mc_per_bin_parallel_inf (the elements f consumed through its own begin()).
+int vo_per_bin_parallel_mc_inf(const char* integrand, int dimbins, const uint64_t* res,
+                               const float* rmin, const float* rmax, int nrange,
+                               uint64_t spp, uint64_t seed, float* bins,
+                               double* rec_sum, double* rec_sum2,
+                               uint32_t* rec_len, float* rec_elems, uint64_t rec_cap, uint64_t* rec_used);
+
+// reference monte_carlo(samples,seed) over RangeInfinite, global scatter — src/monte-carlo/monte-carlo.h:65-84.  '+='.
+int vo_monte_carlo_inf(const char* integrand, int dimbins, const uint64_t* res,
+                       const float* rmin, const float* rmax, int nrange, uint64_t samples, uint64_t seed, float* bins);
+
 // reference integrator_newton_cotes(rule) — src/newton-cotes/newton-cotes.h:11-14. rule in
 // {"trapezoidal","simpson","boole"}.  '+='.
 int vo_newton_cotes(const char* integrand, const char* rule, int dimbins, const uint64_t* res,

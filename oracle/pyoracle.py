@@ -50,7 +50,7 @@ class Oracle:
         self.lib.vo_kind.restype = ctypes.c_char_p
         self.kind = self.lib.vo_kind().decode()
         for name in ("vo_mc_per_bin_parallel", "vo_per_bin_parallel_mc", "vo_monte_carlo", "vo_mc_per_bin_parallel_inf",
-                     "vo_newton_cotes", "vo_adaptive_iterations", "vo_crespo2021", "vo_mt_per_bin", "vo_integrand_dim"):
+                     "vo_per_bin_parallel_mc_inf", "vo_monte_carlo_inf", "vo_newton_cotes", "vo_adaptive_iterations", "vo_crespo2021", "vo_mt_per_bin", "vo_integrand_dim"):
             getattr(self.lib, name).restype = ctypes.c_int
 
     def dim(self, integrand):
@@ -112,6 +112,36 @@ class Oracle:
         self._check(rc, "vo_mc_per_bin_parallel_inf")
         if record:
             return bins, s1, s2, lens, elems[: used.value]
+        return bins
+
+    def per_bin_parallel_mc_inf(self, integrand, res, spp, seed, rmin=(), rmax=(), bins=None, record=False, rec_cap=None):
+        res = np.ascontiguousarray(np.asarray(res, dtype=np.uint64))
+        nb = int(np.prod(res))
+        rmin, rmax = _f32(rmin), _f32(rmax)
+        bins = np.zeros(nb, np.float32) if bins is None else np.ascontiguousarray(bins, dtype=np.float32).copy()
+        s1 = s2 = lens = elems = None
+        used = ctypes.c_uint64(0)
+        cap = 0
+        if record:
+            s1 = np.zeros(nb, np.float64); s2 = np.zeros(nb, np.float64)
+            lens = np.zeros(nb * spp, np.uint32)
+            cap = rec_cap if rec_cap is not None else nb * spp * 64
+            elems = np.zeros(cap, np.float32)
+        rc = self.lib.vo_per_bin_parallel_mc_inf(integrand.encode(), len(res), _p(res), _p(rmin), _p(rmax), len(rmin),
+                                                 ctypes.c_uint64(spp), ctypes.c_uint64(seed), _p(bins), _p(s1), _p(s2),
+                                                 _p(lens), _p(elems), ctypes.c_uint64(cap), ctypes.byref(used))
+        self._check(rc, "vo_per_bin_parallel_mc_inf")
+        if record:
+            return bins, s1, s2, lens, elems[: used.value]
+        return bins
+
+    def monte_carlo_inf(self, integrand, res, samples, seed, rmin=(), rmax=(), bins=None):
+        res = np.ascontiguousarray(np.asarray(res, dtype=np.uint64))
+        rmin, rmax = _f32(rmin), _f32(rmax)
+        bins = np.zeros(int(np.prod(res)), np.float32) if bins is None else np.ascontiguousarray(bins, dtype=np.float32).copy()
+        rc = self.lib.vo_monte_carlo_inf(integrand.encode(), len(res), _p(res), _p(rmin), _p(rmax), len(rmin),
+                                         ctypes.c_uint64(samples), ctypes.c_uint64(seed), _p(bins))
+        self._check(rc, "vo_monte_carlo_inf")
         return bins
 
     def newton_cotes(self, integrand, rule, res, rmin, rmax, bins=None):

@@ -154,6 +154,74 @@ extern "C" int vo_mc_per_bin_parallel_inf(const char* integrand, int dimbins, co
     });
 }
 
+extern "C" int vo_per_bin_parallel_mc_inf(const char* integrand, int dimbins, const uint64_t* res,
+                               const float* rmin, const float* rmax, int nrange,
+                               uint64_t spp, uint64_t seed, float* bins,
+                               double* rec_sum, double* rec_sum2,
+                               uint32_t* rec_len, float* rec_elems, uint64_t rec_cap, uint64_t* rec_used) {
+    return dispatch_infinite(integrand, [&] (auto f) -> int {
+        auto run = [&] (auto dbc) -> int {
+            constexpr std::size_t DB = decltype(dbc)::value;
+            auto r = res_array<DB>(res);
+            auto range = viltrum::range_infinite(std::vector<float>(rmin,rmin+nrange), std::vector<float>(rmax,rmax+nrange));
+            auto order = parallel_visit_order<DB>(r);
+            std::size_t nbins = 1; for (auto x : r) nbins *= x;
+            if (rec_sum)  std::fill(rec_sum,  rec_sum+nbins,  0.0);
+            if (rec_sum2) std::fill(rec_sum2, rec_sum2+nbins, 0.0);
+            std::vector<std::vector<float>> per_path(rec_elems || rec_used ? nbins*spp : 0);
+            std::vector<uint32_t> lens(nbins*spp, 0);
+            std::size_t calls = 0;
+            // the value-returning integrate deduces T from function(std::vector<Float>()) (integrate.h:117): the recorder must
+            // only count REAL calls, which come with the reference's RandomSequenceRNG
+            auto recf = [&] (const auto& seq) -> float {
+                using Seq = std::decay_t<decltype(seq)>;
+                if constexpr (std::is_same_v<Seq, std::vector<float>>) { return f(seq); }
+                else {
+                    std::size_t k = calls++;
+                    std::size_t bin = order[k/spp]; std::size_t s = k % spp;
+                    SeqRecorder sr{ per_path.empty() ? nullptr : &per_path[bin*spp+s], &lens[bin*spp+s] };
+                    RecSeq<Seq> rs(seq, sr);
+                    float v = f(rs);
+                    if (rec_sum)  rec_sum[bin]  += double(v);
+                    if (rec_sum2) rec_sum2[bin] += double(v)*double(v);
+                    return v;
+                }
+            };
+            auto acc = [&] (const std::array<std::size_t,DB>& p) -> float& { return bins[tensor_pos(p,r)]; };
+            viltrum::integrate(viltrum::integrator_per_bin_parallel(viltrum::monte_carlo(spp, std::size_t(seed))), acc, r, recf, range);
+            if (rec_len) std::copy(lens.begin(), lens.end(), rec_len);
+            uint64_t used = 0; for (auto l : lens) used += l;
+            if (rec_used) *rec_used = used;
+            if (rec_elems) {
+                if (used > rec_cap) return -3;
+                uint64_t o = 0;
+                for (auto& v : per_path) { std::copy(v.begin(), v.end(), rec_elems+o); o += v.size(); }
+            }
+            return 0;
+        };
+        if (dimbins == 1) return run(std::integral_constant<std::size_t,1>());
+        if (dimbins == 2) return run(std::integral_constant<std::size_t,2>());
+        return -2;
+    });
+}
+
+extern "C" int vo_monte_carlo_inf(const char* integrand, int dimbins, const uint64_t* res,
+                       const float* rmin, const float* rmax, int nrange, uint64_t samples, uint64_t seed, float* bins) {
+    return dispatch_infinite(integrand, [&] (auto f) -> int {
+        auto run = [&] (auto dbc) -> int {
+            constexpr std::size_t DB = decltype(dbc)::value;
+            auto r = res_array<DB>(res);
+            auto range = viltrum::range_infinite(std::vector<float>(rmin,rmin+nrange), std::vector<float>(rmax,rmax+nrange));
+            auto acc = [&] (const std::array<std::size_t,DB>& p) -> float& { return bins[tensor_pos(p,r)]; };
+            viltrum::integrate(viltrum::monte_carlo(samples, std::size_t(seed)), acc, r, f, range);
+            return 0;
+        };
+        if (dimbins == 1) return run(std::integral_constant<std::size_t,1>());
+        if (dimbins == 2) return run(std::integral_constant<std::size_t,2>());
+        return -2;
+    });
+}
+
 // Thread-pool CPU baseline: slab the LAST bin dimension over std::threads; each slab is an
 // independent call of the unmodified single-threaded reference with a sub-range and seed+slab.
 extern "C" int vo_mt_per_bin(const char* path, const char* integrand, int dimbins, const uint64_t* res,

@@ -76,6 +76,11 @@ def main():
             b, s1, s2, lens, elems = R.mc_per_bin_parallel_inf(integ, res, 6, 5, rmin, rmax, record=True)
             V.append(dict(integrand=integ, res=res, rmin=rmin, rmax=rmax, path="mc_per_bin_parallel_inf", spp=6, seed=5,
                           bins=bits(b), sum=bits(s1), sum2=bits(s2), lens=bits(lens), elems=bits(elems)))
+            b, s1, s2, lens, elems = R.per_bin_parallel_mc_inf(integ, res, 6, 5, rmin, rmax, record=True)
+            V.append(dict(integrand=integ, res=res, rmin=rmin, rmax=rmax, path="per_bin_parallel_mc_inf", spp=6, seed=5,
+                          bins=bits(b), sum=bits(s1), sum2=bits(s2), lens=bits(lens), elems=bits(elems)))
+            V.append(dict(integrand=integ, res=res, rmin=rmin, rmax=rmax, path="monte_carlo_inf", samples_n=300, seed=7,
+                          bins=bits(R.monte_carlo_inf(integ, res, 300, 7, rmin, rmax))))
     # SURVEY.md §8(c) known-answer vectors (README-sized cases), kept as decimal strings the survey printed
     path = os.path.join(HERE, "reference_vectors.json")
     with open(path, "w") as f:

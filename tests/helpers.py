@@ -59,6 +59,11 @@ def run_oracle_vector(O, v):
     if path == "mc_per_bin_parallel_inf":
         b, s1, s2, lens, elems = O.mc_per_bin_parallel_inf(integ, res, v["spp"], v["seed"], rmin, rmax, record=True)
         return dict(bins=b, sum=s1, sum2=s2, lens=lens, elems=elems)
+    if path == "per_bin_parallel_mc_inf":
+        b, s1, s2, lens, elems = O.per_bin_parallel_mc_inf(integ, res, v["spp"], v["seed"], rmin, rmax, record=True)
+        return dict(bins=b, sum=s1, sum2=s2, lens=lens, elems=elems)
+    if path == "monte_carlo_inf":
+        return dict(bins=O.monte_carlo_inf(integ, res, v["samples_n"], v["seed"], rmin, rmax))
     raise KeyError(path)
 
 

@@ -50,16 +50,17 @@ def test_replay_golden_reference_vectors(ctx):
     from viltrum_b200 import RangeInfinite
     n = 0
     for v in load_golden():
-        if v["path"] != "mc_per_bin_parallel_inf":
+        if v["path"] not in ("mc_per_bin_parallel_inf", "per_bin_parallel_mc_inf"):
             continue
+        from viltrum_b200 import _capi
         lens = np.asarray(v["lens"], np.uint64)
         offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
         got = np.zeros(int(np.prod(v["res"])), np.float32)
         ctx.mc_per_bin_inf_replay(v["integrand"], got, v["res"], RangeInfinite(v["rmin"], v["rmax"]), v["spp"], offsets,
-                                  np.ascontiguousarray(f32(v["elems"])))
+                                  np.ascontiguousarray(f32(v["elems"])), flavor=_capi.MC_PER_BIN if v["path"] == "mc_per_bin_parallel_inf" else _capi.PER_BIN_MC)
         assert_same_bits(got, f32(v["bins"]), f"{v['integrand']} {v['res']}")
         n += 1
-    assert n == 4
+    assert n == 8
 
 
 def test_replay_detects_short_sequences(ctx, port):
@@ -131,3 +132,41 @@ def test_wavefront_kernel_equals_generic_kernel(ctx):
         ctx.mc_per_bin_inf("walk", a, res, RangeInfinite(), spp, 5)
         ctx.mc_per_bin_inf("walk_plain", b, res, RangeInfinite(), spp, 5)
         assert_same_bits(a, b, f"wavefront vs generic {res}")
+
+
+@pytest.mark.parametrize("integ,res,spp,rmin,rmax", [("walk", [48, 40], 256, (), ()), ("decay", [64], 512, (), ()),
+                                                     ("walk", [20, 16], 128, (0.1, 0.2, 0.0), (0.9, 0.7, 1.0))])
+def test_wrapper_spelling_over_infinite_range_a20(ctx, port, integ, res, spp, rmin, rmax):
+    """integrator_per_bin_parallel(monte_carlo(spp,seed)) over RangeInfinite ('=', scaled by the bin box's
+    own volume) — statistical parity with the oracle and bit-exact replay of the oracle's recorded sequences."""
+    from viltrum_b200 import RangeInfinite, integrate, integrator_per_bin_parallel, monte_carlo, _capi
+    rng = RangeInfinite(list(rmin), list(rmax))
+    nb = int(np.prod(res))
+    g = np.full(nb, 9.0, np.float32); s1 = np.zeros(nb, np.float32); s2 = np.zeros(nb, np.float32)
+    integrate(integrator_per_bin_parallel(monte_carlo(spp, seed=21)), g, res, integ, rng, ctx=ctx, sum_f=s1, sum_f2=s2)
+    r, r1, r2, lens, elems = port.per_bin_parallel_mc_inf(integ, res, spp, 4, rmin, rmax, record=True)
+    vol = float(np.prod(np.asarray(rmax, np.float32) - np.asarray(rmin, np.float32))) if len(rmin) else 1.0
+    assert_statistically_equal(g, r, mc_variance(s1, s2, spp, vol), mc_variance(r1, r2, spp, vol), f"a20 {integ} {res}")
+    offsets = np.concatenate([[0], np.cumsum(lens.astype(np.uint64))]).astype(np.uint64)
+    got = np.full(nb, 3.0, np.float32)
+    ctx.mc_per_bin_inf_replay(integ, got, res, rng, spp, offsets, np.ascontiguousarray(elems), flavor=_capi.PER_BIN_MC)
+    assert_same_bits(got, r, "a20 replay")
+
+
+@pytest.mark.parametrize("integ,res,rmin,rmax", [("walk", [16, 12], (), ()), ("decay", [10], (), ()), ("walk", [8, 8], (0.1, 0.2, 0.0), (0.9, 0.7, 1.0))])
+def test_global_scatter_over_infinite_range(ctx, port, integ, res, rmin, rmax):
+    """monte_carlo(n,seed) over RangeInfinite (monte-carlo.h:65-84): bin from the first dimbins sequence elements"""
+    from viltrum_b200 import RangeInfinite, integrate, monte_carlo
+    rng = RangeInfinite(list(rmin), list(rmax))
+    nb = int(np.prod(res)); n = 1 << 22
+    g = np.zeros(nb, np.float32)
+    integrate(monte_carlo(n, seed=5), g, res, integ, rng, ctx=ctx)
+    ref_n = 400000
+    r = port.monte_carlo_inf(integ, res, ref_n, 3, rmin, rmax)
+    # the oracle run is the noisy one: per-bin sigma ~ |f| * sqrt(nb/ref_n)
+    sigma = (np.abs(r).mean() + 1.0) * np.sqrt(nb / ref_n) * 1.5
+    assert np.max(np.abs(g - r)) < 6 * sigma, (np.max(np.abs(g - r)), sigma)
+    assert abs(float(g.mean()) - float(r.mean())) < 6 * sigma / np.sqrt(nb) + 1e-3
+    acc = np.full(nb, 2.0, np.float32)
+    integrate(monte_carlo(n, seed=5), acc, res, integ, rng, ctx=ctx)
+    assert np.allclose(acc - 2.0, g, rtol=1e-4, atol=1e-4)          # '+=' ; float atomics reorder sums

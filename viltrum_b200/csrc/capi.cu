@@ -334,7 +334,7 @@ extern "C" int vb200_mc_per_bin_inf(vb200_ctx* ctx, const vb200_integrand* f, co
     if (f->dim != -1) return fail(ctx, VB200_ERR_INVALID, "vb200_mc_per_bin_inf needs a sequence integrand");
     int rc = check_domain(ctx, p->domain, -1); if (rc) return rc;
     if (p->spp == 0 || p->spp > 0xffffffffull) return fail(ctx, VB200_ERR_INVALID, "spp invalid");
-    if (p->flavor != VB200_MC_PER_BIN) return fail(ctx, VB200_ERR_UNSUPPORTED, "infinite ranges: only the monte_carlo_per_bin_parallel flavor is implemented");
+    if (p->flavor != VB200_MC_PER_BIN && p->flavor != VB200_PER_BIN_MC) return fail(ctx, VB200_ERR_INVALID, "unknown flavor %d", p->flavor);
     const uint64_t total = nbins_of(p->domain);
     uint64_t begin, end; rc = resolve_shard(ctx, p->shard, total, &begin, &end); if (rc) return rc;
     if (begin == end) return VB200_OK;
@@ -343,7 +343,9 @@ extern "C" int vb200_mc_per_bin_inf(vb200_ctx* ctx, const vb200_integrand* f, co
     a.spp = uint32_t(p->spp); a.lanes_per_bin = pick_lanes_per_bin(ctx, p->spp, total);   // from the WHOLE grid: the summation order, hence the bits, must not depend on the shard
     a.key0 = uint32_t(p->seed); a.key1 = uint32_t(p->seed >> 32);
     a.factor = double(range_volume(p->domain, p->domain.dim)) / double(p->spp);      // range-infinite.h:22-23; :77
-    return run_sampler(ctx, f, VB200_K_WALK, a, /*accumulate '+='*/ true, bins, bins_mem, sum_f, sum_f2);
+    a.flavor = p->flavor;
+    // '+=' for MonteCarloPerBinParallel, '=' for IntegratorPerBinParallel(MonteCarlo)
+    return run_sampler(ctx, f, VB200_K_WALK, a, p->flavor == VB200_MC_PER_BIN, bins, bins_mem, sum_f, sum_f2);
 }
 
 extern "C" int vb200_mc_per_bin_inf_replay(vb200_ctx* ctx, const vb200_integrand* f, const vb200_mc_params* p,
@@ -357,7 +359,7 @@ extern "C" int vb200_mc_per_bin_inf_replay(vb200_ctx* ctx, const vb200_integrand
     if (begin == end) return VB200_OK;
     const uint64_t npaths = (end - begin) * p->spp;
     vb200_walk_replay_launch a; std::memset(&a, 0, sizeof(a));
-    a.domain = finish_domain(p->domain); a.bin_begin = begin; a.bin_end = end; a.nbins_total = total; a.spp = uint32_t(p->spp);
+    a.domain = finish_domain(p->domain); a.bin_begin = begin; a.bin_end = end; a.nbins_total = total; a.spp = uint32_t(p->spp); a.flavor = p->flavor;
     a.factor = double(range_volume(p->domain, p->domain.dim)) / double(p->spp);
     if (mem == VB200_HOST) {
         const uint64_t nel = offsets[npaths];
@@ -385,8 +387,8 @@ extern "C" int vb200_mc_per_bin_inf_replay(vb200_ctx* ctx, const vb200_integrand
 extern "C" int vb200_monte_carlo(vb200_ctx* ctx, const vb200_integrand* f, const vb200_mc_params* p, float* bins, int bins_mem) {
     if (!ctx || !f || !p) return fail(ctx, VB200_ERR_INVALID, "NULL argument");
     VB200_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (f->dim <= 0) return fail(ctx, VB200_ERR_UNSUPPORTED, "global Monte Carlo over infinite ranges is not implemented");
-    int rc = check_domain(ctx, p->domain, f->dim); if (rc) return rc;
+    if (f->dim == 0) return fail(ctx, VB200_ERR_INVALID, "integrand has dimension 0");
+    int rc = check_domain(ctx, p->domain, f->dim > 0 ? f->dim : -1); if (rc) return rc;
     if (p->spp == 0) return fail(ctx, VB200_ERR_INVALID, "samples=0");
     const uint64_t total = nbins_of(p->domain);
     uint64_t sb, se; rc = resolve_shard(ctx, p->shard, p->spp, &sb, &se); if (rc) return rc;
@@ -401,7 +403,7 @@ extern "C" int vb200_monte_carlo(vb200_ctx* ctx, const vb200_integrand* f, const
         VB200_CUDA(ctx, cudaMemsetAsync(dev, 0, total * sizeof(float), ctx->stream));
     }
     a.out = dev;
-    if (se > sb) { rc = call_thunk(ctx, f, VB200_K_MC_SCATTER, &a); if (rc) return rc; }
+    if (se > sb) { rc = call_thunk(ctx, f, f->dim > 0 ? VB200_K_MC_SCATTER : VB200_K_WALK_SCATTER, &a); if (rc) return rc; }
     if (bins_mem == VB200_HOST) {
         float* h = nullptr; rc = reserve_pinned(ctx, total * sizeof(float), reinterpret_cast<void**>(&h)); if (rc) return rc;
         VB200_CUDA(ctx, cudaMemcpyAsync(h, dev, total * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));

@@ -161,18 +161,18 @@ class Context:
         p = self._mc_params(len(rng.min), res, rng, spp, 0, flavor, shard)
         self.check(self._L.vb200_mc_per_bin_replay(self._h, self.integrand(f, exact), ctypes.byref(p), s, smem, b, mem))
 
-    def mc_per_bin_inf(self, f, bins, res, rng, spp, seed, shard=None, sum_f=None, sum_f2=None, exact=False):
+    def mc_per_bin_inf(self, f, bins, res, rng, spp, seed, shard=None, sum_f=None, sum_f2=None, exact=False, flavor=C.MC_PER_BIN):
         if self._empty(shard):
             return
         b, mem, _k = _buffer(bins)
         s1, m1, _k1 = _buffer(sum_f); s2, m2, _k2 = _buffer(sum_f2)
-        p = self._mc_params(len(rng.min), res, rng, spp, seed, C.MC_PER_BIN, shard)
+        p = self._mc_params(len(rng.min), res, rng, spp, seed, flavor, shard)
         self.check(self._L.vb200_mc_per_bin_inf(self._h, self.integrand(f, exact), ctypes.byref(p), b, mem, s1, s2))
 
-    def mc_per_bin_inf_replay(self, f, bins, res, rng, spp, offsets, elems, shard=None, exact=True):
+    def mc_per_bin_inf_replay(self, f, bins, res, rng, spp, offsets, elems, shard=None, exact=True, flavor=C.MC_PER_BIN):
         b, mem, _k = _buffer(bins)
         o, omem, _ko = _buffer(offsets, np.uint64); e, emem, _ke = _buffer(elems)
-        p = self._mc_params(len(rng.min), res, rng, spp, 0, C.MC_PER_BIN, shard)
+        p = self._mc_params(len(rng.min), res, rng, spp, 0, flavor, shard)
         self.check(self._L.vb200_mc_per_bin_inf_replay(self._h, self.integrand(f, exact), ctypes.byref(p), o, e, emem, b, mem))
 
     def monte_carlo(self, f, bins, res, rng, samples, seed, shard=None, exact=False):
@@ -305,7 +305,10 @@ class IntegratorPerBinParallel:
     def integrate(self, ctx, bins, res, f, rng, shard=None, **kw):
         if not isinstance(self.inner, MonteCarlo):
             raise NotImplementedError("integrator_per_bin_parallel: only monte_carlo(...) inner integrators are on the hot path")
-        ctx.mc_per_bin(f, bins, res, rng, self.inner.samples, self.inner.seed, C.PER_BIN_MC, shard=shard, **kw)
+        if isinstance(rng, RangeInfinite):
+            ctx.mc_per_bin_inf(f, bins, res, rng, self.inner.samples, self.inner.seed, shard=shard, flavor=C.PER_BIN_MC, **kw)
+        else:
+            ctx.mc_per_bin(f, bins, res, rng, self.inner.samples, self.inner.seed, C.PER_BIN_MC, shard=shard, **kw)
 
 
 @dataclass
