@@ -73,6 +73,36 @@ struct SmoothEdge2 {
     }
 };
 
+// ---- double-precision family (Range<double,DIM>, north_star: Newton-Cotes within 1e-12 in fp64) ------------------------------
+// Same shapes with double constants; these are integrands in their own right (0.55 != 0.55f), named like the float ones and
+// selected by the *_f64 entry points.
+template<typename T> struct X2Y2T { static constexpr int dim = 2; T operator()(const std::array<T,2>& x) const { return x[0]*x[0] + x[1]*x[1]; } };
+template<typename T> struct Ind2T { static constexpr int dim = 2; T operator()(const std::array<T,2>& x) const { return ((x[0]+x[1])<T(1))?T(1):T(0); } };
+template<typename T> struct Cubic1T { static constexpr int dim = 1; T operator()(const std::array<T,1>& x) const { return (T(4)*x[0]*x[0]-T(1))*x[0] + T(0.25); } };
+template<typename T> struct Poly3T { static constexpr int dim = 3; T operator()(const std::array<T,3>& x) const { return x[0]*x[1] + x[1]*x[2]*x[2] + T(0.5); } };
+template<typename T> struct SmoothEdge2T {
+    static constexpr int dim = 2;
+    T operator()(const std::array<T,2>& p) const {
+        T x=p[0], y=p[1];
+        T s=T(0.5)+T(8)*x*(T(1)-x)*y*(T(1)-y)*(T(1)-T(2)*(x-y)*(x-y));
+        T dx=x-T(0.45), dy=y-T(0.55);
+        return s+((dx*dx+dy*dy<T(0.09))?T(0.75):T(0));
+    }
+};
+template<typename T, int K> struct Shade4T {
+    static constexpr int dim = 4;
+    T operator()(const std::array<T,4>& x) const {
+        T a=x[0]-T(0.5), b=x[1]-T(0.5);
+        T edge=T(0.55)+T(0.35)*(a*a-b*b)+T(0.2)*a*b;
+        T vis=(x[2]+T(0.5)*x[3]<edge)?T(1):T(0);
+        T t=x[2]*(T(1)-x[3]);
+        T lobe=T(1)/T(K);
+        for (int k=K-2;k>=0;--k) lobe=lobe*t+T(1)/T(k+1);
+        T alb=T(0.25)+T(0.75)*x[0]*x[1];
+        return vis*lobe*alb;
+    }
+};
+
 // Infinite-dimensional random walk with Russian roulette.
 struct Walk {
     template<typename Seq> float operator()(const Seq& seq) const {

@@ -378,17 +378,30 @@ extern "C" int vo_monte_carlo_inf(const char* integrand, int dimbins, const uint
 namespace {
 
 enum Rule { TRAPEZOIDAL=2, SIMPSON=3, BOOLE=5 };   // value == samples per dimension
-
-// rules.h:14 / :64 / :256 — literals are double, result rounded to float at return
-inline float rule_apply(int S, const float* p) {
-    switch (S) {
-        case 2: return float((p[0]+p[1])/2.0);                                               // float add, double divide
-        case 3: return float((double(p[0])+4.0*double(p[1])+double(p[2]))/6.0);
-        default: return float((7.0*double(p[0])+32.0*double(p[1])+12.0*double(p[2])+32.0*double(p[3])+7.0*double(p[4]))/90.0);
+// Everything below is a template over the scalar type T = Float = value_type of the reference (float or double): the
+// float(...) casts of the fp32 restatement become T(...), i.e. no-ops when the reference itself computes in double.
+template<typename T> using FiniteFnT = T (*)(const T*);
+template<typename T> inline T volume_of_t(int d, const T* a, const T* b) { T v=T(1); for (int i=0;i<d;++i) v*=(b[i]-a[i]); return v; }
+template<typename T> inline void bin_box_t(int d, int db, const T* rmin, const T* rmax, const uint64_t* res, const uint64_t* pos, T* a, T* b) {
+    for (int i=0;i<d;++i) { a[i]=rmin[i]; b[i]=rmax[i]; }
+    for (int i=0;i<db;++i) {
+        T drange = (rmax[i]-rmin[i])/T(res[i]);
+        a[i] = rmin[i] + T(pos[i])*drange;
+        b[i] = rmin[i] + T(pos[i]+1)*drange;
     }
 }
-// rules.h:27-32 / :77-83 / :272-280 — integer literals: float arithmetic, left to right
-inline void rule_coefficients(int S, const float* p, float* c) {
+
+
+// rules.h:14 / :64 / :256 — literals are double, result rounded to T at return
+template<typename T> inline T rule_apply(int S, const T* p) {
+    switch (S) {
+        case 2: return T((p[0]+p[1])/2.0);                                               // T add, double divide
+        case 3: return T((double(p[0])+4.0*double(p[1])+double(p[2]))/6.0);
+        default: return T((7.0*double(p[0])+32.0*double(p[1])+12.0*double(p[2])+32.0*double(p[3])+7.0*double(p[4]))/90.0);
+    }
+}
+// rules.h:27-32 / :77-83 / :272-280 — integer literals: T arithmetic, left to right
+template<typename T> inline void rule_coefficients(int S, const T* p, T* c) {
     switch (S) {
         case 2: c[0]=p[0]; c[1]=p[1]-p[0]; break;
         case 3: c[0]=p[0]; c[1]=-3*p[0]+4*p[1]-p[2]; c[2]=2*p[0]-4*p[1]+2*p[2]; break;
@@ -400,34 +413,34 @@ inline void rule_coefficients(int S, const float* p, float* c) {
             c[4]=32*p[0]/3 - 128*p[1]/3 + 64*p[2] - 128*p[3]/3 + 32*p[4]/3;
     }
 }
-// rules.h:35-38 / :86-89 / :283-286 — Horner in float
-inline float rule_at(int S, float t, const float* p) {
-    float c[5]; rule_coefficients(S,p,c);
+// rules.h:35-38 / :86-89 / :283-286 — Horner in T
+template<typename T> inline T rule_at(int S, T t, const T* p) {
+    T c[5]; rule_coefficients(S,p,c);
     switch (S) {
         case 2: return c[1]*t + c[0];
         case 3: return (c[2]*t + c[1])*t + c[0];
         default: return (((c[4]*t + c[3])*t + c[2])*t + c[1])*t + c[0];
     }
 }
-// rules.h:41-44 / :97-100 / :289-293 — antiderivative difference; c*b is float, the /k.0 promotes to double
-inline float rule_subrange(int S, float a, float b, const float* p) {
-    float c[5]; rule_coefficients(S,p,c);
+// rules.h:41-44 / :97-100 / :289-293 — antiderivative difference; c*b is T, the /k.0 promotes to double
+template<typename T> inline T rule_subrange(int S, T a, T b, const T* p) {
+    T c[5]; rule_coefficients(S,p,c);
     switch (S) {
-        case 2: return float((c[1]*b/2.0 + c[0])*b - (c[1]*a/2.0 + c[0])*a);
-        case 3: return float(((c[2]*b/3.0 + c[1]/2.0)*b + c[0])*b - ((c[2]*a/3.0 + c[1]/2.0)*a + c[0])*a);
-        default: return float(((((c[4]*b/5.0 + c[3]/4.0)*b + c[2]/3.0)*b + c[1]/2.0)*b + c[0])*b -
+        case 2: return T((c[1]*b/2.0 + c[0])*b - (c[1]*a/2.0 + c[0])*a);
+        case 3: return T(((c[2]*b/3.0 + c[1]/2.0)*b + c[0])*b - ((c[2]*a/3.0 + c[1]/2.0)*a + c[0])*a);
+        default: return T(((((c[4]*b/5.0 + c[3]/4.0)*b + c[2]/3.0)*b + c[1]/2.0)*b + c[0])*b -
                               ((((c[4]*a/5.0 + c[3]/4.0)*a + c[2]/3.0)*a + c[1]/2.0)*a + c[0])*a);
     }
 }
 // nested.h:17-23
-inline float nested_low(int SH, int SL, const float* p) {
-    float plow[5];
+template<typename T> inline T nested_low(int SH, int SL, const T* p) {
+    T plow[5];
     for (int i=0;i<SL;++i) plow[i] = p[i*(SH-1)/(SL-1)];
     return rule_apply(SL,plow);
 }
 // error-metric.h:10-13 / :30-37
-inline float metric_absolute(float a, float b) { return std::abs(b-a); }
-inline float metric_relative(float a, float b) {
+template<typename T> inline T metric_absolute(T a, T b) { return std::abs(b-a); }
+template<typename T> inline T metric_relative(T a, T b) {
     const double min_val = 1.e-37;
     if (std::max(std::abs(a),std::abs(b)) < min_val) return std::abs(b-a);
     else return std::abs(b-a)/std::max(std::abs(a),std::abs(b));
@@ -436,19 +449,19 @@ inline float metric_relative(float a, float b) {
 inline uint64_t ipow(int s, int d) { uint64_t r=1; for (int i=0;i<d;++i) r*=uint64_t(s); return r; }
 
 // A region = box + S^D samples, dim-0-fastest (region.h:23-68, multiarray.h:20-25)
-struct Region {
-    std::vector<float> rmin, rmax, data;
-    float volume;                     // Range::_volume, float product
-    float err = 0.0f; uint32_t errdim = 0;
+template<typename T> struct RegionT {
+    std::vector<T> rmin, rmax, data;
+    T volume;                     // Range::_volume, T product
+    T err = T(0); uint32_t errdim = 0;
 };
 
 // fold a multiarray along dimension `dim` with a per-line functor; shape in/out are S^nd / S^(nd-1), dim-0-fastest
 // (fold.h:24-35: result index = base index with `dim` removed)
-template<typename LineFn>
-std::vector<float> fold_dim(const std::vector<float>& in, int S, int nd, int dim, LineFn&& fn) {
+template<typename T, typename LineFn>
+std::vector<T> fold_dim(const std::vector<T>& in, int S, int nd, int dim, LineFn&& fn) {
     uint64_t inner = ipow(S,dim), outer = ipow(S,nd-1-dim);
-    std::vector<float> out(inner*outer);
-    float line[5];
+    std::vector<T> out(inner*outer);
+    T line[5];
     for (uint64_t o=0;o<outer;++o) for (uint64_t i=0;i<inner;++i) {
         for (int e=0;e<S;++e) line[e] = in[i + uint64_t(e)*inner + o*inner*uint64_t(S)];
         out[i + o*inner] = fn(line);
@@ -456,20 +469,20 @@ std::vector<float> fold_dim(const std::vector<float>& in, int S, int nd, int dim
     return out;
 }
 // fold_all(q): fold dimension 0 repeatedly (fold.h:87-108) — the lowest remaining dim is always innermost
-inline float fold_all_rule(std::vector<float> v, int S, int nd) {
-    while (nd>0) { v = fold_dim(v,S,nd,0,[&] (const float* l) { return rule_apply(S,l); }); --nd; }
+template<typename T> inline T fold_all_rule(std::vector<T> v, int S, int nd) {
+    while (nd>0) { v = fold_dim(v,S,nd,0,[&] (const T* l) { return rule_apply(S,l); }); --nd; }
     return v[0];
 }
 
-// region.h:40-46 (f_in_range) + fill.h:45-72: normalised coords double(i)/double(S-1), mapped in double, rounded to float
-inline void region_point(const Region& r, int D, const double* p, float* x) {
-    for (int i=0;i<D;++i) x[i] = float(p[i]*double(r.rmax[i]-r.rmin[i]) + double(r.rmin[i]));
+// region.h:40-46 (f_in_range) + fill.h:45-72: normalised coords double(i)/double(S-1), mapped in double, rounded to T
+template<typename T> inline void region_point(const RegionT<T>& r, int D, const double* p, T* x) {
+    for (int i=0;i<D;++i) x[i] = T(p[i]*double(r.rmax[i]-r.rmin[i]) + double(r.rmin[i]));
 }
-Region make_region(FiniteFn f, int S, int D, const float* a, const float* b) {
-    Region r; r.rmin.assign(a,a+D); r.rmax.assign(b,b+D); r.volume = volume_of(D,a,b);
+template<typename T> RegionT<T> make_region(FiniteFnT<T> f, int S, int D, const T* a, const T* b) {
+    RegionT<T> r; r.rmin.assign(a,a+D); r.rmax.assign(b,b+D); r.volume = volume_of_t(D,a,b);
     uint64_t n = ipow(S,D); r.data.resize(n);
     for (uint64_t k=0;k<n;++k) {
-        double p[8]; float x[8]; uint64_t t=k;
+        double p[8]; T x[8]; uint64_t t=k;
         for (int d=0;d<D;++d) { p[d] = double(t%uint64_t(S))/double(S-1); t/=uint64_t(S); }
         region_point(r,D,p,x);
         r.data[k] = f(x);
@@ -479,18 +492,18 @@ Region make_region(FiniteFn f, int S, int D, const float* a, const float* b) {
 
 // region.h:345-359 + split.h:13-49, parts == 2.  Children reuse the parent's samples at even positions along
 // `dim` and evaluate f at the odd ones with coordinates derived from the PARENT range (v = i/(2(S-1))).
-void split_region(FiniteFn f, int S, int D, const Region& r, int dim, Region out[2]) {
+template<typename T> void split_region(FiniteFnT<T> f, int S, int D, const RegionT<T>& r, int dim, RegionT<T> out[2]) {
     uint64_t n = ipow(S,D), inner = ipow(S,dim);
     int full = 2*(S-1)+1;
-    for (int c=0;c<2;++c) { out[c].rmin=r.rmin; out[c].rmax=r.rmax; out[c].data.assign(n,0.0f); }
+    for (int c=0;c<2;++c) { out[c].rmin=r.rmin; out[c].rmax=r.rmax; out[c].data.assign(n,T(0)); }
     // slab(i) of the conceptual (2S-1)-wide array: from parent if i even, fresh evaluations if odd
     for (int i=0;i<full;++i) {
         for (uint64_t k=0;k<n/uint64_t(S);++k) {           // index over the other D-1 dims, dim-0-fastest
             uint64_t lo = k%inner, hi = k/inner;            // position below / above `dim`
-            float v;
+            T v;
             if (i%2==0) v = r.data[lo + uint64_t(i/2)*inner + hi*inner*uint64_t(S)];
             else {
-                double p[8]; float x[8]; uint64_t t=k;
+                double p[8]; T x[8]; uint64_t t=k;
                 for (int d=0;d<D;++d) {
                     if (d==dim) p[d] = double(i)/double(full-1);
                     else { p[d] = double(t%uint64_t(S))/double(S-1); t/=uint64_t(S); }
@@ -502,37 +515,37 @@ void split_region(FiniteFn f, int S, int D, const Region& r, int dim, Region out
             if (i>=S-1) out[1].data[lo + uint64_t(i-(S-1))*inner + hi*inner*uint64_t(S)] = v;
         }
     }
-    float d = (r.rmax[dim]-r.rmin[dim])/float(2);                              // region.h:351
-    float mid = r.rmin[dim] + d*float(1);                                      // :353 (i+1 == 1)
+    T d = (r.rmax[dim]-r.rmin[dim])/T(2);                              // region.h:351
+    T mid = r.rmin[dim] + d*T(1);                                      // :353 (i+1 == 1)
     out[0].rmax[dim] = mid; out[1].rmin[dim] = mid;                            // :353-355 ; last child keeps parent max
-    for (int c=0;c<2;++c) out[c].volume = volume_of(D,out[c].rmin.data(),out[c].rmax.data());
+    for (int c=0;c<2;++c) out[c].volume = volume_of_t(D,out[c].rmin.data(),out[c].rmax.data());
 }
 
 // region.h:387-393: volume * fold(error along dim).fold_all(high rule)
-float region_error(const Region& r, int SH, int SL, int D, int dim, bool relative) {
-    auto e = fold_dim(r.data,SH,D,dim,[&] (const float* l) {
-        float h = rule_apply(SH,l), lo = nested_low(SH,SL,l);
+template<typename T> T region_error(const RegionT<T>& r, int SH, int SL, int D, int dim, bool relative) {
+    auto e = fold_dim(r.data,SH,D,dim,[&] (const T* l) {
+        T h = rule_apply(SH,l), lo = nested_low(SH,SL,l);
         return relative ? metric_relative(h,lo) : metric_absolute(h,lo);       // nested.h:31-33
     });
     return r.volume*fold_all_rule(e,SH,D-1);
 }
 // error-heuristic.h:15-18 -> region.h:401-411 (first maximal dim, strict >)
-void heuristic_default(Region& r, int SH, int SL, int D, bool relative) {
-    float max_err = 0; uint32_t max_dim = 0;
-    for (int d=0; d<D; ++d) { float err = region_error(r,SH,SL,D,d,relative); if (err>max_err) { max_err=err; max_dim=uint32_t(d); } }
+template<typename T> void heuristic_default(RegionT<T>& r, int SH, int SL, int D, bool relative) {
+    T max_err = 0; uint32_t max_dim = 0;
+    for (int d=0; d<D; ++d) { T err = region_error(r,SH,SL,D,d,relative); if (err>max_err) { max_err=err; max_dim=uint32_t(d); } }
     r.err = max_err; r.errdim = max_dim;
 }
 // error-heuristic.h:29-46 (last maximal dim, >=)
-void heuristic_size(Region& r, int SH, int SL, int D, bool relative, double size_weight) {
+template<typename T> void heuristic_size(RegionT<T>& r, int SH, int SL, int D, bool relative, double size_weight) {
     const double min_size = 1.e-37;
-    float max_err = region_error(r,SH,SL,D,0,relative);
-    float w0 = r.rmax[0]-r.rmin[0];
+    T max_err = region_error(r,SH,SL,D,0,relative);
+    T w0 = r.rmax[0]-r.rmin[0];
     if (w0<min_size || std::isnan(w0)) max_err = 0;
-    else max_err = float(double(max_err) + size_weight*double(std::abs(r.rmax[0]-r.rmin[0])));
+    else max_err = T(double(max_err) + size_weight*double(std::abs(r.rmax[0]-r.rmin[0])));
     uint32_t max_dim = 0;
-    float err = max_err;
+    T err = max_err;
     for (int d=1; d<D; ++d) {
-        err = float(double(region_error(r,SH,SL,D,d,relative)) + size_weight*double(std::abs(r.rmax[d]-r.rmin[d])));
+        err = T(double(region_error(r,SH,SL,D,d,relative)) + size_weight*double(std::abs(r.rmax[d]-r.rmin[d])));
         if ((r.rmax[d]-r.rmin[d])<min_size) err = 0;
         if (err>=max_err) { max_err=err; max_dim=uint32_t(d); }
     }
@@ -548,22 +561,22 @@ bool parse_heuristic(const char* h, double sw, Heuristic& out) {
     if (!std::strcmp(h,"size_relative"))    { out.size=true;  out.relative=true;  return true; }
     return false;
 }
-void apply_heuristic(Region& r, int SH, int SL, int D, const Heuristic& h) {
+template<typename T> void apply_heuristic(RegionT<T>& r, int SH, int SL, int D, const Heuristic& h) {
     if (h.size) heuristic_size(r,SH,SL,D,h.relative,h.size_weight); else heuristic_default(r,SH,SL,D,h.relative);
 }
 
 // libstdc++ bits/stl_heap.h:135-148 (__push_heap) with comparator a.err < b.err
-void heap_push(std::vector<Region>& h) {
-    std::size_t hole = h.size()-1; Region value = std::move(h[hole]);
+template<typename T> void heap_push(std::vector<RegionT<T>>& h) {
+    std::size_t hole = h.size()-1; RegionT<T> value = std::move(h[hole]);
     std::size_t parent = (hole-1)/2;
     while (hole>0 && h[parent].err < value.err) { h[hole] = std::move(h[parent]); hole = parent; parent = (hole-1)/2; }
     h[hole] = std::move(value);
 }
 // libstdc++ bits/stl_heap.h:254-267 (pop_heap -> __pop_heap) + :224-250 (__adjust_heap); caller pops the back
-void heap_pop(std::vector<Region>& h) {
+template<typename T> void heap_pop(std::vector<RegionT<T>>& h) {
     if (h.size()<2) return;
     std::size_t last = h.size()-1;
-    Region value = std::move(h[last]); h[last] = std::move(h[0]);
+    RegionT<T> value = std::move(h[last]); h[last] = std::move(h[0]);
     std::size_t len = last, hole = 0, child = 0;
     while (child < (len-1)/2) {
         child = 2*(child+1);
@@ -578,14 +591,14 @@ void heap_pop(std::vector<Region>& h) {
 }
 
 // regions-generator-adaptive-heap.h:18-45
-std::vector<Region> generate_adaptive(FiniteFn f, int SH, int SL, int D, const float* rmin, const float* rmax,
+template<typename T> std::vector<RegionT<T>> generate_adaptive(FiniteFnT<T> f, int SH, int SL, int D, const T* rmin, const T* rmax,
                                       const Heuristic& h, uint64_t iterations) {
-    std::vector<Region> heap; heap.reserve(iterations+1);
+    std::vector<RegionT<T>> heap; heap.reserve(iterations+1);
     heap.push_back(make_region(f,SH,D,rmin,rmax));
     apply_heuristic(heap[0],SH,SL,D,h);
     for (uint64_t i=0;i<iterations;++i) {
-        Region r = heap.front();                                               // :33
-        Region sub[2]; split_region(f,SH,D,r,int(r.errdim),sub);               // :34
+        RegionT<T> r = heap.front();                                               // :33
+        RegionT<T> sub[2]; split_region(f,SH,D,r,int(r.errdim),sub);               // :34
         heap_pop(heap); heap.pop_back();                                       // :35
         for (int c=0;c<2;++c) {                                                // :36-40
             apply_heuristic(sub[c],SH,SL,D,h);
@@ -596,54 +609,54 @@ std::vector<Region> generate_adaptive(FiniteFn f, int SH, int SL, int D, const f
 }
 
 // range.h:45-53
-inline float pos_in_range1(float lo, float hi, float p) { return (lo>=hi) ? lo : (p-lo)/(hi-lo); }
+template<typename T> inline T pos_in_range1(T lo, T hi, T p) { return (lo>=hi) ? lo : (p-lo)/(hi-lo); }
 
 // region.h:141-169 (integral_subrange -> sub_last): fold subrange(a_d,b_d) over dim D-1, ..., 0; times volume
-float region_integral_subrange(const Region& r, int S, int D, const float* a, const float* b) {
-    std::vector<float> v = r.data;
+template<typename T> T region_integral_subrange(const RegionT<T>& r, int S, int D, const T* a, const T* b) {
+    std::vector<T> v = r.data;
     for (int d=D-1; d>=0; --d) {
-        float na = pos_in_range1(r.rmin[d],r.rmax[d],a[d]), nb = pos_in_range1(r.rmin[d],r.rmax[d],b[d]);
-        v = fold_dim(v,S,d+1,d,[&] (const float* l) { return rule_subrange(S,na,nb,l); });
+        T na = pos_in_range1(r.rmin[d],r.rmax[d],a[d]), nb = pos_in_range1(r.rmin[d],r.rmax[d],b[d]);
+        v = fold_dim(v,S,d+1,d,[&] (const T* l) { return rule_subrange(S,na,nb,l); });
     }
     return r.volume*v[0];
 }
 // region.h:86-112 (approximation_at -> app_at): fold at(pos_d) over dim 0, 1, ..., D-1; times volume_from(D) == 1
-float region_approximation_at(const Region& r, int S, int D, const float* pos) {
-    std::vector<float> v = r.data;
+template<typename T> T region_approximation_at(const RegionT<T>& r, int S, int D, const T* pos) {
+    std::vector<T> v = r.data;
     for (int d=0; d<D; ++d) {
-        float t = pos_in_range1(r.rmin[d],r.rmax[d],pos[d]);
-        v = fold_dim(v,S,D-d,0,[&] (const float* l) { return rule_at(S,t,l); });
+        T t = pos_in_range1(r.rmin[d],r.rmax[d],pos[d]);
+        v = fold_dim(v,S,D-d,0,[&] (const T* l) { return rule_at(S,t,l); });
     }
-    return v[0]*1.0f;
+    return v[0]*T(1);
 }
 
 // region.h:454-463
-void pixels_in_region(const Region& r, int db, const uint64_t* res, const float* rmin, const float* rmax, uint64_t* start, uint64_t* end) {
+template<typename T> void pixels_in_region(const RegionT<T>& r, int db, const uint64_t* res, const T* rmin, const T* rmax, uint64_t* start, uint64_t* end) {
     for (int i=0;i<db;++i) {
-        start[i] = std::max(uint64_t(0), uint64_t(float(res[i])*(r.rmin[i]-rmin[i])/(rmax[i]-rmin[i])));
-        end[i]   = std::max(start[i]+1, std::min(res[i], uint64_t(0.99f + (float(res[i])*(r.rmax[i]-rmin[i])/(rmax[i]-rmin[i])))));
+        start[i] = std::max(uint64_t(0), uint64_t(T(res[i])*(r.rmin[i]-rmin[i])/(rmax[i]-rmin[i])));
+        end[i]   = std::max(start[i]+1, std::min(res[i], uint64_t(T(0.99f) + (T(res[i])*(r.rmax[i]-rmin[i])/(rmax[i]-rmin[i])))));
     }
 }
 // range.h:92-101 ; false when the intersection is empty (range.h:70-75)
-bool intersect(int D, const float* a1, const float* b1, const float* a2, const float* b2, float* a, float* b) {
+template<typename T> bool intersect(int D, const T* a1, const T* b1, const T* a2, const T* b2, T* a, T* b) {
     bool empty = false;
     for (int d=0;d<D;++d) { a[d] = std::max(a1[d],a2[d]); b[d] = std::max(a[d], std::min(b1[d],b2[d])); if (a[d]>=b[d]) empty = true; }
     return !empty;
 }
 
 // regions-integrator-sequential.h:38-58
-void integrate_regions_sequential(const std::vector<Region>& regions, int S, int D, int db, const uint64_t* res,
-                                  const float* rmin, const float* rmax, float* bins) {
+template<typename T> void integrate_regions_sequential(const std::vector<RegionT<T>>& regions, int S, int D, int db, const uint64_t* res,
+                                  const T* rmin, const T* rmax, T* bins) {
     uint64_t factor = nbins_of(db,res);
-    for (const Region& r : regions) {
+    for (const RegionT<T>& r : regions) {
         uint64_t st[8], en[8]; pixels_in_region(r,db,res,rmin,rmax,st,en);
         uint64_t pos[8]; for (int i=0;i<db;++i) pos[i]=st[i];
         while (true) {
-            float ba[8], bb[8], ia[8], ib[8];
-            bin_box(D,db,rmin,rmax,res,pos,ba,bb);
+            T ba[8], bb[8], ia[8], ib[8];
+            bin_box_t(D,db,rmin,rmax,res,pos,ba,bb);
             if (intersect(D,ba,bb,r.rmin.data(),r.rmax.data(),ia,ib)) {
                 uint64_t lin=0, prod=1; for (int i=0;i<db;++i) { lin+=pos[i]*prod; prod*=res[i]; }
-                bins[lin] = float(double(bins[lin]) + double(factor)*double(region_integral_subrange(r,S,D,ia,ib)));   // :54
+                bins[lin] = T(double(bins[lin]) + double(factor)*double(region_integral_subrange(r,S,D,ia,ib)));   // :54
             }
             int d=0; for (; d<db; ++d) { if (++pos[d] >= en[d]) pos[d]=st[d]; else break; }
             if (d==db) break;
@@ -651,10 +664,10 @@ void integrate_regions_sequential(const std::vector<Region>& regions, int S, int
     }
 }
 
-void export_regions(const std::vector<Region>& regions, int D,
-                    float* reg_min, float* reg_max, float* reg_err, uint32_t* reg_dim, float* reg_data) {
+template<typename T> void export_regions(const std::vector<RegionT<T>>& regions, int D,
+                    T* reg_min, T* reg_max, T* reg_err, uint32_t* reg_dim, T* reg_data) {
     uint64_t n = 0;
-    for (const Region& r : regions) {
+    for (const RegionT<T>& r : regions) {
         if (reg_min) std::copy(r.rmin.begin(), r.rmin.end(), reg_min+n*uint64_t(D));
         if (reg_max) std::copy(r.rmax.begin(), r.rmax.end(), reg_max+n*uint64_t(D));
         if (reg_err) reg_err[n] = r.err;
@@ -673,8 +686,8 @@ extern "C" int vo_newton_cotes(const char* integrand, const char* rule, int dimb
     int D = F->dim; if (dimbins<1 || dimbins>D) return -2;
     int S = !std::strcmp(rule,"trapezoidal") ? 2 : !std::strcmp(rule,"simpson") ? 3 : !std::strcmp(rule,"boole") ? 5 : 0;
     if (!S) return -2;
-    std::vector<Region> regions; regions.push_back(make_region(F->fn,S,D,rmin,rmax));
-    integrate_regions_sequential(regions,S,D,dimbins,res,rmin,rmax,bins);
+    std::vector<RegionT<float>> regions; regions.push_back(make_region<float>(F->fn,S,D,rmin,rmax));
+    integrate_regions_sequential<float>(regions,S,D,dimbins,res,rmin,rmax,bins);
     return 0;
 }
 
@@ -689,9 +702,52 @@ extern "C" int vo_adaptive_iterations(const char* integrand, const char* rule, c
     else if (!std::strcmp(rule,"boole_simpson")) { SH=5; SL=3; }
     else return -2;
     Heuristic h; if (!parse_heuristic(heuristic,size_weight,h)) return -2;
-    auto regions = generate_adaptive(F->fn,SH,SL,D,rmin,rmax,h,iterations);
-    export_regions(regions,D,reg_min,reg_max,reg_err,reg_dim,reg_data);
-    if (bins) integrate_regions_sequential(regions,SH,D,dimbins,res,rmin,rmax,bins);
+    auto regions = generate_adaptive<float>(F->fn,SH,SL,D,rmin,rmax,h,iterations);
+    export_regions<float>(regions,D,reg_min,reg_max,reg_err,reg_dim,reg_data);
+    if (bins) integrate_regions_sequential<float>(regions,SH,D,dimbins,res,rmin,rmax,bins);
+    return 0;
+}
+
+// ---- double precision (Range<double,DIM>): the same templates with T = double -----------------------------------------------
+namespace {
+template<typename F> double call_finite_d(const double* x) {
+    std::array<double,F::dim> a; for (int i=0;i<F::dim;++i) a[i]=x[i];
+    return F()(a);
+}
+struct FiniteIntegrandD { const char* name; int dim; FiniteFnT<double> fn; };
+const FiniteIntegrandD FINITE_D[] = {
+    {"x2y2",2,call_finite_d<vo::X2Y2T<double>>}, {"ind2",2,call_finite_d<vo::Ind2T<double>>}, {"cubic1",1,call_finite_d<vo::Cubic1T<double>>},
+    {"poly3",3,call_finite_d<vo::Poly3T<double>>}, {"smooth_edge2",2,call_finite_d<vo::SmoothEdge2T<double>>},
+    {"shade4_16",4,call_finite_d<vo::Shade4T<double,16>>},
+};
+const FiniteIntegrandD* find_finite_d(const char* n) { for (auto& f : FINITE_D) if (!std::strcmp(f.name,n)) return &f; return nullptr; }
+}
+
+extern "C" int vo_newton_cotes_f64(const char* integrand, const char* rule, int dimbins, const uint64_t* res,
+                        const double* rmin, const double* rmax, double* bins) {
+    auto F = find_finite_d(integrand); if (!F) return -1;
+    int D = F->dim; if (dimbins<1 || dimbins>D) return -2;
+    int S = !std::strcmp(rule,"trapezoidal") ? 2 : !std::strcmp(rule,"simpson") ? 3 : !std::strcmp(rule,"boole") ? 5 : 0;
+    if (!S) return -2;
+    std::vector<RegionT<double>> regions; regions.push_back(make_region<double>(F->fn,S,D,rmin,rmax));
+    integrate_regions_sequential<double>(regions,S,D,dimbins,res,rmin,rmax,bins);
+    return 0;
+}
+
+extern "C" int vo_adaptive_iterations_f64(const char* integrand, const char* rule, const char* heuristic, double size_weight,
+                               uint64_t iterations, int dimbins, const uint64_t* res,
+                               const double* rmin, const double* rmax, double* bins,
+                               double* reg_min, double* reg_max, double* reg_err, uint32_t* reg_dim, double* reg_data) {
+    auto F = find_finite_d(integrand); if (!F) return -1;
+    int D = F->dim; if (dimbins<1 || dimbins>D) return -2;
+    int SH, SL;
+    if (!std::strcmp(rule,"simpson_trapezoidal")) { SH=3; SL=2; }
+    else if (!std::strcmp(rule,"boole_simpson")) { SH=5; SL=3; }
+    else return -2;
+    Heuristic h; if (!parse_heuristic(heuristic,size_weight,h)) return -2;
+    auto regions = generate_adaptive<double>(F->fn,SH,SL,D,rmin,rmax,h,iterations);
+    export_regions<double>(regions,D,reg_min,reg_max,reg_err,reg_dim,reg_data);
+    if (bins) integrate_regions_sequential<double>(regions,SH,D,dimbins,res,rmin,rmax,bins);
     return 0;
 }
 
@@ -706,8 +762,8 @@ extern "C" int vo_crespo2021(const char* integrand, uint64_t iterations, uint64_
     int D = F->dim; if (dimbins<1 || dimbins>D) return -2;
     const int S = 3, SL = 2;
     Heuristic h{true,true,1.e-5};                                              // integrator-crespo2021.h:12
-    auto regions = generate_adaptive(F->fn,S,SL,D,rmin,rmax,h,iterations);
-    export_regions(regions,D,reg_min,reg_max,reg_err,reg_dim,reg_data);
+    auto regions = generate_adaptive<float>(F->fn,S,SL,D,rmin,rmax,h,iterations);
+    export_regions<float>(regions,D,reg_min,reg_max,reg_err,reg_dim,reg_data);
 
     uint64_t nb = nbins_of(dimbins,res);
     uint64_t factor = nb;
@@ -738,7 +794,7 @@ extern "C" int vo_crespo2021(const char* integrand, uint64_t iterations, uint64_
         std::vector<std::array<float,8>> ia(n), ib(n);
         float approximation = 0.0f;                                            // :77
         for (std::size_t i=0;i<n;++i) {                                        // :78-88
-            const Region& r = regions[list[i]];
+            const RegionT<float>& r = regions[list[i]];
             if (intersect(D,ba,bb,r.rmin.data(),r.rmax.data(),ia[i].data(),ib[i].data()))
                 approximation = float(double(approximation) + double(factor)*double(region_integral_subrange(r,S,D,ia[i].data(),ib[i].data())));
         }
@@ -750,7 +806,7 @@ extern "C" int vo_crespo2021(const char* integrand, uint64_t iterations, uint64_
         for (uint64_t s=0;s<spp;++s) {                                         // :92-101
             uint64_t chosen = uniform_int(rng,0,n-1);                          // region-russian-roulette.h:14,18-21
             double rrfactor = double(n);
-            const Region& r = regions[list[chosen]];
+            const RegionT<float>& r = regions[list[chosen]];
             float x[8];
             for (int i=0;i<D;++i) x[i] = uniform_real(rng,ia[chosen][i],ib[chosen][i]);   // region-sampling.h:13-17
             float sfactor = volume_of(D,ia[chosen].data(),ib[chosen].data());              // :18

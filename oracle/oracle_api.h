@@ -76,6 +76,15 @@ int vo_adaptive_iterations(const char* integrand, const char* rule, const char* 
                            const float* rmin, const float* rmax, float* bins,
                            float* reg_min, float* reg_max, float* reg_err, uint32_t* reg_dim, float* reg_data);
 
+// Double-precision twins (Range<double,DIM>, double integrand, double bins) of vo_newton_cotes / vo_adaptive_iterations.
+// Integrands: "x2y2", "ind2", "cubic1", "poly3", "smooth_edge2", "shade4_16" (the double family of integrands.h).
+int vo_newton_cotes_f64(const char* integrand, const char* rule, int dimbins, const uint64_t* res,
+                        const double* rmin, const double* rmax, double* bins);
+int vo_adaptive_iterations_f64(const char* integrand, const char* rule, const char* heuristic, double size_weight,
+                               uint64_t iterations, int dimbins, const uint64_t* res,
+                               const double* rmin, const double* rmax, double* bins,
+                               double* reg_min, double* reg_max, double* reg_err, uint32_t* reg_dim, double* reg_data);
+
 // reference integrator_crespo2021(iterations,spp,seed) — src/control-variates/integrator-crespo2021.h:7-22,
 // src/control-variates/regions-integrator-parallel-variance-reduction.h:32-109.  bins overwritten ('=').
 // Records (per bin, tensor order): rec_nregions [nbins]; rec_approx [nbins] (control-variate integral);

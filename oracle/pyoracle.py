@@ -167,6 +167,30 @@ class Oracle:
         self._check(rc, "vo_adaptive_iterations")
         return bins, reg
 
+    # ---- double precision twins ----
+    def newton_cotes_f64(self, integrand, rule, res, rmin, rmax, bins=None):
+        res = np.ascontiguousarray(np.asarray(res, dtype=np.uint64)); nb = int(np.prod(res))
+        rmin = np.ascontiguousarray(rmin, np.float64); rmax = np.ascontiguousarray(rmax, np.float64)
+        bins = np.zeros(nb, np.float64) if bins is None else np.ascontiguousarray(bins, dtype=np.float64).copy()
+        self.lib.vo_newton_cotes_f64.restype = ctypes.c_int
+        rc = self.lib.vo_newton_cotes_f64(integrand.encode(), rule.encode(), len(res), _p(res), _p(rmin), _p(rmax), _p(bins))
+        self._check(rc, "vo_newton_cotes_f64")
+        return bins
+
+    def adaptive_iterations_f64(self, integrand, rule, heuristic, iterations, res, rmin, rmax, size_weight=1e-5, bins=None):
+        res = np.ascontiguousarray(np.asarray(res, dtype=np.uint64)); nb = int(np.prod(res))
+        rmin = np.ascontiguousarray(rmin, np.float64); rmax = np.ascontiguousarray(rmax, np.float64)
+        d = len(rmin); n = iterations + 1; sd = RULE_SAMPLES[rule] ** d
+        bins = np.zeros(nb, np.float64) if bins is None else np.ascontiguousarray(bins, dtype=np.float64).copy()
+        reg = dict(min=np.zeros((n, d), np.float64), max=np.zeros((n, d), np.float64), err=np.zeros(n, np.float64),
+                   dim=np.zeros(n, np.uint32), data=np.zeros((n, sd), np.float64))
+        self.lib.vo_adaptive_iterations_f64.restype = ctypes.c_int
+        rc = self.lib.vo_adaptive_iterations_f64(integrand.encode(), rule.encode(), heuristic.encode(), ctypes.c_double(size_weight),
+                                                 ctypes.c_uint64(iterations), len(res), _p(res), _p(rmin), _p(rmax), _p(bins),
+                                                 _p(reg["min"]), _p(reg["max"]), _p(reg["err"]), _p(reg["dim"]), _p(reg["data"]))
+        self._check(rc, "vo_adaptive_iterations_f64")
+        return bins, reg
+
     def crespo2021(self, integrand, iterations, spp, seed, res, rmin, rmax, record=False):
         res, rmin, rmax, nb = self._setup(res, rmin, rmax)
         d = self.dim(integrand)

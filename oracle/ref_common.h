@@ -104,6 +104,24 @@ inline int dispatch_finite_bins(const char* name, int dimbins, Fn&& fn) {
     });
 }
 
+// double family (Range<double,DIM>)
+template<typename Fn>
+inline int dispatch_finite_d(const char* name, int dimbins, Fn&& fn) {
+    auto go = [&] (auto f) -> int {
+        using F = decltype(f);
+        if (dimbins == 1) return fn(f, std::integral_constant<std::size_t,1>());
+        if constexpr (F::dim >= 2) { if (dimbins == 2) return fn(f, std::integral_constant<std::size_t,2>()); }
+        return -2;
+    };
+    if (!std::strcmp(name,"x2y2"))         return go(vo::X2Y2T<double>());
+    if (!std::strcmp(name,"ind2"))         return go(vo::Ind2T<double>());
+    if (!std::strcmp(name,"cubic1"))       return go(vo::Cubic1T<double>());
+    if (!std::strcmp(name,"poly3"))        return go(vo::Poly3T<double>());
+    if (!std::strcmp(name,"smooth_edge2")) return go(vo::SmoothEdge2T<double>());
+    if (!std::strcmp(name,"shade4_16"))    return go(vo::Shade4T<double,16>());
+    return -1;
+}
+
 template<typename Fn>
 inline int dispatch_infinite(const char* name, Fn&& fn) {
     if (!std::strcmp(name,"walk"))  return fn(vo::Walk());

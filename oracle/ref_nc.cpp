@@ -59,3 +59,54 @@ extern "C" int vo_adaptive_iterations(const char* integrand, const char* rule, c
         return -2;
     });
 }
+
+// ---- double precision: the same reference templates instantiated with Range<double,DIM> ------------------------------------
+extern "C" int vo_newton_cotes_f64(const char* integrand, const char* rule, int dimbins, const uint64_t* res,
+                        const double* rmin, const double* rmax, double* bins) {
+    return dispatch_finite_d(integrand, dimbins, [&] (auto f, auto dbc) -> int {
+        using F = decltype(f);
+        constexpr std::size_t D = F::dim;
+        constexpr std::size_t DB = decltype(dbc)::value;
+        auto r = res_array<DB>(res);
+        std::array<double,D> a, b; for (std::size_t i=0;i<D;++i) { a[i]=rmin[i]; b[i]=rmax[i]; }
+        auto range = viltrum::range(a,b);
+        auto acc = [&] (const std::array<std::size_t,DB>& p) -> double& { return bins[tensor_pos(p,r)]; };
+        if (!std::strcmp(rule,"trapezoidal")) viltrum::integrate(viltrum::integrator_newton_cotes(viltrum::trapezoidal), acc, r, f, range);
+        else if (!std::strcmp(rule,"simpson")) viltrum::integrate(viltrum::integrator_newton_cotes(viltrum::simpson), acc, r, f, range);
+        else if (!std::strcmp(rule,"boole"))   viltrum::integrate(viltrum::integrator_newton_cotes(viltrum::boole), acc, r, f, range);
+        else return -2;
+        return 0;
+    });
+}
+
+extern "C" int vo_adaptive_iterations_f64(const char* integrand, const char* rule, const char* heuristic, double size_weight,
+                               uint64_t iterations, int dimbins, const uint64_t* res,
+                               const double* rmin, const double* rmax, double* bins,
+                               double* reg_min, double* reg_max, double* reg_err, uint32_t* reg_dim, double* reg_data) {
+    RegionSinkT<double> sink; sink.reg_min=reg_min; sink.reg_max=reg_max; sink.reg_err=reg_err; sink.reg_dim=reg_dim; sink.reg_data=reg_data;
+    return dispatch_finite_d(integrand, dimbins, [&] (auto f, auto dbc) -> int {
+        using F = decltype(f);
+        constexpr std::size_t D = F::dim;
+        constexpr std::size_t DB = decltype(dbc)::value;
+        using namespace viltrum;
+        auto r = res_array<DB>(res);
+        std::array<double,D> a, b; for (std::size_t i=0;i<D;++i) { a[i]=rmin[i]; b[i]=rmax[i]; }
+        auto range = viltrum::range(a,b);
+        auto acc = [&] (const std::array<std::size_t,DB>& p) -> double& { return bins[tensor_pos(p,r)]; };
+        DumpLoggerT<double> logger(&sink);
+        auto run = [&] (auto rl, auto eh) -> int {
+            viltrum::integrate(integrator_adaptive_iterations(rl, eh, std::size_t(iterations)), acc, r, f, range, logger);
+            return 0;
+        };
+        auto with_rule = [&] (auto rl) -> int {
+            if (!std::strcmp(heuristic,"default_absolute")) return run(rl, error_heuristic_default(error_metric_absolute()));
+            if (!std::strcmp(heuristic,"default_relative")) return run(rl, error_heuristic_default(error_metric_relative()));
+            if (!std::strcmp(heuristic,"size_absolute"))    return run(rl, error_heuristic_size(error_metric_absolute(),size_weight));
+            if (!std::strcmp(heuristic,"size_relative"))    return run(rl, error_heuristic_size(error_metric_relative(),size_weight));
+            return -2;
+        };
+        if (!std::strcmp(rule,"simpson_trapezoidal")) return with_rule(nested(simpson,trapezoidal));
+        if (!std::strcmp(rule,"boole_simpson"))       return with_rule(nested(boole,simpson));
+        return -2;
+    });
+}

@@ -9,16 +9,19 @@ namespace vref {
 template<class T, class=void> struct is_region_seq : std::false_type {};
 template<class T> struct is_region_seq<T, std::void_t<decltype(std::declval<T>().begin()->range())>> : std::true_type {};
 
-struct RegionSink {
-    float* reg_min=nullptr; float* reg_max=nullptr; float* reg_err=nullptr; uint32_t* reg_dim=nullptr; float* reg_data=nullptr;
+template<typename T>
+struct RegionSinkT {
+    T* reg_min=nullptr; T* reg_max=nullptr; T* reg_err=nullptr; uint32_t* reg_dim=nullptr; T* reg_data=nullptr;
     const void* base=nullptr;       // address of element 0 of the logged region vector
     std::size_t count=0;
 };
+using RegionSink = RegionSinkT<float>;
 
-class DumpLogger {
-    RegionSink* sink;
+template<typename T>
+class DumpLoggerT {
+    RegionSinkT<T>* sink;
 public:
-    DumpLogger(RegionSink* s) : sink(s) {}
+    DumpLoggerT(RegionSinkT<T>* s) : sink(s) {}
     std::string name() const { return ""; }
     void set_name(const std::string&) {}
     template<typename Number> void log_progress(const Number&, const Number& = Number(1)) {}
@@ -35,7 +38,7 @@ public:
                     if (sink->reg_min) sink->reg_min[n*D+i] = r.range().min(i);
                     if (sink->reg_max) sink->reg_max[n*D+i] = r.range().max(i);
                 }
-                if constexpr (std::is_same_v<std::decay_t<decltype(r.extra())>, std::tuple<float,std::size_t>>) {
+                if constexpr (std::is_same_v<std::decay_t<decltype(r.extra())>, std::tuple<T,std::size_t>>) {
                     if (sink->reg_err) sink->reg_err[n] = std::get<0>(r.extra());
                     if (sink->reg_dim) sink->reg_dim[n] = uint32_t(std::get<1>(r.extra()));
                 }
@@ -51,5 +54,6 @@ public:
         }
     }
 };
+using DumpLogger = DumpLoggerT<float>;
 
 } // namespace vref
