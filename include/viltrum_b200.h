@@ -95,6 +95,7 @@ enum {
 };
 
 #define VB200_INTEGRAND_EXACT 1u   /* thunks were compiled with --fmad=false: bit-exact twin of a CPU build with -ffp-contract=off */
+#define VB200_INTEGRAND_F64   2u   /* functor is double f(std::array<double,dim>): points/values of the eval thunk are doubles */
 
 typedef struct vb200_integrand {
     uint32_t        abi_version;    /* VB200_ABI_VERSION */
@@ -126,6 +127,15 @@ typedef struct vb200_domain {
                                               (monte-carlo-per-bin-parallel.h:46-47); callers may leave it 0 */
     int32_t  reserved;
 } vb200_domain;
+
+/* double-precision twin (Range<double,DIM>) for the Newton-Cotes region family */
+typedef struct vb200_domain_f64 {
+    int32_t  dim;
+    int32_t  dimbins;
+    double   rmin[VB200_MAX_DIM];
+    double   rmax[VB200_MAX_DIM];
+    uint64_t res[VB200_MAX_DIMBINS];
+} vb200_domain_f64;
 
 /* Bin-grid shard handled by one call/GPU: linear bin indices [begin,end) in tensor order.  {0,0} = whole grid.
  * Philox counters are keyed by the GLOBAL bin index, so results do not depend on how the grid is sharded. */
@@ -227,6 +237,20 @@ void     vb200_regions_free(vb200_regions* r);
 int vb200_regions_integrate_bins(vb200_ctx* ctx, const vb200_regions* r, const vb200_domain* domain, const vb200_shard* shard,
                                  float* bins, int bins_mem);
 
+/* ---- double precision (north_star: Newton-Cotes within 1e-12 in fp64) ---------------------------------------------------- */
+/* The same region family for Range<double,DIM>: integrands flagged VB200_INTEGRAND_F64 (functor over std::array<double,DIM>
+ * returning double), double bins, every rule/fold/accumulation in double exactly as the reference does for Float = double.
+ * vb200_regions_count/dim/samples/free work on both kinds of table. */
+int vb200_regions_generate_single_f64(vb200_ctx* ctx, const vb200_integrand* f, const vb200_domain_f64* domain, int rule, vb200_regions** out);
+int vb200_regions_upload_f64(vb200_ctx* ctx, int dim, int rule, uint64_t count,
+                             const double* rmin, const double* rmax, const double* err, const uint32_t* errdim, const double* data,
+                             vb200_regions** out);
+int vb200_regions_download_f64(vb200_ctx* ctx, const vb200_regions* r, double* rmin, double* rmax, double* err, uint32_t* errdim, double* data);
+int vb200_regions_integrate_bins_f64(vb200_ctx* ctx, const vb200_regions* r, const vb200_domain_f64* domain, const vb200_shard* shard,
+                                     double* bins, int bins_mem);
+/* double-precision built-in integrands: "x2y2", "ind2", "cubic1", "poly3", "smooth_edge2", "shade4_16" */
+const vb200_integrand* vb200_builtin_integrand_f64(const char* name, int exact);
+
 /* ---- control variates + residual Monte Carlo (rows a15-a18) --------------------------------------------- */
 typedef struct vb200_cv_params {
     vb200_domain domain;
@@ -299,9 +323,9 @@ typedef struct vb200_walk_replay_launch {
 
 typedef struct vb200_eval_launch {
     uint64_t n;
-    int32_t  dim; int32_t reserved;
-    const float* points;              /* device, SoA: points[d*n + i] */
-    float*   values;                  /* device, [n] */
+    int32_t  dim; int32_t f64;        /* f64 != 0: points/values are doubles (VB200_INTEGRAND_F64 integrands) */
+    const void* points;               /* device, SoA: points[d*n + i] */
+    void*    values;                  /* device, [n] */
 } vb200_eval_launch;
 
 typedef struct vb200_greedy_launch {

@@ -170,14 +170,17 @@ mc_replay_kernel(const F f, const vb200_replay_launch a) {
 
 // K-eval — values[i] = f(points[:, i]); points are SoA (points[d*n+i]) so loads and the store are coalesced.
 // Serves the region generators (fill / batched split evaluation) and the control-variate residual pass.
-template<class F, int DIM, bool EXACT>
+// T = float, or double for VB200_INTEGRAND_F64 integrands.
+template<class F, int DIM, class T, bool EXACT>
 __global__ void __launch_bounds__(256)
 eval_points_kernel(const F f, const vb200_eval_launch a) {
+    const T* __restrict__ points = static_cast<const T*>(a.points);
+    T* __restrict__ values = static_cast<T*>(a.values);
     for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n; i += uint64_t(gridDim.x) * blockDim.x) {
-        std::array<float, DIM> x;
+        std::array<T, DIM> x;
 #pragma unroll
-        for (int d = 0; d < DIM; ++d) x[d] = a.points[uint64_t(d) * a.n + i];
-        a.values[i] = f(x);
+        for (int d = 0; d < DIM; ++d) x[d] = points[uint64_t(d) * a.n + i];
+        values[i] = f(x);
     }
 }
 

@@ -3,11 +3,13 @@
 //                                   coefficients (monomial form), at (Horner), subrange (antiderivative difference)
 //   Nested<H,L>::low / error        (src/nested/nested.h:17-33)
 //   error_metric_absolute/relative  (src/nested/error-metric.h:10-41)
-// The reference mixes float and double inside these expressions (double literals in the weights and in the
-// antiderivative, integer literals in the coefficients — SURVEY.md App. A #11) and rounds back to float at every
+// The reference mixes its Float type and double inside these expressions (double literals in the weights and in the
+// antiderivative, integer literals in the coefficients — SURVEY.md App. A #11) and rounds back to Float at every
 // return.  The bit-exact modes (greedy refinement order, region->bin integration, control-variate replay) only work
 // if every one of those roundings happens here too, so each operation is spelled with an explicit round-to-nearest
 // intrinsic: the results do not depend on whether the including TU is compiled with --fmad=true or false.
+// Everything is a template over T = Float = value_type (float, or double for Range<double,DIM>: then the promotions
+// are no-ops and the whole expression is evaluated in double, exactly as upstream).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -23,78 +25,98 @@ __device__ __forceinline__ double ds(double a, double b) { return __dsub_rn(a, b
 __device__ __forceinline__ double dd(double a, double b) { return __ddiv_rn(a, b); }
 __device__ __forceinline__ float  d2f(double a) { return __double2float_rn(a); }
 
+// arithmetic in T with explicit rounding
+__device__ __forceinline__ float  mul(float a, float b) { return fm(a, b); }
+__device__ __forceinline__ float  add(float a, float b) { return fa(a, b); }
+__device__ __forceinline__ float  sub(float a, float b) { return fs(a, b); }
+__device__ __forceinline__ float  quo(float a, float b) { return fd(a, b); }
+__device__ __forceinline__ double mul(double a, double b) { return dm(a, b); }
+__device__ __forceinline__ double add(double a, double b) { return da(a, b); }
+__device__ __forceinline__ double sub(double a, double b) { return ds(a, b); }
+__device__ __forceinline__ double quo(double a, double b) { return dd(a, b); }
+template<class T> __device__ __forceinline__ T from_double(double a);
+template<> __device__ __forceinline__ float  from_double<float>(double a) { return d2f(a); }
+template<> __device__ __forceinline__ double from_double<double>(double a) { return a; }
+__device__ __forceinline__ float  absv(float a) { return fabsf(a); }
+__device__ __forceinline__ double absv(double a) { return fabs(a); }
+__device__ __forceinline__ float  maxv(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double maxv(double a, double b) { return fmax(a, b); }
+__device__ __forceinline__ float  minv(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ double minv(double a, double b) { return fmin(a, b); }
+
 // quadrature weights, rules.h:14 / :64 / :256
-template<int S> __device__ __forceinline__ float apply(const float* p);
-template<> __device__ __forceinline__ float apply<2>(const float* p) { return d2f(dd(double(fa(p[0], p[1])), 2.0)); }
-template<> __device__ __forceinline__ float apply<3>(const float* p) { return d2f(dd(da(da(double(p[0]), dm(4.0, double(p[1]))), double(p[2])), 6.0)); }
-template<> __device__ __forceinline__ float apply<5>(const float* p) {
-    double s = dm(7.0, double(p[0]));
-    s = da(s, dm(32.0, double(p[1]))); s = da(s, dm(12.0, double(p[2]))); s = da(s, dm(32.0, double(p[3]))); s = da(s, dm(7.0, double(p[4])));
-    return d2f(dd(s, 90.0));
+template<int S, class T> __device__ __forceinline__ T apply(const T* p) {
+    if constexpr (S == 2) return from_double<T>(dd(double(add(p[0], p[1])), 2.0));
+    else if constexpr (S == 3) return from_double<T>(dd(da(da(double(p[0]), dm(4.0, double(p[1]))), double(p[2])), 6.0));
+    else {
+        double s = dm(7.0, double(p[0]));
+        s = da(s, dm(32.0, double(p[1]))); s = da(s, dm(12.0, double(p[2]))); s = da(s, dm(32.0, double(p[3]))); s = da(s, dm(7.0, double(p[4])));
+        return from_double<T>(dd(s, 90.0));
+    }
 }
 
-// monomial coefficients, rules.h:27-32 / :77-83 / :272-280 (integer literals -> float arithmetic, left to right)
-template<int S> __device__ __forceinline__ void coefficients(const float* p, float* c);
-template<> __device__ __forceinline__ void coefficients<2>(const float* p, float* c) { c[0] = p[0]; c[1] = fs(p[1], p[0]); }
-template<> __device__ __forceinline__ void coefficients<3>(const float* p, float* c) {
-    c[0] = p[0];
-    c[1] = fs(fa(fm(-3.0f, p[0]), fm(4.0f, p[1])), p[2]);
-    c[2] = fa(fs(fm(2.0f, p[0]), fm(4.0f, p[1])), fm(2.0f, p[2]));
-}
-template<> __device__ __forceinline__ void coefficients<5>(const float* p, float* c) {
-    c[0] = p[0];
-    c[1] = fs(fa(fs(fa(fd(fm(-25.0f, p[0]), 3.0f), fm(16.0f, p[1])), fm(12.0f, p[2])), fd(fm(16.0f, p[3]), 3.0f)), p[4]);
-    c[2] = fa(fs(fa(fs(fd(fm(70.0f, p[0]), 3.0f), fd(fm(208.0f, p[1]), 3.0f)), fm(76.0f, p[2])), fd(fm(112.0f, p[3]), 3.0f)), fd(fm(22.0f, p[4]), 3.0f));
-    c[3] = fs(fa(fs(fa(fd(fm(-80.0f, p[0]), 3.0f), fm(96.0f, p[1])), fm(128.0f, p[2])), fd(fm(224.0f, p[3]), 3.0f)), fm(16.0f, p[4]));
-    c[4] = fa(fs(fa(fs(fd(fm(32.0f, p[0]), 3.0f), fd(fm(128.0f, p[1]), 3.0f)), fm(64.0f, p[2])), fd(fm(128.0f, p[3]), 3.0f)), fd(fm(32.0f, p[4]), 3.0f));
+// monomial coefficients, rules.h:27-32 / :77-83 / :272-280 (integer literals -> arithmetic in T, left to right)
+template<int S, class T> __device__ __forceinline__ void coefficients(const T* p, T* c) {
+    if constexpr (S == 2) { c[0] = p[0]; c[1] = sub(p[1], p[0]); }
+    else if constexpr (S == 3) {
+        c[0] = p[0];
+        c[1] = sub(add(mul(T(-3), p[0]), mul(T(4), p[1])), p[2]);
+        c[2] = add(sub(mul(T(2), p[0]), mul(T(4), p[1])), mul(T(2), p[2]));
+    } else {
+        c[0] = p[0];
+        c[1] = sub(add(sub(add(quo(mul(T(-25), p[0]), T(3)), mul(T(16), p[1])), mul(T(12), p[2])), quo(mul(T(16), p[3]), T(3))), p[4]);
+        c[2] = add(sub(add(sub(quo(mul(T(70), p[0]), T(3)), quo(mul(T(208), p[1]), T(3))), mul(T(76), p[2])), quo(mul(T(112), p[3]), T(3))), quo(mul(T(22), p[4]), T(3)));
+        c[3] = sub(add(sub(add(quo(mul(T(-80), p[0]), T(3)), mul(T(96), p[1])), mul(T(128), p[2])), quo(mul(T(224), p[3]), T(3))), mul(T(16), p[4]));
+        c[4] = add(sub(add(sub(quo(mul(T(32), p[0]), T(3)), quo(mul(T(128), p[1]), T(3))), mul(T(64), p[2])), quo(mul(T(128), p[3]), T(3))), quo(mul(T(32), p[4]), T(3)));
+    }
 }
 
-// Horner evaluation in float, rules.h:35-38 / :86-89 / :283-286
-template<int S> __device__ __forceinline__ float at(float t, const float* p) {
-    float c[S]; coefficients<S>(p, c);
-    float v = c[S - 1];
+// Horner evaluation in T, rules.h:35-38 / :86-89 / :283-286
+template<int S, class T> __device__ __forceinline__ T at(T t, const T* p) {
+    T c[S]; coefficients<S, T>(p, c);
+    T v = c[S - 1];
 #pragma unroll
-    for (int k = S - 2; k >= 0; --k) v = fa(fm(v, t), c[k]);
+    for (int k = S - 2; k >= 0; --k) v = add(mul(v, t), c[k]);
     return v;
 }
 
-// antiderivative at x of the interpolating polynomial: (((c4*x/5.0 + c3/4.0)*x + c2/3.0)*x + c1/2.0)*x + c0)*x  — c*x is a float
-// product, the division by the double literal promotes the rest (rules.h:41-44 / :97-100 / :289-293)
-template<int S> __device__ __forceinline__ double antiderivative(const float* c, float x) {
-    double u = dd(double(fm(c[S - 1], x)), double(S));
+// antiderivative at x of the interpolating polynomial: (((c4*x/5.0 + c3/4.0)*x + c2/3.0)*x + c1/2.0)*x + c0)*x  — c*x is a product in T,
+// the division by the double literal promotes the rest (rules.h:41-44 / :97-100 / :289-293)
+template<int S, class T> __device__ __forceinline__ double antiderivative(const T* c, T x) {
+    double u = dd(double(mul(c[S - 1], x)), double(S));
 #pragma unroll
     for (int k = S - 2; k >= 1; --k) { u = da(u, dd(double(c[k]), double(k + 1))); u = dm(u, double(x)); }
     u = da(u, double(c[0]));
     return dm(u, double(x));
 }
-template<int S> __device__ __forceinline__ float subrange(float a, float b, const float* p) {
-    float c[S]; coefficients<S>(p, c);
-    return d2f(ds(antiderivative<S>(c, b), antiderivative<S>(c, a)));
+template<int S, class T> __device__ __forceinline__ T subrange(T a, T b, const T* p) {
+    T c[S]; coefficients<S, T>(p, c);
+    return from_double<T>(ds(antiderivative<S, T>(c, b), antiderivative<S, T>(c, a)));
 }
 
 // nested.h:17-23
-template<int SH, int SL> __device__ __forceinline__ float low(const float* p) {
-    float q[SL];
+template<int SH, int SL, class T> __device__ __forceinline__ T low(const T* p) {
+    T q[SL];
 #pragma unroll
     for (int i = 0; i < SL; ++i) q[i] = p[i * (SH - 1) / (SL - 1)];
-    return apply<SL>(q);
+    return apply<SL, T>(q);
 }
 
 // error-metric.h:10-13 / :30-37
-__device__ __forceinline__ float metric(bool relative, float a, float b) {
-    const float diff = fabsf(fs(b, a));
+template<class T> __device__ __forceinline__ T metric(bool relative, T a, T b) {
+    const T diff = absv(sub(b, a));
     if (!relative) return diff;
-    const float m = fmaxf(fabsf(a), fabsf(b));
+    const T m = maxv(absv(a), absv(b));
     if (double(m) < 1.e-37) return diff;
-    return fd(diff, m);
+    return quo(diff, m);
 }
 // nested.h:31-33
-template<int SH, int SL> __device__ __forceinline__ float line_error(bool relative, const float* p) {
-    return metric(relative, apply<SH>(p), low<SH, SL>(p));
+template<int SH, int SL, class T> __device__ __forceinline__ T line_error(bool relative, const T* p) {
+    return metric<T>(relative, apply<SH, T>(p), low<SH, SL, T>(p));
 }
 
 // range.h:45-53
-__device__ __forceinline__ float pos_in_range(float lo, float hi, float p) { return (lo >= hi) ? lo : fd(fs(p, lo), fs(hi, lo)); }
+template<class T> __device__ __forceinline__ T pos_in_range(T lo, T hi, T p) { return (lo >= hi) ? lo : quo(sub(p, lo), sub(hi, lo)); }
 
 __host__ __device__ constexpr int ipow(int s, int d) { return d <= 0 ? 1 : s * ipow(s, d - 1); }
 

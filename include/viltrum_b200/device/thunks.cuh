@@ -95,9 +95,9 @@ struct FiniteThunks {
 
     static int eval(const vb200_integrand* self, const void* args, void* stream) {
         const vb200_eval_launch& a = *static_cast<const vb200_eval_launch*>(args);
-        if (a.dim != DIM) return int(cudaErrorInvalidValue);
+        if (a.dim != DIM || a.f64) return int(cudaErrorInvalidValue);
         if (a.n == 0) return 0;
-        auto k = device::eval_points_kernel<F, DIM, EXACT>;
+        auto k = device::eval_points_kernel<F, DIM, float, EXACT>;
         const int grid = persistent_grid(k, 256, (a.n + 255) / 256, 0);
         k<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(functor(self), a);
         return int(cudaGetLastError());
@@ -125,6 +125,22 @@ struct FiniteThunks {
         const vb200_greedy_launch& a = *static_cast<const vb200_greedy_launch*>(args);
         if (a.dim != DIM) return int(cudaErrorInvalidValue);
         return device::launch_greedy<F, DIM, EXACT>(functor(self), a, static_cast<cudaStream_t>(stream));
+    }
+};
+
+// double-precision integrands (functor over std::array<double,DIM> returning double): the Newton-Cotes region family only
+template<class F, int DIM, bool EXACT>
+struct FiniteThunks64 {
+    static_assert(std::is_trivially_copyable<F>::value, "integrand functors cross the C ABI by value: must be trivially copyable");
+    static F functor(const vb200_integrand* self) { return *static_cast<const F*>(self->functor); }
+    static int eval(const vb200_integrand* self, const void* args, void* stream) {
+        const vb200_eval_launch& a = *static_cast<const vb200_eval_launch*>(args);
+        if (a.dim != DIM || !a.f64) return int(cudaErrorInvalidValue);
+        if (a.n == 0) return 0;
+        auto k = device::eval_points_kernel<F, DIM, double, EXACT>;
+        const int grid = persistent_grid(k, 256, (a.n + 255) / 256, 0);
+        k<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(functor(self), a);
+        return int(cudaGetLastError());
     }
 };
 
@@ -214,6 +230,23 @@ public:
     explicit Integrand(const F& f, const char* name = "user integrand") : f_(f) { bind(name); }
     Integrand(const Integrand& o) : f_(o.f_) { bind(o.d_.name); }
     Integrand& operator=(const Integrand& o) { f_ = o.f_; bind(o.d_.name); return *this; }
+    const vb200_integrand* c_abi() const { return &d_; }
+};
+
+// double-precision integrand: double operator()(const std::array<double,DIM>&) const
+template<class F, int DIM, bool EXACT = kExactTU>
+class Integrand64 {
+    F f_; vb200_integrand d_;
+    void bind(const char* name) {
+        std::memset(&d_, 0, sizeof(d_));
+        d_.abi_version = VB200_ABI_VERSION; d_.dim = DIM; d_.functor = &f_; d_.functor_bytes = uint32_t(sizeof(F));
+        d_.flags = (EXACT ? VB200_INTEGRAND_EXACT : 0u) | VB200_INTEGRAND_F64; d_.name = name;
+        d_.launch[VB200_K_EVAL_POINTS] = &detail::FiniteThunks64<F, DIM, EXACT>::eval;
+    }
+public:
+    explicit Integrand64(const F& f, const char* name = "user integrand (f64)") : f_(f) { bind(name); }
+    Integrand64(const Integrand64& o) : f_(o.f_) { bind(o.d_.name); }
+    Integrand64& operator=(const Integrand64& o) { f_ = o.f_; bind(o.d_.name); return *this; }
     const vb200_integrand* c_abi() const { return &d_; }
 };
 

@@ -26,6 +26,8 @@ SYMBOLS = [
     "vb200_monte_carlo", "vb200_regions_generate_adaptive", "vb200_regions_generate_single", "vb200_regions_upload",
     "vb200_regions_count", "vb200_regions_dim", "vb200_regions_samples", "vb200_regions_download", "vb200_regions_free",
     "vb200_regions_integrate_bins", "vb200_cv_integrate", "vb200_cv_replay",
+    "vb200_regions_generate_single_f64", "vb200_regions_upload_f64", "vb200_regions_download_f64", "vb200_regions_integrate_bins_f64",
+    "vb200_builtin_integrand_f64",
 ]
 
 
@@ -33,6 +35,11 @@ class Domain(ctypes.Structure):
     _fields_ = [("dim", ctypes.c_int32), ("dimbins", ctypes.c_int32), ("rmin", ctypes.c_float * MAX_DIM),
                 ("rmax", ctypes.c_float * MAX_DIM), ("res", ctypes.c_uint64 * MAX_DIMBINS),
                 ("drange", ctypes.c_float * MAX_DIMBINS), ("reserved", ctypes.c_int32)]
+
+
+class Domain64(ctypes.Structure):
+    _fields_ = [("dim", ctypes.c_int32), ("dimbins", ctypes.c_int32), ("rmin", ctypes.c_double * MAX_DIM),
+                ("rmax", ctypes.c_double * MAX_DIM), ("res", ctypes.c_uint64 * MAX_DIMBINS)]
 
 
 class Shard(ctypes.Structure):
@@ -97,10 +104,26 @@ def lib():
         L.vb200_regions_download.argtypes = [vp, vp, vp, vp, vp, vp, vp]; L.vb200_regions_download.restype = i32
         L.vb200_regions_free.argtypes = [vp]; L.vb200_regions_free.restype = None
         L.vb200_regions_integrate_bins.argtypes = [vp, vp, ctypes.POINTER(Domain), ctypes.POINTER(Shard), vp, i32]; L.vb200_regions_integrate_bins.restype = i32
+        L.vb200_regions_generate_single_f64.argtypes = [vp, vp, ctypes.POINTER(Domain64), i32, ctypes.POINTER(vp)]; L.vb200_regions_generate_single_f64.restype = i32
+        L.vb200_regions_upload_f64.argtypes = [vp, i32, i32, u64, vp, vp, vp, vp, vp, ctypes.POINTER(vp)]; L.vb200_regions_upload_f64.restype = i32
+        L.vb200_regions_download_f64.argtypes = [vp, vp, vp, vp, vp, vp, vp]; L.vb200_regions_download_f64.restype = i32
+        L.vb200_regions_integrate_bins_f64.argtypes = [vp, vp, ctypes.POINTER(Domain64), ctypes.POINTER(Shard), vp, i32]; L.vb200_regions_integrate_bins_f64.restype = i32
+        L.vb200_builtin_integrand_f64.argtypes = [ctypes.c_char_p, i32]; L.vb200_builtin_integrand_f64.restype = vp
         L.vb200_cv_integrate.argtypes = [vp, vp, vp, ctypes.POINTER(CvParams), vp, i32, vp, vp]; L.vb200_cv_integrate.restype = i32
         L.vb200_cv_replay.argtypes = [vp, vp, vp, ctypes.POINTER(CvParams), vp, vp, i32, vp, i32]; L.vb200_cv_replay.restype = i32
         _lib = L
     return _lib
+
+
+def make_domain64(dim, res, rmin, rmax):
+    d = Domain64()
+    d.dim = int(dim); d.dimbins = len(res)
+    for i, r in enumerate(res):
+        d.res[i] = int(r)
+    for i in range(MAX_DIM):
+        d.rmin[i] = float(rmin[i]) if i < len(rmin) else 0.0
+        d.rmax[i] = float(rmax[i]) if i < len(rmax) else 1.0
+    return d
 
 
 def make_domain(dim, res, rmin=(), rmax=()):

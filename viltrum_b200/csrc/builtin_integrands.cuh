@@ -39,6 +39,32 @@ struct SmoothEdge2 {
         return s+((dx*dx+dy*dy<.09f)?.75f:0.0f);
     }
 };
+// ---- double-precision family (Range<double,DIM>): same shapes, double constants --------------------------------------------
+struct X2Y2d { __host__ __device__ double operator()(const std::array<double,2>& x) const { return x[0]*x[0] + x[1]*x[1]; } };
+struct Ind2d { __host__ __device__ double operator()(const std::array<double,2>& x) const { return ((x[0]+x[1])<1.0)?1.0:0.0; } };
+struct Cubic1d { __host__ __device__ double operator()(const std::array<double,1>& x) const { return (4.0*x[0]*x[0]-1.0)*x[0] + 0.25; } };
+struct Poly3d { __host__ __device__ double operator()(const std::array<double,3>& x) const { return x[0]*x[1] + x[1]*x[2]*x[2] + 0.5; } };
+struct SmoothEdge2d {
+    __host__ __device__ double operator()(const std::array<double,2>& p) const {
+        const double x = p[0], y = p[1];
+        const double s = 0.5+8.0*x*(1.0-x)*y*(1.0-y)*(1.0-2.0*(x-y)*(x-y));
+        const double dx = x-0.45, dy = y-0.55;
+        return s+((dx*dx+dy*dy<0.09)?0.75:0.0);
+    }
+};
+template<int K> struct Shade4d {
+    __host__ __device__ double operator()(const std::array<double,4>& x) const {
+        const double a = x[0]-0.5, b = x[1]-0.5;
+        const double edge = 0.55+0.35*(a*a-b*b)+0.2*a*b;
+        const double vis = (x[2]+0.5*x[3]<edge)?1.0:0.0;
+        const double t = x[2]*(1.0-x[3]);
+        double lobe = 1.0/double(K);
+        for (int k=K-2;k>=0;--k) lobe = lobe*t+1.0/double(k+1);
+        const double alb = 0.25+0.75*x[0]*x[1];
+        return vis*lobe*alb;
+    }
+};
+
 struct Walk {
     template<typename Seq> __host__ __device__ float operator()(const Seq& seq) const {
         auto it = seq.begin(); const float px = *it; ++it; const float py = *it; ++it;

@@ -10,8 +10,10 @@ struct Entry { const char* name; const vb200_integrand* desc; };
 
 #ifdef VILTRUM_B200_EXACT
 #define VB200_BUILTIN_TABLE builtin_table_exact
+#define VB200_BUILTIN_TABLE64 builtin_table64_exact
 #else
 #define VB200_BUILTIN_TABLE builtin_table_fast
+#define VB200_BUILTIN_TABLE64 builtin_table64_fast
 #endif
 
 static const Entry* make_table(int* count) {
@@ -36,6 +38,22 @@ static const Entry* make_table(int* count) {
     return table;
 }
 
+static const Entry* make_table64(int* count) {
+    static const Integrand64<X2Y2d,2> x2y2{X2Y2d(), "x2y2"};
+    static const Integrand64<Ind2d,2> ind2{Ind2d(), "ind2"};
+    static const Integrand64<Cubic1d,1> cubic1{Cubic1d(), "cubic1"};
+    static const Integrand64<Poly3d,3> poly3{Poly3d(), "poly3"};
+    static const Integrand64<SmoothEdge2d,2> smooth_edge2{SmoothEdge2d(), "smooth_edge2"};
+    static const Integrand64<Shade4d<16>,4> shade4_16{Shade4d<16>(), "shade4_16"};
+    static const Entry table[] = {
+        {"x2y2", x2y2.c_abi()}, {"ind2", ind2.c_abi()}, {"cubic1", cubic1.c_abi()}, {"poly3", poly3.c_abi()},
+        {"smooth_edge2", smooth_edge2.c_abi()}, {"shade4_16", shade4_16.c_abi()},
+    };
+    *count = int(sizeof(table)/sizeof(table[0]));
+    return table;
+}
+
 }}}
 
+extern "C" const viltrum::b200::builtin::Entry* VB200_BUILTIN_TABLE64(int* count) { return viltrum::b200::builtin::make_table64(count); }
 extern "C" const viltrum::b200::builtin::Entry* VB200_BUILTIN_TABLE(int* count) { return viltrum::b200::builtin::make_table(count); }

@@ -222,6 +222,14 @@ extern "C" const vb200_integrand* vb200_builtin_integrand(const char* name, int 
     for (int i = 0; i < n; ++i) if (!std::strcmp(t[i].name, name)) return t[i].desc;
     return nullptr;
 }
+extern "C" const BuiltinEntry* builtin_table64_fast(int* count);
+extern "C" const BuiltinEntry* builtin_table64_exact(int* count);
+extern "C" const vb200_integrand* vb200_builtin_integrand_f64(const char* name, int exact) {
+    if (!name) return nullptr;
+    int n = 0; const BuiltinEntry* t = exact ? builtin_table64_exact(&n) : builtin_table64_fast(&n);
+    for (int i = 0; i < n; ++i) if (!std::strcmp(t[i].name, name)) return t[i].desc;
+    return nullptr;
+}
 extern "C" int vb200_builtin_count(void) { int n = 0; builtin_table_fast(&n); return n; }
 extern "C" const char* vb200_builtin_name(int index) { int n = 0; const BuiltinEntry* t = builtin_table_fast(&n); return (index >= 0 && index < n) ? t[index].name : nullptr; }
 

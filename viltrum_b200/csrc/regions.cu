@@ -25,7 +25,7 @@ int rule_samples(int rule, int* SH, int* SL) {
     return -1;
 }
 
-int regions_alloc(vb200_ctx* ctx, int dim, int rule, uint64_t capacity, vb200_regions** out) {
+int regions_alloc(vb200_ctx* ctx, int dim, int rule, uint64_t capacity, vb200_regions** out, bool f64) {
     int SH, SL;
     if (rule_samples(rule, &SH, &SL)) return fail(ctx, VB200_ERR_INVALID, "unknown rule %d", rule);
     if (dim < 1 || dim > VB200_MAX_DIM) return fail(ctx, VB200_ERR_INVALID, "region dimension %d outside 1..%d", dim, VB200_MAX_DIM);
@@ -33,11 +33,14 @@ int regions_alloc(vb200_ctx* ctx, int dim, int rule, uint64_t capacity, vb200_re
     if (sd > 15625) return fail(ctx, VB200_ERR_UNSUPPORTED, "%llu samples per region: beyond the reference's own limit (VILTRUM_MAX_DIMENSIONS_REGION, region.h:16-18)", (unsigned long long)sd);
     vb200_regions* r = new (std::nothrow) vb200_regions;
     if (!r) return fail(ctx, VB200_ERR_NOMEM, "out of host memory");
-    r->ctx = ctx; r->dim = dim; r->rule = rule; r->SH = SH; r->SL = SL; r->sd = int(sd); r->capacity = capacity; r->count = 0;
+    r->ctx = ctx; r->dim = dim; r->rule = rule; r->SH = SH; r->SL = SL; r->sd = int(sd); r->capacity = capacity; r->count = 0; r->f64 = f64;
     cudaError_t e;
-    if ((e = dmalloc(ctx, &r->rmin, capacity * dim * sizeof(float))) != cudaSuccess || (e = dmalloc(ctx, &r->rmax, capacity * dim * sizeof(float))) != cudaSuccess ||
+    if (f64 ? ((e = dmalloc(ctx, &r->rmin64, capacity * dim * sizeof(double))) != cudaSuccess || (e = dmalloc(ctx, &r->rmax64, capacity * dim * sizeof(double))) != cudaSuccess ||
+               (e = dmalloc(ctx, &r->data64, capacity * sd * sizeof(double))) != cudaSuccess || (e = dmalloc(ctx, &r->err64, capacity * sizeof(double))) != cudaSuccess ||
+               (e = dmalloc(ctx, &r->errdim, capacity * sizeof(uint32_t))) != cudaSuccess)
+            : ((e = dmalloc(ctx, &r->rmin, capacity * dim * sizeof(float))) != cudaSuccess || (e = dmalloc(ctx, &r->rmax, capacity * dim * sizeof(float))) != cudaSuccess ||
         (e = dmalloc(ctx, &r->data, capacity * sd * sizeof(float))) != cudaSuccess || (e = dmalloc(ctx, &r->err, capacity * sizeof(float))) != cudaSuccess ||
-        (e = dmalloc(ctx, &r->errdim, capacity * sizeof(uint32_t))) != cudaSuccess) {
+        (e = dmalloc(ctx, &r->errdim, capacity * sizeof(uint32_t))) != cudaSuccess)) {
         cudaGetLastError(); vb200_regions_free(r);
         return fail(ctx, VB200_ERR_NOMEM, "region table of %llu regions x %llu samples does not fit: %s", (unsigned long long)capacity, (unsigned long long)sd, cudaGetErrorString(e));
     }
@@ -51,33 +54,33 @@ extern "C" void vb200_regions_free(vb200_regions* r) {
     if (!r) return;
     vb200_ctx* ctx = r->ctx;       // stream-ordered frees: work already enqueued on the context's stream still sees the table
     dfree(ctx, r->rmin); dfree(ctx, r->rmax); dfree(ctx, r->data); dfree(ctx, r->err); dfree(ctx, r->errdim);
+    dfree(ctx, r->rmin64); dfree(ctx, r->rmax64); dfree(ctx, r->data64); dfree(ctx, r->err64);
     delete r;
 }
 extern "C" uint64_t vb200_regions_count(const vb200_regions* r) { return r ? r->count : 0; }
 extern "C" int vb200_regions_dim(const vb200_regions* r) { return r ? r->dim : 0; }
 extern "C" int vb200_regions_samples(const vb200_regions* r) { return r ? r->sd : 0; }
 
-extern "C" int vb200_regions_upload(vb200_ctx* ctx, int dim, int rule, uint64_t count,
-                                    const float* rmin, const float* rmax, const float* err, const uint32_t* errdim, const float* data,
-                                    vb200_regions** out) {
+template<class T>
+static int regions_upload_t(vb200_ctx* ctx, int dim, int rule, uint64_t count, const T* rmin, const T* rmax, const T* err, const uint32_t* errdim, const T* data, vb200_regions** out) {
     if (!ctx || !out || !rmin || !rmax || !data || count == 0) return fail(ctx, VB200_ERR_INVALID, "NULL/empty argument");
     VB200_CUDA(ctx, cudaSetDevice(ctx->device));
     vb200_regions* r = nullptr;
-    int rc = regions_alloc(ctx, dim, rule, count, &r); if (rc) return rc;
+    int rc = regions_alloc(ctx, dim, rule, count, &r, sizeof(T) == 8); if (rc) return rc;
     const uint64_t sd = uint64_t(r->sd);
-    std::vector<float> t(count * (sd > uint64_t(dim) ? sd : uint64_t(dim)));
-    auto up = [&] (float* dst, const float* src, uint64_t width) -> cudaError_t {       // AoS [count][width] -> SoA [width][count]
+    std::vector<T> t(count * (sd > uint64_t(dim) ? sd : uint64_t(dim)));
+    auto up = [&] (T* dst, const T* src, uint64_t width) -> cudaError_t {       // AoS [count][width] -> SoA [width][count]
         for (uint64_t i = 0; i < count; ++i) for (uint64_t k = 0; k < width; ++k) t[k * count + i] = src[i * width + k];
-        return cudaMemcpyAsync(dst, t.data(), count * width * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+        return cudaMemcpyAsync(dst, t.data(), count * width * sizeof(T), cudaMemcpyHostToDevice, ctx->stream);
     };
     cudaError_t e;
-    if ((e = up(r->rmin, rmin, dim)) != cudaSuccess || (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess ||
-        (e = up(r->rmax, rmax, dim)) != cudaSuccess || (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess ||
-        (e = up(r->data, data, sd)) != cudaSuccess || (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) {
+    if ((e = up(RegCols<T>::rmin(r), rmin, dim)) != cudaSuccess || (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess ||
+        (e = up(RegCols<T>::rmax(r), rmax, dim)) != cudaSuccess || (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess ||
+        (e = up(RegCols<T>::data(r), data, sd)) != cudaSuccess || (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) {
         vb200_regions_free(r); return fail(ctx, VB200_ERR_CUDA, "region upload failed: %s", cudaGetErrorString(e));
     }
-    if (err) VB200_CUDA(ctx, cudaMemcpyAsync(r->err, err, count * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    else VB200_CUDA(ctx, cudaMemsetAsync(r->err, 0, count * sizeof(float), ctx->stream));
+    if (err) VB200_CUDA(ctx, cudaMemcpyAsync(RegCols<T>::err(r), err, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    else VB200_CUDA(ctx, cudaMemsetAsync(RegCols<T>::err(r), 0, count * sizeof(T), ctx->stream));
     if (errdim) VB200_CUDA(ctx, cudaMemcpyAsync(r->errdim, errdim, count * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     else VB200_CUDA(ctx, cudaMemsetAsync(r->errdim, 0, count * sizeof(uint32_t), ctx->stream));
     VB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -85,64 +88,91 @@ extern "C" int vb200_regions_upload(vb200_ctx* ctx, int dim, int rule, uint64_t 
     *out = r;
     return VB200_OK;
 }
+extern "C" int vb200_regions_upload(vb200_ctx* ctx, int dim, int rule, uint64_t count,
+                                    const float* rmin, const float* rmax, const float* err, const uint32_t* errdim, const float* data, vb200_regions** out) {
+    return regions_upload_t<float>(ctx, dim, rule, count, rmin, rmax, err, errdim, data, out);
+}
+extern "C" int vb200_regions_upload_f64(vb200_ctx* ctx, int dim, int rule, uint64_t count,
+                                        const double* rmin, const double* rmax, const double* err, const uint32_t* errdim, const double* data, vb200_regions** out) {
+    return regions_upload_t<double>(ctx, dim, rule, count, rmin, rmax, err, errdim, data, out);
+}
 
-extern "C" int vb200_regions_download(vb200_ctx* ctx, const vb200_regions* r, float* rmin, float* rmax, float* err, uint32_t* errdim, float* data) {
+template<class T>
+static int regions_download_t(vb200_ctx* ctx, const vb200_regions* r, T* rmin, T* rmax, T* err, uint32_t* errdim, T* data) {
     if (!ctx || !r) return fail(ctx, VB200_ERR_INVALID, "NULL argument");
+    if (r->f64 != (sizeof(T) == 8)) return fail(ctx, VB200_ERR_INVALID, "region table holds %s values", r->f64 ? "double" : "float");
     VB200_CUDA(ctx, cudaSetDevice(ctx->device));
     const uint64_t n = r->count, cap = r->capacity, sd = uint64_t(r->sd), dim = uint64_t(r->dim);
-    std::vector<float> t;
-    auto down = [&] (float* dst, const float* src, uint64_t width) -> int {              // SoA [width][cap] -> AoS [n][width]
+    std::vector<T> t;
+    auto down = [&] (T* dst, const T* src, uint64_t width) -> int {              // SoA [width][cap] -> AoS [n][width]
         t.resize(width * cap);
-        VB200_CUDA(ctx, cudaMemcpyAsync(t.data(), src, width * cap * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        VB200_CUDA(ctx, cudaMemcpyAsync(t.data(), src, width * cap * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
         VB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         for (uint64_t i = 0; i < n; ++i) for (uint64_t k = 0; k < width; ++k) dst[i * width + k] = t[k * cap + i];
         return VB200_OK;
     };
     int rc;
-    if (rmin && (rc = down(rmin, r->rmin, dim))) return rc;
-    if (rmax && (rc = down(rmax, r->rmax, dim))) return rc;
-    if (data && (rc = down(data, r->data, sd))) return rc;
-    if (err) VB200_CUDA(ctx, cudaMemcpyAsync(err, r->err, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (rmin && (rc = down(rmin, RegCols<T>::rmin(r), dim))) return rc;
+    if (rmax && (rc = down(rmax, RegCols<T>::rmax(r), dim))) return rc;
+    if (data && (rc = down(data, RegCols<T>::data(r), sd))) return rc;
+    if (err) VB200_CUDA(ctx, cudaMemcpyAsync(err, RegCols<T>::err(r), n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
     if (errdim) VB200_CUDA(ctx, cudaMemcpyAsync(errdim, r->errdim, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     VB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return VB200_OK;
 }
+extern "C" int vb200_regions_download(vb200_ctx* ctx, const vb200_regions* r, float* rmin, float* rmax, float* err, uint32_t* errdim, float* data) {
+    return regions_download_t<float>(ctx, r, rmin, rmax, err, errdim, data);
+}
+extern "C" int vb200_regions_download_f64(vb200_ctx* ctx, const vb200_regions* r, double* rmin, double* rmax, double* err, uint32_t* errdim, double* data) {
+    return regions_download_t<double>(ctx, r, rmin, rmax, err, errdim, data);
+}
 
 // ---- regions_generator_single: one region over the whole range (regions-generator-single.h:12-20) --------------------
-// sample points of region.h:40-46 + fill.h:45-72: p = double(i)/double(S-1); x = float(p*(max-min) + min), (max-min) a float difference
-__global__ void region_grid_points_kernel(int S, int dim, uint64_t n, const float* rmin, const float* rmax, uint64_t cap, uint64_t region, float* points) {
+// sample points of region.h:40-46 + fill.h:45-72: p = double(i)/double(S-1); x = Float(p*(max-min) + min), (max-min) a difference in Float
+template<class T>
+__global__ void region_grid_points_kernel(int S, int dim, uint64_t n, const T* rmin, const T* rmax, uint64_t cap, uint64_t region, T* points) {
     const uint64_t k = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (k >= n) return;
     uint64_t t = k;
     for (int d = 0; d < dim; ++d) {
         const double p = R::dd(double(t % uint64_t(S)), double(S - 1)); t /= uint64_t(S);
-        const float lo = rmin[uint64_t(d) * cap + region], hi = rmax[uint64_t(d) * cap + region];
-        points[uint64_t(d) * n + k] = R::d2f(R::da(R::dm(p, double(R::fs(hi, lo))), double(lo)));
+        const T lo = rmin[uint64_t(d) * cap + region], hi = rmax[uint64_t(d) * cap + region];
+        points[uint64_t(d) * n + k] = R::from_double<T>(R::da(R::dm(p, double(R::sub(hi, lo))), double(lo)));
     }
 }
 
-extern "C" int vb200_regions_generate_single(vb200_ctx* ctx, const vb200_integrand* f, const vb200_domain* domain, int rule, vb200_regions** out) {
-    if (!ctx || !f || !domain || !out) return fail(ctx, VB200_ERR_INVALID, "NULL argument");
+template<class T>
+static int generate_single_t(vb200_ctx* ctx, const vb200_integrand* f, int dim, const T* rmin, const T* rmax, int rule, vb200_regions** out) {
     VB200_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (f->dim <= 0 || domain->dim != f->dim) return fail(ctx, VB200_ERR_INVALID, "range has %d dimensions, integrand takes %d", domain->dim, f->dim);
+    const bool f64 = sizeof(T) == 8;
+    if (f->dim <= 0 || dim != f->dim) return fail(ctx, VB200_ERR_INVALID, "range has %d dimensions, integrand takes %d", dim, f->dim);
+    if (bool(f->flags & VB200_INTEGRAND_F64) != f64) return fail(ctx, VB200_ERR_INVALID, "integrand '%s' computes in %s, the range is %s", f->name ? f->name : "?", (f->flags & VB200_INTEGRAND_F64) ? "double" : "float", f64 ? "double" : "float");
     vb200_regions* r = nullptr;
-    int rc = regions_alloc(ctx, f->dim, rule, 1, &r); if (rc) return rc;
+    int rc = regions_alloc(ctx, f->dim, rule, 1, &r, f64); if (rc) return rc;
     auto bail = [&] (int code) { vb200_regions_free(r); return code; };
-    if (cudaMemcpyAsync(r->rmin, domain->rmin, f->dim * sizeof(float), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
-        cudaMemcpyAsync(r->rmax, domain->rmax, f->dim * sizeof(float), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+    if (cudaMemcpyAsync(RegCols<T>::rmin(r), rmin, f->dim * sizeof(T), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+        cudaMemcpyAsync(RegCols<T>::rmax(r), rmax, f->dim * sizeof(T), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
         return bail(fail(ctx, VB200_ERR_CUDA, "range upload failed"));
     const uint64_t n = uint64_t(r->sd);
-    void* pts = nullptr; rc = reserve(ctx, 3, n * f->dim * sizeof(float), &pts); if (rc) return bail(rc);
-    region_grid_points_kernel<<<unsigned((n + 255) / 256), 256, 0, ctx->stream>>>(r->SH, f->dim, n, r->rmin, r->rmax, 1, 0, static_cast<float*>(pts));
+    void* pts = nullptr; rc = reserve(ctx, 3, n * f->dim * sizeof(T), &pts); if (rc) return bail(rc);
+    region_grid_points_kernel<T><<<unsigned((n + 255) / 256), 256, 0, ctx->stream>>>(r->SH, f->dim, n, RegCols<T>::rmin(r), RegCols<T>::rmax(r), 1, 0, static_cast<T*>(pts));
     ctx->launches++;
     vb200_eval_launch ev; std::memset(&ev, 0, sizeof(ev));
-    ev.n = n; ev.dim = f->dim; ev.points = static_cast<const float*>(pts); ev.values = r->data;       // capacity 1: data[k*1+0]
+    ev.n = n; ev.dim = f->dim; ev.f64 = f64 ? 1 : 0; ev.points = pts; ev.values = RegCols<T>::data(r);       // capacity 1: data[k*1+0]
     rc = call_thunk(ctx, f, VB200_K_EVAL_POINTS, &ev); if (rc) return bail(rc);
-    if (cudaMemsetAsync(r->err, 0, sizeof(float), ctx->stream) != cudaSuccess || cudaMemsetAsync(r->errdim, 0, sizeof(uint32_t), ctx->stream) != cudaSuccess ||
+    if (cudaMemsetAsync(RegCols<T>::err(r), 0, sizeof(T), ctx->stream) != cudaSuccess || cudaMemsetAsync(r->errdim, 0, sizeof(uint32_t), ctx->stream) != cudaSuccess ||
         cudaStreamSynchronize(ctx->stream) != cudaSuccess) return bail(fail(ctx, VB200_ERR_CUDA, "single-region generation failed: %s", cudaGetErrorString(cudaGetLastError())));
     r->count = 1;
     *out = r;
     return VB200_OK;
+}
+extern "C" int vb200_regions_generate_single(vb200_ctx* ctx, const vb200_integrand* f, const vb200_domain* domain, int rule, vb200_regions** out) {
+    if (!ctx || !f || !domain || !out) return fail(ctx, VB200_ERR_INVALID, "NULL argument");
+    return generate_single_t<float>(ctx, f, domain->dim, domain->rmin, domain->rmax, rule, out);
+}
+extern "C" int vb200_regions_generate_single_f64(vb200_ctx* ctx, const vb200_integrand* f, const vb200_domain_f64* domain, int rule, vb200_regions** out) {
+    if (!ctx || !f || !domain || !out) return fail(ctx, VB200_ERR_INVALID, "NULL argument");
+    return generate_single_t<double>(ctx, f, domain->dim, domain->rmin, domain->rmax, rule, out);
 }
 
 // =====================================================================================================================
@@ -153,34 +183,35 @@ namespace {
 // one fold level of Region::sub_last over a NON-binned dimension: the bin box spans the region's whole extent there, so the
 // normalised limits are exactly 0 and 1 (pos_in_range(min)=0, pos_in_range(max)=1) and the result is the same for every
 // bin — computed once per region instead of once per (bin, region) pair.  in: [S^m][cap] -> out: [S^(m-1)][cap].
-template<int S>
-__global__ void fold_last_dim_kernel(uint64_t nregions, uint64_t cap, int lower /* S^(m-1) */, const float* __restrict__ in, float* __restrict__ out) {
+template<int S, class T>
+__global__ void fold_last_dim_kernel(uint64_t nregions, uint64_t cap, int lower /* S^(m-1) */, const T* __restrict__ in, T* __restrict__ out) {
     const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const int k = blockIdx.y;
     if (i >= nregions) return;
-    float line[S];
+    T line[S];
 #pragma unroll
     for (int j = 0; j < S; ++j) line[j] = in[(uint64_t(k) + uint64_t(j) * uint64_t(lower)) * cap + i];
-    out[uint64_t(k) * cap + i] = R::subrange<S>(0.0f, 1.0f, line);
+    out[uint64_t(k) * cap + i] = R::subrange<S, T>(T(0), T(1), line);
 }
 
 // Range::volume (range.h:21-25) and pixels_in_region (region.h:454-463) per region
-__global__ void region_boxes_kernel(uint64_t nregions, uint64_t cap, int dim, int db, vb200_domain dom,
-                                    const float* __restrict__ rmin, const float* __restrict__ rmax,
-                                    float* __restrict__ volume, uint32_t* __restrict__ pstart, uint32_t* __restrict__ pend) {
+template<class T>
+__global__ void region_boxes_kernel(uint64_t nregions, uint64_t cap, int dim, int db, DomT<T> dom,
+                                    const T* __restrict__ rmin, const T* __restrict__ rmax,
+                                    T* __restrict__ volume, uint32_t* __restrict__ pstart, uint32_t* __restrict__ pend) {
     const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= nregions) return;
-    float v = 1.0f;
-    for (int d = 0; d < dim; ++d) v = R::fm(v, R::fs(rmax[uint64_t(d) * cap + i], rmin[uint64_t(d) * cap + i]));
+    T v = T(1);
+    for (int d = 0; d < dim; ++d) v = R::mul(v, R::sub(rmax[uint64_t(d) * cap + i], rmin[uint64_t(d) * cap + i]));
     volume[i] = v;
     for (int d = 0; d < db; ++d) {
-        const float res = float(dom.res[d]);
-        const float ext = R::fs(dom.rmax[d], dom.rmin[d]);
-        const float fs_ = R::fd(R::fm(res, R::fs(rmin[uint64_t(d) * cap + i], dom.rmin[d])), ext);
-        const float fe_ = R::fa(0.99f, R::fd(R::fm(res, R::fs(rmax[uint64_t(d) * cap + i], dom.rmin[d])), ext));
-        // size_t(float): negative / NaN inputs are undefined upstream; clamp them to 0 here
-        uint64_t s = fs_ > 0.0f ? uint64_t(fs_) : 0ull;
-        uint64_t e = fe_ > 0.0f ? uint64_t(fe_) : 0ull;
+        const T res = T(dom.res[d]);
+        const T ext = R::sub(dom.rmax[d], dom.rmin[d]);
+        const T fs_ = R::quo(R::mul(res, R::sub(rmin[uint64_t(d) * cap + i], dom.rmin[d])), ext);
+        const T fe_ = R::add(T(0.99f), R::quo(R::mul(res, R::sub(rmax[uint64_t(d) * cap + i], dom.rmin[d])), ext));     // 0.99f is a float literal upstream
+        // size_t(Float): negative / NaN inputs are undefined upstream; clamp them to 0 here
+        uint64_t s = fs_ > T(0) ? uint64_t(fs_) : 0ull;
+        uint64_t e = fe_ > T(0) ? uint64_t(fe_) : 0ull;
         if (e > dom.res[d]) e = dom.res[d];
         if (e < s + 1) e = s + 1;
         pstart[uint64_t(d) * cap + i] = uint32_t(s < 0xffffffffull ? s : 0xffffffffull);
@@ -298,53 +329,53 @@ __global__ void __launch_bounds__(1024) tile_sort_kernel(const uint64_t* __restr
 
 // closed-form integral of the region's (marginalised) tensor-product interpolant over bin ∩ region:
 // Region::integral_subrange -> sub_last (region.h:141-169), folding subrange(a_d,b_d) over the binned dims DB-1, ..., 0.
-template<int S, int DB>
-__device__ __forceinline__ float patch_subrange(const float* patch, const float (&na)[3], const float (&nb)[3]) {
-    if (DB == 1) return R::subrange<S>(na[0], nb[0], patch);
+template<int S, int DB, class T>
+__device__ __forceinline__ T patch_subrange(const T* patch, const T (&na)[3], const T (&nb)[3]) {
+    if (DB == 1) return R::subrange<S, T>(na[0], nb[0], patch);
     if (DB == 2) {
-        float t[S];
+        T t[S];
 #pragma unroll
         for (int i0 = 0; i0 < S; ++i0) {
-            float line[S];
+            T line[S];
 #pragma unroll
             for (int i1 = 0; i1 < S; ++i1) line[i1] = patch[i0 + S * i1];
-            t[i0] = R::subrange<S>(na[1], nb[1], line);
+            t[i0] = R::subrange<S, T>(na[1], nb[1], line);
         }
-        return R::subrange<S>(na[0], nb[0], t);
+        return R::subrange<S, T>(na[0], nb[0], t);
     }
-    float t1[S];
+    T t1[S];
 #pragma unroll
     for (int i0 = 0; i0 < S; ++i0) {
-        float t2[S];
+        T t2[S];
 #pragma unroll
         for (int i1 = 0; i1 < S; ++i1) {
-            float line[S];
+            T line[S];
 #pragma unroll
             for (int i2 = 0; i2 < S; ++i2) line[i2] = patch[i0 + S * i1 + S * S * i2];
-            t2[i1] = R::subrange<S>(na[2], nb[2], line);
+            t2[i1] = R::subrange<S, T>(na[2], nb[2], line);
         }
-        t1[i0] = R::subrange<S>(na[1], nb[1], t2);
+        t1[i0] = R::subrange<S, T>(na[1], nb[1], t2);
     }
-    return R::subrange<S>(na[0], nb[0], t1);
+    return R::subrange<S, T>(na[0], nb[0], t1);
 }
 
-template<int S, int DB> struct Staged {
+template<int S, int DB, class T> struct Staged {
     static constexpr int P = (DB == 1 ? S : DB == 2 ? S * S : S * S * S);
-    float patch[P]; float rmin[DB], rmax[DB]; float volume; uint32_t ps[DB], pe[DB];
+    T patch[P]; T rmin[DB], rmax[DB]; T volume; uint32_t ps[DB], pe[DB];
 };
 
 // K8/K10: one CTA per bin tile, one thread per bin.  The tile's region list is staged through shared memory in chunks
 // (patches + boxes: the "region tree" a bin needs), every thread walks the chunk in table order, keeps the regions whose
 // pixel box contains its bin and accumulates nbins * integral_subrange(bin ∩ region) with the reference's promotions:
 //   bins(pos) += double(factor) * float        (regions-integrator-sequential.h:54; ...-variance-reduction.h:80)
-template<int S, int DB>
-__global__ void __launch_bounds__(256) walk_accumulate_kernel(TileGeom g, vb200_domain dom, uint64_t cap, uint64_t begin, uint64_t end, uint64_t nbins_total,
-                                                              const float* __restrict__ patches, const float* __restrict__ rmin, const float* __restrict__ rmax,
-                                                              const float* __restrict__ volume, const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ pend,
+template<int S, int DB, class T>
+__global__ void __launch_bounds__(256) walk_accumulate_kernel(TileGeom g, DomT<T> dom, uint64_t cap, uint64_t begin, uint64_t end, uint64_t nbins_total,
+                                                              const T* __restrict__ patches, const T* __restrict__ rmin, const T* __restrict__ rmax,
+                                                              const T* __restrict__ volume, const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ pend,
                                                               const uint64_t* __restrict__ offsets, const uint32_t* __restrict__ list,
-                                                              int mode, float* __restrict__ out, float* __restrict__ approx, uint32_t* __restrict__ count) {
-    using St = Staged<S, DB>;
-    constexpr int CHUNK = (St::P > 64) ? 16 : 64;
+                                                              int mode, T* __restrict__ out, T* __restrict__ approx, uint32_t* __restrict__ count) {
+    using St = Staged<S, DB, T>;
+    constexpr int CHUNK = (St::P * sizeof(T) > 256) ? 16 : 64;
     __shared__ St s_reg[CHUNK];
     const uint64_t t = blockIdx.x;
     uint32_t o[3]; tile_origin(g, t, o);
@@ -354,13 +385,13 @@ __global__ void __launch_bounds__(256) walk_accumulate_kernel(TileGeom g, vb200_
     bool live = true; uint64_t bin = 0, prod = 1;
     for (int d = 0; d < DB; ++d) { live = live && pos[d] < g.res[d]; bin += uint64_t(pos[d]) * prod; prod *= g.res[d]; }
     live = live && bin >= begin && bin < end;
-    float ba[DB], bb[DB];
+    T ba[DB], bb[DB];
 #pragma unroll
-    for (int d = 0; d < DB; ++d) {       // bin box: min + float(pos)*drange (regions-integrator-sequential.h:42-51)
-        ba[d] = R::fa(dom.rmin[d], R::fm(float(pos[d]), dom.drange[d]));
-        bb[d] = R::fa(dom.rmin[d], R::fm(float(pos[d] + 1u), dom.drange[d]));
+    for (int d = 0; d < DB; ++d) {       // bin box: min + Float(pos)*drange (regions-integrator-sequential.h:42-51)
+        ba[d] = R::add(dom.rmin[d], R::mul(T(pos[d]), dom.drange[d]));
+        bb[d] = R::add(dom.rmin[d], R::mul(T(pos[d] + 1u), dom.drange[d]));
     }
-    float acc = (mode == 0 && live) ? out[bin] : 0.0f;
+    T acc = (mode == 0 && live) ? out[bin] : T(0);
     uint32_t cnt = 0;
     const double factor = double(nbins_total);
     const uint64_t lo = offsets[t], hi = offsets[t + 1];
@@ -389,18 +420,18 @@ __global__ void __launch_bounds__(256) walk_accumulate_kernel(TileGeom g, vb200_
                 if (!inside) continue;
                 ++cnt;
                 // Range::intersection (range.h:92-101) in the binned dims; the other dims are the region's own extent
-                float na[3], nb[3]; bool empty = false;
+                T na[3], nb[3]; bool empty = false;
 #pragma unroll
                 for (int d = 0; d < DB; ++d) {
-                    const float a = fmaxf(ba[d], rg.rmin[d]);
-                    const float b = fmaxf(a, fminf(bb[d], rg.rmax[d]));
+                    const T a = R::maxv(ba[d], rg.rmin[d]);
+                    const T b = R::maxv(a, R::minv(bb[d], rg.rmax[d]));
                     empty = empty || (a >= b);
-                    na[d] = R::pos_in_range(rg.rmin[d], rg.rmax[d], a);
-                    nb[d] = R::pos_in_range(rg.rmin[d], rg.rmax[d], b);
+                    na[d] = R::pos_in_range<T>(rg.rmin[d], rg.rmax[d], a);
+                    nb[d] = R::pos_in_range<T>(rg.rmin[d], rg.rmax[d], b);
                 }
                 if (empty) continue;                                             // regions-integrator-sequential.h:54 `if (!empty())`
-                const float integral = R::fm(rg.volume, patch_subrange<S, DB>(rg.patch, na, nb));
-                acc = R::d2f(R::da(double(acc), R::dm(factor, double(integral))));
+                const T integral = R::mul(rg.volume, patch_subrange<S, DB, T>(rg.patch, na, nb));
+                acc = R::from_double<T>(R::da(double(acc), R::dm(factor, double(integral))));
             }
         }
     }
@@ -410,17 +441,17 @@ __global__ void __launch_bounds__(256) walk_accumulate_kernel(TileGeom g, vb200_
     }
 }
 
-template<int S, int DB>
-int launch_accumulate(vb200_ctx* ctx, const vb200_regions* r, const BinWalk& w, const TileGeom& g, const vb200_domain& dom,
-                      uint64_t begin, uint64_t end, uint64_t total, int mode, float* out, float* approx, uint32_t* count) {
-    walk_accumulate_kernel<S, DB><<<unsigned(w.ntiles), 256, 0, ctx->stream>>>(g, dom, w.cap, begin, end, total, w.patches, r->rmin, r->rmax, w.volume,
-                                                                                w.pstart, w.pend, w.tile_offset, w.tile_list, mode, out, approx, count);
+template<int S, int DB, class T>
+int launch_accumulate(vb200_ctx* ctx, const vb200_regions* r, const BinWalkT<T>& w, const TileGeom& g, const DomT<T>& dom,
+                      uint64_t begin, uint64_t end, uint64_t total, int mode, T* out, T* approx, uint32_t* count) {
+    walk_accumulate_kernel<S, DB, T><<<unsigned(w.ntiles), 256, 0, ctx->stream>>>(g, dom, w.cap, begin, end, total, w.patches, RegCols<T>::rmin(r), RegCols<T>::rmax(r), w.volume,
+                                                                                   w.pstart, w.pend, w.tile_offset, w.tile_list, mode, out, approx, count);
     ctx->launches++;
     VB200_CUDA(ctx, cudaGetLastError());
     return VB200_OK;
 }
 
-TileGeom make_geom(const BinWalk& w, const vb200_domain& dom) {
+template<class T> TileGeom make_geom(const BinWalkT<T>& w, const DomT<T>& dom) {
     TileGeom g; g.db = w.db;
     for (int d = 0; d < 3; ++d) { g.tile[d] = w.tile[d]; g.tiles[d] = w.tiles[d]; g.res[d] = d < w.db ? uint32_t(dom.res[d]) : 1u; }
     return g;
@@ -430,50 +461,50 @@ TileGeom make_geom(const BinWalk& w, const vb200_domain& dom) {
 
 namespace vb200 {
 
-void walk_free(BinWalk* w) {
+template<class T> void walk_free_t(BinWalkT<T>* w) {
     vb200_ctx* ctx = w->ctx;
-    if (!ctx) { *w = BinWalk(); return; }
+    if (!ctx) { *w = BinWalkT<T>(); return; }
     dfree(ctx, w->patches); dfree(ctx, w->volume); dfree(ctx, w->pstart); dfree(ctx, w->pend); dfree(ctx, w->tile_offset); dfree(ctx, w->tile_list);
     dfree(ctx, w->scratch[0]); dfree(ctx, w->scratch[1]);
-    *w = BinWalk();
+    *w = BinWalkT<T>();
 }
 
-int walk_build(vb200_ctx* ctx, const vb200_regions* r, const vb200_domain& dom, uint64_t begin, uint64_t end, BinWalk* w) {
-    *w = BinWalk();
+template<class T> int walk_build_t(vb200_ctx* ctx, const vb200_regions* r, const DomT<T>& dom, uint64_t begin, uint64_t end, BinWalkT<T>* w) {
+    *w = BinWalkT<T>();
     w->ctx = ctx;
     const int S = r->SH, D = r->dim, db = dom.dimbins;
     const uint64_t n = r->count, cap = r->capacity;
     w->S = S; w->db = db; w->nregions = n; w->cap = cap;
     int patch = 1; for (int i = 0; i < db; ++i) patch *= S;
     w->patch = patch;
-    auto bail = [&] (int code) { walk_free(w); return code; };
+    auto bail = [&] (int code) { walk_free_t<T>(w); return code; };
 #define VB200_TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return bail(fail(ctx, VB200_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__))); } while (0)
     // 1. marginalise the non-binned dimensions D-1 .. db (each fold rounds to float, exactly like the lazy reference folds)
-    const float* cur = r->data;
+    const T* cur = RegCols<T>::data(r);
     if (D > db) {
         uint64_t biggest = 1; for (int i = 0; i < D - 1; ++i) biggest *= uint64_t(S);
-        VB200_TRY(dmalloc(ctx, &w->scratch[0], biggest * cap * sizeof(float)));
-        if (D - db > 1) VB200_TRY(dmalloc(ctx, &w->scratch[1], (biggest / uint64_t(S)) * cap * sizeof(float)));
+        VB200_TRY(dmalloc(ctx, &w->scratch[0], biggest * cap * sizeof(T)));
+        if (D - db > 1) VB200_TRY(dmalloc(ctx, &w->scratch[1], (biggest / uint64_t(S)) * cap * sizeof(T)));
         int which = 0;
         for (int m = D; m > db; --m) {
             int lower = 1; for (int i = 0; i < m - 1; ++i) lower *= S;
-            float* dst = w->scratch[which];
+            T* dst = w->scratch[which];
             dim3 grid(unsigned((n + 127) / 128), unsigned(lower));
-            if (S == 2) fold_last_dim_kernel<2><<<grid, 128, 0, ctx->stream>>>(n, cap, lower, cur, dst);
-            else if (S == 3) fold_last_dim_kernel<3><<<grid, 128, 0, ctx->stream>>>(n, cap, lower, cur, dst);
-            else fold_last_dim_kernel<5><<<grid, 128, 0, ctx->stream>>>(n, cap, lower, cur, dst);
+            if (S == 2) fold_last_dim_kernel<2, T><<<grid, 128, 0, ctx->stream>>>(n, cap, lower, cur, dst);
+            else if (S == 3) fold_last_dim_kernel<3, T><<<grid, 128, 0, ctx->stream>>>(n, cap, lower, cur, dst);
+            else fold_last_dim_kernel<5, T><<<grid, 128, 0, ctx->stream>>>(n, cap, lower, cur, dst);
             ctx->launches++;
             VB200_TRY(cudaGetLastError());
             cur = dst; which ^= 1;
         }
     }
-    VB200_TRY(dmalloc(ctx, &w->patches, uint64_t(patch) * cap * sizeof(float)));
-    VB200_TRY(cudaMemcpyAsync(w->patches, cur, uint64_t(patch) * cap * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    VB200_TRY(dmalloc(ctx, &w->patches, uint64_t(patch) * cap * sizeof(T)));
+    VB200_TRY(cudaMemcpyAsync(w->patches, cur, uint64_t(patch) * cap * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
     // 2. volumes + pixel boxes
-    VB200_TRY(dmalloc(ctx, &w->volume, cap * sizeof(float)));
+    VB200_TRY(dmalloc(ctx, &w->volume, cap * sizeof(T)));
     VB200_TRY(dmalloc(ctx, &w->pstart, uint64_t(db) * cap * sizeof(uint32_t)));
     VB200_TRY(dmalloc(ctx, &w->pend, uint64_t(db) * cap * sizeof(uint32_t)));
-    region_boxes_kernel<<<unsigned((n + 255) / 256), 256, 0, ctx->stream>>>(n, cap, D, db, dom, r->rmin, r->rmax, w->volume, w->pstart, w->pend);
+    region_boxes_kernel<T><<<unsigned((n + 255) / 256), 256, 0, ctx->stream>>>(n, cap, D, db, dom, RegCols<T>::rmin(r), RegCols<T>::rmax(r), w->volume, w->pstart, w->pend);
     ctx->launches++;
     VB200_TRY(cudaGetLastError());
     // 3. tiles of 256 bins and their ordered region lists
@@ -481,7 +512,7 @@ int walk_build(vb200_ctx* ctx, const vb200_regions* r, const vb200_domain& dom, 
     w->ntiles = 1;
     for (int d = 0; d < 3; ++d) { w->tiles[d] = d < db ? uint32_t((dom.res[d] + w->tile[d] - 1) / w->tile[d]) : 1u; w->ntiles *= w->tiles[d]; }
     if (w->ntiles > 0x7fffffffull) return bail(fail(ctx, VB200_ERR_UNSUPPORTED, "bin grid too large for the tile walk"));
-    const TileGeom g = make_geom(*w, dom);
+    const TileGeom g = make_geom<T>(*w, dom);
     VB200_TRY(dmalloc(ctx, &w->tile_offset, (w->ntiles + 1) * sizeof(uint64_t)));
     unsigned long long* counts = reinterpret_cast<unsigned long long*>(w->tile_offset);
     // every (tile, region) pair tested by brute force keeps table order for free; beyond ~2.7e8 pairs bin the regions into
@@ -525,22 +556,65 @@ int walk_build(vb200_ctx* ctx, const vb200_regions* r, const vb200_domain& dom, 
     return VB200_OK;
 }
 
-int walk_accumulate(vb200_ctx* ctx, const vb200_regions* r, const BinWalk& w, const vb200_domain& dom, uint64_t begin, uint64_t end,
-                    int mode, float* out, float* approx, uint32_t* count) {
-    const TileGeom g = make_geom(w, dom);
+template<class T> int walk_accumulate_t(vb200_ctx* ctx, const vb200_regions* r, const BinWalkT<T>& w, const DomT<T>& dom, uint64_t begin, uint64_t end,
+                                        int mode, T* out, T* approx, uint32_t* count) {
+    const TileGeom g = make_geom<T>(w, dom);
     const uint64_t total = nbins_of(dom);
-#define VB200_WALK(SS, DD) if (w.S == SS && w.db == DD) return launch_accumulate<SS, DD>(ctx, r, w, g, dom, begin, end, total, mode, out, approx, count);
+#define VB200_WALK(SS, DD) if (w.S == SS && w.db == DD) return launch_accumulate<SS, DD, T>(ctx, r, w, g, dom, begin, end, total, mode, out, approx, count);
     VB200_WALK(2, 1) VB200_WALK(2, 2) VB200_WALK(2, 3) VB200_WALK(3, 1) VB200_WALK(3, 2) VB200_WALK(3, 3) VB200_WALK(5, 1) VB200_WALK(5, 2) VB200_WALK(5, 3)
 #undef VB200_WALK
     return fail(ctx, VB200_ERR_UNSUPPORTED, "no bin walk for rule with %d samples and %d binned dimensions", w.S, w.db);
 }
 
+// the two scalar types the library computes in
+template int walk_build_t<float>(vb200_ctx*, const vb200_regions*, const DomT<float>&, uint64_t, uint64_t, BinWalkT<float>*);
+template int walk_build_t<double>(vb200_ctx*, const vb200_regions*, const DomT<double>&, uint64_t, uint64_t, BinWalkT<double>*);
+template void walk_free_t<float>(BinWalkT<float>*);
+template void walk_free_t<double>(BinWalkT<double>*);
+template int walk_accumulate_t<float>(vb200_ctx*, const vb200_regions*, const BinWalkT<float>&, const DomT<float>&, uint64_t, uint64_t, int, float*, float*, uint32_t*);
+template int walk_accumulate_t<double>(vb200_ctx*, const vb200_regions*, const BinWalkT<double>&, const DomT<double>&, uint64_t, uint64_t, int, double*, double*, uint32_t*);
+
 } // namespace vb200
+
+// Range<double,DIM>: RegionsIntegratorSequential with Float = value_type = double — every fold, the bin boxes and the running
+// '+=' are evaluated in double, as upstream
+extern "C" int vb200_regions_integrate_bins_f64(vb200_ctx* ctx, const vb200_regions* r, const vb200_domain_f64* domain, const vb200_shard* shard,
+                                                double* bins, int bins_mem) {
+    if (!ctx || !r || !domain || !bins) return fail(ctx, VB200_ERR_INVALID, "NULL argument");
+    VB200_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!r->f64) return fail(ctx, VB200_ERR_INVALID, "region table holds float values: use vb200_regions_integrate_bins");
+    if (domain->dim != r->dim || domain->dimbins < 1 || domain->dimbins > VB200_MAX_DIMBINS || domain->dimbins > domain->dim)
+        return fail(ctx, VB200_ERR_INVALID, "range has %d dimensions (%d binned), regions have %d", domain->dim, domain->dimbins, r->dim);
+    for (int i = 0; i < domain->dimbins; ++i) if (domain->res[i] == 0 || domain->res[i] > 0xffffffffull) return fail(ctx, VB200_ERR_INVALID, "resolution[%d] invalid", i);
+    const DomT<double> dom = to_dom(*domain);
+    const uint64_t total = nbins_of(dom);
+    uint64_t begin, end; vb200_shard s = shard ? *shard : vb200_shard{0, 0};
+    int rc = resolve_shard(ctx, s, total, &begin, &end); if (rc) return rc;
+    if (begin == end || r->count == 0) return VB200_OK;
+    const uint64_t n = end - begin;
+    double* dev_base = bins;
+    if (bins_mem == VB200_HOST) {
+        void* d = nullptr; rc = reserve(ctx, 0, n * sizeof(double), &d); if (rc) return rc;
+        VB200_CUDA(ctx, cudaMemcpyAsync(d, bins + begin, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));     // '+=' continues from the current contents
+        dev_base = static_cast<double*>(d) - begin;
+    } else if (bins_mem != VB200_DEVICE) return fail(ctx, VB200_ERR_INVALID, "bad memory-space flag %d", bins_mem);
+    BinWalkT<double> w;
+    rc = walk_build_t<double>(ctx, r, dom, begin, end, &w); if (rc) return rc;
+    rc = walk_accumulate_t<double>(ctx, r, w, dom, begin, end, 0, dev_base, nullptr, nullptr);
+    if (!rc && bins_mem == VB200_HOST) {
+        cudaError_t e = cudaMemcpyAsync(bins + begin, dev_base + begin, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e != cudaSuccess) rc = fail(ctx, VB200_ERR_CUDA, "copy back failed: %s", cudaGetErrorString(e));
+    }
+    if (!rc) { cudaError_t e = cudaStreamSynchronize(ctx->stream); if (e != cudaSuccess) rc = fail(ctx, VB200_ERR_CUDA, "region->bin integration (f64) failed: %s", cudaGetErrorString(e)); }
+    walk_free_t<double>(&w);
+    return rc;
+}
 
 extern "C" int vb200_regions_integrate_bins(vb200_ctx* ctx, const vb200_regions* r, const vb200_domain* domain, const vb200_shard* shard,
                                             float* bins, int bins_mem) {
     if (!ctx || !r || !domain || !bins) return fail(ctx, VB200_ERR_INVALID, "NULL argument");
     VB200_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (r->f64) return fail(ctx, VB200_ERR_INVALID, "region table holds double values: use vb200_regions_integrate_bins_f64");
     int rc = check_domain(ctx, *domain, r->dim); if (rc) return rc;
     const vb200_domain dom = finish_domain(*domain);
     const uint64_t total = nbins_of(dom);

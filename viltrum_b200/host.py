@@ -195,6 +195,30 @@ class Context:
         self.check(self._L.vb200_regions_generate_single(self._h, self.integrand(f, exact), ctypes.byref(d), C.RULES[rule], ctypes.byref(h)))
         return Regions(self, h)
 
+    # -- double precision (Range<double,DIM>): Newton-Cotes region family -------------------------------------------------
+    def integrand64(self, name, exact=True):
+        p = self._L.vb200_builtin_integrand_f64(name.encode(), 1 if exact else 0)
+        if not p:
+            raise KeyError(f"unknown double-precision built-in integrand '{name}'")
+        return p
+
+    def regions_generate_single_f64(self, f, rng, rule, exact=True):
+        d = C.make_domain64(len(rng.min), [1], rng.min, rng.max)
+        h = ctypes.c_void_p()
+        self.check(self._L.vb200_regions_generate_single_f64(self._h, self.integrand64(f, exact), ctypes.byref(d), C.RULES[rule], ctypes.byref(h)))
+        return Regions(self, h, f64=True)
+
+    def regions_upload_f64(self, rule, rmin, rmax, err, errdim, data):
+        rmin = np.ascontiguousarray(rmin, np.float64); rmax = np.ascontiguousarray(rmax, np.float64)
+        n, dim = rmin.shape
+        err = np.ascontiguousarray(err if err is not None else np.zeros(n), np.float64)
+        errdim = np.ascontiguousarray(errdim if errdim is not None else np.zeros(n), np.uint32)
+        data = np.ascontiguousarray(data, np.float64)
+        h = ctypes.c_void_p()
+        self.check(self._L.vb200_regions_upload_f64(self._h, dim, C.RULES[rule], n, rmin.ctypes.data, rmax.ctypes.data, err.ctypes.data,
+                                                    errdim.ctypes.data, data.ctypes.data, ctypes.byref(h)))
+        return Regions(self, h, f64=True)
+
     def regions_upload(self, rule, rmin, rmax, err, errdim, data):
         rmin = np.ascontiguousarray(rmin, np.float32); rmax = np.ascontiguousarray(rmax, np.float32)
         n, dim = rmin.shape
@@ -210,8 +234,8 @@ class Context:
 class Regions:
     """Device-resident leaf table (vb200_regions)."""
 
-    def __init__(self, ctx, handle):
-        self.ctx, self._h = ctx, handle
+    def __init__(self, ctx, handle, f64=False):
+        self.ctx, self._h, self.f64 = ctx, handle, f64
 
     def __len__(self):
         return int(self.ctx._L.vb200_regions_count(self._h))
@@ -226,14 +250,22 @@ class Regions:
 
     def download(self):
         n, d, sd = len(self), self.dim, self.samples
-        out = dict(min=np.zeros((n, d), np.float32), max=np.zeros((n, d), np.float32), err=np.zeros(n, np.float32),
-                   dim=np.zeros(n, np.uint32), data=np.zeros((n, sd), np.float32))
-        self.ctx.check(self.ctx._L.vb200_regions_download(self.ctx._h, self._h, out["min"].ctypes.data, out["max"].ctypes.data,
-                                                          out["err"].ctypes.data, out["dim"].ctypes.data, out["data"].ctypes.data))
+        ft = np.float64 if self.f64 else np.float32
+        out = dict(min=np.zeros((n, d), ft), max=np.zeros((n, d), ft), err=np.zeros(n, ft),
+                   dim=np.zeros(n, np.uint32), data=np.zeros((n, sd), ft))
+        fn = self.ctx._L.vb200_regions_download_f64 if self.f64 else self.ctx._L.vb200_regions_download
+        self.ctx.check(fn(self.ctx._h, self._h, out["min"].ctypes.data, out["max"].ctypes.data,
+                          out["err"].ctypes.data, out["dim"].ctypes.data, out["data"].ctypes.data))
         return out
 
     def integrate_bins(self, bins, res, rng, shard=None):
         if Context._empty(shard):
+            return
+        if self.f64:
+            b, mem, _k = _buffer(bins, np.float64)
+            d = C.make_domain64(len(rng.min), res, rng.min, rng.max)
+            s = C.Shard(); s.begin, s.end = (shard if shard else (0, 0))
+            self.ctx.check(self.ctx._L.vb200_regions_integrate_bins_f64(self.ctx._h, self._h, ctypes.byref(d), ctypes.byref(s), b, mem))
             return
         b, mem, _k = _buffer(bins)
         d = C.make_domain(len(rng.min), res, rng.min, rng.max)
