@@ -13,6 +13,7 @@ struct SmoothEdge2 {
         return s+((dx*dx+dy*dy<.09f)?.75f:0.0f);
     }
 };
+struct X2Y2d { __host__ __device__ double operator()(const std::array<double,2>& x) const { return x[0]*x[0] + x[1]*x[1]; } };
 struct CountLogger : viltrum::LoggerNull {           // the reference hands the region list to Logger::log (integrator-region-based.h:19)
     std::size_t* regions;
     template<typename Data> void log(const Data& d) { *regions = d.size(); }
@@ -27,9 +28,13 @@ int main(int argc, char** argv) {
               img, img.resolution(), SmoothEdge2(), range_primary<2>(), logger);
     std::vector<float> fixed(16, 0.0f);
     integrate(integrator_newton_cotes(simpson), fixed, [] __host__ __device__ (float x, float y) { return x*x + y*y; }, range_primary<2>());
+    // Range<double,DIM> + double integrand: the fp64 Newton-Cotes path (1e-12 gate)
+    std::vector<double> fixed64(16, 0.0);
+    integrate(integrator_newton_cotes(boole), fixed64, X2Y2d(), range_primary<2,double>());
+    std::printf("fp64 boole bin 0: %.15f (analytic %.15f)\n", fixed64[0], 1.0/768.0 + 1.0/3.0);
     double m = 0; for (float v : img.raw_data()) m += v; m /= img.size();
     const double analytic = 0.5 + 2.0/9.0 - 2.0/45.0 + 0.75*3.14159265358979*0.09;
     std::printf("adaptive: %zu regions, mean of bins %.6f should be close to %.6f; simpson bin 0 %.6f\n", nregions, m, analytic, fixed[0]);
     if (argc > 3) { FILE* f = std::fopen(argv[3], "wb"); std::fwrite(img.raw_data().data(), 4, img.size(), f); std::fclose(f); }
-    return (std::fabs(m-analytic) < 1e-3 && nregions == iterations+1) ? 0 : 1;
+    return (std::fabs(m-analytic) < 1e-3 && nregions == iterations+1 && std::fabs(fixed64[0] - (1.0/768.0 + 1.0/3.0)) < 1e-13) ? 0 : 1;
 }

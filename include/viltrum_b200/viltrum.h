@@ -165,11 +165,20 @@ inline vb200_domain make_domain(const RangeInfinite<Float>& r, const std::array<
     for (std::size_t i = 0; i < DIMBINS; ++i) d.res[i] = res[i];
     return d;
 }
+template<std::size_t DIM, std::size_t DIMBINS>
+inline vb200_domain_f64 make_domain64(const Range<double,DIM>& r, const std::array<std::size_t,DIMBINS>& res) {
+    static_assert(DIM <= VB200_MAX_DIM && DIMBINS <= VB200_MAX_DIMBINS && DIMBINS <= DIM, "unsupported dimensionality");
+    vb200_domain_f64 d; std::memset(&d, 0, sizeof(d));
+    d.dim = int(DIM); d.dimbins = int(DIMBINS);
+    for (std::size_t i = 0; i < DIM; ++i) { d.rmin[i] = r.min(i); d.rmax[i] = r.max(i); }
+    for (std::size_t i = 0; i < DIMBINS; ++i) d.res[i] = res[i];
+    return d;
+}
 template<std::size_t DIMBINS> inline std::size_t bin_count(const std::array<std::size_t,DIMBINS>& res) { std::size_t n = 1; for (auto r : res) n *= r; return n; }
 
 // applies a flat device result (tensor order) to the caller's bins through the accessor: bins(pos) op= v
-template<bool ACCUMULATE, typename Bins, std::size_t DIMBINS>
-inline void apply_bins(Bins& bins, const std::array<std::size_t,DIMBINS>& res, const std::vector<float>& flat) {
+template<bool ACCUMULATE, typename Bins, std::size_t DIMBINS, typename V>
+inline void apply_bins(Bins& bins, const std::array<std::size_t,DIMBINS>& res, const std::vector<V>& flat) {
     std::array<std::size_t,DIMBINS> pos; pos.fill(0);
     vb200_shard sh = current_shard(); const std::size_t n = flat.size();
     const std::size_t b = (sh.begin == 0 && sh.end == 0) ? 0 : std::size_t(sh.begin), e = (sh.begin == 0 && sh.end == 0) ? n : std::size_t(sh.end);
@@ -187,9 +196,11 @@ template<typename F, std::size_t N> struct ScalarAdapter {
 };
 template<typename F, std::size_t N, typename = void> struct takes_array : std::false_type {};
 template<typename F, std::size_t N> struct takes_array<F, N, std::void_t<decltype(std::declval<const F&>()(std::declval<const std::array<float,N>&>()))>> : std::true_type {};
+template<typename F, std::size_t N, typename = void> struct takes_array_d : std::false_type {};
+template<typename F, std::size_t N> struct takes_array_d<F, N, std::void_t<decltype(std::declval<const F&>()(std::declval<const std::array<double,N>&>()))>> : std::true_type {};
 template<std::size_t DIM, typename F>
 inline auto adapt(const F& f) {
-    if constexpr (takes_array<F, DIM>::value) return f;
+    if constexpr (takes_array<F, DIM>::value || takes_array_d<F, DIM>::value) return f;
     else return ScalarAdapter<F, DIM>{f};
 }
 
@@ -341,8 +352,23 @@ template<typename EM> struct error_heuristic_size { static constexpr int id = VB
 // integrator_newton_cotes(rule) — reference src/newton-cotes/newton-cotes.h:11-19 ('+=')
 template<typename Rule> class IntegratorNewtonCotes {
 public:
-    template<typename Bins, std::size_t DIMBINS, typename F, typename Float, std::size_t DIM, typename Logger>
-    void integrate(Bins& bins, const std::array<std::size_t,DIMBINS>& res, const F& f, const Range<Float,DIM>& range, Logger& logger) const {
+    // Range<double,DIM> with a double integrand: the fp64 path (every rule and fold in double, as upstream)
+    template<typename Bins, std::size_t DIMBINS, typename F, std::size_t DIM, typename Logger>
+    void integrate(Bins& bins, const std::array<std::size_t,DIMBINS>& res, const F& f, const Range<double,DIM>& range, Logger& logger) const {
+        auto& ctx = b200::default_context();
+        b200::Integrand64<F, int(DIM)> g(f);
+        vb200_domain_f64 dom = b200::make_domain64(range, res);
+        b200::RegionsHandle regs;
+        ctx.check(vb200_regions_generate_single_f64(ctx.get(), g.c_abi(), &dom, Rule::id, &regs.r));
+        std::vector<double> flat(b200::bin_count(res), 0.0);
+        vb200_shard sh = b200::current_shard();
+        ctx.check(vb200_regions_integrate_bins_f64(ctx.get(), regs.r, &dom, &sh, flat.data(), VB200_HOST));
+        b200::apply_bins<true>(bins, res, flat);
+        logger.log_progress(std::size_t(1), std::size_t(1));
+    }
+    template<typename Bins, std::size_t DIMBINS, typename F, std::size_t DIM, typename Logger>
+    void integrate(Bins& bins, const std::array<std::size_t,DIMBINS>& res, const F& f, const Range<float,DIM>& range, Logger& logger) const {
+        using Float = float;
         auto& ctx = b200::default_context();
         b200::Integrand<F, int(DIM)> g(f);
         vb200_domain dom = b200::make_domain(range, res);
