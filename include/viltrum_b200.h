@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define VB200_ABI_VERSION 1u
+#define VB200_ABI_VERSION 2u
 #define VB200_MAX_DIM      8     /* finite integrands: 1..8 dimensions (reference VILTRUM_MAX_DIMENSIONS_REGION = 6, region.h:16-18) */
 #define VB200_MAX_DIMBINS  3     /* reference binned overloads go up to 3-D containers (integrate.h:132-167) */
 
@@ -272,6 +272,20 @@ int vb200_cv_replay(vb200_ctx* ctx, const vb200_integrand* f, const vb200_region
                     const uint32_t* chosen, const float* samples, int mem, float* bins, int bins_mem);
 
 /* ---- kernel launch structs (filled by the library, consumed by the thunks) ------------------------------ */
+/* Chunk completion signalling of the sampling kernels (end-to-end path with VB200_HOST bins): the kernel stores its bins
+ * straight into pinned, device-mapped host memory; the shard's tiles (one warp step = 32/lanes_per_bin bins) are grouped
+ * into chunks of 2^chunk_shift consecutive tiles, every finished tile bumps its chunk's counter behind a system-scope fence,
+ * and the warp that completes a chunk publishes `epoch` in the chunk's host-mapped flag.  The host applies the
+ * reference's '+=' / '=' to a chunk as soon as its flag shows up, while the same launch is still computing the rest. */
+typedef struct vb200_chunk_signal {
+    uint32_t  enabled;                /* 0: no signalling (device-resident output) */
+    uint32_t  chunk_shift;            /* tiles per chunk = 1 << chunk_shift */
+    uint32_t* done;                   /* device [chunks], zeroed by the driver: finished tiles per chunk */
+    uint32_t* flag;                   /* host-mapped [chunks]: set to epoch when every tile of the chunk has been stored */
+    uint32_t  epoch;                  /* changes with every call, so the flags never need clearing */
+    uint32_t  reserved;
+} vb200_chunk_signal;
+
 typedef struct vb200_mc_launch {
     vb200_domain domain;
     uint64_t bin_begin, bin_end;      /* shard */
@@ -288,6 +302,7 @@ typedef struct vb200_mc_launch {
     int32_t  grid_hint;               /* CTAs to launch (0 = let the thunk size it from occupancy) */
     int32_t  reserved;
     unsigned long long* tile_counter; /* device, zeroed by the driver before the launch: dynamic tile scheduler */
+    vb200_chunk_signal signal;
 } vb200_mc_launch;
 
 typedef struct vb200_replay_launch {
@@ -309,6 +324,7 @@ typedef struct vb200_walk_launch {
     float*   out; float* sum_f; float* sum_f2;
     unsigned long long* tile_counter; /* device, zeroed by the driver before the launch */
     int32_t  flavor; int32_t reserved;
+    vb200_chunk_signal signal;
 } vb200_walk_launch;
 
 typedef struct vb200_walk_replay_launch {

@@ -53,6 +53,23 @@ __device__ __forceinline__ void bin_box(const vb200_domain& dom, uint64_t bin, f
     }
 }
 
+// End of a warp's tile on the end-to-end path (vb200_chunk_signal): the lanes' bin stores went to host-mapped memory; order them
+// before the chunk counter at system scope, and let the warp that completes a chunk raise the chunk's host flag.
+__device__ __forceinline__ void signal_tile_done(const vb200_chunk_signal& c, uint64_t tile, uint64_t ntiles, uint32_t lane) {
+    if (!c.enabled) return;
+    __syncwarp();                                   // the storing lanes' writes happen-before lane 0's fence
+    if (lane == 0) {
+        __threadfence_system();
+        const uint64_t chunk = tile >> c.chunk_shift;
+        const uint64_t first = chunk << c.chunk_shift, per = 1ull << c.chunk_shift;
+        const uint32_t count = uint32_t(ntiles - first < per ? ntiles - first : per);
+        if (atomicAdd(&c.done[chunk], 1u) + 1u == count) {
+            __threadfence_system();
+            *reinterpret_cast<volatile uint32_t*>(&c.flag[chunk]) = c.epoch;
+        }
+    }
+}
+
 // EXACT only tags the instantiation (the same template is compiled twice into the library, once in a TU built
 // with --fmad=false); it keeps the two sets of kernel symbols apart.
 //
@@ -139,6 +156,7 @@ mc_per_bin_kernel(const F f, const vb200_mc_launch a) {
                 if (a.sum_f2) a.sum_f2[bin - a.bin_begin] = sum2;
             }
         }
+        signal_tile_done(a.signal, tile, ntiles, lane);
         if (lane == 0) tile = atomicAdd(a.tile_counter, 1ull);
         tile = __shfl_sync(0xffffffffu, tile, 0);
     }

@@ -115,6 +115,7 @@ walk_kernel(const F f, const vb200_walk_launch a) {
                 if (a.sum_f2) a.sum_f2[bin - a.bin_begin] = sum2;
             }
         }
+        signal_tile_done(a.signal, tile, ntiles, lane);
         if (lane == 0) tile = atomicAdd(a.tile_counter, 1ull);
         tile = __shfl_sync(0xffffffffu, tile, 0);
     }
@@ -196,6 +197,7 @@ walk_wavefront_kernel(const F f, const vb200_walk_launch a) {
                 if (a.sum_f2) a.sum_f2[bin - a.bin_begin] = sum2;
             }
         }
+        signal_tile_done(a.signal, tile, ntiles, lane);
         if (lane == 0) tile = atomicAdd(a.tile_counter, 1ull);
         tile = __shfl_sync(0xffffffffu, tile, 0);
     }

@@ -4,7 +4,36 @@
 #include <string>
 #include <cstdio>
 #include <cstdarg>
+#include <atomic>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <vector>
 #include "../../include/viltrum_b200.h"
+
+namespace vb200 {
+// Host side of the end-to-end sampling path: the kernel raises one host-mapped flag per chunk of bins; whoever claims a chunk
+// spins on its flag and then applies the reference's '+=' / '=' to the caller's bins.  One thread cannot keep up with the
+// kernel (a 4 MiB '+=' pass takes longer than the 0.34 ms the B200 needs to produce it), so a few pooled workers share the chunks.
+struct HostPass {
+    volatile uint32_t* flags = nullptr; uint32_t epoch = 0;
+    uint64_t chunks = 0, bins_per_chunk = 0, n = 0;
+    float* dst = nullptr; const float* src = nullptr; bool accumulate = false;
+    std::atomic<uint64_t> next{0}, finished{0};
+    std::atomic<int> abort{0};
+    void run(bool poll_stream, cudaStream_t stream, cudaError_t* stream_error);
+};
+struct HostPool {
+    std::vector<std::thread> workers;
+    std::mutex m; std::condition_variable cv;
+    HostPass* job = nullptr; uint64_t job_id = 0; bool stop = false;
+    std::atomic<int> active{0};
+    void start(int nworkers);
+    void publish(HostPass* j);
+    void retire();              // no worker touches the job after this returns
+    ~HostPool();
+};
+}
 
 struct vb200_ctx {
     int device = 0;
@@ -18,9 +47,14 @@ struct vb200_ctx {
     // pinned host staging (D2H of bins lands here first so the copy is truly asynchronous)
     void* pinned = nullptr; size_t pinned_bytes = 0;
     int32_t* d_flag = nullptr;      // device error flag for replay kernels
-    unsigned long long* d_counter = nullptr;   // dynamic tile schedulers of the sampling kernels: one ticket counter per chunk
-    static constexpr int kMaxChunks = 8;
-    cudaEvent_t chunk_done[kMaxChunks] = {};
+    // sampling kernels: d_counter[0] = dynamic tile scheduler ticket; the kMaxChunks uint32 words behind it (d_done) count the
+    // finished tiles per chunk of the end-to-end path; h_flags (pinned, device-mapped) receive the per-chunk completion epochs
+    unsigned long long* d_counter = nullptr;
+    uint32_t* d_done = nullptr;
+    uint32_t* h_flags = nullptr;
+    uint32_t epoch = 0;
+    static constexpr int kMaxChunks = 64;
+    vb200::HostPool pool;
 };
 
 namespace vb200 {
