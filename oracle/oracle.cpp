@@ -26,6 +26,8 @@
 #include <thread>
 #include <algorithm>
 #include <functional>
+#include <memory>
+#include <cstdlib>
 #include "integrands.h"
 #include "oracle_api.h"
 
@@ -478,7 +480,7 @@ template<typename T> inline T fold_all_rule(std::vector<T> v, int S, int nd) {
 template<typename T> inline void region_point(const RegionT<T>& r, int D, const double* p, T* x) {
     for (int i=0;i<D;++i) x[i] = T(p[i]*double(r.rmax[i]-r.rmin[i]) + double(r.rmin[i]));
 }
-template<typename T> RegionT<T> make_region(FiniteFnT<T> f, int S, int D, const T* a, const T* b) {
+template<typename T, typename Fn> RegionT<T> make_region(Fn&& f, int S, int D, const T* a, const T* b) {
     RegionT<T> r; r.rmin.assign(a,a+D); r.rmax.assign(b,b+D); r.volume = volume_of_t(D,a,b);
     uint64_t n = ipow(S,D); r.data.resize(n);
     for (uint64_t k=0;k<n;++k) {
@@ -492,7 +494,7 @@ template<typename T> RegionT<T> make_region(FiniteFnT<T> f, int S, int D, const 
 
 // region.h:345-359 + split.h:13-49, parts == 2.  Children reuse the parent's samples at even positions along
 // `dim` and evaluate f at the odd ones with coordinates derived from the PARENT range (v = i/(2(S-1))).
-template<typename T> void split_region(FiniteFnT<T> f, int S, int D, const RegionT<T>& r, int dim, RegionT<T> out[2]) {
+template<typename T, typename Fn> void split_region(Fn&& f, int S, int D, const RegionT<T>& r, int dim, RegionT<T> out[2]) {
     uint64_t n = ipow(S,D), inner = ipow(S,dim);
     int full = 2*(S-1)+1;
     for (int c=0;c<2;++c) { out[c].rmin=r.rmin; out[c].rmax=r.rmax; out[c].data.assign(n,T(0)); }
@@ -591,14 +593,14 @@ template<typename T> void heap_pop(std::vector<RegionT<T>>& h) {
 }
 
 // regions-generator-adaptive-heap.h:18-45
-template<typename T> std::vector<RegionT<T>> generate_adaptive(FiniteFnT<T> f, int SH, int SL, int D, const T* rmin, const T* rmax,
+template<typename T, typename Fn> std::vector<RegionT<T>> generate_adaptive(Fn&& f, int SH, int SL, int D, const T* rmin, const T* rmax,
                                       const Heuristic& h, uint64_t iterations) {
     std::vector<RegionT<T>> heap; heap.reserve(iterations+1);
-    heap.push_back(make_region(f,SH,D,rmin,rmax));
+    heap.push_back(make_region<T>(f,SH,D,rmin,rmax));
     apply_heuristic(heap[0],SH,SL,D,h);
     for (uint64_t i=0;i<iterations;++i) {
         RegionT<T> r = heap.front();                                               // :33
-        RegionT<T> sub[2]; split_region(f,SH,D,r,int(r.errdim),sub);               // :34
+        RegionT<T> sub[2]; split_region<T>(f,SH,D,r,int(r.errdim),sub);               // :34
         heap_pop(heap); heap.pop_back();                                       // :35
         for (int c=0;c<2;++c) {                                                // :36-40
             apply_heuristic(sub[c],SH,SL,D,h);
@@ -754,17 +756,14 @@ extern "C" int vo_adaptive_iterations_f64(const char* integrand, const char* rul
 // =========================================================================================================
 // Control variates: integrator-crespo2021.h:7-22 -> regions-integrator-parallel-variance-reduction.h:32-109
 // =========================================================================================================
-extern "C" int vo_crespo2021(const char* integrand, uint64_t iterations, uint64_t spp, uint64_t seed,
-                  int dimbins, const uint64_t* res, const float* rmin, const float* rmax, float* bins,
-                  uint32_t* rec_nregions, float* rec_approx, uint32_t* rec_chosen, float* rec_samples,
-                  float* reg_min, float* reg_max, float* reg_err, uint32_t* reg_dim, float* reg_data) {
-    auto F = find_finite(integrand); if (!F) return -1;
-    int D = F->dim; if (dimbins<1 || dimbins>D) return -2;
-    const int S = 3, SL = 2;
-    Heuristic h{true,true,1.e-5};                                              // integrator-crespo2021.h:12
-    auto regions = generate_adaptive<float>(F->fn,S,SL,D,rmin,rmax,h,iterations);
-    export_regions<float>(regions,D,reg_min,reg_max,reg_err,reg_dim,reg_data);
-
+namespace {
+// RegionsIntegratorParallelVarianceReduction::integrate_regions (regions-integrator-parallel-variance-reduction.h:32-109) with
+// rr_uniform_region / cv_optimize_weight / region_sampling_uniform over a D-dimensional region table.
+// make_residual(seed) returns the per-bin callable f_regdim(x) (:69).
+template<typename MakeResidual>
+void cv_integrate_regions(const std::vector<RegionT<float>>& regions, int S, int D, int dimbins, const uint64_t* res,
+                          const float* rmin, const float* rmax, uint64_t spp, uint64_t seed, MakeResidual&& make_residual, float* bins,
+                          uint32_t* rec_nregions, float* rec_approx, uint32_t* rec_chosen, float* rec_samples) {
     uint64_t nb = nbins_of(dimbins,res);
     uint64_t factor = nb;
     // bin -> region lists, regions visited in list order (:53-57, serial PSTL backend)
@@ -787,7 +786,9 @@ extern "C" int vo_crespo2021(const char* integrand, uint64_t iterations, uint64_
     for (uint64_t k=0;k<nb;++k) {                                              // variance_reduction(pos) :67-103
         uint64_t pos[8]; unflatten(k,dimbins,res,pos);
         MT19937 rng{uint64_t(bin_seed[k])};
-        (void)rng();        // monte_carlo_per_bin(rng,1) reseeds itself from the bin RNG: one draw (:69, monte-carlo-per-bin.h:28)
+        // monte_carlo_per_bin(rng,1) seeds itself from the bin RNG: one draw (:69, monte-carlo-per-bin.h:28); what it then does
+        // with that seed is the caller's business (nothing for a full-dimensional region table, the rest estimator for Fubini)
+        auto f_regdim = make_residual(uint64_t(uint32_t(rng())));
         float ba[8], bb[8]; bin_box(D,dimbins,rmin,rmax,res,pos,ba,bb);       // :71-73
         const auto& list = perbin[k];
         std::size_t n = list.size();
@@ -812,7 +813,7 @@ extern "C" int vo_crespo2021(const char* integrand, uint64_t iterations, uint64_
             float sfactor = volume_of(D,ia[chosen].data(),ib[chosen].data());              // :18
             if (rec_chosen) rec_chosen[k*spp+s] = list[chosen];
             if (rec_samples) for (int i=0;i<D;++i) rec_samples[(k*spp+s)*D+i] = x[i];
-            float fs = float(double(F->fn(x))*double(factor)*rrfactor*double(sfactor));                      // :98
+            float fs = float(double(f_regdim(x))*double(factor)*rrfactor*double(sfactor));                      // :98
             float as = float(double(region_approximation_at(r,S,D,x))*double(factor)*rrfactor*double(sfactor)); // :99
             // push (weight-strategy.h:56-69); NormDefault = abs (norm.h:12)
             if (size==0) { k_f = std::abs(fs); k_app = std::abs(as); }
@@ -837,6 +838,182 @@ extern "C" int vo_crespo2021(const char* integrand, uint64_t iterations, uint64_
         }
         bins[k] = result;                                                      // :102 ('=')
     }
+}
+} // namespace
+
+extern "C" int vo_crespo2021(const char* integrand, uint64_t iterations, uint64_t spp, uint64_t seed,
+                  int dimbins, const uint64_t* res, const float* rmin, const float* rmax, float* bins,
+                  uint32_t* rec_nregions, float* rec_approx, uint32_t* rec_chosen, float* rec_samples,
+                  float* reg_min, float* reg_max, float* reg_err, uint32_t* reg_dim, float* reg_data) {
+    auto F = find_finite(integrand); if (!F) return -1;
+    int D = F->dim; if (dimbins<1 || dimbins>D) return -2;
+    const int S = 3, SL = 2;
+    Heuristic h{true,true,1.e-5};                                              // integrator-crespo2021.h:12
+    auto regions = generate_adaptive<float>(F->fn,S,SL,D,rmin,rmax,h,iterations);
+    export_regions<float>(regions,D,reg_min,reg_max,reg_err,reg_dim,reg_data);
+
+    cv_integrate_regions(regions,S,D,dimbins,res,rmin,rmax,spp,seed,[&] (uint64_t) { return F->fn; },bins,rec_nregions,rec_approx,rec_chosen,rec_samples);
+    return 0;
+}
+
+// =========================================================================================================
+// Fubini family: fubini.h:51-101, regions-generator-fubini.h:7-28, integrator-crespo2021.h:24-44
+// =========================================================================================================
+namespace {
+
+// Every copy of a MonteCarlo / MonteCarloPerBin integrator RESEEDS: new.rng = mt19937(size_t(old.rng()))
+// (monte-carlo.h:30-33, monte-carlo-per-bin.h:26-33).  A chain of k copies therefore leaves the last copy seeded by
+// s_k, s_{i+1} = first output of mt19937(s_i).  The depths below count the copies between the user's monte_carlo(m, seed)
+// and the object that finally evaluates (constructor argument, [=] capture in function_split_and_integrate_at,
+// detail::adapt's by-value return, ...): 3 for the rest integrator of integrator_fubini and of regions_generator_fubini, 1 for the
+// first integrator of integrator_fubini and for the residual's monte_carlo_per_bin.  They are pinned by the bit-exact tests against
+// the unmodified reference (tests/test_oracle_vs_reference.py).
+inline uint64_t reseed_chain(uint64_t seed, int depth) {
+    for (int i=0;i<depth;++i) { MT19937 g(seed); seed = uint64_t(g()); }
+    return seed;
+}
+
+// the integrand split at N: finite (f over dim D > N) or a sequence integrand
+struct SplitIntegrand {
+    const FiniteIntegrand* fin = nullptr; const InfIntegrand* inf = nullptr;
+    int N = 0, D = 0;                                   // D: total finite dimension (finite case)
+    const float* rmin = nullptr; const float* rmax = nullptr; int nrange = 0;      // full range
+    float rest_min(int j) const { int i = N+j; return inf ? (i<nrange ? rmin[i] : 0.0f) : rmin[i]; }      // range_split_at (fubini.h:18-49)
+    float rest_max(int j) const { int i = N+j; return inf ? (i<nrange ? rmax[i] : 1.0f) : rmax[i]; }
+    int rest_explicit() const { return inf ? std::max(0, nrange-N) : D-N; }
+    float rest_volume() const { float v = 1.0f; for (int j=0;j<rest_explicit();++j) v *= (rest_max(j)-rest_min(j)); return v; }
+    // f(x ⊕ rest) with the rest elements produced by next(j)
+    template<typename Next> float eval(const float* x, Next&& next) const {
+        if (!inf) { float full[8]; for (int i=0;i<N;++i) full[i]=x[i]; for (int j=0;j<D-N;++j) full[N+j] = next(j); return fin->fn(full); }
+        int idx = 0;
+        LazySeq seq;
+        seq.next = [&] () -> float { int i = idx++; return i<N ? x[i] : next(i-N); };          // concat(x, xr)  (concat.h:9-45)
+        return inf->fn(seq);
+    }
+};
+
+// g(x) = viltrum::integrate(monte_carlo(m) copy holding `rng`, f(x ⊕ ·), range_rest)   (fubini.h:57-75; monte-carlo.h:39-84, one bin)
+inline float rest_monte_carlo(const SplitIntegrand& f, const float* x, uint64_t m, MT19937& rng) {
+    double factor = 1.0*double(f.rest_volume())/double(m);                      // monte-carlo.h:43-45 / :70-72
+    float sol = 0.0f;
+    for (uint64_t s=0;s<m;++s) {
+        float v;
+        if (!f.inf) {
+            float xr[8]; for (int j=0;j<f.D-f.N;++j) xr[j] = uniform_real(rng,f.rest_min(j),f.rest_max(j));     // :50-53
+            v = f.eval(x,[&] (int j) { return xr[j]; });
+        } else {
+            MT19937 seqrng{uint64_t(uint32_t(rng()))};                          // :75 random_sequence(range, seed) -> mt19937(seed)
+            v = f.eval(x,[&] (int j) { return uniform_real(seqrng,f.rest_min(j),f.rest_max(j)); });    // random-sequence-rng.h:30,35
+        }
+        sol = float(double(sol) + double(v)*factor);                            // :59 / :81
+    }
+    return sol;
+}
+
+// g(x) through monte_carlo_per_bin(rng,1) over the rest (regions-integrator-parallel-variance-reduction.h:69; monte-carlo-per-bin.h:41-97, one bin)
+inline float rest_monte_carlo_per_bin(const SplitIntegrand& f, const float* x, uint64_t m, MT19937& rng) {
+    double factor = double(f.rest_volume())/double(m);
+    // the single bin's sub-range rebuilds dimension 0 of the rest: [min + 0*drange, min + 1*drange]
+    float a0 = f.rest_min(0), b0 = f.rest_max(0);
+    { float drange = (b0-a0)/float(1); float lo = a0 + float(0)*drange, hi = a0 + float(1)*drange; a0 = lo; b0 = hi; }
+    auto lo_at = [&] (int j) { return j==0 ? a0 : f.rest_min(j); };
+    auto hi_at = [&] (int j) { return j==0 ? b0 : f.rest_max(j); };
+    float sol = 0.0f;
+    for (uint64_t s=0;s<m;++s) {
+        float v;
+        if (!f.inf) {
+            float xr[8]; for (int j=0;j<f.D-f.N;++j) xr[j] = uniform_real(rng,lo_at(j),hi_at(j));
+            v = f.eval(x,[&] (int j) { return xr[j]; });
+        } else {
+            // Concat::begin() builds the rest iterator at once (concat.h:40), and RandomSequenceRefDis draws its element 0 on
+            // construction from the SHARED generator (random-sequence-ref-dis.h:27-28): one draw per sample even when f stops
+            // inside the first N elements
+            const float e0 = uniform_real(rng,0.0f,1.0f)*(hi_at(0)-lo_at(0))+lo_at(0);
+            v = f.eval(x,[&] (int j) { return j==0 ? e0 : uniform_real(rng,0.0f,1.0f)*(hi_at(j)-lo_at(j))+lo_at(j); });   // :28,32
+        }
+        sol = float(double(sol) + double(v)*factor);
+    }
+    return sol;
+}
+
+int setup_split(const char* integrand, int nfirst, int dimbins, const float* rmin, const float* rmax, int nrange, SplitIntegrand& f) {
+    f.fin = find_finite(integrand); f.inf = f.fin ? nullptr : find_inf(integrand);
+    if (!f.fin && !f.inf) return -1;
+    f.N = nfirst; f.D = f.fin ? f.fin->dim : 0; f.rmin = rmin; f.rmax = rmax; f.nrange = f.fin ? f.D : nrange;
+    if (nfirst<1 || nfirst>4 || (f.fin && nfirst>=f.D) || dimbins<1 || dimbins>nfirst || dimbins>2) return -2;
+    return 0;
+}
+// first-part range: the first N entries (implicit [0,1] for infinite ranges)
+void first_range(const SplitIntegrand& f, float* a, float* b) {
+    for (int i=0;i<f.N;++i) { a[i] = i<f.nrange ? f.rmin[i] : 0.0f; b[i] = i<f.nrange ? f.rmax[i] : 1.0f; }
+}
+
+} // namespace
+
+extern "C" int vo_fubini_adaptive_mc(const char* integrand, int nfirst, const char* rule, const char* heuristic, double size_weight,
+                          uint64_t iterations, uint64_t mc_samples, uint64_t mc_seed, int dimbins, const uint64_t* res,
+                          const float* rmin, const float* rmax, int nrange, float* bins) {
+    SplitIntegrand f; int rc = setup_split(integrand,nfirst,dimbins,rmin,rmax,nrange,f); if (rc) return rc;
+    int SH, SL;
+    if (!std::strcmp(rule,"simpson_trapezoidal")) { SH=3; SL=2; }
+    else if (!std::strcmp(rule,"boole_simpson")) { SH=5; SL=3; }
+    else return -2;
+    Heuristic h; if (!parse_heuristic(heuristic,size_weight,h)) return -2;
+    float a[8], b[8]; first_range(f,a,b);
+    MT19937 rng(reseed_chain(mc_seed, 3));
+    auto g = [&] (const float* x) -> float { return rest_monte_carlo(f,x,mc_samples,rng); };
+    auto regions = generate_adaptive<float>(g,SH,SL,f.N,a,b,h,iterations);
+    integrate_regions_sequential<float>(regions,SH,f.N,dimbins,res,a,b,bins);
+    return 0;
+}
+
+extern "C" int vo_fubini_mc_mc(const char* integrand, int nfirst, uint64_t spp, uint64_t seed, uint64_t mc_samples, uint64_t mc_seed,
+                    int dimbins, const uint64_t* res, const float* rmin, const float* rmax, int nrange, float* bins) {
+    SplitIntegrand f; int rc = setup_split(integrand,nfirst,dimbins,rmin,rmax,nrange,f); if (rc) return rc;
+    float ra[8], rb[8]; first_range(f,ra,rb);
+    MT19937 rest_rng(reseed_chain(mc_seed, 3));
+    // monte_carlo_per_bin_parallel over the first N dimensions (monte-carlo-per-bin-parallel.h:41-71) with f = g
+    uint64_t nb = nbins_of(dimbins,res);
+    double factor = volume_of(f.N,ra,rb)/double(spp);
+    MT19937 master(reseed_chain(seed, 1));          // IntegratorFubini copies the first integrator too (fubini.h:83-84)
+    std::vector<uint32_t> perbin_seed(nb);
+    for (uint64_t k=0;k<nb;++k) perbin_seed[k] = uint32_t(master());
+    // bins are visited in the reference's for_each(parallel) order (serial PSTL backend): dim 0 outer, the rest inside (foreach.h:56-67);
+    // the order matters here because the rest integrator's stream runs through all evaluations
+    std::vector<uint64_t> order;
+    if (dimbins == 1) for (uint64_t k=0;k<nb;++k) order.push_back(k);
+    else for (uint64_t d0=0; d0<res[0]; ++d0) for (uint64_t d1=0; d1<res[1]; ++d1) order.push_back(d0 + d1*res[0]);
+    for (uint64_t k : order) {
+        uint64_t pos[8]; unflatten(k,dimbins,res,pos);
+        MT19937 local(perbin_seed[k]);
+        float a[8], b[8]; bin_box(f.N,dimbins,ra,rb,res,pos,a,b);
+        for (uint64_t s=0;s<spp;++s) {
+            float x[8];
+            for (int i=0;i<f.N;++i) x[i] = uniform_real(local,a[i],b[i]);
+            float v = rest_monte_carlo(f,x,mc_samples,rest_rng);
+            bins[k] = float(double(bins[k]) + double(v)*factor);
+        }
+    }
+    return 0;
+}
+
+extern "C" int vo_crespo2021_infinite(const char* integrand, int nfirst, uint64_t iterations, uint64_t mc_samples, uint64_t spp, uint64_t seed,
+                           int dimbins, const uint64_t* res, const float* rmin, const float* rmax, int nrange, float* bins) {
+    SplitIntegrand f; int rc = setup_split(integrand,nfirst,dimbins,rmin,rmax,nrange,f); if (rc) return rc;
+    const int S = 3, SL = 2;
+    Heuristic h{true,true,1.e-5};                                              // integrator-crespo2021.h:31
+    float a[8], b[8]; first_range(f,a,b);
+    // generator: monte_carlo(mc_samples, 2*seed+1) (integrator-crespo2021.h:34) copied into RegionsGeneratorFubini, into
+    // IntegratorRegionBased and into the [=] closure of function_split_and_integrate_at
+    MT19937 gen_rng(reseed_chain(2*seed+1, 3));
+    auto g = [&] (const float* x) -> float { return rest_monte_carlo(f,x,mc_samples,gen_rng); };
+    auto regions = generate_adaptive<float>(g,S,SL,f.N,a,b,h,iterations);
+    // residual: monte_carlo_per_bin(bin rng, 1) captured by value in the closure (one more reseeding copy)
+    const int depth = 1;
+    cv_integrate_regions(regions,S,f.N,dimbins,res,a,b,spp,seed,[&] (uint64_t s1) {
+        auto rng = std::make_shared<MT19937>(reseed_chain(s1, depth));
+        return [&f,rng] (const float* x) -> float { return rest_monte_carlo_per_bin(f,x,1,*rng); };
+    },bins,nullptr,nullptr,nullptr,nullptr);
     return 0;
 }
 

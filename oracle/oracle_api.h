@@ -95,6 +95,24 @@ int vo_crespo2021(const char* integrand, uint64_t iterations, uint64_t spp, uint
                   uint32_t* rec_nregions, float* rec_approx, uint32_t* rec_chosen, float* rec_samples,
                   float* reg_min, float* reg_max, float* reg_err, uint32_t* reg_dim, float* reg_data);
 
+// ---- Fubini family ---------------------------------------------------------------------------------
+// The integrand's first `nfirst` dimensions are handled by a "first" integrator over g(x) = integral of f(x, rest) estimated by
+// monte_carlo(mc_samples, mc_seed) over the remaining dimensions — finite (named finite integrand, dim > nfirst, rmin/rmax have
+// dim entries, nrange ignored) or infinite (named sequence integrand, rmin/rmax have nrange explicit entries).
+// reference src/combination/fubini.h:51-101 (function_split_and_integrate_at, IntegratorFubini).
+//   first = integrator_adaptive_iterations(nested rule, heuristic, iterations)        '+='
+int vo_fubini_adaptive_mc(const char* integrand, int nfirst, const char* rule, const char* heuristic, double size_weight,
+                          uint64_t iterations, uint64_t mc_samples, uint64_t mc_seed, int dimbins, const uint64_t* res,
+                          const float* rmin, const float* rmax, int nrange, float* bins);
+//   first = monte_carlo_per_bin_parallel(spp, seed)                                    '+='
+int vo_fubini_mc_mc(const char* integrand, int nfirst, uint64_t spp, uint64_t seed, uint64_t mc_samples, uint64_t mc_seed,
+                    int dimbins, const uint64_t* res, const float* rmin, const float* rmax, int nrange, float* bins);
+// reference integrator_crespo2021_infinite<nfirst>(iterations, mc_samples, spp, seed) — src/control-variates/integrator-crespo2021.h:24-44,
+// src/combination/regions-generator-fubini.h:7-28; the residual pass evaluates f through monte_carlo_per_bin(rng,1) over the
+// rest (regions-integrator-parallel-variance-reduction.h:69).  '='.
+int vo_crespo2021_infinite(const char* integrand, int nfirst, uint64_t iterations, uint64_t mc_samples, uint64_t spp, uint64_t seed,
+                           int dimbins, const uint64_t* res, const float* rmin, const float* rmax, int nrange, float* bins);
+
 // Multi-threaded CPU baseline used by bench.py (--impl reference / cpu_baseline): slabs the bin grid along the
 // LAST bin dimension over nthreads std::threads, each calling the single-threaded entry point above on its
 // slab with seed+slab.  path in {"mc_per_bin_parallel","per_bin_parallel_mc",

@@ -208,6 +208,40 @@ class Oracle:
             return bins, reg, dict(nregions=nreg, approx=approx, chosen=chosen, samples=samples)
         return bins, reg
 
+    # ---- Fubini family: first `nfirst` dims by the named first integrator, the rest by monte_carlo(mc_samples, mc_seed) ----
+    def _fubini_args(self, integrand, res, rmin, rmax):
+        res = np.ascontiguousarray(np.asarray(res, dtype=np.uint64))
+        d = self.dim(integrand)
+        if d > 0 and len(rmin) == 0:
+            rmin, rmax = [0.0] * d, [1.0] * d
+        rmin, rmax = _f32(rmin), _f32(rmax)
+        return res, rmin, rmax, np.zeros(int(np.prod(res)), np.float32)
+
+    def fubini_adaptive_mc(self, integrand, nfirst, rule, heuristic, iterations, mc_samples, mc_seed, res, rmin=(), rmax=(), size_weight=1e-5):
+        res, rmin, rmax, bins = self._fubini_args(integrand, res, rmin, rmax)
+        self.lib.vo_fubini_adaptive_mc.restype = ctypes.c_int
+        rc = self.lib.vo_fubini_adaptive_mc(integrand.encode(), int(nfirst), rule.encode(), heuristic.encode(), ctypes.c_double(size_weight),
+                                            ctypes.c_uint64(iterations), ctypes.c_uint64(mc_samples), ctypes.c_uint64(mc_seed),
+                                            len(res), _p(res), _p(rmin), _p(rmax), len(rmin), _p(bins))
+        self._check(rc, "vo_fubini_adaptive_mc")
+        return bins
+
+    def fubini_mc_mc(self, integrand, nfirst, spp, seed, mc_samples, mc_seed, res, rmin=(), rmax=()):
+        res, rmin, rmax, bins = self._fubini_args(integrand, res, rmin, rmax)
+        self.lib.vo_fubini_mc_mc.restype = ctypes.c_int
+        rc = self.lib.vo_fubini_mc_mc(integrand.encode(), int(nfirst), ctypes.c_uint64(spp), ctypes.c_uint64(seed), ctypes.c_uint64(mc_samples),
+                                      ctypes.c_uint64(mc_seed), len(res), _p(res), _p(rmin), _p(rmax), len(rmin), _p(bins))
+        self._check(rc, "vo_fubini_mc_mc")
+        return bins
+
+    def crespo2021_infinite(self, integrand, nfirst, iterations, mc_samples, spp, seed, res, rmin=(), rmax=()):
+        res, rmin, rmax, bins = self._fubini_args(integrand, res, rmin, rmax)
+        self.lib.vo_crespo2021_infinite.restype = ctypes.c_int
+        rc = self.lib.vo_crespo2021_infinite(integrand.encode(), int(nfirst), ctypes.c_uint64(iterations), ctypes.c_uint64(mc_samples),
+                                             ctypes.c_uint64(spp), ctypes.c_uint64(seed), len(res), _p(res), _p(rmin), _p(rmax), len(rmin), _p(bins))
+        self._check(rc, "vo_crespo2021_infinite")
+        return bins
+
     def mt_per_bin(self, path, integrand, res, spp, seed, nthreads, rmin=(), rmax=()):
         res = np.ascontiguousarray(np.asarray(res, dtype=np.uint64))
         rmin, rmax = _f32(rmin), _f32(rmax)

@@ -81,6 +81,18 @@ def main():
                           bins=bits(b), sum=bits(s1), sum2=bits(s2), lens=bits(lens), elems=bits(elems)))
             V.append(dict(integrand=integ, res=res, rmin=rmin, rmax=rmax, path="monte_carlo_inf", samples_n=300, seed=7,
                           bins=bits(R.monte_carlo_inf(integ, res, 300, 7, rmin, rmax))))
+    # Fubini family: finite and infinite rests
+    FUB = [("poly3", 1, [4], [0.1] * 3, [0.9] * 3), ("shade4_16", 2, [4, 3], [0.0] * 4, [1.0] * 4), ("shade5_16", 3, [2, 2], [0.0] * 5, [1.0] * 5),
+           ("decay", 1, [5], [], []), ("walk", 2, [3, 2], [], []), ("walk", 2, [2, 2], [0.1, 0.2, 0.0], [0.9, 0.7, 1.0])]
+    for integ, n, res, rmin, rmax in FUB:
+        base = dict(integrand=integ, res=res, rmin=rmin, rmax=rmax, nfirst=n)
+        V.append(dict(base, path="fubini_adaptive_mc", rule="simpson_trapezoidal", heuristic="default_absolute", iterations=12, size_weight=1e-5,
+                      mc_samples=6, mc_seed=5, bins=bits(R.fubini_adaptive_mc(integ, n, "simpson_trapezoidal", "default_absolute", 12, 6, 5, res, rmin, rmax))))
+        V.append(dict(base, path="fubini_mc_mc", spp=5, seed=3, mc_samples=4, mc_seed=5, bins=bits(R.fubini_mc_mc(integ, n, 5, 3, 4, 5, res, rmin, rmax))))
+        if rmin and R.dim(integ) < 0:
+            continue      # upstream crashes ("Empty interection", null region) for RangeInfinite with explicit non-primary entries
+        V.append(dict(base, path="crespo2021_infinite", iterations=10, mc_samples=4, spp=8, seed=7,
+                      bins=bits(R.crespo2021_infinite(integ, n, 10, 4, 8, 7, res, rmin, rmax))))
     # SURVEY.md §8(c) known-answer vectors (README-sized cases), kept as decimal strings the survey printed
     path = os.path.join(HERE, "reference_vectors.json")
     with open(path, "w") as f:

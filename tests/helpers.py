@@ -64,6 +64,12 @@ def run_oracle_vector(O, v):
         return dict(bins=b, sum=s1, sum2=s2, lens=lens, elems=elems)
     if path == "monte_carlo_inf":
         return dict(bins=O.monte_carlo_inf(integ, res, v["samples_n"], v["seed"], rmin, rmax))
+    if path == "fubini_adaptive_mc":
+        return dict(bins=O.fubini_adaptive_mc(integ, v["nfirst"], v["rule"], v["heuristic"], v["iterations"], v["mc_samples"], v["mc_seed"], res, rmin, rmax, v["size_weight"]))
+    if path == "fubini_mc_mc":
+        return dict(bins=O.fubini_mc_mc(integ, v["nfirst"], v["spp"], v["seed"], v["mc_samples"], v["mc_seed"], res, rmin, rmax))
+    if path == "crespo2021_infinite":
+        return dict(bins=O.crespo2021_infinite(integ, v["nfirst"], v["iterations"], v["mc_samples"], v["spp"], v["seed"], res, rmin, rmax))
     raise KeyError(path)
 
 

@@ -82,3 +82,25 @@ def test_crespo2021(port, reference, integ, res, it, spp):
     assert_same_bits(a[0], b[0], "bins"); assert_same_bits(b[0], c[0], "recording harness == preset")
     for k in ("nregions", "approx", "chosen", "samples"):
         assert_same_bits(a[2][k], b[2][k], k)
+
+
+FUBINI = [("poly3", 1, [4], None), ("poly3", 2, [3, 2], None), ("shade4_16", 2, [4, 3], None), ("shade5_16", 3, [2, 2], None), ("shade5_16", 2, [3], None),
+          ("decay", 1, [5], ((), ())), ("decay", 2, [3, 2], ((), ())), ("walk", 2, [3, 2], ((), ())), ("walk", 2, [2, 2], ((0.1, 0.2, 0.0), (0.9, 0.7, 1.0))),
+          ("walk", 1, [4], ((0.2,), (0.8,)))]
+
+
+@pytest.mark.parametrize("integ,n,res,rng", FUBINI)
+def test_fubini_family(port, reference, integ, n, res, rng):
+    """integrator_fubini<N> and integrator_crespo2021_infinite<N>: every reseeding copy of the rest integrator is restated"""
+    rmin, rmax = _range(port, integ) if rng is None else rng
+    for h, rule in (("default_absolute", "simpson_trapezoidal"), ("size_relative", "boole_simpson")):
+        if rule == "boole_simpson" and n >= 3:
+            continue
+        a = port.fubini_adaptive_mc(integ, n, rule, h, 20, 5, 9, res, rmin, rmax)
+        b = reference.fubini_adaptive_mc(integ, n, rule, h, 20, 5, 9, res, rmin, rmax)
+        assert_same_bits(a, b, f"fubini adaptive {rule} {h}")
+    assert_same_bits(port.fubini_mc_mc(integ, n, 6, 3, 5, 9, res, rmin, rmax), reference.fubini_mc_mc(integ, n, 6, 3, 5, 9, res, rmin, rmax), "fubini mc/mc")
+    if rng is not None and len(rng[0]) > 0:
+        return      # upstream crashes ("Empty interection", null region) for RangeInfinite with explicit non-primary entries
+    assert_same_bits(port.crespo2021_infinite(integ, n, 24, 4, 16, 11, res, rmin, rmax), reference.crespo2021_infinite(integ, n, 24, 4, 16, 11, res, rmin, rmax),
+                     "crespo2021_infinite")
