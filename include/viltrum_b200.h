@@ -114,6 +114,19 @@ const vb200_integrand* vb200_builtin_integrand(const char* name, int exact);
 int                    vb200_builtin_count(void);
 const char*            vb200_builtin_name(int index);
 
+/* Fubini adapter over a built-in integrand (reference src/combination/fubini.h:51-75,
+ * function_split_and_integrate_at<nfirst>(f, monte_carlo(mc_samples, seed), range_rest)): the returned descriptor is an
+ * nfirst-dimensional integrand  g(x) = vol(rest)/mc_samples * sum_s f(x (+) r_s)  with r_s uniform in the rest range —
+ * rest_min/rest_max have nrest entries: exactly dim-nfirst for finite integrands, 0..VB200_MAX_DIM explicit entries (implicit [0,1]
+ * beyond) for sequence integrands.  It goes wherever an integrand goes: vb200_mc_per_bin (integrator_fubini<N>(monte_carlo_per_bin, ..)),
+ * vb200_regions_generate_adaptive (regions_generator_fubini<N>), vb200_cv_integrate with mc_samples = 1 (the residual pass of
+ * integrator_crespo2021_infinite<N>, integrator-crespo2021.h:24-44).  Available: ("poly3",1|2) ("shade4_16"|"shade4_64",2)
+ * ("shade5_16",2|3) ("decay",1|2) ("walk",1|2).  NULL if unknown.  Free with vb200_integrand_free (a no-op for every other descriptor).
+ * C++ callers wrap their own functors with viltrum::integrator_fubini / integrator_crespo2021_infinite (include/viltrum_b200/viltrum.h). */
+const vb200_integrand* vb200_builtin_fubini(const char* name, int nfirst, const float* rest_min, const float* rest_max, int nrest,
+                                            uint64_t mc_samples, uint64_t seed);
+void                   vb200_integrand_free(const vb200_integrand* f);
+
 /* ---- shared parameter blocks -------------------------------------------------------------------------- */
 /* Integration box + bin grid.  For infinite ranges `dim` is the number of explicit entries of rmin/rmax
  * (reference RangeInfinite: implicit [0,1] tail, range-infinite.h:31-37) and may be 0. */

@@ -27,7 +27,7 @@ SYMBOLS = [
     "vb200_regions_count", "vb200_regions_dim", "vb200_regions_samples", "vb200_regions_download", "vb200_regions_free",
     "vb200_regions_integrate_bins", "vb200_cv_integrate", "vb200_cv_replay",
     "vb200_regions_generate_single_f64", "vb200_regions_upload_f64", "vb200_regions_download_f64", "vb200_regions_integrate_bins_f64",
-    "vb200_builtin_integrand_f64",
+    "vb200_builtin_integrand_f64", "vb200_builtin_fubini", "vb200_integrand_free",
 ]
 
 
@@ -109,6 +109,8 @@ def lib():
         L.vb200_regions_download_f64.argtypes = [vp, vp, vp, vp, vp, vp, vp]; L.vb200_regions_download_f64.restype = i32
         L.vb200_regions_integrate_bins_f64.argtypes = [vp, vp, ctypes.POINTER(Domain64), ctypes.POINTER(Shard), vp, i32]; L.vb200_regions_integrate_bins_f64.restype = i32
         L.vb200_builtin_integrand_f64.argtypes = [ctypes.c_char_p, i32]; L.vb200_builtin_integrand_f64.restype = vp
+        L.vb200_builtin_fubini.argtypes = [ctypes.c_char_p, i32, vp, vp, i32, u64, u64]; L.vb200_builtin_fubini.restype = vp
+        L.vb200_integrand_free.argtypes = [vp]; L.vb200_integrand_free.restype = None
         L.vb200_cv_integrate.argtypes = [vp, vp, vp, ctypes.POINTER(CvParams), vp, i32, vp, vp]; L.vb200_cv_integrate.restype = i32
         L.vb200_cv_replay.argtypes = [vp, vp, vp, ctypes.POINTER(CvParams), vp, vp, i32, vp, i32]; L.vb200_cv_replay.restype = i32
         _lib = L

@@ -28,6 +28,7 @@ SOURCES = [
     ("cv.cu", ["--fmad=false"]),
     ("refine_batched.cu", ["--fmad=false"]),
     ("builtin_fast.cu", []),
+    ("builtin_fubini.cu", []),
     ("builtin_exact.cu", ["--fmad=false", "-DVILTRUM_B200_EXACT"]),
 ]
 

@@ -130,6 +130,8 @@ class Context:
         return out.value
 
     def integrand(self, name, exact=False):
+        if isinstance(name, FubiniIntegrand):      # an adapter descriptor made by vb200_builtin_fubini (always the fast flavour)
+            return name.ptr
         p = self._L.vb200_builtin_integrand(name.encode(), 1 if exact else 0)
         if not p:
             raise KeyError(f"unknown built-in integrand '{name}' (have: {builtin_names()})")
@@ -229,6 +231,40 @@ class Context:
         self.check(self._L.vb200_regions_upload(self._h, dim, C.RULES[rule], n, rmin.ctypes.data, rmax.ctypes.data, err.ctypes.data,
                                                 errdim.ctypes.data, data.ctypes.data, ctypes.byref(h)))
         return Regions(self, h)
+
+
+def range_split_at(n, rng):
+    """range_split_at<N>(range) — reference src/combination/fubini.h:18-49: (first N dimensions, the rest)"""
+    if isinstance(rng, RangeInfinite):
+        lo = [rng.min[i] if i < len(rng.min) else 0.0 for i in range(n)]
+        hi = [rng.max[i] if i < len(rng.max) else 1.0 for i in range(n)]
+        return Range(lo, hi), RangeInfinite(list(rng.min[n:]), list(rng.max[n:]))
+    return Range(list(rng.min[:n]), list(rng.max[:n])), Range(list(rng.min[n:]), list(rng.max[n:]))
+
+
+class FubiniIntegrand:
+    """function_split_and_integrate_at<N>(f, monte_carlo(mc_samples, seed), range_rest) over a built-in integrand — reference
+    src/combination/fubini.h:51-75: the N-dimensional integrand g(x) = vol(rest)/m * sum_s f(x (+) r_s) (vb200_builtin_fubini)."""
+
+    def __init__(self, ctx, name, nfirst, rest, mc_samples, seed):
+        lo = np.ascontiguousarray(rest.min, np.float32); hi = np.ascontiguousarray(rest.max, np.float32)
+        self._L = ctx._L
+        self.name, self.nfirst = name, nfirst
+        self.ptr = self._L.vb200_builtin_fubini(name.encode(), int(nfirst), lo.ctypes.data if len(lo) else None, hi.ctypes.data if len(hi) else None,
+                                                len(lo), int(mc_samples), int(seed) & 0xFFFFFFFFFFFFFFFF)
+        if not self.ptr:
+            raise KeyError(f"no built-in Fubini adapter for ('{name}', nfirst={nfirst}) with {len(lo)} rest entries")
+
+    def free(self):
+        if getattr(self, "ptr", None):
+            self._L.vb200_integrand_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 class Regions:
@@ -443,6 +479,66 @@ class IntegratorCrespo2021:
         finally:
             if logger is None:
                 regs.free()
+
+
+@dataclass
+class IntegratorFubini:
+    """integrator_fubini<N>(first, monte_carlo(m, seed)) — reference src/combination/fubini.h:78-101: `first` integrates the first N
+    dimensions of g(x) = the Monte-Carlo estimate of the integral of f(x, .) over the rest (finite or infinite)."""
+    nfirst: int
+    first: object
+    rest: MonteCarlo
+
+    def integrate(self, ctx, bins, res, f, rng, shard=None, **kw):
+        if len(res) > self.nfirst:
+            raise ValueError("Fubini does not work with that many dimensions on bin resolution")      # fubini.h:88
+        first_rng, rest_rng = range_split_at(self.nfirst, rng)
+        g = FubiniIntegrand(ctx, f, self.nfirst, rest_rng, self.rest.samples, self.rest.seed)
+        try:
+            kw.pop("exact", None)
+            self.first.integrate(ctx, bins, res, g, first_rng, shard=shard, **kw)
+        finally:
+            g.free()
+
+
+@dataclass
+class IntegratorCrespo2021Infinite:
+    """integrator_crespo2021_infinite<N>(iterations, mc_samples, spp, seed) — reference src/control-variates/integrator-crespo2021.h:24-44:
+    the region table is generated over the first N dimensions from g estimated with monte_carlo(mc_samples, 2*seed+1)
+    (regions_generator_fubini<N>, regions-generator-fubini.h:7-28); the residual pass evaluates f with ONE sample of the rest per
+    residual sample (monte_carlo_per_bin(rng,1), regions-integrator-parallel-variance-reduction.h:69).  '='."""
+    nfirst: int
+    iterations: int
+    mc_samples: int
+    spp: int
+    seed: int = 0
+    batch: int = 1
+
+    def integrate(self, ctx, bins, res, f, rng, shard=None, logger=None, **kw):
+        first_rng, rest_rng = range_split_at(self.nfirst, rng)
+        g_gen = FubiniIntegrand(ctx, f, self.nfirst, rest_rng, self.mc_samples, 2 * self.seed + 1)
+        g_res = FubiniIntegrand(ctx, f, self.nfirst, rest_rng, 1, self.seed + 0x9E3779B97F4A7C15)
+        gen = IntegratorAdaptiveIterations(nested("simpson", "trapezoidal"), error_heuristic_size(error_metric_relative(), 1e-5),
+                                           self.iterations, self.batch)
+        regs = None
+        try:
+            regs = gen.generate(ctx, g_gen, first_rng)
+            if logger is not None:
+                logger.log(regs)
+            kw.pop("exact", None)
+            regs.cv_integrate(g_res, bins, res, first_rng, self.spp, self.seed, shard=shard, **kw)
+        finally:
+            if regs is not None and logger is None:
+                regs.free()
+            g_gen.free(); g_res.free()
+
+
+def integrator_fubini(nfirst, first, rest):
+    return IntegratorFubini(nfirst, first, rest)
+
+
+def integrator_crespo2021_infinite(nfirst, iterations, mc_samples, spp, seed=0, batch=1):
+    return IntegratorCrespo2021Infinite(nfirst, iterations, mc_samples, spp, seed, batch)
 
 
 def monte_carlo(samples, seed=0):
