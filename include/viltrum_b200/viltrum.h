@@ -5,7 +5,8 @@
 //     viltrum::integrate(integrator, bins, resolution, integrand, range[, logger])        reference src/integrate.h:72-103
 //     viltrum::integrate(integrator, std::vector<T>& bins, integrand, range[, logger])    reference src/integrate.h:132-137,169-173
 //     monte_carlo, monte_carlo_per_bin_parallel, integrator_per_bin_parallel, integrator_newton_cotes,
-//     integrator_adaptive_iterations, integrator_crespo2021, nested, trapezoidal / simpson / boole,
+//     integrator_adaptive_iterations, integrator_crespo2021, integrator_fubini<N>, integrator_crespo2021_infinite<N>,
+//     range_split_at<N>, nested, trapezoidal / simpson / boole,
 //     error_heuristic_default / error_heuristic_size, error_metric_absolute / error_metric_relative,
 //     range, range_all, range_primary, range_infinite, range_primary_infinite, tensor, LoggerNull, LoggerProgress
 // — with every integrator's integrate(bins, resolution, f, range, logger) member forwarding to libviltrum_b200.so through
@@ -35,6 +36,7 @@
 #include <cmath>
 #include "../viltrum_b200.h"
 #include "device/thunks.cuh"
+#include "device/fubini.cuh"
 
 namespace viltrum {
 
@@ -224,6 +226,8 @@ inline std::vector<RegionView<DIM>> download_regions(Context& ctx, const vb200_r
     return out;
 }
 struct RegionsHandle { vb200_regions* r = nullptr; ~RegionsHandle() { vb200_regions_free(r); } };
+// the one-bin accessor of the value-returning integrate overloads (integrate.h:105-123)
+struct SingleBin { float* value; float& operator()(const std::array<std::size_t,1>&) const { return *value; } };
 
 } // namespace b200
 
@@ -440,6 +444,82 @@ public:
 };
 inline IntegratorCrespo2021 integrator_crespo2021(std::size_t iterations, std::size_t spp, std::size_t seed = 0, std::size_t = 16) { return IntegratorCrespo2021(iterations, spp, seed); }
 
+// ---- Fubini family (reference src/combination/fubini.h:18-101, regions-generator-fubini.h:7-28, integrator-crespo2021.h:24-44) ---
+template<std::size_t N, typename Float, std::size_t DIM>
+std::tuple<Range<Float,N>, Range<Float,DIM-N>> range_split_at(const Range<Float,DIM>& range) {
+    std::array<Float,N> a, b; std::array<Float,DIM-N> ra, rb;
+    for (std::size_t i = 0; i < N; ++i) { a[i] = range.min(i); b[i] = range.max(i); }
+    for (std::size_t i = N; i < DIM; ++i) { ra[i-N] = range.min(i); rb[i-N] = range.max(i); }
+    return std::tuple<Range<Float,N>, Range<Float,DIM-N>>(Range<Float,N>(a,b), Range<Float,DIM-N>(ra,rb));
+}
+template<std::size_t N, typename Float>
+std::tuple<Range<Float,N>, RangeInfinite<Float>> range_split_at(const RangeInfinite<Float>& range) {
+    std::array<Float,N> a, b;
+    for (std::size_t i = 0; i < N; ++i) { a[i] = range.min(i); b[i] = range.max(i); }
+    std::vector<Float> ra = range.min(), rb = range.max();
+    ra.erase(ra.begin(), ra.begin() + std::min(N, ra.size())); rb.erase(rb.begin(), rb.begin() + std::min(N, rb.size()));
+    return std::tuple<Range<Float,N>, RangeInfinite<Float>>(Range<Float,N>(a,b), RangeInfinite<Float>(ra,rb));
+}
+namespace b200 {
+// function_split_and_integrate_at<N>(f, monte_carlo(m, seed), range_rest) as a device functor (device/fubini.cuh)
+template<std::size_t N, typename F, std::size_t R>
+auto fubini_function(const F& f, const Range<float,R>& rest, unsigned long m, std::size_t seed) {
+    return make_fubini_finite<int(N), int(R)>(f, rest.min().data(), rest.max().data(), m, seed);
+}
+template<std::size_t N, typename F>
+auto fubini_function(const F& f, const RangeInfinite<float>& rest, unsigned long m, std::size_t seed) {
+    std::vector<float> lo, hi; const std::size_t n = std::max(rest.min().size(), rest.max().size());
+    if (n > VB200_MAX_DIM) throw std::runtime_error("viltrum_b200: at most 8 explicit entries in an infinite range");
+    for (std::size_t i = 0; i < n; ++i) { lo.push_back(rest.min(i)); hi.push_back(rest.max(i)); }
+    return make_fubini_infinite<int(N)>(f, lo.data(), hi.data(), int(n), m, seed);
+}
+}
+// integrator_fubini<N>(first, monte_carlo(m, seed)) — fubini.h:78-101: `first` integrates g(x) = MC estimate of the rest integral
+template<typename First, std::size_t N> class IntegratorFubini {
+    First first; MonteCarlo rest;
+public:
+    IntegratorFubini(const First& f, const MonteCarlo& r) : first(f), rest(r) {}
+    template<typename Bins, std::size_t DIMBINS, typename F, typename R, typename Logger>
+    void integrate(Bins& bins, const std::array<std::size_t,DIMBINS>& res, const F& f, const R& range, Logger& logger) const {
+        static_assert(N >= DIMBINS, "Fubini does not work with that many dimensions on bin resolution");      // fubini.h:88
+        auto split = range_split_at<N>(range);
+        first.integrate(bins, res, b200::fubini_function<N>(f, std::get<1>(split), rest.sample_count(), rest.seed()), std::get<0>(split), logger);
+    }
+};
+template<std::size_t N, typename First> IntegratorFubini<First,N> integrator_fubini(const First& first, const MonteCarlo& rest) { return IntegratorFubini<First,N>(first, rest); }
+
+// integrator_crespo2021_infinite<N>(iterations, mc_samples, spp, seed) — integrator-crespo2021.h:24-44 ('=')
+template<std::size_t N> class IntegratorCrespo2021Infinite {
+    std::size_t iterations, mc_samples, spp, seed_;
+public:
+    IntegratorCrespo2021Infinite(std::size_t it, std::size_t m, std::size_t s, std::size_t seed) : iterations(it), mc_samples(m), spp(s), seed_(seed) {}
+    template<typename Bins, std::size_t DIMBINS, typename F, typename R, typename Logger>
+    void integrate(Bins& bins, const std::array<std::size_t,DIMBINS>& res, const F& f, const R& range, Logger& logger) const {
+        auto& ctx = b200::default_context();
+        auto split = range_split_at<N>(range);
+        const Range<float,N>& first = std::get<0>(split);
+        // regions_generator_fubini<N>(adaptive heap, monte_carlo(mc_samples, 2*seed+1))
+        auto g_gen = b200::fubini_function<N>(f, std::get<1>(split), mc_samples, 2*seed_+1);
+        b200::Integrand<decltype(g_gen), int(N)> gen(g_gen);
+        b200::RegionsHandle regs;
+        using EH = error_heuristic_size<error_metric_relative>;
+        IntegratorAdaptiveIterations<Nested<Simpson,Trapezoidal>, EH>(EH(error_metric_relative(), 1.e-5), iterations).generate(ctx, gen, first, regs);
+        if constexpr (!std::is_same<Logger, LoggerNull>::value) logger.log(b200::download_regions<N>(ctx, regs.r));
+        // residual: f through monte_carlo_per_bin(rng, 1) over the rest (regions-integrator-parallel-variance-reduction.h:69)
+        auto g_res = b200::fubini_function<N>(f, std::get<1>(split), 1ul, seed_ + std::size_t(0x9E3779B97F4A7C15ull));
+        b200::Integrand<decltype(g_res), int(N)> resid(g_res);
+        vb200_cv_params p; std::memset(&p, 0, sizeof(p));
+        p.domain = b200::make_domain(first, res); p.shard = b200::current_shard(); p.spp = spp; p.seed = seed_;
+        std::vector<float> flat(b200::bin_count(res), 0.0f);
+        ctx.check(vb200_cv_integrate(ctx.get(), resid.c_abi(), regs.r, &p, flat.data(), VB200_HOST, nullptr, nullptr));
+        b200::apply_bins<false>(bins, res, flat);
+        logger.log_progress(std::size_t(1), std::size_t(1));
+    }
+};
+template<std::size_t N> IntegratorCrespo2021Infinite<N> integrator_crespo2021_infinite(std::size_t iterations, std::size_t mc_samples, std::size_t spp, std::size_t seed = 0, std::size_t = 16) {
+    return IntegratorCrespo2021Infinite<N>(iterations, mc_samples, spp, seed);
+}
+
 // ---- the front door (reference src/integrate.h:72-173) ------------------------------------------------------------------------
 template<typename Integrator, typename Bins, std::size_t DIMBINS, typename F, typename Float, std::size_t DIM, typename Logger>
 void integrate(const Integrator& integrator, Bins& bins, const std::array<std::size_t,DIMBINS>& resolution, const F& function, const Range<Float,DIM>& range, Logger& logger) {
@@ -461,7 +541,7 @@ void integrate(const Integrator& integrator, Bins& bins, const std::array<std::s
 template<typename Integrator, typename F, typename Float, std::size_t DIM, typename Logger>
 float integrate(const Integrator& integrator, const F& function, const Range<Float,DIM>& range, Logger& logger) {
     float sol(0.0f);
-    auto bins = [&sol] (const std::array<std::size_t,1>&) -> float& { return sol; };
+    b200::SingleBin bins{&sol};
     std::array<std::size_t,1> res{1};
     integrate(integrator, bins, res, function, range, logger);
     return sol;
@@ -469,7 +549,7 @@ float integrate(const Integrator& integrator, const F& function, const Range<Flo
 template<typename Integrator, typename F, typename Float, typename Logger>
 float integrate(const Integrator& integrator, const F& function, const RangeInfinite<Float>& range, Logger& logger) {
     float sol(0.0f);
-    auto bins = [&sol] (const std::array<std::size_t,1>&) -> float& { return sol; };
+    b200::SingleBin bins{&sol};
     std::array<std::size_t,1> res{1};
     integrate(integrator, bins, res, function, range, logger);
     return sol;

@@ -710,6 +710,52 @@ extern "C" int vo_adaptive_iterations(const char* integrand, const char* rule, c
     return 0;
 }
 
+// integrator-adaptive-tolerance.h:15-39
+namespace {
+struct ToleranceRun {
+    FiniteFn f; int SH, SL, D, dimbins; const uint64_t* res; const float* rmin; const float* rmax; Heuristic h; float tolerance;
+    float* bins; uint64_t nleaves = 0; uint64_t reg_cap; float *reg_min, *reg_max, *reg_err; uint32_t* reg_dim; float* reg_data;
+    bool overflow = false, too_deep = false;
+    void visit(RegionT<float>& r, int depth) {
+        apply_heuristic(r,SH,SL,D,h);                                           // :18
+        if (r.err < tolerance) {                                                // :19
+            std::vector<RegionT<float>> one(1,r);
+            integrate_regions_sequential<float>(one,SH,D,dimbins,res,rmin,rmax,bins);      // :21
+            if (nleaves < reg_cap) {
+                uint64_t n = nleaves;
+                if (reg_min) std::copy(r.rmin.begin(), r.rmin.end(), reg_min+n*uint64_t(D));
+                if (reg_max) std::copy(r.rmax.begin(), r.rmax.end(), reg_max+n*uint64_t(D));
+                if (reg_err) reg_err[n] = r.err;
+                if (reg_dim) reg_dim[n] = r.errdim;
+                if (reg_data) std::copy(r.data.begin(), r.data.end(), reg_data+n*r.data.size());
+            } else if (reg_min || reg_max || reg_err || reg_dim || reg_data) overflow = true;
+            ++nleaves;
+        } else {
+            if (depth >= 128) { too_deep = true; return; }
+            RegionT<float> sub[2]; split_region<float>(f,SH,D,r,int(r.errdim),sub);          // :25
+            for (int c=0;c<2 && !too_deep;++c) visit(sub[c],depth+1);                        // :26
+        }
+    }
+};
+}
+extern "C" int vo_adaptive_tolerance(const char* integrand, const char* rule, const char* heuristic, double size_weight, float tolerance,
+                          int dimbins, const uint64_t* res, const float* rmin, const float* rmax, float* bins, uint64_t* nleaves,
+                          uint64_t reg_cap, float* reg_min, float* reg_max, float* reg_err, uint32_t* reg_dim, float* reg_data) {
+    auto F = find_finite(integrand); if (!F) return -1;
+    int D = F->dim; if (dimbins<1 || dimbins>D) return -2;
+    ToleranceRun run;
+    if (!std::strcmp(rule,"simpson_trapezoidal")) { run.SH=3; run.SL=2; }
+    else if (!std::strcmp(rule,"boole_simpson")) { run.SH=5; run.SL=3; }
+    else return -2;
+    if (!parse_heuristic(heuristic,size_weight,run.h)) return -2;
+    run.f=F->fn; run.D=D; run.dimbins=dimbins; run.res=res; run.rmin=rmin; run.rmax=rmax; run.tolerance=tolerance; run.bins=bins;
+    run.reg_cap=reg_cap; run.reg_min=reg_min; run.reg_max=reg_max; run.reg_err=reg_err; run.reg_dim=reg_dim; run.reg_data=reg_data;
+    RegionT<float> root = make_region<float>(F->fn,run.SH,D,rmin,rmax);       // :37
+    run.visit(root,0);
+    if (nleaves) *nleaves = run.nleaves;
+    return run.too_deep ? -4 : run.overflow ? -3 : 0;
+}
+
 // ---- double precision (Range<double,DIM>): the same templates with T = double -----------------------------------------------
 namespace {
 template<typename F> double call_finite_d(const double* x) {

@@ -76,6 +76,16 @@ int vo_adaptive_iterations(const char* integrand, const char* rule, const char* 
                            const float* rmin, const float* rmax, float* bins,
                            float* reg_min, float* reg_max, float* reg_err, uint32_t* reg_dim, float* reg_data);
 
+// reference integrator_adaptive_tolerance(nested(H,L), heuristic, tolerance) — src/nested/integrator-adaptive-tolerance.h:15-39: depth-first
+// recursion, a region is integrated into the bins ('+=', sequential integrator) as soon as its heuristic error drops below the
+// tolerance, otherwise split along the heuristic's dimension (child 0 first).  *nleaves = number of integrated regions.
+// The port also returns the leaves in visiting order (reg_* with capacity reg_cap regions; may be NULL); the reference harness
+// only counts them (the reference never hands its leaves to the logger) and leaves reg_* untouched.  Returns -3 if the leaf list
+// exceeds reg_cap (bins and *nleaves are still complete), -4 if the recursion exceeds 128 levels.
+int vo_adaptive_tolerance(const char* integrand, const char* rule, const char* heuristic, double size_weight, float tolerance,
+                          int dimbins, const uint64_t* res, const float* rmin, const float* rmax, float* bins, uint64_t* nleaves,
+                          uint64_t reg_cap, float* reg_min, float* reg_max, float* reg_err, uint32_t* reg_dim, float* reg_data);
+
 // Double-precision twins (Range<double,DIM>, double integrand, double bins) of vo_newton_cotes / vo_adaptive_iterations.
 // Integrands: "x2y2", "ind2", "cubic1", "poly3", "smooth_edge2", "shade4_16" (the double family of integrands.h).
 int vo_newton_cotes_f64(const char* integrand, const char* rule, int dimbins, const uint64_t* res,

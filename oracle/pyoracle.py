@@ -167,6 +167,26 @@ class Oracle:
         self._check(rc, "vo_adaptive_iterations")
         return bins, reg
 
+    def adaptive_tolerance(self, integrand, rule, heuristic, tolerance, res, rmin, rmax, size_weight=1e-5, bins=None, reg_cap=0):
+        """returns (bins, nleaves, regions or None); regions (leaves in the reference's depth-first visiting order) only from the port"""
+        res, rmin, rmax, nb = self._setup(res, rmin, rmax)
+        bins = np.zeros(nb, np.float32) if bins is None else np.ascontiguousarray(bins, dtype=np.float32).copy()
+        d = self.dim(integrand); sd = RULE_SAMPLES[rule] ** d
+        reg = None
+        if reg_cap and self.kind == "port":
+            reg = dict(min=np.zeros((reg_cap, d), np.float32), max=np.zeros((reg_cap, d), np.float32), err=np.zeros(reg_cap, np.float32),
+                       dim=np.zeros(reg_cap, np.uint32), data=np.zeros((reg_cap, sd), np.float32))
+        n = ctypes.c_uint64(0)
+        self.lib.vo_adaptive_tolerance.restype = ctypes.c_int
+        rc = self.lib.vo_adaptive_tolerance(integrand.encode(), rule.encode(), heuristic.encode(), ctypes.c_double(size_weight), ctypes.c_float(tolerance),
+                                            len(res), _p(res), _p(rmin), _p(rmax), _p(bins), ctypes.byref(n), ctypes.c_uint64(reg_cap if reg else 0),
+                                            _p(reg["min"]) if reg else None, _p(reg["max"]) if reg else None, _p(reg["err"]) if reg else None,
+                                            _p(reg["dim"]) if reg else None, _p(reg["data"]) if reg else None)
+        self._check(rc, "vo_adaptive_tolerance")
+        if reg:
+            reg = {k: v[: n.value] for k, v in reg.items()}
+        return bins, int(n.value), reg
+
     # ---- double precision twins ----
     def newton_cotes_f64(self, integrand, rule, res, rmin, rmax, bins=None):
         res = np.ascontiguousarray(np.asarray(res, dtype=np.uint64)); nb = int(np.prod(res))

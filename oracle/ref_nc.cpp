@@ -60,6 +60,46 @@ extern "C" int vo_adaptive_iterations(const char* integrand, const char* rule, c
     });
 }
 
+// integrator_adaptive_tolerance — the reference never logs its leaves; every integrated leaf reports progress once
+// (integrator-adaptive-tolerance.h:23), which is what the counting logger below counts.
+namespace {
+struct LeafCountLogger {
+    uint64_t* n;
+    std::string name() const { return ""; }
+    void set_name(const std::string&) {}
+    template<typename Number> void log_progress(const Number&, const Number& = Number(1)) { ++*n; }
+    template<typename Data> void log(const Data&) {}
+};
+}
+extern "C" int vo_adaptive_tolerance(const char* integrand, const char* rule, const char* heuristic, double size_weight, float tolerance,
+                          int dimbins, const uint64_t* res, const float* rmin, const float* rmax, float* bins, uint64_t* nleaves,
+                          uint64_t, float*, float*, float*, uint32_t*, float*) {
+    uint64_t count = 0;
+    int rc = dispatch_finite_bins(integrand, dimbins, [&] (auto f, auto dbc) -> int {
+        using F = decltype(f);
+        constexpr std::size_t D = F::dim;
+        constexpr std::size_t DB = decltype(dbc)::value;
+        using namespace viltrum;
+        auto r = res_array<DB>(res);
+        auto range = range_array<D>(rmin, rmax);
+        auto acc = [&] (const std::array<std::size_t,DB>& p) -> float& { return bins[tensor_pos(p,r)]; };
+        LeafCountLogger logger{&count};
+        auto run = [&] (auto rl, auto eh) -> int { viltrum::integrate(integrator_adaptive_tolerance(rl, eh, tolerance), acc, r, f, range, logger); return 0; };
+        auto with_rule = [&] (auto rl) -> int {
+            if (!std::strcmp(heuristic,"default_absolute")) return run(rl, error_heuristic_default(error_metric_absolute()));
+            if (!std::strcmp(heuristic,"default_relative")) return run(rl, error_heuristic_default(error_metric_relative()));
+            if (!std::strcmp(heuristic,"size_absolute"))    return run(rl, error_heuristic_size(error_metric_absolute(),size_weight));
+            if (!std::strcmp(heuristic,"size_relative"))    return run(rl, error_heuristic_size(error_metric_relative(),size_weight));
+            return -2;
+        };
+        if (!std::strcmp(rule,"simpson_trapezoidal")) return with_rule(nested(simpson,trapezoidal));
+        if (!std::strcmp(rule,"boole_simpson"))       return with_rule(nested(boole,simpson));
+        return -2;
+    });
+    if (nleaves) *nleaves = count;
+    return rc;
+}
+
 // ---- double precision: the same reference templates instantiated with Range<double,DIM> ------------------------------------
 extern "C" int vo_newton_cotes_f64(const char* integrand, const char* rule, int dimbins, const uint64_t* res,
                         const double* rmin, const double* rmax, double* bins) {

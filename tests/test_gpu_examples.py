@@ -54,3 +54,8 @@ def test_adaptive_newton_cotes_config3_bit_exact(ctx, port, tmp_path):
 
 def test_crespo2021_config4(ctx):
     assert "control variates: mean of bins" in run("crespo2021", 64, 2048, 16)
+
+
+def test_fubini_family(ctx):
+    out = run("fubini")
+    assert "crespo2021_infinite<2>" in out and "fubini<1>(adaptive, monte_carlo(256)) finite" in out
