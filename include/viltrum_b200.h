@@ -230,6 +230,21 @@ typedef struct vb200_adaptive_params {
 } vb200_adaptive_params;
 
 int vb200_regions_generate_adaptive(vb200_ctx* ctx, const vb200_integrand* f, const vb200_adaptive_params* p, vb200_regions** out);
+/* integrator_adaptive_tolerance(nested(h,l), heuristic, tolerance) — reference src/nested/integrator-adaptive-tolerance.h:15-39: regions
+ * are split (along the heuristic's dimension) until their heuristic error is below `tolerance`.  The reference recurses depth first;
+ * here every round splits all failing regions at once and the leaves are finally sorted into the reference's depth-first order by
+ * their root-to-leaf path, so vb200_regions_integrate_bins on the result reproduces the reference's bins bit for bit (EXACT
+ * integrand).  Fails with VB200_ERR_UNSUPPORTED past 128 levels of subdivision and VB200_ERR_NOMEM past max_regions. */
+typedef struct vb200_tolerance_params {
+    vb200_domain domain;        /* dimbins/res unused by the generator */
+    int32_t  rule;              /* nested pair */
+    int32_t  heuristic;         /* vb200_heuristic */
+    int32_t  metric;            /* vb200_metric */
+    float    tolerance;         /* the reference stores it as float (integrator-adaptive-tolerance.h:13) */
+    double   size_weight;
+    uint64_t max_regions;       /* 0 = 2^27 */
+} vb200_tolerance_params;
+int vb200_regions_generate_tolerance(vb200_ctx* ctx, const vb200_integrand* f, const vb200_tolerance_params* p, vb200_regions** out);
 /* regions_generator_single (reference src/newton-cotes/regions-generator-single.h:12-20): one region over the range */
 int vb200_regions_generate_single(vb200_ctx* ctx, const vb200_integrand* f, const vb200_domain* domain, int rule, vb200_regions** out);
 /* upload an externally produced table (tests: the reference's own region list) */

@@ -5,7 +5,7 @@
 //     viltrum::integrate(integrator, bins, resolution, integrand, range[, logger])        reference src/integrate.h:72-103
 //     viltrum::integrate(integrator, std::vector<T>& bins, integrand, range[, logger])    reference src/integrate.h:132-137,169-173
 //     monte_carlo, monte_carlo_per_bin_parallel, integrator_per_bin_parallel, integrator_newton_cotes,
-//     integrator_adaptive_iterations, integrator_crespo2021, integrator_fubini<N>, integrator_crespo2021_infinite<N>,
+//     integrator_adaptive_iterations, integrator_adaptive_tolerance, integrator_crespo2021, integrator_fubini<N>, integrator_crespo2021_infinite<N>,
 //     range_split_at<N>, nested, trapezoidal / simpson / boole,
 //     error_heuristic_default / error_heuristic_size, error_metric_absolute / error_metric_relative,
 //     range, range_all, range_primary, range_infinite, range_primary_infinite, tensor, LoggerNull, LoggerProgress
@@ -420,6 +420,33 @@ public:
 template<typename R, typename EH> auto integrator_adaptive_iterations(const R&, const EH& eh, std::size_t iterations) { return IntegratorAdaptiveIterations<R,EH>(eh, iterations); }
 template<typename R, typename EH> auto integrator_adaptive_iterations_parallel(const R&, const EH& eh, std::size_t iterations, std::size_t = 16) { return IntegratorAdaptiveIterations<R,EH>(eh, iterations); }
 template<typename R> auto integrator_adaptive_iterations(const R& r, std::size_t iterations) { return integrator_adaptive_iterations(r, error_heuristic_default<error_metric_absolute>(error_metric_absolute()), iterations); }
+
+// integrator_adaptive_tolerance(nested(h,l), error_heuristic, tolerance) — reference src/nested/integrator-adaptive-tolerance.h:41-59 ('+=').
+// Leaves come back in the reference's depth-first order, so the bins match the reference bit for bit in an exact build.
+template<typename Rule, typename EH> class IntegratorAdaptiveTolerance {
+    EH eh; float tolerance;
+public:
+    IntegratorAdaptiveTolerance(const EH& e, float tol) : eh(e), tolerance(tol) {}
+    template<typename Bins, std::size_t DIMBINS, typename F, typename Float, std::size_t DIM, typename Logger>
+    void integrate(Bins& bins, const std::array<std::size_t,DIMBINS>& res, const F& f, const Range<Float,DIM>& range, Logger& logger) const {
+        auto& ctx = b200::default_context();
+        b200::Integrand<F, int(DIM)> g(f);
+        vb200_tolerance_params p; std::memset(&p, 0, sizeof(p));
+        std::array<std::size_t,1> one{1}; p.domain = b200::make_domain(range, one);
+        p.rule = Rule::id; p.heuristic = EH::id; p.metric = EH::metric::id; p.tolerance = tolerance; p.size_weight = eh.size_weight;
+        b200::RegionsHandle regs;
+        ctx.check(vb200_regions_generate_tolerance(ctx.get(), g.c_abi(), &p, &regs.r));
+        vb200_domain dom = b200::make_domain(range, res);
+        std::vector<float> flat(b200::bin_count(res), 0.0f);
+        vb200_shard sh = b200::current_shard();
+        ctx.check(vb200_regions_integrate_bins(ctx.get(), regs.r, &dom, &sh, flat.data(), VB200_HOST));
+        b200::apply_bins<true>(bins, res, flat);
+        logger.log_progress(range.volume(), range.volume());
+    }
+};
+template<typename R, typename EH, typename = typename EH::metric> auto integrator_adaptive_tolerance(const R&, const EH& eh, float tolerance = 1.e-3f) { return IntegratorAdaptiveTolerance<R,EH>(eh, tolerance); }
+template<typename R> auto integrator_adaptive_tolerance(const R& r, float tolerance = 1.e-3f) { return integrator_adaptive_tolerance(r, error_heuristic_default<error_metric_absolute>(error_metric_absolute()), tolerance); }
+template<typename R> auto integrator_adaptive_tolerance(const R& r, double tolerance) { return integrator_adaptive_tolerance(r, float(tolerance)); }
 
 // integrator_crespo2021(iterations, spp, seed) — reference src/control-variates/integrator-crespo2021.h:7-22 ('=')
 class IntegratorCrespo2021 {

@@ -81,6 +81,14 @@ def main():
                           bins=bits(b), sum=bits(s1), sum2=bits(s2), lens=bits(lens), elems=bits(elems)))
             V.append(dict(integrand=integ, res=res, rmin=rmin, rmax=rmax, path="monte_carlo_inf", samples_n=300, seed=7,
                           bins=bits(R.monte_carlo_inf(integ, res, 300, 7, rmin, rmax))))
+    # integrator_adaptive_tolerance: bins + number of leaves
+    for integ, res, lo, hi, rule, h, tol in (("x2y2", [5], 0.0, 1.0, "simpson_trapezoidal", "default_absolute", 1e-5), ("smooth_edge2", [8, 8], 0.0, 1.0, "boole_simpson", "size_relative", 2e-4),
+                                             ("ind2", [6, 5], 0.0, 1.0, "simpson_trapezoidal", "default_absolute", 2e-4), ("shade4_16", [4, 4], 0.0, 1.0, "simpson_trapezoidal", "size_relative", 4e-3),
+                                             ("cubic1", [7], -0.5, 1.25, "boole_simpson", "default_relative", 1e-6), ("poly3", [3, 2], 0.1, 0.9, "simpson_trapezoidal", "size_absolute", 1e-5)):
+        d = R.dim(integ)
+        b, n, _ = R.adaptive_tolerance(integ, rule, h, tol, res, [lo] * d, [hi] * d)
+        V.append(dict(integrand=integ, res=res, rmin=[lo] * d, rmax=[hi] * d, path="adaptive_tolerance", rule=rule, heuristic=h, tolerance=tol, size_weight=1e-5,
+                      bins=bits(b), nleaves=n))
     # Fubini family: finite and infinite rests
     FUB = [("poly3", 1, [4], [0.1] * 3, [0.9] * 3), ("shade4_16", 2, [4, 3], [0.0] * 4, [1.0] * 4), ("shade5_16", 3, [2, 2], [0.0] * 5, [1.0] * 5),
            ("decay", 1, [5], [], []), ("walk", 2, [3, 2], [], []), ("walk", 2, [2, 2], [0.1, 0.2, 0.0], [0.9, 0.7, 1.0])]

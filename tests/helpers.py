@@ -64,6 +64,9 @@ def run_oracle_vector(O, v):
         return dict(bins=b, sum=s1, sum2=s2, lens=lens, elems=elems)
     if path == "monte_carlo_inf":
         return dict(bins=O.monte_carlo_inf(integ, res, v["samples_n"], v["seed"], rmin, rmax))
+    if path == "adaptive_tolerance":
+        b, n, _ = O.adaptive_tolerance(integ, v["rule"], v["heuristic"], v["tolerance"], res, rmin, rmax, v["size_weight"])
+        return dict(bins=b, nleaves=n)
     if path == "fubini_adaptive_mc":
         return dict(bins=O.fubini_adaptive_mc(integ, v["nfirst"], v["rule"], v["heuristic"], v["iterations"], v["mc_samples"], v["mc_seed"], res, rmin, rmax, v["size_weight"]))
     if path == "fubini_mc_mc":
@@ -79,6 +82,6 @@ def golden_field(v, key):
         return f64(x)
     if key in ("reg_dim", "nregions", "chosen", "lens"):
         return np.asarray(x, dtype=np.uint32)
-    if key == "reg_data_checksum":
+    if key in ("reg_data_checksum", "nleaves"):
         return x
     return f32(x)

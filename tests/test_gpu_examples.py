@@ -45,11 +45,14 @@ def test_walk_config5(ctx):
 
 def test_adaptive_newton_cotes_config3_bit_exact(ctx, port, tmp_path):
     f = tmp_path / "bins.f32"
-    out = run("adaptive_newton_cotes", 64, 20000, f)
+    g = tmp_path / "tol.f32"
+    out = run("adaptive_newton_cotes", 64, 20000, f, g)
     assert "20001 regions" in out
     got = np.fromfile(f, np.float32)
     want, _ = port.adaptive_iterations("smooth_edge2", "boole_simpson", "size_relative", 20000, [64, 64], [0, 0], [1, 1])
     assert_same_bits(got, want, "C++ drop-in (user functor, exact build) vs oracle")
+    want_tol, _, _ = port.adaptive_tolerance("smooth_edge2", "boole_simpson", "default_absolute", 1e-7, [64, 64], [0, 0], [1, 1])
+    assert_same_bits(np.fromfile(g, np.float32), want_tol, "integrator_adaptive_tolerance, C++ drop-in vs oracle")
 
 
 def test_crespo2021_config4(ctx):

@@ -104,3 +104,18 @@ def test_fubini_family(port, reference, integ, n, res, rng):
         return      # upstream crashes ("Empty interection", null region) for RangeInfinite with explicit non-primary entries
     assert_same_bits(port.crespo2021_infinite(integ, n, 24, 4, 16, 11, res, rmin, rmax), reference.crespo2021_infinite(integ, n, 24, 4, 16, 11, res, rmin, rmax),
                      "crespo2021_infinite")
+
+
+@pytest.mark.parametrize("integ,res", FINITE)
+def test_adaptive_tolerance(port, reference, integ, res):
+    """integrator_adaptive_tolerance: depth-first recursion; the reference exposes its bins and (through log_progress) its leaf count"""
+    rmin, rmax = _range(port, integ)
+    d = port.dim(integ)
+    for rule, h, tol in (("simpson_trapezoidal", "default_absolute", 3e-5 if d < 4 else 2e-2), ("boole_simpson", "size_relative", 3e-4), ("simpson_trapezoidal", "size_absolute", 1e-4 if d < 4 else 3e-2)):
+        if d >= 4 and rule == "boole_simpson":
+            continue
+        a = port.adaptive_tolerance(integ, rule, h, tol, res, rmin, rmax, reg_cap=200000)
+        b = reference.adaptive_tolerance(integ, rule, h, tol, res, rmin, rmax)
+        assert a[1] == b[1] and len(a[2]["err"]) == a[1], f"{rule} {h}: leaves {a[1]} vs {b[1]}"
+        assert_same_bits(a[0], b[0], f"{rule} {h} bins")
+        assert np.all(a[2]["err"] < np.float32(tol))

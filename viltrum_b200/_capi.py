@@ -27,7 +27,7 @@ SYMBOLS = [
     "vb200_regions_count", "vb200_regions_dim", "vb200_regions_samples", "vb200_regions_download", "vb200_regions_free",
     "vb200_regions_integrate_bins", "vb200_cv_integrate", "vb200_cv_replay",
     "vb200_regions_generate_single_f64", "vb200_regions_upload_f64", "vb200_regions_download_f64", "vb200_regions_integrate_bins_f64",
-    "vb200_builtin_integrand_f64", "vb200_builtin_fubini", "vb200_integrand_free",
+    "vb200_builtin_integrand_f64", "vb200_builtin_fubini", "vb200_integrand_free", "vb200_regions_generate_tolerance",
 ]
 
 
@@ -54,6 +54,11 @@ class McParams(ctypes.Structure):
 class AdaptiveParams(ctypes.Structure):
     _fields_ = [("domain", Domain), ("rule", ctypes.c_int32), ("heuristic", ctypes.c_int32), ("metric", ctypes.c_int32),
                 ("batch", ctypes.c_int32), ("size_weight", ctypes.c_double), ("iterations", ctypes.c_uint64)]
+
+
+class ToleranceParams(ctypes.Structure):
+    _fields_ = [("domain", Domain), ("rule", ctypes.c_int32), ("heuristic", ctypes.c_int32), ("metric", ctypes.c_int32),
+                ("tolerance", ctypes.c_float), ("size_weight", ctypes.c_double), ("max_regions", ctypes.c_uint64)]
 
 
 class CvParams(ctypes.Structure):
@@ -96,6 +101,7 @@ def lib():
         L.vb200_mc_per_bin_inf_replay.argtypes = [vp, vp, ctypes.POINTER(McParams), vp, vp, i32, vp, i32]; L.vb200_mc_per_bin_inf_replay.restype = i32
         L.vb200_monte_carlo.argtypes = [vp, vp, ctypes.POINTER(McParams), vp, i32]; L.vb200_monte_carlo.restype = i32
         L.vb200_regions_generate_adaptive.argtypes = [vp, vp, ctypes.POINTER(AdaptiveParams), ctypes.POINTER(vp)]; L.vb200_regions_generate_adaptive.restype = i32
+        L.vb200_regions_generate_tolerance.argtypes = [vp, vp, ctypes.POINTER(ToleranceParams), ctypes.POINTER(vp)]; L.vb200_regions_generate_tolerance.restype = i32
         L.vb200_regions_generate_single.argtypes = [vp, vp, ctypes.POINTER(Domain), i32, ctypes.POINTER(vp)]; L.vb200_regions_generate_single.restype = i32
         L.vb200_regions_upload.argtypes = [vp, i32, i32, u64, vp, vp, vp, vp, vp, ctypes.POINTER(vp)]; L.vb200_regions_upload.restype = i32
         L.vb200_regions_count.argtypes = [vp]; L.vb200_regions_count.restype = u64

@@ -18,6 +18,7 @@
 #include <cstring>
 #include <vector>
 #include <algorithm>
+#include <cub/device/device_radix_sort.cuh>
 
 using namespace vb200;
 namespace R = viltrum::b200::device::rules;
@@ -262,6 +263,135 @@ int run_rounds(vb200_ctx* ctx, const vb200_integrand* f, const vb200_adaptive_pa
     return VB200_OK;
 }
 
+// ---- tolerance-driven refinement (integrator_adaptive_tolerance, reference src/nested/integrator-adaptive-tolerance.h:15-39) --------
+// The reference recurses depth first: a region whose heuristic error is below the tolerance is integrated, any other is split and
+// its children visited in order.  Whether a region is split depends on that region alone, so the LEAF SET is the same in any
+// visiting order: here every round splits all regions that still fail the test at once (same kernels as the batched top-k mode),
+// every region carries its root-to-leaf path as a 128-bit key (bit d = which child at depth d), and a final radix sort of the
+// left-aligned keys puts the leaves into the reference's depth-first order — the region->bin accumulation that follows then adds
+// them in the reference's order, bit for bit.
+__global__ void tol_select_kernel(const float* __restrict__ err, const uint32_t* __restrict__ depth, uint64_t n, float tolerance,
+                                  unsigned* __restrict__ sel, unsigned* __restrict__ counters /* [0]=count [1]=max depth */) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (!(err[i] < tolerance)) {                       // integrator-adaptive-tolerance.h:19 (a NaN error is split, as upstream)
+        sel[atomicAdd(&counters[0], 1u)] = unsigned(i);
+        atomicMax(&counters[1], depth[i]);
+    }
+}
+__global__ void tol_paths_kernel(const unsigned* __restrict__ sel, uint64_t nsel, uint64_t n_old, unsigned long long* __restrict__ key_hi,
+                                 unsigned long long* __restrict__ key_lo, uint32_t* __restrict__ depth) {
+    const uint64_t r = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (r >= nsel) return;
+    const unsigned slot = sel[r]; const uint64_t slot1 = n_old + r;
+    const uint32_t d = depth[slot];
+    unsigned long long hi = key_hi[slot], lo = key_lo[slot];
+    key_hi[slot1] = d < 64 ? hi | (1ull << (63 - d)) : hi;
+    key_lo[slot1] = d < 64 ? lo : lo | (1ull << (127 - d));
+    depth[slot] = d + 1; depth[slot1] = d + 1;         // child 0 keeps the parent's bits (a 0 appended), child 1 sets bit d
+}
+__global__ void tol_iota_kernel(unsigned* idx, uint64_t n) { const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; if (i < n) idx[i] = unsigned(i); }
+__global__ void tol_gather_keys_kernel(const unsigned long long* __restrict__ key, const unsigned* __restrict__ idx, unsigned long long* __restrict__ out, uint64_t n) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; if (i < n) out[i] = key[idx[i]];
+}
+// column gather: dst[k][i] = src[k][perm[i]]   (blockIdx.y strides over the columns)
+template<class T>
+__global__ void tol_permute_kernel(const T* __restrict__ src, uint64_t src_cap, T* __restrict__ dst, uint64_t dst_cap, const unsigned* __restrict__ perm, uint64_t n, int columns) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t j = perm[i];
+    for (int k = blockIdx.y; k < columns; k += gridDim.y) dst[uint64_t(k) * dst_cap + i] = src[uint64_t(k) * src_cap + j];
+}
+
+struct TolState {
+    vb200_regions* r = nullptr;
+    unsigned long long *key_hi = nullptr, *key_lo = nullptr; uint32_t* depth = nullptr;
+};
+
+// re-stride the SoA table (and the path columns) to a larger capacity
+static int tol_grow(vb200_ctx* ctx, TolState& t, uint64_t n, uint64_t new_cap) {
+    vb200_regions* o = t.r; vb200_regions* g = nullptr;
+    int rc = regions_alloc(ctx, o->dim, o->rule, new_cap, &g); if (rc) return rc;
+    unsigned long long *kh = nullptr, *kl = nullptr; uint32_t* dp = nullptr;
+    if (dmalloc(ctx, &kh, new_cap * 8) != cudaSuccess || dmalloc(ctx, &kl, new_cap * 8) != cudaSuccess || dmalloc(ctx, &dp, new_cap * 4) != cudaSuccess) {
+        cudaGetLastError(); dfree(ctx, kh); dfree(ctx, kl); dfree(ctx, dp); vb200_regions_free(g);
+        return fail(ctx, VB200_ERR_NOMEM, "tolerance refinement: %llu region slots do not fit", (unsigned long long)new_cap);
+    }
+    cudaStream_t s = ctx->stream;
+    const size_t w = n * sizeof(float);
+    VB200_CUDA(ctx, cudaMemcpy2DAsync(g->rmin, new_cap * 4, o->rmin, o->capacity * 4, w, o->dim, cudaMemcpyDeviceToDevice, s));
+    VB200_CUDA(ctx, cudaMemcpy2DAsync(g->rmax, new_cap * 4, o->rmax, o->capacity * 4, w, o->dim, cudaMemcpyDeviceToDevice, s));
+    VB200_CUDA(ctx, cudaMemcpy2DAsync(g->data, new_cap * 4, o->data, o->capacity * 4, w, o->sd, cudaMemcpyDeviceToDevice, s));
+    VB200_CUDA(ctx, cudaMemcpyAsync(g->err, o->err, w, cudaMemcpyDeviceToDevice, s));
+    VB200_CUDA(ctx, cudaMemcpyAsync(g->errdim, o->errdim, n * 4, cudaMemcpyDeviceToDevice, s));
+    VB200_CUDA(ctx, cudaMemcpyAsync(kh, t.key_hi, n * 8, cudaMemcpyDeviceToDevice, s));
+    VB200_CUDA(ctx, cudaMemcpyAsync(kl, t.key_lo, n * 8, cudaMemcpyDeviceToDevice, s));
+    VB200_CUDA(ctx, cudaMemcpyAsync(dp, t.depth, n * 4, cudaMemcpyDeviceToDevice, s));
+    dfree(ctx, t.key_hi); dfree(ctx, t.key_lo); dfree(ctx, t.depth); vb200_regions_free(o);
+    t.r = g; t.key_hi = kh; t.key_lo = kl; t.depth = dp;
+    return VB200_OK;
+}
+
+template<int SH, int SL, int DIM>
+int run_tolerance(vb200_ctx* ctx, const vb200_integrand* f, const vb200_tolerance_params* p, TolState& t, uint64_t* n_out) {
+    using Sh = D_::GreedyShape<SH, SL, DIM>;
+    cudaStream_t s = ctx->stream;
+    root_error_kernel<SH, SL, DIM><<<1, 32, (Sh::SD + Sh::L + 4 * DIM) * sizeof(float), s>>>(t.r->capacity, t.r->rmin, t.r->rmax, t.r->data, t.r->err, t.r->errdim, p->heuristic, p->metric, p->size_weight);
+    ctx->launches++;
+    VB200_CUDA(ctx, cudaGetLastError());
+    const size_t per_warp = (3 * Sh::SD + Sh::L + 4 * DIM + 2 * DIM + 2) * sizeof(float);
+    int wpc = int((96u << 10) / per_warp); if (wpc > 8) wpc = 8; if (wpc < 1) wpc = 1;
+    auto kchild = split_children_kernel<SH, SL, DIM>;
+    VB200_CUDA(ctx, cudaFuncSetAttribute(kchild, cudaFuncAttributeMaxDynamicSharedMemorySize, int(per_warp * wpc)));
+    const uint64_t Q = uint64_t(SH - 1) * Sh::L;
+    uint64_t max_batch = (32ull << 20) / Q; if (max_batch < 1) max_batch = 1;
+    const uint64_t limit = p->max_regions ? p->max_regions : (1ull << 27);
+    unsigned* counters = nullptr;
+    if (dmalloc(ctx, &counters, 2 * sizeof(unsigned)) != cudaSuccess) { cudaGetLastError(); return fail(ctx, VB200_ERR_NOMEM, "out of device memory"); }
+    uint64_t n = 1; int rc = VB200_OK;
+    for (;;) {
+        unsigned* sel = nullptr;
+        if (dmalloc(ctx, &sel, n * sizeof(unsigned)) != cudaSuccess) { cudaGetLastError(); rc = fail(ctx, VB200_ERR_NOMEM, "out of device memory"); break; }
+        unsigned h[2] = {0, 0};
+        if (cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned), s) != cudaSuccess) { dfree(ctx, sel); rc = fail(ctx, VB200_ERR_CUDA, "memset failed"); break; }
+        tol_select_kernel<<<unsigned((n + 255) / 256), 256, 0, s>>>(t.r->err, t.depth, n, p->tolerance, sel, counters);
+        ctx->launches++;
+        if (cudaMemcpyAsync(h, counters, sizeof(h), cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) {
+            dfree(ctx, sel); rc = fail(ctx, VB200_ERR_CUDA, "tolerance refinement failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+        const uint64_t nsel = h[0];
+        if (nsel == 0) { dfree(ctx, sel); break; }
+        if (h[1] >= 128) { dfree(ctx, sel); rc = fail(ctx, VB200_ERR_UNSUPPORTED, "tolerance %g not reached after 128 levels of subdivision (the reference would recurse without bound)", double(p->tolerance)); break; }
+        if (n + nsel > limit) { dfree(ctx, sel); rc = fail(ctx, VB200_ERR_NOMEM, "tolerance refinement exceeds %llu regions", (unsigned long long)limit); break; }
+        if (n + nsel > t.r->capacity) { rc = tol_grow(ctx, t, n, std::max<uint64_t>(2 * t.r->capacity, n + nsel)); if (rc) { dfree(ctx, sel); break; } }
+        const uint64_t cap = t.r->capacity;
+        for (uint64_t off = 0; off < nsel && !rc; off += max_batch) {
+            const uint64_t B = std::min<uint64_t>(max_batch, nsel - off), N = B * Q;
+            float *points = nullptr, *vals = nullptr;
+            if (dmalloc(ctx, &points, N * DIM * sizeof(float)) != cudaSuccess || dmalloc(ctx, &vals, N * sizeof(float)) != cudaSuccess) {
+                cudaGetLastError(); dfree(ctx, points); dfree(ctx, vals); rc = fail(ctx, VB200_ERR_NOMEM, "out of device memory"); break; }
+            split_points_kernel<<<unsigned((N + 255) / 256), 256, 0, s>>>(SH, DIM, cap, B, sel + off, t.r->rmin, t.r->rmax, t.r->errdim, points);
+            tol_paths_kernel<<<unsigned((B + 255) / 256), 256, 0, s>>>(sel + off, B, n + off, t.key_hi, t.key_lo, t.depth);
+            ctx->launches += 2;
+            vb200_eval_launch ev; std::memset(&ev, 0, sizeof(ev));
+            ev.n = N; ev.dim = DIM; ev.points = points; ev.values = vals;
+            rc = call_thunk(ctx, f, VB200_K_EVAL_POINTS, &ev);
+            if (!rc) {
+                kchild<<<unsigned((B + wpc - 1) / wpc), wpc * 32, per_warp * wpc, s>>>(cap, B, n + off, sel + off, vals, t.r->rmin, t.r->rmax, t.r->data, t.r->err, t.r->errdim,
+                                                                                       p->heuristic, p->metric, p->size_weight);
+                ctx->launches++;
+                if (cudaGetLastError() != cudaSuccess) rc = fail(ctx, VB200_ERR_CUDA, "split kernel launch failed");
+            }
+            dfree(ctx, points); dfree(ctx, vals);
+        }
+        dfree(ctx, sel);
+        if (rc) break;
+        n += nsel;
+    }
+    dfree(ctx, counters);
+    *n_out = n;
+    return rc;
+}
+
 } // namespace
 
 namespace vb200 {
@@ -322,6 +452,71 @@ int generate_batched(vb200_ctx* ctx, const vb200_integrand* f, const vb200_adapt
     if (e != cudaSuccess) return bail(fail(ctx, VB200_ERR_CUDA, "batched refinement failed: %s", cudaGetErrorString(e)));
     cleanup();
     *out = r;
+    return VB200_OK;
+}
+
+int generate_tolerance(vb200_ctx* ctx, const vb200_integrand* f, const vb200_tolerance_params* p, vb200_regions** out) {
+    const int D = f->dim;
+    TolState t;
+    uint64_t cap = 4096;
+    int rc = regions_alloc(ctx, D, p->rule, cap, &t.r); if (rc) return rc;
+    const int S = t.r->SH; const uint64_t sd = uint64_t(t.r->sd);
+    float *points = nullptr, *vals = nullptr, *lohi = nullptr;
+    auto cleanup = [&] () { dfree(ctx, points); dfree(ctx, vals); dfree(ctx, lohi); dfree(ctx, t.key_hi); dfree(ctx, t.key_lo); dfree(ctx, t.depth); t.key_hi = t.key_lo = nullptr; t.depth = nullptr; };
+    auto bail = [&] (int code) { cudaStreamSynchronize(ctx->stream); cleanup(); vb200_regions_free(t.r); return code; };
+    if (dmalloc(ctx, &t.key_hi, cap * 8) != cudaSuccess || dmalloc(ctx, &t.key_lo, cap * 8) != cudaSuccess || dmalloc(ctx, &t.depth, cap * 4) != cudaSuccess ||
+        dmalloc(ctx, &points, sd * D * sizeof(float)) != cudaSuccess || dmalloc(ctx, &vals, sd * sizeof(float)) != cudaSuccess || dmalloc(ctx, &lohi, 2 * VB200_MAX_DIM * sizeof(float)) != cudaSuccess) {
+        cudaGetLastError(); return bail(fail(ctx, VB200_ERR_NOMEM, "working set of the tolerance refinement does not fit")); }
+    if (cudaMemsetAsync(t.key_hi, 0, 8, ctx->stream) != cudaSuccess || cudaMemsetAsync(t.key_lo, 0, 8, ctx->stream) != cudaSuccess || cudaMemsetAsync(t.depth, 0, 4, ctx->stream) != cudaSuccess)
+        return bail(fail(ctx, VB200_ERR_CUDA, "memset failed"));
+    // root region (integrator-adaptive-tolerance.h:37)
+    float h_lohi[2 * VB200_MAX_DIM];
+    for (int d = 0; d < D; ++d) { h_lohi[d] = p->domain.rmin[d]; h_lohi[VB200_MAX_DIM + d] = p->domain.rmax[d]; }
+    if (cudaMemcpyAsync(lohi, h_lohi, sizeof(h_lohi), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return bail(fail(ctx, VB200_ERR_CUDA, "range upload failed"));
+    root_points_kernel<<<unsigned((sd + 255) / 256), 256, 0, ctx->stream>>>(S, D, sd, lohi, lohi + VB200_MAX_DIM, points);
+    ctx->launches++;
+    vb200_eval_launch ev; std::memset(&ev, 0, sizeof(ev));
+    ev.n = sd; ev.dim = D; ev.points = points; ev.values = vals;
+    rc = call_thunk(ctx, f, VB200_K_EVAL_POINTS, &ev); if (rc) return bail(rc);
+    scatter_root_kernel<<<unsigned((std::max<uint64_t>(sd, uint64_t(D)) + 255) / 256), 256, 0, ctx->stream>>>(sd, cap, D, vals, lohi, lohi + VB200_MAX_DIM, t.r->data, t.r->rmin, t.r->rmax);
+    ctx->launches++;
+    uint64_t n = 0;
+    rc = VB200_ERR_UNSUPPORTED;
+#define VB200_RT(SH_, SL_, DD) if (t.r->SH == SH_ && t.r->SL == SL_ && D == DD) rc = run_tolerance<SH_, SL_, DD>(ctx, f, p, t, &n);
+    VB200_RT(3, 2, 1) VB200_RT(3, 2, 2) VB200_RT(3, 2, 3) VB200_RT(3, 2, 4) VB200_RT(3, 2, 5) VB200_RT(3, 2, 6)
+    VB200_RT(5, 3, 1) VB200_RT(5, 3, 2) VB200_RT(5, 3, 3) VB200_RT(5, 3, 4) VB200_RT(5, 3, 5)
+#undef VB200_RT
+    if (rc == VB200_ERR_UNSUPPORTED && n == 0) return bail(fail(ctx, VB200_ERR_UNSUPPORTED, "tolerance refinement: rule/dimension combination not instantiated"));
+    if (rc) return bail(rc);
+    // leaves -> the reference's depth-first order: stable LSD radix sort of the 128-bit path keys (low word, then high word)
+    cudaStream_t s = ctx->stream;
+    unsigned *idx_a = nullptr, *idx_b = nullptr; unsigned long long *k_in = nullptr, *k_out = nullptr; void* tmp = nullptr; size_t tmp_bytes = 0;
+    vb200_regions* fin = nullptr;
+    auto cleanup2 = [&] () { dfree(ctx, idx_a); dfree(ctx, idx_b); dfree(ctx, k_in); dfree(ctx, k_out); dfree(ctx, tmp); };
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, idx_a, idx_b, int(n), 0, 64, s);
+    if (dmalloc(ctx, &idx_a, n * 4) != cudaSuccess || dmalloc(ctx, &idx_b, n * 4) != cudaSuccess || dmalloc(ctx, &k_in, n * 8) != cudaSuccess ||
+        dmalloc(ctx, &k_out, n * 8) != cudaSuccess || dmalloc_bytes(ctx, &tmp, tmp_bytes) != cudaSuccess) { cudaGetLastError(); cleanup2(); return bail(fail(ctx, VB200_ERR_NOMEM, "out of device memory")); }
+    const unsigned g1 = unsigned((n + 255) / 256);
+    tol_iota_kernel<<<g1, 256, 0, s>>>(idx_a, n);
+    cudaMemcpyAsync(k_in, t.key_lo, n * 8, cudaMemcpyDeviceToDevice, s);
+    cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, idx_a, idx_b, int(n), 0, 64, s);
+    tol_gather_keys_kernel<<<g1, 256, 0, s>>>(t.key_hi, idx_b, k_in, n);
+    cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, idx_b, idx_a, int(n), 0, 64, s);
+    ctx->launches += 4;
+    rc = regions_alloc(ctx, D, p->rule, n, &fin); if (rc) { cleanup2(); return bail(rc); }
+    const uint64_t ocap = t.r->capacity;
+    tol_permute_kernel<float><<<dim3(g1, unsigned(std::min<uint64_t>(sd, 64))), 256, 0, s>>>(t.r->data, ocap, fin->data, n, idx_a, n, int(sd));
+    tol_permute_kernel<float><<<dim3(g1, unsigned(D)), 256, 0, s>>>(t.r->rmin, ocap, fin->rmin, n, idx_a, n, D);
+    tol_permute_kernel<float><<<dim3(g1, unsigned(D)), 256, 0, s>>>(t.r->rmax, ocap, fin->rmax, n, idx_a, n, D);
+    tol_permute_kernel<float><<<dim3(g1, 1), 256, 0, s>>>(t.r->err, ocap, fin->err, n, idx_a, n, 1);
+    tol_permute_kernel<uint32_t><<<dim3(g1, 1), 256, 0, s>>>(t.r->errdim, ocap, fin->errdim, n, idx_a, n, 1);
+    ctx->launches += 5;
+    cudaError_t e = cudaGetLastError(); if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cleanup2();
+    if (e != cudaSuccess) { vb200_regions_free(fin); return bail(fail(ctx, VB200_ERR_CUDA, "tolerance refinement (ordering pass) failed: %s", cudaGetErrorString(e))); }
+    cleanup(); vb200_regions_free(t.r);
+    fin->count = n;
+    *out = fin;
     return VB200_OK;
 }
 

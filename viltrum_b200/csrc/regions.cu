@@ -681,6 +681,18 @@ static int generate_greedy(vb200_ctx* ctx, const vb200_integrand* f, const vb200
     return VB200_OK;
 }
 
+extern "C" int vb200_regions_generate_tolerance(vb200_ctx* ctx, const vb200_integrand* f, const vb200_tolerance_params* p, vb200_regions** out) {
+    if (!ctx || !f || !p || !out) return fail(ctx, VB200_ERR_INVALID, "NULL argument");
+    VB200_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (f->dim <= 0 || p->domain.dim != f->dim) return fail(ctx, VB200_ERR_INVALID, "range has %d dimensions, integrand takes %d", p->domain.dim, f->dim);
+    int SH, SL;
+    if (rule_samples(p->rule, &SH, &SL) || SL == 0) return fail(ctx, VB200_ERR_INVALID, "adaptive refinement needs a nested(high,low) rule (got %d)", p->rule);
+    if (p->heuristic != VB200_HEURISTIC_DEFAULT && p->heuristic != VB200_HEURISTIC_SIZE) return fail(ctx, VB200_ERR_INVALID, "unknown heuristic %d", p->heuristic);
+    if (p->metric != VB200_METRIC_ABSOLUTE && p->metric != VB200_METRIC_RELATIVE) return fail(ctx, VB200_ERR_INVALID, "unknown metric %d", p->metric);
+    if (!(p->tolerance > 0.0f)) return fail(ctx, VB200_ERR_INVALID, "tolerance %g must be positive (no region's error is below it otherwise)", double(p->tolerance));
+    return generate_tolerance(ctx, f, p, out);
+}
+
 extern "C" int vb200_regions_generate_adaptive(vb200_ctx* ctx, const vb200_integrand* f, const vb200_adaptive_params* p, vb200_regions** out) {
     if (!ctx || !f || !p || !out) return fail(ctx, VB200_ERR_INVALID, "NULL argument");
     VB200_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -28,6 +28,8 @@ int rule_samples(int rule, int* SH, int* SL);
 int regions_alloc(vb200_ctx* ctx, int dim, int rule, uint64_t capacity, vb200_regions** out, bool f64 = false);
 // batched top-k refinement (refine_batched.cu); params already validated
 int generate_batched(vb200_ctx* ctx, const vb200_integrand* f, const vb200_adaptive_params* p, vb200_regions** out);
+// tolerance-driven refinement, leaves in the reference's depth-first order (refine_batched.cu); params already validated
+int generate_tolerance(vb200_ctx* ctx, const vb200_integrand* f, const vb200_tolerance_params* p, vb200_regions** out);
 
 // Per-call acceleration structure for "for every bin, visit the regions that touch it, in table order":
 // regions marginalised over the non-binned dimensions (patches), their pixel boxes (region.h:454-463) and per-tile

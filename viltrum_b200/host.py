@@ -191,6 +191,15 @@ class Context:
         self.check(self._L.vb200_regions_generate_adaptive(self._h, self.integrand(f, exact), ctypes.byref(p), ctypes.byref(h)))
         return Regions(self, h)
 
+    def regions_generate_tolerance(self, f, rng, rule, heuristic, metric, tolerance, size_weight=1e-5, max_regions=0, exact=True):
+        p = C.ToleranceParams()
+        p.domain = C.make_domain(len(rng.min), [1], rng.min, rng.max)
+        p.rule, p.heuristic, p.metric = C.RULES[rule], C.HEURISTICS[heuristic], C.METRICS[metric]
+        p.tolerance, p.size_weight, p.max_regions = float(tolerance), float(size_weight), int(max_regions)
+        h = ctypes.c_void_p()
+        self.check(self._L.vb200_regions_generate_tolerance(self._h, self.integrand(f, exact), ctypes.byref(p), ctypes.byref(h)))
+        return Regions(self, h)
+
     def regions_generate_single(self, f, rng, rule, exact=True):
         d = C.make_domain(len(rng.min), [1], rng.min, rng.max)
         h = ctypes.c_void_p()
@@ -461,6 +470,30 @@ class IntegratorAdaptiveIterations:
 
 
 @dataclass
+class IntegratorAdaptiveTolerance:
+    """integrator_adaptive_tolerance(nested_rule, error_heuristic, tolerance) — reference src/nested/integrator-adaptive-tolerance.h:41-59
+    ('+=').  Leaves come out in the reference's depth-first order, so the bins match bit for bit with an exact integrand."""
+    rule: Nested
+    heuristic: ErrorHeuristic
+    tolerance: float = 1e-3
+    max_regions: int = 0
+
+    def generate(self, ctx, f, rng, exact=True):
+        return ctx.regions_generate_tolerance(f, rng, self.rule.name, self.heuristic.kind, self.heuristic.metric.kind, self.tolerance,
+                                              self.heuristic.size_weight, self.max_regions, exact=exact)
+
+    def integrate(self, ctx, bins, res, f, rng, shard=None, exact=True, logger=None, **kw):
+        regs = self.generate(ctx, f, rng, exact=exact)
+        if logger is not None:
+            logger.log(regs)
+        try:
+            regs.integrate_bins(bins, res, rng, shard=shard)
+        finally:
+            if logger is None:
+                regs.free()
+
+
+@dataclass
 class IntegratorCrespo2021:
     """integrator_crespo2021(iterations, spp, seed) — reference src/control-variates/integrator-crespo2021.h:7-22 ('=')"""
     iterations: int
@@ -561,6 +594,14 @@ def integrator_adaptive_iterations(rule, heuristic=None, iterations=None, batch=
     if iterations is None:            # integrator_adaptive_iterations(rule, iterations) overload (integrator-adaptive-iterations.h:22-25)
         heuristic, iterations = error_heuristic_default(error_metric_absolute()), heuristic
     return IntegratorAdaptiveIterations(rule, heuristic, iterations, batch)
+
+
+def integrator_adaptive_tolerance(rule, heuristic=None, tolerance=1e-3, max_regions=0):
+    if not isinstance(heuristic, ErrorHeuristic):        # integrator_adaptive_tolerance(rule, tolerance) overload (integrator-adaptive-tolerance.h:46-54)
+        if heuristic is not None:
+            tolerance = heuristic
+        heuristic = error_heuristic_default(error_metric_absolute())
+    return IntegratorAdaptiveTolerance(rule, heuristic, tolerance, max_regions)
 
 
 def integrator_crespo2021(iterations, spp, seed=0, batch=1):
