@@ -280,11 +280,18 @@ int vb200_regions_integrate_bins_f64(vb200_ctx* ctx, const vb200_regions* r, con
 const vb200_integrand* vb200_builtin_integrand_f64(const char* name, int exact);
 
 /* ---- control variates + residual Monte Carlo (rows a15-a18) --------------------------------------------- */
+typedef enum vb200_cv_weight {
+    VB200_CV_OPTIMIZE_WEIGHT = 0,   /* cv_optimize_weight: alpha = clamp(cov,0,var)/var from the samples (weight-strategy.h:40-110) */
+    VB200_CV_FIXED_WEIGHT = 1       /* cv_fixed_weight(alpha): 0 = plain importance-sampled MC ... 1 = full control variate (weight-strategy.h:7-35) */
+} vb200_cv_weight;
 typedef struct vb200_cv_params {
     vb200_domain domain;
     vb200_shard  shard;
     uint64_t     spp;
     uint64_t     seed;
+    int32_t      weight_strategy;   /* vb200_cv_weight */
+    int32_t      reserved;
+    double       alpha;             /* VB200_CV_FIXED_WEIGHT only */
 } vb200_cv_params;
 
 /* RegionsIntegratorParallelVarianceReduction with rr_uniform_region / cv_optimize_weight / region_sampling_uniform

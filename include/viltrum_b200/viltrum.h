@@ -449,10 +449,16 @@ template<typename R> auto integrator_adaptive_tolerance(const R& r, float tolera
 template<typename R> auto integrator_adaptive_tolerance(const R& r, double tolerance) { return integrator_adaptive_tolerance(r, float(tolerance)); }
 
 // integrator_crespo2021(iterations, spp, seed) — reference src/control-variates/integrator-crespo2021.h:7-22 ('=')
+// control-variate weight policies (reference src/control-variates/weight-strategy.h:7-110)
+struct cv_optimize_weight { static constexpr int id = VB200_CV_OPTIMIZE_WEIGHT; double alpha = 1.0; };
+struct cv_fixed_weight { static constexpr int id = VB200_CV_FIXED_WEIGHT; double alpha; cv_fixed_weight(double a = 1) : alpha(a) {} };
+struct rr_uniform_region {};            // region-russian-roulette.h:9-28
+struct region_sampling_uniform {};      // region-sampling.h:9-20
 class IntegratorCrespo2021 {
-    std::size_t iterations, spp, seed_;
+    std::size_t iterations, spp, seed_; int weight_strategy = VB200_CV_OPTIMIZE_WEIGHT; double alpha = 1.0;
 public:
     IntegratorCrespo2021(std::size_t it, std::size_t s, std::size_t seed) : iterations(it), spp(s), seed_(seed) {}
+    IntegratorCrespo2021(std::size_t it, std::size_t s, std::size_t seed, int ws, double a) : iterations(it), spp(s), seed_(seed), weight_strategy(ws), alpha(a) {}
     template<typename Bins, std::size_t DIMBINS, typename F, typename Float, std::size_t DIM, typename Logger>
     void integrate(Bins& bins, const std::array<std::size_t,DIMBINS>& res, const F& f, const Range<Float,DIM>& range, Logger& logger) const {
         auto& ctx = b200::default_context();
@@ -463,6 +469,7 @@ public:
         if constexpr (!std::is_same<Logger, LoggerNull>::value) logger.log(b200::download_regions<DIM>(ctx, regs.r));
         vb200_cv_params p; std::memset(&p, 0, sizeof(p));
         p.domain = b200::make_domain(range, res); p.shard = b200::current_shard(); p.spp = spp; p.seed = seed_;
+        p.weight_strategy = weight_strategy; p.alpha = alpha;
         std::vector<float> flat(b200::bin_count(res), 0.0f);
         ctx.check(vb200_cv_integrate(ctx.get(), g.c_abi(), regs.r, &p, flat.data(), VB200_HOST, nullptr, nullptr));
         b200::apply_bins<false>(bins, res, flat);
@@ -470,6 +477,14 @@ public:
     }
 };
 inline IntegratorCrespo2021 integrator_crespo2021(std::size_t iterations, std::size_t spp, std::size_t seed = 0, std::size_t = 16) { return IntegratorCrespo2021(iterations, spp, seed); }
+// integrator_adaptive_variance_reduction_parallel(nested(simpson,trapezoidal), error_heuristic_size(relative), iterations, rr_uniform_region(),
+// cv_optimize_weight() | cv_fixed_weight(alpha), region_sampling_uniform(), spp, seed) — reference integrator-adaptive-variance-reduction.h:33-36
+// for the rule / heuristic pair of the crespo2021 preset (other policies: SURVEY.md §8f rank 3, not on the device yet)
+template<typename CV>
+inline IntegratorCrespo2021 integrator_adaptive_variance_reduction_parallel(const Nested<Simpson,Trapezoidal>&, const error_heuristic_size<error_metric_relative>&, std::size_t iterations,
+                                                                            const rr_uniform_region&, const CV& cv, const region_sampling_uniform&, unsigned long spp, std::size_t seed = 0, std::size_t = 16) {
+    return IntegratorCrespo2021(iterations, spp, seed, CV::id, cv.alpha);
+}
 
 // ---- Fubini family (reference src/combination/fubini.h:18-101, regions-generator-fubini.h:7-28, integrator-crespo2021.h:24-44) ---
 template<std::size_t N, typename Float, std::size_t DIM>

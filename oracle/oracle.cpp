@@ -809,7 +809,8 @@ namespace {
 template<typename MakeResidual>
 void cv_integrate_regions(const std::vector<RegionT<float>>& regions, int S, int D, int dimbins, const uint64_t* res,
                           const float* rmin, const float* rmax, uint64_t spp, uint64_t seed, MakeResidual&& make_residual, float* bins,
-                          uint32_t* rec_nregions, float* rec_approx, uint32_t* rec_chosen, float* rec_samples) {
+                          uint32_t* rec_nregions, float* rec_approx, uint32_t* rec_chosen, float* rec_samples,
+                          bool fixed_weight = false, double fixed_alpha = 1.0) {
     uint64_t nb = nbins_of(dimbins,res);
     uint64_t factor = nb;
     // bin -> region lists, regions visited in list order (:53-57, serial PSTL backend)
@@ -849,6 +850,7 @@ void cv_integrate_regions(const std::vector<RegionT<float>>& regions, int S, int
         if (rec_approx) rec_approx[k] = approximation;
         // cv_optimize_weight accumulator (weight-strategy.h:40-101)
         float sum_f=0.0f, sum_app=0.0f; uint64_t size=0;
+        float fixed_sum = 0.0f;                                                // cv_fixed_weight::Accumulator::sum (weight-strategy.h:14-17)
         double k_f=0,k_app=0,e_f=0,e_ap=0,e_ap2=0,e_fap=0;
         for (uint64_t s=0;s<spp;++s) {                                         // :92-101
             uint64_t chosen = uniform_int(rng,0,n-1);                          // region-russian-roulette.h:14,18-21
@@ -868,11 +870,13 @@ void cv_integrate_regions(const std::vector<RegionT<float>>& regions, int S, int
             e_ap2 += (std::abs(as) - k_app)*(std::abs(as) - k_app);
             e_fap += (std::abs(fs) - k_f)*(std::abs(as) - k_app);
             sum_f += fs; sum_app += as;
+            fixed_sum = float(double(fixed_sum) + (double(fs) - fixed_alpha*double(as)));      // sum += f - alpha*app  (weight-strategy.h:20)
             ++size;
         }
         // integral (weight-strategy.h:71-101)
         float result;
-        if (size<2) result = approximation;
+        if (fixed_weight) result = size==0 ? approximation : float(double(fixed_sum)/double(size) + fixed_alpha*double(approximation));   // :24-27
+        else if (size<2) result = approximation;
         else {
             double covariance = (e_fap - (e_f*e_ap)/double(size))/double(size-1);
             double variance   = (e_ap2 - (e_ap*e_ap)/double(size))/double(size-1);
@@ -899,6 +903,18 @@ extern "C" int vo_crespo2021(const char* integrand, uint64_t iterations, uint64_
     export_regions<float>(regions,D,reg_min,reg_max,reg_err,reg_dim,reg_data);
 
     cv_integrate_regions(regions,S,D,dimbins,res,rmin,rmax,spp,seed,[&] (uint64_t) { return F->fn; },bins,rec_nregions,rec_approx,rec_chosen,rec_samples);
+    return 0;
+}
+
+extern "C" int vo_cv_fixed_weight(const char* integrand, uint64_t iterations, uint64_t spp, uint64_t seed, double alpha,
+                       int dimbins, const uint64_t* res, const float* rmin, const float* rmax, float* bins,
+                       uint32_t* rec_nregions, float* rec_approx, uint32_t* rec_chosen, float* rec_samples) {
+    auto F = find_finite(integrand); if (!F) return -1;
+    int D = F->dim; if (dimbins<1 || dimbins>D) return -2;
+    const int S = 3, SL = 2;
+    Heuristic h{true,true,1.e-5};
+    auto regions = generate_adaptive<float>(F->fn,S,SL,D,rmin,rmax,h,iterations);
+    cv_integrate_regions(regions,S,D,dimbins,res,rmin,rmax,spp,seed,[&] (uint64_t) { return F->fn; },bins,rec_nregions,rec_approx,rec_chosen,rec_samples,true,alpha);
     return 0;
 }
 

@@ -105,6 +105,13 @@ int vo_crespo2021(const char* integrand, uint64_t iterations, uint64_t spp, uint
                   uint32_t* rec_nregions, float* rec_approx, uint32_t* rec_chosen, float* rec_samples,
                   float* reg_min, float* reg_max, float* reg_err, uint32_t* reg_dim, float* reg_data);
 
+// The same integrator with cv_fixed_weight(alpha) instead of cv_optimize_weight (reference src/control-variates/weight-strategy.h:7-35):
+// integrator_adaptive_variance_reduction_parallel(nested(simpson,trapezoidal), error_heuristic_size(relative,1e-5), iterations,
+// rr_uniform_region(), cv_fixed_weight(alpha), region_sampling_uniform(), spp, seed).  Records as vo_crespo2021 (rec_approx: port only).
+int vo_cv_fixed_weight(const char* integrand, uint64_t iterations, uint64_t spp, uint64_t seed, double alpha,
+                       int dimbins, const uint64_t* res, const float* rmin, const float* rmax, float* bins,
+                       uint32_t* rec_nregions, float* rec_approx, uint32_t* rec_chosen, float* rec_samples);
+
 // ---- Fubini family ---------------------------------------------------------------------------------
 // The integrand's first `nfirst` dimensions are handled by a "first" integrator over g(x) = integral of f(x, rest) estimated by
 // monte_carlo(mc_samples, mc_seed) over the remaining dimensions — finite (named finite integrand, dim > nfirst, rmin/rmax have

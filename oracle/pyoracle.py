@@ -262,6 +262,22 @@ class Oracle:
         self._check(rc, "vo_crespo2021_infinite")
         return bins
 
+    def cv_fixed_weight(self, integrand, iterations, spp, seed, alpha, res, rmin, rmax, record=False):
+        res, rmin, rmax, nb = self._setup(res, rmin, rmax)
+        d = self.dim(integrand)
+        bins = np.zeros(nb, np.float32)
+        nreg = approx = chosen = samples = None
+        if record:
+            nreg = np.zeros(nb, np.uint32); approx = np.zeros(nb, np.float32)
+            chosen = np.zeros((nb, spp), np.uint32); samples = np.zeros((nb, spp, d), np.float32)
+        self.lib.vo_cv_fixed_weight.restype = ctypes.c_int
+        rc = self.lib.vo_cv_fixed_weight(integrand.encode(), ctypes.c_uint64(iterations), ctypes.c_uint64(spp), ctypes.c_uint64(seed), ctypes.c_double(alpha),
+                                         len(res), _p(res), _p(rmin), _p(rmax), _p(bins), _p(nreg), _p(approx), _p(chosen), _p(samples))
+        self._check(rc, "vo_cv_fixed_weight")
+        if record:
+            return bins, dict(nregions=nreg, approx=approx, chosen=chosen, samples=samples)
+        return bins
+
     def mt_per_bin(self, path, integrand, res, spp, seed, nthreads, rmin=(), rmax=()):
         res = np.ascontiguousarray(np.asarray(res, dtype=np.uint64))
         rmin, rmax = _f32(rmin), _f32(rmax)

@@ -111,3 +111,27 @@ extern "C" int vo_crespo2021(const char* integrand, uint64_t iterations, uint64_
         return 0;
     });
 }
+
+extern "C" int vo_cv_fixed_weight(const char* integrand, uint64_t iterations, uint64_t spp, uint64_t seed, double alpha,
+                       int dimbins, const uint64_t* res, const float* rmin, const float* rmax, float* bins,
+                       uint32_t* rec_nregions, float* rec_approx, uint32_t* rec_chosen, float* rec_samples) {
+    RegionSink sink;
+    return dispatch_finite_bins(integrand, dimbins, [&] (auto f, auto dbc) -> int {
+        using F = decltype(f);
+        constexpr std::size_t D = F::dim;
+        constexpr std::size_t DB = decltype(dbc)::value;
+        using namespace viltrum;
+        auto r = res_array<DB>(res);
+        auto range = range_array<D>(rmin, rmax);
+        auto acc = [&] (const std::array<std::size_t,DB>& p) -> float& { return bins[tensor_pos(p,r)]; };
+        CvRecorder rec; rec.db = int(DB); rec.spp = spp; rec.dim = D; rec.sink = &sink;
+        for (std::size_t i=0;i<DB;++i) { rec.rmin[i]=rmin[i]; rec.res[i]=r[i]; rec.drange[i]=(rmax[i]-rmin[i])/float(r[i]); }
+        rec.nregions=rec_nregions; rec.approx=nullptr; rec.chosen=rec_chosen; rec.samples=rec_samples;
+        DumpLogger logger(&sink);
+        auto integrator = integrator_region_based(
+            regions_generator_adaptive_heap(nested(simpson,trapezoidal), error_heuristic_size(error_metric_relative(),1.e-5), std::size_t(iterations)),
+            regions_integrator_parallel_variance_reduction(RecRR(&rec), cv_fixed_weight(alpha), RecRS(&rec), std::mt19937(std::size_t(seed)), (unsigned long)spp, std::size_t(16)));
+        viltrum::integrate(integrator, acc, r, f, range, logger);
+        return 0;
+    });
+}

@@ -81,6 +81,12 @@ def main():
                           bins=bits(b), sum=bits(s1), sum2=bits(s2), lens=bits(lens), elems=bits(elems)))
             V.append(dict(integrand=integ, res=res, rmin=rmin, rmax=rmax, path="monte_carlo_inf", samples_n=300, seed=7,
                           bins=bits(R.monte_carlo_inf(integ, res, 300, 7, rmin, rmax))))
+    # cv_fixed_weight: bins + the recorded region choices / sample points for the replay mode
+    for integ, res, it, spp, alpha in (("x2y2", [5], 12, 6, 1.0), ("smooth_edge2", [6, 6], 30, 4, 0.5), ("shade4_16", [3, 3], 8, 4, 0.0), ("poly3", [3, 2], 12, 4, 0.75)):
+        d = R.dim(integ)
+        b, rec = R.cv_fixed_weight(integ, it, spp, 9, alpha, res, [0.0] * d, [1.0] * d, record=True)
+        V.append(dict(integrand=integ, res=res, rmin=[0.0] * d, rmax=[1.0] * d, path="cv_fixed_weight", iterations=it, spp=spp, seed=9, alpha=alpha,
+                      bins=bits(b), nregions=bits(rec["nregions"]), chosen=bits(rec["chosen"]), samples=bits(rec["samples"])))
     # integrator_adaptive_tolerance: bins + number of leaves
     for integ, res, lo, hi, rule, h, tol in (("x2y2", [5], 0.0, 1.0, "simpson_trapezoidal", "default_absolute", 1e-5), ("smooth_edge2", [8, 8], 0.0, 1.0, "boole_simpson", "size_relative", 2e-4),
                                              ("ind2", [6, 5], 0.0, 1.0, "simpson_trapezoidal", "default_absolute", 2e-4), ("shade4_16", [4, 4], 0.0, 1.0, "simpson_trapezoidal", "size_relative", 4e-3),

@@ -64,6 +64,9 @@ def run_oracle_vector(O, v):
         return dict(bins=b, sum=s1, sum2=s2, lens=lens, elems=elems)
     if path == "monte_carlo_inf":
         return dict(bins=O.monte_carlo_inf(integ, res, v["samples_n"], v["seed"], rmin, rmax))
+    if path == "cv_fixed_weight":
+        b, rec = O.cv_fixed_weight(integ, v["iterations"], v["spp"], v["seed"], v["alpha"], res, rmin, rmax, record=True)
+        return dict(bins=b, nregions=rec["nregions"], chosen=rec["chosen"], samples=rec["samples"])
     if path == "adaptive_tolerance":
         b, n, _ = O.adaptive_tolerance(integ, v["rule"], v["heuristic"], v["tolerance"], res, rmin, rmax, v["size_weight"])
         return dict(bins=b, nleaves=n)

@@ -111,3 +111,44 @@ def test_crespo2021_full_pipeline_device_bins_and_sharding(ctx):
     ref = np.zeros(nb, np.float32)
     ctx.mc_per_bin("shade5_64", ref, res, _rng("shade5_64"), 4096, 4)
     assert np.mean((a - ref) ** 2) < 0.5 * np.mean((mc - ref) ** 2)
+
+
+@pytest.mark.parametrize("alpha", [1.0, 0.5, 0.0])
+def test_cv_fixed_weight_replay_bit_exact_and_statistics(ctx, port, alpha):
+    """cv_fixed_weight(alpha) (weight-strategy.h:7-35): replay of the oracle's choices is bit-exact; the Philox path is the same estimator"""
+    from viltrum_b200 import integrate, integrator_crespo2021, cv_fixed_weight
+    integ, res, it, spp = "shade4_16", [12, 12], 150, 16
+    d = DIMS[integ]; nb = int(np.prod(res))
+    want, rec = port.cv_fixed_weight(integ, it, spp, 11, alpha, res, [0.0] * d, [1.0] * d, record=True)
+    regs = ctx.regions_generate_adaptive(integ, _rng(integ), "simpson_trapezoidal", "size", "relative", it, 1e-5, batch=1, exact=True)
+    out = np.full(nb, 3.0, np.float32)
+    regs.cv_replay(integ, out, res, _rng(integ), spp, np.ascontiguousarray(rec["chosen"]), np.ascontiguousarray(rec["samples"]), fixed_alpha=alpha)
+    assert_same_bits(out, want, f"cv_fixed_weight({alpha}) replay")
+    regs.free()
+    K = 16
+    refs = np.stack([port.cv_fixed_weight(integ, it, spp, 100 + s, alpha, res, [0.0] * d, [1.0] * d) for s in range(K)]).astype(np.float64)
+    gpus = []
+    for s in range(K):
+        b = np.zeros(nb, np.float32)
+        integrate(integrator_crespo2021(it, spp, seed=s, cv=cv_fixed_weight(alpha)), b, res, integ, _rng(integ), ctx=ctx)
+        gpus.append(b.astype(np.float64))
+    gpus = np.stack(gpus)
+    assert_statistically_equal(gpus.mean(axis=0), refs.mean(axis=0), gpus.var(axis=0, ddof=1) / K, refs.var(axis=0, ddof=1) / K, f"cv_fixed_weight({alpha})")
+    ratio = (gpus.var(axis=0, ddof=1).mean() + 1e-30) / (refs.var(axis=0, ddof=1).mean() + 1e-30)
+    assert 0.7 < ratio < 1.4, f"variance ratio {ratio:.3f}"
+
+
+def test_cv_fixed_weight_golden_reference_vectors(ctx):
+    from viltrum_b200 import Range
+    n = 0
+    for v in load_golden():
+        if v["path"] != "cv_fixed_weight":
+            continue
+        d = len(v["rmin"]); nb = int(np.prod(v["res"])); spp = v["spp"]
+        regs = ctx.regions_generate_adaptive(v["integrand"], Range(v["rmin"], v["rmax"]), "simpson_trapezoidal", "size", "relative", v["iterations"], 1e-5, batch=1, exact=True)
+        out = np.zeros(nb, np.float32)
+        regs.cv_replay(v["integrand"], out, v["res"], Range(v["rmin"], v["rmax"]), spp, np.asarray(v["chosen"], np.uint32).reshape(nb, spp),
+                       np.ascontiguousarray(f32(v["samples"]).reshape(nb, spp, d)), fixed_alpha=v["alpha"])
+        assert_same_bits(out, f32(v["bins"]), f"{v['integrand']} alpha={v['alpha']}")
+        regs.free(); n += 1
+    assert n == 4

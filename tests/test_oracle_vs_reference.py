@@ -119,3 +119,14 @@ def test_adaptive_tolerance(port, reference, integ, res):
         assert a[1] == b[1] and len(a[2]["err"]) == a[1], f"{rule} {h}: leaves {a[1]} vs {b[1]}"
         assert_same_bits(a[0], b[0], f"{rule} {h} bins")
         assert np.all(a[2]["err"] < np.float32(tol))
+
+
+@pytest.mark.parametrize("integ,res,it,spp,alpha", [("x2y2", [5], 16, 64, 1.0), ("x2y2", [4, 3], 40, 16, 0.5), ("smooth_edge2", [8, 8], 200, 8, 0.0),
+                                                     ("shade4_16", [3, 4], 60, 8, 0.25), ("shade5_16", [5, 4], 120, 8, 0.75), ("cubic1", [7], 20, 4, 1.0), ("x2y2", [2, 3], 10, 0, 1.0)])
+def test_cv_fixed_weight(port, reference, integ, res, it, spp, alpha):
+    rmin, rmax = _range(port, integ)
+    a = port.cv_fixed_weight(integ, it, spp, 11, alpha, res, rmin, rmax, record=True)
+    b = reference.cv_fixed_weight(integ, it, spp, 11, alpha, res, rmin, rmax, record=True)
+    assert_same_bits(a[0], b[0], "bins")
+    for k in ("nregions", "chosen", "samples"):
+        assert_same_bits(a[1][k], b[1][k], k)

@@ -171,12 +171,13 @@ __global__ void __launch_bounds__(128) cv_samples_kernel(vb200_domain dom, uint6
 __global__ void __launch_bounds__(128) cv_accumulate_kernel(uint64_t begin, uint64_t nb, uint32_t spp, uint64_t nbins_total,
                                                             const uint32_t* __restrict__ count, const float* __restrict__ approx,
                                                             const float* __restrict__ fval, const float* __restrict__ app, const float* __restrict__ weight,
-                                                            float* __restrict__ out) {
+                                                            float* __restrict__ out, int fixed_weight, double fixed_alpha) {
     const uint64_t b = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (b >= nb) return;
     const double factor = double(nbins_total), rrfactor = double(count[b]);
     const float approximation = approx[b];
     float sum_f = 0.0f, sum_app = 0.0f; uint64_t size = 0;
+    float fixed_sum = 0.0f;                 // cv_fixed_weight::Accumulator::sum (weight-strategy.h:14-21)
     double k_f = 0, k_app = 0, e_f = 0, e_ap = 0, e_ap2 = 0, e_fap = 0;
     for (uint32_t j = 0; j < spp; ++j) {
         const uint64_t i = uint64_t(j) * nb + b;
@@ -191,10 +192,12 @@ __global__ void __launch_bounds__(128) cv_accumulate_kernel(uint64_t begin, uint
         e_ap2 = R::da(e_ap2, R::dm(R::ds(na, k_app), R::ds(na, k_app)));
         e_fap = R::da(e_fap, R::dm(R::ds(nf, k_f), R::ds(na, k_app)));
         sum_f = R::fa(sum_f, fs); sum_app = R::fa(sum_app, as);
+        fixed_sum = R::d2f(R::da(double(fixed_sum), R::ds(double(fs), R::dm(fixed_alpha, double(as)))));      // sum += f - alpha*app (:20)
         ++size;
     }
     float result;
-    if (size < 2) result = approximation;                                               // weight-strategy.h:95
+    if (fixed_weight) result = size == 0 ? approximation : R::d2f(R::da(R::dd(double(fixed_sum), double(size)), R::dm(fixed_alpha, double(approximation))));   // :24-27
+    else if (size < 2) result = approximation;                                          // weight-strategy.h:95
     else {
         const double n = double(size), n1 = double(size - 1);
         const double covariance = R::dd(R::ds(e_fap, R::dd(R::dm(e_f, e_ap), n)), n1);
@@ -253,6 +256,7 @@ int cv_run(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r, con
     if (r->f64 || (f->flags & VB200_INTEGRAND_F64)) return fail(ctx, VB200_ERR_UNSUPPORTED, "control variates are computed in fp32: double region tables / integrands are not supported");
     int rc = check_domain(ctx, p->domain, r->dim); if (rc) return rc;
     if (p->spp > 0xffffffffull) return fail(ctx, VB200_ERR_INVALID, "spp invalid");
+    if (p->weight_strategy != VB200_CV_OPTIMIZE_WEIGHT && p->weight_strategy != VB200_CV_FIXED_WEIGHT) return fail(ctx, VB200_ERR_INVALID, "unknown control-variate weight strategy %d", p->weight_strategy);
     const vb200_domain dom = finish_domain(p->domain);
     const uint64_t total = nbins_of(dom);
     uint64_t begin, end; rc = resolve_shard(ctx, p->shard, total, &begin, &end); if (rc) return rc;
@@ -310,7 +314,8 @@ int cv_run(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r, con
             ev.n = N; ev.dim = D; ev.points = points.as<float>(); ev.values = fval.as<float>();
             rc = call_thunk(ctx, f, VB200_K_EVAL_POINTS, &ev); if (rc) return rc;
             cv_accumulate_kernel<<<unsigned((nb + 127) / 128), 128, 0, ctx->stream>>>(s0, nb, spp, total, cnt, d_approx.as<float>() + (s0 - begin),
-                                                                                        fval.as<float>(), app.as<float>(), weight.as<float>(), st.dev_base);
+                                                                                        fval.as<float>(), app.as<float>(), weight.as<float>(), st.dev_base,
+                                                                                        p->weight_strategy == VB200_CV_FIXED_WEIGHT ? 1 : 0, p->alpha);
             ctx->launches++; VB200_CUDA(ctx, cudaGetLastError());
         }
         VB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // the slab buffers die here

@@ -317,25 +317,27 @@ class Regions:
         s = C.Shard(); s.begin, s.end = (shard if shard else (0, 0))
         self.ctx.check(self.ctx._L.vb200_regions_integrate_bins(self.ctx._h, self._h, ctypes.byref(d), ctypes.byref(s), b, mem))
 
-    def _cv_params(self, res, rng, spp, seed, shard):
+    def _cv_params(self, res, rng, spp, seed, shard, fixed_alpha=None):
         p = C.CvParams()
         p.domain = C.make_domain(len(rng.min), res, rng.min, rng.max)
         p.shard.begin, p.shard.end = (shard if shard else (0, 0))
         p.spp, p.seed = int(spp), int(seed) & 0xFFFFFFFFFFFFFFFF
+        if fixed_alpha is not None:          # cv_fixed_weight(alpha) instead of cv_optimize_weight (weight-strategy.h:7-35)
+            p.weight_strategy, p.alpha = C.CV_FIXED_WEIGHT, float(fixed_alpha)
         return p
 
-    def cv_integrate(self, f, bins, res, rng, spp, seed, shard=None, nregions=None, approx=None, exact=False):
+    def cv_integrate(self, f, bins, res, rng, spp, seed, shard=None, nregions=None, approx=None, exact=False, fixed_alpha=None):
         if Context._empty(shard):
             return
         b, mem, _k = _buffer(bins)
         n, _m, _kn = _buffer(nregions, np.uint32); a, _m2, _ka = _buffer(approx)
-        p = self._cv_params(res, rng, spp, seed, shard)
+        p = self._cv_params(res, rng, spp, seed, shard, fixed_alpha)
         self.ctx.check(self.ctx._L.vb200_cv_integrate(self.ctx._h, self.ctx.integrand(f, exact), self._h, ctypes.byref(p), b, mem, n, a))
 
-    def cv_replay(self, f, bins, res, rng, spp, chosen, samples, shard=None, exact=True):
+    def cv_replay(self, f, bins, res, rng, spp, chosen, samples, shard=None, exact=True, fixed_alpha=None):
         b, mem, _k = _buffer(bins)
         c, cmem, _kc = _buffer(chosen, np.uint32); s, _sm, _ks = _buffer(samples)
-        p = self._cv_params(res, rng, spp, 0, shard)
+        p = self._cv_params(res, rng, spp, 0, shard, fixed_alpha)
         self.ctx.check(self.ctx._L.vb200_cv_replay(self.ctx._h, self.ctx.integrand(f, exact), self._h, ctypes.byref(p), c, s, cmem, b, mem))
 
     def free(self):
@@ -494,12 +496,29 @@ class IntegratorAdaptiveTolerance:
 
 
 @dataclass
+class CvFixedWeight:
+    """cv_fixed_weight(alpha) — reference src/control-variates/weight-strategy.h:7-35"""
+    alpha: float = 1.0
+
+
+def cv_fixed_weight(alpha=1.0):
+    return CvFixedWeight(alpha)
+
+
+def cv_optimize_weight():
+    """cv_optimize_weight() — reference src/control-variates/weight-strategy.h:40-110 (the default)"""
+    return None
+
+
+@dataclass
 class IntegratorCrespo2021:
-    """integrator_crespo2021(iterations, spp, seed) — reference src/control-variates/integrator-crespo2021.h:7-22 ('=')"""
+    """integrator_crespo2021(iterations, spp, seed) — reference src/control-variates/integrator-crespo2021.h:7-22 ('=').
+    cv=cv_fixed_weight(alpha) gives integrator_adaptive_variance_reduction_parallel(..., rr_uniform_region(), cv_fixed_weight(alpha), ...)."""
     iterations: int
     spp: int
     seed: int = 0
     batch: int = 1
+    cv: Optional[CvFixedWeight] = None
 
     def integrate(self, ctx, bins, res, f, rng, shard=None, exact=False, logger=None, **kw):
         gen = IntegratorAdaptiveIterations(nested("simpson", "trapezoidal"), error_heuristic_size(error_metric_relative(), 1e-5),
@@ -508,7 +527,8 @@ class IntegratorCrespo2021:
         if logger is not None:
             logger.log(regs)
         try:
-            regs.cv_integrate(f, bins, res, rng, self.spp, self.seed, shard=shard, exact=exact, **kw)
+            regs.cv_integrate(f, bins, res, rng, self.spp, self.seed, shard=shard, exact=exact,
+                              fixed_alpha=self.cv.alpha if self.cv is not None else None, **kw)
         finally:
             if logger is None:
                 regs.free()
@@ -604,8 +624,8 @@ def integrator_adaptive_tolerance(rule, heuristic=None, tolerance=1e-3, max_regi
     return IntegratorAdaptiveTolerance(rule, heuristic, tolerance, max_regions)
 
 
-def integrator_crespo2021(iterations, spp, seed=0, batch=1):
-    return IntegratorCrespo2021(iterations, spp, seed, batch)
+def integrator_crespo2021(iterations, spp, seed=0, batch=1, cv=None):
+    return IntegratorCrespo2021(iterations, spp, seed, batch, cv)
 
 
 # ---- multi-GPU partitioning (one process per GPU) ---------------------------------------------------
