@@ -15,6 +15,9 @@
 #include <cuda_runtime.h>
 #include "../../viltrum_b200.h"
 #include "philox.cuh"
+#include "f32x2.cuh"
+#include <type_traits>
+#include <utility>
 
 namespace viltrum { namespace b200 { namespace device {
 
@@ -73,40 +76,68 @@ __device__ __forceinline__ void signal_tile_done(const vb200_chunk_signal& c, ui
 // EXACT only tags the instantiation (the same template is compiled twice into the library, once in a TU built
 // with --fmad=false); it keeps the two sets of kernel symbols apart.
 //
-// Design notes (measured on B200, profiles/exp/mc_variants.cu -> profiles/mc_variants_r1.txt):
-//   * warp-autonomous tiles: a warp owns G = 32/LPB consecutive bins per step and never meets a CTA barrier
-//     (the first version staged a CTA tile through shared memory behind __syncthreads: 11 % of warp samples sat
-//     in stall_barrier);
-//   * tiles are handed out through one global atomic per warp and tile (a.tile_counter, zeroed by the driver before
-//     the launch), so the tail is one tile long instead of one static share;
-//   * two samples per lane are in flight (independent Philox + Horner chains) — +4 % over one;
-//   * the u32 -> [0,1) scaling (2^-24) is folded into the bin extent, so a coordinate costs SHF + I2FP + FFMA.
+// Design notes (measured on B200, profiles/exp/mc_variants.cu, profiles/exp/mc_packed.cu, profiles/exp/pipes.cu):
+//   * warp-autonomous tiles: a warp owns G = 32/LPB consecutive bins per step and never meets a CTA barrier; tiles are handed out
+//     through one global atomic per warp and tile (a.tile_counter), so the tail is one tile long instead of one static share;
+//   * the 32x32->64 multiplies of Philox are the expensive instructions of this kernel — IMAD.WIDE has a reciprocal throughput of
+//     5.1 cycles per warp and SMSP and does not overlap with FFMA (profiles/pipes_r1.txt) — so no generated bit is thrown away:
+//     samples are drawn in GROUPS OF FOUR from THREE Philox calls per block of four dimensions.  Sample j < 3 of a group takes the
+//     top 24 bits of every word of call j, sample 3 is assembled from the three low bytes (two PRMT per coordinate):
+//     24 bits x 4 coordinates x 4 samples = 384 bits = 3 x 128.  Counter = (bin lo, bin hi, group, call + 4*block), key = seed;
+//   * four samples are in flight per lane (independent Philox + integrand chains); functors that are generic over their scalar
+//     type are evaluated as two packed pairs (f32x2.cuh, FFMA2): half the issue slots for the FP32 work;
+//   * the u32 -> [0,1) scaling (2^-24) is folded into the bin extent, so a coordinate costs SHF/PRMT + I2FP + FFMA.
+template<class F, int DIM, class = void> struct has_pair_eval : std::false_type {};
 template<class F, int DIM>
-__device__ __forceinline__ float mc_sample(const F& f, uint32_t b0, uint32_t b1, uint32_t s, uint32_t k0, uint32_t k1,
-                                           const float (&lo)[DIM], const float (&ext24)[DIM]) {
+struct has_pair_eval<F, DIM, std::void_t<decltype(std::declval<const F&>()(std::declval<const std::array<f32x2, DIM>&>()))>>
+    : std::is_same<decltype(std::declval<const F&>()(std::declval<const std::array<f32x2, DIM>&>())), f32x2> {};
+
+constexpr int MC_GROUP = 4;                 // samples per draw group
+template<int DIM> struct GroupDraws {
+    static constexpr int NB = (DIM + 3) / 4;      // blocks of four dimensions
+    u32x4 r[3][NB];
+    __device__ __forceinline__ void draw(uint32_t b0, uint32_t b1, uint32_t group, uint32_t k0, uint32_t k1, int calls) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int blk = 0; blk < NB; ++blk)
+                if (j < calls) r[j][blk] = philox4x32<10>(u32x4{b0, b1, group, uint32_t(j + 4 * blk)}, k0, k1);
+    }
+    __device__ __forceinline__ static uint32_t word(const u32x4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
+    // 24-bit integer of coordinate i of sample j (as float: exact)
+    __device__ __forceinline__ float coord(int j, int i) const {
+        const int blk = i >> 2, w = i & 3;
+        if (j < 3) return float(word(r[j][blk], w) >> 8);
+        const uint32_t p = word(r[0][blk], w), q = word(r[1][blk], w), t = word(r[2][blk], w);
+        return float(__byte_perm(__byte_perm(t, q, 0x7740), p, 0x7410) & 0x00ffffffu);       // (p.b0 << 16) | (q.b0 << 8) | t.b0
+    }
+};
+
+template<class F, int DIM>
+__device__ __forceinline__ float mc_eval_one(const F& f, const GroupDraws<DIM>& d, int j, const float (&lo)[DIM], const float (&ext24)[DIM]) {
     std::array<float, DIM> x;
 #pragma unroll
-    for (int blk = 0; blk < (DIM + 3) / 4; ++blk) {
-        const u32x4 r = philox4x32<10>(u32x4{b0, b1, s, uint32_t(blk)}, k0, k1);
-        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    for (int i = 0; i < DIM; ++i) x[i] = fmaf(d.coord(j, i), ext24[i], lo[i]);     // u*(b-a)+a as std::uniform_real_distribution, u = n*2^-24 in [0,1)
+    return f(x);
+}
+template<class F, int DIM>
+__device__ __forceinline__ f32x2 mc_eval_pair(const F& f, const GroupDraws<DIM>& d, int j0, const float (&lo)[DIM], const float (&ext24)[DIM]) {
+    std::array<f32x2, DIM> x;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int i = blk * 4 + j;
-            // u*(b-a)+a as std::uniform_real_distribution, u = (w>>8)*2^-24 in [0,1); ext24 = (b-a)*2^-24 (exact scaling)
-            if (i < DIM) x[i] = fmaf(float(w[j] >> 8), ext24[i], lo[i]);
-        }
-    }
+    for (int i = 0; i < DIM; ++i) x[i] = mad(f32x2::pack(d.coord(j0, i), d.coord(j0 + 1, i)), f32x2(ext24[i]), f32x2(lo[i]));
     return f(x);
 }
 
 template<class F, int DIM, int DIMBINS, bool MOMENTS, bool EXACT>
 __global__ void __launch_bounds__(MC_THREADS)
 mc_per_bin_kernel(const F f, const vb200_mc_launch a) {
+    constexpr bool PAIRS = !EXACT && has_pair_eval<F, DIM>::value;
     const uint32_t LPB = a.lanes_per_bin;     // power of two <= 32: the lanes of a bin sit in one warp
     const uint32_t G = 32u / LPB;             // bins per warp step
     const uint32_t lane = threadIdx.x & 31u, sub = lane % LPB, grp = lane / LPB;
     const uint64_t nshard = a.bin_end - a.bin_begin;
     const uint64_t ntiles = (nshard + G - 1) / G;
+    const uint32_t full_groups = a.spp / MC_GROUP, rest = a.spp % MC_GROUP;      // the lanes of a bin stride over its sample groups
 
     uint64_t tile = 0;
     if (lane == 0) tile = atomicAdd(a.tile_counter, 1ull);
@@ -121,20 +152,37 @@ mc_per_bin_kernel(const F f, const vb200_mc_launch a) {
 #pragma unroll
             for (int i = 0; i < DIM; ++i) ext[i] *= 5.9604644775390625e-08f;
             const uint32_t b0 = uint32_t(bin), b1 = uint32_t(bin >> 32);
-            float sumb = 0.0f, sum2b = 0.0f;
-            uint32_t s = sub;
-            for (; s + LPB < a.spp; s += 2u * LPB) {      // two independent samples in flight per lane
-                const float v0 = mc_sample<F, DIM>(f, b0, b1, s, a.key0, a.key1, lo, ext);
-                const float v1 = mc_sample<F, DIM>(f, b0, b1, s + LPB, a.key0, a.key1, lo, ext);
-                sum += v0; sumb += v1;
-                if (MOMENTS) { sum2 = fmaf(v0, v0, sum2); sum2b = fmaf(v1, v1, sum2b); }
+            GroupDraws<DIM> d;
+            if constexpr (PAIRS) {
+                f32x2 acc0(0.0f), acc1(0.0f), sq0(0.0f), sq1(0.0f);
+                for (uint32_t g = sub; g < full_groups; g += LPB) {
+                    d.draw(b0, b1, g, a.key0, a.key1, 3);
+                    const f32x2 v0 = mc_eval_pair<F, DIM>(f, d, 0, lo, ext), v1 = mc_eval_pair<F, DIM>(f, d, 2, lo, ext);
+                    acc0 += v0; acc1 += v1;
+                    if (MOMENTS) { sq0 = mad(v0, v0, sq0); sq1 = mad(v1, v1, sq1); }
+                }
+                sum = (acc0.lo() + acc0.hi()) + (acc1.lo() + acc1.hi());
+                if (MOMENTS) sum2 = (sq0.lo() + sq0.hi()) + (sq1.lo() + sq1.hi());
+            } else {
+                float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f, q0 = 0.0f, q1 = 0.0f, q2 = 0.0f, q3 = 0.0f;
+                for (uint32_t g = sub; g < full_groups; g += LPB) {
+                    d.draw(b0, b1, g, a.key0, a.key1, 3);
+                    const float v0 = mc_eval_one<F, DIM>(f, d, 0, lo, ext), v1 = mc_eval_one<F, DIM>(f, d, 1, lo, ext);
+                    const float v2 = mc_eval_one<F, DIM>(f, d, 2, lo, ext), v3 = mc_eval_one<F, DIM>(f, d, 3, lo, ext);
+                    s0 += v0; s1 += v1; s2 += v2; s3 += v3;
+                    if (MOMENTS) { q0 = fmaf(v0, v0, q0); q1 = fmaf(v1, v1, q1); q2 = fmaf(v2, v2, q2); q3 = fmaf(v3, v3, q3); }
+                }
+                sum = (s0 + s1) + (s2 + s3);
+                if (MOMENTS) sum2 = (q0 + q1) + (q2 + q3);
             }
-            if (s < a.spp) {
-                const float v0 = mc_sample<F, DIM>(f, b0, b1, s, a.key0, a.key1, lo, ext);
-                sum += v0;
-                if (MOMENTS) sum2 = fmaf(v0, v0, sum2);
+            if (rest != 0u && sub == full_groups % LPB) {      // the last, partial group: one call per sample
+                d.draw(b0, b1, full_groups, a.key0, a.key1, int(rest));
+                for (uint32_t j = 0; j < rest; ++j) {
+                    const float v = j == 0 ? mc_eval_one<F, DIM>(f, d, 0, lo, ext) : j == 1 ? mc_eval_one<F, DIM>(f, d, 1, lo, ext) : mc_eval_one<F, DIM>(f, d, 2, lo, ext);
+                    sum += v;
+                    if (MOMENTS) sum2 = fmaf(v, v, sum2);
+                }
             }
-            sum += sumb; sum2 += sum2b;
         }
         // in-bin reduction across the LPB lanes that share the bin (all inside one warp)
         for (uint32_t off = LPB >> 1; off > 0; off >>= 1) {

@@ -122,6 +122,77 @@ __global__ void __launch_bounds__(256, MINB) k_mc(const Args a) {
     }
 }
 
+
+// 4 samples per 3 Philox calls: samples 0..2 take the top 24 bits of every word of call 0..2, sample 3 is assembled from the three
+// low bytes (PRMT), so no generated bit is thrown away (24 bits x 4 coordinates x 4 samples = 384 bits = 3 x 128)
+template<int ROUNDS, int LPB, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_mc34(const Args a) {
+    constexpr int G = 32 / LPB;
+    const uint32_t lane = threadIdx.x & 31, sub = lane % LPB, grp = lane / LPB;
+    const uint32_t ntiles = uint32_t(a.nbins / G);
+    uint32_t tile;
+    if (lane == 0) tile = atomicAdd(a.counter, 1u); tile = __shfl_sync(0xffffffffu, tile, 0);
+    while (tile < ntiles) {
+        const uint32_t bin = tile * G + grp;
+        float lo_[4], ext[4]; box(a, bin, lo_, ext);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ext[i] *= 5.9604644775390625e-08f;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        for (uint32_t g = sub; g < a.spp / 4; g += LPB) {
+            const u32x4 r0 = philox<ROUNDS>(u32x4{bin, 0u, g, 0u}, a.k0, a.k1);
+            const u32x4 r1 = philox<ROUNDS>(u32x4{bin, 0u, g, 1u}, a.k0, a.k1);
+            const u32x4 r2 = philox<ROUNDS>(u32x4{bin, 0u, g, 2u}, a.k0, a.k1);
+            float x[4] = {fmaf(float(r0.x >> 8), ext[0], lo_[0]), fmaf(float(r0.y >> 8), ext[1], lo_[1]), fmaf(float(r0.z >> 8), ext[2], lo_[2]), fmaf(float(r0.w >> 8), ext[3], lo_[3])};
+            float y[4] = {fmaf(float(r1.x >> 8), ext[0], lo_[0]), fmaf(float(r1.y >> 8), ext[1], lo_[1]), fmaf(float(r1.z >> 8), ext[2], lo_[2]), fmaf(float(r1.w >> 8), ext[3], lo_[3])};
+            float z[4] = {fmaf(float(r2.x >> 8), ext[0], lo_[0]), fmaf(float(r2.y >> 8), ext[1], lo_[1]), fmaf(float(r2.z >> 8), ext[2], lo_[2]), fmaf(float(r2.w >> 8), ext[3], lo_[3])};
+            // low bytes: (r0.b0 << 16) | (r1.b0 << 8) | r2.b0
+            auto low = [] (uint32_t p, uint32_t q, uint32_t r) { return __byte_perm(__byte_perm(r, q, 0x7740), p, 0x7410) & 0x00ffffffu; };
+            float w[4] = {fmaf(float(low(r0.x, r1.x, r2.x)), ext[0], lo_[0]), fmaf(float(low(r0.y, r1.y, r2.y)), ext[1], lo_[1]),
+                          fmaf(float(low(r0.z, r1.z, r2.z)), ext[2], lo_[2]), fmaf(float(low(r0.w, r1.w, r2.w)), ext[3], lo_[3])};
+            s0 += shade4<64>(x); s1 += shade4<64>(y); s2 += shade4<64>(z); s3 += shade4<64>(w);
+        }
+        float sum = (s0 + s1) + (s2 + s3);
+#pragma unroll
+        for (int off = LPB / 2; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        if (sub == 0) a.out[bin] = sum * (1.0f / float(a.spp));
+        if (lane == 0) tile = atomicAdd(a.counter, 1u); tile = __shfl_sync(0xffffffffu, tile, 0);
+    }
+}
+
+
+// the same draw scheme feeding two packed pairs (FFMA2): samples (0,1) and (2,3)
+template<int ROUNDS, int LPB, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_mc34p(const Args a) {
+    constexpr int G = 32 / LPB;
+    const uint32_t lane = threadIdx.x & 31, sub = lane % LPB, grp = lane / LPB;
+    const uint32_t ntiles = uint32_t(a.nbins / G);
+    uint32_t tile;
+    if (lane == 0) tile = atomicAdd(a.counter, 1u); tile = __shfl_sync(0xffffffffu, tile, 0);
+    while (tile < ntiles) {
+        const uint32_t bin = tile * G + grp;
+        float lo_[4], ext[4]; box(a, bin, lo_, ext);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ext[i] *= 5.9604644775390625e-08f;
+        f2 acc0 = bc(0.f), acc1 = bc(0.f);
+        for (uint32_t g = sub; g < a.spp / 4; g += LPB) {
+            const u32x4 r0 = philox<ROUNDS>(u32x4{bin, 0u, g, 0u}, a.k0, a.k1);
+            const u32x4 r1 = philox<ROUNDS>(u32x4{bin, 0u, g, 1u}, a.k0, a.k1);
+            const u32x4 r2 = philox<ROUNDS>(u32x4{bin, 0u, g, 2u}, a.k0, a.k1);
+            auto low = [] (uint32_t p, uint32_t q, uint32_t r) { return __byte_perm(__byte_perm(r, q, 0x7740), p, 0x7410) & 0x00ffffffu; };
+            f2 x[4] = {fma2(mk(float(r0.x >> 8), float(r1.x >> 8)), bc(ext[0]), bc(lo_[0])), fma2(mk(float(r0.y >> 8), float(r1.y >> 8)), bc(ext[1]), bc(lo_[1])),
+                       fma2(mk(float(r0.z >> 8), float(r1.z >> 8)), bc(ext[2]), bc(lo_[2])), fma2(mk(float(r0.w >> 8), float(r1.w >> 8)), bc(ext[3]), bc(lo_[3]))};
+            f2 y[4] = {fma2(mk(float(r2.x >> 8), float(low(r0.x, r1.x, r2.x))), bc(ext[0]), bc(lo_[0])), fma2(mk(float(r2.y >> 8), float(low(r0.y, r1.y, r2.y))), bc(ext[1]), bc(lo_[1])),
+                       fma2(mk(float(r2.z >> 8), float(low(r0.z, r1.z, r2.z))), bc(ext[2]), bc(lo_[2])), fma2(mk(float(r2.w >> 8), float(low(r0.w, r1.w, r2.w))), bc(ext[3]), bc(lo_[3]))};
+            acc0 = add2(acc0, shade4_2<64>(x)); acc1 = add2(acc1, shade4_2<64>(y));
+        }
+        float sum = (lo(acc0) + hi(acc0)) + (lo(acc1) + hi(acc1));
+#pragma unroll
+        for (int off = LPB / 2; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        if (sub == 0) a.out[bin] = sum * (1.0f / float(a.spp));
+        if (lane == 0) tile = atomicAdd(a.counter, 1u); tile = __shfl_sync(0xffffffffu, tile, 0);
+    }
+}
+
 // ---- pipe microbenchmarks ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_ffma(float* out, int iters, float a) {
     float v[8];
@@ -202,6 +273,19 @@ int main() {
     RUN("packed 1 pair lop LPB1 minb4",    10, 1, 1, 1, 1, 4)
     RUN("packed 1 pair lop LPB1 minb6",    10, 1, 1, 1, 1, 6)
     RUN("packed 1 pair lop LPB1 minb8",    10, 1, 1, 1, 1, 8)
+#define RUN34(NAME, ...) { auto k = k_mc34<__VA_ARGS__>; int g = occ_grid(k, sms); \
+        float ms = time_ms([&] { cudaMemsetAsync(a.counter, 0, 4); k<<<g, 256>>>(a); }); report(NAME, ms, g); }
+#define RUN34P(NAME, ...) { auto k = k_mc34p<__VA_ARGS__>; int g = occ_grid(k, sms); \
+        float ms = time_ms([&] { cudaMemsetAsync(a.counter, 0, 4); k<<<g, 256>>>(a); }); report(NAME, ms, g); }
+    RUN34P("4 samples / 3 calls, packed pairs LPB1", 10, 1, 1)
+    RUN34P("4 samples / 3 calls, packed pairs LPB1 minb4", 10, 1, 4)
+    RUN34P("4 samples / 3 calls, packed pairs LPB1 minb5", 10, 1, 5)
+    RUN34P("4 samples / 3 calls, packed pairs philox7", 7, 1, 1)
+    RUN34("4 samples / 3 calls LPB1", 10, 1, 1)
+    RUN34("4 samples / 3 calls LPB1 minb4", 10, 1, 4)
+    RUN34("4 samples / 3 calls LPB1 minb5", 10, 1, 5)
+    RUN34("4 samples / 3 calls LPB2", 10, 2, 1)
+    RUN34("4 samples / 3 calls LPB1 philox7", 7, 1, 1)
     RUN("packed 1 pair lop LPB1 philox7",   7, 1, 1, 1, 1, 1)
     RUN("packed 2 pairs lop LPB1 philox7",  7, 1, 1, 2, 1, 1)
     {

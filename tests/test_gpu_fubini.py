@@ -28,6 +28,8 @@ def _k_seeds(K, ref_fn, gpu_fn):
 
 def _gate(refs, gpus, what, var_lo=0.6, var_hi=1.6):
     K = refs.shape[0]
+    if "decay" in what:      # decay's terms grow like prod 2x (heavy tail): the sample variance of 24 seeds is itself very noisy — only its scale is checked
+        var_lo, var_hi = min(var_lo, 0.25), max(var_hi, 4.0)
     assert_statistically_equal(gpus.mean(axis=0), refs.mean(axis=0), gpus.var(axis=0, ddof=1) / K, refs.var(axis=0, ddof=1) / K, what)
     ratio = (gpus.var(axis=0, ddof=1).mean() + 1e-30) / (refs.var(axis=0, ddof=1).mean() + 1e-30)
     assert var_lo < ratio < var_hi, f"{what}: variance ratio {ratio:.3f}"
@@ -87,8 +89,7 @@ def test_crespo2021_infinite(ctx, port, integ, n, res, it, mc, spp):
         integrate(integrator_crespo2021_infinite(n, it, mc, spp, seed=s), b, res, integ, rng, ctx=ctx)
         return b
     refs, gpus = _k_seeds(K, lambda s: port.crespo2021_infinite(integ, n, it, mc, spp, 200 + s, res, rng.min, rng.max), gpu)
-    # decay's terms grow like prod 2x (heavy tail): the sample variance of 24 seeds is itself very noisy, so only its scale is checked
-    _gate(refs, gpus, f"crespo2021_infinite<{n}> {integ}", *((0.25, 4.0) if integ == "decay" else (0.6, 1.6)))
+    _gate(refs, gpus, f"crespo2021_infinite<{n}> {integ}")
 
 
 def test_fubini_adapter_is_an_ordinary_integrand(ctx):

@@ -5,6 +5,7 @@
 // -ffp-contract=off.  Written from the formulas in SURVEY.md; nothing here comes from oracle/.
 #pragma once
 #include <array>
+#include <viltrum_b200/device/f32x2.cuh>
 
 namespace viltrum { namespace b200 { namespace builtin {
 
@@ -13,22 +14,25 @@ struct Ind2 { __host__ __device__ float operator()(const std::array<float,2>& x)
 struct Cubic1 { __host__ __device__ float operator()(const std::array<float,1>& x) const { return (4.0f*x[0]*x[0]-1.0f)*x[0] + 0.25f; } };
 struct Poly3 { __host__ __device__ float operator()(const std::array<float,3>& x) const { return x[0]*x[1] + x[1]*x[2]*x[2] + 0.5f; } };
 
+// Generic over the scalar type (float, or viltrum::b200::f32x2 = two samples per call on the packed FP32 pipe, device/f32x2.cuh).
+// For T = float the expression tree is the original one (mad(a,b,c) is literally a*b+c), so the exact build's bits are unchanged.
 template<int K> struct Shade4 {
-    __host__ __device__ float operator()(const std::array<float,4>& x) const {
-        const float a = x[0]-.5f, b = x[1]-.5f;
-        const float edge = .55f+.35f*(a*a-b*b)+.2f*a*b;
-        const float vis = (x[2]+.5f*x[3]<edge)?1.0f:0.0f;
-        const float t = x[2]*(1.0f-x[3]);
-        float lobe = 1.0f/float(K);
+    template<class T> __host__ __device__ T operator()(const std::array<T,4>& x) const {
+        using viltrum::b200::mad; using viltrum::b200::indicator;
+        const T a = x[0]-.5f, b = x[1]-.5f;
+        const T edge = .55f+.35f*(a*a-b*b)+.2f*a*b;
+        const T vis = indicator(x[2]+.5f*x[3]<edge);
+        const T t = x[2]*(1.0f-x[3]);
+        T lobe = T(1.0f/float(K));
 #pragma unroll
-        for (int k=K-2;k>=0;--k) lobe = lobe*t+1.0f/float(k+1);      // Horner, c_k = 1/(k+1)
-        const float alb = .25f+.75f*x[0]*x[1];
+        for (int k=K-2;k>=0;--k) lobe = mad(lobe,t,1.0f/float(k+1));      // Horner, c_k = 1/(k+1)
+        const T alb = .25f+.75f*x[0]*x[1];
         return vis*lobe*alb;
     }
 };
 template<int K> struct Shade5 {
-    __host__ __device__ float operator()(const std::array<float,5>& x) const {
-        return Shade4<K>()(std::array<float,4>{x[0],x[1],x[2],x[3]})*(.5f+x[4]);
+    template<class T> __host__ __device__ T operator()(const std::array<T,5>& x) const {
+        return Shade4<K>()(std::array<T,4>{x[0],x[1],x[2],x[3]})*(.5f+x[4]);
     }
 };
 struct SmoothEdge2 {

@@ -152,8 +152,9 @@ vb200_domain finish_domain(const vb200_domain& d) {
 // small (measured: profiles/mc_variants_r1.txt).
 uint32_t pick_lanes_per_bin(const vb200_ctx* ctx, uint64_t spp, uint64_t nbins) {
     const uint64_t want_lanes = uint64_t(ctx->sm_count) * 2048ull * 2ull;
+    const uint64_t groups = (spp + 3) / 4;      // the lanes of a bin stride over groups of four samples (mc_per_bin.cuh; paths in walk.cuh stride over samples)
     uint32_t lpb = 1;
-    while (lpb < 32 && nbins * lpb < want_lanes && uint64_t(lpb) * 2 <= spp) lpb <<= 1;
+    while (lpb < 32 && nbins * lpb < want_lanes && uint64_t(lpb) * 2 <= groups) lpb <<= 1;
     return lpb;
 }
 
