@@ -12,7 +12,9 @@ no data-path collective — SURVEY.md §8e).
 
 Prints ONE JSON line (rank 0).  `value` = device-resident throughput (bins stay in HBM), `e2e` = the same call with
 HOST bins through the C ABI (device->host copy of the 4 MiB bin slab and the host-side '+=' inside the timed region).
-`roofline` is the FP32 (non-tensor) issue roofline SURVEY.md §8(d) names for this kernel; `cpu_baseline` is the
+`roofline` is the FP32 (non-tensor) roofline SURVEY.md §8(d) names for this kernel (bound "fp32": this path has no tensor-core work
+and moves 4 B per 64 evaluations, so neither of the contract's "hbm"/"tensor" bounds describes it; the achieved HBM GB/s is reported
+beside it); `cpu_baseline` is the
 reference's CPU path timed on this box's host cores (rank 0, N=1, bounded sample).
 """
 import argparse
@@ -36,8 +38,8 @@ WORKLOADS = {
 }
 METRIC = "integrand evals/sec (per-bin MC, 1024x1024 bins x 64 spp, shade4<64>)"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the ncu --set full capture summarised in
-# profiles/ncu_c2_mc_per_bin_r1.txt / profiles/ncu_c5_walk_r1.txt (algorithmic bytes: 4 B per bin)
-NCU_TRAFFIC_BYTES = {"c2": 4213504, "c5": 16792576}
+# profiles/ncu_c2_mc_per_bin_r1b.txt / profiles/ncu_c5_walk_r1.txt (algorithmic bytes: 4 B per bin)
+NCU_TRAFFIC_BYTES = {"c2": 4220672, "c5": 16792576}
 
 
 def dist_env():
@@ -244,10 +246,10 @@ def main():
             cb = {"error": str(ex)}
     line = {"metric": metric, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "integrand": integ, "bins_per_gpu": res, "spp": spp, "rng": "Philox4x32-10", "parallelism": f"bin-grid slabs x{world}",
+            "config": {"workload": desc, "integrand": integ, "bins_per_gpu": res, "spp": spp, "rng": "Philox4x32-10 (3 calls per group of 4 samples x 4 dimensions: every generated bit is used)", "parallelism": f"bin-grid slabs x{world}",
                        "l2": "flushed between timed steps (256 MiB memset, untimed); per-step CUDA events on the library stream"},
             "e2e": {"value": e2e, "unit": "evals/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(np.dtype(np.uint8).itemsize * 128),
-                    "d2h_bytes_per_step": nb_local * 4, "note": "host bins through vb200_mc_per_bin: kernel + D2H of the bin slab + host '+='; inputs are ~128 B of parameters"},
+                    "d2h_bytes_per_step": nb_local * 4, "note": "host bins through vb200_mc_per_bin: one launch storing into pinned device-mapped memory with per-chunk completion flags + pooled host '+=' into the caller's bins; inputs are ~128 B of parameters"},
             "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cb, "clocks": clocks}
     print(json.dumps(line))
     return 0

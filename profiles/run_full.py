@@ -39,3 +39,30 @@ elif which == "c4":
         print(f"C4 rep{rep}: generation {it} iterations {t1-t0:.3f} s ({(t1-t0)/it*1e6:.2f} us/iter); CV+residual {w}x{w}x{spp}spp {t2-t1:.3f} s = {ev/(t2-t1)/1e6:.1f} M evals/s; "
               f"total {ev/(t2-t0)/1e6:.1f} M evals/s; regions/bin {float(nreg.float().mean()):.1f} pairs {float(nreg.double().sum()):.3e}; mean {float(bins.mean()):.5f}", flush=True)
         regs.free()
+elif which == "tol":
+    # integrator_adaptive_tolerance on the C3 integrand: every failing region of a round is split at once, leaves sorted into DFS order
+    tol = float(sys.argv[2]) if len(sys.argv) > 2 else 1e-10
+    w = int(sys.argv[3]) if len(sys.argv) > 3 else 512
+    rng = Range([0, 0], [1, 1])
+    for rep in range(2):
+        t0 = tic()
+        regs = ctx.regions_generate_tolerance("smooth_edge2", rng, "boole_simpson", "default", "absolute", tol, 1e-5, exact=True)
+        t1 = tic()
+        bins = torch.zeros(w * w, dtype=torch.float32, device="cuda")
+        regs.integrate_bins(bins, [w, w], rng)
+        t2 = tic()
+        print(f"TOL rep{rep}: tolerance {tol:g}: {len(regs)} leaves in {t1-t0:.4f} s ({len(regs)/(t1-t0)/1e6:.2f} M leaves/s), region->bin ({w}x{w}) {t2-t1:.4f} s, mean {float(bins.mean()):.6f}", flush=True)
+        regs.free()
+elif which == "fub":
+    # integrator_crespo2021_infinite<2> on the C5 integrand (random walk): region table over the first two dimensions from a noisy g
+    from viltrum_b200 import integrate, integrator_crespo2021_infinite, RangeInfinite
+    it = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
+    w = int(sys.argv[3]) if len(sys.argv) > 3 else 512
+    mc = int(sys.argv[4]) if len(sys.argv) > 4 else 16
+    spp = int(sys.argv[5]) if len(sys.argv) > 5 else 64
+    for rep in range(2):
+        bins = torch.zeros(w * w, dtype=torch.float32, device="cuda")
+        t0 = tic()
+        integrate(integrator_crespo2021_infinite(2, it, mc, spp, seed=rep, batch=batch), bins, [w, w], "walk", RangeInfinite(), ctx=ctx)
+        t1 = tic()
+        print(f"FUB rep{rep}: crespo2021_infinite<2>({it},{mc},{spp}) {w}x{w} bins, batch={batch}: {t1-t0:.4f} s = {w*w*spp/(t1-t0)/1e6:.1f} M residual paths/s, mean {float(bins.mean()):.5f}", flush=True)
