@@ -29,7 +29,8 @@ void HostPass::run(bool poll_stream, cudaStream_t stream, cudaError_t* stream_er
         uint64_t spins = 0;
         while (flags[c] != epoch) {
             if (abort.load(std::memory_order_relaxed)) return;
-            if (poll_stream && (++spins & 0x3fffu) == 0) {       // the kernel may have died: do not spin forever
+            if ((++spins & 0x3ffu) == 0) std::this_thread::yield();      // be polite if the cores are oversubscribed
+            if (poll_stream && (spins & 0x3fffu) == 0) {       // the kernel may have died: do not spin forever
                 const cudaError_t q = cudaStreamQuery(stream);
                 if (q != cudaErrorNotReady && flags[c] != epoch) { *stream_error = (q == cudaSuccess) ? cudaErrorUnknown : q; abort.store(1); return; }
             }
@@ -348,9 +349,12 @@ static int run_sampler(vb200_ctx* ctx, const vb200_integrand* f, int kind, Launc
     // helpers: VB200_HOST_THREADS (total threads incl. the caller's), default 8 or the machine's hardware threads if fewer
     // (measured on the pool's 16-vCPU host, C2: 1 thread 0.67 ms per call, 2: 0.51, 4: 0.42, 8: 0.405; kernel alone 0.343)
     int threads = 8;
-    if (const char* env = std::getenv("VB200_HOST_THREADS")) threads = std::atoi(env);
-    const int hw = int(std::thread::hardware_concurrency());
+    int hw = int(std::thread::hardware_concurrency());
+    // one process per GPU: share the host's cores between the ranks of this node (torchrun exports LOCAL_WORLD_SIZE) — spinning
+    // helpers must never outnumber the cores
+    if (const char* lws = std::getenv("LOCAL_WORLD_SIZE")) { const int n = std::atoi(lws); if (n > 1 && hw > 0) hw = hw / n > 1 ? hw / n : 1; }
     if (hw > 0 && threads > hw) threads = hw;
+    if (const char* env = std::getenv("VB200_HOST_THREADS")) threads = std::atoi(env);
     if (uint64_t(threads) > chunks) threads = int(chunks);
     if (threads < 1) threads = 1;
     if (threads > 1) { ctx->pool.start(threads - 1); ctx->pool.publish(&job); }
