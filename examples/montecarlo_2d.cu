@@ -22,6 +22,16 @@ int main() {
         std::printf("Bin %d: %.5f  %.5f  %.5f  (analytic %.5f)\n", i, sol[i], sol_vec[i], sol_xy[i], analytic);
         if (std::fabs(sol[i]-analytic) > 0.15f || std::fabs(sol_vec[i]-analytic) > 0.006f || std::fabs(sol_xy[i]-analytic) > 0.006f) ++bad;
     }
+    // nested std::vector bins (integrate.h:139-167): a ragged 4 x (<=5) container is squared up to 4 x 5; bin (i,j) of x^2+y^2 over the unit square
+    std::vector<std::vector<float>> grid(4); grid[2].resize(5);
+    viltrum::LoggerNull lognull;
+    viltrum::integrate(viltrum::monte_carlo_per_bin_parallel(4096, 5), grid, X2Y2(), range, lognull);
+    for (std::size_t i = 0; i < 4; ++i) for (std::size_t j = 0; j < 5; ++j) {
+        const double x0 = i/4.0, x1 = (i+1)/4.0, y0 = j/5.0, y1 = (j+1)/5.0;
+        const double want = 20.0*((x1*x1*x1-x0*x0*x0)/3.0*(y1-y0) + (y1*y1*y1-y0*y0*y0)/3.0*(x1-x0));      // nbins x the bin's integral = the mean of f over the bin
+        if (grid[i].size() != 5 || std::fabs(grid[i][j] - want) > 0.02*want + 1e-4) ++bad;
+    }
+    std::printf("nested vector bins: grid[3][4] = %.5f\n", grid[3][4]);
     float single = viltrum::integrate(viltrum::monte_carlo(1u << 20, 3), X2Y2(), range);
     std::printf("single value: %.5f should be close to %.5f\n", single, 2.0f/3.0f);
     if (std::fabs(single - 2.0f/3.0f) > 0.004f) ++bad;

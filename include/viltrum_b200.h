@@ -210,6 +210,10 @@ typedef enum vb200_rule {
     VB200_RULE_TRAPEZOIDAL = 2, VB200_RULE_SIMPSON = 3, VB200_RULE_BOOLE = 5,       /* value = samples per dimension (rules.h) */
     VB200_RULE_SIMPSON_TRAPEZOIDAL = 32, VB200_RULE_BOOLE_SIMPSON = 53              /* nested(high,low) pairs (nested.h:7-34) */
 } vb200_rule;
+/* Steps<Q,N> composite rule (reference src/newton-cotes/rules.h:321-388): n pieces of rule q (q = 2, 3 or 5 samples) per dimension,
+ * (q-1)*n+1 samples per dimension.  Fixed-rule integration only (vb200_regions_generate_single + vb200_regions_integrate_bins). */
+#define VB200_RULE_STEPS(q, n) (0x1000000 | ((q) << 16) | ((n) & 0xffff))
+#define VB200_RULE_IS_STEPS(rule) (((rule) & 0x1000000) != 0)
 typedef enum vb200_heuristic { VB200_HEURISTIC_DEFAULT = 0, VB200_HEURISTIC_SIZE = 1 } vb200_heuristic;   /* error-heuristic.h:10-46 */
 typedef enum vb200_metric { VB200_METRIC_ABSOLUTE = 0, VB200_METRIC_RELATIVE = 1 } vb200_metric;         /* error-metric.h:10-41 */
 

@@ -341,6 +341,9 @@ struct Trapezoidal { static constexpr std::size_t samples = 2; static constexpr 
 struct Simpson { static constexpr std::size_t samples = 3; static constexpr int id = VB200_RULE_SIMPSON; };
 struct Boole { static constexpr std::size_t samples = 5; static constexpr int id = VB200_RULE_BOOLE; };
 static const Trapezoidal trapezoidal{}; static const Simpson simpson{}; static const Boole boole{};
+// steps<N>(rule) — reference rules.h:321-389: N pieces of rule Q per dimension (fixed-rule integration)
+template<typename Q, std::size_t N> struct Steps { static constexpr std::size_t samples = (Q::samples - 1)*N + 1; static constexpr int id = VB200_RULE_STEPS(int(Q::samples), int(N)); };
+template<std::size_t N, typename Q> Steps<Q,N> steps(const Q&) { static_assert(N >= 1 && N <= 65535, "steps<N>: 1 <= N <= 65535"); return Steps<Q,N>(); }
 template<typename H, typename L> struct Nested {
     static constexpr std::size_t samples = H::samples;
     static_assert((std::is_same<H,Simpson>::value && std::is_same<L,Trapezoidal>::value) || (std::is_same<H,Boole>::value && std::is_same<L,Simpson>::value),
@@ -603,6 +606,27 @@ template<typename Integrator, typename T, typename F, typename R, typename Logge
 void integrate(const Integrator& integrator, std::vector<T>& bins, const F& function, const R& range, Logger& logger) {
     auto b = [&bins] (const std::array<std::size_t,1>& i) -> T& { return bins[i[0]]; };
     std::array<std::size_t,1> res{bins.size()};
+    integrate(integrator, b, res, function, range, logger);
+}
+// nested std::vector bins (integrate.h:139-167; like upstream these two exist only with a logger): ragged rows are resized to the longest
+template<typename Integrator, typename T, typename F, typename R, typename Logger>
+void integrate(const Integrator& integrator, std::vector<std::vector<T>>& bins, const F& function, const R& range, Logger& logger) {
+    auto b = [&bins] (const std::array<std::size_t,2>& i) -> T& { return bins[i[0]][i[1]]; };
+    std::size_t max1 = 0;
+    for (const std::vector<T>& v : bins) if (v.size() > max1) max1 = v.size();
+    for (std::vector<T>& v : bins) v.resize(max1);
+    std::array<std::size_t,2> res{bins.size(), max1};
+    integrate(integrator, b, res, function, range, logger);
+}
+template<typename Integrator, typename T, typename F, typename R, typename Logger>
+void integrate(const Integrator& integrator, std::vector<std::vector<std::vector<T>>>& bins, const F& function, const R& range, Logger& logger) {
+    auto b = [&bins] (const std::array<std::size_t,3>& i) -> T& { return bins[i[0]][i[1]][i[2]]; };
+    std::size_t max1 = 0, max2 = 0;
+    for (const auto& v : bins) if (v.size() > max1) max1 = v.size();
+    for (auto& v : bins) v.resize(max1);
+    for (const auto& vv : bins) for (const auto& v : vv) if (v.size() > max2) max2 = v.size();
+    for (auto& vv : bins) for (auto& v : vv) v.resize(max2);
+    std::array<std::size_t,3> res{bins.size(), max1, max2};
     integrate(integrator, b, res, function, range, logger);
 }
 template<typename Integrator, typename T, typename F, typename R>

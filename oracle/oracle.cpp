@@ -28,6 +28,7 @@
 #include <functional>
 #include <memory>
 #include <cstdlib>
+#include <cstdio>
 #include "integrands.h"
 #include "oracle_api.h"
 
@@ -666,6 +667,59 @@ template<typename T> void integrate_regions_sequential(const std::vector<RegionT
     }
 }
 
+// ---- Steps<Q,N> composite rules (rules.h:321-388): (Q-1)*N+1 samples per dimension, N pieces of rule Q ---------------------------
+template<typename T> inline T steps_subrange(int Q, int N, T a, T b, const T* p) {                    // rules.h:359-384
+    std::size_t ia = std::min(std::size_t(a*N), std::size_t(N-1));
+    std::size_t ib = std::min(std::size_t(b*N), std::size_t(N-1));
+    T a_local = T(a*N) - T(ia);
+    T b_local = T(b*N) - T(ib);
+    if (ia == ib) return rule_subrange(Q,a_local,b_local,p+ia*(Q-1))/N;
+    T sol = rule_subrange(Q,a_local,T(1),p+ia*(Q-1))/N;
+    for (std::size_t i = ia+1; i<ib; ++i) sol += rule_apply(Q,p+i*(Q-1))/N;
+    sol += rule_subrange(Q,T(0),b_local,p+ib*(Q-1))/N;
+    return sol;
+}
+// Region::integral_subrange with a Steps rule (region.h:141-169: fold subrange over dim D-1, ..., 0; times the region's volume)
+template<typename T> T region_integral_subrange_steps(const RegionT<T>& r, int Q, int N, int D, const T* a, const T* b) {
+    const int S = (Q-1)*N+1;
+    std::vector<T> v = r.data;
+    std::vector<T> line(S);
+    for (int d=D-1; d>=0; --d) {
+        T na = pos_in_range1(r.rmin[d],r.rmax[d],a[d]), nb = pos_in_range1(r.rmin[d],r.rmax[d],b[d]);
+        uint64_t inner = ipow(S,d);                      // dims below d; d is the last remaining dimension
+        std::vector<T> out(inner);
+        for (uint64_t i=0;i<inner;++i) {
+            for (int e=0;e<S;++e) line[e] = v[i + uint64_t(e)*inner];
+            out[i] = steps_subrange(Q,N,na,nb,line.data());
+        }
+        v.swap(out);
+    }
+    return r.volume*v[0];
+}
+template<typename T> void integrate_steps_region(const RegionT<T>& r, int Q, int N, int D, int db, const uint64_t* res, const T* rmin, const T* rmax, T* bins) {
+    uint64_t factor = nbins_of(db,res);
+    uint64_t st[8], en[8]; pixels_in_region(r,db,res,rmin,rmax,st,en);
+    uint64_t pos[8]; for (int i=0;i<db;++i) pos[i]=st[i];
+    while (true) {
+        T ba[8], bb[8], ia[8], ib[8];
+        bin_box_t(D,db,rmin,rmax,res,pos,ba,bb);
+        if (intersect(D,ba,bb,r.rmin.data(),r.rmax.data(),ia,ib)) {
+            uint64_t lin=0, prod=1; for (int i=0;i<db;++i) { lin+=pos[i]*prod; prod*=res[i]; }
+            bins[lin] = T(double(bins[lin]) + double(factor)*double(region_integral_subrange_steps(r,Q,N,D,ia,ib)));   // regions-integrator-sequential.h:54
+        }
+        int d=0; for (; d<db; ++d) { if (++pos[d] >= en[d]) pos[d]=st[d]; else break; }
+        if (d==db) break;
+    }
+}
+// "steps<N>_<rule>" -> (Q, N)
+inline bool parse_steps(const char* rule, int* Q, int* N) {
+    int n = 0; char base[32] = {0};
+    if (std::sscanf(rule,"steps%d_%31s",&n,base) != 2 || n < 1) return false;
+    int q = !std::strcmp(base,"trapezoidal") ? 2 : !std::strcmp(base,"simpson") ? 3 : !std::strcmp(base,"boole") ? 5 : 0;
+    if (!q) return false;
+    *Q = q; *N = n; return true;
+}
+
 template<typename T> void export_regions(const std::vector<RegionT<T>>& regions, int D,
                     T* reg_min, T* reg_max, T* reg_err, uint32_t* reg_dim, T* reg_data) {
     uint64_t n = 0;
@@ -686,6 +740,12 @@ extern "C" int vo_newton_cotes(const char* integrand, const char* rule, int dimb
                     const float* rmin, const float* rmax, float* bins) {
     auto F = find_finite(integrand); if (!F) return -1;
     int D = F->dim; if (dimbins<1 || dimbins>D) return -2;
+    int SQ, SN;
+    if (parse_steps(rule,&SQ,&SN)) {                                           // integrator_newton_cotes(steps<N>(rule)), rules.h:321-388
+        RegionT<float> r = make_region<float>(F->fn,(SQ-1)*SN+1,D,rmin,rmax);
+        integrate_steps_region<float>(r,SQ,SN,D,dimbins,res,rmin,rmax,bins);
+        return 0;
+    }
     int S = !std::strcmp(rule,"trapezoidal") ? 2 : !std::strcmp(rule,"simpson") ? 3 : !std::strcmp(rule,"boole") ? 5 : 0;
     if (!S) return -2;
     std::vector<RegionT<float>> regions; regions.push_back(make_region<float>(F->fn,S,D,rmin,rmax));

@@ -16,6 +16,13 @@ extern "C" int vo_newton_cotes(const char* integrand, const char* rule, int dimb
         if (!std::strcmp(rule,"trapezoidal")) viltrum::integrate(viltrum::integrator_newton_cotes(viltrum::trapezoidal), acc, r, f, range);
         else if (!std::strcmp(rule,"simpson")) viltrum::integrate(viltrum::integrator_newton_cotes(viltrum::simpson), acc, r, f, range);
         else if (!std::strcmp(rule,"boole"))   viltrum::integrate(viltrum::integrator_newton_cotes(viltrum::boole), acc, r, f, range);
+        // composite rules steps<N>(rule) (rules.h:321-388): a fixed menu of instantiations (N is a template argument upstream)
+        else if (!std::strcmp(rule,"steps2_boole"))        viltrum::integrate(viltrum::integrator_newton_cotes(viltrum::steps<2>(viltrum::boole)), acc, r, f, range);
+        else if (!std::strcmp(rule,"steps3_simpson"))      viltrum::integrate(viltrum::integrator_newton_cotes(viltrum::steps<3>(viltrum::simpson)), acc, r, f, range);
+        else if (!std::strcmp(rule,"steps4_trapezoidal"))  viltrum::integrate(viltrum::integrator_newton_cotes(viltrum::steps<4>(viltrum::trapezoidal)), acc, r, f, range);
+        else if (!std::strcmp(rule,"steps8_simpson"))      { if constexpr (D <= 3) viltrum::integrate(viltrum::integrator_newton_cotes(viltrum::steps<8>(viltrum::simpson)), acc, r, f, range); else return -2; }
+        else if (!std::strcmp(rule,"steps16_trapezoidal")) { if constexpr (D <= 3) viltrum::integrate(viltrum::integrator_newton_cotes(viltrum::steps<16>(viltrum::trapezoidal)), acc, r, f, range); else return -2; }
+        else if (!std::strcmp(rule,"steps1_boole"))        viltrum::integrate(viltrum::integrator_newton_cotes(viltrum::steps<1>(viltrum::boole)), acc, r, f, range);
         else return -2;
         return 0;
     });

@@ -81,6 +81,14 @@ def main():
                           bins=bits(b), sum=bits(s1), sum2=bits(s2), lens=bits(lens), elems=bits(elems)))
             V.append(dict(integrand=integ, res=res, rmin=rmin, rmax=rmax, path="monte_carlo_inf", samples_n=300, seed=7,
                           bins=bits(R.monte_carlo_inf(integ, res, 300, 7, rmin, rmax))))
+    # Steps<Q,N> composite rules: integrator_newton_cotes(steps<N>(rule))
+    for integ, res, lo, hi in (("x2y2", [5], 0.0, 1.0), ("x2y2", [4, 3], 0.05, 1.1), ("smooth_edge2", [8, 8], 0.0, 1.0), ("cubic1", [7], -0.5, 1.25),
+                               ("poly3", [3, 2], 0.1, 0.9), ("ind2", [6, 5], 0.0, 1.0), ("shade4_16", [3, 4], 0.0, 1.0)):
+        d = R.dim(integ)
+        for rule in ("steps2_boole", "steps3_simpson", "steps4_trapezoidal", "steps16_trapezoidal"):
+            if d >= 4 and rule == "steps16_trapezoidal":
+                continue
+            V.append(dict(integrand=integ, res=res, rmin=[lo] * d, rmax=[hi] * d, path="newton_cotes", rule=rule, bins=bits(R.newton_cotes(integ, rule, res, [lo] * d, [hi] * d))))
     # cv_fixed_weight: bins + the recorded region choices / sample points for the replay mode
     for integ, res, it, spp, alpha in (("x2y2", [5], 12, 6, 1.0), ("smooth_edge2", [6, 6], 30, 4, 0.5), ("shade4_16", [3, 3], 8, 4, 0.0), ("poly3", [3, 2], 12, 4, 0.75)):
         d = R.dim(integ)

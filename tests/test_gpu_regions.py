@@ -236,3 +236,43 @@ def test_region_major_tile_lists_keep_table_order(ctx, port, integ, res, rule, i
     if want is not None:
         assert_same_bits(major, want, "== oracle")
     regs.free()
+
+
+@pytest.mark.parametrize("integ,res,lo,hi", [("x2y2", [5], 0.0, 1.0), ("x2y2", [40, 30], 0.05, 1.1), ("smooth_edge2", [64, 64], 0.0, 1.0), ("cubic1", [300], -0.5, 1.25),
+                                             ("poly3", [9, 7], 0.1, 0.9), ("shade4_16", [12, 10], 0.0, 1.0), ("ind2", [1], 0.0, 1.0), ("ind2", [33, 17], 0.0, 1.0)])
+@pytest.mark.parametrize("rule", ["steps1_boole", "steps2_boole", "steps3_simpson", "steps4_trapezoidal", "steps7_boole", "steps20_simpson", "steps64_trapezoidal"])
+def test_steps_composite_rules(ctx, port, integ, res, lo, hi, rule):
+    """integrator_newton_cotes(steps<N>(rule)) (rules.h:321-388): bit-exact against the oracle (any N: the port takes N at run time)"""
+    from viltrum_b200 import integrate, integrator_newton_cotes
+    d = DIMS[integ]
+    n = int(rule[5:].split("_")[0]); q = {"trapezoidal": 2, "simpson": 3, "boole": 5}[rule.split("_")[1]]
+    if ((q - 1) * n + 1) ** d > 1 << 22:
+        pytest.skip("more samples than a composite-rule table holds")
+    init = np.linspace(-0.5, 0.5, int(np.prod(res))).astype(np.float32)
+    want = port.newton_cotes(integ, rule, res, [lo] * d, [hi] * d, bins=init)
+    got = init.copy()
+    integrate(integrator_newton_cotes(rule), got, res, integ, _rng(integ, lo, hi), ctx=ctx)
+    assert_same_bits(got, want, f"{integ} {rule}")
+    # sharded
+    nb = len(init)
+    if nb >= 4:
+        parts = init.copy()
+        integrate(integrator_newton_cotes(rule), parts, res, integ, _rng(integ, lo, hi), ctx=ctx, shard=(0, nb // 3))
+        integrate(integrator_newton_cotes(rule), parts, res, integ, _rng(integ, lo, hi), ctx=ctx, shard=(nb // 3, nb))
+        assert_same_bits(parts, want, "sharded")
+
+
+def test_steps_golden_reference_vectors_and_survey_kat(ctx):
+    from viltrum_b200 import integrate, integrator_newton_cotes, steps, Range
+    n = 0
+    for v in load_golden():
+        if v["path"] != "newton_cotes" or not v["rule"].startswith("steps"):
+            continue
+        got = np.zeros(int(np.prod(v["res"])), np.float32)
+        integrate(integrator_newton_cotes(v["rule"]), got, v["res"], v["integrand"], Range(v["rmin"], v["rmax"]), ctx=ctx)
+        assert_same_bits(got, f32(v["bins"]), f"{v['integrand']} {v['rule']} vs the unmodified reference"); n += 1
+    assert n == 27
+    # SURVEY.md §8(c): steps<2>(boole) on x^2+y^2, 5 bins
+    got = np.zeros(5, np.float32)
+    integrate(integrator_newton_cotes(steps(2, "boole")), got, [5], "x2y2", Range([0, 0], [1, 1]), ctx=ctx)
+    assert_same_bits(got, np.array([0.346666217, 0.42666626, 0.586666465, 0.826666653, 1.14666629], np.float32), "SURVEY KAT")

@@ -130,3 +130,14 @@ def test_cv_fixed_weight(port, reference, integ, res, it, spp, alpha):
     assert_same_bits(a[0], b[0], "bins")
     for k in ("nregions", "chosen", "samples"):
         assert_same_bits(a[1][k], b[1][k], k)
+
+
+@pytest.mark.parametrize("integ,res", FINITE)
+def test_steps_composite_rules(port, reference, integ, res):
+    """integrator_newton_cotes(steps<N>(rule)) — rules.h:321-388"""
+    rmin, rmax = _range(port, integ)
+    d = port.dim(integ)
+    for rule in ("steps1_boole", "steps2_boole", "steps3_simpson", "steps4_trapezoidal", "steps8_simpson", "steps16_trapezoidal"):
+        if d >= 4 and rule in ("steps8_simpson", "steps16_trapezoidal"):
+            continue
+        assert_same_bits(port.newton_cotes(integ, rule, res, rmin, rmax), reference.newton_cotes(integ, rule, res, rmin, rmax), rule)

@@ -13,6 +13,16 @@ MC_PER_BIN, PER_BIN_MC = 0, 1
 CV_OPTIMIZE_WEIGHT, CV_FIXED_WEIGHT = 0, 1
 RULES = {"trapezoidal": 2, "simpson": 3, "boole": 5, "simpson_trapezoidal": 32, "boole_simpson": 53}
 RULE_SAMPLES = {2: 2, 3: 3, 5: 5, 32: 3, 53: 5}
+
+
+def rule_id(name):
+    """'simpson', 'boole_simpson', ... or 'steps<N>_<rule>' (Steps<Q,N>, reference src/newton-cotes/rules.h:321-388) -> vb200_rule code"""
+    if isinstance(name, int):
+        return name
+    if name.startswith("steps"):
+        n, base = name[5:].split("_", 1)
+        return 0x1000000 | (RULES[base] << 16) | (int(n) & 0xffff)
+    return RULES[name]
 HEURISTICS = {"default": 0, "size": 1}
 METRICS = {"absolute": 0, "relative": 1}
 

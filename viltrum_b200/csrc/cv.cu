@@ -253,6 +253,7 @@ int cv_run(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r, con
            float* bins, int bins_mem, uint32_t* nregions, float* approx_out) {
     VB200_CUDA(ctx, cudaSetDevice(ctx->device));
     if (f->dim <= 0 || f->dim != r->dim) return fail(ctx, VB200_ERR_INVALID, "integrand takes %d dimensions, regions have %d", f->dim, r->dim);
+    if (VB200_RULE_IS_STEPS(r->rule)) return fail(ctx, VB200_ERR_UNSUPPORTED, "control variates over a composite (steps) rule table are not supported");
     if (r->f64 || (f->flags & VB200_INTEGRAND_F64)) return fail(ctx, VB200_ERR_UNSUPPORTED, "control variates are computed in fp32: double region tables / integrands are not supported");
     int rc = check_domain(ctx, p->domain, r->dim); if (rc) return rc;
     if (p->spp > 0xffffffffull) return fail(ctx, VB200_ERR_INVALID, "spp invalid");

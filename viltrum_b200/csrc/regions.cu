@@ -15,6 +15,11 @@ namespace R = viltrum::b200::device::rules;
 namespace vb200 {
 
 int rule_samples(int rule, int* SH, int* SL) {
+    if (VB200_RULE_IS_STEPS(rule)) {       // Steps<Q,N>: samples = (Q::samples - 1)*N + 1 (rules.h:326)
+        const int q = (rule >> 16) & 0xff, n = rule & 0xffff;
+        if ((q != 2 && q != 3 && q != 5) || n < 1) return -1;
+        *SH = (q - 1) * n + 1; *SL = 0; return 0;
+    }
     switch (rule) {
         case VB200_RULE_TRAPEZOIDAL: *SH = 2; *SL = 0; return 0;
         case VB200_RULE_SIMPSON: *SH = 3; *SL = 0; return 0;
@@ -29,8 +34,8 @@ int regions_alloc(vb200_ctx* ctx, int dim, int rule, uint64_t capacity, vb200_re
     int SH, SL;
     if (rule_samples(rule, &SH, &SL)) return fail(ctx, VB200_ERR_INVALID, "unknown rule %d", rule);
     if (dim < 1 || dim > VB200_MAX_DIM) return fail(ctx, VB200_ERR_INVALID, "region dimension %d outside 1..%d", dim, VB200_MAX_DIM);
-    uint64_t sd = 1; for (int i = 0; i < dim; ++i) sd *= uint64_t(SH);
-    if (sd > 15625) return fail(ctx, VB200_ERR_UNSUPPORTED, "%llu samples per region: beyond the reference's own limit (VILTRUM_MAX_DIMENSIONS_REGION, region.h:16-18)", (unsigned long long)sd);
+    uint64_t sd = 1; for (int i = 0; i < dim; ++i) { sd *= uint64_t(SH); if (sd > (1ull << 40)) break; }
+    if (VB200_RULE_IS_STEPS(rule) ? (sd > (1ull << 22) || capacity != 1) : sd > 15625) return fail(ctx, VB200_ERR_UNSUPPORTED, "%llu samples per region: beyond the reference's own limit (VILTRUM_MAX_DIMENSIONS_REGION, region.h:16-18)", (unsigned long long)sd);
     vb200_regions* r = new (std::nothrow) vb200_regions;
     if (!r) return fail(ctx, VB200_ERR_NOMEM, "out of host memory");
     r->ctx = ctx; r->dim = dim; r->rule = rule; r->SH = SH; r->SL = SL; r->sd = int(sd); r->capacity = capacity; r->count = 0; r->f64 = f64;
@@ -610,6 +615,106 @@ extern "C" int vb200_regions_integrate_bins_f64(vb200_ctx* ctx, const vb200_regi
     return rc;
 }
 
+// ---- Steps<Q,N> composite rules: one region over the whole range, one thread per bin ---------------------------------------------
+namespace {
+// Steps::subrange (rules.h:359-384) over a line whose elements are produced on demand (the folds of the dimensions above it)
+template<int Q, class Elem>
+__device__ __forceinline__ float steps_subrange(float a, float b, uint32_t N, Elem&& elem) {
+    const float fN = float(N);
+    const float aN = R::fm(a, fN), bN = R::fm(b, fN);
+    uint32_t ia = uint32_t(aN > 0.0f ? (unsigned long long)aN : 0ull), ib = uint32_t(bN > 0.0f ? (unsigned long long)bN : 0ull);
+    if (ia > N - 1) ia = N - 1;
+    if (ib > N - 1) ib = N - 1;
+    const float a_local = R::fs(aN, float(ia)), b_local = R::fs(bN, float(ib));
+    float l[Q];
+#pragma unroll
+    for (int k = 0; k < Q; ++k) l[k] = elem(ia * uint32_t(Q - 1) + uint32_t(k));
+    if (ia == ib) return R::fd(R::subrange<Q, float>(a_local, b_local, l), fN);
+    float sol = R::fd(R::subrange<Q, float>(a_local, 1.0f, l), fN);
+    for (uint32_t i = ia + 1; i < ib; ++i) {
+#pragma unroll
+        for (int k = 0; k < Q; ++k) l[k] = elem(i * uint32_t(Q - 1) + uint32_t(k));
+        sol = R::fa(sol, R::fd(R::apply<Q, float>(l), fN));
+    }
+#pragma unroll
+    for (int k = 0; k < Q; ++k) l[k] = elem(ib * uint32_t(Q - 1) + uint32_t(k));
+    return R::fa(sol, R::fd(R::subrange<Q, float>(0.0f, b_local, l), fN));
+}
+// Region::sub_last (region.h:141-151): subrange folded over dimension D-1 first ... dimension 0 last; evaluated depth first
+template<int Q, int D, int LEVEL> struct StepsFold {
+    struct Elem {
+        const float* data; uint64_t base, stride; uint32_t S, N; const float* a; const float* b;
+        __device__ __forceinline__ float operator()(uint32_t j) const { return StepsFold<Q, D, LEVEL + 1>::eval(data, base + uint64_t(j) * stride, S, N, a, b); }
+    };
+    // NOT inlined: every level calls the next one from 3*Q sites, so inlining the recursion would multiply the code by (3Q)^D
+    __device__ __noinline__ static float eval(const float* __restrict__ data, uint64_t base, uint32_t S, uint32_t N, const float* a, const float* b) {
+        uint64_t stride = 1;
+#pragma unroll
+        for (int i = 0; i < LEVEL; ++i) stride *= S;
+        return steps_subrange<Q>(a[LEVEL], b[LEVEL], N, Elem{data, base, stride, S, N, a, b});
+    }
+};
+template<int Q, int D> struct StepsFold<Q, D, D> {
+    __device__ __forceinline__ static float eval(const float* __restrict__ data, uint64_t base, uint32_t, uint32_t, const float*, const float*) { return __ldg(data + base); }
+};
+
+template<int Q, int D>
+__global__ void __launch_bounds__(128) steps_integrate_kernel(vb200_domain dom, uint64_t begin, uint64_t end, uint64_t nbins_total, uint32_t S, uint32_t N,
+                                                              const float* __restrict__ rmin, const float* __restrict__ rmax, const float* __restrict__ data, float* __restrict__ out) {
+    const uint64_t bin = begin + uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (bin >= end) return;
+    uint32_t pos[VB200_MAX_DIMBINS]; { uint64_t q = bin; for (int d = 0; d < dom.dimbins; ++d) { pos[d] = uint32_t(q % dom.res[d]); q /= dom.res[d]; } }
+    float a[D], b[D]; float volume = 1.0f; bool empty = false;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        const float lo = rmin[d], hi = rmax[d];                                  // the region = the whole range (capacity 1)
+        volume = R::fm(volume, R::fs(hi, lo));                                     // Range::volume (range.h:21-25)
+        float ba = dom.rmin[d], bb = dom.rmax[d];
+        if (d < dom.dimbins) {
+            // pixels_in_region (region.h:454-463): bins outside [start,end) are never visited
+            const float res = float(dom.res[d]), ext = R::fs(dom.rmax[d], dom.rmin[d]);
+            const float fs_ = R::fd(R::fm(res, R::fs(lo, dom.rmin[d])), ext), fe_ = R::fa(0.99f, R::fd(R::fm(res, R::fs(hi, dom.rmin[d])), ext));
+            uint64_t s = fs_ > 0.0f ? uint64_t(fs_) : 0ull, e = fe_ > 0.0f ? uint64_t(fe_) : 0ull;
+            if (e > dom.res[d]) e = dom.res[d];
+            if (e < s + 1) e = s + 1;
+            if (pos[d] < s || pos[d] >= e) empty = true;
+            ba = R::fa(dom.rmin[d], R::fm(float(pos[d]), dom.drange[d])); bb = R::fa(dom.rmin[d], R::fm(float(pos[d] + 1u), dom.drange[d]));
+        }
+        const float ia = fmaxf(ba, lo), ib = fmaxf(ia, fminf(bb, hi));             // Range::intersection (range.h:92-101)
+        if (ia >= ib) empty = true;
+        a[d] = R::pos_in_range(lo, hi, ia); b[d] = R::pos_in_range(lo, hi, ib);
+    }
+    if (empty) return;
+    const float integral = R::fm(volume, StepsFold<Q, D, 0>::eval(data, 0, S, N, a, b));
+    out[bin] = R::d2f(R::da(double(out[bin]), R::dm(double(nbins_total), double(integral))));      // regions-integrator-sequential.h:54
+}
+
+template<int Q>
+int steps_dispatch(vb200_ctx* ctx, const vb200_regions* r, const vb200_domain& dom, uint64_t begin, uint64_t end, uint64_t total, float* out) {
+    const unsigned grid = unsigned((end - begin + 127) / 128);
+    const uint32_t S = uint32_t(r->SH), N = uint32_t(r->rule & 0xffff);
+    switch (r->dim) {
+        case 1: steps_integrate_kernel<Q, 1><<<grid, 128, 0, ctx->stream>>>(dom, begin, end, total, S, N, r->rmin, r->rmax, r->data, out); break;
+        case 2: steps_integrate_kernel<Q, 2><<<grid, 128, 0, ctx->stream>>>(dom, begin, end, total, S, N, r->rmin, r->rmax, r->data, out); break;
+        case 3: steps_integrate_kernel<Q, 3><<<grid, 128, 0, ctx->stream>>>(dom, begin, end, total, S, N, r->rmin, r->rmax, r->data, out); break;
+        case 4: steps_integrate_kernel<Q, 4><<<grid, 128, 0, ctx->stream>>>(dom, begin, end, total, S, N, r->rmin, r->rmax, r->data, out); break;
+        default: return fail(ctx, VB200_ERR_UNSUPPORTED, "composite (steps) rules are instantiated for 1..4 dimensions");
+    }
+    ctx->launches++;
+    VB200_CUDA(ctx, cudaGetLastError());
+    return VB200_OK;
+}
+int steps_integrate(vb200_ctx* ctx, const vb200_regions* r, const vb200_domain& dom, uint64_t begin, uint64_t end, uint64_t total, float* out) {
+    if (r->count != 1 || r->capacity != 1) return fail(ctx, VB200_ERR_UNSUPPORTED, "composite (steps) rules describe a single region");
+    switch ((r->rule >> 16) & 0xff) {
+        case 2: return steps_dispatch<2>(ctx, r, dom, begin, end, total, out);
+        case 3: return steps_dispatch<3>(ctx, r, dom, begin, end, total, out);
+        case 5: return steps_dispatch<5>(ctx, r, dom, begin, end, total, out);
+    }
+    return fail(ctx, VB200_ERR_INVALID, "bad steps rule %d", r->rule);
+}
+}
+
 extern "C" int vb200_regions_integrate_bins(vb200_ctx* ctx, const vb200_regions* r, const vb200_domain* domain, const vb200_shard* shard,
                                             float* bins, int bins_mem) {
     if (!ctx || !r || !domain || !bins) return fail(ctx, VB200_ERR_INVALID, "NULL argument");
@@ -623,6 +728,12 @@ extern "C" int vb200_regions_integrate_bins(vb200_ctx* ctx, const vb200_regions*
     if (begin == end || r->count == 0) return VB200_OK;
     // '+=' continues from the bins' current contents in the reference's float(double(acc)+...) chain: upload them
     BinStage st; rc = stage_bins_in(ctx, bins, bins_mem, begin, end, /*upload=*/true, &st); if (rc) return rc;
+    if (VB200_RULE_IS_STEPS(r->rule)) {
+        rc = steps_integrate(ctx, r, dom, begin, end, total, st.dev_base);
+        if (!rc) rc = stage_bins_out(ctx, st);
+        if (!rc && !st.staged) { cudaError_t e = cudaStreamSynchronize(ctx->stream); if (e != cudaSuccess) rc = fail(ctx, VB200_ERR_CUDA, "steps integration failed: %s", cudaGetErrorString(e)); }
+        return rc;
+    }
     BinWalk w;
     rc = walk_build(ctx, r, dom, begin, end, &w); if (rc) return rc;
     rc = walk_accumulate(ctx, r, w, dom, begin, end, 0, st.dev_base, nullptr, nullptr);

@@ -203,7 +203,7 @@ class Context:
     def regions_generate_single(self, f, rng, rule, exact=True):
         d = C.make_domain(len(rng.min), [1], rng.min, rng.max)
         h = ctypes.c_void_p()
-        self.check(self._L.vb200_regions_generate_single(self._h, self.integrand(f, exact), ctypes.byref(d), C.RULES[rule], ctypes.byref(h)))
+        self.check(self._L.vb200_regions_generate_single(self._h, self.integrand(f, exact), ctypes.byref(d), C.rule_id(rule), ctypes.byref(h)))
         return Regions(self, h)
 
     # -- double precision (Range<double,DIM>): Newton-Cotes region family -------------------------------------------------
@@ -604,6 +604,11 @@ def monte_carlo_per_bin_parallel(spp, seed=0):
 
 def integrator_per_bin_parallel(inner):
     return IntegratorPerBinParallel(inner)
+
+
+def steps(n, rule):
+    """steps<N>(rule) — reference src/newton-cotes/rules.h:386-389: N pieces of `rule` per dimension (fixed-rule integration only)"""
+    return f"steps{int(n)}_{rule}"
 
 
 def integrator_newton_cotes(rule):
