@@ -25,6 +25,12 @@ int main(int argc, char** argv) {
     viltrum::integrate(viltrum::monte_carlo_per_bin_parallel(spp, 0), a, a.resolution(), Shade4<64>(), viltrum::range_primary<4>());
     viltrum::integrate(viltrum::integrator_per_bin_parallel(viltrum::monte_carlo(spp, 0)), b, b.resolution(), Shade4<64>(), viltrum::range_primary<4>());
     viltrum::integrate(viltrum::monte_carlo_per_bin_parallel(spp, 1), c, c.resolution(), Tinted{2.0f}, viltrum::range_primary<4>());
+    // pinned bins: the kernel accumulates into the tensor's own storage over PCIe (no staging, no host pass); same bits as `a` for the same seed
+    viltrum::tensor<float,2> p({w,w}, 0.0f);
+    viltrum::b200::pin_bins(p);
+    viltrum::integrate(viltrum::monte_carlo_per_bin_parallel(spp, 0), p, p.resolution(), Shade4<64>(), viltrum::range_primary<4>());
+    viltrum::b200::unpin_bins(p);
+    if (p.raw_data() != a.raw_data()) { std::printf("pinned bins differ from staged bins\n"); return 2; }
     double ma = 0, mb = 0, mc = 0;
     for (float v : a.raw_data()) ma += v; for (float v : b.raw_data()) mb += v; for (float v : c.raw_data()) mc += v;
     ma /= a.size(); mb /= b.size(); mc /= c.size();

@@ -67,6 +67,14 @@ int         vb200_sm_count(const vb200_ctx* ctx);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 uint64_t    vb200_launch_count(const vb200_ctx* ctx);
 
+/* Pin and map a caller-owned host buffer (cudaHostRegister, mapped + portable) for the lifetime of the registration.  The sampling
+ * drivers (vb200_mc_per_bin, vb200_mc_per_bin_inf) recognise VB200_HOST bins that lie inside a registered buffer and let the kernel
+ * apply the reference's '+=' / '=' to them directly over PCIe (zero-copy read-modify-write): no staging buffer and no host-side pass,
+ * which is what limits the end-to-end rate when several ranks share one host.  The buffer must stay allocated until
+ * vb200_host_unregister / vb200_destroy.  Unregistered VB200_HOST bins keep working through the staged path. */
+int         vb200_host_register(vb200_ctx* ctx, void* ptr, size_t bytes);
+int         vb200_host_unregister(vb200_ctx* ctx, void* ptr);
+
 /* Measured FP32 (non-tensor) peak of the device: a dependent-FFMA chain kernel (8 independent chains per thread, all SMs fully
  * occupied), timed with CUDA events on the context's stream; best of `reps`.  This is the roofline denominator bench.py reports
  * next to the nominal 2*128*SMs*clock figure (MEASURED_PEAKS.json carries HBM and bf16-tensor peaks only). */

@@ -143,6 +143,14 @@ public:
 // one context per process and device, created on first use (one process per GPU)
 inline int& current_device() { static int d = 0; return d; }
 inline Context& default_context() { static Context c(current_device()); return c; }
+// (addition) pin + map a tensor's storage so that the per-bin samplers write their bins into it directly over PCIe, without the
+// staged copy and the host-side '+=' pass (vb200_host_register).  Unpin before the tensor is destroyed or resized.
+template<typename T, std::size_t DIMBINS> inline void pin_bins(tensor<T,DIMBINS>& t) {
+    auto& ctx = default_context(); ctx.check(vb200_host_register(ctx.get(), t.data(), t.size()*sizeof(T)));
+}
+template<typename T, std::size_t DIMBINS> inline void unpin_bins(tensor<T,DIMBINS>& t) {
+    auto& ctx = default_context(); ctx.check(vb200_host_unregister(ctx.get(), t.data()));
+}
 // bin-grid shard handled by this process ({0,0} = whole grid): multi-GPU runs set it per rank
 inline vb200_shard& current_shard() { static vb200_shard s{0, 0}; return s; }
 

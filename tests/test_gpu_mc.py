@@ -185,3 +185,34 @@ def test_full_size_properties(ctx):
     ctx.mc_per_bin("shade4_64", e, res, rng, spp, 1)
     assert not np.array_equal(a, e) and abs(float(e.mean(dtype=np.float64)) - 0.14326) < 2e-4   # same image, independent noise
     assert float(np.mean(a > 0)) > 0.9
+
+
+def test_registered_host_bins_zero_copy_path(ctx):
+    """vb200_host_register: the kernel applies '+=' / '=' to the caller's pinned bins in place; same bits as the staged path, shards included"""
+    from viltrum_b200 import _capi, Vb200Error
+    res, spp = [96, 80], 37
+    nb = res[0] * res[1]
+    rng = _rng(None, "shade4_16")
+    init = np.linspace(-1, 1, nb).astype(np.float32)
+    for flavor in (_capi.MC_PER_BIN, _capi.PER_BIN_MC):
+        staged = init.copy()
+        ctx.mc_per_bin("shade4_16", staged, res, rng, spp, 5, flavor)
+        pinned = init.copy()
+        ctx.host_register(pinned)
+        try:
+            ctx.mc_per_bin("shade4_16", pinned, res, rng, spp, 5, flavor, shard=(0, 3000))
+            ctx.mc_per_bin("shade4_16", pinned, res, rng, spp, 5, flavor, shard=(3000, nb))
+        finally:
+            ctx.host_unregister(pinned)
+        assert np.array_equal(staged.view(np.uint32), pinned.view(np.uint32))
+    from viltrum_b200 import RangeInfinite
+    a = np.zeros(64, np.float32); b = np.zeros(64, np.float32)
+    ctx.mc_per_bin_inf("walk", a, [8, 8], RangeInfinite(), 32, 3)
+    ctx.host_register(b)
+    ctx.mc_per_bin_inf("walk", b, [8, 8], RangeInfinite(), 32, 3)
+    with pytest.raises(Vb200Error):
+        ctx.host_register(b)            # twice
+    ctx.host_unregister(b)
+    with pytest.raises(Vb200Error):
+        ctx.host_unregister(b)          # not registered any more
+    assert np.array_equal(a, b)

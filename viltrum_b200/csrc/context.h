@@ -9,6 +9,7 @@
 #include <mutex>
 #include <condition_variable>
 #include <vector>
+#include <utility>
 #include "../../include/viltrum_b200.h"
 
 namespace vb200 {
@@ -55,6 +56,8 @@ struct vb200_ctx {
     uint32_t epoch = 0;
     static constexpr int kMaxChunks = 64;
     vb200::HostPool pool;
+    // caller-owned host buffers pinned and mapped by vb200_host_register: (base, bytes)
+    std::vector<std::pair<char*, size_t>> registered;
 };
 
 namespace vb200 {

@@ -123,6 +123,13 @@ class Context:
     def launch_count(self):
         return self._L.vb200_launch_count(self._h)
 
+    def host_register(self, array):
+        """pin + map a numpy array (vb200_host_register): samplers then write their bins into it directly over PCIe, with no host-side pass"""
+        self.check(self._L.vb200_host_register(self._h, array.ctypes.data, array.nbytes))
+
+    def host_unregister(self, array):
+        self.check(self._L.vb200_host_unregister(self._h, array.ctypes.data))
+
     def measure_fp32_peak(self, reps=5):
         """measured dependent-FFMA peak of this GPU in TFLOP/s (vb200_measure_fp32_peak)"""
         out = ctypes.c_double(0.0)
