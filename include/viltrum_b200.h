@@ -347,7 +347,8 @@ typedef struct vb200_mc_launch {
     float*   sum_f;                   /* device or NULL, base of shard */
     float*   sum_f2;
     int32_t  grid_hint;               /* CTAs to launch (0 = let the thunk size it from occupancy) */
-    int32_t  reserved;
+    int32_t  narrow_binned;           /* 1: coordinates of the binned dimensions carry 16 random bits (every binned dimension of the
+                                       * WHOLE grid has >= 256 bins, so the lattice along it still has >= 2^24 points); 0: 24 bits */
     unsigned long long* tile_counter; /* device, zeroed by the driver before the launch: dynamic tile scheduler */
     vb200_chunk_signal signal;
 } vb200_mc_launch;

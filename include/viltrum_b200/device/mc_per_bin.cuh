@@ -81,57 +81,75 @@ __device__ __forceinline__ void signal_tile_done(const vb200_chunk_signal& c, ui
 //     through one global atomic per warp and tile (a.tile_counter), so the tail is one tile long instead of one static share;
 //   * the 32x32->64 multiplies of Philox are the expensive instructions of this kernel — IMAD.WIDE has a reciprocal throughput of
 //     5.1 cycles per warp and SMSP and does not overlap with FFMA (profiles/pipes_r1.txt) — so no generated bit is thrown away:
-//     samples are drawn in GROUPS OF FOUR from THREE Philox calls per block of four dimensions.  Sample j < 3 of a group takes the
-//     top 24 bits of every word of call j, sample 3 is assembled from the three low bytes (two PRMT per coordinate):
-//     24 bits x 4 coordinates x 4 samples = 384 bits = 3 x 128.  Counter = (bin lo, bin hi, group, call + 4*block), key = seed;
-//   * four samples are in flight per lane (independent Philox + integrand chains); functors that are generic over their scalar
-//     type are evaluated as two packed pairs (f32x2.cuh, FFMA2): half the issue slots for the FP32 work;
-//   * the u32 -> [0,1) scaling (2^-24) is folded into the bin extent, so a coordinate costs SHF/PRMT + I2FP + FFMA.
+//     samples are drawn in GROUPS OF EIGHT whose Philox words are cut into 24-bit and (binned dimensions of fine grids) 16-bit
+//     coordinate fields, see GroupDraws.  Counter = (bin lo, bin hi, group, call), key = seed;
+//   * functors that are generic over their scalar type are evaluated as packed pairs (f32x2.cuh, FFMA2): half the issue slots
+//     for the FP32 work; two pairs (or four scalar samples) are in flight per lane;
+//   * the integer -> [0,1) scaling (2^-24 / 2^-16) is folded into the bin extent, so a coordinate costs SHF/LOP/PRMT + I2FP + FFMA.
 template<class F, int DIM, class = void> struct has_pair_eval : std::false_type {};
 template<class F, int DIM>
 struct has_pair_eval<F, DIM, std::void_t<decltype(std::declval<const F&>()(std::declval<const std::array<f32x2, DIM>&>()))>>
     : std::is_same<decltype(std::declval<const F&>()(std::declval<const std::array<f32x2, DIM>&>())), f32x2> {};
 
-constexpr int MC_GROUP = 4;                 // samples per draw group
-template<int DIM> struct GroupDraws {
-    static constexpr int NB = (DIM + 3) / 4;      // blocks of four dimensions
-    u32x4 r[3][NB];
-    __device__ __forceinline__ void draw(uint32_t b0, uint32_t b1, uint32_t group, uint32_t k0, uint32_t k1, int calls) {
+constexpr int MC_GROUP = 8;                 // samples per draw group
+// One draw group = 8 samples of one bin.  The group's random words w[0..4*CALLS) are the outputs of CALLS Philox calls with the
+// counters (bin lo, bin hi, group, call), and every word is cut into coordinate fields so that no generated bit is thrown away:
+//   * 24-bit fields (the reference's generate_canonical<float,24> lattice): three words give four fields — the top 24 bits of
+//     each word and a fourth assembled from the three low bytes (two PRMT);
+//   * 16-bit fields for the first NARROW dimensions: two per word.  The driver picks NARROW = dimbins only when every binned
+//     dimension has >= 256 bins, so that the sample lattice along such a dimension (resolution x 2^16 points over the range)
+//     is at least as fine as the reference's (2^24 points over the bin, which float rounding of lo + u*(hi-lo) coarsens to
+//     ~2^24 over the range anyway); NARROW = 0 otherwise.
+// Words per group: 4*NARROW + 6*(DIM-NARROW).  4-D integrand over a 2-D bin grid: 20 words = 5 calls per 8 samples
+// (all-24-bit: 24 words = 6 calls, the round-1b "4 samples per 3 calls").
+template<int DIM, int NARROW> struct GroupDraws {
+    static constexpr int WIDE = DIM - NARROW;
+    static constexpr int W16 = 4 * NARROW;          // first W16 words: 16-bit fields
+    static constexpr int W24 = 6 * WIDE;            // then W24 words: 24-bit fields, in triples
+    static constexpr int CALLS = (W16 + W24 + 3) / 4;
+    uint32_t w[4 * CALLS];
+    __device__ __forceinline__ void draw(uint32_t b0, uint32_t b1, uint32_t group, uint32_t k0, uint32_t k1) {
 #pragma unroll
-        for (int j = 0; j < 3; ++j)
-#pragma unroll
-            for (int blk = 0; blk < NB; ++blk)
-                if (j < calls) r[j][blk] = philox4x32<10>(u32x4{b0, b1, group, uint32_t(j + 4 * blk)}, k0, k1);
+        for (int c = 0; c < CALLS; ++c) {
+            const u32x4 r = philox4x32<10>(u32x4{b0, b1, group, uint32_t(c)}, k0, k1);
+            w[4 * c] = r.x; w[4 * c + 1] = r.y; w[4 * c + 2] = r.z; w[4 * c + 3] = r.w;
+        }
     }
-    __device__ __forceinline__ static uint32_t word(const u32x4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
-    // 24-bit integer of coordinate i of sample j (as float: exact)
+    // integer n of coordinate i of sample j as a float (exact): 24-bit fields give n, 16-bit fields (i < NARROW) give 2^23 + n,
+    // built straight from the bits with one LOP3/PRMT (cvt.f32.u16 becomes I2F.U16 on the quarter-rate XU pipe); the kernel folds
+    // the 2^23 into the bin's lower corner (bias()).  Samples 2p and 2p+1 share the word of a 16-bit field.
+    __device__ __forceinline__ static constexpr float bias(int i) { return i < NARROW ? 8388608.0f : 0.0f; }
     __device__ __forceinline__ float coord(int j, int i) const {
-        const int blk = i >> 2, w = i & 3;
-        if (j < 3) return float(word(r[j][blk], w) >> 8);
-        const uint32_t p = word(r[0][blk], w), q = word(r[1][blk], w), t = word(r[2][blk], w);
-        return float(__byte_perm(__byte_perm(t, q, 0x7740), p, 0x7410) & 0x00ffffffu);       // (p.b0 << 16) | (q.b0 << 8) | t.b0
+        if (i < NARROW) {
+            const uint32_t v = w[(j >> 1) * NARROW + i];
+            return __uint_as_float((j & 1) ? __byte_perm(v, 0x4b000000u, 0x7632) : ((v & 0xffffu) | 0x4b000000u));
+        }
+        const int m = j * WIDE + (i - NARROW), base = W16 + 3 * (m >> 2), q = m & 3;
+        if (q < 3) return float(w[base + q] >> 8);
+        return float(__byte_perm(__byte_perm(w[base + 2], w[base + 1], 0x7740), w[base], 0x7410) & 0x00ffffffu);   // (w0.b0 << 16) | (w1.b0 << 8) | w2.b0
     }
 };
 
-template<class F, int DIM>
-__device__ __forceinline__ float mc_eval_one(const F& f, const GroupDraws<DIM>& d, int j, const float (&lo)[DIM], const float (&ext24)[DIM]) {
+template<class F, int DIM, int NARROW>
+__device__ __forceinline__ float mc_eval_one(const F& f, const GroupDraws<DIM, NARROW>& d, int j, const float (&lo)[DIM], const float (&exts)[DIM]) {
     std::array<float, DIM> x;
 #pragma unroll
-    for (int i = 0; i < DIM; ++i) x[i] = fmaf(d.coord(j, i), ext24[i], lo[i]);     // u*(b-a)+a as std::uniform_real_distribution, u = n*2^-24 in [0,1)
+    for (int i = 0; i < DIM; ++i) x[i] = fmaf(d.coord(j, i), exts[i], lo[i]);     // u*(b-a)+a as std::uniform_real_distribution, u = n*2^-bits in [0,1)
     return f(x);
 }
-template<class F, int DIM>
-__device__ __forceinline__ f32x2 mc_eval_pair(const F& f, const GroupDraws<DIM>& d, int j0, const float (&lo)[DIM], const float (&ext24)[DIM]) {
+template<class F, int DIM, int NARROW>
+__device__ __forceinline__ f32x2 mc_eval_pair(const F& f, const GroupDraws<DIM, NARROW>& d, int j0, const float (&lo)[DIM], const float (&exts)[DIM]) {
     std::array<f32x2, DIM> x;
 #pragma unroll
-    for (int i = 0; i < DIM; ++i) x[i] = mad(f32x2::pack(d.coord(j0, i), d.coord(j0 + 1, i)), f32x2(ext24[i]), f32x2(lo[i]));
+    for (int i = 0; i < DIM; ++i) x[i] = mad(f32x2::pack(d.coord(j0, i), d.coord(j0 + 1, i)), f32x2(exts[i]), f32x2(lo[i]));
     return f(x);
 }
 
-template<class F, int DIM, int DIMBINS, bool MOMENTS, bool EXACT>
+template<class F, int DIM, int DIMBINS, bool MOMENTS, bool EXACT, bool NARROW>
 __global__ void __launch_bounds__(MC_THREADS)
 mc_per_bin_kernel(const F f, const vb200_mc_launch a) {
     constexpr bool PAIRS = !EXACT && has_pair_eval<F, DIM>::value;
+    constexpr int NB = NARROW ? DIMBINS : 0;  // dimensions drawn as 16-bit fields
     const uint32_t LPB = a.lanes_per_bin;     // power of two <= 32: the lanes of a bin sit in one warp
     const uint32_t G = 32u / LPB;             // bins per warp step
     const uint32_t lane = threadIdx.x & 31u, sub = lane % LPB, grp = lane / LPB;
@@ -150,37 +168,49 @@ mc_per_bin_kernel(const F f, const vb200_mc_launch a) {
             float lo[DIM], ext[DIM];
             bin_box<DIM, DIMBINS>(a.domain, bin, lo, ext, volume);
 #pragma unroll
-            for (int i = 0; i < DIM; ++i) ext[i] *= 5.9604644775390625e-08f;
+            for (int i = 0; i < DIM; ++i) {       // 2^-16 / 2^-24 folded into the extent, the 16-bit fields' 2^23 into the lower corner
+                ext[i] *= (i < NB ? 1.52587890625e-05f : 5.9604644775390625e-08f);
+                lo[i] = fmaf(-GroupDraws<DIM, NB>::bias(i), ext[i], lo[i]);
+            }
             const uint32_t b0 = uint32_t(bin), b1 = uint32_t(bin >> 32);
-            GroupDraws<DIM> d;
+            GroupDraws<DIM, NB> d;
             if constexpr (PAIRS) {
                 f32x2 acc0(0.0f), acc1(0.0f), sq0(0.0f), sq1(0.0f);
                 for (uint32_t g = sub; g < full_groups; g += LPB) {
-                    d.draw(b0, b1, g, a.key0, a.key1, 3);
-                    const f32x2 v0 = mc_eval_pair<F, DIM>(f, d, 0, lo, ext), v1 = mc_eval_pair<F, DIM>(f, d, 2, lo, ext);
+                    d.draw(b0, b1, g, a.key0, a.key1);
+                    const f32x2 v0 = mc_eval_pair<F, DIM, NB>(f, d, 0, lo, ext), v1 = mc_eval_pair<F, DIM, NB>(f, d, 2, lo, ext);
                     acc0 += v0; acc1 += v1;
                     if (MOMENTS) { sq0 = mad(v0, v0, sq0); sq1 = mad(v1, v1, sq1); }
+                    const f32x2 v2 = mc_eval_pair<F, DIM, NB>(f, d, 4, lo, ext), v3 = mc_eval_pair<F, DIM, NB>(f, d, 6, lo, ext);
+                    acc0 += v2; acc1 += v3;
+                    if (MOMENTS) { sq0 = mad(v2, v2, sq0); sq1 = mad(v3, v3, sq1); }
                 }
                 sum = (acc0.lo() + acc0.hi()) + (acc1.lo() + acc1.hi());
                 if (MOMENTS) sum2 = (sq0.lo() + sq0.hi()) + (sq1.lo() + sq1.hi());
             } else {
                 float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f, q0 = 0.0f, q1 = 0.0f, q2 = 0.0f, q3 = 0.0f;
                 for (uint32_t g = sub; g < full_groups; g += LPB) {
-                    d.draw(b0, b1, g, a.key0, a.key1, 3);
-                    const float v0 = mc_eval_one<F, DIM>(f, d, 0, lo, ext), v1 = mc_eval_one<F, DIM>(f, d, 1, lo, ext);
-                    const float v2 = mc_eval_one<F, DIM>(f, d, 2, lo, ext), v3 = mc_eval_one<F, DIM>(f, d, 3, lo, ext);
-                    s0 += v0; s1 += v1; s2 += v2; s3 += v3;
-                    if (MOMENTS) { q0 = fmaf(v0, v0, q0); q1 = fmaf(v1, v1, q1); q2 = fmaf(v2, v2, q2); q3 = fmaf(v3, v3, q3); }
+                    d.draw(b0, b1, g, a.key0, a.key1);
+#pragma unroll
+                    for (int h = 0; h < MC_GROUP; h += 4) {
+                        const float v0 = mc_eval_one<F, DIM, NB>(f, d, h, lo, ext), v1 = mc_eval_one<F, DIM, NB>(f, d, h + 1, lo, ext);
+                        const float v2 = mc_eval_one<F, DIM, NB>(f, d, h + 2, lo, ext), v3 = mc_eval_one<F, DIM, NB>(f, d, h + 3, lo, ext);
+                        s0 += v0; s1 += v1; s2 += v2; s3 += v3;
+                        if (MOMENTS) { q0 = fmaf(v0, v0, q0); q1 = fmaf(v1, v1, q1); q2 = fmaf(v2, v2, q2); q3 = fmaf(v3, v3, q3); }
+                    }
                 }
                 sum = (s0 + s1) + (s2 + s3);
                 if (MOMENTS) sum2 = (q0 + q1) + (q2 + q3);
             }
-            if (rest != 0u && sub == full_groups % LPB) {      // the last, partial group: one call per sample
-                d.draw(b0, b1, full_groups, a.key0, a.key1, int(rest));
-                for (uint32_t j = 0; j < rest; ++j) {
-                    const float v = j == 0 ? mc_eval_one<F, DIM>(f, d, 0, lo, ext) : j == 1 ? mc_eval_one<F, DIM>(f, d, 1, lo, ext) : mc_eval_one<F, DIM>(f, d, 2, lo, ext);
-                    sum += v;
-                    if (MOMENTS) sum2 = fmaf(v, v, sum2);
+            if (rest != 0u && sub == full_groups % LPB) {      // the last, partial group: its first `rest` samples
+                d.draw(b0, b1, full_groups, a.key0, a.key1);
+#pragma unroll
+                for (int j = 0; j < MC_GROUP - 1; ++j) {
+                    if (uint32_t(j) < rest) {
+                        const float v = mc_eval_one<F, DIM, NB>(f, d, j, lo, ext);
+                        sum += v;
+                        if (MOMENTS) sum2 = fmaf(v, v, sum2);
+                    }
                 }
             }
         }

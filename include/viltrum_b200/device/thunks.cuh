@@ -54,9 +54,9 @@ struct FiniteThunks {
     // not default-constructible)
     static F functor(const vb200_integrand* self) { return *static_cast<const F*>(self->functor); }
 
-    template<int DB, bool MOMENTS>
+    template<int DB, bool MOMENTS, bool NARROW>
     static int launch_mc(const F& f, const vb200_mc_launch& a, cudaStream_t st) {
-        auto k = device::mc_per_bin_kernel<F, DIM, DB, MOMENTS, EXACT>;
+        auto k = device::mc_per_bin_kernel<F, DIM, DB, MOMENTS, EXACT, NARROW>;
         const uint64_t bins_per_cta = uint64_t(device::MC_THREADS) / a.lanes_per_bin;     // one warp step of every warp
         const uint64_t ctas = (a.bin_end - a.bin_begin + bins_per_cta - 1) / bins_per_cta;
         const int grid = persistent_grid(k, device::MC_THREADS, ctas, a.grid_hint);
@@ -65,7 +65,9 @@ struct FiniteThunks {
     }
     template<int DB>
     static int mc_db(const F& f, const vb200_mc_launch& a, cudaStream_t st) {
-        return (a.sum_f || a.sum_f2) ? launch_mc<DB, true>(f, a, st) : launch_mc<DB, false>(f, a, st);
+        // a.narrow_binned: 16-bit draws for the binned dimensions (driver: every binned dimension has >= 256 bins)
+        if (a.narrow_binned) return (a.sum_f || a.sum_f2) ? launch_mc<DB, true, true>(f, a, st) : launch_mc<DB, false, true>(f, a, st);
+        return (a.sum_f || a.sum_f2) ? launch_mc<DB, true, false>(f, a, st) : launch_mc<DB, false, false>(f, a, st);
     }
     static int mc(const vb200_integrand* self, const void* args, void* stream) {
         const vb200_mc_launch& a = *static_cast<const vb200_mc_launch*>(args);

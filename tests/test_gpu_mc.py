@@ -43,6 +43,32 @@ def test_counter_layout_and_affine_map(ctx):
     assert np.allclose(bins, want, rtol=3e-7, atol=0)
 
 
+def test_counter_layout_narrow_fields(ctx):
+    """Grids with >= 256 bins along every binned dimension draw the in-bin coordinates as 16-bit fields (mc_per_bin.cuh GroupDraws):
+    spp=1 -> sample 0 of bin b takes the low halves of words 0 and 1 of Philox(key=seed, ctr=(b,0,0,0)) — predicted on the host."""
+    from viltrum_b200 import _capi, Range
+    L = _capi.lib()
+    res, seed = [256, 300], 0x0FEDCBA987654321
+    nb = res[0] * res[1]
+    bins = np.zeros(nb, np.float32)
+    ctx.mc_per_bin("x2y2", bins, res, Range([0.25, -1.0], [2.0, 3.0]), 1, seed)
+    vol = np.float32(np.float32(2.0 - 0.25) * np.float32(3.0 + 1.0))
+    for b in range(0, nb, 97):
+        c = (ctypes.c_uint32 * 4)(b, 0, 0, 0); k = (ctypes.c_uint32 * 2)(seed & 0xffffffff, seed >> 32); o = (ctypes.c_uint32 * 4)()
+        L.vb200_philox4x32_10(c, k, o)
+        p = [b % res[0], b // res[0]]
+        x = []
+        for i, (lo, hi, r) in enumerate(((0.25, 2.0, res[0]), (-1.0, 3.0, res[1]))):
+            dr = np.float32(np.float32(hi - lo) / np.float32(r))
+            a = np.float32(lo) + np.float32(p[i]) * dr; bb = np.float32(lo) + np.float32(p[i] + 1) * dr
+            x.append(np.float32(np.float64(o[i] & 0xffff) * 2.0 ** -16 * np.float64(np.float32(bb - a)) + np.float64(a)))
+            assert a <= x[i] <= bb
+        f = np.float64(x[0]) ** 2 + np.float64(x[1]) ** 2
+        want = f * np.float64(vol)
+        # the kernel folds the fields' 2^23 offset into the bin corner: the sample may sit a fraction of a lattice step away
+        assert abs(bins[b] - want) <= 2e-6 * abs(want), (b, bins[b], want)
+
+
 @pytest.mark.parametrize("integ,res,spp", [("shade4_64", [256, 256], 64), ("shade4_16", [64, 48], 37), ("x2y2", [100], 256),
                                            ("poly3", [12, 10, 6], 32), ("shade5_16", [32, 32], 16), ("ind2", [24, 24], 128)])
 @pytest.mark.parametrize("flavor", ["mc_per_bin_parallel", "per_bin_parallel_mc"])

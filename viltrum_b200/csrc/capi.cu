@@ -151,9 +151,9 @@ vb200_domain finish_domain(const vb200_domain& d) {
 // Lanes of one warp that share a bin.  Every bin costs a fixed set-up (bin box, scaling, tile ticket) worth about one
 // sample, so as few lanes per bin as possible — but enough lanes in total to fill the chip twice over when the grid is
 // small (measured: profiles/mc_variants_r1.txt).
-uint32_t pick_lanes_per_bin(const vb200_ctx* ctx, uint64_t spp, uint64_t nbins) {
+uint32_t pick_lanes_per_bin(const vb200_ctx* ctx, uint64_t spp, uint64_t nbins, uint32_t group) {
     const uint64_t want_lanes = uint64_t(ctx->sm_count) * 2048ull * 2ull;
-    const uint64_t groups = (spp + 3) / 4;      // the lanes of a bin stride over groups of four samples (mc_per_bin.cuh; paths in walk.cuh stride over samples)
+    const uint64_t groups = (spp + group - 1) / group;      // the lanes of a bin stride over draw groups of eight samples (mc_per_bin.cuh); paths in walk.cuh stride over samples (group = 4 bounds their lanes)
     uint32_t lpb = 1;
     while (lpb < 32 && nbins * lpb < want_lanes && uint64_t(lpb) * 2 <= groups) lpb <<= 1;
     return lpb;
@@ -434,7 +434,9 @@ extern "C" int vb200_mc_per_bin(vb200_ctx* ctx, const vb200_integrand* f, const 
 
     vb200_mc_launch a; std::memset(&a, 0, sizeof(a));
     a.domain = finish_domain(p->domain); a.bin_begin = begin; a.bin_end = end; a.nbins_total = total;
-    a.spp = uint32_t(p->spp); a.lanes_per_bin = pick_lanes_per_bin(ctx, p->spp, total);   // from the WHOLE grid: the summation order, hence the bits, must not depend on the shard
+    a.spp = uint32_t(p->spp); a.lanes_per_bin = pick_lanes_per_bin(ctx, p->spp, total, 8);   // from the WHOLE grid: the summation order, hence the bits, must not depend on the shard
+    a.narrow_binned = 1;                        // 16-bit draws inside a bin only where the grid itself supplies >= 8 bits per binned dimension
+    for (int i = 0; i < p->domain.dimbins; ++i) if (p->domain.res[i] < 256) a.narrow_binned = 0;
     a.key0 = uint32_t(p->seed); a.key1 = uint32_t(p->seed >> 32);
     a.flavor = p->flavor;
     a.factor = double(range_volume(p->domain, p->domain.dim)) / double(p->spp);     // monte-carlo-per-bin-parallel.h:45
@@ -482,7 +484,7 @@ extern "C" int vb200_mc_per_bin_inf(vb200_ctx* ctx, const vb200_integrand* f, co
     if (begin == end) return VB200_OK;
     vb200_walk_launch a; std::memset(&a, 0, sizeof(a));
     a.domain = finish_domain(p->domain); a.bin_begin = begin; a.bin_end = end; a.nbins_total = total;
-    a.spp = uint32_t(p->spp); a.lanes_per_bin = pick_lanes_per_bin(ctx, p->spp, total);   // from the WHOLE grid: the summation order, hence the bits, must not depend on the shard
+    a.spp = uint32_t(p->spp); a.lanes_per_bin = pick_lanes_per_bin(ctx, p->spp, total, 4);   // from the WHOLE grid: the summation order, hence the bits, must not depend on the shard
     a.key0 = uint32_t(p->seed); a.key1 = uint32_t(p->seed >> 32);
     a.factor = double(range_volume(p->domain, p->domain.dim)) / double(p->spp);      // range-infinite.h:22-23; :77
     a.flavor = p->flavor;

@@ -80,7 +80,7 @@ int check_domain(vb200_ctx* ctx, const vb200_domain& d, int integrand_dim);
 vb200_domain finish_domain(const vb200_domain& d);
 int resolve_shard(vb200_ctx* ctx, const vb200_shard& s, uint64_t total, uint64_t* begin, uint64_t* end);
 int call_thunk(vb200_ctx* ctx, const vb200_integrand* f, int kind, const void* args);
-uint32_t pick_lanes_per_bin(const vb200_ctx* ctx, uint64_t spp, uint64_t nbins);
+uint32_t pick_lanes_per_bin(const vb200_ctx* ctx, uint64_t spp, uint64_t nbins, uint32_t group);
 // bins staging helpers: returns the device pointer to use as "base of the full grid"
 struct BinStage { float* dev_base = nullptr; bool staged = false; uint64_t begin = 0, end = 0; float* host = nullptr; };
 int stage_bins_in(vb200_ctx* ctx, float* bins, int mem, uint64_t begin, uint64_t end, bool upload, BinStage* st);
