@@ -92,6 +92,9 @@ struct has_pair_eval<F, DIM, std::void_t<decltype(std::declval<const F&>()(std::
     : std::is_same<decltype(std::declval<const F&>()(std::declval<const std::array<f32x2, DIM>&>())), f32x2> {};
 
 constexpr int MC_GROUP = 8;                 // samples per draw group
+#ifndef VB200_MC_ROUNDS
+#define VB200_MC_ROUNDS 10                  // Philox4x32-10; experiment builds (profiles/exp) measure 7, the product ships 10
+#endif
 // One draw group = 8 samples of one bin.  The group's random words w[0..4*CALLS) are the outputs of CALLS Philox calls with the
 // counters (bin lo, bin hi, group, call), and every word is cut into coordinate fields so that no generated bit is thrown away:
 //   * 24-bit fields (the reference's generate_canonical<float,24> lattice): three words give four fields — the top 24 bits of
@@ -111,7 +114,11 @@ template<int DIM, int NARROW> struct GroupDraws {
     __device__ __forceinline__ void draw(uint32_t b0, uint32_t b1, uint32_t group, uint32_t k0, uint32_t k1) {
 #pragma unroll
         for (int c = 0; c < CALLS; ++c) {
-            const u32x4 r = philox4x32<10>(u32x4{b0, b1, group, uint32_t(c)}, k0, k1);
+#ifdef VB200_MC_CTR_B
+            const u32x4 r = philox4x32<VB200_MC_ROUNDS>(u32x4{b0, group, b1, uint32_t(c)}, k0, k1);
+#else
+            const u32x4 r = philox4x32<VB200_MC_ROUNDS>(u32x4{b0, b1, group, uint32_t(c)}, k0, k1);
+#endif
             w[4 * c] = r.x; w[4 * c + 1] = r.y; w[4 * c + 2] = r.z; w[4 * c + 3] = r.w;
         }
     }
@@ -145,8 +152,11 @@ __device__ __forceinline__ f32x2 mc_eval_pair(const F& f, const GroupDraws<DIM, 
     return f(x);
 }
 
+#ifndef VB200_MC_MINB
+#define VB200_MC_MINB 1
+#endif
 template<class F, int DIM, int DIMBINS, bool MOMENTS, bool EXACT, bool NARROW>
-__global__ void __launch_bounds__(MC_THREADS)
+__global__ void __launch_bounds__(MC_THREADS, VB200_MC_MINB)
 mc_per_bin_kernel(const F f, const vb200_mc_launch a) {
     constexpr bool PAIRS = !EXACT && has_pair_eval<F, DIM>::value;
     constexpr int NB = NARROW ? DIMBINS : 0;  // dimensions drawn as 16-bit fields

@@ -65,6 +65,13 @@ inline float canonical(MT19937& g) {              // generate_canonical<float,24
     return r;
 }
 inline float uniform_real(MT19937& g, float a, float b) { return canonical(g)*(b-a)+a; }
+inline double canonical_double(MT19937& g) {      // generate_canonical<double,53>, two 32-bit draws (bits/random.tcc:3349-3381)
+    double sum = 0.0, tmp = 1.0;
+    for (int k=0;k<2;++k) { sum += double(g())*tmp; tmp *= 4294967296.0; }
+    double r = sum/tmp;
+    if (r >= 1.0) r = std::nextafter(1.0, 0.0);
+    return r;
+}
 
 inline uint64_t uniform_int(MT19937& g, uint64_t a, uint64_t b) {  // uniform_int_distribution<size_t>(a,b), 32-bit urng
     uint64_t urange = b-a;
@@ -532,6 +539,12 @@ template<typename T> T region_error(const RegionT<T>& r, int SH, int SL, int D, 
     });
     return r.volume*fold_all_rule(e,SH,D-1);
 }
+// region.h:420-424 Region::error(): volume * (fold_all(high) - fold_all(low))
+template<typename T> T region_error_total(const RegionT<T>& r, int SH, int SL, int D) {
+    std::vector<T> v = r.data; int nd = D;
+    while (nd>0) { v = fold_dim(v,SH,nd,0,[&] (const T* l) { return nested_low(SH,SL,l); }); --nd; }
+    return r.volume*(fold_all_rule(r.data,SH,D) - v[0]);
+}
 // error-heuristic.h:15-18 -> region.h:401-411 (first maximal dim, strict >)
 template<typename T> void heuristic_default(RegionT<T>& r, int SH, int SL, int D, bool relative) {
     T max_err = 0; uint32_t max_dim = 0;
@@ -870,7 +883,8 @@ template<typename MakeResidual>
 void cv_integrate_regions(const std::vector<RegionT<float>>& regions, int S, int D, int dimbins, const uint64_t* res,
                           const float* rmin, const float* rmax, uint64_t spp, uint64_t seed, MakeResidual&& make_residual, float* bins,
                           uint32_t* rec_nregions, float* rec_approx, uint32_t* rec_chosen, float* rec_samples,
-                          bool fixed_weight = false, double fixed_alpha = 1.0) {
+                          bool fixed_weight = false, double fixed_alpha = 1.0, int rr_policy = 0, int SL = 2) {
+    // rr_policy: 0 rr_uniform_region, 1 rr_integral_region, 2 rr_error_region (region-russian-roulette.h:9-28 / :30-67 / :69-106)
     uint64_t nb = nbins_of(dimbins,res);
     uint64_t factor = nb;
     // bin -> region lists, regions visited in list order (:53-57, serial PSTL backend)
@@ -908,13 +922,40 @@ void cv_integrate_regions(const std::vector<RegionT<float>>& regions, int S, int
         }
         if (rec_nregions) rec_nregions[k] = uint32_t(n);
         if (rec_approx) rec_approx[k] = approximation;
+        // weighted roulettes: RR constructor (region-russian-roulette.h:42-53 / :81-92) + std::discrete_distribution
+        // (libstdc++ bits/random.tcc:2657-2678 _M_initialize: fewer than two weights -> always 0 with probability 1, no draw)
+        std::vector<double> prob, cp;
+        if (rr_policy != 0) {
+            std::vector<double> wts(n);
+            for (std::size_t i=0;i<n;++i) {
+                const RegionT<float>& r = regions[list[i]];
+                if (rr_policy == 1) wts[i] = std::abs(region_integral_subrange(r,S,D,ia[i].data(),ib[i].data()));           // :45 NormDefault = abs
+                else wts[i] = std::abs(region_error_total(r,S,SL,D))*volume_of(D,ia[i].data(),ib[i].data())/r.volume;         // :86, float arithmetic
+            }
+            double sum = 0.0; for (double w : wts) sum += w;
+            if (sum<=0.0) for (double& w : wts) w = 1.0;
+            else for (double& w : wts) w = std::max(w,0.01*sum/double(n));
+            if (n>=2) {
+                double total = 0.0; for (double w : wts) total += w;            // std::accumulate(.., 0.0)
+                prob.resize(n); cp.resize(n);
+                for (std::size_t i=0;i<n;++i) prob[i] = wts[i]/total;           // __normalize
+                double run = 0.0; for (std::size_t i=0;i<n;++i) { run = (i==0) ? prob[0] : run + prob[i]; cp[i] = run; }   // std::partial_sum
+                cp[n-1] = 1.0;
+            }
+        }
         // cv_optimize_weight accumulator (weight-strategy.h:40-101)
         float sum_f=0.0f, sum_app=0.0f; uint64_t size=0;
         float fixed_sum = 0.0f;                                                // cv_fixed_weight::Accumulator::sum (weight-strategy.h:14-17)
         double k_f=0,k_app=0,e_f=0,e_ap=0,e_ap2=0,e_fap=0;
         for (uint64_t s=0;s<spp;++s) {                                         // :92-101
-            uint64_t chosen = uniform_int(rng,0,n-1);                          // region-russian-roulette.h:14,18-21
-            double rrfactor = double(n);
+            uint64_t chosen; double rrfactor;
+            if (rr_policy == 0) { chosen = uniform_int(rng,0,n-1); rrfactor = double(n); }     // region-russian-roulette.h:14,18-21
+            else if (cp.empty()) { chosen = 0; rrfactor = 1.0/1.0; }                             // probabilities() == {1.0}
+            else {
+                double pr = canonical_double(rng);                                               // _Adaptor<URNG,double>
+                chosen = uint64_t(std::lower_bound(cp.begin(),cp.end(),pr) - cp.begin());        // bits/random.tcc:2709-2713
+                rrfactor = 1.0/prob[chosen];                                                     // region-russian-roulette.h:59
+            }
             const RegionT<float>& r = regions[list[chosen]];
             float x[8];
             for (int i=0;i<D;++i) x[i] = uniform_real(rng,ia[chosen][i],ib[chosen][i]);   // region-sampling.h:13-17
@@ -975,6 +1016,20 @@ extern "C" int vo_cv_fixed_weight(const char* integrand, uint64_t iterations, ui
     Heuristic h{true,true,1.e-5};
     auto regions = generate_adaptive<float>(F->fn,S,SL,D,rmin,rmax,h,iterations);
     cv_integrate_regions(regions,S,D,dimbins,res,rmin,rmax,spp,seed,[&] (uint64_t) { return F->fn; },bins,rec_nregions,rec_approx,rec_chosen,rec_samples,true,alpha);
+    return 0;
+}
+
+extern "C" int vo_cv_policies(const char* integrand, uint64_t iterations, uint64_t spp, uint64_t seed, int rr_policy, int weight_strategy, double alpha,
+                   int dimbins, const uint64_t* res, const float* rmin, const float* rmax, float* bins,
+                   uint32_t* rec_nregions, float* rec_approx, uint32_t* rec_chosen, float* rec_samples) {
+    auto F = find_finite(integrand); if (!F) return -1;
+    int D = F->dim; if (dimbins<1 || dimbins>D) return -2;
+    if (rr_policy<0 || rr_policy>2 || weight_strategy<0 || weight_strategy>1) return -3;
+    const int S = 3, SL = 2;
+    Heuristic h{true,true,1.e-5};
+    auto regions = generate_adaptive<float>(F->fn,S,SL,D,rmin,rmax,h,iterations);
+    cv_integrate_regions(regions,S,D,dimbins,res,rmin,rmax,spp,seed,[&] (uint64_t) { return F->fn; },bins,rec_nregions,rec_approx,rec_chosen,rec_samples,
+                         weight_strategy==1,alpha,rr_policy,SL);
     return 0;
 }
 

@@ -278,6 +278,27 @@ class Oracle:
             return bins, dict(nregions=nreg, approx=approx, chosen=chosen, samples=samples)
         return bins
 
+    RR_POLICIES = {"uniform": 0, "integral": 1, "error": 2}
+
+    def cv_policies(self, integrand, iterations, spp, seed, rr, res, rmin, rmax, fixed_alpha=None, record=False):
+        """integrator_adaptive_variance_reduction_parallel(nested(simpson,trapezoidal), size/relative 1e-5, iterations, rr_<rr>_region(),
+        cv_optimize_weight() | cv_fixed_weight(fixed_alpha), region_sampling_uniform(), spp, seed)"""
+        res, rmin, rmax, nb = self._setup(res, rmin, rmax)
+        d = self.dim(integrand)
+        bins = np.zeros(nb, np.float32)
+        nreg = approx = chosen = samples = None
+        if record:
+            nreg = np.zeros(nb, np.uint32); approx = np.zeros(nb, np.float32)
+            chosen = np.zeros((nb, spp), np.uint32); samples = np.zeros((nb, spp, d), np.float32)
+        self.lib.vo_cv_policies.restype = ctypes.c_int
+        rc = self.lib.vo_cv_policies(integrand.encode(), ctypes.c_uint64(iterations), ctypes.c_uint64(spp), ctypes.c_uint64(seed),
+                                     ctypes.c_int(self.RR_POLICIES[rr]), ctypes.c_int(0 if fixed_alpha is None else 1), ctypes.c_double(1.0 if fixed_alpha is None else fixed_alpha),
+                                     len(res), _p(res), _p(rmin), _p(rmax), _p(bins), _p(nreg), _p(approx), _p(chosen), _p(samples))
+        self._check(rc, "vo_cv_policies")
+        if record:
+            return bins, dict(nregions=nreg, approx=approx, chosen=chosen, samples=samples)
+        return bins
+
     def mt_per_bin(self, path, integrand, res, spp, seed, nthreads, rmin=(), rmax=()):
         res = np.ascontiguousarray(np.asarray(res, dtype=np.uint64))
         rmin, rmax = _f32(rmin), _f32(rmax)

@@ -29,14 +29,15 @@ struct CvRecorder {
     }
 };
 
-class RecRR {
-    CvRecorder* rec; viltrum::rr_uniform_region inner;
+template<typename Inner>
+class RecRRT {
+    CvRecorder* rec; Inner inner;
 public:
-    RecRR(CvRecorder* r) : rec(r) {}
+    RecRRT(CvRecorder* r, const Inner& i = Inner()) : rec(r), inner(i) {}
     class RR {
-        viltrum::rr_uniform_region::RR inner;
+        typename Inner::RR inner;
     public:
-        RR(viltrum::rr_uniform_region::RR&& i) : inner(std::move(i)) {}
+        RR(typename Inner::RR&& i) : inner(std::move(i)) {}
         template<typename RNG> std::tuple<std::size_t,double> choose(RNG& rng) { return inner.choose(rng); }
     };
     template<typename Regions> RR russian_roulette(const Regions& regions) const {
@@ -44,6 +45,7 @@ public:
         return RR(inner.russian_roulette(regions));
     }
 };
+using RecRR = RecRRT<viltrum::rr_uniform_region>;
 
 class RecRS {
     CvRecorder* rec; viltrum::region_sampling_uniform inner;
@@ -132,6 +134,40 @@ extern "C" int vo_cv_fixed_weight(const char* integrand, uint64_t iterations, ui
             regions_generator_adaptive_heap(nested(simpson,trapezoidal), error_heuristic_size(error_metric_relative(),1.e-5), std::size_t(iterations)),
             regions_integrator_parallel_variance_reduction(RecRR(&rec), cv_fixed_weight(alpha), RecRS(&rec), std::mt19937(std::size_t(seed)), (unsigned long)spp, std::size_t(16)));
         viltrum::integrate(integrator, acc, r, f, range, logger);
+        return 0;
+    });
+}
+
+extern "C" int vo_cv_policies(const char* integrand, uint64_t iterations, uint64_t spp, uint64_t seed, int rr_policy, int weight_strategy, double alpha,
+                   int dimbins, const uint64_t* res, const float* rmin, const float* rmax, float* bins,
+                   uint32_t* rec_nregions, float* rec_approx, uint32_t* rec_chosen, float* rec_samples) {
+    if (rr_policy<0 || rr_policy>2 || weight_strategy<0 || weight_strategy>1) return -3;
+    RegionSink sink;
+    return dispatch_finite_bins(integrand, dimbins, [&] (auto f, auto dbc) -> int {
+        using F = decltype(f);
+        constexpr std::size_t D = F::dim;
+        constexpr std::size_t DB = decltype(dbc)::value;
+        using namespace viltrum;
+        auto r = res_array<DB>(res);
+        auto range = range_array<D>(rmin, rmax);
+        auto acc = [&] (const std::array<std::size_t,DB>& p) -> float& { return bins[tensor_pos(p,r)]; };
+        CvRecorder rec; rec.db = int(DB); rec.spp = spp; rec.dim = D; rec.sink = &sink;
+        for (std::size_t i=0;i<DB;++i) { rec.rmin[i]=rmin[i]; rec.res[i]=r[i]; rec.drange[i]=(rmax[i]-rmin[i])/float(r[i]); }
+        rec.nregions=rec_nregions; rec.approx=nullptr; rec.chosen=rec_chosen; rec.samples=rec_samples;
+        DumpLogger logger(&sink);
+        auto run = [&] (auto rr, auto cv) {
+            auto integrator = integrator_region_based(
+                regions_generator_adaptive_heap(nested(simpson,trapezoidal), error_heuristic_size(error_metric_relative(),1.e-5), std::size_t(iterations)),
+                regions_integrator_parallel_variance_reduction(std::move(rr), std::move(cv), RecRS(&rec), std::mt19937(std::size_t(seed)), (unsigned long)spp, std::size_t(16)));
+            viltrum::integrate(integrator, acc, r, f, range, logger);
+        };
+        auto with_cv = [&] (auto rr) {
+            if (weight_strategy == 1) run(std::move(rr), cv_fixed_weight(alpha));
+            else { rec.approx = rec_approx; run(std::move(rr), RecCV(&rec)); }
+        };
+        if (rr_policy == 0) with_cv(RecRRT<rr_uniform_region>(&rec));
+        else if (rr_policy == 1) with_cv(RecRRT<rr_integral_region<>>(&rec));
+        else with_cv(RecRRT<rr_error_region<>>(&rec));
         return 0;
     });
 }
