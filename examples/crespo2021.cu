@@ -28,5 +28,14 @@ int main(int argc, char** argv) {
     for (std::size_t i = 0; i < cv.size(); ++i) { m += cv.raw_data()[i]; double r = ref.raw_data()[i]; ecv += (cv.raw_data()[i]-r)*(cv.raw_data()[i]-r); emc += (mc.raw_data()[i]-r)*(mc.raw_data()[i]-r); }
     m /= cv.size();
     std::printf("control variates: mean of bins %.5f should be close to 0.14326; MSE vs 8192-spp reference: CV %.3e, plain MC at the same spp %.3e\n", m, ecv/cv.size(), emc/cv.size());
-    return (std::fabs(m-0.14326) < 3e-3 && ecv < emc) ? 0 : 1;
+    // the other Russian-roulette policies, spelled as in the reference's main/compilation-tests/multiple-parameters-2d.cc:62,74
+    tensor<float,2> ri({w,w}, 0.0f), re({w,w}, 0.0f);
+    integrate(integrator_adaptive_variance_reduction_parallel(nested(simpson,trapezoidal), iterations, rr_integral_region(), cv_optimize_weight(), spp, 0), ri, ri.resolution(), Shade5<64>(), range_primary<5>());
+    integrate(integrator_adaptive_variance_reduction_parallel(nested(simpson,trapezoidal), error_heuristic_size(error_metric_relative(),1.e-5), iterations, rr_error_region(), cv_fixed_weight(1.0), region_sampling_uniform(), spp, 0),
+              re, re.resolution(), Shade5<64>(), range_primary<5>());
+    double mi = 0, me = 0, ei = 0, ee = 0;
+    for (std::size_t i = 0; i < ri.size(); ++i) { double r = ref.raw_data()[i]; mi += ri.raw_data()[i]; me += re.raw_data()[i]; ei += (ri.raw_data()[i]-r)*(ri.raw_data()[i]-r); ee += (re.raw_data()[i]-r)*(re.raw_data()[i]-r); }
+    mi /= ri.size(); me /= re.size();
+    std::printf("rr_integral_region + cv_optimize_weight: mean %.5f, MSE %.3e; rr_error_region + cv_fixed_weight(1): mean %.5f, MSE %.3e\n", mi, ei/ri.size(), me, ee/re.size());
+    return (std::fabs(m-0.14326) < 3e-3 && ecv < emc && std::fabs(mi-0.14326) < 3e-3 && std::fabs(me-0.14326) < 3e-3) ? 0 : 1;
 }

@@ -296,17 +296,22 @@ typedef enum vb200_cv_weight {
     VB200_CV_OPTIMIZE_WEIGHT = 0,   /* cv_optimize_weight: alpha = clamp(cov,0,var)/var from the samples (weight-strategy.h:40-110) */
     VB200_CV_FIXED_WEIGHT = 1       /* cv_fixed_weight(alpha): 0 = plain importance-sampled MC ... 1 = full control variate (weight-strategy.h:7-35) */
 } vb200_cv_weight;
+typedef enum vb200_rr_policy {      /* Russian roulette among the regions that touch a bin (reference src/control-variates/region-russian-roulette.h) */
+    VB200_RR_UNIFORM = 0,           /* rr_uniform_region  :9-28   every region equally likely */
+    VB200_RR_INTEGRAL = 1,          /* rr_integral_region :30-67  probability ~ |integral of the interpolant over bin ∩ region| (floored at 1 % of the mean) */
+    VB200_RR_ERROR = 2              /* rr_error_region    :69-106 probability ~ |Region::error()| * vol(bin ∩ region)/vol(region) (same floor); nested rules only */
+} vb200_rr_policy;
 typedef struct vb200_cv_params {
     vb200_domain domain;
     vb200_shard  shard;
     uint64_t     spp;
     uint64_t     seed;
     int32_t      weight_strategy;   /* vb200_cv_weight */
-    int32_t      reserved;
+    int32_t      rr_policy;         /* vb200_rr_policy (0 = the crespo2021 preset) */
     double       alpha;             /* VB200_CV_FIXED_WEIGHT only */
 } vb200_cv_params;
 
-/* RegionsIntegratorParallelVarianceReduction with rr_uniform_region / cv_optimize_weight / region_sampling_uniform
+/* RegionsIntegratorParallelVarianceReduction with rr_uniform_region | rr_integral_region | rr_error_region / cv_optimize_weight | cv_fixed_weight / region_sampling_uniform
  * (reference src/control-variates/regions-integrator-parallel-variance-reduction.h:32-109; the integrator_crespo2021
  * preset, integrator-crespo2021.h:7-22).  bins overwritten ('=').  Optional per-bin records (same memory space as
  * bins, may be NULL): nregions (uint32), approx (float, the control-variate integral). */

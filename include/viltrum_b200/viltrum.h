@@ -463,38 +463,57 @@ template<typename R> auto integrator_adaptive_tolerance(const R& r, double toler
 // control-variate weight policies (reference src/control-variates/weight-strategy.h:7-110)
 struct cv_optimize_weight { static constexpr int id = VB200_CV_OPTIMIZE_WEIGHT; double alpha = 1.0; };
 struct cv_fixed_weight { static constexpr int id = VB200_CV_FIXED_WEIGHT; double alpha; cv_fixed_weight(double a = 1) : alpha(a) {} };
-struct rr_uniform_region {};            // region-russian-roulette.h:9-28
+// Russian roulette among the regions of a bin (reference src/control-variates/region-russian-roulette.h)
+struct rr_uniform_region { static constexpr int id = VB200_RR_UNIFORM; };       // :9-28
+struct rr_integral_region { static constexpr int id = VB200_RR_INTEGRAL; };     // :30-67  (NormDefault)
+struct rr_error_region { static constexpr int id = VB200_RR_ERROR; };           // :69-106 (NormDefault)
 struct region_sampling_uniform {};      // region-sampling.h:9-20
-class IntegratorCrespo2021 {
-    std::size_t iterations, spp, seed_; int weight_strategy = VB200_CV_OPTIMIZE_WEIGHT; double alpha = 1.0;
+// integrator_region_based(regions_generator_adaptive_heap(rule, heuristic, iterations), regions_integrator_parallel_variance_reduction(RR, CV,
+// region_sampling_uniform, spp, seed)) — reference integrator-adaptive-variance-reduction.h:11-49, regions-integrator-parallel-variance-reduction.h:32-109
+template<typename Rule, typename EH> class IntegratorAdaptiveVarianceReduction {
+    EH eh; std::size_t iterations, spp, seed_; int weight_strategy = VB200_CV_OPTIMIZE_WEIGHT; double alpha = 1.0; int rr = VB200_RR_UNIFORM;
 public:
-    IntegratorCrespo2021(std::size_t it, std::size_t s, std::size_t seed) : iterations(it), spp(s), seed_(seed) {}
-    IntegratorCrespo2021(std::size_t it, std::size_t s, std::size_t seed, int ws, double a) : iterations(it), spp(s), seed_(seed), weight_strategy(ws), alpha(a) {}
+    IntegratorAdaptiveVarianceReduction(const EH& e, std::size_t it, std::size_t s, std::size_t seed, int ws = VB200_CV_OPTIMIZE_WEIGHT, double a = 1.0, int rr_policy = VB200_RR_UNIFORM)
+        : eh(e), iterations(it), spp(s), seed_(seed), weight_strategy(ws), alpha(a), rr(rr_policy) {}
     template<typename Bins, std::size_t DIMBINS, typename F, typename Float, std::size_t DIM, typename Logger>
     void integrate(Bins& bins, const std::array<std::size_t,DIMBINS>& res, const F& f, const Range<Float,DIM>& range, Logger& logger) const {
         auto& ctx = b200::default_context();
         b200::Integrand<F, int(DIM)> g(f);
         b200::RegionsHandle regs;
-        using EH = error_heuristic_size<error_metric_relative>;
-        IntegratorAdaptiveIterations<Nested<Simpson,Trapezoidal>, EH>(EH(error_metric_relative(), 1.e-5), iterations).generate(ctx, g, range, regs);
+        IntegratorAdaptiveIterations<Rule, EH>(eh, iterations).generate(ctx, g, range, regs);
         if constexpr (!std::is_same<Logger, LoggerNull>::value) logger.log(b200::download_regions<DIM>(ctx, regs.r));
         vb200_cv_params p; std::memset(&p, 0, sizeof(p));
         p.domain = b200::make_domain(range, res); p.shard = b200::current_shard(); p.spp = spp; p.seed = seed_;
-        p.weight_strategy = weight_strategy; p.alpha = alpha;
+        p.weight_strategy = weight_strategy; p.alpha = alpha; p.rr_policy = rr;
         std::vector<float> flat(b200::bin_count(res), 0.0f);
         ctx.check(vb200_cv_integrate(ctx.get(), g.c_abi(), regs.r, &p, flat.data(), VB200_HOST, nullptr, nullptr));
         b200::apply_bins<false>(bins, res, flat);
         logger.log_progress(std::size_t(1), std::size_t(1));
     }
 };
-inline IntegratorCrespo2021 integrator_crespo2021(std::size_t iterations, std::size_t spp, std::size_t seed = 0, std::size_t = 16) { return IntegratorCrespo2021(iterations, spp, seed); }
-// integrator_adaptive_variance_reduction_parallel(nested(simpson,trapezoidal), error_heuristic_size(relative), iterations, rr_uniform_region(),
-// cv_optimize_weight() | cv_fixed_weight(alpha), region_sampling_uniform(), spp, seed) — reference integrator-adaptive-variance-reduction.h:33-36
-// for the rule / heuristic pair of the crespo2021 preset (other policies: SURVEY.md §8f rank 3, not on the device yet)
-template<typename CV>
-inline IntegratorCrespo2021 integrator_adaptive_variance_reduction_parallel(const Nested<Simpson,Trapezoidal>&, const error_heuristic_size<error_metric_relative>&, std::size_t iterations,
-                                                                            const rr_uniform_region&, const CV& cv, const region_sampling_uniform&, unsigned long spp, std::size_t seed = 0, std::size_t = 16) {
-    return IntegratorCrespo2021(iterations, spp, seed, CV::id, cv.alpha);
+using IntegratorCrespo2021 = IntegratorAdaptiveVarianceReduction<Nested<Simpson,Trapezoidal>, error_heuristic_size<error_metric_relative>>;
+inline IntegratorCrespo2021 integrator_crespo2021(std::size_t iterations, std::size_t spp, std::size_t seed = 0, std::size_t = 16) {
+    return IntegratorCrespo2021(error_heuristic_size<error_metric_relative>(error_metric_relative(), 1.e-5), iterations, spp, seed);
+}
+// the reference's overloads that take a seed (integrator-adaptive-variance-reduction.h:21-49); RR = rr_uniform_region | rr_integral_region |
+// rr_error_region, CV = cv_optimize_weight | cv_fixed_weight(alpha); region_sampling_uniform only (importance / MIS sampling: SURVEY.md §8f rank 3, not built)
+template<typename RR, typename CV, typename R, typename EH, typename = decltype(RR::id), typename = decltype(CV::id), typename = decltype(EH::id)>
+auto integrator_adaptive_variance_reduction_parallel(const R&, const EH& eh, std::size_t iterations, const RR&, const CV& cv, const region_sampling_uniform&, unsigned long spp, std::size_t seed = 0, std::size_t = 16) {
+    return IntegratorAdaptiveVarianceReduction<R, EH>(eh, iterations, spp, seed, CV::id, cv.alpha, RR::id);
+}
+template<typename RR, typename CV, typename R, typename EH, typename = decltype(RR::id), typename = decltype(CV::id), typename = decltype(EH::id)>
+auto integrator_adaptive_variance_reduction_parallel(const R&, const EH& eh, std::size_t iterations, const RR&, const CV& cv, unsigned long spp, std::size_t seed = 0, std::size_t = 16) {
+    return IntegratorAdaptiveVarianceReduction<R, EH>(eh, iterations, spp, seed, CV::id, cv.alpha, RR::id);
+}
+template<typename RR, typename CV, typename R, typename = decltype(RR::id), typename = decltype(CV::id), typename = decltype(R::id)>
+auto integrator_adaptive_variance_reduction_parallel(const R&, std::size_t iterations, const RR&, const CV& cv, const region_sampling_uniform&, unsigned long spp, std::size_t seed = 0, std::size_t = 16) {
+    using EH = error_heuristic_default<error_metric_absolute>;
+    return IntegratorAdaptiveVarianceReduction<R, EH>(EH(error_metric_absolute()), iterations, spp, seed, CV::id, cv.alpha, RR::id);
+}
+template<typename RR, typename CV, typename R, typename = decltype(RR::id), typename = decltype(CV::id), typename = decltype(R::id)>
+auto integrator_adaptive_variance_reduction_parallel(const R&, std::size_t iterations, const RR&, const CV& cv, unsigned long spp, std::size_t seed = 0, std::size_t = 16) {
+    using EH = error_heuristic_default<error_metric_absolute>;
+    return IntegratorAdaptiveVarianceReduction<R, EH>(EH(error_metric_absolute()), iterations, spp, seed, CV::id, cv.alpha, RR::id);
 }
 
 // ---- Fubini family (reference src/combination/fubini.h:18-101, regions-generator-fubini.h:7-28, integrator-crespo2021.h:24-44) ---

@@ -67,6 +67,9 @@ def run_oracle_vector(O, v):
     if path == "cv_fixed_weight":
         b, rec = O.cv_fixed_weight(integ, v["iterations"], v["spp"], v["seed"], v["alpha"], res, rmin, rmax, record=True)
         return dict(bins=b, nregions=rec["nregions"], chosen=rec["chosen"], samples=rec["samples"])
+    if path == "cv_policies":
+        b, rec = O.cv_policies(integ, v["iterations"], v["spp"], v["seed"], v["rr"], res, rmin, rmax, fixed_alpha=v["alpha"], record=True)
+        return dict(bins=b, nregions=rec["nregions"], chosen=rec["chosen"], samples=rec["samples"])
     if path == "adaptive_tolerance":
         b, n, _ = O.adaptive_tolerance(integ, v["rule"], v["heuristic"], v["tolerance"], res, rmin, rmax, v["size_weight"])
         return dict(bins=b, nleaves=n)

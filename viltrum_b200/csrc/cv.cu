@@ -44,6 +44,16 @@ __global__ void cv_ranks_kernel(uint64_t begin, uint64_t nb, uint32_t spp, uint3
     rank[i] = __umulhi(r.x, count[b]);
 }
 
+// weighted roulettes (rr_integral_region / rr_error_region): the raw 32-bit draw of every residual sample; the walk turns it into
+// u * sum(w') and picks the region by inverse CDF (regions.cu walk_rr_kernel)
+__global__ void cv_raw_kernel(uint64_t begin, uint64_t nb, uint32_t spp, uint32_t k0, uint32_t k1, uint32_t* __restrict__ raw) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= nb * spp) return;
+    const uint64_t b = i % nb; const uint32_t j = uint32_t(i / nb);
+    const uint64_t bin = begin + b;
+    raw[i] = philox4x32<10>(u32x4{uint32_t(bin), uint32_t(bin >> 32), j, 0u}, k0, k1).x;
+}
+
 // rank -> region id.  One CTA per bin tile, one thread per bin; the tile's ordered region list is staged in chunks of 64
 // pixel boxes, each thread builds the 64-bit mask of the regions that contain its bin and resolves the ranks that fall
 // inside the chunk with find-nth-set.
@@ -171,10 +181,10 @@ __global__ void __launch_bounds__(128) cv_samples_kernel(vb200_domain dom, uint6
 __global__ void __launch_bounds__(128) cv_accumulate_kernel(uint64_t begin, uint64_t nb, uint32_t spp, uint64_t nbins_total,
                                                             const uint32_t* __restrict__ count, const float* __restrict__ approx,
                                                             const float* __restrict__ fval, const float* __restrict__ app, const float* __restrict__ weight,
-                                                            float* __restrict__ out, int fixed_weight, double fixed_alpha) {
+                                                            float* __restrict__ out, int fixed_weight, double fixed_alpha, const double* __restrict__ rrf) {
     const uint64_t b = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (b >= nb) return;
-    const double factor = double(nbins_total), rrfactor = double(count[b]);
+    const double factor = double(nbins_total), rr_uniform = double(count[b]);         // rr_uniform_region: rr.max()+1 (region-russian-roulette.h:19)
     const float approximation = approx[b];
     float sum_f = 0.0f, sum_app = 0.0f; uint64_t size = 0;
     float fixed_sum = 0.0f;                 // cv_fixed_weight::Accumulator::sum (weight-strategy.h:14-21)
@@ -182,6 +192,7 @@ __global__ void __launch_bounds__(128) cv_accumulate_kernel(uint64_t begin, uint
     for (uint32_t j = 0; j < spp; ++j) {
         const uint64_t i = uint64_t(j) * nb + b;
         const double sf = double(weight[i]);
+        const double rrfactor = rrf ? rrf[i] : rr_uniform;                             // weighted roulettes: 1/probability of the chosen region
         // f(sample)*double(factor)*rrfactor*sfactor, rounded to the Sample type (…-variance-reduction.h:97-100)
         const float fs = R::d2f(R::dm(R::dm(R::dm(double(fval[i]), factor), rrfactor), sf));
         const float as = R::d2f(R::dm(R::dm(R::dm(double(app[i]), factor), rrfactor), sf));
@@ -258,6 +269,8 @@ int cv_run(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r, con
     int rc = check_domain(ctx, p->domain, r->dim); if (rc) return rc;
     if (p->spp > 0xffffffffull) return fail(ctx, VB200_ERR_INVALID, "spp invalid");
     if (p->weight_strategy != VB200_CV_OPTIMIZE_WEIGHT && p->weight_strategy != VB200_CV_FIXED_WEIGHT) return fail(ctx, VB200_ERR_INVALID, "unknown control-variate weight strategy %d", p->weight_strategy);
+    if (p->rr_policy != VB200_RR_UNIFORM && p->rr_policy != VB200_RR_INTEGRAL && p->rr_policy != VB200_RR_ERROR) return fail(ctx, VB200_ERR_INVALID, "unknown Russian-roulette policy %d", p->rr_policy);
+    const int policy = p->rr_policy;
     const vb200_domain dom = finish_domain(p->domain);
     const uint64_t total = nbins_of(dom);
     uint64_t begin, end; rc = resolve_shard(ctx, p->shard, total, &begin, &end); if (rc) return rc;
@@ -276,11 +289,22 @@ int cv_run(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r, con
     rc = walk_build(ctx, r, dom, begin, end, &w); if (rc) return rc;
     struct WalkGuard { BinWalk* w; ~WalkGuard() { walk_free(w); } } guard{&w};
     rc = walk_accumulate(ctx, r, w, dom, begin, end, 1, nullptr, d_approx.as<float>(), d_count.as<uint32_t>()); if (rc) return rc;
+    // weighted roulettes: per-bin sum of the pair weights, then of the clamped weights (two more walks, nothing per pair is stored)
+    DevBuf d_wsum, d_csum, d_rerr;
+    if (policy != VB200_RR_UNIFORM && spp > 0) {
+        if ((rc = d_wsum.alloc(ctx, nshard * sizeof(double))) || (rc = d_csum.alloc(ctx, nshard * sizeof(double)))) return rc;
+        if (policy == VB200_RR_ERROR) { if ((rc = d_rerr.alloc(ctx, r->count * sizeof(float))) || (rc = region_total_errors(ctx, r, w, d_rerr.as<float>()))) return rc; }
+        for (int pass = 1; pass <= 2; ++pass) {
+            rc = walk_rr_pass(ctx, r, w, dom, begin, end, begin, policy, pass, d_rerr.as<float>(), d_count.as<uint32_t>(), d_wsum.as<double>(), d_csum.as<double>(), 0, nullptr, nullptr);
+            if (rc) return rc;
+        }
+    }
 
     if (spp > 0) {
         uint64_t slab = (32ull << 20) / spp; if (slab < 1) slab = 1; if (slab > nshard) slab = nshard;
         const uint64_t NS = slab * spp;
-        DevBuf rank, chosen, points, weight, app, fval, rchosen, rpoints;
+        DevBuf rank, chosen, points, weight, app, fval, rchosen, rpoints, rrf;
+        if (policy != VB200_RR_UNIFORM) { if ((rc = rrf.alloc(ctx, NS * sizeof(double)))) return rc; }
         if ((rc = chosen.alloc(ctx, NS * 4)) || (rc = points.alloc(ctx, NS * D * 4)) || (rc = weight.alloc(ctx, NS * 4)) || (rc = app.alloc(ctx, NS * 4)) || (rc = fval.alloc(ctx, NS * 4))) return rc;
         if (!replay) { if ((rc = rank.alloc(ctx, NS * 4))) return rc; }
         else if (replay_mem == VB200_HOST) { if ((rc = rchosen.alloc(ctx, NS * 4)) || (rc = rpoints.alloc(ctx, NS * D * 4))) return rc; }
@@ -290,7 +314,13 @@ int cv_run(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r, con
             const uint64_t s1 = s0 + slab < end ? s0 + slab : end, nb = s1 - s0, N = nb * spp;
             const uint32_t* cnt = d_count.as<uint32_t>() + (s0 - begin);
             const float* rp = nullptr;
-            if (!replay) {
+            if (!replay && policy != VB200_RR_UNIFORM) {
+                cv_raw_kernel<<<unsigned((N + 255) / 256), 256, 0, ctx->stream>>>(s0, nb, spp, uint32_t(p->seed), uint32_t(p->seed >> 32), rank.as<uint32_t>());
+                ctx->launches++; VB200_CUDA(ctx, cudaGetLastError());
+                VB200_CUDA(ctx, cudaMemsetAsync(chosen.p, 0, N * 4, ctx->stream));
+                rc = walk_rr_pass(ctx, r, w, dom, s0, s1, begin, policy, 3, d_rerr.as<float>(), d_count.as<uint32_t>(), d_wsum.as<double>(), d_csum.as<double>(), spp,
+                                  rank.as<uint32_t>(), chosen.as<uint32_t>()); if (rc) return rc;
+            } else if (!replay) {
                 cv_ranks_kernel<<<unsigned((N + 255) / 256), 256, 0, ctx->stream>>>(s0, nb, spp, uint32_t(p->seed), uint32_t(p->seed >> 32), cnt, rank.as<uint32_t>());
                 ctx->launches++; VB200_CUDA(ctx, cudaGetLastError());
                 VB200_CUDA(ctx, cudaMemsetAsync(chosen.p, 0, N * 4, ctx->stream));
@@ -311,12 +341,17 @@ int cv_run(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r, con
             }
             rc = dispatch_samples(ctx, replay, dom, s0, nb, spp, uint32_t(p->seed), uint32_t(p->seed >> 32), r, aos.as<float>(), chosen.as<uint32_t>(), rp,
                                   points.as<float>(), weight.as<float>(), app.as<float>()); if (rc) return rc;
+            if (policy != VB200_RR_UNIFORM) {
+                rc = rr_factors(ctx, r, w, dom, s0, nb, begin, policy, spp, d_rerr.as<float>(), d_count.as<uint32_t>(), d_wsum.as<double>(), d_csum.as<double>(),
+                                chosen.as<uint32_t>(), rrf.as<double>()); if (rc) return rc;
+            }
             vb200_eval_launch ev; std::memset(&ev, 0, sizeof(ev));
             ev.n = N; ev.dim = D; ev.points = points.as<float>(); ev.values = fval.as<float>();
             rc = call_thunk(ctx, f, VB200_K_EVAL_POINTS, &ev); if (rc) return rc;
             cv_accumulate_kernel<<<unsigned((nb + 127) / 128), 128, 0, ctx->stream>>>(s0, nb, spp, total, cnt, d_approx.as<float>() + (s0 - begin),
                                                                                         fval.as<float>(), app.as<float>(), weight.as<float>(), st.dev_base,
-                                                                                        p->weight_strategy == VB200_CV_FIXED_WEIGHT ? 1 : 0, p->alpha);
+                                                                                        p->weight_strategy == VB200_CV_FIXED_WEIGHT ? 1 : 0, p->alpha,
+                                                                                        policy != VB200_RR_UNIFORM ? rrf.as<double>() : nullptr);
             ctx->launches++; VB200_CUDA(ctx, cudaGetLastError());
         }
         VB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // the slab buffers die here

@@ -456,6 +456,175 @@ int launch_accumulate(vb200_ctx* ctx, const vb200_regions* r, const BinWalkT<T>&
     return VB200_OK;
 }
 
+// ---- weighted Russian roulette among the regions of a bin -------------------------------------------------
+//   rr_integral_region  region-russian-roulette.h:30-67   weight = |integral_subrange(bin ∩ region)|                       (policy 1)
+//   rr_error_region     region-russian-roulette.h:69-106  weight = |region.error()| * vol(bin ∩ region) / vol(region)       (policy 2)
+// then, per bin: sum; w' = sum <= 0 ? 1 : max(w, 0.01*sum/n); std::discrete_distribution over w' (probabilities w'/sum(w')).
+// The weights are never materialised (1e9 pairs at BASELINE config 4): three more walks over the tile lists recompute them —
+// pass 1 sum(w), pass 2 sum(w'), pass 3 the per-sample inverse-CDF pick — all in table order, all sums in double like upstream.
+template<int S, int DB> struct StagedW {
+    static constexpr int P = (DB == 1 ? S : DB == 2 ? S * S : S * S * S);
+    float patch[P]; float rmin[DB], rmax[DB]; float volume; uint32_t ps[DB], pe[DB];
+    float ext[VB200_MAX_DIM]; float rerr; uint32_t id;
+};
+
+template<int S, int DB, class RG>
+__device__ __forceinline__ double pair_weight(int policy, int next, const float (&ba)[DB], const float (&bb)[DB], const RG& rg) {
+    float na[3], nb[3]; float vol = 1.0f;
+#pragma unroll
+    for (int d = 0; d < DB; ++d) {           // Range::intersection (range.h:92-101)
+        const float a = R::maxv(ba[d], rg.rmin[d]);
+        const float b = R::maxv(a, R::minv(bb[d], rg.rmax[d]));
+        na[d] = R::pos_in_range<float>(rg.rmin[d], rg.rmax[d], a);
+        nb[d] = R::pos_in_range<float>(rg.rmin[d], rg.rmax[d], b);
+        vol = R::fm(vol, R::fs(b, a));
+    }
+    if (policy == 1) return double(fabsf(R::fm(rg.volume, patch_subrange<S, DB, float>(rg.patch, na, nb))));       // :45, NormDefault = abs
+    for (int e = 0; e < next; ++e) vol = R::fm(vol, rg.ext[e]);                                                     // Range::volume, dimension order
+    return double(R::fd(R::fm(fabsf(rg.rerr), vol), rg.volume));                                                    // :86 (float arithmetic)
+}
+
+template<int S, int DB>
+__global__ void __launch_bounds__(256) walk_rr_kernel(TileGeom g, DomT<float> dom, uint64_t cap, uint64_t begin, uint64_t end, uint64_t base, int D, int policy, int pass,
+                                                      const float* __restrict__ patches, const float* __restrict__ rmin, const float* __restrict__ rmax,
+                                                      const float* __restrict__ volume, const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ pend,
+                                                      const uint64_t* __restrict__ offsets, const uint32_t* __restrict__ list, const float* __restrict__ rerr,
+                                                      const uint32_t* __restrict__ count, double* __restrict__ wsum, double* __restrict__ csum,
+                                                      uint32_t spp, const uint32_t* __restrict__ raw, uint32_t* __restrict__ chosen) {
+    using St = StagedW<S, DB>;
+    constexpr int CHUNK = (St::P * sizeof(float) > 256) ? 16 : 32;
+    __shared__ St s_reg[CHUNK];
+    const uint64_t t = blockIdx.x;
+    uint32_t o[3]; tile_origin(g, t, o);
+    if (!tile_in_shard(g, o, begin, end)) return;
+    uint32_t pos[3] = {0, 0, 0}; { uint32_t k = threadIdx.x; for (int d = 0; d < DB; ++d) { pos[d] = o[d] + k % g.tile[d]; k /= g.tile[d]; } }
+    bool live = true; uint64_t bin = 0, prod = 1;
+    for (int d = 0; d < DB; ++d) { live = live && pos[d] < g.res[d]; bin += uint64_t(pos[d]) * prod; prod *= g.res[d]; }
+    live = live && bin >= begin && bin < end;
+    float ba[DB], bb[DB];
+#pragma unroll
+    for (int d = 0; d < DB; ++d) {
+        ba[d] = R::add(dom.rmin[d], R::mul(float(pos[d]), dom.drange[d]));
+        bb[d] = R::add(dom.rmin[d], R::mul(float(pos[d] + 1u), dom.drange[d]));
+    }
+    const int next = D - DB;
+    const uint64_t nb = end - begin, b = bin - begin;
+    double acc = 0.0, floor_w = 0.0, total = 0.0; bool flat = false;
+    if (live && pass >= 2) {
+        const double ws = wsum[bin - base];
+        flat = ws <= 0.0;                                                                   // :49 / :88
+        floor_w = R::dd(R::dm(0.01, ws), double(count[bin - base]));                        // :50 / :89
+        if (pass == 3) total = csum[bin - base];
+    }
+    uint32_t last_id = 0;
+    const uint64_t lo = offsets[t], hi = offsets[t + 1];
+    for (uint64_t cb = lo; cb < hi; cb += CHUNK) {
+        const int n = int(min(uint64_t(CHUNK), hi - cb));
+        __syncthreads();
+        for (int k = threadIdx.x; k < n * St::P; k += blockDim.x) {
+            const int j = k / St::P, q = k % St::P;
+            s_reg[j].patch[q] = patches[uint64_t(q) * cap + list[cb + j]];
+        }
+        for (int j = threadIdx.x; j < n; j += blockDim.x) {
+            const uint64_t r = list[cb + j];
+            for (int d = 0; d < DB; ++d) {
+                s_reg[j].rmin[d] = rmin[uint64_t(d) * cap + r]; s_reg[j].rmax[d] = rmax[uint64_t(d) * cap + r];
+                s_reg[j].ps[d] = pstart[uint64_t(d) * cap + r]; s_reg[j].pe[d] = pend[uint64_t(d) * cap + r];
+            }
+            for (int e = 0; e < next; ++e) s_reg[j].ext[e] = R::fs(rmax[uint64_t(DB + e) * cap + r], rmin[uint64_t(DB + e) * cap + r]);
+            s_reg[j].volume = volume[r]; s_reg[j].rerr = rerr ? rerr[r] : 0.0f; s_reg[j].id = uint32_t(r);
+        }
+        __syncthreads();
+        if (!live) continue;
+        double cum[CHUNK]; unsigned char which[CHUNK]; int k = 0;
+        const double c0 = acc;
+        for (int j = 0; j < n; ++j) {
+            const St& rg = s_reg[j];
+            bool inside = true;
+#pragma unroll
+            for (int d = 0; d < DB; ++d) inside = inside && pos[d] >= rg.ps[d] && pos[d] < rg.pe[d];
+            if (!inside) continue;
+            double w = pair_weight<S, DB>(policy, next, ba, bb, rg);
+            if (pass >= 2) w = flat ? 1.0 : fmax(w, floor_w);
+            acc = R::da(acc, w);
+            if (pass == 3) { cum[k] = acc; which[k] = (unsigned char)j; ++k; last_id = rg.id; }
+        }
+        if (pass == 3 && k > 0) {
+            for (uint32_t sidx = 0; sidx < spp; ++sidx) {
+                const double tgt = R::dm(R::dm(double(raw[uint64_t(sidx) * nb + b]), 2.3283064365386963e-10), total);
+                if (tgt >= c0 && tgt < acc) {
+                    int i = 0; while (i < k - 1 && !(cum[i] > tgt)) ++i;
+                    chosen[uint64_t(sidx) * nb + b] = s_reg[which[i]].id;
+                }
+            }
+        }
+    }
+    if (!live) return;
+    if (pass == 1) wsum[bin - base] = acc;
+    else if (pass == 2) csum[bin - base] = acc;
+    else for (uint32_t sidx = 0; sidx < spp; ++sidx) {       // u * total rounded up to the total itself: the last region
+        const double tgt = R::dm(R::dm(double(raw[uint64_t(sidx) * nb + b]), 2.3283064365386963e-10), total);
+        if (!(tgt < acc)) chosen[uint64_t(sidx) * nb + b] = last_id;
+    }
+}
+
+// rrfactor = 1.0 / probabilities()[choice] of every residual sample (region-russian-roulette.h:59 / :98), probabilities = w'/sum(w')
+// (libstdc++ discrete_distribution: bits/random.tcc:2657-2678; fewer than two weights -> {1.0})
+template<int S, int DB>
+__global__ void __launch_bounds__(128) rr_factor_kernel(DomT<float> dom, uint64_t cap, uint64_t s0, uint64_t nb, uint64_t base, int D, int policy, uint32_t spp,
+                                                        const float* __restrict__ patches, const float* __restrict__ rmin, const float* __restrict__ rmax,
+                                                        const float* __restrict__ volume, const float* __restrict__ rerr, const uint32_t* __restrict__ count,
+                                                        const double* __restrict__ wsum, const double* __restrict__ csum, const uint32_t* __restrict__ chosen,
+                                                        double* __restrict__ rrf) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= nb * spp) return;
+    const uint64_t b = i % nb, bin = s0 + b;
+    const uint32_t n = count[bin - base];
+    if (n < 2) { rrf[i] = 1.0; return; }
+    const uint64_t r = chosen[i];
+    uint32_t pos[3]; { uint64_t q = bin; for (int d = 0; d < DB; ++d) { pos[d] = uint32_t(q % dom.res[d]); q /= dom.res[d]; } }
+    StagedW<S, DB> rg; float ba[DB], bb[DB];
+#pragma unroll
+    for (int d = 0; d < DB; ++d) {
+        ba[d] = R::add(dom.rmin[d], R::mul(float(pos[d]), dom.drange[d]));
+        bb[d] = R::add(dom.rmin[d], R::mul(float(pos[d] + 1u), dom.drange[d]));
+        rg.rmin[d] = rmin[uint64_t(d) * cap + r]; rg.rmax[d] = rmax[uint64_t(d) * cap + r];
+    }
+#pragma unroll
+    for (int q = 0; q < StagedW<S, DB>::P; ++q) rg.patch[q] = patches[uint64_t(q) * cap + r];
+    const int next = D - DB;
+    for (int e = 0; e < next; ++e) rg.ext[e] = R::fs(rmax[uint64_t(DB + e) * cap + r], rmin[uint64_t(DB + e) * cap + r]);
+    rg.volume = volume[r]; rg.rerr = rerr ? rerr[r] : 0.0f;
+    const double ws = wsum[bin - base];
+    double w = pair_weight<S, DB>(policy, next, ba, bb, rg);
+    w = (ws <= 0.0) ? 1.0 : fmax(w, R::dd(R::dm(0.01, ws), double(n)));
+    rrf[i] = R::dd(1.0, R::dd(w, csum[bin - base]));
+}
+
+// Region::error() (region.h:420-424): volume * (fold_all(high rule) - fold_all(low rule)); one thread per region, folds of
+// dimension 0 in place (fold.h:87-108)
+template<int SH, int SL>
+__global__ void __launch_bounds__(64) region_total_error_kernel(uint64_t n, uint64_t cap, int sd, const float* __restrict__ data, const float* __restrict__ volume, float* __restrict__ rerr) {
+    const uint64_t r = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    float v[729];
+    float res[2];
+    for (int which = 0; which < 2; ++which) {
+        for (int k = 0; k < sd; ++k) v[k] = data[uint64_t(k) * cap + r];
+        for (int m = sd / SH; m >= 1; m /= SH) {
+            for (int o = 0; o < m; ++o) {
+                float line[SH];
+#pragma unroll
+                for (int e = 0; e < SH; ++e) line[e] = v[o * SH + e];
+                v[o] = which == 0 ? R::apply<SH, float>(line) : R::low<SH, SL, float>(line);
+            }
+            if (m == 1) break;
+        }
+        res[which] = v[0];
+    }
+    rerr[r] = R::fm(volume[r], R::fs(res[0], res[1]));
+}
+
 template<class T> TileGeom make_geom(const BinWalkT<T>& w, const DomT<T>& dom) {
     TileGeom g; g.db = w.db;
     for (int d = 0; d < 3; ++d) { g.tile[d] = w.tile[d]; g.tiles[d] = w.tiles[d]; g.res[d] = d < w.db ? uint32_t(dom.res[d]) : 1u; }
@@ -569,6 +738,41 @@ template<class T> int walk_accumulate_t(vb200_ctx* ctx, const vb200_regions* r, 
     VB200_WALK(2, 1) VB200_WALK(2, 2) VB200_WALK(2, 3) VB200_WALK(3, 1) VB200_WALK(3, 2) VB200_WALK(3, 3) VB200_WALK(5, 1) VB200_WALK(5, 2) VB200_WALK(5, 3)
 #undef VB200_WALK
     return fail(ctx, VB200_ERR_UNSUPPORTED, "no bin walk for rule with %d samples and %d binned dimensions", w.S, w.db);
+}
+
+// ---- weighted Russian roulette (rr_integral_region / rr_error_region): host side of the kernels above --------------------------
+int region_total_errors(vb200_ctx* ctx, const vb200_regions* r, const BinWalk& w, float* rerr) {
+    if (r->SL <= 0) return fail(ctx, VB200_ERR_UNSUPPORTED, "rr_error_region needs a nested rule (Region::error(), region.h:420)");
+    if (r->sd > 729) return fail(ctx, VB200_ERR_UNSUPPORTED, "rr_error_region: %d samples per region exceed the kernel's scratch", r->sd);
+    const unsigned grid = unsigned((r->count + 63) / 64);
+    if (r->SH == 3 && r->SL == 2) region_total_error_kernel<3, 2><<<grid, 64, 0, ctx->stream>>>(r->count, r->capacity, r->sd, r->data, w.volume, rerr);
+    else if (r->SH == 5 && r->SL == 3) region_total_error_kernel<5, 3><<<grid, 64, 0, ctx->stream>>>(r->count, r->capacity, r->sd, r->data, w.volume, rerr);
+    else return fail(ctx, VB200_ERR_UNSUPPORTED, "rr_error_region: no kernel for the nested pair (%d,%d)", r->SH, r->SL);
+    ctx->launches++;
+    VB200_CUDA(ctx, cudaGetLastError());
+    return VB200_OK;
+}
+
+int walk_rr_pass(vb200_ctx* ctx, const vb200_regions* r, const BinWalk& w, const vb200_domain& domain, uint64_t begin, uint64_t end, uint64_t base, int policy, int pass,
+                 const float* rerr, const uint32_t* count, double* wsum, double* csum, uint32_t spp, const uint32_t* raw, uint32_t* chosen) {
+    const DomT<float> dom = to_dom(domain);
+    const TileGeom g = make_geom<float>(w, dom);
+#define VB200_RRW(SS, DD) if (w.S == SS && w.db == DD) { walk_rr_kernel<SS, DD><<<unsigned(w.ntiles), 256, 0, ctx->stream>>>(g, dom, w.cap, begin, end, base, r->dim, policy, pass, \
+        w.patches, r->rmin, r->rmax, w.volume, w.pstart, w.pend, w.tile_offset, w.tile_list, rerr, count, wsum, csum, spp, raw, chosen); ctx->launches++; VB200_CUDA(ctx, cudaGetLastError()); return VB200_OK; }
+    VB200_RRW(2, 1) VB200_RRW(2, 2) VB200_RRW(2, 3) VB200_RRW(3, 1) VB200_RRW(3, 2) VB200_RRW(3, 3) VB200_RRW(5, 1) VB200_RRW(5, 2) VB200_RRW(5, 3)
+#undef VB200_RRW
+    return fail(ctx, VB200_ERR_UNSUPPORTED, "no weighted roulette walk for rule with %d samples and %d binned dimensions", w.S, w.db);
+}
+
+int rr_factors(vb200_ctx* ctx, const vb200_regions* r, const BinWalk& w, const vb200_domain& domain, uint64_t s0, uint64_t nb, uint64_t base, int policy, uint32_t spp,
+               const float* rerr, const uint32_t* count, const double* wsum, const double* csum, const uint32_t* chosen, double* rrf) {
+    const DomT<float> dom = to_dom(domain);
+    const unsigned grid = unsigned((nb * spp + 127) / 128);
+#define VB200_RRF(SS, DD) if (w.S == SS && w.db == DD) { rr_factor_kernel<SS, DD><<<grid, 128, 0, ctx->stream>>>(dom, w.cap, s0, nb, base, r->dim, policy, spp, \
+        w.patches, r->rmin, r->rmax, w.volume, rerr, count, wsum, csum, chosen, rrf); ctx->launches++; VB200_CUDA(ctx, cudaGetLastError()); return VB200_OK; }
+    VB200_RRF(2, 1) VB200_RRF(2, 2) VB200_RRF(2, 3) VB200_RRF(3, 1) VB200_RRF(3, 2) VB200_RRF(3, 3) VB200_RRF(5, 1) VB200_RRF(5, 2) VB200_RRF(5, 3)
+#undef VB200_RRF
+    return fail(ctx, VB200_ERR_UNSUPPORTED, "no weighted roulette kernel for rule with %d samples and %d binned dimensions", w.S, w.db);
 }
 
 // the two scalar types the library computes in

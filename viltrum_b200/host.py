@@ -324,8 +324,9 @@ class Regions:
         s = C.Shard(); s.begin, s.end = (shard if shard else (0, 0))
         self.ctx.check(self.ctx._L.vb200_regions_integrate_bins(self.ctx._h, self._h, ctypes.byref(d), ctypes.byref(s), b, mem))
 
-    def _cv_params(self, res, rng, spp, seed, shard, fixed_alpha=None):
+    def _cv_params(self, res, rng, spp, seed, shard, fixed_alpha=None, rr="uniform"):
         p = C.CvParams()
+        p.rr_policy = C.RR_POLICIES[rr]      # rr_uniform_region / rr_integral_region / rr_error_region (region-russian-roulette.h:9-106)
         p.domain = C.make_domain(len(rng.min), res, rng.min, rng.max)
         p.shard.begin, p.shard.end = (shard if shard else (0, 0))
         p.spp, p.seed = int(spp), int(seed) & 0xFFFFFFFFFFFFFFFF
@@ -333,18 +334,18 @@ class Regions:
             p.weight_strategy, p.alpha = C.CV_FIXED_WEIGHT, float(fixed_alpha)
         return p
 
-    def cv_integrate(self, f, bins, res, rng, spp, seed, shard=None, nregions=None, approx=None, exact=False, fixed_alpha=None):
+    def cv_integrate(self, f, bins, res, rng, spp, seed, shard=None, nregions=None, approx=None, exact=False, fixed_alpha=None, rr="uniform"):
         if Context._empty(shard):
             return
         b, mem, _k = _buffer(bins)
         n, _m, _kn = _buffer(nregions, np.uint32); a, _m2, _ka = _buffer(approx)
-        p = self._cv_params(res, rng, spp, seed, shard, fixed_alpha)
+        p = self._cv_params(res, rng, spp, seed, shard, fixed_alpha, rr)
         self.ctx.check(self.ctx._L.vb200_cv_integrate(self.ctx._h, self.ctx.integrand(f, exact), self._h, ctypes.byref(p), b, mem, n, a))
 
-    def cv_replay(self, f, bins, res, rng, spp, chosen, samples, shard=None, exact=True, fixed_alpha=None):
+    def cv_replay(self, f, bins, res, rng, spp, chosen, samples, shard=None, exact=True, fixed_alpha=None, rr="uniform"):
         b, mem, _k = _buffer(bins)
         c, cmem, _kc = _buffer(chosen, np.uint32); s, _sm, _ks = _buffer(samples)
-        p = self._cv_params(res, rng, spp, 0, shard, fixed_alpha)
+        p = self._cv_params(res, rng, spp, 0, shard, fixed_alpha, rr)
         self.ctx.check(self.ctx._L.vb200_cv_replay(self.ctx._h, self.ctx.integrand(f, exact), self._h, ctypes.byref(p), c, s, cmem, b, mem))
 
     def free(self):
@@ -517,6 +518,21 @@ def cv_optimize_weight():
     return None
 
 
+def rr_uniform_region():
+    """rr_uniform_region() — reference src/control-variates/region-russian-roulette.h:9-28 (the crespo2021 preset)"""
+    return "uniform"
+
+
+def rr_integral_region():
+    """rr_integral_region() — reference src/control-variates/region-russian-roulette.h:30-67"""
+    return "integral"
+
+
+def rr_error_region():
+    """rr_error_region() — reference src/control-variates/region-russian-roulette.h:69-106"""
+    return "error"
+
+
 @dataclass
 class IntegratorCrespo2021:
     """integrator_crespo2021(iterations, spp, seed) — reference src/control-variates/integrator-crespo2021.h:7-22 ('=').
@@ -526,6 +542,7 @@ class IntegratorCrespo2021:
     seed: int = 0
     batch: int = 1
     cv: Optional[CvFixedWeight] = None
+    rr: str = "uniform"
 
     def integrate(self, ctx, bins, res, f, rng, shard=None, exact=False, logger=None, **kw):
         gen = IntegratorAdaptiveIterations(nested("simpson", "trapezoidal"), error_heuristic_size(error_metric_relative(), 1e-5),
@@ -535,7 +552,7 @@ class IntegratorCrespo2021:
             logger.log(regs)
         try:
             regs.cv_integrate(f, bins, res, rng, self.spp, self.seed, shard=shard, exact=exact,
-                              fixed_alpha=self.cv.alpha if self.cv is not None else None, **kw)
+                              fixed_alpha=self.cv.alpha if self.cv is not None else None, rr=self.rr, **kw)
         finally:
             if logger is None:
                 regs.free()
@@ -638,6 +655,17 @@ def integrator_adaptive_tolerance(rule, heuristic=None, tolerance=1e-3, max_regi
 
 def integrator_crespo2021(iterations, spp, seed=0, batch=1, cv=None):
     return IntegratorCrespo2021(iterations, spp, seed, batch, cv)
+
+
+def integrator_adaptive_variance_reduction_parallel(rule, heuristic, iterations, rr, cv, spp, seed=0, batch=1):
+    """integrator_adaptive_variance_reduction_parallel(nested(simpson,trapezoidal), error_heuristic_size(relative), iterations, RR, CV,
+    region_sampling_uniform(), spp, seed) — reference src/control-variates/integrator-adaptive-variance-reduction.h: the crespo2021 rule /
+    heuristic pair with RR = rr_uniform_region() | rr_integral_region() | rr_error_region() and CV = cv_optimize_weight() | cv_fixed_weight(a)."""
+    if getattr(rule, "name", rule) != "simpson_trapezoidal":
+        raise ValueError("the device control-variate path is built for nested(simpson, trapezoidal)")
+    if not (isinstance(heuristic, ErrorHeuristic) and heuristic.kind == "size" and heuristic.metric.kind == "relative"):
+        raise ValueError("the device control-variate path is built for error_heuristic_size(error_metric_relative())")
+    return IntegratorCrespo2021(iterations, spp, seed, batch, cv, rr)
 
 
 # ---- multi-GPU partitioning (one process per GPU; SURVEY.md §8e) ---------------------------------------------------
