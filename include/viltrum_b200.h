@@ -299,7 +299,8 @@ typedef enum vb200_cv_weight {
 typedef enum vb200_rr_policy {      /* Russian roulette among the regions that touch a bin (reference src/control-variates/region-russian-roulette.h) */
     VB200_RR_UNIFORM = 0,           /* rr_uniform_region  :9-28   every region equally likely */
     VB200_RR_INTEGRAL = 1,          /* rr_integral_region :30-67  probability ~ |integral of the interpolant over bin ∩ region| (floored at 1 % of the mean) */
-    VB200_RR_ERROR = 2              /* rr_error_region    :69-106 probability ~ |Region::error()| * vol(bin ∩ region)/vol(region) (same floor); nested rules only */
+    VB200_RR_ERROR = 2,             /* rr_error_region    :69-106 probability ~ |Region::error()| * vol(bin ∩ region)/vol(region) (same floor); nested rules only */
+    VB200_RR_PDF = 3                /* rr_pdf_region      :108-147 probability ~ integral over bin ∩ region of the shifted |interpolant| (Simpson-based rules only; factor_prob 0.01f) */
 } vb200_rr_policy;
 typedef struct vb200_cv_params {
     vb200_domain domain;
@@ -311,7 +312,7 @@ typedef struct vb200_cv_params {
     double       alpha;             /* VB200_CV_FIXED_WEIGHT only */
 } vb200_cv_params;
 
-/* RegionsIntegratorParallelVarianceReduction with rr_uniform_region | rr_integral_region | rr_error_region / cv_optimize_weight | cv_fixed_weight / region_sampling_uniform
+/* RegionsIntegratorParallelVarianceReduction with rr_uniform_region | rr_integral_region | rr_error_region | rr_pdf_region / cv_optimize_weight | cv_fixed_weight / region_sampling_uniform
  * (reference src/control-variates/regions-integrator-parallel-variance-reduction.h:32-109; the integrator_crespo2021
  * preset, integrator-crespo2021.h:7-22).  bins overwritten ('=').  Optional per-bin records (same memory space as
  * bins, may be NULL): nregions (uint32), approx (float, the control-variate integral). */

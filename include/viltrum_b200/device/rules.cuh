@@ -94,6 +94,24 @@ template<int S, class T> __device__ __forceinline__ T subrange(T a, T b, const T
     return from_double<T>(ds(antiderivative<S, T>(c, b), antiderivative<S, T>(c, a)));
 }
 
+// Simpson::pdf_points + pdf_integral_subrange (rules.h:104-154): |p| (NormDefault), shifted down by the minimum of its parabola where
+// that minimum is negative and inside (0,1), integrated over [t0,t1]
+template<class T> __device__ __forceinline__ T simpson_pdf_integral_subrange(T t0, T t1, const T* p) {
+    T q[3] = {absv(p[0]), absv(p[1]), absv(p[2])};
+    T cs[3]; coefficients<3, T>(q, cs);
+    T ymin = T(0);
+    if (cs[2] > T(0)) {
+        const T tmin = from_double<T>(dd(double(-cs[1]), dm(2.0, double(cs[2]))));       // -cs[1]/(2.0*cs[2]), double literal (rules.h:123)
+        if (tmin > T(0) && tmin < T(1)) {
+            const T ytmin = add(mul(add(mul(cs[2], tmin), cs[1]), tmin), cs[0]);
+            if (ytmin < ymin) ymin = ytmin;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) q[i] = sub(q[i], ymin);
+    return subrange<3, T>(t0, t1, q);
+}
+
 // nested.h:17-23
 template<int SH, int SL, class T> __device__ __forceinline__ T low(const T* p) {
     T q[SL];

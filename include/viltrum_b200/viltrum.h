@@ -467,6 +467,7 @@ struct cv_fixed_weight { static constexpr int id = VB200_CV_FIXED_WEIGHT; double
 struct rr_uniform_region { static constexpr int id = VB200_RR_UNIFORM; };       // :9-28
 struct rr_integral_region { static constexpr int id = VB200_RR_INTEGRAL; };     // :30-67  (NormDefault)
 struct rr_error_region { static constexpr int id = VB200_RR_ERROR; };           // :69-106 (NormDefault)
+struct rr_pdf_region { static constexpr int id = VB200_RR_PDF; };               // :108-147 (factor_prob = 0.01, NormDefault)
 struct region_sampling_uniform {};      // region-sampling.h:9-20
 // integrator_region_based(regions_generator_adaptive_heap(rule, heuristic, iterations), regions_integrator_parallel_variance_reduction(RR, CV,
 // region_sampling_uniform, spp, seed)) — reference integrator-adaptive-variance-reduction.h:11-49, regions-integrator-parallel-variance-reduction.h:32-109
@@ -496,7 +497,7 @@ inline IntegratorCrespo2021 integrator_crespo2021(std::size_t iterations, std::s
     return IntegratorCrespo2021(error_heuristic_size<error_metric_relative>(error_metric_relative(), 1.e-5), iterations, spp, seed);
 }
 // the reference's overloads that take a seed (integrator-adaptive-variance-reduction.h:21-49); RR = rr_uniform_region | rr_integral_region |
-// rr_error_region, CV = cv_optimize_weight | cv_fixed_weight(alpha); region_sampling_uniform only (importance / MIS sampling: SURVEY.md §8f rank 3, not built)
+// rr_error_region | rr_pdf_region, CV = cv_optimize_weight | cv_fixed_weight(alpha); region_sampling_uniform only (importance / MIS sampling: SURVEY.md §8f rank 3, not built)
 template<typename RR, typename CV, typename R, typename EH, typename = decltype(RR::id), typename = decltype(CV::id), typename = decltype(EH::id)>
 auto integrator_adaptive_variance_reduction_parallel(const R&, const EH& eh, std::size_t iterations, const RR&, const CV& cv, const region_sampling_uniform&, unsigned long spp, std::size_t seed = 0, std::size_t = 16) {
     return IntegratorAdaptiveVarianceReduction<R, EH>(eh, iterations, spp, seed, CV::id, cv.alpha, RR::id);

@@ -636,6 +636,27 @@ template<typename T> T region_integral_subrange(const RegionT<T>& r, int S, int 
     }
     return r.volume*v[0];
 }
+// Simpson::pdf_points / pdf_integral_subrange (rules.h:104-154): |p| shifted so that its parabola never dips below zero, integrated over [t0,t1]
+template<typename T> inline T simpson_pdf_integral_subrange(T t0, T t1, const T* p) {
+    T q[3]; for (int i=0;i<3;++i) q[i] = std::abs(p[i]);                        // NormDefault (norm.h:12)
+    T cs[5]; rule_coefficients(3,q,cs);
+    T ymin = 0;
+    if (cs[2] > 0) {
+        T tmin = T(-cs[1]/(2.0*cs[2]));                                        // rules.h:123 (double literal)
+        if ((tmin > 0) && (tmin < 1)) { T ytmin = (cs[2]*tmin + cs[1])*tmin + cs[0]; if (ytmin < ymin) ymin = ytmin; }
+    }
+    for (int i=0;i<3;++i) q[i] -= ymin;
+    return rule_subrange(3,t0,t1,q);
+}
+// region.h:277-302 (pdf_integral_subrange -> pdf_sub): fold pdf_integral_subrange(a_d,b_d) over dim D-1, ..., 0; times volume
+template<typename T> T region_pdf_integral_subrange(const RegionT<T>& r, int D, const T* a, const T* b) {
+    std::vector<T> v = r.data;
+    for (int d=D-1; d>=0; --d) {
+        T na = pos_in_range1(r.rmin[d],r.rmax[d],a[d]), nb = pos_in_range1(r.rmin[d],r.rmax[d],b[d]);
+        v = fold_dim(v,3,d+1,d,[&] (const T* l) { return simpson_pdf_integral_subrange(na,nb,l); });
+    }
+    return r.volume*v[0];
+}
 // region.h:86-112 (approximation_at -> app_at): fold at(pos_d) over dim 0, 1, ..., D-1; times volume_from(D) == 1
 template<typename T> T region_approximation_at(const RegionT<T>& r, int S, int D, const T* pos) {
     std::vector<T> v = r.data;
@@ -884,7 +905,7 @@ void cv_integrate_regions(const std::vector<RegionT<float>>& regions, int S, int
                           const float* rmin, const float* rmax, uint64_t spp, uint64_t seed, MakeResidual&& make_residual, float* bins,
                           uint32_t* rec_nregions, float* rec_approx, uint32_t* rec_chosen, float* rec_samples,
                           bool fixed_weight = false, double fixed_alpha = 1.0, int rr_policy = 0, int SL = 2) {
-    // rr_policy: 0 rr_uniform_region, 1 rr_integral_region, 2 rr_error_region (region-russian-roulette.h:9-28 / :30-67 / :69-106)
+    // rr_policy: 0 rr_uniform_region, 1 rr_integral_region, 2 rr_error_region, 3 rr_pdf_region (region-russian-roulette.h:9-28 / :30-67 / :69-106 / :108-147)
     uint64_t nb = nbins_of(dimbins,res);
     uint64_t factor = nb;
     // bin -> region lists, regions visited in list order (:53-57, serial PSTL backend)
@@ -930,10 +951,13 @@ void cv_integrate_regions(const std::vector<RegionT<float>>& regions, int S, int
             for (std::size_t i=0;i<n;++i) {
                 const RegionT<float>& r = regions[list[i]];
                 if (rr_policy == 1) wts[i] = std::abs(region_integral_subrange(r,S,D,ia[i].data(),ib[i].data()));           // :45 NormDefault = abs
-                else wts[i] = std::abs(region_error_total(r,S,SL,D))*volume_of(D,ia[i].data(),ib[i].data())/r.volume;         // :86, float arithmetic
+                else if (rr_policy == 2) wts[i] = std::abs(region_error_total(r,S,SL,D))*volume_of(D,ia[i].data(),ib[i].data())/r.volume;   // :86, float arithmetic
+                else wts[i] = region_pdf_integral_subrange(r,D,ia[i].data(),ib[i].data());                                     // :125 (Simpson only)
             }
             double sum = 0.0; for (double w : wts) sum += w;
+            const float factor_prob = 0.01f;                                    // rr_pdf_region keeps its floor as a FLOAT member (:111)
             if (sum<=0.0) for (double& w : wts) w = 1.0;
+            else if (rr_policy == 3) for (double& w : wts) w = std::max(w,factor_prob*sum/double(n));
             else for (double& w : wts) w = std::max(w,0.01*sum/double(n));
             if (n>=2) {
                 double total = 0.0; for (double w : wts) total += w;            // std::accumulate(.., 0.0)
@@ -1024,7 +1048,7 @@ extern "C" int vo_cv_policies(const char* integrand, uint64_t iterations, uint64
                    uint32_t* rec_nregions, float* rec_approx, uint32_t* rec_chosen, float* rec_samples) {
     auto F = find_finite(integrand); if (!F) return -1;
     int D = F->dim; if (dimbins<1 || dimbins>D) return -2;
-    if (rr_policy<0 || rr_policy>2 || weight_strategy<0 || weight_strategy>1) return -3;
+    if (rr_policy<0 || rr_policy>3 || weight_strategy<0 || weight_strategy>1) return -3;
     const int S = 3, SL = 2;
     Heuristic h{true,true,1.e-5};
     auto regions = generate_adaptive<float>(F->fn,S,SL,D,rmin,rmax,h,iterations);

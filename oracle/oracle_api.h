@@ -114,8 +114,8 @@ int vo_cv_fixed_weight(const char* integrand, uint64_t iterations, uint64_t spp,
 
 // The same integrator with the Russian-roulette policy and the weight strategy chosen by the caller:
 // integrator_adaptive_variance_reduction_parallel(nested(simpson,trapezoidal), error_heuristic_size(relative,1e-5), iterations,
-// RR, CV, region_sampling_uniform(), spp, seed) with RR = rr_uniform_region (0) / rr_integral_region (1) / rr_error_region (2)
-// (reference src/control-variates/region-russian-roulette.h:9-106) and CV = cv_optimize_weight (weight_strategy 0) / cv_fixed_weight(alpha) (1).
+// RR, CV, region_sampling_uniform(), spp, seed) with RR = rr_uniform_region (0) / rr_integral_region (1) / rr_error_region (2) / rr_pdf_region (3)
+// (reference src/control-variates/region-russian-roulette.h:9-147) and CV = cv_optimize_weight (weight_strategy 0) / cv_fixed_weight(alpha) (1).
 int vo_cv_policies(const char* integrand, uint64_t iterations, uint64_t spp, uint64_t seed, int rr_policy, int weight_strategy, double alpha,
                    int dimbins, const uint64_t* res, const float* rmin, const float* rmax, float* bins,
                    uint32_t* rec_nregions, float* rec_approx, uint32_t* rec_chosen, float* rec_samples);

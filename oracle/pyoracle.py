@@ -278,7 +278,7 @@ class Oracle:
             return bins, dict(nregions=nreg, approx=approx, chosen=chosen, samples=samples)
         return bins
 
-    RR_POLICIES = {"uniform": 0, "integral": 1, "error": 2}
+    RR_POLICIES = {"uniform": 0, "integral": 1, "error": 2, "pdf": 3}
 
     def cv_policies(self, integrand, iterations, spp, seed, rr, res, rmin, rmax, fixed_alpha=None, record=False):
         """integrator_adaptive_variance_reduction_parallel(nested(simpson,trapezoidal), size/relative 1e-5, iterations, rr_<rr>_region(),

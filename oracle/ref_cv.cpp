@@ -141,7 +141,7 @@ extern "C" int vo_cv_fixed_weight(const char* integrand, uint64_t iterations, ui
 extern "C" int vo_cv_policies(const char* integrand, uint64_t iterations, uint64_t spp, uint64_t seed, int rr_policy, int weight_strategy, double alpha,
                    int dimbins, const uint64_t* res, const float* rmin, const float* rmax, float* bins,
                    uint32_t* rec_nregions, float* rec_approx, uint32_t* rec_chosen, float* rec_samples) {
-    if (rr_policy<0 || rr_policy>2 || weight_strategy<0 || weight_strategy>1) return -3;
+    if (rr_policy<0 || rr_policy>3 || weight_strategy<0 || weight_strategy>1) return -3;
     RegionSink sink;
     return dispatch_finite_bins(integrand, dimbins, [&] (auto f, auto dbc) -> int {
         using F = decltype(f);
@@ -167,7 +167,8 @@ extern "C" int vo_cv_policies(const char* integrand, uint64_t iterations, uint64
         };
         if (rr_policy == 0) with_cv(RecRRT<rr_uniform_region>(&rec));
         else if (rr_policy == 1) with_cv(RecRRT<rr_integral_region<>>(&rec));
-        else with_cv(RecRRT<rr_error_region<>>(&rec));
+        else if (rr_policy == 2) with_cv(RecRRT<rr_error_region<>>(&rec));
+        else with_cv(RecRRT<rr_pdf_region<>>(&rec));
         return 0;
     });
 }

@@ -97,7 +97,8 @@ def main():
                       bins=bits(b), nregions=bits(rec["nregions"]), chosen=bits(rec["chosen"]), samples=bits(rec["samples"])))
     # rr_integral_region / rr_error_region with either weight strategy: bins + recorded choices / sample points
     for integ, res, it, spp, rr, alpha in (("x2y2", [5], 12, 6, "integral", None), ("smooth_edge2", [6, 6], 30, 4, "error", None), ("shade4_16", [3, 3], 8, 4, "integral", 0.0),
-                                           ("poly3", [3, 2], 12, 4, "error", 1.0), ("ind2", [5, 4], 20, 5, "integral", 0.5), ("shade5_16", [2, 3], 6, 3, "error", None)):
+                                           ("poly3", [3, 2], 12, 4, "error", 1.0), ("ind2", [5, 4], 20, 5, "integral", 0.5), ("shade5_16", [2, 3], 6, 3, "error", None),
+                                           ("smooth_edge2", [5, 5], 25, 4, "pdf", None), ("shade4_16", [3, 2], 10, 5, "pdf", 0.0), ("cubic1", [6], 9, 4, "pdf", 1.0)):
         d = R.dim(integ)
         b, rec = R.cv_policies(integ, it, spp, 9, rr, res, [0.0] * d, [1.0] * d, fixed_alpha=alpha, record=True)
         V.append(dict(integrand=integ, res=res, rmin=[0.0] * d, rmax=[1.0] * d, path="cv_policies", iterations=it, spp=spp, seed=9, rr=rr, alpha=alpha,

@@ -158,7 +158,7 @@ RR_CASES = [("x2y2", [12, 9], 40, 16), ("ind2", [24, 20], 300, 8), ("smooth_edge
             ("shade5_16", [20, 16], 400, 8), ("cubic1", [70], 50, 4), ("poly3", [9, 6], 120, 8), ("x2y2", [2, 3], 0, 5), ("x2y2", [40], 3, 6)]
 
 
-@pytest.mark.parametrize("rr", ["integral", "error"])
+@pytest.mark.parametrize("rr", ["integral", "error", "pdf"])
 @pytest.mark.parametrize("fixed_alpha", [None, 0.0])
 @pytest.mark.parametrize("integ,res,it,spp", RR_CASES)
 def test_weighted_roulette_replay_bit_exact(ctx, port, integ, res, it, spp, rr, fixed_alpha):
@@ -178,18 +178,18 @@ def test_weighted_roulette_replay_bit_exact(ctx, port, integ, res, it, spp, rr, 
     regs.free()
 
 
-@pytest.mark.parametrize("rr", ["integral", "error"])
+@pytest.mark.parametrize("rr", ["integral", "error", "pdf"])
 @pytest.mark.parametrize("integ,res,it,spp,fixed_alpha", [("shade4_16", [24, 24], 600, 16, None), ("smooth_edge2", [32, 32], 500, 16, None), ("ind2", [16, 16], 200, 32, 0.0),
                                                            ("shade5_16", [16, 16], 500, 16, 1.0)])
 def test_weighted_roulette_statistical_parity(ctx, port, integ, res, it, spp, fixed_alpha, rr):
     """Philox path: the region is picked by inverse CDF over the clamped weights in table order — same estimator as the reference's
     std::discrete_distribution: K seeds of both, bin-wise means within 3 sigma, matching variance."""
     from viltrum_b200 import (integrate, integrator_adaptive_variance_reduction_parallel, nested, error_heuristic_size, error_metric_relative,
-                              cv_fixed_weight, cv_optimize_weight, rr_integral_region, rr_error_region)
+                              cv_fixed_weight, cv_optimize_weight, rr_integral_region, rr_error_region, rr_pdf_region)
     d = DIMS[integ]; nb = int(np.prod(res))
     K = 16
     refs = np.stack([port.cv_policies(integ, it, spp, 100 + s, rr, res, [0.0] * d, [1.0] * d, fixed_alpha=fixed_alpha) for s in range(K)]).astype(np.float64)
-    policy = rr_integral_region() if rr == "integral" else rr_error_region()
+    policy = {"integral": rr_integral_region, "error": rr_error_region, "pdf": rr_pdf_region}[rr]()
     cv = cv_optimize_weight() if fixed_alpha is None else cv_fixed_weight(fixed_alpha)
     gpus = []
     for s in range(K):
@@ -209,7 +209,7 @@ def test_weighted_roulette_sharding_and_device_bins(ctx):
     from viltrum_b200.host import IntegratorCrespo2021
     res, it, spp = [64, 48], 1500, 8
     nb = res[0] * res[1]
-    for rr in ("integral", "error"):
+    for rr in ("integral", "error", "pdf"):
         whole = torch.full((nb,), -1.0, dtype=torch.float32, device="cuda")
         integrate(IntegratorCrespo2021(it, spp, 3, 1, None, rr), whole, res, "shade5_16", _rng("shade5_16"), ctx=ctx)
         parts = torch.zeros(nb, dtype=torch.float32, device="cuda")
@@ -219,7 +219,7 @@ def test_weighted_roulette_sharding_and_device_bins(ctx):
         assert_same_bits(parts.cpu().numpy(), whole.cpu().numpy(), f"sharded rr_{rr}_region")
         # rr_error_region concentrates the samples on few regions: with 8 spp the optimized-weight estimator is visibly biased (upstream too,
         # test_weighted_roulette_statistical_parity pins it against the reference); rr_integral_region stays close to the true mean
-        assert abs(float(whole.mean()) - 0.14326) < (4e-3 if rr == "integral" else 2.5e-2)
+        assert abs(float(whole.mean()) - 0.14326) < (2.5e-2 if rr == "error" else 4e-3)
 
 
 def test_weighted_roulette_golden_reference_vectors(ctx):
@@ -235,4 +235,4 @@ def test_weighted_roulette_golden_reference_vectors(ctx):
                        np.ascontiguousarray(f32(v["samples"]).reshape(nb, spp, d)), fixed_alpha=v["alpha"], rr=v["rr"])
         assert_same_bits(out, f32(v["bins"]), f"{v['integrand']} rr={v['rr']} alpha={v['alpha']}")
         regs.free(); n += 1
-    assert n == 6
+    assert n == 9

@@ -132,11 +132,11 @@ def test_cv_fixed_weight(port, reference, integ, res, it, spp, alpha):
         assert_same_bits(a[1][k], b[1][k], k)
 
 
-@pytest.mark.parametrize("rr", ["uniform", "integral", "error"])
+@pytest.mark.parametrize("rr", ["uniform", "integral", "error", "pdf"])
 @pytest.mark.parametrize("integ,res,it,spp,alpha", [("x2y2", [16], 64, 16, None), ("shade4_16", [8, 6], 200, 8, 0.0), ("smooth_edge2", [12, 12], 300, 7, None),
                                                      ("poly3", [5, 4], 50, 5, 0.7), ("ind2", [6, 6], 100, 9, None), ("x2y2", [3, 3], 0, 4, 1.0), ("shade5_16", [4, 3], 80, 6, None)])
 def test_cv_policies(port, reference, integ, res, it, spp, alpha, rr):
-    """rr_uniform_region / rr_integral_region / rr_error_region x cv_optimize_weight / cv_fixed_weight — region-russian-roulette.h:9-106
+    """rr_uniform_region / rr_integral_region / rr_error_region / rr_pdf_region x cv_optimize_weight / cv_fixed_weight — region-russian-roulette.h:9-147
     (std::discrete_distribution and generate_canonical<double,53> restated in the port)"""
     rmin, rmax = _range(port, integ)
     a = port.cv_policies(integ, it, spp, 11, rr, res, rmin, rmax, fixed_alpha=alpha, record=True)

@@ -4,7 +4,7 @@ include/viltrum_b200.h) and the C++17 drop-in headers (include/viltrum_b200/vilt
 the thin host-side mirror used by the tests and the benchmark (ctypes over the C ABI, numpy/torch buffers)."""
 from .host import (Context, Regions, integrate, monte_carlo, monte_carlo_per_bin_parallel, integrator_per_bin_parallel,  # noqa: F401
                    integrator_newton_cotes, integrator_adaptive_iterations, integrator_crespo2021, nested,
-                   integrator_fubini, integrator_crespo2021_infinite, integrator_adaptive_tolerance, cv_fixed_weight, cv_optimize_weight, rr_uniform_region, rr_integral_region, rr_error_region,
+                   integrator_fubini, integrator_crespo2021_infinite, integrator_adaptive_tolerance, cv_fixed_weight, cv_optimize_weight, rr_uniform_region, rr_integral_region, rr_error_region, rr_pdf_region,
                    integrator_adaptive_variance_reduction_parallel, steps, FubiniIntegrand, range_split_at,
                    error_heuristic_default, error_heuristic_size, error_metric_absolute, error_metric_relative,
                    range_primary, range_primary_infinite, Range, RangeInfinite, builtin_names, shard_for_rank, sample_shard_for_rank)

@@ -11,7 +11,7 @@ MAX_DIM, MAX_DIMBINS, K_COUNT = 8, 3, 8
 HOST, DEVICE = 0, 1
 MC_PER_BIN, PER_BIN_MC = 0, 1
 CV_OPTIMIZE_WEIGHT, CV_FIXED_WEIGHT = 0, 1
-RR_POLICIES = {"uniform": 0, "integral": 1, "error": 2}     # vb200_rr_policy
+RR_POLICIES = {"uniform": 0, "integral": 1, "error": 2, "pdf": 3}     # vb200_rr_policy
 RULES = {"trapezoidal": 2, "simpson": 3, "boole": 5, "simpson_trapezoidal": 32, "boole_simpson": 53}
 RULE_SAMPLES = {2: 2, 3: 3, 5: 5, 32: 3, 53: 5}
 

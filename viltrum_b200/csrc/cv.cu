@@ -269,7 +269,7 @@ int cv_run(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r, con
     int rc = check_domain(ctx, p->domain, r->dim); if (rc) return rc;
     if (p->spp > 0xffffffffull) return fail(ctx, VB200_ERR_INVALID, "spp invalid");
     if (p->weight_strategy != VB200_CV_OPTIMIZE_WEIGHT && p->weight_strategy != VB200_CV_FIXED_WEIGHT) return fail(ctx, VB200_ERR_INVALID, "unknown control-variate weight strategy %d", p->weight_strategy);
-    if (p->rr_policy != VB200_RR_UNIFORM && p->rr_policy != VB200_RR_INTEGRAL && p->rr_policy != VB200_RR_ERROR) return fail(ctx, VB200_ERR_INVALID, "unknown Russian-roulette policy %d", p->rr_policy);
+    if (p->rr_policy != VB200_RR_UNIFORM && p->rr_policy != VB200_RR_INTEGRAL && p->rr_policy != VB200_RR_ERROR && p->rr_policy != VB200_RR_PDF) return fail(ctx, VB200_ERR_INVALID, "unknown Russian-roulette policy %d", p->rr_policy);
     const int policy = p->rr_policy;
     const vb200_domain dom = finish_domain(p->domain);
     const uint64_t total = nbins_of(dom);
@@ -290,12 +290,13 @@ int cv_run(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r, con
     struct WalkGuard { BinWalk* w; ~WalkGuard() { walk_free(w); } } guard{&w};
     rc = walk_accumulate(ctx, r, w, dom, begin, end, 1, nullptr, d_approx.as<float>(), d_count.as<uint32_t>()); if (rc) return rc;
     // weighted roulettes: per-bin sum of the pair weights, then of the clamped weights (two more walks, nothing per pair is stored)
-    DevBuf d_wsum, d_csum, d_rerr;
+    DevBuf d_wsum, d_csum, d_rerr, d_pdf;
     if (policy != VB200_RR_UNIFORM && spp > 0) {
+        if (policy == VB200_RR_PDF) { float* pp = nullptr; rc = walk_pdf_patches(ctx, r, w, &pp); d_pdf.p = pp; d_pdf.owner = ctx; if (rc) return rc; }
         if ((rc = d_wsum.alloc(ctx, nshard * sizeof(double))) || (rc = d_csum.alloc(ctx, nshard * sizeof(double)))) return rc;
         if (policy == VB200_RR_ERROR) { if ((rc = d_rerr.alloc(ctx, r->count * sizeof(float))) || (rc = region_total_errors(ctx, r, w, d_rerr.as<float>()))) return rc; }
         for (int pass = 1; pass <= 2; ++pass) {
-            rc = walk_rr_pass(ctx, r, w, dom, begin, end, begin, policy, pass, d_rerr.as<float>(), d_count.as<uint32_t>(), d_wsum.as<double>(), d_csum.as<double>(), 0, nullptr, nullptr);
+            rc = walk_rr_pass(ctx, r, w, dom, begin, end, begin, policy, pass, d_rerr.as<float>(), d_pdf.as<float>(), d_count.as<uint32_t>(), d_wsum.as<double>(), d_csum.as<double>(), 0, nullptr, nullptr);
             if (rc) return rc;
         }
     }
@@ -318,7 +319,7 @@ int cv_run(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r, con
                 cv_raw_kernel<<<unsigned((N + 255) / 256), 256, 0, ctx->stream>>>(s0, nb, spp, uint32_t(p->seed), uint32_t(p->seed >> 32), rank.as<uint32_t>());
                 ctx->launches++; VB200_CUDA(ctx, cudaGetLastError());
                 VB200_CUDA(ctx, cudaMemsetAsync(chosen.p, 0, N * 4, ctx->stream));
-                rc = walk_rr_pass(ctx, r, w, dom, s0, s1, begin, policy, 3, d_rerr.as<float>(), d_count.as<uint32_t>(), d_wsum.as<double>(), d_csum.as<double>(), spp,
+                rc = walk_rr_pass(ctx, r, w, dom, s0, s1, begin, policy, 3, d_rerr.as<float>(), d_pdf.as<float>(), d_count.as<uint32_t>(), d_wsum.as<double>(), d_csum.as<double>(), spp,
                                   rank.as<uint32_t>(), chosen.as<uint32_t>()); if (rc) return rc;
             } else if (!replay) {
                 cv_ranks_kernel<<<unsigned((N + 255) / 256), 256, 0, ctx->stream>>>(s0, nb, spp, uint32_t(p->seed), uint32_t(p->seed >> 32), cnt, rank.as<uint32_t>());
@@ -342,7 +343,7 @@ int cv_run(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r, con
             rc = dispatch_samples(ctx, replay, dom, s0, nb, spp, uint32_t(p->seed), uint32_t(p->seed >> 32), r, aos.as<float>(), chosen.as<uint32_t>(), rp,
                                   points.as<float>(), weight.as<float>(), app.as<float>()); if (rc) return rc;
             if (policy != VB200_RR_UNIFORM) {
-                rc = rr_factors(ctx, r, w, dom, s0, nb, begin, policy, spp, d_rerr.as<float>(), d_count.as<uint32_t>(), d_wsum.as<double>(), d_csum.as<double>(),
+                rc = rr_factors(ctx, r, w, dom, s0, nb, begin, policy, spp, d_rerr.as<float>(), d_pdf.as<float>(), d_count.as<uint32_t>(), d_wsum.as<double>(), d_csum.as<double>(),
                                 chosen.as<uint32_t>(), rrf.as<double>()); if (rc) return rc;
             }
             vb200_eval_launch ev; std::memset(&ev, 0, sizeof(ev));

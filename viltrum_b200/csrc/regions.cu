@@ -199,6 +199,19 @@ __global__ void fold_last_dim_kernel(uint64_t nregions, uint64_t cap, int lower 
     out[uint64_t(k) * cap + i] = R::subrange<S, T>(T(0), T(1), line);
 }
 
+// the same fold level for Region::pdf_integral_subrange -> pdf_sub (region.h:277-302; Simpson only): the line integral of the
+// shifted absolute parabola instead of the signed one
+template<class T>
+__global__ void pdf_fold_last_dim_kernel(uint64_t nregions, uint64_t cap, int lower, const T* __restrict__ in, T* __restrict__ out) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    if (i >= nregions) return;
+    T line[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) line[j] = in[(uint64_t(k) + uint64_t(j) * uint64_t(lower)) * cap + i];
+    out[uint64_t(k) * cap + i] = R::simpson_pdf_integral_subrange<T>(T(0), T(1), line);
+}
+
 // Range::volume (range.h:21-25) and pixels_in_region (region.h:454-463) per region
 template<class T>
 __global__ void region_boxes_kernel(uint64_t nregions, uint64_t cap, int dim, int db, DomT<T> dom,
@@ -364,6 +377,38 @@ __device__ __forceinline__ T patch_subrange(const T* patch, const T (&na)[3], co
     return R::subrange<S, T>(na[0], nb[0], t1);
 }
 
+// Region::pdf_integral_subrange -> pdf_sub over the binned dims of a pdf patch (Simpson), same fold order as patch_subrange
+template<int DB>
+__device__ __forceinline__ float pdf_patch_subrange(const float* patch, const float (&na)[3], const float (&nb)[3]) {
+    constexpr int S = 3;
+    if (DB == 1) return R::simpson_pdf_integral_subrange<float>(na[0], nb[0], patch);
+    if (DB == 2) {
+        float t[S];
+#pragma unroll
+        for (int i0 = 0; i0 < S; ++i0) {
+            float line[S];
+#pragma unroll
+            for (int i1 = 0; i1 < S; ++i1) line[i1] = patch[i0 + S * i1];
+            t[i0] = R::simpson_pdf_integral_subrange<float>(na[1], nb[1], line);
+        }
+        return R::simpson_pdf_integral_subrange<float>(na[0], nb[0], t);
+    }
+    float t1[S];
+#pragma unroll
+    for (int i0 = 0; i0 < S; ++i0) {
+        float t2[S];
+#pragma unroll
+        for (int i1 = 0; i1 < S; ++i1) {
+            float line[S];
+#pragma unroll
+            for (int i2 = 0; i2 < S; ++i2) line[i2] = patch[i0 + S * i1 + S * S * i2];
+            t2[i1] = R::simpson_pdf_integral_subrange<float>(na[2], nb[2], line);
+        }
+        t1[i0] = R::simpson_pdf_integral_subrange<float>(na[1], nb[1], t2);
+    }
+    return R::simpson_pdf_integral_subrange<float>(na[0], nb[0], t1);
+}
+
 template<int S, int DB, class T> struct Staged {
     static constexpr int P = (DB == 1 ? S : DB == 2 ? S * S : S * S * S);
     T patch[P]; T rmin[DB], rmax[DB]; T volume; uint32_t ps[DB], pe[DB];
@@ -459,7 +504,8 @@ int launch_accumulate(vb200_ctx* ctx, const vb200_regions* r, const BinWalkT<T>&
 // ---- weighted Russian roulette among the regions of a bin -------------------------------------------------
 //   rr_integral_region  region-russian-roulette.h:30-67   weight = |integral_subrange(bin ∩ region)|                       (policy 1)
 //   rr_error_region     region-russian-roulette.h:69-106  weight = |region.error()| * vol(bin ∩ region) / vol(region)       (policy 2)
-// then, per bin: sum; w' = sum <= 0 ? 1 : max(w, 0.01*sum/n); std::discrete_distribution over w' (probabilities w'/sum(w')).
+//   rr_pdf_region       region-russian-roulette.h:108-147 weight = pdf_integral_subrange(bin ∩ region) (Simpson; `patches` = pdf patches) (policy 3)
+// then, per bin: sum; w' = sum <= 0 ? 1 : max(w, floor_factor*sum/n)  (floor_factor 0.01; double(0.01f) for rr_pdf_region); std::discrete_distribution over w' (probabilities w'/sum(w')).
 // The weights are never materialised (1e9 pairs at BASELINE config 4): three more walks over the tile lists recompute them —
 // pass 1 sum(w), pass 2 sum(w'), pass 3 the per-sample inverse-CDF pick — all in table order, all sums in double like upstream.
 template<int S, int DB> struct StagedW {
@@ -480,12 +526,16 @@ __device__ __forceinline__ double pair_weight(int policy, int next, const float 
         vol = R::fm(vol, R::fs(b, a));
     }
     if (policy == 1) return double(fabsf(R::fm(rg.volume, patch_subrange<S, DB, float>(rg.patch, na, nb))));       // :45, NormDefault = abs
+    if (policy == 3) {                                                                                              // :125, the patch is the pdf patch
+        if constexpr (S == 3) return double(R::fm(rg.volume, pdf_patch_subrange<DB>(rg.patch, na, nb)));
+        else return 0.0;
+    }
     for (int e = 0; e < next; ++e) vol = R::fm(vol, rg.ext[e]);                                                     // Range::volume, dimension order
     return double(R::fd(R::fm(fabsf(rg.rerr), vol), rg.volume));                                                    // :86 (float arithmetic)
 }
 
 template<int S, int DB>
-__global__ void __launch_bounds__(256) walk_rr_kernel(TileGeom g, DomT<float> dom, uint64_t cap, uint64_t begin, uint64_t end, uint64_t base, int D, int policy, int pass,
+__global__ void __launch_bounds__(256) walk_rr_kernel(TileGeom g, DomT<float> dom, uint64_t cap, uint64_t begin, uint64_t end, uint64_t base, int D, int policy, int pass, double floor_factor,
                                                       const float* __restrict__ patches, const float* __restrict__ rmin, const float* __restrict__ rmax,
                                                       const float* __restrict__ volume, const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ pend,
                                                       const uint64_t* __restrict__ offsets, const uint32_t* __restrict__ list, const float* __restrict__ rerr,
@@ -513,7 +563,7 @@ __global__ void __launch_bounds__(256) walk_rr_kernel(TileGeom g, DomT<float> do
     if (live && pass >= 2) {
         const double ws = wsum[bin - base];
         flat = ws <= 0.0;                                                                   // :49 / :88
-        floor_w = R::dd(R::dm(0.01, ws), double(count[bin - base]));                        // :50 / :89
+        floor_w = R::dd(R::dm(floor_factor, ws), double(count[bin - base]));                // :50 / :89 / :130
         if (pass == 3) total = csum[bin - base];
     }
     uint32_t last_id = 0;
@@ -571,7 +621,7 @@ __global__ void __launch_bounds__(256) walk_rr_kernel(TileGeom g, DomT<float> do
 // rrfactor = 1.0 / probabilities()[choice] of every residual sample (region-russian-roulette.h:59 / :98), probabilities = w'/sum(w')
 // (libstdc++ discrete_distribution: bits/random.tcc:2657-2678; fewer than two weights -> {1.0})
 template<int S, int DB>
-__global__ void __launch_bounds__(128) rr_factor_kernel(DomT<float> dom, uint64_t cap, uint64_t s0, uint64_t nb, uint64_t base, int D, int policy, uint32_t spp,
+__global__ void __launch_bounds__(128) rr_factor_kernel(DomT<float> dom, uint64_t cap, uint64_t s0, uint64_t nb, uint64_t base, int D, int policy, double floor_factor, uint32_t spp,
                                                         const float* __restrict__ patches, const float* __restrict__ rmin, const float* __restrict__ rmax,
                                                         const float* __restrict__ volume, const float* __restrict__ rerr, const uint32_t* __restrict__ count,
                                                         const double* __restrict__ wsum, const double* __restrict__ csum, const uint32_t* __restrict__ chosen,
@@ -597,7 +647,7 @@ __global__ void __launch_bounds__(128) rr_factor_kernel(DomT<float> dom, uint64_
     rg.volume = volume[r]; rg.rerr = rerr ? rerr[r] : 0.0f;
     const double ws = wsum[bin - base];
     double w = pair_weight<S, DB>(policy, next, ba, bb, rg);
-    w = (ws <= 0.0) ? 1.0 : fmax(w, R::dd(R::dm(0.01, ws), double(n)));
+    w = (ws <= 0.0) ? 1.0 : fmax(w, R::dd(R::dm(floor_factor, ws), double(n)));
     rrf[i] = R::dd(1.0, R::dd(w, csum[bin - base]));
 }
 
@@ -753,23 +803,61 @@ int region_total_errors(vb200_ctx* ctx, const vb200_regions* r, const BinWalk& w
     return VB200_OK;
 }
 
+// pdf patches [3^db][cap] for rr_pdf_region: the region samples folded over the non-binned dimensions D-1 .. db with the pdf line
+// integral over [0,1] (the same for every bin, like BinWalk::patches).  The caller frees *out with dfree.
+int walk_pdf_patches(vb200_ctx* ctx, const vb200_regions* r, const BinWalk& w, float** out) {
+    *out = nullptr;
+    if (r->SH != 3) return fail(ctx, VB200_ERR_UNSUPPORTED, "rr_pdf_region needs a Simpson-based rule (only Simpson defines pdf_integral_subrange, rules.h:151)");
+    const int D = r->dim, db = w.db; const uint64_t n = r->count, cap = r->capacity;
+    float* bufs[2] = {nullptr, nullptr};
+    const float* cur = r->data;
+    uint64_t biggest = 1; for (int i = 0; i < D - 1; ++i) biggest *= 3;
+    int which = 0;
+    auto cleanup = [&] (float* keep) { for (float* b : bufs) if (b && b != keep) dfree(ctx, b); };
+    for (int m = D; m > db; --m) {
+        int lower = 1; for (int i = 0; i < m - 1; ++i) lower *= 3;
+        if (!bufs[which] && dmalloc(ctx, &bufs[which], biggest * cap * sizeof(float)) != cudaSuccess) { cudaGetLastError(); cleanup(nullptr); return fail(ctx, VB200_ERR_NOMEM, "cudaMalloc failed (pdf patches)"); }
+        dim3 grid(unsigned((n + 127) / 128), unsigned(lower));
+        pdf_fold_last_dim_kernel<float><<<grid, 128, 0, ctx->stream>>>(n, cap, lower, cur, bufs[which]);
+        ctx->launches++;
+        cur = bufs[which]; which ^= 1;
+    }
+    if (cur == r->data) {      // every dimension is binned: the pdf patch is the sample table itself
+        if (dmalloc(ctx, &bufs[0], uint64_t(r->sd) * cap * sizeof(float)) != cudaSuccess) { cudaGetLastError(); return fail(ctx, VB200_ERR_NOMEM, "cudaMalloc failed (pdf patches)"); }
+        cudaMemcpyAsync(bufs[0], r->data, uint64_t(r->sd) * cap * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream);
+        cur = bufs[0];
+    }
+    cleanup(const_cast<float*>(cur));
+    *out = const_cast<float*>(cur);
+    VB200_CUDA(ctx, cudaGetLastError());
+    return VB200_OK;
+}
+
+static double rr_floor_factor(int policy) { return policy == VB200_RR_PDF ? double(0.01f) : 0.01; }    // rr_pdf_region keeps factor_prob as a float (:111)
+
 int walk_rr_pass(vb200_ctx* ctx, const vb200_regions* r, const BinWalk& w, const vb200_domain& domain, uint64_t begin, uint64_t end, uint64_t base, int policy, int pass,
-                 const float* rerr, const uint32_t* count, double* wsum, double* csum, uint32_t spp, const uint32_t* raw, uint32_t* chosen) {
+                 const float* rerr, const float* pdf_patches, const uint32_t* count, double* wsum, double* csum, uint32_t spp, const uint32_t* raw, uint32_t* chosen) {
     const DomT<float> dom = to_dom(domain);
     const TileGeom g = make_geom<float>(w, dom);
-#define VB200_RRW(SS, DD) if (w.S == SS && w.db == DD) { walk_rr_kernel<SS, DD><<<unsigned(w.ntiles), 256, 0, ctx->stream>>>(g, dom, w.cap, begin, end, base, r->dim, policy, pass, \
-        w.patches, r->rmin, r->rmax, w.volume, w.pstart, w.pend, w.tile_offset, w.tile_list, rerr, count, wsum, csum, spp, raw, chosen); ctx->launches++; VB200_CUDA(ctx, cudaGetLastError()); return VB200_OK; }
+    if (policy == VB200_RR_PDF && (w.S != 3 || !pdf_patches)) return fail(ctx, VB200_ERR_UNSUPPORTED, "rr_pdf_region needs a Simpson-based rule (only Simpson defines pdf_integral_subrange, rules.h:151)");
+    const float* patches = policy == VB200_RR_PDF ? pdf_patches : w.patches;
+    const double ff = rr_floor_factor(policy);
+#define VB200_RRW(SS, DD) if (w.S == SS && w.db == DD) { walk_rr_kernel<SS, DD><<<unsigned(w.ntiles), 256, 0, ctx->stream>>>(g, dom, w.cap, begin, end, base, r->dim, policy, pass, ff, \
+        patches, r->rmin, r->rmax, w.volume, w.pstart, w.pend, w.tile_offset, w.tile_list, rerr, count, wsum, csum, spp, raw, chosen); ctx->launches++; VB200_CUDA(ctx, cudaGetLastError()); return VB200_OK; }
     VB200_RRW(2, 1) VB200_RRW(2, 2) VB200_RRW(2, 3) VB200_RRW(3, 1) VB200_RRW(3, 2) VB200_RRW(3, 3) VB200_RRW(5, 1) VB200_RRW(5, 2) VB200_RRW(5, 3)
 #undef VB200_RRW
     return fail(ctx, VB200_ERR_UNSUPPORTED, "no weighted roulette walk for rule with %d samples and %d binned dimensions", w.S, w.db);
 }
 
 int rr_factors(vb200_ctx* ctx, const vb200_regions* r, const BinWalk& w, const vb200_domain& domain, uint64_t s0, uint64_t nb, uint64_t base, int policy, uint32_t spp,
-               const float* rerr, const uint32_t* count, const double* wsum, const double* csum, const uint32_t* chosen, double* rrf) {
+               const float* rerr, const float* pdf_patches, const uint32_t* count, const double* wsum, const double* csum, const uint32_t* chosen, double* rrf) {
     const DomT<float> dom = to_dom(domain);
+    if (policy == VB200_RR_PDF && (w.S != 3 || !pdf_patches)) return fail(ctx, VB200_ERR_UNSUPPORTED, "rr_pdf_region needs a Simpson-based rule");
+    const float* patches = policy == VB200_RR_PDF ? pdf_patches : w.patches;
+    const double ff = rr_floor_factor(policy);
     const unsigned grid = unsigned((nb * spp + 127) / 128);
-#define VB200_RRF(SS, DD) if (w.S == SS && w.db == DD) { rr_factor_kernel<SS, DD><<<grid, 128, 0, ctx->stream>>>(dom, w.cap, s0, nb, base, r->dim, policy, spp, \
-        w.patches, r->rmin, r->rmax, w.volume, rerr, count, wsum, csum, chosen, rrf); ctx->launches++; VB200_CUDA(ctx, cudaGetLastError()); return VB200_OK; }
+#define VB200_RRF(SS, DD) if (w.S == SS && w.db == DD) { rr_factor_kernel<SS, DD><<<grid, 128, 0, ctx->stream>>>(dom, w.cap, s0, nb, base, r->dim, policy, ff, spp, \
+        patches, r->rmin, r->rmax, w.volume, rerr, count, wsum, csum, chosen, rrf); ctx->launches++; VB200_CUDA(ctx, cudaGetLastError()); return VB200_OK; }
     VB200_RRF(2, 1) VB200_RRF(2, 2) VB200_RRF(2, 3) VB200_RRF(3, 1) VB200_RRF(3, 2) VB200_RRF(3, 3) VB200_RRF(5, 1) VB200_RRF(5, 2) VB200_RRF(5, 3)
 #undef VB200_RRF
     return fail(ctx, VB200_ERR_UNSUPPORTED, "no weighted roulette kernel for rule with %d samples and %d binned dimensions", w.S, w.db);

@@ -78,16 +78,17 @@ inline void walk_free(BinWalk* w) { walk_free_t<float>(w); }
 inline int walk_accumulate(vb200_ctx* ctx, const vb200_regions* r, const BinWalk& w, const vb200_domain& dom, uint64_t begin, uint64_t end,
                            int mode, float* out, float* approx, uint32_t* count) { return walk_accumulate_t<float>(ctx, r, w, to_dom(dom), begin, end, mode, out, approx, count); }
 
-// Weighted Russian roulette among the regions of a bin (rr_integral_region = policy 1, rr_error_region = policy 2; reference
-// src/control-variates/region-russian-roulette.h:30-106).  Per-bin arrays are indexed by bin - base.
+// Weighted Russian roulette among the regions of a bin (rr_integral_region = policy 1, rr_error_region = policy 2, rr_pdf_region = policy 3;
+// reference src/control-variates/region-russian-roulette.h:30-147).  Per-bin arrays are indexed by bin - base.
 //   region_total_errors: rerr[r] = Region::error() (policy 2 only)
 //   walk_rr_pass: pass 1 -> wsum[bin] = sum of the pair weights; pass 2 -> csum[bin] = sum of the clamped weights; pass 3 -> chosen[j*nb+b]
 //                 (sample-major over the slab [begin,end)) = the region whose cumulative clamped weight first exceeds raw[j*nb+b]*2^-32*csum
 //   rr_factors: rrf[j*nb+b] = 1.0 / (w'(bin, chosen) / csum[bin])  (1.0 where fewer than two regions touch the bin)
 int region_total_errors(vb200_ctx* ctx, const vb200_regions* r, const BinWalk& w, float* rerr);
+int walk_pdf_patches(vb200_ctx* ctx, const vb200_regions* r, const BinWalk& w, float** out);   // rr_pdf_region (policy 3): [3^db][cap], freed by the caller (dfree)
 int walk_rr_pass(vb200_ctx* ctx, const vb200_regions* r, const BinWalk& w, const vb200_domain& dom, uint64_t begin, uint64_t end, uint64_t base, int policy, int pass,
-                 const float* rerr, const uint32_t* count, double* wsum, double* csum, uint32_t spp, const uint32_t* raw, uint32_t* chosen);
+                 const float* rerr, const float* pdf_patches, const uint32_t* count, double* wsum, double* csum, uint32_t spp, const uint32_t* raw, uint32_t* chosen);
 int rr_factors(vb200_ctx* ctx, const vb200_regions* r, const BinWalk& w, const vb200_domain& dom, uint64_t s0, uint64_t nb, uint64_t base, int policy, uint32_t spp,
-               const float* rerr, const uint32_t* count, const double* wsum, const double* csum, const uint32_t* chosen, double* rrf);
+               const float* rerr, const float* pdf_patches, const uint32_t* count, const double* wsum, const double* csum, const uint32_t* chosen, double* rrf);
 
 } // namespace vb200

@@ -533,6 +533,11 @@ def rr_error_region():
     return "error"
 
 
+def rr_pdf_region():
+    """rr_pdf_region() — reference src/control-variates/region-russian-roulette.h:108-147 (factor_prob = 0.01)"""
+    return "pdf"
+
+
 @dataclass
 class IntegratorCrespo2021:
     """integrator_crespo2021(iterations, spp, seed) — reference src/control-variates/integrator-crespo2021.h:7-22 ('=').
@@ -660,7 +665,7 @@ def integrator_crespo2021(iterations, spp, seed=0, batch=1, cv=None):
 def integrator_adaptive_variance_reduction_parallel(rule, heuristic, iterations, rr, cv, spp, seed=0, batch=1):
     """integrator_adaptive_variance_reduction_parallel(nested(simpson,trapezoidal), error_heuristic_size(relative), iterations, RR, CV,
     region_sampling_uniform(), spp, seed) — reference src/control-variates/integrator-adaptive-variance-reduction.h: the crespo2021 rule /
-    heuristic pair with RR = rr_uniform_region() | rr_integral_region() | rr_error_region() and CV = cv_optimize_weight() | cv_fixed_weight(a)."""
+    heuristic pair with RR = rr_uniform_region() | rr_integral_region() | rr_error_region() | rr_pdf_region() and CV = cv_optimize_weight() | cv_fixed_weight(a)."""
     if getattr(rule, "name", rule) != "simpson_trapezoidal":
         raise ValueError("the device control-variate path is built for nested(simpson, trapezoidal)")
     if not (isinstance(heuristic, ErrorHeuristic) and heuristic.kind == "size" and heuristic.metric.kind == "relative"):
