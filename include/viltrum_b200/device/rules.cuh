@@ -25,6 +25,27 @@ __device__ __forceinline__ double ds(double a, double b) { return __dsub_rn(a, b
 __device__ __forceinline__ double dd(double a, double b) { return __ddiv_rn(a, b); }
 __device__ __forceinline__ float  d2f(double a) { return __double2float_rn(a); }
 
+// a / K for the small integer constants of the rules (2, 3, 4, 5, 6, 90), correctly rounded without the division subroutine:
+// powers of two are exact multiplications; otherwise Markstein's sequence q0 = RN(a*y), r = a - K*q0 (exact in one FMA),
+// q = RN(q0 + r*y) with y = RN(1/K), which is the correctly rounded quotient for every K here (no all-ones significand) as long as
+// nothing under- or overflows — checked against a/K on 4e8 random doubles (profiles/exp/divtest.c) and guarded by magnitude, with
+// the true division as the fallback (zeros, infinities, NaNs, denormal neighbourhoods).
+template<int K> __device__ __forceinline__ double divc(double a) {
+    if constexpr (K == 2) return __dmul_rn(a, 0.5);
+    else if constexpr (K == 4) return __dmul_rn(a, 0.25);
+    else {
+        constexpr double y = 1.0 / double(K);
+        const double m = fabs(a);
+        if (!(m >= 1e290) && !(m > 0.0 && m <= 1e-290)) {       // zeros and NaNs take the fast path too (q0 = +-0 / NaN is already the answer)
+            const double q0 = __dmul_rn(a, y);
+            const double r = __fma_rn(-double(K), q0, a);
+            const double q = __fma_rn(r, y, q0);
+            return r == 0.0 ? q0 : q;                            // keeps the sign of a zero quotient
+        }
+        return __ddiv_rn(a, double(K));
+    }
+}
+
 // arithmetic in T with explicit rounding
 __device__ __forceinline__ float  mul(float a, float b) { return fm(a, b); }
 __device__ __forceinline__ float  add(float a, float b) { return fa(a, b); }
@@ -46,12 +67,12 @@ __device__ __forceinline__ double minv(double a, double b) { return fmin(a, b); 
 
 // quadrature weights, rules.h:14 / :64 / :256
 template<int S, class T> __device__ __forceinline__ T apply(const T* p) {
-    if constexpr (S == 2) return from_double<T>(dd(double(add(p[0], p[1])), 2.0));
-    else if constexpr (S == 3) return from_double<T>(dd(da(da(double(p[0]), dm(4.0, double(p[1]))), double(p[2])), 6.0));
+    if constexpr (S == 2) return from_double<T>(divc<2>(double(add(p[0], p[1]))));
+    else if constexpr (S == 3) return from_double<T>(divc<6>(da(da(double(p[0]), dm(4.0, double(p[1]))), double(p[2]))));
     else {
         double s = dm(7.0, double(p[0]));
         s = da(s, dm(32.0, double(p[1]))); s = da(s, dm(12.0, double(p[2]))); s = da(s, dm(32.0, double(p[3]))); s = da(s, dm(7.0, double(p[4])));
-        return from_double<T>(dd(s, 90.0));
+        return from_double<T>(divc<90>(s));
     }
 }
 
@@ -82,10 +103,16 @@ template<int S, class T> __device__ __forceinline__ T at(T t, const T* p) {
 
 // antiderivative at x of the interpolating polynomial: (((c4*x/5.0 + c3/4.0)*x + c2/3.0)*x + c1/2.0)*x + c0)*x  — c*x is a product in T,
 // the division by the double literal promotes the rest (rules.h:41-44 / :97-100 / :289-293)
+template<int S, int K> struct AntiStep {       // the Horner steps k = K .. 1, unrolled at compile time so that every divisor is a constant
+    template<class T> __device__ __forceinline__ static double run(double u, const T* c, T x) {
+        u = da(u, divc<K + 1>(double(c[K]))); u = dm(u, double(x));
+        return AntiStep<S, K - 1>::run(u, c, x);
+    }
+};
+template<int S> struct AntiStep<S, 0> { template<class T> __device__ __forceinline__ static double run(double u, const T*, T) { return u; } };
 template<int S, class T> __device__ __forceinline__ double antiderivative(const T* c, T x) {
-    double u = dd(double(mul(c[S - 1], x)), double(S));
-#pragma unroll
-    for (int k = S - 2; k >= 1; --k) { u = da(u, dd(double(c[k]), double(k + 1))); u = dm(u, double(x)); }
+    double u = divc<S>(double(mul(c[S - 1], x)));
+    u = AntiStep<S, S - 2>::run(u, c, x);
     u = da(u, double(c[0]));
     return dm(u, double(x));
 }
