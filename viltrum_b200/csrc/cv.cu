@@ -18,6 +18,7 @@
 #include <viltrum_b200/device/philox.cuh>
 #include <cstring>
 #include <vector>
+#include <cub/device/device_radix_sort.cuh>
 
 using namespace vb200;
 namespace R = viltrum::b200::device::rules;
@@ -140,17 +141,22 @@ __device__ __forceinline__ float approximation_at(const float* __restrict__ data
 
 // residual samples: chosen region -> bin ∩ region box -> uniform point, weight, interpolant value.
 // REPLAY: points are given (AoS [bin][spp][D]), only weights/interpolant are computed.
+// The samples are visited in REGION-SORTED order (thread t handles sample sorted_index[t] of region sorted_region[t]): the lanes of a
+// warp then read the same region — its box and its S^D interpolation samples (972 B at C4) come through L1 as broadcasts instead of
+// 32 different gathers per load instruction.  What a sample computes depends only on (bin, sample number, region), so the order
+// changes no bit; outputs are written at the sorted position t (coalesced) and brought back by cv_unsort_kernel.
 template<int S, int D, bool REPLAY>
 __global__ void __launch_bounds__(128) cv_samples_kernel(vb200_domain dom, uint64_t begin, uint64_t nb, uint32_t spp, uint32_t k0, uint32_t k1,
                                                          uint64_t cap, const float* __restrict__ rmin, const float* __restrict__ rmax, const float* __restrict__ aos,
-                                                         const uint32_t* __restrict__ chosen, const float* __restrict__ replay_points,
+                                                         const uint32_t* __restrict__ sorted_region, const uint32_t* __restrict__ sorted_index, const float* __restrict__ replay_points,
                                                          float* __restrict__ points, float* __restrict__ weight, float* __restrict__ app) {
-    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const uint64_t tpos = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const uint64_t N = nb * spp;
-    if (i >= N) return;
+    if (tpos >= N) return;
+    const uint64_t i = sorted_index[tpos];
     const uint64_t b = i % nb; const uint32_t j = uint32_t(i / nb);
     const uint64_t bin = begin + b;
-    const uint32_t r = chosen[i];
+    const uint32_t r = sorted_region[tpos];
     // bin box in the binned dims (…-variance-reduction.h:71-73), region extent elsewhere; Range::intersection (range.h:92-101)
     uint32_t pos[VB200_MAX_DIMBINS]; { uint64_t q = bin; for (int d = 0; d < dom.dimbins; ++d) { pos[d] = uint32_t(q % dom.res[d]); q /= dom.res[d]; } }
     float a[D], w[D], t[D], x[D];
@@ -171,16 +177,28 @@ __global__ void __launch_bounds__(128) cv_samples_kernel(vb200_domain dom, uint6
             x[d] = R::fa(R::fm(viltrum::b200::u01(u), w[d]), ia);                 // uniform_real_distribution: u*(b-a)+a (region-sampling.h:13-17)
         }
         t[d] = R::pos_in_range(lo, hi, x[d]);
-        points[uint64_t(d) * N + i] = x[d];
+        points[uint64_t(d) * N + tpos] = x[d];
     }
-    weight[i] = vol;
-    app[i] = approximation_at<S, D>(aos + uint64_t(r) * uint64_t(R::ipow(S, D)), t);
+    weight[tpos] = vol;
+    app[tpos] = approximation_at<S, D>(aos + uint64_t(r) * uint64_t(R::ipow(S, D)), t);
+}
+
+__global__ void cv_iota_kernel(uint64_t n, uint32_t* __restrict__ idx) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) idx[i] = uint32_t(i);
+}
+
+// region-sorted position -> sample-major position [j][bin]: one 16-byte record (f, interpolant, weight) per sample
+__global__ void cv_unsort_kernel(uint64_t n, const uint32_t* __restrict__ sorted_index, const float* __restrict__ fval, const float* __restrict__ app,
+                                 const float* __restrict__ weight, float4* __restrict__ rec) {
+    const uint64_t t = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t < n) rec[sorted_index[t]] = make_float4(fval[t], app[t], weight[t], 0.0f);
 }
 
 // cv_optimize_weight::Accumulator (weight-strategy.h:40-110) — one thread per bin, samples in order, moments in double
 __global__ void __launch_bounds__(128) cv_accumulate_kernel(uint64_t begin, uint64_t nb, uint32_t spp, uint64_t nbins_total,
                                                             const uint32_t* __restrict__ count, const float* __restrict__ approx,
-                                                            const float* __restrict__ fval, const float* __restrict__ app, const float* __restrict__ weight,
+                                                            const float4* __restrict__ rec /* (f, interpolant, weight) */,
                                                             float* __restrict__ out, int fixed_weight, double fixed_alpha, const double* __restrict__ rrf) {
     const uint64_t b = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (b >= nb) return;
@@ -191,11 +209,12 @@ __global__ void __launch_bounds__(128) cv_accumulate_kernel(uint64_t begin, uint
     double k_f = 0, k_app = 0, e_f = 0, e_ap = 0, e_ap2 = 0, e_fap = 0;
     for (uint32_t j = 0; j < spp; ++j) {
         const uint64_t i = uint64_t(j) * nb + b;
-        const double sf = double(weight[i]);
+        const float4 smp = rec[i];
+        const double sf = double(smp.z);
         const double rrfactor = rrf ? rrf[i] : rr_uniform;                             // weighted roulettes: 1/probability of the chosen region
         // f(sample)*double(factor)*rrfactor*sfactor, rounded to the Sample type (…-variance-reduction.h:97-100)
-        const float fs = R::d2f(R::dm(R::dm(R::dm(double(fval[i]), factor), rrfactor), sf));
-        const float as = R::d2f(R::dm(R::dm(R::dm(double(app[i]), factor), rrfactor), sf));
+        const float fs = R::d2f(R::dm(R::dm(R::dm(double(smp.x), factor), rrfactor), sf));
+        const float as = R::d2f(R::dm(R::dm(R::dm(double(smp.y), factor), rrfactor), sf));
         const double nf = double(fabsf(fs)), na = double(fabsf(as));                     // NormDefault (norm.h:12)
         if (size == 0) { k_f = nf; k_app = na; }
         e_f = R::da(e_f, R::ds(nf, k_f));
@@ -231,19 +250,19 @@ __global__ void transpose_chosen_kernel(uint64_t nb, uint32_t spp, const uint32_
 
 template<int S, int D>
 int launch_samples(vb200_ctx* ctx, bool replay, const vb200_domain& dom, uint64_t begin, uint64_t nb, uint32_t spp, uint32_t k0, uint32_t k1,
-                   const vb200_regions* r, const float* aos, const uint32_t* chosen, const float* replay_points, float* points, float* weight, float* app) {
+                   const vb200_regions* r, const float* aos, const uint32_t* sreg, const uint32_t* sidx, const float* replay_points, float* points, float* weight, float* app) {
     const uint64_t N = nb * spp;
     const unsigned grid = unsigned((N + 127) / 128);
-    if (replay) cv_samples_kernel<S, D, true><<<grid, 128, 0, ctx->stream>>>(dom, begin, nb, spp, k0, k1, r->capacity, r->rmin, r->rmax, aos, chosen, replay_points, points, weight, app);
-    else cv_samples_kernel<S, D, false><<<grid, 128, 0, ctx->stream>>>(dom, begin, nb, spp, k0, k1, r->capacity, r->rmin, r->rmax, aos, chosen, replay_points, points, weight, app);
+    if (replay) cv_samples_kernel<S, D, true><<<grid, 128, 0, ctx->stream>>>(dom, begin, nb, spp, k0, k1, r->capacity, r->rmin, r->rmax, aos, sreg, sidx, replay_points, points, weight, app);
+    else cv_samples_kernel<S, D, false><<<grid, 128, 0, ctx->stream>>>(dom, begin, nb, spp, k0, k1, r->capacity, r->rmin, r->rmax, aos, sreg, sidx, replay_points, points, weight, app);
     ctx->launches++;
     VB200_CUDA(ctx, cudaGetLastError());
     return VB200_OK;
 }
 
 int dispatch_samples(vb200_ctx* ctx, bool replay, const vb200_domain& dom, uint64_t begin, uint64_t nb, uint32_t spp, uint32_t k0, uint32_t k1,
-                     const vb200_regions* r, const float* aos, const uint32_t* chosen, const float* replay_points, float* points, float* weight, float* app) {
-#define VB200_CVS(SS, DD) if (r->SH == SS && r->dim == DD) return launch_samples<SS, DD>(ctx, replay, dom, begin, nb, spp, k0, k1, r, aos, chosen, replay_points, points, weight, app);
+                     const vb200_regions* r, const float* aos, const uint32_t* sreg, const uint32_t* sidx, const float* replay_points, float* points, float* weight, float* app) {
+#define VB200_CVS(SS, DD) if (r->SH == SS && r->dim == DD) return launch_samples<SS, DD>(ctx, replay, dom, begin, nb, spp, k0, k1, r, aos, sreg, sidx, replay_points, points, weight, app);
     VB200_CVS(3, 1) VB200_CVS(3, 2) VB200_CVS(3, 3) VB200_CVS(3, 4) VB200_CVS(3, 5) VB200_CVS(3, 6)
     VB200_CVS(5, 1) VB200_CVS(5, 2) VB200_CVS(5, 3) VB200_CVS(5, 4)
     VB200_CVS(2, 1) VB200_CVS(2, 2) VB200_CVS(2, 3) VB200_CVS(2, 4) VB200_CVS(2, 5) VB200_CVS(2, 6)
@@ -304,8 +323,16 @@ int cv_run(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r, con
     if (spp > 0) {
         uint64_t slab = (32ull << 20) / spp; if (slab < 1) slab = 1; if (slab > nshard) slab = nshard;
         const uint64_t NS = slab * spp;
-        DevBuf rank, chosen, points, weight, app, fval, rchosen, rpoints, rrf;
+        DevBuf rank, chosen, points, weight, app, fval, rchosen, rpoints, rrf, sreg, sidx, iota, rec, sort_tmp;
         if (policy != VB200_RR_UNIFORM) { if ((rc = rrf.alloc(ctx, NS * sizeof(double)))) return rc; }
+        // region-sorted visiting order of the residual samples (cv_samples_kernel): radix sort of (region, sample position) pairs
+        if (NS > 0x7fffffffull) return fail(ctx, VB200_ERR_UNSUPPORTED, "control variates: slab of %llu samples too large", (unsigned long long)NS);
+        if ((rc = sreg.alloc(ctx, NS * 4)) || (rc = sidx.alloc(ctx, NS * 4)) || (rc = iota.alloc(ctx, NS * 4)) || (rc = rec.alloc(ctx, NS * sizeof(float4)))) return rc;
+        int region_bits = 1; while ((1ull << region_bits) < r->count && region_bits < 32) ++region_bits;
+        size_t sort_bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, chosen.as<uint32_t>(), sreg.as<uint32_t>(), iota.as<uint32_t>(), sidx.as<uint32_t>(), int(NS), 0, region_bits, ctx->stream);
+        if ((rc = sort_tmp.alloc(ctx, sort_bytes))) return rc;
+        cv_iota_kernel<<<unsigned((NS + 255) / 256), 256, 0, ctx->stream>>>(NS, iota.as<uint32_t>()); ctx->launches++; VB200_CUDA(ctx, cudaGetLastError());
         if ((rc = chosen.alloc(ctx, NS * 4)) || (rc = points.alloc(ctx, NS * D * 4)) || (rc = weight.alloc(ctx, NS * 4)) || (rc = app.alloc(ctx, NS * 4)) || (rc = fval.alloc(ctx, NS * 4))) return rc;
         if (!replay) { if ((rc = rank.alloc(ctx, NS * 4))) return rc; }
         else if (replay_mem == VB200_HOST) { if ((rc = rchosen.alloc(ctx, NS * 4)) || (rc = rpoints.alloc(ctx, NS * D * 4))) return rc; }
@@ -340,7 +367,10 @@ int cv_run(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r, con
                 ctx->launches++; VB200_CUDA(ctx, cudaGetLastError());
                 rp = src_p;
             }
-            rc = dispatch_samples(ctx, replay, dom, s0, nb, spp, uint32_t(p->seed), uint32_t(p->seed >> 32), r, aos.as<float>(), chosen.as<uint32_t>(), rp,
+            { size_t tb = sort_bytes;
+              VB200_CUDA(ctx, cub::DeviceRadixSort::SortPairs(sort_tmp.p, tb, chosen.as<uint32_t>(), sreg.as<uint32_t>(), iota.as<uint32_t>(), sidx.as<uint32_t>(), int(N), 0, region_bits, ctx->stream));
+              ctx->launches += 1 + (region_bits + 7) / 8; }
+            rc = dispatch_samples(ctx, replay, dom, s0, nb, spp, uint32_t(p->seed), uint32_t(p->seed >> 32), r, aos.as<float>(), sreg.as<uint32_t>(), sidx.as<uint32_t>(), rp,
                                   points.as<float>(), weight.as<float>(), app.as<float>()); if (rc) return rc;
             if (policy != VB200_RR_UNIFORM) {
                 rc = rr_factors(ctx, r, w, dom, s0, nb, begin, policy, spp, d_rerr.as<float>(), d_pdf.as<float>(), d_count.as<uint32_t>(), d_wsum.as<double>(), d_csum.as<double>(),
@@ -349,8 +379,10 @@ int cv_run(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r, con
             vb200_eval_launch ev; std::memset(&ev, 0, sizeof(ev));
             ev.n = N; ev.dim = D; ev.points = points.as<float>(); ev.values = fval.as<float>();
             rc = call_thunk(ctx, f, VB200_K_EVAL_POINTS, &ev); if (rc) return rc;
+            cv_unsort_kernel<<<unsigned((N + 255) / 256), 256, 0, ctx->stream>>>(N, sidx.as<uint32_t>(), fval.as<float>(), app.as<float>(), weight.as<float>(), rec.as<float4>());
+            ctx->launches++; VB200_CUDA(ctx, cudaGetLastError());
             cv_accumulate_kernel<<<unsigned((nb + 127) / 128), 128, 0, ctx->stream>>>(s0, nb, spp, total, cnt, d_approx.as<float>() + (s0 - begin),
-                                                                                        fval.as<float>(), app.as<float>(), weight.as<float>(), st.dev_base,
+                                                                                        rec.as<float4>(), st.dev_base,
                                                                                         p->weight_strategy == VB200_CV_FIXED_WEIGHT ? 1 : 0, p->alpha,
                                                                                         policy != VB200_RR_UNIFORM ? rrf.as<double>() : nullptr);
             ctx->launches++; VB200_CUDA(ctx, cudaGetLastError());
