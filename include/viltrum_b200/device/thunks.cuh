@@ -155,8 +155,21 @@ struct InfiniteThunks {
 
     template<int DB, bool MOMENTS> static auto wavefront_or_plain(std::true_type) { return device::walk_wavefront_kernel<F, DB, MOMENTS, EXACT>; }
     template<int DB, bool MOMENTS> static auto wavefront_or_plain(std::false_type) { return device::walk_kernel<F, DB, MOMENTS, EXACT>; }
+    template<class K>
+    static int launch_walk_kernel(K k, const F& f, const vb200_walk_launch& a, cudaStream_t st) {
+        const uint64_t bins_per_cta = uint64_t(device::MC_THREADS) / a.lanes_per_bin;
+        const uint64_t ctas = (a.bin_end - a.bin_begin + bins_per_cta - 1) / bins_per_cta;
+        const int grid = persistent_grid(k, device::MC_THREADS, ctas, a.grid_hint);
+        k<<<grid, device::MC_THREADS, 0, st>>>(f, a);
+        return int(cudaGetLastError());
+    }
     template<int DB, bool MOMENTS>
     static int launch_walk(const F& f, const vb200_walk_launch& a, cudaStream_t st) {
+        // state machines that consume 2 + 2 elements per begin()/step() are fed whole Philox blocks (one generator call per lane and
+        // iteration, immediate refill) as long as every explicit range entry sits in block 0
+        if constexpr (device::has_block_steps<F>::value) {
+            if (a.domain.dim <= 4 && DB <= 4) return launch_walk_kernel(device::walk_block_kernel<F, DB, MOMENTS, EXACT>, f, a, st);
+        }
         // functors that also describe themselves as a state machine get the wavefront kernel (lane refill)
         auto k = wavefront_or_plain<DB, MOMENTS>(std::integral_constant<bool, device::has_steps<F>::value>());
         const uint64_t bins_per_cta = uint64_t(device::MC_THREADS) / a.lanes_per_bin;

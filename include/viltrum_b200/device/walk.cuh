@@ -203,6 +203,99 @@ walk_wavefront_kernel(const F f, const vb200_walk_launch a) {
     }
 }
 
+// ---- block-fed wavefront variant: ONE Philox call per lane and loop iteration, immediate refill -----------------------------------
+// A state-machine functor may also declare how many sequence elements its parts consume:
+//     static constexpr int elements_begin = 2;    // begin() reads exactly this many
+//     static constexpr int elements_step  = 2;    // step() reads at most this many (fewer only when it returns false)
+// With 2 + 2 the element stream of a path falls into Philox blocks the kernel can hand out whole: block 0 = begin() + one roulette round,
+// every later block = two rounds.  Every lane then draws exactly one block per loop iteration — the generator (the expensive part:
+// 20 IMAD.WIDE) runs convergent at full lane utilisation — a lane whose path ended is re-armed with its next sample in the very next
+// iteration (no batching needed: begin() costs no extra generator call), and the functor reads its elements through an iterator over
+// four registers instead of the general PhiloxSequence iterator (no per-element block/range bookkeeping).  Elements are the same
+// Philox words mapped with the same expressions, paths are summed per lane in the same order: bins are bit-identical to walk_kernel's.
+// Requires every explicit range entry to sit in block 0 (domain.dim <= 4, checked by the launcher).
+template<class F, class = void> struct has_block_steps : std::false_type {};
+template<class F> struct has_block_steps<F, std::void_t<typename F::State, decltype(F::elements_begin), decltype(F::elements_step)>>
+    : std::integral_constant<bool, F::elements_begin == 2 && F::elements_step == 2> {};
+
+struct BlockIterator {          // the iterator protocol of the reference's sequences (*it, ++it) over one Philox block held in registers
+    float e0, e1, e2, e3; int i;
+    __device__ __forceinline__ float operator*() const { return i == 0 ? e0 : i == 1 ? e1 : i == 2 ? e2 : e3; }
+    __device__ __forceinline__ BlockIterator& operator++() { ++i; return *this; }
+};
+
+template<class F, int DIMBINS, bool MOMENTS, bool EXACT>
+__global__ void __launch_bounds__(MC_THREADS)
+walk_block_kernel(const F f, const vb200_walk_launch a) {
+    const uint32_t LPB = a.lanes_per_bin, G = 32u / LPB;
+    const uint32_t lane = threadIdx.x & 31u, sub = lane % LPB, grp = lane / LPB;
+    const uint64_t nshard = a.bin_end - a.bin_begin;
+    const uint64_t ntiles = (nshard + G - 1) / G;
+    uint64_t tile = 0;
+    if (lane == 0) tile = atomicAdd(a.tile_counter, 1ull);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    while (tile < ntiles) {
+        const uint64_t bin = a.bin_begin + tile * G + grp;
+        const bool live = bin < a.bin_end;
+        float sum = 0.0f, sum2 = 0.0f, volume = 1.0f;
+        // element -> value map of block 0: v = fmaf(u, scale, offset); binned dimensions use the bin box, other explicit entries their
+        // range, everything else [0,1) (scale 1, offset 0: fmaf(u,1,0) == u)
+        float sc[4] = {1.0f, 1.0f, 1.0f, 1.0f}, of[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (live) {
+            float lo[DIMBINS], ext[DIMBINS];
+            volume = walk_bin_box<DIMBINS>(a.domain, bin, lo, ext);
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                if (d < DIMBINS) { sc[d] = ext[d]; of[d] = lo[d]; }
+                else if (d < a.domain.dim) { sc[d] = a.domain.rmax[d] - a.domain.rmin[d]; of[d] = a.domain.rmin[d]; }
+            }
+        }
+        const uint32_t b0 = uint32_t(bin), b1 = uint32_t(bin >> 32);
+        uint32_t next = live ? sub : a.spp;          // next sample this lane will start
+        uint32_t s = 0, blk = 0;
+        bool alive = false;
+        typename F::State st;
+        while (true) {
+            const bool starting = !alive && next < a.spp;
+            if (!__any_sync(0xffffffffu, alive || starting)) break;
+            if (starting) { s = next; next += LPB; blk = 0; }
+            const u32x4 r = philox4x32<10>(u32x4{b0, b1, s, blk}, a.key0, a.key1);
+            BlockIterator it;
+            it.e0 = u01(r.x); it.e1 = u01(r.y); it.e2 = u01(r.z); it.e3 = u01(r.w); it.i = 0;
+            if (blk == 0) {       // PhiloxSequence::const_iterator::load: fmaf(u, extent, lower)
+                it.e0 = fmaf(it.e0, sc[0], of[0]); it.e1 = fmaf(it.e1, sc[1], of[1]); it.e2 = fmaf(it.e2, sc[2], of[2]); it.e3 = fmaf(it.e3, sc[3], of[3]);
+            }
+            ++blk;
+            bool ended = false;
+            if (starting) { st = f.begin(it); alive = true; }            // elements 0,1
+            else if (alive) { if (!f.step(st, it)) ended = true; }       // elements 0,1 (or only 0)
+            it.i = 2;
+            if (alive && !ended) { if (!f.step(st, it)) ended = true; }  // elements 2,3 (or only 2)
+            if (ended) {
+                const float v = f.end(st);
+                sum += v;
+                if (MOMENTS) sum2 = fmaf(v, v, sum2);
+                alive = false;
+            }
+        }
+        for (uint32_t off = LPB >> 1; off > 0; off >>= 1) {
+            sum += __shfl_xor_sync(0xffffffffu, sum, off);
+            if (MOMENTS) sum2 += __shfl_xor_sync(0xffffffffu, sum2, off);
+        }
+        if (live && sub == 0) {
+            const float v = walk_bin_value(a, sum, volume);
+            a.out[bin] = a.accumulate ? float(double(a.out[bin]) + double(v)) : v;
+            if (MOMENTS) {
+                if (a.sum_f)  a.sum_f[bin - a.bin_begin]  = sum;
+                if (a.sum_f2) a.sum_f2[bin - a.bin_begin] = sum2;
+            }
+        }
+        signal_tile_done(a.signal, tile, ntiles, lane);
+        if (lane == 0) tile = atomicAdd(a.tile_counter, 1ull);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+    }
+}
+
 // Replay of recorded sequences (the reference's own element values): one thread per bin, paths in order,
 // bins(p) += f(seq)*factor with float(double(acc)+double(f)*factor)  (monte-carlo-per-bin-parallel.h:96).
 struct RecordedSequence {

@@ -123,15 +123,23 @@ def test_global_scatter_split_samples_sum_to_whole(ctx):
 
 
 def test_wavefront_kernel_equals_generic_kernel(ctx):
-    """'walk' carries the state-machine form (wavefront kernel, lane refill), 'walk_plain' only operator()(seq) (generic per-lane
-    kernel): same Philox elements, same per-lane summation order -> bit-identical bins."""
-    from viltrum_b200 import RangeInfinite
-    for res, spp in (([64, 48], 256), ([100], 37), ([9, 7, 5], 64)):
+    """'walk' carries the state-machine form AND its element counts (block-fed wavefront kernel: one Philox block per lane and iteration,
+    immediate refill), 'walk_steps' the state machine only (wavefront kernel with batched refill through the general iterator),
+    'walk_plain' only operator()(seq) (generic per-lane kernel): same Philox elements, same per-lane summation order ->
+    bit-identical bins, also over explicit range entries (in block 0: block kernel; beyond: the launcher falls back) and both flavors."""
+    from viltrum_b200 import RangeInfinite, _capi
+    cases = [([64, 48], 256, (), ()), ([100], 37, (), ()), ([9, 7, 5], 64, (), ()), ([20, 16], 128, (0.1, 0.2, 0.0), (0.9, 0.7, 1.0)),
+             ([12, 10], 33, (0.1, 0.2, 0.0, 0.0, 0.25), (0.9, 0.7, 1.0, 1.0, 0.75)), ([5], 1000, (-1.0,), (2.0,))]
+    for res, spp, rmin, rmax in cases:
         nb = int(np.prod(res))
-        a = np.zeros(nb, np.float32); b = np.zeros(nb, np.float32)
-        ctx.mc_per_bin_inf("walk", a, res, RangeInfinite(), spp, 5)
-        ctx.mc_per_bin_inf("walk_plain", b, res, RangeInfinite(), spp, 5)
-        assert_same_bits(a, b, f"wavefront vs generic {res}")
+        rng = RangeInfinite(list(rmin), list(rmax))
+        for flavor in (_capi.MC_PER_BIN, _capi.PER_BIN_MC):
+            out = {}
+            for name in ("walk", "walk_steps", "walk_plain"):
+                out[name] = np.zeros(nb, np.float32)
+                ctx.mc_per_bin_inf(name, out[name], res, rng, spp, 5, flavor=flavor)
+            assert_same_bits(out["walk"], out["walk_plain"], f"block-fed vs generic {res} {rmin}")
+            assert_same_bits(out["walk_steps"], out["walk_plain"], f"wavefront vs generic {res} {rmin}")
 
 
 @pytest.mark.parametrize("integ,res,spp,rmin,rmax", [("walk", [48, 40], 256, (), ()), ("decay", [64], 512, (), ()),

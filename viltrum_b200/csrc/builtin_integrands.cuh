@@ -80,6 +80,7 @@ struct Walk {
     }
     // the same path as a state machine (include/viltrum_b200/device/walk.cuh, wavefront kernel): identical arithmetic
     struct State { float alb, pos, L; };
+    static constexpr int elements_begin = 2, elements_step = 2;      // whole Philox blocks: walk_block_kernel
     template<typename It> __host__ __device__ State begin(It& it) const {
         const float px = *it; ++it; const float py = *it; ++it;
         return State{.4f+.5f*(4.0f*px*(1.0f-px))*(.25f+.75f*py), .5f, 0.0f};
@@ -89,6 +90,15 @@ struct Walk {
         const float s = *it; ++it; st.pos = .5f*st.pos+.5f*s; st.L += .25f+st.pos*st.pos;
         return true;
     }
+    __host__ __device__ float end(const State& st) const { return st.L; }
+};
+// same integrand with the state-machine form but WITHOUT the element counts: keeps walk_wavefront_kernel (batched refill through the
+// general iterator) measurable and tested
+struct WalkSteps {
+    template<typename Seq> __host__ __device__ float operator()(const Seq& seq) const { return Walk()(seq); }
+    using State = Walk::State;
+    template<typename It> __host__ __device__ State begin(It& it) const { return Walk().begin(it); }
+    template<typename It> __host__ __device__ bool step(State& st, It& it) const { return Walk().step(st, it); }
     __host__ __device__ float end(const State& st) const { return st.L; }
 };
 // same integrand WITHOUT the state-machine form: keeps the generic per-lane kernel measurable and tested
