@@ -38,8 +38,8 @@ WORKLOADS = {
 }
 METRIC = "integrand evals/sec (per-bin MC, 1024x1024 bins x 64 spp, shade4<64>)"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the ncu --set full capture summarised in
-# profiles/ncu_c2_mc_per_bin_r1c.txt / profiles/ncu_c5_walk_r1.txt (algorithmic bytes: 4 B per bin)
-NCU_TRAFFIC_BYTES = {"c2": 4231936, "c5": 16792576}
+# profiles/ncu_c2_mc_per_bin_r1c.txt / profiles/ncu_c5_walk_block_r1c.txt (algorithmic bytes: 4 B per bin)
+NCU_TRAFFIC_BYTES = {"c2": 4231936, "c5": 16796672}
 
 
 def dist_env():
