@@ -13,6 +13,21 @@ struct Walk {
                        float s=*it; ++it; pos=.5f*pos+.5f*s; L+=.25f+pos*pos; }
         return L;
     }
+    // OPTIONAL (viltrum_b200 extension): the same path as a state machine with its element counts.  operator()(seq) alone runs on the generic
+    // per-lane kernel; with begin/step/end the lanes of a warp refill independently, and with elements_begin/elements_step = 2/2 (or 0/2)
+    // every lane is fed one whole Philox block per iteration (include/viltrum_b200/device/walk.cuh).  Same arithmetic -> same bins, bit for bit.
+    struct State { float alb, pos, L; };
+    static constexpr int elements_begin = 2, elements_step = 2;
+    template<typename It> __host__ __device__ State begin(It& it) const {
+        float px=*it; ++it; float py=*it; ++it;
+        return State{.4f+.5f*(4.0f*px*(1.0f-px))*(.25f+.75f*py), .5f, 0.0f};
+    }
+    template<typename It> __host__ __device__ bool step(State& st, It& it) const {
+        float u=*it; ++it; if (u>=st.alb) return false;
+        float s=*it; ++it; st.pos=.5f*st.pos+.5f*s; st.L+=.25f+st.pos*st.pos;
+        return true;
+    }
+    __host__ __device__ float end(const State& st) const { return st.L; }
 };
 struct Decay {                                       // reference main/doc/montecarlo-infd.cc:8-22
     float decaying_factor;

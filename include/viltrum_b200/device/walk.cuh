@@ -205,10 +205,10 @@ walk_wavefront_kernel(const F f, const vb200_walk_launch a) {
 
 // ---- block-fed wavefront variant: ONE Philox call per lane and loop iteration, immediate refill -----------------------------------
 // A state-machine functor may also declare how many sequence elements its parts consume:
-//     static constexpr int elements_begin = 2;    // begin() reads exactly this many
+//     static constexpr int elements_begin = 2;    // begin() reads exactly this many (2, or 0)
 //     static constexpr int elements_step  = 2;    // step() reads at most this many (fewer only when it returns false)
 // With 2 + 2 the element stream of a path falls into Philox blocks the kernel can hand out whole: block 0 = begin() + one roulette round,
-// every later block = two rounds.  Every lane then draws exactly one block per loop iteration — the generator (the expensive part:
+// every later block = two rounds (with 0 + 2 every block is two rounds).  Every lane then draws exactly one block per loop iteration — the generator (the expensive part:
 // 20 IMAD.WIDE) runs convergent at full lane utilisation — a lane whose path ended is re-armed with its next sample in the very next
 // iteration (no batching needed: begin() costs no extra generator call), and the functor reads its elements through an iterator over
 // four registers instead of the general PhiloxSequence iterator (no per-element block/range bookkeeping).  Elements are the same
@@ -216,7 +216,7 @@ walk_wavefront_kernel(const F f, const vb200_walk_launch a) {
 // Requires every explicit range entry to sit in block 0 (domain.dim <= 4, checked by the launcher).
 template<class F, class = void> struct has_block_steps : std::false_type {};
 template<class F> struct has_block_steps<F, std::void_t<typename F::State, decltype(F::elements_begin), decltype(F::elements_step)>>
-    : std::integral_constant<bool, F::elements_begin == 2 && F::elements_step == 2> {};
+    : std::integral_constant<bool, (F::elements_begin == 2 || F::elements_begin == 0) && F::elements_step == 2> {};
 
 struct BlockIterator {          // the iterator protocol of the reference's sequences (*it, ++it) over one Philox block held in registers
     float e0, e1, e2, e3; int i;
@@ -267,7 +267,10 @@ walk_block_kernel(const F f, const vb200_walk_launch a) {
             }
             ++blk;
             bool ended = false;
-            if (starting) { st = f.begin(it); alive = true; }            // elements 0,1
+            if (starting) {                                              // elements 0,1 — or none, then the first round takes them
+                st = f.begin(it); alive = true;
+                if constexpr (F::elements_begin == 0) { if (!f.step(st, it)) ended = true; }
+            }
             else if (alive) { if (!f.step(st, it)) ended = true; }       // elements 0,1 (or only 0)
             it.i = 2;
             if (alive && !ended) { if (!f.step(st, it)) ended = true; }  // elements 2,3 (or only 2)

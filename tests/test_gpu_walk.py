@@ -140,6 +140,10 @@ def test_wavefront_kernel_equals_generic_kernel(ctx):
                 ctx.mc_per_bin_inf(name, out[name], res, rng, spp, 5, flavor=flavor)
             assert_same_bits(out["walk"], out["walk_plain"], f"block-fed vs generic {res} {rmin}")
             assert_same_bits(out["walk_steps"], out["walk_plain"], f"wavefront vs generic {res} {rmin}")
+            d = np.zeros(nb, np.float32); dp = np.zeros(nb, np.float32)       # 'decay': begin() reads nothing, two elements per round
+            ctx.mc_per_bin_inf("decay", d, res, rng, spp, 9, flavor=flavor)
+            ctx.mc_per_bin_inf("decay_plain", dp, res, rng, spp, 9, flavor=flavor)
+            assert_same_bits(d, dp, f"block-fed vs generic decay {res} {rmin}")
 
 
 @pytest.mark.parametrize("integ,res,spp,rmin,rmax", [("walk", [48, 40], 256, (), ()), ("decay", [64], 512, (), ()),

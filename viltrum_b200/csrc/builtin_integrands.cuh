@@ -111,6 +111,20 @@ struct Decay {
         while ((*x) < 0.75f) { ++x; term *= 2.0f*(*x); ++x; sum += term; }
         return sum;
     }
+    // the same series as a state machine that reads nothing in begin() and two elements per round (walk_block_kernel)
+    struct State { float sum, term; };
+    static constexpr int elements_begin = 0, elements_step = 2;
+    template<typename It> __host__ __device__ State begin(It&) const { return State{0.0f, 1.0f}; }
+    template<typename It> __host__ __device__ bool step(State& st, It& x) const {
+        if (!((*x) < 0.75f)) return false;
+        ++x; st.term *= 2.0f*(*x); ++x; st.sum += st.term;
+        return true;
+    }
+    __host__ __device__ float end(const State& st) const { return st.sum; }
+};
+// operator()(seq) only: the generic per-lane kernel
+struct DecayPlain {
+    template<typename Seq> __host__ __device__ float operator()(const Seq& seq) const { return Decay()(seq); }
 };
 
 }}} // namespace viltrum::b200::builtin

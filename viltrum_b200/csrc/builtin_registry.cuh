@@ -30,11 +30,12 @@ static const Entry* make_table(int* count) {
     static const InfiniteIntegrand<Decay> decay{Decay(), "decay"};
     static const InfiniteIntegrand<WalkPlain> walk_plain{WalkPlain(), "walk_plain"};
     static const InfiniteIntegrand<WalkSteps> walk_steps{WalkSteps(), "walk_steps"};
+    static const InfiniteIntegrand<DecayPlain> decay_plain{DecayPlain(), "decay_plain"};
     static const Entry table[] = {
         {"x2y2", x2y2.c_abi()}, {"ind2", ind2.c_abi()}, {"cubic1", cubic1.c_abi()}, {"poly3", poly3.c_abi()},
         {"shade4_16", shade4_16.c_abi()}, {"shade4_64", shade4_64.c_abi()}, {"shade5_16", shade5_16.c_abi()},
         {"shade5_64", shade5_64.c_abi()}, {"smooth_edge2", smooth_edge2.c_abi()}, {"walk", walk.c_abi()}, {"decay", decay.c_abi()}, {"walk_plain", walk_plain.c_abi()},
-        {"walk_steps", walk_steps.c_abi()},
+        {"walk_steps", walk_steps.c_abi()}, {"decay_plain", decay_plain.c_abi()},
     };
     *count = int(sizeof(table)/sizeof(table[0]));
     return table;
