@@ -414,11 +414,35 @@ template<int S, int DB, class T> struct Staged {
     T patch[P]; T rmin[DB], rmax[DB]; T volume; uint32_t ps[DB], pe[DB];
 };
 
+// integral of region `rg` over (bin at `pos`) ∩ region, exactly as the reference evaluates it; false = empty intersection (skipped upstream)
+template<int S, int DB, class T, class RG>
+__device__ __forceinline__ bool pair_integral(const DomT<T>& dom, const uint32_t (&pos)[3], const RG& rg, T* integral) {
+    // Range::intersection (range.h:92-101) in the binned dims; the other dims are the region's own extent
+    T na[3], nb[3]; bool empty = false;
+#pragma unroll
+    for (int d = 0; d < DB; ++d) {       // bin box: min + Float(pos)*drange (regions-integrator-sequential.h:42-51)
+        const T lo = R::add(dom.rmin[d], R::mul(T(pos[d]), dom.drange[d]));
+        const T hi = R::add(dom.rmin[d], R::mul(T(pos[d] + 1u), dom.drange[d]));
+        const T a = R::maxv(lo, rg.rmin[d]);
+        const T b = R::maxv(a, R::minv(hi, rg.rmax[d]));
+        empty = empty || (a >= b);
+        na[d] = R::pos_in_range<T>(rg.rmin[d], rg.rmax[d], a);
+        nb[d] = R::pos_in_range<T>(rg.rmin[d], rg.rmax[d], b);
+    }
+    *integral = R::mul(rg.volume, patch_subrange<S, DB, T>(rg.patch, na, nb));
+    return !empty;
+}
+
 // K8/K10: one CTA per bin tile, one thread per bin.  The tile's region list is staged through shared memory in chunks
 // (patches + boxes: the "region tree" a bin needs), every thread walks the chunk in table order, keeps the regions whose
 // pixel box contains its bin and accumulates nbins * integral_subrange(bin ∩ region) with the reference's promotions:
 //   bins(pos) += double(factor) * float        (regions-integrator-sequential.h:54; ...-variance-reduction.h:80)
-template<int S, int DB, class T>
+// Small regions (<= KS bins of this tile: the slivers a tolerance-driven refinement piles up along a discontinuity) are integrated by a
+// thread per (region, bin) pair first, 256 at once, and the bin threads only pick the values up in table order — otherwise a chunk of
+// 64 slivers that all touch the same few bins is 64 integrals evaluated one after the other by a single lane (measured: 88 ms -> see
+// profiles/results_r1.md for an 841 644-leaf table at 512x512 bins).  The summation order per bin, hence every bit, is unchanged.
+// SMALL = false compiles that path out (tables of few large regions, e.g. BASELINE config 4: fewer registers, more resident CTAs).
+template<int S, int DB, class T, bool SMALL>
 __global__ void __launch_bounds__(256) walk_accumulate_kernel(TileGeom g, DomT<T> dom, uint64_t cap, uint64_t begin, uint64_t end, uint64_t nbins_total,
                                                               const T* __restrict__ patches, const T* __restrict__ rmin, const T* __restrict__ rmax,
                                                               const T* __restrict__ volume, const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ pend,
@@ -426,7 +450,12 @@ __global__ void __launch_bounds__(256) walk_accumulate_kernel(TileGeom g, DomT<T
                                                               int mode, T* __restrict__ out, T* __restrict__ approx, uint32_t* __restrict__ count) {
     using St = Staged<S, DB, T>;
     constexpr int CHUNK = (St::P * sizeof(T) > 256) ? 16 : 64;
+    constexpr int KS = 4;
     __shared__ St s_reg[CHUNK];
+    __shared__ T s_contrib[CHUNK][KS];
+    __shared__ unsigned char s_area[CHUNK];            // bins of this tile the region covers if that is 1..KS, else 0 (bin threads integrate it themselves)
+    __shared__ unsigned char s_ok[CHUNK][KS];          // 0 = empty intersection
+    __shared__ uint32_t s_lo[CHUNK][DB], s_w[CHUNK][DB];
     const uint64_t t = blockIdx.x;
     uint32_t o[3]; tile_origin(g, t, o);
     if (!tile_in_shard(g, o, begin, end)) return;
@@ -435,12 +464,6 @@ __global__ void __launch_bounds__(256) walk_accumulate_kernel(TileGeom g, DomT<T
     bool live = true; uint64_t bin = 0, prod = 1;
     for (int d = 0; d < DB; ++d) { live = live && pos[d] < g.res[d]; bin += uint64_t(pos[d]) * prod; prod *= g.res[d]; }
     live = live && bin >= begin && bin < end;
-    T ba[DB], bb[DB];
-#pragma unroll
-    for (int d = 0; d < DB; ++d) {       // bin box: min + Float(pos)*drange (regions-integrator-sequential.h:42-51)
-        ba[d] = R::add(dom.rmin[d], R::mul(T(pos[d]), dom.drange[d]));
-        bb[d] = R::add(dom.rmin[d], R::mul(T(pos[d] + 1u), dom.drange[d]));
-    }
     T acc = (mode == 0 && live) ? out[bin] : T(0);
     uint32_t cnt = 0;
     const double factor = double(nbins_total);
@@ -452,15 +475,39 @@ __global__ void __launch_bounds__(256) walk_accumulate_kernel(TileGeom g, DomT<T
             const int j = k / St::P, q = k % St::P;
             s_reg[j].patch[q] = patches[uint64_t(q) * cap + list[base + j]];
         }
+        int small = 0;
         for (int j = threadIdx.x; j < n; j += blockDim.x) {
             const uint64_t r = list[base + j];
+            uint32_t area = 1;
             for (int d = 0; d < DB; ++d) {
                 s_reg[j].rmin[d] = rmin[uint64_t(d) * cap + r]; s_reg[j].rmax[d] = rmax[uint64_t(d) * cap + r];
-                s_reg[j].ps[d] = pstart[uint64_t(d) * cap + r]; s_reg[j].pe[d] = pend[uint64_t(d) * cap + r];
+                const uint32_t ps = pstart[uint64_t(d) * cap + r], pe = pend[uint64_t(d) * cap + r];
+                s_reg[j].ps[d] = ps; s_reg[j].pe[d] = pe;
+                // the part of the region's pixel box inside this tile (and inside the grid)
+                const uint32_t a0 = max(ps, o[d]), a1 = min(min(pe, o[d] + g.tile[d]), g.res[d]);
+                s_lo[j][d] = a0; s_w[j][d] = a1 > a0 ? a1 - a0 : 0u;
+                area = (s_w[j][d] == 0u || area > KS) ? (s_w[j][d] == 0u ? 0u : KS + 1u) : area * s_w[j][d];
             }
             s_reg[j].volume = volume[r];
+            const bool is_small = SMALL && area >= 1u && area <= KS;
+            s_area[j] = (unsigned char)(is_small ? area : 0u);
+            small |= is_small ? 1 : 0;
         }
-        __syncthreads();
+        const int any_small = __syncthreads_or(small);
+        if (SMALL && any_small) {
+            // one thread per (region, covered bin) pair
+            for (int item = threadIdx.x; item < n * KS; item += blockDim.x) {
+                const int j = item / KS, k = item % KS;
+                if (k < int(s_area[j])) {
+                    uint32_t p[3] = {0, 0, 0}; uint32_t kk = uint32_t(k);
+#pragma unroll
+                    for (int d = 0; d < DB; ++d) { p[d] = s_lo[j][d] + kk % s_w[j][d]; kk /= s_w[j][d]; }
+                    T v; const bool ok = pair_integral<S, DB, T>(dom, p, s_reg[j], &v);
+                    s_contrib[j][k] = v; s_ok[j][k] = ok ? 1 : 0;
+                }
+            }
+            __syncthreads();
+        }
         if (live) {
             for (int j = 0; j < n; ++j) {
                 const St& rg = s_reg[j];
@@ -469,18 +516,16 @@ __global__ void __launch_bounds__(256) walk_accumulate_kernel(TileGeom g, DomT<T
                 for (int d = 0; d < DB; ++d) inside = inside && pos[d] >= rg.ps[d] && pos[d] < rg.pe[d];
                 if (!inside) continue;
                 ++cnt;
-                // Range::intersection (range.h:92-101) in the binned dims; the other dims are the region's own extent
-                T na[3], nb[3]; bool empty = false;
+                T integral; bool ok;
+                if (SMALL && s_area[j] != 0) {
+                    uint32_t k = 0, stride = 1;
 #pragma unroll
-                for (int d = 0; d < DB; ++d) {
-                    const T a = R::maxv(ba[d], rg.rmin[d]);
-                    const T b = R::maxv(a, R::minv(bb[d], rg.rmax[d]));
-                    empty = empty || (a >= b);
-                    na[d] = R::pos_in_range<T>(rg.rmin[d], rg.rmax[d], a);
-                    nb[d] = R::pos_in_range<T>(rg.rmin[d], rg.rmax[d], b);
+                    for (int d = 0; d < DB; ++d) { k += (pos[d] - s_lo[j][d]) * stride; stride *= s_w[j][d]; }
+                    integral = s_contrib[j][k]; ok = s_ok[j][k] != 0;
+                } else {
+                    ok = pair_integral<S, DB, T>(dom, pos, rg, &integral);
                 }
-                if (empty) continue;                                             // regions-integrator-sequential.h:54 `if (!empty())`
-                const T integral = R::mul(rg.volume, patch_subrange<S, DB, T>(rg.patch, na, nb));
+                if (!ok) continue;                                             // regions-integrator-sequential.h:54 `if (!empty())`
                 acc = R::from_double<T>(R::da(double(acc), R::dm(factor, double(integral))));
             }
         }
@@ -494,7 +539,11 @@ __global__ void __launch_bounds__(256) walk_accumulate_kernel(TileGeom g, DomT<T
 template<int S, int DB, class T>
 int launch_accumulate(vb200_ctx* ctx, const vb200_regions* r, const BinWalkT<T>& w, const TileGeom& g, const DomT<T>& dom,
                       uint64_t begin, uint64_t end, uint64_t total, int mode, T* out, T* approx, uint32_t* count) {
-    walk_accumulate_kernel<S, DB, T><<<unsigned(w.ntiles), 256, 0, ctx->stream>>>(g, dom, w.cap, begin, end, total, w.patches, RegCols<T>::rmin(r), RegCols<T>::rmax(r), w.volume,
+    // regions that cover only a few bins each are integrated pair-parallel (SMALL); tables of few large regions keep the leaner kernel
+    const bool small = r->count * 4ull >= total;
+    if (small) walk_accumulate_kernel<S, DB, T, true><<<unsigned(w.ntiles), 256, 0, ctx->stream>>>(g, dom, w.cap, begin, end, total, w.patches, RegCols<T>::rmin(r), RegCols<T>::rmax(r), w.volume,
+                                                                                   w.pstart, w.pend, w.tile_offset, w.tile_list, mode, out, approx, count);
+    else walk_accumulate_kernel<S, DB, T, false><<<unsigned(w.ntiles), 256, 0, ctx->stream>>>(g, dom, w.cap, begin, end, total, w.patches, RegCols<T>::rmin(r), RegCols<T>::rmax(r), w.volume,
                                                                                    w.pstart, w.pend, w.tile_offset, w.tile_list, mode, out, approx, count);
     ctx->launches++;
     VB200_CUDA(ctx, cudaGetLastError());
