@@ -6,6 +6,8 @@
 //     viltrum::integrate(integrator, std::vector<T>& bins, integrand, range[, logger])    reference src/integrate.h:132-137,169-173
 //     monte_carlo, monte_carlo_per_bin_parallel, integrator_per_bin_parallel, integrator_newton_cotes,
 //     integrator_adaptive_iterations, integrator_adaptive_tolerance, integrator_crespo2021, integrator_fubini<N>, integrator_crespo2021_infinite<N>,
+//     integrator_adaptive_variance_reduction_parallel with rr_uniform_region / rr_integral_region / rr_error_region / rr_pdf_region,
+//     cv_optimize_weight / cv_fixed_weight, region_sampling_uniform,
 //     range_split_at<N>, nested, trapezoidal / simpson / boole,
 //     error_heuristic_default / error_heuristic_size, error_metric_absolute / error_metric_relative,
 //     range, range_all, range_primary, range_infinite, range_primary_infinite, tensor, LoggerNull, LoggerProgress
