@@ -276,3 +276,24 @@ def test_steps_golden_reference_vectors_and_survey_kat(ctx):
     got = np.zeros(5, np.float32)
     integrate(integrator_newton_cotes(steps(2, "boole")), got, [5], "x2y2", Range([0, 0], [1, 1]), ctx=ctx)
     assert_same_bits(got, np.array([0.346666217, 0.42666626, 0.586666465, 0.826666653, 1.14666629], np.float32), "SURVEY KAT")
+
+
+def test_single_launch_selection_equals_multi_kernel_selection(ctx):
+    """Tables of <= 8192 regions are selected by one single-CTA launch per round (select_small_kernel); VB200_SELECT_SMALL_MAX=0 forces
+    the histogram / pick / count / scan / write kernels for every round: identical region tables, bit for bit and in order."""
+    import os
+    from viltrum_b200 import Range
+    for integ, rule, d, it in (("smooth_edge2", "boole_simpson", 2, 30000), ("shade4_16", "simpson_trapezoidal", 4, 9000), ("x2y2", "simpson_trapezoidal", 2, 700)):
+        rng = Range([0.0] * d, [1.0] * d)
+        tabs = []
+        for knob in (None, "0", "100"):
+            if knob is None:
+                os.environ.pop("VB200_SELECT_SMALL_MAX", None)
+            else:
+                os.environ["VB200_SELECT_SMALL_MAX"] = knob
+            regs = ctx.regions_generate_adaptive(integ, rng, rule, "size", "relative", it, 1e-5, batch=0, exact=True)
+            tabs.append(regs.download()); regs.free()
+        os.environ.pop("VB200_SELECT_SMALL_MAX", None)
+        for other in tabs[1:]:
+            for k in ("min", "max", "err", "dim", "data"):
+                assert_same_bits(tabs[0][k], other[k], f"{integ} {k}")

@@ -115,6 +115,55 @@ __global__ void __launch_bounds__(1024) select_write_kernel(const float* __restr
     else if (eq && be < k_eq) sel[bg + be] = unsigned(i);
 }
 
+// The same selection for small tables in ONE launch of one CTA (keys in shared memory): the first ~35 of the ~60 rounds of a 10^6-split
+// refinement hold fewer than 8192 regions and were eleven tiny launches each — launch latency, not work.  Same threshold, same ties in
+// table order, hence the same sel[] as select_hist/pick/count/scan/write.
+constexpr unsigned SELECT_SMALL_MAX = 8192;
+__global__ void __launch_bounds__(1024) select_small_kernel(const float* __restrict__ keys, unsigned n, unsigned long long k, SelectState* st, unsigned* __restrict__ sel) {
+    __shared__ unsigned s_key[SELECT_SMALL_MAX];
+    __shared__ unsigned s_hist[256];
+    __shared__ unsigned s_pv, s_pm, s_wgt[32], s_weq[32], s_base_gt, s_base_eq;
+    __shared__ unsigned long long s_k;
+    const unsigned tid = threadIdx.x;
+    for (unsigned i = tid; i < n; i += 1024) s_key[i] = __float_as_uint(keys[i]);
+    if (tid == 0) { s_pv = 0; s_pm = 0; s_k = k; }
+    __syncthreads();
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        if (tid < 256) s_hist[tid] = 0;
+        __syncthreads();
+        const unsigned pv = s_pv, pm = s_pm;
+        for (unsigned i = tid; i < n; i += 1024) { const unsigned kk = s_key[i]; if ((kk & pm) == pv) atomicAdd(&s_hist[(kk >> shift) & 255u], 1u); }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long kk = s_k, cum = 0; int d = 255;
+            for (; d > 0; --d) { if (cum + s_hist[d] >= kk) break; cum += s_hist[d]; }
+            s_k = kk - cum; s_pv |= unsigned(d) << shift; s_pm |= 255u << shift;
+        }
+        __syncthreads();
+    }
+    const unsigned T = s_pv; const unsigned long long k_eq = s_k;
+    if (tid == 0) { s_base_gt = 0; s_base_eq = 0; st->prefix_val = T; st->prefix_mask = s_pm; st->k = k_eq; }
+    __syncthreads();
+    const unsigned lane = tid & 31u, warp = tid >> 5;
+    for (unsigned base = 0; base < n; base += 1024) {
+        const unsigned i = base + tid;
+        const unsigned key = i < n ? s_key[i] : 0u;
+        const bool gt = i < n && key > T, eq = i < n && key == T;
+        const unsigned mg = __ballot_sync(0xffffffffu, gt), me = __ballot_sync(0xffffffffu, eq);
+        if (lane == 0) { s_wgt[warp] = __popc(mg); s_weq[warp] = __popc(me); }
+        __syncthreads();
+        unsigned bg = s_base_gt, be = s_base_eq;
+        for (unsigned w = 0; w < warp; ++w) { bg += s_wgt[w]; be += s_weq[w]; }
+        bg += __popc(mg & ((1u << lane) - 1u)); be += __popc(me & ((1u << lane) - 1u));
+        const unsigned long long ties_before = be < k_eq ? be : k_eq;
+        if (gt) sel[bg + ties_before] = i;
+        else if (eq && be < k_eq) sel[bg + be] = i;
+        __syncthreads();
+        if (tid == 1023) { s_base_gt = bg + (gt ? 1u : 0u); s_base_eq = be + (eq ? 1u : 0u); }
+        __syncthreads();
+    }
+}
+
 // sample points of all selected splits: point q of split r = odd position i = 2*(q / L)+1 along the split dimension,
 // other-dims index o = q % L; coordinates from the PARENT range (split.h:22, region.h:40-46)
 __global__ void split_points_kernel(int S, int dim, uint64_t cap, uint64_t nsel, const unsigned* __restrict__ sel,
@@ -230,24 +279,32 @@ int run_rounds(vb200_ctx* ctx, const vb200_integrand* f, const vb200_adaptive_pa
     VB200_CUDA(ctx, cudaFuncSetAttribute(kchild, cudaFuncAttributeMaxDynamicSharedMemorySize, int(per_warp * wpc)));
     const uint64_t Q = uint64_t(SH - 1) * Sh::L;
     uint64_t n = 1, left = p->iterations;
+    uint64_t small_max = SELECT_SMALL_MAX;
+    if (const char* env = std::getenv("VB200_SELECT_SMALL_MAX")) small_max = std::min<uint64_t>(std::strtoull(env, nullptr, 10), SELECT_SMALL_MAX);     // test knob
     while (left > 0) {
         uint64_t B = n / 4; if (B < 1) B = 1; if (B > left) B = left; if (B > max_batch) B = max_batch;
         if (p->batch > 1 && B > uint64_t(p->batch)) B = uint64_t(p->batch);
         // 1. radix top-k
-        select_init_kernel<<<1, 256, 0, s>>>(st, B, hist);
-        const unsigned hgrid = unsigned(std::min<uint64_t>((n + 255) / 256, uint64_t(ctx->sm_count) * 8));
-        for (int shift = 24; shift >= 0; shift -= 8) {
-            select_hist_kernel<<<hgrid, 256, 0, s>>>(r->err, n, st, shift, hist);
-            select_pick_kernel<<<1, 256, 0, s>>>(st, shift, hist);
+        if (n <= small_max) {
+            select_small_kernel<<<1, 1024, 0, s>>>(r->err, unsigned(n), B, st, sel);
+            ctx->launches += 1;
+        } else {
+            select_init_kernel<<<1, 256, 0, s>>>(st, B, hist);
+            const unsigned hgrid = unsigned(std::min<uint64_t>((n + 255) / 256, uint64_t(ctx->sm_count) * 8));
+            for (int shift = 24; shift >= 0; shift -= 8) {
+                select_hist_kernel<<<hgrid, 256, 0, s>>>(r->err, n, st, shift, hist);
+                select_pick_kernel<<<1, 256, 0, s>>>(st, shift, hist);
+            }
+            const unsigned nctas = unsigned((n + 1023) / 1024);
+            select_count_kernel<<<nctas, 256, 0, s>>>(r->err, n, st, cta_gt, cta_eq);
+            select_scan_kernel<<<1, 1024, 0, s>>>(cta_gt, cta_eq, nctas);
+            select_write_kernel<<<nctas, 1024, 0, s>>>(r->err, n, st, cta_gt, cta_eq, sel);
+            ctx->launches += 12;
         }
-        const unsigned nctas = unsigned((n + 1023) / 1024);
-        select_count_kernel<<<nctas, 256, 0, s>>>(r->err, n, st, cta_gt, cta_eq);
-        select_scan_kernel<<<1, 1024, 0, s>>>(cta_gt, cta_eq, nctas);
-        select_write_kernel<<<nctas, 1024, 0, s>>>(r->err, n, st, cta_gt, cta_eq, sel);
         // 2. new sample points of all B splits, one integrand launch
         const uint64_t N = B * Q;
         split_points_kernel<<<unsigned((N + 255) / 256), 256, 0, s>>>(SH, DIM, cap, B, sel, r->rmin, r->rmax, r->errdim, points);
-        ctx->launches += 13;
+        ctx->launches += 1;
         VB200_CUDA(ctx, cudaGetLastError());
         vb200_eval_launch ev; std::memset(&ev, 0, sizeof(ev));
         ev.n = N; ev.dim = DIM; ev.points = points; ev.values = vals;
