@@ -456,6 +456,13 @@ __global__ void __launch_bounds__(256) walk_accumulate_kernel(TileGeom g, DomT<T
     __shared__ unsigned char s_area[CHUNK];            // bins of this tile the region covers if that is 1..KS, else 0 (bin threads integrate it themselves)
     __shared__ unsigned char s_ok[CHUNK][KS];          // 0 = empty intersection
     __shared__ uint32_t s_lo[CHUNK][DB], s_w[CHUNK][DB];
+    // LARGE regions over a 2-D bin grid (!SMALL): the first fold of integral_subrange — along bin dimension 1 — only depends on the bin's
+    // ROW, so the 16 bins of a tile row would repeat it; it is evaluated once per (region, row, line) by the whole CTA and shared
+    // (3.4x fewer line integrals at S = 3; same operations on the same operands, so the same bits).
+    constexpr bool ROWS = !SMALL && DB == 2 && sizeof(T) == 4;
+    constexpr int TR = 16;
+    __shared__ T s_t[ROWS ? CHUNK : 1][ROWS ? TR : 1][ROWS ? S : 1];
+    __shared__ unsigned char s_e1[ROWS ? CHUNK : 1][ROWS ? TR : 1];
     const uint64_t t = blockIdx.x;
     uint32_t o[3]; tile_origin(g, t, o);
     if (!tile_in_shard(g, o, begin, end)) return;
@@ -508,6 +515,21 @@ __global__ void __launch_bounds__(256) walk_accumulate_kernel(TileGeom g, DomT<T
             }
             __syncthreads();
         }
+        if constexpr (ROWS) {
+            for (int item = threadIdx.x; item < n * TR * S; item += blockDim.x) {
+                const int j = item / (TR * S), rem = item % (TR * S), ry = rem / S, i0 = rem % S;
+                const St& rg = s_reg[j];
+                const uint32_t p1 = o[1] + uint32_t(ry);
+                const T lo1 = R::add(dom.rmin[1], R::mul(T(p1), dom.drange[1])), hi1 = R::add(dom.rmin[1], R::mul(T(p1 + 1u), dom.drange[1]));
+                const T a = R::maxv(lo1, rg.rmin[1]), b = R::maxv(a, R::minv(hi1, rg.rmax[1]));
+                T line[S];
+#pragma unroll
+                for (int i1 = 0; i1 < S; ++i1) line[i1] = rg.patch[i0 + S * i1];
+                s_t[j][ry][i0] = R::subrange<S, T>(R::pos_in_range<T>(rg.rmin[1], rg.rmax[1], a), R::pos_in_range<T>(rg.rmin[1], rg.rmax[1], b), line);
+                if (i0 == 0) s_e1[j][ry] = (a >= b) ? 1 : 0;
+            }
+            __syncthreads();
+        }
         if (live) {
             for (int j = 0; j < n; ++j) {
                 const St& rg = s_reg[j];
@@ -517,7 +539,16 @@ __global__ void __launch_bounds__(256) walk_accumulate_kernel(TileGeom g, DomT<T
                 if (!inside) continue;
                 ++cnt;
                 T integral; bool ok;
-                if (SMALL && s_area[j] != 0) {
+                if constexpr (ROWS) {
+                    const int ry = int(pos[1] - o[1]);
+                    const T lo0 = R::add(dom.rmin[0], R::mul(T(pos[0]), dom.drange[0])), hi0 = R::add(dom.rmin[0], R::mul(T(pos[0] + 1u), dom.drange[0]));
+                    const T a = R::maxv(lo0, rg.rmin[0]), b = R::maxv(a, R::minv(hi0, rg.rmax[0]));
+                    T tt[S];
+#pragma unroll
+                    for (int i0 = 0; i0 < S; ++i0) tt[i0] = s_t[j][ry][i0];
+                    integral = R::mul(rg.volume, R::subrange<S, T>(R::pos_in_range<T>(rg.rmin[0], rg.rmax[0], a), R::pos_in_range<T>(rg.rmin[0], rg.rmax[0], b), tt));
+                    ok = !((a >= b) || s_e1[j][ry] != 0);
+                } else if (SMALL && s_area[j] != 0) {
                     uint32_t k = 0, stride = 1;
 #pragma unroll
                     for (int d = 0; d < DB; ++d) { k += (pos[d] - s_lo[j][d]) * stride; stride *= s_w[j][d]; }
