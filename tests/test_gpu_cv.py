@@ -236,3 +236,19 @@ def test_weighted_roulette_golden_reference_vectors(ctx):
         assert_same_bits(out, f32(v["bins"]), f"{v['integrand']} rr={v['rr']} alpha={v['alpha']}")
         regs.free(); n += 1
     assert n == 9
+
+
+def test_grouped_rank_resolution_equals_chunkwise_resolution(ctx):
+    """cv_resolve_grouped_kernel (masks of 16 chunks per pass) picks exactly the regions cv_resolve_kernel picks: identical bins, also for
+    tile lists longer than one group and for 1-D / 3-D bin grids."""
+    import os
+    from viltrum_b200 import integrate, integrator_crespo2021
+    for integ, res, it, spp in (("shade5_16", [64, 64], 6000, 16), ("smooth_edge2", [24, 24], 5000, 8), ("x2y2", [300], 2000, 32), ("poly3", [12, 10, 6], 3000, 8)):
+        nb = int(np.prod(res)); outs = []
+        for legacy in ("1", "0"):
+            os.environ["VB200_CV_RESOLVE_LEGACY"] = legacy
+            b = np.zeros(nb, np.float32)
+            integrate(integrator_crespo2021(it, spp, seed=4, batch=0), b, res, integ, _rng(integ), ctx=ctx)
+            outs.append(b)
+        os.environ.pop("VB200_CV_RESOLVE_LEGACY", None)
+        assert_same_bits(outs[0], outs[1], f"grouped vs chunkwise resolution {integ} {res}")
