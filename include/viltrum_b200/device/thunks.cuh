@@ -108,7 +108,7 @@ struct FiniteThunks {
     template<int DB>
     static int launch_scatter(const F& f, const vb200_scatter_launch& a, cudaStream_t st) {
         auto k = device::mc_scatter_kernel<F, DIM, DB, EXACT>;
-        const uint64_t n = a.sample_end - a.sample_begin;
+        const uint64_t n = (a.sample_end - a.sample_begin + 7) / 8 + 1;      // one thread per group of eight samples
         const int grid = persistent_grid(k, 256, (n + 255) / 256, a.grid_hint);
         k<<<grid, 256, 0, st>>>(f, a);
         return int(cudaGetLastError());
