@@ -433,24 +433,69 @@ __device__ __forceinline__ bool pair_integral(const DomT<T>& dom, const uint32_t
     return !empty;
 }
 
+// Pre-pass of the SMALL path: one thread per (tile-list entry, k) over the WHOLE grid integrates the k-th bin a small region covers
+// inside its tile (at most KS = 4 bins), so the slivers that crowd one tile along a discontinuity (20 000 in a single 16x16 tile of the
+// tolerance benchmark) are spread over all SMs instead of being one CTA's serial work.  contrib[e*4+k] / ok[e*4+k]; area[e] = 0 marks
+// an entry whose region is not small there (the bin threads integrate it themselves).
+constexpr int WALK_KS = 4;
+template<int S, int DB, class T>
+__global__ void __launch_bounds__(256) walk_small_pairs_kernel(TileGeom g, DomT<T> dom, uint64_t cap, uint64_t ntiles, uint64_t nentries,
+                                                               const T* __restrict__ patches, const T* __restrict__ rmin, const T* __restrict__ rmax,
+                                                               const T* __restrict__ volume, const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ pend,
+                                                               const uint64_t* __restrict__ offsets, const uint32_t* __restrict__ list,
+                                                               T* __restrict__ contrib, unsigned char* __restrict__ ok, unsigned char* __restrict__ area_out) {
+    const uint64_t item = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const uint64_t e = item / WALK_KS; const int k = int(item % WALK_KS);
+    if (e >= nentries) return;
+    // tile of this entry: last t with offsets[t] <= e
+    uint64_t lo = 0, hi = ntiles;
+    while (hi - lo > 1) { const uint64_t mid = (lo + hi) >> 1; if (offsets[mid] <= e) lo = mid; else hi = mid; }
+    uint32_t o[3]; tile_origin(g, lo, o);
+    const uint64_t r = list[e];
+    uint32_t blo[DB], bw[DB]; uint32_t area = 1;
+    Staged<S, DB, T> rg;
+#pragma unroll
+    for (int d = 0; d < DB; ++d) {
+        const uint32_t ps = pstart[uint64_t(d) * cap + r], pe = pend[uint64_t(d) * cap + r];
+        const uint32_t a0 = max(ps, o[d]), a1 = min(min(pe, o[d] + g.tile[d]), g.res[d]);
+        blo[d] = a0; bw[d] = a1 > a0 ? a1 - a0 : 0u;
+        area = (bw[d] == 0u || area > uint32_t(WALK_KS)) ? (bw[d] == 0u ? 0u : uint32_t(WALK_KS) + 1u) : area * bw[d];
+    }
+    const bool small = area >= 1u && area <= uint32_t(WALK_KS);
+    if (k == 0) area_out[e] = (unsigned char)(small ? area : 0u);
+    if (!small || uint32_t(k) >= area) return;
+#pragma unroll
+    for (int d = 0; d < DB; ++d) { rg.rmin[d] = rmin[uint64_t(d) * cap + r]; rg.rmax[d] = rmax[uint64_t(d) * cap + r]; }
+#pragma unroll
+    for (int q = 0; q < Staged<S, DB, T>::P; ++q) rg.patch[q] = patches[uint64_t(q) * cap + r];
+    rg.volume = volume[r];
+    uint32_t p[3] = {0, 0, 0}; uint32_t kk = uint32_t(k);
+#pragma unroll
+    for (int d = 0; d < DB; ++d) { p[d] = blo[d] + kk % bw[d]; kk /= bw[d]; }
+    T v; const bool good = pair_integral<S, DB, T>(dom, p, rg, &v);
+    contrib[item] = v; ok[item] = good ? 1 : 0;
+}
+
 // K8/K10: one CTA per bin tile, one thread per bin.  The tile's region list is staged through shared memory in chunks
 // (patches + boxes: the "region tree" a bin needs), every thread walks the chunk in table order, keeps the regions whose
 // pixel box contains its bin and accumulates nbins * integral_subrange(bin ∩ region) with the reference's promotions:
 //   bins(pos) += double(factor) * float        (regions-integrator-sequential.h:54; ...-variance-reduction.h:80)
 // Small regions (<= KS bins of this tile: the slivers a tolerance-driven refinement piles up along a discontinuity) are integrated by a
-// thread per (region, bin) pair first, 256 at once, and the bin threads only pick the values up in table order — otherwise a chunk of
-// 64 slivers that all touch the same few bins is 64 integrals evaluated one after the other by a single lane (measured: 88 ms -> see
-// profiles/results_r1.md for an 841 644-leaf table at 512x512 bins).  The summation order per bin, hence every bit, is unchanged.
+// thread per (region, bin) pair in a grid-wide pre-pass (walk_small_pairs_kernel) and the bin threads only pick the values up in table
+// order — otherwise a chunk of 64 slivers that all touch the same few bins is 64 integrals evaluated one after the other by a single
+// lane (measured: 88 ms -> see profiles/results_r1.md for an 841 644-leaf table at 512x512 bins).  The summation order per bin, hence
+// every bit, is unchanged.
 // SMALL = false compiles that path out (tables of few large regions, e.g. BASELINE config 4: fewer registers, more resident CTAs).
 template<int S, int DB, class T, bool SMALL>
 __global__ void __launch_bounds__(256) walk_accumulate_kernel(TileGeom g, DomT<T> dom, uint64_t cap, uint64_t begin, uint64_t end, uint64_t nbins_total,
                                                               const T* __restrict__ patches, const T* __restrict__ rmin, const T* __restrict__ rmax,
                                                               const T* __restrict__ volume, const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ pend,
                                                               const uint64_t* __restrict__ offsets, const uint32_t* __restrict__ list,
-                                                              int mode, T* __restrict__ out, T* __restrict__ approx, uint32_t* __restrict__ count) {
+                                                              int mode, T* __restrict__ out, T* __restrict__ approx, uint32_t* __restrict__ count,
+                                                              const T* __restrict__ g_contrib, const unsigned char* __restrict__ g_ok, const unsigned char* __restrict__ g_area) {
     using St = Staged<S, DB, T>;
     constexpr int CHUNK = (St::P * sizeof(T) > 256) ? 16 : 64;
-    constexpr int KS = 4;
+    constexpr int KS = WALK_KS;
     __shared__ St s_reg[CHUNK];
     __shared__ T s_contrib[CHUNK][KS];
     __shared__ unsigned char s_area[CHUNK];            // bins of this tile the region covers if that is 1..KS, else 0 (bin threads integrate it themselves)
@@ -480,12 +525,11 @@ __global__ void __launch_bounds__(256) walk_accumulate_kernel(TileGeom g, DomT<T
         __syncthreads();
         for (int k = threadIdx.x; k < n * St::P; k += blockDim.x) {
             const int j = k / St::P, q = k % St::P;
+            if (SMALL && g_area[base + j] != 0) continue;       // integrated by the pre-pass: nobody reads its patch here
             s_reg[j].patch[q] = patches[uint64_t(q) * cap + list[base + j]];
         }
-        int small = 0;
         for (int j = threadIdx.x; j < n; j += blockDim.x) {
             const uint64_t r = list[base + j];
-            uint32_t area = 1;
             for (int d = 0; d < DB; ++d) {
                 s_reg[j].rmin[d] = rmin[uint64_t(d) * cap + r]; s_reg[j].rmax[d] = rmax[uint64_t(d) * cap + r];
                 const uint32_t ps = pstart[uint64_t(d) * cap + r], pe = pend[uint64_t(d) * cap + r];
@@ -493,28 +537,17 @@ __global__ void __launch_bounds__(256) walk_accumulate_kernel(TileGeom g, DomT<T
                 // the part of the region's pixel box inside this tile (and inside the grid)
                 const uint32_t a0 = max(ps, o[d]), a1 = min(min(pe, o[d] + g.tile[d]), g.res[d]);
                 s_lo[j][d] = a0; s_w[j][d] = a1 > a0 ? a1 - a0 : 0u;
-                area = (s_w[j][d] == 0u || area > KS) ? (s_w[j][d] == 0u ? 0u : KS + 1u) : area * s_w[j][d];
             }
             s_reg[j].volume = volume[r];
-            const bool is_small = SMALL && area >= 1u && area <= KS;
-            s_area[j] = (unsigned char)(is_small ? area : 0u);
-            small |= is_small ? 1 : 0;
+            s_area[j] = SMALL ? g_area[base + j] : (unsigned char)0;
         }
-        const int any_small = __syncthreads_or(small);
-        if (SMALL && any_small) {
-            // one thread per (region, covered bin) pair
+        if constexpr (SMALL) {       // the small regions' integrals come from the grid-wide pre-pass (walk_small_pairs_kernel)
             for (int item = threadIdx.x; item < n * KS; item += blockDim.x) {
                 const int j = item / KS, k = item % KS;
-                if (k < int(s_area[j])) {
-                    uint32_t p[3] = {0, 0, 0}; uint32_t kk = uint32_t(k);
-#pragma unroll
-                    for (int d = 0; d < DB; ++d) { p[d] = s_lo[j][d] + kk % s_w[j][d]; kk /= s_w[j][d]; }
-                    T v; const bool ok = pair_integral<S, DB, T>(dom, p, s_reg[j], &v);
-                    s_contrib[j][k] = v; s_ok[j][k] = ok ? 1 : 0;
-                }
+                if (k < int(g_area[base + j])) { s_contrib[j][k] = g_contrib[(base + j) * KS + k]; s_ok[j][k] = g_ok[(base + j) * KS + k]; }
             }
-            __syncthreads();
         }
+        __syncthreads();
         if constexpr (ROWS) {
             for (int item = threadIdx.x; item < n * TR * S; item += blockDim.x) {
                 const int j = item / (TR * S), rem = item % (TR * S), ry = rem / S, i0 = rem % S;
@@ -571,11 +604,26 @@ template<int S, int DB, class T>
 int launch_accumulate(vb200_ctx* ctx, const vb200_regions* r, const BinWalkT<T>& w, const TileGeom& g, const DomT<T>& dom,
                       uint64_t begin, uint64_t end, uint64_t total, int mode, T* out, T* approx, uint32_t* count) {
     // regions that cover only a few bins each are integrated pair-parallel (SMALL); tables of few large regions keep the leaner kernel
-    const bool small = r->count * 4ull >= total;
-    if (small) walk_accumulate_kernel<S, DB, T, true><<<unsigned(w.ntiles), 256, 0, ctx->stream>>>(g, dom, w.cap, begin, end, total, w.patches, RegCols<T>::rmin(r), RegCols<T>::rmax(r), w.volume,
-                                                                                   w.pstart, w.pend, w.tile_offset, w.tile_list, mode, out, approx, count);
-    else walk_accumulate_kernel<S, DB, T, false><<<unsigned(w.ntiles), 256, 0, ctx->stream>>>(g, dom, w.cap, begin, end, total, w.patches, RegCols<T>::rmin(r), RegCols<T>::rmax(r), w.volume,
-                                                                                   w.pstart, w.pend, w.tile_offset, w.tile_list, mode, out, approx, count);
+    const bool small = r->count * 4ull >= total && w.pairs > 0;
+    if (small) {
+        T* contrib = nullptr; unsigned char* ok = nullptr; unsigned char* area = nullptr;
+        const uint64_t items = w.pairs * uint64_t(WALK_KS);
+        if (dmalloc(ctx, &contrib, items * sizeof(T)) != cudaSuccess || dmalloc(ctx, &ok, items) != cudaSuccess || dmalloc(ctx, &area, w.pairs) != cudaSuccess) {
+            cudaGetLastError(); dfree(ctx, contrib); dfree(ctx, ok); dfree(ctx, area);
+            return fail(ctx, VB200_ERR_NOMEM, "cudaMalloc failed (small-region contributions)");
+        }
+        walk_small_pairs_kernel<S, DB, T><<<unsigned((items + 255) / 256), 256, 0, ctx->stream>>>(g, dom, w.cap, w.ntiles, w.pairs, w.patches, RegCols<T>::rmin(r), RegCols<T>::rmax(r), w.volume,
+                                                                                                   w.pstart, w.pend, w.tile_offset, w.tile_list, contrib, ok, area);
+        walk_accumulate_kernel<S, DB, T, true><<<unsigned(w.ntiles), 256, 0, ctx->stream>>>(g, dom, w.cap, begin, end, total, w.patches, RegCols<T>::rmin(r), RegCols<T>::rmax(r), w.volume,
+                                                                                   w.pstart, w.pend, w.tile_offset, w.tile_list, mode, out, approx, count, contrib, ok, area);
+        ctx->launches += 2;
+        const cudaError_t e = cudaGetLastError();
+        dfree(ctx, contrib); dfree(ctx, ok); dfree(ctx, area);      // stream-ordered frees: after the kernels above
+        VB200_CUDA(ctx, e);
+        return VB200_OK;
+    }
+    walk_accumulate_kernel<S, DB, T, false><<<unsigned(w.ntiles), 256, 0, ctx->stream>>>(g, dom, w.cap, begin, end, total, w.patches, RegCols<T>::rmin(r), RegCols<T>::rmax(r), w.volume,
+                                                                                   w.pstart, w.pend, w.tile_offset, w.tile_list, mode, out, approx, count, nullptr, nullptr, nullptr);
     ctx->launches++;
     VB200_CUDA(ctx, cudaGetLastError());
     return VB200_OK;
