@@ -252,3 +252,29 @@ def test_grouped_rank_resolution_equals_chunkwise_resolution(ctx):
             outs.append(b)
         os.environ.pop("VB200_CV_RESOLVE_LEGACY", None)
         assert_same_bits(outs[0], outs[1], f"grouped vs chunkwise resolution {integ} {res}")
+
+
+@pytest.mark.parametrize("rule", ["boole_simpson", "simpson_trapezoidal"])
+@pytest.mark.parametrize("rr", ["uniform", "integral", "error"])
+def test_control_variates_over_other_rules_converge(ctx, rule, rr):
+    """The residual pass takes any nested rule's table (the C++ factories are generic over rule and heuristic; the oracle's CV entry
+    points only cover the crespo2021 pair): with cv_fixed_weight(1) — an unbiased estimator whatever the roulette — the estimate must
+    agree with a 16 384-spp per-bin Monte Carlo reference, bin by bin, and beat plain MC at the same sample count."""
+    integ, res, it, spp = "smooth_edge2", [24, 24], 400, 16
+    nb = res[0] * res[1]
+    regs = ctx.regions_generate_adaptive(integ, _rng(integ), rule, "default", "absolute", it, 1e-5, batch=1, exact=True)
+    est = np.stack([np.zeros(nb, np.float32) for _ in range(8)])
+    for s in range(8):
+        regs.cv_integrate(integ, est[s], res, _rng(integ), spp, 50 + s, rr=rr, fixed_alpha=1.0)
+    regs.free()
+    ref = np.zeros(nb, np.float32); s1 = np.zeros(nb, np.float32); s2 = np.zeros(nb, np.float32)
+    ctx.mc_per_bin(integ, ref, res, _rng(integ), 16384, 3, sum_f=s1, sum_f2=s2)
+    mc = np.zeros(nb, np.float32)
+    ctx.mc_per_bin(integ, mc, res, _rng(integ), spp, 4)
+    mean = est.astype(np.float64).mean(axis=0)
+    sem = est.astype(np.float64).std(axis=0, ddof=1) / np.sqrt(8) + 2e-3 * np.abs(ref) + 1e-4
+    z = (mean - ref) / sem
+    assert np.mean(np.abs(z) < 4) > 0.97 and np.max(np.abs(z)) < 12, f"{rule} rr={rr}: z max {np.max(np.abs(z)):.2f}"
+    assert abs(float(mean.mean()) - float(ref.mean())) < 3e-3
+    if rr != "error":       # rr_error_region's 1/probability factors (up to 100x the mean) can cost more variance than the control variate saves
+        assert np.mean((est[0] - ref) ** 2) < np.mean((mc - ref) ** 2)
