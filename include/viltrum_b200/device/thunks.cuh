@@ -11,6 +11,7 @@
 // (add --fmad=false and define VILTRUM_B200_EXACT for the bit-exact twin).
 #pragma once
 #include <cstring>
+#include <cstdlib>
 #include <type_traits>
 #include <cuda_runtime.h>
 #include "../../viltrum_b200.h"
@@ -168,7 +169,21 @@ struct InfiniteThunks {
         // state machines that consume 2 + 2 elements per begin()/step() are fed whole Philox blocks (one generator call per lane and
         // iteration, immediate refill) as long as every explicit range entry sits in block 0
         if constexpr (device::has_block_steps<F>::value) {
-            if (a.domain.dim <= 4 && DB <= 4) return launch_walk_kernel(device::walk_block_kernel<F, DB, MOMENTS, EXACT>, f, a, st);
+            if (a.domain.dim <= 4 && DB <= 4) {
+                // one lane per bin (every large grid): the two-tile window keeps the lanes of a warp busy across the uneven lengths of
+                // their bins.  Needs enough tiles per warp to still balance the tail through the ticket counter; VB200_WALK_WINDOW=0/1
+                // switches it off / forces it (tests compare both kernels bit for bit).
+                if (a.lanes_per_bin == 1) {
+                    auto kw = device::walk_block_window_kernel<F, DB, MOMENTS, EXACT>;
+                    const uint64_t tiles = (a.bin_end - a.bin_begin + 31u) / 32u;
+                    const uint64_t ctas = (tiles + device::MC_THREADS / 32 - 1) / (device::MC_THREADS / 32);
+                    const int grid = persistent_grid(kw, device::MC_THREADS, ctas, a.grid_hint);
+                    bool window = tiles >= 6ull * uint64_t(grid) * (device::MC_THREADS / 32);
+                    if (const char* env = std::getenv("VB200_WALK_WINDOW")) window = env[0] != '0';
+                    if (window) { kw<<<grid, device::MC_THREADS, 0, st>>>(f, a); return int(cudaGetLastError()); }
+                }
+                return launch_walk_kernel(device::walk_block_kernel<F, DB, MOMENTS, EXACT>, f, a, st);
+            }
         }
         // functors that also describe themselves as a state machine get the wavefront kernel (lane refill)
         auto k = wavefront_or_plain<DB, MOMENTS>(std::integral_constant<bool, device::has_steps<F>::value>());

@@ -299,6 +299,112 @@ walk_block_kernel(const F f, const vb200_walk_launch a) {
     }
 }
 
+// ---- block-fed kernel, one lane per bin, with a two-tile window (the shipped C5 path) -----------------------------------------------
+// With one lane per bin (every large grid: pick_lanes_per_bin) a bin is `spp` sequential paths of random length, so the 32 lanes of a
+// tile finish at different times and walk_block_kernel idles the early ones until the slowest is through (ncu: 27.5 of 32 lanes active
+// at C5).  Here a warp holds TWO tiles: a lane that has stored its bin of the current tile moves straight on to its bin of the next one
+// and only waits if it has finished that one too while some lane is still in the current tile (a full bin's lead: it does not happen
+// at C5's 256 paths per bin).  When every lane has left the current tile the warp signals it (end-to-end path: chunk flags), the next
+// tile becomes the current one and a new ticket is drawn.  Tiles, tickets, elements and the per-bin summation order (one lane, samples
+// in order) are walk_block_kernel's at lanes_per_bin = 1: bits identical.
+template<class F, int DIMBINS, bool MOMENTS, bool EXACT>
+__global__ void __launch_bounds__(MC_THREADS)
+walk_block_window_kernel(const F f, const vb200_walk_launch a) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t nshard = a.bin_end - a.bin_begin;
+    const uint64_t ntiles = (nshard + 31u) / 32u;
+    // the bin box of this lane's bin in tile t (all lanes together: the index divisions run convergent, once per tile)
+    auto prepare = [&](uint64_t t, float (&lo)[DIMBINS], float (&ext)[DIMBINS], float& vol) -> bool {
+        const uint64_t b = a.bin_begin + t * 32u + lane;
+        if (t >= ntiles || b >= a.bin_end) return false;
+        vol = walk_bin_box<DIMBINS>(a.domain, b, lo, ext);
+        return true;
+    };
+    unsigned long long t2 = 0;
+    if (lane == 0) t2 = atomicAdd(a.tile_counter, 2ull);          // tickets are consecutive: the first two in one atomic
+    t2 = __shfl_sync(0xffffffffu, t2, 0);
+    uint64_t tile_cur = t2, tile_nxt = t2 + 1;
+    uint32_t base = 0;                    // warp-uniform: tiles this warp has retired
+    uint32_t pos = 0;                     // per lane: base = in the current tile, base + 1 = in the next one, base + 2 = through with both (waits)
+    // element -> value map of block 0: v = fmaf(u, scale, offset); binned dimensions use the bin box, other explicit entries their
+    // range, everything else [0,1) (scale 1, offset 0: fmaf(u,1,0) == u)
+    float sc[4] = {1.0f, 1.0f, 1.0f, 1.0f}, of[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int d = DIMBINS; d < 4; ++d)
+        if (d < a.domain.dim) { sc[d] = a.domain.rmax[d] - a.domain.rmin[d]; of[d] = a.domain.rmin[d]; }
+    float n_lo[DIMBINS], n_ext[DIMBINS], n_vol = 1.0f, volume = 1.0f;     // n_*: this lane's bin of the NEXT tile, prepared ahead
+    float sum = 0.0f, sum2 = 0.0f;
+    bool alive = false;
+    bool has_bin = prepare(tile_cur, n_lo, n_ext, volume);
+    uint64_t bin = a.bin_begin + tile_cur * 32u + lane;
+#pragma unroll
+    for (int d = 0; d < DIMBINS && d < 4; ++d) { sc[d] = n_ext[d]; of[d] = n_lo[d]; }
+    if (!has_bin) pos = 1;
+    bool n_live = prepare(tile_nxt, n_lo, n_ext, n_vol);
+    uint32_t b0 = uint32_t(bin), b1 = uint32_t(bin >> 32), next = 0, s = 0, blk = 0;
+    typename F::State st;
+    bool service = true;                  // first pass: lanes without a bin in the first tile, warps without a tile
+    while (true) {
+        const bool done = has_bin && !alive && next >= a.spp;
+        if (service || __any_sync(0xffffffffu, done)) {
+            service = false;
+            if (done) {
+                const float v = walk_bin_value(a, sum, volume);
+                a.out[bin] = a.accumulate ? float(double(a.out[bin]) + double(v)) : v;
+                if (MOMENTS) {
+                    if (a.sum_f)  a.sum_f[bin - a.bin_begin]  = sum;
+                    if (a.sum_f2) a.sum_f2[bin - a.bin_begin] = sum2;
+                }
+                has_bin = false; ++pos;
+            }
+            while (true) {                // warp-uniform: move free lanes into the next tile; retire the current tile once everybody has left it
+                if (!has_bin && pos == base + 1u) {
+                    if (n_live) {
+#pragma unroll
+                        for (int d = 0; d < DIMBINS && d < 4; ++d) { sc[d] = n_ext[d]; of[d] = n_lo[d]; }
+                        volume = n_vol;
+                        bin = a.bin_begin + tile_nxt * 32u + lane; b0 = uint32_t(bin); b1 = uint32_t(bin >> 32);
+                        sum = 0.0f; sum2 = 0.0f; next = 0; has_bin = true;
+                    }
+                    else ++pos;           // no bin for this lane there (ragged last tile, or past the last ticket)
+                }
+                if (!__all_sync(0xffffffffu, pos > base)) break;
+                if (tile_cur >= ntiles) return;                        // tickets only grow: nothing left for this warp
+                signal_tile_done(a.signal, tile_cur, ntiles, lane);
+                tile_cur = tile_nxt;
+                unsigned long long t = 0;
+                if (lane == 0) t = atomicAdd(a.tile_counter, 1ull);
+                tile_nxt = __shfl_sync(0xffffffffu, t, 0);
+                ++base;
+                n_live = prepare(tile_nxt, n_lo, n_ext, n_vol);
+            }
+        }
+        const bool starting = has_bin && !alive && next < a.spp;
+        if (starting) { s = next; ++next; blk = 0; }
+        const u32x4 r = philox4x32<10>(u32x4{b0, b1, s, blk}, a.key0, a.key1);
+        BlockIterator it;
+        it.e0 = u01(r.x); it.e1 = u01(r.y); it.e2 = u01(r.z); it.e3 = u01(r.w); it.i = 0;
+        if (blk == 0) {       // PhiloxSequence::const_iterator::load: fmaf(u, extent, lower)
+            it.e0 = fmaf(it.e0, sc[0], of[0]); it.e1 = fmaf(it.e1, sc[1], of[1]); it.e2 = fmaf(it.e2, sc[2], of[2]); it.e3 = fmaf(it.e3, sc[3], of[3]);
+        }
+        ++blk;
+        bool ended = false;
+        if (starting) {                                              // elements 0,1 — or none, then the first round takes them
+            st = f.begin(it); alive = true;
+            if constexpr (F::elements_begin == 0) { if (!f.step(st, it)) ended = true; }
+        }
+        else if (alive) { if (!f.step(st, it)) ended = true; }       // elements 0,1 (or only 0)
+        it.i = 2;
+        if (alive && !ended) { if (!f.step(st, it)) ended = true; }  // elements 2,3 (or only 2)
+        if (ended) {
+            const float v = f.end(st);
+            sum += v;
+            if (MOMENTS) sum2 = fmaf(v, v, sum2);
+            alive = false;
+        }
+    }
+}
+
 // Replay of recorded sequences (the reference's own element values): one thread per bin, paths in order,
 // bins(p) += f(seq)*factor with float(double(acc)+double(f)*factor)  (monte-carlo-per-bin-parallel.h:96).
 struct RecordedSequence {

@@ -182,3 +182,37 @@ def test_global_scatter_over_infinite_range(ctx, port, integ, res, rmin, rmax):
     acc = np.full(nb, 2.0, np.float32)
     integrate(monte_carlo(n, seed=5), acc, res, integ, rng, ctx=ctx)
     assert np.allclose(acc - 2.0, g, rtol=1e-4, atol=1e-4)          # '+=' ; float atomics reorder sums
+
+
+def test_window_kernel_equals_tile_kernel(ctx, monkeypatch):
+    """One lane per bin (what every large grid gets; forced here with VB200_LANES_PER_BIN=1): the two-tile window kernel
+    (walk_block_window_kernel: a lane moves on to its bin of the warp's next tile instead of idling) against the tile-at-a-time
+    block kernel and the generic kernel — same elements, same per-bin summation order -> bit-identical bins and moments; device bins,
+    host bins (end-to-end path: chunk flags raised per retired tile), ragged shards, both flavors, accumulate, more warps than tiles."""
+    import torch
+    from viltrum_b200 import RangeInfinite, _capi
+    monkeypatch.setenv("VB200_LANES_PER_BIN", "1")
+    cases = [([64, 48], 64, (), ()), ([1000], 37, (), ()), ([9, 7, 5], 40, (), ()), ([50, 41], 96, (0.1, 0.2, 0.0), (0.9, 0.7, 1.0)),
+             ([3], 500, (-1.0,), (2.0,)), ([256, 200], 32, (), ())]
+    for res, spp, rmin, rmax in cases:
+        nb = int(np.prod(res))
+        rng = RangeInfinite(list(rmin), list(rmax))
+        shards = [None, (0, nb // 3 + 1), (nb // 3 + 1, nb)]
+        for flavor in (_capi.MC_PER_BIN, _capi.PER_BIN_MC):
+            for name, plain in (("walk", "walk_plain"), ("decay", "decay_plain")):
+                got = {}
+                for window in ("1", "0"):
+                    monkeypatch.setenv("VB200_WALK_WINDOW", window)
+                    h = np.full(nb, 0.25, np.float32); s1 = np.zeros(nb, np.float32); s2 = np.zeros(nb, np.float32)
+                    ctx.mc_per_bin_inf(name, h, res, rng, spp, 11, flavor=flavor, sum_f=s1, sum_f2=s2)        # host bins
+                    d = torch.full((nb,), 0.25, dtype=torch.float32, device="cuda")
+                    for sh in shards[1:]:
+                        ctx.mc_per_bin_inf(name, d, res, rng, spp, 11, flavor=flavor, shard=sh)                # device bins, ragged shards
+                    ctx.synchronize()
+                    got[window] = (h, s1, s2, d.cpu().numpy())
+                ref = np.full(nb, 0.25, np.float32)
+                ctx.mc_per_bin_inf(plain, ref, res, rng, spp, 11, flavor=flavor)
+                for k, what in enumerate(("host bins", "sum f", "sum f^2", "sharded device bins")):
+                    assert_same_bits(got["1"][k], got["0"][k], f"window vs tile kernel: {what} {name} {res} {rmin} flavor {flavor}")
+                assert_same_bits(got["1"][0], ref, f"window vs generic kernel {name} {res} {rmin} flavor {flavor}")
+                assert_same_bits(got["1"][3], ref, f"window (sharded) vs generic kernel {name} {res} {rmin} flavor {flavor}")

@@ -155,7 +155,11 @@ uint32_t pick_lanes_per_bin(const vb200_ctx* ctx, uint64_t spp, uint64_t nbins, 
     const uint64_t want_lanes = uint64_t(ctx->sm_count) * 2048ull * 2ull;
     const uint64_t groups = (spp + group - 1) / group;      // the lanes of a bin stride over draw groups of eight samples (mc_per_bin.cuh); paths in walk.cuh stride over samples (group = 4 bounds their lanes)
     uint32_t lpb = 1;
-    while (lpb < 32 && nbins * lpb < want_lanes && uint64_t(lpb) * 2 <= groups) lpb <<= 1;
+    // VB200_LANES_PER_BIN (tuning / test knob): upper bound on the lanes that share a bin; 1 gives small grids the summation order —
+    // and the kernels — of the large ones
+    uint32_t cap = 32;
+    if (const char* env = std::getenv("VB200_LANES_PER_BIN")) { const long v = std::atol(env); if (v >= 1 && v <= 32) cap = uint32_t(v); }
+    while (lpb < 32 && lpb * 2 <= cap && nbins * lpb < want_lanes && uint64_t(lpb) * 2 <= groups) lpb <<= 1;
     return lpb;
 }
 
