@@ -174,7 +174,8 @@ struct InfiniteThunks {
                 // their bins.  Needs enough tiles per warp to still balance the tail through the ticket counter; VB200_WALK_WINDOW=0/1
                 // switches it off / forces it (tests compare both kernels bit for bit).
                 if (a.lanes_per_bin == 1) {
-                    auto kw = device::walk_block_window_kernel<F, DB, MOMENTS, EXACT>;
+                    auto kw = a.domain.dim > DB ? device::walk_block_window_kernel<F, DB, MOMENTS, EXACT, true>
+                                                : device::walk_block_window_kernel<F, DB, MOMENTS, EXACT, false>;
                     const uint64_t tiles = (a.bin_end - a.bin_begin + 31u) / 32u;
                     const uint64_t ctas = (tiles + device::MC_THREADS / 32 - 1) / (device::MC_THREADS / 32);
                     const int grid = persistent_grid(kw, device::MC_THREADS, ctas, a.grid_hint);

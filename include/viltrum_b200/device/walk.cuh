@@ -307,7 +307,9 @@ walk_block_kernel(const F f, const vb200_walk_launch a) {
 // at C5's 256 paths per bin).  When every lane has left the current tile the warp signals it (end-to-end path: chunk flags), the next
 // tile becomes the current one and a new ticket is drawn.  Tiles, tickets, elements and the per-bin summation order (one lane, samples
 // in order) are walk_block_kernel's at lanes_per_bin = 1: bits identical.
-template<class F, int DIMBINS, bool MOMENTS, bool EXACT>
+// TAIL: the range has explicit entries beyond the binned dimensions (elements DIMBINS..3 of block 0 are mapped too); without them those
+// elements keep [0,1) — fmaf(u, 1, 0) == u — and block 0 costs DIMBINS predicated FFMAs instead of a divergent branch.
+template<class F, int DIMBINS, bool MOMENTS, bool EXACT, bool TAIL>
 __global__ void __launch_bounds__(MC_THREADS)
 walk_block_window_kernel(const F f, const vb200_walk_launch a) {
     const uint32_t lane = threadIdx.x & 31u;
@@ -329,9 +331,11 @@ walk_block_window_kernel(const F f, const vb200_walk_launch a) {
     // element -> value map of block 0: v = fmaf(u, scale, offset); binned dimensions use the bin box, other explicit entries their
     // range, everything else [0,1) (scale 1, offset 0: fmaf(u,1,0) == u)
     float sc[4] = {1.0f, 1.0f, 1.0f, 1.0f}, of[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (TAIL) {
 #pragma unroll
-    for (int d = DIMBINS; d < 4; ++d)
-        if (d < a.domain.dim) { sc[d] = a.domain.rmax[d] - a.domain.rmin[d]; of[d] = a.domain.rmin[d]; }
+        for (int d = DIMBINS; d < 4; ++d)
+            if (d < a.domain.dim) { sc[d] = a.domain.rmax[d] - a.domain.rmin[d]; of[d] = a.domain.rmin[d]; }
+    }
     float n_lo[DIMBINS], n_ext[DIMBINS], n_vol = 1.0f, volume = 1.0f;     // n_*: this lane's bin of the NEXT tile, prepared ahead
     float sum = 0.0f, sum2 = 0.0f;
     bool alive = false;
@@ -341,67 +345,78 @@ walk_block_window_kernel(const F f, const vb200_walk_launch a) {
     for (int d = 0; d < DIMBINS && d < 4; ++d) { sc[d] = n_ext[d]; of[d] = n_lo[d]; }
     if (!has_bin) pos = 1;
     bool n_live = prepare(tile_nxt, n_lo, n_ext, n_vol);
-    uint32_t b0 = uint32_t(bin), b1 = uint32_t(bin >> 32), next = 0, s = 0, blk = 0;
+    uint32_t b1 = uint32_t(bin >> 32), next = 0, blk = 0;
+    // first Philox round from cached products (philox4x32_from_products): counter = (bin lo, bin hi, sample, block)
+    uint64_t p_bin = uint64_t(uint32_t(bin)) * philox_m0();      // M0 * bin lo: fixed while the lane works on this bin
+    const PhiloxKeys<10> keys = philox_key_schedule<10>(a.key0, a.key1);
+    uint64_t p_next = 0, p_s = 0;                                 // M1 * next, M1 * (sample in flight): samples count up, so += M1
     typename F::State st;
-    bool service = true;                  // first pass: lanes without a bin in the first tile, warps without a tile
     while (true) {
-        const bool done = has_bin && !alive && next >= a.spp;
-        if (service || __any_sync(0xffffffffu, done)) {
-            service = false;
-            if (done) {
-                const float v = walk_bin_value(a, sum, volume);
-                a.out[bin] = a.accumulate ? float(double(a.out[bin]) + double(v)) : v;
-                if (MOMENTS) {
-                    if (a.sum_f)  a.sum_f[bin - a.bin_begin]  = sum;
-                    if (a.sum_f2) a.sum_f2[bin - a.bin_begin] = sum2;
-                }
-                has_bin = false; ++pos;
+        // ---- service: first pass, and whenever some lane is through with its bin -----------------------------------------------------
+        if (has_bin && !alive && next >= a.spp) {
+            const float v = walk_bin_value(a, sum, volume);
+            a.out[bin] = a.accumulate ? float(double(a.out[bin]) + double(v)) : v;
+            if (MOMENTS) {
+                if (a.sum_f)  a.sum_f[bin - a.bin_begin]  = sum;
+                if (a.sum_f2) a.sum_f2[bin - a.bin_begin] = sum2;
             }
-            while (true) {                // warp-uniform: move free lanes into the next tile; retire the current tile once everybody has left it
-                if (!has_bin && pos == base + 1u) {
-                    if (n_live) {
+            has_bin = false; ++pos;
+        }
+        while (true) {                    // warp-uniform: move free lanes into the next tile; retire the current tile once everybody has left it
+            if (!has_bin && pos == base + 1u) {
+                if (n_live) {
 #pragma unroll
-                        for (int d = 0; d < DIMBINS && d < 4; ++d) { sc[d] = n_ext[d]; of[d] = n_lo[d]; }
-                        volume = n_vol;
-                        bin = a.bin_begin + tile_nxt * 32u + lane; b0 = uint32_t(bin); b1 = uint32_t(bin >> 32);
-                        sum = 0.0f; sum2 = 0.0f; next = 0; has_bin = true;
-                    }
-                    else ++pos;           // no bin for this lane there (ragged last tile, or past the last ticket)
+                    for (int d = 0; d < DIMBINS && d < 4; ++d) { sc[d] = n_ext[d]; of[d] = n_lo[d]; }
+                    volume = n_vol;
+                    bin = a.bin_begin + tile_nxt * 32u + lane; b1 = uint32_t(bin >> 32);
+                    p_bin = uint64_t(uint32_t(bin)) * philox_m0(); p_next = 0;
+                    sum = 0.0f; sum2 = 0.0f; next = 0; has_bin = true;
                 }
-                if (!__all_sync(0xffffffffu, pos > base)) break;
-                if (tile_cur >= ntiles) return;                        // tickets only grow: nothing left for this warp
-                signal_tile_done(a.signal, tile_cur, ntiles, lane);
-                tile_cur = tile_nxt;
-                unsigned long long t = 0;
-                if (lane == 0) t = atomicAdd(a.tile_counter, 1ull);
-                tile_nxt = __shfl_sync(0xffffffffu, t, 0);
-                ++base;
-                n_live = prepare(tile_nxt, n_lo, n_ext, n_vol);
+                else ++pos;               // no bin for this lane there (ragged last tile, or past the last ticket)
             }
+            if (!__all_sync(0xffffffffu, pos > base)) break;
+            if (tile_cur >= ntiles) return;                            // tickets only grow: nothing left for this warp
+            signal_tile_done(a.signal, tile_cur, ntiles, lane);
+            tile_cur = tile_nxt;
+            unsigned long long t = 0;
+            if (lane == 0) t = atomicAdd(a.tile_counter, 1ull);
+            tile_nxt = __shfl_sync(0xffffffffu, t, 0);
+            ++base;
+            n_live = prepare(tile_nxt, n_lo, n_ext, n_vol);
         }
-        const bool starting = has_bin && !alive && next < a.spp;
-        if (starting) { s = next; ++next; blk = 0; }
-        const u32x4 r = philox4x32<10>(u32x4{b0, b1, s, blk}, a.key0, a.key1);
-        BlockIterator it;
-        it.e0 = u01(r.x); it.e1 = u01(r.y); it.e2 = u01(r.z); it.e3 = u01(r.w); it.i = 0;
-        if (blk == 0) {       // PhiloxSequence::const_iterator::load: fmaf(u, extent, lower)
-            it.e0 = fmaf(it.e0, sc[0], of[0]); it.e1 = fmaf(it.e1, sc[1], of[1]); it.e2 = fmaf(it.e2, sc[2], of[2]); it.e3 = fmaf(it.e3, sc[3], of[3]);
-        }
-        ++blk;
-        bool ended = false;
-        if (starting) {                                              // elements 0,1 — or none, then the first round takes them
-            st = f.begin(it); alive = true;
-            if constexpr (F::elements_begin == 0) { if (!f.step(st, it)) ended = true; }
-        }
-        else if (alive) { if (!f.step(st, it)) ended = true; }       // elements 0,1 (or only 0)
-        it.i = 2;
-        if (alive && !ended) { if (!f.step(st, it)) ended = true; }  // elements 2,3 (or only 2)
-        if (ended) {
-            const float v = f.end(st);
-            sum += v;
-            if (MOMENTS) sum2 = fmaf(v, v, sum2);
-            alive = false;
-        }
+        // ---- hot loop: one Philox block per lane and iteration, until a lane has finished its bin (some lane always owns a bin here) ----
+        do {
+            const bool starting = has_bin && !alive && next < a.spp;
+            if (starting) { p_s = p_next; p_next += philox_m1(); ++next; blk = 0; }
+            const u32x4 r = philox4x32_from_products<10>(p_bin, p_s, b1, blk, keys);
+            BlockIterator it;
+            it.e0 = u01(r.x); it.e1 = u01(r.y); it.e2 = u01(r.z); it.e3 = u01(r.w); it.i = 0;
+            if (TAIL) {
+                if (blk == 0) {       // PhiloxSequence::const_iterator::load: fmaf(u, extent, lower)
+                    it.e0 = fmaf(it.e0, sc[0], of[0]); it.e1 = fmaf(it.e1, sc[1], of[1]); it.e2 = fmaf(it.e2, sc[2], of[2]); it.e3 = fmaf(it.e3, sc[3], of[3]);
+                }
+            } else {
+                const bool first = blk == 0;
+                if (DIMBINS > 0) it.e0 = first ? fmaf(it.e0, sc[0], of[0]) : it.e0;
+                if (DIMBINS > 1) it.e1 = first ? fmaf(it.e1, sc[1], of[1]) : it.e1;
+                if (DIMBINS > 2) it.e2 = first ? fmaf(it.e2, sc[2], of[2]) : it.e2;
+            }
+            ++blk;
+            bool ended = false;
+            if (starting) {                                              // elements 0,1 — or none, then the first round takes them
+                st = f.begin(it); alive = true;
+                if constexpr (F::elements_begin == 0) { if (!f.step(st, it)) ended = true; }
+            }
+            else if (alive) { if (!f.step(st, it)) ended = true; }       // elements 0,1 (or only 0)
+            it.i = 2;
+            if (alive && !ended) { if (!f.step(st, it)) ended = true; }  // elements 2,3 (or only 2)
+            if (ended) {
+                const float v = f.end(st);
+                sum += v;
+                if (MOMENTS) sum2 = fmaf(v, v, sum2);
+                alive = false;
+            }
+        } while (!__any_sync(0xffffffffu, has_bin && !alive && next >= a.spp));
     }
 }
 

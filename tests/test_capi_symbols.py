@@ -76,3 +76,38 @@ def test_no_product_module_touches_the_oracle():
                     if re.search(r"pyoracle|liboracle|oracle_api|#include\s+\"[^\"]*oracle/", t):
                         bad.append(os.path.join(d, f))
     assert not bad, bad
+
+
+def test_philox_from_cached_products_equals_philox(tmp_path):
+    """philox4x32_from_products (first-round products kept in registers by the walk kernel: M0 * bin per bin, M1 * sample advanced
+    by a 64-bit add) is the same function as philox4x32<10>: host build of the header, 10^6 random counters and sample runs."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "p.cpp"
+    src.write_text(r'''
+#include <cstdio>
+#include <cstdint>
+#include "viltrum_b200/device/philox.cuh"
+using namespace viltrum::b200;
+int main() {
+    uint64_t x = 88172645463325252ull; auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return uint32_t(x >> 16); };
+    for (int i = 0; i < 1000000; ++i) {
+        const uint32_t b0 = rnd(), b1 = rnd(), blk = rnd() & 15u, k0 = rnd(), k1 = rnd();
+        uint32_t s = (i & 1) ? rnd() : 0u;
+        uint64_t p1 = uint64_t(s) * philox_m1();
+        const uint64_t p0 = uint64_t(b0) * philox_m0();
+        for (int j = 0; j < 3; ++j, ++s, p1 += philox_m1()) {
+            if (s == 0xffffffffu) break;
+            const u32x4 a = philox4x32<10>(u32x4{b0, b1, s, blk}, k0, k1);
+            const u32x4 b = philox4x32_from_products<10>(p0, p1, b1, blk, k0, k1);
+            if (a.x != b.x || a.y != b.y || a.z != b.z || a.w != b.w) { std::printf("mismatch at %d\n", i); return 1; }
+        }
+    }
+    std::printf("ok\n"); return 0;
+}
+''')
+    exe = tmp_path / "p"
+    subprocess.run(["g++", "-std=c++17", "-O2", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout
