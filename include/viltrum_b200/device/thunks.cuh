@@ -173,7 +173,7 @@ struct InfiniteThunks {
                 // one lane per bin (every large grid): the two-tile window keeps the lanes of a warp busy across the uneven lengths of
                 // their bins.  Needs enough tiles per warp to still balance the tail through the ticket counter; VB200_WALK_WINDOW=0/1
                 // switches it off / forces it (tests compare both kernels bit for bit).
-                if (a.lanes_per_bin == 1) {
+                if (a.lanes_per_bin == 1 && a.spp < 0xffffffffu) {
                     auto kw = a.domain.dim > DB ? device::walk_block_window_kernel<F, DB, MOMENTS, EXACT, true>
                                                 : device::walk_block_window_kernel<F, DB, MOMENTS, EXACT, false>;
                     const uint64_t tiles = (a.bin_end - a.bin_begin + 31u) / 32u;

@@ -344,8 +344,9 @@ walk_block_window_kernel(const F f, const vb200_walk_launch a) {
 #pragma unroll
     for (int d = 0; d < DIMBINS && d < 4; ++d) { sc[d] = n_ext[d]; of[d] = n_lo[d]; }
     if (!has_bin) pos = 1;
+    const uint32_t idle = a.spp + 1u;       // `next` of a lane without a bin: neither < spp (would start a path) nor == spp (bin finished)
     bool n_live = prepare(tile_nxt, n_lo, n_ext, n_vol);
-    uint32_t b1 = uint32_t(bin >> 32), next = 0, blk = 0;
+    uint32_t b1 = uint32_t(bin >> 32), next = has_bin ? 0u : idle, blk = 0;
     // first Philox round from cached products (philox4x32_from_products): counter = (bin lo, bin hi, sample, block)
     uint64_t p_bin = uint64_t(uint32_t(bin)) * philox_m0();      // M0 * bin lo: fixed while the lane works on this bin
     const PhiloxKeys<10> keys = philox_key_schedule<10>(a.key0, a.key1);
@@ -353,14 +354,14 @@ walk_block_window_kernel(const F f, const vb200_walk_launch a) {
     typename F::State st;
     while (true) {
         // ---- service: first pass, and whenever some lane is through with its bin -----------------------------------------------------
-        if (has_bin && !alive && next >= a.spp) {
+        if (!alive && next == a.spp) {
             const float v = walk_bin_value(a, sum, volume);
             a.out[bin] = a.accumulate ? float(double(a.out[bin]) + double(v)) : v;
             if (MOMENTS) {
                 if (a.sum_f)  a.sum_f[bin - a.bin_begin]  = sum;
                 if (a.sum_f2) a.sum_f2[bin - a.bin_begin] = sum2;
             }
-            has_bin = false; ++pos;
+            has_bin = false; next = idle; ++pos;
         }
         while (true) {                    // warp-uniform: move free lanes into the next tile; retire the current tile once everybody has left it
             if (!has_bin && pos == base + 1u) {
@@ -386,7 +387,7 @@ walk_block_window_kernel(const F f, const vb200_walk_launch a) {
         }
         // ---- hot loop: one Philox block per lane and iteration, until a lane has finished its bin (some lane always owns a bin here) ----
         do {
-            const bool starting = has_bin && !alive && next < a.spp;
+            const bool starting = !alive && next < a.spp;
             if (starting) { p_s = p_next; p_next += philox_m1(); ++next; blk = 0; }
             const u32x4 r = philox4x32_from_products<10>(p_bin, p_s, b1, blk, keys);
             BlockIterator it;
@@ -402,21 +403,20 @@ walk_block_window_kernel(const F f, const vb200_walk_launch a) {
                 if (DIMBINS > 2) it.e2 = first ? fmaf(it.e2, sc[2], of[2]) : it.e2;
             }
             ++blk;
-            bool ended = false;
+            const bool inflight = alive || starting;
             if (starting) {                                              // elements 0,1 — or none, then the first round takes them
                 st = f.begin(it); alive = true;
-                if constexpr (F::elements_begin == 0) { if (!f.step(st, it)) ended = true; }
+                if constexpr (F::elements_begin == 0) alive = f.step(st, it);
             }
-            else if (alive) { if (!f.step(st, it)) ended = true; }       // elements 0,1 (or only 0)
+            else if (alive) alive = f.step(st, it);                      // elements 0,1 (or only 0)
             it.i = 2;
-            if (alive && !ended) { if (!f.step(st, it)) ended = true; }  // elements 2,3 (or only 2)
-            if (ended) {
+            if (alive) alive = f.step(st, it);                           // elements 2,3 (or only 2)
+            if (inflight && !alive) {                                    // the path ended in this block
                 const float v = f.end(st);
                 sum += v;
                 if (MOMENTS) sum2 = fmaf(v, v, sum2);
-                alive = false;
             }
-        } while (!__any_sync(0xffffffffu, has_bin && !alive && next >= a.spp));
+        } while (!__any_sync(0xffffffffu, !alive && next == a.spp));
     }
 }
 
