@@ -309,8 +309,11 @@ walk_block_kernel(const F f, const vb200_walk_launch a) {
 // in order) are walk_block_kernel's at lanes_per_bin = 1: bits identical.
 // TAIL: the range has explicit entries beyond the binned dimensions (elements DIMBINS..3 of block 0 are mapped too); without them those
 // elements keep [0,1) — fmaf(u, 1, 0) == u — and block 0 costs DIMBINS predicated FFMAs instead of a divergent branch.
+#ifndef WALK_WINDOW_MIN_CTAS
+#define WALK_WINDOW_MIN_CTAS 5
+#endif
 template<class F, int DIMBINS, bool MOMENTS, bool EXACT, bool TAIL>
-__global__ void __launch_bounds__(MC_THREADS)
+__global__ void __launch_bounds__(MC_THREADS, WALK_WINDOW_MIN_CTAS)
 walk_block_window_kernel(const F f, const vb200_walk_launch a) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t nshard = a.bin_end - a.bin_begin;
