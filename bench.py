@@ -38,8 +38,10 @@ WORKLOADS = {
 }
 METRIC = "integrand evals/sec (per-bin MC, 1024x1024 bins x 64 spp, shade4<64>)"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the ncu --set full capture summarised in
-# profiles/ncu_c2_mc_per_bin_r1c.txt / profiles/ncu_c5_walk_block_r1c.txt (algorithmic bytes: 4 B per bin)
-NCU_TRAFFIC_BYTES = {"c2": 4231936, "c5": 16796672}
+# profiles/ncu_c2_mc_per_bin_r1c.txt / profiles/ncu_c5_walk_window_r1d.txt (algorithmic bytes: 4 B per bin)
+NCU_TRAFFIC_BYTES = {"c2": 4231936, "c5": 16922112}
+RNG_NOTE = {"mc": "Philox4x32-10, 5 calls per group of 8 samples: 24-bit fields for the free dimensions, 16-bit fields inside a bin of a >=256-bin axis (every generated bit is used)",
+            "walk": "Philox4x32-10, counter (bin, sample, block): one block of four 24-bit elements per lane and loop iteration, first-round products cached (18 multiplies per block)"}
 
 
 def dist_env():
@@ -250,7 +252,7 @@ def main():
             cb = {"error": str(ex)}
     line = {"metric": metric, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "integrand": integ, "bins_per_gpu": res, "spp": spp, "rng": "Philox4x32-10, 5 calls per group of 8 samples: 24-bit fields for the free dimensions, 16-bit fields inside a bin of a >=256-bin axis (every generated bit is used)", "parallelism": f"bin-grid slabs x{world}",
+            "config": {"workload": desc, "integrand": integ, "bins_per_gpu": res, "spp": spp, "rng": RNG_NOTE["walk" if args.workload == "c5" else "mc"], "parallelism": f"bin-grid slabs x{world}",
                        "l2": "flushed between timed steps (256 MiB memset, untimed); per-step CUDA events on the library stream"},
             "e2e": {"value": e2e, "unit": "evals/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": 128, "d2h_bytes_per_step": nb_local * 4,
                     "pinned_value": e2e_pinned, "pinned_ms_per_step": ms_e2e_pinned,
