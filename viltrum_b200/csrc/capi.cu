@@ -2,6 +2,7 @@
 // Nothing in here evaluates an integrand: kernels templated on the functor are reached through the launch thunks
 // in the vb200_integrand table.  There is no CPU fallback anywhere in this library.
 #include "context.h"
+#include <chrono>
 #include <viltrum_b200/device/philox.cuh>
 #include <cstring>
 #include <cstdlib>
@@ -376,10 +377,10 @@ static int run_sampler(vb200_ctx* ctx, const vb200_integrand* f, int kind, Launc
     a.accumulate = 0;
     a.out = h - begin;                                   // kernels index from the base of the full grid
     a.sum_f = sum_f ? h + n : nullptr; a.sum_f2 = sum_f2 ? h + 2 * n : nullptr;
-    // chunking: tiles of G = 32/lanes_per_bin bins; chunks of 2^shift tiles, about 64 Ki bins each (the host pass over one chunk is
-    // ~10 us, the exposed tail), at most kMaxChunks of them.  VB200_E2E_CHUNK_BINS overrides the target (tuning knob).
+    // chunking: tiles of G = 32/lanes_per_bin bins; chunks of 2^shift tiles, about 16 Ki bins each (the host pass over one chunk is
+    // ~15 us, the exposed tail), at most kMaxChunks of them.  VB200_E2E_CHUNK_BINS overrides the target (tuning knob).
     const uint64_t G = 32u / a.lanes_per_bin, ntiles = (n + G - 1) / G;
-    uint64_t target_bins = 64u * 1024u;
+    uint64_t target_bins = 16u * 1024u;                 // measured on the pool's 16-vCPU host (profiles/results_r1.md, round 1d): one host thread adds ~1 bin/ns, so a 64 Ki chunk is a 60 us tail
     if (const char* env = std::getenv("VB200_E2E_CHUNK_BINS")) { const long long v = std::atoll(env); if (v > 0) target_bins = uint64_t(v); }
     uint32_t shift = 0;
     while ((G << (shift + 1)) <= target_bins) ++shift;
@@ -403,9 +404,15 @@ static int run_sampler(vb200_ctx* ctx, const vb200_integrand* f, int kind, Launc
     if (const char* env = std::getenv("VB200_HOST_THREADS")) threads = std::atoi(env);
     if (uint64_t(threads) > chunks) threads = int(chunks);
     if (threads < 1) threads = 1;
+    // VB200_E2E_TRACE=1: one line of timestamps per call on stderr (us since the launch returned) — where the end-to-end time goes
+    static const bool trace = std::getenv("VB200_E2E_TRACE") != nullptr;
+    const auto t_launch = std::chrono::steady_clock::now();
+    auto us = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::micro>(t - t_launch).count(); };
     if (threads > 1) { ctx->pool.start(threads - 1); ctx->pool.publish(&job); }
+    const auto t_pub = std::chrono::steady_clock::now();
     cudaError_t stream_error = cudaSuccess;
     job.run(true, ctx->stream, &stream_error);
+    const auto t_run = std::chrono::steady_clock::now();
     uint64_t spins = 0;
     while (job.finished.load(std::memory_order_acquire) != chunks && !job.abort.load()) {
         if ((++spins & 0x3fffu) == 0) {
@@ -416,9 +423,16 @@ static int run_sampler(vb200_ctx* ctx, const vb200_integrand* f, int kind, Launc
         __builtin_ia32_pause();
 #endif
     }
+    const auto t_fin = std::chrono::steady_clock::now();
     if (threads > 1) ctx->pool.retire();
+    const auto t_ret = std::chrono::steady_clock::now();
     if (job.abort.load()) { cudaStreamSynchronize(ctx->stream); return fail(ctx, VB200_ERR_CUDA, "sampling kernel failed or ended without completing its chunks: %s", cudaGetErrorString(stream_error)); }
     VB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (trace) {
+        const auto t_sync = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[vb200 e2e] chunks %llu x %llu bins, %d threads: published %.1f, own pass done %.1f, all chunks done %.1f, pool retired %.1f, stream synced %.1f us\n",
+                     (unsigned long long)chunks, (unsigned long long)(G << shift), threads, us(t_pub), us(t_run), us(t_fin), us(t_ret), us(t_sync));
+    }
     if (sum_f)  std::memcpy(sum_f, h + n, n * sizeof(float));
     if (sum_f2) std::memcpy(sum_f2, h + 2 * n, n * sizeof(float));
     return VB200_OK;

@@ -54,7 +54,7 @@ struct vb200_ctx {
     uint32_t* d_done = nullptr;
     uint32_t* h_flags = nullptr;
     uint32_t epoch = 0;
-    static constexpr int kMaxChunks = 64;
+    static constexpr int kMaxChunks = 1024;
     vb200::HostPool pool;
     // caller-owned host buffers pinned and mapped by vb200_host_register: (base, bytes)
     std::vector<std::pair<char*, size_t>> registered;
