@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define VB200_ABI_VERSION 2u
+#define VB200_ABI_VERSION 3u
 #define VB200_MAX_DIM      8     /* finite integrands: 1..8 dimensions (reference VILTRUM_MAX_DIMENSIONS_REGION = 6, region.h:16-18) */
 #define VB200_MAX_DIMBINS  3     /* reference binned overloads go up to 3-D containers (integrate.h:132-167) */
 
@@ -80,9 +80,13 @@ int         vb200_host_unregister(vb200_ctx* ctx, void* ptr);
  * next to the nominal 2*128*SMs*clock figure (MEASURED_PEAKS.json carries HBM and bf16-tensor peaks only). */
 int         vb200_measure_fp32_peak(vb200_ctx* ctx, int reps, double* tflops);
 
-/* Host-side evaluation of the library's counter-based generator (Philox4x32-10, include/viltrum_b200/device/philox.cuh),
- * for known-answer tests and for callers that want to predict which sample a (seed, bin, sample) triple maps to. */
+/* Host-side evaluation of the library's generators (include/viltrum_b200/device/philox.cuh, xoshiro.cuh, threefry.cuh), for
+ * known-answer tests and for callers that want to predict which sample a (seed, bin, sample) triple maps to.
+ * vb200_xoshiro128pp: advances `state` n times and stores the n outputs.  vb200_threefry4x32: the experiment generator of
+ * profiles/exp/k1_mix.cu (rounds = 12, 13 or 20), not used by the shipped kernels. */
 void        vb200_philox4x32_10(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]);
+void        vb200_xoshiro128pp(uint32_t state[4], uint64_t n, uint32_t* out);
+int         vb200_threefry4x32(int rounds, const uint32_t counter[4], const uint32_t key[4], uint32_t out[4]);
 
 /* ---- integrands --------------------------------------------------------------------------------------- */
 struct vb200_integrand;
@@ -170,13 +174,27 @@ typedef enum vb200_mc_flavor {
 } vb200_mc_flavor;
 
 /* ---- per-bin Monte Carlo (SURVEY.md §8a rows a2,a3,a4) ------------------------------------------------- */
+/* Sampler options of vb200_mc_per_bin (bit flags; 0 = the fastest configuration).
+ *   Random streams.  Default: every (bin, lane sub-stream) owns an xoshiro128++ stream whose 128-bit state is
+ *   Philox4x32-10(key = seed, counter = (bin lo, bin hi, sub-stream, 'strm')) — the reference's own scheme (a per-bin generator seeded
+ *   from a master stream, monte-carlo-per-bin-parallel.h:50-58; xoshiro128++ is one of the generators it vendors, src/rng/XoshiroCpp.hpp:531)
+ *   with a counter-based master, so a bin's samples do not depend on how the grid is sharded.  Add / rotate / xor only: the generator
+ *   runs on the ALU pipe next to the integrand's FFMA2 (60 % of FP32 peak on C2 against 53 % with pure Philox, profiles/k1_rng_r2.txt).
+ *   VB200_MC_RNG_PHILOX: every word is Philox4x32-10(key = seed, counter = (bin lo, bin hi, sample group, call)) — stateless, a sample's
+ *   coordinates depend on (seed, bin, sample index) only.
+ *   Sample lattice.  Default: coordinates of the binned dimensions carry 16 random bits inside the bin when every binned dimension of the
+ *   WHOLE grid has >= 256 bins (the lattice along such a dimension still has >= 2^24 points over the range, the reference's
+ *   generate_canonical<float,24> resolution), 24 bits otherwise; non-binned dimensions always 24.  VB200_MC_LATTICE24: 24 bits everywhere. */
+#define VB200_MC_RNG_PHILOX 1
+#define VB200_MC_LATTICE24  2
+
 typedef struct vb200_mc_params {
     vb200_domain domain;
     vb200_shard  shard;
     uint64_t     spp;
-    uint64_t     seed;          /* Philox key; counter = (bin index, sample index, draw block) */
+    uint64_t     seed;          /* generator key (Philox key = (seed lo, seed hi)) */
     int32_t      flavor;        /* vb200_mc_flavor: also fixes the write semantics ('+=' vs '=') */
-    int32_t      reserved;
+    int32_t      options;       /* VB200_MC_* flags above (vb200_mc_per_bin only; the other drivers ignore them) */
 } vb200_mc_params;
 
 /* bins: base of the full grid.  sum_f / sum_f2 (optional, may be NULL; same memory space as bins): raw per-bin
@@ -357,6 +375,8 @@ typedef struct vb200_mc_launch {
                                        * WHOLE grid has >= 256 bins, so the lattice along it still has >= 2^24 points); 0: 24 bits */
     unsigned long long* tile_counter; /* device, zeroed by the driver before the launch: dynamic tile scheduler */
     vb200_chunk_signal signal;
+    int32_t  rng;                     /* 0: xoshiro128++ stream per (bin, lane sub-stream) seeded by Philox; 1: Philox4x32-10 per draw group */
+    int32_t  reserved;
 } vb200_mc_launch;
 
 typedef struct vb200_replay_launch {

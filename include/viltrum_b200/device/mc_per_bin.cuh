@@ -15,6 +15,8 @@
 #include <cuda_runtime.h>
 #include "../../viltrum_b200.h"
 #include "philox.cuh"
+#include "threefry.cuh"
+#include "xoshiro.cuh"
 #include "f32x2.cuh"
 #include <type_traits>
 #include <utility>
@@ -95,6 +97,15 @@ constexpr int MC_GROUP = 8;                 // samples per draw group
 #ifndef VB200_MC_ROUNDS
 #define VB200_MC_ROUNDS 10                  // Philox4x32-10; experiment builds (profiles/exp) measure 7, the product ships 10
 #endif
+#ifndef VB200_MC_TF_NUM
+#define VB200_MC_TF_NUM 0                   // share of a group's generator calls drawn from Threefry4x32: NUM/DEN, rounded
+#endif
+#ifndef VB200_MC_TF_DEN
+#define VB200_MC_TF_DEN 5
+#endif
+#ifndef VB200_MC_TF_ROUNDS
+#define VB200_MC_TF_ROUNDS 12
+#endif
 // One draw group = 8 samples of one bin.  The group's random words w[0..4*CALLS) are the outputs of CALLS Philox calls with the
 // counters (bin lo, bin hi, group, call), and every word is cut into coordinate fields so that no generated bit is thrown away:
 //   * 24-bit fields (the reference's generate_canonical<float,24> lattice): three words give four fields — the top 24 bits of
@@ -105,21 +116,38 @@ constexpr int MC_GROUP = 8;                 // samples per draw group
 //     ~2^24 over the range anyway); NARROW = 0 otherwise.
 // Words per group: 4*NARROW + 6*(DIM-NARROW).  4-D integrand over a 2-D bin grid: 20 words = 5 calls per 8 samples
 // (all-24-bit: 24 words = 6 calls, the round-1b "4 samples per 3 calls").
-template<int DIM, int NARROW> struct GroupDraws {
+enum { MC_RNG_PHILOX = 0, MC_RNG_XOSHIRO = 1 };     // vb200_mc_rng
+template<int DIM, int NARROW, int RNG = MC_RNG_PHILOX> struct GroupDraws {
     static constexpr int WIDE = DIM - NARROW;
     static constexpr int W16 = 4 * NARROW;          // first W16 words: 16-bit fields
     static constexpr int W24 = 6 * WIDE;            // then W24 words: 24-bit fields, in triples
     static constexpr int CALLS = (W16 + W24 + 3) / 4;
     uint32_t w[4 * CALLS];
-    __device__ __forceinline__ void draw(uint32_t b0, uint32_t b1, uint32_t group, uint32_t k0, uint32_t k1) {
+    // RNG = MC_RNG_PHILOX: stateless, the words of group g are Philox4x32-10(key = seed, counter = (bin lo, bin hi, g, call)).
+    //   Experiment knob (profiles/exp/k1_mix.cu, profiles/k1_rng_r2.txt): the LAST TF of the CALLS calls can come from Threefry4x32-12
+    //   (ALU pipe) instead; measured no faster than pure Philox, so the product builds with TF = 0.
+    // RNG = MC_RNG_XOSHIRO: one xoshiro128++ stream per (bin, lane sub-stream), seeded by begin() with
+    //   Philox4x32-10(key = seed, counter = (bin lo, bin hi, sub, 'strm')); draw() takes the next W16 + W24 words of the stream.
+    static constexpr int TF = (CALLS * VB200_MC_TF_NUM + VB200_MC_TF_DEN / 2) / VB200_MC_TF_DEN;
+    uint32_t b0, b1, k0, k1;
+    Xoshiro128pp x;
+    __device__ __forceinline__ void begin(uint32_t bin_lo, uint32_t bin_hi, uint32_t sub, uint32_t key0, uint32_t key1) {
+        b0 = bin_lo; b1 = bin_hi; k0 = key0; k1 = key1;
+        if constexpr (RNG == MC_RNG_XOSHIRO) x.seed(philox4x32<10>(u32x4{bin_lo, bin_hi, sub, 0x7374726du}, key0, key1));
+    }
+    __device__ __forceinline__ void draw(uint32_t group) {
+        if constexpr (RNG == MC_RNG_XOSHIRO) {
 #pragma unroll
-        for (int c = 0; c < CALLS; ++c) {
-#ifdef VB200_MC_CTR_B
-            const u32x4 r = philox4x32<VB200_MC_ROUNDS>(u32x4{b0, group, b1, uint32_t(c)}, k0, k1);
-#else
-            const u32x4 r = philox4x32<VB200_MC_ROUNDS>(u32x4{b0, b1, group, uint32_t(c)}, k0, k1);
-#endif
-            w[4 * c] = r.x; w[4 * c + 1] = r.y; w[4 * c + 2] = r.z; w[4 * c + 3] = r.w;
+            for (int i = 0; i < W16 + W24; ++i) w[i] = x.next();
+        } else {
+            const ThreefryKeys tk = threefry_key_schedule(k0, k1, 0x76696c74u, 0x72756d21u);      // key words 2,3: "vilt" "rum!"
+#pragma unroll
+            for (int c = 0; c < CALLS; ++c) {
+                u32x4 r;
+                if (c >= CALLS - TF) r = threefry4x32<VB200_MC_TF_ROUNDS>(u32x4{b0, b1, group, uint32_t(c)}, tk);
+                else r = philox4x32<VB200_MC_ROUNDS>(u32x4{b0, b1, group, uint32_t(c)}, k0, k1);
+                w[4 * c] = r.x; w[4 * c + 1] = r.y; w[4 * c + 2] = r.z; w[4 * c + 3] = r.w;
+            }
         }
     }
     // integer n of coordinate i of sample j as a float (exact): 24-bit fields give n, 16-bit fields (i < NARROW) give 2^23 + n,
@@ -137,15 +165,15 @@ template<int DIM, int NARROW> struct GroupDraws {
     }
 };
 
-template<class F, int DIM, int NARROW>
-__device__ __forceinline__ float mc_eval_one(const F& f, const GroupDraws<DIM, NARROW>& d, int j, const float (&lo)[DIM], const float (&exts)[DIM]) {
+template<class F, int DIM, class Draws>
+__device__ __forceinline__ float mc_eval_one(const F& f, const Draws& d, int j, const float (&lo)[DIM], const float (&exts)[DIM]) {
     std::array<float, DIM> x;
 #pragma unroll
     for (int i = 0; i < DIM; ++i) x[i] = fmaf(d.coord(j, i), exts[i], lo[i]);     // u*(b-a)+a as std::uniform_real_distribution, u = n*2^-bits in [0,1)
     return f(x);
 }
-template<class F, int DIM, int NARROW>
-__device__ __forceinline__ f32x2 mc_eval_pair(const F& f, const GroupDraws<DIM, NARROW>& d, int j0, const float (&lo)[DIM], const float (&exts)[DIM]) {
+template<class F, int DIM, class Draws>
+__device__ __forceinline__ f32x2 mc_eval_pair(const F& f, const Draws& d, int j0, const float (&lo)[DIM], const float (&exts)[DIM]) {
     std::array<f32x2, DIM> x;
 #pragma unroll
     for (int i = 0; i < DIM; ++i) x[i] = mad(f32x2::pack(d.coord(j0, i), d.coord(j0 + 1, i)), f32x2(exts[i]), f32x2(lo[i]));
@@ -153,9 +181,9 @@ __device__ __forceinline__ f32x2 mc_eval_pair(const F& f, const GroupDraws<DIM, 
 }
 
 #ifndef VB200_MC_MINB
-#define VB200_MC_MINB 1
+#define VB200_MC_MINB 3                     // 3 CTAs/SM (<= 85 registers): measured within 1 % of the best occupancy for both generators (profiles/k1_rng_r2.txt)
 #endif
-template<class F, int DIM, int DIMBINS, bool MOMENTS, bool EXACT, bool NARROW>
+template<class F, int DIM, int DIMBINS, bool MOMENTS, bool EXACT, bool NARROW, int RNG = MC_RNG_PHILOX>
 __global__ void __launch_bounds__(MC_THREADS, VB200_MC_MINB)
 mc_per_bin_kernel(const F f, const vb200_mc_launch a) {
     constexpr bool PAIRS = !EXACT && has_pair_eval<F, DIM>::value;
@@ -183,15 +211,16 @@ mc_per_bin_kernel(const F f, const vb200_mc_launch a) {
                 lo[i] = fmaf(-GroupDraws<DIM, NB>::bias(i), ext[i], lo[i]);
             }
             const uint32_t b0 = uint32_t(bin), b1 = uint32_t(bin >> 32);
-            GroupDraws<DIM, NB> d;
+            GroupDraws<DIM, NB, RNG> d;
+            d.begin(b0, b1, sub, a.key0, a.key1);
             if constexpr (PAIRS) {
                 f32x2 acc0(0.0f), acc1(0.0f), sq0(0.0f), sq1(0.0f);
                 for (uint32_t g = sub; g < full_groups; g += LPB) {
-                    d.draw(b0, b1, g, a.key0, a.key1);
-                    const f32x2 v0 = mc_eval_pair<F, DIM, NB>(f, d, 0, lo, ext), v1 = mc_eval_pair<F, DIM, NB>(f, d, 2, lo, ext);
+                    d.draw(g);
+                    const f32x2 v0 = mc_eval_pair<F, DIM>(f, d, 0, lo, ext), v1 = mc_eval_pair<F, DIM>(f, d, 2, lo, ext);
                     acc0 += v0; acc1 += v1;
                     if (MOMENTS) { sq0 = mad(v0, v0, sq0); sq1 = mad(v1, v1, sq1); }
-                    const f32x2 v2 = mc_eval_pair<F, DIM, NB>(f, d, 4, lo, ext), v3 = mc_eval_pair<F, DIM, NB>(f, d, 6, lo, ext);
+                    const f32x2 v2 = mc_eval_pair<F, DIM>(f, d, 4, lo, ext), v3 = mc_eval_pair<F, DIM>(f, d, 6, lo, ext);
                     acc0 += v2; acc1 += v3;
                     if (MOMENTS) { sq0 = mad(v2, v2, sq0); sq1 = mad(v3, v3, sq1); }
                 }
@@ -200,11 +229,11 @@ mc_per_bin_kernel(const F f, const vb200_mc_launch a) {
             } else {
                 float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f, q0 = 0.0f, q1 = 0.0f, q2 = 0.0f, q3 = 0.0f;
                 for (uint32_t g = sub; g < full_groups; g += LPB) {
-                    d.draw(b0, b1, g, a.key0, a.key1);
+                    d.draw(g);
 #pragma unroll
                     for (int h = 0; h < MC_GROUP; h += 4) {
-                        const float v0 = mc_eval_one<F, DIM, NB>(f, d, h, lo, ext), v1 = mc_eval_one<F, DIM, NB>(f, d, h + 1, lo, ext);
-                        const float v2 = mc_eval_one<F, DIM, NB>(f, d, h + 2, lo, ext), v3 = mc_eval_one<F, DIM, NB>(f, d, h + 3, lo, ext);
+                        const float v0 = mc_eval_one<F, DIM>(f, d, h, lo, ext), v1 = mc_eval_one<F, DIM>(f, d, h + 1, lo, ext);
+                        const float v2 = mc_eval_one<F, DIM>(f, d, h + 2, lo, ext), v3 = mc_eval_one<F, DIM>(f, d, h + 3, lo, ext);
                         s0 += v0; s1 += v1; s2 += v2; s3 += v3;
                         if (MOMENTS) { q0 = fmaf(v0, v0, q0); q1 = fmaf(v1, v1, q1); q2 = fmaf(v2, v2, q2); q3 = fmaf(v3, v3, q3); }
                     }
@@ -213,11 +242,11 @@ mc_per_bin_kernel(const F f, const vb200_mc_launch a) {
                 if (MOMENTS) sum2 = (q0 + q1) + (q2 + q3);
             }
             if (rest != 0u && sub == full_groups % LPB) {      // the last, partial group: its first `rest` samples
-                d.draw(b0, b1, full_groups, a.key0, a.key1);
+                d.draw(full_groups);
 #pragma unroll
                 for (int j = 0; j < MC_GROUP - 1; ++j) {
                     if (uint32_t(j) < rest) {
-                        const float v = mc_eval_one<F, DIM, NB>(f, d, j, lo, ext);
+                        const float v = mc_eval_one<F, DIM>(f, d, j, lo, ext);
                         sum += v;
                         if (MOMENTS) sum2 = fmaf(v, v, sum2);
                     }

@@ -46,7 +46,8 @@ mc_scatter_kernel(const F f, const vb200_scatter_launch a) {
     const uint64_t g_begin = a.sample_begin / MC_GROUP, g_end = (a.sample_end + MC_GROUP - 1) / MC_GROUP;
     for (uint64_t g = g_begin + uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; g < g_end; g += uint64_t(gridDim.x) * blockDim.x) {
         GroupDraws<DIM, 0> d;
-        d.draw(uint32_t(g), uint32_t(g >> 32), 0xffffffffu, a.key0, a.key1);
+        d.begin(uint32_t(g), uint32_t(g >> 32), 0u, a.key0, a.key1);
+        d.draw(0xffffffffu);
 #pragma unroll
         for (int j = 0; j < MC_GROUP; j += 2) {
             float xa[DIMBINS], xb[DIMBINS], va, vb;

@@ -55,14 +55,19 @@ struct FiniteThunks {
     // not default-constructible)
     static F functor(const vb200_integrand* self) { return *static_cast<const F*>(self->functor); }
 
-    template<int DB, bool MOMENTS, bool NARROW>
-    static int launch_mc(const F& f, const vb200_mc_launch& a, cudaStream_t st) {
-        auto k = device::mc_per_bin_kernel<F, DIM, DB, MOMENTS, EXACT, NARROW>;
+    template<int DB, bool MOMENTS, bool NARROW, int RNG>
+    static int launch_mc_rng(const F& f, const vb200_mc_launch& a, cudaStream_t st) {
+        auto k = device::mc_per_bin_kernel<F, DIM, DB, MOMENTS, EXACT, NARROW, RNG>;
         const uint64_t bins_per_cta = uint64_t(device::MC_THREADS) / a.lanes_per_bin;     // one warp step of every warp
         const uint64_t ctas = (a.bin_end - a.bin_begin + bins_per_cta - 1) / bins_per_cta;
         const int grid = persistent_grid(k, device::MC_THREADS, ctas, a.grid_hint);
         k<<<grid, device::MC_THREADS, 0, st>>>(f, a);
         return int(cudaGetLastError());
+    }
+    template<int DB, bool MOMENTS, bool NARROW>
+    static int launch_mc(const F& f, const vb200_mc_launch& a, cudaStream_t st) {
+        return a.rng == device::MC_RNG_PHILOX ? launch_mc_rng<DB, MOMENTS, NARROW, device::MC_RNG_PHILOX>(f, a, st)
+                                              : launch_mc_rng<DB, MOMENTS, NARROW, device::MC_RNG_XOSHIRO>(f, a, st);
     }
     template<int DB>
     static int mc_db(const F& f, const vb200_mc_launch& a, cudaStream_t st) {

@@ -155,6 +155,9 @@ template<typename T, std::size_t DIMBINS> inline void unpin_bins(tensor<T,DIMBIN
 }
 // bin-grid shard handled by this process ({0,0} = whole grid): multi-GPU runs set it per rank
 inline vb200_shard& current_shard() { static vb200_shard s{0, 0}; return s; }
+// process-wide sampler options of the per-bin Monte-Carlo integrators (vb200_mc_params.options, VB200_MC_* flags): 0 = xoshiro128++ streams
+// keyed by Philox + 16-bit in-bin lattice on fine grids; VB200_MC_RNG_PHILOX = every draw from Philox4x32-10; VB200_MC_LATTICE24
+inline int32_t& mc_options() { static int32_t o = 0; return o; }
 
 template<typename Float, std::size_t DIM, std::size_t DIMBINS>
 inline vb200_domain make_domain(const Range<Float,DIM>& r, const std::array<std::size_t,DIMBINS>& res) {
@@ -283,7 +286,7 @@ class MonteCarloPerBinParallel {
     void run(Bins& bins, const std::array<std::size_t,DIMBINS>& res, const G& g, const vb200_domain& dom, Logger& logger) const {
         auto& ctx = b200::default_context();
         vb200_mc_params p; std::memset(&p, 0, sizeof(p));
-        p.domain = dom; p.shard = b200::current_shard(); p.spp = samples; p.seed = seed_; p.flavor = VB200_MC_PER_BIN;
+        p.domain = dom; p.shard = b200::current_shard(); p.spp = samples; p.seed = seed_; p.flavor = VB200_MC_PER_BIN; p.options = b200::mc_options();
         logger.log_progress(std::size_t(0), std::size_t(1));
         if constexpr (std::is_same<Bins, tensor<float,DIMBINS>>::value) {      // fast path: the library accumulates straight into the tensor
             ctx.check(INF ? vb200_mc_per_bin_inf(ctx.get(), g.c_abi(), &p, bins.data(), VB200_HOST, nullptr, nullptr)
@@ -323,7 +326,7 @@ public:
         auto& ctx = b200::default_context();
         b200::Integrand<F, int(DIM)> g(f);
         vb200_mc_params p; std::memset(&p, 0, sizeof(p));
-        p.domain = b200::make_domain(range, res); p.shard = b200::current_shard(); p.spp = inner.sample_count(); p.seed = inner.seed(); p.flavor = VB200_PER_BIN_MC;
+        p.domain = b200::make_domain(range, res); p.shard = b200::current_shard(); p.spp = inner.sample_count(); p.seed = inner.seed(); p.flavor = VB200_PER_BIN_MC; p.options = b200::mc_options();
         std::vector<float> flat(b200::bin_count(res), 0.0f);
         logger.log_progress(std::size_t(0), std::size_t(1));
         ctx.check(vb200_mc_per_bin(ctx.get(), g.c_abi(), &p, flat.data(), VB200_HOST, nullptr, nullptr));

@@ -146,6 +146,15 @@ int vo_mt_per_bin(const char* path, const char* integrand, int dimbins, const ui
                   const float* rmin, const float* rmax, int nrange, uint64_t spp, uint64_t seed,
                   int nthreads, float* bins);
 
+
+// ---- timing legs (reference builds only; the port does not export them) -----------------------------------------------------
+// vo_set_threads: threads behind the reference's std::for_each(par_unseq, ...) loops in oracle/_ref/libviltrum_ref_mt.so (the same
+// harness over the same unmodified reference, with oracle/pstl_threads/execution as the parallel-STL back end upstream takes from
+// TBB); returns the value in effect (always 1 in the serial build).  vo_phase_times: t[0] = seconds until the last region-based call
+// handed its region list to Logger::log (generation), t[1] = seconds of the whole call.
+int  vo_set_threads(int n);
+void vo_phase_times(double* t);
+
 #ifdef __cplusplus
 }
 #endif

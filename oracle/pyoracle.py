@@ -4,6 +4,8 @@ ctypes loader for the two CPU checkers (see oracle/oracle_api.h):
 
   * ``load("port")``       -> oracle/liboracle.so            plain restatement (oracle/oracle.cpp)
   * ``load("reference")``  -> oracle/_ref/libviltrum_ref.so  the unmodified reference
+  * ``load("reference-mt")`` -> oracle/_ref/libviltrum_ref_mt.so  the same, with a std::thread back end under the reference's
+    std::for_each(par_unseq, ...) loops (upstream: TBB) — bench.py's multi-threaded CPU baseline, never used by the parity tests
 
 Only tests/, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` legs may import
 this module.  Nothing under viltrum_b200/ does.
@@ -16,6 +18,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 PORT_SO = os.path.join(HERE, "liboracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libviltrum_ref.so")
+REF_MT_SO = os.path.join(HERE, "_ref", "libviltrum_ref_mt.so")      # timing baseline only (bench.py): see oracle/pstl_threads/execution
+_PATHS = {"port": PORT_SO, "reference": REF_SO, "reference-mt": REF_MT_SO}
 REFERENCE_ROOT = "/root/reference"
 
 RULE_SAMPLES = {"trapezoidal": 2, "simpson": 3, "boole": 5, "simpson_trapezoidal": 3, "boole_simpson": 5}
@@ -23,14 +27,14 @@ RULE_SAMPLES = {"trapezoidal": 2, "simpson": 3, "boole": 5, "simpson_trapezoidal
 
 def build(kind="port"):
     """(Re)build a checker with oracle/Makefile.  'reference' needs /root/reference (authoring container only)."""
-    target = {"port": "port", "reference": "ref"}[kind]
-    if kind == "reference" and not os.path.isdir(REFERENCE_ROOT):
+    target = {"port": "port", "reference": "ref", "reference-mt": "ref"}[kind]
+    if kind != "port" and not os.path.isdir(REFERENCE_ROOT):
         raise RuntimeError("/root/reference is absent: the reference checker can only be built in the authoring container")
     subprocess.run(["make", "-s", "-j8", "-C", HERE, target], check=True)
 
 
 def available(kind):
-    return os.path.exists(PORT_SO if kind == "port" else REF_SO)
+    return os.path.exists(_PATHS[kind])
 
 
 def _p(a):
@@ -55,6 +59,22 @@ class Oracle:
 
     def dim(self, integrand):
         return self.lib.vo_integrand_dim(integrand.encode())
+
+    def set_threads(self, n):
+        """threads behind the reference's par_unseq loops (reference-mt build; 1 elsewhere)"""
+        if not hasattr(self.lib, "vo_set_threads"):
+            return 1
+        self.lib.vo_set_threads.restype = ctypes.c_int
+        return self.lib.vo_set_threads(int(n))
+
+    def phase_times(self):
+        """(seconds until the last region-based call logged its region list = generation, seconds of the whole call); reference builds only"""
+        if not hasattr(self.lib, "vo_phase_times"):
+            return None
+        t = (ctypes.c_double * 2)()
+        self.lib.vo_phase_times.restype = None
+        self.lib.vo_phase_times(t)
+        return float(t[0]), float(t[1])
 
     @staticmethod
     def _setup(res, rmin, rmax):
@@ -315,7 +335,7 @@ _cache = {}
 def load(kind="port"):
     """kind: 'port' (restatement, built on demand) or 'reference' (prebuilt .so, or built when /root/reference exists)."""
     if kind not in _cache:
-        path = PORT_SO if kind == "port" else REF_SO
+        path = _PATHS[kind]
         if not os.path.exists(path):
             build(kind)
         _cache[kind] = Oracle(path)

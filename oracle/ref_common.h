@@ -38,6 +38,17 @@
 
 namespace vref {
 
+// Phase clock of the timing legs (bench.py cpu_baseline / --impl reference): every region-based entry point notes when it
+// started, when the reference handed its region list to Logger::log (= generation done, integrator-region-based.h:19) and when
+// it returned; vo_phase_times() reads the three back.
+struct PhaseClock { double t_begin = 0, t_log = 0, t_end = 0; };
+inline PhaseClock g_phase;
+inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+struct PhaseTimer {
+    PhaseTimer() { g_phase.t_begin = now_s(); g_phase.t_log = g_phase.t_end = 0; }
+    ~PhaseTimer() { g_phase.t_end = now_s(); if (g_phase.t_log == 0) g_phase.t_log = g_phase.t_begin; }
+};
+
 template<std::size_t DB>
 inline std::size_t tensor_pos(const std::array<std::size_t,DB>& p, const std::array<std::size_t,DB>& res) {
     std::size_t pos=0, prod=1;

@@ -6,7 +6,15 @@
 
 using namespace vref;
 
+#ifdef VREF_MT
+extern "C" const char* vo_kind(void) { return "reference-mt"; }
+// threads behind the reference's std::for_each(par_unseq, ...) loops (oracle/pstl_threads/execution); n <= 0 keeps the current value
+extern "C" int vo_set_threads(int n) { if (n > 0) vref_pstl::threads() = n; return vref_pstl::threads(); }
+#else
 extern "C" const char* vo_kind(void) { return "reference"; }
+extern "C" int vo_set_threads(int) { return 1; }
+#endif
+extern "C" void vo_phase_times(double* t) { t[0] = g_phase.t_log - g_phase.t_begin; t[1] = g_phase.t_end - g_phase.t_begin; }
 
 extern "C" int vo_integrand_dim(const char* name) {
     int d = dispatch_finite(name, [] (auto f) -> int { return decltype(f)::dim; });
@@ -44,6 +52,16 @@ int per_bin_finite(const char* integrand, int dimbins, const uint64_t* res,
         std::size_t nbins = 1; for (auto x : r) nbins *= x;
         if (rec_sum)  std::fill(rec_sum,  rec_sum+nbins,  0.0);
         if (rec_sum2) std::fill(rec_sum2, rec_sum2+nbins, 0.0);
+        if (!rec_samples && !rec_sum && !rec_sum2) {      // nothing to record (the timing legs): the integrand itself, no wrapper
+            if constexpr (KIND == 0)
+                viltrum::integrate(viltrum::monte_carlo_per_bin_parallel(spp, std::size_t(seed)), acc, r, f, range);
+            else
+                viltrum::integrate(viltrum::integrator_per_bin_parallel(viltrum::monte_carlo(spp, std::size_t(seed))), acc, r, f, range);
+            return 0;
+        }
+#ifdef VREF_MT
+        return -4;      // the recording wrapper counts calls in visiting order: serial build only
+#endif
         if constexpr (KIND == 0)
             viltrum::integrate(viltrum::monte_carlo_per_bin_parallel(spp, std::size_t(seed)), acc, r, recf, range);
         else
@@ -137,6 +155,13 @@ extern "C" int vo_mc_per_bin_parallel_inf(const char* integrand, int dimbins, co
                 return v;
             };
             auto acc = [&] (const std::array<std::size_t,DB>& p) -> float& { return bins[tensor_pos(p,r)]; };
+            if (!rec_sum && !rec_sum2 && !rec_len && !rec_elems && !rec_used) {      // timing legs: the integrand itself
+                viltrum::integrate(viltrum::monte_carlo_per_bin_parallel(spp, std::size_t(seed)), acc, r, f, range);
+                return 0;
+            }
+#ifdef VREF_MT
+            return -4;
+#endif
             viltrum::integrate(viltrum::monte_carlo_per_bin_parallel(spp, std::size_t(seed)), acc, r, recf, range);
             if (rec_len) std::copy(lens.begin(), lens.end(), rec_len);
             uint64_t used = 0; for (auto l : lens) used += l;

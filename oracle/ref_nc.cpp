@@ -46,6 +46,7 @@ extern "C" int vo_adaptive_iterations(const char* integrand, const char* rule, c
                            uint64_t iterations, int dimbins, const uint64_t* res,
                            const float* rmin, const float* rmax, float* bins,
                            float* reg_min, float* reg_max, float* reg_err, uint32_t* reg_dim, float* reg_data) {
+    PhaseTimer phase;
     RegionSink sink; sink.reg_min=reg_min; sink.reg_max=reg_max; sink.reg_err=reg_err; sink.reg_dim=reg_dim; sink.reg_data=reg_data;
     return dispatch_finite_bins(integrand, dimbins, [&] (auto f, auto dbc) -> int {
         constexpr std::size_t DB = decltype(dbc)::value;

@@ -27,6 +27,7 @@ public:
     template<typename Number> void log_progress(const Number&, const Number& = Number(1)) {}
     template<typename Data> void log(const Data& d) {
         if constexpr (is_region_seq<Data>::value) {
+            g_phase.t_log = now_s();
             using Reg = std::decay_t<decltype(*d.begin())>;
             constexpr std::size_t D = Reg::dimensions;
             constexpr std::size_t S = Reg::rule::samples;

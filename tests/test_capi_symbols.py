@@ -40,6 +40,37 @@ def test_builtin_integrands_registered():
     assert not L.vb200_builtin_integrand(b"nope", 0)
 
 
+def test_xoshiro128pp_matches_the_reference_vendored_generator():
+    """vb200_xoshiro128pp (the per-bin stream generator of the default sampler) against outputs of the reference's own
+    Xoshiro128PlusPlus (src/rng/XoshiroCpp.hpp:531-589), tests/golden/rng_vectors.json (generator script beside it)"""
+    import json
+    from viltrum_b200 import _capi
+    L = _capi.lib()
+    vec = json.load(open(os.path.join(ROOT, "tests", "golden", "rng_vectors.json")))["vectors"]
+    assert len(vec) >= 5
+    for v in vec:
+        st = (ctypes.c_uint32 * 4)(*v["state"]); n = len(v["outputs"]); out = (ctypes.c_uint32 * n)()
+        L.vb200_xoshiro128pp(st, 17, out)                       # in two calls: the state carries over
+        L.vb200_xoshiro128pp(st, n - 17, ctypes.cast(ctypes.addressof(out) + 17 * 4, ctypes.POINTER(ctypes.c_uint32)))
+        assert list(out) == v["outputs"]
+
+
+def test_threefry_known_answers():
+    # Random123 kat_vectors for threefry4x32 (20 and 13 rounds); the 12-round variant of the experiment harness shares the code
+    from viltrum_b200 import _capi
+    L = _capi.lib()
+    pi = [0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344]; pik = [0xa4093822, 0x299f31d0, 0x082efa98, 0xec4e6c89]
+    kat = [(20, [0] * 4, [0] * 4, [0x9c6ca96a, 0xe17eae66, 0xfc10ecd4, 0x5256a7d8]),
+           (20, [0xffffffff] * 4, [0xffffffff] * 4, [0x2a881696, 0x57012287, 0xf6c7446e, 0xa16a6732]),
+           (20, pi, pik, [0x59cd1dbb, 0xb8879579, 0x86b5d00c, 0xac8b6d84]),
+           (13, [0] * 4, [0] * 4, [0x531c7e4f, 0x39491ee5, 0x2c855a92, 0x3d6abf9a])]
+    for rounds, c, k, want in kat:
+        o = (ctypes.c_uint32 * 4)()
+        assert L.vb200_threefry4x32(rounds, (ctypes.c_uint32 * 4)(*c), (ctypes.c_uint32 * 4)(*k), o) == 0
+        assert list(o) == want
+    assert L.vb200_threefry4x32(7, (ctypes.c_uint32 * 4)(), (ctypes.c_uint32 * 4)(), (ctypes.c_uint32 * 4)()) != 0
+
+
 def test_philox_known_answers():
     # Random123 kat_vectors for philox4x32-10
     from viltrum_b200 import _capi

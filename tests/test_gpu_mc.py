@@ -24,7 +24,7 @@ def test_counter_layout_and_affine_map(ctx):
     L = _capi.lib()
     res, seed = [7, 5], 0x1234567890ABCDEF
     bins = np.zeros(35, np.float32)
-    ctx.mc_per_bin("x2y2", bins, res, Range([0.25, -1.0], [2.0, 3.0]), 1, seed)
+    ctx.mc_per_bin("x2y2", bins, res, Range([0.25, -1.0], [2.0, 3.0]), 1, seed, generator="philox")
     want = np.zeros(35, np.float32)
     for b in range(35):
         c = (ctypes.c_uint32 * 4)(b, 0, 0, 0); k = (ctypes.c_uint32 * 2)(seed & 0xffffffff, seed >> 32); o = (ctypes.c_uint32 * 4)()
@@ -51,7 +51,7 @@ def test_counter_layout_narrow_fields(ctx):
     res, seed = [256, 300], 0x0FEDCBA987654321
     nb = res[0] * res[1]
     bins = np.zeros(nb, np.float32)
-    ctx.mc_per_bin("x2y2", bins, res, Range([0.25, -1.0], [2.0, 3.0]), 1, seed)
+    ctx.mc_per_bin("x2y2", bins, res, Range([0.25, -1.0], [2.0, 3.0]), 1, seed, generator="philox")
     vol = np.float32(np.float32(2.0 - 0.25) * np.float32(3.0 + 1.0))
     for b in range(0, nb, 97):
         c = (ctypes.c_uint32 * 4)(b, 0, 0, 0); k = (ctypes.c_uint32 * 2)(seed & 0xffffffff, seed >> 32); o = (ctypes.c_uint32 * 4)()
@@ -69,16 +69,45 @@ def test_counter_layout_narrow_fields(ctx):
         assert abs(bins[b] - want) <= 2e-6 * abs(want), (b, bins[b], want)
 
 
+@pytest.mark.parametrize("lattice24", [False, True])
+def test_stream_layout_xoshiro(ctx, lattice24):
+    """Default generator: one xoshiro128++ stream per (bin, lane sub-stream), state = Philox4x32-10(key=seed, ctr=(bin lo, bin hi, sub, 'strm')).
+    spp=1 -> the sample of bin b is cut from the first words of sub-stream 0 (16-bit fields on this >= 256-bin grid, 24-bit fields with
+    VB200_MC_LATTICE24) — predicted on the host through vb200_philox4x32_10 + vb200_xoshiro128pp."""
+    from viltrum_b200 import _capi, Range
+    L = _capi.lib()
+    res, seed = [256, 300], 0x0FEDCBA987654321
+    nb = res[0] * res[1]
+    bins = np.zeros(nb, np.float32)
+    ctx.mc_per_bin("x2y2", bins, res, Range([0.25, -1.0], [2.0, 3.0]), 1, seed, lattice24=lattice24)
+    vol = np.float32(np.float32(2.0 - 0.25) * np.float32(3.0 + 1.0))
+    for b in range(0, nb, 97):
+        c = (ctypes.c_uint32 * 4)(b, 0, 0, 0x7374726d); k = (ctypes.c_uint32 * 2)(seed & 0xffffffff, seed >> 32); st = (ctypes.c_uint32 * 4)()
+        L.vb200_philox4x32_10(c, k, st)
+        o = (ctypes.c_uint32 * 2)()
+        L.vb200_xoshiro128pp(st, 2, o)
+        p = [b % res[0], b // res[0]]
+        x = []
+        for i, (lo, hi, r) in enumerate(((0.25, 2.0, res[0]), (-1.0, 3.0, res[1]))):
+            dr = np.float32(np.float32(hi - lo) / np.float32(r))
+            a = np.float32(lo) + np.float32(p[i]) * dr; bb = np.float32(lo) + np.float32(p[i] + 1) * dr
+            u = np.float64(o[i] >> 8) * 2.0 ** -24 if lattice24 else np.float64(o[i] & 0xffff) * 2.0 ** -16
+            x.append(np.float32(u * np.float64(np.float32(bb - a)) + np.float64(a)))
+        want = (np.float64(x[0]) ** 2 + np.float64(x[1]) ** 2) * np.float64(vol)
+        assert abs(bins[b] - want) <= 2e-6 * abs(want), (b, bins[b], want)
+
+
+@pytest.mark.parametrize("generator", ["xoshiro", "philox"])
 @pytest.mark.parametrize("integ,res,spp", [("shade4_64", [256, 256], 64), ("shade4_16", [64, 48], 37), ("x2y2", [100], 256),
                                            ("poly3", [12, 10, 6], 32), ("shade5_16", [32, 32], 16), ("ind2", [24, 24], 128)])
 @pytest.mark.parametrize("flavor", ["mc_per_bin_parallel", "per_bin_parallel_mc"])
-def test_statistical_parity(ctx, port, integ, res, spp, flavor):
+def test_statistical_parity(ctx, port, integ, res, spp, flavor, generator):
     from viltrum_b200 import _capi
     rng = _rng(None, integ, 0.0, 1.0)
     nb = int(np.prod(res))
     g = np.zeros(nb, np.float32); s1 = np.zeros(nb, np.float32); s2 = np.zeros(nb, np.float32)
     fl = _capi.MC_PER_BIN if flavor == "mc_per_bin_parallel" else _capi.PER_BIN_MC
-    ctx.mc_per_bin(integ, g, res, rng, spp, 1234, fl, sum_f=s1, sum_f2=s2)
+    ctx.mc_per_bin(integ, g, res, rng, spp, 1234, fl, sum_f=s1, sum_f2=s2, generator=generator)
     if len(res) <= 2:
         r, _, r1, r2 = getattr(port, flavor)(integ, res, rng.min, rng.max, spp, 99, record=True)
     else:   # the oracle bins over <= 2 dims: compare per-bin against an independent GPU seed instead, and the mean against the oracle
@@ -127,19 +156,35 @@ def test_replay_golden_reference_vectors(ctx):
     assert n >= 20
 
 
-def test_sharding_is_invisible(ctx):
-    """Philox counters are keyed by the global bin index: any split of the grid gives the same bits."""
+@pytest.mark.parametrize("generator", ["xoshiro", "philox"])
+def test_sharding_is_invisible(ctx, generator):
+    """Streams / counters are keyed by the global bin index: any split of the grid gives the same bits."""
     res, spp = [50, 30], 48
     rng = _rng(None, "shade4_16")
     full = np.zeros(1500, np.float32)
-    ctx.mc_per_bin("shade4_16", full, res, rng, spp, 5)
+    ctx.mc_per_bin("shade4_16", full, res, rng, spp, 5, generator=generator)
     parts = np.zeros(1500, np.float32)
     for lo, hi in ((0, 1), (1, 700), (700, 701), (701, 1500)):
-        ctx.mc_per_bin("shade4_16", parts, res, rng, spp, 5, shard=(lo, hi))
+        ctx.mc_per_bin("shade4_16", parts, res, rng, spp, 5, shard=(lo, hi), generator=generator)
     assert_same_bits(full, parts, "sharded vs whole")
     other = np.zeros(1500, np.float32)
-    ctx.mc_per_bin("shade4_16", other, res, rng, spp, 6)
+    ctx.mc_per_bin("shade4_16", other, res, rng, spp, 6, generator=generator)
     assert not np.array_equal(full, other)
+
+
+def test_generators_are_distinct_streams_of_the_same_estimator(ctx):
+    """the two generators must not share samples, and option bits outside the ABI are rejected"""
+    from viltrum_b200 import Vb200Error, _capi
+    res, spp = [64, 64], 64
+    rng = _rng(None, "shade4_16")
+    a = np.zeros(4096, np.float32); b = np.zeros(4096, np.float32)
+    ctx.mc_per_bin("shade4_16", a, res, rng, spp, 5, generator="xoshiro")
+    ctx.mc_per_bin("shade4_16", b, res, rng, spp, 5, generator="philox")
+    assert not np.array_equal(a, b)
+    assert abs(float(a.mean()) - float(b.mean())) < 5e-3
+    p = ctx._mc_params(4, res, rng, spp, 5, _capi.MC_PER_BIN, None, options=8)
+    import ctypes as ct
+    assert ctx._L.vb200_mc_per_bin(ctx._h, ctx.integrand("shade4_16"), ct.byref(p), a.ctypes.data, _capi.HOST, None, None) == -2
 
 
 def test_write_semantics_and_device_path(ctx):
@@ -211,6 +256,30 @@ def test_full_size_properties(ctx):
     ctx.mc_per_bin("shade4_64", e, res, rng, spp, 1)
     assert not np.array_equal(a, e) and abs(float(e.mean(dtype=np.float64)) - 0.14326) < 2e-4   # same image, independent noise
     assert float(np.mean(a > 0)) > 0.9
+
+
+@pytest.mark.parametrize("flavor", ["mc_per_bin_parallel", "per_bin_parallel_mc"])
+@pytest.mark.parametrize("generator", ["xoshiro", "philox"])
+def test_full_size_per_bin_parity_against_the_reference(ctx, flavor, generator):
+    """BASELINE config 2 at FULL size: every one of the 2^20 bins against the unmodified reference's own estimate of the same bin
+    (oracle/_ref, multi-threaded build: its MC bins are bit-identical to the serial build's because the per-bin seeds are drawn up
+    front, monte-carlo-per-bin-parallel.h:50-54).  The grid has >= 256 bins per axis, so this is the 16-bit in-bin lattice.
+    Variances: the GPU's own per-bin moments on both sides (same estimator, same spp)."""
+    import pyoracle
+    from viltrum_b200 import _capi
+    kind = "reference-mt" if pyoracle.available("reference-mt") else ("reference" if pyoracle.available("reference") else None)
+    if kind is None:
+        pytest.skip("oracle/_ref was not built (needs /root/reference at build time)")
+    O = pyoracle.load(kind)
+    O.set_threads(len(__import__("os").sched_getaffinity(0)))
+    res, spp, nb = [1024, 1024], 64, 1 << 20
+    rng = _rng(None, "shade4_64")
+    ref = getattr(O, flavor)("shade4_64", res, rng.min, rng.max, spp, 2024)
+    g = np.zeros(nb, np.float32); s1 = np.zeros(nb, np.float32); s2 = np.zeros(nb, np.float32)
+    fl = _capi.MC_PER_BIN if flavor == "mc_per_bin_parallel" else _capi.PER_BIN_MC
+    ctx.mc_per_bin("shade4_64", g, res, rng, spp, 7, fl, sum_f=s1, sum_f2=s2, generator=generator)
+    var = mc_variance(s1, s2, spp, 1.0)
+    assert_statistically_equal(g, ref, var, var, f"C2 full size {flavor} {generator}")
 
 
 def test_registered_host_bins_zero_copy_path(ctx):

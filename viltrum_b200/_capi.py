@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(HERE, "libviltrum_b200.so")
 MAX_DIM, MAX_DIMBINS, K_COUNT = 8, 3, 8
 HOST, DEVICE = 0, 1
 MC_PER_BIN, PER_BIN_MC = 0, 1
+MC_RNG_PHILOX, MC_LATTICE24 = 1, 2      # vb200_mc_params.options
 CV_OPTIMIZE_WEIGHT, CV_FIXED_WEIGHT = 0, 1
 RR_POLICIES = {"uniform": 0, "integral": 1, "error": 2, "pdf": 3}     # vb200_rr_policy
 RULES = {"trapezoidal": 2, "simpson": 3, "boole": 5, "simpson_trapezoidal": 32, "boole_simpson": 53}
@@ -33,7 +34,7 @@ STATUS = {0: "VB200_OK", -1: "VB200_ERR_NO_DEVICE", -2: "VB200_ERR_INVALID", -3:
 # every symbol include/viltrum_b200.h declares (tests/test_capi_symbols.py checks the header against this list and the .so)
 SYMBOLS = [
     "vb200_create", "vb200_destroy", "vb200_last_error", "vb200_stream", "vb200_synchronize", "vb200_sm_count",
-    "vb200_launch_count", "vb200_host_register", "vb200_host_unregister", "vb200_measure_fp32_peak", "vb200_philox4x32_10", "vb200_builtin_integrand", "vb200_builtin_count", "vb200_builtin_name",
+    "vb200_launch_count", "vb200_host_register", "vb200_host_unregister", "vb200_measure_fp32_peak", "vb200_philox4x32_10", "vb200_xoshiro128pp", "vb200_threefry4x32", "vb200_builtin_integrand", "vb200_builtin_count", "vb200_builtin_name",
     "vb200_mc_per_bin", "vb200_mc_per_bin_replay", "vb200_mc_per_bin_inf", "vb200_mc_per_bin_inf_replay",
     "vb200_monte_carlo", "vb200_regions_generate_adaptive", "vb200_regions_generate_single", "vb200_regions_upload",
     "vb200_regions_count", "vb200_regions_dim", "vb200_regions_samples", "vb200_regions_download", "vb200_regions_free",
@@ -60,7 +61,7 @@ class Shard(ctypes.Structure):
 
 class McParams(ctypes.Structure):
     _fields_ = [("domain", Domain), ("shard", Shard), ("spp", ctypes.c_uint64), ("seed", ctypes.c_uint64),
-                ("flavor", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("flavor", ctypes.c_int32), ("options", ctypes.c_int32)]
 
 
 class AdaptiveParams(ctypes.Structure):
@@ -107,6 +108,8 @@ def lib():
         L.vb200_host_unregister.argtypes = [vp, vp]; L.vb200_host_unregister.restype = i32
         L.vb200_measure_fp32_peak.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double)]; L.vb200_measure_fp32_peak.restype = i32
         L.vb200_philox4x32_10.argtypes = [ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]; L.vb200_philox4x32_10.restype = None
+        L.vb200_xoshiro128pp.argtypes = [ctypes.POINTER(ctypes.c_uint32), u64, ctypes.POINTER(ctypes.c_uint32)]; L.vb200_xoshiro128pp.restype = None
+        L.vb200_threefry4x32.argtypes = [i32, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]; L.vb200_threefry4x32.restype = i32
         L.vb200_builtin_integrand.argtypes = [ctypes.c_char_p, i32]; L.vb200_builtin_integrand.restype = vp
         L.vb200_builtin_count.argtypes = []; L.vb200_builtin_count.restype = i32
         L.vb200_builtin_name.argtypes = [i32]; L.vb200_builtin_name.restype = ctypes.c_char_p

@@ -4,6 +4,8 @@
 #include "context.h"
 #include <chrono>
 #include <viltrum_b200/device/philox.cuh>
+#include <viltrum_b200/device/xoshiro.cuh>
+#include <viltrum_b200/device/threefry.cuh>
 #include <cstring>
 #include <cstdlib>
 #include <cmath>
@@ -314,6 +316,22 @@ extern "C" void vb200_philox4x32_10(const uint32_t counter[4], const uint32_t ke
     out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
 }
 
+extern "C" void vb200_xoshiro128pp(uint32_t state[4], uint64_t n, uint32_t* out) {
+    viltrum::b200::Xoshiro128pp x{state[0], state[1], state[2], state[3]};
+    for (uint64_t i = 0; i < n; ++i) out[i] = x.next();
+    state[0] = x.s0; state[1] = x.s1; state[2] = x.s2; state[3] = x.s3;
+}
+extern "C" int vb200_threefry4x32(int rounds, const uint32_t counter[4], const uint32_t key[4], uint32_t out[4]) {
+    using namespace viltrum::b200;
+    const ThreefryKeys t = threefry_key_schedule(key[0], key[1], key[2], key[3]);
+    const u32x4 c{counter[0], counter[1], counter[2], counter[3]};
+    u32x4 r;
+    if (rounds == 12) r = threefry4x32<12>(c, t); else if (rounds == 13) r = threefry4x32<13>(c, t); else if (rounds == 20) r = threefry4x32<20>(c, t);
+    else return VB200_ERR_INVALID;
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+    return VB200_OK;
+}
+
 // ---- built-in integrands ----------------------------------------------------------------------------------
 struct BuiltinEntry { const char* name; const vb200_integrand* desc; };
 extern "C" const BuiltinEntry* builtin_table_fast(int* count);
@@ -453,7 +471,9 @@ extern "C" int vb200_mc_per_bin(vb200_ctx* ctx, const vb200_integrand* f, const 
     vb200_mc_launch a; std::memset(&a, 0, sizeof(a));
     a.domain = finish_domain(p->domain); a.bin_begin = begin; a.bin_end = end; a.nbins_total = total;
     a.spp = uint32_t(p->spp); a.lanes_per_bin = pick_lanes_per_bin(ctx, p->spp, total, 8);   // from the WHOLE grid: the summation order, hence the bits, must not depend on the shard
-    a.narrow_binned = 1;                        // 16-bit draws inside a bin only where the grid itself supplies >= 8 bits per binned dimension
+    if (p->options & ~(VB200_MC_RNG_PHILOX | VB200_MC_LATTICE24)) return fail(ctx, VB200_ERR_INVALID, "unknown option bits 0x%x", unsigned(p->options));
+    a.rng = (p->options & VB200_MC_RNG_PHILOX) ? 1 : 0;
+    a.narrow_binned = (p->options & VB200_MC_LATTICE24) ? 0 : 1;      // 16-bit draws inside a bin only where the grid itself supplies >= 8 bits per binned dimension
     for (int i = 0; i < p->domain.dimbins; ++i) if (p->domain.res[i] < 256) a.narrow_binned = 0;
     a.key0 = uint32_t(p->seed); a.key1 = uint32_t(p->seed >> 32);
     a.flavor = p->flavor;

@@ -145,24 +145,34 @@ class Context:
         return p
 
     # -- raw drivers (1:1 with the C ABI) --------------------------------------------------------------------------
-    def _mc_params(self, dim, res, rng, spp, seed, flavor, shard):
+    def _mc_params(self, dim, res, rng, spp, seed, flavor, shard, options=0):
         p = C.McParams()
         p.domain = C.make_domain(dim, res, rng.min, rng.max)
         p.shard.begin, p.shard.end = (shard if shard else (0, 0))
-        p.spp, p.seed, p.flavor = int(spp), int(seed) & 0xFFFFFFFFFFFFFFFF, flavor
+        p.spp, p.seed, p.flavor, p.options = int(spp), int(seed) & 0xFFFFFFFFFFFFFFFF, flavor, int(options)
         return p
+
+    @staticmethod
+    def mc_options(rng="xoshiro", lattice24=False):
+        """vb200_mc_params.options: rng = 'xoshiro' (default: one xoshiro128++ stream per bin and lane sub-stream, seeded by Philox4x32-10)
+        or 'philox' (every draw is Philox4x32-10 of (bin, sample group, call)); lattice24 = True keeps 24 random bits per coordinate
+        even inside the bins of a fine grid."""
+        if rng not in ("xoshiro", "philox"):
+            raise ValueError(f"rng must be 'xoshiro' or 'philox' (got {rng!r})")
+        return (C.MC_RNG_PHILOX if rng == "philox" else 0) | (C.MC_LATTICE24 if lattice24 else 0)
 
     @staticmethod
     def _empty(shard):
         """an explicit empty shard (a rank with no rows): nothing to do — {0,0} in the C ABI means 'whole grid'"""
         return shard is not None and shard[0] == shard[1]
 
-    def mc_per_bin(self, f, bins, res, rng, spp, seed, flavor=C.MC_PER_BIN, shard=None, sum_f=None, sum_f2=None, exact=False):
+    def mc_per_bin(self, f, bins, res, rng, spp, seed, flavor=C.MC_PER_BIN, shard=None, sum_f=None, sum_f2=None, exact=False,
+                   generator="xoshiro", lattice24=False):
         if self._empty(shard):
             return
         b, mem, _k = _buffer(bins)
         s1, m1, _k1 = _buffer(sum_f); s2, m2, _k2 = _buffer(sum_f2)
-        p = self._mc_params(len(rng.min), res, rng, spp, seed, flavor, shard)
+        p = self._mc_params(len(rng.min), res, rng, spp, seed, flavor, shard, self.mc_options(generator, lattice24))
         self.check(self._L.vb200_mc_per_bin(self._h, self.integrand(f, exact), ctypes.byref(p), b, mem, s1, s2))
 
     def mc_per_bin_replay(self, f, bins, res, rng, spp, samples, flavor=C.MC_PER_BIN, shard=None, exact=True):
