@@ -273,8 +273,14 @@ class Bench:
             regs.integrate_bins(bins, self.gres, self.rng, shard=self.shard)
             regs.free()
         elif w["kind"] == "cv":
-            # every rank generates the (identical) table: generation cannot be sharded and T_gen + T_cv/N beats T_gen + T_broadcast + T_cv/N
-            regs = ctx.regions_generate_adaptive(w["integrand"], self.rng, "simpson_trapezoidal", "size", "relative", w["iterations"], 1e-5, batch=self.batch, exact=True)
+            # default: every rank generates the (identical, deterministic) table — generation cannot be sharded, so T_gen + T_cv/N beats
+            # T_gen + T_broadcast + T_cv/N.  --table broadcast: rank 0 generates, vb200_regions_broadcast (NCCL over NVLink) hands it out.
+            if self.args.table == "broadcast" and self.world > 1:
+                regs = ctx.regions_generate_adaptive(w["integrand"], self.rng, "simpson_trapezoidal", "size", "relative", w["iterations"], 1e-5, batch=self.batch,
+                                                     exact=True) if self.rank == 0 else None
+                regs = ctx.regions_broadcast(regs, 0)
+            else:
+                regs = ctx.regions_generate_adaptive(w["integrand"], self.rng, "simpson_trapezoidal", "size", "relative", w["iterations"], 1e-5, batch=self.batch, exact=True)
             regs.cv_integrate(w["integrand"], bins, self.gres, self.rng, w["spp"], seed, shard=self.shard,
                               nregions=self.d_nreg if (self.d_nreg is not None and not isinstance(bins, np.ndarray)) else None)
             regs.free()
@@ -409,6 +415,9 @@ class Bench:
                     "l2": "flushed between timed steps (256 MiB memset, untimed); per-step CUDA events on the library stream"})
         if w["kind"] in ("nc", "cv"):
             cfg["generation"] = "batched top-k refinement (batch = 0); the exact greedy mode (batch = 1) is timed beside it in exact_mode"
+        if w["kind"] == "cv" and self.world > 1:
+            cfg["table"] = ("rank 0 generates, vb200_regions_broadcast (ncclBroadcast over NVLink) hands the table out" if args.table == "broadcast"
+                            else "every rank generates the identical table (no exchange)")
         if philox is not None:
             cfg["philox_value"] = philox
         rec = {"metric": METRIC.get(self.name, f"integrand evals/sec ({w['desc']})"), "value": value, "unit": unit, "n_gpus": self.world, "steps": args.steps, "warmup": args.warmup,
@@ -437,6 +446,8 @@ def main():
     ap.add_argument("--exact", action="store_true", help="c3: also time the exact greedy mode (seconds)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cv", action="store_true", help="default run: skip the C4 record under 'cv'")
+    ap.add_argument("--table", default="replicate", choices=["replicate", "broadcast"],
+                    help="c4 at N > 1: every rank generates the region table (default) or rank 0 generates and vb200_regions_broadcast hands it out")
     args = ap.parse_args()
     rank, local_rank, world = dist_env()
     primary = args.workload or "c2"
@@ -463,6 +474,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     ctx = Context(local_rank)
+    if world > 1 and args.table == "broadcast":
+        ctx.comm_init_from_torch()           # the library's own NCCL communicator; the rendezvous token travels through torch.distributed
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
     sampler = ClockSampler(local_rank) if rank == 0 else None

@@ -139,6 +139,21 @@ const vb200_integrand* vb200_builtin_fubini(const char* name, int nfirst, const 
                                             uint64_t mc_samples, uint64_t seed);
 void                   vb200_integrand_free(const vb200_integrand* f);
 
+/* ---- multi-GPU: one process per GPU, an optional NCCL communicator per context --------------------------- */
+/* The per-bin paths shard over independent bins (vb200_shard) and need no communicator.  The two exchanges of the design — the
+ * split-sample allreduce of vb200_monte_carlo (VB200_MC_ALLREDUCE) and vb200_regions_broadcast — run over a communicator the context
+ * owns.  vb200_comm_unique_id (one rank) makes the 128-byte rendezvous token (ncclGetUniqueId); hand it to every rank by whatever
+ * the host application has (torch.distributed / MPI broadcast, a file), then every rank calls vb200_comm_init(ctx, id, rank, world)
+ * (ncclCommInitRank on the context's device; collective).  NCCL is bound at run time with dlopen("libnccl.so.2") — the copy the process
+ * already carries (PyTorch's) or the system's; VB200_NCCL_LIB overrides the path; VB200_ERR_UNSUPPORTED if none is found. */
+#define VB200_COMM_ID_BYTES 128
+int vb200_comm_unique_id(vb200_ctx* ctx, void* id /* VB200_COMM_ID_BYTES out */);
+int vb200_comm_init(vb200_ctx* ctx, const void* id, int rank, int world);
+int vb200_comm_destroy(vb200_ctx* ctx);
+int vb200_comm_rank(const vb200_ctx* ctx);
+int vb200_comm_size(const vb200_ctx* ctx);      /* 1 without a communicator */
+int vb200_nccl_version(void);                   /* ncclGetVersion of the bound library, 0 if NCCL could not be loaded */
+
 /* ---- shared parameter blocks -------------------------------------------------------------------------- */
 /* Integration box + bin grid.  For infinite ranges `dim` is the number of explicit entries of rmin/rmax
  * (reference RangeInfinite: implicit [0,1] tail, range-infinite.h:31-37) and may be 0. */
@@ -162,9 +177,12 @@ typedef struct vb200_domain_f64 {
     uint64_t res[VB200_MAX_DIMBINS];
 } vb200_domain_f64;
 
-/* Bin-grid shard handled by one call/GPU: linear bin indices [begin,end) in tensor order.  {0,0} = whole grid.
- * Philox counters are keyed by the GLOBAL bin index, so results do not depend on how the grid is sharded. */
+/* Bin-grid shard handled by one call/GPU: linear bin indices [begin,end) in tensor order.  {0,0} = whole grid (a zero-initialised
+ * parameter block integrates everything).  begin == end != 0 is an EMPTY shard: the call does nothing — a rank that owns no rows, or an
+ * empty sample share in vb200_monte_carlo; write an empty shard that starts at the origin as VB200_SHARD_EMPTY ({UINT64_MAX, UINT64_MAX}).
+ * Random streams are keyed by the GLOBAL bin index, so results do not depend on how the grid is sharded. */
 typedef struct vb200_shard { uint64_t begin, end; } vb200_shard;
+#define VB200_SHARD_EMPTY_INDEX 0xffffffffffffffffull
 
 typedef enum vb200_mc_flavor {
     VB200_MC_PER_BIN = 0,     /* monte_carlo_per_bin_parallel(spp,seed): bins(p) += sum f * vol(range)/spp
@@ -187,6 +205,11 @@ typedef enum vb200_mc_flavor {
  *   generate_canonical<float,24> resolution), 24 bits otherwise; non-binned dimensions always 24.  VB200_MC_LATTICE24: 24 bits everywhere. */
 #define VB200_MC_RNG_PHILOX 1
 #define VB200_MC_LATTICE24  2
+/* vb200_monte_carlo only — split-sample mode across the context's communicator (vb200_comm_init): this rank draws samples
+ * [spp*rank/world, spp*(rank+1)/world) of the global sample counter, the partial grids are summed with ncclAllReduce over NVLink, and every
+ * rank applies the '+=' of the TOTAL to its bins: the one allreduce of the design (SURVEY.md §8e "few bins, many samples").  shard stays {0,0}. */
+#define VB200_MC_ALLREDUCE  4
+enum { VB200_RNG_XOSHIRO = 0, VB200_RNG_PHILOX = 1 };      /* vb200_mc_launch.rng */
 
 typedef struct vb200_mc_params {
     vb200_domain domain;
@@ -244,7 +267,10 @@ typedef enum vb200_heuristic { VB200_HEURISTIC_DEFAULT = 0, VB200_HEURISTIC_SIZE
 typedef enum vb200_metric { VB200_METRIC_ABSOLUTE = 0, VB200_METRIC_RELATIVE = 1 } vb200_metric;         /* error-metric.h:10-41 */
 
 /* Leaf table produced by a generator ("region tree" of north_star = this flat table).
- * Device resident, SoA; order is the reference's heap-array order in exact mode. */
+ * Device resident, SoA; order is the reference's heap-array order in exact mode.
+ * Lifetime: a table belongs to the context that made it.  Free it with vb200_regions_free before or after vb200_destroy — destroying
+ * the context releases the device memory of every outstanding table and leaves the handles valid only for vb200_regions_free
+ * (count/dim/samples then read 0 regions); every other use of a table after its context is gone is an error. */
 typedef struct vb200_regions vb200_regions;
 
 typedef struct vb200_adaptive_params {
@@ -294,6 +320,13 @@ void     vb200_regions_free(vb200_regions* r);
  * so the float summation order — and the bits — match the reference.  Also serves RegionsIntegratorParallelRegions. */
 int vb200_regions_integrate_bins(vb200_ctx* ctx, const vb200_regions* r, const vb200_domain* domain, const vb200_shard* shard,
                                  float* bins, int bins_mem);
+
+/* Region-table broadcast over the context's communicator (SURVEY.md §8e "CV residual": one table, bins slabbed over the GPUs; reference
+ * regions-integrator-parallel-variance-reduction.h:53-63 builds every bin's list from the one table): the root passes its table, every
+ * other rank passes *r == NULL and receives a new single-precision table of the same shape (free it with vb200_regions_free).
+ * Collective; enqueued on the context's stream.  Generating the (deterministic) table on every rank instead costs no exchange at all
+ * and is what bench.py times by default — DESIGN.md §6 has both numbers. */
+int vb200_regions_broadcast(vb200_ctx* ctx, vb200_regions** r, int root);
 
 /* ---- double precision (north_star: Newton-Cotes within 1e-12 in fp64) ---------------------------------------------------- */
 /* The same region family for Range<double,DIM>: integrands flagged VB200_INTEGRAND_F64 (functor over std::array<double,DIM>
@@ -351,7 +384,7 @@ int vb200_cv_replay(vb200_ctx* ctx, const vb200_integrand* f, const vb200_region
 typedef struct vb200_chunk_signal {
     uint32_t  enabled;                /* 0: no signalling (device-resident output) */
     uint32_t  chunk_shift;            /* tiles per chunk = 1 << chunk_shift */
-    uint32_t* done;                   /* device [chunks], zeroed by the driver: finished tiles per chunk */
+    uint32_t* done;                   /* device [chunks], zero at launch: finished tiles per chunk (the warp that completes a chunk zeroes its counter again) */
     uint32_t* flag;                   /* host-mapped [chunks]: set to epoch when every tile of the chunk has been stored */
     uint32_t  epoch;                  /* changes with every call, so the flags never need clearing */
     uint32_t  reserved;
@@ -373,9 +406,10 @@ typedef struct vb200_mc_launch {
     int32_t  grid_hint;               /* CTAs to launch (0 = let the thunk size it from occupancy) */
     int32_t  narrow_binned;           /* 1: coordinates of the binned dimensions carry 16 random bits (every binned dimension of the
                                        * WHOLE grid has >= 256 bins, so the lattice along it still has >= 2^24 points); 0: 24 bits */
-    unsigned long long* tile_counter; /* device, zeroed by the driver before the launch: dynamic tile scheduler */
+    unsigned long long* tile_counter; /* device, two words, zero at launch: [0] tile tickets, [1] warps that are through — the kernel zeroes both again when
+                                       * its last warp leaves, so the driver clears them once per context, not once per call */
     vb200_chunk_signal signal;
-    int32_t  rng;                     /* 0: xoshiro128++ stream per (bin, lane sub-stream) seeded by Philox; 1: Philox4x32-10 per draw group */
+    int32_t  rng;                     /* VB200_RNG_XOSHIRO: xoshiro128++ stream per (bin, lane sub-stream) seeded by Philox; VB200_RNG_PHILOX: Philox4x32-10 per draw group */
     int32_t  reserved;
 } vb200_mc_launch;
 

@@ -69,6 +69,7 @@ __device__ __forceinline__ void signal_tile_done(const vb200_chunk_signal& c, ui
         const uint64_t first = chunk << c.chunk_shift, per = 1ull << c.chunk_shift;
         const uint32_t count = uint32_t(ntiles - first < per ? ntiles - first : per);
         if (atomicAdd(&c.done[chunk], 1u) + 1u == count) {
+            c.done[chunk] = 0u;                     // self-resetting: nobody else touches this chunk's counter in this launch
             __threadfence_system();
             *reinterpret_cast<volatile uint32_t*>(&c.flag[chunk]) = c.epoch;
         }
@@ -116,8 +117,8 @@ constexpr int MC_GROUP = 8;                 // samples per draw group
 //     ~2^24 over the range anyway); NARROW = 0 otherwise.
 // Words per group: 4*NARROW + 6*(DIM-NARROW).  4-D integrand over a 2-D bin grid: 20 words = 5 calls per 8 samples
 // (all-24-bit: 24 words = 6 calls, the round-1b "4 samples per 3 calls").
-enum { MC_RNG_PHILOX = 0, MC_RNG_XOSHIRO = 1 };     // vb200_mc_rng
-template<int DIM, int NARROW, int RNG = MC_RNG_PHILOX> struct GroupDraws {
+enum { MC_RNG_XOSHIRO = VB200_RNG_XOSHIRO, MC_RNG_PHILOX = VB200_RNG_PHILOX };     // template argument = vb200_mc_launch.rng
+template<int DIM, int NARROW, int RNG = MC_RNG_PHILOX> struct GroupDraws {      // (the scatter kernel keeps the stateless Philox default)
     static constexpr int WIDE = DIM - NARROW;
     static constexpr int W16 = 4 * NARROW;          // first W16 words: 16-bit fields
     static constexpr int W24 = 6 * WIDE;            // then W24 words: 24-bit fields, in triples
@@ -180,8 +181,14 @@ __device__ __forceinline__ f32x2 mc_eval_pair(const F& f, const Draws& d, int j0
     return f(x);
 }
 
+#ifndef VB200_MC_PIPELINE
+#define VB200_MC_PIPELINE 0
+#endif
+#ifndef VB200_MC_CHAINS
+#define VB200_MC_CHAINS 2
+#endif
 #ifndef VB200_MC_MINB
-#define VB200_MC_MINB 3                     // 3 CTAs/SM (<= 85 registers): measured within 1 % of the best occupancy for both generators (profiles/k1_rng_r2.txt)
+#define VB200_MC_MINB 4                     // 4 CTAs/SM (64 registers, no spills for the 4-D / 5-D built-ins): 0.5-1 % ahead of 2-3 CTAs/SM for the xoshiro kernel (profiles/k1_rng_r2.txt)
 #endif
 template<class F, int DIM, int DIMBINS, bool MOMENTS, bool EXACT, bool NARROW, int RNG = MC_RNG_PHILOX>
 __global__ void __launch_bounds__(MC_THREADS, VB200_MC_MINB)
@@ -195,10 +202,14 @@ mc_per_bin_kernel(const F f, const vb200_mc_launch a) {
     const uint64_t ntiles = (nshard + G - 1) / G;
     const uint32_t full_groups = a.spp / MC_GROUP, rest = a.spp % MC_GROUP;      // the lanes of a bin stride over its sample groups
 
-    uint64_t tile = 0;
+    // dynamic tile scheduler: tickets from a.tile_counter[0].  The ticket of the NEXT tile is drawn before the current tile is worked on, so
+    // the atomic's round trip hides behind ~25 us of sampling.  The counters reset themselves: a.tile_counter[1] counts the warps that have
+    // drawn their last ticket, and the last of them zeroes both words — the driver never has to clear them between launches.
+    uint64_t tile = 0, next = 0;
     if (lane == 0) tile = atomicAdd(a.tile_counter, 1ull);
     tile = __shfl_sync(0xffffffffu, tile, 0);
     while (tile < ntiles) {
+        if (lane == 0) next = atomicAdd(a.tile_counter, 1ull);
         const uint64_t bin = a.bin_begin + tile * G + grp;
         const bool live = bin < a.bin_end;
         float sum = 0.0f, sum2 = 0.0f, volume = 1.0f;
@@ -215,14 +226,31 @@ mc_per_bin_kernel(const F f, const vb200_mc_launch a) {
             d.begin(b0, b1, sub, a.key0, a.key1);
             if constexpr (PAIRS) {
                 f32x2 acc0(0.0f), acc1(0.0f), sq0(0.0f), sq1(0.0f);
+#if VB200_MC_PIPELINE
+                // software pipeline: the words of the NEXT group are drawn while the current group is evaluated — two independent
+                // instruction streams in one basic block (generator: ALU pipe, integrand: FMA pipe), which ptxas interleaves
+                if (sub < full_groups) d.draw(sub);
+                for (uint32_t g = sub; g < full_groups; g += LPB) {
+                    const GroupDraws<DIM, NB, RNG> cur = d;
+                    if (g + LPB < full_groups) d.draw(g + LPB);
+#else
                 for (uint32_t g = sub; g < full_groups; g += LPB) {
                     d.draw(g);
-                    const f32x2 v0 = mc_eval_pair<F, DIM>(f, d, 0, lo, ext), v1 = mc_eval_pair<F, DIM>(f, d, 2, lo, ext);
+                    const GroupDraws<DIM, NB, RNG>& cur = d;
+#endif
+#if VB200_MC_CHAINS == 4
+                    const f32x2 v0 = mc_eval_pair<F, DIM>(f, cur, 0, lo, ext), v1 = mc_eval_pair<F, DIM>(f, cur, 2, lo, ext),
+                                v2 = mc_eval_pair<F, DIM>(f, cur, 4, lo, ext), v3 = mc_eval_pair<F, DIM>(f, cur, 6, lo, ext);
+                    acc0 += v0; acc1 += v1; acc0 += v2; acc1 += v3;
+                    if (MOMENTS) { sq0 = mad(v0, v0, sq0); sq1 = mad(v1, v1, sq1); sq0 = mad(v2, v2, sq0); sq1 = mad(v3, v3, sq1); }
+#else
+                    const f32x2 v0 = mc_eval_pair<F, DIM>(f, cur, 0, lo, ext), v1 = mc_eval_pair<F, DIM>(f, cur, 2, lo, ext);
                     acc0 += v0; acc1 += v1;
                     if (MOMENTS) { sq0 = mad(v0, v0, sq0); sq1 = mad(v1, v1, sq1); }
-                    const f32x2 v2 = mc_eval_pair<F, DIM>(f, d, 4, lo, ext), v3 = mc_eval_pair<F, DIM>(f, d, 6, lo, ext);
+                    const f32x2 v2 = mc_eval_pair<F, DIM>(f, cur, 4, lo, ext), v3 = mc_eval_pair<F, DIM>(f, cur, 6, lo, ext);
                     acc0 += v2; acc1 += v3;
                     if (MOMENTS) { sq0 = mad(v2, v2, sq0); sq1 = mad(v3, v3, sq1); }
+#endif
                 }
                 sum = (acc0.lo() + acc0.hi()) + (acc1.lo() + acc1.hi());
                 if (MOMENTS) sum2 = (sq0.lo() + sq0.hi()) + (sq1.lo() + sq1.hi());
@@ -274,8 +302,11 @@ mc_per_bin_kernel(const F f, const vb200_mc_launch a) {
             }
         }
         signal_tile_done(a.signal, tile, ntiles, lane);
-        if (lane == 0) tile = atomicAdd(a.tile_counter, 1ull);
-        tile = __shfl_sync(0xffffffffu, tile, 0);
+        tile = __shfl_sync(0xffffffffu, next, 0);
+    }
+    if (lane == 0) {
+        const unsigned long long finished = atomicAdd(a.tile_counter + 1, 1ull) + 1ull;
+        if (finished == uint64_t(gridDim.x) * (MC_THREADS / 32)) { a.tile_counter[0] = 0ull; a.tile_counter[1] = 0ull; }
     }
 }
 

@@ -66,8 +66,8 @@ struct FiniteThunks {
     }
     template<int DB, bool MOMENTS, bool NARROW>
     static int launch_mc(const F& f, const vb200_mc_launch& a, cudaStream_t st) {
-        return a.rng == device::MC_RNG_PHILOX ? launch_mc_rng<DB, MOMENTS, NARROW, device::MC_RNG_PHILOX>(f, a, st)
-                                              : launch_mc_rng<DB, MOMENTS, NARROW, device::MC_RNG_XOSHIRO>(f, a, st);
+        return a.rng == VB200_RNG_PHILOX ? launch_mc_rng<DB, MOMENTS, NARROW, device::MC_RNG_PHILOX>(f, a, st)
+                                         : launch_mc_rng<DB, MOMENTS, NARROW, device::MC_RNG_XOSHIRO>(f, a, st);
     }
     template<int DB>
     static int mc_db(const F& f, const vb200_mc_launch& a, cudaStream_t st) {

@@ -155,6 +155,15 @@ template<typename T, std::size_t DIMBINS> inline void unpin_bins(tensor<T,DIMBIN
 }
 // bin-grid shard handled by this process ({0,0} = whole grid): multi-GPU runs set it per rank
 inline vb200_shard& current_shard() { static vb200_shard s{0, 0}; return s; }
+// slab of `rank` out of `world`: whole rows of the LAST bin dimension, one contiguous range of linear bin indices; a rank beyond the
+// number of rows gets the explicit empty shard (VB200_SHARD_EMPTY_INDEX), never {0,0} (= whole grid)
+template<std::size_t DIMBINS>
+inline vb200_shard shard_for_rank(const std::array<std::size_t,DIMBINS>& res, std::size_t rank, std::size_t world) {
+    std::size_t stride = 1; for (std::size_t i = 0; i + 1 < DIMBINS; ++i) stride *= res[i];
+    const std::size_t rows = res[DIMBINS-1], lo = rows * rank / world, hi = rows * (rank + 1) / world;
+    if (lo == hi) return vb200_shard{VB200_SHARD_EMPTY_INDEX, VB200_SHARD_EMPTY_INDEX};
+    return vb200_shard{uint64_t(lo) * stride, uint64_t(hi) * stride};
+}
 // process-wide sampler options of the per-bin Monte-Carlo integrators (vb200_mc_params.options, VB200_MC_* flags): 0 = xoshiro128++ streams
 // keyed by Philox + 16-bit in-bin lattice on fine grids; VB200_MC_RNG_PHILOX = every draw from Philox4x32-10; VB200_MC_LATTICE24
 inline int32_t& mc_options() { static int32_t o = 0; return o; }
@@ -196,6 +205,7 @@ template<bool ACCUMULATE, typename Bins, std::size_t DIMBINS, typename V>
 inline void apply_bins(Bins& bins, const std::array<std::size_t,DIMBINS>& res, const std::vector<V>& flat) {
     std::array<std::size_t,DIMBINS> pos; pos.fill(0);
     vb200_shard sh = current_shard(); const std::size_t n = flat.size();
+    if (sh.begin == VB200_SHARD_EMPTY_INDEX && sh.end == VB200_SHARD_EMPTY_INDEX) return;      // explicit empty shard
     const std::size_t b = (sh.begin == 0 && sh.end == 0) ? 0 : std::size_t(sh.begin), e = (sh.begin == 0 && sh.end == 0) ? n : std::size_t(sh.end);
     for (std::size_t k = 0; k < n; ++k) {
         if (k >= b && k < e) { if (ACCUMULATE) bins(pos) += flat[k]; else bins(pos) = flat[k]; }

@@ -86,10 +86,11 @@ class Oracle:
             raise RuntimeError(f"{what} failed in {self.kind} oracle: rc={rc}")
 
     def _per_bin(self, fn, integrand, res, rmin, rmax, spp, seed, bins, record):
+        """record = True: (bins, samples, sum f, sum f^2); record = "moments": the same without the sample points (samples = None)"""
         res, rmin, rmax, nb = self._setup(res, rmin, rmax)
         d = self.dim(integrand)
         bins = np.zeros(nb, np.float32) if bins is None else np.ascontiguousarray(bins, dtype=np.float32).copy()
-        samples = np.zeros((nb, spp, d), np.float32) if record else None
+        samples = np.zeros((nb, spp, d), np.float32) if record is True else None
         s1 = np.zeros(nb, np.float64) if record else None
         s2 = np.zeros(nb, np.float64) if record else None
         rc = fn(integrand.encode(), len(res), _p(res), _p(rmin), _p(rmax), ctypes.c_uint64(spp), ctypes.c_uint64(seed),
@@ -121,7 +122,9 @@ class Oracle:
         s1 = s2 = lens = elems = None
         used = ctypes.c_uint64(0)
         cap = 0
-        if record:
+        if record == "moments":      # per-bin sum f, sum f^2 only (the one kind of record the multi-threaded build can take)
+            s1 = np.zeros(nb, np.float64); s2 = np.zeros(nb, np.float64)
+        elif record:
             s1 = np.zeros(nb, np.float64); s2 = np.zeros(nb, np.float64)
             lens = np.zeros(nb * spp, np.uint32)
             cap = rec_cap if rec_cap is not None else nb * spp * 64
@@ -130,6 +133,8 @@ class Oracle:
                                                  ctypes.c_uint64(spp), ctypes.c_uint64(seed), _p(bins), _p(s1), _p(s2),
                                                  _p(lens), _p(elems), ctypes.c_uint64(cap), ctypes.byref(used))
         self._check(rc, "vo_mc_per_bin_parallel_inf")
+        if record == "moments":
+            return bins, s1, s2
         if record:
             return bins, s1, s2, lens, elems[: used.value]
         return bins

@@ -60,7 +60,26 @@ int per_bin_finite(const char* integrand, int dimbins, const uint64_t* res,
             return 0;
         }
 #ifdef VREF_MT
-        return -4;      // the recording wrapper counts calls in visiting order: serial build only
+        // multi-threaded build: calls arrive in no particular order, so the bin of a sample is found from its coordinates (a sample that
+        // float rounding puts exactly on a bin's upper edge is booked to the neighbour: ~1e-7 of the samples, irrelevant for the moments)
+        if (rec_samples) return -4;
+        {
+            float rmn[DB], inv[DB];
+            for (std::size_t i=0;i<DB;++i) { rmn[i] = rmin[i]; inv[i] = float(r[i])/(rmax[i]-rmin[i]); }
+            auto posf = [&] (const std::array<float,D>& x) -> float {
+                float v = f(x);
+                std::size_t bin = 0, prod = 1;
+                for (std::size_t i=0;i<DB;++i) { std::size_t k = std::size_t((x[i]-rmn[i])*inv[i]); if (k >= r[i]) k = r[i]-1; bin += k*prod; prod *= r[i]; }
+                if (rec_sum)  rec_sum[bin]  += double(v);
+                if (rec_sum2) rec_sum2[bin] += double(v)*double(v);
+                return v;
+            };
+            if constexpr (KIND == 0)
+                viltrum::integrate(viltrum::monte_carlo_per_bin_parallel(spp, std::size_t(seed)), acc, r, posf, range);
+            else
+                viltrum::integrate(viltrum::integrator_per_bin_parallel(viltrum::monte_carlo(spp, std::size_t(seed))), acc, r, posf, range);
+            return 0;
+        }
 #endif
         if constexpr (KIND == 0)
             viltrum::integrate(viltrum::monte_carlo_per_bin_parallel(spp, std::size_t(seed)), acc, r, recf, range);
@@ -155,12 +174,31 @@ extern "C" int vo_mc_per_bin_parallel_inf(const char* integrand, int dimbins, co
                 return v;
             };
             auto acc = [&] (const std::array<std::size_t,DB>& p) -> float& { return bins[tensor_pos(p,r)]; };
-            if (!rec_sum && !rec_sum2 && !rec_len && !rec_elems && !rec_used) {      // timing legs: the integrand itself
+            if (!rec_sum && !rec_sum2 && !rec_len && !rec_elems) {      // timing legs: the integrand itself
                 viltrum::integrate(viltrum::monte_carlo_per_bin_parallel(spp, std::size_t(seed)), acc, r, f, range);
+                if (rec_used) *rec_used = 0;
                 return 0;
             }
 #ifdef VREF_MT
-            return -4;
+            // multi-threaded build: per-bin moments only, the bin found from the first DB elements the integrand itself consumed
+            if (rec_len || rec_elems) return -4;
+            {
+                float rmn[DB], inv[DB];
+                for (std::size_t i=0;i<DB;++i) { float a = i<std::size_t(nrange)?rmin[i]:0.0f, b = i<std::size_t(nrange)?rmax[i]:1.0f; rmn[i] = a; inv[i] = float(r[i])/(b-a); }
+                auto posf = [&] (const auto& seq) -> float {
+                    std::vector<float> seen; seen.reserve(16);
+                    RecSeq<std::decay_t<decltype(seq)>> rs(seq, SeqRecorder{&seen, nullptr});
+                    float v = f(rs);
+                    std::size_t bin = 0, prod = 1;
+                    for (std::size_t i=0;i<DB;++i) { std::size_t k = i<seen.size() ? std::size_t((seen[i]-rmn[i])*inv[i]) : 0; if (k >= r[i]) k = r[i]-1; bin += k*prod; prod *= r[i]; }
+                    if (rec_sum)  rec_sum[bin]  += double(v);
+                    if (rec_sum2) rec_sum2[bin] += double(v)*double(v);
+                    return v;
+                };
+                viltrum::integrate(viltrum::monte_carlo_per_bin_parallel(spp, std::size_t(seed)), acc, r, posf, range);
+                if (rec_used) *rec_used = 0;
+                return 0;
+            }
 #endif
             viltrum::integrate(viltrum::monte_carlo_per_bin_parallel(spp, std::size_t(seed)), acc, r, recf, range);
             if (rec_len) std::copy(lens.begin(), lens.end(), rec_len);

@@ -22,21 +22,20 @@ int main(int argc, char** argv) {
     a.domain.res[0] = a.domain.res[1] = 1024; a.domain.drange[0] = a.domain.drange[1] = 1.0f / 1024.0f;
     a.bin_begin = 0; a.bin_end = a.nbins_total = 1u << 20; a.spp = 64; a.lanes_per_bin = 1; a.key0 = 1; a.key1 = 2;
     a.flavor = VB200_MC_PER_BIN; a.accumulate = 0; a.factor = 1.0 / 64.0; a.narrow_binned = 1;
-    cudaMalloc(&a.out, a.nbins_total * 4); cudaMalloc(&a.tile_counter, 8);
+    cudaMalloc(&a.out, a.nbins_total * 4); cudaMalloc(&a.tile_counter, 16); cudaMemset(a.tile_counter, 0, 16);
     #ifndef K1_RNG
-#define K1_RNG 0
+#define K1_RNG 1      // device::MC_RNG_PHILOX; 0 = MC_RNG_XOSHIRO
 #endif
     auto k = device::mc_per_bin_kernel<builtin::Shade4<64>, 4, 2, false, false, true, K1_RNG>;
     cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, k);
     int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, device::MC_THREADS, 0);
     const int grid = occ * sms;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    auto launch = [&] { cudaMemsetAsync(a.tile_counter, 0, 8); k<<<grid, device::MC_THREADS>>>(builtin::Shade4<64>(), a); };
+    auto launch = [&] { k<<<grid, device::MC_THREADS>>>(builtin::Shade4<64>(), a); };      // the kernel resets its scheduler words itself
     for (int i = 0; i < 5; ++i) launch();
     cudaDeviceSynchronize();
     float best = 1e30f, tot = 0;
     for (int i = 0; i < reps; ++i) {
-        cudaMemsetAsync(a.tile_counter, 0, 8);
         cudaEventRecord(e0); k<<<grid, device::MC_THREADS>>>(builtin::Shade4<64>(), a); cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1); tot += ms; if (ms < best) best = ms;
     }

@@ -89,6 +89,33 @@ def test_statistical_parity_with_the_reference_estimator(ctx, port, integ, res, 
     assert 0.7 < ratio < 1.4, f"variance ratio {ratio:.3f}"
 
 
+def test_config4_shape_256x256_against_sixteen_reference_seeds(ctx):
+    """BASELINE config 4's shape on a 256x256 grid (integrator_crespo2021 over shade5<64>; 2048 iterations and 16 spp so that sixteen runs of the
+    UNMODIFIED reference fit a test — its multi-threaded build, ~1 s per seed): per-bin means over K = 16 seeds of either side within
+    3 sigma of their standard errors, z histogram centred with unit variance, equal noise levels.  The GPU side uses the exact greedy
+    generator, i.e. the reference's own region table."""
+    import os
+    import pyoracle
+    from viltrum_b200 import integrate, integrator_crespo2021
+    if not pyoracle.available("reference-mt"):
+        pytest.skip("oracle/_ref/libviltrum_ref_mt.so was not built (needs /root/reference at build time)")
+    O = pyoracle.load("reference-mt")
+    O.set_threads(len(os.sched_getaffinity(0)))
+    integ, res, it, spp, K = "shade5_64", [256, 256], 2048, 16, 16
+    nb = res[0] * res[1]
+    refs = np.stack([O.crespo2021(integ, it, spp, 100 + s, res, [0.0] * 5, [1.0] * 5)[0] for s in range(K)]).astype(np.float64)
+    gpus = []
+    for s in range(K):
+        b = np.zeros(nb, np.float32)
+        integrate(integrator_crespo2021(it, spp, seed=s), b, res, integ, _rng(integ), ctx=ctx)
+        gpus.append(b.astype(np.float64))
+    gpus = np.stack(gpus)
+    var_r = refs.var(axis=0, ddof=1) / K; var_g = gpus.var(axis=0, ddof=1) / K
+    assert_statistically_equal(gpus.mean(axis=0), refs.mean(axis=0), var_g, var_r, "C4 shape 256x256, K=16")
+    ratio = (gpus.var(axis=0, ddof=1).mean() + 1e-30) / (refs.var(axis=0, ddof=1).mean() + 1e-30)
+    assert 0.8 < ratio < 1.25, f"variance ratio {ratio:.3f}"
+
+
 def test_crespo2021_full_pipeline_device_bins_and_sharding(ctx):
     """config 4 shape, reduced (shade5<64>, 128x128 bins, 4096 iterations, 16 spp): device-resident bins, shards reproduce the whole"""
     import torch

@@ -217,9 +217,14 @@ def test_batched_refinement_converges(ctx, port, integ, rule, res, it, mean_tol,
 
 @pytest.mark.parametrize("integ,res,rule,it", [("smooth_edge2", [64, 64], "boole_simpson", 3000), ("shade5_16", [40, 36], "simpson_trapezoidal", 500),
                                                ("poly3", [20, 18, 10], "simpson_trapezoidal", 300), ("x2y2", [600], "simpson_trapezoidal", 70000)])
-def test_region_major_tile_lists_keep_table_order(ctx, port, integ, res, rule, it, monkeypatch):
+@pytest.mark.parametrize("smem_limit", [None, 0, 64])
+def test_region_major_tile_lists_keep_table_order(ctx, port, integ, res, rule, it, smem_limit, monkeypatch):
     """large tables bin regions into tiles with atomics and sort every tile list back into table order (shared-memory bitonic
-    sort; global-memory fallback beyond 32768 regions per tile — the 1-D case): bins stay bit-identical to the brute-force path."""
+    sort; global-memory sort beyond 32768 regions per tile): bins stay bit-identical to the brute-force path.  smem_limit = 0 / 64
+    (VB200_TILE_SORT_SMEM_LIMIT) sends every list / every list longer than 64 ids down the global-memory path, so that its
+    all-ascending network sees non-power-of-two lengths of every size (the largest tile list of the 1-D case holds 32 625 ids)."""
+    if smem_limit is not None:
+        monkeypatch.setenv("VB200_TILE_SORT_SMEM_LIMIT", str(smem_limit))
     d = DIMS[integ]
     if len(res) <= 2:
         want, reg = port.adaptive_iterations(integ, rule, "size_relative", it, res, [0.0] * d, [1.0] * d)

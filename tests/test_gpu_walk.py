@@ -216,3 +216,20 @@ def test_window_kernel_equals_tile_kernel(ctx, monkeypatch):
                     assert_same_bits(got["1"][k], got["0"][k], f"window vs tile kernel: {what} {name} {res} {rmin} flavor {flavor}")
                 assert_same_bits(got["1"][0], ref, f"window vs generic kernel {name} {res} {rmin} flavor {flavor}")
                 assert_same_bits(got["1"][3], ref, f"window (sharded) vs generic kernel {name} {res} {rmin} flavor {flavor}")
+
+
+def test_full_size_per_bin_parity_against_the_reference(ctx):
+    """BASELINE config 5 at FULL size (2048x2048 bins, 256 spp): every bin within 3 sigma of the unmodified reference's estimate of the same
+    bin, each side with its own per-bin moments (oracle/_ref multi-threaded build; ~20 s of host time)."""
+    import os
+    import pyoracle
+    from viltrum_b200 import RangeInfinite
+    if not pyoracle.available("reference-mt"):
+        pytest.skip("oracle/_ref/libviltrum_ref_mt.so was not built (needs /root/reference at build time)")
+    O = pyoracle.load("reference-mt")
+    O.set_threads(len(os.sched_getaffinity(0)))
+    res, spp, nb = [2048, 2048], 256, 1 << 22
+    ref, r1, r2 = O.mc_per_bin_parallel_inf("walk", res, spp, 77, record="moments")
+    g = np.zeros(nb, np.float32); s1 = np.zeros(nb, np.float32); s2 = np.zeros(nb, np.float32)
+    ctx.mc_per_bin_inf("walk", g, res, RangeInfinite(), spp, 5, sum_f=s1, sum_f2=s2)
+    assert_statistically_equal(g, ref, mc_variance(s1, s2, spp, 1.0), mc_variance(r1, r2, spp, 1.0), "C5 full size")

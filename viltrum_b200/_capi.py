@@ -10,7 +10,17 @@ LIB_PATH = os.path.join(HERE, "libviltrum_b200.so")
 MAX_DIM, MAX_DIMBINS, K_COUNT = 8, 3, 8
 HOST, DEVICE = 0, 1
 MC_PER_BIN, PER_BIN_MC = 0, 1
-MC_RNG_PHILOX, MC_LATTICE24 = 1, 2      # vb200_mc_params.options
+MC_RNG_PHILOX, MC_LATTICE24, MC_ALLREDUCE = 1, 2, 4      # vb200_mc_params.options
+COMM_ID_BYTES = 128
+SHARD_EMPTY_INDEX = 0xFFFFFFFFFFFFFFFF   # VB200_SHARD_EMPTY_INDEX: {EMPTY, EMPTY} = explicit empty shard ({0,0} = whole grid)
+
+
+def shard_pair(shard):
+    """(begin, end) for a vb200_shard: None -> {0,0} (whole grid); an empty range -> the explicit empty encoding"""
+    if not shard:
+        return 0, 0
+    b, e = int(shard[0]), int(shard[1])
+    return (SHARD_EMPTY_INDEX, SHARD_EMPTY_INDEX) if b == e else (b, e)
 CV_OPTIMIZE_WEIGHT, CV_FIXED_WEIGHT = 0, 1
 RR_POLICIES = {"uniform": 0, "integral": 1, "error": 2, "pdf": 3}     # vb200_rr_policy
 RULES = {"trapezoidal": 2, "simpson": 3, "boole": 5, "simpson_trapezoidal": 32, "boole_simpson": 53}
@@ -41,6 +51,7 @@ SYMBOLS = [
     "vb200_regions_integrate_bins", "vb200_cv_integrate", "vb200_cv_replay",
     "vb200_regions_generate_single_f64", "vb200_regions_upload_f64", "vb200_regions_download_f64", "vb200_regions_integrate_bins_f64",
     "vb200_builtin_integrand_f64", "vb200_builtin_fubini", "vb200_integrand_free", "vb200_regions_generate_tolerance",
+    "vb200_comm_unique_id", "vb200_comm_init", "vb200_comm_destroy", "vb200_comm_rank", "vb200_comm_size", "vb200_nccl_version", "vb200_regions_broadcast",
 ]
 
 
@@ -110,6 +121,13 @@ def lib():
         L.vb200_philox4x32_10.argtypes = [ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]; L.vb200_philox4x32_10.restype = None
         L.vb200_xoshiro128pp.argtypes = [ctypes.POINTER(ctypes.c_uint32), u64, ctypes.POINTER(ctypes.c_uint32)]; L.vb200_xoshiro128pp.restype = None
         L.vb200_threefry4x32.argtypes = [i32, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]; L.vb200_threefry4x32.restype = i32
+        L.vb200_comm_unique_id.argtypes = [vp, vp]; L.vb200_comm_unique_id.restype = i32
+        L.vb200_comm_init.argtypes = [vp, vp, i32, i32]; L.vb200_comm_init.restype = i32
+        L.vb200_comm_destroy.argtypes = [vp]; L.vb200_comm_destroy.restype = i32
+        L.vb200_comm_rank.argtypes = [vp]; L.vb200_comm_rank.restype = i32
+        L.vb200_comm_size.argtypes = [vp]; L.vb200_comm_size.restype = i32
+        L.vb200_nccl_version.argtypes = []; L.vb200_nccl_version.restype = i32
+        L.vb200_regions_broadcast.argtypes = [vp, ctypes.POINTER(vp), i32]; L.vb200_regions_broadcast.restype = i32
         L.vb200_builtin_integrand.argtypes = [ctypes.c_char_p, i32]; L.vb200_builtin_integrand.restype = vp
         L.vb200_builtin_count.argtypes = []; L.vb200_builtin_count.restype = i32
         L.vb200_builtin_name.argtypes = [i32]; L.vb200_builtin_name.restype = ctypes.c_char_p

@@ -24,6 +24,7 @@ COMMON = ["-std=c++17", "-O3", "-lineinfo", "--expt-relaxed-constexpr", "-Xcompi
 # (source, extra flags).  builtin_exact.cu is the --fmad=false twin used by the bit-exact parity modes.
 SOURCES = [
     ("capi.cu", []),
+    ("comm.cu", []),
     ("regions.cu", ["--fmad=false"]),
     ("cv.cu", ["--fmad=false"]),
     ("refine_batched.cu", ["--fmad=false"]),
@@ -62,7 +63,7 @@ def build(force=False, verbose=False):
         results = list(ex.map(lambda t: _compile(t[0], t[1], force, newest), SOURCES))
     objs = [o for o, _ in results]
     if force or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
-        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart"]
+        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -2,11 +2,13 @@
 // Nothing in here evaluates an integrand: kernels templated on the functor are reached through the launch thunks
 // in the vb200_integrand table.  There is no CPU fallback anywhere in this library.
 #include "context.h"
+#include "regions.h"
 #include <chrono>
 #include <viltrum_b200/device/philox.cuh>
 #include <viltrum_b200/device/xoshiro.cuh>
 #include <viltrum_b200/device/threefry.cuh>
 #include <cstring>
+#include <algorithm>
 #include <cstdlib>
 #include <cmath>
 #include <new>
@@ -21,7 +23,7 @@ namespace vb200 {
 int fail(vb200_ctx* ctx, int status, const char* fmt, ...) {
     char buf[1024];
     va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
-    if (ctx) ctx->error = buf; else g_create_error = buf;
+    if (ctx) { ctx->error = buf; ctx->counters_dirty = true; } else g_create_error = buf;      // after any failure the sampler's scheduler words are cleared again
     return status;
 }
 
@@ -127,6 +129,7 @@ int check_domain(vb200_ctx* ctx, const vb200_domain& d, int integrand_dim) {
 
 int resolve_shard(vb200_ctx* ctx, const vb200_shard& s, uint64_t total, uint64_t* begin, uint64_t* end) {
     if (s.begin == 0 && s.end == 0) { *begin = 0; *end = total; return VB200_OK; }
+    if (s.begin == VB200_SHARD_EMPTY_INDEX && s.end == VB200_SHARD_EMPTY_INDEX) { *begin = 0; *end = 0; return VB200_OK; }      // explicit empty shard
     if (s.begin > s.end || s.end > total) return fail(ctx, VB200_ERR_INVALID, "shard [%llu,%llu) outside [0,%llu)", (unsigned long long)s.begin, (unsigned long long)s.end, (unsigned long long)total);
     *begin = s.begin; *end = s.end;
     return VB200_OK;
@@ -206,7 +209,7 @@ extern "C" int vb200_create(int device, vb200_ctx** out) {
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess ||
         (e = cudaMalloc(&ctx->d_flag, sizeof(int32_t))) != cudaSuccess ||
-        (e = cudaMalloc(&ctx->d_counter, sizeof(unsigned long long) + vb200_ctx::kMaxChunks * sizeof(uint32_t))) != cudaSuccess ||
+        (e = cudaMalloc(&ctx->d_counter, 2 * sizeof(unsigned long long) + vb200_ctx::kMaxChunks * sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaHostAlloc(&ctx->h_flags, vb200_ctx::kMaxChunks * sizeof(uint32_t), cudaHostAllocMapped | cudaHostAllocPortable)) != cudaSuccess) {
         int rc = fail(nullptr, VB200_ERR_CUDA, "context setup on device %d failed: %s", device, cudaGetErrorString(e));
         delete ctx; return rc;
@@ -216,7 +219,7 @@ extern "C" int vb200_create(int device, vb200_ctx** out) {
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         cudaGetLastError();
     }
-    ctx->d_done = reinterpret_cast<uint32_t*>(ctx->d_counter + 1);
+    ctx->d_done = reinterpret_cast<uint32_t*>(ctx->d_counter + 2);
     std::memset(ctx->h_flags, 0, vb200_ctx::kMaxChunks * sizeof(uint32_t));
     *out = ctx;
     return VB200_OK;
@@ -226,6 +229,8 @@ extern "C" void vb200_destroy(vb200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    vb200::orphan_regions(ctx);
+    vb200::comm_release(ctx);
     for (auto& s : ctx->scratch) if (s) cudaFree(s);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->d_flag) cudaFree(ctx->d_flag);
@@ -374,7 +379,13 @@ static int run_sampler(vb200_ctx* ctx, const vb200_integrand* f, int kind, Launc
     const uint64_t begin = a.bin_begin, end = a.bin_end, n = end - begin;
     if (bins_mem != VB200_HOST && bins_mem != VB200_DEVICE) return fail(ctx, VB200_ERR_INVALID, "bad memory-space flag %d", bins_mem);
     if (!bins) return fail(ctx, VB200_ERR_INVALID, "bins pointer is NULL");
-    VB200_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long) + vb200_ctx::kMaxChunks * sizeof(uint32_t), ctx->stream));
+    // the finite sampler resets its scheduler words itself (mc_per_bin.cuh); the walk kernels still want them cleared, and so does the first
+    // call after a failed launch
+    if (kind != VB200_K_MC_PER_BIN || ctx->counters_dirty) {
+        VB200_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, 2 * sizeof(unsigned long long) + vb200_ctx::kMaxChunks * sizeof(uint32_t), ctx->stream));
+        ctx->counters_dirty = false;
+    }
+    if (kind != VB200_K_MC_PER_BIN) ctx->counters_dirty = true;      // walk kernels leave their tickets behind
     a.tile_counter = ctx->d_counter;
     std::memset(&a.signal, 0, sizeof(a.signal));
     if (bins_mem == VB200_DEVICE) {
@@ -472,7 +483,7 @@ extern "C" int vb200_mc_per_bin(vb200_ctx* ctx, const vb200_integrand* f, const 
     a.domain = finish_domain(p->domain); a.bin_begin = begin; a.bin_end = end; a.nbins_total = total;
     a.spp = uint32_t(p->spp); a.lanes_per_bin = pick_lanes_per_bin(ctx, p->spp, total, 8);   // from the WHOLE grid: the summation order, hence the bits, must not depend on the shard
     if (p->options & ~(VB200_MC_RNG_PHILOX | VB200_MC_LATTICE24)) return fail(ctx, VB200_ERR_INVALID, "unknown option bits 0x%x", unsigned(p->options));
-    a.rng = (p->options & VB200_MC_RNG_PHILOX) ? 1 : 0;
+    a.rng = (p->options & VB200_MC_RNG_PHILOX) ? VB200_RNG_PHILOX : VB200_RNG_XOSHIRO;
     a.narrow_binned = (p->options & VB200_MC_LATTICE24) ? 0 : 1;      // 16-bit draws inside a bin only where the grid itself supplies >= 8 bits per binned dimension
     for (int i = 0; i < p->domain.dimbins; ++i) if (p->domain.res[i] < 256) a.narrow_binned = 0;
     a.key0 = uint32_t(p->seed); a.key1 = uint32_t(p->seed >> 32);
@@ -537,6 +548,8 @@ extern "C" int vb200_mc_per_bin_inf_replay(vb200_ctx* ctx, const vb200_integrand
     if (f->dim != -1) return fail(ctx, VB200_ERR_INVALID, "sequence replay needs a sequence integrand");
     int rc = check_domain(ctx, p->domain, -1); if (rc) return rc;
     const uint64_t total = nbins_of(p->domain);
+    if (p->spp == 0 || p->spp > 0xffffffffull) return fail(ctx, VB200_ERR_INVALID, "spp invalid");
+    if (p->flavor != VB200_MC_PER_BIN && p->flavor != VB200_PER_BIN_MC) return fail(ctx, VB200_ERR_INVALID, "unknown flavor %d", p->flavor);
     uint64_t begin, end; rc = resolve_shard(ctx, p->shard, total, &begin, &end); if (rc) return rc;
     if (begin == end) return VB200_OK;
     const uint64_t npaths = (end - begin) * p->spp;
@@ -565,6 +578,21 @@ extern "C" int vb200_mc_per_bin_inf_replay(vb200_ctx* ctx, const vb200_integrand
     return VB200_OK;
 }
 
+// bins[i] = float(double(bins[i]) + double(add[i])): the reference's '+=' onto device-resident bins
+__global__ void add_into_kernel(float* __restrict__ bins, const float* __restrict__ add, uint64_t n) {
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x)
+        bins[i] = __double2float_rn(__dadd_rn(double(bins[i]), double(add[i])));
+}
+namespace vb200 {
+int add_into(vb200_ctx* ctx, float* bins, const float* add, uint64_t n) {
+    const unsigned grid = unsigned(std::min<uint64_t>((n + 255) / 256, uint64_t(ctx->sm_count) * 8));
+    add_into_kernel<<<grid, 256, 0, ctx->stream>>>(bins, add, n);
+    ctx->launches++;
+    VB200_CUDA(ctx, cudaGetLastError());
+    return VB200_OK;
+}
+}
+
 // ---- global Monte Carlo (scatter) ---------------------------------------------------------------------------
 extern "C" int vb200_monte_carlo(vb200_ctx* ctx, const vb200_integrand* f, const vb200_mc_params* p, float* bins, int bins_mem) {
     if (!ctx || !f || !p) return fail(ctx, VB200_ERR_INVALID, "NULL argument");
@@ -573,19 +601,31 @@ extern "C" int vb200_monte_carlo(vb200_ctx* ctx, const vb200_integrand* f, const
     int rc = check_domain(ctx, p->domain, f->dim > 0 ? f->dim : -1); if (rc) return rc;
     if (p->spp == 0) return fail(ctx, VB200_ERR_INVALID, "samples=0");
     const uint64_t total = nbins_of(p->domain);
-    uint64_t sb, se; rc = resolve_shard(ctx, p->shard, p->spp, &sb, &se); if (rc) return rc;
+    if (p->options & ~VB200_MC_ALLREDUCE) return fail(ctx, VB200_ERR_INVALID, "unknown option bits 0x%x", unsigned(p->options));
+    const bool allreduce = (p->options & VB200_MC_ALLREDUCE) != 0;
+    uint64_t sb, se;
+    if (allreduce) {      // split-sample mode: this rank's share of the global sample counter; the partial grids are summed over the communicator
+        if (!ctx->comm) return fail(ctx, VB200_ERR_INVALID, "VB200_MC_ALLREDUCE needs a communicator: call vb200_comm_init first");
+        if (p->shard.begin != 0 || p->shard.end != 0) return fail(ctx, VB200_ERR_INVALID, "VB200_MC_ALLREDUCE derives the sample shard from the communicator: leave shard {0,0}");
+        sb = uint64_t((unsigned __int128)p->spp * unsigned(ctx->comm_rank) / unsigned(ctx->comm_size));          // = host.py sample_shard_for_rank
+        se = uint64_t((unsigned __int128)p->spp * unsigned(ctx->comm_rank + 1) / unsigned(ctx->comm_size));
+    } else { rc = resolve_shard(ctx, p->shard, p->spp, &sb, &se); if (rc) return rc; }
     vb200_scatter_launch a; std::memset(&a, 0, sizeof(a));
     a.domain = finish_domain(p->domain); a.sample_begin = sb; a.sample_end = se; a.nbins_total = total;
     a.key0 = uint32_t(p->seed); a.key1 = uint32_t(p->seed >> 32);
     a.factor = double(total) * double(range_volume(p->domain, p->domain.dim)) / double(p->spp);     // monte-carlo.h:43-45
     float* dev = bins;
-    if (bins_mem == VB200_HOST) {
+    if (bins_mem == VB200_HOST || allreduce) {      // a zeroed partial grid: the '+=' onto the caller's bins comes after the sum over ranks
         void* d = nullptr; rc = reserve(ctx, 0, total * sizeof(float), &d); if (rc) return rc;
         dev = static_cast<float*>(d);
         VB200_CUDA(ctx, cudaMemsetAsync(dev, 0, total * sizeof(float), ctx->stream));
     }
     a.out = dev;
     if (se > sb) { rc = call_thunk(ctx, f, f->dim > 0 ? VB200_K_MC_SCATTER : VB200_K_WALK_SCATTER, &a); if (rc) return rc; }
+    if (allreduce) {
+        rc = comm_allreduce_sum(ctx, dev, total); if (rc) return rc;
+        if (bins_mem == VB200_DEVICE) { rc = vb200::add_into(ctx, bins, dev, total); if (rc) return rc; }
+    }
     if (bins_mem == VB200_HOST) {
         float* h = nullptr; rc = reserve_pinned(ctx, total * sizeof(float), reinterpret_cast<void**>(&h)); if (rc) return rc;
         VB200_CUDA(ctx, cudaMemcpyAsync(h, dev, total * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));

@@ -54,10 +54,16 @@ struct vb200_ctx {
     uint32_t* d_done = nullptr;
     uint32_t* h_flags = nullptr;
     uint32_t epoch = 0;
+    bool counters_dirty = true;     // d_counter / d_done need a memset before the next sampling launch
     static constexpr int kMaxChunks = 1024;
     vb200::HostPool pool;
     // caller-owned host buffers pinned and mapped by vb200_host_register: (base, bytes)
     std::vector<std::pair<char*, size_t>> registered;
+    // region tables handed out and not yet freed: vb200_destroy releases their device memory and orphans them, so that a late
+    // vb200_regions_free (a Python finaliser running after Context.close) only deletes the host record
+    std::vector<struct vb200_regions*> live_regions;
+    // optional NCCL communicator (vb200_comm_init; comm.cu): one rank per process and GPU
+    void* comm = nullptr; int comm_rank = 0, comm_size = 1;
 };
 
 namespace vb200 {
@@ -85,5 +91,8 @@ uint32_t pick_lanes_per_bin(const vb200_ctx* ctx, uint64_t spp, uint64_t nbins, 
 struct BinStage { float* dev_base = nullptr; bool staged = false; uint64_t begin = 0, end = 0; float* host = nullptr; };
 int stage_bins_in(vb200_ctx* ctx, float* bins, int mem, uint64_t begin, uint64_t end, bool upload, BinStage* st);
 int stage_bins_out(vb200_ctx* ctx, const BinStage& st);
+void comm_release(vb200_ctx* ctx);
+int comm_allreduce_sum(vb200_ctx* ctx, float* dev, uint64_t count);
+int add_into(vb200_ctx* ctx, float* bins, const float* add, uint64_t n);
 
 } // namespace vb200

@@ -39,6 +39,7 @@ int regions_alloc(vb200_ctx* ctx, int dim, int rule, uint64_t capacity, vb200_re
     vb200_regions* r = new (std::nothrow) vb200_regions;
     if (!r) return fail(ctx, VB200_ERR_NOMEM, "out of host memory");
     r->ctx = ctx; r->dim = dim; r->rule = rule; r->SH = SH; r->SL = SL; r->sd = int(sd); r->capacity = capacity; r->count = 0; r->f64 = f64;
+    ctx->live_regions.push_back(r);
     cudaError_t e;
     if (f64 ? ((e = dmalloc(ctx, &r->rmin64, capacity * dim * sizeof(double))) != cudaSuccess || (e = dmalloc(ctx, &r->rmax64, capacity * dim * sizeof(double))) != cudaSuccess ||
                (e = dmalloc(ctx, &r->data64, capacity * sd * sizeof(double))) != cudaSuccess || (e = dmalloc(ctx, &r->err64, capacity * sizeof(double))) != cudaSuccess ||
@@ -55,9 +56,24 @@ int regions_alloc(vb200_ctx* ctx, int dim, int rule, uint64_t capacity, vb200_re
 
 } // namespace vb200
 
+namespace vb200 {
+// called by vb200_destroy: the context is going away — release the device memory of every outstanding table and cut the link
+void orphan_regions(vb200_ctx* ctx) {
+    for (vb200_regions* r : ctx->live_regions) {
+        cudaFree(r->rmin); cudaFree(r->rmax); cudaFree(r->data); cudaFree(r->err); cudaFree(r->errdim);
+        cudaFree(r->rmin64); cudaFree(r->rmax64); cudaFree(r->data64); cudaFree(r->err64);
+        r->rmin = r->rmax = r->data = r->err = nullptr; r->errdim = nullptr; r->rmin64 = r->rmax64 = r->data64 = r->err64 = nullptr;
+        r->ctx = nullptr; r->count = 0;
+    }
+    ctx->live_regions.clear();
+}
+}
+
 extern "C" void vb200_regions_free(vb200_regions* r) {
     if (!r) return;
     vb200_ctx* ctx = r->ctx;       // stream-ordered frees: work already enqueued on the context's stream still sees the table
+    if (!ctx) { delete r; return; }      // the context was destroyed first: vb200_destroy already released the device memory
+    for (size_t i = 0; i < ctx->live_regions.size(); ++i) if (ctx->live_regions[i] == r) { ctx->live_regions[i] = ctx->live_regions.back(); ctx->live_regions.pop_back(); break; }
     dfree(ctx, r->rmin); dfree(ctx, r->rmax); dfree(ctx, r->data); dfree(ctx, r->err); dfree(ctx, r->errdim);
     dfree(ctx, r->rmin64); dfree(ctx, r->rmax64); dfree(ctx, r->data64); dfree(ctx, r->err64);
     delete r;
@@ -84,11 +100,13 @@ static int regions_upload_t(vb200_ctx* ctx, int dim, int rule, uint64_t count, c
         (e = up(RegCols<T>::data(r), data, sd)) != cudaSuccess || (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) {
         vb200_regions_free(r); return fail(ctx, VB200_ERR_CUDA, "region upload failed: %s", cudaGetErrorString(e));
     }
-    if (err) VB200_CUDA(ctx, cudaMemcpyAsync(RegCols<T>::err(r), err, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
-    else VB200_CUDA(ctx, cudaMemsetAsync(RegCols<T>::err(r), 0, count * sizeof(T), ctx->stream));
-    if (errdim) VB200_CUDA(ctx, cudaMemcpyAsync(r->errdim, errdim, count * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-    else VB200_CUDA(ctx, cudaMemsetAsync(r->errdim, 0, count * sizeof(uint32_t), ctx->stream));
-    VB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if ((e = err ? cudaMemcpyAsync(RegCols<T>::err(r), err, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream)
+                 : cudaMemsetAsync(RegCols<T>::err(r), 0, count * sizeof(T), ctx->stream)) != cudaSuccess ||
+        (e = errdim ? cudaMemcpyAsync(r->errdim, errdim, count * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream)
+                    : cudaMemsetAsync(r->errdim, 0, count * sizeof(uint32_t), ctx->stream)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) {
+        vb200_regions_free(r); return fail(ctx, VB200_ERR_CUDA, "region upload failed: %s", cudaGetErrorString(e));
+    }
     r->count = count;
     *out = r;
     return VB200_OK;
@@ -315,34 +333,47 @@ __global__ void region_major_kernel(TileGeom g, uint64_t nregions, uint64_t cap,
         else list[offsets[t] + atomicAdd(&cursor[t], 1ull)] = uint32_t(r);
     }
 }
-// restore table order inside every tile list: bitonic sort, in shared memory when the list fits (<= 32768 ids), in place
-// in global memory otherwise (rare: one tile touched by more than 32768 regions)
-__global__ void __launch_bounds__(1024) tile_sort_kernel(const uint64_t* __restrict__ offsets, uint32_t* __restrict__ list) {
+// restore table order inside every tile list: bitonic sort in shared memory when the padded list fits (<= smem_limit ids, 32768 in
+// production), otherwise in place in global memory (rare: one tile touched by more than 32768 regions).  The global path cannot
+// materialise the padding up to a power of two, so it runs the ALL-ASCENDING form of the network — the first step of every merge
+// compares i with i ^ (k-1), the following ones i with i ^ j, every comparator orders (low index, high index) ascending — for which
+// virtual +inf entries behind the end are never moved: a comparator that reaches past `len` is a no-op.  (The alternating-direction
+// form used in shared memory would have to move +inf DOWN in its descending blocks; round 1 shipped that form here and lost ids
+// for every non-power-of-two length)
+__global__ void __launch_bounds__(1024) tile_sort_kernel(const uint64_t* __restrict__ offsets, uint32_t* __restrict__ list, uint32_t smem_limit) {
     extern __shared__ uint32_t s_ids[];
     const uint64_t lo = offsets[blockIdx.x], len = offsets[blockIdx.x + 1] - lo;
     if (len < 2) return;
     uint64_t P = 1; while (P < len) P <<= 1;
     uint32_t* a = list + lo;
-    const bool in_smem = P <= 32768;
-    if (in_smem) {
+    if (P <= smem_limit) {
         for (uint64_t i = threadIdx.x; i < P; i += blockDim.x) s_ids[i] = i < len ? a[i] : 0xffffffffu;
         __syncthreads();
+        for (uint64_t k = 2; k <= P; k <<= 1) for (uint64_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint64_t i = threadIdx.x; i < P; i += blockDim.x) {
+                const uint64_t l = i ^ j;
+                if (l > i) {
+                    const bool up = (i & k) == 0;
+                    const uint32_t x = s_ids[i], y = s_ids[l];
+                    if ((x > y) == up) { s_ids[i] = y; s_ids[l] = x; }
+                }
+            }
+            __syncthreads();
+        }
+        for (uint64_t i = threadIdx.x; i < len; i += blockDim.x) a[i] = s_ids[i];
+        return;
     }
     for (uint64_t k = 2; k <= P; k <<= 1) for (uint64_t j = k >> 1; j > 0; j >>= 1) {
-        for (uint64_t i = threadIdx.x; i < P; i += blockDim.x) {
-            const uint64_t l = i ^ j;
-            if (l > i) {
-                const bool up = (i & k) == 0;
-                if (in_smem) { const uint32_t x = s_ids[i], y = s_ids[l]; if ((x > y) == up) { s_ids[i] = y; s_ids[l] = x; } }
-                else {      // virtual padding: positions >= len hold +inf
-                    const uint32_t x = i < len ? a[i] : 0xffffffffu, y = l < len ? a[l] : 0xffffffffu;
-                    if ((x > y) == up) { if (i < len) a[i] = y; if (l < len) a[l] = x; }
-                }
+        const uint64_t mask = (j == (k >> 1)) ? (k - 1) : j;
+        for (uint64_t i = threadIdx.x; i < len; i += blockDim.x) {
+            const uint64_t l = i ^ mask;
+            if (l > i && l < len) {
+                const uint32_t x = a[i], y = a[l];
+                if (x > y) { a[i] = y; a[l] = x; }
             }
         }
         __syncthreads();
     }
-    if (in_smem) for (uint64_t i = threadIdx.x; i < len; i += blockDim.x) a[i] = s_ids[i];
 }
 
 // closed-form integral of the region's (marginalised) tensor-product interpolant over bin ∩ region:
@@ -893,7 +924,9 @@ template<class T> int walk_build_t(vb200_ctx* ctx, const vb200_regions* r, const
         cudaError_t e1 = cudaMemsetAsync(cursor, 0, w->ntiles * sizeof(unsigned long long), ctx->stream);
         region_major_kernel<true><<<unsigned((n + 255) / 256), 256, 0, ctx->stream>>>(g, n, cap, begin, end, w->pstart, w->pend, nullptr, w->tile_offset, cursor, w->tile_list);
         cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4);
-        tile_sort_kernel<<<unsigned(w->ntiles), 1024, 32768 * 4, ctx->stream>>>(w->tile_offset, w->tile_list);
+        uint32_t smem_limit = 32768;        // VB200_TILE_SORT_SMEM_LIMIT: test knob that sends shorter lists down the global-memory path
+        if (const char* env = std::getenv("VB200_TILE_SORT_SMEM_LIMIT")) { const long v = std::atol(env); if (v >= 0 && v < 32768) smem_limit = uint32_t(v); }
+        tile_sort_kernel<<<unsigned(w->ntiles), 1024, 32768 * 4, ctx->stream>>>(w->tile_offset, w->tile_list, smem_limit);
         ctx->launches += 2;
         cudaError_t e2 = cudaGetLastError(), e3 = cudaStreamSynchronize(ctx->stream);
         dfree(ctx, cursor);

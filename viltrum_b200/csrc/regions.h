@@ -26,6 +26,7 @@ namespace vb200 {
 
 int rule_samples(int rule, int* SH, int* SL);
 int regions_alloc(vb200_ctx* ctx, int dim, int rule, uint64_t capacity, vb200_regions** out, bool f64 = false);
+void orphan_regions(vb200_ctx* ctx);
 // batched top-k refinement (refine_batched.cu); params already validated
 int generate_batched(vb200_ctx* ctx, const vb200_integrand* f, const vb200_adaptive_params* p, vb200_regions** out);
 // tolerance-driven refinement, leaves in the reference's depth-first order (refine_batched.cu); params already validated

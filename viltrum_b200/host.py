@@ -136,6 +136,48 @@ class Context:
         self.check(self._L.vb200_measure_fp32_peak(self._h, int(reps), ctypes.byref(out)))
         return out.value
 
+    # -- multi-GPU: an optional NCCL communicator owned by the context (one process per GPU) ------------------------------------
+    def comm_unique_id(self):
+        """128-byte rendezvous token (ncclGetUniqueId): make it on one rank, hand it to the others"""
+        buf = (ctypes.c_ubyte * C.COMM_ID_BYTES)()
+        self.check(self._L.vb200_comm_unique_id(self._h, buf))
+        return bytes(buf)
+
+    def comm_init(self, token, rank, world):
+        """ncclCommInitRank on this context's device (collective)"""
+        buf = (ctypes.c_ubyte * C.COMM_ID_BYTES).from_buffer_copy(token)
+        self.check(self._L.vb200_comm_init(self._h, buf, int(rank), int(world)))
+
+    def comm_init_from_torch(self):
+        """convenience for hosts that already run torch.distributed: rank 0 makes the token, the process group's broadcast hands it out"""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        t = torch.zeros(C.COMM_ID_BYTES, dtype=torch.uint8)
+        if rank == 0:
+            t = torch.frombuffer(bytearray(self.comm_unique_id()), dtype=torch.uint8).clone()
+        dev = torch.device("cuda", self.device) if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = t.to(dev)
+        dist.broadcast(t, 0)
+        self.comm_init(bytes(t.cpu().numpy().tobytes()), rank, world)
+
+    def comm_destroy(self):
+        self.check(self._L.vb200_comm_destroy(self._h))
+
+    @property
+    def comm_rank(self):
+        return self._L.vb200_comm_rank(self._h)
+
+    @property
+    def comm_size(self):
+        return self._L.vb200_comm_size(self._h)
+
+    def regions_broadcast(self, regions, root=0):
+        """vb200_regions_broadcast: the root passes its Regions, the other ranks pass None and receive a new table"""
+        h = regions._h if regions is not None else ctypes.c_void_p()
+        self.check(self._L.vb200_regions_broadcast(self._h, ctypes.byref(h), int(root)))
+        return regions if regions is not None else Regions(self, h)
+
     def integrand(self, name, exact=False):
         if isinstance(name, FubiniIntegrand):      # an adapter descriptor made by vb200_builtin_fubini (always the fast flavour)
             return name.ptr
@@ -148,7 +190,7 @@ class Context:
     def _mc_params(self, dim, res, rng, spp, seed, flavor, shard, options=0):
         p = C.McParams()
         p.domain = C.make_domain(dim, res, rng.min, rng.max)
-        p.shard.begin, p.shard.end = (shard if shard else (0, 0))
+        p.shard.begin, p.shard.end = C.shard_pair(shard)
         p.spp, p.seed, p.flavor, p.options = int(spp), int(seed) & 0xFFFFFFFFFFFFFFFF, flavor, int(options)
         return p
 
@@ -176,6 +218,8 @@ class Context:
         self.check(self._L.vb200_mc_per_bin(self._h, self.integrand(f, exact), ctypes.byref(p), b, mem, s1, s2))
 
     def mc_per_bin_replay(self, f, bins, res, rng, spp, samples, flavor=C.MC_PER_BIN, shard=None, exact=True):
+        if self._empty(shard):
+            return
         b, mem, _k = _buffer(bins); s, smem, _ks = _buffer(samples)
         p = self._mc_params(len(rng.min), res, rng, spp, 0, flavor, shard)
         self.check(self._L.vb200_mc_per_bin_replay(self._h, self.integrand(f, exact), ctypes.byref(p), s, smem, b, mem))
@@ -189,14 +233,19 @@ class Context:
         self.check(self._L.vb200_mc_per_bin_inf(self._h, self.integrand(f, exact), ctypes.byref(p), b, mem, s1, s2))
 
     def mc_per_bin_inf_replay(self, f, bins, res, rng, spp, offsets, elems, shard=None, exact=True, flavor=C.MC_PER_BIN):
+        if self._empty(shard):
+            return
         b, mem, _k = _buffer(bins)
         o, omem, _ko = _buffer(offsets, np.uint64); e, emem, _ke = _buffer(elems)
         p = self._mc_params(len(rng.min), res, rng, spp, 0, flavor, shard)
         self.check(self._L.vb200_mc_per_bin_inf_replay(self._h, self.integrand(f, exact), ctypes.byref(p), o, e, emem, b, mem))
 
-    def monte_carlo(self, f, bins, res, rng, samples, seed, shard=None, exact=False):
+    def monte_carlo(self, f, bins, res, rng, samples, seed, shard=None, exact=False, allreduce=False):
+        """allreduce=True: split-sample mode over the context's communicator (VB200_MC_ALLREDUCE) — every rank ends with bins += the TOTAL"""
+        if self._empty(shard):
+            return
         b, mem, _k = _buffer(bins)
-        p = self._mc_params(len(rng.min), res, rng, samples, seed, C.MC_PER_BIN, shard)
+        p = self._mc_params(len(rng.min), res, rng, samples, seed, C.MC_PER_BIN, shard, C.MC_ALLREDUCE if allreduce else 0)
         self.check(self._L.vb200_monte_carlo(self._h, self.integrand(f, exact), ctypes.byref(p), b, mem))
 
     def regions_generate_adaptive(self, f, rng, rule, heuristic, metric, iterations, size_weight=1e-5, batch=1, exact=True):
@@ -326,19 +375,19 @@ class Regions:
         if self.f64:
             b, mem, _k = _buffer(bins, np.float64)
             d = C.make_domain64(len(rng.min), res, rng.min, rng.max)
-            s = C.Shard(); s.begin, s.end = (shard if shard else (0, 0))
+            s = C.Shard(); s.begin, s.end = C.shard_pair(shard)
             self.ctx.check(self.ctx._L.vb200_regions_integrate_bins_f64(self.ctx._h, self._h, ctypes.byref(d), ctypes.byref(s), b, mem))
             return
         b, mem, _k = _buffer(bins)
         d = C.make_domain(len(rng.min), res, rng.min, rng.max)
-        s = C.Shard(); s.begin, s.end = (shard if shard else (0, 0))
+        s = C.Shard(); s.begin, s.end = C.shard_pair(shard)
         self.ctx.check(self.ctx._L.vb200_regions_integrate_bins(self.ctx._h, self._h, ctypes.byref(d), ctypes.byref(s), b, mem))
 
     def _cv_params(self, res, rng, spp, seed, shard, fixed_alpha=None, rr="uniform"):
         p = C.CvParams()
         p.rr_policy = C.RR_POLICIES[rr]      # rr_uniform_region / rr_integral_region / rr_error_region (region-russian-roulette.h:9-106)
         p.domain = C.make_domain(len(rng.min), res, rng.min, rng.max)
-        p.shard.begin, p.shard.end = (shard if shard else (0, 0))
+        p.shard.begin, p.shard.end = C.shard_pair(shard)
         p.spp, p.seed = int(spp), int(seed) & 0xFFFFFFFFFFFFFFFF
         if fixed_alpha is not None:          # cv_fixed_weight(alpha) instead of cv_optimize_weight (weight-strategy.h:7-35)
             p.weight_strategy, p.alpha = C.CV_FIXED_WEIGHT, float(fixed_alpha)
@@ -353,6 +402,8 @@ class Regions:
         self.ctx.check(self.ctx._L.vb200_cv_integrate(self.ctx._h, self.ctx.integrand(f, exact), self._h, ctypes.byref(p), b, mem, n, a))
 
     def cv_replay(self, f, bins, res, rng, spp, chosen, samples, shard=None, exact=True, fixed_alpha=None, rr="uniform"):
+        if Context._empty(shard):
+            return
         b, mem, _k = _buffer(bins)
         c, cmem, _kc = _buffer(chosen, np.uint32); s, _sm, _ks = _buffer(samples)
         p = self._cv_params(res, rng, spp, 0, shard, fixed_alpha, rr)
@@ -360,7 +411,7 @@ class Regions:
 
     def free(self):
         if self._h:
-            self.ctx._L.vb200_regions_free(self._h)
+            self.ctx._L.vb200_regions_free(self._h)      # safe after Context.close(): the library orphans outstanding tables in vb200_destroy
             self._h = None
 
     def __del__(self):
@@ -687,7 +738,7 @@ def integrator_adaptive_variance_reduction_parallel(rule, heuristic, iterations,
 def shard_for_rank(resolution, rank, world):
     """Bin-grid slab of `rank`: a contiguous range [begin, end) of linear bin indices (tensor order) made of whole rows of the
     LAST bin dimension, so that every rank owns one contiguous block of the flat bin array.  Ranks beyond the number of rows
-    get an empty shard (begin == end != 0 is passed explicitly; {0,0} would mean 'whole grid')."""
+    get an empty shard (begin == end; the drivers pass it to the C ABI as VB200_SHARD_EMPTY, {0,0} would mean 'whole grid')."""
     resolution = [int(r) for r in resolution]
     rows = resolution[-1]
     stride = 1
