@@ -188,7 +188,7 @@ __device__ __forceinline__ f32x2 mc_eval_pair(const F& f, const Draws& d, int j0
 #define VB200_MC_CHAINS 2
 #endif
 #ifndef VB200_MC_MINB
-#define VB200_MC_MINB 4                     // 4 CTAs/SM (64 registers, no spills for the 4-D / 5-D built-ins): 0.5-1 % ahead of 2-3 CTAs/SM for the xoshiro kernel (profiles/k1_rng_r2.txt)
+#define VB200_MC_MINB 3                     // 3 CTAs/SM (<= 85 registers: room for heavier user functors and the Fubini adapters); 4 CTAs/SM at 64 registers is within 1 % (profiles/k1_rng_r2.txt)
 #endif
 template<class F, int DIM, int DIMBINS, bool MOMENTS, bool EXACT, bool NARROW, int RNG = MC_RNG_PHILOX>
 __global__ void __launch_bounds__(MC_THREADS, VB200_MC_MINB)
@@ -202,14 +202,14 @@ mc_per_bin_kernel(const F f, const vb200_mc_launch a) {
     const uint64_t ntiles = (nshard + G - 1) / G;
     const uint32_t full_groups = a.spp / MC_GROUP, rest = a.spp % MC_GROUP;      // the lanes of a bin stride over its sample groups
 
-    // dynamic tile scheduler: tickets from a.tile_counter[0].  The ticket of the NEXT tile is drawn before the current tile is worked on, so
-    // the atomic's round trip hides behind ~25 us of sampling.  The counters reset themselves: a.tile_counter[1] counts the warps that have
-    // drawn their last ticket, and the last of them zeroes both words — the driver never has to clear them between launches.
-    uint64_t tile = 0, next = 0;
+    // dynamic tile scheduler: tickets from a.tile_counter[0].  The counters reset themselves: a.tile_counter[1] counts the warps that have
+    // drawn their last ticket, and the last of them zeroes both words — the driver never has to clear them between launches.  (Drawing the
+    // next ticket ahead of the current tile, to hide the atomic's round trip, was measured and dropped: two more live registers cost the
+    // loop more than the hidden latency gave back, profiles/k1_rng_r2.txt.)
+    uint64_t tile = 0;
     if (lane == 0) tile = atomicAdd(a.tile_counter, 1ull);
     tile = __shfl_sync(0xffffffffu, tile, 0);
     while (tile < ntiles) {
-        if (lane == 0) next = atomicAdd(a.tile_counter, 1ull);
         const uint64_t bin = a.bin_begin + tile * G + grp;
         const bool live = bin < a.bin_end;
         float sum = 0.0f, sum2 = 0.0f, volume = 1.0f;
@@ -302,7 +302,8 @@ mc_per_bin_kernel(const F f, const vb200_mc_launch a) {
             }
         }
         signal_tile_done(a.signal, tile, ntiles, lane);
-        tile = __shfl_sync(0xffffffffu, next, 0);
+        if (lane == 0) tile = atomicAdd(a.tile_counter, 1ull);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
     }
     if (lane == 0) {
         const unsigned long long finished = atomicAdd(a.tile_counter + 1, 1ull) + 1ull;

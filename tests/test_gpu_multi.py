@@ -41,6 +41,6 @@ def test_comm_entry_points_without_a_communicator(ctx=None):
     b = np.zeros(10, np.float32); w = np.zeros(10, np.float32)
     c.monte_carlo("x2y2", b, [10], Range([0, 0], [1, 1]), 8192, 0, allreduce=True)
     c.monte_carlo("x2y2", w, [10], Range([0, 0], [1, 1]), 8192, 0)
-    assert np.array_equal(b, w)
+    assert np.allclose(b, w, rtol=1e-6)          # same samples; the order of the float atomics differs run to run
     c.comm_destroy()
     c.close()

@@ -202,13 +202,43 @@ __device__ __forceinline__ float approximation_at(const float* __restrict__ data
     return R::fm(ApproxLevel<S, D - 1>::eval(data, t), 1.0f);      // * volume_from(DIM) == 1  (region.h:47-51,91-92)
 }
 
+// Throughput form of approximation_at (FAST integrands: statistical parity only): the tensor-product interpolant as a separable
+// contraction with the Lagrange basis of the rule's nodes k/(S-1) — S + S^2 + ... + S^D FMAs (363 at S = 3, D = 5: SURVEY.md §8d's
+// F_contract) instead of a monomial refit plus Horner per line with every rounding spelled out (~1200 operations).
+template<int S> __device__ __forceinline__ void lagrange_basis(float t, float* L) {
+#pragma unroll
+    for (int k = 0; k < S; ++k) {
+        float v = 1.0f;
+#pragma unroll
+        for (int m = 0; m < S; ++m) if (m != k) v *= (t * float(S - 1) - float(m)) * (1.0f / float(k - m));
+        L[k] = v;
+    }
+}
+template<int S, int LEVEL> struct FastLevel {
+    static constexpr int STRIDE = R::ipow(S, LEVEL);
+    __device__ __forceinline__ static float eval(const float* __restrict__ data, const float (*L)[S]) {
+        float v = 0.0f;
+#pragma unroll
+        for (int e = 0; e < S; ++e) v = fmaf(L[LEVEL][e], FastLevel<S, LEVEL - 1>::eval(data + e * STRIDE, L), v);
+        return v;
+    }
+};
+template<int S> struct FastLevel<S, 0> {
+    __device__ __forceinline__ static float eval(const float* __restrict__ data, const float (*L)[S]) {
+        float v = 0.0f;
+#pragma unroll
+        for (int e = 0; e < S; ++e) v = fmaf(L[0][e], __ldg(data + e), v);
+        return v;
+    }
+};
+
 // residual samples: chosen region -> bin ∩ region box -> uniform point, weight, interpolant value.
 // REPLAY: points are given (AoS [bin][spp][D]), only weights/interpolant are computed.
 // The samples are visited in REGION-SORTED order (thread t handles sample sorted_index[t] of region sorted_region[t]): the lanes of a
 // warp then read the same region — its box and its S^D interpolation samples (972 B at C4) come through L1 as broadcasts instead of
 // 32 different gathers per load instruction.  What a sample computes depends only on (bin, sample number, region), so the order
 // changes no bit; outputs are written at the sorted position t (coalesced) and brought back by cv_unsort_kernel.
-template<int S, int D, bool REPLAY>
+template<int S, int D, bool REPLAY, bool FAST = false>
 __global__ void __launch_bounds__(128) cv_samples_kernel(vb200_domain dom, uint64_t begin, uint64_t nb, uint32_t spp, uint32_t k0, uint32_t k1,
                                                          uint64_t cap, const float* __restrict__ rmin, const float* __restrict__ rmax, const float* __restrict__ aos,
                                                          const uint32_t* __restrict__ sorted_region, const uint32_t* __restrict__ sorted_index, const float* __restrict__ replay_points,
@@ -225,6 +255,26 @@ __global__ void __launch_bounds__(128) cv_samples_kernel(vb200_domain dom, uint6
     float a[D], w[D], t[D], x[D];
     float vol = 1.0f;
     u32x4 rnd{0, 0, 0, 0};
+    if constexpr (FAST) {        // plain fp32 + FMA; the same samples (same Philox words), the same estimator
+        float L[D][S];
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            const float lo = rmin[uint64_t(d) * cap + r], hi = rmax[uint64_t(d) * cap + r];
+            float ba = dom.rmin[d], bb = dom.rmax[d];
+            if (d < dom.dimbins) { ba = fmaf(float(pos[d]), dom.drange[d], dom.rmin[d]); bb = fmaf(float(pos[d] + 1u), dom.drange[d], dom.rmin[d]); }
+            const float ia = fmaxf(ba, lo), ib = fmaxf(ia, fminf(bb, hi));
+            const float wd = ib - ia;
+            vol *= wd;
+            if ((d & 3) == 0) rnd = philox4x32<10>(u32x4{uint32_t(bin), uint32_t(bin >> 32), j, uint32_t(1 + d / 4)}, k0, k1);
+            const uint32_t u = (d & 3) == 0 ? rnd.x : (d & 3) == 1 ? rnd.y : (d & 3) == 2 ? rnd.z : rnd.w;
+            const float xd = fmaf(viltrum::b200::u01(u), wd, ia);
+            points[uint64_t(d) * N + tpos] = xd;
+            lagrange_basis<S>(hi > lo ? (xd - lo) / (hi - lo) : 0.0f, L[d]);
+        }
+        weight[tpos] = vol;
+        app[tpos] = FastLevel<S, D - 1>::eval(aos + uint64_t(r) * uint64_t(R::ipow(S, D)), L);
+        return;
+    }
 #pragma unroll
     for (int d = 0; d < D; ++d) {
         const float lo = rmin[uint64_t(d) * cap + r], hi = rmax[uint64_t(d) * cap + r];
@@ -312,20 +362,21 @@ __global__ void transpose_chosen_kernel(uint64_t nb, uint32_t spp, const uint32_
 }
 
 template<int S, int D>
-int launch_samples(vb200_ctx* ctx, bool replay, const vb200_domain& dom, uint64_t begin, uint64_t nb, uint32_t spp, uint32_t k0, uint32_t k1,
+int launch_samples(vb200_ctx* ctx, bool replay, bool fast, const vb200_domain& dom, uint64_t begin, uint64_t nb, uint32_t spp, uint32_t k0, uint32_t k1,
                    const vb200_regions* r, const float* aos, const uint32_t* sreg, const uint32_t* sidx, const float* replay_points, float* points, float* weight, float* app) {
     const uint64_t N = nb * spp;
     const unsigned grid = unsigned((N + 127) / 128);
     if (replay) cv_samples_kernel<S, D, true><<<grid, 128, 0, ctx->stream>>>(dom, begin, nb, spp, k0, k1, r->capacity, r->rmin, r->rmax, aos, sreg, sidx, replay_points, points, weight, app);
+    else if (fast) cv_samples_kernel<S, D, false, true><<<grid, 128, 0, ctx->stream>>>(dom, begin, nb, spp, k0, k1, r->capacity, r->rmin, r->rmax, aos, sreg, sidx, replay_points, points, weight, app);
     else cv_samples_kernel<S, D, false><<<grid, 128, 0, ctx->stream>>>(dom, begin, nb, spp, k0, k1, r->capacity, r->rmin, r->rmax, aos, sreg, sidx, replay_points, points, weight, app);
     ctx->launches++;
     VB200_CUDA(ctx, cudaGetLastError());
     return VB200_OK;
 }
 
-int dispatch_samples(vb200_ctx* ctx, bool replay, const vb200_domain& dom, uint64_t begin, uint64_t nb, uint32_t spp, uint32_t k0, uint32_t k1,
+int dispatch_samples(vb200_ctx* ctx, bool replay, bool fast, const vb200_domain& dom, uint64_t begin, uint64_t nb, uint32_t spp, uint32_t k0, uint32_t k1,
                      const vb200_regions* r, const float* aos, const uint32_t* sreg, const uint32_t* sidx, const float* replay_points, float* points, float* weight, float* app) {
-#define VB200_CVS(SS, DD) if (r->SH == SS && r->dim == DD) return launch_samples<SS, DD>(ctx, replay, dom, begin, nb, spp, k0, k1, r, aos, sreg, sidx, replay_points, points, weight, app);
+#define VB200_CVS(SS, DD) if (r->SH == SS && r->dim == DD) return launch_samples<SS, DD>(ctx, replay, fast, dom, begin, nb, spp, k0, k1, r, aos, sreg, sidx, replay_points, points, weight, app);
     VB200_CVS(3, 1) VB200_CVS(3, 2) VB200_CVS(3, 3) VB200_CVS(3, 4) VB200_CVS(3, 5) VB200_CVS(3, 6)
     VB200_CVS(5, 1) VB200_CVS(5, 2) VB200_CVS(5, 3) VB200_CVS(5, 4)
     VB200_CVS(2, 1) VB200_CVS(2, 2) VB200_CVS(2, 3) VB200_CVS(2, 4) VB200_CVS(2, 5) VB200_CVS(2, 6)
@@ -370,7 +421,13 @@ int cv_run(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r, con
     BinWalk w;
     rc = walk_build(ctx, r, dom, begin, end, &w); if (rc) return rc;
     struct WalkGuard { BinWalk* w; ~WalkGuard() { walk_free(w); } } guard{&w};
-    rc = walk_accumulate(ctx, r, w, dom, begin, end, 1, nullptr, d_approx.as<float>(), d_count.as<uint32_t>()); if (rc) return rc;
+    // FAST integrands (the throughput path: statistical parity) take the fp32 forms of the two arithmetic-heavy kernels — the bin walk and
+    // the interpolant under the residual samples; EXACT integrands and replay keep every rounding of the reference (VB200_CV_EXACT=1 forces that)
+    const char* force_exact = std::getenv("VB200_CV_EXACT");
+    const bool fast = !replay && !(f->flags & VB200_INTEGRAND_EXACT) && !(force_exact && force_exact[0] == '1');
+    if (!(fast && walk_accumulate_fast(ctx, r, w, dom, begin, end, 1, nullptr, d_approx.as<float>(), d_count.as<uint32_t>(), &rc)))
+        rc = walk_accumulate(ctx, r, w, dom, begin, end, 1, nullptr, d_approx.as<float>(), d_count.as<uint32_t>());
+    if (rc) return rc;
     // weighted roulettes: per-bin sum of the pair weights, then of the clamped weights (two more walks, nothing per pair is stored)
     DevBuf d_wsum, d_csum, d_rerr, d_pdf;
     if (policy != VB200_RR_UNIFORM && spp > 0) {
@@ -440,7 +497,7 @@ int cv_run(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r, con
             { size_t tb = sort_bytes;
               VB200_CUDA(ctx, cub::DeviceRadixSort::SortPairs(sort_tmp.p, tb, chosen.as<uint32_t>(), sreg.as<uint32_t>(), iota.as<uint32_t>(), sidx.as<uint32_t>(), int(N), 0, region_bits, ctx->stream));
               ctx->launches += 1 + (region_bits + 7) / 8; }
-            rc = dispatch_samples(ctx, replay, dom, s0, nb, spp, uint32_t(p->seed), uint32_t(p->seed >> 32), r, aos.as<float>(), sreg.as<uint32_t>(), sidx.as<uint32_t>(), rp,
+            rc = dispatch_samples(ctx, replay, fast, dom, s0, nb, spp, uint32_t(p->seed), uint32_t(p->seed >> 32), r, aos.as<float>(), sreg.as<uint32_t>(), sidx.as<uint32_t>(), rp,
                                   points.as<float>(), weight.as<float>(), app.as<float>()); if (rc) return rc;
             if (policy != VB200_RR_UNIFORM) {
                 rc = rr_factors(ctx, r, w, dom, s0, nb, begin, policy, spp, d_rerr.as<float>(), d_pdf.as<float>(), d_count.as<uint32_t>(), d_wsum.as<double>(), d_csum.as<double>(),

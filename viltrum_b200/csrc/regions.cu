@@ -631,6 +631,116 @@ __global__ void __launch_bounds__(256) walk_accumulate_kernel(TileGeom g, DomT<T
     }
 }
 
+// ---- throughput form of the walk (control variates of a FAST integrand: statistical parity, no bit contract) ------------------------
+// The same tile walk in plain fp32 with FMAs: the antiderivative of a line's interpolant is evaluated in float (the reference promotes it
+// to double, which is what makes the exact kernel issue-bound on FP64 and float<->double conversions: 6.0 ms at BASELINE config 4), the
+// reciprocal extents of a region are computed once when it is staged, and the line fold along bin dimension 1 leaves its MONOMIAL
+// coefficients pre-divided for the antiderivative in shared memory, so a (bin, region) pair costs an inside test, two clamps, two
+// 3-term Horner evaluations and one FMA into the running sum.  Per-chunk partial sums go into a double accumulator (one DADD per 16
+// regions), so the control variate of a bin is good to ~1e-7 relative.  2-D bin grids, any S.
+template<int S> struct FastLine { float c[S]; };      // c[k] = monomial coefficient k of the line, divided by k+1
+template<int S> __device__ __forceinline__ void fast_coefficients(const float* p, float* c) {
+    if constexpr (S == 2) { c[0] = p[0]; c[1] = p[1] - p[0]; }
+    else if constexpr (S == 3) { c[0] = p[0]; c[1] = fmaf(4.0f, p[1], fmaf(-3.0f, p[0], -p[2])); c[2] = fmaf(-4.0f, p[1], 2.0f * (p[0] + p[2])); }
+    else {
+        constexpr float k3 = 1.0f / 3.0f;
+        c[0] = p[0];
+        c[1] = (-25.0f * p[0] + 48.0f * p[1] - 36.0f * p[2] + 16.0f * p[3] - 3.0f * p[4]) * k3;
+        c[2] = (70.0f * p[0] - 208.0f * p[1] + 228.0f * p[2] - 112.0f * p[3] + 22.0f * p[4]) * k3;
+        c[3] = (-80.0f * p[0] + 288.0f * p[1] - 384.0f * p[2] + 224.0f * p[3] - 48.0f * p[4]) * k3;
+        c[4] = (32.0f * p[0] - 128.0f * p[1] + 192.0f * p[2] - 128.0f * p[3] + 32.0f * p[4]) * k3;
+    }
+}
+// integral over [a,b] (normalised) of the polynomial with pre-divided coefficients q[k] = c[k]/(k+1): F(b) - F(a), F(x) = x * Horner(q, x)
+template<int S> __device__ __forceinline__ float fast_subrange(float a, float b, const float* q) {
+    float fa = q[S - 1], fb = q[S - 1];
+#pragma unroll
+    for (int k = S - 2; k >= 0; --k) { fa = fmaf(fa, a, q[k]); fb = fmaf(fb, b, q[k]); }
+    return fmaf(fb, b, -fa * a);
+}
+template<int S>
+__global__ void __launch_bounds__(256) walk_accumulate_fast_kernel(TileGeom g, DomT<float> dom, uint64_t cap, uint64_t begin, uint64_t end, uint64_t nbins_total,
+                                                                   const float* __restrict__ patches, const float* __restrict__ rmin, const float* __restrict__ rmax,
+                                                                   const float* __restrict__ volume, const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ pend,
+                                                                   const uint64_t* __restrict__ offsets, const uint32_t* __restrict__ list,
+                                                                   int mode, float* __restrict__ out, float* __restrict__ approx, uint32_t* __restrict__ count) {
+    constexpr int CHUNK = 16, TR = 16, P = S * S;
+    struct Reg { float patch[P]; float rmin[2], rmax[2], inv[2]; float scale; uint32_t ps[2], pe[2]; };
+    __shared__ Reg s_reg[CHUNK];
+    __shared__ FastLine<S> s_q[CHUNK][TR];          // pre-divided coefficients of the dimension-1 fold, per (region, tile row)
+    __shared__ unsigned char s_e1[CHUNK][TR];       // empty intersection along dimension 1
+    const uint64_t t = blockIdx.x;
+    uint32_t o[3]; tile_origin(g, t, o);
+    if (!tile_in_shard(g, o, begin, end)) return;
+    uint32_t pos[2]; pos[0] = o[0] + threadIdx.x % g.tile[0]; pos[1] = o[1] + threadIdx.x / g.tile[0];
+    bool live = pos[0] < g.res[0] && pos[1] < g.res[1];
+    const uint64_t bin = uint64_t(pos[0]) + uint64_t(pos[1]) * g.res[0];
+    live = live && bin >= begin && bin < end;
+    const float lo0 = fmaf(float(pos[0]), dom.drange[0], dom.rmin[0]), hi0 = fmaf(float(pos[0] + 1u), dom.drange[0], dom.rmin[0]);
+    const int ry = int(pos[1] - o[1]);
+    double acc = (mode == 0 && live) ? double(out[bin]) : 0.0;
+    uint32_t cnt = 0;
+    const float factor = float(nbins_total);
+    const uint64_t lo = offsets[t], hi = offsets[t + 1];
+    for (uint64_t base = lo; base < hi; base += CHUNK) {
+        const int n = int(min(uint64_t(CHUNK), hi - base));
+        __syncthreads();
+        for (int k = threadIdx.x; k < n * P; k += blockDim.x) { const int j = k / P, q = k % P; s_reg[j].patch[q] = patches[uint64_t(q) * cap + list[base + j]]; }
+        for (int j = threadIdx.x; j < n; j += blockDim.x) {
+            const uint64_t r = list[base + j];
+#pragma unroll
+            for (int d = 0; d < 2; ++d) {
+                const float a = rmin[uint64_t(d) * cap + r], b = rmax[uint64_t(d) * cap + r];
+                s_reg[j].rmin[d] = a; s_reg[j].rmax[d] = b; s_reg[j].inv[d] = b > a ? 1.0f / (b - a) : 0.0f;
+                s_reg[j].ps[d] = pstart[uint64_t(d) * cap + r]; s_reg[j].pe[d] = pend[uint64_t(d) * cap + r];
+            }
+            s_reg[j].scale = volume[r] * factor;
+        }
+        __syncthreads();
+        for (int item = threadIdx.x; item < n * TR; item += blockDim.x) {       // fold along bin dimension 1, once per (region, tile row)
+            const int j = item / TR, row = item % TR;
+            const Reg& rg = s_reg[j];
+            const uint32_t p1 = o[1] + uint32_t(row);
+            const float lo1 = fmaf(float(p1), dom.drange[1], dom.rmin[1]), hi1 = fmaf(float(p1 + 1u), dom.drange[1], dom.rmin[1]);
+            const float a = fmaxf(lo1, rg.rmin[1]), b = fmaxf(a, fminf(hi1, rg.rmax[1]));
+            const float na = (a - rg.rmin[1]) * rg.inv[1], nb = (b - rg.rmin[1]) * rg.inv[1];
+            float tt[S];
+#pragma unroll
+            for (int i0 = 0; i0 < S; ++i0) {
+                float line[S], c[S];
+#pragma unroll
+                for (int i1 = 0; i1 < S; ++i1) line[i1] = rg.patch[i0 + S * i1];
+                fast_coefficients<S>(line, c);
+#pragma unroll
+                for (int k = 0; k < S; ++k) c[k] *= 1.0f / float(k + 1);
+                tt[i0] = fast_subrange<S>(na, nb, c);
+            }
+            float c[S]; fast_coefficients<S>(tt, c);
+#pragma unroll
+            for (int k = 0; k < S; ++k) s_q[j][row].c[k] = c[k] * (rg.scale / float(k + 1));      // volume * nbins folded in
+            s_e1[j][row] = (a >= b) ? 1 : 0;
+        }
+        __syncthreads();
+        if (live) {
+            float part = 0.0f;
+#pragma unroll 4
+            for (int j = 0; j < n; ++j) {
+                const Reg& rg = s_reg[j];
+                if (!(pos[0] >= rg.ps[0] && pos[0] < rg.pe[0] && pos[1] >= rg.ps[1] && pos[1] < rg.pe[1])) continue;
+                ++cnt;
+                const float a = fmaxf(lo0, rg.rmin[0]), b = fmaxf(a, fminf(hi0, rg.rmax[0]));
+                if (a >= b || s_e1[j][ry]) continue;                          // empty intersection: skipped upstream (regions-integrator-sequential.h:54)
+                part += fast_subrange<S>((a - rg.rmin[0]) * rg.inv[0], (b - rg.rmin[0]) * rg.inv[0], s_q[j][ry].c);
+            }
+            acc += double(part);
+        }
+    }
+    if (live) {
+        if (mode == 0) out[bin] = float(acc);
+        else { approx[bin - begin] = float(acc); count[bin - begin] = cnt; }
+    }
+}
+
 template<int S, int DB, class T>
 int launch_accumulate(vb200_ctx* ctx, const vb200_regions* r, const BinWalkT<T>& w, const TileGeom& g, const DomT<T>& dom,
                       uint64_t begin, uint64_t end, uint64_t total, int mode, T* out, T* approx, uint32_t* count) {
@@ -949,6 +1059,24 @@ template<class T> int walk_accumulate_t(vb200_ctx* ctx, const vb200_regions* r, 
     VB200_WALK(2, 1) VB200_WALK(2, 2) VB200_WALK(2, 3) VB200_WALK(3, 1) VB200_WALK(3, 2) VB200_WALK(3, 3) VB200_WALK(5, 1) VB200_WALK(5, 2) VB200_WALK(5, 3)
 #undef VB200_WALK
     return fail(ctx, VB200_ERR_UNSUPPORTED, "no bin walk for rule with %d samples and %d binned dimensions", w.S, w.db);
+}
+
+// throughput form (fp32 + FMA, no bit contract): 2-D bin grids of 16x16 tiles; false = shape not covered, the caller takes the exact walk
+bool walk_accumulate_fast(vb200_ctx* ctx, const vb200_regions* r, const BinWalk& w, const vb200_domain& dom_, uint64_t begin, uint64_t end,
+                          int mode, float* out, float* approx, uint32_t* count, int* rc) {
+    *rc = VB200_OK;
+    if (w.db != 2 || w.tile[0] != 16 || w.tile[1] != 16 || (w.S != 2 && w.S != 3 && w.S != 5)) return false;
+    const DomT<float> dom = to_dom(dom_);
+    const TileGeom g = make_geom<float>(w, dom);
+    const uint64_t total = nbins_of(dom);
+#define VB200_FASTWALK(SS) if (w.S == SS) walk_accumulate_fast_kernel<SS><<<unsigned(w.ntiles), 256, 0, ctx->stream>>>(g, dom, w.cap, begin, end, total, w.patches, r->rmin, r->rmax, w.volume, \
+                                                                                                        w.pstart, w.pend, w.tile_offset, w.tile_list, mode, out, approx, count);
+    VB200_FASTWALK(2) VB200_FASTWALK(3) VB200_FASTWALK(5)
+#undef VB200_FASTWALK
+    ctx->launches++;
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) *rc = fail(ctx, VB200_ERR_CUDA, "fast bin walk failed to launch: %s", cudaGetErrorString(e));
+    return true;
 }
 
 // ---- weighted Russian roulette (rr_integral_region / rr_error_region): host side of the kernels above --------------------------

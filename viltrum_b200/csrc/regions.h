@@ -79,6 +79,10 @@ inline void walk_free(BinWalk* w) { walk_free_t<float>(w); }
 inline int walk_accumulate(vb200_ctx* ctx, const vb200_regions* r, const BinWalk& w, const vb200_domain& dom, uint64_t begin, uint64_t end,
                            int mode, float* out, float* approx, uint32_t* count) { return walk_accumulate_t<float>(ctx, r, w, to_dom(dom), begin, end, mode, out, approx, count); }
 
+// throughput form of mode 0/1 in plain fp32 (regions.cu walk_accumulate_fast_kernel): returns false when the shape is not covered
+bool walk_accumulate_fast(vb200_ctx* ctx, const vb200_regions* r, const BinWalk& w, const vb200_domain& dom, uint64_t begin, uint64_t end,
+                          int mode, float* out, float* approx, uint32_t* count, int* rc);
+
 // Weighted Russian roulette among the regions of a bin (rr_integral_region = policy 1, rr_error_region = policy 2, rr_pdf_region = policy 3;
 // reference src/control-variates/region-russian-roulette.h:30-147).  Per-bin arrays are indexed by bin - base.
 //   region_total_errors: rerr[r] = Region::error() (policy 2 only)
