@@ -30,9 +30,10 @@ def test_replay_and_control_variate_integral_bit_exact(ctx, port, integ, res, it
     got_reg = regs.download()
     assert_same_bits(got_reg["min"], reg["min"], "region table")
     nb = int(np.prod(res))
-    # (a) control-variate integral and per-bin region counts from the Philox path's own bin walk
+    # (a) control-variate integral and per-bin region counts from the Philox path's own bin walk (EXACT integrand: the exact-arithmetic
+    # kernels; FAST integrands take the fp32 forms, test_fast_forms_agree_with_the_exact_arithmetic)
     bins = np.zeros(nb, np.float32); nreg = np.zeros(nb, np.uint32); approx = np.zeros(nb, np.float32)
-    regs.cv_integrate(integ, bins, res, _rng(integ), spp, 5, nregions=nreg, approx=approx)
+    regs.cv_integrate(integ, bins, res, _rng(integ), spp, 5, nregions=nreg, approx=approx, exact=True)
     assert np.array_equal(nreg, rec["nregions"]), "regions per bin (pixels_in_region)"
     assert_same_bits(approx, rec["approx"], "control-variate integral per bin")
     # (b) replay of the reference's region choices and sample points
@@ -62,7 +63,7 @@ def test_replay_golden_reference_vectors(ctx):
                        np.asarray(v["chosen"], np.uint32).reshape(nb, spp), np.ascontiguousarray(f32(v["samples"]).reshape(nb, spp, d)))
         assert_same_bits(out, f32(v["bins"]), f"{v['integrand']} {v['res']}")
         bins = np.zeros(nb, np.float32); nreg = np.zeros(nb, np.uint32); approx = np.zeros(nb, np.float32)
-        regs.cv_integrate(v["integrand"], bins, v["res"], Range(v["rmin"], v["rmax"]), spp, 1, nregions=nreg, approx=approx)
+        regs.cv_integrate(v["integrand"], bins, v["res"], Range(v["rmin"], v["rmax"]), spp, 1, nregions=nreg, approx=approx, exact=True)
         assert np.array_equal(nreg, np.asarray(v["nregions"], np.uint32)); assert_same_bits(approx, f32(v["approx"]), "approx")
         regs.free(); n += 1
     assert n == 10
@@ -87,6 +88,54 @@ def test_statistical_parity_with_the_reference_estimator(ctx, port, integ, res, 
     # and the noise levels match: same estimator => same variance (ratio of pooled variances near 1)
     ratio = (gpus.var(axis=0, ddof=1).mean() + 1e-30) / (refs.var(axis=0, ddof=1).mean() + 1e-30)
     assert 0.7 < ratio < 1.4, f"variance ratio {ratio:.3f}"
+
+
+@pytest.mark.parametrize("integ,res,it,spp", [("shade5_64", [128, 128], 4096, 32), ("shade4_16", [100, 70], 1500, 16), ("smooth_edge2", [64, 48], 800, 8)])
+def test_fast_forms_agree_with_the_exact_arithmetic(ctx, integ, res, it, spp, monkeypatch):
+    """FAST integrands take the fp32 forms of the bin walk and of the interpolant (regions.cu walk_accumulate_fast_kernel, cv.cu FastLevel);
+    VB200_CV_EXACT=1 sends the same call down the exact-arithmetic kernels.  Same region table, same Philox words, same estimator: the
+    control-variate integral agrees to float rounding of a ~1000-term sum, and the bins agree except where a sample point that moved by
+    an ulp crosses the integrand's discontinuity."""
+    d = DIMS[integ]; nb = res[0] * res[1]
+    regs = ctx.regions_generate_adaptive(integ, _rng(integ), "simpson_trapezoidal", "size", "relative", it, 1e-5, batch=1, exact=True)
+    monkeypatch.setenv("VB200_CV_TILE", "0")      # the sample-major pipeline on both sides: it draws the same regions in either arithmetic
+    fast = np.zeros(nb, np.float32); fa = np.zeros(nb, np.float32); fn = np.zeros(nb, np.uint32)
+    regs.cv_integrate(integ, fast, res, _rng(integ), spp, 11, nregions=fn, approx=fa)
+    monkeypatch.setenv("VB200_CV_EXACT", "1")
+    exact = np.zeros(nb, np.float32); ea = np.zeros(nb, np.float32); en = np.zeros(nb, np.uint32)
+    regs.cv_integrate(integ, exact, res, _rng(integ), spp, 11, nregions=en, approx=ea)
+    regs.free()
+    assert np.array_equal(fn, en)
+    assert np.allclose(fa, ea, rtol=3e-5, atol=3e-6), float(np.max(np.abs(fa - ea)))
+    close = np.isclose(fast, exact, rtol=2e-3, atol=2e-4)
+    assert close.mean() > 0.995, f"{(~close).sum()} of {nb} bins differ"
+    assert abs(float(fast.mean(dtype=np.float64)) - float(exact.mean(dtype=np.float64))) < 1e-4
+
+
+@pytest.mark.parametrize("integ,res,it,spp", [("shade5_64", [128, 128], 4096, 48), ("shade4_16", [100, 70], 1500, 16), ("smooth_edge2", [64, 48], 800, 70), ("shade5_16", [33, 20], 300, 3)])
+def test_tile_major_residual_pass_against_the_sample_major_pipeline(ctx, integ, res, it, spp, monkeypatch):
+    """cv_tile_samples_kernel / cv_tile_accumulate_kernel (regions drawn by rejection from the tile list, tile-local counting sort, no
+    device-wide sort) against the sample-major pipeline (VB200_CV_TILE=0): the same estimator with different random streams — per-bin
+    means over K = 12 seeds within 3 sigma, equal noise; shards that cut tile rows reproduce the whole bit for bit; ragged grids, passes of
+    fewer than 64 samples per bin."""
+    nb = res[0] * res[1]; K = 12
+    regs = ctx.regions_generate_adaptive(integ, _rng(integ), "simpson_trapezoidal", "size", "relative", it, 1e-5, batch=1, exact=True)
+    tiles, flats = [], []
+    for s_ in range(K):
+        b = np.zeros(nb, np.float32); regs.cv_integrate(integ, b, res, _rng(integ), spp, 300 + s_); tiles.append(b.astype(np.float64))
+    cut = (nb // 3) + 7
+    parts = np.zeros(nb, np.float32)
+    regs.cv_integrate(integ, parts, res, _rng(integ), spp, 300, shard=(0, cut))
+    regs.cv_integrate(integ, parts, res, _rng(integ), spp, 300, shard=(cut, nb))
+    assert_same_bits(parts, tiles[0].astype(np.float32), "sharded tile-major vs whole")
+    monkeypatch.setenv("VB200_CV_TILE", "0")
+    for s_ in range(K):
+        b = np.zeros(nb, np.float32); regs.cv_integrate(integ, b, res, _rng(integ), spp, 700 + s_); flats.append(b.astype(np.float64))
+    regs.free()
+    tiles = np.stack(tiles); flats = np.stack(flats)
+    assert_statistically_equal(tiles.mean(axis=0), flats.mean(axis=0), tiles.var(axis=0, ddof=1) / K, flats.var(axis=0, ddof=1) / K, f"tile-major vs sample-major {integ}")
+    ratio = (tiles.var(axis=0, ddof=1).mean() + 1e-30) / (flats.var(axis=0, ddof=1).mean() + 1e-30)
+    assert 0.75 < ratio < 1.33, f"variance ratio {ratio:.3f}"
 
 
 def test_config4_shape_256x256_against_sixteen_reference_seeds(ctx):

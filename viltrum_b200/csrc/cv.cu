@@ -19,6 +19,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <vector>
+#include <algorithm>
 #include <cub/device/device_radix_sort.cuh>
 
 using namespace vb200;
@@ -214,20 +215,20 @@ template<int S> __device__ __forceinline__ void lagrange_basis(float t, float* L
         L[k] = v;
     }
 }
-template<int S, int LEVEL> struct FastLevel {
+template<int S, int LEVEL, bool LDG = true> struct FastLevel {      // LDG: region data in global memory (read-only path); else shared memory
     static constexpr int STRIDE = R::ipow(S, LEVEL);
     __device__ __forceinline__ static float eval(const float* __restrict__ data, const float (*L)[S]) {
         float v = 0.0f;
 #pragma unroll
-        for (int e = 0; e < S; ++e) v = fmaf(L[LEVEL][e], FastLevel<S, LEVEL - 1>::eval(data + e * STRIDE, L), v);
+        for (int e = 0; e < S; ++e) v = fmaf(L[LEVEL][e], FastLevel<S, LEVEL - 1, LDG>::eval(data + e * STRIDE, L), v);
         return v;
     }
 };
-template<int S> struct FastLevel<S, 0> {
+template<int S, bool LDG> struct FastLevel<S, 0, LDG> {
     __device__ __forceinline__ static float eval(const float* __restrict__ data, const float (*L)[S]) {
         float v = 0.0f;
 #pragma unroll
-        for (int e = 0; e < S; ++e) v = fmaf(L[0][e], __ldg(data + e), v);
+        for (int e = 0; e < S; ++e) v = fmaf(L[0][e], LDG ? __ldg(data + e) : data[e], v);
         return v;
     }
 };
@@ -308,26 +309,15 @@ __global__ void cv_unsort_kernel(uint64_t n, const uint32_t* __restrict__ sorted
     if (t < n) rec[sorted_index[t]] = make_float4(fval[t], app[t], weight[t], 0.0f);
 }
 
-// cv_optimize_weight::Accumulator (weight-strategy.h:40-110) — one thread per bin, samples in order, moments in double
-__global__ void __launch_bounds__(128) cv_accumulate_kernel(uint64_t begin, uint64_t nb, uint32_t spp, uint64_t nbins_total,
-                                                            const uint32_t* __restrict__ count, const float* __restrict__ approx,
-                                                            const float4* __restrict__ rec /* (f, interpolant, weight) */,
-                                                            float* __restrict__ out, int fixed_weight, double fixed_alpha, const double* __restrict__ rrf) {
-    const uint64_t b = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (b >= nb) return;
-    const double factor = double(nbins_total), rr_uniform = double(count[b]);         // rr_uniform_region: rr.max()+1 (region-russian-roulette.h:19)
-    const float approximation = approx[b];
-    float sum_f = 0.0f, sum_app = 0.0f; uint64_t size = 0;
-    float fixed_sum = 0.0f;                 // cv_fixed_weight::Accumulator::sum (weight-strategy.h:14-21)
+// cv_optimize_weight::Accumulator (weight-strategy.h:40-110) / cv_fixed_weight::Accumulator (:7-35): samples in order, moments in double
+struct CvAccumulator {
+    float sum_f = 0.0f, sum_app = 0.0f, fixed_sum = 0.0f; uint64_t size = 0;
     double k_f = 0, k_app = 0, e_f = 0, e_ap = 0, e_ap2 = 0, e_fap = 0;
-    for (uint32_t j = 0; j < spp; ++j) {
-        const uint64_t i = uint64_t(j) * nb + b;
-        const float4 smp = rec[i];
-        const double sf = double(smp.z);
-        const double rrfactor = rrf ? rrf[i] : rr_uniform;                             // weighted roulettes: 1/probability of the chosen region
-        // f(sample)*double(factor)*rrfactor*sfactor, rounded to the Sample type (…-variance-reduction.h:97-100)
-        const float fs = R::d2f(R::dm(R::dm(R::dm(double(smp.x), factor), rrfactor), sf));
-        const float as = R::d2f(R::dm(R::dm(R::dm(double(smp.y), factor), rrfactor), sf));
+    // f(sample)*double(factor)*rrfactor*sfactor, rounded to the Sample type (…-variance-reduction.h:97-100)
+    __device__ __forceinline__ void push(float f, float app, float sfactor, double factor, double rrfactor, double fixed_alpha) {
+        const double sf = double(sfactor);
+        const float fs = R::d2f(R::dm(R::dm(R::dm(double(f), factor), rrfactor), sf));
+        const float as = R::d2f(R::dm(R::dm(R::dm(double(app), factor), rrfactor), sf));
         const double nf = double(fabsf(fs)), na = double(fabsf(as));                     // NormDefault (norm.h:12)
         if (size == 0) { k_f = nf; k_app = na; }
         e_f = R::da(e_f, R::ds(nf, k_f));
@@ -338,10 +328,9 @@ __global__ void __launch_bounds__(128) cv_accumulate_kernel(uint64_t begin, uint
         fixed_sum = R::d2f(R::da(double(fixed_sum), R::ds(double(fs), R::dm(fixed_alpha, double(as)))));      // sum += f - alpha*app (:20)
         ++size;
     }
-    float result;
-    if (fixed_weight) result = size == 0 ? approximation : R::d2f(R::da(R::dd(double(fixed_sum), double(size)), R::dm(fixed_alpha, double(approximation))));   // :24-27
-    else if (size < 2) result = approximation;                                          // weight-strategy.h:95
-    else {
+    __device__ __forceinline__ float result(float approximation, int fixed_weight, double fixed_alpha) const {
+        if (fixed_weight) return size == 0 ? approximation : R::d2f(R::da(R::dd(double(fixed_sum), double(size)), R::dm(fixed_alpha, double(approximation))));   // :24-27
+        if (size < 2) return approximation;                                              // weight-strategy.h:95
         const double n = double(size), n1 = double(size - 1);
         const double covariance = R::dd(R::ds(e_fap, R::dd(R::dm(e_f, e_ap), n)), n1);
         const double variance = R::dd(R::ds(e_ap2, R::dd(R::dm(e_ap, e_ap), n)), n1);
@@ -349,9 +338,229 @@ __global__ void __launch_bounds__(128) cv_accumulate_kernel(uint64_t begin, uint
         const double v = fmax(0.0, variance);
         if (v <= 0.0) alpha = 1.0;
         else alpha = R::dd(fmin(v, fmax(0.0, covariance)), v);
-        result = R::d2f(R::da(R::dd(R::ds(double(sum_f), R::dm(alpha, double(sum_app))), n), R::dm(alpha, double(approximation))));
+        return R::d2f(R::da(R::dd(R::ds(double(sum_f), R::dm(alpha, double(sum_app))), n), R::dm(alpha, double(approximation))));
     }
-    out[begin + b] = result;                                                             // '=' (…-variance-reduction.h:102)
+};
+
+// one thread per bin folds its samples (sample-major records) in order
+__global__ void __launch_bounds__(128) cv_accumulate_kernel(uint64_t begin, uint64_t nb, uint32_t spp, uint64_t nbins_total,
+                                                            const uint32_t* __restrict__ count, const float* __restrict__ approx,
+                                                            const float4* __restrict__ rec /* (f, interpolant, weight) */,
+                                                            float* __restrict__ out, int fixed_weight, double fixed_alpha, const double* __restrict__ rrf) {
+    const uint64_t b = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    const double factor = double(nbins_total), rr_uniform = double(count[b]);         // rr_uniform_region: rr.max()+1 (region-russian-roulette.h:19)
+    CvAccumulator acc;
+    for (uint32_t j = 0; j < spp; ++j) {
+        const uint64_t i = uint64_t(j) * nb + b;
+        const float4 smp = rec[i];
+        acc.push(smp.x, smp.y, smp.z, factor, rrf ? rrf[i] : rr_uniform, fixed_alpha);  // weighted roulettes: 1/probability of the chosen region
+    }
+    out[begin + b] = acc.result(approx[b], fixed_weight, fixed_alpha);                   // '=' (…-variance-reduction.h:102)
+}
+
+// ---- tile-major residual pass (throughput path: FAST integrand, rr_uniform_region, 2-D bin grid) ------------------------------------
+// The sample-major pipeline above sorts ALL residual samples of a slab by region with a device-wide radix sort, evaluates them in that
+// order and scatters 16-byte records back (sort 1.5 ms + un-sort 2.7 ms of BASELINE config 4's 23 ms).  Here a CTA owns one
+// 16x16 bin tile and does, per pass of J samples per bin and entirely in shared memory: the draw of every sample's region
+// from the tile's region list, a counting sort of the pass's samples by their position in that list (so that consecutive
+// threads evaluate the same region: its box and interpolation samples arrive as L1 broadcasts), and the sample points / weights /
+// interpolant values, which go to global memory in that tile-local order together with the sample each slot belongs to.  After the
+// integrand's launch over those points, cv_tile_accumulate_kernel brings a tile's values back into sample order through shared memory
+// and one thread per bin folds them in the reference's order.  No device-wide sort, no scattered global traffic.
+constexpr int CVT_BINS = 256, CVT_MAXLIST = 4096, CVT_MAXPASS = 64, CVT_ACCPASS = 32, CVT_SLOTS = 4;
+struct CvTileArgs {
+    TileGeomCv g; vb200_domain dom; uint64_t cap, begin, end, tile0, nbins_total; uint32_t spp, J, k0, k1;
+    const uint32_t* pstart; const uint32_t* pend; const uint64_t* offsets; const uint32_t* list; const uint32_t* count;      // count: indexed by bin - count_base
+    uint64_t count_base;
+    const float* rmin; const float* rmax; const float* aos;
+    float* points; float* weight; float* app; unsigned short* owner;      // [slots] per array, points SoA [d][slots]; slots = tiles * 256 * spp
+    uint64_t slots;
+};
+template<int S, int D>
+__global__ void __launch_bounds__(256) cv_tile_samples_kernel(const CvTileArgs a) {
+    extern __shared__ unsigned char cvt_smem[];
+    unsigned short* s_rank   = reinterpret_cast<unsigned short*>(cvt_smem);                 // [J][256] the pass's sample ids sorted by list position
+    unsigned short* s_choice = s_rank + a.J * CVT_BINS;                              // [J][256] position in the tile's region list (0xffff = no sample)
+    unsigned short* s_hist   = s_choice + a.J * CVT_BINS;                            // [L] samples per list entry, then their running offsets
+    uint32_t* s_box = reinterpret_cast<uint32_t*>(s_hist + CVT_MAXLIST);                     // [L] pixel boxes of the list entries, tile-local bytes
+    float* s_region = reinterpret_cast<float*>(s_box);                                       // [8 warps][CVT_SLOTS] region records of the evaluation phase (the boxes are done with by then)
+    __shared__ uint32_t s_scan[CVT_BINS];
+    const uint64_t t = a.tile0 + blockIdx.x;
+    const TileGeomCv& g = a.g;
+    const uint32_t tid = threadIdx.x;
+    uint32_t o[2]; o[0] = uint32_t(t % g.tiles[0]) * g.tile[0]; o[1] = uint32_t(t / g.tiles[0]) * g.tile[1];
+    uint32_t pos[2]; pos[0] = o[0] + tid % g.tile[0]; pos[1] = o[1] + tid / g.tile[0];
+    const uint64_t bin = uint64_t(pos[0]) + uint64_t(pos[1]) * g.res[0];
+    const bool live = pos[0] < g.res[0] && pos[1] < g.res[1] && bin >= a.begin && bin < a.end;
+    const uint32_t cnt = live ? a.count[bin - a.count_base] : 0u;
+    const uint64_t lo = a.offsets[t], hi = a.offsets[t + 1];
+    const uint32_t L = uint32_t(hi - lo);
+    const uint64_t slot_tile = uint64_t(blockIdx.x) * CVT_BINS * a.spp;
+    for (uint32_t j0 = 0; j0 < a.spp; j0 += a.J) {
+        const uint32_t J = min(a.J, a.spp - j0);
+        // 1.+2. region of every sample: rr_uniform_region picks uniformly among the regions that touch the bin (region-russian-roulette.h:9-28).
+        //    Drawn here by rejection from the TILE's list — a uniform candidate entry is accepted iff its pixel box contains the bin — which
+        //    is uniform over the bin's own regions without ever enumerating them (~80 % of a tile's entries contain a given bin at BASELINE
+        //    config 4: 1.25 candidates per sample, four candidates per Philox call).  A sample still without a region after 16 candidates
+        //    (a bin that few of its tile's regions touch) falls back to rank + linear scan, exactly as the sample-major pipeline resolves it.
+        for (uint32_t i = tid; i < L; i += CVT_BINS) {
+            const uint32_t r = a.list[lo + i];
+            const uint32_t x0 = max(a.pstart[r], o[0]) - o[0], x1 = min(a.pend[r], o[0] + 16u) - o[0];
+            const uint32_t y0 = max(a.pstart[a.cap + r], o[1]) - o[1], y1 = min(a.pend[a.cap + r], o[1] + 16u) - o[1];
+            s_box[i] = x0 | (x1 << 8) | (y0 << 16) | (y1 << 24);                // the entry's pixel box inside the tile, one byte per edge
+            s_hist[i] = 0;
+        }
+        __syncthreads();
+        const uint32_t bx = tid % 16u, by = tid / 16u;
+        auto contains = [&] (uint32_t i) -> bool {
+            const uint32_t bxw = s_box[i];
+            return bx >= (bxw & 255u) && bx < ((bxw >> 8) & 255u) && by >= ((bxw >> 16) & 255u) && by < (bxw >> 24);
+        };
+        for (uint32_t j = 0; j < J; ++j) {
+            uint32_t idx = 0xffffu;
+            if (cnt > 0u) {
+                for (uint32_t blk = 0; blk < 4u && idx == 0xffffu; ++blk) {
+                    const u32x4 c = philox4x32<10>(u32x4{uint32_t(bin), uint32_t(bin >> 32), j0 + j, 0x80u + blk}, a.k0, a.k1);
+                    const uint32_t cand[4] = {__umulhi(c.x, L), __umulhi(c.y, L), __umulhi(c.z, L), __umulhi(c.w, L)};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) if (idx == 0xffffu && contains(cand[q])) idx = cand[q];
+                }
+                if (idx == 0xffffu) {          // rank among the bin's regions, resolved by a scan of the list (rare)
+                    uint32_t rk = __umulhi(philox4x32<10>(u32x4{uint32_t(bin), uint32_t(bin >> 32), j0 + j, 0u}, a.k0, a.k1).x, cnt);
+                    for (uint32_t i = 0; i < L; ++i) if (contains(i)) { if (rk == 0u) { idx = i; break; } --rk; }
+                }
+            }
+            s_choice[j * CVT_BINS + tid] = (unsigned short)idx;
+            if (idx != 0xffffu) atomicAdd(reinterpret_cast<unsigned int*>(s_hist) + (idx >> 1), (idx & 1u) ? 0x10000u : 1u);      // 16-bit counters, two per word
+        }
+        __syncthreads();
+        // 3. counting sort of the pass's samples by list position: exclusive scan of the counters, then every sample takes its slot
+        {
+            const uint32_t per = (L + CVT_BINS - 1) / CVT_BINS, b0 = tid * per, b1 = min(b0 + per, L);
+            uint32_t sum = 0; for (uint32_t i = b0; i < b1; ++i) sum += s_hist[i];
+            s_scan[tid] = sum; __syncthreads();
+            for (uint32_t off = 1; off < CVT_BINS; off <<= 1) { const uint32_t v = tid >= off ? s_scan[tid - off] : 0u; __syncthreads(); s_scan[tid] += v; __syncthreads(); }
+            uint32_t run = s_scan[tid] - sum;
+            for (uint32_t i = b0; i < b1; ++i) { const uint32_t c = s_hist[i]; s_hist[i] = (unsigned short)run; run += c; }
+        }
+        const uint32_t total = s_scan[CVT_BINS - 1];
+        __syncthreads();
+        for (uint32_t j = 0; j < J; ++j) {                                       // s_rank is free now: it becomes the sorted list of sample ids
+            const uint32_t idx = s_choice[j * CVT_BINS + tid];
+            if (idx != 0xffffu) {
+                const unsigned int old = atomicAdd(reinterpret_cast<unsigned int*>(s_hist) + (idx >> 1), (idx & 1u) ? 0x10000u : 1u);
+                const uint32_t p = (idx & 1u) ? (old >> 16) : (old & 0xffffu);
+                s_rank[p] = (unsigned short)(j * CVT_BINS + tid);
+            }
+        }
+        __syncthreads();
+        // 4. the samples, in list order.  A warp takes 32 consecutive sorted samples; they belong to a handful of consecutive list entries
+        //    (~14 samples per region at BASELINE config 4), whose interpolation samples and boxes the warp first copies into its own
+        //    shared-memory slots (coalesced 1 KB reads, once per region and warp) — the evaluation then reads shared memory, where lanes on
+        //    the same region broadcast and lanes on different regions hit different banks (odd slot stride), instead of issuing 243 global
+        //    loads that each touch as many cache lines as the warp has regions.
+        const uint64_t slot_pass = slot_tile + uint64_t(j0) * CVT_BINS;
+        constexpr int SD = R::ipow(S, D), SLOT = (SD + 2 * D) | 1;                   // data, rmin, rmax; odd stride
+        float* s_slots = s_region + (tid >> 5) * (CVT_SLOTS * SLOT);
+        const uint32_t lane = tid & 31u;
+        for (uint32_t pbase = (tid >> 5) * 32u; pbase < J * CVT_BINS; pbase += CVT_BINS) {
+            const uint32_t pp = pbase + lane;
+            const uint64_t slot = slot_pass + pp;
+            const bool valid = pp < total;
+            uint32_t sid = 0, idx = 0xffffffffu;
+            if (valid) { sid = s_rank[pp]; idx = s_choice[sid]; }
+            else {
+                a.owner[slot] = 0xffffu; a.weight[slot] = 0.0f; a.app[slot] = 0.0f;
+#pragma unroll
+                for (int d = 0; d < D; ++d) a.points[uint64_t(d) * a.slots + slot] = a.dom.rmin[d];
+            }
+            const uint32_t prev = __shfl_up_sync(0xffffffffu, idx, 1);
+            const unsigned heads = __ballot_sync(0xffffffffu, valid && (lane == 0 || idx != prev));
+            const int k = __popc(heads);
+            const int mine = __popc(heads & (0xffffffffu >> (31 - lane))) - 1;       // which of the warp's regions this lane's sample uses
+            for (int r0 = 0; r0 < k; r0 += CVT_SLOTS) {
+                __syncwarp();
+                for (int q = 0; q < CVT_SLOTS && r0 + q < k; ++q) {
+                    const int head = __fns(heads, 0, r0 + q + 1);
+                    const uint32_t e_idx = __shfl_sync(0xffffffffu, idx, head);
+                    const uint64_t r = a.list[lo + e_idx];
+                    float* dst = s_slots + q * SLOT;
+                    for (int i = lane; i < SD; i += 32) dst[i] = __ldg(a.aos + r * uint64_t(SD) + i);
+                    if (lane < D) dst[SD + lane] = a.rmin[uint64_t(lane) * a.cap + r];
+                    else if (lane < 2 * D) dst[SD + lane] = a.rmax[uint64_t(lane - D) * a.cap + r];
+                }
+                __syncwarp();
+                if (valid && mine >= r0 && mine < r0 + CVT_SLOTS) {
+                    const float* reg = s_slots + (mine - r0) * SLOT;
+                    const uint32_t j = sid / CVT_BINS, bt = sid % CVT_BINS;
+                    uint32_t bp[2]; bp[0] = o[0] + bt % g.tile[0]; bp[1] = o[1] + bt / g.tile[0];
+                    const uint64_t sbin = uint64_t(bp[0]) + uint64_t(bp[1]) * g.res[0];
+                    float Lg[D][S]; float vol = 1.0f; u32x4 rnd{0, 0, 0, 0};
+#pragma unroll
+                    for (int d = 0; d < D; ++d) {
+                        const float rlo = reg[SD + d], rhi = reg[SD + D + d];
+                        float ba = a.dom.rmin[d], bb = a.dom.rmax[d];
+                        if (d < 2) { ba = fmaf(float(bp[d]), a.dom.drange[d], a.dom.rmin[d]); bb = fmaf(float(bp[d] + 1u), a.dom.drange[d], a.dom.rmin[d]); }
+                        const float ia = fmaxf(ba, rlo), ib = fmaxf(ia, fminf(bb, rhi)), wd = ib - ia;
+                        vol *= wd;
+                        if ((d & 3) == 0) rnd = philox4x32<10>(u32x4{uint32_t(sbin), uint32_t(sbin >> 32), j0 + j, uint32_t(1 + d / 4)}, a.k0, a.k1);
+                        const uint32_t u = (d & 3) == 0 ? rnd.x : (d & 3) == 1 ? rnd.y : (d & 3) == 2 ? rnd.z : rnd.w;
+                        const float xd = fmaf(viltrum::b200::u01(u), wd, ia);
+                        a.points[uint64_t(d) * a.slots + slot] = xd;
+                        lagrange_basis<S>(rhi > rlo ? (xd - rlo) / (rhi - rlo) : 0.0f, Lg[d]);
+                    }
+                    a.weight[slot] = vol;
+                    a.app[slot] = FastLevel<S, D - 1, false>::eval(reg, Lg);
+                    a.owner[slot] = (unsigned short)sid;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// one CTA per tile: the pass's (f, interpolant, weight) come back into sample order through shared memory, one thread per bin folds them
+__global__ void __launch_bounds__(256) cv_tile_accumulate_kernel(TileGeomCv g, uint64_t begin, uint64_t end, uint64_t tile0, uint64_t nbins_total, uint32_t spp, uint32_t J,
+                                                                 const uint32_t* __restrict__ count, const float* __restrict__ approx, uint64_t count_base,
+                                                                 const float* __restrict__ fval, const float* __restrict__ app, const float* __restrict__ weight,
+                                                                 const unsigned short* __restrict__ owner, float* __restrict__ out, int fixed_weight, double fixed_alpha) {
+    extern __shared__ unsigned char cvt_smem[];
+    float* s_f = reinterpret_cast<float*>(cvt_smem); float* s_a = s_f + CVT_ACCPASS * CVT_BINS; float* s_w = s_a + CVT_ACCPASS * CVT_BINS;
+    const uint64_t t = tile0 + blockIdx.x;
+    const uint32_t tid = threadIdx.x;
+    uint32_t pos[2]; pos[0] = uint32_t(t % g.tiles[0]) * g.tile[0] + tid % g.tile[0]; pos[1] = uint32_t(t / g.tiles[0]) * g.tile[1] + tid / g.tile[0];
+    const uint64_t bin = uint64_t(pos[0]) + uint64_t(pos[1]) * g.res[0];
+    const bool live = pos[0] < g.res[0] && pos[1] < g.res[1] && bin >= begin && bin < end;
+    const uint32_t cnt = live ? count[bin - count_base] : 0u;
+    const double factor = double(nbins_total), rr_uniform = double(cnt);
+    CvAccumulator acc;
+    const uint64_t slot_tile = uint64_t(blockIdx.x) * CVT_BINS * spp;
+    for (uint32_t j0 = 0; j0 < spp; j0 += J) {
+        const uint32_t Jp = min(J, spp - j0);
+        const uint64_t slot_pass = slot_tile + uint64_t(j0) * CVT_BINS;
+        for (uint32_t h0 = 0; h0 < Jp; h0 += CVT_ACCPASS) {      // the pass's samples h0 .. h0+31 of every bin at a time (96 KB of shared memory)
+            const uint32_t Jh = min(uint32_t(CVT_ACCPASS), Jp - h0);
+            __syncthreads();
+            for (uint32_t pb = tid; pb < Jp * CVT_BINS; pb += 8 * CVT_BINS) {       // eight slots per thread at a time: the loads of a batch are in flight together
+                uint32_t sid[8]; float vf[8], va[8], vw[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { const uint32_t p = pb + u * CVT_BINS; sid[u] = p < Jp * CVT_BINS ? owner[slot_pass + p] : 0xffffu; }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t p = pb + u * CVT_BINS, j = sid[u] / CVT_BINS;
+                    const bool take = sid[u] != 0xffffu && j >= h0 && j < h0 + Jh;
+                    sid[u] = take ? sid[u] - h0 * CVT_BINS : 0xffffffffu;
+                    if (take) { vf[u] = fval[slot_pass + p]; va[u] = app[slot_pass + p]; vw[u] = weight[slot_pass + p]; }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) if (sid[u] != 0xffffffffu) { s_f[sid[u]] = vf[u]; s_a[sid[u]] = va[u]; s_w[sid[u]] = vw[u]; }
+            }
+            __syncthreads();
+            if (cnt > 0u) for (uint32_t j = 0; j < Jh; ++j) acc.push(s_f[j * CVT_BINS + tid], s_a[j * CVT_BINS + tid], s_w[j * CVT_BINS + tid], factor, rr_uniform, fixed_alpha);
+        }
+    }
+    if (live) out[bin] = acc.result(approx[bin - count_base], fixed_weight, fixed_alpha);
 }
 
 __global__ void transpose_chosen_kernel(uint64_t nb, uint32_t spp, const uint32_t* __restrict__ in /* [bin][spp] */, uint32_t* __restrict__ out /* [spp][bin] */) {
@@ -390,6 +599,65 @@ struct DevBuf {
     int alloc(vb200_ctx* ctx, size_t bytes) { owner = ctx; if (dmalloc(ctx, &p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return fail(ctx, VB200_ERR_NOMEM, "cudaMalloc of %zu bytes failed", bytes); } return VB200_OK; }
     template<class T> T* as() const { return static_cast<T*>(p); }
 };
+
+template<int S, int D> int launch_tile_samples(vb200_ctx* ctx, const CvTileArgs& a, unsigned ntiles) {
+    constexpr int SLOT = (R::ipow(S, D) + 2 * D) | 1;
+    const size_t smem = size_t(a.J) * CVT_BINS * 2 * 2 + size_t(CVT_MAXLIST) * 2 + std::max(size_t(CVT_MAXLIST) * 4, size_t(8) * CVT_SLOTS * SLOT * 4);
+    auto k = cv_tile_samples_kernel<S, D>;
+    VB200_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    k<<<ntiles, 256, smem, ctx->stream>>>(a);
+    ctx->launches++;
+    VB200_CUDA(ctx, cudaGetLastError());
+    return VB200_OK;
+}
+// the slab loop of the tile-major residual pass; VB200_ERR_UNSUPPORTED = no kernel for this (S, D): the caller takes the sample-major pipeline
+int cv_tile_run(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r, const vb200_cv_params* p, const vb200_domain& dom, const BinWalk& w,
+                uint64_t begin, uint64_t end, uint64_t total, uint32_t spp, const float* aos, const uint32_t* count, const float* approx, float* out) {
+    const int D = r->dim;
+    if (!((r->SH == 3 && D >= 2 && D <= 6) || (r->SH == 2 && D >= 2 && D <= 6) || (r->SH == 5 && D >= 2 && D <= 4))) return VB200_ERR_UNSUPPORTED;
+    const uint64_t res0 = dom.res[0], tiles_x = w.tiles[0];
+    const uint64_t row0 = begin / res0, row1 = (end - 1) / res0 + 1;                      // bin rows the shard touches
+    // slabs of whole tile rows, <= ~32 Mi sample slots each
+    uint64_t tile_rows_per_slab = (32ull << 20) / (uint64_t(spp) * CVT_BINS * tiles_x); if (tile_rows_per_slab < 1) tile_rows_per_slab = 1;
+    const uint64_t ty0 = row0 / 16, ty1 = (row1 - 1) / 16 + 1;
+    if (tile_rows_per_slab > ty1 - ty0) tile_rows_per_slab = ty1 - ty0;
+    const uint64_t slots = tile_rows_per_slab * tiles_x * CVT_BINS * spp;
+    if (slots > 0x7fffffffull * 4) return VB200_ERR_UNSUPPORTED;
+    DevBuf points, weight, app, fval, owner;
+    int rc;
+    if ((rc = points.alloc(ctx, slots * D * 4)) || (rc = weight.alloc(ctx, slots * 4)) || (rc = app.alloc(ctx, slots * 4)) || (rc = fval.alloc(ctx, slots * 4)) || (rc = owner.alloc(ctx, slots * 2))) return rc;
+    const uint32_t J = spp < uint32_t(CVT_MAXPASS) ? spp : uint32_t(CVT_MAXPASS);
+    const size_t smem_acc = size_t(CVT_ACCPASS) * CVT_BINS * 4 * 3;
+    VB200_CUDA(ctx, cudaFuncSetAttribute(cv_tile_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_acc)));
+    for (uint64_t ty = ty0; ty < ty1; ty += tile_rows_per_slab) {
+        const uint64_t tye = ty + tile_rows_per_slab < ty1 ? ty + tile_rows_per_slab : ty1;
+        const unsigned ntiles = unsigned((tye - ty) * tiles_x);
+        CvTileArgs a; std::memset(&a, 0, sizeof(a));
+        a.g = make_geom_cv(w, dom); a.dom = dom; a.cap = w.cap; a.begin = begin; a.end = end; a.tile0 = ty * tiles_x; a.nbins_total = total;
+        a.spp = spp; a.J = J; a.k0 = uint32_t(p->seed); a.k1 = uint32_t(p->seed >> 32);
+        a.pstart = w.pstart; a.pend = w.pend; a.offsets = w.tile_offset; a.list = w.tile_list; a.count = count; a.count_base = begin;
+        a.rmin = r->rmin; a.rmax = r->rmax; a.aos = aos;
+        a.points = points.as<float>(); a.weight = weight.as<float>(); a.app = app.as<float>(); a.owner = owner.as<unsigned short>();
+        a.slots = uint64_t(ntiles) * CVT_BINS * spp;
+        rc = VB200_ERR_UNSUPPORTED;
+#define VB200_CVT(SS, DD) if (r->SH == SS && D == DD) rc = launch_tile_samples<SS, DD>(ctx, a, ntiles);
+        VB200_CVT(3, 2) VB200_CVT(3, 3) VB200_CVT(3, 4) VB200_CVT(3, 5) VB200_CVT(3, 6)
+        VB200_CVT(2, 2) VB200_CVT(2, 3) VB200_CVT(2, 4) VB200_CVT(2, 5) VB200_CVT(2, 6)
+        VB200_CVT(5, 2) VB200_CVT(5, 3) VB200_CVT(5, 4)
+#undef VB200_CVT
+        if (rc) return rc;
+        vb200_eval_launch ev; std::memset(&ev, 0, sizeof(ev));
+        ev.n = a.slots; ev.dim = D; ev.points = points.as<float>(); ev.values = fval.as<float>();
+        rc = call_thunk(ctx, f, VB200_K_EVAL_POINTS, &ev); if (rc) return rc;
+        cv_tile_accumulate_kernel<<<ntiles, 256, smem_acc, ctx->stream>>>(a.g, begin, end, a.tile0, total, spp, J, count, approx, begin,
+                                                                            fval.as<float>(), app.as<float>(), weight.as<float>(), owner.as<unsigned short>(), out,
+                                                                            p->weight_strategy == VB200_CV_FIXED_WEIGHT ? 1 : 0, p->alpha);
+        ctx->launches++;
+        VB200_CUDA(ctx, cudaGetLastError());
+    }
+    VB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // the slab buffers die here
+    return VB200_OK;
+}
 
 // bins of a shard are processed in slabs so that the per-sample buffers stay bounded (<= ~32 Mi samples at a time)
 int cv_run(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r, const vb200_cv_params* p, bool replay,
@@ -440,6 +708,14 @@ int cv_run(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r, con
         }
     }
 
+    // tile-major residual pass (cv_tile_samples_kernel): the throughput path of the crespo2021 preset over a 2-D bin grid
+    const char* tile_env = std::getenv("VB200_CV_TILE");       // test knob: 0 = keep the sample-major pipeline
+    const bool tile_path = fast && policy == VB200_RR_UNIFORM && spp > 0 && w.db == 2 && w.tile[0] == 16 && w.tile[1] == 16 && w.max_list <= uint64_t(CVT_MAXLIST) &&
+                           (r->SH == 2 || r->SH == 3 || r->SH == 5) && !(tile_env && tile_env[0] == '0');
+    if (tile_path) {
+        rc = cv_tile_run(ctx, f, r, p, dom, w, begin, end, total, spp, aos.as<float>(), d_count.as<uint32_t>(), d_approx.as<float>(), st.dev_base);
+        if (rc != VB200_ERR_UNSUPPORTED) { if (rc) return rc; goto residual_done; }
+    }
     if (spp > 0) {
         uint64_t slab = (32ull << 20) / spp; if (slab < 1) slab = 1; if (slab > nshard) slab = nshard;
         const uint64_t NS = slab * spp;
@@ -519,6 +795,7 @@ int cv_run(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r, con
         // no residual samples: bins = approximation (weight-strategy.h:95, size < 2)
         VB200_CUDA(ctx, cudaMemcpyAsync(st.dev_base + begin, d_approx.p, nshard * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
     }
+residual_done:
     auto copy_out = [&] (void* dst, const void* src, size_t bytes) -> int {
         VB200_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, bins_mem == VB200_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, ctx->stream));
         return VB200_OK;

@@ -1024,7 +1024,8 @@ template<class T> int walk_build_t(vb200_ctx* ctx, const vb200_regions* r, const
     std::vector<uint64_t> h(w->ntiles + 1);
     VB200_TRY(cudaMemcpyAsync(h.data(), counts, w->ntiles * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
     VB200_TRY(cudaStreamSynchronize(ctx->stream));
-    uint64_t run = 0; for (uint64_t t = 0; t < w->ntiles; ++t) { const uint64_t c = h[t]; h[t] = run; run += c; } h[w->ntiles] = run;
+    uint64_t run = 0; w->max_list = 0;
+    for (uint64_t t = 0; t < w->ntiles; ++t) { const uint64_t c = h[t]; if (c > w->max_list) w->max_list = c; h[t] = run; run += c; } h[w->ntiles] = run;
     w->pairs = run;
     VB200_TRY(cudaMemcpyAsync(w->tile_offset, h.data(), (w->ntiles + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
     VB200_TRY(dmalloc(ctx, &w->tile_list, (run + 1) * sizeof(uint32_t)));

@@ -65,6 +65,7 @@ template<class T> struct BinWalkT {
     uint64_t* tile_offset = nullptr;       // [ntiles+1]
     uint32_t* tile_list = nullptr;         // region ids, ascending inside each tile
     uint64_t pairs = 0;                    // total (tile, region) entries
+    uint64_t max_list = 0;                 // longest tile list
     T* scratch[2] = {nullptr, nullptr};
 };
 using BinWalk = BinWalkT<float>;
