@@ -263,7 +263,17 @@ typedef enum vb200_rule {
  * (q-1)*n+1 samples per dimension.  Fixed-rule integration only (vb200_regions_generate_single + vb200_regions_integrate_bins). */
 #define VB200_RULE_STEPS(q, n) (0x1000000 | ((q) << 16) | ((n) & 0xffff))
 #define VB200_RULE_IS_STEPS(rule) (((rule) & 0x1000000) != 0)
-typedef enum vb200_heuristic { VB200_HEURISTIC_DEFAULT = 0, VB200_HEURISTIC_SIZE = 1 } vb200_heuristic;   /* error-heuristic.h:10-46 */
+typedef enum vb200_heuristic { VB200_HEURISTIC_DEFAULT = 0, VB200_HEURISTIC_SIZE = 1,                     /* error-heuristic.h:10-46 */
+                               VB200_HEURISTIC_MIXED = 2 } vb200_heuristic;                                 /* error_heuristic_mixed, error-heuristic.h:49-98 */
+/* error_heuristic_mixed(metric_bins, metric_rest, dimension, bins_weight, size_weight, size_threshold_bins, size_threshold_rest, error_increase_factor):
+ * vb200_adaptive_params.metric is the bins metric and .size_weight the size weight; the rest comes from this block (reference defaults:
+ * dimension 2, bins_weight 1.0, size_weight 1e-3, thresholds 1/1024 and 1/16, increase factor 1e4).  Its keys are doubles upstream; the exact
+ * mode (batch = 1) keeps them as doubles, the batched mode orders by the key rounded to float. */
+typedef struct vb200_mixed_heuristic {
+    int32_t metric_rest;            /* vb200_metric of the non-binned dimensions */
+    int32_t dimension;              /* first dimension that takes the rest metric */
+    double  bins_weight, size_threshold_bins, size_threshold_rest, error_increase_factor;
+} vb200_mixed_heuristic;
 typedef enum vb200_metric { VB200_METRIC_ABSOLUTE = 0, VB200_METRIC_RELATIVE = 1 } vb200_metric;         /* error-metric.h:10-41 */
 
 /* Leaf table produced by a generator ("region tree" of north_star = this flat table).
@@ -283,7 +293,17 @@ typedef struct vb200_adaptive_params {
                                    >1 = batched with at most this many splits per round */
     double   size_weight;       /* error_heuristic_size weight (reference default 1e-5) */
     uint64_t iterations;        /* number of splits: the table ends with iterations+1 regions */
+    vb200_mixed_heuristic mixed;/* VB200_HEURISTIC_MIXED only */
 } vb200_adaptive_params;
+/* Range<double,DIM>: the same generator over a VB200_INTEGRAND_F64 integrand — every sample, error and heap key a double, as upstream for
+ * Float = double.  Exact greedy mode only (batch must be 1); the table is a double table (vb200_regions_*_f64). */
+typedef struct vb200_adaptive_params_f64 {
+    vb200_domain_f64 domain;
+    int32_t  rule, heuristic, metric, batch;
+    double   size_weight;
+    uint64_t iterations;
+    vb200_mixed_heuristic mixed;
+} vb200_adaptive_params_f64;
 
 int vb200_regions_generate_adaptive(vb200_ctx* ctx, const vb200_integrand* f, const vb200_adaptive_params* p, vb200_regions** out);
 /* integrator_adaptive_tolerance(nested(h,l), heuristic, tolerance) — reference src/nested/integrator-adaptive-tolerance.h:15-39: regions
@@ -333,6 +353,7 @@ int vb200_regions_broadcast(vb200_ctx* ctx, vb200_regions** r, int root);
  * returning double), double bins, every rule/fold/accumulation in double exactly as the reference does for Float = double.
  * vb200_regions_count/dim/samples/free work on both kinds of table. */
 int vb200_regions_generate_single_f64(vb200_ctx* ctx, const vb200_integrand* f, const vb200_domain_f64* domain, int rule, vb200_regions** out);
+int vb200_regions_generate_adaptive_f64(vb200_ctx* ctx, const vb200_integrand* f, const vb200_adaptive_params_f64* p, vb200_regions** out);
 int vb200_regions_upload_f64(vb200_ctx* ctx, int dim, int rule, uint64_t count,
                              const double* rmin, const double* rmax, const double* err, const uint32_t* errdim, const double* data,
                              vb200_regions** out);
@@ -457,14 +478,21 @@ typedef struct vb200_greedy_launch {
     double   size_weight;
     uint64_t iterations;
     uint64_t capacity;                /* region slots: 2*iterations+1 (a split retires the parent slot and opens two) */
-    /* working set of the persistent kernel, region-major so that one region is a few contiguous lines: */
-    float*   range;                   /* device [capacity][2*dim]: min[0..dim), max[0..dim) */
-    float*   data;                    /* device [capacity][S^dim], the reference's multiarray order (dim 0 fastest) */
-    float*   err;                     /* device [capacity] heuristic value */
-    unsigned long long* heap;         /* device [iterations+2]: binary heap entries (id | dim<<28) << 32 | float bits of the key;
-                                         array order = the reference's output order (regions-generator-adaptive-heap.h:44) */
+    /* working set of the persistent kernel, region-major so that one region is a few contiguous lines; float or double per f64: */
+    void*    range;                   /* device [capacity][2*dim]: min[0..dim), max[0..dim) */
+    void*    data;                    /* device [capacity][S^dim], the reference's multiarray order (dim 0 fastest) */
+    void*    err;                     /* device [capacity] heuristic value in the table's scalar type (float-key runs) */
+    void*    heap;                    /* device [iterations+2]: binary heap entries — 8 bytes (id | dim<<28) << 32 | float bits of the key, or, when the
+                                         keys are doubles (f64 tables, VB200_HEURISTIC_MIXED), 16 bytes {double bits, id | dim<<28}; array order = the
+                                         reference's output order (regions-generator-adaptive-heap.h:44) */
     uint64_t* heap_size;              /* device scalar: entries in the heap when the kernel ends (iterations+1) */
     float    range_min[VB200_MAX_DIM], range_max[VB200_MAX_DIM];
+    /* ABI 3: */
+    int32_t  f64;                     /* 1: double table (range_min64/range_max64, functor over std::array<double,dim>) */
+    int32_t  metric_rest, mixed_dimension, reserved;
+    double   mixed_bins_weight, mixed_threshold_bins, mixed_threshold_rest, mixed_error_increase;
+    double   range_min64[VB200_MAX_DIM], range_max64[VB200_MAX_DIM];
+    void*    key64;                   /* device [capacity] double heuristic values (double-key runs), else NULL */
 } vb200_greedy_launch;
 
 typedef struct vb200_scatter_launch {

@@ -15,6 +15,7 @@
 // bit-identical to the reference's (tests/test_gpu_regions.py).
 #pragma once
 #include <array>
+#include <type_traits>
 #include <cuda_runtime.h>
 #include "../../viltrum_b200.h"
 #include "rules.cuh"
@@ -24,36 +25,53 @@ namespace viltrum { namespace b200 { namespace device {
 constexpr int GREEDY_THREADS = 256;
 constexpr unsigned GREEDY_ID_MASK = 0x0fffffffu;
 
-struct GreedyHeap {
-    unsigned long long* g;      // global entries
-    unsigned long long* s;      // shared-memory cache of entries [0, cached)
+// Heap entries.  Float keys (error_heuristic_default / _size over Range<float>): one 64-bit word, (id | dim << 28) << 32 | key bits.
+// Double keys (Range<double>, and error_heuristic_mixed, whose key is a double upstream, error-heuristic.h:73-96): 16 bytes.
+struct GreedyEntry32 {
+    typedef unsigned long long type; typedef float key_type;
+    __device__ __forceinline__ static type make(unsigned id_dim, float k) { return (static_cast<unsigned long long>(id_dim) << 32) | __float_as_uint(k); }
+    __device__ __forceinline__ static float key(type e) { return __uint_as_float(unsigned(e)); }
+    __device__ __forceinline__ static unsigned id_dim(type e) { return unsigned(e >> 32); }
+};
+struct GreedyEntry64 {
+    typedef ulonglong2 type; typedef double key_type;
+    __device__ __forceinline__ static type make(unsigned id_dim, double k) { return make_ulonglong2(static_cast<unsigned long long>(__double_as_longlong(k)), id_dim); }
+    __device__ __forceinline__ static double key(type e) { return __longlong_as_double(static_cast<long long>(e.x)); }
+    __device__ __forceinline__ static unsigned id_dim(type e) { return unsigned(e.y); }
+};
+
+template<class E = GreedyEntry32>
+struct GreedyHeapT {
+    typedef typename E::type entry; typedef typename E::key_type key_type;
+    entry* g;      // global entries
+    entry* s;      // shared-memory cache of entries [0, cached)
     long long cached;
     long long n;
-    __device__ __forceinline__ unsigned long long get(long long i) const { return i < cached ? s[i] : g[i]; }
-    __device__ __forceinline__ void set(long long i, unsigned long long v) { if (i < cached) s[i] = v; else g[i] = v; }
-    __device__ __forceinline__ static float key(unsigned long long e) { return __uint_as_float(unsigned(e)); }
+    __device__ __forceinline__ entry get(long long i) const { return i < cached ? s[i] : g[i]; }
+    __device__ __forceinline__ void set(long long i, entry v) { if (i < cached) s[i] = v; else g[i] = v; }
+    __device__ __forceinline__ static key_type key(entry e) { return E::key(e); }
 
     // libstdc++ __push_heap (stl_heap.h:135-148), comparator a.err < b.err
-    __device__ void sift_up(long long hole, unsigned long long value) {
-        const float vk = key(value);
+    __device__ void sift_up(long long hole, entry value) {
+        const key_type vk = key(value);
         long long parent = (hole - 1) / 2;
         while (hole > 0) {
-            const unsigned long long pe = get(parent);
+            const entry pe = get(parent);
             if (!(key(pe) < vk)) break;
             set(hole, pe); hole = parent; parent = (hole - 1) / 2;
         }
         set(hole, value);
     }
-    __device__ void push(unsigned long long value) { ++n; sift_up(n - 1, value); }
+    __device__ void push(entry value) { ++n; sift_up(n - 1, value); }
     // libstdc++ pop_heap -> __pop_heap -> __adjust_heap (stl_heap.h:224-267) followed by the caller's pop_back
     __device__ void pop() {
         if (n > 1) {
-            const unsigned long long value = get(n - 1);
+            const entry value = get(n - 1);
             const long long len = n - 1;
             long long hole = 0, child = 0;
             while (child < (len - 1) / 2) {
                 child = 2 * (child + 1);
-                unsigned long long ce = get(child); const unsigned long long le = get(child - 1);
+                entry ce = get(child); const entry le = get(child - 1);
                 if (key(ce) < key(le)) { --child; ce = le; }
                 set(hole, ce); hole = child;
             }
@@ -63,6 +81,7 @@ struct GreedyHeap {
         --n;
     }
 };
+typedef GreedyHeapT<GreedyEntry32> GreedyHeap;
 
 template<int SH, int SL, int DIM>
 struct GreedyShape {
@@ -72,119 +91,159 @@ struct GreedyShape {
     static constexpr int WIDE = (2 * SH - 1) * L;     // samples of the two children side by side
 };
 
-// normalised grid coordinate -> point, with the PARENT's range (region.h:40-46): x = float(p*(max-min) + min)
-__device__ __forceinline__ float grid_coord(double p, float lo, float hi) {
-    return rules::d2f(rules::da(rules::dm(p, double(rules::fs(hi, lo))), double(lo)));
+// normalised grid coordinate -> point, with the PARENT's range (region.h:40-46): x = Float(p*(max-min) + min)
+template<class T>
+__device__ __forceinline__ T grid_coord(double p, T lo, T hi) {
+    return rules::from_double<T>(rules::da(rules::dm(p, double(rules::sub(hi, lo))), double(lo)));
 }
 
 // error of one region along `dim` (region.h:387-393): per line metric(high,low), folded over the other dims with the high
-// rule, times the volume.  One warp; `work` holds L floats.
-template<int SH, int SL, int DIM>
-__device__ float region_error_warp(const float* data, float volume, int dim, bool relative, float* work, unsigned lane) {
+// rule, times the volume.  One warp; `work` holds L values.
+template<int SH, int SL, int DIM, class T = float>
+__device__ T region_error_warp(const T* data, T volume, int dim, bool relative, T* work, unsigned lane) {
     using Sh = GreedyShape<SH, SL, DIM>;
     int inner = 1; for (int i = 0; i < dim; ++i) inner *= SH;
     for (int o = lane; o < Sh::L; o += 32) {
         const int lo = o % inner, hi = o / inner;
-        float line[SH];
+        T line[SH];
 #pragma unroll
         for (int e = 0; e < SH; ++e) line[e] = data[lo + e * inner + hi * inner * SH];
-        work[o] = rules::line_error<SH, SL>(relative, line);
+        work[o] = rules::line_error<SH, SL, T>(relative, line);
     }
     __syncwarp();
     // fold_all(high rule): fold dimension 0 of the remaining array until one value is left (fold.h:87-108)
     for (int n = Sh::L / SH; n >= 1; n /= SH) {
-        float v[(Sh::L / SH + 31) / 32 > 0 ? (Sh::L / SH + 31) / 32 : 1];
+        T v[(Sh::L / SH + 31) / 32 > 0 ? (Sh::L / SH + 31) / 32 : 1];
         int c = 0;
-        for (int o = lane; o < n; o += 32, ++c) v[c] = rules::apply<SH>(work + o * SH);
+        for (int o = lane; o < n; o += 32, ++c) v[c] = rules::apply<SH, T>(work + o * SH);
         __syncwarp();
         c = 0;
         for (int o = lane; o < n; o += 32, ++c) work[o] = v[c];
         __syncwarp();
         if (n == 1) break;
     }
-    return rules::fm(volume, work[0]);
+    return rules::mul(volume, work[0]);
 }
 
-// error_heuristic_size (error-heuristic.h:29-46) / error_heuristic_default -> max_error_dimension (region.h:401-411)
-template<int DIM>
-__device__ void heuristic_pick(const float* E, const float* rng /* min[DIM], max[DIM] */, int heuristic, double size_weight, float* out_err, unsigned* out_dim) {
+// error_heuristic_size (error-heuristic.h:29-46) / error_heuristic_default -> max_error_dimension (region.h:401-411); key type = Float
+template<int DIM, class T = float>
+__device__ void heuristic_pick(const T* E, const T* rng /* min[DIM], max[DIM] */, int heuristic, double size_weight, T* out_err, unsigned* out_dim) {
     const double min_size = 1.e-37;
     if (heuristic == VB200_HEURISTIC_SIZE) {
-        float max_err = E[0];
-        const float w0 = rules::fs(rng[DIM], rng[0]);
-        if (double(w0) < min_size || isnan(w0)) max_err = 0.0f;
-        else max_err = rules::d2f(rules::da(double(max_err), rules::dm(size_weight, double(fabsf(w0)))));
+        T max_err = E[0];
+        const T w0 = rules::sub(rng[DIM], rng[0]);
+        if (double(w0) < min_size || isnan(w0)) max_err = T(0);
+        else max_err = rules::from_double<T>(rules::da(double(max_err), rules::dm(size_weight, double(rules::absv(w0)))));
         unsigned max_dim = 0;
         for (int d = 1; d < DIM; ++d) {
-            const float w = rules::fs(rng[DIM + d], rng[d]);
-            float err = rules::d2f(rules::da(double(E[d]), rules::dm(size_weight, double(fabsf(w)))));
-            if (double(w) < min_size) err = 0.0f;
+            const T w = rules::sub(rng[DIM + d], rng[d]);
+            T err = rules::from_double<T>(rules::da(double(E[d]), rules::dm(size_weight, double(rules::absv(w)))));
+            if (double(w) < min_size) err = T(0);
             if (err >= max_err) { max_err = err; max_dim = unsigned(d); }
         }
         *out_err = max_err; *out_dim = max_dim;
     } else {
-        float max_err = 0.0f; unsigned max_dim = 0;
+        T max_err = T(0); unsigned max_dim = 0;
         for (int d = 0; d < DIM; ++d) if (E[d] > max_err) { max_err = E[d]; max_dim = unsigned(d); }
         *out_err = max_err; *out_dim = max_dim;
     }
 }
+// error_heuristic_mixed (error-heuristic.h:49-98): the key is a DOUBLE upstream (Float * double + double + double * Float).  E[d] holds the error
+// along d under the metric that dimension takes (bins metric for d < dimension and for d = 0, rest metric beyond).
+struct MixedParams { int dimension; double bins_weight, size_weight, size_threshold_bins, size_threshold_rest, error_increase_factor; };
+template<int DIM, class T>
+__device__ void heuristic_pick_mixed(const T* E, const T* rng, const MixedParams& m, double* out_err, unsigned* out_dim) {
+    double size_bins = 1.0, size_rest = 1.0;
+    const int nb = m.dimension < DIM ? m.dimension : DIM;
+    for (int d = 0; d < nb; ++d) size_bins = rules::dm(size_bins, double(rules::absv(rules::sub(rng[DIM + d], rng[d]))));
+    for (int d = m.dimension; d < DIM; ++d) size_rest = rules::dm(size_rest, double(rules::absv(rules::sub(rng[DIM + d], rng[d]))));
+    double add_bins = m.error_increase_factor, add_rest = m.error_increase_factor;
+    if (size_bins < m.size_threshold_bins) add_bins = 0.0;
+    if (size_rest < m.size_threshold_rest) add_rest = 0.0;
+    if (isnan(size_bins)) add_bins = 0.0;
+    if (isnan(size_rest)) add_rest = 0.0;
+    double max_err = rules::da(rules::da(rules::dm(double(E[0]), m.bins_weight), add_bins), rules::dm(m.size_weight, double(rules::sub(rng[DIM], rng[0]))));
+    unsigned max_dim = 0;
+    for (int d = 1; d < DIM; ++d) {
+        const double sz = rules::dm(m.size_weight, double(rules::sub(rng[DIM + d], rng[d])));
+        const double err = d < m.dimension ? rules::da(rules::da(rules::dm(double(E[d]), m.bins_weight), add_bins), sz)
+                                           : rules::da(rules::da(double(E[d]), add_rest), sz);
+        if (err >= max_err) { max_err = err; max_dim = unsigned(d); }
+    }
+    *out_err = max_err; *out_dim = max_dim;
+}
 
-template<class F, int DIM, int SH, int SL, bool EXACT>
+// T = float or double (the Float of the range); MIXED selects error_heuristic_mixed (double keys).  Keys are doubles whenever T is double or MIXED.
+template<class F, int DIM, int SH, int SL, bool EXACT, class T = float, bool MIXED = false>
 __global__ void __launch_bounds__(GREEDY_THREADS, 1)
 greedy_kernel(const F f, const vb200_greedy_launch a, const int heap_cached) {
     using Sh = GreedyShape<SH, SL, DIM>;
+    constexpr bool KEY64 = MIXED || sizeof(T) == 8;
+    using E = typename std::conditional<KEY64, GreedyEntry64, GreedyEntry32>::type;
+    using Heap = GreedyHeapT<E>;
+    using Key = typename E::key_type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned long long* s_heap = reinterpret_cast<unsigned long long*>(smem_raw);
-    float* s_parent = reinterpret_cast<float*>(s_heap + heap_cached);       // [SD]
-    float* s_child = s_parent + Sh::SD;                                     // [2][SD]
-    float* s_work = s_child + 2 * Sh::SD;                                   // [2*DIM][L]
-    float* s_prange = s_work + 2 * DIM * Sh::L;                             // [2*DIM]
-    float* s_crange = s_prange + 2 * DIM;                                   // [2][2*DIM]
-    float* s_E = s_crange + 4 * DIM;                                        // [2][DIM]
-    float* s_vol = s_E + 2 * DIM;                                           // [2]
+    typename E::type* s_heap = reinterpret_cast<typename E::type*>(smem_raw);
+    T* s_parent = reinterpret_cast<T*>(s_heap + heap_cached);           // [SD]
+    T* s_child = s_parent + Sh::SD;                                     // [2][SD]
+    T* s_work = s_child + 2 * Sh::SD;                                   // [2*DIM][L]
+    T* s_prange = s_work + 2 * DIM * Sh::L;                             // [2*DIM]
+    T* s_crange = s_prange + 2 * DIM;                                   // [2][2*DIM]
+    T* s_E = s_crange + 4 * DIM;                                        // [2][DIM]
+    T* s_vol = s_E + 2 * DIM;                                           // [2]
     __shared__ unsigned s_top_id, s_top_dim;
-    __shared__ GreedyHeap heap;
+    __shared__ Heap heap;
 
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, nwarps = GREEDY_THREADS / 32;
-    const bool relative = a.metric == VB200_METRIC_RELATIVE;
+    const bool relative = a.metric == VB200_METRIC_RELATIVE, relative_rest = a.metric_rest == VB200_METRIC_RELATIVE;
+    const MixedParams mixed{a.mixed_dimension, a.mixed_bins_weight, a.size_weight, a.mixed_threshold_bins, a.mixed_threshold_rest, a.mixed_error_increase};
+    // metric of dimension d: error_heuristic_mixed uses the bins metric for d = 0 and d < dimension, the rest metric beyond (error-heuristic.h:81-88)
+    auto rel_of = [&] (int d) -> bool { return MIXED ? ((d == 0 || d < mixed.dimension) ? relative : relative_rest) : relative; };
+    auto pick = [&] (const T* Ev, const T* rng, Key* key, unsigned* dim) {
+        if constexpr (MIXED) heuristic_pick_mixed<DIM, T>(Ev, rng, mixed, key, dim);
+        else { T e; heuristic_pick<DIM, T>(Ev, rng, a.heuristic, a.size_weight, &e, dim); *key = Key(e); }
+    };
+    T* g_range = static_cast<T*>(a.range); T* g_data = static_cast<T*>(a.data); T* g_err = static_cast<T*>(a.err);
+    const T* rmin_ = reinterpret_cast<const T*>(sizeof(T) == 8 ? static_cast<const void*>(a.range_min64) : static_cast<const void*>(a.range_min));
+    const T* rmax_ = reinterpret_cast<const T*>(sizeof(T) == 8 ? static_cast<const void*>(a.range_max64) : static_cast<const void*>(a.range_max));
 
     // ---- initial region over the whole range (regions-generator-adaptive-heap.h:27-31) ----
-    if (tid == 0) { heap.g = a.heap; heap.s = s_heap; heap.cached = heap_cached; heap.n = 0; }
-    if (tid < 2 * DIM) s_crange[tid] = tid < DIM ? a.range_min[tid] : a.range_max[tid - DIM];
+    if (tid == 0) { heap.g = static_cast<typename E::type*>(a.heap); heap.s = s_heap; heap.cached = heap_cached; heap.n = 0; }
+    if (tid < 2 * DIM) s_crange[tid] = tid < DIM ? rmin_[tid] : rmax_[tid - DIM];
     __syncthreads();
     for (int k = tid; k < Sh::SD; k += GREEDY_THREADS) {
-        std::array<float, DIM> x; int t = k;
+        std::array<T, DIM> x; int t = k;
 #pragma unroll
-        for (int d = 0; d < DIM; ++d) { x[d] = grid_coord(rules::dd(double(t % SH), double(SH - 1)), s_crange[d], s_crange[DIM + d]); t /= SH; }
+        for (int d = 0; d < DIM; ++d) { x[d] = grid_coord<T>(rules::dd(double(t % SH), double(SH - 1)), s_crange[d], s_crange[DIM + d]); t /= SH; }
         s_child[k] = f(x);
     }
-    if (tid == 0) { float v = 1.0f; for (int d = 0; d < DIM; ++d) v = rules::fm(v, rules::fs(s_crange[DIM + d], s_crange[d])); s_vol[0] = v; }
+    if (tid == 0) { T v = T(1); for (int d = 0; d < DIM; ++d) v = rules::mul(v, rules::sub(s_crange[DIM + d], s_crange[d])); s_vol[0] = v; }
     __syncthreads();
     for (int d = warp; d < DIM; d += nwarps) {
-        const float e = region_error_warp<SH, SL, DIM>(s_child, s_vol[0], d, relative, s_work + d * Sh::L, lane);
+        const T e = region_error_warp<SH, SL, DIM, T>(s_child, s_vol[0], d, rel_of(d), s_work + d * Sh::L, lane);
         if (lane == 0) s_E[d] = e;
     }
     __syncthreads();
     if (tid == 0) {
-        float err; unsigned dim; heuristic_pick<DIM>(s_E, s_crange, a.heuristic, a.size_weight, &err, &dim);
-        a.err[0] = err;
-        heap.push((static_cast<unsigned long long>(0u | (dim << 28)) << 32) | __float_as_uint(err));
+        Key err; unsigned dim; pick(s_E, s_crange, &err, &dim);
+        if constexpr (KEY64) static_cast<double*>(a.key64)[0] = double(err); else g_err[0] = T(err);
+        heap.push(E::make(0u | (dim << 28), err));
     }
-    for (int k = tid; k < Sh::SD; k += GREEDY_THREADS) a.data[k] = s_child[k];
-    if (tid < 2 * DIM) a.range[tid] = s_crange[tid];
+    for (int k = tid; k < Sh::SD; k += GREEDY_THREADS) g_data[k] = s_child[k];
+    if (tid < 2 * DIM) g_range[tid] = s_crange[tid];
     __syncthreads();
 
     // ---- iterations ----
     unsigned long long next_slot = 1;
     for (unsigned long long it = 0; it < a.iterations; ++it) {
-        if (tid == 0) { const unsigned long long e = heap.get(0); s_top_id = unsigned(e >> 32) & GREEDY_ID_MASK; s_top_dim = unsigned(e >> 60); }
+        if (tid == 0) { const unsigned idd = E::id_dim(heap.get(0)); s_top_id = idd & GREEDY_ID_MASK; s_top_dim = idd >> 28; }
         __syncthreads();
         const unsigned top = s_top_id; const int dim = int(s_top_dim);
         // warp 0 pops while the others fetch the parent (the pop does not depend on the split: heap.front() was copied first, :33-35)
         if (warp == 0) { if (lane == 0) heap.pop(); }
         else {
-            for (int k = tid - 32; k < Sh::SD; k += GREEDY_THREADS - 32) s_parent[k] = a.data[static_cast<unsigned long long>(top) * Sh::SD + k];
-            if (tid - 32 < 2 * DIM) s_prange[tid - 32] = a.range[static_cast<unsigned long long>(top) * (2 * DIM) + (tid - 32)];
+            for (int k = tid - 32; k < Sh::SD; k += GREEDY_THREADS - 32) s_parent[k] = g_data[static_cast<unsigned long long>(top) * Sh::SD + k];
+            if (tid - 32 < 2 * DIM) s_prange[tid - 32] = g_range[static_cast<unsigned long long>(top) * (2 * DIM) + (tid - 32)];
         }
         __syncthreads();
         // split along `dim` (split.h:13-49): the (2S-1)-wide array; even positions are the parent's samples, odd ones new evaluations
@@ -192,16 +251,16 @@ greedy_kernel(const F f, const vb200_greedy_launch a, const int heap_cached) {
         for (int item = tid; item < Sh::WIDE; item += GREEDY_THREADS) {
             const int i = item / Sh::L, o = item % Sh::L;            // position along `dim` (0..2S-2), index over the other dims
             const int lo = o % inner, hi = o / inner;
-            float v;
+            T v;
             if ((i & 1) == 0) v = s_parent[lo + (i / 2) * inner + hi * inner * SH];
             else {
-                std::array<float, DIM> x; int t = o;
+                std::array<T, DIM> x; int t = o;
 #pragma unroll
                 for (int d = 0; d < DIM; ++d) {
                     double p;
                     if (d == dim) p = rules::dd(double(i), double(2 * (SH - 1)));
                     else { p = rules::dd(double(t % SH), double(SH - 1)); t /= SH; }
-                    x[d] = grid_coord(p, s_prange[d], s_prange[DIM + d]);
+                    x[d] = grid_coord<T>(p, s_prange[d], s_prange[DIM + d]);
                 }
                 v = f(x);
             }
@@ -210,30 +269,30 @@ greedy_kernel(const F f, const vb200_greedy_launch a, const int heap_cached) {
         }
         // child ranges (region.h:349-357): d = (max-min)/Float(2); child 0 = [min, min+d*1], child 1 = [min+d*1, max]
         if (tid < 2) {
-            const float pmin = s_prange[dim], pmax = s_prange[DIM + dim];
-            const float mid = rules::fa(pmin, rules::fm(rules::fd(rules::fs(pmax, pmin), 2.0f), 1.0f));
-            float* cr = s_crange + tid * 2 * DIM;
+            const T pmin = s_prange[dim], pmax = s_prange[DIM + dim];
+            const T mid = rules::add(pmin, rules::mul(rules::quo(rules::sub(pmax, pmin), T(2)), T(1)));
+            T* cr = s_crange + tid * 2 * DIM;
             for (int d = 0; d < 2 * DIM; ++d) cr[d] = s_prange[d];
             if (tid == 0) cr[DIM + dim] = mid; else cr[dim] = mid;
-            float v = 1.0f; for (int d = 0; d < DIM; ++d) v = rules::fm(v, rules::fs(cr[DIM + d], cr[d]));
+            T v = T(1); for (int d = 0; d < DIM; ++d) v = rules::mul(v, rules::sub(cr[DIM + d], cr[d]));
             s_vol[tid] = v;
         }
         __syncthreads();
         // nested-rule error of both children along every dimension: one warp per (child, dimension)
         for (int job = warp; job < 2 * DIM; job += nwarps) {
             const int c = job / DIM, d = job % DIM;
-            const float e = region_error_warp<SH, SL, DIM>(s_child + c * Sh::SD, s_vol[c], d, relative, s_work + job * Sh::L, lane);
+            const T e = region_error_warp<SH, SL, DIM, T>(s_child + c * Sh::SD, s_vol[c], d, rel_of(d), s_work + job * Sh::L, lane);
             if (lane == 0) s_E[c * DIM + d] = e;
         }
         __syncthreads();
         // store the children (slots next_slot, next_slot+1) and push them in ascending coordinate order (:36-40)
-        for (int k = tid; k < 2 * Sh::SD; k += GREEDY_THREADS) a.data[next_slot * Sh::SD + k] = s_child[k];
-        if (tid < 4 * DIM) a.range[next_slot * (2 * DIM) + tid] = s_crange[tid];
+        for (int k = tid; k < 2 * Sh::SD; k += GREEDY_THREADS) g_data[next_slot * Sh::SD + k] = s_child[k];
+        if (tid < 4 * DIM) g_range[next_slot * (2 * DIM) + tid] = s_crange[tid];
         if (tid == 0) {
             for (int c = 0; c < 2; ++c) {
-                float err; unsigned d; heuristic_pick<DIM>(s_E + c * DIM, s_crange + c * 2 * DIM, a.heuristic, a.size_weight, &err, &d);
-                a.err[next_slot + c] = err;
-                heap.push((static_cast<unsigned long long>(unsigned(next_slot + c) | (d << 28)) << 32) | __float_as_uint(err));
+                Key err; unsigned d; pick(s_E + c * DIM, s_crange + c * 2 * DIM, &err, &d);
+                if constexpr (KEY64) static_cast<double*>(a.key64)[next_slot + c] = double(err); else g_err[next_slot + c] = T(err);
+                heap.push(E::make(unsigned(next_slot + c) | (d << 28), err));
             }
         }
         next_slot += 2;
@@ -241,34 +300,44 @@ greedy_kernel(const F f, const vb200_greedy_launch a, const int heap_cached) {
     }
     // flush the cached top of the heap
     const long long n = heap.n;
-    for (long long i = tid; i < n && i < heap_cached; i += GREEDY_THREADS) a.heap[i] = s_heap[i];
+    for (long long i = tid; i < n && i < heap_cached; i += GREEDY_THREADS) static_cast<typename E::type*>(a.heap)[i] = s_heap[i];
     if (tid == 0) *a.heap_size = static_cast<uint64_t>(n);
 }
 
-template<class F, int DIM, int SH, int SL, bool EXACT>
+template<class F, int DIM, int SH, int SL, bool EXACT, class T, bool MIXED>
 inline int launch_greedy_rule(const F& f, const vb200_greedy_launch& a, cudaStream_t st) {
     using Sh = GreedyShape<SH, SL, DIM>;
+    constexpr bool KEY64 = MIXED || sizeof(T) == 8;
+    constexpr size_t ENTRY = KEY64 ? 16 : 8;
     if (a.capacity > GREEDY_ID_MASK) return int(cudaErrorInvalidValue);
-    auto k = greedy_kernel<F, DIM, SH, SL, EXACT>;
-    const size_t fixed = sizeof(float) * size_t(3 * Sh::SD + 2 * DIM * Sh::L + 2 * DIM + 4 * DIM + 2 * DIM + 2) + 64;
+    auto k = greedy_kernel<F, DIM, SH, SL, EXACT, T, MIXED>;
+    const size_t fixed = sizeof(T) * size_t(3 * Sh::SD + 2 * DIM * Sh::L + 2 * DIM + 4 * DIM + 2 * DIM + 2) + 64;
     int dev = 0, max_smem = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (size_t(max_smem) < fixed + 1024) return int(cudaErrorInvalidConfiguration);     // region too large for the one-CTA working set
-    // cache as many complete top levels of the heap as fit: 2^k - 1 entries of 8 bytes
+    // cache as many complete top levels of the heap as fit: 2^k - 1 entries
     size_t room = size_t(max_smem) - fixed - 1024;
-    int cached = 1; while (size_t(2 * cached + 1) * 8 <= room && cached < (1 << 15)) cached = 2 * cached + 1;
-    const size_t smem = size_t(cached) * 8 + fixed;
+    int cached = 1; while (size_t(2 * cached + 1) * ENTRY <= room && cached < (1 << 15)) cached = 2 * cached + 1;
+    const size_t smem = size_t(cached) * ENTRY + fixed;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return int(e);
     k<<<1, GREEDY_THREADS, smem, st>>>(f, a, cached);
     return int(cudaGetLastError());
 }
 
-template<class F, int DIM, bool EXACT>
+template<class F, int DIM, bool EXACT, class T = float>
 inline int launch_greedy(const F& f, const vb200_greedy_launch& a, cudaStream_t st) {
-    if constexpr (DIM <= 6) { if (a.rule == VB200_RULE_SIMPSON_TRAPEZOIDAL) return launch_greedy_rule<F, DIM, 3, 2, EXACT>(f, a, st); }
-    if constexpr (DIM <= 5) { if (a.rule == VB200_RULE_BOOLE_SIMPSON) return launch_greedy_rule<F, DIM, 5, 3, EXACT>(f, a, st); }
+    const bool mixed = a.heuristic == VB200_HEURISTIC_MIXED;
+    if constexpr (DIM <= 6) {
+        if (a.rule == VB200_RULE_SIMPSON_TRAPEZOIDAL) return mixed ? launch_greedy_rule<F, DIM, 3, 2, EXACT, T, true>(f, a, st) : launch_greedy_rule<F, DIM, 3, 2, EXACT, T, false>(f, a, st);
+    }
+    if constexpr (DIM <= 5 && sizeof(T) == 4) {
+        if (a.rule == VB200_RULE_BOOLE_SIMPSON) return mixed ? launch_greedy_rule<F, DIM, 5, 3, EXACT, T, true>(f, a, st) : launch_greedy_rule<F, DIM, 5, 3, EXACT, T, false>(f, a, st);
+    }
+    if constexpr (DIM <= 4 && sizeof(T) == 8) {      // doubles: twice the shared memory per sample
+        if (a.rule == VB200_RULE_BOOLE_SIMPSON) return mixed ? launch_greedy_rule<F, DIM, 5, 3, EXACT, T, true>(f, a, st) : launch_greedy_rule<F, DIM, 5, 3, EXACT, T, false>(f, a, st);
+    }
     return int(cudaErrorNotSupported);
 }
 

@@ -131,8 +131,8 @@ struct FiniteThunks {
 
     static int greedy(const vb200_integrand* self, const void* args, void* stream) {
         const vb200_greedy_launch& a = *static_cast<const vb200_greedy_launch*>(args);
-        if (a.dim != DIM) return int(cudaErrorInvalidValue);
-        return device::launch_greedy<F, DIM, EXACT>(functor(self), a, static_cast<cudaStream_t>(stream));
+        if (a.dim != DIM || a.f64) return int(cudaErrorInvalidValue);
+        return device::launch_greedy<F, DIM, EXACT, float>(functor(self), a, static_cast<cudaStream_t>(stream));
     }
 };
 
@@ -149,6 +149,12 @@ struct FiniteThunks64 {
         const int grid = persistent_grid(k, 256, (a.n + 255) / 256, 0);
         k<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(functor(self), a);
         return int(cudaGetLastError());
+    }
+    // Range<double,DIM> through regions-generator-adaptive-heap.h:18-45: the greedy kernel with T = double
+    static int greedy(const vb200_integrand* self, const void* args, void* stream) {
+        const vb200_greedy_launch& a = *static_cast<const vb200_greedy_launch*>(args);
+        if (a.dim != DIM || !a.f64) return int(cudaErrorInvalidValue);
+        return device::launch_greedy<F, DIM, EXACT, double>(functor(self), a, static_cast<cudaStream_t>(stream));
     }
 };
 
@@ -278,6 +284,7 @@ class Integrand64 {
         d_.abi_version = VB200_ABI_VERSION; d_.dim = DIM; d_.functor = &f_; d_.functor_bytes = uint32_t(sizeof(F));
         d_.flags = (EXACT ? VB200_INTEGRAND_EXACT : 0u) | VB200_INTEGRAND_F64; d_.name = name;
         d_.launch[VB200_K_EVAL_POINTS] = &detail::FiniteThunks64<F, DIM, EXACT>::eval;
+        d_.launch[VB200_K_ADAPTIVE_EXACT] = &detail::FiniteThunks64<F, DIM, EXACT>::greedy;
     }
 public:
     explicit Integrand64(const F& f, const char* name = "user integrand (f64)") : f_(f) { bind(name); }

@@ -376,8 +376,19 @@ template<typename H, typename L> struct Nested {
 template<typename H, typename L> Nested<H,L> nested(const H&, const L&) { return Nested<H,L>(); }
 struct error_metric_absolute { static constexpr int id = VB200_METRIC_ABSOLUTE; };
 struct error_metric_relative { static constexpr int id = VB200_METRIC_RELATIVE; error_metric_relative(double = 1.e-37) {} };
-template<typename EM> struct error_heuristic_default { static constexpr int id = VB200_HEURISTIC_DEFAULT; double size_weight = 0; error_heuristic_default(const EM&) {} using metric = EM; };
-template<typename EM> struct error_heuristic_size { static constexpr int id = VB200_HEURISTIC_SIZE; double size_weight; error_heuristic_size(const EM&, double sw = 1.e-5, double = 1.e-37) : size_weight(sw) {} using metric = EM; };
+template<typename EM> struct error_heuristic_default { static constexpr int id = VB200_HEURISTIC_DEFAULT; double size_weight = 0; error_heuristic_default(const EM&) {} using metric = EM;
+    void fill(vb200_mixed_heuristic&) const {} };
+template<typename EM> struct error_heuristic_size { static constexpr int id = VB200_HEURISTIC_SIZE; double size_weight; error_heuristic_size(const EM&, double sw = 1.e-5, double = 1.e-37) : size_weight(sw) {} using metric = EM;
+    void fill(vb200_mixed_heuristic&) const {} };
+// error_heuristic_mixed(metric_bins, metric_rest, dimension, bins_weight, size_weight, size_bins, size_rest, error_increase_factor) — reference
+// src/nested/error-heuristic.h:49-98, same argument order and defaults
+template<typename EMB, typename EMR> struct error_heuristic_mixed {
+    static constexpr int id = VB200_HEURISTIC_MIXED; using metric = EMB;
+    double size_weight; vb200_mixed_heuristic m;
+    error_heuristic_mixed(const EMB&, const EMR&, unsigned int dim = 2, double bins_w = 1.0, double sw = 1.e-3, double size_bins = 1.0/1024.0, double size_rest = 1.0/16.0,
+                          double error_increase_factor = 1.e4) : size_weight(sw), m{EMR::id, int(dim), bins_w, size_bins, size_rest, error_increase_factor} {}
+    void fill(vb200_mixed_heuristic& out) const { out = m; }
+};
 
 // integrator_newton_cotes(rule) — reference src/newton-cotes/newton-cotes.h:11-19 ('+=')
 template<typename Rule> class IntegratorNewtonCotes {
@@ -426,10 +437,29 @@ public:
         vb200_adaptive_params p; std::memset(&p, 0, sizeof(p));
         std::array<std::size_t,1> one{1}; p.domain = b200::make_domain(range, one);
         p.rule = Rule::id; p.heuristic = EH::id; p.metric = EH::metric::id; p.batch = batch; p.size_weight = eh.size_weight; p.iterations = iterations;
+        eh.fill(p.mixed);
         ctx.check(vb200_regions_generate_adaptive(ctx.get(), g.c_abi(), &p, &regs.r));
     }
-    template<typename Bins, std::size_t DIMBINS, typename F, typename Float, std::size_t DIM, typename Logger>
-    void integrate(Bins& bins, const std::array<std::size_t,DIMBINS>& res, const F& f, const Range<Float,DIM>& range, Logger& logger) const {
+    // Range<double,DIM> with a double integrand: the greedy generator and the region->bin accumulation in double, as upstream for Float = double
+    template<typename Bins, std::size_t DIMBINS, typename F, std::size_t DIM, typename Logger>
+    void integrate(Bins& bins, const std::array<std::size_t,DIMBINS>& res, const F& f, const Range<double,DIM>& range, Logger& logger) const {
+        auto& ctx = b200::default_context();
+        b200::Integrand64<F, int(DIM)> g(f);
+        vb200_adaptive_params_f64 p; std::memset(&p, 0, sizeof(p));
+        std::array<std::size_t,1> one{1}; p.domain = b200::make_domain64(range, one);
+        p.rule = Rule::id; p.heuristic = EH::id; p.metric = EH::metric::id; p.batch = 1; p.size_weight = eh.size_weight; p.iterations = iterations;
+        eh.fill(p.mixed);
+        b200::RegionsHandle regs;
+        ctx.check(vb200_regions_generate_adaptive_f64(ctx.get(), g.c_abi(), &p, &regs.r));
+        vb200_domain_f64 dom = b200::make_domain64(range, res);
+        std::vector<double> flat(b200::bin_count(res), 0.0);
+        vb200_shard sh = b200::current_shard();
+        ctx.check(vb200_regions_integrate_bins_f64(ctx.get(), regs.r, &dom, &sh, flat.data(), VB200_HOST));
+        b200::apply_bins<true>(bins, res, flat);
+        logger.log_progress(iterations, iterations);
+    }
+    template<typename Bins, std::size_t DIMBINS, typename F, std::size_t DIM, typename Logger>
+    void integrate(Bins& bins, const std::array<std::size_t,DIMBINS>& res, const F& f, const Range<float,DIM>& range, Logger& logger) const {
         auto& ctx = b200::default_context();
         b200::Integrand<F, int(DIM)> g(f);
         b200::RegionsHandle regs;

@@ -22,6 +22,7 @@
 #include <cstring>
 #include <cmath>
 #include <vector>
+#include <string>
 #include <array>
 #include <thread>
 #include <algorithm>
@@ -463,6 +464,7 @@ template<typename T> struct RegionT {
     std::vector<T> rmin, rmax, data;
     T volume;                     // Range::_volume, T product
     T err = T(0); uint32_t errdim = 0;
+    double key = 0.0;             // what the heap orders by: double(err) for the Float-keyed heuristics, error_heuristic_mixed's own double key
 };
 
 // fold a multiarray along dimension `dim` with a per-line functor; shape in/out are S^nd / S^(nd-1), dim-0-fastest
@@ -549,7 +551,7 @@ template<typename T> T region_error_total(const RegionT<T>& r, int SH, int SL, i
 template<typename T> void heuristic_default(RegionT<T>& r, int SH, int SL, int D, bool relative) {
     T max_err = 0; uint32_t max_dim = 0;
     for (int d=0; d<D; ++d) { T err = region_error(r,SH,SL,D,d,relative); if (err>max_err) { max_err=err; max_dim=uint32_t(d); } }
-    r.err = max_err; r.errdim = max_dim;
+    r.err = max_err; r.errdim = max_dim; r.key = double(max_err);
 }
 // error-heuristic.h:29-46 (last maximal dim, >=)
 template<typename T> void heuristic_size(RegionT<T>& r, int SH, int SL, int D, bool relative, double size_weight) {
@@ -565,12 +567,41 @@ template<typename T> void heuristic_size(RegionT<T>& r, int SH, int SL, int D, b
         if ((r.rmax[d]-r.rmin[d])<min_size) err = 0;
         if (err>=max_err) { max_err=err; max_dim=uint32_t(d); }
     }
-    r.err = max_err; r.errdim = max_dim;
+    r.err = max_err; r.errdim = max_dim; r.key = double(max_err);
+}
+// error-heuristic.h:49-98 error_heuristic_mixed: two metrics (bins: d = 0 and d < dimension; rest: beyond), a DOUBLE key
+struct MixedArgs { int dimension = 2; double bins_weight = 1.0, size_threshold_bins = 1.0/1024.0, size_threshold_rest = 1.0/16.0, error_increase_factor = 1.e4; };
+MixedArgs g_mixed;
+template<typename T> void heuristic_mixed(RegionT<T>& r, int SH, int SL, int D, bool rel_bins, bool rel_rest, double size_weight, const MixedArgs& m) {
+    double size_bins = 1.0, size_rest = 1.0;
+    for (int d=0; d<std::min(m.dimension,D); ++d) size_bins *= std::abs(r.rmax[d]-r.rmin[d]);                      // :73-74
+    for (int d=m.dimension; d<D; ++d) size_rest *= std::abs(r.rmax[d]-r.rmin[d]);                                  // :75-76
+    double add_bins = m.error_increase_factor, add_rest = m.error_increase_factor;                                 // :78-83
+    if (size_bins<m.size_threshold_bins) add_bins = 0.0;
+    if (size_rest<m.size_threshold_rest) add_rest = 0.0;
+    if (std::isnan(size_bins)) add_bins = 0.0;
+    if (std::isnan(size_rest)) add_rest = 0.0;
+    double max_err = region_error(r,SH,SL,D,0,rel_bins)*m.bins_weight + add_bins + size_weight*(r.rmax[0]-r.rmin[0]);    // :85-86
+    uint32_t max_dim = 0;
+    double err = max_err;
+    for (int d=1; d<D; ++d) {                                                                                      // :90-97
+        if (d<m.dimension) err = region_error(r,SH,SL,D,d,rel_bins)*m.bins_weight + add_bins + size_weight*(r.rmax[d]-r.rmin[d]);
+        else err = region_error(r,SH,SL,D,d,rel_rest) + add_rest + size_weight*(r.rmax[d]-r.rmin[d]);
+        if (err>=max_err) { max_err=err; max_dim=uint32_t(d); }
+    }
+    r.err = T(max_err); r.errdim = max_dim; r.key = max_err;
 }
 
-struct Heuristic { bool size; bool relative; double size_weight; };
+struct Heuristic { bool size; bool relative; double size_weight; bool mixed = false; bool relative_rest = false; MixedArgs margs; };
 bool parse_heuristic(const char* h, double sw, Heuristic& out) {
-    out.size_weight = sw;
+    out.size_weight = sw; out.mixed = false;
+    if (!std::strncmp(h,"mixed_",6)) {                 // mixed_<bins metric>_<rest metric>; the other arguments come from vo_set_mixed
+        const char* rest = std::strchr(h+6,'_'); if (!rest) return false;
+        std::string mb(h+6, rest), mr(rest+1);
+        if ((mb!="absolute" && mb!="relative") || (mr!="absolute" && mr!="relative")) return false;
+        out.mixed = true; out.size = false; out.relative = mb=="relative"; out.relative_rest = mr=="relative"; out.margs = g_mixed;
+        return true;
+    }
     if (!std::strcmp(h,"default_absolute")) { out.size=false; out.relative=false; return true; }
     if (!std::strcmp(h,"default_relative")) { out.size=false; out.relative=true;  return true; }
     if (!std::strcmp(h,"size_absolute"))    { out.size=true;  out.relative=false; return true; }
@@ -578,6 +609,7 @@ bool parse_heuristic(const char* h, double sw, Heuristic& out) {
     return false;
 }
 template<typename T> void apply_heuristic(RegionT<T>& r, int SH, int SL, int D, const Heuristic& h) {
+    if (h.mixed) { heuristic_mixed(r,SH,SL,D,h.relative,h.relative_rest,h.size_weight,h.margs); return; }
     if (h.size) heuristic_size(r,SH,SL,D,h.relative,h.size_weight); else heuristic_default(r,SH,SL,D,h.relative);
 }
 
@@ -585,7 +617,7 @@ template<typename T> void apply_heuristic(RegionT<T>& r, int SH, int SL, int D, 
 template<typename T> void heap_push(std::vector<RegionT<T>>& h) {
     std::size_t hole = h.size()-1; RegionT<T> value = std::move(h[hole]);
     std::size_t parent = (hole-1)/2;
-    while (hole>0 && h[parent].err < value.err) { h[hole] = std::move(h[parent]); hole = parent; parent = (hole-1)/2; }
+    while (hole>0 && h[parent].key < value.key) { h[hole] = std::move(h[parent]); hole = parent; parent = (hole-1)/2; }
     h[hole] = std::move(value);
 }
 // libstdc++ bits/stl_heap.h:254-267 (pop_heap -> __pop_heap) + :224-250 (__adjust_heap); caller pops the back
@@ -596,13 +628,13 @@ template<typename T> void heap_pop(std::vector<RegionT<T>>& h) {
     std::size_t len = last, hole = 0, child = 0;
     while (child < (len-1)/2) {
         child = 2*(child+1);
-        if (h[child].err < h[child-1].err) --child;
+        if (h[child].key < h[child-1].key) --child;
         h[hole] = std::move(h[child]); hole = child;
     }
     if ((len&1)==0 && child==(len-2)/2) { child = 2*(child+1); h[hole] = std::move(h[child-1]); hole = child-1; }
     // __push_heap(first, hole, top=0, value)
     std::size_t parent = (hole-1)/2;
-    while (hole>0 && h[parent].err < value.err) { h[hole] = std::move(h[parent]); hole = parent; parent = (hole-1)/2; }
+    while (hole>0 && h[parent].key < value.key) { h[hole] = std::move(h[parent]); hole = parent; parent = (hole-1)/2; }
     h[hole] = std::move(value);
 }
 
@@ -785,6 +817,11 @@ extern "C" int vo_newton_cotes(const char* integrand, const char* rule, int dimb
     std::vector<RegionT<float>> regions; regions.push_back(make_region<float>(F->fn,S,D,rmin,rmax));
     integrate_regions_sequential<float>(regions,S,D,dimbins,res,rmin,rmax,bins);
     return 0;
+}
+
+extern "C" void vo_set_mixed(int dimension, double bins_weight, double size_threshold_bins, double size_threshold_rest, double error_increase_factor) {
+    g_mixed.dimension = dimension; g_mixed.bins_weight = bins_weight; g_mixed.size_threshold_bins = size_threshold_bins;
+    g_mixed.size_threshold_rest = size_threshold_rest; g_mixed.error_increase_factor = error_increase_factor;
 }
 
 extern "C" int vo_adaptive_iterations(const char* integrand, const char* rule, const char* heuristic, double size_weight,

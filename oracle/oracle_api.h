@@ -67,14 +67,18 @@ int vo_newton_cotes(const char* integrand, const char* rule, int dimbins, const 
 // src/nested/integrator-adaptive-iterations.h:12-15, src/nested/regions-generator-adaptive-heap.h:18-45,
 // src/newton-cotes/regions-integrator-sequential.h:38-58.
 //   rule      in {"simpson_trapezoidal","boole_simpson"}
-//   heuristic in {"default_absolute","default_relative","size_absolute","size_relative"}
-//   size_weight only used by size_* (reference default 1e-5)
+//   heuristic in {"default_absolute","default_relative","size_absolute","size_relative"} or "mixed_<bins metric>_<rest metric>" =
+//             error_heuristic_mixed (error-heuristic.h:49-98) whose remaining constructor arguments come from vo_set_mixed (reference defaults
+//             until it is called); reg_err then holds the double key rounded to float
+//   size_weight only used by size_* and mixed_* (reference defaults 1e-5 / 1e-3)
 // Region list (iterations+1 regions, in the reference's heap-array order):
 //   reg_min/reg_max [n*dim], reg_err [n], reg_dim [n], reg_data [n*S^dim] (dim-0-fastest samples).
 int vo_adaptive_iterations(const char* integrand, const char* rule, const char* heuristic, double size_weight,
                            uint64_t iterations, int dimbins, const uint64_t* res,
                            const float* rmin, const float* rmax, float* bins,
                            float* reg_min, float* reg_max, float* reg_err, uint32_t* reg_dim, float* reg_data);
+
+void vo_set_mixed(int dimension, double bins_weight, double size_threshold_bins, double size_threshold_rest, double error_increase_factor);
 
 // reference integrator_adaptive_tolerance(nested(H,L), heuristic, tolerance) — src/nested/integrator-adaptive-tolerance.h:15-39: depth-first
 // recursion, a region is integrated into the bins ('+=', sequential integrator) as soon as its heuristic error drops below the

@@ -60,6 +60,12 @@ class Oracle:
     def dim(self, integrand):
         return self.lib.vo_integrand_dim(integrand.encode())
 
+    def set_mixed(self, dimension=2, bins_weight=1.0, size_threshold_bins=1.0 / 1024.0, size_threshold_rest=1.0 / 16.0, error_increase_factor=1.e4):
+        """constructor arguments of error_heuristic_mixed for the next 'mixed_<bins>_<rest>' heuristic (size_weight travels with the call)"""
+        self.lib.vo_set_mixed.restype = None
+        self.lib.vo_set_mixed(int(dimension), ctypes.c_double(bins_weight), ctypes.c_double(size_threshold_bins), ctypes.c_double(size_threshold_rest),
+                              ctypes.c_double(error_increase_factor))
+
     def set_threads(self, n):
         """threads behind the reference's par_unseq loops (reference-mt build; 1 elsewhere)"""
         if not hasattr(self.lib, "vo_set_threads"):

@@ -4,6 +4,11 @@
 
 using namespace vref;
 
+namespace { struct MixedArgs { int dimension = 2; double bins_weight = 1.0, tb = 1.0/1024.0, tr = 1.0/16.0, factor = 1.e4; } g_mixed; }
+extern "C" void vo_set_mixed(int dimension, double bins_weight, double size_threshold_bins, double size_threshold_rest, double error_increase_factor) {
+    g_mixed.dimension = dimension; g_mixed.bins_weight = bins_weight; g_mixed.tb = size_threshold_bins; g_mixed.tr = size_threshold_rest; g_mixed.factor = error_increase_factor;
+}
+
 extern "C" int vo_newton_cotes(const char* integrand, const char* rule, int dimbins, const uint64_t* res,
                     const float* rmin, const float* rmax, float* bins) {
     return dispatch_finite_bins(integrand, dimbins, [&] (auto f, auto dbc) -> int {
@@ -60,6 +65,15 @@ extern "C" int vo_adaptive_iterations(const char* integrand, const char* rule, c
                 return run_adaptive<decltype(f),DB>(f, rule, error_heuristic_size(error_metric_absolute(),size_weight), iterations,res,rmin,rmax,bins,sink);
             if (!std::strcmp(heuristic,"size_relative"))
                 return run_adaptive<decltype(f),DB>(f, rule, error_heuristic_size(error_metric_relative(),size_weight), iterations,res,rmin,rmax,bins,sink);
+#define RUN(EH) run_adaptive<decltype(f),DB>(f, rule, EH, iterations,res,rmin,rmax,bins,sink)
+            if (!std::strncmp(heuristic,"mixed_",6)) {      // error_heuristic_mixed(bins metric, rest metric, ...) — error-heuristic.h:49-98; extra arguments from vo_set_mixed
+                const unsigned dm = unsigned(g_mixed.dimension);
+                if (!std::strcmp(heuristic,"mixed_absolute_absolute")) return RUN(error_heuristic_mixed(error_metric_absolute(), error_metric_absolute(), dm, g_mixed.bins_weight, size_weight, g_mixed.tb, g_mixed.tr, g_mixed.factor));
+                if (!std::strcmp(heuristic,"mixed_absolute_relative")) return RUN(error_heuristic_mixed(error_metric_absolute(), error_metric_relative(), dm, g_mixed.bins_weight, size_weight, g_mixed.tb, g_mixed.tr, g_mixed.factor));
+                if (!std::strcmp(heuristic,"mixed_relative_absolute")) return RUN(error_heuristic_mixed(error_metric_relative(), error_metric_absolute(), dm, g_mixed.bins_weight, size_weight, g_mixed.tb, g_mixed.tr, g_mixed.factor));
+                if (!std::strcmp(heuristic,"mixed_relative_relative")) return RUN(error_heuristic_mixed(error_metric_relative(), error_metric_relative(), dm, g_mixed.bins_weight, size_weight, g_mixed.tb, g_mixed.tr, g_mixed.factor));
+            }
+#undef RUN
             return -2;
         };
         if (!std::strcmp(rule,"simpson_trapezoidal")) return with_rule(nested(simpson,trapezoidal));
@@ -151,6 +165,15 @@ extern "C" int vo_adaptive_iterations_f64(const char* integrand, const char* rul
             if (!std::strcmp(heuristic,"default_relative")) return run(rl, error_heuristic_default(error_metric_relative()));
             if (!std::strcmp(heuristic,"size_absolute"))    return run(rl, error_heuristic_size(error_metric_absolute(),size_weight));
             if (!std::strcmp(heuristic,"size_relative"))    return run(rl, error_heuristic_size(error_metric_relative(),size_weight));
+#define RUN(EH) run(rl, EH)
+            if (!std::strncmp(heuristic,"mixed_",6)) {      // error_heuristic_mixed(bins metric, rest metric, ...) — error-heuristic.h:49-98; extra arguments from vo_set_mixed
+                const unsigned dm = unsigned(g_mixed.dimension);
+                if (!std::strcmp(heuristic,"mixed_absolute_absolute")) return RUN(error_heuristic_mixed(error_metric_absolute(), error_metric_absolute(), dm, g_mixed.bins_weight, size_weight, g_mixed.tb, g_mixed.tr, g_mixed.factor));
+                if (!std::strcmp(heuristic,"mixed_absolute_relative")) return RUN(error_heuristic_mixed(error_metric_absolute(), error_metric_relative(), dm, g_mixed.bins_weight, size_weight, g_mixed.tb, g_mixed.tr, g_mixed.factor));
+                if (!std::strcmp(heuristic,"mixed_relative_absolute")) return RUN(error_heuristic_mixed(error_metric_relative(), error_metric_absolute(), dm, g_mixed.bins_weight, size_weight, g_mixed.tb, g_mixed.tr, g_mixed.factor));
+                if (!std::strcmp(heuristic,"mixed_relative_relative")) return RUN(error_heuristic_mixed(error_metric_relative(), error_metric_relative(), dm, g_mixed.bins_weight, size_weight, g_mixed.tb, g_mixed.tr, g_mixed.factor));
+            }
+#undef RUN
             return -2;
         };
         if (!std::strcmp(rule,"simpson_trapezoidal")) return with_rule(nested(simpson,trapezoidal));

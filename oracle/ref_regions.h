@@ -39,8 +39,9 @@ public:
                     if (sink->reg_min) sink->reg_min[n*D+i] = r.range().min(i);
                     if (sink->reg_max) sink->reg_max[n*D+i] = r.range().max(i);
                 }
-                if constexpr (std::is_same_v<std::decay_t<decltype(r.extra())>, std::tuple<T,std::size_t>>) {
-                    if (sink->reg_err) sink->reg_err[n] = std::get<0>(r.extra());
+                if constexpr (std::is_same_v<std::decay_t<decltype(r.extra())>, std::tuple<T,std::size_t>> ||
+                              std::is_same_v<std::decay_t<decltype(r.extra())>, std::tuple<double,std::size_t>>) {      // error_heuristic_mixed keys are doubles
+                    if (sink->reg_err) sink->reg_err[n] = T(std::get<0>(r.extra()));
                     if (sink->reg_dim) sink->reg_dim[n] = uint32_t(std::get<1>(r.extra()));
                 }
                 if (sink->reg_data) {

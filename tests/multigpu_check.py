@@ -42,7 +42,7 @@ def main():
         assert torch.equal(lo, hi), "ranks disagree on the reduced bins"
         dev = torch.ones(nb, dtype=torch.float32, device="cuda")                    # device-resident bins
         ctx.monte_carlo("x2y2", dev, res, rng2, samples, 5, allreduce=True); ctx.synchronize()
-        assert np.array_equal(dev.cpu().numpy(), part)
+        assert np.allclose(dev.cpu().numpy(), part, rtol=2e-6, atol=1e-7)        # same samples; the float atomics of the scatter add in a different order every run
     # -- 3. region-table broadcast ---------------------------------------------------------------------------------------------
     rng5 = Range([0.0] * 5, [1.0] * 5)
     mine = ctx.regions_generate_adaptive("shade5_16", rng5, "simpson_trapezoidal", "size", "relative", 3000, 1e-5, batch=0, exact=True)

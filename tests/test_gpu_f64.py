@@ -60,6 +60,36 @@ def test_region_to_bin_integration_fp64_identical_leaf_table(ctx, port, integ, r
     regs.free()
 
 
+@pytest.mark.parametrize("integ,rule,h,it,lo,hi", [("smooth_edge2", "boole_simpson", "size_relative", 3000, 0.0, 1.0), ("x2y2", "simpson_trapezoidal", "default_absolute", 200, 0.05, 1.1),
+                                                   ("poly3", "simpson_trapezoidal", "size_relative", 300, 0.0, 1.0), ("shade4_16", "simpson_trapezoidal", "size_relative", 400, 0.0, 1.0),
+                                                   ("ind2", "boole_simpson", "default_relative", 500, 0.0, 1.0), ("cubic1", "boole_simpson", "size_absolute", 300, -0.5, 1.25),
+                                                   ("smooth_edge2", "simpson_trapezoidal", "mixed_relative_absolute", 500, 0.0, 1.0), ("x2y2", "boole_simpson", "size_relative", 0, 0.0, 1.0)])
+def test_greedy_refinement_fp64_reproduces_the_reference_subdivision(ctx, port, integ, rule, h, it, lo, hi):
+    """Range<double,DIM> through regions-generator-adaptive-heap.h:18-45: every sample, error and heap key a double (the greedy kernel with
+    T = double, 16-byte heap entries) — region list (ranges, samples, errors, split dimensions, order) and bins bit-identical to the oracle,
+    which is bit-exact against the unmodified reference instantiated with Range<double,DIM>; hence inside north_star's 1e-12 gate."""
+    d = DIMS[integ]
+    res = [6] * min(d, 2)
+    init = np.linspace(0, 1, int(np.prod(res)))
+    mixed = None
+    if h.startswith("mixed"):
+        mixed = dict(dimension=1, bins_weight=1.5, size_threshold_bins=1.0 / 32, size_threshold_rest=1.0 / 8, error_increase_factor=100.0)
+        port.set_mixed(**mixed)
+    want, reg = port.adaptive_iterations_f64(integ, rule, h, it, res, [lo] * d, [hi] * d, size_weight=1e-4, bins=init)
+    parts = h.split("_")
+    regs = ctx.regions_generate_adaptive_f64(integ, _rng(integ, lo, hi), rule, parts[0], parts[1], it, 1e-4, exact=True,
+                                             mixed=dict(mixed, metric_rest=parts[2]) if mixed else None)
+    assert len(regs) == it + 1
+    got = regs.download()
+    for k in ("min", "max", "err", "dim", "data"):
+        assert_same_bits(got[k], reg[k], f"{integ} {rule} {h} fp64 region {k}")
+    bins = init.copy()
+    regs.integrate_bins(bins, res, _rng(integ, lo, hi))
+    assert_same_bits(bins, want, "fp64 bins")
+    assert np.allclose(bins, want, rtol=1e-12, atol=0)
+    regs.free()
+
+
 def test_type_mismatch_is_rejected(ctx):
     from viltrum_b200 import Vb200Error, Range
     regs = ctx.regions_generate_single_f64("x2y2", Range([0, 0], [1, 1]), "simpson")

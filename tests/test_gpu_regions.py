@@ -126,6 +126,43 @@ def test_greedy_refinement_reproduces_the_reference_subdivision(ctx, port, integ
     regs.free()
 
 
+MIXED_CASES = [("shade4_16", "simpson_trapezoidal", "relative", "absolute", 200, dict(dimension=2, bins_weight=1.0, size_threshold_bins=1.0 / 64, size_threshold_rest=1.0 / 4, error_increase_factor=1.e4), 1e-3),
+               ("smooth_edge2", "boole_simpson", "absolute", "relative", 600, dict(dimension=1, bins_weight=0.5, size_threshold_bins=1.0 / 32, size_threshold_rest=1.0 / 8, error_increase_factor=10.0), 1e-3),
+               ("shade5_16", "simpson_trapezoidal", "relative", "relative", 300, dict(dimension=2, bins_weight=2.0, size_threshold_bins=1.0 / 1024, size_threshold_rest=1.0 / 16, error_increase_factor=1.e4), 1e-5),
+               ("poly3", "simpson_trapezoidal", "absolute", "absolute", 150, dict(dimension=5, bins_weight=1.0, size_threshold_bins=0.5, size_threshold_rest=0.5, error_increase_factor=1.0), 0.0),
+               ("x2y2", "boole_simpson", "relative", "absolute", 64, dict(dimension=0, bins_weight=1.0, size_threshold_bins=1.0 / 16, size_threshold_rest=1.0 / 16, error_increase_factor=3.0), 1e-2)]
+
+
+@pytest.mark.parametrize("integ,rule,mb,mr,it,margs,sw", MIXED_CASES)
+def test_greedy_refinement_with_error_heuristic_mixed(ctx, port, integ, rule, mb, mr, it, margs, sw):
+    """error_heuristic_mixed (reference src/nested/error-heuristic.h:49-98): two metrics, size thresholds, a DOUBLE heap key — the exact mode
+    keeps 16-byte heap entries with double keys and reproduces the subdivision bit for bit (err = the key rounded to float); the batched
+    mode takes the same heuristic with float keys (leaves tile the domain)."""
+    from viltrum_b200 import error_heuristic_mixed, error_metric_absolute, error_metric_relative
+    d = DIMS[integ]
+    res = [4] * min(d, 2)
+    port.set_mixed(**margs)
+    want_bins, want = port.adaptive_iterations(integ, rule, f"mixed_{mb}_{mr}", it, res, [0.0] * d, [1.0] * d, size_weight=sw)
+    regs = ctx.regions_generate_adaptive(integ, _rng(integ), rule, "mixed", mb, it, sw, batch=1, exact=True, mixed=dict(margs, metric_rest=mr))
+    got = regs.download()
+    for k in ("min", "max", "err", "dim", "data"):
+        assert_same_bits(got[k], want[k], f"{integ} {rule} mixed region {k}")
+    bins = np.zeros(int(np.prod(res)), np.float32)
+    regs.integrate_bins(bins, res, _rng(integ))
+    assert_same_bits(bins, want_bins, "bins")
+    regs.free()
+    # the same heuristic through the host-side mirror of the reference's factory, batched mode
+    mk = {"absolute": error_metric_absolute, "relative": error_metric_relative}
+    h = error_heuristic_mixed(mk[mb](), mk[mr](), margs["dimension"], margs["bins_weight"], sw, margs["size_threshold_bins"], margs["size_threshold_rest"], margs["error_increase_factor"])
+    from viltrum_b200 import IntegratorAdaptiveIterations, nested
+    hi, lo = rule.split("_")
+    batched = IntegratorAdaptiveIterations(nested(hi, lo), h, it, batch=0).generate(ctx, integ, _rng(integ))
+    t = batched.download()
+    vol = np.prod(t["max"].astype(np.float64) - t["min"].astype(np.float64), axis=1)
+    assert len(batched) == it + 1 and abs(vol.sum() - 1.0) < 1e-5 and vol.min() > 0
+    batched.free()
+
+
 def test_greedy_refinement_golden_reference_tables(ctx):
     """region lists dumped from the UNMODIFIED reference through Logger::log (tests/golden/reference_vectors.json)"""
     from viltrum_b200 import Range

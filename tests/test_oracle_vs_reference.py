@@ -61,6 +61,31 @@ def test_newton_cotes_and_adaptive(port, reference, integ, res):
                 assert_same_bits(a[1][k], b[1][k], f"{rule} {h} region {k}")
 
 
+@pytest.mark.parametrize("integ,rule,mb,mr,it,margs,sw", [
+    ("shade4_16", "simpson_trapezoidal", "relative", "absolute", 120, dict(dimension=2, bins_weight=1.0, size_threshold_bins=1.0 / 64, size_threshold_rest=1.0 / 4, error_increase_factor=1.e4), 1e-3),
+    ("smooth_edge2", "boole_simpson", "absolute", "relative", 400, dict(dimension=1, bins_weight=0.5, size_threshold_bins=1.0 / 32, size_threshold_rest=1.0 / 8, error_increase_factor=10.0), 1e-3),
+    ("poly3", "simpson_trapezoidal", "absolute", "absolute", 150, dict(dimension=5, bins_weight=1.0, size_threshold_bins=0.5, size_threshold_rest=0.5, error_increase_factor=1.0), 0.0),
+    ("x2y2", "boole_simpson", "relative", "absolute", 64, dict(dimension=0, bins_weight=1.0, size_threshold_bins=1.0 / 16, size_threshold_rest=1.0 / 16, error_increase_factor=3.0), 1e-2)])
+def test_error_heuristic_mixed(port, reference, integ, rule, mb, mr, it, margs, sw):
+    """error_heuristic_mixed (error-heuristic.h:49-98; no caller or test upstream): the port's restatement against the reference's own template,
+    float and double ranges"""
+    rmin, rmax = _range(port, integ)
+    d = port.dim(integ)
+    res = [5] * min(d, 2)
+    port.set_mixed(**margs); reference.set_mixed(**margs)
+    a = port.adaptive_iterations(integ, rule, f"mixed_{mb}_{mr}", it, res, rmin, rmax, size_weight=sw)
+    b = reference.adaptive_iterations(integ, rule, f"mixed_{mb}_{mr}", it, res, rmin, rmax, size_weight=sw)
+    assert_same_bits(a[0], b[0], "mixed bins")
+    for k in ("min", "max", "err", "dim", "data"):
+        assert_same_bits(a[1][k], b[1][k], f"mixed region {k}")
+    if integ in ("smooth_edge2", "poly3", "x2y2"):
+        a = port.adaptive_iterations_f64(integ, rule, f"mixed_{mb}_{mr}", it, res, rmin, rmax, size_weight=sw)
+        b = reference.adaptive_iterations_f64(integ, rule, f"mixed_{mb}_{mr}", it, res, rmin, rmax, size_weight=sw)
+        assert_same_bits(a[0], b[0], "mixed bins f64")
+        for k in ("min", "max", "err", "dim", "data"):
+            assert_same_bits(a[1][k], b[1][k], f"mixed region {k} f64")
+
+
 def test_heap_order_with_ties(port, reference):
     # SURVEY.md App. B: >99% tied keys on smooth_edge2 — the region ORDER is decided by libstdc++ heap mechanics
     a = port.adaptive_iterations("smooth_edge2", "boole_simpson", "size_relative", 5000, [16, 16], [0, 0], [1, 1])

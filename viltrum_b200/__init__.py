@@ -6,6 +6,6 @@ from .host import (Context, Regions, integrate, monte_carlo, monte_carlo_per_bin
                    integrator_newton_cotes, integrator_adaptive_iterations, integrator_crespo2021, nested,
                    integrator_fubini, integrator_crespo2021_infinite, integrator_adaptive_tolerance, cv_fixed_weight, cv_optimize_weight, rr_uniform_region, rr_integral_region, rr_error_region, rr_pdf_region,
                    integrator_adaptive_variance_reduction_parallel, steps, FubiniIntegrand, range_split_at,
-                   error_heuristic_default, error_heuristic_size, error_metric_absolute, error_metric_relative,
+                   error_heuristic_default, error_heuristic_size, error_heuristic_mixed, error_metric_absolute, error_metric_relative,
                    range_primary, range_primary_infinite, Range, RangeInfinite, builtin_names, shard_for_rank, sample_shard_for_rank)
 from ._capi import Vb200Error  # noqa: F401

@@ -35,7 +35,7 @@ def rule_id(name):
         n, base = name[5:].split("_", 1)
         return 0x1000000 | (RULES[base] << 16) | (int(n) & 0xffff)
     return RULES[name]
-HEURISTICS = {"default": 0, "size": 1}
+HEURISTICS = {"default": 0, "size": 1, "mixed": 2}
 METRICS = {"absolute": 0, "relative": 1}
 
 STATUS = {0: "VB200_OK", -1: "VB200_ERR_NO_DEVICE", -2: "VB200_ERR_INVALID", -3: "VB200_ERR_CUDA",
@@ -51,6 +51,7 @@ SYMBOLS = [
     "vb200_regions_integrate_bins", "vb200_cv_integrate", "vb200_cv_replay",
     "vb200_regions_generate_single_f64", "vb200_regions_upload_f64", "vb200_regions_download_f64", "vb200_regions_integrate_bins_f64",
     "vb200_builtin_integrand_f64", "vb200_builtin_fubini", "vb200_integrand_free", "vb200_regions_generate_tolerance",
+    "vb200_regions_generate_adaptive_f64",
     "vb200_comm_unique_id", "vb200_comm_init", "vb200_comm_destroy", "vb200_comm_rank", "vb200_comm_size", "vb200_nccl_version", "vb200_regions_broadcast",
 ]
 
@@ -75,9 +76,19 @@ class McParams(ctypes.Structure):
                 ("flavor", ctypes.c_int32), ("options", ctypes.c_int32)]
 
 
+class MixedHeuristic(ctypes.Structure):
+    _fields_ = [("metric_rest", ctypes.c_int32), ("dimension", ctypes.c_int32), ("bins_weight", ctypes.c_double), ("size_threshold_bins", ctypes.c_double),
+                ("size_threshold_rest", ctypes.c_double), ("error_increase_factor", ctypes.c_double)]
+
+
 class AdaptiveParams(ctypes.Structure):
     _fields_ = [("domain", Domain), ("rule", ctypes.c_int32), ("heuristic", ctypes.c_int32), ("metric", ctypes.c_int32),
-                ("batch", ctypes.c_int32), ("size_weight", ctypes.c_double), ("iterations", ctypes.c_uint64)]
+                ("batch", ctypes.c_int32), ("size_weight", ctypes.c_double), ("iterations", ctypes.c_uint64), ("mixed", MixedHeuristic)]
+
+
+class AdaptiveParams64(ctypes.Structure):
+    _fields_ = [("domain", Domain64), ("rule", ctypes.c_int32), ("heuristic", ctypes.c_int32), ("metric", ctypes.c_int32),
+                ("batch", ctypes.c_int32), ("size_weight", ctypes.c_double), ("iterations", ctypes.c_uint64), ("mixed", MixedHeuristic)]
 
 
 class ToleranceParams(ctypes.Structure):
@@ -137,6 +148,7 @@ def lib():
         L.vb200_mc_per_bin_inf_replay.argtypes = [vp, vp, ctypes.POINTER(McParams), vp, vp, i32, vp, i32]; L.vb200_mc_per_bin_inf_replay.restype = i32
         L.vb200_monte_carlo.argtypes = [vp, vp, ctypes.POINTER(McParams), vp, i32]; L.vb200_monte_carlo.restype = i32
         L.vb200_regions_generate_adaptive.argtypes = [vp, vp, ctypes.POINTER(AdaptiveParams), ctypes.POINTER(vp)]; L.vb200_regions_generate_adaptive.restype = i32
+        L.vb200_regions_generate_adaptive_f64.argtypes = [vp, vp, ctypes.POINTER(AdaptiveParams64), ctypes.POINTER(vp)]; L.vb200_regions_generate_adaptive_f64.restype = i32
         L.vb200_regions_generate_tolerance.argtypes = [vp, vp, ctypes.POINTER(ToleranceParams), ctypes.POINTER(vp)]; L.vb200_regions_generate_tolerance.restype = i32
         L.vb200_regions_generate_single.argtypes = [vp, vp, ctypes.POINTER(Domain), i32, ctypes.POINTER(vp)]; L.vb200_regions_generate_single.restype = i32
         L.vb200_regions_upload.argtypes = [vp, i32, i32, u64, vp, vp, vp, vp, vp, ctypes.POINTER(vp)]; L.vb200_regions_upload.restype = i32

@@ -183,12 +183,30 @@ __global__ void split_points_kernel(int S, int dim, uint64_t cap, uint64_t nsel,
     }
 }
 
+// heuristic of a region from its per-dimension errors: error_heuristic_default / _size (float keys) or _mixed (a double key upstream, rounded
+// to float here: the batched mode orders by float keys and is not bit-exact with the greedy order anyway)
+struct HeurArgs { int heuristic, metric, metric_rest; double size_weight; D_::MixedParams mixed; };
+inline HeurArgs heur_args(int heuristic, int metric, double size_weight, const vb200_mixed_heuristic& m) {
+    HeurArgs h; h.heuristic = heuristic; h.metric = metric; h.metric_rest = m.metric_rest; h.size_weight = size_weight;
+    h.mixed = D_::MixedParams{m.dimension, m.bins_weight, size_weight, m.size_threshold_bins, m.size_threshold_rest, m.error_increase_factor};
+    return h;
+}
+__device__ __forceinline__ bool heur_relative(const HeurArgs& h, int d) {
+    if (h.heuristic == VB200_HEURISTIC_MIXED) return ((d == 0 || d < h.mixed.dimension) ? h.metric : h.metric_rest) == VB200_METRIC_RELATIVE;
+    return h.metric == VB200_METRIC_RELATIVE;
+}
+template<int DIM>
+__device__ __forceinline__ void heur_pick(const HeurArgs& h, const float* E, const float* rng, float* e, unsigned* d) {
+    if (h.heuristic == VB200_HEURISTIC_MIXED) { double k; D_::heuristic_pick_mixed<DIM, float>(E, rng, h.mixed, &k, d); *e = float(k); }
+    else D_::heuristic_pick<DIM>(E, rng, h.heuristic, h.size_weight, e, d);
+}
+
 // one warp per split: build both children (region.h:345-359, split.h:13-49), store child 0 over the parent and child 1 in a
 // new slot, then evaluate both children's error heuristics (region.h:387-411, error-heuristic.h:10-46)
 template<int SH, int SL, int DIM>
 __global__ void split_children_kernel(uint64_t cap, uint64_t nsel, uint64_t n_old, const unsigned* __restrict__ sel, const float* __restrict__ vals,
                                       float* __restrict__ rmin, float* __restrict__ rmax, float* __restrict__ data, float* __restrict__ err, uint32_t* __restrict__ errdim,
-                                      int heuristic, int metric, double size_weight) {
+                                      const HeurArgs hr) {
     using Sh = D_::GreedyShape<SH, SL, DIM>;
     extern __shared__ float smem[];
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
@@ -232,13 +250,13 @@ __global__ void split_children_kernel(uint64_t cap, uint64_t nsel, uint64_t n_ol
         rmin[uint64_t(lane) * cap + slot1] = s_crange[2 * DIM + lane]; rmax[uint64_t(lane) * cap + slot1] = s_crange[3 * DIM + lane];
     }
     for (int c = 0; c < 2; ++c) for (int d = 0; d < DIM; ++d) {
-        const float e = D_::region_error_warp<SH, SL, DIM>(s_child + c * Sh::SD, s_vol[c], d, metric == VB200_METRIC_RELATIVE, s_work, lane);
+        const float e = D_::region_error_warp<SH, SL, DIM>(s_child + c * Sh::SD, s_vol[c], d, heur_relative(hr, d), s_work, lane);
         if (lane == 0) s_E[c * DIM + d] = e;
         __syncwarp();
     }
     if (lane < 2) {
         float e; unsigned d;
-        D_::heuristic_pick<DIM>(s_E + lane * DIM, s_crange + lane * 2 * DIM, heuristic, size_weight, &e, &d);
+        heur_pick<DIM>(hr, s_E + lane * DIM, s_crange + lane * 2 * DIM, &e, &d);
         const uint64_t s = lane == 0 ? uint64_t(slot) : slot1;
         err[s] = e; errdim[s] = d;
     }
@@ -247,7 +265,7 @@ __global__ void split_children_kernel(uint64_t cap, uint64_t nsel, uint64_t n_ol
 // the root region: samples are already in data[.][0]; compute its heuristic
 template<int SH, int SL, int DIM>
 __global__ void root_error_kernel(uint64_t cap, const float* __restrict__ rmin, const float* __restrict__ rmax, const float* __restrict__ data,
-                                  float* __restrict__ err, uint32_t* __restrict__ errdim, int heuristic, int metric, double size_weight) {
+                                  float* __restrict__ err, uint32_t* __restrict__ errdim, const HeurArgs hr) {
     using Sh = D_::GreedyShape<SH, SL, DIM>;
     extern __shared__ float smem[];
     float* s_data = smem; float* s_work = s_data + Sh::SD; float* s_range = s_work + Sh::L; float* s_E = s_range + 2 * DIM;
@@ -257,11 +275,11 @@ __global__ void root_error_kernel(uint64_t cap, const float* __restrict__ rmin, 
     __syncwarp();
     float vol = 1.0f; for (int d = 0; d < DIM; ++d) vol = R::fm(vol, R::fs(s_range[DIM + d], s_range[d]));
     for (int d = 0; d < DIM; ++d) {
-        const float e = D_::region_error_warp<SH, SL, DIM>(s_data, vol, d, metric == VB200_METRIC_RELATIVE, s_work, lane);
+        const float e = D_::region_error_warp<SH, SL, DIM>(s_data, vol, d, heur_relative(hr, d), s_work, lane);
         if (lane == 0) s_E[d] = e;
         __syncwarp();
     }
-    if (lane == 0) { float e; unsigned d; D_::heuristic_pick<DIM>(s_E, s_range, heuristic, size_weight, &e, &d); err[0] = e; errdim[0] = d; }
+    if (lane == 0) { float e; unsigned d; heur_pick<DIM>(hr, s_E, s_range, &e, &d); err[0] = e; errdim[0] = d; }
 }
 
 template<int SH, int SL, int DIM>
@@ -270,7 +288,7 @@ int run_rounds(vb200_ctx* ctx, const vb200_integrand* f, const vb200_adaptive_pa
     using Sh = D_::GreedyShape<SH, SL, DIM>;
     const uint64_t cap = r->capacity;
     cudaStream_t s = ctx->stream;
-    root_error_kernel<SH, SL, DIM><<<1, 32, (Sh::SD + Sh::L + 4 * DIM) * sizeof(float), s>>>(cap, r->rmin, r->rmax, r->data, r->err, r->errdim, p->heuristic, p->metric, p->size_weight);
+    root_error_kernel<SH, SL, DIM><<<1, 32, (Sh::SD + Sh::L + 4 * DIM) * sizeof(float), s>>>(cap, r->rmin, r->rmax, r->data, r->err, r->errdim, heur_args(p->heuristic, p->metric, p->size_weight, p->mixed));
     ctx->launches++;
     VB200_CUDA(ctx, cudaGetLastError());
     const size_t per_warp = (3 * Sh::SD + Sh::L + 4 * DIM + 2 * DIM + 2) * sizeof(float);
@@ -311,7 +329,7 @@ int run_rounds(vb200_ctx* ctx, const vb200_integrand* f, const vb200_adaptive_pa
         int rc = call_thunk(ctx, f, VB200_K_EVAL_POINTS, &ev); if (rc) return rc;
         // 3. children + heuristics
         kchild<<<unsigned((B + wpc - 1) / wpc), wpc * 32, per_warp * wpc, s>>>(cap, B, n, sel, vals, r->rmin, r->rmax, r->data, r->err, r->errdim,
-                                                                               p->heuristic, p->metric, p->size_weight);
+                                                                               heur_args(p->heuristic, p->metric, p->size_weight, p->mixed));
         ctx->launches++;
         VB200_CUDA(ctx, cudaGetLastError());
         n += B; left -= B;
@@ -393,7 +411,7 @@ template<int SH, int SL, int DIM>
 int run_tolerance(vb200_ctx* ctx, const vb200_integrand* f, const vb200_tolerance_params* p, TolState& t, uint64_t* n_out) {
     using Sh = D_::GreedyShape<SH, SL, DIM>;
     cudaStream_t s = ctx->stream;
-    root_error_kernel<SH, SL, DIM><<<1, 32, (Sh::SD + Sh::L + 4 * DIM) * sizeof(float), s>>>(t.r->capacity, t.r->rmin, t.r->rmax, t.r->data, t.r->err, t.r->errdim, p->heuristic, p->metric, p->size_weight);
+    root_error_kernel<SH, SL, DIM><<<1, 32, (Sh::SD + Sh::L + 4 * DIM) * sizeof(float), s>>>(t.r->capacity, t.r->rmin, t.r->rmax, t.r->data, t.r->err, t.r->errdim, heur_args(p->heuristic, p->metric, p->size_weight, vb200_mixed_heuristic{}));
     ctx->launches++;
     VB200_CUDA(ctx, cudaGetLastError());
     const size_t per_warp = (3 * Sh::SD + Sh::L + 4 * DIM + 2 * DIM + 2) * sizeof(float);
@@ -434,7 +452,7 @@ int run_tolerance(vb200_ctx* ctx, const vb200_integrand* f, const vb200_toleranc
             rc = call_thunk(ctx, f, VB200_K_EVAL_POINTS, &ev);
             if (!rc) {
                 kchild<<<unsigned((B + wpc - 1) / wpc), wpc * 32, per_warp * wpc, s>>>(cap, B, n + off, sel + off, vals, t.r->rmin, t.r->rmax, t.r->data, t.r->err, t.r->errdim,
-                                                                                       p->heuristic, p->metric, p->size_weight);
+                                                                                       heur_args(p->heuristic, p->metric, p->size_weight, vb200_mixed_heuristic{}));
                 ctx->launches++;
                 if (cudaGetLastError() != cudaSuccess) rc = fail(ctx, VB200_ERR_CUDA, "split kernel launch failed");
             }

@@ -1327,50 +1327,76 @@ extern "C" int vb200_regions_integrate_bins(vb200_ctx* ctx, const vb200_regions*
 
 // ---- adaptive refinement ------------------------------------------------------------------------------------------------
 // heap-array order -> region table (SoA): region h of the output is the region the h-th heap entry points at
-// (the reference returns the heap vector as is, regions-generator-adaptive-heap.h:44)
-__global__ void compact_heap_order_kernel(uint64_t n, uint64_t cap_out, int dim, int sd, const unsigned long long* __restrict__ heap,
-                                          const float* __restrict__ range, const float* __restrict__ data,
-                                          float* __restrict__ rmin, float* __restrict__ rmax, float* __restrict__ odata,
-                                          float* __restrict__ err, uint32_t* __restrict__ errdim) {
+// (the reference returns the heap vector as is, regions-generator-adaptive-heap.h:44).  T = scalar type of the table; KEY64: 16-byte
+// heap entries with double keys (double tables and error_heuristic_mixed), whose key goes to err[] rounded to T.
+template<class T, bool KEY64>
+__global__ void compact_heap_order_kernel(uint64_t n, uint64_t cap_out, int dim, int sd, const void* __restrict__ heap_,
+                                          const T* __restrict__ range, const T* __restrict__ data,
+                                          T* __restrict__ rmin, T* __restrict__ rmax, T* __restrict__ odata,
+                                          T* __restrict__ err, uint32_t* __restrict__ errdim) {
     const uint64_t h = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (h >= n) return;
-    const unsigned long long e = heap[h];
-    const uint64_t id = (e >> 32) & 0x0fffffffull;
+    uint64_t id; uint32_t ed; T key;
+    if constexpr (KEY64) {
+        const ulonglong2 e = static_cast<const ulonglong2*>(heap_)[h];
+        id = e.y & 0x0fffffffull; ed = uint32_t(e.y >> 28) & 0xfu; key = T(__longlong_as_double(static_cast<long long>(e.x)));
+    } else {
+        const unsigned long long e = static_cast<const unsigned long long*>(heap_)[h];
+        id = (e >> 32) & 0x0fffffffull; ed = uint32_t(e >> 60); key = T(__uint_as_float(unsigned(e)));
+    }
     if (blockIdx.y == 0) {
-        err[h] = __uint_as_float(unsigned(e)); errdim[h] = uint32_t(e >> 60);
+        err[h] = key; errdim[h] = ed;
         for (int d = 0; d < dim; ++d) { rmin[uint64_t(d) * cap_out + h] = range[id * uint64_t(2 * dim) + d]; rmax[uint64_t(d) * cap_out + h] = range[id * uint64_t(2 * dim) + dim + d]; }
     }
     for (int k = blockIdx.y; k < sd; k += gridDim.y) odata[uint64_t(k) * cap_out + h] = data[id * uint64_t(sd) + k];
 }
 
-static int generate_greedy(vb200_ctx* ctx, const vb200_integrand* f, const vb200_adaptive_params* p, vb200_regions** out) {
+// exact greedy mode (batch = 1) for float and double tables; `dmin/dmax` are the range in the table's type
+template<class T>
+static int generate_greedy_t(vb200_ctx* ctx, const vb200_integrand* f, int rule, int heuristic, int metric, double size_weight, uint64_t iterations,
+                             const vb200_mixed_heuristic& mixed, const T* dmin, const T* dmax, vb200_regions** out) {
+    constexpr bool F64 = sizeof(T) == 8;
+    const bool key64 = F64 || heuristic == VB200_HEURISTIC_MIXED;
     vb200_regions* r = nullptr;
-    const uint64_t n = p->iterations + 1, cap = 2 * p->iterations + 1;
-    int rc = regions_alloc(ctx, f->dim, p->rule, n, &r); if (rc) return rc;
+    const uint64_t n = iterations + 1, cap = 2 * iterations + 1;
+    int rc = regions_alloc(ctx, f->dim, rule, n, &r, F64); if (rc) return rc;
     const int D = f->dim; const uint64_t sd = uint64_t(r->sd);
-    float *range = nullptr, *data = nullptr, *err = nullptr; unsigned long long* heap = nullptr; uint64_t* hsize = nullptr;
-    auto cleanup = [&] () { dfree(ctx, range); dfree(ctx, data); dfree(ctx, err); dfree(ctx, heap); dfree(ctx, hsize); };
+    T *range = nullptr, *data = nullptr, *err = nullptr; double* key = nullptr; void* heap = nullptr; uint64_t* hsize = nullptr;
+    auto cleanup = [&] () { dfree(ctx, range); dfree(ctx, data); dfree(ctx, err); dfree(ctx, key); dfree(ctx, heap); dfree(ctx, hsize); };
     auto bail = [&] (int code) { cleanup(); vb200_regions_free(r); return code; };
-    if (dmalloc(ctx, &range, cap * 2 * D * sizeof(float)) != cudaSuccess || dmalloc(ctx, &data, cap * sd * sizeof(float)) != cudaSuccess ||
-        dmalloc(ctx, &err, cap * sizeof(float)) != cudaSuccess || dmalloc(ctx, &heap, (n + 1) * sizeof(unsigned long long)) != cudaSuccess ||
+    if (dmalloc(ctx, &range, cap * 2 * D * sizeof(T)) != cudaSuccess || dmalloc(ctx, &data, cap * sd * sizeof(T)) != cudaSuccess ||
+        dmalloc(ctx, &err, cap * sizeof(T)) != cudaSuccess || (key64 && dmalloc(ctx, &key, cap * sizeof(double)) != cudaSuccess) ||
+        dmalloc_bytes(ctx, &heap, (n + 1) * (key64 ? 16 : 8)) != cudaSuccess ||
         dmalloc(ctx, &hsize, sizeof(uint64_t)) != cudaSuccess) { cudaGetLastError(); return bail(fail(ctx, VB200_ERR_NOMEM, "working set of the greedy refinement (%llu region slots) does not fit", (unsigned long long)cap)); }
     vb200_greedy_launch a; std::memset(&a, 0, sizeof(a));
-    a.dim = D; a.rule = p->rule; a.heuristic = p->heuristic; a.metric = p->metric; a.size_weight = p->size_weight;
-    a.iterations = p->iterations; a.capacity = cap; a.range = range; a.data = data; a.err = err; a.heap = heap; a.heap_size = hsize;
-    for (int d = 0; d < D; ++d) { a.range_min[d] = p->domain.rmin[d]; a.range_max[d] = p->domain.rmax[d]; }
+    a.dim = D; a.rule = rule; a.heuristic = heuristic; a.metric = metric; a.size_weight = size_weight;
+    a.iterations = iterations; a.capacity = cap; a.range = range; a.data = data; a.err = err; a.heap = heap; a.heap_size = hsize; a.key64 = key;
+    a.f64 = F64 ? 1 : 0; a.metric_rest = mixed.metric_rest; a.mixed_dimension = mixed.dimension; a.mixed_bins_weight = mixed.bins_weight;
+    a.mixed_threshold_bins = mixed.size_threshold_bins; a.mixed_threshold_rest = mixed.size_threshold_rest; a.mixed_error_increase = mixed.error_increase_factor;
+    for (int d = 0; d < D; ++d) {
+        if (F64) { a.range_min64[d] = double(dmin[d]); a.range_max64[d] = double(dmax[d]); }
+        else { a.range_min[d] = float(dmin[d]); a.range_max[d] = float(dmax[d]); }
+    }
     rc = call_thunk(ctx, f, VB200_K_ADAPTIVE_EXACT, &a); if (rc) return bail(rc);
     uint64_t got = 0;
     if (cudaMemcpyAsync(&got, hsize, sizeof(got), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess)
         return bail(fail(ctx, VB200_ERR_CUDA, "greedy refinement kernel failed: %s", cudaGetErrorString(cudaGetLastError())));
     if (got != n) return bail(fail(ctx, VB200_ERR_CUDA, "greedy refinement ended with %llu regions, expected %llu", (unsigned long long)got, (unsigned long long)n));
     dim3 grid(unsigned((n + 255) / 256), unsigned(sd < 32 ? sd : 32));
-    compact_heap_order_kernel<<<grid, 256, 0, ctx->stream>>>(n, n, D, int(sd), heap, range, data, r->rmin, r->rmax, r->data, r->err, r->errdim);
+    if (key64) compact_heap_order_kernel<T, true><<<grid, 256, 0, ctx->stream>>>(n, n, D, int(sd), heap, range, data, RegCols<T>::rmin(r), RegCols<T>::rmax(r), RegCols<T>::data(r), RegCols<T>::err(r), r->errdim);
+    else compact_heap_order_kernel<T, false><<<grid, 256, 0, ctx->stream>>>(n, n, D, int(sd), heap, range, data, RegCols<T>::rmin(r), RegCols<T>::rmax(r), RegCols<T>::data(r), RegCols<T>::err(r), r->errdim);
     ctx->launches++;
     if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess)
         return bail(fail(ctx, VB200_ERR_CUDA, "heap-order compaction failed: %s", cudaGetErrorString(cudaGetLastError())));
     cleanup();
     r->count = n;
     *out = r;
+    return VB200_OK;
+}
+static int check_mixed(vb200_ctx* ctx, int heuristic, const vb200_mixed_heuristic& m) {
+    if (heuristic != VB200_HEURISTIC_MIXED) return VB200_OK;
+    if (m.metric_rest != VB200_METRIC_ABSOLUTE && m.metric_rest != VB200_METRIC_RELATIVE) return fail(ctx, VB200_ERR_INVALID, "error_heuristic_mixed: unknown rest metric %d", m.metric_rest);
+    if (m.dimension < 0) return fail(ctx, VB200_ERR_INVALID, "error_heuristic_mixed: dimension %d", m.dimension);
     return VB200_OK;
 }
 
@@ -1392,10 +1418,27 @@ extern "C" int vb200_regions_generate_adaptive(vb200_ctx* ctx, const vb200_integ
     if (f->dim <= 0 || p->domain.dim != f->dim) return fail(ctx, VB200_ERR_INVALID, "range has %d dimensions, integrand takes %d", p->domain.dim, f->dim);
     int SH, SL;
     if (rule_samples(p->rule, &SH, &SL) || SL == 0) return fail(ctx, VB200_ERR_INVALID, "adaptive refinement needs a nested(high,low) rule (got %d)", p->rule);
-    if (p->heuristic != VB200_HEURISTIC_DEFAULT && p->heuristic != VB200_HEURISTIC_SIZE) return fail(ctx, VB200_ERR_INVALID, "unknown heuristic %d", p->heuristic);
+    if (p->heuristic != VB200_HEURISTIC_DEFAULT && p->heuristic != VB200_HEURISTIC_SIZE && p->heuristic != VB200_HEURISTIC_MIXED) return fail(ctx, VB200_ERR_INVALID, "unknown heuristic %d", p->heuristic);
     if (p->metric != VB200_METRIC_ABSOLUTE && p->metric != VB200_METRIC_RELATIVE) return fail(ctx, VB200_ERR_INVALID, "unknown metric %d", p->metric);
+    if (int rcm = check_mixed(ctx, p->heuristic, p->mixed)) return rcm;
+    if (f->flags & VB200_INTEGRAND_F64) return fail(ctx, VB200_ERR_INVALID, "double-precision integrand: use vb200_regions_generate_adaptive_f64");
     if (p->iterations >= (1ull << 27)) return fail(ctx, VB200_ERR_UNSUPPORTED, "more than 2^27 iterations");
-    if (p->batch == 1) return generate_greedy(ctx, f, p, out);
+    if (p->batch == 1) return generate_greedy_t<float>(ctx, f, p->rule, p->heuristic, p->metric, p->size_weight, p->iterations, p->mixed, p->domain.rmin, p->domain.rmax, out);
     if (p->batch < 0) return fail(ctx, VB200_ERR_INVALID, "batch=%d", p->batch);
     return generate_batched(ctx, f, p, out);
+}
+
+extern "C" int vb200_regions_generate_adaptive_f64(vb200_ctx* ctx, const vb200_integrand* f, const vb200_adaptive_params_f64* p, vb200_regions** out) {
+    if (!ctx || !f || !p || !out) return fail(ctx, VB200_ERR_INVALID, "NULL argument");
+    VB200_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!(f->flags & VB200_INTEGRAND_F64)) return fail(ctx, VB200_ERR_INVALID, "vb200_regions_generate_adaptive_f64 needs a double-precision integrand");
+    if (f->dim <= 0 || p->domain.dim != f->dim) return fail(ctx, VB200_ERR_INVALID, "range has %d dimensions, integrand takes %d", p->domain.dim, f->dim);
+    int SH, SL;
+    if (rule_samples(p->rule, &SH, &SL) || SL == 0) return fail(ctx, VB200_ERR_INVALID, "adaptive refinement needs a nested(high,low) rule (got %d)", p->rule);
+    if (p->heuristic != VB200_HEURISTIC_DEFAULT && p->heuristic != VB200_HEURISTIC_SIZE && p->heuristic != VB200_HEURISTIC_MIXED) return fail(ctx, VB200_ERR_INVALID, "unknown heuristic %d", p->heuristic);
+    if (p->metric != VB200_METRIC_ABSOLUTE && p->metric != VB200_METRIC_RELATIVE) return fail(ctx, VB200_ERR_INVALID, "unknown metric %d", p->metric);
+    if (int rcm = check_mixed(ctx, p->heuristic, p->mixed)) return rcm;
+    if (p->iterations >= (1ull << 27)) return fail(ctx, VB200_ERR_UNSUPPORTED, "more than 2^27 iterations");
+    if (p->batch != 1) return fail(ctx, VB200_ERR_UNSUPPORTED, "double-precision adaptive generation runs in the exact greedy mode only (batch = 1)");
+    return generate_greedy_t<double>(ctx, f, p->rule, p->heuristic, p->metric, p->size_weight, p->iterations, p->mixed, p->domain.rmin, p->domain.rmax, out);
 }

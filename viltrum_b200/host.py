@@ -248,14 +248,38 @@ class Context:
         p = self._mc_params(len(rng.min), res, rng, samples, seed, C.MC_PER_BIN, shard, C.MC_ALLREDUCE if allreduce else 0)
         self.check(self._L.vb200_monte_carlo(self._h, self.integrand(f, exact), ctypes.byref(p), b, mem))
 
-    def regions_generate_adaptive(self, f, rng, rule, heuristic, metric, iterations, size_weight=1e-5, batch=1, exact=True):
+    @staticmethod
+    def _fill_mixed(p, mixed):
+        """mixed = dict(metric_rest, dimension, bins_weight, size_threshold_bins, size_threshold_rest, error_increase_factor) — error_heuristic_mixed's
+        constructor arguments with the reference's defaults (error-heuristic.h:62-68)"""
+        m = dict(metric_rest="absolute", dimension=2, bins_weight=1.0, size_threshold_bins=1.0 / 1024.0, size_threshold_rest=1.0 / 16.0, error_increase_factor=1.e4)
+        m.update(mixed or {})
+        p.mixed.metric_rest, p.mixed.dimension = C.METRICS[m["metric_rest"]], int(m["dimension"])
+        p.mixed.bins_weight, p.mixed.size_threshold_bins = float(m["bins_weight"]), float(m["size_threshold_bins"])
+        p.mixed.size_threshold_rest, p.mixed.error_increase_factor = float(m["size_threshold_rest"]), float(m["error_increase_factor"])
+
+    def regions_generate_adaptive(self, f, rng, rule, heuristic, metric, iterations, size_weight=1e-5, batch=1, exact=True, mixed=None):
         p = C.AdaptiveParams()
         p.domain = C.make_domain(len(rng.min), [1], rng.min, rng.max)
         p.rule, p.heuristic, p.metric = C.RULES[rule], C.HEURISTICS[heuristic], C.METRICS[metric]
         p.batch, p.size_weight, p.iterations = int(batch), float(size_weight), int(iterations)
+        if heuristic == "mixed":
+            self._fill_mixed(p, mixed)
         h = ctypes.c_void_p()
         self.check(self._L.vb200_regions_generate_adaptive(self._h, self.integrand(f, exact), ctypes.byref(p), ctypes.byref(h)))
         return Regions(self, h)
+
+    def regions_generate_adaptive_f64(self, f, rng, rule, heuristic, metric, iterations, size_weight=1e-5, exact=True, mixed=None):
+        """Range<double,DIM> through the exact greedy generator (vb200_regions_generate_adaptive_f64): a double region table"""
+        p = C.AdaptiveParams64()
+        p.domain = C.make_domain64(len(rng.min), [1], rng.min, rng.max)
+        p.rule, p.heuristic, p.metric = C.RULES[rule], C.HEURISTICS[heuristic], C.METRICS[metric]
+        p.batch, p.size_weight, p.iterations = 1, float(size_weight), int(iterations)
+        if heuristic == "mixed":
+            self._fill_mixed(p, mixed)
+        h = ctypes.c_void_p()
+        self.check(self._L.vb200_regions_generate_adaptive_f64(self._h, self.integrand64(f, exact), ctypes.byref(p), ctypes.byref(h)))
+        return Regions(self, h, f64=True)
 
     def regions_generate_tolerance(self, f, rng, rule, heuristic, metric, tolerance, size_weight=1e-5, max_regions=0, exact=True):
         p = C.ToleranceParams()
@@ -502,6 +526,15 @@ def error_heuristic_size(metric, size_weight=1e-5):
     return ErrorHeuristic("size", metric, size_weight)
 
 
+def error_heuristic_mixed(metric_bins, metric_rest, dimension=2, bins_weight=1.0, size_weight=1.e-3, size_threshold_bins=1.0 / 1024.0,
+                          size_threshold_rest=1.0 / 16.0, error_increase_factor=1.e4):
+    """error_heuristic_mixed(...) — reference src/nested/error-heuristic.h:49-98, same argument order and defaults"""
+    h = ErrorHeuristic("mixed", metric_bins, size_weight)
+    h.mixed = dict(metric_rest=metric_rest.kind, dimension=dimension, bins_weight=bins_weight, size_threshold_bins=size_threshold_bins,
+                   size_threshold_rest=size_threshold_rest, error_increase_factor=error_increase_factor)
+    return h
+
+
 @dataclass
 class IntegratorNewtonCotes:
     """integrator_newton_cotes(rule) — reference src/newton-cotes/newton-cotes.h:11-14 ('+=')"""
@@ -527,7 +560,7 @@ class IntegratorAdaptiveIterations:
 
     def generate(self, ctx, f, rng, exact=True):
         return ctx.regions_generate_adaptive(f, rng, self.rule.name, self.heuristic.kind, self.heuristic.metric.kind,
-                                             self.iterations, self.heuristic.size_weight, self.batch, exact=exact)
+                                             self.iterations, self.heuristic.size_weight, self.batch, exact=exact, mixed=getattr(self.heuristic, "mixed", None))
 
     def integrate(self, ctx, bins, res, f, rng, shard=None, exact=True, logger=None, **kw):
         regs = self.generate(ctx, f, rng, exact=exact)
