@@ -249,8 +249,11 @@ class Bench:
         # (BASELINE configs[3]: "bins sharded over 8 GPUs"); --scaling overrides
         self.scaling = args.scaling or ("weak" if w["kind"] in ("mc", "walk") else "strong")
         res = list(w["res"])
-        self.gres = [res[0], res[1] * world] if self.scaling == "weak" else res
-        self.shard = shard_for_rank(self.gres, rank, world)
+        # region-based workloads under --scaling weak: N replicas, every rank integrates the whole grid with its own seed (the region table does not
+        # shard, so "more bins" would change the regions per bin); the per-bin samplers stack the ranks' slabs into one taller grid instead
+        self.replicas = self.scaling == "weak" and w["kind"] in ("nc", "cv") and world > 1
+        self.gres = [res[0], res[1] * world] if (self.scaling == "weak" and not self.replicas) else res
+        self.shard = (0, self.gres[0] * self.gres[1]) if self.replicas else shard_for_rank(self.gres, rank, world)
         self.nb_local = self.shard[1] - self.shard[0]
         self.nb_global = self.gres[0] * self.gres[1]
         d = {"mc": 4, "cv": 5, "nc": 2}.get(w["kind"])
@@ -281,7 +284,7 @@ class Bench:
                 regs = ctx.regions_broadcast(regs, 0)
             else:
                 regs = ctx.regions_generate_adaptive(w["integrand"], self.rng, "simpson_trapezoidal", "size", "relative", w["iterations"], 1e-5, batch=self.batch, exact=True)
-            regs.cv_integrate(w["integrand"], bins, self.gres, self.rng, w["spp"], seed, shard=self.shard,
+            regs.cv_integrate(w["integrand"], bins, self.gres, self.rng, w["spp"], seed + 7919 * (self.rank if self.replicas else 0), shard=self.shard,
                               nregions=self.d_nreg if (self.d_nreg is not None and not isinstance(bins, np.ndarray)) else None)
             regs.free()
 
@@ -336,9 +339,10 @@ class Bench:
 
     def units(self):
         w = self.w
+        rep = self.world if self.replicas else 1
         if w["kind"] == "nc":
-            return w["iterations"]
-        return self.nb_global * w["spp"]
+            return w["iterations"] * rep
+        return self.nb_global * w["spp"] * rep
 
     def run(self, peaks, fp32_peak, fma_peak, sm_max):
         args, w, ctx = self.args, self.w, self.ctx
@@ -411,7 +415,8 @@ class Bench:
             roof["peak_measured_fma"] = fma_peak
             roof["frac_of_measured_fma"] = (roof["achieved"] / fma_peak) if fma_peak else None
         cfg = config_of(self.name)
-        cfg.update({"rng": RNG_NOTE[w["kind"]] if w["kind"] in RNG_NOTE else None, "parallelism": f"bin-grid slabs x{self.world} ({self.scaling} scaling: global grid {self.gres[0]}x{self.gres[1]})",
+        cfg.update({"rng": RNG_NOTE[w["kind"]] if w["kind"] in RNG_NOTE else None, "parallelism": (f"{self.world} replicas of the whole {self.gres[0]}x{self.gres[1]} grid, one per GPU, own seeds (weak scaling of a path whose region table does not shard)" if self.replicas
+                                    else f"bin-grid slabs x{self.world} ({self.scaling} scaling: global grid {self.gres[0]}x{self.gres[1]})"),
                     "l2": "flushed between timed steps (256 MiB memset, untimed); per-step CUDA events on the library stream"})
         if w["kind"] in ("nc", "cv"):
             cfg["generation"] = "batched top-k refinement (batch = 0); the exact greedy mode (batch = 1) is timed beside it in exact_mode"

@@ -372,8 +372,17 @@ typedef enum vb200_rr_policy {      /* Russian roulette among the regions that t
     VB200_RR_UNIFORM = 0,           /* rr_uniform_region  :9-28   every region equally likely */
     VB200_RR_INTEGRAL = 1,          /* rr_integral_region :30-67  probability ~ |integral of the interpolant over bin ∩ region| (floored at 1 % of the mean) */
     VB200_RR_ERROR = 2,             /* rr_error_region    :69-106 probability ~ |Region::error()| * vol(bin ∩ region)/vol(region) (same floor); nested rules only */
-    VB200_RR_PDF = 3                /* rr_pdf_region      :108-147 probability ~ integral over bin ∩ region of the shifted |interpolant| (Simpson-based rules only; factor_prob 0.01f) */
+    VB200_RR_PDF = 3,               /* rr_pdf_region      :108-147 probability ~ integral over bin ∩ region of the shifted |interpolant| (Simpson-based rules only; factor_prob 0.01f) */
+    VB200_RR_STRATIFIED = 4         /* region_stratification_uniform (region-stratification.h:9-25), the allocation of RegionsIntegratorParallelVarianceReductionOptimized
+                                       (…-variance-reduction-optimized.h:120-133): spp/n samples per region of the bin, the remainder from one random start, each
+                                       residual term weighted by spp / (samples of its region) */
 } vb200_rr_policy;
+typedef enum vb200_rs_policy {      /* where inside bin ∩ region a residual sample falls (reference src/control-variates/region-sampling.h) */
+    VB200_RS_UNIFORM = 0,           /* region_sampling_uniform          :9-20   weight = volume                                              */
+    VB200_RS_IMPORTANCE = 1,        /* region_sampling_importance       :22-44  position ~ |interpolant| (Simpson::sample), weight = 1/pdf   */
+    VB200_RS_MIS = 2,               /* region_sampling_mis(power,cutoff):85-135 importance position or uniform position, constant MIS weight */
+    VB200_RS_RUSSIAN_ROULETTE = 3   /* region_sampling_russian_roulette :46-83                                                               */
+} vb200_rs_policy;
 typedef struct vb200_cv_params {
     vb200_domain domain;
     vb200_shard  shard;
@@ -382,6 +391,10 @@ typedef struct vb200_cv_params {
     int32_t      weight_strategy;   /* vb200_cv_weight */
     int32_t      rr_policy;         /* vb200_rr_policy (0 = the crespo2021 preset) */
     double       alpha;             /* VB200_CV_FIXED_WEIGHT only */
+    int32_t      rs_policy;         /* vb200_rs_policy (0 = the crespo2021 preset); the non-uniform ones need a Simpson-based table of <= 5 dimensions
+                                       and have statistical parity only (the reference inverts a cubic CDF with pow/acos/cos) */
+    int32_t      reserved;
+    double       rs_power, rs_cutoff; /* VB200_RS_MIS: region_sampling_mis(power = 1, cutoff = 0) */
 } vb200_cv_params;
 
 /* RegionsIntegratorParallelVarianceReduction with rr_uniform_region | rr_integral_region | rr_error_region | rr_pdf_region / cv_optimize_weight | cv_fixed_weight / region_sampling_uniform

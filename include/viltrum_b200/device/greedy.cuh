@@ -173,6 +173,12 @@ __device__ void heuristic_pick_mixed(const T* E, const T* rng, const MixedParams
     *out_err = max_err; *out_dim = max_dim;
 }
 
+#ifdef VB200_GREEDY_TIMING      // experiment builds (profiles/exp/greedy_phases.cu): cycles thread 0 spends between the barriers of an iteration
+__device__ unsigned long long vb200_greedy_clock[8];
+#define VB200_GT(k) do { if (tid == 0) { const long long now_ = clock64(); vb200_greedy_clock[k] += (unsigned long long)(now_ - t_prev_); t_prev_ = now_; } } while (0)
+#else
+#define VB200_GT(k) do {} while (0)
+#endif
 // T = float or double (the Float of the range); MIXED selects error_heuristic_mixed (double keys).  Keys are doubles whenever T is double or MIXED.
 template<class F, int DIM, int SH, int SL, bool EXACT, class T = float, bool MIXED = false>
 __global__ void __launch_bounds__(GREEDY_THREADS, 1)
@@ -235,9 +241,13 @@ greedy_kernel(const F f, const vb200_greedy_launch a, const int heap_cached) {
 
     // ---- iterations ----
     unsigned long long next_slot = 1;
+#ifdef VB200_GREEDY_TIMING
+    long long t_prev_ = clock64();
+#endif
     for (unsigned long long it = 0; it < a.iterations; ++it) {
         if (tid == 0) { const unsigned idd = E::id_dim(heap.get(0)); s_top_id = idd & GREEDY_ID_MASK; s_top_dim = idd >> 28; }
         __syncthreads();
+        VB200_GT(0);
         const unsigned top = s_top_id; const int dim = int(s_top_dim);
         // warp 0 pops while the others fetch the parent (the pop does not depend on the split: heap.front() was copied first, :33-35)
         if (warp == 0) { if (lane == 0) heap.pop(); }
@@ -245,7 +255,9 @@ greedy_kernel(const F f, const vb200_greedy_launch a, const int heap_cached) {
             for (int k = tid - 32; k < Sh::SD; k += GREEDY_THREADS - 32) s_parent[k] = g_data[static_cast<unsigned long long>(top) * Sh::SD + k];
             if (tid - 32 < 2 * DIM) s_prange[tid - 32] = g_range[static_cast<unsigned long long>(top) * (2 * DIM) + (tid - 32)];
         }
+        VB200_GT(1);
         __syncthreads();
+        VB200_GT(2);
         // split along `dim` (split.h:13-49): the (2S-1)-wide array; even positions are the parent's samples, odd ones new evaluations
         int inner = 1; for (int i = 0; i < dim; ++i) inner *= SH;
         for (int item = tid; item < Sh::WIDE; item += GREEDY_THREADS) {
@@ -278,6 +290,7 @@ greedy_kernel(const F f, const vb200_greedy_launch a, const int heap_cached) {
             s_vol[tid] = v;
         }
         __syncthreads();
+        VB200_GT(3);
         // nested-rule error of both children along every dimension: one warp per (child, dimension)
         for (int job = warp; job < 2 * DIM; job += nwarps) {
             const int c = job / DIM, d = job % DIM;
@@ -285,6 +298,7 @@ greedy_kernel(const F f, const vb200_greedy_launch a, const int heap_cached) {
             if (lane == 0) s_E[c * DIM + d] = e;
         }
         __syncthreads();
+        VB200_GT(4);
         // store the children (slots next_slot, next_slot+1) and push them in ascending coordinate order (:36-40)
         for (int k = tid; k < 2 * Sh::SD; k += GREEDY_THREADS) g_data[next_slot * Sh::SD + k] = s_child[k];
         if (tid < 4 * DIM) g_range[next_slot * (2 * DIM) + tid] = s_crange[tid];
@@ -296,7 +310,9 @@ greedy_kernel(const F f, const vb200_greedy_launch a, const int heap_cached) {
             }
         }
         next_slot += 2;
+        VB200_GT(5);
         __syncthreads();
+        VB200_GT(6);
     }
     // flush the cached top of the heap
     const long long n = heap.n;

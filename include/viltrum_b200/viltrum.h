@@ -513,14 +513,22 @@ struct rr_uniform_region { static constexpr int id = VB200_RR_UNIFORM; };       
 struct rr_integral_region { static constexpr int id = VB200_RR_INTEGRAL; };     // :30-67  (NormDefault)
 struct rr_error_region { static constexpr int id = VB200_RR_ERROR; };           // :69-106 (NormDefault)
 struct rr_pdf_region { static constexpr int id = VB200_RR_PDF; };               // :108-147 (factor_prob = 0.01, NormDefault)
-struct region_sampling_uniform {};      // region-sampling.h:9-20
+// where inside bin ∩ region a residual sample falls (reference src/control-variates/region-sampling.h:9-135); NormDefault
+struct region_sampling_uniform { static constexpr int id = VB200_RS_UNIFORM; double power = 1, cutoff = 0; };                      // :9-20
+struct region_sampling_importance { static constexpr int id = VB200_RS_IMPORTANCE; double power = 1, cutoff = 0; };                // :22-44
+struct region_sampling_russian_roulette { static constexpr int id = VB200_RS_RUSSIAN_ROULETTE; double power = 1, cutoff = 0; };    // :46-83
+struct region_sampling_mis { static constexpr int id = VB200_RS_MIS; double power, cutoff; region_sampling_mis(double p = 1, double c = 0) : power(p), cutoff(c) {} };   // :85-135
+// region_stratification_uniform (region-stratification.h:9-25): the sample allocation of the ...Optimized integrators, in the RR slot of their factories
+struct region_stratification_uniform { static constexpr int id = VB200_RR_STRATIFIED; };
 // integrator_region_based(regions_generator_adaptive_heap(rule, heuristic, iterations), regions_integrator_parallel_variance_reduction(RR, CV,
 // region_sampling_uniform, spp, seed)) — reference integrator-adaptive-variance-reduction.h:11-49, regions-integrator-parallel-variance-reduction.h:32-109
 template<typename Rule, typename EH> class IntegratorAdaptiveVarianceReduction {
     EH eh; std::size_t iterations, spp, seed_; int weight_strategy = VB200_CV_OPTIMIZE_WEIGHT; double alpha = 1.0; int rr = VB200_RR_UNIFORM;
+    int rs = VB200_RS_UNIFORM; double rs_power = 1.0, rs_cutoff = 0.0;
 public:
-    IntegratorAdaptiveVarianceReduction(const EH& e, std::size_t it, std::size_t s, std::size_t seed, int ws = VB200_CV_OPTIMIZE_WEIGHT, double a = 1.0, int rr_policy = VB200_RR_UNIFORM)
-        : eh(e), iterations(it), spp(s), seed_(seed), weight_strategy(ws), alpha(a), rr(rr_policy) {}
+    IntegratorAdaptiveVarianceReduction(const EH& e, std::size_t it, std::size_t s, std::size_t seed, int ws = VB200_CV_OPTIMIZE_WEIGHT, double a = 1.0, int rr_policy = VB200_RR_UNIFORM,
+                                        int rs_policy = VB200_RS_UNIFORM, double power = 1.0, double cutoff = 0.0)
+        : eh(e), iterations(it), spp(s), seed_(seed), weight_strategy(ws), alpha(a), rr(rr_policy), rs(rs_policy), rs_power(power), rs_cutoff(cutoff) {}
     template<typename Bins, std::size_t DIMBINS, typename F, typename Float, std::size_t DIM, typename Logger>
     void integrate(Bins& bins, const std::array<std::size_t,DIMBINS>& res, const F& f, const Range<Float,DIM>& range, Logger& logger) const {
         auto& ctx = b200::default_context();
@@ -530,7 +538,7 @@ public:
         if constexpr (!std::is_same<Logger, LoggerNull>::value) logger.log(b200::download_regions<DIM>(ctx, regs.r));
         vb200_cv_params p; std::memset(&p, 0, sizeof(p));
         p.domain = b200::make_domain(range, res); p.shard = b200::current_shard(); p.spp = spp; p.seed = seed_;
-        p.weight_strategy = weight_strategy; p.alpha = alpha; p.rr_policy = rr;
+        p.weight_strategy = weight_strategy; p.alpha = alpha; p.rr_policy = rr; p.rs_policy = rs; p.rs_power = rs_power; p.rs_cutoff = rs_cutoff;
         std::vector<float> flat(b200::bin_count(res), 0.0f);
         ctx.check(vb200_cv_integrate(ctx.get(), g.c_abi(), regs.r, &p, flat.data(), VB200_HOST, nullptr, nullptr));
         b200::apply_bins<false>(bins, res, flat);
@@ -542,19 +550,25 @@ inline IntegratorCrespo2021 integrator_crespo2021(std::size_t iterations, std::s
     return IntegratorCrespo2021(error_heuristic_size<error_metric_relative>(error_metric_relative(), 1.e-5), iterations, spp, seed);
 }
 // the reference's overloads that take a seed (integrator-adaptive-variance-reduction.h:21-49); RR = rr_uniform_region | rr_integral_region |
-// rr_error_region | rr_pdf_region, CV = cv_optimize_weight | cv_fixed_weight(alpha); region_sampling_uniform only (importance / MIS sampling: SURVEY.md §8f rank 3, not built)
-template<typename RR, typename CV, typename R, typename EH, typename = decltype(RR::id), typename = decltype(CV::id), typename = decltype(EH::id)>
-auto integrator_adaptive_variance_reduction_parallel(const R&, const EH& eh, std::size_t iterations, const RR&, const CV& cv, const region_sampling_uniform&, unsigned long spp, std::size_t seed = 0, std::size_t = 16) {
-    return IntegratorAdaptiveVarianceReduction<R, EH>(eh, iterations, spp, seed, CV::id, cv.alpha, RR::id);
+// rr_error_region | rr_pdf_region | region_stratification_uniform, CV = cv_optimize_weight | cv_fixed_weight(alpha), RS = region_sampling_uniform | _importance |
+// _mis(power, cutoff) | _russian_roulette (the ...optimized factories of integrator-adaptive-variance-reduction-optimized.h:11-30 are the same call with
+// region_stratification_uniform() in the RR slot)
+template<typename RR, typename CV, typename RS, typename R, typename EH, typename = decltype(RR::id), typename = decltype(CV::id), typename = decltype(EH::id), typename = decltype(RS::id)>
+auto integrator_adaptive_variance_reduction_parallel(const R&, const EH& eh, std::size_t iterations, const RR&, const CV& cv, const RS& rs, unsigned long spp, std::size_t seed = 0, std::size_t = 16) {
+    return IntegratorAdaptiveVarianceReduction<R, EH>(eh, iterations, spp, seed, CV::id, cv.alpha, RR::id, RS::id, rs.power, rs.cutoff);
+}
+template<typename RR, typename CV, typename RS, typename R, typename EH, typename = decltype(RR::id), typename = decltype(CV::id), typename = decltype(EH::id), typename = decltype(RS::id)>
+auto integrator_adaptive_variance_reduction_parallel_optimized(const R& r, const EH& eh, std::size_t iterations, const RR& rr, const CV& cv, const RS& rs, unsigned long spp, std::size_t seed = 0, std::size_t n = 16) {
+    return integrator_adaptive_variance_reduction_parallel(r, eh, iterations, rr, cv, rs, spp, seed, n);
 }
 template<typename RR, typename CV, typename R, typename EH, typename = decltype(RR::id), typename = decltype(CV::id), typename = decltype(EH::id)>
 auto integrator_adaptive_variance_reduction_parallel(const R&, const EH& eh, std::size_t iterations, const RR&, const CV& cv, unsigned long spp, std::size_t seed = 0, std::size_t = 16) {
     return IntegratorAdaptiveVarianceReduction<R, EH>(eh, iterations, spp, seed, CV::id, cv.alpha, RR::id);
 }
-template<typename RR, typename CV, typename R, typename = decltype(RR::id), typename = decltype(CV::id), typename = decltype(R::id)>
-auto integrator_adaptive_variance_reduction_parallel(const R&, std::size_t iterations, const RR&, const CV& cv, const region_sampling_uniform&, unsigned long spp, std::size_t seed = 0, std::size_t = 16) {
+template<typename RR, typename CV, typename RS, typename R, typename = decltype(RR::id), typename = decltype(CV::id), typename = decltype(R::id), typename = decltype(RS::id)>
+auto integrator_adaptive_variance_reduction_parallel(const R&, std::size_t iterations, const RR&, const CV& cv, const RS& rs, unsigned long spp, std::size_t seed = 0, std::size_t = 16) {
     using EH = error_heuristic_default<error_metric_absolute>;
-    return IntegratorAdaptiveVarianceReduction<R, EH>(EH(error_metric_absolute()), iterations, spp, seed, CV::id, cv.alpha, RR::id);
+    return IntegratorAdaptiveVarianceReduction<R, EH>(EH(error_metric_absolute()), iterations, spp, seed, CV::id, cv.alpha, RR::id, RS::id, rs.power, rs.cutoff);
 }
 template<typename RR, typename CV, typename R, typename = decltype(RR::id), typename = decltype(CV::id), typename = decltype(R::id)>
 auto integrator_adaptive_variance_reduction_parallel(const R&, std::size_t iterations, const RR&, const CV& cv, unsigned long spp, std::size_t seed = 0, std::size_t = 16) {
@@ -608,9 +622,9 @@ template<std::size_t N, typename First> IntegratorFubini<First,N> integrator_fub
 
 // integrator_crespo2021_infinite<N>(iterations, mc_samples, spp, seed) — integrator-crespo2021.h:24-44 ('=')
 template<std::size_t N> class IntegratorCrespo2021Infinite {
-    std::size_t iterations, mc_samples, spp, seed_;
+    std::size_t iterations, mc_samples, spp, seed_; int rr = VB200_RR_UNIFORM;
 public:
-    IntegratorCrespo2021Infinite(std::size_t it, std::size_t m, std::size_t s, std::size_t seed) : iterations(it), mc_samples(m), spp(s), seed_(seed) {}
+    IntegratorCrespo2021Infinite(std::size_t it, std::size_t m, std::size_t s, std::size_t seed, int rr_policy = VB200_RR_UNIFORM) : iterations(it), mc_samples(m), spp(s), seed_(seed), rr(rr_policy) {}
     template<typename Bins, std::size_t DIMBINS, typename F, typename R, typename Logger>
     void integrate(Bins& bins, const std::array<std::size_t,DIMBINS>& res, const F& f, const R& range, Logger& logger) const {
         auto& ctx = b200::default_context();
@@ -627,7 +641,7 @@ public:
         auto g_res = b200::fubini_function<N>(f, std::get<1>(split), 1ul, seed_ + std::size_t(0x9E3779B97F4A7C15ull));
         b200::Integrand<decltype(g_res), int(N)> resid(g_res);
         vb200_cv_params p; std::memset(&p, 0, sizeof(p));
-        p.domain = b200::make_domain(first, res); p.shard = b200::current_shard(); p.spp = spp; p.seed = seed_;
+        p.domain = b200::make_domain(first, res); p.shard = b200::current_shard(); p.spp = spp; p.seed = seed_; p.rr_policy = rr;
         std::vector<float> flat(b200::bin_count(res), 0.0f);
         ctx.check(vb200_cv_integrate(ctx.get(), resid.c_abi(), regs.r, &p, flat.data(), VB200_HOST, nullptr, nullptr));
         b200::apply_bins<false>(bins, res, flat);
@@ -636,6 +650,16 @@ public:
 };
 template<std::size_t N> IntegratorCrespo2021Infinite<N> integrator_crespo2021_infinite(std::size_t iterations, std::size_t mc_samples, std::size_t spp, std::size_t seed = 0, std::size_t = 16) {
     return IntegratorCrespo2021Infinite<N>(iterations, mc_samples, spp, seed);
+}
+
+// integrator_adaptive_fubini_variance_reduction_parallel_optimized<N>(nested(simpson,trapezoidal), error_heuristic_size(relative), iterations, mc_samples,
+// region_stratification_uniform(), cv_optimize_weight(), region_sampling_uniform(), spp, seed) — reference integrator-adaptive-fubini-variance-reduction-optimized.h:17-23
+template<std::size_t N, typename R, typename EH, typename CV, typename RS>
+IntegratorCrespo2021Infinite<N> integrator_adaptive_fubini_variance_reduction_parallel_optimized(const R&, const EH&, std::size_t iterations, unsigned long mc_samples, const region_stratification_uniform&,
+                                                                                                  const CV&, const RS&, unsigned long spp, std::size_t seed = 0, std::size_t = 16) {
+    static_assert(std::is_same<R, Nested<Simpson,Trapezoidal>>::value && std::is_same<EH, error_heuristic_size<error_metric_relative>>::value && CV::id == VB200_CV_OPTIMIZE_WEIGHT && RS::id == VB200_RS_UNIFORM,
+                  "the device pipeline of the infinite-range control variates is built for the crespo2021 preset (simpson/trapezoidal, size/relative, cv_optimize_weight, region_sampling_uniform)");
+    return IntegratorCrespo2021Infinite<N>(iterations, mc_samples, spp, seed, VB200_RR_STRATIFIED);
 }
 
 // ---- the front door (reference src/integrate.h:72-173) ------------------------------------------------------------------------

@@ -151,6 +151,19 @@ int vo_mt_per_bin(const char* path, const char* integrand, int dimbins, const ui
                   int nthreads, float* bins);
 
 
+// ---- remaining control-variate policies (reference builds only: no port restatement — Simpson::sample inverts a cubic CDF with pow/acos/cos, so
+// only statistical parity is on offer and the tests compare against the unmodified reference directly) ------------------------------------------
+// integrator_region_based(regions_generator_adaptive_heap(nested(simpson,trapezoidal), size/relative 1e-5, iterations),
+//   regions_integrator_parallel_variance_reduction(rr_uniform_region(), cv_optimize_weight(), RS, mt19937(seed), spp)) with RS = region_sampling_uniform (0) /
+//   _importance (1) / _mis(power, cutoff) (2) / _russian_roulette (3) — reference src/control-variates/region-sampling.h:9-135.  '='.
+int vo_cv_sampling(const char* integrand, uint64_t iterations, uint64_t spp, uint64_t seed, int rs_policy, double power, double cutoff,
+                   int dimbins, const uint64_t* res, const float* rmin, const float* rmax, float* bins);
+// integrator_adaptive_fubini_variance_reduction_parallel_optimized<nfirst>(nested(simpson,trapezoidal), size/relative 1e-5, iterations, mc_samples,
+//   region_stratification_uniform(), cv_optimize_weight(), region_sampling_uniform(), spp, seed) over a sequence integrand and an infinite range —
+//   reference src/control-variates/integrator-adaptive-fubini-variance-reduction-optimized.h:17-23, regions-integrator-parallel-variance-reduction-optimized.h:70-142.  '='.
+int vo_cv_optimized_infinite(const char* integrand, int nfirst, uint64_t iterations, uint64_t mc_samples, uint64_t spp, uint64_t seed,
+                             int dimbins, const uint64_t* res, const float* rmin, const float* rmax, int nrange, float* bins);
+
 // ---- timing legs (reference builds only; the port does not export them) -----------------------------------------------------
 // vo_set_threads: threads behind the reference's std::for_each(par_unseq, ...) loops in oracle/_ref/libviltrum_ref_mt.so (the same
 // harness over the same unmodified reference, with oracle/pstl_threads/execution as the parallel-STL back end upstream takes from

@@ -330,6 +330,26 @@ class Oracle:
             return bins, dict(nregions=nreg, approx=approx, chosen=chosen, samples=samples)
         return bins
 
+    def cv_sampling(self, integrand, iterations, spp, seed, rs, res, rmin, rmax, power=1.0, cutoff=0.0):
+        """crespo2021 pipeline with region_sampling_<rs> (reference builds only)"""
+        res, rmin, rmax, nb = self._setup(res, rmin, rmax)
+        bins = np.zeros(nb, np.float32)
+        self.lib.vo_cv_sampling.restype = ctypes.c_int
+        rc = self.lib.vo_cv_sampling(integrand.encode(), ctypes.c_uint64(iterations), ctypes.c_uint64(spp), ctypes.c_uint64(seed),
+                                     ctypes.c_int({"uniform": 0, "importance": 1, "mis": 2, "russian_roulette": 3}[rs]), ctypes.c_double(power), ctypes.c_double(cutoff),
+                                     len(res), _p(res), _p(rmin), _p(rmax), _p(bins))
+        self._check(rc, "vo_cv_sampling")
+        return bins
+
+    def cv_optimized_infinite(self, integrand, nfirst, iterations, mc_samples, spp, seed, res, rmin=(), rmax=()):
+        """integrator_adaptive_fubini_variance_reduction_parallel_optimized<nfirst> (reference builds only)"""
+        res, rmin, rmax, bins = self._fubini_args(integrand, res, rmin, rmax)
+        self.lib.vo_cv_optimized_infinite.restype = ctypes.c_int
+        rc = self.lib.vo_cv_optimized_infinite(integrand.encode(), int(nfirst), ctypes.c_uint64(iterations), ctypes.c_uint64(mc_samples),
+                                               ctypes.c_uint64(spp), ctypes.c_uint64(seed), len(res), _p(res), _p(rmin), _p(rmax), len(rmin), _p(bins))
+        self._check(rc, "vo_cv_optimized_infinite")
+        return bins
+
     def mt_per_bin(self, path, integrand, res, spp, seed, nthreads, rmin=(), rmax=()):
         res = np.ascontiguousarray(np.asarray(res, dtype=np.uint64))
         rmin, rmax = _f32(rmin), _f32(rmax)

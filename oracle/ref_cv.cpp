@@ -173,3 +173,32 @@ extern "C" int vo_cv_policies(const char* integrand, uint64_t iterations, uint64
         return 0;
     });
 }
+
+
+// The crespo2021 pipeline with the region-SAMPLING policy chosen by the caller (reference src/control-variates/region-sampling.h:9-135):
+// rs_policy 0 region_sampling_uniform, 1 region_sampling_importance, 2 region_sampling_mis(power, cutoff), 3 region_sampling_russian_roulette;
+// rr_uniform_region, cv_optimize_weight.  No recording (the importance samplers draw through Simpson::sample: statistical parity only).
+extern "C" int vo_cv_sampling(const char* integrand, uint64_t iterations, uint64_t spp, uint64_t seed, int rs_policy, double power, double cutoff,
+                   int dimbins, const uint64_t* res, const float* rmin, const float* rmax, float* bins) {
+    if (rs_policy < 0 || rs_policy > 3) return -3;
+    return dispatch_finite_bins(integrand, dimbins, [&] (auto f, auto dbc) -> int {
+        using F = decltype(f);
+        constexpr std::size_t D = F::dim;
+        constexpr std::size_t DB = decltype(dbc)::value;
+        using namespace viltrum;
+        auto r = res_array<DB>(res);
+        auto range = range_array<D>(rmin, rmax);
+        auto acc = [&] (const std::array<std::size_t,DB>& p) -> float& { return bins[tensor_pos(p,r)]; };
+        auto run = [&] (auto rs) {
+            auto integrator = integrator_region_based(
+                regions_generator_adaptive_heap(nested(simpson,trapezoidal), error_heuristic_size(error_metric_relative(),1.e-5), std::size_t(iterations)),
+                regions_integrator_parallel_variance_reduction(rr_uniform_region(), cv_optimize_weight(), std::move(rs), std::mt19937(std::size_t(seed)), (unsigned long)spp, std::size_t(16)));
+            viltrum::integrate(integrator, acc, r, f, range);
+        };
+        if (rs_policy == 0) run(region_sampling_uniform());
+        else if (rs_policy == 1) run(region_sampling_importance<>());
+        else if (rs_policy == 2) run(region_sampling_mis<>(power, cutoff));
+        else run(region_sampling_russian_roulette<>());
+        return 0;
+    });
+}

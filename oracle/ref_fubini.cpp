@@ -96,3 +96,30 @@ extern "C" int vo_crespo2021_infinite(const char* integrand, int nfirst, uint64_
         return 0;
     });
 }
+
+
+// reference integrator_adaptive_fubini_variance_reduction_parallel_optimized<N>(nested(simpson,trapezoidal), error_heuristic_size(relative,1e-5),
+// iterations, mc_samples, region_stratification_uniform(), cv_optimize_weight(), region_sampling_uniform(), spp, seed) —
+// src/control-variates/integrator-adaptive-fubini-variance-reduction-optimized.h:17-23 -> RegionsIntegratorParallelVarianceReductionOptimized
+// (…-variance-reduction-optimized.h:70-142).  Infinite ranges only: over a finite rest the class does not compile upstream (Range::DIM, :27).  '='.
+extern "C" int vo_cv_optimized_infinite(const char* integrand, int nfirst, uint64_t iterations, uint64_t mc_samples, uint64_t spp, uint64_t seed,
+                             int dimbins, const uint64_t* res, const float* rmin, const float* rmax, int nrange, float* bins) {
+    return dispatch_infinite(integrand, [&] (auto f) -> int {
+        auto range = viltrum::range_infinite(std::vector<float>(rmin, rmin+nrange), std::vector<float>(rmax, rmax+nrange));
+        auto go = [&] (auto nc, auto dbc) -> int {
+            constexpr std::size_t N = decltype(nc)::value;
+            constexpr std::size_t DB = decltype(dbc)::value;
+            using namespace viltrum;
+            Acc<DB> acc{bins, res_array<DB>(res)};
+            viltrum::integrate(integrator_adaptive_fubini_variance_reduction_parallel_optimized<N>(nested(simpson,trapezoidal), error_heuristic_size(error_metric_relative(),1.e-5),
+                                   std::size_t(iterations), (unsigned long)mc_samples, region_stratification_uniform(), cv_optimize_weight(), region_sampling_uniform(),
+                                   (unsigned long)spp, std::size_t(seed)), acc, acc.r, f, range);
+            return 0;
+        };
+        if (nfirst == 1 && dimbins == 1) return go(std::integral_constant<std::size_t,1>(), std::integral_constant<std::size_t,1>());
+        if (nfirst == 2 && dimbins == 1) return go(std::integral_constant<std::size_t,2>(), std::integral_constant<std::size_t,1>());
+        if (nfirst == 2 && dimbins == 2) return go(std::integral_constant<std::size_t,2>(), std::integral_constant<std::size_t,2>());
+        if (nfirst == 3 && dimbins == 2) return go(std::integral_constant<std::size_t,3>(), std::integral_constant<std::size_t,2>());
+        return -2;
+    });
+}

@@ -19,3 +19,4 @@ for f in sorted(glob.glob('gpurun_out/r2m_bench_*_n$N.json')):
     except Exception as e:
         print(f, 'FAILED', e)
 PY
+timeout 600 python -m pytest tests/test_gpu_regions.py tests/test_gpu_multi.py -m gpu -q -k "mixed or nccl or comm" > gpurun_out/r2m_tests_n$N.log 2>&1; tail -4 gpurun_out/r2m_tests_n$N.log

@@ -138,6 +138,74 @@ def test_tile_major_residual_pass_against_the_sample_major_pipeline(ctx, integ, 
     assert 0.75 < ratio < 1.33, f"variance ratio {ratio:.3f}"
 
 
+def _k_seed_gate(gpus, refs, what, ratio_bounds=(0.6, 1.6)):
+    K = gpus.shape[0]
+    assert np.all(np.isfinite(gpus)), f"{what}: non-finite GPU bins"
+    assert_statistically_equal(gpus.mean(axis=0), refs.mean(axis=0), gpus.var(axis=0, ddof=1) / K, refs.var(axis=0, ddof=1) / K, what)
+    ratio = (gpus.var(axis=0, ddof=1).mean() + 1e-30) / (refs.var(axis=0, ddof=1).mean() + 1e-30)
+    assert ratio_bounds[0] < ratio < ratio_bounds[1], f"{what}: variance ratio {ratio:.3f}"
+
+
+@pytest.mark.parametrize("integ,res,it,spp,rs,power,cutoff", [("smooth_edge2", [24, 24], 300, 16, "importance", 1.0, 0.0), ("smooth_edge2", [24, 24], 300, 16, "mis", 1.0, 0.0),
+                                                              ("smooth_edge2", [24, 24], 300, 16, "mis", 2.0, 0.1), ("smooth_edge2", [24, 24], 300, 16, "russian_roulette", 1.0, 0.0),
+                                                              ("smooth_edge2", [40, 10], 120, 64, "importance", 1.0, 0.0), ("cubic1", [20], 30, 8, "importance", 1.0, 0.0)])
+def test_region_sampling_policies_against_the_reference(ctx, integ, res, it, spp, rs, power, cutoff):
+    """region_sampling_importance / _mis(power, cutoff) / _russian_roulette (reference src/control-variates/region-sampling.h:22-135, Simpson::sample
+    rules.h:184-247, Region::sample_subrange / pdf_subrange region.h:220-343): K = 16 seeds of the device path against K = 16 seeds of the
+    UNMODIFIED reference, per-bin means within 3 sigma of their standard errors, matching noise (statistical parity: the reference inverts a
+    cubic CDF with pow/acos/cos).  Integrands on which the reference's samplers stay finite (on shade4 / ind2 half of its bins come out NaN) and
+    whose residual is not down at float rounding (polynomials the Simpson interpolant reproduces leave nothing to compare)."""
+    import pyoracle
+    from viltrum_b200 import integrate, integrator_adaptive_variance_reduction_parallel, nested, error_heuristic_size, error_metric_relative, RegionSampling
+    if not pyoracle.available("reference"):
+        pytest.skip("oracle/_ref was not built (needs /root/reference at build time)")
+    O = pyoracle.load("reference")
+    d = DIMS[integ]; nb = int(np.prod(res)); K = 16
+    refs = np.stack([O.cv_sampling(integ, it, spp, 100 + s_, rs, res, [0.0] * d, [1.0] * d, power, cutoff) for s_ in range(K)]).astype(np.float64)
+    gpus = []
+    for s_ in range(K):
+        b = np.zeros(nb, np.float32)
+        integ_obj = integrator_adaptive_variance_reduction_parallel(nested("simpson", "trapezoidal"), error_heuristic_size(error_metric_relative(), 1e-5), it, "uniform", None, spp,
+                                                                    seed=s_, rs=RegionSampling(rs, power, cutoff))
+        integrate(integ_obj, b, res, integ, _rng(integ), ctx=ctx)
+        gpus.append(b.astype(np.float64))
+    _k_seed_gate(np.stack(gpus), refs, f"region_sampling_{rs} {integ}")
+
+
+def test_region_sampling_importance_stays_finite_on_a_discontinuous_integrand(ctx):
+    """shade4<16>: the reference's importance / MIS samplers return NaN for about half of the bins (0/0 where a region's interpolant vanishes);
+    the device path gives zero weight to such a sample instead and must agree with the uniform sampler's estimate"""
+    from viltrum_b200 import RegionSampling
+    res, it, spp = [16, 16], 400, 32
+    regs = ctx.regions_generate_adaptive("shade4_16", _rng("shade4_16"), "simpson_trapezoidal", "size", "relative", it, 1e-5, batch=1, exact=True)
+    uni = np.zeros(256, np.float32); regs.cv_integrate("shade4_16", uni, res, _rng("shade4_16"), spp, 3)
+    for rs in ("importance", "mis", "russian_roulette"):
+        b = np.zeros(256, np.float32); regs.cv_integrate("shade4_16", b, res, _rng("shade4_16"), spp, 3, rs=rs)
+        assert np.all(np.isfinite(b)) and abs(float(b.mean()) - float(uni.mean())) < 0.01, (rs, float(b.mean()), float(uni.mean()))
+    regs.free()
+
+
+@pytest.mark.parametrize("integ,n,res,it,m,spp", [("walk", 2, [8, 8], 100, 4, 16), ("walk", 2, [6, 6], 30, 4, 100), ("decay", 1, [12], 40, 4, 64)])
+def test_optimized_stratified_allocation_against_the_reference(ctx, integ, n, res, it, m, spp):
+    """integrator_adaptive_fubini_variance_reduction_parallel_optimized<N> (reference integrator-adaptive-fubini-variance-reduction-optimized.h:17-23;
+    RegionsIntegratorParallelVarianceReductionOptimized + region_stratification_uniform, …-optimized.h:70-142, region-stratification.h:9-25): spp/n
+    samples per region of a bin plus the remainder from a random start, both regimes (spp below and above the regions per bin); K = 24 seeds."""
+    import pyoracle
+    from viltrum_b200 import integrate, integrator_adaptive_fubini_variance_reduction_parallel_optimized, RangeInfinite
+    if not pyoracle.available("reference"):
+        pytest.skip("oracle/_ref was not built (needs /root/reference at build time)")
+    O = pyoracle.load("reference")
+    nb = int(np.prod(res)); K = 24
+    refs = np.stack([O.cv_optimized_infinite(integ, n, it, m, spp, 50 + s_, res) for s_ in range(K)]).astype(np.float64)
+    gpus = []
+    for s_ in range(K):
+        b = np.zeros(nb, np.float32)
+        integrate(integrator_adaptive_fubini_variance_reduction_parallel_optimized(n, it, m, spp, seed=s_), b, res, integ, RangeInfinite(), ctx=ctx)
+        gpus.append(b.astype(np.float64))
+    # the decay integrand is heavy tailed: its variance over 24 seeds is itself noisy (the reference's two allocations differ by 2x at 8 spp)
+    _k_seed_gate(np.stack(gpus), refs, f"optimized {integ}", ratio_bounds=(0.4, 2.5))
+
+
 def test_config4_shape_256x256_against_sixteen_reference_seeds(ctx):
     """BASELINE config 4's shape on a 256x256 grid (integrator_crespo2021 over shade5<64>; 2048 iterations and 16 spp so that sixteen runs of the
     UNMODIFIED reference fit a test — its multi-threaded build, ~1 s per seed): per-bin means over K = 16 seeds of either side within

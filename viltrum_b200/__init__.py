@@ -7,5 +7,7 @@ from .host import (Context, Regions, integrate, monte_carlo, monte_carlo_per_bin
                    integrator_fubini, integrator_crespo2021_infinite, integrator_adaptive_tolerance, cv_fixed_weight, cv_optimize_weight, rr_uniform_region, rr_integral_region, rr_error_region, rr_pdf_region,
                    integrator_adaptive_variance_reduction_parallel, steps, FubiniIntegrand, range_split_at,
                    error_heuristic_default, error_heuristic_size, error_heuristic_mixed, error_metric_absolute, error_metric_relative,
-                   range_primary, range_primary_infinite, Range, RangeInfinite, builtin_names, shard_for_rank, sample_shard_for_rank)
+                   range_primary, range_primary_infinite, Range, RangeInfinite, builtin_names, shard_for_rank, sample_shard_for_rank,
+                   region_sampling_uniform, region_sampling_importance, region_sampling_mis, region_sampling_russian_roulette, region_stratification_uniform,
+                   integrator_adaptive_fubini_variance_reduction_parallel_optimized, IntegratorAdaptiveIterations, RegionSampling)
 from ._capi import Vb200Error  # noqa: F401

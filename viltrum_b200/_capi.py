@@ -22,7 +22,8 @@ def shard_pair(shard):
     b, e = int(shard[0]), int(shard[1])
     return (SHARD_EMPTY_INDEX, SHARD_EMPTY_INDEX) if b == e else (b, e)
 CV_OPTIMIZE_WEIGHT, CV_FIXED_WEIGHT = 0, 1
-RR_POLICIES = {"uniform": 0, "integral": 1, "error": 2, "pdf": 3}     # vb200_rr_policy
+RR_POLICIES = {"uniform": 0, "integral": 1, "error": 2, "pdf": 3, "stratified": 4}     # vb200_rr_policy
+RS_POLICIES = {"uniform": 0, "importance": 1, "mis": 2, "russian_roulette": 3}          # vb200_rs_policy
 RULES = {"trapezoidal": 2, "simpson": 3, "boole": 5, "simpson_trapezoidal": 32, "boole_simpson": 53}
 RULE_SAMPLES = {2: 2, 3: 3, 5: 5, 32: 3, 53: 5}
 
@@ -98,7 +99,8 @@ class ToleranceParams(ctypes.Structure):
 
 class CvParams(ctypes.Structure):
     _fields_ = [("domain", Domain), ("shard", Shard), ("spp", ctypes.c_uint64), ("seed", ctypes.c_uint64),
-                ("weight_strategy", ctypes.c_int32), ("rr_policy", ctypes.c_int32), ("alpha", ctypes.c_double)]
+                ("weight_strategy", ctypes.c_int32), ("rr_policy", ctypes.c_int32), ("alpha", ctypes.c_double),
+                ("rs_policy", ctypes.c_int32), ("reserved", ctypes.c_int32), ("rs_power", ctypes.c_double), ("rs_cutoff", ctypes.c_double)]
 
 
 class Vb200Error(RuntimeError):

@@ -47,6 +47,34 @@ __global__ void cv_ranks_kernel(uint64_t begin, uint64_t nb, uint32_t spp, uint3
     rank[i] = __umulhi(r.x, count[b]);
 }
 
+// region_stratification_uniform::samples_per_region (reference src/control-variates/region-stratification.h:9-25), the allocation of
+// RegionsIntegratorParallelVarianceReductionOptimized (…-variance-reduction-optimized.h:120-133): every region of the bin takes
+// spp / n samples and the spp % n left over go to the regions start, start+1, ... (mod n) for ONE random start per bin; regions are
+// visited in list order, so sample j belongs to the region whose running sample count first exceeds j.  rank = that region's position
+// in the bin's list, rrf = double(spp) / double(samples of that region) — the factor the residual terms carry upstream (:127-128).
+__global__ void cv_stratified_ranks_kernel(uint64_t begin, uint64_t nb, uint32_t spp, uint32_t k0, uint32_t k1, const uint32_t* __restrict__ count,
+                                           uint32_t* __restrict__ rank, double* __restrict__ rrf) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= nb * spp) return;
+    const uint64_t b = i % nb; const uint32_t j = uint32_t(i / nb);
+    const uint64_t bin = begin + b;
+    const uint32_t n = count[b];
+    if (n == 0) { rank[i] = 0; rrf[i] = 1.0; return; }
+    const uint32_t base = spp / n, rem = spp % n;
+    const uint32_t start = rem > 0 ? __umulhi(philox4x32<10>(u32x4{uint32_t(bin), uint32_t(bin >> 32), 0xfffffffeu, 0u}, k0, k1).x, n) : 0u;
+    // samples held by the regions before position p: p*base + |[0,p) ∩ ([start, start+rem) mod n)|
+    auto before = [&] (uint32_t p) -> uint64_t {
+        const uint32_t e = start + rem;                     // < 2n
+        uint32_t extra = e <= n ? (p > start ? min(p, e) - start : 0u) : ((p > start ? p - start : 0u) + min(p, e - n));
+        return uint64_t(p) * base + extra;
+    };
+    uint32_t lo = 0, hi = n;                                // largest p with before(p) <= j
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (before(mid) <= j) lo = mid; else hi = mid; }
+    const uint32_t mine = uint32_t(before(lo + 1) - before(lo));
+    rank[i] = lo;
+    rrf[i] = double(spp) / double(mine);
+}
+
 // weighted roulettes (rr_integral_region / rr_error_region): the raw 32-bit draw of every residual sample; the walk turns it into
 // u * sum(w') and picks the region by inverse CDF (regions.cu walk_rr_kernel)
 __global__ void cv_raw_kernel(uint64_t begin, uint64_t nb, uint32_t spp, uint32_t k0, uint32_t k1, uint32_t* __restrict__ raw) {
@@ -232,6 +260,170 @@ template<int S, bool LDG> struct FastLevel<S, 0, LDG> {
         return v;
     }
 };
+
+// ---- importance sampling of a region's interpolant -----------------------------------------------------------
+//   Simpson::pdf_points / pdf_unnormalized / cdf / inv_cdf / sample            reference src/newton-cotes/rules.h:104-247
+//   Region::sample_subrange / sample_marginal / pdf_subrange / pdf_at           reference src/newton-cotes/region.h:220-343
+//   region_sampling_importance / _mis / _russian_roulette                       reference src/control-variates/region-sampling.h:22-135
+// A sample is drawn dimension by dimension from the |interpolant| restricted to bin ∩ region: the marginal of dimension k (the other
+// dimensions folded with pdf_integral_subrange) is a parabola whose CDF — a cubic — is inverted in closed form (Cardano / Viète), then the
+// array is conditioned on the drawn coordinate (fold with pdf_unnormalized) and the next dimension follows.  pow/acos/cos make a bit
+// contract impossible: plain fp32 with the library's fast intrinsics, statistical parity only.
+namespace imp {
+__device__ __forceinline__ void coeff3(const float* p, float* c) { c[0] = p[0]; c[1] = -3.0f * p[0] + 4.0f * p[1] - p[2]; c[2] = 2.0f * p[0] - 4.0f * p[1] + 2.0f * p[2]; }
+// rules.h:104-147 with NormDefault: |p|, shifted down by the (negative, interior) minimum of its parabola
+__device__ __forceinline__ void pdf_points(const float* p, float* q) {
+    q[0] = fabsf(p[0]); q[1] = fabsf(p[1]); q[2] = fabsf(p[2]);
+    float c[3]; coeff3(q, c);
+    float ymin = 0.0f;
+    if (c[2] > 0.0f) {
+        const float tmin = -c[1] / (2.0f * c[2]);
+        if (tmin > 0.0f && tmin < 1.0f) { const float y = (c[2] * tmin + c[1]) * tmin + c[0]; if (y < ymin) ymin = y; }
+    }
+    q[0] -= ymin; q[1] -= ymin; q[2] -= ymin;
+}
+__device__ __forceinline__ float cdf3(float t, const float* c) { return ((c[2] * t * (1.0f / 3.0f) + c[1] * 0.5f) * t + c[0]) * t; }       // rules.h:173-177
+__device__ __forceinline__ float pdf_integral(float t0, float t1, const float* p) { float q[3], c[3]; pdf_points(p, q); coeff3(q, c); return cdf3(t1, c) - cdf3(t0, c); }   // :150-154
+__device__ __forceinline__ float pdf_unnormalized(float t, const float* p) { float q[3], c[3]; pdf_points(p, q); coeff3(q, c); return (c[2] * t + c[1]) * t + c[0]; }       // :157-161
+__device__ __forceinline__ float cuberoot(float x) { return x < 0.0f ? -powf(-x, 1.0f / 3.0f) : powf(x, 1.0f / 3.0f); }
+// rules.h:184-247: x = s*cdf(t1) + (1-s)*cdf(t0), roots of cdf(t) - x, the first one inside [t0,t1] (1e-5 slack), else uniform
+__device__ float sample1(float s, float t0, float t1, const float* p) {
+    float q[3], cf[3]; pdf_points(p, q); coeff3(q, cf);
+    const float x = s * cdf3(t1, cf) + (1.0f - s) * cdf3(t0, cf);
+    float a = cf[2] * (1.0f / 3.0f), b = cf[1] * 0.5f, c = cf[0], d = -x;
+    const float sum = a + b + c + d; a /= sum; b /= sum; c /= sum; d /= sum;
+    float sol[3]; int ns = 0;
+    if (fabsf(a) < 1.e-3f) {
+        if (fabsf(b) < 1.e-3f) { if (fabsf(c) >= 1.e-3f) sol[ns++] = -d / c; }
+        else { const float disc = c * c - 4.0f * b * d; if (disc >= 0.0f) { const float sq = sqrtf(disc); sol[ns++] = (-c + sq) / (2.0f * b); sol[ns++] = (-c - sq) / (2.0f * b); } }
+    } else {
+        const float pp = c / a - b * b / (3.0f * a * a);
+        const float qq = 2.0f * b * b * b / (27.0f * a * a * a) - b * c / (3.0f * a * a) + d / a;
+        const float sqr = 0.25f * qq * qq + pp * pp * pp * (1.0f / 27.0f);
+        if (sqr >= 0.0f) sol[ns++] = cuberoot(-0.5f * qq - sqrtf(sqr)) + cuberoot(-0.5f * qq + sqrtf(sqr)) - b / (3.0f * a);
+        else for (int i = 0; i < 3; ++i) sol[ns++] = 2.0f * sqrtf(-pp / 3.0f) * cosf(acosf(3.0f * qq / (2.0f * pp) * sqrtf(-3.0f / pp)) * (1.0f / 3.0f) - 6.2831853071795865f * float(i) / 3.0f) - b / (3.0f * a);
+    }
+    for (int i = 0; i < ns; ++i) {
+        float r = sol[i];
+        if (r < t0 && fabsf(t0 - r) < 1.e-5f) r = t0;
+        if (r > t1 && fabsf(r - t1) < 1.e-5f) r = t1;
+        if (r >= t0 && r <= t1 && !isnan(r)) return r;
+    }
+    return s * (t1 - t0) + t0;
+}
+// one region: data[3^D] (dimension 0 fastest), normalised box [a,b]^D of bin ∩ region.  u[D] uniforms -> normalised position pos[D];
+// returns pdf_at(pos) / pdf_sub(a,b) = the density of pos in NORMALISED coordinates times 1 (the caller divides by the region's volume).
+template<int D>
+__device__ float sample_and_pdf(const float* __restrict__ data, const float* a, const float* b, const float* u, bool importance_pos, float* pos, float* pdf_sub_out) {
+    constexpr int N = R::ipow(3, D);
+    float arr[N];      // the array still to be sampled: dimensions k..D-1, conditioned on pos[0..k)
+    for (int i = 0; i < N; ++i) arr[i] = __ldg(data + i);
+    float pdf_at = 0.0f, pdf_sub = 0.0f;
+    int n = N;
+    for (int k = 0; k < D; ++k) {
+        // marginal of dimension k: fold the last dimensions with pdf_integral over their [a,b] (region.h:221-240)
+        float m[N];
+        for (int i = 0; i < n; ++i) m[i] = arr[i];
+        int len = n;
+        for (int dd = D - 1; dd > k; --dd) {
+            const int outn = len / 3;
+            for (int o = 0; o < outn; ++o) { const float line[3] = {m[o], m[o + outn], m[o + 2 * outn]}; m[o] = pdf_integral(a[dd], b[dd], line); }
+            len = outn;
+        }
+        // m[0..3) is the marginal along dimension k
+        if (k == 0) pdf_sub = pdf_integral(a[0], b[0], m);                                   // region.h:268-279 (pdf_sub: every dimension folded over [a,b])
+        pos[k] = importance_pos ? sample1(u[k], a[k], b[k], m) : u[k] * (b[k] - a[k]) + a[k];
+        // condition on pos[k]: fold dimension 0 of arr with pdf_unnormalized (region.h:250-254)
+        const int outn = n / 3;
+        for (int o = 0; o < outn; ++o) { const float line[3] = {arr[3 * o], arr[3 * o + 1], arr[3 * o + 2]}; arr[o] = pdf_unnormalized(pos[k], line); }
+        n = outn;
+    }
+    // pdf_at (region.h:300-313): the folds are not linear (|.| and the shift of pdf_points), so the density is evaluated the reference's way —
+    // pdf_unnormalized over the LAST dimension first — rather than read off the conditioning chain above
+    for (int i = 0; i < N; ++i) arr[i] = __ldg(data + i);
+    int len = N;
+    for (int dd = D - 1; dd >= 0; --dd) {
+        const int outn = len / 3;
+        for (int o = 0; o < outn; ++o) { const float line[3] = {arr[o], arr[o + outn], arr[o + 2 * outn]}; arr[o] = pdf_unnormalized(pos[dd], line); }
+        len = outn;
+    }
+    pdf_at = arr[0];
+    *pdf_sub_out = pdf_sub;
+    return pdf_at;
+}
+}
+
+// residual samples under region_sampling_importance (RS = 1), region_sampling_mis (2) or region_sampling_russian_roulette (3); Simpson
+// tables.  Same inputs and outputs as cv_samples_kernel; weight = the policy's sample weight (1/pdf, the constant MIS weight, ...).
+template<int D, int RS>
+__global__ void __launch_bounds__(128) cv_samples_importance_kernel(vb200_domain dom, uint64_t begin, uint64_t nb, uint32_t spp, uint32_t k0, uint32_t k1,
+                                                                    uint64_t cap, const float* __restrict__ rmin, const float* __restrict__ rmax, const float* __restrict__ aos,
+                                                                    const uint32_t* __restrict__ sorted_region, const uint32_t* __restrict__ sorted_index,
+                                                                    float* __restrict__ points, float* __restrict__ weight, float* __restrict__ app, double power, double cutoff) {
+    const uint64_t tpos = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const uint64_t N = nb * spp;
+    if (tpos >= N) return;
+    const uint64_t i = sorted_index[tpos];
+    const uint64_t b = i % nb; const uint32_t j = uint32_t(i / nb);
+    const uint64_t bin = begin + b;
+    const uint32_t r = sorted_region[tpos];
+    uint32_t pos[VB200_MAX_DIMBINS]; { uint64_t q = bin; for (int d = 0; d < dom.dimbins; ++d) { pos[d] = uint32_t(q % dom.res[d]); q /= dom.res[d]; } }
+    float lo[D], hi[D], ia[D], ib[D], na[D], nbn[D], u[D + 1], L[D][3];
+    float vol = 1.0f, rvol = 1.0f;
+    u32x4 rnd{0, 0, 0, 0};
+#pragma unroll
+    for (int d = 0; d <= D; ++d) {
+        if ((d & 3) == 0) rnd = philox4x32<10>(u32x4{uint32_t(bin), uint32_t(bin >> 32), j, uint32_t(1 + d / 4)}, k0, k1);
+        u[d] = viltrum::b200::u01((d & 3) == 0 ? rnd.x : (d & 3) == 1 ? rnd.y : (d & 3) == 2 ? rnd.z : rnd.w);
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        lo[d] = rmin[uint64_t(d) * cap + r]; hi[d] = rmax[uint64_t(d) * cap + r];
+        float ba = dom.rmin[d], bb = dom.rmax[d];
+        if (d < dom.dimbins) { ba = fmaf(float(pos[d]), dom.drange[d], dom.rmin[d]); bb = fmaf(float(pos[d] + 1u), dom.drange[d], dom.rmin[d]); }
+        ia[d] = fmaxf(ba, lo[d]); ib[d] = fmaxf(ia[d], fminf(bb, hi[d]));
+        vol *= ib[d] - ia[d]; rvol *= hi[d] - lo[d];
+        const float inv = hi[d] > lo[d] ? 1.0f / (hi[d] - lo[d]) : 0.0f;
+        na[d] = (ia[d] - lo[d]) * inv; nbn[d] = (ib[d] - lo[d]) * inv;
+    }
+    const float* data = aos + uint64_t(r) * uint64_t(R::ipow(3, D));
+    float x[D], w;
+    bool uniform_pos = false;
+    if (RS == 1 && vol < 1.e-5f) { uniform_pos = true; w = vol; }                             // region-sampling.h:31-32: tiny subranges are sampled uniformly
+    else {
+        float t[D], pdf_sub;
+        const float pdf_at = imp::sample_and_pdf<D>(data, na, nbn, u, true, t, &pdf_sub);
+        const float pdf_imp = pdf_at / (rvol * pdf_sub);                                       // Region::pdf_subrange (region.h:333-337)
+        // a region whose interpolant vanishes over the box has no density to sample (0/0: the reference returns NaN there): uniform sampling instead
+        if (!(pdf_sub > 0.0f) || !(pdf_imp == pdf_imp) || isinf(pdf_imp)) { uniform_pos = true; w = vol; }
+        else if (RS == 1) w = pdf_imp < 1.e-5f ? 0.0f : 1.0f / pdf_imp;                        // :42
+        else if (RS == 3) {                                                                    // region_sampling_russian_roulette :46-83
+            const float pdf_importance = rvol * pdf_sub, pdf_uniform = vol;
+            if (u[D] < pdf_importance / (pdf_importance + pdf_uniform)) w = pdf_imp < 1.e-10f ? 0.0f : 1.0f / pdf_imp;
+            else { uniform_pos = true; w = vol; }                                              // pdf = 1/volume
+        } else {                                                                               // region_sampling_mis :85-135
+            const float pdf_uni = 1.0f / vol;
+            float mi = powf(pdf_imp, float(power)), mu = powf(pdf_uni, float(power)), ms = mi + mu;
+            if (mi < float(cutoff) * ms) { mi = 0.0f; ms = mu; }
+            if (mu < float(cutoff) * ms) { mu = 0.0f; ms = mi; }
+            const float p_imp = pdf_imp > 1.e-10f ? mi / pdf_imp : 0.0f, p_uni = mu * vol, p_sum = p_imp + p_uni;
+            w = p_sum / ms;
+            if (u[D] < p_uni / p_sum) uniform_pos = true;
+        }
+        if (!uniform_pos) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) x[d] = fmaf(t[d], hi[d] - lo[d], lo[d]);               // Range::pos_from_range
+        }
+    }
+    if (uniform_pos) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) x[d] = fmaf(u[d], ib[d] - ia[d], ia[d]);
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d) { points[uint64_t(d) * N + tpos] = x[d]; lagrange_basis<3>(hi[d] > lo[d] ? (x[d] - lo[d]) / (hi[d] - lo[d]) : 0.0f, L[d]); }
+    weight[tpos] = w;
+    app[tpos] = FastLevel<3, D - 1>::eval(data, L);
+}
 
 // residual samples: chosen region -> bin ∩ region box -> uniform point, weight, interpolant value.
 // REPLAY: points are given (AoS [bin][spp][D]), only weights/interpolant are computed.
@@ -593,6 +785,30 @@ int dispatch_samples(vb200_ctx* ctx, bool replay, bool fast, const vb200_domain&
     return fail(ctx, VB200_ERR_UNSUPPORTED, "control variates: no kernel for %d samples per dimension in %d dimensions", r->SH, r->dim);
 }
 
+template<int D>
+int launch_importance(vb200_ctx* ctx, int rs, double power, double cutoff, const vb200_domain& dom, uint64_t begin, uint64_t nb, uint32_t spp, uint32_t k0, uint32_t k1,
+                      const vb200_regions* r, const float* aos, const uint32_t* sreg, const uint32_t* sidx, float* points, float* weight, float* app) {
+    const uint64_t N = nb * spp;
+    const unsigned grid = unsigned((N + 127) / 128);
+    if (rs == VB200_RS_IMPORTANCE) cv_samples_importance_kernel<D, 1><<<grid, 128, 0, ctx->stream>>>(dom, begin, nb, spp, k0, k1, r->capacity, r->rmin, r->rmax, aos, sreg, sidx, points, weight, app, power, cutoff);
+    else if (rs == VB200_RS_MIS) cv_samples_importance_kernel<D, 2><<<grid, 128, 0, ctx->stream>>>(dom, begin, nb, spp, k0, k1, r->capacity, r->rmin, r->rmax, aos, sreg, sidx, points, weight, app, power, cutoff);
+    else cv_samples_importance_kernel<D, 3><<<grid, 128, 0, ctx->stream>>>(dom, begin, nb, spp, k0, k1, r->capacity, r->rmin, r->rmax, aos, sreg, sidx, points, weight, app, power, cutoff);
+    ctx->launches++;
+    VB200_CUDA(ctx, cudaGetLastError());
+    return VB200_OK;
+}
+int dispatch_importance(vb200_ctx* ctx, int rs, double power, double cutoff, const vb200_domain& dom, uint64_t begin, uint64_t nb, uint32_t spp, uint32_t k0, uint32_t k1,
+                        const vb200_regions* r, const float* aos, const uint32_t* sreg, const uint32_t* sidx, float* points, float* weight, float* app) {
+    switch (r->dim) {
+        case 1: return launch_importance<1>(ctx, rs, power, cutoff, dom, begin, nb, spp, k0, k1, r, aos, sreg, sidx, points, weight, app);
+        case 2: return launch_importance<2>(ctx, rs, power, cutoff, dom, begin, nb, spp, k0, k1, r, aos, sreg, sidx, points, weight, app);
+        case 3: return launch_importance<3>(ctx, rs, power, cutoff, dom, begin, nb, spp, k0, k1, r, aos, sreg, sidx, points, weight, app);
+        case 4: return launch_importance<4>(ctx, rs, power, cutoff, dom, begin, nb, spp, k0, k1, r, aos, sreg, sidx, points, weight, app);
+        case 5: return launch_importance<5>(ctx, rs, power, cutoff, dom, begin, nb, spp, k0, k1, r, aos, sreg, sidx, points, weight, app);
+    }
+    return fail(ctx, VB200_ERR_UNSUPPORTED, "importance sampling is instantiated for 1..5 dimensions");
+}
+
 struct DevBuf {
     void* p = nullptr; vb200_ctx* owner = nullptr;
     ~DevBuf() { if (owner) dfree(owner, p); }
@@ -670,8 +886,16 @@ int cv_run(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r, con
     int rc = check_domain(ctx, p->domain, r->dim); if (rc) return rc;
     if (p->spp > 0xffffffffull) return fail(ctx, VB200_ERR_INVALID, "spp invalid");
     if (p->weight_strategy != VB200_CV_OPTIMIZE_WEIGHT && p->weight_strategy != VB200_CV_FIXED_WEIGHT) return fail(ctx, VB200_ERR_INVALID, "unknown control-variate weight strategy %d", p->weight_strategy);
-    if (p->rr_policy != VB200_RR_UNIFORM && p->rr_policy != VB200_RR_INTEGRAL && p->rr_policy != VB200_RR_ERROR && p->rr_policy != VB200_RR_PDF) return fail(ctx, VB200_ERR_INVALID, "unknown Russian-roulette policy %d", p->rr_policy);
+    if (p->rr_policy < VB200_RR_UNIFORM || p->rr_policy > VB200_RR_STRATIFIED) return fail(ctx, VB200_ERR_INVALID, "unknown Russian-roulette policy %d", p->rr_policy);
+    if (p->rs_policy < VB200_RS_UNIFORM || p->rs_policy > VB200_RS_RUSSIAN_ROULETTE) return fail(ctx, VB200_ERR_INVALID, "unknown region-sampling policy %d", p->rs_policy);
+    if (p->rs_policy != VB200_RS_UNIFORM) {
+        if (replay) return fail(ctx, VB200_ERR_UNSUPPORTED, "replay feeds recorded sample points: it implies region_sampling_uniform weights");
+        if (r->SH != 3) return fail(ctx, VB200_ERR_UNSUPPORTED, "importance sampling of a region needs a Simpson-based table (Simpson::sample, rules.h:184-247)");
+        if (r->dim > 5) return fail(ctx, VB200_ERR_UNSUPPORTED, "importance sampling is instantiated for up to 5 dimensions");
+    }
+    if (p->rr_policy == VB200_RR_STRATIFIED && replay) return fail(ctx, VB200_ERR_UNSUPPORTED, "replay of the stratified allocation is not supported");
     const int policy = p->rr_policy;
+    const bool weighted = policy == VB200_RR_INTEGRAL || policy == VB200_RR_ERROR || policy == VB200_RR_PDF;
     const vb200_domain dom = finish_domain(p->domain);
     const uint64_t total = nbins_of(dom);
     uint64_t begin, end; rc = resolve_shard(ctx, p->shard, total, &begin, &end); if (rc) return rc;
@@ -698,7 +922,7 @@ int cv_run(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r, con
     if (rc) return rc;
     // weighted roulettes: per-bin sum of the pair weights, then of the clamped weights (two more walks, nothing per pair is stored)
     DevBuf d_wsum, d_csum, d_rerr, d_pdf;
-    if (policy != VB200_RR_UNIFORM && spp > 0) {
+    if (weighted && spp > 0) {
         if (policy == VB200_RR_PDF) { float* pp = nullptr; rc = walk_pdf_patches(ctx, r, w, &pp); d_pdf.p = pp; d_pdf.owner = ctx; if (rc) return rc; }
         if ((rc = d_wsum.alloc(ctx, nshard * sizeof(double))) || (rc = d_csum.alloc(ctx, nshard * sizeof(double)))) return rc;
         if (policy == VB200_RR_ERROR) { if ((rc = d_rerr.alloc(ctx, r->count * sizeof(float))) || (rc = region_total_errors(ctx, r, w, d_rerr.as<float>()))) return rc; }
@@ -710,7 +934,7 @@ int cv_run(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r, con
 
     // tile-major residual pass (cv_tile_samples_kernel): the throughput path of the crespo2021 preset over a 2-D bin grid
     const char* tile_env = std::getenv("VB200_CV_TILE");       // test knob: 0 = keep the sample-major pipeline
-    const bool tile_path = fast && policy == VB200_RR_UNIFORM && spp > 0 && w.db == 2 && w.tile[0] == 16 && w.tile[1] == 16 && w.max_list <= uint64_t(CVT_MAXLIST) &&
+    const bool tile_path = fast && policy == VB200_RR_UNIFORM && p->rs_policy == VB200_RS_UNIFORM && spp > 0 && w.db == 2 && w.tile[0] == 16 && w.tile[1] == 16 && w.max_list <= uint64_t(CVT_MAXLIST) &&
                            (r->SH == 2 || r->SH == 3 || r->SH == 5) && !(tile_env && tile_env[0] == '0');
     if (tile_path) {
         rc = cv_tile_run(ctx, f, r, p, dom, w, begin, end, total, spp, aos.as<float>(), d_count.as<uint32_t>(), d_approx.as<float>(), st.dev_base);
@@ -738,14 +962,15 @@ int cv_run(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r, con
             const uint64_t s1 = s0 + slab < end ? s0 + slab : end, nb = s1 - s0, N = nb * spp;
             const uint32_t* cnt = d_count.as<uint32_t>() + (s0 - begin);
             const float* rp = nullptr;
-            if (!replay && policy != VB200_RR_UNIFORM) {
+            if (!replay && weighted) {
                 cv_raw_kernel<<<unsigned((N + 255) / 256), 256, 0, ctx->stream>>>(s0, nb, spp, uint32_t(p->seed), uint32_t(p->seed >> 32), rank.as<uint32_t>());
                 ctx->launches++; VB200_CUDA(ctx, cudaGetLastError());
                 VB200_CUDA(ctx, cudaMemsetAsync(chosen.p, 0, N * 4, ctx->stream));
                 rc = walk_rr_pass(ctx, r, w, dom, s0, s1, begin, policy, 3, d_rerr.as<float>(), d_pdf.as<float>(), d_count.as<uint32_t>(), d_wsum.as<double>(), d_csum.as<double>(), spp,
                                   rank.as<uint32_t>(), chosen.as<uint32_t>()); if (rc) return rc;
             } else if (!replay) {
-                cv_ranks_kernel<<<unsigned((N + 255) / 256), 256, 0, ctx->stream>>>(s0, nb, spp, uint32_t(p->seed), uint32_t(p->seed >> 32), cnt, rank.as<uint32_t>());
+                if (policy == VB200_RR_STRATIFIED) cv_stratified_ranks_kernel<<<unsigned((N + 255) / 256), 256, 0, ctx->stream>>>(s0, nb, spp, uint32_t(p->seed), uint32_t(p->seed >> 32), cnt, rank.as<uint32_t>(), rrf.as<double>());
+                else cv_ranks_kernel<<<unsigned((N + 255) / 256), 256, 0, ctx->stream>>>(s0, nb, spp, uint32_t(p->seed), uint32_t(p->seed >> 32), cnt, rank.as<uint32_t>());
                 ctx->launches++; VB200_CUDA(ctx, cudaGetLastError());
                 VB200_CUDA(ctx, cudaMemsetAsync(chosen.p, 0, N * 4, ctx->stream));
                 const char* legacy = std::getenv("VB200_CV_RESOLVE_LEGACY");       // test knob: the chunk-by-chunk kernel
@@ -773,9 +998,14 @@ int cv_run(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r, con
             { size_t tb = sort_bytes;
               VB200_CUDA(ctx, cub::DeviceRadixSort::SortPairs(sort_tmp.p, tb, chosen.as<uint32_t>(), sreg.as<uint32_t>(), iota.as<uint32_t>(), sidx.as<uint32_t>(), int(N), 0, region_bits, ctx->stream));
               ctx->launches += 1 + (region_bits + 7) / 8; }
-            rc = dispatch_samples(ctx, replay, fast, dom, s0, nb, spp, uint32_t(p->seed), uint32_t(p->seed >> 32), r, aos.as<float>(), sreg.as<uint32_t>(), sidx.as<uint32_t>(), rp,
-                                  points.as<float>(), weight.as<float>(), app.as<float>()); if (rc) return rc;
-            if (policy != VB200_RR_UNIFORM) {
+            if (p->rs_policy != VB200_RS_UNIFORM)
+                rc = dispatch_importance(ctx, p->rs_policy, p->rs_power, p->rs_cutoff, dom, s0, nb, spp, uint32_t(p->seed), uint32_t(p->seed >> 32), r, aos.as<float>(), sreg.as<uint32_t>(), sidx.as<uint32_t>(),
+                                         points.as<float>(), weight.as<float>(), app.as<float>());
+            else
+                rc = dispatch_samples(ctx, replay, fast, dom, s0, nb, spp, uint32_t(p->seed), uint32_t(p->seed >> 32), r, aos.as<float>(), sreg.as<uint32_t>(), sidx.as<uint32_t>(), rp,
+                                      points.as<float>(), weight.as<float>(), app.as<float>());
+            if (rc) return rc;
+            if (weighted) {
                 rc = rr_factors(ctx, r, w, dom, s0, nb, begin, policy, spp, d_rerr.as<float>(), d_pdf.as<float>(), d_count.as<uint32_t>(), d_wsum.as<double>(), d_csum.as<double>(),
                                 chosen.as<uint32_t>(), rrf.as<double>()); if (rc) return rc;
             }

@@ -134,10 +134,30 @@ __global__ void __launch_bounds__(1024) select_small_kernel(const float* __restr
         const unsigned pv = s_pv, pm = s_pm;
         for (unsigned i = tid; i < n; i += 1024) { const unsigned kk = s_key[i]; if ((kk & pm) == pv) atomicAdd(&s_hist[(kk >> shift) & 255u], 1u); }
         __syncthreads();
-        if (tid == 0) {
-            unsigned long long kk = s_k, cum = 0; int d = 255;
-            for (; d > 0; --d) { if (cum + s_hist[d] >= kk) break; cum += s_hist[d]; }
-            s_k = kk - cum; s_pv |= unsigned(d) << shift; s_pm |= 255u << shift;
+        if (tid < 32) {
+            // the digit d whose bucket holds the k-th largest key: the largest d >= 1 with suffix(d) = sum_{i >= d} hist[i] >= k, else 0; cum = suffix(d+1).
+            // Lane l owns buckets 8l..8l+7; a shuffle suffix scan over the lanes, then eight buckets per lane (was a 256-step loop on one thread).
+            unsigned h[8]; unsigned own = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { h[q] = s_hist[8 * tid + q]; own += h[q]; }
+            unsigned above = own;                                   // inclusive suffix over lanes >= tid
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) { const unsigned v = __shfl_down_sync(0xffffffffu, above, off); if (tid + off < 32) above += v; }
+            above -= own;                                           // buckets of the lanes above this one
+            const unsigned long long kk = s_k;
+            int best = -1; unsigned long long best_cum = 0; unsigned long long run = above;
+#pragma unroll
+            for (int q = 7; q >= 0; --q) { if (best < 0 && run + h[q] >= kk) { best = 8 * int(tid) + q; best_cum = run; } run += h[q]; }
+            if (best == 0) best = -1;                               // d = 0 is the fall-through, never a match (the loop stops at d > 0)
+            const unsigned hit = __ballot_sync(0xffffffffu, best >= 0);
+            int d = 0; unsigned long long cum = 0;
+            if (hit) {
+                const int src = 31 - __clz(int(hit));               // the highest lane with a match holds the largest d
+                d = __shfl_sync(0xffffffffu, best, src); cum = __shfl_sync(0xffffffffu, best_cum, src);
+            } else {                                                // everything above bucket 0
+                cum = __shfl_sync(0xffffffffu, run, 0) - s_hist[0];
+            }
+            if (tid == 0) { s_k = kk - cum; s_pv |= unsigned(d) << shift; s_pm |= 255u << shift; }
         }
         __syncthreads();
     }
@@ -210,10 +230,10 @@ __global__ void split_children_kernel(uint64_t cap, uint64_t nsel, uint64_t n_ol
     using Sh = D_::GreedyShape<SH, SL, DIM>;
     extern __shared__ float smem[];
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
-    float* s_parent = smem + size_t(warp) * (3 * Sh::SD + Sh::L + 4 * DIM + 2 * DIM + 2);
+    float* s_parent = smem + size_t(warp) * (3 * Sh::SD + 2 * DIM * Sh::L + 4 * DIM + 2 * DIM + 2);
     float* s_child = s_parent + Sh::SD;
-    float* s_work = s_child + 2 * Sh::SD;
-    float* s_crange = s_work + Sh::L;          // [2][2*DIM]
+    float* s_work = s_child + 2 * Sh::SD;      // [2*DIM][L]
+    float* s_crange = s_work + 2 * DIM * Sh::L;          // [2][2*DIM]
     float* s_E = s_crange + 4 * DIM;           // [2][DIM]
     float* s_vol = s_E + 2 * DIM;              // [2]
     const uint64_t r = uint64_t(blockIdx.x) * wpc + warp;
@@ -249,11 +269,33 @@ __global__ void split_children_kernel(uint64_t cap, uint64_t nsel, uint64_t n_ol
         rmin[uint64_t(lane) * cap + slot] = s_crange[lane]; rmax[uint64_t(lane) * cap + slot] = s_crange[DIM + lane];
         rmin[uint64_t(lane) * cap + slot1] = s_crange[2 * DIM + lane]; rmax[uint64_t(lane) * cap + slot1] = s_crange[3 * DIM + lane];
     }
-    for (int c = 0; c < 2; ++c) for (int d = 0; d < DIM; ++d) {
-        const float e = D_::region_error_warp<SH, SL, DIM>(s_child + c * Sh::SD, s_vol[c], d, heur_relative(hr, d), s_work, lane);
-        if (lane == 0) s_E[c * DIM + d] = e;
-        __syncwarp();
+    // nested-rule error of both children along every dimension (region.h:387-393), all 2*DIM of them side by side: the line errors are
+    // 2*DIM*L independent tasks, every level of the fold_all that follows 2*DIM*n — instead of ten folds one after the other, most of whose
+    // steps keep a handful of lanes busy.  Every value is computed by the same operations as in region_error_warp, hence the same bits.
+    constexpr int CD = 2 * DIM;
+    for (int t = lane; t < CD * Sh::L; t += 32) {
+        const int cd = t / Sh::L, o = t % Sh::L, c = cd / DIM, d = cd % DIM;
+        int inn = 1; for (int i = 0; i < d; ++i) inn *= SH;
+        const int lo = o % inn, hi = o / inn;
+        float line[SH];
+#pragma unroll
+        for (int e = 0; e < SH; ++e) line[e] = s_child[c * Sh::SD + lo + e * inn + hi * inn * SH];
+        s_work[cd * Sh::L + o] = R::line_error<SH, SL>(heur_relative(hr, d), line);
     }
+    __syncwarp();
+    for (int n = Sh::L / SH; n >= 1; n /= SH) {                     // fold_all(high rule): fold dimension 0 until one value is left (fold.h:87-108)
+        constexpr int MAXT = (CD * (Sh::L / SH) + 31) / 32;
+        float v[MAXT > 0 ? MAXT : 1];
+        int k = 0;
+        for (int t = lane; t < CD * n; t += 32, ++k) { const int cd = t / n, o = t % n; v[k] = R::apply<SH>(s_work + cd * Sh::L + o * SH); }
+        __syncwarp();
+        k = 0;
+        for (int t = lane; t < CD * n; t += 32, ++k) { const int cd = t / n, o = t % n; s_work[cd * Sh::L + o] = v[k]; }
+        __syncwarp();
+        if (n == 1) break;
+    }
+    if (lane < CD) s_E[lane] = R::fm(s_vol[lane / DIM], s_work[lane * Sh::L]);
+    __syncwarp();
     if (lane < 2) {
         float e; unsigned d;
         heur_pick<DIM>(hr, s_E + lane * DIM, s_crange + lane * 2 * DIM, &e, &d);
@@ -291,7 +333,7 @@ int run_rounds(vb200_ctx* ctx, const vb200_integrand* f, const vb200_adaptive_pa
     root_error_kernel<SH, SL, DIM><<<1, 32, (Sh::SD + Sh::L + 4 * DIM) * sizeof(float), s>>>(cap, r->rmin, r->rmax, r->data, r->err, r->errdim, heur_args(p->heuristic, p->metric, p->size_weight, p->mixed));
     ctx->launches++;
     VB200_CUDA(ctx, cudaGetLastError());
-    const size_t per_warp = (3 * Sh::SD + Sh::L + 4 * DIM + 2 * DIM + 2) * sizeof(float);
+    const size_t per_warp = (3 * Sh::SD + 2 * DIM * Sh::L + 4 * DIM + 2 * DIM + 2) * sizeof(float);
     int wpc = int((96u << 10) / per_warp); if (wpc > 8) wpc = 8; if (wpc < 1) wpc = 1;
     auto kchild = split_children_kernel<SH, SL, DIM>;
     VB200_CUDA(ctx, cudaFuncSetAttribute(kchild, cudaFuncAttributeMaxDynamicSharedMemorySize, int(per_warp * wpc)));
@@ -414,7 +456,7 @@ int run_tolerance(vb200_ctx* ctx, const vb200_integrand* f, const vb200_toleranc
     root_error_kernel<SH, SL, DIM><<<1, 32, (Sh::SD + Sh::L + 4 * DIM) * sizeof(float), s>>>(t.r->capacity, t.r->rmin, t.r->rmax, t.r->data, t.r->err, t.r->errdim, heur_args(p->heuristic, p->metric, p->size_weight, vb200_mixed_heuristic{}));
     ctx->launches++;
     VB200_CUDA(ctx, cudaGetLastError());
-    const size_t per_warp = (3 * Sh::SD + Sh::L + 4 * DIM + 2 * DIM + 2) * sizeof(float);
+    const size_t per_warp = (3 * Sh::SD + 2 * DIM * Sh::L + 4 * DIM + 2 * DIM + 2) * sizeof(float);
     int wpc = int((96u << 10) / per_warp); if (wpc > 8) wpc = 8; if (wpc < 1) wpc = 1;
     auto kchild = split_children_kernel<SH, SL, DIM>;
     VB200_CUDA(ctx, cudaFuncSetAttribute(kchild, cudaFuncAttributeMaxDynamicSharedMemorySize, int(per_warp * wpc)));

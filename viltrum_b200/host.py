@@ -407,9 +407,10 @@ class Regions:
         s = C.Shard(); s.begin, s.end = C.shard_pair(shard)
         self.ctx.check(self.ctx._L.vb200_regions_integrate_bins(self.ctx._h, self._h, ctypes.byref(d), ctypes.byref(s), b, mem))
 
-    def _cv_params(self, res, rng, spp, seed, shard, fixed_alpha=None, rr="uniform"):
+    def _cv_params(self, res, rng, spp, seed, shard, fixed_alpha=None, rr="uniform", rs="uniform", rs_power=1.0, rs_cutoff=0.0):
         p = C.CvParams()
-        p.rr_policy = C.RR_POLICIES[rr]      # rr_uniform_region / rr_integral_region / rr_error_region (region-russian-roulette.h:9-106)
+        p.rr_policy = C.RR_POLICIES[rr]      # rr_uniform_region / rr_integral_region / rr_error_region / rr_pdf_region (region-russian-roulette.h:9-147), "stratified"
+        p.rs_policy, p.rs_power, p.rs_cutoff = C.RS_POLICIES[rs], float(rs_power), float(rs_cutoff)      # region-sampling.h:9-135
         p.domain = C.make_domain(len(rng.min), res, rng.min, rng.max)
         p.shard.begin, p.shard.end = C.shard_pair(shard)
         p.spp, p.seed = int(spp), int(seed) & 0xFFFFFFFFFFFFFFFF
@@ -417,12 +418,13 @@ class Regions:
             p.weight_strategy, p.alpha = C.CV_FIXED_WEIGHT, float(fixed_alpha)
         return p
 
-    def cv_integrate(self, f, bins, res, rng, spp, seed, shard=None, nregions=None, approx=None, exact=False, fixed_alpha=None, rr="uniform"):
+    def cv_integrate(self, f, bins, res, rng, spp, seed, shard=None, nregions=None, approx=None, exact=False, fixed_alpha=None, rr="uniform",
+                     rs="uniform", rs_power=1.0, rs_cutoff=0.0):
         if Context._empty(shard):
             return
         b, mem, _k = _buffer(bins)
         n, _m, _kn = _buffer(nregions, np.uint32); a, _m2, _ka = _buffer(approx)
-        p = self._cv_params(res, rng, spp, seed, shard, fixed_alpha, rr)
+        p = self._cv_params(res, rng, spp, seed, shard, fixed_alpha, rr, rs, rs_power, rs_cutoff)
         self.ctx.check(self.ctx._L.vb200_cv_integrate(self.ctx._h, self.ctx.integrand(f, exact), self._h, ctypes.byref(p), b, mem, n, a))
 
     def cv_replay(self, f, bins, res, rng, spp, chosen, samples, shard=None, exact=True, fixed_alpha=None, rr="uniform"):
@@ -632,6 +634,35 @@ def rr_pdf_region():
     return "pdf"
 
 
+def region_stratification_uniform():
+    """region_stratification_uniform() — reference src/control-variates/region-stratification.h:9-25 (the Optimized integrator's allocation)"""
+    return "stratified"
+
+
+@dataclass
+class RegionSampling:
+    """region_sampling_uniform / _importance / _mis(power, cutoff) / _russian_roulette — reference src/control-variates/region-sampling.h:9-135"""
+    kind: str = "uniform"
+    power: float = 1.0
+    cutoff: float = 0.0
+
+
+def region_sampling_uniform():
+    return RegionSampling("uniform")
+
+
+def region_sampling_importance():
+    return RegionSampling("importance")
+
+
+def region_sampling_mis(power=1.0, cutoff=0.0):
+    return RegionSampling("mis", power, cutoff)
+
+
+def region_sampling_russian_roulette():
+    return RegionSampling("russian_roulette")
+
+
 @dataclass
 class IntegratorCrespo2021:
     """integrator_crespo2021(iterations, spp, seed) — reference src/control-variates/integrator-crespo2021.h:7-22 ('=').
@@ -642,6 +673,7 @@ class IntegratorCrespo2021:
     batch: int = 1
     cv: Optional[CvFixedWeight] = None
     rr: str = "uniform"
+    rs: Optional["RegionSampling"] = None
 
     def integrate(self, ctx, bins, res, f, rng, shard=None, exact=False, logger=None, **kw):
         gen = IntegratorAdaptiveIterations(nested("simpson", "trapezoidal"), error_heuristic_size(error_metric_relative(), 1e-5),
@@ -650,8 +682,9 @@ class IntegratorCrespo2021:
         if logger is not None:
             logger.log(regs)
         try:
+            rs = self.rs or RegionSampling()
             regs.cv_integrate(f, bins, res, rng, self.spp, self.seed, shard=shard, exact=exact,
-                              fixed_alpha=self.cv.alpha if self.cv is not None else None, rr=self.rr, **kw)
+                              fixed_alpha=self.cv.alpha if self.cv is not None else None, rr=self.rr, rs=rs.kind, rs_power=rs.power, rs_cutoff=rs.cutoff, **kw)
         finally:
             if logger is None:
                 regs.free()
@@ -709,6 +742,22 @@ class IntegratorCrespo2021Infinite:
             g_gen.free(); g_res.free()
 
 
+@dataclass
+class IntegratorFubiniVarianceReductionOptimized(IntegratorCrespo2021Infinite):
+    """integrator_adaptive_fubini_variance_reduction_parallel_optimized<N>(nested(simpson,trapezoidal), error_heuristic_size(relative), iterations,
+    mc_samples, region_stratification_uniform(), cv, region_sampling_uniform(), spp, seed) — reference
+    src/control-variates/integrator-adaptive-fubini-variance-reduction-optimized.h:9-23: the crespo2021_infinite pipeline with the stratified
+    allocation of RegionsIntegratorParallelVarianceReductionOptimized in place of the per-sample Russian roulette."""
+
+    def integrate(self, ctx, bins, res, f, rng, shard=None, logger=None, **kw):
+        kw = dict(kw); kw["rr"] = "stratified"
+        super().integrate(ctx, bins, res, f, rng, shard=shard, logger=logger, **kw)
+
+
+def integrator_adaptive_fubini_variance_reduction_parallel_optimized(nfirst, iterations, mc_samples, spp, seed=0, batch=1):
+    return IntegratorFubiniVarianceReductionOptimized(nfirst, iterations, mc_samples, spp, seed, batch)
+
+
 def integrator_fubini(nfirst, first, rest):
     return IntegratorFubini(nfirst, first, rest)
 
@@ -756,7 +805,7 @@ def integrator_crespo2021(iterations, spp, seed=0, batch=1, cv=None):
     return IntegratorCrespo2021(iterations, spp, seed, batch, cv)
 
 
-def integrator_adaptive_variance_reduction_parallel(rule, heuristic, iterations, rr, cv, spp, seed=0, batch=1):
+def integrator_adaptive_variance_reduction_parallel(rule, heuristic, iterations, rr, cv, spp, seed=0, batch=1, rs=None):
     """integrator_adaptive_variance_reduction_parallel(nested(simpson,trapezoidal), error_heuristic_size(relative), iterations, RR, CV,
     region_sampling_uniform(), spp, seed) — reference src/control-variates/integrator-adaptive-variance-reduction.h: the crespo2021 rule /
     heuristic pair with RR = rr_uniform_region() | rr_integral_region() | rr_error_region() | rr_pdf_region() and CV = cv_optimize_weight() | cv_fixed_weight(a)."""
@@ -764,7 +813,7 @@ def integrator_adaptive_variance_reduction_parallel(rule, heuristic, iterations,
         raise ValueError("the device control-variate path is built for nested(simpson, trapezoidal)")
     if not (isinstance(heuristic, ErrorHeuristic) and heuristic.kind == "size" and heuristic.metric.kind == "relative"):
         raise ValueError("the device control-variate path is built for error_heuristic_size(error_metric_relative())")
-    return IntegratorCrespo2021(iterations, spp, seed, batch, cv, rr)
+    return IntegratorCrespo2021(iterations, spp, seed, batch, cv, rr, rs)
 
 
 # ---- multi-GPU partitioning (one process per GPU) ---------------------------------------------------
