@@ -40,42 +40,45 @@ struct GreedyEntry64 {
     __device__ __forceinline__ static unsigned id_dim(type e) { return unsigned(e.y); }
 };
 
+// The heap is operated by ONE thread and lives in that thread's registers (pointers, cache size, count): kept in shared memory, every
+// get/set re-read those fields behind each store — ~290 cycles per heap level, 5200 of the 10200 cycles of a BASELINE-config-3 iteration
+// (profiles/greedy_phases_r2.txt).  Indices are 32-bit (capacity <= 2^28).
 template<class E = GreedyEntry32>
 struct GreedyHeapT {
     typedef typename E::type entry; typedef typename E::key_type key_type;
     entry* g;      // global entries
     entry* s;      // shared-memory cache of entries [0, cached)
-    long long cached;
-    long long n;
-    __device__ __forceinline__ entry get(long long i) const { return i < cached ? s[i] : g[i]; }
-    __device__ __forceinline__ void set(long long i, entry v) { if (i < cached) s[i] = v; else g[i] = v; }
+    unsigned cached;
+    unsigned n;
+    __device__ __forceinline__ entry get(unsigned i) const { return i < cached ? s[i] : g[i]; }
+    __device__ __forceinline__ void set(unsigned i, entry v) { if (i < cached) s[i] = v; else g[i] = v; }
     __device__ __forceinline__ static key_type key(entry e) { return E::key(e); }
 
     // libstdc++ __push_heap (stl_heap.h:135-148), comparator a.err < b.err
-    __device__ void sift_up(long long hole, entry value) {
+    __device__ __forceinline__ void sift_up(unsigned hole, entry value) {
         const key_type vk = key(value);
-        long long parent = (hole - 1) / 2;
         while (hole > 0) {
+            const unsigned parent = (hole - 1u) >> 1;
             const entry pe = get(parent);
             if (!(key(pe) < vk)) break;
-            set(hole, pe); hole = parent; parent = (hole - 1) / 2;
+            set(hole, pe); hole = parent;
         }
         set(hole, value);
     }
-    __device__ void push(entry value) { ++n; sift_up(n - 1, value); }
+    __device__ __forceinline__ void push(entry value) { ++n; sift_up(n - 1u, value); }
     // libstdc++ pop_heap -> __pop_heap -> __adjust_heap (stl_heap.h:224-267) followed by the caller's pop_back
-    __device__ void pop() {
-        if (n > 1) {
-            const entry value = get(n - 1);
-            const long long len = n - 1;
-            long long hole = 0, child = 0;
-            while (child < (len - 1) / 2) {
-                child = 2 * (child + 1);
-                entry ce = get(child); const entry le = get(child - 1);
+    __device__ __forceinline__ void pop() {
+        if (n > 1u) {
+            const entry value = get(n - 1u);
+            const unsigned len = n - 1u;
+            unsigned hole = 0, child = 0;
+            while (child < (len - 1u) / 2u) {
+                child = 2u * (child + 1u);
+                entry ce = get(child); const entry le = get(child - 1u);
                 if (key(ce) < key(le)) { --child; ce = le; }
                 set(hole, ce); hole = child;
             }
-            if ((len & 1) == 0 && child == (len - 2) / 2) { child = 2 * (child + 1); set(hole, get(child - 1)); hole = child - 1; }
+            if ((len & 1u) == 0u && child == (len - 2u) / 2u) { child = 2u * (child + 1u); set(hole, get(child - 1u)); hole = child - 1u; }
             sift_up(hole, value);
         }
         --n;
@@ -198,7 +201,9 @@ greedy_kernel(const F f, const vb200_greedy_launch a, const int heap_cached) {
     T* s_E = s_crange + 4 * DIM;                                        // [2][DIM]
     T* s_vol = s_E + 2 * DIM;                                           // [2]
     __shared__ unsigned s_top_id, s_top_dim;
-    __shared__ Heap heap;
+    __shared__ unsigned s_pick_dim[2];
+    __shared__ double s_pick_key[2];          // heap keys of the two children (exactly representable: Key is float or double)
+    Heap heap;                                // thread 0's registers
 
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, nwarps = GREEDY_THREADS / 32;
     const bool relative = a.metric == VB200_METRIC_RELATIVE, relative_rest = a.metric_rest == VB200_METRIC_RELATIVE;
@@ -209,18 +214,20 @@ greedy_kernel(const F f, const vb200_greedy_launch a, const int heap_cached) {
         if constexpr (MIXED) heuristic_pick_mixed<DIM, T>(Ev, rng, mixed, key, dim);
         else { T e; heuristic_pick<DIM, T>(Ev, rng, a.heuristic, a.size_weight, &e, dim); *key = Key(e); }
     };
+    // i / m for the grid positions: m = S-1 or 2(S-1) is a power of two for S = 3, 5, so the division is an exact multiplication
+    auto frac = [] (int i, int m) -> double { return ((m & (m - 1)) == 0) ? rules::dm(double(i), 1.0 / double(m)) : rules::dd(double(i), double(m)); };
     T* g_range = static_cast<T*>(a.range); T* g_data = static_cast<T*>(a.data); T* g_err = static_cast<T*>(a.err);
     const T* rmin_ = reinterpret_cast<const T*>(sizeof(T) == 8 ? static_cast<const void*>(a.range_min64) : static_cast<const void*>(a.range_min));
     const T* rmax_ = reinterpret_cast<const T*>(sizeof(T) == 8 ? static_cast<const void*>(a.range_max64) : static_cast<const void*>(a.range_max));
 
     // ---- initial region over the whole range (regions-generator-adaptive-heap.h:27-31) ----
-    if (tid == 0) { heap.g = static_cast<typename E::type*>(a.heap); heap.s = s_heap; heap.cached = heap_cached; heap.n = 0; }
+    heap.g = static_cast<typename E::type*>(a.heap); heap.s = s_heap; heap.cached = unsigned(heap_cached); heap.n = 0;
     if (tid < 2 * DIM) s_crange[tid] = tid < DIM ? rmin_[tid] : rmax_[tid - DIM];
     __syncthreads();
     for (int k = tid; k < Sh::SD; k += GREEDY_THREADS) {
         std::array<T, DIM> x; int t = k;
 #pragma unroll
-        for (int d = 0; d < DIM; ++d) { x[d] = grid_coord<T>(rules::dd(double(t % SH), double(SH - 1)), s_crange[d], s_crange[DIM + d]); t /= SH; }
+        for (int d = 0; d < DIM; ++d) { x[d] = grid_coord<T>(frac(t % SH, SH - 1), s_crange[d], s_crange[DIM + d]); t /= SH; }
         s_child[k] = f(x);
     }
     if (tid == 0) { T v = T(1); for (int d = 0; d < DIM; ++d) v = rules::mul(v, rules::sub(s_crange[DIM + d], s_crange[d])); s_vol[0] = v; }
@@ -234,90 +241,102 @@ greedy_kernel(const F f, const vb200_greedy_launch a, const int heap_cached) {
         Key err; unsigned dim; pick(s_E, s_crange, &err, &dim);
         if constexpr (KEY64) static_cast<double*>(a.key64)[0] = double(err); else g_err[0] = T(err);
         heap.push(E::make(0u | (dim << 28), err));
+        s_top_id = 0u; s_top_dim = dim;
     }
     for (int k = tid; k < Sh::SD; k += GREEDY_THREADS) g_data[k] = s_child[k];
     if (tid < 2 * DIM) g_range[tid] = s_crange[tid];
-    __syncthreads();
 
     // ---- iterations ----
+    // Two CTA barriers per iteration.  Between B1 and B2 warp 0 pops the heap (thread 0; the pop does not depend on the split: heap.front()
+    // was copied first, :33-35) WHILE warps 1..7 fetch the parent, evaluate the split, fold both children's errors and pick their
+    // heuristics (barrier 1 of 224 threads between those steps); between B2 and B1 thread 0 pushes the two children and publishes the
+    // next top while the other threads store the children to the region arrays.
+    constexpr int WORKERS = GREEDY_THREADS - 32;
+    auto worker_sync = [] () { asm volatile("bar.sync 1, %0;" :: "n"(WORKERS) : "memory"); };
     unsigned long long next_slot = 1;
 #ifdef VB200_GREEDY_TIMING
     long long t_prev_ = clock64();
 #endif
     for (unsigned long long it = 0; it < a.iterations; ++it) {
-        if (tid == 0) { const unsigned idd = E::id_dim(heap.get(0)); s_top_id = idd & GREEDY_ID_MASK; s_top_dim = idd >> 28; }
-        __syncthreads();
+        __syncthreads();                                                   // B1: top published, previous children stored
         VB200_GT(0);
         const unsigned top = s_top_id; const int dim = int(s_top_dim);
-        // warp 0 pops while the others fetch the parent (the pop does not depend on the split: heap.front() was copied first, :33-35)
-        if (warp == 0) { if (lane == 0) heap.pop(); }
-        else {
-            for (int k = tid - 32; k < Sh::SD; k += GREEDY_THREADS - 32) s_parent[k] = g_data[static_cast<unsigned long long>(top) * Sh::SD + k];
-            if (tid - 32 < 2 * DIM) s_prange[tid - 32] = g_range[static_cast<unsigned long long>(top) * (2 * DIM) + (tid - 32)];
-        }
-        VB200_GT(1);
-        __syncthreads();
-        VB200_GT(2);
-        // split along `dim` (split.h:13-49): the (2S-1)-wide array; even positions are the parent's samples, odd ones new evaluations
-        int inner = 1; for (int i = 0; i < dim; ++i) inner *= SH;
-        for (int item = tid; item < Sh::WIDE; item += GREEDY_THREADS) {
-            const int i = item / Sh::L, o = item % Sh::L;            // position along `dim` (0..2S-2), index over the other dims
-            const int lo = o % inner, hi = o / inner;
-            T v;
-            if ((i & 1) == 0) v = s_parent[lo + (i / 2) * inner + hi * inner * SH];
-            else {
-                std::array<T, DIM> x; int t = o;
+        if (warp == 0) {
+            if (lane == 0) heap.pop();
+            VB200_GT(1);
+        } else {
+            const int wt = int(tid) - 32;
+            for (int k = wt; k < Sh::SD; k += WORKERS) s_parent[k] = g_data[static_cast<unsigned long long>(top) * Sh::SD + k];
+            if (wt < 2 * DIM) s_prange[wt] = g_range[static_cast<unsigned long long>(top) * (2 * DIM) + wt];
+            worker_sync();
+            // split along `dim` (split.h:13-49): the (2S-1)-wide array; even positions are the parent's samples, odd ones new evaluations
+            int inner = 1; for (int i = 0; i < dim; ++i) inner *= SH;
+            for (int item = wt; item < Sh::WIDE; item += WORKERS) {
+                const int i = item / Sh::L, o = item % Sh::L;            // position along `dim` (0..2S-2), index over the other dims
+                const int lo = o % inner, hi = o / inner;
+                T v;
+                if ((i & 1) == 0) v = s_parent[lo + (i / 2) * inner + hi * inner * SH];
+                else {
+                    std::array<T, DIM> x; int t = o;
 #pragma unroll
-                for (int d = 0; d < DIM; ++d) {
-                    double p;
-                    if (d == dim) p = rules::dd(double(i), double(2 * (SH - 1)));
-                    else { p = rules::dd(double(t % SH), double(SH - 1)); t /= SH; }
-                    x[d] = grid_coord<T>(p, s_prange[d], s_prange[DIM + d]);
+                    for (int d = 0; d < DIM; ++d) {
+                        double p;
+                        if (d == dim) p = frac(i, 2 * (SH - 1));
+                        else { p = frac(t % SH, SH - 1); t /= SH; }
+                        x[d] = grid_coord<T>(p, s_prange[d], s_prange[DIM + d]);
+                    }
+                    v = f(x);
                 }
-                v = f(x);
+                if (i <= SH - 1) s_child[lo + i * inner + hi * inner * SH] = v;
+                if (i >= SH - 1) s_child[Sh::SD + lo + (i - (SH - 1)) * inner + hi * inner * SH] = v;
             }
-            if (i <= SH - 1) s_child[lo + i * inner + hi * inner * SH] = v;
-            if (i >= SH - 1) s_child[Sh::SD + lo + (i - (SH - 1)) * inner + hi * inner * SH] = v;
+            // child ranges (region.h:349-357): d = (max-min)/Float(2); child 0 = [min, min+d*1], child 1 = [min+d*1, max]; the last worker warp
+            if (wt >= WORKERS - 2) {
+                const int c = wt - (WORKERS - 2);
+                const T pmin = s_prange[dim], pmax = s_prange[DIM + dim];
+                const T mid = rules::add(pmin, rules::mul(rules::quo(rules::sub(pmax, pmin), T(2)), T(1)));
+                T* cr = s_crange + c * 2 * DIM;
+                for (int d = 0; d < 2 * DIM; ++d) cr[d] = s_prange[d];
+                if (c == 0) cr[DIM + dim] = mid; else cr[dim] = mid;
+                T v = T(1); for (int d = 0; d < DIM; ++d) v = rules::mul(v, rules::sub(cr[DIM + d], cr[d]));
+                s_vol[c] = v;
+            }
+            worker_sync();
+            // nested-rule error of both children along every dimension: one worker warp per (child, dimension)
+            for (int job = int(warp) - 1; job < 2 * DIM; job += int(nwarps) - 1) {
+                const int c = job / DIM, d = job % DIM;
+                const T e = region_error_warp<SH, SL, DIM, T>(s_child + c * Sh::SD, s_vol[c], d, rel_of(d), s_work + job * Sh::L, lane);
+                if (lane == 0) s_E[c * DIM + d] = e;
+            }
+            worker_sync();
+            if (wt < 2) {                                                   // the two children's heuristics side by side (:36-40)
+                Key err; unsigned d; pick(s_E + wt * DIM, s_crange + wt * 2 * DIM, &err, &d);
+                s_pick_key[wt] = double(err); s_pick_dim[wt] = d;
+            }
         }
-        // child ranges (region.h:349-357): d = (max-min)/Float(2); child 0 = [min, min+d*1], child 1 = [min+d*1, max]
-        if (tid < 2) {
-            const T pmin = s_prange[dim], pmax = s_prange[DIM + dim];
-            const T mid = rules::add(pmin, rules::mul(rules::quo(rules::sub(pmax, pmin), T(2)), T(1)));
-            T* cr = s_crange + tid * 2 * DIM;
-            for (int d = 0; d < 2 * DIM; ++d) cr[d] = s_prange[d];
-            if (tid == 0) cr[DIM + dim] = mid; else cr[dim] = mid;
-            T v = T(1); for (int d = 0; d < DIM; ++d) v = rules::mul(v, rules::sub(cr[DIM + d], cr[d]));
-            s_vol[tid] = v;
-        }
-        __syncthreads();
-        VB200_GT(3);
-        // nested-rule error of both children along every dimension: one warp per (child, dimension)
-        for (int job = warp; job < 2 * DIM; job += nwarps) {
-            const int c = job / DIM, d = job % DIM;
-            const T e = region_error_warp<SH, SL, DIM, T>(s_child + c * Sh::SD, s_vol[c], d, rel_of(d), s_work + job * Sh::L, lane);
-            if (lane == 0) s_E[c * DIM + d] = e;
-        }
-        __syncthreads();
-        VB200_GT(4);
-        // store the children (slots next_slot, next_slot+1) and push them in ascending coordinate order (:36-40)
-        for (int k = tid; k < 2 * Sh::SD; k += GREEDY_THREADS) g_data[next_slot * Sh::SD + k] = s_child[k];
-        if (tid < 4 * DIM) g_range[next_slot * (2 * DIM) + tid] = s_crange[tid];
+        __syncthreads();                                                   // B2: popped; children, errors and picks ready
+        VB200_GT(2);
         if (tid == 0) {
             for (int c = 0; c < 2; ++c) {
-                Key err; unsigned d; pick(s_E + c * DIM, s_crange + c * 2 * DIM, &err, &d);
-                if constexpr (KEY64) static_cast<double*>(a.key64)[next_slot + c] = double(err); else g_err[next_slot + c] = T(err);
+                const Key err = Key(s_pick_key[c]); const unsigned d = s_pick_dim[c];
                 heap.push(E::make(unsigned(next_slot + c) | (d << 28), err));
             }
+            const unsigned idd = E::id_dim(heap.get(0)); s_top_id = idd & GREEDY_ID_MASK; s_top_dim = idd >> 28;
+            VB200_GT(3);
+        } else {
+            // store the children (slots next_slot, next_slot+1)
+            for (int k = int(tid) - 1; k < 2 * Sh::SD; k += GREEDY_THREADS - 1) g_data[next_slot * Sh::SD + k] = s_child[k];
+            if (tid - 1 < 4 * DIM) g_range[next_slot * (2 * DIM) + (tid - 1)] = s_crange[tid - 1];
+            if (tid - 1 < 2) { if constexpr (KEY64) static_cast<double*>(a.key64)[next_slot + (tid - 1)] = s_pick_key[tid - 1]; else g_err[next_slot + (tid - 1)] = T(s_pick_key[tid - 1]); }
         }
         next_slot += 2;
-        VB200_GT(5);
-        __syncthreads();
-        VB200_GT(6);
     }
+    __syncthreads();
     // flush the cached top of the heap
-    const long long n = heap.n;
-    for (long long i = tid; i < n && i < heap_cached; i += GREEDY_THREADS) static_cast<typename E::type*>(a.heap)[i] = s_heap[i];
-    if (tid == 0) *a.heap_size = static_cast<uint64_t>(n);
+    if (tid == 0) { s_top_id = heap.n; *a.heap_size = static_cast<uint64_t>(heap.n); }
+    __syncthreads();
+    const unsigned n = s_top_id;
+    for (unsigned i = tid; i < n && i < unsigned(heap_cached); i += GREEDY_THREADS) static_cast<typename E::type*>(a.heap)[i] = s_heap[i];
 }
 
 template<class F, int DIM, int SH, int SL, bool EXACT, class T, bool MIXED>

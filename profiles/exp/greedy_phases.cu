@@ -1,7 +1,7 @@
 // Experiment harness (not product): the PRODUCT's greedy_kernel (include/viltrum_b200/device/greedy.cuh) on BASELINE config 3's shape
 // (smooth_edge2, nested(boole,simpson), size/relative 1e-5) with per-phase cycle counters of thread 0 (-DVB200_GREEDY_TIMING).
-//   phases: 0 top read + barrier | 1 pop (thread 0) | 2 barrier after pop/fetch | 3 split evaluation + barrier | 4 child errors + barrier |
-//           5 stores + heuristics + two pushes | 6 closing barrier
+//   phases (thread 0's clock): 0 barrier B1 | 1 pop | 2 wait at barrier B2 (the workers' fetch + split + errors + picks, if longer than the pop) |
+//           3 two pushes + next top.  (Round-2 first capture, old kernel: top 302, pop 5223, split 970, errors 1378, pushes+stores 2001 of 10234 cycles.)
 #define VB200_GREEDY_TIMING
 #include <cstdio>
 #include <cstring>
