@@ -245,13 +245,14 @@ class Bench:
         w = self.w
         from viltrum_b200 import Range, RangeInfinite, shard_for_rank, _capi
         self.capi = _capi
-        # scaling: c2/c5 weak by default (every rank owns a full-size slab of a grid N times as tall: independent bins, no collective), c3/c4 strong
+        # scaling: c2 weak by default (every rank owns a full-size slab of a grid N times as tall: independent bins, no collective), c5 weak as replicas, c3/c4 strong
         # (BASELINE configs[3]: "bins sharded over 8 GPUs"); --scaling overrides
         self.scaling = args.scaling or ("weak" if w["kind"] in ("mc", "walk") else "strong")
         res = list(w["res"])
         # region-based workloads under --scaling weak: N replicas, every rank integrates the whole grid with its own seed (the region table does not
         # shard, so "more bins" would change the regions per bin); the per-bin samplers stack the ranks' slabs into one taller grid instead
-        self.replicas = self.scaling == "weak" and w["kind"] in ("nc", "cv") and world > 1
+        # (the walk integrand's path length depends on where a bin sits in the image: slabs of a taller grid would not be equal work, so it is replicated too)
+        self.replicas = self.scaling == "weak" and w["kind"] in ("nc", "cv", "walk") and world > 1
         self.gres = [res[0], res[1] * world] if (self.scaling == "weak" and not self.replicas) else res
         self.shard = (0, self.gres[0] * self.gres[1]) if self.replicas else shard_for_rank(self.gres, rank, world)
         self.nb_local = self.shard[1] - self.shard[0]
@@ -262,6 +263,7 @@ class Bench:
         self.h_bins = np.zeros(self.nb_global, np.float32)
         self.d_nreg = torch.zeros(self.nb_global, dtype=torch.int32, device="cuda") if w["kind"] == "cv" else None
         self.generator = "xoshiro"
+        self.ktimer = False
 
     # one step = one integrator call
     def step(self, bins, seed):
@@ -270,7 +272,7 @@ class Bench:
             ctx.mc_per_bin(w["integrand"], bins, self.gres, self.rng, w["spp"], seed, self.capi.MC_PER_BIN if w["path"] == "mc_per_bin_parallel" else self.capi.PER_BIN_MC,
                            shard=self.shard, generator=self.generator)
         elif w["kind"] == "walk":
-            ctx.mc_per_bin_inf(w["integrand"], bins, self.gres, self.rng, w["spp"], seed, shard=self.shard)
+            ctx.mc_per_bin_inf(w["integrand"], bins, self.gres, self.rng, w["spp"], seed + 7919 * (self.rank if self.replicas else 0), shard=self.shard)
         elif w["kind"] == "nc":
             regs = ctx.regions_generate_adaptive(w["integrand"], self.rng, "boole_simpson", "size", "relative", w["iterations"], 1e-5, batch=self.batch, exact=True)
             regs.integrate_bins(bins, self.gres, self.rng, shard=self.shard)
@@ -309,6 +311,8 @@ class Bench:
             for i in range(warmup):
                 self.step(bins, i)
             self.barrier()
+            if self.ktimer:
+                self.ctx.kernel_timer_read()                                       # drop the warm-up launches
             evs = []
             for i in range(steps):
                 self.flush.zero_()
@@ -348,7 +352,12 @@ class Bench:
         args, w, ctx = self.args, self.w, self.ctx
         unit = "regions/s" if w["kind"] == "nc" else ("paths/s" if w["kind"] == "walk" else "evals/s")
         l0 = ctx.launch_count
+        if w["kind"] == "cv":                                                      # event pairs around the heaviest kernel's launches (vb200_kernel_timer)
+            ctx.kernel_timer(True); self.ktimer = True
         ms_dev = self.timed(self.d_bins, args.steps, args.warmup)
+        k_ms, k_launches = (0.0, 0)
+        if self.ktimer:
+            k_ms, k_launches = ctx.kernel_timer_read(); ctx.kernel_timer(False); self.ktimer = False
         launches = ctx.launch_count - l0 - 0
         launches_per_step = launches / float(args.steps + args.warmup)
         ms_sus, n_sus = self.sustained(self.d_bins, ms_dev, args.sustain)
@@ -394,14 +403,29 @@ class Bench:
                     "note": "issue bound by the generator and the per-lane roulette (~6 flops per random number): the FP32 fraction is low by construction (SURVEY.md §8d)"}
         elif w["kind"] == "cv":
             pairs = float(self.d_nreg.double().sum().item())                       # (bin, region) pairs of this rank's slab
-            flops = pairs * F_PAIR + self.nb_local * w["spp"] * (F_F5 + F_APPROX + 20)
-            achieved = flops / per_gpu_s / 1e12
             table_bytes = (w["iterations"] + 1) * 243 * 4
-            roof = {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak, "traffic": None,
-                    "pairs": pairs, "regions_per_bin": pairs / self.nb_local, "flops_per_pair": F_PAIR, "flops_per_residual_sample": F_F5 + F_APPROX + 20,
-                    "pairs_per_s": pairs / per_gpu_s, "hbm_gbs_achieved": (table_bytes + self.nb_local * 4) / per_gpu_s / 1e9, "hbm_gbs_peak": peaks.get("hbm_gbs"),
-                    "note": "whole step (generation + region->bin control variate + residual MC); algorithmic flops = pairs*876 + bins*spp*(158+846+20), the separable "
-                            "tensor-contraction counts of SURVEY.md §8(d); HBM figure = region table read once + bins"}
+            f_sample = F_F5 + F_APPROX + 20
+            samples_step = self.nb_local * w["spp"]
+            if k_launches:
+                # dominant kernel = the tile-major residual pass: draws the sample, picks its region, evaluates f and the region's interpolant,
+                # books the moments.  Its own duration (CUDA events around each of its launches inside the timed region), not the step's.
+                k_ms_launch = k_ms / k_launches
+                samples_launch = samples_step * args.steps / float(k_launches)
+                achieved = samples_launch * f_sample / (k_ms_launch * 1e-3) / 1e12
+                roof = {"bound": "fp32", "kernel": "cv_tile_samples_kernel<3,5>", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+                        "traffic": NCU_TRAFFIC_BYTES.get(self.name), "kernel_ms_per_launch": k_ms_launch, "kernel_launches_per_step": k_launches / float(args.steps),
+                        "kernel_share_of_step": (k_ms / args.steps) / ms_dev, "samples_per_launch": samples_launch, "flops_per_residual_sample": f_sample,
+                        "smem_gbs_achieved": samples_launch * 972 / (k_ms_launch * 1e-3) / 1e9,
+                        "note": "per launch: residual samples x (158 integrand + 846 interpolant + 20) flop, SURVEY.md §8(d); every sample also reads its region's 243 "
+                                "coefficients (972 B) from shared memory (smem_gbs_achieved; 148 SMs x 128 B/clk = 37 TB/s)"}
+            else:
+                achieved = samples_step * f_sample / per_gpu_s / 1e12
+                roof = {"bound": "fp32", "kernel": "whole step (sample-major residual pipeline)", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                        "frac": achieved / fp32_peak, "traffic": None, "flops_per_residual_sample": f_sample}
+            # the region->bin control-variate pass: regions are marginalised over the non-binned dimensions once (243 -> 9 values), so a
+            # (bin, region) pair costs a 2-D patch integral, not the 876 flop of SURVEY.md §8(d)'s 5-D contraction: reported as pairs/s only
+            roof.update({"pairs": pairs, "regions_per_bin": pairs / self.nb_local, "pairs_per_s": pairs / per_gpu_s,
+                         "hbm_gbs_achieved": (table_bytes + self.nb_local * 4) / per_gpu_s / 1e9, "hbm_gbs_peak": peaks.get("hbm_gbs")})
         elif w["kind"] == "nc":
             bytes_alg = w["iterations"] * 376.0 + (w["iterations"] + 1) * 120.0 + self.nb_local * 4
             achieved = bytes_alg / per_gpu_s / 1e9
@@ -415,7 +439,7 @@ class Bench:
             roof["peak_measured_fma"] = fma_peak
             roof["frac_of_measured_fma"] = (roof["achieved"] / fma_peak) if fma_peak else None
         cfg = config_of(self.name)
-        cfg.update({"rng": RNG_NOTE[w["kind"]] if w["kind"] in RNG_NOTE else None, "parallelism": (f"{self.world} replicas of the whole {self.gres[0]}x{self.gres[1]} grid, one per GPU, own seeds (weak scaling of a path whose region table does not shard)" if self.replicas
+        cfg.update({"rng": RNG_NOTE[w["kind"]] if w["kind"] in RNG_NOTE else None, "parallelism": (f"{self.world} replicas of the whole {self.gres[0]}x{self.gres[1]} grid, one per GPU, own seeds (weak scaling: " + ("the path length of a walk depends on the bin's place in the image, so slabs of a taller grid would not be equal work)" if w["kind"] == "walk" else "the region table does not shard)") if self.replicas
                                     else f"bin-grid slabs x{self.world} ({self.scaling} scaling: global grid {self.gres[0]}x{self.gres[1]})"),
                     "l2": "flushed between timed steps (256 MiB memset, untimed); per-step CUDA events on the library stream"})
         if w["kind"] in ("nc", "cv"):

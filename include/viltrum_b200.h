@@ -66,6 +66,12 @@ int         vb200_synchronize(vb200_ctx* ctx);
 int         vb200_sm_count(const vb200_ctx* ctx);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 uint64_t    vb200_launch_count(const vb200_ctx* ctx);
+/* Per-kernel device time of the residual-sampling kernel of vb200_cv_integrate (the heaviest kernel of the control-variate pipeline; its
+ * roofline in bench.py needs the kernel's own duration, not the step's).  While enabled, every launch of that kernel is bracketed by a pair
+ * of CUDA events on the context's stream (no synchronisation, two event records per launch); vb200_kernel_timer_read synchronises the
+ * stream, returns the summed duration and the number of launches since the last read, and releases the events. */
+int         vb200_kernel_timer(vb200_ctx* ctx, int enable);
+int         vb200_kernel_timer_read(vb200_ctx* ctx, double* ms_total, uint64_t* launches);
 
 /* Pin and map a caller-owned host buffer (cudaHostRegister, mapped + portable) for the lifetime of the registration.  The sampling
  * drivers (vb200_mc_per_bin, vb200_mc_per_bin_inf) recognise VB200_HOST bins that lie inside a registered buffer and let the kernel

@@ -148,13 +148,15 @@ def _k_seed_gate(gpus, refs, what, ratio_bounds=(0.6, 1.6)):
 
 @pytest.mark.parametrize("integ,res,it,spp,rs,power,cutoff", [("smooth_edge2", [24, 24], 300, 16, "importance", 1.0, 0.0), ("smooth_edge2", [24, 24], 300, 16, "mis", 1.0, 0.0),
                                                               ("smooth_edge2", [24, 24], 300, 16, "mis", 2.0, 0.1), ("smooth_edge2", [24, 24], 300, 16, "russian_roulette", 1.0, 0.0),
-                                                              ("smooth_edge2", [40, 10], 120, 64, "importance", 1.0, 0.0), ("cubic1", [20], 30, 8, "importance", 1.0, 0.0)])
+                                                              ("smooth_edge2", [40, 10], 120, 64, "importance", 1.0, 0.0), ("smooth_edge2", [16, 16], 40, 32, "importance", 1.0, 0.0),
+                                                              ("smooth_edge2", [16, 16], 40, 32, "russian_roulette", 1.0, 0.0)])
 def test_region_sampling_policies_against_the_reference(ctx, integ, res, it, spp, rs, power, cutoff):
     """region_sampling_importance / _mis(power, cutoff) / _russian_roulette (reference src/control-variates/region-sampling.h:22-135, Simpson::sample
     rules.h:184-247, Region::sample_subrange / pdf_subrange region.h:220-343): K = 16 seeds of the device path against K = 16 seeds of the
     UNMODIFIED reference, per-bin means within 3 sigma of their standard errors, matching noise (statistical parity: the reference inverts a
     cubic CDF with pow/acos/cos).  Integrands on which the reference's samplers stay finite (on shade4 / ind2 half of its bins come out NaN) and
-    whose residual is not down at float rounding (polynomials the Simpson interpolant reproduces leave nothing to compare)."""
+    whose residual is not down at float rounding (polynomials the Simpson interpolant reproduces, and cubic1 after 30 splits, leave only
+    rounding noise plus one heavy-tailed outlier of the reference to compare); the [16, 16] cases have fewer regions than bins."""
     import pyoracle
     from viltrum_b200 import integrate, integrator_adaptive_variance_reduction_parallel, nested, error_heuristic_size, error_metric_relative, RegionSampling
     if not pyoracle.available("reference"):

@@ -45,7 +45,7 @@ STATUS = {0: "VB200_OK", -1: "VB200_ERR_NO_DEVICE", -2: "VB200_ERR_INVALID", -3:
 # every symbol include/viltrum_b200.h declares (tests/test_capi_symbols.py checks the header against this list and the .so)
 SYMBOLS = [
     "vb200_create", "vb200_destroy", "vb200_last_error", "vb200_stream", "vb200_synchronize", "vb200_sm_count",
-    "vb200_launch_count", "vb200_host_register", "vb200_host_unregister", "vb200_measure_fp32_peak", "vb200_philox4x32_10", "vb200_xoshiro128pp", "vb200_threefry4x32", "vb200_builtin_integrand", "vb200_builtin_count", "vb200_builtin_name",
+    "vb200_launch_count", "vb200_kernel_timer", "vb200_kernel_timer_read", "vb200_host_register", "vb200_host_unregister", "vb200_measure_fp32_peak", "vb200_philox4x32_10", "vb200_xoshiro128pp", "vb200_threefry4x32", "vb200_builtin_integrand", "vb200_builtin_count", "vb200_builtin_name",
     "vb200_mc_per_bin", "vb200_mc_per_bin_replay", "vb200_mc_per_bin_inf", "vb200_mc_per_bin_inf_replay",
     "vb200_monte_carlo", "vb200_regions_generate_adaptive", "vb200_regions_generate_single", "vb200_regions_upload",
     "vb200_regions_count", "vb200_regions_dim", "vb200_regions_samples", "vb200_regions_download", "vb200_regions_free",
@@ -128,6 +128,8 @@ def lib():
         L.vb200_synchronize.argtypes = [vp]; L.vb200_synchronize.restype = i32
         L.vb200_sm_count.argtypes = [vp]; L.vb200_sm_count.restype = i32
         L.vb200_launch_count.argtypes = [vp]; L.vb200_launch_count.restype = u64
+        L.vb200_kernel_timer.argtypes = [vp, i32]; L.vb200_kernel_timer.restype = i32
+        L.vb200_kernel_timer_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]; L.vb200_kernel_timer_read.restype = i32
         L.vb200_host_register.argtypes = [vp, vp, ctypes.c_size_t]; L.vb200_host_register.restype = i32
         L.vb200_host_unregister.argtypes = [vp, vp]; L.vb200_host_unregister.restype = i32
         L.vb200_measure_fp32_peak.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double)]; L.vb200_measure_fp32_peak.restype = i32

@@ -247,6 +247,26 @@ extern "C" int vb200_synchronize(vb200_ctx* ctx) { if (!ctx) return VB200_ERR_IN
 extern "C" int vb200_sm_count(const vb200_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 extern "C" uint64_t vb200_launch_count(const vb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+static void ktimer_drop(vb200_ctx* ctx) {
+    for (auto& e : ctx->ktimer_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    ctx->ktimer_events.clear();
+}
+extern "C" int vb200_kernel_timer(vb200_ctx* ctx, int enable) {
+    if (!ctx) return VB200_ERR_INVALID;
+    ctx->ktimer = enable != 0;
+    if (!ctx->ktimer) { cudaStreamSynchronize(ctx->stream); ktimer_drop(ctx); }
+    return VB200_OK;
+}
+extern "C" int vb200_kernel_timer_read(vb200_ctx* ctx, double* ms_total, uint64_t* launches) {
+    if (!ctx || !ms_total || !launches) return ctx ? vb200::fail(ctx, VB200_ERR_INVALID, "vb200_kernel_timer_read: null output") : VB200_ERR_INVALID;
+    VB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double ms = 0.0;
+    for (auto& e : ctx->ktimer_events) { float t = 0.f; VB200_CUDA(ctx, cudaEventElapsedTime(&t, e.first, e.second)); ms += t; }
+    *ms_total = ms; *launches = ctx->ktimer_events.size();
+    ktimer_drop(ctx);
+    return VB200_OK;
+}
+
 extern "C" int vb200_host_register(vb200_ctx* ctx, void* ptr, size_t bytes) {
     if (!ctx || !ptr || bytes == 0) return fail(ctx, VB200_ERR_INVALID, "NULL/empty buffer");
     VB200_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -64,6 +64,9 @@ struct vb200_ctx {
     std::vector<struct vb200_regions*> live_regions;
     // optional NCCL communicator (vb200_comm_init; comm.cu): one rank per process and GPU
     void* comm = nullptr; int comm_rank = 0, comm_size = 1;
+    // vb200_kernel_timer: event pairs around the launches of the residual-sampling kernel
+    bool ktimer = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ktimer_events;
 };
 
 namespace vb200 {

@@ -821,8 +821,11 @@ template<int S, int D> int launch_tile_samples(vb200_ctx* ctx, const CvTileArgs&
     const size_t smem = size_t(a.J) * CVT_BINS * 2 * 2 + size_t(CVT_MAXLIST) * 2 + std::max(size_t(CVT_MAXLIST) * 4, size_t(8) * CVT_SLOTS * SLOT * 4);
     auto k = cv_tile_samples_kernel<S, D>;
     VB200_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ctx->ktimer) { VB200_CUDA(ctx, cudaEventCreate(&e0)); VB200_CUDA(ctx, cudaEventCreate(&e1)); VB200_CUDA(ctx, cudaEventRecord(e0, ctx->stream)); }
     k<<<ntiles, 256, smem, ctx->stream>>>(a);
     ctx->launches++;
+    if (ctx->ktimer) { VB200_CUDA(ctx, cudaEventRecord(e1, ctx->stream)); ctx->ktimer_events.emplace_back(e0, e1); }
     VB200_CUDA(ctx, cudaGetLastError());
     return VB200_OK;
 }

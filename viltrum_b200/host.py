@@ -123,6 +123,17 @@ class Context:
     def launch_count(self):
         return self._L.vb200_launch_count(self._h)
 
+    def kernel_timer(self, enable):
+        """event pairs around every launch of the residual-sampling kernel of cv_integrate (vb200_kernel_timer)"""
+        self.check(self._L.vb200_kernel_timer(self._h, 1 if enable else 0))
+
+    def kernel_timer_read(self):
+        """(summed milliseconds, launches) since the last read; synchronises the stream"""
+        import ctypes
+        ms = ctypes.c_double(0.0); n = ctypes.c_uint64(0)
+        self.check(self._L.vb200_kernel_timer_read(self._h, ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, int(n.value)
+
     def host_register(self, array):
         """pin + map a numpy array (vb200_host_register): samplers then write their bins into it directly over PCIe, with no host-side pass"""
         self.check(self._L.vb200_host_register(self._h, array.ctypes.data, array.nbytes))
