@@ -551,6 +551,35 @@ __global__ void __launch_bounds__(128) cv_accumulate_kernel(uint64_t begin, uint
     out[begin + b] = acc.result(approx[b], fixed_weight, fixed_alpha);                   // '=' (…-variance-reduction.h:102)
 }
 
+// The same contraction over a region record in SHARED memory, read as 128-bit words: the S^D values are consumed strictly in storage order
+// (dimension 0 fastest), every level keeps one running sum.  Same operations in the same order as FastLevel (identical bits), a quarter
+// of the shared-memory wavefronts — which is what bounds the tile-major residual kernel.  `data` must be 16-byte aligned and readable up to
+// the next multiple of four values.
+template<int S, int D>
+__device__ __forceinline__ float fast_eval_stream(const float* __restrict__ data, const float (*L)[S]) {
+    constexpr int SD = R::ipow(S, D);
+    const float4* d4 = reinterpret_cast<const float4*>(data);
+    float acc[D];
+#pragma unroll
+    for (int l = 0; l < D; ++l) acc[l] = 0.0f;
+    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < SD; ++i) {
+        if ((i & 3) == 0) c = d4[i >> 2];
+        const float x = (i & 3) == 0 ? c.x : (i & 3) == 1 ? c.y : (i & 3) == 2 ? c.z : c.w;
+        acc[0] = fmaf(L[0][i % S], x, acc[0]);
+        int q = i;
+#pragma unroll
+        for (int l = 1; l < D; ++l) {
+            if (q % S != S - 1) break;
+            q /= S;
+            acc[l] = fmaf(L[l][q % S], acc[l - 1], acc[l]);
+            acc[l - 1] = 0.0f;
+        }
+    }
+    return acc[D - 1];
+}
+
 // ---- tile-major residual pass (throughput path: FAST integrand, rr_uniform_region, 2-D bin grid) ------------------------------------
 // The sample-major pipeline above sorts ALL residual samples of a slab by region with a device-wide radix sort, evaluates them in that
 // order and scatters 16-byte records back (sort 1.5 ms + un-sort 2.7 ms of BASELINE config 4's 23 ms).  Here a CTA owns one
@@ -561,6 +590,7 @@ __global__ void __launch_bounds__(128) cv_accumulate_kernel(uint64_t begin, uint
 // integrand's launch over those points, cv_tile_accumulate_kernel brings a tile's values back into sample order through shared memory
 // and one thread per bin folds them in the reference's order.  No device-wide sort, no scattered global traffic.
 constexpr int CVT_BINS = 256, CVT_MAXLIST = 4096, CVT_MAXPASS = 64, CVT_ACCPASS = 32, CVT_SLOTS = 4;
+constexpr int cvt_slot_words(int sd, int d) { return ((sd + 2 * d + 7) / 8) * 8 + 4; }
 struct CvTileArgs {
     TileGeomCv g; vb200_domain dom; uint64_t cap, begin, end, tile0, nbins_total; uint32_t spp, J, k0, k1;
     const uint32_t* pstart; const uint32_t* pend; const uint64_t* offsets; const uint32_t* list; const uint32_t* count;      // count: indexed by bin - count_base
@@ -571,7 +601,7 @@ struct CvTileArgs {
 };
 template<int S, int D>
 __global__ void __launch_bounds__(256) cv_tile_samples_kernel(const CvTileArgs a) {
-    extern __shared__ unsigned char cvt_smem[];
+    extern __shared__ __align__(16) unsigned char cvt_smem[];
     unsigned short* s_rank   = reinterpret_cast<unsigned short*>(cvt_smem);                 // [J][256] the pass's sample ids sorted by list position
     unsigned short* s_choice = s_rank + a.J * CVT_BINS;                              // [J][256] position in the tile's region list (0xffff = no sample)
     unsigned short* s_hist   = s_choice + a.J * CVT_BINS;                            // [L] samples per list entry, then their running offsets
@@ -653,7 +683,8 @@ __global__ void __launch_bounds__(256) cv_tile_samples_kernel(const CvTileArgs a
         //    the same region broadcast and lanes on different regions hit different banks (odd slot stride), instead of issuing 243 global
         //    loads that each touch as many cache lines as the warp has regions.
         const uint64_t slot_pass = slot_tile + uint64_t(j0) * CVT_BINS;
-        constexpr int SD = R::ipow(S, D), SLOT = (SD + 2 * D) | 1;                   // data, rmin, rmax; odd stride
+        constexpr int SD = R::ipow(S, D), SLOT = cvt_slot_words(SD, D);            // data, rmin, rmax; stride = 4 (mod 8) words: 16-byte aligned records whose
+                                                                                  // 128-bit reads fall into different banks for the CVT_SLOTS records of a warp
         float* s_slots = s_region + (tid >> 5) * (CVT_SLOTS * SLOT);
         const uint32_t lane = tid & 31u;
         for (uint32_t pbase = (tid >> 5) * 32u; pbase < J * CVT_BINS; pbase += CVT_BINS) {
@@ -696,14 +727,16 @@ __global__ void __launch_bounds__(256) cv_tile_samples_kernel(const CvTileArgs a
                         if (d < 2) { ba = fmaf(float(bp[d]), a.dom.drange[d], a.dom.rmin[d]); bb = fmaf(float(bp[d] + 1u), a.dom.drange[d], a.dom.rmin[d]); }
                         const float ia = fmaxf(ba, rlo), ib = fmaxf(ia, fminf(bb, rhi)), wd = ib - ia;
                         vol *= wd;
-                        if ((d & 3) == 0) rnd = philox4x32<10>(u32x4{uint32_t(sbin), uint32_t(sbin >> 32), j0 + j, uint32_t(1 + d / 4)}, a.k0, a.k1);
-                        const uint32_t u = (d & 3) == 0 ? rnd.x : (d & 3) == 1 ? rnd.y : (d & 3) == 2 ? rnd.z : rnd.w;
+                        // a float coordinate takes 24 bits: one Philox block feeds five of them (the top 24 bits of each word + the four low bytes)
+                        if (d % 5 == 0) rnd = philox4x32<10>(u32x4{uint32_t(sbin), uint32_t(sbin >> 32), j0 + j, uint32_t(1 + d / 5)}, a.k0, a.k1);
+                        const uint32_t u = d % 5 == 0 ? rnd.x : d % 5 == 1 ? rnd.y : d % 5 == 2 ? rnd.z : d % 5 == 3 ? rnd.w
+                                         : (((rnd.x & 255u) << 24) | ((rnd.y & 255u) << 16) | ((rnd.z & 255u) << 8));
                         const float xd = fmaf(viltrum::b200::u01(u), wd, ia);
                         a.points[uint64_t(d) * a.slots + slot] = xd;
                         lagrange_basis<S>(rhi > rlo ? (xd - rlo) / (rhi - rlo) : 0.0f, Lg[d]);
                     }
                     a.weight[slot] = vol;
-                    a.app[slot] = FastLevel<S, D - 1, false>::eval(reg, Lg);
+                    a.app[slot] = fast_eval_stream<S, D>(reg, Lg);
                     a.owner[slot] = (unsigned short)sid;
                 }
             }
@@ -817,7 +850,7 @@ struct DevBuf {
 };
 
 template<int S, int D> int launch_tile_samples(vb200_ctx* ctx, const CvTileArgs& a, unsigned ntiles) {
-    constexpr int SLOT = (R::ipow(S, D) + 2 * D) | 1;
+    constexpr int SLOT = cvt_slot_words(R::ipow(S, D), D);
     const size_t smem = size_t(a.J) * CVT_BINS * 2 * 2 + size_t(CVT_MAXLIST) * 2 + std::max(size_t(CVT_MAXLIST) * 4, size_t(8) * CVT_SLOTS * SLOT * 4);
     auto k = cv_tile_samples_kernel<S, D>;
     VB200_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
