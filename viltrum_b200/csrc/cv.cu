@@ -599,8 +599,11 @@ struct CvTileArgs {
     float* points; float* weight; float* app; unsigned short* owner;      // [slots] per array, points SoA [d][slots]; slots = tiles * 256 * spp
     uint64_t slots;
 };
+#ifndef VB200_CVT_MINB
+#define VB200_CVT_MINB 2      // resident CTAs per SM the residual kernel is compiled for (shared memory allows two; measured 1: 2.98, 2: 2.10, 3: 2.12 ms per launch, profiles/results_r2.md)
+#endif
 template<int S, int D>
-__global__ void __launch_bounds__(256) cv_tile_samples_kernel(const CvTileArgs a) {
+__global__ void __launch_bounds__(256, VB200_CVT_MINB) cv_tile_samples_kernel(const CvTileArgs a) {
     extern __shared__ __align__(16) unsigned char cvt_smem[];
     unsigned short* s_rank   = reinterpret_cast<unsigned short*>(cvt_smem);                 // [J][256] the pass's sample ids sorted by list position
     unsigned short* s_choice = s_rank + a.J * CVT_BINS;                              // [J][256] position in the tile's region list (0xffff = no sample)
@@ -699,19 +702,37 @@ __global__ void __launch_bounds__(256) cv_tile_samples_kernel(const CvTileArgs a
                 for (int d = 0; d < D; ++d) a.points[uint64_t(d) * a.slots + slot] = a.dom.rmin[d];
             }
             const uint32_t prev = __shfl_up_sync(0xffffffffu, idx, 1);
-            const unsigned heads = __ballot_sync(0xffffffffu, valid && (lane == 0 || idx != prev));
+            const bool is_head = valid && (lane == 0 || idx != prev);
+            const unsigned heads = __ballot_sync(0xffffffffu, is_head);
             const int k = __popc(heads);
             const int mine = __popc(heads & (0xffffffffu >> (31 - lane))) - 1;       // which of the warp's regions this lane's sample uses
+            const uint32_t rid = valid ? a.list[lo + idx] : 0u;                      // every lane looks its own region up: one round trip, not one per region
+            constexpr int NV = (SD + 31) / 32;
             for (int r0 = 0; r0 < k; r0 += CVT_SLOTS) {
                 __syncwarp();
-                for (int q = 0; q < CVT_SLOTS && r0 + q < k; ++q) {
-                    const int head = __fns(heads, 0, r0 + q + 1);
-                    const uint32_t e_idx = __shfl_sync(0xffffffffu, idx, head);
-                    const uint64_t r = a.list[lo + e_idx];
-                    float* dst = s_slots + q * SLOT;
-                    for (int i = lane; i < SD; i += 32) dst[i] = __ldg(a.aos + r * uint64_t(SD) + i);
-                    if (lane < D) dst[SD + lane] = a.rmin[uint64_t(lane) * a.cap + r];
-                    else if (lane < 2 * D) dst[SD + lane] = a.rmax[uint64_t(lane - D) * a.cap + r];
+                // all of the round's loads first, then the stores: one memory round trip per round of CVT_SLOTS regions
+                float v[CVT_SLOTS][NV], rg[CVT_SLOTS];
+                unsigned have = 0;
+#pragma unroll
+                for (int q = 0; q < CVT_SLOTS; ++q) {
+                    const unsigned hm = __ballot_sync(0xffffffffu, is_head && mine == r0 + q);      // the lane that heads region r0 + q, if there is one
+                    const uint64_t r = __shfl_sync(0xffffffffu, rid, hm ? __ffs(int(hm)) - 1 : 0);
+                    if (hm) {
+                        have |= 1u << q;
+#pragma unroll
+                        for (int t = 0; t < NV; ++t) if (t * 32 + int(lane) < SD) v[q][t] = __ldg(a.aos + r * uint64_t(SD) + t * 32 + lane);
+                        if (lane < D) rg[q] = a.rmin[uint64_t(lane) * a.cap + r];
+                        else if (lane < 2 * D) rg[q] = a.rmax[uint64_t(lane - D) * a.cap + r];
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < CVT_SLOTS; ++q) {
+                    if (have & (1u << q)) {
+                        float* dst = s_slots + q * SLOT;
+#pragma unroll
+                        for (int t = 0; t < NV; ++t) if (t * 32 + int(lane) < SD) dst[t * 32 + lane] = v[q][t];
+                        if (lane < 2 * D) dst[SD + lane] = rg[q];
+                    }
                 }
                 __syncwarp();
                 if (valid && mine >= r0 && mine < r0 + CVT_SLOTS) {
@@ -733,7 +754,7 @@ __global__ void __launch_bounds__(256) cv_tile_samples_kernel(const CvTileArgs a
                                          : (((rnd.x & 255u) << 24) | ((rnd.y & 255u) << 16) | ((rnd.z & 255u) << 8));
                         const float xd = fmaf(viltrum::b200::u01(u), wd, ia);
                         a.points[uint64_t(d) * a.slots + slot] = xd;
-                        lagrange_basis<S>(rhi > rlo ? (xd - rlo) / (rhi - rlo) : 0.0f, Lg[d]);
+                        lagrange_basis<S>(rhi > rlo ? __fdividef(xd - rlo, rhi - rlo) : 0.0f, Lg[d]);
                     }
                     a.weight[slot] = vol;
                     a.app[slot] = fast_eval_stream<S, D>(reg, Lg);
@@ -878,7 +899,8 @@ int cv_tile_run(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r
     DevBuf points, weight, app, fval, owner;
     int rc;
     if ((rc = points.alloc(ctx, slots * D * 4)) || (rc = weight.alloc(ctx, slots * 4)) || (rc = app.alloc(ctx, slots * 4)) || (rc = fval.alloc(ctx, slots * 4)) || (rc = owner.alloc(ctx, slots * 2))) return rc;
-    const uint32_t J = spp < uint32_t(CVT_MAXPASS) ? spp : uint32_t(CVT_MAXPASS);
+    uint32_t J = spp < uint32_t(CVT_MAXPASS) ? spp : uint32_t(CVT_MAXPASS);
+    if (const char* e = std::getenv("VB200_CVT_J")) { const long v = std::atol(e); if (v >= 1 && v <= CVT_MAXPASS && uint32_t(v) < J) J = uint32_t(v); }      // samples per bin and pass (tuning knob)
     const size_t smem_acc = size_t(CVT_ACCPASS) * CVT_BINS * 4 * 3;
     VB200_CUDA(ctx, cudaFuncSetAttribute(cv_tile_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_acc)));
     for (uint64_t ty = ty0; ty < ty1; ty += tile_rows_per_slab) {
