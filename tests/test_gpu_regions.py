@@ -320,6 +320,28 @@ def test_steps_golden_reference_vectors_and_survey_kat(ctx):
     assert_same_bits(got, np.array([0.346666217, 0.42666626, 0.586666465, 0.826666653, 1.14666629], np.float32), "SURVEY KAT")
 
 
+def test_cta_per_split_rounds_equal_warp_per_split_rounds(ctx):
+    """Rounds of few splits of large regions give every split a CTA instead of a warp (split_children_kernel<.., CTA = true>); VB200_SPLIT_CTA_MAX=0
+    forces a warp per split everywhere, a huge value a CTA per split everywhere: identical region tables, bit for bit and in order
+    (batched refinement and tolerance-driven refinement)."""
+    import os
+    from viltrum_b200 import Range
+    for integ, rule, d, it in (("shade5_64", "simpson_trapezoidal", 5, 6000), ("shade4_16", "simpson_trapezoidal", 4, 9000), ("poly3", "boole_simpson", 3, 2500)):
+        rng = Range([0.0] * d, [1.0] * d)
+        tabs = []
+        for knob in (None, "0", "100000000"):
+            if knob is None:
+                os.environ.pop("VB200_SPLIT_CTA_MAX", None)
+            else:
+                os.environ["VB200_SPLIT_CTA_MAX"] = knob
+            regs = ctx.regions_generate_adaptive(integ, rng, rule, "size", "relative", it, 1e-5, batch=0, exact=True)
+            tabs.append(regs.download()); regs.free()
+        os.environ.pop("VB200_SPLIT_CTA_MAX", None)
+        for other in tabs[1:]:
+            for k in ("min", "max", "err", "dim", "data"):
+                assert_same_bits(tabs[0][k], other[k], f"{integ} {k}")
+
+
 def test_single_launch_selection_equals_multi_kernel_selection(ctx):
     """Tables of <= 8192 regions are selected by one single-CTA launch per round (select_small_kernel); VB200_SELECT_SMALL_MAX=0 forces
     the histogram / pick / count / scan / write kernels for every round: identical region tables, bit for bit and in order."""

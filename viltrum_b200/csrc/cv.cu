@@ -642,9 +642,18 @@ __global__ void __launch_bounds__(256, VB200_CVT_MINB) cv_tile_samples_kernel(co
             const uint32_t bxw = s_box[i];
             return bx >= (bxw & 255u) && bx < ((bxw >> 8) & 255u) && by >= ((bxw >> 16) & 255u) && by < (bxw >> 24);
         };
+        u32x4 first{0, 0, 0, 0};
         for (uint32_t j = 0; j < J; ++j) {
             uint32_t idx = 0xffffu;
             if (cnt > 0u) {
+                // the first candidate of four consecutive samples comes from ONE Philox block (most samples accept it); later candidates from the sample's own blocks
+                const uint32_t gj = j0 + j;                   // sample number within the bin: word gj % 4 of block gj / 4
+                if ((gj & 3u) == 0u || j == 0u) first = philox4x32<10>(u32x4{uint32_t(bin), uint32_t(bin >> 32), gj >> 2, 0x7fu}, a.k0, a.k1);
+                {
+                    const uint32_t w = (gj & 3u) == 0u ? first.x : (gj & 3u) == 1u ? first.y : (gj & 3u) == 2u ? first.z : first.w;
+                    const uint32_t cand0 = __umulhi(w, L);
+                    if (contains(cand0)) idx = cand0;
+                }
                 for (uint32_t blk = 0; blk < 4u && idx == 0xffffu; ++blk) {
                     const u32x4 c = philox4x32<10>(u32x4{uint32_t(bin), uint32_t(bin >> 32), j0 + j, 0x80u + blk}, a.k0, a.k1);
                     const uint32_t cand[4] = {__umulhi(c.x, L), __umulhi(c.y, L), __umulhi(c.z, L), __umulhi(c.w, L)};

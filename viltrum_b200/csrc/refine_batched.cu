@@ -221,33 +221,38 @@ __device__ __forceinline__ void heur_pick(const HeurArgs& h, const float* E, con
     else D_::heuristic_pick<DIM>(E, rng, h.heuristic, h.size_weight, e, d);
 }
 
-// one warp per split: build both children (region.h:345-359, split.h:13-49), store child 0 over the parent and child 1 in a
-// new slot, then evaluate both children's error heuristics (region.h:387-411, error-heuristic.h:10-46)
-template<int SH, int SL, int DIM>
+// one GROUP of threads per split — a warp (CTA = false: the throughput form, 8 splits per CTA) or a whole CTA (CTA = true: rounds with few
+// splits, where a lone warp's ~30 us of dependent work per split is the round's whole duration): build both children (region.h:345-359,
+// split.h:13-49), store child 0 over the parent and child 1 in a new slot, then evaluate both children's error heuristics
+// (region.h:387-411, error-heuristic.h:10-46).  Same operations on the same operands either way, hence the same bits.
+template<int SH, int SL, int DIM, bool CTA>
 __global__ void split_children_kernel(uint64_t cap, uint64_t nsel, uint64_t n_old, const unsigned* __restrict__ sel, const float* __restrict__ vals,
                                       float* __restrict__ rmin, float* __restrict__ rmax, float* __restrict__ data, float* __restrict__ err, uint32_t* __restrict__ errdim,
                                       const HeurArgs hr) {
     using Sh = D_::GreedyShape<SH, SL, DIM>;
     extern __shared__ float smem[];
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
-    float* s_parent = smem + size_t(warp) * (3 * Sh::SD + 2 * DIM * Sh::L + 4 * DIM + 2 * DIM + 2);
+    const unsigned warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    const unsigned lane = CTA ? threadIdx.x : (threadIdx.x & 31u);          // index within the group
+    const int G = CTA ? int(blockDim.x) : 32;                                // threads of the group
+    auto gsync = [] () { if constexpr (CTA) __syncthreads(); else __syncwarp(); };
+    float* s_parent = smem + (CTA ? size_t(0) : size_t(warp) * (3 * Sh::SD + 2 * DIM * Sh::L + 4 * DIM + 2 * DIM + 2));
     float* s_child = s_parent + Sh::SD;
     float* s_work = s_child + 2 * Sh::SD;      // [2*DIM][L]
     float* s_crange = s_work + 2 * DIM * Sh::L;          // [2][2*DIM]
     float* s_E = s_crange + 4 * DIM;           // [2][DIM]
     float* s_vol = s_E + 2 * DIM;              // [2]
-    const uint64_t r = uint64_t(blockIdx.x) * wpc + warp;
+    const uint64_t r = CTA ? uint64_t(blockIdx.x) : uint64_t(blockIdx.x) * wpc + warp;
     if (r >= nsel) return;
     const unsigned slot = sel[r]; const uint64_t slot1 = n_old + r;
     const int dim = int(errdim[slot]);
-    for (int k = lane; k < Sh::SD; k += 32) s_parent[k] = data[uint64_t(k) * cap + slot];
+    for (int k = lane; k < Sh::SD; k += G) s_parent[k] = data[uint64_t(k) * cap + slot];
     float prange[2 * DIM];
 #pragma unroll
     for (int d = 0; d < DIM; ++d) { prange[d] = rmin[uint64_t(d) * cap + slot]; prange[DIM + d] = rmax[uint64_t(d) * cap + slot]; }
-    __syncwarp();
+    gsync();
     int inner = 1; for (int i = 0; i < dim; ++i) inner *= SH;
     constexpr int Q = (SH - 1) * Sh::L;
-    for (int item = lane; item < Sh::WIDE; item += 32) {
+    for (int item = lane; item < Sh::WIDE; item += G) {
         const int i = item / Sh::L, o = item % Sh::L;
         const int lo = o % inner, hi = o / inner;
         const float v = (i & 1) == 0 ? s_parent[lo + (i / 2) * inner + hi * inner * SH] : vals[r * uint64_t(Q) + uint64_t((i / 2) * Sh::L + o)];
@@ -263,8 +268,8 @@ __global__ void split_children_kernel(uint64_t cap, uint64_t nsel, uint64_t n_ol
         float v = 1.0f; for (int d = 0; d < DIM; ++d) v = R::fm(v, R::fs(cr[DIM + d], cr[d]));
         s_vol[lane] = v;
     }
-    __syncwarp();
-    for (int k = lane; k < Sh::SD; k += 32) { data[uint64_t(k) * cap + slot] = s_child[k]; data[uint64_t(k) * cap + slot1] = s_child[Sh::SD + k]; }
+    gsync();
+    for (int k = lane; k < Sh::SD; k += G) { data[uint64_t(k) * cap + slot] = s_child[k]; data[uint64_t(k) * cap + slot1] = s_child[Sh::SD + k]; }
     if (lane < DIM) {
         rmin[uint64_t(lane) * cap + slot] = s_crange[lane]; rmax[uint64_t(lane) * cap + slot] = s_crange[DIM + lane];
         rmin[uint64_t(lane) * cap + slot1] = s_crange[2 * DIM + lane]; rmax[uint64_t(lane) * cap + slot1] = s_crange[3 * DIM + lane];
@@ -273,7 +278,7 @@ __global__ void split_children_kernel(uint64_t cap, uint64_t nsel, uint64_t n_ol
     // 2*DIM*L independent tasks, every level of the fold_all that follows 2*DIM*n — instead of ten folds one after the other, most of whose
     // steps keep a handful of lanes busy.  Every value is computed by the same operations as in region_error_warp, hence the same bits.
     constexpr int CD = 2 * DIM;
-    for (int t = lane; t < CD * Sh::L; t += 32) {
+    for (int t = lane; t < CD * Sh::L; t += G) {
         const int cd = t / Sh::L, o = t % Sh::L, c = cd / DIM, d = cd % DIM;
         int inn = 1; for (int i = 0; i < d; ++i) inn *= SH;
         const int lo = o % inn, hi = o / inn;
@@ -282,26 +287,32 @@ __global__ void split_children_kernel(uint64_t cap, uint64_t nsel, uint64_t n_ol
         for (int e = 0; e < SH; ++e) line[e] = s_child[c * Sh::SD + lo + e * inn + hi * inn * SH];
         s_work[cd * Sh::L + o] = R::line_error<SH, SL>(heur_relative(hr, d), line);
     }
-    __syncwarp();
+    gsync();
     for (int n = Sh::L / SH; n >= 1; n /= SH) {                     // fold_all(high rule): fold dimension 0 until one value is left (fold.h:87-108)
         constexpr int MAXT = (CD * (Sh::L / SH) + 31) / 32;
         float v[MAXT > 0 ? MAXT : 1];
         int k = 0;
-        for (int t = lane; t < CD * n; t += 32, ++k) { const int cd = t / n, o = t % n; v[k] = R::apply<SH>(s_work + cd * Sh::L + o * SH); }
-        __syncwarp();
+        for (int t = lane; t < CD * n; t += G, ++k) { const int cd = t / n, o = t % n; v[k] = R::apply<SH>(s_work + cd * Sh::L + o * SH); }
+        gsync();
         k = 0;
-        for (int t = lane; t < CD * n; t += 32, ++k) { const int cd = t / n, o = t % n; s_work[cd * Sh::L + o] = v[k]; }
-        __syncwarp();
+        for (int t = lane; t < CD * n; t += G, ++k) { const int cd = t / n, o = t % n; s_work[cd * Sh::L + o] = v[k]; }
+        gsync();
         if (n == 1) break;
     }
     if (lane < CD) s_E[lane] = R::fm(s_vol[lane / DIM], s_work[lane * Sh::L]);
-    __syncwarp();
+    gsync();
     if (lane < 2) {
         float e; unsigned d;
         heur_pick<DIM>(hr, s_E + lane * DIM, s_crange + lane * 2 * DIM, &e, &d);
         const uint64_t s = lane == 0 ? uint64_t(slot) : slot1;
         err[s] = e; errdim[s] = d;
     }
+}
+// rounds of at most this many splits give every split a CTA (VB200_SPLIT_CTA_MAX overrides: tuning / test knob)
+constexpr uint64_t SPLIT_CTA_MAX = 4736;      // measured on C4 (ms per step): 0: 10.76, 296: 10.18, 1184: 10.05, 4736: 10.00, always: 10.01
+inline uint64_t split_cta_max() {
+    if (const char* e = std::getenv("VB200_SPLIT_CTA_MAX")) return std::strtoull(e, nullptr, 10);
+    return SPLIT_CTA_MAX;
 }
 
 // the root region: samples are already in data[.][0]; compute its heuristic
@@ -335,8 +346,11 @@ int run_rounds(vb200_ctx* ctx, const vb200_integrand* f, const vb200_adaptive_pa
     VB200_CUDA(ctx, cudaGetLastError());
     const size_t per_warp = (3 * Sh::SD + 2 * DIM * Sh::L + 4 * DIM + 2 * DIM + 2) * sizeof(float);
     int wpc = int((96u << 10) / per_warp); if (wpc > 8) wpc = 8; if (wpc < 1) wpc = 1;
-    auto kchild = split_children_kernel<SH, SL, DIM>;
+    auto kchild = split_children_kernel<SH, SL, DIM, false>;
+    auto kchild_cta = split_children_kernel<SH, SL, DIM, true>;
     VB200_CUDA(ctx, cudaFuncSetAttribute(kchild, cudaFuncAttributeMaxDynamicSharedMemorySize, int(per_warp * wpc)));
+    VB200_CUDA(ctx, cudaFuncSetAttribute(kchild_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, int(per_warp)));
+    const uint64_t cta_max = split_cta_max();
     const uint64_t Q = uint64_t(SH - 1) * Sh::L;
     uint64_t n = 1, left = p->iterations;
     uint64_t small_max = SELECT_SMALL_MAX;
@@ -370,8 +384,11 @@ int run_rounds(vb200_ctx* ctx, const vb200_integrand* f, const vb200_adaptive_pa
         ev.n = N; ev.dim = DIM; ev.points = points; ev.values = vals;
         int rc = call_thunk(ctx, f, VB200_K_EVAL_POINTS, &ev); if (rc) return rc;
         // 3. children + heuristics
-        kchild<<<unsigned((B + wpc - 1) / wpc), wpc * 32, per_warp * wpc, s>>>(cap, B, n, sel, vals, r->rmin, r->rmax, r->data, r->err, r->errdim,
-                                                                               heur_args(p->heuristic, p->metric, p->size_weight, p->mixed));
+        if (2 * DIM * Sh::L >= 128 && B <= cta_max)      // few splits of large regions: a CTA per split (the round lasts as long as its slowest split)
+            kchild_cta<<<unsigned(B), 256, per_warp, s>>>(cap, B, n, sel, vals, r->rmin, r->rmax, r->data, r->err, r->errdim, heur_args(p->heuristic, p->metric, p->size_weight, p->mixed));
+        else
+            kchild<<<unsigned((B + wpc - 1) / wpc), wpc * 32, per_warp * wpc, s>>>(cap, B, n, sel, vals, r->rmin, r->rmax, r->data, r->err, r->errdim,
+                                                                                   heur_args(p->heuristic, p->metric, p->size_weight, p->mixed));
         ctx->launches++;
         VB200_CUDA(ctx, cudaGetLastError());
         n += B; left -= B;
@@ -458,8 +475,11 @@ int run_tolerance(vb200_ctx* ctx, const vb200_integrand* f, const vb200_toleranc
     VB200_CUDA(ctx, cudaGetLastError());
     const size_t per_warp = (3 * Sh::SD + 2 * DIM * Sh::L + 4 * DIM + 2 * DIM + 2) * sizeof(float);
     int wpc = int((96u << 10) / per_warp); if (wpc > 8) wpc = 8; if (wpc < 1) wpc = 1;
-    auto kchild = split_children_kernel<SH, SL, DIM>;
+    auto kchild = split_children_kernel<SH, SL, DIM, false>;
+    auto kchild_cta = split_children_kernel<SH, SL, DIM, true>;
     VB200_CUDA(ctx, cudaFuncSetAttribute(kchild, cudaFuncAttributeMaxDynamicSharedMemorySize, int(per_warp * wpc)));
+    VB200_CUDA(ctx, cudaFuncSetAttribute(kchild_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, int(per_warp)));
+    const uint64_t cta_max = split_cta_max();
     const uint64_t Q = uint64_t(SH - 1) * Sh::L;
     uint64_t max_batch = (32ull << 20) / Q; if (max_batch < 1) max_batch = 1;
     const uint64_t limit = p->max_regions ? p->max_regions : (1ull << 27);
@@ -493,8 +513,12 @@ int run_tolerance(vb200_ctx* ctx, const vb200_integrand* f, const vb200_toleranc
             ev.n = N; ev.dim = DIM; ev.points = points; ev.values = vals;
             rc = call_thunk(ctx, f, VB200_K_EVAL_POINTS, &ev);
             if (!rc) {
-                kchild<<<unsigned((B + wpc - 1) / wpc), wpc * 32, per_warp * wpc, s>>>(cap, B, n + off, sel + off, vals, t.r->rmin, t.r->rmax, t.r->data, t.r->err, t.r->errdim,
-                                                                                       heur_args(p->heuristic, p->metric, p->size_weight, vb200_mixed_heuristic{}));
+                if (2 * DIM * Sh::L >= 128 && B <= cta_max)
+                    kchild_cta<<<unsigned(B), 256, per_warp, s>>>(cap, B, n + off, sel + off, vals, t.r->rmin, t.r->rmax, t.r->data, t.r->err, t.r->errdim,
+                                                                  heur_args(p->heuristic, p->metric, p->size_weight, vb200_mixed_heuristic{}));
+                else
+                    kchild<<<unsigned((B + wpc - 1) / wpc), wpc * 32, per_warp * wpc, s>>>(cap, B, n + off, sel + off, vals, t.r->rmin, t.r->rmax, t.r->data, t.r->err, t.r->errdim,
+                                                                                           heur_args(p->heuristic, p->metric, p->size_weight, vb200_mixed_heuristic{}));
                 ctx->launches++;
                 if (cudaGetLastError() != cudaSuccess) rc = fail(ctx, VB200_ERR_CUDA, "split kernel launch failed");
             }
