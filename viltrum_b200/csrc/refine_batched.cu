@@ -186,19 +186,25 @@ __global__ void __launch_bounds__(1024) select_small_kernel(const float* __restr
 
 // sample points of all selected splits: point q of split r = odd position i = 2*(q / L)+1 along the split dimension,
 // other-dims index o = q % L; coordinates from the PARENT range (split.h:22, region.h:40-46)
-__global__ void split_points_kernel(int S, int dim, uint64_t cap, uint64_t nsel, const unsigned* __restrict__ sel,
+// i / m for the grid positions (region.h:40-46): m = S-1 or 2(S-1) is a power of two for S = 3, 5, so the double division is an exact multiplication
+__device__ __forceinline__ double grid_frac(int i, int m) { return ((m & (m - 1)) == 0) ? R::dm(double(i), 1.0 / double(m)) : R::dd(double(i), double(m)); }
+template<int S, int DIM>
+__global__ void split_points_kernel(uint64_t cap, uint64_t nsel, const unsigned* __restrict__ sel,
                                     const float* __restrict__ rmin, const float* __restrict__ rmax, const uint32_t* __restrict__ errdim, float* __restrict__ points) {
-    int L = 1; for (int i = 0; i < dim - 1; ++i) L *= S;
-    const uint64_t Q = uint64_t(S - 1) * L, N = nsel * Q;
+    constexpr int L = R::ipow(S, DIM - 1);
+    constexpr unsigned Q = unsigned(S - 1) * L;
+    const uint64_t N = nsel * Q;
     const uint64_t t = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (t >= N) return;
-    const uint64_t r = t / Q; const int q = int(t % Q);
+    const uint64_t r = N <= 0xffffffffull ? uint64_t(unsigned(t) / Q) : t / Q;         // Q is a compile-time constant: multiply-shift, 32-bit where it fits
+    const int q = int(t - r * Q);
     const unsigned slot = sel[r]; const int sd = int(errdim[slot]);
     const int i = 2 * (q / L) + 1; int o = q % L;
-    for (int d = 0; d < dim; ++d) {
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
         double p;
-        if (d == sd) p = R::dd(double(i), double(2 * (S - 1)));
-        else { p = R::dd(double(o % S), double(S - 1)); o /= S; }
+        if (d == sd) p = grid_frac(i, 2 * (S - 1));
+        else { p = grid_frac(o % S, S - 1); o /= S; }
         points[uint64_t(d) * N + t] = D_::grid_coord(p, rmin[uint64_t(d) * cap + slot], rmax[uint64_t(d) * cap + slot]);
     }
 }
@@ -377,7 +383,7 @@ int run_rounds(vb200_ctx* ctx, const vb200_integrand* f, const vb200_adaptive_pa
         }
         // 2. new sample points of all B splits, one integrand launch
         const uint64_t N = B * Q;
-        split_points_kernel<<<unsigned((N + 255) / 256), 256, 0, s>>>(SH, DIM, cap, B, sel, r->rmin, r->rmax, r->errdim, points);
+        split_points_kernel<SH, DIM><<<unsigned((N + 255) / 256), 256, 0, s>>>(cap, B, sel, r->rmin, r->rmax, r->errdim, points);
         ctx->launches += 1;
         VB200_CUDA(ctx, cudaGetLastError());
         vb200_eval_launch ev; std::memset(&ev, 0, sizeof(ev));
@@ -506,7 +512,7 @@ int run_tolerance(vb200_ctx* ctx, const vb200_integrand* f, const vb200_toleranc
             float *points = nullptr, *vals = nullptr;
             if (dmalloc(ctx, &points, N * DIM * sizeof(float)) != cudaSuccess || dmalloc(ctx, &vals, N * sizeof(float)) != cudaSuccess) {
                 cudaGetLastError(); dfree(ctx, points); dfree(ctx, vals); rc = fail(ctx, VB200_ERR_NOMEM, "out of device memory"); break; }
-            split_points_kernel<<<unsigned((N + 255) / 256), 256, 0, s>>>(SH, DIM, cap, B, sel + off, t.r->rmin, t.r->rmax, t.r->errdim, points);
+            split_points_kernel<SH, DIM><<<unsigned((N + 255) / 256), 256, 0, s>>>(cap, B, sel + off, t.r->rmin, t.r->rmax, t.r->errdim, points);
             tol_paths_kernel<<<unsigned((B + 255) / 256), 256, 0, s>>>(sel + off, B, n + off, t.key_hi, t.key_lo, t.depth);
             ctx->launches += 2;
             vb200_eval_launch ev; std::memset(&ev, 0, sizeof(ev));

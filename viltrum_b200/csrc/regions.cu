@@ -664,11 +664,16 @@ __global__ void __launch_bounds__(256) walk_accumulate_fast_kernel(TileGeom g, D
                                                                    const float* __restrict__ volume, const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ pend,
                                                                    const uint64_t* __restrict__ offsets, const uint32_t* __restrict__ list,
                                                                    int mode, float* __restrict__ out, float* __restrict__ approx, uint32_t* __restrict__ count) {
-    constexpr int CHUNK = 16, TR = 16, P = S * S;
+    // The integral of a region's S x S patch over bin (x, y) of the tile separates: sum_k q[region][y][k] * (b^(k+1) - a^(k+1)), where q are the
+    // pre-divided coefficients of the patch folded along bin dimension 1 over row y (they depend on (region, row) only) and [a, b] is the bin's
+    // normalised extent along dimension 0 (it depends on (region, column) only).  Both tables and the region's pixel box — as a row mask and
+    // a column mask — are built once per chunk of regions by the whole CTA; a (bin, region) pair is then a mask test and an S-term dot product.
+    constexpr int CHUNK = 32, TR = 16, P = S * S, SP = S <= 4 ? 4 : 8;
     struct Reg { float patch[P]; float rmin[2], rmax[2], inv[2]; float scale; uint32_t ps[2], pe[2]; };
     __shared__ Reg s_reg[CHUNK];
-    __shared__ FastLine<S> s_q[CHUNK][TR];          // pre-divided coefficients of the dimension-1 fold, per (region, tile row)
-    __shared__ unsigned char s_e1[CHUNK][TR];       // empty intersection along dimension 1
+    __shared__ __align__(16) float s_q[CHUNK][TR][SP];      // per (region, tile row): coefficients c[k] / (k+1) * volume * nbins; zero where the row misses the region
+    __shared__ __align__(16) float s_p[CHUNK][TR][SP];      // per (region, tile column): b^(k+1) - a^(k+1); zero where the column misses the region
+    __shared__ uint32_t s_mask[CHUNK];                      // pixel box: rows in the low half, columns in the high half
     const uint64_t t = blockIdx.x;
     uint32_t o[3]; tile_origin(g, t, o);
     if (!tile_in_shard(g, o, begin, end)) return;
@@ -676,8 +681,8 @@ __global__ void __launch_bounds__(256) walk_accumulate_fast_kernel(TileGeom g, D
     bool live = pos[0] < g.res[0] && pos[1] < g.res[1];
     const uint64_t bin = uint64_t(pos[0]) + uint64_t(pos[1]) * g.res[0];
     live = live && bin >= begin && bin < end;
-    const float lo0 = fmaf(float(pos[0]), dom.drange[0], dom.rmin[0]), hi0 = fmaf(float(pos[0] + 1u), dom.drange[0], dom.rmin[0]);
-    const int ry = int(pos[1] - o[1]);
+    const int cx = int(pos[0] - o[0]), ry = int(pos[1] - o[1]);
+    const uint32_t mybit = (1u << ry), mycol = (0x10000u << cx);
     double acc = (mode == 0 && live) ? double(out[bin]) : 0.0;
     uint32_t cnt = 0;
     const float factor = float(nbins_total);
@@ -688,49 +693,70 @@ __global__ void __launch_bounds__(256) walk_accumulate_fast_kernel(TileGeom g, D
         for (int k = threadIdx.x; k < n * P; k += blockDim.x) { const int j = k / P, q = k % P; s_reg[j].patch[q] = patches[uint64_t(q) * cap + list[base + j]]; }
         for (int j = threadIdx.x; j < n; j += blockDim.x) {
             const uint64_t r = list[base + j];
+            uint32_t m = 0;
 #pragma unroll
             for (int d = 0; d < 2; ++d) {
                 const float a = rmin[uint64_t(d) * cap + r], b = rmax[uint64_t(d) * cap + r];
                 s_reg[j].rmin[d] = a; s_reg[j].rmax[d] = b; s_reg[j].inv[d] = b > a ? 1.0f / (b - a) : 0.0f;
-                s_reg[j].ps[d] = pstart[uint64_t(d) * cap + r]; s_reg[j].pe[d] = pend[uint64_t(d) * cap + r];
+                const uint32_t ps = pstart[uint64_t(d) * cap + r], pe = pend[uint64_t(d) * cap + r];
+                // bins [ps, pe) of the grid -> bits of the tile's 16 rows / columns
+                const uint32_t l0 = ps > o[d] ? min(ps - o[d], 16u) : 0u, l1 = pe > o[d] ? min(pe - o[d], 16u) : 0u;
+                const uint32_t bits = l1 > l0 ? (((1u << l1) - 1u) & ~((1u << l0) - 1u)) : 0u;
+                m |= d == 0 ? (bits << 16) : bits;
             }
             s_reg[j].scale = volume[r] * factor;
+            s_mask[j] = m;
         }
         __syncthreads();
-        for (int item = threadIdx.x; item < n * TR; item += blockDim.x) {       // fold along bin dimension 1, once per (region, tile row)
+        for (int item = threadIdx.x; item < n * TR; item += blockDim.x) {       // per (region, tile row): the fold along bin dimension 1; per (region, column): the powers
             const int j = item / TR, row = item % TR;
             const Reg& rg = s_reg[j];
-            const uint32_t p1 = o[1] + uint32_t(row);
-            const float lo1 = fmaf(float(p1), dom.drange[1], dom.rmin[1]), hi1 = fmaf(float(p1 + 1u), dom.drange[1], dom.rmin[1]);
-            const float a = fmaxf(lo1, rg.rmin[1]), b = fmaxf(a, fminf(hi1, rg.rmax[1]));
-            const float na = (a - rg.rmin[1]) * rg.inv[1], nb = (b - rg.rmin[1]) * rg.inv[1];
-            float tt[S];
+            {
+                const uint32_t p1 = o[1] + uint32_t(row);
+                const float lo1 = fmaf(float(p1), dom.drange[1], dom.rmin[1]), hi1 = fmaf(float(p1 + 1u), dom.drange[1], dom.rmin[1]);
+                const float a = fmaxf(lo1, rg.rmin[1]), b = fmaxf(a, fminf(hi1, rg.rmax[1]));
+                const float na = (a - rg.rmin[1]) * rg.inv[1], nb = (b - rg.rmin[1]) * rg.inv[1];
+                float tt[S];
 #pragma unroll
-            for (int i0 = 0; i0 < S; ++i0) {
-                float line[S], c[S];
+                for (int i0 = 0; i0 < S; ++i0) {
+                    float line[S], c[S];
 #pragma unroll
-                for (int i1 = 0; i1 < S; ++i1) line[i1] = rg.patch[i0 + S * i1];
-                fast_coefficients<S>(line, c);
+                    for (int i1 = 0; i1 < S; ++i1) line[i1] = rg.patch[i0 + S * i1];
+                    fast_coefficients<S>(line, c);
 #pragma unroll
-                for (int k = 0; k < S; ++k) c[k] *= 1.0f / float(k + 1);
-                tt[i0] = fast_subrange<S>(na, nb, c);
+                    for (int k = 0; k < S; ++k) c[k] *= 1.0f / float(k + 1);
+                    tt[i0] = fast_subrange<S>(na, nb, c);
+                }
+                float c[S]; fast_coefficients<S>(tt, c);
+                const float sc = (a >= b) ? 0.0f : rg.scale;                    // empty intersection: skipped upstream (regions-integrator-sequential.h:54)
+#pragma unroll
+                for (int k = 0; k < SP; ++k) s_q[j][row][k] = k < S ? c[k] * (sc / float(k + 1)) : 0.0f;      // volume * nbins folded in
             }
-            float c[S]; fast_coefficients<S>(tt, c);
+            {
+                const uint32_t p0 = o[0] + uint32_t(row);                       // the same index as a column
+                const float lo0 = fmaf(float(p0), dom.drange[0], dom.rmin[0]), hi0 = fmaf(float(p0 + 1u), dom.drange[0], dom.rmin[0]);
+                const float a = fmaxf(lo0, rg.rmin[0]), b = fmaxf(a, fminf(hi0, rg.rmax[0]));
+                const float na = (a - rg.rmin[0]) * rg.inv[0], nb = (b - rg.rmin[0]) * rg.inv[0];
+                float pa = na, pb = nb;
 #pragma unroll
-            for (int k = 0; k < S; ++k) s_q[j][row].c[k] = c[k] * (rg.scale / float(k + 1));      // volume * nbins folded in
-            s_e1[j][row] = (a >= b) ? 1 : 0;
+                for (int k = 0; k < SP; ++k) { s_p[j][row][k] = (k < S && a < b) ? pb - pa : 0.0f; pa *= na; pb *= nb; }
+            }
         }
         __syncthreads();
         if (live) {
             float part = 0.0f;
 #pragma unroll 4
             for (int j = 0; j < n; ++j) {
-                const Reg& rg = s_reg[j];
-                if (!(pos[0] >= rg.ps[0] && pos[0] < rg.pe[0] && pos[1] >= rg.ps[1] && pos[1] < rg.pe[1])) continue;
+                const uint32_t m = s_mask[j];
+                if (!((m & mybit) && (m & mycol))) continue;
                 ++cnt;
-                const float a = fmaxf(lo0, rg.rmin[0]), b = fmaxf(a, fminf(hi0, rg.rmax[0]));
-                if (a >= b || s_e1[j][ry]) continue;                          // empty intersection: skipped upstream (regions-integrator-sequential.h:54)
-                part += fast_subrange<S>((a - rg.rmin[0]) * rg.inv[0], (b - rg.rmin[0]) * rg.inv[0], s_q[j][ry].c);
+                const float4 q0 = *reinterpret_cast<const float4*>(&s_q[j][ry][0]), p0 = *reinterpret_cast<const float4*>(&s_p[j][cx][0]);
+                float v = q0.x * p0.x;
+                v = fmaf(q0.y, p0.y, v);
+                if constexpr (S >= 3) v = fmaf(q0.z, p0.z, v);
+                if constexpr (S >= 4) v = fmaf(q0.w, p0.w, v);
+                if constexpr (S >= 5) { v = fmaf(s_q[j][ry][4], s_p[j][cx][4], v); }
+                part += v;
             }
             acc += double(part);
         }
