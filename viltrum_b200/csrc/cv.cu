@@ -580,6 +580,14 @@ __device__ __forceinline__ float fast_eval_stream(const float* __restrict__ data
     return acc[D - 1];
 }
 
+// region-major copy of the ranges, ranges[r][0..D) = min, [D..2D) = max: the residual kernel stages a region's box with one 8*D-byte read
+__global__ void ranges_to_aos_kernel(uint64_t n, uint64_t cap, int dim, const float* __restrict__ rmin, const float* __restrict__ rmax, float* __restrict__ out) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n * uint64_t(2 * dim)) return;
+    const uint64_t r = i / uint64_t(2 * dim); const int k = int(i % uint64_t(2 * dim));
+    out[i] = k < dim ? rmin[uint64_t(k) * cap + r] : rmax[uint64_t(k - dim) * cap + r];
+}
+
 // ---- tile-major residual pass (throughput path: FAST integrand, rr_uniform_region, 2-D bin grid) ------------------------------------
 // The sample-major pipeline above sorts ALL residual samples of a slab by region with a device-wide radix sort, evaluates them in that
 // order and scatters 16-byte records back (sort 1.5 ms + un-sort 2.7 ms of BASELINE config 4's 23 ms).  Here a CTA owns one
@@ -595,7 +603,7 @@ struct CvTileArgs {
     TileGeomCv g; vb200_domain dom; uint64_t cap, begin, end, tile0, nbins_total; uint32_t spp, J, k0, k1;
     const uint32_t* pstart; const uint32_t* pend; const uint64_t* offsets; const uint32_t* list; const uint32_t* count;      // count: indexed by bin - count_base
     uint64_t count_base;
-    const float* rmin; const float* rmax; const float* aos;
+    const float* ranges; const float* aos;            // region-major: ranges[r][2*D], aos[r][S^D]
     float* points; float* weight; float* app; unsigned short* owner;      // [slots] per array, points SoA [d][slots]; slots = tiles * 256 * spp
     uint64_t slots;
 };
@@ -730,8 +738,7 @@ __global__ void __launch_bounds__(256, VB200_CVT_MINB) cv_tile_samples_kernel(co
                         have |= 1u << q;
 #pragma unroll
                         for (int t = 0; t < NV; ++t) if (t * 32 + int(lane) < SD) v[q][t] = __ldg(a.aos + r * uint64_t(SD) + t * 32 + lane);
-                        if (lane < D) rg[q] = a.rmin[uint64_t(lane) * a.cap + r];
-                        else if (lane < 2 * D) rg[q] = a.rmax[uint64_t(lane - D) * a.cap + r];
+                        if (lane < 2 * D) rg[q] = __ldg(a.ranges + r * uint64_t(2 * D) + lane);
                     }
                 }
 #pragma unroll
@@ -905,8 +912,11 @@ int cv_tile_run(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r
     if (tile_rows_per_slab > ty1 - ty0) tile_rows_per_slab = ty1 - ty0;
     const uint64_t slots = tile_rows_per_slab * tiles_x * CVT_BINS * spp;
     if (slots > 0x7fffffffull * 4) return VB200_ERR_UNSUPPORTED;
-    DevBuf points, weight, app, fval, owner;
+    DevBuf points, weight, app, fval, owner, ranges;
     int rc;
+    if ((rc = ranges.alloc(ctx, r->count * uint64_t(2 * D) * 4))) return rc;
+    { const uint64_t n = r->count * uint64_t(2 * D);
+      ranges_to_aos_kernel<<<unsigned((n + 255) / 256), 256, 0, ctx->stream>>>(r->count, r->capacity, D, r->rmin, r->rmax, ranges.as<float>()); ctx->launches++; VB200_CUDA(ctx, cudaGetLastError()); }
     if ((rc = points.alloc(ctx, slots * D * 4)) || (rc = weight.alloc(ctx, slots * 4)) || (rc = app.alloc(ctx, slots * 4)) || (rc = fval.alloc(ctx, slots * 4)) || (rc = owner.alloc(ctx, slots * 2))) return rc;
     uint32_t J = spp < uint32_t(CVT_MAXPASS) ? spp : uint32_t(CVT_MAXPASS);
     if (const char* e = std::getenv("VB200_CVT_J")) { const long v = std::atol(e); if (v >= 1 && v <= CVT_MAXPASS && uint32_t(v) < J) J = uint32_t(v); }      // samples per bin and pass (tuning knob)
@@ -919,7 +929,7 @@ int cv_tile_run(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r
         a.g = make_geom_cv(w, dom); a.dom = dom; a.cap = w.cap; a.begin = begin; a.end = end; a.tile0 = ty * tiles_x; a.nbins_total = total;
         a.spp = spp; a.J = J; a.k0 = uint32_t(p->seed); a.k1 = uint32_t(p->seed >> 32);
         a.pstart = w.pstart; a.pend = w.pend; a.offsets = w.tile_offset; a.list = w.tile_list; a.count = count; a.count_base = begin;
-        a.rmin = r->rmin; a.rmax = r->rmax; a.aos = aos;
+        a.ranges = ranges.as<float>(); a.aos = aos;
         a.points = points.as<float>(); a.weight = weight.as<float>(); a.app = app.as<float>(); a.owner = owner.as<unsigned short>();
         a.slots = uint64_t(ntiles) * CVT_BINS * spp;
         rc = VB200_ERR_UNSUPPORTED;
