@@ -424,3 +424,23 @@ def test_control_variates_over_other_rules_converge(ctx, rule, rr):
     assert abs(float(mean.mean()) - float(ref.mean())) < 3e-3
     if rr != "error":       # rr_error_region's 1/probability factors (up to 100x the mean) can cost more variance than the control variate saves
         assert np.mean((est[0] - ref) ** 2) < np.mean((mc - ref) ** 2)
+
+
+def test_kernel_timer_brackets_the_residual_kernel(ctx):
+    """vb200_kernel_timer / vb200_kernel_timer_read (what bench.py's C4 roofline is computed from): launches of the tile-major residual kernel are
+    counted and timed only while the timer is on, reading clears the record"""
+    res, it, spp = [64, 64], 600, 16
+    regs = ctx.regions_generate_adaptive("shade5_16", _rng("shade5_16"), "simpson_trapezoidal", "size", "relative", it, 1e-5, batch=0, exact=True)
+    b = np.zeros(res[0] * res[1], np.float32)
+    regs.cv_integrate("shade5_16", b, res, _rng("shade5_16"), spp, 1)
+    assert ctx.kernel_timer_read() == (0.0, 0)
+    ctx.kernel_timer(True)
+    regs.cv_integrate("shade5_16", b, res, _rng("shade5_16"), spp, 2)
+    regs.cv_integrate("shade5_16", b, res, _rng("shade5_16"), spp, 3)
+    ms, n = ctx.kernel_timer_read()
+    assert n >= 2 and 0.0 < ms < 1000.0, (ms, n)
+    assert ctx.kernel_timer_read() == (0.0, 0)
+    ctx.kernel_timer(False)
+    regs.cv_integrate("shade5_16", b, res, _rng("shade5_16"), spp, 4)
+    assert ctx.kernel_timer_read() == (0.0, 0)
+    regs.free()

@@ -686,7 +686,7 @@ __global__ void __launch_bounds__(256, VB200_CVT_MINB) cv_tile_samples_kernel(co
         // 1.+2. region of every sample: rr_uniform_region picks uniformly among the regions that touch the bin (region-russian-roulette.h:9-28).
         //    Drawn here by rejection from the TILE's list — a uniform candidate entry is accepted iff its pixel box contains the bin — which
         //    is uniform over the bin's own regions without ever enumerating them (~80 % of a tile's entries contain a given bin at BASELINE
-        //    config 4: 1.25 candidates per sample, four candidates per Philox call).  A sample still without a region after 16 candidates
+        //    config 4: 1.25 candidates per sample).  A sample still without a region after 17 candidates
         //    (a bin that few of its tile's regions touch) falls back to rank + linear scan, exactly as the sample-major pipeline resolves it.
         for (uint32_t i = tid; i < L; i += CVT_BINS) {
             const uint32_t r = a.list[lo + i];
