@@ -57,7 +57,7 @@ METRIC = {"c2": "integrand evals/sec (per-bin MC, 1024x1024 bins x 64 spp, shade
           "c3": "regions/sec (nested Newton-Cotes adaptive refinement, 10^6 iterations, 512x512 bins)",
           "c5": "paths/sec (range_infinite random walk, 2048x2048 bins x 256 spp)"}
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the ncu --set full captures under profiles/
-NCU_TRAFFIC_BYTES = {"c2": 36864 + 4194304, "c5": 16922112, "c4": 110365696 + 950292224}      # dram read + write of the dominant kernel per launch (profiles/ncu_*)
+NCU_TRAFFIC_BYTES = {"c2": 36864 + 4194304, "c5": 16922112, "c4": 100966400 + 949487616}      # dram read + write of the dominant kernel per launch (profiles/ncu_*)
 RNG_NOTE = {"mc": "xoshiro128++ stream per (bin, lane sub-stream), state = Philox4x32-10(key=seed, counter=(bin, sub-stream)); 20 words per group of 8 samples: 24-bit fields for "
                   "the free dimensions, 16-bit fields inside a bin of a >=256-bin axis (VB200_MC_RNG_PHILOX selects Philox4x32-10 for every draw: see config.philox_value)",
             "walk": "Philox4x32-10, counter (bin, sample, block): one block of four 24-bit elements per lane and loop iteration, first-round products cached (18 multiplies per block)",
