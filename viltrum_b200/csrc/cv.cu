@@ -837,9 +837,9 @@ __global__ void __launch_bounds__(256, VB200_CVT_MINB) cv_tile_samples_kernel(co
 __global__ void __launch_bounds__(256) cv_tile_accumulate_kernel(TileGeomCv g, uint64_t begin, uint64_t end, uint64_t tile0, uint64_t nbins_total, uint32_t spp, uint32_t J,
                                                                  const uint32_t* __restrict__ count, const float* __restrict__ approx, uint64_t count_base,
                                                                  const float* __restrict__ fval, const float* __restrict__ app, const float* __restrict__ weight,
-                                                                 const unsigned short* __restrict__ owner, float* __restrict__ out, int fixed_weight, double fixed_alpha) {
+                                                                 const unsigned short* __restrict__ owner, float* __restrict__ out, int fixed_weight, double fixed_alpha, uint32_t accpass) {
     extern __shared__ unsigned char cvt_smem[];
-    float* s_f = reinterpret_cast<float*>(cvt_smem); float* s_a = s_f + CVT_ACCPASS * CVT_BINS; float* s_w = s_a + CVT_ACCPASS * CVT_BINS;
+    float* s_f = reinterpret_cast<float*>(cvt_smem); float* s_a = s_f + accpass * CVT_BINS; float* s_w = s_a + accpass * CVT_BINS;
     const uint64_t t = tile0 + blockIdx.x;
     const uint32_t tid = threadIdx.x;
     uint32_t pos[2]; pos[0] = uint32_t(t % g.tiles[0]) * g.tile[0] + tid % g.tile[0]; pos[1] = uint32_t(t / g.tiles[0]) * g.tile[1] + tid / g.tile[0];
@@ -852,8 +852,8 @@ __global__ void __launch_bounds__(256) cv_tile_accumulate_kernel(TileGeomCv g, u
     for (uint32_t j0 = 0; j0 < spp; j0 += J) {
         const uint32_t Jp = min(J, spp - j0);
         const uint64_t slot_pass = slot_tile + uint64_t(j0) * CVT_BINS;
-        for (uint32_t h0 = 0; h0 < Jp; h0 += CVT_ACCPASS) {      // the pass's samples h0 .. h0+31 of every bin at a time (96 KB of shared memory)
-            const uint32_t Jh = min(uint32_t(CVT_ACCPASS), Jp - h0);
+        for (uint32_t h0 = 0; h0 < Jp; h0 += accpass) {      // the pass's samples h0 .. h0+accpass-1 of every bin at a time (3 KB of shared memory per sample row)
+            const uint32_t Jh = min(accpass, Jp - h0);
             __syncthreads();
             for (uint32_t pb = tid; pb < Jp * CVT_BINS; pb += 8 * CVT_BINS) {       // eight slots per thread at a time: the loads of a batch are in flight together
                 uint32_t sid[8]; float vf[8], va[8], vw[8];
@@ -971,7 +971,9 @@ int cv_tile_run(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r
     if ((rc = points.alloc(ctx, slots * D * 4)) || (rc = weight.alloc(ctx, slots * 4)) || (rc = app.alloc(ctx, slots * 4)) || (rc = fval.alloc(ctx, slots * 4)) || (rc = owner.alloc(ctx, slots * 2))) return rc;
     uint32_t J = spp < uint32_t(CVT_MAXPASS) ? spp : uint32_t(CVT_MAXPASS);
     if (const char* e = std::getenv("VB200_CVT_J")) { const long v = std::atol(e); if (v >= 1 && v <= CVT_MAXPASS && uint32_t(v) < J) J = uint32_t(v); }      // samples per bin and pass (tuning knob)
-    const size_t smem_acc = size_t(CVT_ACCPASS) * CVT_BINS * 4 * 3;
+    uint32_t accpass = CVT_ACCPASS;
+    if (const char* e = std::getenv("VB200_CVT_ACCPASS")) { const long v = std::atol(e); if (v >= 1 && v <= 64) accpass = uint32_t(v); }      // tuning knob
+    const size_t smem_acc = size_t(accpass) * CVT_BINS * 4 * 3;
     VB200_CUDA(ctx, cudaFuncSetAttribute(cv_tile_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_acc)));
     for (uint64_t ty = ty0; ty < ty1; ty += tile_rows_per_slab) {
         const uint64_t tye = ty + tile_rows_per_slab < ty1 ? ty + tile_rows_per_slab : ty1;
@@ -995,7 +997,7 @@ int cv_tile_run(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r
         rc = call_thunk(ctx, f, VB200_K_EVAL_POINTS, &ev); if (rc) return rc;
         cv_tile_accumulate_kernel<<<ntiles, 256, smem_acc, ctx->stream>>>(a.g, begin, end, a.tile0, total, spp, J, count, approx, begin,
                                                                             fval.as<float>(), app.as<float>(), weight.as<float>(), owner.as<unsigned short>(), out,
-                                                                            p->weight_strategy == VB200_CV_FIXED_WEIGHT ? 1 : 0, p->alpha);
+                                                                            p->weight_strategy == VB200_CV_FIXED_WEIGHT ? 1 : 0, p->alpha, accpass);
         ctx->launches++;
         VB200_CUDA(ctx, cudaGetLastError());
     }

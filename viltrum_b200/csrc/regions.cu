@@ -349,14 +349,13 @@ __global__ void __launch_bounds__(1024) tile_sort_kernel(const uint64_t* __restr
     if (P <= smem_limit) {
         for (uint64_t i = threadIdx.x; i < P; i += blockDim.x) s_ids[i] = i < len ? a[i] : 0xffffffffu;
         __syncthreads();
-        for (uint64_t k = 2; k <= P; k <<= 1) for (uint64_t j = k >> 1; j > 0; j >>= 1) {
-            for (uint64_t i = threadIdx.x; i < P; i += blockDim.x) {
-                const uint64_t l = i ^ j;
-                if (l > i) {
-                    const bool up = (i & k) == 0;
-                    const uint32_t x = s_ids[i], y = s_ids[l];
-                    if ((x > y) == up) { s_ids[i] = y; s_ids[l] = x; }
-                }
+        const uint32_t P32 = uint32_t(P), half = P32 >> 1;
+        for (uint32_t k = 2; k <= P32; k <<= 1) for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t p = threadIdx.x; p < half; p += blockDim.x) {       // one thread per comparator: i has bit j clear, its partner has it set
+                const uint32_t i = ((p & ~(j - 1u)) << 1) | (p & (j - 1u)), l = i | j;
+                const bool up = (i & k) == 0;
+                const uint32_t x = s_ids[i], y = s_ids[l];
+                if ((x > y) == up) { s_ids[i] = y; s_ids[l] = x; }
             }
             __syncthreads();
         }
@@ -1063,7 +1062,10 @@ template<class T> int walk_build_t(vb200_ctx* ctx, const vb200_regions* r, const
         cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4);
         uint32_t smem_limit = 32768;        // VB200_TILE_SORT_SMEM_LIMIT: test knob that sends shorter lists down the global-memory path
         if (const char* env = std::getenv("VB200_TILE_SORT_SMEM_LIMIT")) { const long v = std::atol(env); if (v >= 0 && v < 32768) smem_limit = uint32_t(v); }
-        tile_sort_kernel<<<unsigned(w->ntiles), 1024, 32768 * 4, ctx->stream>>>(w->tile_offset, w->tile_list, smem_limit);
+        // shared memory for the longest padded list only (the lengths are on the host): two CTAs per SM instead of one for lists of a few thousand ids
+        uint64_t pmax = 1; while (pmax < w->max_list) pmax <<= 1;
+        const size_t sort_smem = size_t(std::min<uint64_t>(pmax, smem_limit)) * 4;
+        tile_sort_kernel<<<unsigned(w->ntiles), 1024, sort_smem, ctx->stream>>>(w->tile_offset, w->tile_list, smem_limit);
         ctx->launches += 2;
         cudaError_t e2 = cudaGetLastError(), e3 = cudaStreamSynchronize(ctx->stream);
         dfree(ctx, cursor);
