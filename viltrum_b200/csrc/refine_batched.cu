@@ -46,17 +46,30 @@ __global__ void __launch_bounds__(256) select_hist_kernel(const float* __restric
     if (s_hist[threadIdx.x]) atomicAdd(&hist[threadIdx.x], s_hist[threadIdx.x]);
 }
 // walk the digits from the top: the digit where the cumulative count reaches k holds the k-th largest key
-__global__ void select_pick_kernel(SelectState* st, int shift, unsigned* hist) {
-    __shared__ unsigned s_h[256];
-    s_h[threadIdx.x] = hist[threadIdx.x];
+__global__ void __launch_bounds__(256) select_pick_kernel(SelectState* st, int shift, unsigned* hist) {
+    // inclusive suffix sums S[d] = hist[d] + ... + hist[255] (Hillis-Steele over 256 threads); the digit is the largest d >= 1 with S[d] >= k,
+    // or 0 — what a serial walk from 255 down finds, without its 255 dependent steps
+    __shared__ unsigned long long s_s[256];
+    __shared__ int s_d;
+    const unsigned d = threadIdx.x;
+    const unsigned h = hist[d];
+    s_s[d] = h;
+    if (d == 0) s_d = 0;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned long long k = st->k, cum = 0; int d = 255;
-        for (; d > 0; --d) { if (cum + s_h[d] >= k) break; cum += s_h[d]; }
-        st->k = k - cum; st->prefix_val |= unsigned(d) << shift; st->prefix_mask |= 255u << shift;
+    for (unsigned off = 1; off < 256; off <<= 1) {
+        const unsigned long long v = d + off < 256 ? s_s[d + off] : 0ull;
+        __syncthreads();
+        s_s[d] += v;
+        __syncthreads();
     }
+    const unsigned long long k = st->k;
+    if (d >= 1 && s_s[d] >= k) atomicMax(&s_d, int(d));
     __syncthreads();
-    if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+    if (d == unsigned(s_d)) {
+        const unsigned long long cum = s_s[d] - h;          // keys in the digits above d
+        st->k = k - cum; st->prefix_val |= d << shift; st->prefix_mask |= 255u << shift;
+    }
+    hist[d] = 0;
 }
 // per-CTA counts of keys above the threshold and equal to it (CTA = 1024 consecutive regions)
 __global__ void __launch_bounds__(256) select_count_kernel(const float* __restrict__ keys, uint64_t n, const SelectState* __restrict__ st, unsigned* __restrict__ cta_gt, unsigned* __restrict__ cta_eq) {
