@@ -28,48 +28,60 @@ namespace {
 
 struct SelectState { unsigned prefix_val, prefix_mask; unsigned long long k; };
 
+// Radix top-k over the float keys' bits, eight bits per pass, most significant first.  Every pass has its own 256-bin histogram (hist[pass][256]),
+// so no kernel is needed between two passes: a CTA that starts pass p replays the p digit picks made so far from the finished histograms
+// (a 256-thread suffix scan each) instead of reading a state a single-CTA launch would have had to write.  One pick launch after the last
+// pass writes the final state for the count / write kernels.
 __global__ void select_init_kernel(SelectState* st, unsigned long long k, unsigned* hist) {
     if (threadIdx.x == 0) { st->prefix_val = 0; st->prefix_mask = 0; st->k = k; }
-    if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+    for (unsigned i = threadIdx.x; i < 4 * 256; i += blockDim.x) hist[i] = 0;
 }
-// histogram of the next 8-bit digit among the keys that match the prefix found so far
-__global__ void __launch_bounds__(256) select_hist_kernel(const float* __restrict__ keys, uint64_t n, const SelectState* __restrict__ st, int shift, unsigned* __restrict__ hist) {
-    __shared__ unsigned s_hist[256];
-    s_hist[threadIdx.x] = 0;
-    __syncthreads();
-    const unsigned pv = st->prefix_val, pm = st->prefix_mask;
-    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
-        const unsigned k = __float_as_uint(keys[i]);
-        if ((k & pm) == pv) atomicAdd(&s_hist[(k >> shift) & 255u], 1u);
-    }
-    __syncthreads();
-    if (s_hist[threadIdx.x]) atomicAdd(&hist[threadIdx.x], s_hist[threadIdx.x]);
-}
-// walk the digits from the top: the digit where the cumulative count reaches k holds the k-th largest key
-__global__ void __launch_bounds__(256) select_pick_kernel(SelectState* st, int shift, unsigned* hist) {
-    // inclusive suffix sums S[d] = hist[d] + ... + hist[255] (Hillis-Steele over 256 threads); the digit is the largest d >= 1 with S[d] >= k,
-    // or 0 — what a serial walk from 255 down finds, without its 255 dependent steps
-    __shared__ unsigned long long s_s[256];
-    __shared__ int s_d;
+// The digit d whose bucket holds the k-th largest key among the keys of one histogram: the largest d >= 1 with hist[d] + ... + hist[255] >= k,
+// else 0 (what a serial walk from 255 down finds); k is reduced by the keys above that digit.  All 256 threads of the CTA call it.
+__device__ __forceinline__ void select_pick_digit(const unsigned* __restrict__ hist, int shift, unsigned long long& k, unsigned& pv, unsigned& pm,
+                                                  unsigned long long* s_s, int* s_d, unsigned long long* s_cum) {
     const unsigned d = threadIdx.x;
     const unsigned h = hist[d];
+    __syncthreads();                                       // the previous pick's readers are done with the scratch
     s_s[d] = h;
-    if (d == 0) s_d = 0;
+    if (d == 0) *s_d = 0;
     __syncthreads();
-    for (unsigned off = 1; off < 256; off <<= 1) {
+    for (unsigned off = 1; off < 256; off <<= 1) {         // inclusive suffix sums (Hillis-Steele)
         const unsigned long long v = d + off < 256 ? s_s[d + off] : 0ull;
         __syncthreads();
         s_s[d] += v;
         __syncthreads();
     }
-    const unsigned long long k = st->k;
-    if (d >= 1 && s_s[d] >= k) atomicMax(&s_d, int(d));
+    if (d >= 1 && s_s[d] >= k) atomicMax(s_d, int(d));
     __syncthreads();
-    if (d == unsigned(s_d)) {
-        const unsigned long long cum = s_s[d] - h;          // keys in the digits above d
-        st->k = k - cum; st->prefix_val |= d << shift; st->prefix_mask |= 255u << shift;
+    if (d == unsigned(*s_d)) *s_cum = s_s[d] - h;          // keys in the digits above d
+    __syncthreads();
+    k -= *s_cum; pv |= unsigned(*s_d) << shift; pm |= 255u << shift;
+}
+// histogram of pass `pass` (digit at bit 24 - 8 pass) among the keys that match the prefix found by the earlier passes
+__global__ void __launch_bounds__(256) select_hist_kernel(const float* __restrict__ keys, uint64_t n, unsigned long long k0, int pass, unsigned* __restrict__ hist) {
+    __shared__ unsigned s_hist[256];
+    __shared__ unsigned long long s_s[256], s_cum;
+    __shared__ int s_d;
+    s_hist[threadIdx.x] = 0;
+    unsigned long long k = k0; unsigned pv = 0, pm = 0;
+    for (int q = 0; q < pass; ++q) select_pick_digit(hist + q * 256, 24 - 8 * q, k, pv, pm, s_s, &s_d, &s_cum);
+    __syncthreads();
+    const int shift = 24 - 8 * pass;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
+        const unsigned key = __float_as_uint(keys[i]);
+        if ((key & pm) == pv) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
     }
-    hist[d] = 0;
+    __syncthreads();
+    if (s_hist[threadIdx.x]) atomicAdd(&hist[pass * 256 + threadIdx.x], s_hist[threadIdx.x]);
+}
+// after the last pass: the four picks once more, written down for the count / write kernels
+__global__ void __launch_bounds__(256) select_pick_kernel(SelectState* st, unsigned long long k0, const unsigned* __restrict__ hist) {
+    __shared__ unsigned long long s_s[256], s_cum;
+    __shared__ int s_d;
+    unsigned long long k = k0; unsigned pv = 0, pm = 0;
+    for (int q = 0; q < 4; ++q) select_pick_digit(hist + q * 256, 24 - 8 * q, k, pv, pm, s_s, &s_d, &s_cum);
+    if (threadIdx.x == 0) { st->k = k; st->prefix_val = pv; st->prefix_mask = pm; }
 }
 // per-CTA counts of keys above the threshold and equal to it (CTA = 1024 consecutive regions)
 __global__ void __launch_bounds__(256) select_count_kernel(const float* __restrict__ keys, uint64_t n, const SelectState* __restrict__ st, unsigned* __restrict__ cta_gt, unsigned* __restrict__ cta_eq) {
@@ -384,15 +396,13 @@ int run_rounds(vb200_ctx* ctx, const vb200_integrand* f, const vb200_adaptive_pa
         } else {
             select_init_kernel<<<1, 256, 0, s>>>(st, B, hist);
             const unsigned hgrid = unsigned(std::min<uint64_t>((n + 255) / 256, uint64_t(ctx->sm_count) * 8));
-            for (int shift = 24; shift >= 0; shift -= 8) {
-                select_hist_kernel<<<hgrid, 256, 0, s>>>(r->err, n, st, shift, hist);
-                select_pick_kernel<<<1, 256, 0, s>>>(st, shift, hist);
-            }
+            for (int pass = 0; pass < 4; ++pass) select_hist_kernel<<<hgrid, 256, 0, s>>>(r->err, n, B, pass, hist);
+            select_pick_kernel<<<1, 256, 0, s>>>(st, B, hist);
             const unsigned nctas = unsigned((n + 1023) / 1024);
             select_count_kernel<<<nctas, 256, 0, s>>>(r->err, n, st, cta_gt, cta_eq);
             select_scan_kernel<<<1, 1024, 0, s>>>(cta_gt, cta_eq, nctas);
             select_write_kernel<<<nctas, 1024, 0, s>>>(r->err, n, st, cta_gt, cta_eq, sel);
-            ctx->launches += 12;
+            ctx->launches += 9;
         }
         // 2. new sample points of all B splits, one integrand launch
         const uint64_t N = B * Q;
@@ -585,7 +595,7 @@ int generate_batched(vb200_ctx* ctx, const vb200_integrand* f, const vb200_adapt
     auto cleanup = [&] () { dfree(ctx, st); dfree(ctx, hist); dfree(ctx, cta_gt); dfree(ctx, cta_eq); dfree(ctx, sel); dfree(ctx, points); dfree(ctx, vals); dfree(ctx, lohi); };
     auto bail = [&] (int code) { cudaStreamSynchronize(ctx->stream); cleanup(); vb200_regions_free(r); return code; };
     const uint64_t nctas_max = (cap + 1023) / 1024;
-    if (dmalloc(ctx, &st, sizeof(SelectState)) != cudaSuccess || dmalloc(ctx, &hist, 256 * sizeof(unsigned)) != cudaSuccess ||
+    if (dmalloc(ctx, &st, sizeof(SelectState)) != cudaSuccess || dmalloc(ctx, &hist, 4 * 256 * sizeof(unsigned)) != cudaSuccess ||
         dmalloc(ctx, &cta_gt, nctas_max * sizeof(unsigned)) != cudaSuccess || dmalloc(ctx, &cta_eq, nctas_max * sizeof(unsigned)) != cudaSuccess ||
         dmalloc(ctx, &sel, std::min<uint64_t>(max_batch, cap) * sizeof(unsigned)) != cudaSuccess || dmalloc(ctx, &points, maxN * D * sizeof(float)) != cudaSuccess ||
         dmalloc(ctx, &vals, maxN * sizeof(float)) != cudaSuccess || dmalloc(ctx, &lohi, 2 * VB200_MAX_DIM * sizeof(float)) != cudaSuccess) {
