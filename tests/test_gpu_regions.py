@@ -350,14 +350,17 @@ def test_single_launch_selection_equals_multi_kernel_selection(ctx):
     for integ, rule, d, it in (("smooth_edge2", "boole_simpson", 2, 30000), ("shade4_16", "simpson_trapezoidal", 4, 9000), ("x2y2", "simpson_trapezoidal", 2, 700)):
         rng = Range([0.0] * d, [1.0] * d)
         tabs = []
-        for knob in (None, "0", "100"):
+        for knob in (None, "0", "100", "scan"):
+            os.environ.pop("VB200_SELECT_FUSED_MAX", None)
             if knob is None:
                 os.environ.pop("VB200_SELECT_SMALL_MAX", None)
+            elif knob == "scan":                                  # multi-kernel selection with the separate scan of the per-CTA counts (tables of > 4 M regions)
+                os.environ["VB200_SELECT_SMALL_MAX"] = "0"; os.environ["VB200_SELECT_FUSED_MAX"] = "0"
             else:
                 os.environ["VB200_SELECT_SMALL_MAX"] = knob
             regs = ctx.regions_generate_adaptive(integ, rng, rule, "size", "relative", it, 1e-5, batch=0, exact=True)
             tabs.append(regs.download()); regs.free()
-        os.environ.pop("VB200_SELECT_SMALL_MAX", None)
+        os.environ.pop("VB200_SELECT_SMALL_MAX", None); os.environ.pop("VB200_SELECT_FUSED_MAX", None)
         for other in tabs[1:]:
             for k in ("min", "max", "err", "dim", "data"):
                 assert_same_bits(tabs[0][k], other[k], f"{integ} {k}")

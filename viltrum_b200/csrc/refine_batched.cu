@@ -30,8 +30,8 @@ struct SelectState { unsigned prefix_val, prefix_mask; unsigned long long k; };
 
 // Radix top-k over the float keys' bits, eight bits per pass, most significant first.  Every pass has its own 256-bin histogram (hist[pass][256]),
 // so no kernel is needed between two passes: a CTA that starts pass p replays the p digit picks made so far from the finished histograms
-// (a 256-thread suffix scan each) instead of reading a state a single-CTA launch would have had to write.  One pick launch after the last
-// pass writes the final state for the count / write kernels.
+// (a 256-thread suffix scan each) instead of reading a state a single-CTA launch would have had to write; the count kernel replays all four and
+// its first CTA writes the final state for the write kernel.
 __global__ void select_init_kernel(SelectState* st, unsigned long long k, unsigned* hist) {
     if (threadIdx.x == 0) { st->prefix_val = 0; st->prefix_mask = 0; st->k = k; }
     for (unsigned i = threadIdx.x; i < 4 * 256; i += blockDim.x) hist[i] = 0;
@@ -75,24 +75,23 @@ __global__ void __launch_bounds__(256) select_hist_kernel(const float* __restric
     __syncthreads();
     if (s_hist[threadIdx.x]) atomicAdd(&hist[pass * 256 + threadIdx.x], s_hist[threadIdx.x]);
 }
-// after the last pass: the four picks once more, written down for the count / write kernels
-__global__ void __launch_bounds__(256) select_pick_kernel(SelectState* st, unsigned long long k0, const unsigned* __restrict__ hist) {
+// per-CTA counts of keys above the threshold and equal to it (CTA = 1024 consecutive regions)
+__global__ void __launch_bounds__(256) select_count_kernel(const float* __restrict__ keys, uint64_t n, unsigned long long k0, const unsigned* __restrict__ hist, SelectState* __restrict__ st,
+                                                           unsigned* __restrict__ cta_gt, unsigned* __restrict__ cta_eq) {
+    __shared__ unsigned s_gt, s_eq;
     __shared__ unsigned long long s_s[256], s_cum;
     __shared__ int s_d;
+    if (threadIdx.x == 0) { s_gt = 0; s_eq = 0; }
+    // the four digit picks once more: the threshold is complete now; CTA 0 writes it down for the write kernel
     unsigned long long k = k0; unsigned pv = 0, pm = 0;
     for (int q = 0; q < 4; ++q) select_pick_digit(hist + q * 256, 24 - 8 * q, k, pv, pm, s_s, &s_d, &s_cum);
-    if (threadIdx.x == 0) { st->k = k; st->prefix_val = pv; st->prefix_mask = pm; }
-}
-// per-CTA counts of keys above the threshold and equal to it (CTA = 1024 consecutive regions)
-__global__ void __launch_bounds__(256) select_count_kernel(const float* __restrict__ keys, uint64_t n, const SelectState* __restrict__ st, unsigned* __restrict__ cta_gt, unsigned* __restrict__ cta_eq) {
-    __shared__ unsigned s_gt, s_eq;
-    if (threadIdx.x == 0) { s_gt = 0; s_eq = 0; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { st->k = k; st->prefix_val = pv; st->prefix_mask = pm; }
     __syncthreads();
-    const unsigned T = st->prefix_val;
+    const unsigned T = pv;
     unsigned gt = 0, eq = 0;
     for (int j = 0; j < 4; ++j) {
         const uint64_t i = uint64_t(blockIdx.x) * 1024 + j * 256 + threadIdx.x;
-        if (i < n) { const unsigned k = __float_as_uint(keys[i]); gt += k > T; eq += k == T; }
+        if (i < n) { const unsigned kk = __float_as_uint(keys[i]); gt += kk > T; eq += kk == T; }
     }
     atomicAdd(&s_gt, gt); atomicAdd(&s_eq, eq);
     __syncthreads();
@@ -120,9 +119,12 @@ __global__ void __launch_bounds__(1024) select_scan_kernel(unsigned* cta_gt, uns
 }
 // ordered compaction: selected = key > T, or key == T and fewer than k_eq equal keys precede it in table order.
 // Output position: (#selected-by-'>' before) + (#selected ties before); both are monotone in the index, so sel[] is sorted.
+// SCANNED: cta_gt / cta_eq hold exclusive prefixes (select_scan_kernel ran); otherwise they hold the raw per-CTA counts and every CTA sums the
+// entries before its own (tables of up to a few million regions: a few thousand entries — cheaper than one more launch).
+template<bool SCANNED>
 __global__ void __launch_bounds__(1024) select_write_kernel(const float* __restrict__ keys, uint64_t n, const SelectState* __restrict__ st,
                                                             const unsigned* __restrict__ cta_gt, const unsigned* __restrict__ cta_eq, unsigned* __restrict__ sel) {
-    __shared__ unsigned s_wgt[32], s_weq[32];
+    __shared__ unsigned s_wgt[32], s_weq[32], s_pg[32], s_pe[32];
     const unsigned T = st->prefix_val; const unsigned long long k_eq = st->k;
     const uint64_t i = uint64_t(blockIdx.x) * 1024 + threadIdx.x;
     const unsigned key = i < n ? __float_as_uint(keys[i]) : 0u;
@@ -130,8 +132,17 @@ __global__ void __launch_bounds__(1024) select_write_kernel(const float* __restr
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned mg = __ballot_sync(0xffffffffu, gt), me = __ballot_sync(0xffffffffu, eq);
     if (lane == 0) { s_wgt[warp] = __popc(mg); s_weq[warp] = __popc(me); }
+    unsigned bg = 0, be = 0;
+    if constexpr (!SCANNED) {
+        unsigned pg = 0, pe = 0;
+        for (unsigned c = threadIdx.x; c < blockIdx.x; c += 1024) { pg += cta_gt[c]; pe += cta_eq[c]; }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) { pg += __shfl_xor_sync(0xffffffffu, pg, off); pe += __shfl_xor_sync(0xffffffffu, pe, off); }
+        if (lane == 0) { s_pg[warp] = pg; s_pe[warp] = pe; }
+    }
     __syncthreads();
-    unsigned bg = cta_gt[blockIdx.x], be = cta_eq[blockIdx.x];
+    if constexpr (SCANNED) { bg = cta_gt[blockIdx.x]; be = cta_eq[blockIdx.x]; }
+    else { for (unsigned w = 0; w < 32; ++w) { bg += s_pg[w]; be += s_pe[w]; } }
     for (unsigned w = 0; w < warp; ++w) { bg += s_wgt[w]; be += s_weq[w]; }
     bg += __popc(mg & ((1u << lane) - 1u)); be += __popc(me & ((1u << lane) - 1u));
     // ties are taken in table order: tie number `be` is selected iff be < k_eq; ties before it that were selected: min(be, k_eq)
@@ -386,6 +397,8 @@ int run_rounds(vb200_ctx* ctx, const vb200_integrand* f, const vb200_adaptive_pa
     uint64_t n = 1, left = p->iterations;
     uint64_t small_max = SELECT_SMALL_MAX;
     if (const char* env = std::getenv("VB200_SELECT_SMALL_MAX")) small_max = std::min<uint64_t>(std::strtoull(env, nullptr, 10), SELECT_SMALL_MAX);     // test knob
+    unsigned fused_max = 4096;      // per-CTA counts up to which the write kernel sums its own prefix (VB200_SELECT_FUSED_MAX: test knob for the scan kernel's path)
+    if (const char* env = std::getenv("VB200_SELECT_FUSED_MAX")) fused_max = unsigned(std::strtoul(env, nullptr, 10));
     while (left > 0) {
         uint64_t B = n / 4; if (B < 1) B = 1; if (B > left) B = left; if (B > max_batch) B = max_batch;
         if (p->batch > 1 && B > uint64_t(p->batch)) B = uint64_t(p->batch);
@@ -397,12 +410,16 @@ int run_rounds(vb200_ctx* ctx, const vb200_integrand* f, const vb200_adaptive_pa
             select_init_kernel<<<1, 256, 0, s>>>(st, B, hist);
             const unsigned hgrid = unsigned(std::min<uint64_t>((n + 255) / 256, uint64_t(ctx->sm_count) * 8));
             for (int pass = 0; pass < 4; ++pass) select_hist_kernel<<<hgrid, 256, 0, s>>>(r->err, n, B, pass, hist);
-            select_pick_kernel<<<1, 256, 0, s>>>(st, B, hist);
             const unsigned nctas = unsigned((n + 1023) / 1024);
-            select_count_kernel<<<nctas, 256, 0, s>>>(r->err, n, st, cta_gt, cta_eq);
-            select_scan_kernel<<<1, 1024, 0, s>>>(cta_gt, cta_eq, nctas);
-            select_write_kernel<<<nctas, 1024, 0, s>>>(r->err, n, st, cta_gt, cta_eq, sel);
-            ctx->launches += 9;
+            select_count_kernel<<<nctas, 256, 0, s>>>(r->err, n, B, hist, st, cta_gt, cta_eq);
+            if (nctas <= fused_max) {
+                select_write_kernel<false><<<nctas, 1024, 0, s>>>(r->err, n, st, cta_gt, cta_eq, sel);
+                ctx->launches += 7;
+            } else {
+                select_scan_kernel<<<1, 1024, 0, s>>>(cta_gt, cta_eq, nctas);
+                select_write_kernel<true><<<nctas, 1024, 0, s>>>(r->err, n, st, cta_gt, cta_eq, sel);
+                ctx->launches += 8;
+            }
         }
         // 2. new sample points of all B splits, one integrand launch
         const uint64_t N = B * Q;
