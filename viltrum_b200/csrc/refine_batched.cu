@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(1024) select_scan_kernel(unsigned* cta_gt, uns
 // entries before its own (tables of up to a few million regions: a few thousand entries — cheaper than one more launch).
 template<bool SCANNED>
 __global__ void __launch_bounds__(1024) select_write_kernel(const float* __restrict__ keys, uint64_t n, const SelectState* __restrict__ st,
-                                                            const unsigned* __restrict__ cta_gt, const unsigned* __restrict__ cta_eq, unsigned* __restrict__ sel) {
+                                                            const unsigned* __restrict__ cta_gt, const unsigned* __restrict__ cta_eq, unsigned* __restrict__ sel, unsigned* __restrict__ hist) {
     __shared__ unsigned s_wgt[32], s_weq[32], s_pg[32], s_pe[32];
     const unsigned T = st->prefix_val; const unsigned long long k_eq = st->k;
     const uint64_t i = uint64_t(blockIdx.x) * 1024 + threadIdx.x;
@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(1024) select_write_kernel(const float* __restr
     const unsigned long long ties_before = be < k_eq ? be : k_eq;
     if (gt) sel[bg + ties_before] = unsigned(i);
     else if (eq && be < k_eq) sel[bg + be] = unsigned(i);
+    if (blockIdx.x == 0) hist[threadIdx.x] = 0;            // 4 x 256 bins: nobody reads them after the count kernel; clean for the next round
 }
 
 // The same selection for small tables in ONE launch of one CTA (keys in shared memory): the first ~35 of the ~60 rounds of a 10^6-split
@@ -397,6 +398,7 @@ int run_rounds(vb200_ctx* ctx, const vb200_integrand* f, const vb200_adaptive_pa
     uint64_t n = 1, left = p->iterations;
     uint64_t small_max = SELECT_SMALL_MAX;
     if (const char* env = std::getenv("VB200_SELECT_SMALL_MAX")) small_max = std::min<uint64_t>(std::strtoull(env, nullptr, 10), SELECT_SMALL_MAX);     // test knob
+    bool hist_clean = false;
     unsigned fused_max = 4096;      // per-CTA counts up to which the write kernel sums its own prefix (VB200_SELECT_FUSED_MAX: test knob for the scan kernel's path)
     if (const char* env = std::getenv("VB200_SELECT_FUSED_MAX")) fused_max = unsigned(std::strtoul(env, nullptr, 10));
     while (left > 0) {
@@ -407,18 +409,18 @@ int run_rounds(vb200_ctx* ctx, const vb200_integrand* f, const vb200_adaptive_pa
             select_small_kernel<<<1, 1024, 0, s>>>(r->err, unsigned(n), B, st, sel);
             ctx->launches += 1;
         } else {
-            select_init_kernel<<<1, 256, 0, s>>>(st, B, hist);
+            if (!hist_clean) { select_init_kernel<<<1, 256, 0, s>>>(st, B, hist); ctx->launches++; hist_clean = true; }      // later rounds: the write kernel leaves the histograms zeroed
             const unsigned hgrid = unsigned(std::min<uint64_t>((n + 255) / 256, uint64_t(ctx->sm_count) * 8));
             for (int pass = 0; pass < 4; ++pass) select_hist_kernel<<<hgrid, 256, 0, s>>>(r->err, n, B, pass, hist);
             const unsigned nctas = unsigned((n + 1023) / 1024);
             select_count_kernel<<<nctas, 256, 0, s>>>(r->err, n, B, hist, st, cta_gt, cta_eq);
             if (nctas <= fused_max) {
-                select_write_kernel<false><<<nctas, 1024, 0, s>>>(r->err, n, st, cta_gt, cta_eq, sel);
-                ctx->launches += 7;
+                select_write_kernel<false><<<nctas, 1024, 0, s>>>(r->err, n, st, cta_gt, cta_eq, sel, hist);
+                ctx->launches += 6;
             } else {
                 select_scan_kernel<<<1, 1024, 0, s>>>(cta_gt, cta_eq, nctas);
-                select_write_kernel<true><<<nctas, 1024, 0, s>>>(r->err, n, st, cta_gt, cta_eq, sel);
-                ctx->launches += 8;
+                select_write_kernel<true><<<nctas, 1024, 0, s>>>(r->err, n, st, cta_gt, cta_eq, sel, hist);
+                ctx->launches += 7;
             }
         }
         // 2. new sample points of all B splits, one integrand launch
