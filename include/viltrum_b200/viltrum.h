@@ -378,7 +378,8 @@ struct error_metric_absolute { static constexpr int id = VB200_METRIC_ABSOLUTE; 
 struct error_metric_relative { static constexpr int id = VB200_METRIC_RELATIVE; error_metric_relative(double = 1.e-37) {} };
 template<typename EM> struct error_heuristic_default { static constexpr int id = VB200_HEURISTIC_DEFAULT; double size_weight = 0; error_heuristic_default(const EM&) {} using metric = EM;
     void fill(vb200_mixed_heuristic&) const {} };
-template<typename EM> struct error_heuristic_size { static constexpr int id = VB200_HEURISTIC_SIZE; double size_weight; error_heuristic_size(const EM&, double sw = 1.e-5, double = 1.e-37) : size_weight(sw) {} using metric = EM;
+template<typename EM> struct error_heuristic_size { static constexpr int id = VB200_HEURISTIC_SIZE; double size_weight; error_heuristic_size(const EM&, double sw = 1.e-5,
+        double = 1.e-37) : size_weight(sw) {} using metric = EM;
     void fill(vb200_mixed_heuristic&) const {} };
 // error_heuristic_mixed(metric_bins, metric_rest, dimension, bins_weight, size_weight, size_bins, size_rest, error_increase_factor) — reference
 // src/nested/error-heuristic.h:49-98, same argument order and defaults
@@ -474,8 +475,10 @@ public:
     }
 };
 template<typename R, typename EH> auto integrator_adaptive_iterations(const R&, const EH& eh, std::size_t iterations) { return IntegratorAdaptiveIterations<R,EH>(eh, iterations); }
-template<typename R, typename EH> auto integrator_adaptive_iterations_parallel(const R&, const EH& eh, std::size_t iterations, std::size_t = 16) { return IntegratorAdaptiveIterations<R,EH>(eh, iterations); }
-template<typename R> auto integrator_adaptive_iterations(const R& r, std::size_t iterations) { return integrator_adaptive_iterations(r, error_heuristic_default<error_metric_absolute>(error_metric_absolute()), iterations); }
+template<typename R, typename EH> auto integrator_adaptive_iterations_parallel(const R&, const EH& eh, std::size_t iterations,
+        std::size_t = 16) { return IntegratorAdaptiveIterations<R,EH>(eh, iterations); }
+template<typename R> auto integrator_adaptive_iterations(const R& r, std::size_t iterations) { return integrator_adaptive_iterations(r,
+        error_heuristic_default<error_metric_absolute>(error_metric_absolute()), iterations); }
 
 // integrator_adaptive_tolerance(nested(h,l), error_heuristic, tolerance) — reference src/nested/integrator-adaptive-tolerance.h:41-59 ('+=').
 // Leaves come back in the reference's depth-first order, so the bins match the reference bit for bit in an exact build.
@@ -500,8 +503,10 @@ public:
         logger.log_progress(range.volume(), range.volume());
     }
 };
-template<typename R, typename EH, typename = typename EH::metric> auto integrator_adaptive_tolerance(const R&, const EH& eh, float tolerance = 1.e-3f) { return IntegratorAdaptiveTolerance<R,EH>(eh, tolerance); }
-template<typename R> auto integrator_adaptive_tolerance(const R& r, float tolerance = 1.e-3f) { return integrator_adaptive_tolerance(r, error_heuristic_default<error_metric_absolute>(error_metric_absolute()), tolerance); }
+template<typename R, typename EH, typename = typename EH::metric> auto integrator_adaptive_tolerance(const R&, const EH& eh,
+        float tolerance = 1.e-3f) { return IntegratorAdaptiveTolerance<R,EH>(eh, tolerance); }
+template<typename R> auto integrator_adaptive_tolerance(const R& r, float tolerance = 1.e-3f) { return integrator_adaptive_tolerance(r,
+        error_heuristic_default<error_metric_absolute>(error_metric_absolute()), tolerance); }
 template<typename R> auto integrator_adaptive_tolerance(const R& r, double tolerance) { return integrator_adaptive_tolerance(r, float(tolerance)); }
 
 // integrator_crespo2021(iterations, spp, seed) — reference src/control-variates/integrator-crespo2021.h:7-22 ('=')
@@ -558,7 +563,8 @@ auto integrator_adaptive_variance_reduction_parallel(const R&, const EH& eh, std
     return IntegratorAdaptiveVarianceReduction<R, EH>(eh, iterations, spp, seed, CV::id, cv.alpha, RR::id, RS::id, rs.power, rs.cutoff);
 }
 template<typename RR, typename CV, typename RS, typename R, typename EH, typename = decltype(RR::id), typename = decltype(CV::id), typename = decltype(EH::id), typename = decltype(RS::id)>
-auto integrator_adaptive_variance_reduction_parallel_optimized(const R& r, const EH& eh, std::size_t iterations, const RR& rr, const CV& cv, const RS& rs, unsigned long spp, std::size_t seed = 0, std::size_t n = 16) {
+auto integrator_adaptive_variance_reduction_parallel_optimized(const R& r, const EH& eh, std::size_t iterations, const RR& rr, const CV& cv, const RS& rs,
+        unsigned long spp, std::size_t seed = 0, std::size_t n = 16) {
     return integrator_adaptive_variance_reduction_parallel(r, eh, iterations, rr, cv, rs, spp, seed, n);
 }
 template<typename RR, typename CV, typename R, typename EH, typename = decltype(RR::id), typename = decltype(CV::id), typename = decltype(EH::id)>
@@ -624,7 +630,8 @@ template<std::size_t N, typename First> IntegratorFubini<First,N> integrator_fub
 template<std::size_t N> class IntegratorCrespo2021Infinite {
     std::size_t iterations, mc_samples, spp, seed_; int rr = VB200_RR_UNIFORM;
 public:
-    IntegratorCrespo2021Infinite(std::size_t it, std::size_t m, std::size_t s, std::size_t seed, int rr_policy = VB200_RR_UNIFORM) : iterations(it), mc_samples(m), spp(s), seed_(seed), rr(rr_policy) {}
+    IntegratorCrespo2021Infinite(std::size_t it, std::size_t m, std::size_t s, std::size_t seed, int rr_policy = VB200_RR_UNIFORM) : iterations(it), mc_samples(m),
+            spp(s), seed_(seed), rr(rr_policy) {}
     template<typename Bins, std::size_t DIMBINS, typename F, typename R, typename Logger>
     void integrate(Bins& bins, const std::array<std::size_t,DIMBINS>& res, const F& f, const R& range, Logger& logger) const {
         auto& ctx = b200::default_context();
@@ -655,9 +662,11 @@ template<std::size_t N> IntegratorCrespo2021Infinite<N> integrator_crespo2021_in
 // integrator_adaptive_fubini_variance_reduction_parallel_optimized<N>(nested(simpson,trapezoidal), error_heuristic_size(relative), iterations, mc_samples,
 // region_stratification_uniform(), cv_optimize_weight(), region_sampling_uniform(), spp, seed) — reference integrator-adaptive-fubini-variance-reduction-optimized.h:17-23
 template<std::size_t N, typename R, typename EH, typename CV, typename RS>
-IntegratorCrespo2021Infinite<N> integrator_adaptive_fubini_variance_reduction_parallel_optimized(const R&, const EH&, std::size_t iterations, unsigned long mc_samples, const region_stratification_uniform&,
+IntegratorCrespo2021Infinite<N> integrator_adaptive_fubini_variance_reduction_parallel_optimized(const R&, const EH&, std::size_t iterations, unsigned long mc_samples,
+        const region_stratification_uniform&,
                                                                                                   const CV&, const RS&, unsigned long spp, std::size_t seed = 0, std::size_t = 16) {
-    static_assert(std::is_same<R, Nested<Simpson,Trapezoidal>>::value && std::is_same<EH, error_heuristic_size<error_metric_relative>>::value && CV::id == VB200_CV_OPTIMIZE_WEIGHT && RS::id == VB200_RS_UNIFORM,
+    static_assert(std::is_same<R, Nested<Simpson,Trapezoidal>>::value && std::is_same<EH, error_heuristic_size<error_metric_relative>>::value
+            && CV::id == VB200_CV_OPTIMIZE_WEIGHT && RS::id == VB200_RS_UNIFORM,
                   "the device pipeline of the infinite-range control variates is built for the crespo2021 preset (simpson/trapezoidal, size/relative, cv_optimize_weight, region_sampling_uniform)");
     return IntegratorCrespo2021Infinite<N>(iterations, mc_samples, spp, seed, VB200_RR_STRATIFIED);
 }

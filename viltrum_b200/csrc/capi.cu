@@ -201,7 +201,8 @@ extern "C" int vb200_create(int device, vb200_ctx** out) {
     *out = nullptr;
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
-    if (e != cudaSuccess || n == 0) { cudaGetLastError(); return fail(nullptr, VB200_ERR_NO_DEVICE, "no CUDA device available (%s); viltrum_b200 has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"); }
+    if (e != cudaSuccess || n == 0) { cudaGetLastError(); return fail(nullptr, VB200_ERR_NO_DEVICE, "no CUDA device available (%s); viltrum_b200 has no CPU fallback",
+            e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"); }
     if (device < 0 || device >= n) return fail(nullptr, VB200_ERR_INVALID, "device %d outside 0..%d", device, n - 1);
     vb200_ctx* ctx = new (std::nothrow) vb200_ctx;
     if (!ctx) return fail(nullptr, VB200_ERR_NOMEM, "out of host memory");
@@ -475,7 +476,8 @@ static int run_sampler(vb200_ctx* ctx, const vb200_integrand* f, int kind, Launc
     const auto t_fin = std::chrono::steady_clock::now();
     if (threads > 1) ctx->pool.retire();
     const auto t_ret = std::chrono::steady_clock::now();
-    if (job.abort.load()) { cudaStreamSynchronize(ctx->stream); return fail(ctx, VB200_ERR_CUDA, "sampling kernel failed or ended without completing its chunks: %s", cudaGetErrorString(stream_error)); }
+    if (job.abort.load()) { cudaStreamSynchronize(ctx->stream); return fail(ctx, VB200_ERR_CUDA, "sampling kernel failed or ended without completing its chunks: %s",
+            cudaGetErrorString(stream_error)); }
     VB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (trace) {
         const auto t_sync = std::chrono::steady_clock::now();

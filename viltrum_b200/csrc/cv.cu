@@ -911,8 +911,10 @@ int launch_importance(vb200_ctx* ctx, int rs, double power, double cutoff, const
                       const vb200_regions* r, const float* aos, const uint32_t* sreg, const uint32_t* sidx, float* points, float* weight, float* app) {
     const uint64_t N = nb * spp;
     const unsigned grid = unsigned((N + 127) / 128);
-    if (rs == VB200_RS_IMPORTANCE) cv_samples_importance_kernel<D, 1><<<grid, 128, 0, ctx->stream>>>(dom, begin, nb, spp, k0, k1, r->capacity, r->rmin, r->rmax, aos, sreg, sidx, points, weight, app, power, cutoff);
-    else if (rs == VB200_RS_MIS) cv_samples_importance_kernel<D, 2><<<grid, 128, 0, ctx->stream>>>(dom, begin, nb, spp, k0, k1, r->capacity, r->rmin, r->rmax, aos, sreg, sidx, points, weight, app, power, cutoff);
+    if (rs == VB200_RS_IMPORTANCE) cv_samples_importance_kernel<D, 1><<<grid, 128, 0, ctx->stream>>>(dom, begin, nb, spp, k0, k1, r->capacity, r->rmin, r->rmax, aos,
+            sreg, sidx, points, weight, app, power, cutoff);
+    else if (rs == VB200_RS_MIS) cv_samples_importance_kernel<D, 2><<<grid, 128, 0, ctx->stream>>>(dom, begin, nb, spp, k0, k1, r->capacity, r->rmin, r->rmax, aos, sreg,
+            sidx, points, weight, app, power, cutoff);
     else cv_samples_importance_kernel<D, 3><<<grid, 128, 0, ctx->stream>>>(dom, begin, nb, spp, k0, k1, r->capacity, r->rmin, r->rmax, aos, sreg, sidx, points, weight, app, power, cutoff);
     ctx->launches++;
     VB200_CUDA(ctx, cudaGetLastError());
@@ -933,7 +935,8 @@ int dispatch_importance(vb200_ctx* ctx, int rs, double power, double cutoff, con
 struct DevBuf {
     void* p = nullptr; vb200_ctx* owner = nullptr;
     ~DevBuf() { if (owner) dfree(owner, p); }
-    int alloc(vb200_ctx* ctx, size_t bytes) { owner = ctx; if (dmalloc(ctx, &p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return fail(ctx, VB200_ERR_NOMEM, "cudaMalloc of %zu bytes failed", bytes); } return VB200_OK; }
+    int alloc(vb200_ctx* ctx, size_t bytes) { owner = ctx; if (dmalloc(ctx, &p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return fail(ctx, VB200_ERR_NOMEM,
+            "cudaMalloc of %zu bytes failed", bytes); } return VB200_OK; }
     template<class T> T* as() const { return static_cast<T*>(p); }
 };
 
@@ -968,7 +971,8 @@ int cv_tile_run(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r
     if ((rc = ranges.alloc(ctx, r->count * uint64_t(2 * D) * 4))) return rc;
     { const uint64_t n = r->count * uint64_t(2 * D);
       ranges_to_aos_kernel<<<unsigned((n + 255) / 256), 256, 0, ctx->stream>>>(r->count, r->capacity, D, r->rmin, r->rmax, ranges.as<float>()); ctx->launches++; VB200_CUDA(ctx, cudaGetLastError()); }
-    if ((rc = points.alloc(ctx, slots * D * 4)) || (rc = weight.alloc(ctx, slots * 4)) || (rc = app.alloc(ctx, slots * 4)) || (rc = fval.alloc(ctx, slots * 4)) || (rc = owner.alloc(ctx, slots * 2))) return rc;
+    if ((rc = points.alloc(ctx, slots * D * 4)) || (rc = weight.alloc(ctx, slots * 4)) || (rc = app.alloc(ctx, slots * 4)) || (rc = fval.alloc(ctx, slots * 4))
+            || (rc = owner.alloc(ctx, slots * 2))) return rc;
     uint32_t J = spp < uint32_t(CVT_MAXPASS) ? spp : uint32_t(CVT_MAXPASS);
     if (const char* e = std::getenv("VB200_CVT_J")) { const long v = std::atol(e); if (v >= 1 && v <= CVT_MAXPASS && uint32_t(v) < J) J = uint32_t(v); }      // samples per bin and pass (tuning knob)
     uint32_t accpass = CVT_ACCPASS;
@@ -1015,7 +1019,8 @@ int cv_run(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r, con
     if (r->f64 || (f->flags & VB200_INTEGRAND_F64)) return fail(ctx, VB200_ERR_UNSUPPORTED, "control variates are computed in fp32: double region tables / integrands are not supported");
     int rc = check_domain(ctx, p->domain, r->dim); if (rc) return rc;
     if (p->spp > 0xffffffffull) return fail(ctx, VB200_ERR_INVALID, "spp invalid");
-    if (p->weight_strategy != VB200_CV_OPTIMIZE_WEIGHT && p->weight_strategy != VB200_CV_FIXED_WEIGHT) return fail(ctx, VB200_ERR_INVALID, "unknown control-variate weight strategy %d", p->weight_strategy);
+    if (p->weight_strategy != VB200_CV_OPTIMIZE_WEIGHT && p->weight_strategy != VB200_CV_FIXED_WEIGHT) return fail(ctx, VB200_ERR_INVALID,
+            "unknown control-variate weight strategy %d", p->weight_strategy);
     if (p->rr_policy < VB200_RR_UNIFORM || p->rr_policy > VB200_RR_STRATIFIED) return fail(ctx, VB200_ERR_INVALID, "unknown Russian-roulette policy %d", p->rr_policy);
     if (p->rs_policy < VB200_RS_UNIFORM || p->rs_policy > VB200_RS_RUSSIAN_ROULETTE) return fail(ctx, VB200_ERR_INVALID, "unknown region-sampling policy %d", p->rs_policy);
     if (p->rs_policy != VB200_RS_UNIFORM) {
@@ -1057,14 +1062,16 @@ int cv_run(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r, con
         if ((rc = d_wsum.alloc(ctx, nshard * sizeof(double))) || (rc = d_csum.alloc(ctx, nshard * sizeof(double)))) return rc;
         if (policy == VB200_RR_ERROR) { if ((rc = d_rerr.alloc(ctx, r->count * sizeof(float))) || (rc = region_total_errors(ctx, r, w, d_rerr.as<float>()))) return rc; }
         for (int pass = 1; pass <= 2; ++pass) {
-            rc = walk_rr_pass(ctx, r, w, dom, begin, end, begin, policy, pass, d_rerr.as<float>(), d_pdf.as<float>(), d_count.as<uint32_t>(), d_wsum.as<double>(), d_csum.as<double>(), 0, nullptr, nullptr);
+            rc = walk_rr_pass(ctx, r, w, dom, begin, end, begin, policy, pass, d_rerr.as<float>(), d_pdf.as<float>(), d_count.as<uint32_t>(), d_wsum.as<double>(),
+                    d_csum.as<double>(), 0, nullptr, nullptr);
             if (rc) return rc;
         }
     }
 
     // tile-major residual pass (cv_tile_samples_kernel): the throughput path of the crespo2021 preset over a 2-D bin grid
     const char* tile_env = std::getenv("VB200_CV_TILE");       // test knob: 0 = keep the sample-major pipeline
-    const bool tile_path = fast && policy == VB200_RR_UNIFORM && p->rs_policy == VB200_RS_UNIFORM && spp > 0 && w.db == 2 && w.tile[0] == 16 && w.tile[1] == 16 && w.max_list <= uint64_t(CVT_MAXLIST) &&
+    const bool tile_path = fast && policy == VB200_RR_UNIFORM && p->rs_policy == VB200_RS_UNIFORM && spp > 0 && w.db == 2 && w.tile[0] == 16 && w.tile[1] == 16
+            && w.max_list <= uint64_t(CVT_MAXLIST) &&
                            (r->SH == 2 || r->SH == 3 || r->SH == 5) && !(tile_env && tile_env[0] == '0');
     if (tile_path) {
         rc = cv_tile_run(ctx, f, r, p, dom, w, begin, end, total, spp, aos.as<float>(), d_count.as<uint32_t>(), d_approx.as<float>(), st.dev_base);
@@ -1099,19 +1106,26 @@ int cv_run(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r, con
                 rc = walk_rr_pass(ctx, r, w, dom, s0, s1, begin, policy, 3, d_rerr.as<float>(), d_pdf.as<float>(), d_count.as<uint32_t>(), d_wsum.as<double>(), d_csum.as<double>(), spp,
                                   rank.as<uint32_t>(), chosen.as<uint32_t>()); if (rc) return rc;
             } else if (!replay) {
-                if (policy == VB200_RR_STRATIFIED) cv_stratified_ranks_kernel<<<unsigned((N + 255) / 256), 256, 0, ctx->stream>>>(s0, nb, spp, uint32_t(p->seed), uint32_t(p->seed >> 32), cnt, rank.as<uint32_t>(), rrf.as<double>());
+                if (policy == VB200_RR_STRATIFIED) cv_stratified_ranks_kernel<<<unsigned((N + 255) / 256), 256, 0, ctx->stream>>>(s0, nb, spp, uint32_t(p->seed),
+                        uint32_t(p->seed >> 32), cnt, rank.as<uint32_t>(), rrf.as<double>());
                 else cv_ranks_kernel<<<unsigned((N + 255) / 256), 256, 0, ctx->stream>>>(s0, nb, spp, uint32_t(p->seed), uint32_t(p->seed >> 32), cnt, rank.as<uint32_t>());
                 ctx->launches++; VB200_CUDA(ctx, cudaGetLastError());
                 VB200_CUDA(ctx, cudaMemsetAsync(chosen.p, 0, N * 4, ctx->stream));
                 const char* legacy = std::getenv("VB200_CV_RESOLVE_LEGACY");       // test knob: the chunk-by-chunk kernel
                 if (legacy && legacy[0] == '1') {
-                    if (w.db == 1) cv_resolve_kernel<1><<<unsigned(w.ntiles), 256, 0, ctx->stream>>>(g, w.cap, s0, s1, spp, w.pstart, w.pend, w.tile_offset, w.tile_list, rank.as<uint32_t>(), chosen.as<uint32_t>());
-                    else if (w.db == 2) cv_resolve_kernel<2><<<unsigned(w.ntiles), 256, 0, ctx->stream>>>(g, w.cap, s0, s1, spp, w.pstart, w.pend, w.tile_offset, w.tile_list, rank.as<uint32_t>(), chosen.as<uint32_t>());
-                    else cv_resolve_kernel<3><<<unsigned(w.ntiles), 256, 0, ctx->stream>>>(g, w.cap, s0, s1, spp, w.pstart, w.pend, w.tile_offset, w.tile_list, rank.as<uint32_t>(), chosen.as<uint32_t>());
+                    if (w.db == 1) cv_resolve_kernel<1><<<unsigned(w.ntiles), 256, 0, ctx->stream>>>(g, w.cap, s0, s1, spp, w.pstart, w.pend, w.tile_offset, w.tile_list,
+                            rank.as<uint32_t>(), chosen.as<uint32_t>());
+                    else if (w.db == 2) cv_resolve_kernel<2><<<unsigned(w.ntiles), 256, 0, ctx->stream>>>(g, w.cap, s0, s1, spp, w.pstart, w.pend, w.tile_offset,
+                            w.tile_list, rank.as<uint32_t>(), chosen.as<uint32_t>());
+                    else cv_resolve_kernel<3><<<unsigned(w.ntiles), 256, 0, ctx->stream>>>(g, w.cap, s0, s1, spp, w.pstart, w.pend, w.tile_offset, w.tile_list,
+                            rank.as<uint32_t>(), chosen.as<uint32_t>());
                 } else {
-                    if (w.db == 1) cv_resolve_grouped_kernel<1, 16><<<unsigned(w.ntiles), 256, 0, ctx->stream>>>(g, w.cap, s0, s1, spp, w.pstart, w.pend, w.tile_offset, w.tile_list, rank.as<uint32_t>(), chosen.as<uint32_t>());
-                    else if (w.db == 2) cv_resolve_grouped_kernel<2, 16><<<unsigned(w.ntiles), 256, 0, ctx->stream>>>(g, w.cap, s0, s1, spp, w.pstart, w.pend, w.tile_offset, w.tile_list, rank.as<uint32_t>(), chosen.as<uint32_t>());
-                    else cv_resolve_grouped_kernel<3, 16><<<unsigned(w.ntiles), 256, 0, ctx->stream>>>(g, w.cap, s0, s1, spp, w.pstart, w.pend, w.tile_offset, w.tile_list, rank.as<uint32_t>(), chosen.as<uint32_t>());
+                    if (w.db == 1) cv_resolve_grouped_kernel<1, 16><<<unsigned(w.ntiles), 256, 0, ctx->stream>>>(g, w.cap, s0, s1, spp, w.pstart, w.pend, w.tile_offset,
+                            w.tile_list, rank.as<uint32_t>(), chosen.as<uint32_t>());
+                    else if (w.db == 2) cv_resolve_grouped_kernel<2, 16><<<unsigned(w.ntiles), 256, 0, ctx->stream>>>(g, w.cap, s0, s1, spp, w.pstart, w.pend,
+                            w.tile_offset, w.tile_list, rank.as<uint32_t>(), chosen.as<uint32_t>());
+                    else cv_resolve_grouped_kernel<3, 16><<<unsigned(w.ntiles), 256, 0, ctx->stream>>>(g, w.cap, s0, s1, spp, w.pstart, w.pend, w.tile_offset,
+                            w.tile_list, rank.as<uint32_t>(), chosen.as<uint32_t>());
                 }
                 ctx->launches++; VB200_CUDA(ctx, cudaGetLastError());
             } else {
@@ -1126,10 +1140,12 @@ int cv_run(vb200_ctx* ctx, const vb200_integrand* f, const vb200_regions* r, con
                 rp = src_p;
             }
             { size_t tb = sort_bytes;
-              VB200_CUDA(ctx, cub::DeviceRadixSort::SortPairs(sort_tmp.p, tb, chosen.as<uint32_t>(), sreg.as<uint32_t>(), iota.as<uint32_t>(), sidx.as<uint32_t>(), int(N), 0, region_bits, ctx->stream));
+              VB200_CUDA(ctx, cub::DeviceRadixSort::SortPairs(sort_tmp.p, tb, chosen.as<uint32_t>(), sreg.as<uint32_t>(), iota.as<uint32_t>(), sidx.as<uint32_t>(),
+                      int(N), 0, region_bits, ctx->stream));
               ctx->launches += 1 + (region_bits + 7) / 8; }
             if (p->rs_policy != VB200_RS_UNIFORM)
-                rc = dispatch_importance(ctx, p->rs_policy, p->rs_power, p->rs_cutoff, dom, s0, nb, spp, uint32_t(p->seed), uint32_t(p->seed >> 32), r, aos.as<float>(), sreg.as<uint32_t>(), sidx.as<uint32_t>(),
+                rc = dispatch_importance(ctx, p->rs_policy, p->rs_power, p->rs_cutoff, dom, s0, nb, spp, uint32_t(p->seed), uint32_t(p->seed >> 32), r, aos.as<float>(),
+                        sreg.as<uint32_t>(), sidx.as<uint32_t>(),
                                          points.as<float>(), weight.as<float>(), app.as<float>());
             else
                 rc = dispatch_samples(ctx, replay, fast, dom, s0, nb, spp, uint32_t(p->seed), uint32_t(p->seed >> 32), r, aos.as<float>(), sreg.as<uint32_t>(), sidx.as<uint32_t>(), rp,

@@ -384,7 +384,8 @@ int run_rounds(vb200_ctx* ctx, const vb200_integrand* f, const vb200_adaptive_pa
     using Sh = D_::GreedyShape<SH, SL, DIM>;
     const uint64_t cap = r->capacity;
     cudaStream_t s = ctx->stream;
-    root_error_kernel<SH, SL, DIM><<<1, 32, (Sh::SD + Sh::L + 4 * DIM) * sizeof(float), s>>>(cap, r->rmin, r->rmax, r->data, r->err, r->errdim, heur_args(p->heuristic, p->metric, p->size_weight, p->mixed));
+    root_error_kernel<SH, SL, DIM><<<1, 32, (Sh::SD + Sh::L + 4 * DIM) * sizeof(float), s>>>(cap, r->rmin, r->rmax, r->data, r->err, r->errdim, heur_args(p->heuristic,
+            p->metric, p->size_weight, p->mixed));
     ctx->launches++;
     VB200_CUDA(ctx, cudaGetLastError());
     const size_t per_warp = (3 * Sh::SD + 2 * DIM * Sh::L + 4 * DIM + 2 * DIM + 2) * sizeof(float);
@@ -518,7 +519,8 @@ template<int SH, int SL, int DIM>
 int run_tolerance(vb200_ctx* ctx, const vb200_integrand* f, const vb200_tolerance_params* p, TolState& t, uint64_t* n_out) {
     using Sh = D_::GreedyShape<SH, SL, DIM>;
     cudaStream_t s = ctx->stream;
-    root_error_kernel<SH, SL, DIM><<<1, 32, (Sh::SD + Sh::L + 4 * DIM) * sizeof(float), s>>>(t.r->capacity, t.r->rmin, t.r->rmax, t.r->data, t.r->err, t.r->errdim, heur_args(p->heuristic, p->metric, p->size_weight, vb200_mixed_heuristic{}));
+    root_error_kernel<SH, SL, DIM><<<1, 32, (Sh::SD + Sh::L + 4 * DIM) * sizeof(float), s>>>(t.r->capacity, t.r->rmin, t.r->rmax, t.r->data, t.r->err, t.r->errdim,
+            heur_args(p->heuristic, p->metric, p->size_weight, vb200_mixed_heuristic{}));
     ctx->launches++;
     VB200_CUDA(ctx, cudaGetLastError());
     const size_t per_warp = (3 * Sh::SD + 2 * DIM * Sh::L + 4 * DIM + 2 * DIM + 2) * sizeof(float);
@@ -545,7 +547,8 @@ int run_tolerance(vb200_ctx* ctx, const vb200_integrand* f, const vb200_toleranc
             dfree(ctx, sel); rc = fail(ctx, VB200_ERR_CUDA, "tolerance refinement failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
         const uint64_t nsel = h[0];
         if (nsel == 0) { dfree(ctx, sel); break; }
-        if (h[1] >= 128) { dfree(ctx, sel); rc = fail(ctx, VB200_ERR_UNSUPPORTED, "tolerance %g not reached after 128 levels of subdivision (the reference would recurse without bound)", double(p->tolerance)); break; }
+        if (h[1] >= 128) { dfree(ctx, sel); rc = fail(ctx, VB200_ERR_UNSUPPORTED,
+                "tolerance %g not reached after 128 levels of subdivision (the reference would recurse without bound)", double(p->tolerance)); break; }
         if (n + nsel > limit) { dfree(ctx, sel); rc = fail(ctx, VB200_ERR_NOMEM, "tolerance refinement exceeds %llu regions", (unsigned long long)limit); break; }
         if (n + nsel > t.r->capacity) { rc = tol_grow(ctx, t, n, std::max<uint64_t>(2 * t.r->capacity, n + nsel)); if (rc) { dfree(ctx, sel); break; } }
         const uint64_t cap = t.r->capacity;
@@ -651,10 +654,12 @@ int generate_tolerance(vb200_ctx* ctx, const vb200_integrand* f, const vb200_tol
     int rc = regions_alloc(ctx, D, p->rule, cap, &t.r); if (rc) return rc;
     const int S = t.r->SH; const uint64_t sd = uint64_t(t.r->sd);
     float *points = nullptr, *vals = nullptr, *lohi = nullptr;
-    auto cleanup = [&] () { dfree(ctx, points); dfree(ctx, vals); dfree(ctx, lohi); dfree(ctx, t.key_hi); dfree(ctx, t.key_lo); dfree(ctx, t.depth); t.key_hi = t.key_lo = nullptr; t.depth = nullptr; };
+    auto cleanup = [&] () { dfree(ctx, points); dfree(ctx, vals); dfree(ctx, lohi); dfree(ctx, t.key_hi); dfree(ctx, t.key_lo); dfree(ctx, t.depth);
+            t.key_hi = t.key_lo = nullptr; t.depth = nullptr; };
     auto bail = [&] (int code) { cudaStreamSynchronize(ctx->stream); cleanup(); vb200_regions_free(t.r); return code; };
     if (dmalloc(ctx, &t.key_hi, cap * 8) != cudaSuccess || dmalloc(ctx, &t.key_lo, cap * 8) != cudaSuccess || dmalloc(ctx, &t.depth, cap * 4) != cudaSuccess ||
-        dmalloc(ctx, &points, sd * D * sizeof(float)) != cudaSuccess || dmalloc(ctx, &vals, sd * sizeof(float)) != cudaSuccess || dmalloc(ctx, &lohi, 2 * VB200_MAX_DIM * sizeof(float)) != cudaSuccess) {
+        dmalloc(ctx, &points, sd * D * sizeof(float)) != cudaSuccess || dmalloc(ctx, &vals, sd * sizeof(float)) != cudaSuccess || dmalloc(ctx, &lohi,
+                2 * VB200_MAX_DIM * sizeof(float)) != cudaSuccess) {
         cudaGetLastError(); return bail(fail(ctx, VB200_ERR_NOMEM, "working set of the tolerance refinement does not fit")); }
     if (cudaMemsetAsync(t.key_hi, 0, 8, ctx->stream) != cudaSuccess || cudaMemsetAsync(t.key_lo, 0, 8, ctx->stream) != cudaSuccess || cudaMemsetAsync(t.depth, 0, 4, ctx->stream) != cudaSuccess)
         return bail(fail(ctx, VB200_ERR_CUDA, "memset failed"));
@@ -684,7 +689,8 @@ int generate_tolerance(vb200_ctx* ctx, const vb200_integrand* f, const vb200_tol
     auto cleanup2 = [&] () { dfree(ctx, idx_a); dfree(ctx, idx_b); dfree(ctx, k_in); dfree(ctx, k_out); dfree(ctx, tmp); };
     cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, idx_a, idx_b, int(n), 0, 64, s);
     if (dmalloc(ctx, &idx_a, n * 4) != cudaSuccess || dmalloc(ctx, &idx_b, n * 4) != cudaSuccess || dmalloc(ctx, &k_in, n * 8) != cudaSuccess ||
-        dmalloc(ctx, &k_out, n * 8) != cudaSuccess || dmalloc_bytes(ctx, &tmp, tmp_bytes) != cudaSuccess) { cudaGetLastError(); cleanup2(); return bail(fail(ctx, VB200_ERR_NOMEM, "out of device memory")); }
+        dmalloc(ctx, &k_out, n * 8) != cudaSuccess || dmalloc_bytes(ctx, &tmp, tmp_bytes) != cudaSuccess) { cudaGetLastError(); cleanup2(); return bail(fail(ctx,
+                VB200_ERR_NOMEM, "out of device memory")); }
     const unsigned g1 = unsigned((n + 255) / 256);
     tol_iota_kernel<<<g1, 256, 0, s>>>(idx_a, n);
     cudaMemcpyAsync(k_in, t.key_lo, n * 8, cudaMemcpyDeviceToDevice, s);

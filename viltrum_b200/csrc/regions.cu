@@ -35,7 +35,8 @@ int regions_alloc(vb200_ctx* ctx, int dim, int rule, uint64_t capacity, vb200_re
     if (rule_samples(rule, &SH, &SL)) return fail(ctx, VB200_ERR_INVALID, "unknown rule %d", rule);
     if (dim < 1 || dim > VB200_MAX_DIM) return fail(ctx, VB200_ERR_INVALID, "region dimension %d outside 1..%d", dim, VB200_MAX_DIM);
     uint64_t sd = 1; for (int i = 0; i < dim; ++i) { sd *= uint64_t(SH); if (sd > (1ull << 40)) break; }
-    if (VB200_RULE_IS_STEPS(rule) ? (sd > (1ull << 22) || capacity != 1) : sd > 15625) return fail(ctx, VB200_ERR_UNSUPPORTED, "%llu samples per region: beyond the reference's own limit (VILTRUM_MAX_DIMENSIONS_REGION, region.h:16-18)", (unsigned long long)sd);
+    if (VB200_RULE_IS_STEPS(rule) ? (sd > (1ull << 22) || capacity != 1) : sd > 15625) return fail(ctx, VB200_ERR_UNSUPPORTED,
+            "%llu samples per region: beyond the reference's own limit (VILTRUM_MAX_DIMENSIONS_REGION, region.h:16-18)", (unsigned long long)sd);
     vb200_regions* r = new (std::nothrow) vb200_regions;
     if (!r) return fail(ctx, VB200_ERR_NOMEM, "out of host memory");
     r->ctx = ctx; r->dim = dim; r->rule = rule; r->SH = SH; r->SL = SL; r->sd = int(sd); r->capacity = capacity; r->count = 0; r->f64 = f64;
@@ -169,7 +170,8 @@ static int generate_single_t(vb200_ctx* ctx, const vb200_integrand* f, int dim, 
     VB200_CUDA(ctx, cudaSetDevice(ctx->device));
     const bool f64 = sizeof(T) == 8;
     if (f->dim <= 0 || dim != f->dim) return fail(ctx, VB200_ERR_INVALID, "range has %d dimensions, integrand takes %d", dim, f->dim);
-    if (bool(f->flags & VB200_INTEGRAND_F64) != f64) return fail(ctx, VB200_ERR_INVALID, "integrand '%s' computes in %s, the range is %s", f->name ? f->name : "?", (f->flags & VB200_INTEGRAND_F64) ? "double" : "float", f64 ? "double" : "float");
+    if (bool(f->flags & VB200_INTEGRAND_F64) != f64) return fail(ctx, VB200_ERR_INVALID, "integrand '%s' computes in %s, the range is %s", f->name ? f->name : "?",
+            (f->flags & VB200_INTEGRAND_F64) ? "double" : "float", f64 ? "double" : "float");
     vb200_regions* r = nullptr;
     int rc = regions_alloc(ctx, f->dim, rule, 1, &r, f64); if (rc) return rc;
     auto bail = [&] (int code) { vb200_regions_free(r); return code; };
@@ -1069,7 +1071,8 @@ template<class T> int walk_build_t(vb200_ctx* ctx, const vb200_regions* r, const
         ctx->launches += 2;
         cudaError_t e2 = cudaGetLastError(), e3 = cudaStreamSynchronize(ctx->stream);
         dfree(ctx, cursor);
-        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) return bail(fail(ctx, VB200_ERR_CUDA, "tile list construction failed: %s", cudaGetErrorString(e3 != cudaSuccess ? e3 : e2 != cudaSuccess ? e2 : e1)));
+        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) return bail(fail(ctx, VB200_ERR_CUDA, "tile list construction failed: %s",
+                cudaGetErrorString(e3 != cudaSuccess ? e3 : e2 != cudaSuccess ? e2 : e1)));
     } else {
         tile_lists_kernel<true><<<unsigned(w->ntiles), 256, 0, ctx->stream>>>(g, n, cap, begin, end, w->pstart, w->pend, nullptr, w->tile_offset, w->tile_list);
         ctx->launches++;
@@ -1134,7 +1137,8 @@ int walk_pdf_patches(vb200_ctx* ctx, const vb200_regions* r, const BinWalk& w, f
     auto cleanup = [&] (float* keep) { for (float* b : bufs) if (b && b != keep) dfree(ctx, b); };
     for (int m = D; m > db; --m) {
         int lower = 1; for (int i = 0; i < m - 1; ++i) lower *= 3;
-        if (!bufs[which] && dmalloc(ctx, &bufs[which], biggest * cap * sizeof(float)) != cudaSuccess) { cudaGetLastError(); cleanup(nullptr); return fail(ctx, VB200_ERR_NOMEM, "cudaMalloc failed (pdf patches)"); }
+        if (!bufs[which] && dmalloc(ctx, &bufs[which], biggest * cap * sizeof(float)) != cudaSuccess) { cudaGetLastError(); cleanup(nullptr); return fail(ctx,
+                VB200_ERR_NOMEM, "cudaMalloc failed (pdf patches)"); }
         dim3 grid(unsigned((n + 127) / 128), unsigned(lower));
         pdf_fold_last_dim_kernel<float><<<grid, 128, 0, ctx->stream>>>(n, cap, lower, cur, bufs[which]);
         ctx->launches++;
@@ -1157,11 +1161,13 @@ int walk_rr_pass(vb200_ctx* ctx, const vb200_regions* r, const BinWalk& w, const
                  const float* rerr, const float* pdf_patches, const uint32_t* count, double* wsum, double* csum, uint32_t spp, const uint32_t* raw, uint32_t* chosen) {
     const DomT<float> dom = to_dom(domain);
     const TileGeom g = make_geom<float>(w, dom);
-    if (policy == VB200_RR_PDF && (w.S != 3 || !pdf_patches)) return fail(ctx, VB200_ERR_UNSUPPORTED, "rr_pdf_region needs a Simpson-based rule (only Simpson defines pdf_integral_subrange, rules.h:151)");
+    if (policy == VB200_RR_PDF && (w.S != 3 || !pdf_patches)) return fail(ctx, VB200_ERR_UNSUPPORTED,
+            "rr_pdf_region needs a Simpson-based rule (only Simpson defines pdf_integral_subrange, rules.h:151)");
     const float* patches = policy == VB200_RR_PDF ? pdf_patches : w.patches;
     const double ff = rr_floor_factor(policy);
 #define VB200_RRW(SS, DD) if (w.S == SS && w.db == DD) { walk_rr_kernel<SS, DD><<<unsigned(w.ntiles), 256, 0, ctx->stream>>>(g, dom, w.cap, begin, end, base, r->dim, policy, pass, ff, \
-        patches, r->rmin, r->rmax, w.volume, w.pstart, w.pend, w.tile_offset, w.tile_list, rerr, count, wsum, csum, spp, raw, chosen); ctx->launches++; VB200_CUDA(ctx, cudaGetLastError()); return VB200_OK; }
+        patches, r->rmin, r->rmax, w.volume, w.pstart, w.pend, w.tile_offset, w.tile_list, rerr, count, wsum, csum, spp, raw, chosen); ctx->launches++; VB200_CUDA(ctx,
+                cudaGetLastError()); return VB200_OK; }
     VB200_RRW(2, 1) VB200_RRW(2, 2) VB200_RRW(2, 3) VB200_RRW(3, 1) VB200_RRW(3, 2) VB200_RRW(3, 3) VB200_RRW(5, 1) VB200_RRW(5, 2) VB200_RRW(5, 3)
 #undef VB200_RRW
     return fail(ctx, VB200_ERR_UNSUPPORTED, "no weighted roulette walk for rule with %d samples and %d binned dimensions", w.S, w.db);
@@ -1395,7 +1401,8 @@ static int generate_greedy_t(vb200_ctx* ctx, const vb200_integrand* f, int rule,
     if (dmalloc(ctx, &range, cap * 2 * D * sizeof(T)) != cudaSuccess || dmalloc(ctx, &data, cap * sd * sizeof(T)) != cudaSuccess ||
         dmalloc(ctx, &err, cap * sizeof(T)) != cudaSuccess || (key64 && dmalloc(ctx, &key, cap * sizeof(double)) != cudaSuccess) ||
         dmalloc_bytes(ctx, &heap, (n + 1) * (key64 ? 16 : 8)) != cudaSuccess ||
-        dmalloc(ctx, &hsize, sizeof(uint64_t)) != cudaSuccess) { cudaGetLastError(); return bail(fail(ctx, VB200_ERR_NOMEM, "working set of the greedy refinement (%llu region slots) does not fit", (unsigned long long)cap)); }
+        dmalloc(ctx, &hsize, sizeof(uint64_t)) != cudaSuccess) { cudaGetLastError(); return bail(fail(ctx, VB200_ERR_NOMEM,
+                "working set of the greedy refinement (%llu region slots) does not fit", (unsigned long long)cap)); }
     vb200_greedy_launch a; std::memset(&a, 0, sizeof(a));
     a.dim = D; a.rule = rule; a.heuristic = heuristic; a.metric = metric; a.size_weight = size_weight;
     a.iterations = iterations; a.capacity = cap; a.range = range; a.data = data; a.err = err; a.heap = heap; a.heap_size = hsize; a.key64 = key;
@@ -1411,8 +1418,10 @@ static int generate_greedy_t(vb200_ctx* ctx, const vb200_integrand* f, int rule,
         return bail(fail(ctx, VB200_ERR_CUDA, "greedy refinement kernel failed: %s", cudaGetErrorString(cudaGetLastError())));
     if (got != n) return bail(fail(ctx, VB200_ERR_CUDA, "greedy refinement ended with %llu regions, expected %llu", (unsigned long long)got, (unsigned long long)n));
     dim3 grid(unsigned((n + 255) / 256), unsigned(sd < 32 ? sd : 32));
-    if (key64) compact_heap_order_kernel<T, true><<<grid, 256, 0, ctx->stream>>>(n, n, D, int(sd), heap, range, data, RegCols<T>::rmin(r), RegCols<T>::rmax(r), RegCols<T>::data(r), RegCols<T>::err(r), r->errdim);
-    else compact_heap_order_kernel<T, false><<<grid, 256, 0, ctx->stream>>>(n, n, D, int(sd), heap, range, data, RegCols<T>::rmin(r), RegCols<T>::rmax(r), RegCols<T>::data(r), RegCols<T>::err(r), r->errdim);
+    if (key64) compact_heap_order_kernel<T, true><<<grid, 256, 0, ctx->stream>>>(n, n, D, int(sd), heap, range, data, RegCols<T>::rmin(r), RegCols<T>::rmax(r),
+            RegCols<T>::data(r), RegCols<T>::err(r), r->errdim);
+    else compact_heap_order_kernel<T, false><<<grid, 256, 0, ctx->stream>>>(n, n, D, int(sd), heap, range, data, RegCols<T>::rmin(r), RegCols<T>::rmax(r),
+            RegCols<T>::data(r), RegCols<T>::err(r), r->errdim);
     ctx->launches++;
     if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess)
         return bail(fail(ctx, VB200_ERR_CUDA, "heap-order compaction failed: %s", cudaGetErrorString(cudaGetLastError())));
@@ -1446,7 +1455,8 @@ extern "C" int vb200_regions_generate_adaptive(vb200_ctx* ctx, const vb200_integ
     if (f->dim <= 0 || p->domain.dim != f->dim) return fail(ctx, VB200_ERR_INVALID, "range has %d dimensions, integrand takes %d", p->domain.dim, f->dim);
     int SH, SL;
     if (rule_samples(p->rule, &SH, &SL) || SL == 0) return fail(ctx, VB200_ERR_INVALID, "adaptive refinement needs a nested(high,low) rule (got %d)", p->rule);
-    if (p->heuristic != VB200_HEURISTIC_DEFAULT && p->heuristic != VB200_HEURISTIC_SIZE && p->heuristic != VB200_HEURISTIC_MIXED) return fail(ctx, VB200_ERR_INVALID, "unknown heuristic %d", p->heuristic);
+    if (p->heuristic != VB200_HEURISTIC_DEFAULT && p->heuristic != VB200_HEURISTIC_SIZE && p->heuristic != VB200_HEURISTIC_MIXED) return fail(ctx, VB200_ERR_INVALID,
+            "unknown heuristic %d", p->heuristic);
     if (p->metric != VB200_METRIC_ABSOLUTE && p->metric != VB200_METRIC_RELATIVE) return fail(ctx, VB200_ERR_INVALID, "unknown metric %d", p->metric);
     if (int rcm = check_mixed(ctx, p->heuristic, p->mixed)) return rcm;
     if (f->flags & VB200_INTEGRAND_F64) return fail(ctx, VB200_ERR_INVALID, "double-precision integrand: use vb200_regions_generate_adaptive_f64");
@@ -1463,7 +1473,8 @@ extern "C" int vb200_regions_generate_adaptive_f64(vb200_ctx* ctx, const vb200_i
     if (f->dim <= 0 || p->domain.dim != f->dim) return fail(ctx, VB200_ERR_INVALID, "range has %d dimensions, integrand takes %d", p->domain.dim, f->dim);
     int SH, SL;
     if (rule_samples(p->rule, &SH, &SL) || SL == 0) return fail(ctx, VB200_ERR_INVALID, "adaptive refinement needs a nested(high,low) rule (got %d)", p->rule);
-    if (p->heuristic != VB200_HEURISTIC_DEFAULT && p->heuristic != VB200_HEURISTIC_SIZE && p->heuristic != VB200_HEURISTIC_MIXED) return fail(ctx, VB200_ERR_INVALID, "unknown heuristic %d", p->heuristic);
+    if (p->heuristic != VB200_HEURISTIC_DEFAULT && p->heuristic != VB200_HEURISTIC_SIZE && p->heuristic != VB200_HEURISTIC_MIXED) return fail(ctx, VB200_ERR_INVALID,
+            "unknown heuristic %d", p->heuristic);
     if (p->metric != VB200_METRIC_ABSOLUTE && p->metric != VB200_METRIC_RELATIVE) return fail(ctx, VB200_ERR_INVALID, "unknown metric %d", p->metric);
     if (int rcm = check_mixed(ctx, p->heuristic, p->mixed)) return rcm;
     if (p->iterations >= (1ull << 27)) return fail(ctx, VB200_ERR_UNSUPPORTED, "more than 2^27 iterations");
