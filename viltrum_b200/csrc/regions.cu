@@ -1166,8 +1166,7 @@ int walk_rr_pass(vb200_ctx* ctx, const vb200_regions* r, const BinWalk& w, const
     const float* patches = policy == VB200_RR_PDF ? pdf_patches : w.patches;
     const double ff = rr_floor_factor(policy);
 #define VB200_RRW(SS, DD) if (w.S == SS && w.db == DD) { walk_rr_kernel<SS, DD><<<unsigned(w.ntiles), 256, 0, ctx->stream>>>(g, dom, w.cap, begin, end, base, r->dim, policy, pass, ff, \
-        patches, r->rmin, r->rmax, w.volume, w.pstart, w.pend, w.tile_offset, w.tile_list, rerr, count, wsum, csum, spp, raw, chosen); ctx->launches++; VB200_CUDA(ctx,
-                cudaGetLastError()); return VB200_OK; }
+        patches, r->rmin, r->rmax, w.volume, w.pstart, w.pend, w.tile_offset, w.tile_list, rerr, count, wsum, csum, spp, raw, chosen); ctx->launches++; VB200_CUDA(ctx, cudaGetLastError()); return VB200_OK; }
     VB200_RRW(2, 1) VB200_RRW(2, 2) VB200_RRW(2, 3) VB200_RRW(3, 1) VB200_RRW(3, 2) VB200_RRW(3, 3) VB200_RRW(5, 1) VB200_RRW(5, 2) VB200_RRW(5, 3)
 #undef VB200_RRW
     return fail(ctx, VB200_ERR_UNSUPPORTED, "no weighted roulette walk for rule with %d samples and %d binned dimensions", w.S, w.db);
