@@ -226,10 +226,15 @@ extern "C" int vb200_create(int device, vb200_ctx** out) {
     return VB200_OK;
 }
 
+static void ktimer_drop(vb200_ctx* ctx) {
+    for (auto& e : ctx->ktimer_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    ctx->ktimer_events.clear();
+}
 extern "C" void vb200_destroy(vb200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    ktimer_drop(ctx);               // a timer left on: its events go with the context
     vb200::orphan_regions(ctx);
     vb200::comm_release(ctx);
     for (auto& s : ctx->scratch) if (s) cudaFree(s);
@@ -248,10 +253,6 @@ extern "C" int vb200_synchronize(vb200_ctx* ctx) { if (!ctx) return VB200_ERR_IN
 extern "C" int vb200_sm_count(const vb200_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 extern "C" uint64_t vb200_launch_count(const vb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
-static void ktimer_drop(vb200_ctx* ctx) {
-    for (auto& e : ctx->ktimer_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
-    ctx->ktimer_events.clear();
-}
 extern "C" int vb200_kernel_timer(vb200_ctx* ctx, int enable) {
     if (!ctx) return VB200_ERR_INVALID;
     ctx->ktimer = enable != 0;
