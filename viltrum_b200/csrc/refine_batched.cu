@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(1024) select_small_kernel(const float* __restr
             } else {                                                // everything above bucket 0
                 cum = __shfl_sync(0xffffffffu, run, 0) - s_hist[0];
             }
+            __syncwarp();                                           // every lane has read s_k (racecheck: the shuffles above order execution, not memory)
             if (tid == 0) { s_k = kk - cum; s_pv |= unsigned(d) << shift; s_pm |= 255u << shift; }
         }
         __syncthreads();
